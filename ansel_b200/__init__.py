@@ -1,0 +1,122 @@
+"""ansel_b200 -- thin Python plumbing over libb200iop.so (the C ABI in include/b200iop.h).
+
+The product is the C-ABI CUDA library plus the C module adapters in ansel_b200/iop/; this package
+only loads them (ctypes) so tests and bench.py can drive the same entry points a reference
+maintainer would bind from C.  There is no CPU or PyTorch fallback: if the library is missing or
+no sm_100 device is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200iop.so")
+MODLIB_PATH = os.path.join(HERE, "libb200_modules.so")
+
+# ---- error codes (include/b200iop.h) --------------------------------------------------------
+B200_OK, B200_ERR_CUDA, B200_ERR_ARG, B200_ERR_UNSUPPORTED, B200_ERR_NODEVICE, B200_ERR_NOMEM = range(6)
+
+PIPE_NONE, PIPE_EXPORT, PIPE_FULL, PIPE_PREVIEW, PIPE_THUMBNAIL = range(5)
+
+DEMOSAIC_PPG, DEMOSAIC_AMAZE, DEMOSAIC_VNG4, DEMOSAIC_RCD, DEMOSAIC_LMMSE = 0, 1, 2, 5, 6
+
+
+class Roi(C.Structure):
+    """b200_roi_t == dt_iop_roi_t (src/pixel/format.h:48-52)."""
+    _fields_ = [("x", C.c_int), ("y", C.c_int), ("width", C.c_int), ("height", C.c_int), ("scale", C.c_double)]
+
+
+class Tiling(C.Structure):
+    """b200_tiling_t == dt_develop_tiling_t (src/develop/tiling.h:39-58)."""
+    _fields_ = [("factor", C.c_float), ("factor_cl", C.c_float), ("maxbuf", C.c_float), ("maxbuf_cl", C.c_float),
+                ("overhead", C.c_uint), ("overlap", C.c_uint), ("xalign", C.c_uint), ("yalign", C.c_uint)]
+
+
+class Piece(C.Structure):
+    """b200_piece_t: the fields the hot-path process() bodies read."""
+    _fields_ = [("roi_in", Roi), ("roi_out", Roi), ("filters", C.c_uint32), ("xtrans", (C.c_uint8 * 6) * 6),
+                ("channels", C.c_uint32), ("processed_maximum", C.c_float * 4), ("wb_coeffs", C.c_float * 4),
+                ("buf_in_width", C.c_int), ("buf_in_height", C.c_int), ("pipe_type", C.c_int),
+                ("mask_display", C.c_int), ("iscale", C.c_double), ("exif_iso", C.c_float),
+                ("image_flags", C.c_uint32), ("devid", C.c_int), ("data", C.c_void_p), ("data_size", C.c_size_t)]
+
+
+class DemosaicData(C.Structure):
+    """b200_demosaic_data_t == dt_iop_demosaic_data_t (src/iop/demosaic.c:238-247)."""
+    _fields_ = [("green_eq", C.c_uint32), ("color_smoothing", C.c_uint32), ("demosaicing_method", C.c_uint32),
+                ("lmmse_refine", C.c_uint32), ("median_thrs", C.c_float), ("CAM_to_RGB", (C.c_double * 4) * 3),
+                ("dual_thrs", C.c_float)]
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libb200iop error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libb200iop.so (built in-tree by ansel_b200.build).  Fails loudly when absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -m ansel_b200.build` (needs nvcc)")
+        L = C.CDLL(LIB_PATH)
+        L.b200_last_error.restype = C.c_char_p
+        L.b200_roi_filters.restype = C.c_uint32
+        L.b200_roi_filters.argtypes = [C.c_uint32, C.c_int, C.c_int]
+        L.b200_fc.argtypes = [C.c_int, C.c_int, C.c_uint32]
+        for name in ("b200_demosaic_process_host",):
+            getattr(L, name).argtypes = [C.POINTER(Piece), C.c_void_p, C.c_void_p]
+        for name in ("b200_demosaic_process_dev",):
+            getattr(L, name).argtypes = [C.POINTER(Piece), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b200_demosaic_tiling.argtypes = [C.POINTER(Piece), C.POINTER(Tiling)]
+        L.b200_demosaic_tiling.restype = None
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise B200Error(rc, lib().b200_last_error().decode("utf-8", "replace"))
+
+
+def init(ndev: int = 0) -> int:
+    check(lib().b200_init(ndev))
+    return lib().b200_device_count()
+
+
+def make_piece(width: int, height: int, *, filters: int = 0x94949494, roi_x: int = 0, roi_y: int = 0,
+               processed_maximum=(1.0, 1.0, 1.0, 1.0), wb_coeffs=(2.0, 1.0, 1.5, 0.0), channels: int = 1,
+               pipe_type: int = PIPE_EXPORT, exif_iso: float = 100.0, devid: int = -1, data=None,
+               out_width: int | None = None, out_height: int | None = None, scale: float = 1.0) -> Piece:
+    """Fill a b200_piece_t with the fixed metadata of SURVEY.md 8(d)."""
+    p = Piece()
+    p.roi_in = Roi(roi_x, roi_y, width, height, scale)
+    p.roi_out = Roi(0, 0, out_width or width, out_height or height, scale)
+    p.filters = filters
+    p.channels = channels
+    for k in range(4):
+        p.processed_maximum[k] = processed_maximum[k] if k < len(processed_maximum) else 0.0
+        p.wb_coeffs[k] = wb_coeffs[k] if k < len(wb_coeffs) else 0.0
+    p.buf_in_width, p.buf_in_height = width, height
+    p.pipe_type = pipe_type
+    p.mask_display = 0
+    p.iscale = 1.0
+    p.exif_iso = exif_iso
+    p.image_flags = 0
+    p.devid = devid
+    if data is not None:
+        p._keepalive = data  # noqa: keep the ctypes struct alive with the piece
+        p.data = C.cast(C.pointer(data), C.c_void_p)
+        p.data_size = C.sizeof(data)
+    return p
+
+
+def demosaic_data(method: int = DEMOSAIC_RCD) -> DemosaicData:
+    d = DemosaicData()
+    d.demosaicing_method = method
+    return d

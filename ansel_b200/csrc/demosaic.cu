@@ -1,0 +1,121 @@
+// b200_demosaic_*: the demosaic module's process()/process_cl()/tiling_callback() bodies.
+// Reference: src/iop/demosaic.c:1043-1253 (process), :1916-2013 (tiling_callback).
+#include "runtime.h"
+#include <math.h>
+
+namespace b200
+{
+int rcd_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters,
+                     const float processed_maximum[3], cudaStream_t stream);
+}
+using namespace b200;
+
+#define DEMOSAIC_DUAL 2048 /* iop/demosaic.c:109 */
+
+static int check_piece(const b200_piece_t *piece, const void *in, void *out)
+{
+  if(!piece || !in || !out) return fail(B200_ERR_ARG, "demosaic: NULL argument");
+  if(!piece->data || piece->data_size < sizeof(b200_demosaic_data_t))
+    return fail(B200_ERR_ARG, "demosaic: piece->data is not a b200_demosaic_data_t");
+  if(piece->roi_in.width <= 0 || piece->roi_in.height <= 0) return fail(B200_ERR_ARG, "demosaic: empty roi_in");
+  return B200_OK;
+}
+
+extern "C" int b200_demosaic_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream)
+{
+  int rc = check_piece(piece, d_in, d_out);
+  if(rc) return rc;
+  rc = bind_device(piece->devid);
+  if(rc) return rc;
+  const b200_demosaic_data_t *d = (const b200_demosaic_data_t *)piece->data;
+  // demosaic.c:1071 -- fold the ROI origin into the CFA phase for the tile-local algorithms
+  const uint32_t filters = b200_roi_filters(piece->filters, piece->roi_in.x, piece->roi_in.y);
+  if(filters == 9u) return fail(B200_ERR_UNSUPPORTED, "demosaic: X-Trans sensors are not built (SURVEY.md 8f rank 4)");
+  if(d->green_eq != 0) return fail(B200_ERR_UNSUPPORTED, "demosaic: green equilibration is not built (8f rank 4)");
+  if(d->color_smoothing != 0) return fail(B200_ERR_UNSUPPORTED, "demosaic: colour smoothing is not built (8f rank 4)");
+  if(d->demosaicing_method & DEMOSAIC_DUAL) return fail(B200_ERR_UNSUPPORTED, "demosaic: dual demosaic is not built (8f rank 4)");
+  // roi_out has the size of roi_in with origin 0 for the full demosaicers (demosaic.c:1052-1054)
+  if(piece->roi_out.width != piece->roi_in.width || piece->roi_out.height != piece->roi_in.height)
+    return fail(B200_ERR_UNSUPPORTED, "demosaic: roi_out %dx%d != roi_in %dx%d (downsampling paths are not built)",
+                piece->roi_out.width, piece->roi_out.height, piece->roi_in.width, piece->roi_in.height);
+
+  switch(d->demosaicing_method)
+  {
+    case B200_DEMOSAIC_RCD:
+      return rcd_demosaic_dev((const float *)d_in, (float *)d_out, piece->roi_in.width, piece->roi_in.height, filters,
+                              piece->processed_maximum, (cudaStream_t)stream);
+    default:
+      return fail(B200_ERR_UNSUPPORTED, "demosaic: method %u is not built", d->demosaicing_method);
+  }
+}
+
+extern "C" int b200_demosaic_process_host(const b200_piece_t *piece, const void *in, void *out)
+{
+  int rc = check_piece(piece, in, out);
+  if(rc) return rc;
+  rc = bind_device(piece->devid);
+  if(rc) return rc;
+  const size_t npx_in = (size_t)piece->roi_in.width * piece->roi_in.height;
+  const size_t npx_out = (size_t)piece->roi_out.width * piece->roi_out.height;
+  void *d_in = nullptr, *d_out = nullptr;
+  cudaStream_t s;
+  if((rc = host_stream(&s))) return rc;
+  if((rc = scratch(SLOT_IN, npx_in * sizeof(float), &d_in))) return rc;
+  if((rc = scratch(SLOT_OUT, npx_out * 4 * sizeof(float), &d_out))) return rc;
+  if((rc = copy_h2d(d_in, in, npx_in * sizeof(float), s))) return rc;
+  // The caller's cacheline may hold anything; the reference leaves the alpha of the outer 3 px
+  // and (for frames under 16 px) the whole buffer as found.  Start from the caller's bytes only
+  // in the too-small case; otherwise every pixel is overwritten.
+  if(piece->roi_in.width < 16 || piece->roi_in.height < 16)
+    if((rc = copy_h2d(d_out, out, npx_out * 4 * sizeof(float), s))) return rc;
+  if((rc = b200_demosaic_process_dev(piece, d_in, d_out, (void *)s))) return rc;
+  if((rc = copy_d2h(out, d_out, npx_out * 4 * sizeof(float), s))) return rc;
+  B200_CUDA_TRY(cudaStreamSynchronize(s));
+  return B200_OK;
+}
+
+// tiling_callback(), iop/demosaic.c:1916-2013 (Bayer branches for the methods built here)
+extern "C" void b200_demosaic_tiling(const b200_piece_t *piece, b200_tiling_t *tiling)
+{
+  if(!piece || !tiling || !piece->data) return;
+  const b200_demosaic_data_t *d = (const b200_demosaic_data_t *)piece->data;
+  const float ioratio = (float)piece->roi_out.width * piece->roi_out.height
+                        / ((float)piece->roi_in.width * piece->roi_in.height);
+  const float smooth = d->color_smoothing ? ioratio : 0.0f;
+  const float greeneq = ((piece->filters != 9u) && (d->green_eq != 0)) ? 0.25f : 0.0f;
+  const uint32_t method = d->demosaicing_method & ~DEMOSAIC_DUAL;
+
+  tiling->factor = 1.0f + ioratio;
+  tiling->factor += fmaxf(1.0f + greeneq, smooth);
+  tiling->factor_cl = tiling->factor;
+  tiling->maxbuf = 1.0f;
+  tiling->maxbuf_cl = 1.0f;
+  tiling->overhead = 0;
+  if(method == B200_DEMOSAIC_RCD)
+  {
+    // the CPU figure counts per-thread tile scratch; the device keeps its tiles in shared memory
+    tiling->xalign = 2;
+    tiling->yalign = 2;
+    tiling->overlap = 10;
+    tiling->factor_cl = tiling->factor; // no full-frame temporaries on the device (reference: +3, rcd.c:671-686)
+  }
+  else if(method == B200_DEMOSAIC_AMAZE || method == B200_DEMOSAIC_PPG)
+  {
+    tiling->xalign = 2;
+    tiling->yalign = 2;
+    tiling->overlap = 5;
+  }
+  else
+  {
+    tiling->xalign = 6;
+    tiling->yalign = 6;
+    tiling->overlap = 6;
+  }
+  if(d->demosaicing_method & DEMOSAIC_DUAL)
+  {
+    tiling->factor += 1.0f;
+    tiling->xalign = tiling->xalign > 6 ? tiling->xalign : 6;
+    tiling->yalign = tiling->yalign > 6 ? tiling->yalign : 6;
+    tiling->overlap = tiling->overlap > 6 ? tiling->overlap : 6;
+  }
+}

@@ -46,6 +46,9 @@ typedef int64_t gint64;
 #define G_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #define G_BEGIN_DECLS
 #define G_END_DECLS
+typedef struct _GList { void *data; struct _GList *next, *prev; } GList;
+typedef struct _GHashTable GHashTable;
+typedef struct _GSList { void *data; struct _GSList *next; } GSList;
 #define g_malloc malloc
 #define g_malloc0(n) calloc(1, (n))
 #define g_free free
