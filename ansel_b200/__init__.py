@@ -49,11 +49,37 @@ class DemosaicData(C.Structure):
                 ("dual_thrs", C.c_float)]
 
 
+LUT_SAMPLES = 0x10000
+COLORSPACE_LAB = 6
+FP_CONTRACT, FP_STRICT = 0, 1
+
+
+class Conversion(C.Structure):
+    """b200_conversion_t: what a device kernel needs from dt_colorspaces_conversion_t
+    (src/colorprofiles/conversion.c:58-97)."""
+    _fields_ = [("is_matrix", C.c_int), ("has_clipping", C.c_int), ("matrix", (C.c_float * 4) * 3),
+                ("clip_matrix", (C.c_float * 4) * 3), ("lut_source", C.c_void_p * 3),
+                ("coeffs_source", (C.c_float * 3) * 3), ("lut_target", C.c_void_p * 3),
+                ("coeffs_target", (C.c_float * 3) * 3), ("identity", C.c_uint64), ("fp_mode", C.c_int)]
+
+
+class ColorinData(C.Structure):
+    """b200_colorin_data_t (fields of dt_iop_colorin_data_t, src/iop/colorin.c:145-163)."""
+    _fields_ = [("conversion", C.POINTER(Conversion)), ("type", C.c_int), ("blue_mapping", C.c_int)]
+
+
+class ColoroutData(C.Structure):
+    """b200_colorout_data_t (fields of dt_iop_colorout_data_t, src/iop/colorout.c:94-113)."""
+    _fields_ = [("conversion", C.POINTER(Conversion)), ("type", C.c_int)]
+
+
 class B200Error(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libb200iop error {code}: {msg}")
         self.code = code
 
+
+OPS = ("demosaic", "colorin", "colorout")
 
 _lib = None
 
@@ -69,12 +95,15 @@ def lib() -> C.CDLL:
         L.b200_roi_filters.restype = C.c_uint32
         L.b200_roi_filters.argtypes = [C.c_uint32, C.c_int, C.c_int]
         L.b200_fc.argtypes = [C.c_int, C.c_int, C.c_uint32]
-        for name in ("b200_demosaic_process_host",):
-            getattr(L, name).argtypes = [C.POINTER(Piece), C.c_void_p, C.c_void_p]
-        for name in ("b200_demosaic_process_dev",):
-            getattr(L, name).argtypes = [C.POINTER(Piece), C.c_void_p, C.c_void_p, C.c_void_p]
-        L.b200_demosaic_tiling.argtypes = [C.POINTER(Piece), C.POINTER(Tiling)]
-        L.b200_demosaic_tiling.restype = None
+        for op in OPS:
+            getattr(L, f"b200_{op}_process_host").argtypes = [C.POINTER(Piece), C.c_void_p, C.c_void_p]
+            getattr(L, f"b200_{op}_process_dev").argtypes = [C.POINTER(Piece), C.c_void_p, C.c_void_p, C.c_void_p]
+            getattr(L, f"b200_{op}_tiling").argtypes = [C.POINTER(Piece), C.POINTER(Tiling)]
+            getattr(L, f"b200_{op}_tiling").restype = None
+        L.b200_apply_conversion_dev.argtypes = [C.POINTER(Conversion), C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
+                                                C.c_int, C.c_void_p]
+        L.b200_flt32_eval_dev.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.b200_fit_unbounded_coeffs.argtypes = [C.POINTER(C.c_void_p), C.c_void_p]
         _lib = L
     return _lib
 
@@ -119,4 +148,50 @@ def make_piece(width: int, height: int, *, filters: int = 0x94949494, roi_x: int
 def demosaic_data(method: int = DEMOSAIC_RCD) -> DemosaicData:
     d = DemosaicData()
     d.demosaicing_method = method
+    return d
+
+
+def make_conversion(matrix, *, clip_matrix=None, lut_source=None, coeffs_source=None, lut_target=None,
+                    coeffs_target=None, identity: int = 0, fp_mode: int = FP_CONTRACT) -> Conversion:
+    """Fill a b200_conversion_t from numpy arrays (3x3 matrices, 3 x LUT_SAMPLES float32 curves).
+    The arrays are kept alive on the returned struct."""
+    import numpy as np
+    c = Conversion()
+    c.is_matrix = 1
+    c.has_clipping = 1 if clip_matrix is not None else 0
+    keep = []
+    for i in range(3):
+        for j in range(3):
+            c.matrix[i][j] = float(matrix[i][j])
+            c.clip_matrix[i][j] = float(clip_matrix[i][j]) if clip_matrix is not None else 0.0
+            c.coeffs_source[i][j] = float(coeffs_source[i][j]) if coeffs_source is not None else 0.0
+            c.coeffs_target[i][j] = float(coeffs_target[i][j]) if coeffs_target is not None else 0.0
+    for name, lut in (("lut_source", lut_source), ("lut_target", lut_target)):
+        if lut is not None:
+            arr = np.ascontiguousarray(lut, dtype=np.float32)
+            assert arr.shape == (3, LUT_SAMPLES)
+            keep.append(arr)
+            for k in range(3):
+                getattr(c, name)[k] = arr[k].ctypes.data
+    c.identity = identity
+    c.fp_mode = fp_mode
+    c._keepalive = keep  # noqa
+    return c
+
+
+def colorin_data(conversion: Conversion | None, type_: int = 12) -> ColorinData:
+    d = ColorinData()
+    if conversion is not None:
+        d._keepalive = conversion  # noqa
+        d.conversion = C.pointer(conversion)
+    d.type = type_
+    return d
+
+
+def colorout_data(conversion: Conversion | None, type_: int = 1) -> ColoroutData:
+    d = ColoroutData()
+    if conversion is not None:
+        d._keepalive = conversion  # noqa
+        d.conversion = C.pointer(conversion)
+    d.type = type_
     return d

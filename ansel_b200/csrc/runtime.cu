@@ -319,3 +319,37 @@ extern "C" int b200_fc(int row, int col, uint32_t filters)
 {
   return (int)((filters >> (((((unsigned)row << 1) & 14u) + ((unsigned)col & 1u)) << 1)) & 3u);
 }
+
+// ---- device memory for resident chains (dt_opencl_alloc_device / copy_* analogues) ---------
+extern "C" int b200_dev_alloc(void **ptr, size_t bytes)
+{
+  if(!ptr) return fail(B200_ERR_ARG, "dev_alloc: NULL");
+  int rc = bind_device(-1);
+  if(rc) return rc;
+  cudaError_t e = cudaMalloc(ptr, bytes ? bytes : 1);
+  if(e != cudaSuccess)
+  {
+    *ptr = nullptr;
+    return fail(B200_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  }
+  return B200_OK;
+}
+extern "C" void b200_dev_free(void *ptr)
+{
+  if(ptr && g_alive.load()) cudaFree(ptr);
+}
+extern "C" int b200_copy_host_to_device(void *d_dst, const void *h_src, size_t bytes, void *stream)
+{
+  if(!d_dst || !h_src) return fail(B200_ERR_ARG, "copy_host_to_device: NULL");
+  return copy_h2d(d_dst, h_src, bytes, (cudaStream_t)stream);
+}
+extern "C" int b200_copy_device_to_host(void *h_dst, const void *d_src, size_t bytes, void *stream)
+{
+  if(!h_dst || !d_src) return fail(B200_ERR_ARG, "copy_device_to_host: NULL");
+  return copy_d2h(h_dst, d_src, bytes, (cudaStream_t)stream);
+}
+extern "C" int b200_stream_synchronize(void *stream)
+{
+  B200_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return B200_OK;
+}

@@ -1,0 +1,82 @@
+/* Device-resident module chain: the slice of pixelpipe_process_on_GPU() (src/develop/pixelpipe_gpu.c:191-760)
+ * that matters for throughput -- upload the first module's input once, hand each module's output to
+ * the next as a device buffer (the "borrow the cached vRAM payload" protocol, :219-224,317-328), and
+ * read back only the last output (:456-463).  Host pointers in, host pointers out; the modules run
+ * through their process_cl() adapters.  Cache keys, blending and the CPU fallback ladder stay in the
+ * reference's own pixelpipe code and are not reproduced here.
+ */
+#include "dt_surface.h"
+#include <stdlib.h>
+
+typedef int (*b200_process_cl_fn)(struct dt_iop_module_t *, const dt_dev_pixelpipe_t *, const dt_dev_pixelpipe_iop_t *,
+                                  cl_mem, cl_mem);
+
+typedef struct b200_pipe_node_t
+{
+  b200_process_cl_fn process_cl;   /* the module's process_cl() */
+  struct dt_iop_module_t *module;
+  const dt_dev_pixelpipe_iop_t *piece;
+} b200_pipe_node_t;
+
+/* provided by libb200iop.so (device memory for the chain; dt_opencl_alloc_device / copy analogues) */
+int b200_dev_alloc(void **ptr, size_t bytes);
+void b200_dev_free(void *ptr);
+int b200_copy_host_to_device(void *d_dst, const void *h_src, size_t bytes, void *stream);
+int b200_copy_device_to_host(void *h_dst, const void *d_src, size_t bytes, void *stream);
+int b200_stream_synchronize(void *stream);
+
+static size_t buffer_bytes(const dt_iop_buffer_dsc_t *dsc, const dt_iop_roi_t *roi)
+{
+  return dsc->bpp * (size_t)roi->width * (size_t)roi->height; /* pixelpipe_hb.c:985 */
+}
+
+/* state kept between calls so steady-state runs allocate nothing: two ping-pong device buffers */
+typedef struct b200_pipe_buffers_t
+{
+  void *buf[2];
+  size_t cap[2];
+} b200_pipe_buffers_t;
+
+b200_pipe_buffers_t *b200_pipe_buffers_new(void) { return calloc(1, sizeof(b200_pipe_buffers_t)); }
+void b200_pipe_buffers_free(b200_pipe_buffers_t *b)
+{
+  if(!b) return;
+  for(int k = 0; k < 2; k++) b200_dev_free(b->buf[k]);
+  free(b);
+}
+static int ensure(b200_pipe_buffers_t *b, int k, size_t bytes)
+{
+  if(b->cap[k] >= bytes) return 0;
+  b200_dev_free(b->buf[k]);
+  b->buf[k] = NULL;
+  b->cap[k] = 0;
+  if(b200_dev_alloc(&b->buf[k], bytes)) return 1;
+  b->cap[k] = bytes;
+  return 0;
+}
+
+/* Returns 0 on success (process() convention).  host_in is the first node's input cacheline,
+ * host_out the last node's output cacheline. */
+int b200_pixelpipe_process_on_gpu(const dt_dev_pixelpipe_t *pipe, const b200_pipe_node_t *nodes, int n_nodes,
+                                  b200_pipe_buffers_t *bufs, const void *host_in, void *host_out)
+{
+  if(!pipe || !nodes || n_nodes < 1 || !bufs || !host_in || !host_out) return 1;
+  size_t need[2] = { 0, 0 };
+  for(int k = 0; k < n_nodes; k++)
+  {
+    const size_t bi = buffer_bytes(&nodes[k].piece->dsc_in, &nodes[k].piece->roi_in);
+    const size_t bo = buffer_bytes(&nodes[k].piece->dsc_out, &nodes[k].piece->roi_out);
+    if(bi > need[k & 1]) need[k & 1] = bi;
+    if(bo > need[(k + 1) & 1]) need[(k + 1) & 1] = bo;
+  }
+  if(ensure(bufs, 0, need[0]) || ensure(bufs, 1, need[1])) return 1;
+
+  const size_t in_bytes = buffer_bytes(&nodes[0].piece->dsc_in, &nodes[0].piece->roi_in);
+  if(b200_copy_host_to_device(bufs->buf[0], host_in, in_bytes, pipe->stream)) return 1;
+  for(int k = 0; k < n_nodes; k++)
+    if(!nodes[k].process_cl(nodes[k].module, pipe, nodes[k].piece, bufs->buf[k & 1], bufs->buf[(k + 1) & 1])) return 1;
+  const dt_dev_pixelpipe_iop_t *last = nodes[n_nodes - 1].piece;
+  if(b200_copy_device_to_host(host_out, bufs->buf[n_nodes & 1], buffer_bytes(&last->dsc_out, &last->roi_out), pipe->stream))
+    return 1;
+  return b200_stream_synchronize(pipe->stream);
+}

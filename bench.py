@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- the develop-pipe benchmark contract (see DESIGN.md "Measurement").
+
+  python bench.py --gpus N --steps K --warmup W              # this repo's B200 path
+  python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path (oracle/_ref)
+
+Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): one synthetic 45.44 MP RGGB Bayer frame
+(8256x5504, D-natural, seed 20260922) per step through  demosaic(RCD) -> colorin(matrix) ->
+colorout(matrix + sRGB tone curve).  A "step" is one frame through that chain.
+  value : device-resident chain throughput, MP/s, frames already in HBM, CUDA-event timed.
+  e2e   : the same chain through the C module adapters and the device-resident pixelpipe glue
+          (ansel_b200/iop/), host (pinned) buffers in and out, H2D + D2H inside the timed region.
+Multi-GPU (torchrun): frames are independent, each rank develops its own frame per step, no
+data-path collective (weak scaling, SURVEY.md 8e "batch (C5) replicas").
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "megapixels/sec full develop pipe @45MP"
+UNIT = "MP/s"
+WORKLOAD = "C2: 45MP RGGB Bayer (8256x5504) -> demosaic(RCD) -> colorin(matrix) -> colorout(matrix+sRGB TRC)"
+W45, H45 = 8256, 5504
+SEED = 20260922
+ALGO_BYTES_PER_PX = {"demosaic": 20, "colorin": 32, "colorout": 32}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--width", type=int, default=W45)
+    ap.add_argument("--height", type=int, default=H45)
+    ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the reference's own sources compiled by oracle/Makefile (oracle/_ref), else the port
+# ------------------------------------------------------------------------------------------
+class CpuChain:
+    def __init__(self, w, h):
+        import util
+        self.util = util
+        self.w, self.h = w, h
+        self.kind = "reference" if util.ref("fast") is not None else "port"
+        self.enc = util.srgb_encode_lut()
+        self.co_t = util.fit_unbounded_coeffs(self.enc)
+        self.rgb = [util.aligned_empty((h, w, 4)) for _ in range(3)]
+        self.fp = C.POINTER(C.c_float)
+
+    def _conv(self, src, dst, matrix, lut_t=None, co_t=None):
+        u = self.util
+        m = np.ascontiguousarray(matrix, np.float32).reshape(-1)
+        lt = u.fptr(lut_t) if lut_t is not None else None
+        ct = u.fptr(np.ascontiguousarray(co_t, np.float32).reshape(-1)) if co_t is not None else None
+        if self.kind == "reference":
+            f = u.ref("fast").ref_apply_matrix_conversion
+            f.restype = C.c_int
+            f(u.fptr(src), u.fptr(dst), C.c_size_t(self.w), C.c_size_t(self.h), u.fptr(m), None, C.c_int(0), None, None, lt, ct)
+        else:
+            f = u.oracle().orc_apply_matrix_conversion
+            f.restype = C.c_int
+            f(u.fptr(src), u.fptr(dst), C.c_size_t(self.w), C.c_size_t(self.h), u.fptr(m), None, C.c_int(0), None, None, lt, ct,
+              C.c_int(u.FP_CONTRACT))
+
+    def step(self, mosaic):
+        u = self.util
+        pm = (C.c_float * 3)(1.0, 1.0, 1.0)
+        lib = u.ref("fast") if self.kind == "reference" else u.oracle()
+        name = "ref_rcd_demosaic" if self.kind == "reference" else "orc_rcd_demosaic"
+        f = getattr(lib, name)
+        f.restype = C.c_int
+        f(u.fptr(self.rgb[0]), u.fptr(mosaic), self.w, self.h, C.c_uint32(u.BAYER["RGGB"]), pm, C.c_float(0.0))
+        self._conv(self.rgb[0], self.rgb[1], u.MATRIX_CAM_TO_REC2020)
+        self._conv(self.rgb[1], self.rgb[2], u.MATRIX_REC2020_TO_SRGB, self.enc, self.co_t)
+        return self.rgb[2]
+
+
+def time_cpu(chain, mosaic, warm, steps):
+    for _ in range(warm):
+        chain.step(mosaic)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        chain.step(mosaic)
+        ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import util
+    w, h = args.width, args.height
+    mosaic = util.frame_natural(w, h, SEED)
+    chain = CpuChain(w, h)
+    ts = time_cpu(chain, mosaic, max(args.warmup, 1), args.steps)
+    total = float(np.sum(ts))
+    mps = w * h * len(ts) / total / 1e6
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frame": f"{w}x{h}", "cpu_threads": int(os.environ.get("OMP_NUM_THREADS", cores)),
+                   "what": "reference sources compiled in place (oracle/_ref, release flags)" if chain.kind == "reference"
+                   else "oracle port (oracle/_ref not built)"},
+        "cpu_baseline": {"value": mps, "unit": UNIT, "cores": cores, "kind": chain.kind,
+                         "sample": f"{len(ts)} full {w}x{h} frames through the chain, one per step"},
+        "e2e": {"value": mps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# clocks: sample SM clock and throttle reasons during the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop = [], set(), threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {"nvmlClocksEventReasonHwSlowdown": "hw_slowdown", "nvmlClocksEventReasonHwThermalSlowdown": "hw_thermal_slowdown",
+                 "nvmlClocksEventReasonSwThermalSlowdown": "sw_thermal_slowdown", "nvmlClocksEventReasonSwPowerCap": "sw_power_cap",
+                 "nvmlClocksThrottleReasonHwSlowdown": "hw_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown": "hw_thermal_slowdown",
+                 "nvmlClocksThrottleReasonSwThermalSlowdown": "sw_thermal_slowdown", "nvmlClocksThrottleReasonSwPowerCap": "sw_power_cap"}
+        bits = {getattr(nv, k): v for k, v in names.items() if hasattr(nv, k)}
+        while not self.stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for b, name in bits.items():
+                    if r & b:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        if self.nv:
+            self.t.join(timeout=1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import ansel_b200 as ab
+    import ansel_b200.dtsurface as ds
+    import util
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ab.init()
+    L = ab.lib()
+    w, h = args.width, args.height
+    npx = w * h
+
+    mosaic = util.frame_natural(w, h, SEED + rank)
+    filters = util.BAYER["RGGB"]
+    enc = util.srgb_encode_lut()
+    co_t = np.zeros((3, 3), np.float32)
+    lut_ptrs = (C.c_void_p * 3)(*[enc[k].ctypes.data for k in range(3)])
+    L.b200_fit_unbounded_coeffs(lut_ptrs, co_t.ctypes.data)
+    conv_in = ab.make_conversion(util.MATRIX_CAM_TO_REC2020, identity=0x1001)
+    conv_out = ab.make_conversion(util.MATRIX_REC2020_TO_SRGB, lut_target=enc, coeffs_target=co_t, identity=0x1002)
+    d_dem, d_cin, d_cout = ab.demosaic_data(ab.DEMOSAIC_RCD), ab.colorin_data(conv_in), ab.colorout_data(conv_out)
+    p_dem = ab.make_piece(w, h, filters=filters, data=d_dem, devid=local)
+    p_cin = ab.make_piece(w, h, filters=0, channels=4, data=d_cin, devid=local)
+    p_cout = ab.make_piece(w, h, filters=0, channels=4, data=d_cout, devid=local)
+
+    dev = torch.device("cuda", local)
+    t_mosaic = torch.from_numpy(mosaic).to(dev)
+    t_rgb = [torch.empty((h, w, 4), dtype=torch.float32, device=dev) for _ in range(3)]
+    stream = torch.cuda.current_stream().cuda_stream
+    mod_ms = {"demosaic": [], "colorin": [], "colorout": []}
+    launches = [0]
+
+    def step(record=False):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
+        if record:
+            evs[0].record()
+        ab.check(L.b200_demosaic_process_dev(p_dem, t_mosaic.data_ptr(), t_rgb[0].data_ptr(), stream))
+        if record:
+            evs[1].record()
+        ab.check(L.b200_colorin_process_dev(p_cin, t_rgb[0].data_ptr(), t_rgb[1].data_ptr(), stream))
+        if record:
+            evs[2].record()
+        ab.check(L.b200_colorout_process_dev(p_cout, t_rgb[1].data_ptr(), t_rgb[2].data_ptr(), stream))
+        if record:
+            evs[3].record()
+        launches[0] += 4  # rcd_ring_kernel, rcd_tiles_kernel, convert_kernel x2
+        return evs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region: exactly K steps, device-resident ----------------------------------------
+    launches[0] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        all_evs = [step(record=True) for _ in range(args.steps)]
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    for evs in all_evs:
+        mod_ms["demosaic"].append(evs[0].elapsed_time(evs[1]))
+        mod_ms["colorin"].append(evs[1].elapsed_time(evs[2]))
+        mod_ms["colorout"].append(evs[2].elapsed_time(evs[3]))
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    value = world * npx * args.steps / (ms_max * 1e-3) / 1e6
+    gpu_launches = launches[0]
+
+    # ---- e2e: host buffers through the C module adapters + device-resident pipe glue -----------
+    M = ds.modlib()
+    pipe = ds.make_pipe(devid=local, stream=None)
+    nodes = (ds.PipeNode * 3)()
+    pieces = [ds.make_piece_iop("demosaic", w, h, d_dem, channels_in=1, channels_out=4, filters=filters),
+              ds.make_piece_iop("colorin", w, h, d_cin, channels_in=4, channels_out=4),
+              ds.make_piece_iop("colorout", w, h, d_cout, channels_in=4, channels_out=4)]
+    for k, op in enumerate(("demosaic", "colorin", "colorout")):
+        nodes[k].process_cl = C.cast(getattr(M, f"dt_iop_{op}__process_cl"), C.c_void_p)
+        nodes[k].module = pieces[k].module
+        nodes[k].piece = C.pointer(pieces[k])
+    bufs = M.b200_pipe_buffers_new()
+    h_in = torch.from_numpy(mosaic).pin_memory()
+    h_out = torch.empty((h, w, 4), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        rc = M.b200_pixelpipe_process_on_gpu(C.byref(pipe), nodes, 3, bufs, h_in.data_ptr(), h_out.data_ptr())
+        if rc != 0:
+            raise RuntimeError("e2e chain failed: " + L.b200_last_error().decode())
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * npx * args.e2e_steps / float(t_e.item()) / 1e6
+    M.b200_pipe_buffers_free(bufs)
+
+    # ---- roofline of the dominant kernel (RCD tiles) --------------------------------------------
+    peak, peak_src = peaks()
+    dem_ms = float(np.mean(mod_ms["demosaic"]))
+    achieved = ALGO_BYTES_PER_PX["demosaic"] * npx / (dem_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("rcd_tiles_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    per_module = {k: {"ms": float(np.mean(v)), "algorithmic_GBps": ALGO_BYTES_PER_PX[k] * npx / (float(np.mean(v)) * 1e-3) / 1e9,
+                      "frac_of_hbm_peak": ALGO_BYTES_PER_PX[k] * npx / (float(np.mean(v)) * 1e-3) / 1e9 / peak}
+                  for k, v in mod_ms.items()}
+
+    # ---- CPU baseline, rank 0 at N=1 only, bounded sample ---------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        chain = CpuChain(w, h)
+        ts = time_cpu(chain, mosaic, 1, 4)
+        cores = os.cpu_count() or 1
+        cpu = {"value": w * h / float(np.median(ts)) / 1e6, "unit": UNIT, "cores": cores, "kind": chain.kind,
+               "sample": f"4 full {w}x{h} frames through the same chain after 1 warm-up (median), "
+                         f"{'reference sources, release flags, ' if chain.kind == 'reference' else 'oracle port, '}OpenMP on all host threads"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frame": f"{w}x{h}", "frames_per_step": world,
+                       "parallelism": f"{world} independent frame replicas, no data-path collective",
+                       "l2": "inputs larger than L2: 182 MB mosaic + 3 x 727 MB RGBA per step vs 126 MB L2",
+                       "fp": "RCD: C-standard float semantics (no contraction); colour: reference release-build contraction",
+                       "per_module": per_module},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * npx, "d2h_bytes_per_step": 16 * npx,
+                    "steps": args.e2e_steps,
+                    "path": "dt_iop_<op>__process_cl adapters via b200_pixelpipe_process_on_gpu, pinned host buffers"},
+            "gpu_launches": gpu_launches,
+            "clocks": clk.summary(),
+            "roofline": {"bound": "hbm", "kernel": "rcd_tiles_kernel (+rcd_ring_kernel, <1% of the pair)", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX["demosaic"] * npx,
+                         "avg_launch_ms": dem_ms},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

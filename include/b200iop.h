@@ -101,6 +101,17 @@ int b200_device_count(void);
 /* thread-local, never NULL */
 const char *b200_last_error(void);
 
+/* ---- device memory for callers that keep buffers resident between modules --------------------
+ * The counterparts of dt_opencl_alloc_device_buffer / dt_opencl_copy_host_to_device /
+ * dt_opencl_copy_device_to_host (src/common/opencl.c) used by pixelpipe_gpu.c:317-328,456-463.
+ * `stream` is a cudaStream_t (NULL = default).  Pinned host memory is copied asynchronously;
+ * pageable memory is staged. */
+int b200_dev_alloc(void **ptr, size_t bytes);
+void b200_dev_free(void *ptr);
+int b200_copy_host_to_device(void *d_dst, const void *h_src, size_t bytes, void *stream);
+int b200_copy_device_to_host(void *h_dst, const void *d_src, size_t bytes, void *stream);
+int b200_stream_synchronize(void *stream);
+
 /* integer CFA phase: dt_dev_get_roi_filters() develop/imageop.c:139-142 ->
  * dt_rawspeed_crop_dcraw_filters() imageio/imageio_rawspeed.cc:146-151 ->
  * ColorFilterArray::shiftDcrawFilter() external/rawspeed/.../ColorFilterArray.cpp:143-170 */
@@ -136,6 +147,85 @@ int b200_demosaic_process_host(const b200_piece_t *piece, const void *in, void *
 int b200_demosaic_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
 /* tiling_callback(), iop/demosaic.c:1916-2013 */
 void b200_demosaic_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
+
+/* ---- colorin / colorout (src/iop/colorin.c, src/iop/colorout.c) ----------------------------- */
+#define B200_LUT_SAMPLES 0x10000 /* DT_CONVERSION_LUT_SAMPLES, colorprofiles/conversion.h:67 */
+#define B200_COLORSPACE_LAB 6    /* DT_COLORSPACE_LAB, colorprofiles/profile_types.h:179 */
+#define B200_DISPLAY_MASK 1      /* DT_DEV_PIXELPIPE_DISPLAY_MASK bit of pipe->mask_display */
+
+/* How multiply-adds are rounded.  CONTRACT reproduces the reference's release build on an
+ * FMA-capable x86-64 (-ffp-contract=fast, gcc 13; pinned bit-for-bit against that build);
+ * STRICT is the same source under plain C semantics (-ffp-contract=off). */
+enum
+{
+  B200_FP_CONTRACT = 0,
+  B200_FP_STRICT = 1
+};
+
+/* What a device kernel needs from dt_colorspaces_conversion_t (colorprofiles/conversion.c:58-97);
+ * upstream hands these out through dt_colorspaces_conversion_{is_matrix,has_clipping,matrix,
+ * clip_matrix,source_curve,target_curve,source_coeffs,target_coeffs,identity}()
+ * (conversion.c:503-506,770-830).  Curves are HOST pointers to B200_LUT_SAMPLES floats (NULL =
+ * no curve stage on that side; first entry < 0 = that channel is linear); the library keeps a
+ * device copy keyed by `identity`. */
+typedef struct b200_conversion_t
+{
+  int is_matrix;           /* 0 = lcms2 transform: not built here (B200_ERR_UNSUPPORTED) */
+  int has_clipping;
+  float matrix[3][4];      /* dt_colormatrix_t rows: source -> target, or source -> clip when clipping */
+  float clip_matrix[3][4]; /* clip -> target */
+  const float *lut_source[3];
+  float coeffs_source[3][3]; /* {a, b, c} of b * (a x)^c past white, iop_profile.h:559-562 */
+  const float *lut_target[3];
+  float coeffs_target[3][3];
+  uint64_t identity;       /* 0 = do not cache the curves on the device */
+  int fp_mode;             /* B200_FP_CONTRACT (default) or B200_FP_STRICT */
+} b200_conversion_t;
+
+/* the fields of dt_iop_colorin_data_t (iop/colorin.c:145-163) that process() reads */
+typedef struct b200_colorin_data_t
+{
+  const b200_conversion_t *conversion; /* NULL = passthrough (colorin.c:720-723) */
+  int type;                            /* B200_COLORSPACE_LAB = passthrough */
+  int blue_mapping;                    /* legacy hook (colorin.c:690-709): not built, must be 0 */
+} b200_colorin_data_t;
+
+/* the fields of dt_iop_colorout_data_t (iop/colorout.c:94-113) that process() reads */
+typedef struct b200_colorout_data_t
+{
+  const b200_conversion_t *conversion;
+  int type;
+} b200_colorout_data_t;
+
+/* process(), iop/colorin.c:711-734 / iop/colorout.c:373-389: RGBA float in -> RGBA float out, roi_out sized */
+int b200_colorin_process_host(const b200_piece_t *piece, const void *in, void *out);
+int b200_colorin_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
+int b200_colorout_process_host(const b200_piece_t *piece, const void *in, void *out);
+int b200_colorout_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
+/* default_tiling_callback(), develop/tiling.c:1423-1463: factor 2, no overlap */
+void b200_colorin_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
+void b200_colorout_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
+/* dt_colorspaces_apply_conversion(), colorprofiles/conversion.c:762-766, on device buffers */
+int b200_apply_conversion_dev(const b200_conversion_t *conversion, const void *d_in, void *d_out, size_t width,
+                              size_t height, int copy_alpha, void *stream);
+/* dt_ioppr_init_unbounded_coeffs(), colorprofiles/iop_profile.c:303-329: fit {a,b,c} per channel from a
+ * 3 x B200_LUT_SAMPLES curve set (host side, called from commit_params); returns the number of
+ * non-linear channels */
+int b200_fit_unbounded_coeffs(const float *const lut[3], float coeffs[3][3]);
+
+/* ---- the libm the kernels use ------------------------------------------------------------------
+ * Device restatement of glibc 2.39's single-precision expf/exp2f/logf/log2f/powf (the functions the
+ * reference's CPU path calls; see ansel_b200/csrc/flt32_math.cuh).  Exposed so its bit-compatibility
+ * with the host libm can be verified on the machine the pipe runs on. */
+enum
+{
+  B200_FLT32_EXPF = 0,
+  B200_FLT32_EXP2F = 1,
+  B200_FLT32_LOGF = 2,
+  B200_FLT32_LOG2F = 3,
+  B200_FLT32_POWF = 4
+};
+int b200_flt32_eval_dev(int fn, const float *d_x, const float *d_y, float *d_out, size_t n, void *stream);
 
 #ifdef __cplusplus
 }

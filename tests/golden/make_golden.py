@@ -1,0 +1,41 @@
+"""Generate tests/golden/*.npz from the reference's own sources (oracle/_ref, built by
+oracle/Makefile from /root/reference).  Run in the authoring container only:
+
+    python tests/golden/make_golden.py
+
+Inputs are seeded; the outputs are what libref_strict.so / libref_fast.so returned here
+(gcc 13.3, x86-64 with FMA).  /root/reference does not exist on the GPU box, these files do."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import util  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+assert util.ref("strict") is not None, "build oracle/_ref first (make -C oracle ref)"
+
+for k, (name, filters) in enumerate(util.BAYER.items()):
+    w, h = 214 + 2 * k, 135 + k          # three tile columns, two tile rows, ragged edges
+    m = util.frame_natural(w, h, 100 + k, filters=filters)
+    m[::9, ::7] = -0.01
+    pm = np.array([1.0 + 0.1 * k, 1.0, 1.05], np.float32)
+    np.savez_compressed(os.path.join(OUT, f"rcd_{name}.npz"), mosaic=m, pm=pm,
+                        rgb_strict=util.ref_rcd(m, filters, tuple(pm), kind="strict"))
+
+enc = util.srgb_encode_lut()
+co_t = util.fit_unbounded_coeffs(enc)
+img = util.rgba_test_image(96, 64, 9)
+for case, kw in (("colorin_matrix", dict(matrix=util.MATRIX_CAM_TO_REC2020)),
+                 ("colorin_clip", dict(matrix=util.MATRIX_CAM_TO_REC2020, clip=util.MATRIX_CLIP_IN)),
+                 ("colorout_trc", dict(matrix=util.MATRIX_REC2020_TO_SRGB, lut_t=enc, co_t=co_t))):
+    save = dict(rgba=img, matrix=kw["matrix"], out_strict=util.ref_convert(img, kind="strict", **kw),
+                out_fast=util.ref_convert(img, kind="fast", **kw))
+    if "clip" in kw:
+        save["clip"] = kw["clip"]
+    if "lut_t" in kw:
+        save["lut_t_row"] = enc[0]
+        save["co_t"] = co_t
+    np.savez_compressed(os.path.join(OUT, f"color_{case}.npz"), **save)
+print("golden vectors written to", OUT)

@@ -169,3 +169,116 @@ def frame_edge(w: int, h: int, kind: str) -> np.ndarray:
         m[1::4, 1::5] = 1e-41  # subnormal: flushed by FTZ/DAZ on both sides
         return m.astype(np.float32)
     raise ValueError(kind)
+
+
+# ---- colour conversion fixtures and checkers (SURVEY.md 8d "fixed metadata") -----------------
+LUT_SAMPLES = 0x10000
+FP_STRICT, FP_CONTRACT = 0, 1
+
+# camera RGB -> linear Rec2020 (a fixed, plausible composite; rows sum to ~1) and
+# linear Rec2020 -> linear sRGB (ITU-R BT.2087)
+MATRIX_CAM_TO_REC2020 = np.array([[0.7398, 0.1873, 0.0729],
+                                  [0.0825, 0.9672, -0.0497],
+                                  [0.0209, -0.1264, 1.1055]], np.float32)
+MATRIX_REC2020_TO_SRGB = np.array([[1.6605, -0.5876, -0.0728],
+                                   [-0.1246, 1.1329, -0.0083],
+                                   [-0.0182, -0.1006, 1.1187]], np.float32)
+MATRIX_CLIP_IN = np.array([[0.6274, 0.3293, 0.0433],
+                           [0.0691, 0.9195, 0.0114],
+                           [0.0164, 0.0880, 0.8956]], np.float32)
+
+
+def srgb_encode_lut() -> np.ndarray:
+    """sRGB OETF sampled at 65536 points in double, rounded to float (3 identical channels)."""
+    x = np.arange(LUT_SAMPLES, dtype=np.float64) / (LUT_SAMPLES - 1)
+    y = np.where(x <= 0.0031308, 12.92 * x, 1.055 * np.power(x, 1 / 2.4) - 0.055)
+    return np.ascontiguousarray(np.tile(y.astype(np.float32), (3, 1)))
+
+
+def srgb_decode_lut() -> np.ndarray:
+    x = np.arange(LUT_SAMPLES, dtype=np.float64) / (LUT_SAMPLES - 1)
+    y = np.where(x <= 0.04045, x / 12.92, np.power((x + 0.055) / 1.055, 2.4))
+    return np.ascontiguousarray(np.tile(y.astype(np.float32), (3, 1)))
+
+
+def _lut_at(lut: np.ndarray, v: float) -> np.float32:
+    ft = np.float32(min(max(np.float32(v) * np.float32(LUT_SAMPLES - 1), 0), LUT_SAMPLES - 1))
+    t = int(ft) if ft < LUT_SAMPLES - 2 else LUT_SAMPLES - 2
+    f = np.float32(ft - np.float32(t))
+    return np.float32(lut[t] * (np.float32(1) - f) + lut[t + 1] * f)
+
+
+def fit_unbounded_coeffs(lut3: np.ndarray) -> np.ndarray:
+    """dt_ioppr_init_unbounded_coeffs (colorprofiles/iop_profile.c:303-329) + dt_iop_estimate_exp
+    (develop/imageop_math.h:135-165), in float32."""
+    out = np.zeros((3, 3), np.float32)
+    xs = [np.float32(v) for v in (0.7, 0.8, 0.9, 1.0)]
+    for k in range(3):
+        lut = lut3[k]
+        if lut[0] < 0:
+            out[k, 0] = -1.0
+            continue
+        ys = [_lut_at(lut, x) for x in xs]
+        x0, y0 = xs[-1], ys[-1]
+        g, cnt = np.float32(0), 0
+        for x, y in zip(xs[:-1], ys[:-1]):
+            if y / y0 > 0 and x / x0 > 0:
+                g = np.float32(g + np.float32(np.log(np.float32(y / y0))) / np.float32(np.log(np.float32(x / x0))))
+                cnt += 1
+        g = np.float32(g * np.float32(1.0 / cnt)) if cnt else np.float32(1)
+        out[k] = (np.float32(1) / x0, y0, g)
+    return out
+
+
+def aligned_empty(shape, dtype=np.float32, align: int = 64) -> np.ndarray:
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    raw = np.empty(n + align, np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + n].view(dtype).reshape(shape)
+
+
+def _fp_or_null(a):
+    return fptr(a) if a is not None else None
+
+
+def _conv_args(rgba, matrix, clip, lut_s, co_s, lut_t, co_t):
+    h, w = rgba.shape[:2]
+    src = aligned_empty(rgba.shape)
+    src[...] = rgba
+    dst = aligned_empty(rgba.shape)
+    dst[...] = 0
+    keep = [np.ascontiguousarray(a, np.float32) if a is not None else None for a in (matrix, clip, lut_s, co_s, lut_t, co_t)]
+    args = [fptr(src), fptr(dst), C.c_size_t(w), C.c_size_t(h), _fp_or_null(keep[0].reshape(-1)),
+            _fp_or_null(keep[1].reshape(-1) if keep[1] is not None else None), C.c_int(1 if clip is not None else 0),
+            _fp_or_null(keep[2]), _fp_or_null(keep[3].reshape(-1) if keep[3] is not None else None),
+            _fp_or_null(keep[4]), _fp_or_null(keep[5].reshape(-1) if keep[5] is not None else None)]
+    return src, dst, keep, args
+
+
+def oracle_convert(rgba, matrix, clip=None, lut_s=None, co_s=None, lut_t=None, co_t=None, fp=FP_CONTRACT):
+    src, dst, keep, args = _conv_args(rgba, matrix, clip, lut_s, co_s, lut_t, co_t)
+    f = oracle().orc_apply_matrix_conversion
+    f.restype = C.c_int
+    assert f(*args, C.c_int(fp)) == 0
+    return np.array(dst)
+
+
+def ref_convert(rgba, matrix, clip=None, lut_s=None, co_s=None, lut_t=None, co_t=None, kind="fast"):
+    lib = ref(kind)
+    if lib is None:
+        return None
+    src, dst, keep, args = _conv_args(rgba, matrix, clip, lut_s, co_s, lut_t, co_t)
+    f = lib.ref_apply_matrix_conversion
+    f.restype = C.c_int
+    assert f(*args) == 0
+    return np.array(dst)
+
+
+def rgba_test_image(w: int, h: int, seed: int, lo: float = -0.05, hi: float = 1.6) -> np.ndarray:
+    """RGBA floats covering negatives, [0,1], and values past white (the eval_exp branch)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    a = rng.uniform(lo, hi, (h, w, 4)).astype(np.float32)
+    a[..., 3] = rng.uniform(0, 1, (h, w)).astype(np.float32)
+    a[0, 0, :3] = (0.0, 1.0, 1.0)
+    a[0, 1, :3] = (-0.0, 0.5, 2.0)
+    return a
