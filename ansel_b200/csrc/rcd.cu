@@ -33,7 +33,8 @@ constexpr int KEEP = 94;   // RCD_TILEVALID  rcd.c:75
 constexpr int RING = 9;    // RCD_BORDER     rcd.c:73
 constexpr int EDGE = 6;    // RCD_MARGIN     rcd.c:74
 constexpr int H = T / 2;   // width of a half plane row
-constexpr int NT = 448;    // threads per CTA: 4 rows x 112 columns, or 8 rows x 56 site columns
+constexpr int RG = 8;      // row groups: NT = RG x 112 columns, or 2*RG x 56 site columns
+constexpr int NT = RG * T; // threads per CTA
 constexpr int SMEM_FLOATS = 2 * T * T + 4 * (T * T / 2);
 
 constexpr float kEps = 1e-5f;    // rcd.c:81
@@ -87,8 +88,8 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
   const uint32_t f = a.filters;
 
   // thread -> (column, row group) maps; no integer division by runtime values anywhere below
-  const int x112 = tid % T, y4 = tid / T; // 4 row groups over full-width domains
-  const int x56 = tid % H, y8 = tid / H;  // 8 row groups over every-second-column domains
+  const int x112 = tid % T, y4 = tid / T; // RG row groups over full-width domains
+  const int x56 = tid % H, y8 = tid / H;  // 2*RG row groups over every-second-column domains
 
   // ---- clear everything: the reference's never-written scratch is defined as zero ------------
   {
@@ -99,17 +100,17 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
   __syncthreads();
 
   // ---- step 0: load, clamp, normalise (rcd.c:343-351) ---------------------------------------
-  for(int r = y4; r < tr; r += 4)
+  for(int r = y4; r < tr; r += RG)
     if(x112 < tc) cfa[r * T + x112] = fmaxf(0.0f, __ldg(a.in + (size_t)(row0 + r) * a.width + col0 + x112)) * a.revscaler;
   __syncthreads();
 
   // ---- step 1: squared V/H high-pass, then direction strength (rcd.c:353-390) ----------------
-  for(int r = 3 + y4; r < tr - 3; r += 4)
+  for(int r = 3 + y4; r < tr - 3; r += RG)
     if(x112 >= 4 && x112 < tc - 4) vsq[r * T + x112] = hpf2(cfa + r * T + x112, T);
-  for(int r = 4 + y4; r < tr - 4; r += 4)
+  for(int r = 4 + y4; r < tr - 4; r += RG)
     if(x112 >= 3 && x112 < tc - 3) hsq[r * T + x112] = hpf2(cfa + r * T + x112, 1);
   __syncthreads();
-  for(int r = 4 + y4; r < tr - 4; r += 4)
+  for(int r = 4 + y4; r < tr - 4; r += RG)
     if(x112 >= 4 && x112 < tc - 4)
     {
       const int i = r * T + x112;
@@ -121,14 +122,14 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
   // give the borrowed planes back: zero, then green-at-red/blue starts out as the raw value
   for(int k = tid; k < 2 * T * T; k += NT) grb[k] = 0.0f; // grb, pq, pd, qd are contiguous
   __syncthreads();
-  for(int r = y8; r < tr; r += 8)
+  for(int r = y8; r < tr; r += 2 * RG)
   {
     const int c = (fc(r, 0, f) & 1) + 2 * x56;
     if(c < tc) grb[(r * T + c) / 2] = cfa[r * T + c];
   }
 
   // ---- step 2.1: low-pass at red/blue sites (rcd.c:394-402) ----------------------------------
-  for(int r = 2 + y8; r < tr - 2; r += 8)
+  for(int r = 2 + y8; r < tr - 2; r += 2 * RG)
   {
     const int c = 2 + (fc(r, 0, f) & 1) + 2 * x56;
     if(c < tc - 2)
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
   __syncthreads();
 
   // ---- step 3.1: green at red/blue sites (rcd.c:406-437) -------------------------------------
-  for(int r = 4 + y8; r < tr - 4; r += 8)
+  for(int r = 4 + y8; r < tr - 4; r += 2 * RG)
   {
     const int c = 4 + (fc(r, 0, f) & 1) + 2 * x56;
     if(c < tc - 4)
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
   }
 
   // ---- step 4.0: squared diagonal high-pass at every second column from 3 (rcd.c:442-449) -----
-  for(int r = 3 + y8; r < tr - 3; r += 8)
+  for(int r = 3 + y8; r < tr - 3; r += 2 * RG)
   {
     const int c = 3 + 2 * x56;
     if(c < tc - 3)
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
   __syncthreads();
 
   // ---- step 4.1: P/Q direction strength, overwriting the low-pass (rcd.c:451-459) ------------
-  for(int r = 4 + y8; r < tr - 4; r += 8)
+  for(int r = 4 + y8; r < tr - 4; r += 2 * RG)
   {
     const int c = 4 + (fc(r, 0, f) & 1) + 2 * x56;
     if(c < tc - 4)
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
 
   // ---- step 4.2: opposite colour at red/blue sites (rcd.c:462-491) ---------------------------
   // rgb[c] at the diagonal neighbours is that site's own raw value, i.e. cfa.
-  for(int r = 4 + y8; r < tr - 4; r += 8)
+  for(int r = 4 + y8; r < tr - 4; r += 2 * RG)
   {
     const int c = 4 + (fc(r, 0, f) & 1) + 2 * x56;
     if(c < tc - 4)
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
   // ---- step 4.3 fused with the store of the kept interior (rcd.c:494-554) --------------------
   const int ra = (tv == 0 ? EDGE : RING), rb = tr - (tv == a.nv - 1 ? EDGE : RING);
   const int ca = (th == 0 ? EDGE : RING), cb = tc - (th == a.nh - 1 ? EDGE : RING);
-  for(int r = ra + y8; r < rb; r += 8)
+  for(int r = ra + y8; r < rb; r += 2 * RG)
   {
     const int rbpar = fc(r, 0, f) & 1; // column parity of the red/blue sites in this row
     const int native = fc(r, rbpar, f); // 0 or 2: the colour those sites carry

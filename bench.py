@@ -24,8 +24,15 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+# the CPU arm: keep libgomp's threads where they start (OMP_PROC_BIND=close); must be
+# in the environment before the first OpenMP runtime initialises
+os.environ.setdefault("OMP_PROC_BIND", "close")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import warnings  # noqa: E402
+
+warnings.filterwarnings("ignore")  # numpy notices the FTZ/DAZ mode the reference sets on its threads
 
 import numpy as np  # noqa: E402
 
@@ -121,7 +128,7 @@ def run_reference(args):
     w, h = args.width, args.height
     mosaic = util.frame_natural(w, h, SEED)
     chain = CpuChain(w, h)
-    ts = time_cpu(chain, mosaic, max(args.warmup, 1), args.steps)
+    ts = time_cpu(chain, mosaic, max(args.warmup, 2), args.steps)
     total = float(np.sum(ts))
     mps = w * h * len(ts) / total / 1e6
     cores = os.cpu_count() or 1
@@ -131,7 +138,8 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frame": f"{w}x{h}", "cpu_threads": int(os.environ.get("OMP_NUM_THREADS", cores)),
                    "what": "reference sources compiled in place (oracle/_ref, release flags)" if chain.kind == "reference"
-                   else "oracle port (oracle/_ref not built)"},
+                   else "oracle port (oracle/_ref not built)",
+                   "step_ms": [round(1e3 * t, 1) for t in ts]},
         "cpu_baseline": {"value": mps, "unit": UNIT, "cores": cores, "kind": chain.kind,
                          "sample": f"{len(ts)} full {w}x{h} frames through the chain, one per step"},
         "e2e": {"value": mps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
