@@ -24,9 +24,8 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-# the CPU arm: keep libgomp's threads where they start (OMP_PROC_BIND=close); must be
-# in the environment before the first OpenMP runtime initialises
-os.environ.setdefault("OMP_PROC_BIND", "close")
+# The CPU arm uses whatever OpenMP placement the environment asks for (OMP_PROC_BIND / OMP_PLACES /
+# OMP_NUM_THREADS); by default libgomp's own default: all host threads, unbound.
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
