@@ -73,13 +73,27 @@ class ColoroutData(C.Structure):
     _fields_ = [("conversion", C.POINTER(Conversion)), ("type", C.c_int)]
 
 
+DENOISE_BANDS = 7
+DENOISE_NLMEANS, DENOISE_WAVELETS, DENOISE_VARIANCE, DENOISE_NLMEANS_AUTO, DENOISE_WAVELETS_AUTO = range(5)
+DENOISE_RGB, DENOISE_Y0U0V0 = 0, 1
+
+
+class DenoiseProfileData(C.Structure):
+    """b200_denoiseprofile_data_t (members of dt_iop_denoiseprofile_data_t, src/iop/denoiseprofile.c:352-371)."""
+    _fields_ = [("radius", C.c_float), ("nbhood", C.c_float), ("strength", C.c_float), ("shadows", C.c_float),
+                ("bias", C.c_float), ("scattering", C.c_float), ("central_pixel_weight", C.c_float),
+                ("overshooting", C.c_float), ("a", C.c_float * 3), ("b", C.c_float * 3), ("mode", C.c_int),
+                ("force", (C.c_float * DENOISE_BANDS) * 6), ("wb_adaptive_anscombe", C.c_int),
+                ("fix_anscombe_and_nlmeans_norm", C.c_int), ("use_new_vst", C.c_int), ("wavelet_color_mode", C.c_int)]
+
+
 class B200Error(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libb200iop error {code}: {msg}")
         self.code = code
 
 
-OPS = ("demosaic", "colorin", "colorout")
+OPS = ("demosaic", "colorin", "colorout", "denoiseprofile")
 
 _lib = None
 
@@ -102,6 +116,10 @@ def lib() -> C.CDLL:
             getattr(L, f"b200_{op}_tiling").restype = None
         L.b200_apply_conversion_dev.argtypes = [C.POINTER(Conversion), C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
                                                 C.c_int, C.c_void_p]
+        L.b200_eaw_dn_decompose_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int,
+                                                C.c_int, C.c_void_p]
+        L.b200_eaw_synthesize_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                              C.c_void_p]
         L.b200_flt32_eval_dev.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.b200_fit_unbounded_coeffs.argtypes = [C.POINTER(C.c_void_p), C.c_void_p]
         _lib = L
@@ -194,4 +212,41 @@ def colorout_data(conversion: Conversion | None, type_: int = 1) -> ColoroutData
         d._keepalive = conversion  # noqa
         d.conversion = C.pointer(conversion)
     d.type = type_
+    return d
+
+
+def infer_shadows_from_profile(a: float) -> float:
+    """iop/denoiseprofile.c:2659-2662."""
+    import math
+    import numpy as np
+    return float(min(max(0.1 - 0.1 * float(np.log(np.float32(a))), 0.7), 1.8))
+
+
+def infer_bias_from_profile(a: float) -> float:
+    """iop/denoiseprofile.c:2664-2667."""
+    import numpy as np
+    return float(-max(5 + 0.5 * float(np.log(np.float32(a))), 0.0))
+
+
+def denoiseprofile_data(mode: int = DENOISE_WAVELETS, *, a=(1e-4, 1e-4, 1e-4), b=(0.0, 0.0, 0.0), strength: float = 1.0,
+                        radius: float = 1.0, nbhood: float = 7.0, scattering: float = 0.0,
+                        central_pixel_weight: float = 0.1, color_mode: int = DENOISE_Y0U0V0, force: float = 0.5,
+                        use_new_vst: bool = True, shadows: float | None = None, bias: float | None = None) -> DenoiseProfileData:
+    """Parameters of SURVEY.md 8(d): generic Poissonian profile, shadows/bias inferred from it, flat
+    wavelet force curves (the GUI default nodes evaluate to 0.5 on every band)."""
+    d = DenoiseProfileData()
+    d.radius, d.nbhood, d.strength, d.scattering = radius, nbhood, strength, scattering
+    d.central_pixel_weight, d.overshooting = central_pixel_weight, 1.0
+    d.shadows = infer_shadows_from_profile(a[1]) if shadows is None else shadows
+    d.bias = infer_bias_from_profile(a[1]) if bias is None else bias
+    for k in range(3):
+        d.a[k], d.b[k] = a[k], b[k]
+    d.mode = mode
+    for ch in range(6):
+        for band in range(DENOISE_BANDS):
+            d.force[ch][band] = force
+    d.wb_adaptive_anscombe = 1
+    d.fix_anscombe_and_nlmeans_norm = 1
+    d.use_new_vst = 1 if use_new_vst else 0
+    d.wavelet_color_mode = color_mode
     return d

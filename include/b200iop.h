@@ -213,6 +213,53 @@ int b200_apply_conversion_dev(const b200_conversion_t *conversion, const void *d
  * non-linear channels */
 int b200_fit_unbounded_coeffs(const float *const lut[3], float coeffs[3][3]);
 
+/* ---- denoise (profiled) (src/iop/denoiseprofile.c) ------------------------------------------------ */
+#define B200_DENOISE_BANDS 7 /* DT_IOP_DENOISE_PROFILE_BANDS, denoiseprofile.c:109 */
+enum
+{ /* dt_iop_denoiseprofile_mode_t, denoiseprofile.c:120-126 */
+  B200_DENOISE_NLMEANS = 0,
+  B200_DENOISE_WAVELETS = 1,
+  B200_DENOISE_VARIANCE = 2,
+  B200_DENOISE_NLMEANS_AUTO = 3,
+  B200_DENOISE_WAVELETS_AUTO = 4
+};
+enum
+{ /* dt_iop_denoiseprofile_wavelet_mode_t :128-131 and dt_iop_denoiseprofile_channel_t :134-143 */
+  B200_DENOISE_RGB = 0,
+  B200_DENOISE_Y0U0V0 = 1,
+  B200_DENOISE_CH_ALL = 0,
+  B200_DENOISE_CH_R = 1,
+  B200_DENOISE_CH_G = 2,
+  B200_DENOISE_CH_B = 3,
+  B200_DENOISE_CH_Y0 = 4,
+  B200_DENOISE_CH_U0V0 = 5,
+  B200_DENOISE_CH_NONE = 6
+};
+/* The members of dt_iop_denoiseprofile_data_t (denoiseprofile.c:352-371) that process() reads, same
+ * names and meaning; the GUI curve handles of the reference struct are dropped, `force` is what
+ * commit_params evaluates from them (:2864-2872). */
+typedef struct b200_denoiseprofile_data_t
+{
+  float radius, nbhood, strength, shadows, bias, scattering, central_pixel_weight, overshooting;
+  float a[3], b[3];
+  int mode;
+  float force[B200_DENOISE_CH_NONE][B200_DENOISE_BANDS];
+  int wb_adaptive_anscombe, fix_anscombe_and_nlmeans_norm, use_new_vst;
+  int wavelet_color_mode;
+} b200_denoiseprofile_data_t;
+
+/* process(), denoiseprofile.c:2633-2647 -> process_wavelets :1289-1447 / process_nlmeans :1599-1654 */
+int b200_denoiseprofile_process_host(const b200_piece_t *piece, const void *in, void *out);
+int b200_denoiseprofile_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
+/* tiling_callback(), denoiseprofile.c:796-849 */
+void b200_denoiseprofile_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
+/* the two wavelet kernels on their own (pixel/eaw.c:242-326, :157-175): device RGBA buffers.
+ * d_sum_squared receives 4 doubles (sum over pixels of detail^2 per channel). */
+int b200_eaw_dn_decompose_dev(void *d_coarse, const void *d_in, void *d_detail, double *d_sum_squared, int scale,
+                              float inv_sigma2, int width, int height, void *stream);
+int b200_eaw_synthesize_dev(void *d_out, const void *d_in, const void *d_detail, const float threshold[4],
+                            const float boost[4], int width, int height, void *stream);
+
 /* ---- the libm the kernels use ------------------------------------------------------------------
  * Device restatement of glibc 2.39's single-precision expf/exp2f/logf/log2f/powf (the functions the
  * reference's CPU path calls; see ansel_b200/csrc/flt32_math.cuh).  Exposed so its bit-compatibility

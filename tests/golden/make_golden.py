@@ -38,4 +38,12 @@ for case, kw in (("colorin_matrix", dict(matrix=util.MATRIX_CAM_TO_REC2020)),
         save["lut_t_row"] = enc[0]
         save["co_t"] = co_t
     np.savez_compressed(os.path.join(OUT, f"color_{case}.npz"), **save)
+rng = np.random.default_rng(77)
+img = rng.normal(10, 1, (96, 128, 4)).astype(np.float32)
+save = dict(img=img, inv_sigma2=np.float32(1.3), thr=np.array([0.3, 0.2, 0.1, 0.0], np.float32))
+for scale in (0, 3):
+    c, d, _ = util.ref_eaw_decompose(img, scale, 1.3)
+    save[f"coarse_{scale}"], save[f"detail_{scale}"] = c, d
+save["synth"] = util.ref_eaw_synthesize(img, save["detail_0"], (0.3, 0.2, 0.1, 0.0))
+np.savez_compressed(os.path.join(OUT, "eaw.npz"), **save)
 print("golden vectors written to", OUT)

@@ -81,6 +81,19 @@ def test_colour_oracle_equals_reference(kind, fp):
         assert same_bits(r, o).all()
 
 
+@need_ref
+@pytest.mark.parametrize("scale", [0, 2, 5])
+def test_eaw_oracle_equals_reference_strict(scale):
+    rng = np.random.default_rng(scale)
+    img = rng.normal(10, 1, (203, 301, 4)).astype(np.float32)
+    oc, od, osum = util.oracle_eaw_decompose(img, scale, 1.7)
+    rc, rd, rsum = util.ref_eaw_decompose(img, scale, 1.7)
+    assert same_bits(oc, rc).all() and same_bits(od, rd).all()
+    assert np.allclose(osum, rsum, rtol=2e-6)     # the reference sums in float, the oracle in double
+    thr = (0.3, 0.2, 0.1, 0.0)
+    assert same_bits(util.oracle_eaw_synthesize(img, od, thr), util.ref_eaw_synthesize(img, od, thr)).all()
+
+
 # ---- golden vectors: produced by tests/golden/make_golden.py from oracle/_ref, committed ----------
 def _golden(name):
     return np.load(os.path.join(util.GOLDEN_DIR, name))
@@ -106,3 +119,11 @@ def test_colour_oracle_equals_golden(case):
         kw["co_t"] = g["co_t"]
     assert same_bits(util.oracle_convert(g["rgba"], fp=util.FP_STRICT, **kw), g["out_strict"]).all()
     assert same_bits(util.oracle_convert(g["rgba"], fp=util.FP_CONTRACT, **kw), g["out_fast"]).all()
+
+
+def test_eaw_oracle_equals_golden():
+    g = _golden("eaw.npz")
+    for scale in (0, 3):
+        oc, od, _ = util.oracle_eaw_decompose(g["img"], scale, float(g["inv_sigma2"]))
+        assert same_bits(oc, g[f"coarse_{scale}"]).all() and same_bits(od, g[f"detail_{scale}"]).all()
+    assert same_bits(util.oracle_eaw_synthesize(g["img"], g["detail_0"], tuple(g["thr"])), g["synth"]).all()

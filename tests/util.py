@@ -282,3 +282,65 @@ def rgba_test_image(w: int, h: int, seed: int, lo: float = -0.05, hi: float = 1.
     a[0, 0, :3] = (0.0, 1.0, 1.0)
     a[0, 1, :3] = (-0.0, 0.5, 2.0)
     return a
+
+
+# ---- profiled denoise (wavelets) through the checkers ------------------------------------------
+def oracle_eaw_decompose(img: np.ndarray, scale: int, inv_sigma2: float):
+    h, w = img.shape[:2]
+    coarse, detail = np.zeros_like(img), np.zeros_like(img)
+    sums = (C.c_double * 4)()
+    oracle().orc_eaw_dn_decompose(fptr(coarse), fptr(img), fptr(detail), sums, scale, C.c_float(inv_sigma2), w, h)
+    return coarse, detail, np.array(list(sums))
+
+
+def ref_eaw_decompose(img: np.ndarray, scale: int, inv_sigma2: float, kind: str = "strict"):
+    lib = ref(kind)
+    if lib is None:
+        return None
+    h, w = img.shape[:2]
+    coarse, detail = np.zeros_like(img), np.zeros_like(img)
+    sums = (C.c_float * 4)()
+    lib.eaw_dn_decompose(fptr(coarse), fptr(img), fptr(detail), sums, scale, C.c_float(inv_sigma2), w, h)
+    return coarse, detail, np.array(list(sums))
+
+
+def oracle_eaw_synthesize(base: np.ndarray, detail: np.ndarray, thr, boost=(1, 1, 1, 1)):
+    h, w = base.shape[:2]
+    out = np.zeros_like(base)
+    oracle().orc_eaw_synthesize(fptr(out), fptr(base), fptr(detail), (C.c_float * 4)(*thr), (C.c_float * 4)(*boost), w, h)
+    return out
+
+
+def ref_eaw_synthesize(base, detail, thr, boost=(1, 1, 1, 1), kind="strict"):
+    lib = ref(kind)
+    if lib is None:
+        return None
+    h, w = base.shape[:2]
+    out = np.zeros_like(base)
+    lib.eaw_synthesize(fptr(out), fptr(base), fptr(detail), (C.c_float * 4)(*thr), (C.c_float * 4)(*boost), w, h)
+    return out
+
+
+def oracle_denoise_wavelets(rgba: np.ndarray, data, roi_scale=1.0, buf=None, wb=(2.0, 1.0, 1.5, 0.0), pm=(1.0, 1.0, 1.0, 1.0)):
+    """data: ansel_b200.DenoiseProfileData (the public ABI struct)."""
+    h, w = rgba.shape[:2]
+    out = np.zeros_like(rgba)
+    bw, bh = buf if buf else (w, h)
+    f = oracle().orc_denoiseprofile_wavelets
+    f.restype = C.c_int
+    rc = f(fptr(np.ascontiguousarray(rgba)), fptr(out), w, h, C.byref(data), C.c_float(roi_scale), bw, bh,
+           (C.c_float * 4)(*wb), (C.c_float * 4)(*pm))
+    assert rc == 0
+    return out
+
+
+def rgba_scene(w: int, h: int, seed: int, noise: float = 0.02) -> np.ndarray:
+    """A demosaiced-looking RGBA frame: smooth scene + noise, alpha 0 (what demosaic hands to denoise)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    s = _scene(w, h, rng)
+    img = np.empty((h, w, 4), np.float32)
+    for c, g in enumerate((0.5, 1.0, 0.65)):
+        img[..., c] = s * np.float32(g) + rng.standard_normal((h, w), dtype=np.float32) * np.float32(noise)
+    np.clip(img[..., :3], 0.0, None, out=img[..., :3])
+    img[..., 3] = 0.0
+    return img
