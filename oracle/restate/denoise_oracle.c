@@ -9,8 +9,11 @@
  *
  * Pinning: the two eaw functions are checked bit-for-bit against the reference's own eaw.c compiled
  * in place (oracle/_ref).  iop/denoiseprofile.c is one translation unit with its GTK GUI and cannot
- * be compiled here, so the variance-stabilising transforms and the glue of process_wavelets are
- * restated from the source only: PARITY UNPINNED for those.
+ * be compiled whole, so its pixel functions (:852-1286: the VST pairs, compute_wb_factors,
+ * set_up_conversion_matrices, variance_stabilizing_xform) are cut out verbatim at build time
+ * (oracle/ref_shim/slice.py) and compiled; the restatements below match them bit for bit
+ * (tests/test_cpu_oracle_pin.py).  Only the ~40 lines of glue in process_wavelets :1289-1447 that
+ * derive p, compensate_p and the scale count are restated without a compiled counterpart.
  *
  * One deliberate difference: the per-channel sum of squared detail coefficients.  The reference
  * accumulates it in float with an OpenMP reduction (eaw.c:236,253,318-324), so its value depends
@@ -465,3 +468,42 @@ int orc_denoiseprofile_wavelets(const float *in, float *out, int width, int heig
 }
 
 int orc_wavelet_max_scale(float roi_scale, int buf_w, int buf_h) { return wavelet_max_scale(roi_scale, buf_w, buf_h); }
+
+/* ---- entry points used by the pinning tests --------------------------------------------------- */
+/* out[0]=max_scale, [1..4]=wb, [5..8]=p, [9]=a_eff, [10]=b, [11]=bias_eff, [12..23]=toY, [24..35]=toRGB,
+ * [36..39]=aa, [40..43]=bb, [44..50]=sigma_band */
+void orc_dn_plan_export(const b200_denoiseprofile_data_t *d, float roi_scale, int buf_w, int buf_h, const float wb_coeffs[4],
+                        const float pm[4], float out[51])
+{
+  wavelet_plan_t pl;
+  make_plan(&pl, d, roi_scale, buf_w, buf_h, wb_coeffs, pm);
+  out[0] = (float)pl.max_scale;
+  memcpy(out + 1, pl.wb, 16);
+  memcpy(out + 5, pl.p, 16);
+  out[9] = pl.a_eff;
+  out[10] = pl.b;
+  out[11] = pl.bias_eff;
+  memcpy(out + 12, pl.toY, 48);
+  memcpy(out + 24, pl.toRGB, 48);
+  memcpy(out + 36, pl.aa, 16);
+  memcpy(out + 40, pl.bb, 16);
+  memcpy(out + 44, pl.sigma_band, 28);
+}
+void orc_dn_vst(int forward, const b200_denoiseprofile_data_t *d, float roi_scale, int buf_w, int buf_h,
+                const float wb_coeffs[4], const float pm[4], const float *in, float *out, size_t npx)
+{
+  wavelet_plan_t pl;
+  make_plan(&pl, d, roi_scale, buf_w, buf_h, wb_coeffs, pm);
+  if(forward)
+    vst_forward(&pl, d, in, out, npx);
+  else
+  {
+    memcpy(out, in, 16 * npx);
+    vst_backward(&pl, d, out, npx);
+  }
+}
+void orc_dn_wb_factors(float wb[4], const b200_denoiseprofile_data_t *d, const float coeffs[4], const float pm[4],
+                       const float weights[4])
+{
+  wb_factors(wb, d, coeffs, pm, weights);
+}

@@ -127,3 +127,68 @@ def test_eaw_oracle_equals_golden():
         oc, od, _ = util.oracle_eaw_decompose(g["img"], scale, float(g["inv_sigma2"]))
         assert same_bits(oc, g[f"coarse_{scale}"]).all() and same_bits(od, g[f"detail_{scale}"]).all()
     assert same_bits(util.oracle_eaw_synthesize(g["img"], g["detail_0"], tuple(g["thr"])), g["synth"]).all()
+
+
+@need_ref
+@pytest.mark.parametrize("color_mode,new_vst", [(1, True), (0, True), (0, False)])
+def test_denoise_vst_oracle_equals_reference(color_mode, new_vst):
+    """precondition/backtransform{,_v2,_Y0U0V0} cut verbatim from iop/denoiseprofile.c:852-1089."""
+    import ctypes as C
+    import ansel_b200 as ab
+    O, R = util.oracle(), util.ref("strict")
+    f4 = lambda v: (C.c_float * 4)(*v)  # noqa: E731
+    wbc, pm = (2.0, 1.0, 1.5, 0.0), (1.0, 1.0, 1.0, 1.0)
+    img = util.rgba_scene(300, 200, 1)
+    img[..., 3] = 0.3
+    npx = 300 * 200
+    d = ab.denoiseprofile_data(ab.DENOISE_WAVELETS, color_mode=color_mode, use_new_vst=new_vst, b=(0.0, 1e-6, 0.0))
+    plan = np.zeros(51, np.float32)
+    O.orc_dn_plan_export(C.byref(d), C.c_float(1.0), 6000, 4000, f4(wbc), f4(pm), util.fptr(plan))
+    wb, p, a_eff, b, bias = plan[1:5], plan[5:9], plan[9], plan[10], plan[11]
+    toY, toRGB, aa, bb = plan[12:24].copy(), plan[24:36].copy(), plan[36:40], plan[40:44]
+    fwd, back = np.zeros_like(img), np.zeros_like(img)
+    O.orc_dn_vst(1, C.byref(d), C.c_float(1.0), 6000, 4000, f4(wbc), f4(pm), util.fptr(img), util.fptr(fwd), C.c_size_t(npx))
+    O.orc_dn_vst(0, C.byref(d), C.c_float(1.0), 6000, 4000, f4(wbc), f4(pm), util.fptr(fwd), util.fptr(back), C.c_size_t(npx))
+    rf, rb = np.zeros_like(img), fwd.copy()
+    if not new_vst:
+        R.ref_dn_precondition(util.fptr(img), util.fptr(rf), 300, 200, f4(aa), f4(bb))
+        R.ref_dn_backtransform(util.fptr(rb), 300, 200, f4(aa), f4(bb))
+    elif color_mode == 0:
+        R.ref_dn_precondition_v2(util.fptr(img), util.fptr(rf), 300, 200, C.c_float(a_eff), f4(p), C.c_float(b), f4(wb))
+        R.ref_dn_backtransform_v2(util.fptr(rb), 300, 200, C.c_float(a_eff), f4(p), C.c_float(b), C.c_float(bias), f4(wb))
+    else:
+        R.ref_dn_precondition_Y0U0V0(util.fptr(img), util.fptr(rf), 300, 200, C.c_float(a_eff), f4(p), C.c_float(b), util.fptr(toY))
+        R.ref_dn_backtransform_Y0U0V0(util.fptr(rb), 300, 200, C.c_float(a_eff), f4(p), C.c_float(b), C.c_float(bias), f4(wb),
+                                      util.fptr(toRGB))
+    assert same_bits(fwd, rf).all() and same_bits(back, rb).all()
+    assert np.abs(back[..., :3] - img[..., :3]).max() < 1e-3  # the pair is (nearly) an inverse
+
+
+@need_ref
+def test_denoise_plan_pieces_equal_reference():
+    """compute_wb_factors, set_up_conversion_matrices, variance_stabilizing_xform (denoiseprofile.c:1098-1286)."""
+    import ctypes as C
+    import ansel_b200 as ab
+    O, R = util.oracle(), util.ref("strict")
+    f4 = lambda v: (C.c_float * 4)(*v)  # noqa: E731
+    wbc, pm = (2.0, 1.0, 1.5, 0.0), (1.0, 1.0, 1.0, 1.0)
+    d = ab.denoiseprofile_data(ab.DENOISE_WAVELETS)
+    a, b = np.zeros(4, np.float32), np.zeros(4, np.float32)
+    O.orc_dn_wb_factors(util.fptr(a), C.byref(d), f4(wbc), f4(pm), f4((2, 1, 2, 0)))
+    R.ref_dn_wb_factors(util.fptr(b), 1, 1, f4(wbc), f4(pm), f4((2, 1, 2, 0)))
+    assert same_bits(a, b).all()
+    tY, tR = np.zeros(12, np.float32), np.zeros(12, np.float32)
+    R.ref_dn_conversion_matrices(util.fptr(tY), util.fptr(tR), f4(a))
+    plan = np.zeros(51, np.float32)
+    O.orc_dn_plan_export(C.byref(d), C.c_float(1.0), 6000, 4000, f4(wbc), f4(pm), util.fptr(plan))
+    k = np.float32(d.strength) * np.float32(2.5) * np.float32(1.0)
+    assert same_bits((tY / k).astype(np.float32), plan[12:24]).all() and same_bits((tR * k).astype(np.float32), plan[24:36]).all()
+    assert plan[0] == 7
+    force = np.ascontiguousarray(np.array(d.force, np.float32))
+    for cm in (0, 1):
+        d.wavelet_color_mode = cm
+        t1, t2 = np.zeros(4, np.float32), np.zeros(4, np.float32)
+        sums = f4((3e7, 2.5e7, 2.8e7, 1.0))
+        O.orc_wavelet_thresholds(util.fptr(t1), 2, 7, C.c_size_t(45441024), sums, C.c_float(plan[46]), C.byref(d))
+        R.ref_dn_thresholds(util.fptr(t2), 2, 7, C.c_size_t(45441024), sums, cm, util.fptr(force))
+        assert same_bits(t1, t2).all()
