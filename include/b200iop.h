@@ -260,6 +260,68 @@ int b200_eaw_dn_decompose_dev(void *d_coarse, const void *d_in, void *d_detail, 
 int b200_eaw_synthesize_dev(void *d_out, const void *d_in, const void *d_detail, const float threshold[4],
                             const float boost[4], int width, int height, void *stream);
 
+/* ---- filmic rgb (src/iop/filmicrgb.c) ---------------------------------------------------------- */
+/* dt_iop_filmic_rgb_spline_t, filmicrgb.c:216-223 (identical layout, 144 bytes) */
+typedef struct b200_filmic_spline_t
+{
+  float M1[4] __attribute__((aligned(16)));
+  float M2[4] __attribute__((aligned(16)));
+  float M3[4] __attribute__((aligned(16)));
+  float M4[4] __attribute__((aligned(16)));
+  float M5[4] __attribute__((aligned(16)));
+  float latitude_min, latitude_max;
+  float y[5];
+  float x[5];
+  int type[2]; /* dt_iop_filmicrgb_curve_type_t: 0 poly4, 1 poly3, 2 rational, 3 sigmoid */
+} b200_filmic_spline_t;
+
+/* dt_iop_filmicrgb_data_t, filmicrgb.c:360-400 (identical layout, 832 bytes): what commit_params()
+ * :4005-4113 leaves in piece->data is passed through unchanged */
+typedef struct b200_filmicrgb_data_t
+{
+  float max_grad, white_source, grey_source, black_source;
+  float reconstruct_threshold, reconstruct_feather, reconstruct_bloom_vs_details, reconstruct_grey_vs_color,
+      reconstruct_structure_vs_texture;
+  float normalize, dynamic_range, saturation, output_power, contrast, sigma_toe, sigma_shoulder, noise_level;
+  int preserve_color;
+  int version; /* dt_iop_filmicrgb_colorscience_type_t: 5..9 = the AgX (v8) family */
+  int spline_version;
+  int high_quality_reconstruction;
+  int hl_deprecated;
+  float agx_beta_hue;
+  b200_filmic_spline_t spline __attribute__((aligned(64)));
+  int noise_distribution;
+  int softproof_mode, softproof_type;
+  char softproof_filename[512];
+  int softproof_intent;
+} b200_filmicrgb_data_t;
+
+/* RGB <-> XYZ(D50) of a matrix profile: dt_iop_order_iccprofile_info_t.matrix_in / matrix_out
+ * (colorprofiles/iop_profile.h:127-131), rows of a dt_colormatrix_t */
+typedef struct b200_profile_matrices_t
+{
+  float matrix_in[3][4];
+  float matrix_out[3][4];
+} b200_profile_matrices_t;
+
+/* what filmic's process() reads: piece->data plus the two pipe-level profiles it fetches through
+ * dt_ioppr_get_pipe_work_profile_info() and _filmic_get_output_profile() (filmicrgb.c:2714-2715) */
+typedef struct b200_filmicrgb_piece_t
+{
+  b200_filmicrgb_data_t data;
+  b200_profile_matrices_t work_profile;
+  int has_export_profile;          /* 0 = output profile is not a matrix profile: gamut-map in the work space */
+  b200_profile_matrices_t export_profile;
+} b200_filmicrgb_piece_t;
+
+/* process(), filmicrgb.c:2707-2895.  Built: the AgX colour sciences (version 5..9) with the highlight
+ * reconstruction at its deprecation sentinel (hl_deprecated, the default).  v1..v5 and the legacy
+ * reconstruction return B200_ERR_UNSUPPORTED. */
+int b200_filmicrgb_process_host(const b200_piece_t *piece, const void *in, void *out);
+int b200_filmicrgb_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
+/* tiling_callback(), filmicrgb.c:2668-2704 */
+void b200_filmicrgb_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
+
 /* ---- the libm the kernels use ------------------------------------------------------------------
  * Device restatement of glibc 2.39's single-precision expf/exp2f/logf/log2f/powf (the functions the
  * reference's CPU path calls; see ansel_b200/csrc/flt32_math.cuh).  Exposed so its bit-compatibility

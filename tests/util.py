@@ -344,3 +344,110 @@ def rgba_scene(w: int, h: int, seed: int, noise: float = 0.02) -> np.ndarray:
     np.clip(img[..., :3], 0.0, None, out=img[..., :3])
     img[..., 3] = 0.0
     return img
+
+
+# ---- filmic rgb ------------------------------------------------------------------------------------
+# RGB -> XYZ(D50) of linear Rec2020 (the default work profile) and of sRGB (the default output profile)
+REC2020_TO_XYZ_D50 = np.array([[0.6734241, 0.1656411, 0.1251286],
+                               [0.2790177, 0.6753402, 0.0456377],
+                               [-0.0019300, 0.0299784, 0.7973330]])
+SRGB_TO_XYZ_D50 = np.array([[0.4360747, 0.3850649, 0.1430804],
+                            [0.2225045, 0.7168786, 0.0606169],
+                            [0.0139322, 0.0971045, 0.7141733]])
+
+
+def profile_pair(m_in64: np.ndarray):
+    """(matrix_in, matrix_out) as float32 3x3, matrix_out the float64 inverse rounded once."""
+    return np.ascontiguousarray(m_in64, np.float32), np.ascontiguousarray(np.linalg.inv(m_in64), np.float32)
+
+
+def filmic_default_params(**over) -> dict:
+    """$DEFAULT values of dt_iop_filmicrgb_params_t (src/iop/filmicrgb.c:244-274), field order preserved."""
+    p = dict(grey_point_source=18.45, black_point_source=-8.0, white_point_source=4.0, reconstruct_threshold=16.0,
+             reconstruct_feather=3.0, reconstruct_bloom_vs_details=100.0, reconstruct_grey_vs_color=100.0,
+             reconstruct_structure_vs_texture=100.0, security_factor=0.0, grey_point_target=18.45,
+             black_point_target=0.01517634, white_point_target=100.0, output_power=4.0, latitude=10.0, contrast=1.18,
+             saturation=0.0, balance=0.0, noise_level=0.05, preserve_color=1, version=7, auto_hardness=1, custom_grey=0,
+             high_quality_reconstruction=1, noise_distribution=2, shadows=3, highlights=3, compensate_icc_black=0,
+             spline_version=2)
+    p.update(over)
+    return p
+
+
+def filmic_params_blob(p: dict) -> np.ndarray:
+    floats = ["grey_point_source", "black_point_source", "white_point_source", "reconstruct_threshold", "reconstruct_feather",
+              "reconstruct_bloom_vs_details", "reconstruct_grey_vs_color", "reconstruct_structure_vs_texture", "security_factor",
+              "grey_point_target", "black_point_target", "white_point_target", "output_power", "latitude", "contrast",
+              "saturation", "balance", "noise_level"]
+    ints = ["preserve_color", "version", "auto_hardness", "custom_grey", "high_quality_reconstruction", "noise_distribution",
+            "shadows", "highlights", "compensate_icc_black", "spline_version"]
+    blob = np.zeros(112, np.uint8)
+    blob[:72].view(np.float32)[:] = [p[k] for k in floats]
+    blob[72:112].view(np.int32)[:] = [p[k] for k in ints]
+    return blob
+
+
+def ref_filmic_commit(params: dict, kind: str = "strict"):
+    """dt_iop_filmicrgb_data_t (832 bytes) from the reference's own commit_params()."""
+    lib = ref(kind)
+    if lib is None:
+        return None
+    lib.ref_filmic_sizeof_params.restype = C.c_size_t
+    lib.ref_filmic_sizeof_data.restype = C.c_size_t
+    assert lib.ref_filmic_sizeof_params() == 112 and lib.ref_filmic_sizeof_data() == 832
+    blob = filmic_params_blob(params)
+    data = np.zeros(832, np.uint8)
+    lib.ref_filmic_commit(blob.ctypes.data_as(C.c_void_p), data.ctypes.data_as(C.c_void_p))
+    return data
+
+
+def _f9(a):
+    return fptr(np.ascontiguousarray(a, np.float32).reshape(-1).copy()) if a is not None else None
+
+
+def ref_filmic_agx(rgba, data_blob, work, export=None, kind="strict"):
+    lib = ref(kind)
+    h, w = rgba.shape[:2]
+    src, dst = aligned_empty(rgba.shape), aligned_empty(rgba.shape)
+    src[...] = rgba
+    dst[...] = 0
+    keep = [_f9(work[0]), _f9(work[1]), _f9(export[0]) if export else None, _f9(export[1]) if export else None]
+    lib.ref_filmic_agx(fptr(src), fptr(dst), C.c_size_t(w), C.c_size_t(h), data_blob.ctypes.data_as(C.c_void_p), *keep)
+    return np.array(dst)
+
+
+def oracle_filmic_agx(rgba, data_blob, work, export=None):
+    h, w = rgba.shape[:2]
+    src = np.ascontiguousarray(rgba)
+    dst = np.zeros_like(src)
+    keep = [_f9(work[0]), _f9(work[1]), _f9(export[0]) if export else None, _f9(export[1]) if export else None]
+    data = aligned_empty((832,), np.uint8)
+    data[:] = data_blob
+    f = oracle().orc_filmic_agx
+    f.restype = C.c_int
+    rc = f(fptr(src), fptr(dst), C.c_size_t(w), C.c_size_t(h), data.ctypes.data_as(C.c_void_p), *keep)
+    assert rc == 0, rc
+    return dst
+
+
+def filmic_prepare(lib, fn, version, work, export=None):
+    out = np.zeros(72, np.float32)
+    keep = [_f9(work[0]), _f9(work[1]), _f9(export[0]) if export else None, _f9(export[1]) if export else None]
+    getattr(lib, fn)(version, *keep, fptr(out))
+    return out
+
+
+def hdr_rgba(w: int, h: int, seed: int) -> np.ndarray:
+    """Scene-referred RGBA for tone mapping: log-uniform over ~16 EV, some negatives, NaN, huge values."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    ev = rng.uniform(-11, 5, (h, w, 1)).astype(np.float32)
+    base = np.float32(0.1845) * np.exp2(ev)
+    img = (base * rng.uniform(0.3, 1.7, (h, w, 4)).astype(np.float32)).astype(np.float32)
+    neg = rng.random((h, w)) < 0.02
+    img[neg, rng.integers(0, 3)] *= -0.05
+    img[..., 3] = rng.uniform(0, 1, (h, w)).astype(np.float32)
+    img[0, 0, :3] = (np.nan, 0.5, 0.5)
+    img[0, 1, :3] = (1e9, -1e9, 0.0)
+    img[0, 2, :3] = 0.0
+    img[0, 3, :3] = 0.1845
+    return img
