@@ -87,13 +87,24 @@ class DenoiseProfileData(C.Structure):
                 ("fix_anscombe_and_nlmeans_norm", C.c_int), ("use_new_vst", C.c_int), ("wavelet_color_mode", C.c_int)]
 
 
+FILMIC_DATA_BYTES = 832  # sizeof(dt_iop_filmicrgb_data_t) == sizeof(b200_filmicrgb_data_t)
+
+
+class FilmicPiece(C.Structure):
+    """b200_filmicrgb_piece_t: dt_iop_filmicrgb_data_t (opaque, as commit_params left it) + the work and
+    output profile matrices process() fetches from the pipe.  Must live at a 64-byte aligned address."""
+    _fields_ = [("data", C.c_uint8 * FILMIC_DATA_BYTES), ("work_in", (C.c_float * 4) * 3), ("work_out", (C.c_float * 4) * 3),
+                ("has_export_profile", C.c_int), ("export_in", (C.c_float * 4) * 3), ("export_out", (C.c_float * 4) * 3),
+                ("_pad", C.c_uint8 * 60)]
+
+
 class B200Error(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libb200iop error {code}: {msg}")
         self.code = code
 
 
-OPS = ("demosaic", "colorin", "colorout", "denoiseprofile")
+OPS = ("demosaic", "colorin", "colorout", "denoiseprofile", "filmicrgb")
 
 _lib = None
 
@@ -250,3 +261,20 @@ def denoiseprofile_data(mode: int = DENOISE_WAVELETS, *, a=(1e-4, 1e-4, 1e-4), b
     d.use_new_vst = 1 if use_new_vst else 0
     d.wavelet_color_mode = color_mode
     return d
+
+
+def filmic_piece(data_blob, work, export=None) -> FilmicPiece:
+    """data_blob: 832 bytes of dt_iop_filmicrgb_data_t; work/export: (matrix_in, matrix_out) 3x3 arrays."""
+    import numpy as np
+    assert C.sizeof(FilmicPiece) == 1088
+    raw = np.zeros(C.sizeof(FilmicPiece) + 64, np.uint8)
+    off = (-raw.ctypes.data) % 64
+    fp = FilmicPiece.from_buffer(raw, off)
+    fp._keepalive = raw  # noqa
+    C.memmove(C.addressof(fp), np.ascontiguousarray(data_blob, np.uint8).ctypes.data, FILMIC_DATA_BYTES)
+    for dst, src in ((fp.work_in, work[0]), (fp.work_out, work[1])) + (((fp.export_in, export[0]), (fp.export_out, export[1])) if export else ()):
+        for i in range(3):
+            for j in range(3):
+                dst[i][j] = float(src[i][j])
+    fp.has_export_profile = 1 if export else 0
+    return fp

@@ -46,4 +46,15 @@ for scale in (0, 3):
     save[f"coarse_{scale}"], save[f"detail_{scale}"] = c, d
 save["synth"] = util.ref_eaw_synthesize(img, save["detail_0"], (0.3, 0.2, 0.1, 0.0))
 np.savez_compressed(os.path.join(OUT, "eaw.npz"), **save)
+CASES = {"default_v8": {}, "no_bleach": dict(version=5), "high_bleach_hue": dict(version=8, saturation=60.0),
+         "poly_curves": dict(shadows=0, highlights=1), "rational_curves": dict(shadows=2, highlights=2, contrast=1.5),
+         "wide_dr_gamma22": dict(white_point_source=6.0, black_point_source=-10.0, output_power=2.2)}
+np.savez_compressed(os.path.join(OUT, "filmic_data.npz"),
+                    **{k: util.ref_filmic_commit(util.filmic_default_params(**v)) for k, v in CASES.items()})
+work, export = util.profile_pair(util.REC2020_TO_XYZ_D50), util.profile_pair(util.SRGB_TO_XYZ_D50)
+img = util.hdr_rgba(96, 64, 11)
+blob = util.ref_filmic_commit(util.filmic_default_params())
+np.savez_compressed(os.path.join(OUT, "filmic_agx.npz"), img=img, out_export=util.ref_filmic_agx(img, blob, work, export),
+                    out_work=util.ref_filmic_agx(img, blob, work, None),
+                    prepare=util.filmic_prepare(util.ref("strict"), "ref_filmic_prepare", 7, work, export))
 print("golden vectors written to", OUT)

@@ -192,3 +192,46 @@ def test_denoise_plan_pieces_equal_reference():
         O.orc_wavelet_thresholds(util.fptr(t1), 2, 7, C.c_size_t(45441024), sums, C.c_float(plan[46]), C.byref(d))
         R.ref_dn_thresholds(util.fptr(t2), 2, 7, C.c_size_t(45441024), sums, cm, util.fptr(force))
         assert same_bits(t1, t2).all()
+
+
+FILMIC_CASES = {"default_v8": {}, "no_bleach": dict(version=5), "high_bleach_hue": dict(version=8, saturation=60.0),
+                "poly_curves": dict(shadows=0, highlights=1), "rational_curves": dict(shadows=2, highlights=2, contrast=1.5),
+                "wide_dr_gamma22": dict(white_point_source=6.0, black_point_source=-10.0, output_power=2.2)}
+
+
+@need_ref
+@pytest.mark.parametrize("name", list(FILMIC_CASES))
+def test_filmic_oracle_equals_reference(name):
+    """filmic_agx and everything under it, cut verbatim from iop/filmicrgb.c:948-2649; piece->data from the
+    reference's own commit_params (:4005-4113)."""
+    work, export = util.profile_pair(util.REC2020_TO_XYZ_D50), util.profile_pair(util.SRGB_TO_XYZ_D50)
+    img = util.hdr_rgba(400, 300, 5)
+    blob = util.ref_filmic_commit(util.filmic_default_params(**FILMIC_CASES[name]))
+    for e in (export, None):
+        assert same_bits(util.ref_filmic_agx(img, blob, work, e), util.oracle_filmic_agx(img, blob, work, e)).all()
+    for v in (5, 6, 7, 8, 9):
+        assert same_bits(util.filmic_prepare(util.ref("strict"), "ref_filmic_prepare", v, work, export),
+                         util.filmic_prepare(util.oracle(), "orc_filmic_prepare", v, work, export)).all()
+
+
+def test_filmic_oracle_equals_golden():
+    g = _golden("filmic_agx.npz")
+    blob = _golden("filmic_data.npz")["default_v8"]
+    work, export = util.profile_pair(util.REC2020_TO_XYZ_D50), util.profile_pair(util.SRGB_TO_XYZ_D50)
+    assert same_bits(util.oracle_filmic_agx(g["img"], blob, work, export), g["out_export"]).all()
+    assert same_bits(util.oracle_filmic_agx(g["img"], blob, work, None), g["out_work"]).all()
+    assert same_bits(util.filmic_prepare(util.oracle(), "orc_filmic_prepare", 7, work, export), g["prepare"]).all()
+
+
+def test_filmic_abi_layout_matches_reference():
+    import ctypes as C
+    import ansel_b200 as ab
+    assert C.sizeof(ab.FilmicPiece) == 1088
+    r = util.ref("strict")
+    if r is None:
+        pytest.skip("oracle/_ref not built")
+    for fn, want in (("ref_filmic_sizeof_data", 832), ("ref_filmic_offsetof_spline", 128), ("ref_filmic_sizeof_spline", 144),
+                     ("ref_filmic_offsetof_noise_distribution", 272), ("ref_filmic_sizeof_params", 112)):
+        f = getattr(r, fn)
+        f.restype = C.c_size_t
+        assert f() == want
