@@ -49,14 +49,12 @@ typedef struct dt_colorprofiles_settings_t
 static void dt_colorprofiles_get_settings(dt_colorprofiles_settings_t *s) { memset(s, 0, sizeof(*s)); s->mode = DT_PROFILE_NORMAL; }
 #define g_strlcpy(d, s, n) strncpy((d), (s), (n))
 #define DT_PIXEL_APPLY_DPI(x) (x)
-#define dt_pixelpipe_cache_alloc_align_float(n, pipe) ((float *)aligned_alloc(64, (((n) * sizeof(float) + 63) / 64) * 64))
-#define dt_pixelpipe_cache_alloc_align_float_cache(n, id) ((float *)aligned_alloc(64, (((n) * sizeof(float) + 63) / 64) * 64))
-#define dt_pixelpipe_cache_free_align(p) free(p)
 #define dt_control_log(...) ((void)0)
 #define dt_print(...) ((void)0)
 #define _(s) (s)
 static inline float dt_dev_get_module_scale(const dt_dev_pixelpipe_t *pipe, const dt_iop_roi_t *roi) { return pipe->iscale / roi->scale; }
-#define DT_CACHES_PIXELPIPE_CACHE_ALLOC_H
+/* caches/pixelpipe_cache_alloc.h is self-contained; its three extern helpers are defined in ref_nlm.c */
+#include "caches/pixelpipe_cache_alloc.h"
 #include "pixel/bspline.h"
 
 #include "gen_filmicrgb.c"

@@ -451,3 +451,32 @@ def hdr_rgba(w: int, h: int, seed: int) -> np.ndarray:
     img[0, 2, :3] = 0.0
     img[0, 3, :3] = 0.1845
     return img
+
+
+# ---- non-local means ----------------------------------------------------------------------------------
+def _nlm_call(lib, fn, img, scattering, scale, luma, chroma, center_weight, sharpness, P, K, decimate, norm):
+    h, w = img.shape[:2]
+    src = aligned_empty(img.shape)
+    src[...] = img
+    out = aligned_empty(img.shape)
+    out[...] = 0
+    f = getattr(lib, fn)
+    f(fptr(src), fptr(out), w, h, C.c_float(scattering), C.c_float(scale), C.c_float(luma), C.c_float(chroma),
+      C.c_float(center_weight), C.c_float(sharpness), P, K, decimate, (C.c_float * 4)(*norm))
+    return np.array(out)
+
+
+def oracle_nlmeans(img, *, scattering=0.0, scale=1.0, luma=1.0, chroma=1.0, center_weight=0.1, sharpness=0.005, P=1, K=7,
+                   decimate=0, norm=(1.0, 1.0, 1.0, 1.0)):
+    return _nlm_call(oracle(), "orc_nlmeans_denoise", img, scattering, scale, luma, chroma, center_weight, sharpness, P, K, decimate, norm)
+
+
+def ref_nlmeans(img, kind="strict", **kw):
+    lib = ref(kind)
+    if lib is None:
+        return None
+    d = dict(scattering=0.0, scale=1.0, luma=1.0, chroma=1.0, center_weight=0.1, sharpness=0.005, P=1, K=7, decimate=0,
+             norm=(1.0, 1.0, 1.0, 1.0))
+    d.update(kw)
+    return _nlm_call(lib, "ref_nlmeans_denoise", img, d["scattering"], d["scale"], d["luma"], d["chroma"], d["center_weight"],
+                     d["sharpness"], d["P"], d["K"], d["decimate"], d["norm"])
