@@ -131,6 +131,8 @@ def lib() -> C.CDLL:
                                                 C.c_int, C.c_void_p]
         L.b200_eaw_synthesize_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                               C.c_void_p]
+        L.b200_nlmeans_denoise_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                               C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.b200_flt32_eval_dev.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.b200_fit_unbounded_coeffs.argtypes = [C.POINTER(C.c_void_p), C.c_void_p]
         _lib = L

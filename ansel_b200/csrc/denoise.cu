@@ -519,8 +519,11 @@ size_t partial_bytes(int width, int height)
 
 namespace b200
 {
-int nlmeans_denoiseprofile_dev(const float *d_in, float *d_out, int width, int height, float scattering, float scale,
-                               float center_weight, float sharpness, int P, int K, cudaStream_t stream);
+int denoiseprofile_nlmeans_dev(const b200_piece_t *piece, const b200_denoiseprofile_data_t *d, const float *d_in, float *d_out,
+                               cudaStream_t s);
+int nlmeans_denoise_dev(const float *d_in, float *d_out, int width, int height, float scattering, float scale, float luma,
+                        float chroma, float center_weight, float sharpness, int radius, int search_radius, int decimate,
+                        const float norm[4], cudaStream_t stream);
 
 // shared with nlm.cu: forward / backward VST for the NLM mode of denoiseprofile (:1500-1597)
 int denoise_vst_forward(const b200_piece_t *piece, const b200_denoiseprofile_data_t *d, const float *d_in, float *d_out,
@@ -579,6 +582,18 @@ extern "C" int b200_eaw_synthesize_dev(void *d_out, const void *d_in, const void
                                                                      d_thr, make_float4(boost[0], boost[1], boost[2], boost[3]), npx);
   B200_CUDA_TRY(cudaGetLastError());
   return B200_OK;
+}
+
+// nlmeans_denoise(), pixel/nlmeans_core.c:315-532, on device RGBA buffers (d_in != d_out)
+extern "C" int b200_nlmeans_denoise_dev(const void *d_in, void *d_out, int width, int height, float scattering, float scale,
+                                        float luma, float chroma, float center_weight, float sharpness, int patch_radius,
+                                        int search_radius, int decimate, const float norm[4], void *stream)
+{
+  if(!d_in || !d_out || d_in == d_out || width <= 0 || height <= 0 || !norm) return fail(B200_ERR_ARG, "nlmeans_denoise: bad arguments");
+  int rc = bind_device(-1);
+  if(rc) return rc;
+  return nlmeans_denoise_dev((const float *)d_in, (float *)d_out, width, height, scattering, scale, luma, chroma, center_weight,
+                             sharpness, patch_radius, search_radius, decimate, norm, (cudaStream_t)stream);
 }
 
 // process_wavelets(), denoiseprofile.c:1289-1447
@@ -659,7 +674,7 @@ extern "C" int b200_denoiseprofile_process_dev(const b200_piece_t *piece, const 
   if(d->mode == B200_DENOISE_WAVELETS || d->mode == B200_DENOISE_WAVELETS_AUTO)
     return process_wavelets_dev(piece, d, (const float *)d_in, (float *)d_out, s);
   if(d->mode == B200_DENOISE_NLMEANS || d->mode == B200_DENOISE_NLMEANS_AUTO)
-    return fail(B200_ERR_UNSUPPORTED, "denoiseprofile: non-local means mode is not built yet");
+    return denoiseprofile_nlmeans_dev(piece, d, (const float *)d_in, (float *)d_out, s);
   return fail(B200_ERR_UNSUPPORTED, "denoiseprofile: variance-measurement mode (GUI aid) is not built");
 }
 

@@ -259,6 +259,12 @@ int b200_eaw_dn_decompose_dev(void *d_coarse, const void *d_in, void *d_detail, 
                               float inv_sigma2, int width, int height, void *stream);
 int b200_eaw_synthesize_dev(void *d_out, const void *d_in, const void *d_detail, const float threshold[4],
                             const float boost[4], int width, int height, void *stream);
+/* nlmeans_denoise(), pixel/nlmeans_core.c:315-532 (dt_nlmeans_param_t spelled out): device RGBA buffers,
+ * d_in != d_out.  center_weight < 0 selects the denoise (non-local means) iop's weighting (:389-402),
+ * >= 0 the profiled one (:404-420).  Patch radius 0..4. */
+int b200_nlmeans_denoise_dev(const void *d_in, void *d_out, int width, int height, float scattering, float scale, float luma,
+                             float chroma, float center_weight, float sharpness, int patch_radius, int search_radius,
+                             int decimate, const float norm[4], void *stream);
 
 /* ---- filmic rgb (src/iop/filmicrgb.c) ---------------------------------------------------------- */
 /* dt_iop_filmic_rgb_spline_t, filmicrgb.c:216-223 (identical layout, 144 bytes) */

@@ -226,14 +226,22 @@ static int wavelet_max_scale(float roi_scale, int buf_w, int buf_h)
   return max_scale;
 }
 
+static void make_plan_ex(wavelet_plan_t *pl, const b200_denoiseprofile_data_t *d, float roi_scale, int buf_w, int buf_h,
+                         const float wb_coeffs[4], const float pm[4], int nlm);
 static void make_plan(wavelet_plan_t *pl, const b200_denoiseprofile_data_t *d, float roi_scale, int buf_w, int buf_h,
                       const float wb_coeffs[4], const float pm[4])
+{
+  make_plan_ex(pl, d, roi_scale, buf_w, buf_h, wb_coeffs, pm, 0);
+}
+/* nlm = 1: nlmeans_precondition(), denoiseprofile.c:1500-1533 (unit wb weights, no Y0U0V0 matrices, strength*scale) */
+static void make_plan_ex(wavelet_plan_t *pl, const b200_denoiseprofile_data_t *d, float roi_scale, int buf_w, int buf_h,
+                         const float wb_coeffs[4], const float pm[4], int nlm)
 {
   memset(pl, 0, sizeof(*pl));
   pl->max_scale = wavelet_max_scale(roi_scale, buf_w, buf_h);
   const float in_scale = fminf(roi_scale, 1.0f);
-  const float wb_weights[4] = { 2.0f, 1.0f, 2.0f, 0.0f };
-  wb_factors(pl->wb, d, wb_coeffs, pm, wb_weights);
+  const float wb_weights[4] = { 2.0f, 1.0f, 2.0f, 0.0f }, wb_unit[4] = { 1.0f, 1.0f, 1.0f, 0.0f };
+  wb_factors(pl->wb, d, wb_coeffs, pm, nlm ? wb_unit : wb_weights);
   for(int c = 0; c < 3; c++)
   { /* MAX(d->shadows + 0.1 * logf(..), 0.0f): the 0.1 makes it a double expression, :1348-1351 */
     const double v = (double)d->shadows + 0.1 * (double)f32m_logf(in_scale / pl->wb[c]);
@@ -241,6 +249,19 @@ static void make_plan(wavelet_plan_t *pl, const b200_denoiseprofile_data_t *d, f
   }
   pl->p[3] = 0.0f;
   const float compensate_p = 0.05f / f32m_powf(0.05f, d->shadows);
+  if(nlm)
+  {
+    for(int i = 0; i < 4; i++)
+    {
+      pl->wb[i] *= d->strength * in_scale;
+      pl->aa[i] = d->a[1] * pl->wb[i];
+      pl->bb[i] = d->b[1] * pl->wb[i];
+    }
+    pl->a_eff = d->a[1] * compensate_p;
+    pl->b = d->b[1];
+    pl->bias_eff = (float)((double)d->bias - 0.5 * (double)f32m_logf(in_scale));
+    return;
+  }
   float toY[3][4] = { { 1.0f / 3.0f, 1.0f / 3.0f, 1.0f / 3.0f, 0 }, { 0.5f, 0.0f, -0.5f, 0 }, { 0.25f, -0.5f, 0.25f, 0 } };
   float toRGB[3][4] = { { 0 } };
   conversion_matrices(toY, toRGB, pl->wb);
@@ -506,4 +527,49 @@ void orc_dn_wb_factors(float wb[4], const b200_denoiseprofile_data_t *d, const f
                        const float weights[4])
 {
   wb_factors(wb, d, coeffs, pm, weights);
+}
+
+
+/* process_nlmeans_cpu(), denoiseprofile.c:1599-1648 */
+int orc_nlmeans_denoise(const float *inbuf, float *outbuf, int width, int height, float scattering, float scale, float luma,
+                        float chroma, float center_weight, float sharpness, int radius, int search_radius, int decimate,
+                        const float norm[4]);
+int orc_denoiseprofile_nlmeans(const float *in, float *out, int width, int height, const b200_denoiseprofile_data_t *d,
+                               float roi_scale, int pipe_type, const float wb_coeffs[4], const float pm[4])
+{
+  const size_t npx = (size_t)width * height;
+  const float scale = fminf(fminf(roi_scale, 2.0f), 1.0f);
+  const int P = (int)ceilf(d->radius * scale);
+  int K = (int)d->nbhood;
+  float scattering = d->scattering;
+  { /* nlmeans_scattering(), :1474-1499 */
+    const int has_preview = pipe_type == B200_PIPE_PREVIEW;
+    if(has_preview || pipe_type == B200_PIPE_THUMBNAIL)
+    {
+      const int maxk = (K * K * K + 7.0 * K * sqrt(K)) * scattering / 6.0 + K;
+      K = K < 3 ? K : 3;
+      scattering = (maxk - K) * 6.0 / (K * K * K + 7.0 * K * sqrt(K));
+    }
+    if(!has_preview)
+    {
+      const int maxk = (K * K * K + 7.0 * K * sqrt(K)) * scattering / 6.0 + K;
+      K = MAXF((K < 4 ? K : 4), K * scale);
+      scattering = (maxk - K) * 6.0 / (K * K * K + 7.0 * K * sqrt(K));
+    }
+  }
+  float norm = .045f / ((2 * P + 1) * (2 * P + 1));
+  if(!d->fix_anscombe_and_nlmeans_norm) norm = .015f / (2 * P + 1);
+  const float cpw = d->central_pixel_weight * scale;
+  wavelet_plan_t pl;
+  make_plan_ex(&pl, d, roi_scale, width, height, wb_coeffs, pm, 1);
+  b200_denoiseprofile_data_t dd = *d;
+  dd.wavelet_color_mode = B200_DENOISE_RGB; /* the NLM path only has the RGB transforms */
+  float *pre = malloc(16 * npx);
+  if(!pre) return 1;
+  vst_forward(&pl, &dd, in, pre, npx);
+  const float norm2[4] = { 1.0f, 1.0f, 1.0f, 1.0f };
+  orc_nlmeans_denoise(pre, out, width, height, scattering, scale, 1.0f, 1.0f, cpw, norm, P, K, 0, norm2);
+  free(pre);
+  vst_backward(&pl, &dd, out, npx);
+  return 0;
 }

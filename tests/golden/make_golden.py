@@ -57,4 +57,7 @@ blob = util.ref_filmic_commit(util.filmic_default_params())
 np.savez_compressed(os.path.join(OUT, "filmic_agx.npz"), img=img, out_export=util.ref_filmic_agx(img, blob, work, export),
                     out_work=util.ref_filmic_agx(img, blob, work, None),
                     prepare=util.filmic_prepare(util.ref("strict"), "ref_filmic_prepare", 7, work, export))
+img = (util.rgba_scene(150, 130, 21, noise=0.02) * 60).astype(np.float32)
+np.savez_compressed(os.path.join(OUT, "nlmeans.npz"), img=img, out_profiled=util.ref_nlmeans(img),
+                    out_lab=util.ref_nlmeans(img, center_weight=-1.0, sharpness=0.01, luma=0.8, chroma=0.6, K=3, P=2))
 print("golden vectors written to", OUT)

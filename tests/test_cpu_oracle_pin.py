@@ -235,3 +235,22 @@ def test_filmic_abi_layout_matches_reference():
         f = getattr(r, fn)
         f.restype = C.c_size_t
         assert f() == want
+
+
+NLM_CONFIGS = [dict(), dict(P=2, K=4, scattering=0.5), dict(center_weight=-1.0, sharpness=0.01, luma=0.8, chroma=0.6, K=3, P=3),
+               dict(K=2, P=1, scattering=1.0, scale=0.7), dict(P=4, K=2), dict(P=0, K=3), dict(K=5, decimate=1)]
+
+
+@need_ref
+@pytest.mark.parametrize("cfg", range(len(NLM_CONFIGS)))
+def test_nlmeans_oracle_equals_reference(cfg):
+    """pixel/nlmeans_core.c compiled in place; chunked, order-dependent float accumulation."""
+    for (w, h) in ((200, 150), (73, 61), (301, 203)):
+        img = (util.rgba_scene(w, h, 2, noise=0.02) * 60).astype(np.float32)
+        assert same_bits(util.oracle_nlmeans(img, **NLM_CONFIGS[cfg]), util.ref_nlmeans(img, **NLM_CONFIGS[cfg])).all()
+
+
+def test_nlmeans_oracle_equals_golden():
+    g = _golden("nlmeans.npz")
+    assert same_bits(util.oracle_nlmeans(g["img"]), g["out_profiled"]).all()
+    assert same_bits(util.oracle_nlmeans(g["img"], center_weight=-1.0, sharpness=0.01, luma=0.8, chroma=0.6, K=3, P=2), g["out_lab"]).all()

@@ -1,0 +1,94 @@
+"""GPU parity: non-local means (exact replay of the reference's accumulation order) against the oracle,
+bit for bit; the oracle is bit-identical to the reference's nlmeans_core.c compiled in place."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def same_bits(a, b):
+    return (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+
+
+def cuda_nlm(img, *, scattering=0.0, scale=1.0, luma=1.0, chroma=1.0, center_weight=0.1, sharpness=0.005, P=1, K=7, decimate=0,
+             norm=(1.0, 1.0, 1.0, 1.0)):
+    import torch
+    import ansel_b200 as ab
+    ab.init()
+    h, w = img.shape[:2]
+    d_in = torch.from_numpy(np.ascontiguousarray(img)).cuda()
+    d_out = torch.zeros_like(d_in)
+    ab.check(ab.lib().b200_nlmeans_denoise_dev(d_in.data_ptr(), d_out.data_ptr(), w, h, scattering, scale, luma, chroma, center_weight,
+                                               sharpness, P, K, decimate, (C.c_float * 4)(*norm), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    return d_out.cpu().numpy()
+
+
+CONFIGS = [dict(), dict(P=2, K=4, scattering=0.5), dict(center_weight=-1.0, sharpness=0.01, luma=0.8, chroma=0.6, K=3, P=3),
+           dict(K=2, P=1, scattering=1.0, scale=0.7), dict(P=4, K=2), dict(P=0, K=3), dict(K=5, decimate=1)]
+
+
+@pytest.mark.parametrize("cfg", range(len(CONFIGS)))
+@pytest.mark.parametrize("size", [(200, 150), (73, 61), (301, 203), (145, 121), (17, 9)])
+def test_nlmeans_core_bit_exact(built, size, cfg):
+    w, h = size
+    img = (util.rgba_scene(w, h, 2, noise=0.02) * 60).astype(np.float32)
+    kw = CONFIGS[cfg]
+    got = cuda_nlm(img, **kw)
+    want = util.oracle_nlmeans(img, **kw)
+    bad = ~same_bits(got, want)
+    assert not bad.any(), f"{int(bad.sum())} floats differ, first {np.argwhere(bad)[:4].tolist()}"
+
+
+def run_module(img, data, pipe_type=1):
+    import torch
+    import ansel_b200 as ab
+    ab.init()
+    h, w = img.shape[:2]
+    piece = ab.make_piece(w, h, filters=0, channels=4, data=data, devid=0, pipe_type=pipe_type)
+    d_in = torch.from_numpy(img).cuda()
+    d_out = torch.zeros_like(d_in)
+    ab.check(ab.lib().b200_denoiseprofile_process_dev(piece, d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    return d_out.cpu().numpy()
+
+
+def oracle_module(img, data, pipe_type=1, wb=(2.0, 1.0, 1.5, 0.0), pm=(1.0, 1.0, 1.0, 1.0)):
+    h, w = img.shape[:2]
+    out = np.zeros_like(img)
+    f = util.oracle().orc_denoiseprofile_nlmeans
+    f.restype = C.c_int
+    assert f(util.fptr(img), util.fptr(out), w, h, C.byref(data), C.c_float(1.0), pipe_type, (C.c_float * 4)(*wb), (C.c_float * 4)(*pm)) == 0
+    return out
+
+
+@pytest.mark.parametrize("new_vst,pipe", [(True, 1), (False, 1), (True, 4)])
+def test_denoiseprofile_nlmeans_module_bit_exact(built, new_vst, pipe):
+    """mode NLMEANS, radius 1, nbhood 7, scattering 0, strength 1, cpw 0.1."""
+    import ansel_b200 as ab
+    img = util.rgba_scene(900, 600, 5)
+    data = ab.denoiseprofile_data(ab.DENOISE_NLMEANS, use_new_vst=new_vst)
+    got = run_module(img, data, pipe)
+    want = oracle_module(img, data, pipe)
+    assert same_bits(got, want).all()
+    assert np.abs(np.diff(got[..., 1], axis=1)).mean() < 0.9 * np.abs(np.diff(img[..., 1], axis=1)).mean()
+
+
+def test_nlmeans_24mp_bit_exact(built):
+    w, h = util.SIZE_24MP
+    img = (util.rgba_scene(w, h, util.SEEDS[1], noise=0.02) * 60).astype(np.float32)
+    got = cuda_nlm(img)
+    want = util.oracle_nlmeans(img)
+    assert same_bits(got, want).all()
+
+
+def test_nlmeans_45mp_deterministic(built):
+    w, h = util.SIZE_45MP
+    img = (util.rgba_scene(w, h, util.SEEDS[2], noise=0.02) * 60).astype(np.float32)
+    a = cuda_nlm(img)
+    assert np.isfinite(a).all()
+    assert same_bits(a, cuda_nlm(img)).all()
