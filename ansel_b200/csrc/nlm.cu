@@ -115,25 +115,43 @@ __global__ void __launch_bounds__(NT) nlm_chunks_kernel(const __grid_constant__ 
         cs = sum;
       }
       const int lim_a = min(row_top, row_bot);
-      for(int row = row_min; row < row_max; row++)
+      // The recurrence is sequential in `row`, its operands are not: fetch UNR rows' worth of pixels
+      // first (independent loads in flight), then apply the updates in the reference's order.
+      constexpr int UNR = 6;
+      for(int row0 = row_min; row0 < row_max; row0 += UNR)
       {
-        S[(row - row_min) * SSTRIDE + tid] = cs;
-        if(!live) continue;
-        if(row < lim_a)
-        { // :424-440
-          const float4 *b = in + (size_t)(row + 1 + radius) * width + col;
-          cs += pixdiff(__ldg(b), __ldg(b + poff), a.norm);
+        float4 B0[UNR], B1[UNR], T0[UNR], T1[UNR];
+        int kind[UNR];
+#pragma unroll
+        for(int u = 0; u < UNR; u++)
+        {
+          const int row = row0 + u;
+          kind[u] = row >= row_max ? -1 : (row < lim_a ? 1 : (row < row_bot ? 2 : ((row >= row_top && row + 1 < row_max) ? 3 : 0)));
+          if(live && (kind[u] == 1 || kind[u] == 2))
+          {
+            const float4 *b = in + (size_t)(row + 1 + radius) * width + col;
+            B0[u] = __ldg(b);
+            B1[u] = __ldg(b + poff);
+          }
+          if(live && (kind[u] == 2 || kind[u] == 3))
+          {
+            const float4 *t = in + (size_t)(row - radius) * width + col;
+            T0[u] = __ldg(t);
+            T1[u] = __ldg(t + poff);
+          }
         }
-        else if(row < row_bot)
-        { // :441-466
-          const float4 *t = in + (size_t)(row - radius) * width + col;
-          const float4 *b = in + (size_t)(row + 1 + radius) * width + col;
-          cs += diff_of_diffs(__ldg(b), __ldg(b + poff), __ldg(t), __ldg(t + poff), a.norm);
-        }
-        else if(row >= row_top && row + 1 < row_max)
-        { // :467-483
-          const float4 *t = in + (size_t)(row - radius) * width + col;
-          cs -= pixdiff(__ldg(t), __ldg(t + poff), a.norm);
+#pragma unroll
+        for(int u = 0; u < UNR; u++)
+        {
+          if(kind[u] < 0) break;
+          S[(row0 + u - row_min) * SSTRIDE + tid] = cs;
+          if(!live) continue;
+          if(kind[u] == 1)
+            cs += pixdiff(B0[u], B1[u], a.norm); // :424-440
+          else if(kind[u] == 2)
+            cs += diff_of_diffs(B0[u], B1[u], T0[u], T1[u], a.norm); // :441-466
+          else if(kind[u] == 3)
+            cs -= pixdiff(T0[u], T1[u], a.norm); // :467-483
         }
       }
     }

@@ -480,3 +480,38 @@ def ref_nlmeans(img, kind="strict", **kw):
     d.update(kw)
     return _nlm_call(lib, "ref_nlmeans_denoise", img, d["scattering"], d["scale"], d["luma"], d["chroma"], d["center_weight"],
                      d["sharpness"], d["P"], d["K"], d["decimate"], d["norm"])
+
+
+# ---- local Laplacian (local contrast) ---------------------------------------------------------------
+def lab_scene(w: int, h: int, seed: int) -> np.ndarray:
+    """Lab-like RGBA: L in [0, 100] with structure, a/b small, alpha arbitrary."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    s = _scene(w, h, rng)
+    img = np.empty((h, w, 4), np.float32)
+    img[..., 0] = np.clip(s * 70 + rng.standard_normal((h, w), dtype=np.float32) * 1.5, 0, 100)
+    img[..., 1] = rng.uniform(-20, 20, (h, w)).astype(np.float32)
+    img[..., 2] = rng.uniform(-20, 20, (h, w)).astype(np.float32)
+    img[..., 3] = rng.uniform(0, 1, (h, w)).astype(np.float32)
+    return img
+
+
+def _ll_call(lib, fn, img, sigma, shadows, highlights, clarity):
+    h, w = img.shape[:2]
+    src = aligned_empty(img.shape)
+    src[...] = img
+    out = aligned_empty(img.shape)
+    out[...] = 0
+    f = getattr(lib, fn)
+    f.restype = C.c_int
+    assert f(fptr(src), fptr(out), w, h, C.c_float(sigma), C.c_float(shadows), C.c_float(highlights), C.c_float(clarity)) == 0
+    return np.array(out)
+
+
+def oracle_local_laplacian(img, sigma=0.5, shadows=0.5, highlights=0.5, clarity=0.25):
+    """defaults = dt_iop_bilat_params_t $DEFAULTs (midtone, sigma_s, sigma_r, detail), iop/bilat.c:78-86,354"""
+    return _ll_call(oracle(), "orc_local_laplacian", img, sigma, shadows, highlights, clarity)
+
+
+def ref_local_laplacian(img, sigma=0.5, shadows=0.5, highlights=0.5, clarity=0.25, kind="strict"):
+    lib = ref(kind)
+    return None if lib is None else _ll_call(lib, "ref_local_laplacian", img, sigma, shadows, highlights, clarity)
