@@ -98,13 +98,18 @@ class FilmicPiece(C.Structure):
                 ("_pad", C.c_uint8 * 60)]
 
 
+class BilatData(C.Structure):
+    """b200_bilat_data_t == dt_iop_bilat_data_t (src/iop/bilat.c:78-86,108)."""
+    _fields_ = [("mode", C.c_int), ("sigma_r", C.c_float), ("sigma_s", C.c_float), ("detail", C.c_float), ("midtone", C.c_float)]
+
+
 class B200Error(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libb200iop error {code}: {msg}")
         self.code = code
 
 
-OPS = ("demosaic", "colorin", "colorout", "denoiseprofile", "filmicrgb")
+OPS = ("demosaic", "colorin", "colorout", "denoiseprofile", "filmicrgb", "bilat")
 
 _lib = None
 
@@ -280,3 +285,7 @@ def filmic_piece(data_blob, work, export=None) -> FilmicPiece:
                 dst[i][j] = float(src[i][j])
     fp.has_export_profile = 1 if export else 0
     return fp
+
+
+def bilat_data(sigma_r: float = 0.5, sigma_s: float = 0.5, detail: float = 0.25, midtone: float = 0.5, mode: int = 1) -> BilatData:
+    return BilatData(mode, sigma_r, sigma_s, detail, midtone)

@@ -328,6 +328,27 @@ int b200_filmicrgb_process_dev(const b200_piece_t *piece, const void *d_in, void
 /* tiling_callback(), filmicrgb.c:2668-2704 */
 void b200_filmicrgb_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
 
+/* ---- local contrast (src/iop/bilat.c), local-Laplacian mode ------------------------------------ */
+enum
+{ /* dt_iop_bilat_mode_t, bilat.c:71-76 */
+  B200_BILAT_BILATERAL = 0,
+  B200_BILAT_LOCAL_LAPLACIAN = 1
+};
+/* dt_iop_bilat_data_t == dt_iop_bilat_params_t, bilat.c:78-86,108 (identical layout) */
+typedef struct b200_bilat_data_t
+{
+  int mode;      /* default 1 */
+  float sigma_r; /* highlights, default 0.5 */
+  float sigma_s; /* shadows, default 0.5 */
+  float detail;  /* clarity, default 0.25 */
+  float midtone; /* default 0.5 */
+} b200_bilat_data_t;
+/* process(), bilat.c:336-360 -> local_laplacian_internal(), pixel/locallaplacian.c:354-563.  Lab RGBA in/out;
+ * channels 1,2 are copied, channel 3 carried through from the input. */
+int b200_bilat_process_host(const b200_piece_t *piece, const void *in, void *out);
+int b200_bilat_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
+void b200_bilat_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
+
 /* ---- the libm the kernels use ------------------------------------------------------------------
  * Device restatement of glibc 2.39's single-precision expf/exp2f/logf/log2f/powf (the functions the
  * reference's CPU path calls; see ansel_b200/csrc/flt32_math.cuh).  Exposed so its bit-compatibility

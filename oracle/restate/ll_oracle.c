@@ -108,6 +108,9 @@ int orc_local_laplacian(const float *input, float *out, int wd, int ht, float si
   const int mn = wd < ht ? wd : ht;
   int num_levels = 31 - __builtin_clz((unsigned)mn);
   if(num_levels > MAX_LEVELS) num_levels = MAX_LEVELS;
+  /* min(wd,ht) in {2,3}: one level, and the reference then reads padded[-1] (:417) -- undefined there,
+   * refused here and by the CUDA path */
+  if(num_levels < 2) return 2;
   const int last = num_levels - 1;
   const int max_supp = 1 << last;
   const int w = 2 * max_supp + wd, h = 2 * max_supp + ht;

@@ -61,3 +61,6 @@ img = (util.rgba_scene(150, 130, 21, noise=0.02) * 60).astype(np.float32)
 np.savez_compressed(os.path.join(OUT, "nlmeans.npz"), img=img, out_profiled=util.ref_nlmeans(img),
                     out_lab=util.ref_nlmeans(img, center_weight=-1.0, sharpness=0.01, luma=0.8, chroma=0.6, K=3, P=2))
 print("golden vectors written to", OUT)
+img = util.lab_scene(180, 131, 31)
+np.savez_compressed(os.path.join(OUT, "ll.npz"), img=img, out_default=util.ref_local_laplacian(img),
+                    out_strong=util.ref_local_laplacian(img, sigma=0.2, shadows=1.5, highlights=0.1, clarity=1.0))

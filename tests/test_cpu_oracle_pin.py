@@ -254,3 +254,21 @@ def test_nlmeans_oracle_equals_golden():
     g = _golden("nlmeans.npz")
     assert same_bits(util.oracle_nlmeans(g["img"]), g["out_profiled"]).all()
     assert same_bits(util.oracle_nlmeans(g["img"], center_weight=-1.0, sharpness=0.01, luma=0.8, chroma=0.6, K=3, P=2), g["out_lab"]).all()
+
+
+LL_PARAMS = [dict(), dict(sigma=0.2, shadows=1.5, highlights=0.1, clarity=1.0), dict(sigma=0.8, shadows=-0.5, highlights=1.8, clarity=-0.6)]
+
+
+@need_ref
+@pytest.mark.parametrize("p", range(len(LL_PARAMS)))
+def test_local_laplacian_oracle_equals_reference(p):
+    """pixel/locallaplacian.c compiled in place; channel 0 is the filter output, 1,2 copies, 3 untouched."""
+    for (w, h) in ((200, 150), (257, 129), (64, 48), (33, 17), (9, 4), (4, 4)):
+        img = util.lab_scene(w, h, 5)
+        assert same_bits(util.oracle_local_laplacian(img, **LL_PARAMS[p]), util.ref_local_laplacian(img, **LL_PARAMS[p])).all()
+
+
+def test_local_laplacian_oracle_equals_golden():
+    g = _golden("ll.npz")
+    assert same_bits(util.oracle_local_laplacian(g["img"]), g["out_default"]).all()
+    assert same_bits(util.oracle_local_laplacian(g["img"], **LL_PARAMS[1]), g["out_strong"]).all()
