@@ -27,10 +27,16 @@ class Develop(C.Structure):
     _fields_ = [("image_storage", Image), ("gui_attached", C.c_int)]
 
 
+class ProfileInfo(C.Structure):
+    """dt_iop_order_iccprofile_info_t subset (src/colorprofiles/iop_profile.h:122-146)."""
+    _fields_ = [("matrix_in", (C.c_float * 4) * 3), ("matrix_out", (C.c_float * 4) * 3)]
+
+
 class Pipe(C.Structure):
     """dt_dev_pixelpipe_t subset."""
     _fields_ = [("dev", C.POINTER(Develop)), ("type", C.c_int), ("mask_display", C.c_int), ("devid", C.c_int),
-                ("iscale", C.c_float), ("stream", C.c_void_p)]
+                ("iscale", C.c_float), ("stream", C.c_void_p), ("work_profile_info", C.POINTER(ProfileInfo)),
+                ("output_profile_info", C.POINTER(ProfileInfo))]
 
 
 class Module(C.Structure):
@@ -53,6 +59,7 @@ class PipeNode(C.Structure):
 
 
 _mod = None
+ADAPTED_OPS = ("demosaic", "colorin", "colorout", "denoiseprofile", "filmicrgb", "bilat")
 
 
 def modlib() -> C.CDLL:
@@ -67,7 +74,7 @@ def modlib() -> C.CDLL:
         M.b200_pipe_buffers_free.argtypes = [C.c_void_p]
         M.b200_pixelpipe_process_on_gpu.argtypes = [C.POINTER(Pipe), C.POINTER(PipeNode), C.c_int, C.c_void_p,
                                                     C.c_void_p, C.c_void_p]
-        for op in ("demosaic", "colorin", "colorout"):
+        for op in ADAPTED_OPS:
             getattr(M, f"dt_iop_{op}__process").argtypes = [C.POINTER(Module), C.POINTER(Pipe), C.POINTER(PipeIop),
                                                             C.c_void_p, C.c_void_p]
             getattr(M, f"dt_iop_{op}__process_cl").argtypes = [C.POINTER(Module), C.POINTER(Pipe), C.POINTER(PipeIop),
@@ -83,11 +90,26 @@ def modlib() -> C.CDLL:
         assert M.b200_dt_surface_probe(6) == PipeIop.dsc_in.offset
         assert M.b200_dt_surface_probe(8) == C.sizeof(Pipe)
         assert M.b200_dt_surface_probe(9) == C.sizeof(Module)
+        assert M.b200_dt_surface_probe(12) == C.sizeof(ProfileInfo)
+        assert M.b200_dt_surface_probe(13) == Pipe.work_profile_info.offset
         _mod = M
     return _mod
 
 
-def make_pipe(devid: int = 0, pipe_type: int = 1, stream: int | None = None, exif_iso: float = 100.0) -> Pipe:
+def profile_info(matrix_in, matrix_out) -> ProfileInfo:
+    """rows of a dt_colormatrix_t (3x4, last column padding)."""
+    import numpy as np
+    pi = ProfileInfo()
+    for name, m in (("matrix_in", matrix_in), ("matrix_out", matrix_out)):
+        m = np.asarray(m, np.float32)
+        for r in range(3):
+            for c in range(3):
+                getattr(pi, name)[r][c] = float(m[r, c])
+    return pi
+
+
+def make_pipe(devid: int = 0, pipe_type: int = 1, stream: int | None = None, exif_iso: float = 100.0, work_profile=None,
+              output_profile=None) -> Pipe:
     dev = Develop()
     dev.image_storage.exif_iso = exif_iso
     p = Pipe()
@@ -98,6 +120,11 @@ def make_pipe(devid: int = 0, pipe_type: int = 1, stream: int | None = None, exi
     p.devid = devid
     p.iscale = 1.0
     p.stream = stream
+    p._profiles = (work_profile, output_profile)  # noqa
+    if work_profile is not None:
+        p.work_profile_info = C.pointer(work_profile)
+    if output_profile is not None:
+        p.output_profile_info = C.pointer(output_profile)
     return p
 
 

@@ -49,6 +49,13 @@ typedef struct dt_develop_t
   int gui_attached;
 } dt_develop_t;
 
+/* src/colorprofiles/iop_profile.h:122-146: the two matrices filmic's gamut mapping reads */
+typedef struct dt_iop_order_iccprofile_info_t
+{
+  float matrix_in[3][4] __attribute__((aligned(16)));  /* RGB -> XYZ(D50); NaN = not a matrix profile */
+  float matrix_out[3][4] __attribute__((aligned(16))); /* XYZ(D50) -> RGB */
+} dt_iop_order_iccprofile_info_t;
+
 /* src/develop/pixelpipe_hb.h: dt_dev_pixelpipe_t */
 typedef struct dt_dev_pixelpipe_t
 {
@@ -58,7 +65,18 @@ typedef struct dt_dev_pixelpipe_t
   int devid;         /* device reserved for this pipe (dt_opencl_reserve_device_for_pipe analogue) */
   float iscale;
   void *stream;      /* per-pipe CUDA stream, NULL = default stream */
+  dt_iop_order_iccprofile_info_t *work_profile_info;   /* pixelpipe_hb.h: set by colorin's commit */
+  dt_iop_order_iccprofile_info_t *output_profile_info; /* set by colorout's commit */
 } dt_dev_pixelpipe_t;
+/* src/colorprofiles/iop_profile.c: the two getters filmic's process() calls (filmicrgb.c:2714-2715) */
+static inline const dt_iop_order_iccprofile_info_t *dt_ioppr_get_pipe_work_profile_info(const dt_dev_pixelpipe_t *pipe)
+{
+  return pipe->work_profile_info;
+}
+static inline const dt_iop_order_iccprofile_info_t *dt_ioppr_get_pipe_output_profile_info(const dt_dev_pixelpipe_t *pipe)
+{
+  return pipe->output_profile_info;
+}
 
 struct dt_iop_module_t;
 /* src/develop/pixelpipe_hb.h:101-166 */

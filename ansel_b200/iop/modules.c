@@ -37,6 +37,63 @@ ADAPT(demosaic) /* src/iop/demosaic.c:1043 (process), rcd.c:568 (process_rcd_cl)
 ADAPT(colorin)  /* src/iop/colorin.c:711, :590-681 (process_cl) */
 ADAPT(colorout) /* src/iop/colorout.c:373, :288-371 (process_cl) */
 
+ADAPT(denoiseprofile) /* src/iop/denoiseprofile.c:2037 (process), :1880-2035 (process_cl), :1091 (tiling_callback) */
+ADAPT(bilat)          /* src/iop/bilat.c:336 (process), :313-334 (process_cl), :296 (commit: tiling off) */
+
+/* filmic reads two pipe-level profiles next to piece->data (filmicrgb.c:2714-2715); the adapter flattens the
+ * three into the b200_filmicrgb_piece_t the library takes.  A soft-proof profile (data->softproof_mode != 0,
+ * _filmic_get_output_profile :2650-2666) is resolved by the reference's own dt_colorspaces_add_profile() in
+ * the maintainer's tree; here the pipe output profile is what is available. */
+#include <math.h>
+#include <string.h>
+static int filmic_view(b200_filmicrgb_piece_t *fp, b200_piece_t *p, const dt_dev_pixelpipe_t *pipe,
+                       const dt_dev_pixelpipe_iop_t *piece)
+{
+  if(!piece->data || piece->data_size < sizeof(b200_filmicrgb_data_t)) return 1;
+  memcpy(&fp->data, piece->data, sizeof(b200_filmicrgb_data_t));
+  const dt_iop_order_iccprofile_info_t *const work = dt_ioppr_get_pipe_work_profile_info(pipe);
+  const dt_iop_order_iccprofile_info_t *const out = dt_ioppr_get_pipe_output_profile_info(pipe);
+  if(!work) return 1; /* filmicrgb.c:2716: "no work profile" -> process() fails */
+  memcpy(fp->work_profile.matrix_in, work->matrix_in, sizeof(work->matrix_in));
+  memcpy(fp->work_profile.matrix_out, work->matrix_out, sizeof(work->matrix_out));
+  fp->has_export_profile = out && !isnan(out->matrix_in[0][0]) && !isnan(out->matrix_out[0][0]);
+  if(fp->has_export_profile)
+  {
+    memcpy(fp->export_profile.matrix_in, out->matrix_in, sizeof(out->matrix_in));
+    memcpy(fp->export_profile.matrix_out, out->matrix_out, sizeof(out->matrix_out));
+  }
+  else
+    memset(&fp->export_profile, 0, sizeof(fp->export_profile));
+  p->data = fp;
+  p->data_size = sizeof(*fp);
+  return 0;
+}
+int dt_iop_filmicrgb__process(struct dt_iop_module_t *self, const dt_dev_pixelpipe_t *pipe,
+                              const dt_dev_pixelpipe_iop_t *piece, const void *const i, void *const o)
+{
+  b200_piece_t p;
+  b200_filmicrgb_piece_t fp;
+  b200_piece_from_dt(&p, self, pipe, piece);
+  if(filmic_view(&fp, &p, pipe, piece)) return 1;
+  return b200_filmicrgb_process_host(&p, i, o);
+}
+int dt_iop_filmicrgb__process_cl(struct dt_iop_module_t *self, const dt_dev_pixelpipe_t *pipe,
+                                 const dt_dev_pixelpipe_iop_t *piece, cl_mem dev_in, cl_mem dev_out)
+{
+  b200_piece_t p;
+  b200_filmicrgb_piece_t fp;
+  b200_piece_from_dt(&p, self, pipe, piece);
+  if(filmic_view(&fp, &p, pipe, piece)) return FALSE;
+  return b200_filmicrgb_process_dev(&p, dev_in, dev_out, pipe->stream) == 0 ? TRUE : FALSE;
+}
+void dt_iop_filmicrgb__tiling_callback(struct dt_iop_module_t *self, const dt_dev_pixelpipe_t *pipe,
+                                       const dt_dev_pixelpipe_iop_t *piece, dt_develop_tiling_t *tiling)
+{
+  b200_piece_t p;
+  b200_piece_from_dt(&p, self, pipe, piece);
+  b200_filmicrgb_tiling(&p, tiling); /* reads roi_in and the data block's reconstruction settings only */
+}
+
 /* layout probes so non-C callers (tests, bench.py) can verify their mirror of dt_surface.h */
 #include <stddef.h>
 size_t b200_dt_surface_probe(int which)
@@ -55,6 +112,8 @@ size_t b200_dt_surface_probe(int which)
     case 9: return sizeof(dt_iop_module_t);
     case 10: return sizeof(b200_piece_t);
     case 11: return sizeof(b200_conversion_t);
+    case 12: return sizeof(dt_iop_order_iccprofile_info_t);
+    case 13: return offsetof(dt_dev_pixelpipe_t, work_profile_info);
     default: return 0;
   }
 }
