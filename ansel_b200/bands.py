@@ -1,0 +1,152 @@
+"""One frame over several GPUs: row bands + one gather at the end of the chain.
+
+A band is a full-width tile of the reference's tiling engine (src/develop/tiling.c:723-1075): each rank runs
+the module chain on input rows [in_y0,in_y1) with roi_in.y = in_y0, keeps rows [out_y0,out_y1) and the
+finished RGBA bands are exchanged once -- all-gather (every rank ends with the frame) or gather to the
+exporting rank.  No collective inside the data path for the modules built here; modules whose result needs
+whole-frame statistics (wavelet thresholds, the local Laplacian pyramid) are refused in banded mode and run
+as replicas instead (8e: "replicas only (first build)").
+
+The cuts come from b200_band_plan(): on RCD's 94-row block grid when the chain starts with the demosaicer
+and everything after it is pointwise -- then the banded frame is bit-identical to the untiled one -- and
+tiling.c-style (overlap = sum of the modules' tiling_callback overlaps) otherwise.
+
+torch.distributed is the plumbing (NCCL over NVLink on the GPUs; gloo in the CPU tests of this host logic).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+import ansel_b200 as ab
+
+WHOLE_FRAME_OPS = {"bilat"}  # denoiseprofile in wavelet mode is checked per data block
+
+
+class Band(C.Structure):
+    """b200_band_t"""
+    _fields_ = [("out_y0", C.c_int), ("out_y1", C.c_int), ("in_y0", C.c_int), ("in_y1", C.c_int)]
+
+    def __repr__(self):
+        return f"Band(out=[{self.out_y0},{self.out_y1}) in=[{self.in_y0},{self.in_y1}))"
+
+
+def plan(height: int, n_bands: int, grid: int = 1, halo: int = 0, align: int = 1) -> list[Band]:
+    bands = (Band * n_bands)()
+    f = ab.lib().b200_band_plan
+    f.argtypes = [C.c_int] * 5 + [C.POINTER(Band)]
+    ab.check(f(height, n_bands, grid, halo, align, bands))
+    return list(bands)
+
+
+@dataclass
+class Node:
+    op: str            # "demosaic", "colorin", ...
+    data: object       # the ctypes data block behind piece->data
+    channels_in: int = 4
+
+
+def chain_cuts(nodes: list[Node], width: int, height: int) -> tuple[int, int, int]:
+    """(grid, halo, align) for a chain, from each module's own tiling numbers."""
+    L = ab.lib()
+    overlaps, aligns = [], []
+    for n in nodes:
+        if n.op in WHOLE_FRAME_OPS or (n.op == "denoiseprofile" and n.data.mode not in (ab.DENOISE_NLMEANS, ab.DENOISE_NLMEANS_AUTO)):
+            raise NotImplementedError(f"{n.op}: needs whole-frame statistics -- run it as replicas (SURVEY.md 8e)")
+        piece = ab.make_piece(width, height, filters=0x94949494 if n.channels_in == 1 else 0, channels=n.channels_in, data=n.data)
+        t = ab.Tiling()
+        getattr(L, f"b200_{n.op}_tiling")(C.byref(piece), C.byref(t))
+        overlaps.append(int(t.overlap))
+        aligns.append(max(1, int(t.yalign)))
+    align = 1
+    for a in aligns:
+        align = align * a // math.gcd(align, a)
+    if nodes and nodes[0].op == "demosaic" and not any(overlaps[1:]):
+        g, h_, a_ = C.c_int(), C.c_int(), C.c_int()
+        L.b200_demosaic_band_grid(None, C.byref(g), C.byref(h_), C.byref(a_))
+        return g.value, h_.value, a_.value
+    return 1, sum(overlaps), align
+
+
+def _cuda_process(op, piece, src, dst, stream):
+    ab.check(getattr(ab.lib(), f"b200_{op}_process_dev")(C.byref(piece), src.data_ptr(), dst.data_ptr(), stream))
+
+
+class BandedChain:
+    """Runs `nodes` on this rank's band of a width x height frame and assembles the frame.
+
+    process: callable(op, piece, src_tensor, dst_tensor, stream) -- the CUDA library by default; the CPU tests
+    of the sharding logic pass a numpy stand-in (no GPU there, and no CPU fallback in the product).
+    """
+
+    def __init__(self, nodes: list[Node], width: int, height: int, rank: int, world: int, device=None, process=None,
+                 filters: int = 0x94949494):
+        import torch
+        self.torch = torch
+        self.nodes, self.w, self.h, self.rank, self.world = nodes, width, height, rank, world
+        self.device = device if device is not None else torch.device("cpu")
+        self.process = process or _cuda_process
+        self.grid, self.halo, self.align = chain_cuts(nodes, width, height)
+        self.bands = plan(height, world, self.grid, self.halo, self.align)
+        self.band = self.bands[rank]
+        bh = self.band.in_y1 - self.band.in_y0
+        self.pieces = []
+        for n in nodes:
+            p = ab.make_piece(width, max(bh, 1), filters=filters if n.channels_in == 1 else 0, channels=n.channels_in, data=n.data,
+                              roi_y=self.band.in_y0, devid=self.device.index if self.device.type == "cuda" else -1)
+            p.buf_in_width, p.buf_in_height = width, height  # the full frame, as tiling.c leaves piece->buf_in
+            self.pieces.append(p)
+        self.tmp = [torch.empty((max(bh, 1), width, 4), dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.frame = torch.empty((height, width, 4), dtype=torch.float32, device=self.device)
+
+    def band_rows(self, frame_in):
+        """this rank's input rows of a full-frame host/device array"""
+        return frame_in[self.band.in_y0:self.band.in_y1]
+
+    def run_band(self, band_in, stream=0):
+        """chain over the band; returns a view of the rows this rank owns"""
+        b = self.band
+        if b.out_y1 == b.out_y0:
+            return self.tmp[0][:0]
+        src = band_in
+        for k, (n, p) in enumerate(zip(self.nodes, self.pieces)):
+            dst = self.tmp[k & 1]
+            self.process(n.op, p, src, dst, stream)
+            src = dst
+        return src[b.out_y0 - b.in_y0:b.out_y1 - b.in_y0]
+
+    def assemble(self, mine, mode: str = "allgather", dst_rank: int = 0):
+        """mode 'allgather': every rank returns the finished frame; 'gather': only dst_rank does (others None).
+        Bands differ in height (cuts sit on the block grid), so the exchange is one broadcast per band --
+        NCCL runs them back to back on its own stream; the bytes moved equal an all-gather's."""
+        torch = self.torch
+        b = self.band
+        if b.out_y1 > b.out_y0:
+            self.frame[b.out_y0:b.out_y1].copy_(mine)
+        if self.world == 1:
+            return self.frame
+        import torch.distributed as dist
+        if mode == "allgather":
+            works = [dist.broadcast(self.frame[q.out_y0:q.out_y1], src=r, async_op=True)
+                     for r, q in enumerate(self.bands) if q.out_y1 > q.out_y0]
+            for wk in works:
+                wk.wait()
+            return self.frame
+        if mode == "gather":
+            ops = []
+            if self.rank == dst_rank:
+                ops = [dist.P2POp(dist.irecv, self.frame[q.out_y0:q.out_y1], r) for r, q in enumerate(self.bands)
+                       if r != dst_rank and q.out_y1 > q.out_y0]
+            elif b.out_y1 > b.out_y0:
+                ops = [dist.P2POp(dist.isend, self.frame[b.out_y0:b.out_y1], dst_rank)]
+            if ops:
+                for wk in dist.batch_isend_irecv(ops):
+                    wk.wait()
+            return self.frame if self.rank == dst_rank else None
+        raise ValueError(mode)
+
+    def __call__(self, band_in, mode: str = "allgather", stream=0):
+        return self.assemble(self.run_band(band_in, stream), mode)

@@ -349,6 +349,22 @@ int b200_bilat_process_host(const b200_piece_t *piece, const void *in, void *out
 int b200_bilat_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
 void b200_bilat_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
 
+/* ---- sharding one frame over several GPUs ---------------------------------------
+ * Row bands = full-width tiles of the reference's tiling engine (src/develop/tiling.c:723-1075).
+ * A band reads input rows [in_y0,in_y1) with roi_in.y = in_y0 and owns output rows [out_y0,out_y1). */
+#define B200_MAX_BANDS 64
+typedef struct b200_band_t
+{
+  int out_y0, out_y1;
+  int in_y0, in_y1;
+} b200_band_t;
+/* grid == 1: cuts at multiples of `align`, `halo` rows of overlap on both sides (the tiling_callback numbers,
+ * summed over the chained modules).  grid > 1: cuts at k*grid+halo so a module with an internal block grid
+ * (RCD: grid 94, halo 9) gives the same bits as on the untiled frame.  Bands may come out empty when
+ * n_bands exceeds the number of block rows. */
+int b200_band_plan(int height, int n_bands, int grid, int halo, int align, b200_band_t *bands);
+void b200_demosaic_band_grid(const b200_piece_t *piece, int *grid, int *halo, int *align);
+
 /* ---- the libm the kernels use ------------------------------------------------------------------
  * Device restatement of glibc 2.39's single-precision expf/exp2f/logf/log2f/powf (the functions the
  * reference's CPU path calls; see ansel_b200/csrc/flt32_math.cuh).  Exposed so its bit-compatibility
