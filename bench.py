@@ -325,6 +325,39 @@ def run_b200(args):
     e2e_value = world * npx * args.e2e_steps / float(t_e.item()) / 1e6
     M.b200_pipe_buffers_free(bufs)
 
+    # ---- second mode at N>1: ONE frame cut into row bands + all-gather ---------
+    banded = None
+    if world > 1:
+        from ansel_b200 import bands
+        bnodes = [bands.Node("demosaic", d_dem, channels_in=1), bands.Node("colorin", d_cin), bands.Node("colorout", d_cout)]
+        frame0 = util.frame_natural(w, h, SEED)          # the same frame on every rank
+        ch = bands.BandedChain(bnodes, w, h, rank, world, device=dev)
+        t_band = torch.from_numpy(np.ascontiguousarray(ch.band_rows(frame0))).to(dev)
+        for _ in range(3):
+            ch(t_band, stream=stream)
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(args.steps):
+            out_frame = ch(t_band, stream=stream)
+        b1.record()
+        barrier()
+        t_b = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_b, op=dist.ReduceOp.MAX)
+        # every rank must now hold the frame rank 0 computes untiled
+        same = torch.ones(1, dtype=torch.int32, device=dev)
+        if rank == 0:
+            t_full = torch.from_numpy(frame0).to(dev)
+            ab.check(L.b200_demosaic_process_dev(p_dem, t_full.data_ptr(), t_rgb[0].data_ptr(), stream))
+            ab.check(L.b200_colorin_process_dev(p_cin, t_rgb[0].data_ptr(), t_rgb[1].data_ptr(), stream))
+            ab.check(L.b200_colorout_process_dev(p_cout, t_rgb[1].data_ptr(), t_rgb[2].data_ptr(), stream))
+            same[0] = int(torch.equal(out_frame.view(torch.int32), t_rgb[2].view(torch.int32)))
+        dist.broadcast(same, 0)
+        banded = {"value": npx * args.steps / (float(t_b.item()) * 1e-3) / 1e6, "unit": UNIT, "ms_per_frame": float(t_b.item()) / args.steps,
+                  "collective": "all-gather of finished RGBA bands (one ncclBroadcast per band, NVLink)",
+                  "cuts": "RCD 94-row block grid, 9-row halo", "bit_identical_to_untiled": bool(same.item()),
+                  "gathered_bytes_per_frame": 16 * npx}
+
     # ---- roofline of the dominant kernel (RCD tiles) --------------------------------------------
     peak, peak_src = peaks()
     dem_ms = float(np.mean(mod_ms["demosaic"]))
@@ -372,6 +405,8 @@ def run_b200(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if banded is not None:
+            line["banded_one_frame"] = banded
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
