@@ -103,13 +103,21 @@ class BilatData(C.Structure):
     _fields_ = [("mode", C.c_int), ("sigma_r", C.c_float), ("sigma_s", C.c_float), ("detail", C.c_float), ("midtone", C.c_float)]
 
 
+class DiffuseData(C.Structure):
+    """b200_diffuse_data_t == dt_iop_diffuse_params_t (src/iop/diffuse.c:76-109)."""
+    _fields_ = [("iterations", C.c_int), ("sharpness", C.c_float), ("radius", C.c_int), ("regularization", C.c_float),
+                ("variance_threshold", C.c_float), ("anisotropy_first", C.c_float), ("anisotropy_second", C.c_float),
+                ("anisotropy_third", C.c_float), ("anisotropy_fourth", C.c_float), ("threshold", C.c_float), ("first", C.c_float),
+                ("second", C.c_float), ("third", C.c_float), ("fourth", C.c_float), ("radius_center", C.c_int)]
+
+
 class B200Error(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libb200iop error {code}: {msg}")
         self.code = code
 
 
-OPS = ("demosaic", "colorin", "colorout", "denoiseprofile", "filmicrgb", "bilat")
+OPS = ("demosaic", "colorin", "colorout", "denoiseprofile", "filmicrgb", "bilat", "diffuse")
 
 _lib = None
 
@@ -289,3 +297,37 @@ def filmic_piece(data_blob, work, export=None) -> FilmicPiece:
 
 def bilat_data(sigma_r: float = 0.5, sigma_s: float = 0.5, detail: float = 0.25, midtone: float = 0.5, mode: int = 1) -> BilatData:
     return BilatData(mode, sigma_r, sigma_s, detail, midtone)
+
+
+# stock presets of src/iop/diffuse.c init_presets(), values as registered there
+DIFFUSE_PRESETS = {
+    "defaults": dict(),
+    # "lens deblur: soft" :298-320
+    "lens_deblur_soft": dict(iterations=8, radius=8, regularization=1.0, variance_threshold=0.0, anisotropy_first=2.0,
+                             anisotropy_second=0.0, anisotropy_third=2.0, anisotropy_fourth=0.0, first=-0.25, second=0.125,
+                             third=-0.125, fourth=0.0625),
+    # "sharpen demosaicing (AA filter)" :440-461
+    "sharpen_demosaic_aa": dict(iterations=1, radius=8, regularization=1.0, variance_threshold=0.0, anisotropy_first=1.0,
+                                anisotropy_second=1.0, anisotropy_third=1.0, anisotropy_fourth=1.0, first=-0.25, second=-0.25,
+                                third=-0.25, fourth=-0.25),
+    # "denoise: medium" :364-391
+    "denoise_medium": dict(iterations=32, radius=3, radius_center=4, regularization=2.5, variance_threshold=-0.0, anisotropy_first=2.0,
+                           anisotropy_second=0.0, anisotropy_third=2.0, anisotropy_fourth=0.0, first=0.10, second=0.0, third=0.10,
+                           fourth=0.0),
+    # "surface blur" :404-420
+    "surface_blur": dict(iterations=2, radius=32, regularization=4.0, variance_threshold=0.0, anisotropy_first=4.0, anisotropy_second=4.0,
+                         anisotropy_third=4.0, anisotropy_fourth=4.0, first=1.0, second=1.0, third=1.0, fourth=1.0),
+    # "bloom" :422-438
+    "bloom": dict(iterations=1, radius=32, regularization=0.0, variance_threshold=0.0, first=0.5, second=0.5, third=0.5, fourth=0.5),
+}
+
+
+def diffuse_data(**kw) -> DiffuseData:
+    """$DEFAULTs of dt_iop_diffuse_params_t, overridden by keyword."""
+    d = DiffuseData(iterations=1, sharpness=0.0, radius=8, regularization=0.0, variance_threshold=0.0, anisotropy_first=0.0,
+                    anisotropy_second=0.0, anisotropy_third=0.0, anisotropy_fourth=0.0, threshold=0.0, first=0.0, second=0.0,
+                    third=0.0, fourth=0.0, radius_center=0)
+    for k, v in kw.items():
+        assert hasattr(d, k), k
+        setattr(d, k, v)
+    return d

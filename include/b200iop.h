@@ -349,6 +349,28 @@ int b200_bilat_process_host(const b200_piece_t *piece, const void *in, void *out
 int b200_bilat_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
 void b200_bilat_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
 
+/* ---- diffuse or sharpen (src/iop/diffuse.c) ----------------------------------------------------- */
+#define B200_DIFFUSE_MAX_SCALES 10 /* MAX_NUM_SCALES, diffuse.c:75 */
+/* dt_iop_diffuse_data_t == dt_iop_diffuse_params_t, diffuse.c:76-109,132 (identical layout, 60 bytes) */
+typedef struct b200_diffuse_data_t
+{
+  int iterations;           /* default 1 */
+  float sharpness;          /* 0 */
+  int radius;               /* 8 */
+  float regularization;     /* 0 */
+  float variance_threshold; /* 0 */
+  float anisotropy_first, anisotropy_second, anisotropy_third, anisotropy_fourth;
+  float threshold;          /* luminance masking threshold; > 0 (inpainting mask) is not built */
+  float first, second, third, fourth;
+  int radius_center;
+} b200_diffuse_data_t;
+/* process(), diffuse.c:1155-1259: iterations x (a-trous B-spline decomposition into `scales` bands, then the
+ * anisotropic heat PDE band by band from coarse to fine).  zoom = piece->iscale / roi_in.scale. */
+int b200_diffuse_process_host(const b200_piece_t *piece, const void *in, void *out);
+int b200_diffuse_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
+/* tiling_callback(), diffuse.c:585-610 */
+void b200_diffuse_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
+
 /* ---- sharding one frame over several GPUs ---------------------------------------
  * Row bands = full-width tiles of the reference's tiling engine (src/develop/tiling.c:723-1075).
  * A band reads input rows [in_y0,in_y1) with roi_in.y = in_y0 and owns output rows [out_y0,out_y1). */

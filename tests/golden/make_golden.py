@@ -64,3 +64,8 @@ print("golden vectors written to", OUT)
 img = util.lab_scene(180, 131, 31)
 np.savez_compressed(os.path.join(OUT, "ll.npz"), img=img, out_default=util.ref_local_laplacian(img),
                     out_strong=util.ref_local_laplacian(img, sigma=0.2, shadows=1.5, highlights=0.1, clarity=1.0))
+import ansel_b200 as ab  # noqa: E402
+import test_cpu_oracle_pin as pin  # noqa: E402
+img = util.hdr_rgba(140, 101, 41)
+np.savez_compressed(os.path.join(OUT, "diffuse.npz"), img=img,
+                    **{k: util.ref_diffuse(img, ab.diffuse_data(**pin._diffuse_cases()[k])) for k in ("sharpen_demosaic_aa", "gradient_sharpen")})

@@ -272,3 +272,34 @@ def test_local_laplacian_oracle_equals_golden():
     g = _golden("ll.npz")
     assert same_bits(util.oracle_local_laplacian(g["img"]), g["out_default"]).all()
     assert same_bits(util.oracle_local_laplacian(g["img"], **LL_PARAMS[1]), g["out_strong"]).all()
+
+
+def _diffuse_cases():
+    import ansel_b200 as ab
+    out = {}
+    for name, kw in ab.DIFFUSE_PRESETS.items():
+        kw = dict(kw)
+        kw["iterations"] = min(kw.get("iterations", 1), 3)       # the stock counts (up to 32) only repeat the same step
+        out[name] = kw
+    out["gradient_sharpen"] = dict(iterations=2, radius=16, radius_center=4, sharpness=0.3, regularization=3.0, variance_threshold=-1.0,
+                                   anisotropy_first=-3.0, anisotropy_second=2.0, anisotropy_third=-0.5, anisotropy_fourth=5.0,
+                                   first=0.3, second=-0.6, third=0.8, fourth=-1.0)
+    return out
+
+
+@need_ref
+@pytest.mark.parametrize("name", list(_diffuse_cases()))
+def test_diffuse_oracle_equals_reference(name):
+    """iop/diffuse.c process() cut verbatim + pixel/bspline.h; NaN/inf/negative input included (hdr_rgba)."""
+    import ansel_b200 as ab
+    d = ab.diffuse_data(**_diffuse_cases()[name])
+    for (w, h), zoom in (((160, 120), 1.0), ((97, 61), 1.0), ((120, 90), 2.0), ((40, 7), 0.5)):
+        img = util.hdr_rgba(w, h, 3)
+        assert same_bits(util.oracle_diffuse(img, d, iscale=zoom), util.ref_diffuse(img, d, iscale=zoom)).all()
+
+
+def test_diffuse_oracle_equals_golden():
+    import ansel_b200 as ab
+    g = _golden("diffuse.npz")
+    for name in ("sharpen_demosaic_aa", "gradient_sharpen"):
+        assert same_bits(util.oracle_diffuse(g["img"], ab.diffuse_data(**_diffuse_cases()[name])), g[name]).all()

@@ -515,3 +515,30 @@ def oracle_local_laplacian(img, sigma=0.5, shadows=0.5, highlights=0.5, clarity=
 def ref_local_laplacian(img, sigma=0.5, shadows=0.5, highlights=0.5, clarity=0.25, kind="strict"):
     lib = ref(kind)
     return None if lib is None else _ll_call(lib, "ref_local_laplacian", img, sigma, shadows, highlights, clarity)
+
+
+# ---- diffuse or sharpen -------------------------------------------------------------------------------
+def _diffuse_call(lib, fn, img, data, iscale, roi_scale):
+    h, w = img.shape[:2]
+    src = aligned_empty(img.shape)
+    src[...] = img
+    out = aligned_empty(img.shape)
+    out[...] = 0
+    f = getattr(lib, fn)
+    f.restype = C.c_int
+    assert f(fptr(src), fptr(out), w, h, C.byref(data), C.c_float(iscale), C.c_float(roi_scale)) == 0
+    return np.array(out)
+
+
+def oracle_diffuse(img, data, iscale=1.0, roi_scale=1.0):
+    """data: ansel_b200.DiffuseData (== dt_iop_diffuse_params_t)"""
+    return _diffuse_call(oracle(), "orc_diffuse", img, data, iscale, roi_scale)
+
+
+def ref_diffuse(img, data, iscale=1.0, roi_scale=1.0, kind="strict"):
+    lib = ref(kind)
+    if lib is None:
+        return None
+    lib.ref_diffuse_sizeof_params.restype = C.c_size_t
+    assert lib.ref_diffuse_sizeof_params() == C.sizeof(data)
+    return _diffuse_call(lib, "ref_diffuse_process", img, data, iscale, roi_scale)
