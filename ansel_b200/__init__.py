@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200iop.so")
+LIB_PATH = os.environ.get("B200IOP_LIB") or os.path.join(HERE, "libb200iop.so")  # override: development A/B builds only
 MODLIB_PATH = os.path.join(HERE, "libb200_modules.so")
 
 # ---- error codes (include/b200iop.h) --------------------------------------------------------
@@ -111,13 +111,23 @@ class DiffuseData(C.Structure):
                 ("second", C.c_float), ("third", C.c_float), ("fourth", C.c_float), ("radius_center", C.c_int)]
 
 
+class NlmeansData(C.Structure):
+    """b200_nlmeans_data_t == dt_iop_nlmeans_params_t (src/iop/nlmeans.c:81-88)."""
+    _fields_ = [("radius", C.c_float), ("strength", C.c_float), ("luma", C.c_float), ("chroma", C.c_float)]
+
+
+class ProfileMatrices(C.Structure):
+    """b200_profile_matrices_t: rows of dt_colormatrix_t (3x4)."""
+    _fields_ = [("matrix_in", (C.c_float * 4) * 3), ("matrix_out", (C.c_float * 4) * 3)]
+
+
 class B200Error(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libb200iop error {code}: {msg}")
         self.code = code
 
 
-OPS = ("demosaic", "colorin", "colorout", "denoiseprofile", "filmicrgb", "bilat", "diffuse")
+OPS = ("demosaic", "colorin", "colorout", "denoiseprofile", "filmicrgb", "bilat", "diffuse", "nlmeans")
 
 _lib = None
 
@@ -331,3 +341,19 @@ def diffuse_data(**kw) -> DiffuseData:
         assert hasattr(d, k), k
         setattr(d, k, v)
     return d
+
+
+CS_LAB, CS_RGB = 1, 2
+
+
+def nlmeans_data(radius: float = 2.0, strength: float = 50.0, luma: float = 0.5, chroma: float = 1.0) -> NlmeansData:
+    return NlmeansData(radius, strength, luma, chroma)
+
+
+def profile_matrices(matrix_in, matrix_out) -> ProfileMatrices:
+    pm = ProfileMatrices()
+    for name, m in (("matrix_in", matrix_in), ("matrix_out", matrix_out)):
+        for r in range(3):
+            for c in range(3):
+                getattr(pm, name)[r][c] = float(m[r][c])
+    return pm

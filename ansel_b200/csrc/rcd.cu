@@ -33,7 +33,15 @@ constexpr int KEEP = 94;   // RCD_TILEVALID  rcd.c:75
 constexpr int RING = 9;    // RCD_BORDER     rcd.c:73
 constexpr int EDGE = 6;    // RCD_MARGIN     rcd.c:74
 constexpr int H = T / 2;   // width of a half plane row
-constexpr int RG = 8;      // row groups: NT = RG x 112 columns, or 2*RG x 56 site columns
+#ifndef RCD_RG
+#define RCD_RG 8
+#endif
+#ifndef RCD_UNROLL
+#define RCD_UNROLL 1
+#endif
+#define RCD_PRAGMA(x) _Pragma(#x)
+#define RCD_UNROLL_LOOP(n) RCD_PRAGMA(unroll n)
+constexpr int RG = RCD_RG; // row groups: NT = RG x 112 columns, or 2*RG x 56 site columns
 constexpr int NT = RG * T; // threads per CTA
 constexpr int SMEM_FLOATS = 2 * T * T + 4 * (T * T / 2);
 
@@ -106,9 +114,10 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
 
   // ---- step 1: squared V/H high-pass, then direction strength (rcd.c:353-390) ----------------
   for(int r = 3 + y4; r < tr - 3; r += RG)
+  {
     if(x112 >= 4 && x112 < tc - 4) vsq[r * T + x112] = hpf2(cfa + r * T + x112, T);
-  for(int r = 4 + y4; r < tr - 4; r += RG)
-    if(x112 >= 3 && x112 < tc - 3) hsq[r * T + x112] = hpf2(cfa + r * T + x112, 1);
+    if(r >= 4 && r < tr - 4 && x112 >= 3 && x112 < tc - 3) hsq[r * T + x112] = hpf2(cfa + r * T + x112, 1);
+  }
   __syncthreads();
   for(int r = 4 + y4; r < tr - 4; r += RG)
     if(x112 >= 4 && x112 < tc - 4)
@@ -120,7 +129,11 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
     }
   __syncthreads();
   // give the borrowed planes back: zero, then green-at-red/blue starts out as the raw value
-  for(int k = tid; k < 2 * T * T; k += NT) grb[k] = 0.0f; // grb, pq, pd, qd are contiguous
+  {
+    float4 *p = reinterpret_cast<float4 *>(grb); // grb, pq, pd, qd are contiguous
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for(int k = tid; k < 2 * T * T / 4; k += NT) p[k] = z;
+  }
   __syncthreads();
   for(int r = y8; r < tr; r += 2 * RG)
   {
@@ -142,6 +155,7 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
   __syncthreads();
 
   // ---- step 3.1: green at red/blue sites (rcd.c:406-437) -------------------------------------
+  RCD_UNROLL_LOOP(RCD_UNROLL)
   for(int r = 4 + y8; r < tr - 4; r += 2 * RG)
   {
     const int c = 4 + (fc(r, 0, f) & 1) + 2 * x56;
@@ -199,11 +213,16 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
   }
   __syncthreads();
   // pd becomes crb: the opposite colour at red/blue sites, zero where step 4.2 never writes
-  for(int k = tid; k < T * T / 2; k += NT) crb[k] = 0.0f;
+  {
+    float4 *p = reinterpret_cast<float4 *>(crb);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for(int k = tid; k < T * T / 8; k += NT) p[k] = z;
+  }
   __syncthreads();
 
   // ---- step 4.2: opposite colour at red/blue sites (rcd.c:462-491) ---------------------------
   // rgb[c] at the diagonal neighbours is that site's own raw value, i.e. cfa.
+  RCD_UNROLL_LOOP(RCD_UNROLL)
   for(int r = 4 + y8; r < tr - 4; r += 2 * RG)
   {
     const int c = 4 + (fc(r, 0, f) & 1) + 2 * x56;
@@ -234,6 +253,7 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
   // ---- step 4.3 fused with the store of the kept interior (rcd.c:494-554) --------------------
   const int ra = (tv == 0 ? EDGE : RING), rb = tr - (tv == a.nv - 1 ? EDGE : RING);
   const int ca = (th == 0 ? EDGE : RING), cb = tc - (th == a.nh - 1 ? EDGE : RING);
+  RCD_UNROLL_LOOP(RCD_UNROLL)
   for(int r = ra + y8; r < rb; r += 2 * RG)
   {
     const int rbpar = fc(r, 0, f) & 1; // column parity of the red/blue sites in this row

@@ -59,7 +59,7 @@ class PipeNode(C.Structure):
 
 
 _mod = None
-ADAPTED_OPS = ("demosaic", "colorin", "colorout", "denoiseprofile", "filmicrgb", "bilat", "diffuse")
+ADAPTED_OPS = ("demosaic", "colorin", "colorout", "denoiseprofile", "filmicrgb", "bilat", "diffuse", "nlmeans")
 
 
 def modlib() -> C.CDLL:

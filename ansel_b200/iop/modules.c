@@ -39,6 +39,7 @@ ADAPT(colorout) /* src/iop/colorout.c:373, :288-371 (process_cl) */
 
 ADAPT(denoiseprofile) /* src/iop/denoiseprofile.c:2037 (process), :1880-2035 (process_cl), :1091 (tiling_callback) */
 ADAPT(diffuse)        /* src/iop/diffuse.c:1155 (process), :1486 (process_cl), :585 (tiling_callback) */
+ADAPT(nlmeans)        /* src/iop/nlmeans.c:458 (process), :150-398 (process_cl), :400 (tiling_callback) */
 ADAPT(bilat)          /* src/iop/bilat.c:336 (process), :313-334 (process_cl), :296 (commit: tiling off) */
 
 /* filmic reads two pipe-level profiles next to piece->data (filmicrgb.c:2714-2715); the adapter flattens the

@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--height", type=int, default=H45)
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-modules", action="store_true", help="skip the untimed per-module table of the non-C2 modules")
     return ap.parse_args()
 
 
@@ -325,6 +326,36 @@ def run_b200(args):
     e2e_value = world * npx * args.e2e_steps / float(t_e.item()) / 1e6
     M.b200_pipe_buffers_free(bufs)
 
+    # ---- the other modules of SURVEY.md 8a at the same frame size (outside the timed region; N=1 only) ----
+    other = None
+    if world == 1 and not args.no_other_modules:
+        other = {}
+        work, export = util.profile_pair(util.REC2020_TO_XYZ_D50), util.profile_pair(util.SRGB_TO_XYZ_D50)
+        fblob = np.load(os.path.join(util.GOLDEN_DIR, "filmic_data.npz"))["default_v8"]
+        fp = ab.filmic_piece(fblob, work, export)
+        cases = [("denoiseprofile_wavelets", "denoiseprofile", ab.denoiseprofile_data(ab.DENOISE_WAVELETS), 2),
+                 ("denoiseprofile_nlmeans_K7_P1", "denoiseprofile", ab.denoiseprofile_data(ab.DENOISE_NLMEANS, radius=1, nbhood=7), 1),
+                 ("filmicrgb_v8_agx", "filmicrgb", fp, 3),
+                 ("diffuse_sharpen_demosaic_1it_5scales", "diffuse", ab.diffuse_data(**ab.DIFFUSE_PRESETS["sharpen_demosaic_aa"]), 2),
+                 ("bilat_local_laplacian", "bilat", ab.bilat_data(), 2)]
+        t_rgb[0].copy_(torch.rand((h, w, 4), device=dev))
+        for label, op, data, reps in cases:
+            pc = ab.make_piece(w, h, filters=0, channels=4, devid=local)
+            pc.data, pc.data_size = C.addressof(data), C.sizeof(data)
+            fn = getattr(L, f"b200_{op}_process_dev")
+            ab.check(fn(pc, t_rgb[0].data_ptr(), t_rgb[1].data_ptr(), stream))
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                ab.check(fn(pc, t_rgb[0].data_ptr(), t_rgb[1].data_ptr(), stream))
+                a1.record()
+                torch.cuda.synchronize()
+                ts.append(a0.elapsed_time(a1))
+            m = float(np.median(ts))
+            other[label] = {"ms": m, "MP_per_s": npx / m / 1e3, "algorithmic_GBps": 32 * npx / (m * 1e-3) / 1e9}
+
     # ---- second mode at N>1: ONE frame cut into row bands + all-gather ---------
     banded = None
     if world > 1:
@@ -405,6 +436,8 @@ def run_b200(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if other is not None:
+            line["config"]["other_modules_45mp"] = other
         if banded is not None:
             line["banded_one_frame"] = banded
         print(json.dumps(line))

@@ -371,6 +371,35 @@ int b200_diffuse_process_dev(const b200_piece_t *piece, const void *d_in, void *
 /* tiling_callback(), diffuse.c:585-610 */
 void b200_diffuse_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
 
+/* ---- denoise (non-local means) iop (src/iop/nlmeans.c) ------------------------------------------ */
+/* dt_iop_nlmeans_data_t == dt_iop_nlmeans_params_t, nlmeans.c:81-88,98 */
+typedef struct b200_nlmeans_data_t
+{
+  float radius;   /* patch size, default 2 */
+  float strength; /* default 50 */
+  float luma;     /* default 0.5 */
+  float chroma;   /* default 1.0 */
+} b200_nlmeans_data_t;
+/* process() :458-465 -> process_cpu :416-456 -> nlmeans_denoise() in Lab with center_weight = -1.  The
+ * patches are decimated on thumbnail and preview pipes (pipe_type B200_PIPE_THUMBNAIL / B200_PIPE_PREVIEW). */
+int b200_nlmeans_process_host(const b200_piece_t *piece, const void *in, void *out);
+int b200_nlmeans_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
+/* tiling_callback(), nlmeans.c:400-414 */
+void b200_nlmeans_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
+
+/* ---- RGB <-> Lab between modules of different colour space ------------------------------------------
+ * dt_colorspaces_apply_profile(), colorprofiles/iop_profile.c:1300-1359 -> dt_ioppr_transform_matrix :566-596
+ * -> _transform_rgb_to_lab_matrix :376-420 / _transform_lab_to_rgb_matrix :422-464, for the pipe's work
+ * profile.  Built for linear work profiles (nonlinearlut == 0: linear Rec2020, the default, and every other
+ * "linear ..." built-in); a work profile with tone curves returns B200_ERR_UNSUPPORTED.
+ * cst: dt_iop_colorspace_type_t (pixel/format.h): 1 = IOP_CS_LAB, 2 = IOP_CS_RGB.  d_in == d_out allowed.
+ * RGB -> Lab leaves lane 3 as the reference does (not written: in place it keeps the pixel's alpha, which is
+ * what this entry stores); Lab -> RGB copies the input alpha. */
+#define B200_CS_LAB 1
+#define B200_CS_RGB 2
+int b200_colorspace_transform_dev(const void *d_in, void *d_out, int width, int height, int cst_from, int cst_to,
+                                  const b200_profile_matrices_t *work_profile, int nonlinearlut, void *stream);
+
 /* ---- sharding one frame over several GPUs ---------------------------------------
  * Row bands = full-width tiles of the reference's tiling engine (src/develop/tiling.c:723-1075).
  * A band reads input rows [in_y0,in_y1) with roi_in.y = in_y0 and owns output rows [out_y0,out_y1). */

@@ -303,3 +303,38 @@ def test_diffuse_oracle_equals_golden():
     g = _golden("diffuse.npz")
     for name in ("sharpen_demosaic_aa", "gradient_sharpen"):
         assert same_bits(util.oracle_diffuse(g["img"], ab.diffuse_data(**_diffuse_cases()[name])), g[name]).all()
+
+
+WORK_PROFILE = util.profile_pair(util.REC2020_TO_XYZ_D50)
+
+
+@need_ref
+def test_lab_glue_oracle_equals_reference():
+    """colorprofiles/iop_profile.c _transform_rgb_to_lab_matrix / _transform_lab_to_rgb_matrix cut verbatim."""
+    rgb = util.hdr_rgba(333, 217, 6)                     # negatives, zeros, NaN, inf, > 1
+    assert same_bits(util.oracle_rgb_to_lab(rgb, WORK_PROFILE), util.ref_rgb_to_lab(rgb, WORK_PROFILE)).all()
+    lab = util.lab_scene(333, 217, 6)
+    lab[5, 5, :3] = (0.0, 0.0, 0.0)
+    lab[6, 6, :3] = (7.9, -300.0, 250.0)                 # both branches of lab_f_inv
+    lab[7, 7, 0] = np.nan
+    assert same_bits(util.oracle_lab_to_rgb(lab, WORK_PROFILE), util.ref_lab_to_rgb(lab, WORK_PROFILE)).all()
+
+
+def test_lab_glue_oracle_equals_golden():
+    g = _golden("labglue.npz")
+    assert same_bits(util.oracle_rgb_to_lab(g["rgb"], WORK_PROFILE), g["lab_of_rgb"]).all()
+    assert same_bits(util.oracle_lab_to_rgb(g["lab"], WORK_PROFILE), g["rgb_of_lab"]).all()
+
+
+@need_ref
+@pytest.mark.parametrize("scale,pipe,prev", [(1.0, 1, 0), (0.5, 1, 0), (2.5, 2, 0), (0.3, 4, 0), (0.4, 3, 1)])
+def test_nlmeans_iop_oracle_equals_reference(scale, pipe, prev):
+    """iop/nlmeans.c process_cpu cut verbatim: P, K, sharpness, Lab norms, decimation, mask alpha copy."""
+    import ansel_b200 as ab
+    img = util.lab_scene(150, 110, 3)
+    for d in (ab.nlmeans_data(), ab.nlmeans_data(radius=1.0, strength=120.0, luma=1.0, chroma=1.0)):
+        dec = 1 if (pipe == 4 or prev) else 0
+        for mask in (0, 1):
+            got = util.oracle_nlmeans_iop(img, d, scale, dec, mask)
+            want = util.ref_nlmeans_iop(img, d, scale, pipe, prev, mask)
+            assert same_bits(got, want).all()

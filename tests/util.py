@@ -542,3 +542,63 @@ def ref_diffuse(img, data, iscale=1.0, roi_scale=1.0, kind="strict"):
     lib.ref_diffuse_sizeof_params.restype = C.c_size_t
     assert lib.ref_diffuse_sizeof_params() == C.sizeof(data)
     return _diffuse_call(lib, "ref_diffuse_process", img, data, iscale, roi_scale)
+
+
+# ---- RGB <-> Lab glue, denoise (non-local means) iop --------------------------------------------------
+def _glue(lib, fn, img, m, nargs):
+    h, w = img.shape[:2]
+    src = aligned_empty(img.shape)
+    src[...] = img
+    out = aligned_empty(img.shape)
+    out[...] = img            # lane 3 of RGB->Lab is not written by the reference: compare it as "kept"
+    f = getattr(lib, fn)
+    f.restype = C.c_int
+    mats = [(C.c_float * 9)(*np.asarray(x, np.float32).reshape(-1)) for x in m]
+    assert f(fptr(src), fptr(out), w, h, *mats[:nargs]) == 0
+    return np.array(out)
+
+
+def oracle_rgb_to_lab(img, work):
+    return _glue(oracle(), "orc_rgb_to_lab", img, (work[0],), 1)
+
+
+def oracle_lab_to_rgb(img, work):
+    return _glue(oracle(), "orc_lab_to_rgb", img, (work[1],), 1)
+
+
+def ref_rgb_to_lab(img, work, kind="strict"):
+    lib = ref(kind)
+    return None if lib is None else _glue(lib, "ref_rgb_to_lab", img, work, 2)
+
+
+def ref_lab_to_rgb(img, work, kind="strict"):
+    lib = ref(kind)
+    return None if lib is None else _glue(lib, "ref_lab_to_rgb", img, work, 2)
+
+
+def oracle_nlmeans_iop(img, data, roi_scale=1.0, decimate=0, mask_display=0):
+    h, w = img.shape[:2]
+    src = aligned_empty(img.shape)
+    src[...] = img
+    out = aligned_empty(img.shape)
+    out[...] = 0
+    f = oracle().orc_nlmeans_iop
+    f.restype = C.c_int
+    assert f(fptr(src), fptr(out), w, h, C.byref(data), C.c_double(roi_scale), decimate, mask_display) == 0
+    return np.array(out)
+
+
+def ref_nlmeans_iop(img, data, roi_scale=1.0, pipe_type=1, has_preview=0, mask_display=0, kind="strict"):
+    lib = ref(kind)
+    if lib is None:
+        return None
+    h, w = img.shape[:2]
+    src = aligned_empty(img.shape)
+    src[...] = img
+    out = aligned_empty(img.shape)
+    out[...] = 0
+    f = lib.ref_nlmeans_iop
+    f.restype = C.c_int
+    assert f(fptr(src), fptr(out), w, h, (C.c_float * 4)(data.radius, data.strength, data.luma, data.chroma), C.c_double(roi_scale),
+             pipe_type, has_preview, mask_display) == 0
+    return np.array(out)
