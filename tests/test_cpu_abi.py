@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(built):
 def test_module_adapters_export_reference_symbol_names(built):
     import ansel_b200.dtsurface as ds
     M = ds.modlib()
-    for op in ("demosaic", "colorin", "colorout"):
+    for op in ds.ADAPTED_OPS:
         for fn in ("process", "process_cl", "tiling_callback"):
             assert hasattr(M, f"dt_iop_{op}__{fn}")
 
@@ -51,6 +51,19 @@ def test_no_cuda_device_fails_loudly(built):
     assert L.b200_demosaic_process_host(piece, m.ctypes.data, out.ctypes.data) != 0
     assert b"no CUDA device" in L.b200_last_error() or b"CUDA" in L.b200_last_error()
     assert (out == 0).all()
+    # every other module: same refusal, nothing computed on the CPU
+    rgba = np.zeros((64, 64, 4), np.float32)
+    conv = ab.make_conversion(util.MATRIX_CAM_TO_REC2020)
+    blob = np.load(os.path.join(util.GOLDEN_DIR, "filmic_data.npz"))["default_v8"]
+    fp = ab.filmic_piece(blob, util.profile_pair(util.REC2020_TO_XYZ_D50))
+    datas = dict(colorin=ab.colorin_data(conv), colorout=ab.colorout_data(conv), denoiseprofile=ab.denoiseprofile_data(),
+                 nlmeans=ab.nlmeans_data(), filmicrgb=fp, diffuse=ab.diffuse_data(), bilat=ab.bilat_data())
+    for op, data in datas.items():
+        pc = ab.make_piece(64, 64, filters=0, channels=4)
+        pc.data, pc.data_size = C.addressof(data), C.sizeof(data)
+        out[...] = -3.0
+        assert getattr(L, f"b200_{op}_process_host")(pc, rgba.ctypes.data, out.ctypes.data) != 0, op
+        assert (out == -3.0).all(), op
 
 
 def _shift_dcraw(filters, x, y):
@@ -104,6 +117,15 @@ def test_tiling_callbacks_match_reference_contract(built):
     piece = ab.make_piece(6000, 4000, filters=0, channels=4, data=ab.colorin_data(conv))
     L.b200_colorin_tiling(piece, t)
     assert (t.overlap, t.xalign, t.yalign, t.factor) == (0, 1, 1, 2.0)  # tiling.c:1423-1440
+    piece = ab.make_piece(6000, 4000, filters=0, channels=4, data=ab.diffuse_data(radius=8))
+    L.b200_diffuse_tiling(piece, t)
+    assert (t.overlap, t.xalign, t.yalign) == (32, 1, 1) and abs(t.factor - (6.0625 + 5)) < 1e-6  # diffuse.c:585-610: 5 scales
+    piece = ab.make_piece(6000, 4000, filters=0, channels=4, data=ab.nlmeans_data(radius=2.0))
+    L.b200_nlmeans_tiling(piece, t)
+    assert (t.overlap, t.xalign, t.yalign) == (2 + 7, 1, 1) and abs(t.factor - 4.0) < 1e-6    # nlmeans.c:400-414
+    piece = ab.make_piece(6000, 4000, filters=0, channels=4, data=ab.denoiseprofile_data(ab.DENOISE_NLMEANS, radius=1, nbhood=7))
+    L.b200_denoiseprofile_tiling(piece, t)
+    assert t.overlap == 1 + 7                                                                  # denoiseprofile.c:803-811
 
 
 def test_abi_struct_layout_matches_reference_headers(built):
