@@ -348,6 +348,40 @@ extern "C" int b200_copy_device_to_host(void *h_dst, const void *d_src, size_t b
   if(!h_dst || !d_src) return fail(B200_ERR_ARG, "copy_device_to_host: NULL");
   return copy_d2h(h_dst, d_src, bytes, (cudaStream_t)stream);
 }
+extern "C" int b200_stream_create(void **stream)
+{
+  if(!stream) return fail(B200_ERR_ARG, "stream_create: NULL");
+  cudaStream_t s;
+  B200_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *stream = (void *)s;
+  return B200_OK;
+}
+extern "C" void b200_stream_destroy(void *stream)
+{
+  if(stream) cudaStreamDestroy((cudaStream_t)stream);
+}
+extern "C" int b200_event_create(void **event)
+{
+  if(!event) return fail(B200_ERR_ARG, "event_create: NULL");
+  cudaEvent_t e;
+  B200_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  *event = (void *)e;
+  return B200_OK;
+}
+extern "C" void b200_event_destroy(void *event)
+{
+  if(event) cudaEventDestroy((cudaEvent_t)event);
+}
+extern "C" int b200_event_record(void *event, void *stream)
+{
+  B200_CUDA_TRY(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream));
+  return B200_OK;
+}
+extern "C" int b200_stream_wait_event(void *stream, void *event)
+{
+  B200_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0));
+  return B200_OK;
+}
 extern "C" int b200_stream_synchronize(void *stream)
 {
   B200_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));

@@ -74,6 +74,12 @@ def modlib() -> C.CDLL:
         M.b200_pipe_buffers_free.argtypes = [C.c_void_p]
         M.b200_pixelpipe_process_on_gpu.argtypes = [C.POINTER(Pipe), C.POINTER(PipeNode), C.c_int, C.c_void_p,
                                                     C.c_void_p, C.c_void_p]
+        M.b200_pipe_queue_new.restype = C.c_void_p
+        M.b200_pipe_queue_new.argtypes = [C.c_int]
+        M.b200_pipe_queue_free.argtypes = [C.c_void_p]
+        M.b200_pixelpipe_submit.restype = C.c_long
+        M.b200_pixelpipe_submit.argtypes = [C.c_void_p, C.POINTER(Pipe), C.POINTER(PipeNode), C.c_int, C.c_void_p, C.c_void_p]
+        M.b200_pixelpipe_wait.argtypes = [C.c_void_p, C.c_long]
         for op in ADAPTED_OPS:
             getattr(M, f"dt_iop_{op}__process").argtypes = [C.POINTER(Module), C.POINTER(Pipe), C.POINTER(PipeIop),
                                                             C.c_void_p, C.c_void_p]

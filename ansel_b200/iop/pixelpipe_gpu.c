@@ -24,6 +24,12 @@ void b200_dev_free(void *ptr);
 int b200_copy_host_to_device(void *d_dst, const void *h_src, size_t bytes, void *stream);
 int b200_copy_device_to_host(void *h_dst, const void *d_src, size_t bytes, void *stream);
 int b200_stream_synchronize(void *stream);
+int b200_stream_create(void **stream);
+void b200_stream_destroy(void *stream);
+int b200_event_create(void **event);
+void b200_event_destroy(void *event);
+int b200_event_record(void *event, void *stream);
+int b200_stream_wait_event(void *stream, void *event);
 
 static size_t buffer_bytes(const dt_iop_buffer_dsc_t *dsc, const dt_iop_roi_t *roi)
 {
@@ -79,4 +85,90 @@ int b200_pixelpipe_process_on_gpu(const dt_dev_pixelpipe_t *pipe, const b200_pip
   if(b200_copy_device_to_host(host_out, bufs->buf[n_nodes & 1], buffer_bytes(&last->dsc_out, &last->roi_out), pipe->stream))
     return 1;
   return b200_stream_synchronize(pipe->stream);
+}
+
+
+/* ---- several frames in flight --------------------------------------------------------------------
+ * A batch export or the darkroom's preview + full pipes keep more than one pipe busy per
+ * device; the reference gives each pipe its own OpenCL command queue (opencl.c:1641-1725).  Here: `depth` slots,
+ * each with its own stream and ping-pong buffers.  Uploads run ahead on the slot's stream, the module chains
+ * of successive frames are ordered by an event (modules share the calling thread's device scratch), and the
+ * read-back of frame n overlaps upload and compute of frame n+1 -- PCIe is full duplex. */
+#define B200_QUEUE_MAX_DEPTH 8
+typedef struct b200_pipe_queue_t
+{
+  int depth;
+  unsigned long submitted;
+  void *stream[B200_QUEUE_MAX_DEPTH];
+  void *compute_done[B200_QUEUE_MAX_DEPTH];
+  b200_pipe_buffers_t bufs[B200_QUEUE_MAX_DEPTH];
+} b200_pipe_queue_t;
+
+void b200_pipe_queue_free(b200_pipe_queue_t *q)
+{
+  if(!q) return;
+  for(int k = 0; k < q->depth; k++)
+  {
+    if(q->stream[k]) b200_stream_synchronize(q->stream[k]);
+    b200_event_destroy(q->compute_done[k]);
+    b200_stream_destroy(q->stream[k]);
+    for(int j = 0; j < 2; j++) b200_dev_free(q->bufs[k].buf[j]);
+  }
+  free(q);
+}
+b200_pipe_queue_t *b200_pipe_queue_new(int depth)
+{
+  if(depth < 1 || depth > B200_QUEUE_MAX_DEPTH) return NULL;
+  b200_pipe_queue_t *q = calloc(1, sizeof(*q));
+  if(!q) return NULL;
+  q->depth = depth;
+  for(int k = 0; k < depth; k++)
+    if(b200_stream_create(&q->stream[k]) || b200_event_create(&q->compute_done[k]))
+    {
+      b200_pipe_queue_free(q);
+      return NULL;
+    }
+  return q;
+}
+/* Enqueue one frame; returns a ticket >= 0, or -1.  host_in must stay valid until the upload has run and
+ * host_out until b200_pixelpipe_wait(ticket) returns; both should be pinned for the copies to be asynchronous.
+ * Submitting into a slot that is still busy waits for that slot's previous frame first. */
+long b200_pixelpipe_submit(b200_pipe_queue_t *q, const dt_dev_pixelpipe_t *pipe, const b200_pipe_node_t *nodes, int n_nodes,
+                           const void *host_in, void *host_out)
+{
+  if(!q || !pipe || !nodes || n_nodes < 1 || !host_in || !host_out) return -1;
+  const int slot = (int)(q->submitted % (unsigned long)q->depth);
+  void *const st = q->stream[slot];
+  b200_pipe_buffers_t *const bufs = &q->bufs[slot];
+  if(b200_stream_synchronize(st)) return -1;
+  size_t need[2] = { 0, 0 };
+  for(int k = 0; k < n_nodes; k++)
+  {
+    const size_t bi = buffer_bytes(&nodes[k].piece->dsc_in, &nodes[k].piece->roi_in);
+    const size_t bo = buffer_bytes(&nodes[k].piece->dsc_out, &nodes[k].piece->roi_out);
+    if(bi > need[k & 1]) need[k & 1] = bi;
+    if(bo > need[(k + 1) & 1]) need[(k + 1) & 1] = bo;
+  }
+  if(ensure(bufs, 0, need[0]) || ensure(bufs, 1, need[1])) return -1;
+  if(b200_copy_host_to_device(bufs->buf[0], host_in, buffer_bytes(&nodes[0].piece->dsc_in, &nodes[0].piece->roi_in), st)) return -1;
+  if(q->submitted > 0)
+  { /* one module chain at a time on the device */
+    const int prev = (int)((q->submitted - 1) % (unsigned long)q->depth);
+    if(prev != slot && b200_stream_wait_event(st, q->compute_done[prev])) return -1;
+  }
+  dt_dev_pixelpipe_t p = *pipe;
+  p.stream = st;
+  for(int k = 0; k < n_nodes; k++)
+    if(!nodes[k].process_cl(nodes[k].module, &p, nodes[k].piece, bufs->buf[k & 1], bufs->buf[(k + 1) & 1])) return -1;
+  if(b200_event_record(q->compute_done[slot], st)) return -1;
+  const dt_dev_pixelpipe_iop_t *last = nodes[n_nodes - 1].piece;
+  if(b200_copy_device_to_host(host_out, bufs->buf[n_nodes & 1], buffer_bytes(&last->dsc_out, &last->roi_out), st)) return -1;
+  return (long)(q->submitted++);
+}
+/* Block until the frame of `ticket` is in its host_out.  Returns 0 on success. */
+int b200_pixelpipe_wait(b200_pipe_queue_t *q, long ticket)
+{
+  if(!q || ticket < 0 || (unsigned long)ticket >= q->submitted) return 1;
+  if(q->submitted - (unsigned long)ticket > (unsigned long)q->depth) return 0; /* its slot was reused: already waited for */
+  return b200_stream_synchronize(q->stream[(unsigned long)ticket % (unsigned long)q->depth]);
 }

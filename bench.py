@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--width", type=int, default=W45)
     ap.add_argument("--height", type=int, default=H45)
-    ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-modules", action="store_true", help="skip the untimed per-module table of the non-C2 modules")
     return ap.parse_args()
@@ -303,28 +303,48 @@ def run_b200(args):
         nodes[k].process_cl = C.cast(getattr(M, f"dt_iop_{op}__process_cl"), C.c_void_p)
         nodes[k].module = pieces[k].module
         nodes[k].piece = C.pointer(pieces[k])
-    bufs = M.b200_pipe_buffers_new()
+    # two frames in flight (b200_pixelpipe_submit/_wait): the read-back of frame n overlaps upload + compute of
+    # frame n+1.  Every step still uploads its own input and reads its own result back inside the timed region.
+    DEPTH = 2
+    queue = M.b200_pipe_queue_new(DEPTH)
     h_in = torch.from_numpy(mosaic).pin_memory()
-    h_out = torch.empty((h, w, 4), dtype=torch.float32).pin_memory()
+    h_out = [torch.empty((h, w, 4), dtype=torch.float32).pin_memory() for _ in range(DEPTH)]
 
-    def e2e_step():
-        rc = M.b200_pixelpipe_process_on_gpu(C.byref(pipe), nodes, 3, bufs, h_in.data_ptr(), h_out.data_ptr())
-        if rc != 0:
-            raise RuntimeError("e2e chain failed: " + L.b200_last_error().decode())
+    def e2e_run(n):
+        tickets = []
+        for i in range(n):
+            t = M.b200_pixelpipe_submit(queue, C.byref(pipe), nodes, 3, h_in.data_ptr(), h_out[i % DEPTH].data_ptr())
+            if t < 0:
+                raise RuntimeError("e2e chain failed: " + L.b200_last_error().decode())
+            tickets.append(t)
+            if i >= DEPTH - 1:                      # the consumer takes frame i-DEPTH+1 before its buffer is reused
+                if M.b200_pixelpipe_wait(queue, tickets[i - DEPTH + 1]) != 0:
+                    raise RuntimeError("e2e wait failed: " + L.b200_last_error().decode())
+        for t in tickets[-(DEPTH - 1):] if DEPTH > 1 else []:
+            if M.b200_pixelpipe_wait(queue, t) != 0:
+                raise RuntimeError("e2e wait failed: " + L.b200_last_error().decode())
 
-    for _ in range(2):
-        e2e_step()
+    e2e_run(3)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_step()
+    e2e_run(args.e2e_steps)
     barrier()
     e2e_s = time.perf_counter() - t0
+    # the synchronous single-frame call, for reference (one frame at a time: upload, chain, read back)
+    bufs = M.b200_pipe_buffers_new()
+    for _ in range(2):
+        M.b200_pixelpipe_process_on_gpu(C.byref(pipe), nodes, 3, bufs, h_in.data_ptr(), h_out[0].data_ptr())
+    t1 = time.perf_counter()
+    for _ in range(4):
+        if M.b200_pixelpipe_process_on_gpu(C.byref(pipe), nodes, 3, bufs, h_in.data_ptr(), h_out[0].data_ptr()) != 0:
+            raise RuntimeError("e2e chain failed: " + L.b200_last_error().decode())
+    e2e_sync_ms = (time.perf_counter() - t1) / 4 * 1e3
+    M.b200_pipe_buffers_free(bufs)
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = world * npx * args.e2e_steps / float(t_e.item()) / 1e6
-    M.b200_pipe_buffers_free(bufs)
+    M.b200_pipe_queue_free(queue)
 
     # ---- the other modules of SURVEY.md 8a at the same frame size (outside the timed region; N=1 only) ----
     other = None
@@ -426,7 +446,8 @@ def run_b200(args):
                        "per_module": per_module},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * npx, "d2h_bytes_per_step": 16 * npx,
                     "steps": args.e2e_steps,
-                    "path": "dt_iop_<op>__process_cl adapters via b200_pixelpipe_process_on_gpu, pinned host buffers"},
+                    "path": "dt_iop_<op>__process_cl adapters via b200_pixelpipe_submit/_wait, 2 frames in flight, pinned host buffers",
+                    "single_frame_sync_ms": e2e_sync_ms},
             "gpu_launches": gpu_launches,
             "clocks": clk.summary(),
             "roofline": {"bound": "hbm", "kernel": "rcd_tiles_kernel (+rcd_ring_kernel, <1% of the pair)", "achieved": achieved,

@@ -111,6 +111,14 @@ void b200_dev_free(void *ptr);
 int b200_copy_host_to_device(void *d_dst, const void *h_src, size_t bytes, void *stream);
 int b200_copy_device_to_host(void *h_dst, const void *d_src, size_t bytes, void *stream);
 int b200_stream_synchronize(void *stream);
+/* streams and events for callers that keep several frames in flight (the reference's per-device command queues
+ * and dt_opencl_events_*, src/common/opencl.c): non-blocking streams; events without timing */
+int b200_stream_create(void **stream);
+void b200_stream_destroy(void *stream);
+int b200_event_create(void **event);
+void b200_event_destroy(void *event);
+int b200_event_record(void *event, void *stream);
+int b200_stream_wait_event(void *stream, void *event);
 
 /* integer CFA phase: dt_dev_get_roi_filters() develop/imageop.c:139-142 ->
  * dt_rawspeed_crop_dcraw_filters() imageio/imageio_rawspeed.cc:146-151 ->

@@ -138,3 +138,40 @@ def test_scene_referred_chain_device_resident(built):
     want = cur.cpu().numpy()
     assert same_bits(out, want).all()
     assert np.isfinite(out[..., :3]).all() and out[..., :3].min() >= 0.0 and out[..., :3].max() <= 1.001
+
+
+def test_frames_in_flight_equal_one_at_a_time(built):
+    """b200_pixelpipe_submit/_wait with 1, 2 and 3 slots: five different frames, same bits as the synchronous call."""
+    import torch
+    import ansel_b200 as ab
+    import ansel_b200.dtsurface as ds
+    ab.init()
+    M = ds.modlib()
+    w, h = 1204, 806
+    datas, pieces, pipe, _keep = _chain(w, h)
+    order = ("demosaic", "denoiseprofile", "colorin", "filmicrgb", "colorout")   # denoise uses the shared device scratch
+    nodes = (ds.PipeNode * len(order))()
+    for k, op in enumerate(order):
+        nodes[k].process_cl = C.cast(getattr(M, f"dt_iop_{op}__process_cl"), C.c_void_p)
+        nodes[k].module = pieces[op].module
+        nodes[k].piece = C.pointer(pieces[op])
+    frames = [torch.from_numpy(util.frame_natural(w, h, 20 + i)).pin_memory() for i in range(5)]
+    bufs = M.b200_pipe_buffers_new()
+    want = []
+    for f in frames:
+        out = np.zeros((h, w, 4), np.float32)
+        assert M.b200_pixelpipe_process_on_gpu(C.byref(pipe), nodes, len(order), bufs, f.data_ptr(), out.ctypes.data) == 0
+        want.append(out)
+    M.b200_pipe_buffers_free(bufs)
+    for depth in (1, 2, 3):
+        q = M.b200_pipe_queue_new(depth)
+        assert q
+        outs = [torch.zeros((h, w, 4), dtype=torch.float32).pin_memory() for _ in frames]
+        tickets = [M.b200_pixelpipe_submit(q, C.byref(pipe), nodes, len(order), f.data_ptr(), o.data_ptr()) for f, o in zip(frames, outs)]
+        assert tickets == list(range(5))
+        for t in tickets:
+            assert M.b200_pixelpipe_wait(q, t) == 0
+        M.b200_pipe_queue_free(q)
+        for o, wnt in zip(outs, want):
+            assert same_bits(o.numpy(), wnt).all(), depth
+    assert M.b200_pipe_queue_new(0) is None and M.b200_pipe_queue_new(9) is None
