@@ -12,13 +12,18 @@
 //   * no FMA contraction, IEEE division, FTZ on (the reference sets FTZ|DAZ, rcd.c:300): the
 //     library is compiled with --fmad=false -ftz=true -prec-div=true.
 //
-// Shared-memory planes per tile (floats):  cfa[T*T]  vh[T*T]  grb[T*T/2]  pq[T*T/2]  pd[T*T/2]
-// qd[T*T/2]  = 200,704 B  -> one CTA per SM.
-//   grb : green at red/blue sites (rgb[1] there; equals cfa until step 3.1 writes it)
-//   pq  : low-pass, later PQ_Dir -- the reference aliases them too (rcd.c:314)
-//   pd  : P_CDiff_Hpf, later "crb" = the opposite colour at red/blue sites (rgb[2-FC])
-//   qd  : Q_CDiff_Hpf
-// Half-width planes are addressed with flat_index/2 exactly like rcd.c:396,444,453,464.
+// Shared-memory planes per tile, all with a row pitch of 56 floats:
+//   cfaE cfaO   raw values at even / odd columns          vhE vhO   VH_Dir at even / odd columns
+//   grb   green at red/blue sites (rgb[1] there; equals cfa until step 3.1 writes it)
+//   pq    low-pass, later PQ_Dir -- the reference aliases them too (rcd.c:314)
+//   pd    P_CDiff_Hpf, later "crb" = the opposite colour at red/blue sites (rgb[2-FC])
+//   qd    Q_CDiff_Hpf
+// = 8 regions of 6272 floats + 16 floats of padding each = 201,216 B -> one CTA per SM.
+// The half-width planes of the reference are addressed with flat_index/2 (rcd.c:396,444,453,464) =
+// row*56 + (col>>1); the full planes are split by column parity so that they use the SAME index.  Red/blue-
+// site loops (lane stride = 2 columns) then walk every plane with stride 1, and full-width loops put even
+// lanes in the E plane and odd lanes in the O plane, whose base is 16 banks further: no bank conflicts
+// (the interleaved layout paid +49 % shared-memory wavefronts, profiles/r01_rcd_tiles_ncu.md).
 // rgb[0]/rgb[2] at green sites are only ever consumed by the output loop, so step 4.3 is fused
 // into the store and evaluated for kept pixels only.
 //
@@ -43,7 +48,9 @@ constexpr int H = T / 2;   // width of a half plane row
 #define RCD_UNROLL_LOOP(n) RCD_PRAGMA(unroll n)
 constexpr int RG = RCD_RG; // row groups: NT = RG x 112 columns, or 2*RG x 56 site columns
 constexpr int NT = RG * T; // threads per CTA
-constexpr int SMEM_FLOATS = 2 * T * T + 4 * (T * T / 2);
+constexpr int HP = T * H;       // floats in one half plane
+constexpr int RS = HP + 16;     // region stride: consecutive regions sit 16 banks apart
+constexpr int SMEM_FLOATS = 8 * RS;
 
 constexpr float kEps = 1e-5f;    // rcd.c:81
 constexpr float kEpsSq = 1e-10f; // rcd.c:82
@@ -64,9 +71,10 @@ __device__ __forceinline__ int fc(int row, int col, uint32_t f)
 }
 __device__ __forceinline__ float sq(float v) { return v * v; }
 __device__ __forceinline__ float mixf(float a, float b, float c) { return a * (b - c) + c; } // iop/demosaic.c:250-257
-__device__ __forceinline__ float hpf2(const float *p, int s)
+// squared 7-tap high-pass of rcd.c:360-386,442-449 from its taps at -3..3
+__device__ __forceinline__ float hpf2v(float m3, float m2, float m1, float c0, float p1, float p2, float p3)
 {
-  return sq((p[-3 * s] - p[-s] - p[s] + p[3 * s]) - 3.0f * (p[-2 * s] + p[2 * s]) + 6.0f * p[0]);
+  return sq((m3 - m1 - p1 + p3) - 3.0f * (m2 + p2) + 6.0f * c0);
 }
 __device__ __forceinline__ float refine(float centre, float nb)
 {
@@ -78,16 +86,16 @@ __device__ __forceinline__ double dabs(float a, float b) { return (double)fabsf(
 __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
 {
   extern __shared__ __align__(16) float smem[];
-  float *const cfa = smem;
-  float *const vh = cfa + T * T;
-  float *const grb = vh + T * T;
-  float *const pq = grb + T * T / 2;
-  float *const pd = pq + T * T / 2;
-  float *const qd = pd + T * T / 2;
+  float *const cfa = smem;          // E plane at +0, O plane at +RS
+  float *const vh = smem + 2 * RS;  // likewise
+  float *const grb = smem + 4 * RS;
+  float *const pq = smem + 5 * RS;
+  float *const pd = smem + 6 * RS;
+  float *const qd = smem + 7 * RS;
   float *const crb = pd;
-  // scratch views used only during step 1 (grb/pq and pd/qd are idle then)
-  float *const vsq = grb; // full plane: squared vertical high-pass
-  float *const hsq = pd;  // full plane: squared horizontal high-pass
+  // scratch views used only during step 1 (grb/pq and pd/qd are idle then): E/O planes like cfa
+  float *const vsq = grb; // squared vertical high-pass
+  float *const hsq = pd;  // squared horizontal high-pass
 
   const int tid = threadIdx.x;
   const int tv = blockIdx.x / a.nh, th = blockIdx.x - tv * a.nh;
@@ -98,6 +106,11 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
   // thread -> (column, row group) maps; no integer division by runtime values anywhere below
   const int x112 = tid % T, y4 = tid / T; // RG row groups over full-width domains
   const int x56 = tid % H, y8 = tid / H;  // 2*RG row groups over every-second-column domains
+  // full-width domains: element (r, x112) of a split plane sits at fb + r*56; its left/right neighbours
+  // x-1, x+1, x-3, x+3 at fo + r*56 + {0, 1, -1, 2}; x-2, x+2 at fb + r*56 -+ 1
+  const int fpx = x112 & 1;
+  const int fb = fpx * RS + (x112 >> 1);
+  const int fo = (1 - fpx) * RS + (x112 >> 1) + fpx - 1;
 
   // ---- clear everything: the reference's never-written scratch is defined as zero ------------
   {
@@ -109,47 +122,54 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
 
   // ---- step 0: load, clamp, normalise (rcd.c:343-351) ---------------------------------------
   for(int r = y4; r < tr; r += RG)
-    if(x112 < tc) cfa[r * T + x112] = fmaxf(0.0f, __ldg(a.in + (size_t)(row0 + r) * a.width + col0 + x112)) * a.revscaler;
+    if(x112 < tc) cfa[fb + r * H] = fmaxf(0.0f, __ldg(a.in + (size_t)(row0 + r) * a.width + col0 + x112)) * a.revscaler;
   __syncthreads();
 
   // ---- step 1: squared V/H high-pass, then direction strength (rcd.c:353-390) ----------------
   for(int r = 3 + y4; r < tr - 3; r += RG)
   {
-    if(x112 >= 4 && x112 < tc - 4) vsq[r * T + x112] = hpf2(cfa + r * T + x112, T);
-    if(r >= 4 && r < tr - 4 && x112 >= 3 && x112 < tc - 3) hsq[r * T + x112] = hpf2(cfa + r * T + x112, 1);
+    const float *c = cfa + fb + r * H, *o = cfa + fo + r * H;
+    if(x112 >= 4 && x112 < tc - 4) vsq[fb + r * H] = hpf2v(c[-3 * H], c[-2 * H], c[-H], c[0], c[H], c[2 * H], c[3 * H]);
+    if(r >= 4 && r < tr - 4 && x112 >= 3 && x112 < tc - 3) hsq[fb + r * H] = hpf2v(o[-1], c[-1], o[0], c[0], o[1], c[1], o[2]);
   }
   __syncthreads();
   for(int r = 4 + y4; r < tr - 4; r += RG)
     if(x112 >= 4 && x112 < tc - 4)
     {
-      const int i = r * T + x112;
-      const float vs = fmaxf(kEpsSq, vsq[i - T] + vsq[i] + vsq[i + T]);
-      const float hs = fmaxf(kEpsSq, hsq[i - 1] + hsq[i] + hsq[i + 1]);
+      const int i = fb + r * H, j = fo + r * H;
+      const float vs = fmaxf(kEpsSq, vsq[i - H] + vsq[i] + vsq[i + H]);
+      const float hs = fmaxf(kEpsSq, hsq[j] + hsq[i] + hsq[j + 1]);
       vh[i] = vs / (vs + hs);
     }
   __syncthreads();
   // give the borrowed planes back: zero, then green-at-red/blue starts out as the raw value
   {
-    float4 *p = reinterpret_cast<float4 *>(grb); // grb, pq, pd, qd are contiguous
+    float4 *p = reinterpret_cast<float4 *>(grb); // grb, pq, pd, qd (and their padding) are contiguous
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for(int k = tid; k < 2 * T * T / 4; k += NT) p[k] = z;
+    for(int k = tid; k < 4 * RS / 4; k += NT) p[k] = z;
   }
   __syncthreads();
   for(int r = y8; r < tr; r += 2 * RG)
   {
-    const int c = (fc(r, 0, f) & 1) + 2 * x56;
-    if(c < tc) grb[(r * T + c) / 2] = cfa[r * T + c];
+    const int p = fc(r, 0, f) & 1;
+    if(p + 2 * x56 < tc) grb[r * H + x56] = cfa[p * RS + r * H + x56];
   }
+
+  // Red/blue site (r, c), c = base + p + 2*x56 with p = the column parity of those sites in row r:
+  //   h  = r*56 + (c>>1)   index in every half plane and inside a split plane
+  //   sb = p*RS + h        same-parity plane: (r+dr, c+2k) at sb + 56*dr + k
+  //   ob = (1-p)*RS + h + p - 1   other plane: c-1, c+1, c-3, c+3 at ob + {0, 1, -1, 2} (+ 56*dr)
+  //   half-plane neighbours: (c-1)>>1 = h + p - 1, (c+1)>>1 = h + p
 
   // ---- step 2.1: low-pass at red/blue sites (rcd.c:394-402) ----------------------------------
   for(int r = 2 + y8; r < tr - 2; r += 2 * RG)
   {
-    const int c = 2 + (fc(r, 0, f) & 1) + 2 * x56;
-    if(c < tc - 2)
+    const int p = fc(r, 0, f) & 1;
+    if(2 + p + 2 * x56 < tc - 2)
     {
-      const int i = r * T + c;
-      pq[i / 2] = cfa[i] + 0.5f * (cfa[i - T] + cfa[i + T] + cfa[i - 1] + cfa[i + 1])
-                  + 0.25f * (cfa[i - T - 1] + cfa[i - T + 1] + cfa[i + T - 1] + cfa[i + T + 1]);
+      const int h = r * H + 1 + x56;
+      const float *s = cfa + p * RS + h, *o = cfa + (1 - p) * RS + h + p - 1;
+      pq[h] = s[0] + 0.5f * (s[-H] + s[H] + o[0] + o[1]) + 0.25f * (o[-H] + o[1 - H] + o[H] + o[1 + H]);
     }
   }
   __syncthreads();
@@ -158,15 +178,16 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
   RCD_UNROLL_LOOP(RCD_UNROLL)
   for(int r = 4 + y8; r < tr - 4; r += 2 * RG)
   {
-    const int c = 4 + (fc(r, 0, f) & 1) + 2 * x56;
-    if(c < tc - 4)
+    const int p = fc(r, 0, f) & 1;
+    if(4 + p + 2 * x56 < tc - 4)
     {
-      const int i = r * T + c, h = i / 2;
-      const float x = cfa[i];
-      const float u1 = cfa[i - T], u2 = cfa[i - 2 * T], u3 = cfa[i - 3 * T], u4 = cfa[i - 4 * T];
-      const float d1 = cfa[i + T], d2 = cfa[i + 2 * T], d3 = cfa[i + 3 * T], d4 = cfa[i + 4 * T];
-      const float l1 = cfa[i - 1], l2 = cfa[i - 2], l3 = cfa[i - 3], l4 = cfa[i - 4];
-      const float r1 = cfa[i + 1], r2 = cfa[i + 2], r3 = cfa[i + 3], r4 = cfa[i + 4];
+      const int h = r * H + 2 + x56;
+      const float *s = cfa + p * RS + h, *o = cfa + (1 - p) * RS + h + p - 1;
+      const float x = s[0];
+      const float u1 = s[-H], u2 = s[-2 * H], u3 = s[-3 * H], u4 = s[-4 * H];
+      const float d1 = s[H], d2 = s[2 * H], d3 = s[3 * H], d4 = s[4 * H];
+      const float l1 = o[0], l2 = s[-1], l3 = o[-1], l4 = s[-2];
+      const float r1 = o[1], r2 = s[1], r3 = o[2], r4 = s[2];
       const double ud = dabs(u1, d1), lr = dabs(l1, r1);
       const float gn = (float)((double)kEps + ud + dabs(x, u2) + dabs(u1, u3) + dabs(u2, u4));
       const float gs = (float)((double)kEps + ud + dabs(x, d2) + dabs(d1, d3) + dabs(d2, d4));
@@ -174,27 +195,31 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
       const float ge = (float)((double)kEps + lr + dabs(x, r2) + dabs(r1, r3) + dabs(r2, r4));
 
       const float l = pq[h], ll = l + l;
-      const float en = u1 * ll / (kEps + l + pq[h - T]);
-      const float es = d1 * ll / (kEps + l + pq[h + T]);
+      const float en = u1 * ll / (kEps + l + pq[h - 2 * H]);
+      const float es = d1 * ll / (kEps + l + pq[h + 2 * H]);
       const float ew = l1 * ll / (kEps + l + pq[h - 1]);
       const float ee = r1 * ll / (kEps + l + pq[h + 1]);
 
       const float ev = (gs * en + gn * es) / (gn + gs);
       const float eh = (gw * ee + ge * ew) / (ge + gw);
-      const float nb = 0.25f * (vh[i - T - 1] + vh[i - T + 1] + vh[i + T - 1] + vh[i + T + 1]);
-      grb[h] = mixf(refine(vh[i], nb), eh, ev);
+      const float *vo = vh + (1 - p) * RS + h + p - 1; // the four diagonal neighbours are of the other parity
+      const float nb = 0.25f * (vo[-H] + vo[1 - H] + vo[H] + vo[1 + H]);
+      grb[h] = mixf(refine(vh[p * RS + h], nb), eh, ev);
     }
   }
 
   // ---- step 4.0: squared diagonal high-pass at every second column from 3 (rcd.c:442-449) -----
+  // site (r, c), c = 3 + 2*x56 odd, m = c>>1: (r+k, c+k) is in the O plane for even k, the E plane for odd k,
+  // at column index m + ((k+1)>>1); (r+k, c-k) at m + ((1-k)>>1)
   for(int r = 3 + y8; r < tr - 3; r += 2 * RG)
   {
-    const int c = 3 + 2 * x56;
-    if(c < tc - 3)
+    if(3 + 2 * x56 < tc - 3)
     {
-      const int i = r * T + c;
-      pd[i / 2] = hpf2(cfa + i, T + 1);
-      qd[i / 2] = hpf2(cfa + i, T - 1);
+      const int h = r * H + 1 + x56;
+      const float *e = cfa + h, *o = cfa + RS + h;
+      const float c0 = o[0];
+      pd[h] = hpf2v(e[-3 * H - 1], o[-2 * H - 1], e[-H], c0, e[H + 1], o[2 * H + 1], e[3 * H + 2]);
+      qd[h] = hpf2v(e[-3 * H + 2], o[-2 * H + 1], e[-H + 1], c0, e[H], o[2 * H - 1], e[3 * H - 1]);
     }
   }
   __syncthreads();
@@ -202,10 +227,10 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
   // ---- step 4.1: P/Q direction strength, overwriting the low-pass (rcd.c:451-459) ------------
   for(int r = 4 + y8; r < tr - 4; r += 2 * RG)
   {
-    const int c = 4 + (fc(r, 0, f) & 1) + 2 * x56;
-    if(c < tc - 4)
+    const int p = fc(r, 0, f) & 1;
+    if(4 + p + 2 * x56 < tc - 4)
     {
-      const int i = r * T + c, h = i / 2, hu = (i - T - 1) / 2, hd = (i + T - 1) / 2;
+      const int h = r * H + 2 + x56, hu = h - H + p - 1, hd = h + H + p - 1;
       const float ps = fmaxf(kEpsSq, pd[hu] + pd[h] + pd[hd + 1]);
       const float qs = fmaxf(kEpsSq, qd[hu + 1] + qd[h] + qd[hd]);
       pq[h] = ps / (ps + qs);
@@ -216,7 +241,7 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
   {
     float4 *p = reinterpret_cast<float4 *>(crb);
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for(int k = tid; k < T * T / 8; k += NT) p[k] = z;
+    for(int k = tid; k < HP / 4; k += NT) p[k] = z;
   }
   __syncthreads();
 
@@ -225,24 +250,24 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
   RCD_UNROLL_LOOP(RCD_UNROLL)
   for(int r = 4 + y8; r < tr - 4; r += 2 * RG)
   {
-    const int c = 4 + (fc(r, 0, f) & 1) + 2 * x56;
-    if(c < tc - 4)
+    const int p = fc(r, 0, f) & 1;
+    if(4 + p + 2 * x56 < tc - 4)
     {
-      const int i = r * T + c, h = i / 2, hu = (i - T - 1) / 2, hd = (i + T - 1) / 2;
+      const int h = r * H + 2 + x56, hu = h - H + p - 1, hd = h + H + p - 1;
       const float nb = 0.25f * (pq[hu] + pq[hu + 1] + pq[hd] + pq[hd + 1]);
       const float disc = refine(pq[h], nb);
 
-      const int nw = i - T - 1, ne = i - T + 1, sw = i + T - 1, se = i + T + 1;
-      const float cnw = cfa[nw], cne = cfa[ne], csw = cfa[sw], cse = cfa[se];
+      const float *o = cfa + (1 - p) * RS + h + p - 1;
+      const float cnw = o[-H], cne = o[1 - H], csw = o[H], cse = o[1 + H];
       const float g = grb[h];
       const double d_nwse = dabs(cnw, cse), d_nesw = dabs(cne, csw);
-      const float gnw = (float)((double)kEps + d_nwse + dabs(cnw, cfa[i - 3 * T - 3]) + dabs(g, grb[(i - 2 * T - 2) / 2]));
-      const float gne = (float)((double)kEps + d_nesw + dabs(cne, cfa[i - 3 * T + 3]) + dabs(g, grb[(i - 2 * T + 2) / 2]));
-      const float gsw = (float)((double)kEps + d_nesw + dabs(csw, cfa[i + 3 * T - 3]) + dabs(g, grb[(i + 2 * T - 2) / 2]));
-      const float gse = (float)((double)kEps + d_nwse + dabs(cse, cfa[i + 3 * T + 3]) + dabs(g, grb[(i + 2 * T + 2) / 2]));
+      const float gnw = (float)((double)kEps + d_nwse + dabs(cnw, o[-3 * H - 1]) + dabs(g, grb[h - 2 * H - 1]));
+      const float gne = (float)((double)kEps + d_nesw + dabs(cne, o[-3 * H + 2]) + dabs(g, grb[h - 2 * H + 1]));
+      const float gsw = (float)((double)kEps + d_nesw + dabs(csw, o[3 * H - 1]) + dabs(g, grb[h + 2 * H - 1]));
+      const float gse = (float)((double)kEps + d_nwse + dabs(cse, o[3 * H + 2]) + dabs(g, grb[h + 2 * H + 1]));
 
-      const float dnw = cnw - grb[nw / 2], dne = cne - grb[ne / 2];
-      const float dsw = csw - grb[sw / 2], dse = cse - grb[se / 2];
+      const float dnw = cnw - grb[hu], dne = cne - grb[hu + 1];
+      const float dsw = csw - grb[hd], dse = cse - grb[hd + 1];
       const float ep = (gnw * dse + gse * dnw) / (gnw + gse);
       const float eq = (gne * dsw + gsw * dne) / (gne + gsw);
       crb[h] = g + mixf(disc, eq, ep);
@@ -258,16 +283,16 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
   {
     const int rbpar = fc(r, 0, f) & 1; // column parity of the red/blue sites in this row
     const int native = fc(r, rbpar, f); // 0 or 2: the colour those sites carry
+    const int h = r * H + x56;          // both sites of this thread's column pair share it
     // --- the red/blue site of this thread's column pair
     {
       const int c = 2 * x56 + rbpar;
       if(c >= ca && c < cb)
       {
-        const int i = r * T + c;
         float px[3];
-        px[native] = cfa[i];
-        px[1] = grb[i / 2];
-        px[2 - native] = crb[i / 2];
+        px[native] = cfa[rbpar * RS + h];
+        px[1] = grb[h];
+        px[2 - native] = crb[h];
         float4 o = make_float4(a.scaler * fmaxf(0.0f, px[0]), a.scaler * fmaxf(0.0f, px[1]),
                                a.scaler * fmaxf(0.0f, px[2]), 0.0f);
         __stcs(reinterpret_cast<float4 *>(a.out + 4 * ((size_t)(row0 + r) * a.width + col0 + c)), o);
@@ -275,34 +300,34 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
     }
     // --- the green site: red and blue from the four cardinal neighbours
     {
-      const int c = 2 * x56 + (1 - rbpar);
+      const int q = 1 - rbpar, c = 2 * x56 + q;
       if(c >= ca && c < cb)
       {
-        const int i = r * T + c;
-        const float nb = 0.25f * (vh[i - T - 1] + vh[i - T + 1] + vh[i + T - 1] + vh[i + T + 1]);
-        const float disc = refine(vh[i], nb);
-        const float g = cfa[i];
-        const float n1 = (float)((double)kEps + dabs(g, cfa[i - 2 * T]));
-        const float s1 = (float)((double)kEps + dabs(g, cfa[i + 2 * T]));
-        const float w1 = (float)((double)kEps + dabs(g, cfa[i - 2]));
-        const float e1 = (float)((double)kEps + dabs(g, cfa[i + 2]));
-        const float gu = grb[(i - T) / 2], gd = grb[(i + T) / 2], gl = grb[(i - 1) / 2], gr = grb[(i + 1) / 2];
+        const float *s = cfa + q * RS + h;               // the site and its same-column / +-2 column neighbours
+        const float *vo = vh + (1 - q) * RS + h + q - 1; // VH_Dir at the diagonal neighbours
+        const float nb = 0.25f * (vo[-H] + vo[1 - H] + vo[H] + vo[1 + H]);
+        const float disc = refine(vh[q * RS + h], nb);
+        const float g = s[0];
+        const float n1 = (float)((double)kEps + dabs(g, s[-2 * H]));
+        const float s1 = (float)((double)kEps + dabs(g, s[2 * H]));
+        const float w1 = (float)((double)kEps + dabs(g, s[-1]));
+        const float e1 = (float)((double)kEps + dabs(g, s[1]));
+        const int hl = h + q - 1; // half index of the left neighbour; the right one is hl + 1
+        const float gu = grb[h - H], gd = grb[h + H], gl = grb[hl], gr = grb[hl + 1];
 
         // Vertical neighbours carry colour `vcol` natively, horizontal ones carry `native`.
-        // rgb[k] at a site of the other colour is crb there; at its own colour it is cfa.
+        // rgb[k] at a site of the other colour is crb there; at its own colour it is cfa.  Both planes have
+        // a 56-float row pitch, so one base pointer per direction serves either.
         const int vcol = 2 - native;
         float px[3];
         px[1] = g;
 #pragma unroll
         for(int k = 0; k <= 2; k += 2)
         {
-          const float *const pv = (k == vcol) ? cfa : crb; // plane holding rgb[k] above/below
-          const float *const ph = (k == native) ? cfa : crb; // ... left/right
-          const int sv = (k == vcol) ? 0 : 1, sh = (k == native) ? 0 : 1; // crb is half-indexed
-          const float cu1 = pv[(i - T) >> sv], cd1 = pv[(i + T) >> sv];
-          const float cu3 = pv[(i - 3 * T) >> sv], cd3 = pv[(i + 3 * T) >> sv];
-          const float cl1 = ph[(i - 1) >> sh], cr1 = ph[(i + 1) >> sh];
-          const float cl3 = ph[(i - 3) >> sh], cr3 = ph[(i + 3) >> sh];
+          const float *const pv = (k == vcol) ? s : (crb + h);                                   // (r+-1, c), (r+-3, c)
+          const float *const ph = (k == native) ? (cfa + (1 - q) * RS + hl) : (crb + hl);         // c-1, c+1, c-3, c+3 at {0, 1, -1, 2}
+          const float cu1 = pv[-H], cd1 = pv[H], cu3 = pv[-3 * H], cd3 = pv[3 * H];
+          const float cl1 = ph[0], cr1 = ph[1], cl3 = ph[-1], cr3 = ph[2];
           const float sn = fabsf(cu1 - cd1), ew = fabsf(cl1 - cr1);
           const float gn = (float)((double)(n1 + sn) + dabs(cu1, cu3));
           const float gs = (float)((double)(s1 + sn) + dabs(cd1, cd3));
