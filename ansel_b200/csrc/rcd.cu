@@ -112,17 +112,27 @@ __global__ void __launch_bounds__(NT, 1) rcd_tiles_kernel(const rcd_args_t a)
   const int fb = fpx * RS + (x112 >> 1);
   const int fo = (1 - fpx) * RS + (x112 >> 1) + fpx - 1;
 
-  // ---- clear everything: the reference's never-written scratch is defined as zero ------------
-  {
-    float4 *p = reinterpret_cast<float4 *>(smem);
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for(int k = tid; k < SMEM_FLOATS / 4; k += NT) p[k] = z;
-  }
-  __syncthreads();
-
   // ---- step 0: load, clamp, normalise (rcd.c:343-351) ---------------------------------------
-  for(int r = y4; r < tr; r += RG)
-    if(x112 < tc) cfa[fb + r * H] = fmaxf(0.0f, __ldg(a.in + (size_t)(row0 + r) * a.width + col0 + x112)) * a.revscaler;
+  // All of a thread's loads are issued before anything else, so the tile costs one DRAM/L2 round trip, and that
+  // round trip is spent clearing shared memory: the reference's never-written scratch is defined as zero.
+  {
+    constexpr int NR = T / RG;
+    static_assert(NR * RG == T, "row groups must divide the tile");
+    float v[NR];
+    const float *src = a.in + (size_t)(row0 + y4) * a.width + col0 + x112;
+    const size_t pitch = (size_t)RG * a.width;
+#pragma unroll
+    for(int k = 0; k < NR; k++) v[k] = (x112 < tc && y4 + k * RG < tr) ? __ldg(src + k * pitch) : 0.0f;
+    {
+      float4 *p = reinterpret_cast<float4 *>(smem);
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      for(int k = tid; k < SMEM_FLOATS / 4; k += NT) p[k] = z;
+    }
+    __syncthreads();
+#pragma unroll
+    for(int k = 0; k < NR; k++)
+      if(x112 < tc && y4 + k * RG < tr) cfa[fb + (y4 + k * RG) * H] = fmaxf(0.0f, v[k]) * a.revscaler;
+  }
   __syncthreads();
 
   // ---- step 1: squared V/H high-pass, then direction strength (rcd.c:353-390) ----------------
