@@ -71,6 +71,13 @@ def chain_cuts(nodes: list[Node], width: int, height: int) -> tuple[int, int, in
     return 1, sum(overlaps), align
 
 
+class _DeviceArray:
+    """a raw device allocation seen through __cuda_array_interface__ (zero-copy torch.as_tensor)"""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
 def _cuda_process(op, piece, src, dst, stream):
     ab.check(getattr(ab.lib(), f"b200_{op}_process_dev")(C.byref(piece), src.data_ptr(), dst.data_ptr(), stream))
 
@@ -83,7 +90,7 @@ class BandedChain:
     """
 
     def __init__(self, nodes: list[Node], width: int, height: int, rank: int, world: int, device=None, process=None,
-                 filters: int = 0x94949494):
+                 filters: int = 0x94949494, p2p: bool = False):
         import torch
         self.torch = torch
         self.nodes, self.w, self.h, self.rank, self.world = nodes, width, height, rank, world
@@ -100,7 +107,74 @@ class BandedChain:
             p.buf_in_width, p.buf_in_height = width, height  # the full frame, as tiling.c leaves piece->buf_in
             self.pieces.append(p)
         self.tmp = [torch.empty((max(bh, 1), width, 4), dtype=torch.float32, device=self.device) for _ in range(2)]
-        self.frame = torch.empty((height, width, 4), dtype=torch.float32, device=self.device)
+        self.p2p = bool(p2p) and world > 1
+        self._own_ptr, self._peer_ptr = None, {}
+        if not self.p2p:
+            self.frame = torch.empty((height, width, 4), dtype=torch.float32, device=self.device)
+        else:
+            self._map_peer_frames()
+
+    # ---- the gather fused into the last kernel (b200_colorout_process_scatter_dev) -----------------------------
+    def _map_peer_frames(self):
+        """every rank allocates its frame with b200_dev_alloc, exports it over CUDA IPC and maps the others'"""
+        import torch.distributed as dist
+        torch = self.torch
+        if self.nodes[-1].op != "colorout":
+            raise NotImplementedError("p2p gather: the chain must end with colorout (the kernel that carries the scatter)")
+        L = ab.lib()
+        nbytes = self.h * self.w * 16
+        own = C.c_void_p()
+        ab.check(L.b200_dev_alloc(C.byref(own), C.c_size_t(nbytes)))
+        self._own_ptr = own.value
+        self.frame = torch.as_tensor(_DeviceArray(own.value, (self.h, self.w, 4)), device=self.device)
+        handle = (C.c_ubyte * 64)()
+        ab.check(L.b200_ipc_export(own, handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle))
+        for r, hb in enumerate(handles):
+            if r == self.rank:
+                continue
+            p = C.c_void_p()
+            ab.check(L.b200_ipc_import((C.c_ubyte * 64).from_buffer_copy(hb), C.byref(p)))
+            self._peer_ptr[r] = p.value
+        b = self.band
+        self._last_piece = ab.make_piece(self.w, max(b.out_y1 - b.out_y0, 1), filters=0, channels=4, data=self.nodes[-1].data, roi_y=b.out_y0,
+                                         devid=self.device.index)
+        self._last_piece.buf_in_width, self._last_piece.buf_in_height = self.w, self.h
+        row = b.out_y0 * self.w * 16
+        ptrs = [self._own_ptr + row] + [self._peer_ptr[r] + row for r in sorted(self._peer_ptr)]
+        self._dsts = (C.c_void_p * len(ptrs))(*ptrs)
+
+    def close(self):
+        """unmap the peers' frames and free this rank's (p2p mode); collective"""
+        if not self.p2p or self._own_ptr is None:
+            return
+        import torch.distributed as dist
+        L = ab.lib()
+        self.torch.cuda.synchronize()
+        for p in self._peer_ptr.values():
+            L.b200_ipc_release(C.c_void_p(p))
+        dist.barrier()                       # nobody frees a frame a peer still has mapped
+        self.frame = None
+        L.b200_dev_free(C.c_void_p(self._own_ptr))
+        self._own_ptr, self._peer_ptr = None, {}
+
+    def run_scatter(self, band_in, stream=0):
+        """chain over the band; the last module writes the owned rows into every rank's frame itself"""
+        import torch.distributed as dist
+        b = self.band
+        if b.out_y1 > b.out_y0:
+            src = band_in
+            for k, (n, p) in enumerate(zip(self.nodes[:-1], self.pieces[:-1])):
+                dst = self.tmp[k & 1]
+                self.process(n.op, p, src, dst, stream)
+                src = dst
+            kept = src[b.out_y0 - b.in_y0:b.out_y1 - b.in_y0]      # pointwise last module: only the owned rows
+            ab.check(ab.lib().b200_colorout_process_scatter_dev(C.byref(self._last_piece), C.c_void_p(kept.data_ptr()), len(self._dsts),
+                                                               self._dsts, C.c_void_p(stream)))
+        # the stores of every rank must have landed before anyone reads its frame
+        dist.barrier()
+        return self.frame
 
     def band_rows(self, frame_in):
         """this rank's input rows of a full-frame host/device array"""
@@ -149,4 +223,6 @@ class BandedChain:
         raise ValueError(mode)
 
     def __call__(self, band_in, mode: str = "allgather", stream=0):
+        if self.p2p:
+            return self.run_scatter(band_in, stream)
         return self.assemble(self.run_band(band_in, stream), mode)

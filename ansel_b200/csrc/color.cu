@@ -35,6 +35,9 @@ struct conv_args_t
   const float *lut_t[3];
   float co_s[9], co_t[9];
   int decode, encode, clip, copy_alpha;
+  // further destinations of the same pixels: peer GPUs' copies of the frame (b200_apply_conversion_scatter_dev)
+  int n_mirror;
+  float4 *mirror[B200_MAX_SCATTER - 1];
 };
 
 template <bool CONTRACT> __device__ __forceinline__ float4 mat4(const float *m, float x, float y, float z)
@@ -120,6 +123,8 @@ template <bool CONTRACT> __global__ void __launch_bounds__(CONV_THREADS) convert
     }
     if(a.copy_alpha) v.w = alpha_in; // dt_iop_alpha_copy when the pipe displays a mask
     __stcs(a.out + k, v);
+    // the all-gather of the finished band, done by the producer: plain stores into the peers' frames over NVLink
+    for(int m = 0; m < a.n_mirror; m++) a.mirror[m][k] = v;
   }
 }
 
@@ -197,8 +202,23 @@ int device_curves(const float *const host[3], uint64_t identity, int side, cudaS
 
 using namespace b200;
 
+static int apply_conversion(const b200_conversion_t *c, const void *d_in, void *d_out, int n_mirror, void *const *mirrors, size_t width,
+                            size_t height, int copy_alpha, void *stream_);
 extern "C" int b200_apply_conversion_dev(const b200_conversion_t *c, const void *d_in, void *d_out, size_t width,
                                          size_t height, int copy_alpha, void *stream_)
+{
+  return apply_conversion(c, d_in, d_out, 0, nullptr, width, height, copy_alpha, stream_);
+}
+extern "C" int b200_apply_conversion_scatter_dev(const b200_conversion_t *c, const void *d_in, int n_out, void *const *d_outs,
+                                                 size_t width, size_t height, int copy_alpha, void *stream_)
+{
+  if(n_out < 1 || n_out > B200_MAX_SCATTER || !d_outs) return fail(B200_ERR_ARG, "apply_conversion_scatter: 1..%d destinations", B200_MAX_SCATTER);
+  for(int k = 0; k < n_out; k++)
+    if(!d_outs[k]) return fail(B200_ERR_ARG, "apply_conversion_scatter: NULL destination");
+  return apply_conversion(c, d_in, d_outs[0], n_out - 1, d_outs + 1, width, height, copy_alpha, stream_);
+}
+static int apply_conversion(const b200_conversion_t *c, const void *d_in, void *d_out, int n_mirror, void *const *mirrors, size_t width,
+                            size_t height, int copy_alpha, void *stream_)
 {
   if(!c || !d_in || !d_out) return fail(B200_ERR_ARG, "apply_conversion: NULL argument");
   if(!c->is_matrix)
@@ -213,6 +233,8 @@ extern "C" int b200_apply_conversion_dev(const b200_conversion_t *c, const void 
   a.in = (const float4 *)d_in;
   a.out = (float4 *)d_out;
   a.npx = npx;
+  a.n_mirror = n_mirror;
+  for(int k = 0; k < B200_MAX_SCATTER - 1; k++) a.mirror[k] = k < n_mirror ? (float4 *)mirrors[k] : nullptr;
   for(int i = 0; i < 3; i++)
     for(int j = 0; j < 3; j++)
     {
@@ -327,6 +349,15 @@ extern "C" int b200_colorout_process_dev(const b200_piece_t *piece, const void *
 {
   COLOR_CHECK("colorout", b200_colorout_data_t)
   return color_process_dev(piece, d->conversion, d->type, in, out, stream);
+}
+// colorout as the last module of a banded chain: the band goes straight into every GPU's frame
+extern "C" int b200_colorout_process_scatter_dev(const b200_piece_t *piece, const void *in, int n_out, void *const *outs, void *stream)
+{
+  void *out = (n_out > 0 && outs) ? outs[0] : nullptr;
+  COLOR_CHECK("colorout", b200_colorout_data_t)
+  if(d->type == B200_COLORSPACE_LAB || !d->conversion) return fail(B200_ERR_UNSUPPORTED, "colorout scatter: pass-through conversions are not scattered");
+  return b200_apply_conversion_scatter_dev(d->conversion, in, n_out, outs, piece->roi_out.width, piece->roi_out.height,
+                                           piece->mask_display & B200_DISPLAY_MASK, stream);
 }
 extern "C" int b200_colorout_process_host(const b200_piece_t *piece, const void *in, void *out)
 {

@@ -1,6 +1,7 @@
 // libb200iop.so runtime: errors, device binding, per-thread scratch, host<->device staging.
 // Counterpart of the reference's OpenCL runtime (src/common/opencl.c) for CUDA on B200.
 #include "runtime.h"
+#include <string.h>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -347,6 +348,28 @@ extern "C" int b200_copy_device_to_host(void *h_dst, const void *d_src, size_t b
 {
   if(!h_dst || !d_src) return fail(B200_ERR_ARG, "copy_device_to_host: NULL");
   return copy_d2h(h_dst, d_src, bytes, (cudaStream_t)stream);
+}
+extern "C" int b200_ipc_export(void *d_ptr, unsigned char handle[B200_IPC_HANDLE_BYTES])
+{
+  static_assert(sizeof(cudaIpcMemHandle_t) == B200_IPC_HANDLE_BYTES, "IPC handle size");
+  if(!d_ptr || !handle) return fail(B200_ERR_ARG, "ipc_export: NULL");
+  cudaIpcMemHandle_t h;
+  B200_CUDA_TRY(cudaIpcGetMemHandle(&h, d_ptr));
+  memcpy(handle, &h, sizeof(h));
+  return B200_OK;
+}
+extern "C" int b200_ipc_import(const unsigned char handle[B200_IPC_HANDLE_BYTES], void **d_ptr)
+{
+  if(!d_ptr || !handle) return fail(B200_ERR_ARG, "ipc_import: NULL");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  B200_CUDA_TRY(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return B200_OK;
+}
+extern "C" int b200_ipc_release(void *d_ptr)
+{
+  if(d_ptr) B200_CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
+  return B200_OK;
 }
 extern "C" int b200_stream_create(void **stream)
 {

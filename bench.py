@@ -408,6 +408,28 @@ def run_b200(args):
                   "collective": "all-gather of finished RGBA bands (one ncclBroadcast per band, NVLink)",
                   "cuts": "RCD 94-row block grid, 9-row halo", "bit_identical_to_untiled": bool(same.item()),
                   "gathered_bytes_per_frame": 16 * npx}
+        # the same, with the gather fused into colorout's stores (peer frames mapped over CUDA IPC)
+        try:
+            ch2 = bands.BandedChain(bnodes, w, h, rank, world, device=dev, p2p=True)
+            for _ in range(3):
+                ch2(t_band, stream=stream)
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(args.steps):
+                out2 = ch2(t_band, stream=stream)
+            c1.record()
+            barrier()
+            t_c = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t_c, op=dist.ReduceOp.MAX)
+            same2 = torch.tensor([int(torch.equal(out2.view(torch.int32), out_frame.view(torch.int32)))], dtype=torch.int32, device=dev)
+            dist.all_reduce(same2, op=dist.ReduceOp.MIN)
+            ch2.close()
+            banded["fused_p2p"] = {"value": npx * args.steps / (float(t_c.item()) * 1e-3) / 1e6, "ms_per_frame": float(t_c.item()) / args.steps,
+                                   "how": "colorout stores each pixel into every rank's frame (CUDA IPC peer mappings), then one barrier",
+                                   "bit_identical_to_collective": bool(same2.item())}
+        except Exception as e:  # no peer access on this box: keep the NCCL number
+            banded["fused_p2p"] = {"unavailable": str(e)[:200]}
 
     # ---- roofline of the dominant kernel (RCD tiles) --------------------------------------------
     peak, peak_src = peaks()

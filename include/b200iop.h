@@ -422,6 +422,21 @@ typedef struct b200_band_t
  * (RCD: grid 94, halo 9) gives the same bits as on the untiled frame.  Bands may come out empty when
  * n_bands exceeds the number of block rows. */
 int b200_band_plan(int height, int n_bands, int grid, int halo, int align, b200_band_t *bands);
+/* The gather fused into the producing kernel: the last (pointwise) module of a band stores every result pixel
+ * into up to B200_MAX_SCATTER frames -- this GPU's and, through peer mappings, the other GPUs' -- so the
+ * exchange rides on the kernel's own stores over NVLink instead of following it as a collective.
+ * d_outs[k] points at the band's first output row inside frame k.  Peer frames are mapped with the IPC calls
+ * below (one process per GPU); the caller separates the stores from the consumers with a stream
+ * synchronisation and a barrier across the processes. */
+#define B200_MAX_SCATTER 8
+int b200_apply_conversion_scatter_dev(const b200_conversion_t *conv, const void *d_in, int n_out, void *const *d_outs,
+                                      size_t width, size_t height, int copy_alpha, void *stream);
+int b200_colorout_process_scatter_dev(const b200_piece_t *piece, const void *d_in, int n_out, void *const *d_outs, void *stream);
+/* cudaIpcGetMemHandle / OpenMemHandle / CloseMemHandle on a b200_dev_alloc() allocation; handle = 64 opaque bytes */
+#define B200_IPC_HANDLE_BYTES 64
+int b200_ipc_export(void *d_ptr, unsigned char handle[B200_IPC_HANDLE_BYTES]);
+int b200_ipc_import(const unsigned char handle[B200_IPC_HANDLE_BYTES], void **d_ptr);
+int b200_ipc_release(void *d_ptr);
 void b200_demosaic_band_grid(const b200_piece_t *piece, int *grid, int *halo, int *align);
 
 /* ---- the libm the kernels use ------------------------------------------------------------------
