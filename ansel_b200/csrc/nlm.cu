@@ -26,7 +26,19 @@ constexpr int MAX_CH = SLICE_HEIGHT + 9;           // compute_slice_height() ret
 constexpr int MAX_CW = SLICE_WIDTH;
 constexpr int SW = MAX_CW + 2 * MAX_RADIUS + 2;    // 82 columns of column sums, +1 -> odd stride below
 constexpr int SSTRIDE = SW + 1;                    // 83: odd, so lanes = rows hit distinct banks
-constexpr int NT = 128;
+#ifndef NLM_NT
+#define NLM_NT 256
+#endif
+#ifndef NLM_MINB
+#define NLM_MINB 2
+#endif
+#ifndef NLM_UNR
+#define NLM_UNR 2
+#endif
+#ifndef NLM_UB
+#define NLM_UB 2
+#endif
+constexpr int NT = NLM_NT;
 
 struct patch_t
 {
@@ -65,7 +77,7 @@ __device__ __forceinline__ float diff_of_diffs(const float4 p1, const float4 p2,
   return (a0 * a0 - b0 * b0) * n[0] + (a1 * a1 - b1 * b1) * n[1] + (a2 * a2 - b2 * b2) * n[2];
 }
 
-__global__ void __launch_bounds__(NT) nlm_chunks_kernel(const __grid_constant__ nlm_args_t a)
+__global__ void __launch_bounds__(NT, NLM_MINB) nlm_chunks_kernel(const __grid_constant__ nlm_args_t a)
 {
   extern __shared__ __align__(16) float smem[];
   float4 *const tile = reinterpret_cast<float4 *>(smem);           // [MAX_CH][MAX_CW] accumulated RGBA
@@ -117,7 +129,7 @@ __global__ void __launch_bounds__(NT) nlm_chunks_kernel(const __grid_constant__ 
       const int lim_a = min(row_top, row_bot);
       // The recurrence is sequential in `row`, its operands are not: fetch UNR rows' worth of pixels
       // first (independent loads in flight), then apply the updates in the reference's order.
-      constexpr int UNR = 6;
+      constexpr int UNR = NLM_UNR;
       for(int row0 = row_min; row0 < row_max; row0 += UNR)
       {
         float4 B0[UNR], B1[UNR], T0[UNR], T1[UNR];
@@ -175,31 +187,51 @@ __global__ void __launch_bounds__(NT) nlm_chunks_kernel(const __grid_constant__ 
     {
       const int nc = col_max - col_min;
       const int total = nc > 0 ? nrows * nc : 0;
-      for(int idx = tid; idx < total; idx += NT)
+      // operands of UB pixels first (independent loads in flight), then the arithmetic
+      constexpr int UB = NLM_UB;
+      for(int idx0 = tid; idx0 < total; idx0 += UB * NT)
       {
-        const int rr = idx / nc, cc = idx - rr * nc;
-        const int row = row_min + rr, col = col_min + cc;
-        const float distortion = S[rr * SSTRIDE + (col - radius - 1 - cbase)];
-        const float4 *px = in + (size_t)row * width + col;
-        const float4 q = __ldg(px + poff);
-        float wt;
-        if(a.center_weight < 0)
-          wt = fast_mexp2(distortion * a.sharpness); // :389-402
-        else
-        { // :404-420
-          const float4 c = __ldg(px);
-          const float d0 = c.x - q.x, d1 = c.y - q.y, d2 = c.z - q.z;
-          const float pd = d0 * d0 * a.cp_norm + d1 * d1 * a.cp_norm + d2 * d2 * a.cp_norm;
-          const float dissimilarity = (distortion + pd) / (1.0f + a.center_weight);
-          wt = fast_mexp2(fmaxf(0.0f, dissimilarity * a.sharpness - 2.0f));
+        float4 q[UB], c[UB];
+        float dist[UB];
+        int slot[UB];
+#pragma unroll
+        for(int u = 0; u < UB; u++)
+        {
+          const int idx = idx0 + u * NT;
+          slot[u] = -1;
+          if(idx < total)
+          {
+            const int rr = idx / nc, cc = idx - rr * nc;
+            const int row = row_min + rr, col = col_min + cc;
+            const float4 *px = in + (size_t)row * width + col;
+            q[u] = __ldg(px + poff);
+            if(a.center_weight >= 0) c[u] = __ldg(px);
+            dist[u] = S[rr * SSTRIDE + (col - radius - 1 - cbase)];
+            slot[u] = (row - chunk_top) * MAX_CW + (col - chunk_left);
+          }
         }
-        float4 *o = tile + (row - chunk_top) * MAX_CW + (col - chunk_left);
-        float4 v = *o;
-        v.x += q.x * wt;
-        v.y += q.y * wt;
-        v.z += q.z * wt;
-        v.w += 1.0f * wt;
-        *o = v;
+#pragma unroll
+        for(int u = 0; u < UB; u++)
+        {
+          if(slot[u] < 0) continue;
+          float wt;
+          if(a.center_weight < 0)
+            wt = fast_mexp2(dist[u] * a.sharpness); // :389-402
+          else
+          { // :404-420
+            const float d0 = c[u].x - q[u].x, d1 = c[u].y - q[u].y, d2 = c[u].z - q[u].z;
+            const float pd = d0 * d0 * a.cp_norm + d1 * d1 * a.cp_norm + d2 * d2 * a.cp_norm;
+            const float dissimilarity = (dist[u] + pd) / (1.0f + a.center_weight);
+            wt = fast_mexp2(fmaxf(0.0f, dissimilarity * a.sharpness - 2.0f));
+          }
+          float4 *o = tile + slot[u];
+          float4 v = *o;
+          v.x += q[u].x * wt;
+          v.y += q[u].y * wt;
+          v.z += q[u].z * wt;
+          v.w += 1.0f * wt;
+          *o = v;
+        }
       }
     }
     __syncthreads();

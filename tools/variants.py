@@ -1,0 +1,37 @@
+"""Development helper: build libb200iop.so variants of ONE kernel file with different tuning macros and time each.
+    python tools/variants.py build nlm          (here, cross-compiling)
+    python tools/variants.py time nlm           (on the GPU box)"""
+import os, subprocess, sys, glob
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from ansel_b200 import build as B
+SETS = {
+    "rcd": ("rcd.cu", "quick_time.py", {"rg8_u1": ["-DRCD_RG=8", "-DRCD_UNROLL=1"], "rg8_u2": ["-DRCD_RG=8", "-DRCD_UNROLL=2"], "rg7_u1": ["-DRCD_RG=7"]}),
+    "nlm": ("nlm.cu", "time_nlm.py", {
+        "nt128_b2": ["-DNLM_NT=128", "-DNLM_MINB=2", "-DNLM_UNR=6", "-DNLM_UB=4"],
+        "nt128_b4": ["-DNLM_NT=128", "-DNLM_MINB=4", "-DNLM_UNR=4", "-DNLM_UB=4"],
+        "nt256_b1": ["-DNLM_NT=256", "-DNLM_MINB=1", "-DNLM_UNR=6", "-DNLM_UB=4"],
+        "nt256_b2": ["-DNLM_NT=256", "-DNLM_MINB=2", "-DNLM_UNR=4", "-DNLM_UB=4"],
+        "nt256_b2_u2": ["-DNLM_NT=256", "-DNLM_MINB=2", "-DNLM_UNR=2", "-DNLM_UB=2"],
+        "nt192_b2": ["-DNLM_NT=192", "-DNLM_MINB=2", "-DNLM_UNR=4", "-DNLM_UB=4"],
+    }),
+}
+OUT = os.path.join(ROOT, "tools", "variants")
+os.makedirs(OUT, exist_ok=True)
+src, timer, variants = SETS[sys.argv[2]]
+stem = src[:-3]
+if sys.argv[1] == "build":
+    B.build()
+    objs = [o for o in glob.glob(os.path.join(ROOT, "ansel_b200", "build", "*.o")) if not o.endswith(f"/{stem}.o")]
+    for name, defs in variants.items():
+        obj = os.path.join(OUT, f"{stem}_{name}.o")
+        cmd = [B._nvcc()] + [f for f in B.NVCC_FLAGS if f != "-shared"] + defs + ["-Xptxas=-v", "-c", os.path.join(B.CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, check=True)
+        print(name, [l.strip() for l in r.stdout.splitlines() if "registers" in l or "spill" in l][-2:])
+        subprocess.run([B._nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-Xcompiler", "-fPIC", "-o",
+                        os.path.join(OUT, f"libb200iop_{stem}_{name}.so"), obj] + objs, check=True)
+else:
+    for name in variants:
+        env = dict(os.environ, B200IOP_LIB=os.path.join(OUT, f"libb200iop_{stem}_{name}.so"))
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", timer)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        print(name, r.stdout.strip().splitlines()[-1])
