@@ -10,10 +10,16 @@
 // float running column sums updated incrementally down the rows, and a float running sum along each row;
 // contributions are accumulated into the output in patch order.  Bit parity therefore fixes three
 // sequential axes.  Mapping: one CTA per reference chunk, patches in order, and per patch
-//   phase A  threads = columns : the column-sum recurrence down the rows   -> S[row][col] (shared)
-//   phase B1 threads = rows    : the running sum along each row            -> D[row][col] (in place of S)
-//   phase B2 threads = pixels  : weights and accumulation into the chunk's RGBA tile (shared)
-// so every lane does independent work while each recurrence is evaluated in the reference's order.
+//   phase E  all threads       : e_c(r,col) = (in[r][col].c - in[r+dy][col+dx].c)^2 for the chunk + halo rows/cols,
+//                                three planes in shared memory -- every global load of the patch happens here,
+//                                fully parallel, so the two serial phases below never wait on memory
+//   phase A  threads = columns : the column-sum recurrence down the rows, from E        -> S[row][col] (shared)
+//   phase B1 threads = rows    : the running sum along each row                          -> D[row][col] (in place of S)
+//   phase B2 threads = pixels  : weights and accumulation; each thread owns a fixed set of chunk pixels and keeps
+//                                their RGBA sums in registers across all patches
+// pixel_difference() is (d0*d0)*n0 + (d1*d1)*n1 + (d2*d2)*n2 and diff_of_pixels_diff() is
+// (a0*a0 - b0*b0)*n0 + ...: both are functions of the per-channel squares, so E holds exactly the reference's
+// intermediate values and the sums are formed in its order.
 // Not HBM bound by construction (~9 kflop/px at K=7); reported against FP32 issue.
 #include "runtime.h"
 #include <math.h>
@@ -27,18 +33,21 @@ constexpr int MAX_CW = SLICE_WIDTH;
 constexpr int SW = MAX_CW + 2 * MAX_RADIUS + 2;    // 82 columns of column sums, +1 -> odd stride below
 constexpr int SSTRIDE = SW + 1;                    // 83: odd, so lanes = rows hit distinct banks
 #ifndef NLM_NT
-#define NLM_NT 256
+#define NLM_NT 512
 #endif
 #ifndef NLM_MINB
-#define NLM_MINB 2
+#define NLM_MINB 1
 #endif
-#ifndef NLM_UNR
-#define NLM_UNR 2
-#endif
-#ifndef NLM_UB
-#define NLM_UB 2
+#ifndef NLM_UE
+#define NLM_UE 1
 #endif
 constexpr int NT = NLM_NT;
+constexpr int OWN = (MAX_CH * MAX_CW + NT - 1) / NT; // chunk pixels owned by one thread
+constexpr int UE = NLM_UE;
+#ifndef NLM_UB
+#define NLM_UB 1
+#endif
+constexpr int UB = NLM_UB;                            // owned pixels fetched together in phase B2                            // E entries fetched per thread before any is used
 
 struct patch_t
 {
@@ -57,6 +66,7 @@ struct nlm_args_t
   float norm[4];
   float weight[4], invert[4];
   int skip_blend;
+  int rows_e, plane_e; // rows of one E plane (chunk rows + 2*radius + 1), floats per plane (rows_e * SW)
 };
 
 __device__ __forceinline__ float fast_mexp2(float x) // math/math.h:290-301
@@ -80,19 +90,34 @@ __device__ __forceinline__ float diff_of_diffs(const float4 p1, const float4 p2,
 __global__ void __launch_bounds__(NT, NLM_MINB) nlm_chunks_kernel(const __grid_constant__ nlm_args_t a)
 {
   extern __shared__ __align__(16) float smem[];
-  float4 *const tile = reinterpret_cast<float4 *>(smem);           // [MAX_CH][MAX_CW] accumulated RGBA
-  float *const S = smem + 4 * MAX_CH * MAX_CW;                     // [MAX_CH][SSTRIDE] column sums / distortions
+  float *const E0 = smem;                      // [rows_e][SW] squared differences, channel 0
+  float *const E1 = E0 + a.plane_e;
+  float *const E2 = E1 + a.plane_e;
+  float *const S = E2 + a.plane_e;             // [chunk rows][SSTRIDE] column sums / distortions
   const int tid = threadIdx.x;
   const int it = blockIdx.x / a.n_cl, il = blockIdx.x - it * a.n_cl;
   const int chunk_top = it * a.chk_h, chunk_left = il * a.chk_w;
   const int chunk_bot = min(chunk_top + a.chk_h, a.height), chunk_right = min(chunk_left + a.chk_w, a.width);
   const int width = a.width, height = a.height, radius = a.radius;
-  const int cbase = chunk_left - radius - 1;              // column of S[.][0]
+  const int cbase = chunk_left - radius - 1;              // column of S[.][0] and E[.][0]
   const int ncols = (chunk_right + radius) - cbase;       // <= SW
   const float4 *const in = a.in;
+  const float n0 = a.norm[0], n1 = a.norm[1], n2 = a.norm[2];
 
-  for(int k = tid; k < MAX_CH * MAX_CW; k += NT) tile[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncthreads();
+  // the pixels this thread owns: chunk-local (row, col) of pixel tid + k*NT, row-major over the chunk
+  const int cw = chunk_right - chunk_left, ch = chunk_bot - chunk_top;
+  float4 acc[OWN];
+  int own[OWN]; // (image row << 16) | image column, or -1 when the slot lies beyond the chunk (frames < 32768 px a side)
+#pragma unroll
+  for(int k = 0; k < OWN; k++)
+  {
+    acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int idx = tid + k * NT;
+    const int rr = idx / cw;
+    own[k] = rr < ch ? (((chunk_top + rr) << 16) | (chunk_left + (idx - rr * cw))) : -1;
+  }
+  // phase E walks (row, col) entries tid, tid+NT, ... of a ncols-wide grid without dividing in the loop
+  const int e_r0 = tid / ncols, e_c0 = tid - e_r0 * ncols, e_dr = NT / ncols, e_dc = NT - e_dr * ncols;
 
   for(int p = 0; p < a.n_patches; p++)
   {
@@ -106,6 +131,51 @@ __global__ void __launch_bounds__(NT, NLM_MINB) nlm_chunks_kernel(const __grid_c
     const int pcol_max = chunk_right + min(radius, min(width - chunk_right, width - (chunk_right + scol)));
     const long long poff = (long long)srow * width + scol; // patch offset in pixels
     const int nrows = row_max - row_min;
+    const int erow0 = row_min - radius;                     // image row of E[0][.]
+    const int n_erows = nrows + 2 * radius + 1;             // rows row_min-radius .. row_max+radius
+
+    // ---- phase E: squared per-channel differences of every pixel pair the patch touches ---------------
+    {
+      int rr = e_r0, cc = e_c0;
+      while(rr < n_erows)
+      {
+        float4 x[UE], y[UE];
+        int slot[UE];
+#pragma unroll
+        for(int u = 0; u < UE; u++)
+        {
+          slot[u] = -1;
+          if(rr < n_erows)
+          {
+            const int r = erow0 + rr, col = cbase + cc;
+            if(col >= pcol_min && col < pcol_max && r >= 0 && r < height && r + srow >= 0 && r + srow < height)
+            {
+              const float4 *px = in + (size_t)r * width + col;
+              x[u] = __ldg(px);
+              y[u] = __ldg(px + poff);
+              slot[u] = rr * SW + cc;
+            }
+          }
+          rr += e_dr;
+          cc += e_dc;
+          if(cc >= ncols)
+          {
+            cc -= ncols;
+            rr++;
+          }
+        }
+#pragma unroll
+        for(int u = 0; u < UE; u++)
+          if(slot[u] >= 0)
+          {
+            const float d0 = x[u].x - y[u].x, d1 = x[u].y - y[u].y, d2 = x[u].z - y[u].z;
+            E0[slot[u]] = d0 * d0;
+            E1[slot[u]] = d1 * d1;
+            E2[slot[u]] = d2 * d2;
+          }
+      }
+    }
+    __syncthreads();
 
     // ---- phase A: column sums down the rows, one thread per column ---------------------------------
     if(tid < ncols)
@@ -121,49 +191,44 @@ __global__ void __launch_bounds__(NT, NLM_MINB) nlm_chunks_kernel(const __grid_c
         float sum = 0.0f;
         for(int r = rmin; r <= rmax; r++)
         {
-          const float4 *px = in + (size_t)r * width + col;
-          sum += pixdiff(__ldg(px), __ldg(px + poff), a.norm);
+          const int e = (r - erow0) * SW + tid;
+          sum += E0[e] * n0 + E1[e] * n1 + E2[e] * n2; // pixel_difference(), :156-165
         }
         cs = sum;
       }
+      // Rows [row_min, lim_a) add the entering row (:424-440), [lim_a, row_bot) add entering minus leaving
+      // (:441-466), rows >= max(row_top, row_bot) with a successor subtract the leaving row (:467-483).  All three
+      // are the middle formula with the absent row's squares replaced by +0 (x - 0 = x, and -(u+v+w) is formed by
+      // the same roundings as (-u)+(-v)+(-w)), so the loop is branch-free; operands of UA rows are fetched before
+      // any column sum is stored.
       const int lim_a = min(row_top, row_bot);
-      // The recurrence is sequential in `row`, its operands are not: fetch UNR rows' worth of pixels
-      // first (independent loads in flight), then apply the updates in the reference's order.
-      constexpr int UNR = NLM_UNR;
-      for(int row0 = row_min; row0 < row_max; row0 += UNR)
+      #ifndef NLM_UA
+#define NLM_UA 1
+#endif
+      constexpr int UA = NLM_UA;
+      for(int row0 = row_min; row0 < row_max; row0 += UA)
       {
-        float4 B0[UNR], B1[UNR], T0[UNR], T1[UNR];
-        int kind[UNR];
+        float b0[UA], b1[UA], b2[UA], t0[UA], t1[UA], t2[UA];
 #pragma unroll
-        for(int u = 0; u < UNR; u++)
+        for(int u = 0; u < UA; u++)
         {
           const int row = row0 + u;
-          kind[u] = row >= row_max ? -1 : (row < lim_a ? 1 : (row < row_bot ? 2 : ((row >= row_top && row + 1 < row_max) ? 3 : 0)));
-          if(live && (kind[u] == 1 || kind[u] == 2))
-          {
-            const float4 *b = in + (size_t)(row + 1 + radius) * width + col;
-            B0[u] = __ldg(b);
-            B1[u] = __ldg(b + poff);
-          }
-          if(live && (kind[u] == 2 || kind[u] == 3))
-          {
-            const float4 *t = in + (size_t)(row - radius) * width + col;
-            T0[u] = __ldg(t);
-            T1[u] = __ldg(t + poff);
-          }
+          const bool use_b = live && row < row_bot && row < row_max;
+          const bool use_t = live && row >= lim_a && row < row_max && (row < row_bot || (row >= row_top && row + 1 < row_max));
+          const int eb = (row + 1 + radius - erow0) * SW + tid, et = (row - radius - erow0) * SW + tid;
+          b0[u] = use_b ? E0[eb] : 0.0f;
+          b1[u] = use_b ? E1[eb] : 0.0f;
+          b2[u] = use_b ? E2[eb] : 0.0f;
+          t0[u] = use_t ? E0[et] : 0.0f;
+          t1[u] = use_t ? E1[et] : 0.0f;
+          t2[u] = use_t ? E2[et] : 0.0f;
         }
 #pragma unroll
-        for(int u = 0; u < UNR; u++)
+        for(int u = 0; u < UA; u++)
         {
-          if(kind[u] < 0) break;
+          if(row0 + u >= row_max) break;
           S[(row0 + u - row_min) * SSTRIDE + tid] = cs;
-          if(!live) continue;
-          if(kind[u] == 1)
-            cs += pixdiff(B0[u], B1[u], a.norm); // :424-440
-          else if(kind[u] == 2)
-            cs += diff_of_diffs(B0[u], B1[u], T0[u], T1[u], a.norm); // :441-466
-          else if(kind[u] == 3)
-            cs -= pixdiff(T0[u], T1[u], a.norm); // :467-483
+          cs += (b0[u] - t0[u]) * n0 + (b1[u] - t1[u]) * n1 + (b2[u] - t2[u]) * n2;
         }
       }
     }
@@ -175,45 +240,64 @@ __global__ void __launch_bounds__(NT, NLM_MINB) nlm_chunks_kernel(const __grid_c
       float *const Sr = S + tid * SSTRIDE - cbase; // Sr[col] = column sum of `col` for this row
       float distortion = 0.0f;
       for(int i = col_min - radius; i < min(col_min + radius, col_max); i++) distortion += Sr[i];
-      for(int col = col_min; col < col_max; col++)
+      // D[col] is kept in the slot col-radius-1, which is behind every column sum still to be read; the operands of
+      // UC columns are fetched before the first of their results is stored
+      #ifndef NLM_UC
+#define NLM_UC 2
+#endif
+      constexpr int UC = NLM_UC;
+      for(int col0 = col_min; col0 < col_max; col0 += UC)
       {
-        distortion += (Sr[col + radius] - Sr[col - radius - 1]);
-        Sr[col - radius - 1] = distortion; // that slot is never read again: keep D[col] there
+        float hi[UC], lo[UC];
+#pragma unroll
+        for(int u = 0; u < UC; u++)
+          if(col0 + u < col_max)
+          {
+            hi[u] = Sr[col0 + u + radius];
+            lo[u] = Sr[col0 + u - radius - 1];
+          }
+#pragma unroll
+        for(int u = 0; u < UC; u++)
+          if(col0 + u < col_max)
+          {
+            distortion += (hi[u] - lo[u]);
+            Sr[col0 + u - radius - 1] = distortion;
+          }
       }
     }
     __syncthreads();
 
-    // ---- phase B2: weights and accumulation, all threads over the chunk's pixels ------------------
+    // ---- phase B2: weights and accumulation into the owned pixels' registers ---------------------------
+    // (no barrier after it: the next patch's phase E touches neither S nor the accumulators)
+    if(col_min < col_max)
     {
-      const int nc = col_max - col_min;
-      const int total = nc > 0 ? nrows * nc : 0;
-      // operands of UB pixels first (independent loads in flight), then the arithmetic
-      constexpr int UB = NLM_UB;
-      for(int idx0 = tid; idx0 < total; idx0 += UB * NT)
-      {
+#pragma unroll
+      for(int k0 = 0; k0 < OWN; k0 += UB)
+      { // operands of UB owned pixels first (independent loads in flight), then the arithmetic
         float4 q[UB], c[UB];
         float dist[UB];
-        int slot[UB];
+        bool on[UB];
 #pragma unroll
         for(int u = 0; u < UB; u++)
         {
-          const int idx = idx0 + u * NT;
-          slot[u] = -1;
-          if(idx < total)
+          on[u] = false;
+          if(k0 + u < OWN)
           {
-            const int rr = idx / nc, cc = idx - rr * nc;
-            const int row = row_min + rr, col = col_min + cc;
-            const float4 *px = in + (size_t)row * width + col;
-            q[u] = __ldg(px + poff);
-            if(a.center_weight >= 0) c[u] = __ldg(px);
-            dist[u] = S[rr * SSTRIDE + (col - radius - 1 - cbase)];
-            slot[u] = (row - chunk_top) * MAX_CW + (col - chunk_left);
+            const int row = own[k0 + u] >> 16, col = own[k0 + u] & 0xffff;
+            on[u] = own[k0 + u] >= 0 && row >= row_min && row < row_max && col >= col_min && col < col_max;
+            if(on[u])
+            {
+              const float4 *px = in + (size_t)row * width + col;
+              q[u] = __ldg(px + poff);
+              if(a.center_weight >= 0) c[u] = __ldg(px);
+              dist[u] = S[(row - row_min) * SSTRIDE + (col - radius - 1 - cbase)];
+            }
           }
         }
 #pragma unroll
         for(int u = 0; u < UB; u++)
         {
-          if(slot[u] < 0) continue;
+          if(!on[u]) continue;
           float wt;
           if(a.center_weight < 0)
             wt = fast_mexp2(dist[u] * a.sharpness); // :389-402
@@ -224,26 +308,22 @@ __global__ void __launch_bounds__(NT, NLM_MINB) nlm_chunks_kernel(const __grid_c
             const float dissimilarity = (dist[u] + pd) / (1.0f + a.center_weight);
             wt = fast_mexp2(fmaxf(0.0f, dissimilarity * a.sharpness - 2.0f));
           }
-          float4 *o = tile + slot[u];
-          float4 v = *o;
-          v.x += q[u].x * wt;
-          v.y += q[u].y * wt;
-          v.z += q[u].z * wt;
-          v.w += 1.0f * wt;
-          *o = v;
+          acc[k0 + u].x += q[u].x * wt;
+          acc[k0 + u].y += q[u].y * wt;
+          acc[k0 + u].z += q[u].z * wt;
+          acc[k0 + u].w += 1.0f * wt;
         }
       }
     }
-    __syncthreads();
   }
 
   // ---- normalise (and blend) : :485-519 ---------------------------------------------------------------
-  const int cw = chunk_right - chunk_left, ch = chunk_bot - chunk_top;
-  for(int idx = tid; idx < cw * ch; idx += NT)
+#pragma unroll
+  for(int k = 0; k < OWN; k++)
   {
-    const int rr = idx / cw, cc = idx - rr * cw;
-    const float4 v = tile[rr * MAX_CW + cc];
-    const size_t g = (size_t)(chunk_top + rr) * width + chunk_left + cc;
+    if(own[k] < 0) continue;
+    const float4 v = acc[k];
+    const size_t g = (size_t)(own[k] >> 16) * width + (own[k] & 0xffff);
     float4 o;
     if(a.skip_blend)
       o = make_float4(v.x / v.w, v.y / v.w, v.z / v.w, v.w / v.w);
@@ -363,15 +443,19 @@ int nlmeans_denoise_dev(const float *d_in, float *d_out, int width, int height, 
   a.invert[1] = a.invert[2] = 1.0f - chroma;
   a.invert[3] = 0.0f;
   a.skip_blend = (luma == 1.0 && chroma == 1.0) ? 1 : 0;
+  if(width >= 32768 || height >= 32768) return fail(B200_ERR_UNSUPPORTED, "nlmeans: frames beyond 32767 px a side are not supported");
   if(a.chk_h > MAX_CH || a.chk_w > MAX_CW) return fail(B200_ERR_ARG, "nlmeans: chunk %dx%d exceeds the kernel's tile", a.chk_w, a.chk_h);
 
-  const int smem_bytes = (4 * MAX_CH * MAX_CW + MAX_CH * SSTRIDE) * (int)sizeof(float);
+  a.rows_e = a.chk_h + 2 * radius + 1;
+  a.plane_e = a.rows_e * SW;
+  const int smem_bytes = (3 * a.plane_e + a.chk_h * SSTRIDE) * (int)sizeof(float);
   static bool attr_set[16] = { false };
   int dev = 0;
   B200_CUDA_TRY(cudaGetDevice(&dev));
   if(!attr_set[dev & 15])
   {
-    B200_CUDA_TRY(cudaFuncSetAttribute(nlm_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    const int smem_max = (3 * (MAX_CH + 2 * MAX_RADIUS + 1) * SW + MAX_CH * SSTRIDE) * (int)sizeof(float);
+    B200_CUDA_TRY(cudaFuncSetAttribute(nlm_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     attr_set[dev & 15] = true;
   }
   nlm_chunks_kernel<<<(unsigned)(n_ct * a.n_cl), NT, smem_bytes, stream>>>(a);
