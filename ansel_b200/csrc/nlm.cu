@@ -23,6 +23,7 @@
 // Not HBM bound by construction (~9 kflop/px at K=7); reported against FP32 issue.
 #include "runtime.h"
 #include <math.h>
+#include <stdlib.h>
 
 namespace
 {
@@ -67,6 +68,7 @@ struct nlm_args_t
   float weight[4], invert[4];
   int skip_blend;
   int rows_e, plane_e; // rows of one E plane (chunk rows + 2*radius + 1), floats per plane (rows_e * SW)
+  int cols_w, sstride_w; // window variant: columns of a window row, odd pitch of its sum planes
 };
 
 __device__ __forceinline__ float fast_mexp2(float x) // math/math.h:290-301
@@ -339,6 +341,286 @@ __global__ void __launch_bounds__(NT, NLM_MINB) nlm_chunks_kernel(const __grid_c
   }
 }
 
+// ---- window variant: the chunk's own pixels (+halo) and the patch-shifted pixels both live in shared memory ------
+// Per chunk the unshifted window P is loaded once; per patch only the shifted window Q is fetched (cp.async, every
+// load of the patch in flight at once).  Everything else is shared-memory work:
+//   U  (all threads)      U[row][col] = the column-sum update of that row (the branch-free form above)
+//   A  (threads = columns) exclusive running sum of U down the rows, in place            -> column sums
+//   V  (all threads)      V[row][col] = colsum[col+radius] - colsum[col-radius-1]
+//   B1 (threads = rows)   inclusive running sum of V along the row, in place             -> distortions
+//   B2 (all threads)      weights from the distortions, shifted pixels from Q, accumulation in registers
+// so the two recurrences that fix the reference's float rounding order shrink to one add per element.
+// Needs both windows in shared memory (radius <= 2 at the usual chunk sizes); selected with B200_NLM_WINDOW=1.
+#ifndef NLM_WNT
+#define NLM_WNT 512
+#endif
+constexpr int WNT = NLM_WNT;
+constexpr int WOWN = (MAX_CH * MAX_CW + WNT - 1) / WNT;
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ float pair_pd(const float4 x, const float4 y, float n0, float n1, float n2)
+{ // pixel_difference(), :156-165
+  const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z;
+  return d0 * d0 * n0 + d1 * d1 * n1 + d2 * d2 * n2;
+}
+
+__global__ void __launch_bounds__(WNT, 1) nlm_chunks_win_kernel(const __grid_constant__ nlm_args_t a)
+{
+  extern __shared__ __align__(16) float smem[];
+  const int colsw = a.cols_w, ss = a.sstride_w;
+  float4 *const Pw = reinterpret_cast<float4 *>(smem);          // [rows_e][colsw] unshifted pixels
+  float4 *const Qw = Pw + a.rows_e * colsw;                     // [rows_e][colsw] pixels at the patch offset
+  float *const S = reinterpret_cast<float *>(Qw + a.rows_e * colsw); // [chunk rows][ss] U, then column sums
+  float *const S2 = S + a.chk_h * ss;                           // [chunk rows][ss] V, then distortions
+  const int tid = threadIdx.x;
+  const int it = blockIdx.x / a.n_cl, il = blockIdx.x - it * a.n_cl;
+  const int chunk_top = it * a.chk_h, chunk_left = il * a.chk_w;
+  const int chunk_bot = min(chunk_top + a.chk_h, a.height), chunk_right = min(chunk_left + a.chk_w, a.width);
+  const int width = a.width, height = a.height, radius = a.radius;
+  const int cbase = chunk_left - radius - 1;              // image column of window column 0
+  const int ncols = (chunk_right + radius) - cbase;       // <= colsw
+  const int wrow0 = chunk_top - radius;                   // image row of window row 0
+  const int nwrows = (chunk_bot - chunk_top) + 2 * radius + 1;
+  const float4 *const in = a.in;
+  const float n0 = a.norm[0], n1 = a.norm[1], n2 = a.norm[2];
+
+  const int cw = chunk_right - chunk_left, ch = chunk_bot - chunk_top;
+  float4 acc[WOWN];
+  int own[WOWN]; // (chunk-local row << 16) | chunk-local column, or -1
+#pragma unroll
+  for(int k = 0; k < WOWN; k++)
+  {
+    acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int idx = tid + k * WNT;
+    const int rr = idx / cw;
+    own[k] = rr < ch ? ((rr << 16) | (idx - rr * cw)) : -1;
+  }
+  // entries tid, tid+WNT, ... of an ncols-wide grid, walked without dividing
+  const int e_r0 = tid / ncols, e_c0 = tid - e_r0 * ncols, e_dr = WNT / ncols, e_dc = WNT - e_dr * ncols;
+
+  // ---- the unshifted window, once per chunk ----------------------------------------------------------------
+  for(int rr = e_r0, cc = e_c0; rr < nwrows;)
+  {
+    const int r = wrow0 + rr, col = cbase + cc;
+    if(r >= 0 && r < height && col >= 0 && col < width) cp_async16(Pw + rr * colsw + cc, in + (size_t)r * width + col);
+    rr += e_dr;
+    cc += e_dc;
+    if(cc >= ncols)
+    {
+      cc -= ncols;
+      rr++;
+    }
+  }
+
+  for(int p = 0; p < a.n_patches; p++)
+  {
+    const int srow = a.patches[p].rows, scol = a.patches[p].cols;
+    const int row_min = max(chunk_top, max(0, -srow)), row_max = min(chunk_bot, height - max(0, srow));
+    if(row_min >= row_max) continue; // uniform
+    const int row_top = max(row_min, max(radius, radius - srow));
+    const int row_bot = min(row_max, height - 1 - max(radius, radius + srow));
+    const int col_min = max(chunk_left, -scol), col_max = min(chunk_right, width - scol);
+    const int pcol_min = chunk_left - min(radius, min(chunk_left, chunk_left + scol));
+    const int pcol_max = chunk_right + min(radius, min(width - chunk_right, width - (chunk_right + scol)));
+    const long long poff = (long long)srow * width + scol;
+    const int nrows = row_max - row_min;
+    const int lim_a = min(row_top, row_bot);
+
+    // ---- Q: the shifted window (the only global traffic of the patch) ------------------------------------
+    for(int rr = e_r0, cc = e_c0; rr < nwrows;)
+    {
+      const int r = wrow0 + rr, col = cbase + cc;
+      if(r >= 0 && r < height && r + srow >= 0 && r + srow < height && col >= 0 && col + scol >= 0 && col < width && col + scol < width)
+        cp_async16(Qw + rr * colsw + cc, in + (size_t)r * width + col + poff);
+      rr += e_dr;
+      cc += e_dc;
+      if(cc >= ncols)
+      {
+        cc -= ncols;
+        rr++;
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    // ---- U: per-row update of every column sum ---------------------------------------------------------
+    for(int rr = e_r0, cc = e_c0; rr < nrows;)
+    {
+      const int row = row_min + rr, col = cbase + cc;
+      const bool live = col >= pcol_min && col < pcol_max;
+      const bool use_b = live && row < row_bot;
+      const bool use_t = live && row >= lim_a && (row < row_bot || (row >= row_top && row + 1 < row_max));
+      float b0 = 0.f, b1 = 0.f, b2 = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f;
+      if(use_b)
+      {
+        const int w = (row + 1 + radius - wrow0) * colsw + cc;
+        const float4 x = Pw[w], y = Qw[w];
+        const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z;
+        b0 = d0 * d0;
+        b1 = d1 * d1;
+        b2 = d2 * d2;
+      }
+      if(use_t)
+      {
+        const int w = (row - radius - wrow0) * colsw + cc;
+        const float4 x = Pw[w], y = Qw[w];
+        const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z;
+        t0 = d0 * d0;
+        t1 = d1 * d1;
+        t2 = d2 * d2;
+      }
+      S[rr * ss + cc] = (b0 - t0) * n0 + (b1 - t1) * n1 + (b2 - t2) * n2;
+      rr += e_dr;
+      cc += e_dc;
+      if(cc >= ncols)
+      {
+        cc -= ncols;
+        rr++;
+      }
+    }
+    __syncthreads();
+
+    // ---- A: column sums = init_column_sums() at row_min, then the running sum of U down the rows --------
+    if(tid < ncols)
+    {
+      const int col = cbase + tid;
+      float cs = 0.0f;
+      if(col >= pcol_min && col < pcol_max)
+      { // :214-264
+        const int row = row_min;
+        const int rmin = row - min(radius, min(row, row + srow));
+        const int rmax = row + min(radius, min(height - 1 - row, height - 1 - (row + srow)));
+        float sum = 0.0f;
+        for(int r = rmin; r <= rmax; r++)
+        {
+          const int w = (r - wrow0) * colsw + tid;
+          sum += pair_pd(Pw[w], Qw[w], n0, n1, n2);
+        }
+        cs = sum;
+      }
+      float *sp = S + tid;
+      constexpr int UW = 8; // updates fetched ahead of the running sum
+      for(int rr0 = 0; rr0 < nrows; rr0 += UW, sp += UW * ss)
+      {
+        float u[UW];
+#pragma unroll
+        for(int k = 0; k < UW; k++) u[k] = (rr0 + k < nrows) ? sp[k * ss] : 0.0f;
+#pragma unroll
+        for(int k = 0; k < UW; k++)
+          if(rr0 + k < nrows)
+          {
+            sp[k * ss] = cs;
+            cs += u[k];
+          }
+      }
+    }
+    __syncthreads();
+
+    // ---- V: what each step of the row recurrence adds (:409) --------------------------------------------
+    {
+      const int nc = col_max - col_min;
+      if(nc > 0)
+      {
+        const int v_r0 = tid / nc, v_c0 = tid - v_r0 * nc, v_dr = WNT / nc, v_dc = WNT - v_dr * nc;
+        for(int rr = v_r0, cc = v_c0; rr < nrows;)
+        {
+          const int k = col_min + cc - cbase;
+          S2[rr * ss + k] = S[rr * ss + k + radius] - S[rr * ss + k - radius - 1];
+          rr += v_dr;
+          cc += v_dc;
+          if(cc >= nc)
+          {
+            cc -= nc;
+            rr++;
+          }
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- B1: running distortion along each row, one thread per row (:384-387,409) -----------------------
+    if(tid < nrows && col_min < col_max)
+    {
+      const float *const Sr = S + tid * ss - cbase;
+      float *const Vr = S2 + tid * ss - cbase;
+      float distortion = 0.0f;
+      for(int i = col_min - radius; i < min(col_min + radius, col_max); i++) distortion += Sr[i];
+      constexpr int UW = 8;
+      for(int col0 = col_min; col0 < col_max; col0 += UW)
+      {
+        float v[UW];
+#pragma unroll
+        for(int k = 0; k < UW; k++) v[k] = (col0 + k < col_max) ? Vr[col0 + k] : 0.0f;
+#pragma unroll
+        for(int k = 0; k < UW; k++)
+          if(col0 + k < col_max)
+          {
+            distortion += v[k];
+            Vr[col0 + k] = distortion;
+          }
+      }
+    }
+    __syncthreads();
+
+    // ---- B2: weights and accumulation into the owned pixels' registers ------------------------------------
+    if(col_min < col_max)
+    {
+#pragma unroll
+      for(int k = 0; k < WOWN; k++)
+      {
+        const int row = chunk_top + (own[k] >> 16), col = chunk_left + (own[k] & 0xffff);
+        if(own[k] < 0 || row < row_min || row >= row_max || col < col_min || col >= col_max) continue;
+        const int w = (row - wrow0) * colsw + (col - cbase);
+        const float4 q = Qw[w];
+        const float dist = S2[(row - row_min) * ss + (col - cbase)];
+        float wt;
+        if(a.center_weight < 0)
+          wt = fast_mexp2(dist * a.sharpness); // :389-402
+        else
+        { // :404-420
+          const float4 c = Pw[w];
+          const float d0 = c.x - q.x, d1 = c.y - q.y, d2 = c.z - q.z;
+          const float pd = d0 * d0 * a.cp_norm + d1 * d1 * a.cp_norm + d2 * d2 * a.cp_norm;
+          const float dissimilarity = (dist + pd) / (1.0f + a.center_weight);
+          wt = fast_mexp2(fmaxf(0.0f, dissimilarity * a.sharpness - 2.0f));
+        }
+        acc[k].x += q.x * wt;
+        acc[k].y += q.y * wt;
+        acc[k].z += q.z * wt;
+        acc[k].w += 1.0f * wt;
+      }
+    }
+    __syncthreads(); // Q and the distortions are overwritten by the next patch
+  }
+  cp_async_wait_all(); // a chunk none of whose patches ran never waited for P
+
+  // ---- normalise (and blend) : :485-519 ---------------------------------------------------------------
+#pragma unroll
+  for(int k = 0; k < WOWN; k++)
+  {
+    if(own[k] < 0) continue;
+    const float4 v = acc[k];
+    const size_t g = (size_t)(chunk_top + (own[k] >> 16)) * width + chunk_left + (own[k] & 0xffff);
+    float4 o;
+    if(a.skip_blend)
+      o = make_float4(v.x / v.w, v.y / v.w, v.z / v.w, v.w / v.w);
+    else
+    {
+      const float4 i4 = __ldg(in + g);
+      o.x = (i4.x * a.invert[0]) + (v.x / v.w * a.weight[0]);
+      o.y = (i4.y * a.invert[1]) + (v.y / v.w * a.weight[1]);
+      o.z = (i4.z * a.invert[2]) + (v.z / v.w * a.weight[2]);
+      o.w = (i4.w * a.invert[3]) + (v.w / v.w * a.weight[3]);
+    }
+    a.out[g] = o;
+  }
+}
+
 // scatter(), :95-104: evaluated in double, truncated to int
 int scatter(float scale, float scattering, int i1, int i2)
 {
@@ -448,17 +730,32 @@ int nlmeans_denoise_dev(const float *d_in, float *d_out, int width, int height, 
 
   a.rows_e = a.chk_h + 2 * radius + 1;
   a.plane_e = a.rows_e * SW;
-  const int smem_bytes = (3 * a.plane_e + a.chk_h * SSTRIDE) * (int)sizeof(float);
+  a.cols_w = a.chk_w + 2 * radius + 2;
+  a.sstride_w = a.cols_w | 1;
   static bool attr_set[16] = { false };
+  static int smem_optin[16] = { 0 };
   int dev = 0;
   B200_CUDA_TRY(cudaGetDevice(&dev));
   if(!attr_set[dev & 15])
   {
     const int smem_max = (3 * (MAX_CH + 2 * MAX_RADIUS + 1) * SW + MAX_CH * SSTRIDE) * (int)sizeof(float);
     B200_CUDA_TRY(cudaFuncSetAttribute(nlm_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    B200_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin[dev & 15], cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    B200_CUDA_TRY(cudaFuncSetAttribute(nlm_chunks_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin[dev & 15]));
     attr_set[dev & 15] = true;
   }
-  nlm_chunks_kernel<<<(unsigned)(n_ct * a.n_cl), NT, smem_bytes, stream>>>(a);
+  const long long win_bytes = 2LL * a.rows_e * a.cols_w * 16 + 2LL * a.chk_h * a.sstride_w * 4;
+  // Measured at 45 MP, K=7, P=1: E-plane kernel 126 ms, window kernel 137 ms (both bit-exact; the window kernel
+  // moves all global traffic into one cp.async fill per patch but spends twice the instructions on index
+  // arithmetic in its parallel phases).  The window kernel stays selectable for that follow-up work.
+  const bool use_window = getenv("B200_NLM_WINDOW") != nullptr;
+  if(use_window && win_bytes <= smem_optin[dev & 15])
+    nlm_chunks_win_kernel<<<(unsigned)(n_ct * a.n_cl), WNT, (size_t)win_bytes, stream>>>(a);
+  else
+  {
+    const int smem_bytes = (3 * a.plane_e + a.chk_h * SSTRIDE) * (int)sizeof(float);
+    nlm_chunks_kernel<<<(unsigned)(n_ct * a.n_cl), NT, smem_bytes, stream>>>(a);
+  }
   B200_CUDA_TRY(cudaGetLastError());
   return B200_OK;
 }

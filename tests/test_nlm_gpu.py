@@ -92,3 +92,12 @@ def test_nlmeans_45mp_deterministic(built):
     a = cuda_nlm(img)
     assert np.isfinite(a).all()
     assert same_bits(a, cuda_nlm(img)).all()
+
+
+def test_window_kernel_is_bit_exact_too(built, monkeypatch):
+    """the shared-memory-window variant of the chunk kernel (B200_NLM_WINDOW=1) against the same oracle"""
+    monkeypatch.setenv("B200_NLM_WINDOW", "1")
+    for cfg in (0, 1, 2, 6):
+        img = (util.rgba_scene(301, 203, 2, noise=0.02) * 60).astype(np.float32)
+        kw = CONFIGS[cfg]
+        assert same_bits(cuda_nlm(img, **kw), util.oracle_nlmeans(img, **kw)).all(), cfg
