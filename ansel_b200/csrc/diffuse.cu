@@ -29,7 +29,8 @@ constexpr int NT = 256;
 __device__ __forceinline__ float clip0(float v) { return 0.0f > v ? 0.0f : v; } // MAX(0.0f, v)
 __device__ __forceinline__ float max_zero(float v)
 { // dt_simd_max_zero, system/simd.h:107-114
-  return (fabsf(v) <= 3.402823466e+38f) ? (v > 0.0f ? v : 0.0f) : 0.f;
+  const float t = fmaxf(v, 0.0f); // NaN -> 0, -inf -> 0, -0 -> +0 (PTX max), finite -> MAX(v, 0)
+  return t == __int_as_float(0x7f800000) ? 0.0f : t;
 }
 // (int) of a float the way x86 cvttss2si does it: out of range and NaN give INT_MIN
 __device__ __forceinline__ int cvtt(float v) { return (v >= -2147483648.0f && v < 2147483648.0f) ? __float2int_rz(v) : (int)0x80000000; }
@@ -39,29 +40,38 @@ __device__ __forceinline__ float fast_expf(float x)
   return __int_as_float(k0 > 0 ? k0 : 0);
 }
 
-// _bspline_vertical_pass: rows clamped, clip at zero.  grid.y = row, x over the 4*width floats of a row
-__global__ void __launch_bounds__(NT) bspline_vertical_kernel(const float *__restrict__ in, float *__restrict__ tmp, int w4, int height, int mult)
+// The two B-spline passes are pure streaming: one thread per PIXEL (float4), five 16-byte taps.
+__device__ __forceinline__ float bs5(float a, float b, float c, float d, float e)
+{ // sparse_scalar_product(), bspline.h:83-117, clip_negatives
+  return clip0(0.0625f * a + 0.25f * b + 0.375f * c + 0.25f * d + 0.0625f * e);
+}
+// _bspline_vertical_pass: rows clamped, clip at zero.  grid.y = row, x over the pixels of a row
+__global__ void __launch_bounds__(NT) bspline_vertical_kernel(const float4 *__restrict__ in, float4 *__restrict__ tmp, int width, int height, int mult)
 {
-  const int x = blockIdx.x * NT + threadIdx.x, i = blockIdx.y;
-  if(x >= w4) return;
-  const float *b = in + x;
-  const size_t r0 = (size_t)w4 * max(i - 2 * mult, 0), r1 = (size_t)w4 * max(i - mult, 0), r2 = (size_t)w4 * i;
-  const size_t r3 = (size_t)w4 * min(i + mult, height - 1), r4 = (size_t)w4 * min(i + 2 * mult, height - 1);
-  tmp[r2 + x] = clip0(0.0625f * __ldg(b + r0) + 0.25f * __ldg(b + r1) + 0.375f * __ldg(b + r2) + 0.25f * __ldg(b + r3) + 0.0625f * __ldg(b + r4));
+  const int j = blockIdx.x * NT + threadIdx.x, i = blockIdx.y;
+  if(j >= width) return;
+  const float4 *b = in + j;
+  const float4 p0 = __ldg(b + (size_t)width * max(i - 2 * mult, 0)), p1 = __ldg(b + (size_t)width * max(i - mult, 0));
+  const float4 p2 = __ldg(b + (size_t)width * i);
+  const float4 p3 = __ldg(b + (size_t)width * min(i + mult, height - 1)), p4 = __ldg(b + (size_t)width * min(i + 2 * mult, height - 1));
+  tmp[(size_t)width * i + j] = make_float4(bs5(p0.x, p1.x, p2.x, p3.x, p4.x), bs5(p0.y, p1.y, p2.y, p3.y, p4.y), bs5(p0.z, p1.z, p2.z, p3.z, p4.z),
+                                           bs5(p0.w, p1.w, p2.w, p3.w, p4.w));
 }
 // _bspline_horizontal + the HF subtraction of decompose_2D_Bspline
-__global__ void __launch_bounds__(NT) bspline_horizontal_kernel(const float *__restrict__ tmp, const float *__restrict__ in, float *__restrict__ LF,
-                                                                float *__restrict__ HF, int w4, int width, int mult)
+__global__ void __launch_bounds__(NT) bspline_horizontal_kernel(const float4 *__restrict__ tmp, const float4 *__restrict__ in, float4 *__restrict__ LF,
+                                                                float4 *__restrict__ HF, int width, int mult)
 {
-  const int x = blockIdx.x * NT + threadIdx.x;
-  if(x >= w4) return;
-  const size_t row = (size_t)w4 * blockIdx.y;
-  const int j = x >> 2, c = x & 3;
-  const float *t = tmp + row + c;
-  const float lf = clip0(0.0625f * __ldg(t + 4 * max(j - 2 * mult, 0)) + 0.25f * __ldg(t + 4 * max(j - mult, 0)) + 0.375f * __ldg(t + 4 * j)
-                         + 0.25f * __ldg(t + 4 * min(j + mult, width - 1)) + 0.0625f * __ldg(t + 4 * min(j + 2 * mult, width - 1)));
-  LF[row + x] = lf;
-  HF[row + x] = __ldg(in + row + x) - lf;
+  const int j = blockIdx.x * NT + threadIdx.x;
+  if(j >= width) return;
+  const size_t row = (size_t)width * blockIdx.y;
+  const float4 *t = tmp + row;
+  const float4 p0 = __ldg(t + max(j - 2 * mult, 0)), p1 = __ldg(t + max(j - mult, 0)), p2 = __ldg(t + j);
+  const float4 p3 = __ldg(t + min(j + mult, width - 1)), p4 = __ldg(t + min(j + 2 * mult, width - 1));
+  const float4 lf = make_float4(bs5(p0.x, p1.x, p2.x, p3.x, p4.x), bs5(p0.y, p1.y, p2.y, p3.y, p4.y), bs5(p0.z, p1.z, p2.z, p3.z, p4.z),
+                                bs5(p0.w, p1.w, p2.w, p3.w, p4.w));
+  const float4 v = __ldg(in + row + j);
+  LF[row + j] = lf;
+  HF[row + j] = make_float4(v.x - lf.x, v.y - lf.y, v.z - lf.z, v.w - lf.w);
 }
 
 struct pde_t
@@ -240,7 +250,8 @@ extern "C" int b200_diffuse_process_dev(const b200_piece_t *piece, const void *d
   pde.variance_threshold = powf(10.f, d->variance_threshold);
 
   const int w4 = 4 * width;
-  const dim3 grid((w4 + NT - 1) / NT, height);
+  const dim3 grid((w4 + NT - 1) / NT, height);        // PDE: one thread per float
+  const dim3 grid_px((width + NT - 1) / NT, height);  // B-spline passes: one thread per pixel
   for(int it = 0; it < iterations; it++)
   {
     const float *temp_in = it == 0 ? (const float *)d_in : (it % 2 == 0 ? temp1 : temp2);
@@ -252,8 +263,8 @@ extern "C" int b200_diffuse_process_dev(const b200_piece_t *piece, const void *d
     {
       const float *bin = s == 0 ? temp_in : (s % 2 != 0 ? LF_odd : LF_even);
       float *bout = s == 0 ? LF_odd : (s % 2 != 0 ? LF_even : LF_odd);
-      bspline_vertical_kernel<<<grid, NT, 0, st>>>(bin, vtmp, w4, height, 1 << s);
-      bspline_horizontal_kernel<<<grid, NT, 0, st>>>(vtmp, bin, bout, HF[s], w4, width, 1 << s);
+      bspline_vertical_kernel<<<grid_px, NT, 0, st>>>((const float4 *)bin, (float4 *)vtmp, width, height, 1 << s);
+      bspline_horizontal_kernel<<<grid_px, NT, 0, st>>>((const float4 *)vtmp, (const float4 *)bin, (float4 *)bout, (float4 *)HF[s], width, 1 << s);
       residual = bout;
     }
     B200_CUDA_TRY(cudaGetLastError());
