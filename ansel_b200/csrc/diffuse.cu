@@ -10,8 +10,8 @@
 // including the dilated ones (offset 4*mult floats), and the lane count is 4x the pixel count, which hides the
 // latency of the 18-tap PDE gather without shared memory.  The stencil taps re-hit L2 (5 taps x mult rows of
 // 132 KB stay far below 126 MB), so DRAM sees ~1 read + 1 write per pass.
-// Per band and per pixel: vertical pass 16 B in + 16 B out, horizontal pass 32 B in + 32 B out, PDE 32 B in +
-// 16 B out = 144 B; module boundary 32 B/px.  Compute-heavy part is the PDE (~110 flops + 2
+// Per band and per pixel: vertical pass 16 B in + 16 B out, horizontal pass 32 B in + 32 B out, PDE 48 B in +
+// 32 B out = 176 B; module boundary 32 B/px.  Compute-heavy part is the PDE (~110 flops + 2
 // sqrt + 4 div per float).
 //
 // Arithmetic contract: the reference source under C float semantics (no contraction, IEEE div/sqrt), as
@@ -58,8 +58,15 @@ __global__ void __launch_bounds__(NT) bspline_vertical_kernel(const float4 *__re
                                            bs5(p0.w, p1.w, p2.w, p3.w, p4.w));
 }
 // _bspline_horizontal + the HF subtraction of decompose_2D_Bspline
+__device__ __forceinline__ float ratio_sq(float hf, float lf)
+{ // one term of the HF/LF energy of heat_PDE_diffusion(), diffuse.c:826-830
+  const float safe_lf = max_zero(lf - 1e-8f) + 1e-8f;
+  const float ratio = hf / safe_lf;
+  return ratio * ratio;
+}
+// R (optional): the energy terms of the coarsest band, whose LF is this very output
 __global__ void __launch_bounds__(NT) bspline_horizontal_kernel(const float4 *__restrict__ tmp, const float4 *__restrict__ in, float4 *__restrict__ LF,
-                                                                float4 *__restrict__ HF, int width, int mult)
+                                                                float4 *__restrict__ HF, float4 *__restrict__ R, int width, int mult)
 {
   const int j = blockIdx.x * NT + threadIdx.x;
   if(j >= width) return;
@@ -70,8 +77,10 @@ __global__ void __launch_bounds__(NT) bspline_horizontal_kernel(const float4 *__
   const float4 lf = make_float4(bs5(p0.x, p1.x, p2.x, p3.x, p4.x), bs5(p0.y, p1.y, p2.y, p3.y, p4.y), bs5(p0.z, p1.z, p2.z, p3.z, p4.z),
                                 bs5(p0.w, p1.w, p2.w, p3.w, p4.w));
   const float4 v = __ldg(in + row + j);
+  const float4 hf = make_float4(v.x - lf.x, v.y - lf.y, v.z - lf.z, v.w - lf.w);
   LF[row + j] = lf;
-  HF[row + j] = make_float4(v.x - lf.x, v.y - lf.y, v.z - lf.z, v.w - lf.w);
+  HF[row + j] = hf;
+  if(R) R[row + j] = make_float4(ratio_sq(hf.x, lf.x), ratio_sq(hf.y, lf.y), ratio_sq(hf.z, lf.z), ratio_sq(hf.w, lf.w));
 }
 
 struct pde_t
@@ -117,7 +126,11 @@ __device__ __forceinline__ void make_kernel(float c2, float cs, float cos2, floa
 }
 
 // heat_PDE_diffusion(), :760-953, has_mask == 0
-__global__ void __launch_bounds__(NT) heat_pde_kernel(const float *__restrict__ HF, const float *__restrict__ LF, float *__restrict__ out, int w4,
+// R holds (HF/safe(LF))^2 of this band per float -- every pixel's term is needed by its nine neighbours, so it is
+// computed once where LF is produced (the previous, coarser PDE step or the last B-spline pass) instead of nine
+// times here: one IEEE division per float instead of nine.  HFnext/Rnext: the next finer band, whose LF is `out`.
+__global__ void __launch_bounds__(NT) heat_pde_kernel(const float *__restrict__ HF, const float *__restrict__ LF, const float *__restrict__ R,
+                                                      float *__restrict__ out, const float *__restrict__ HFnext, float *__restrict__ Rnext, int w4,
                                                       int width, int height, int mult, const pde_t p)
 {
   const int x = blockIdx.x * NT + threadIdx.x, i = blockIdx.y;
@@ -136,12 +149,9 @@ __global__ void __launch_bounds__(NT) heat_pde_kernel(const float *__restrict__ 
     }
   float energy = 0.f;
 #pragma unroll
-  for(int k = 0; k < 9; k++)
-  {
-    const float safe_lf = max_zero(lf[k] - 1e-8f) + 1e-8f;
-    const float ratio = hf[k] / safe_lf;
-    energy += ratio * ratio;
-  }
+  for(int ii = 0; ii < 3; ii++)
+#pragma unroll
+    for(int jj = 0; jj < 3; jj++) energy += __ldg(R + rn[ii] + cn[jj]);
   energy = max_zero(p.variance_threshold + energy * p.normalized_regularization - 1e-8f) + 1e-8f;
 
   float cs[2], cos2[2], sin2[2], mag[2];
@@ -176,7 +186,9 @@ __global__ void __launch_bounds__(NT) heat_pde_kernel(const float *__restrict__ 
   update = d[2] * p.ABCD[2] + update;
   update = d[3] * p.ABCD[3] + update;
   const float acc = hf[4] * p.strength + update / energy;
-  out[rn[1] + x] = max_zero(acc + lf[4]);
+  const float o = max_zero(acc + lf[4]);
+  out[rn[1] + x] = o;
+  if(Rnext) Rnext[rn[1] + x] = ratio_sq(__ldg(HFnext + rn[1] + x), o);
 }
 
 float sigma_at_step(unsigned s)
@@ -232,11 +244,12 @@ extern "C" int b200_diffuse_process_dev(const b200_piece_t *piece, const void *d
   const int scales = scale_count(d, zoom);
 
   void *base = nullptr;
-  if((rc = scratch(SLOT_TMP0, (size_t)(scales + 5) * n * sizeof(float), &base))) return rc;
+  if((rc = scratch(SLOT_TMP0, (size_t)(scales + 7) * n * sizeof(float), &base))) return rc;
   float *p = (float *)base;
   float *HF[MAX_SCALES];
   for(int s = 0; s < scales; s++, p += n) HF[s] = p;
   float *const LF_odd = p, *const LF_even = p + n, *const temp1 = p + 2 * n, *const temp2 = p + 3 * n, *const vtmp = p + 4 * n;
+  float *Rbuf[2] = { p + 5 * n, p + 6 * n }; // energy terms of the band being solved / of the next one
 
   // wavelets_process() :985-1000, :1057-1075: per-call constants
   pde_t pde;
@@ -264,7 +277,8 @@ extern "C" int b200_diffuse_process_dev(const b200_piece_t *piece, const void *d
       const float *bin = s == 0 ? temp_in : (s % 2 != 0 ? LF_odd : LF_even);
       float *bout = s == 0 ? LF_odd : (s % 2 != 0 ? LF_even : LF_odd);
       bspline_vertical_kernel<<<grid_px, NT, 0, st>>>((const float4 *)bin, (float4 *)vtmp, width, height, 1 << s);
-      bspline_horizontal_kernel<<<grid_px, NT, 0, st>>>((const float4 *)vtmp, (const float4 *)bin, (float4 *)bout, (float4 *)HF[s], width, 1 << s);
+      bspline_horizontal_kernel<<<grid_px, NT, 0, st>>>((const float4 *)vtmp, (const float4 *)bin, (float4 *)bout, (float4 *)HF[s],
+                                                      s == scales - 1 ? (float4 *)Rbuf[0] : nullptr, width, 1 << s);
       residual = bout;
     }
     B200_CUDA_TRY(cudaGetLastError());
@@ -284,7 +298,8 @@ extern "C" int b200_diffuse_process_dev(const b200_piece_t *piece, const void *d
       const float *bin = count == 0 ? residual : (count % 2 != 0 ? temp : residual);
       float *bout = count == 0 ? temp : (count % 2 != 0 ? residual : temp);
       if(s == 0) bout = temp_out;
-      heat_pde_kernel<<<grid, NT, 0, st>>>(HF[s], bin, bout, w4, width, height, 1 << s, pde);
+      heat_pde_kernel<<<grid, NT, 0, st>>>(HF[s], bin, Rbuf[count & 1], bout, s > 0 ? HF[s - 1] : nullptr, s > 0 ? Rbuf[(count + 1) & 1] : nullptr, w4,
+                                           width, height, 1 << s, pde);
       count++;
     }
     B200_CUDA_TRY(cudaGetLastError());
