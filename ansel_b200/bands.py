@@ -90,7 +90,7 @@ class BandedChain:
     """
 
     def __init__(self, nodes: list[Node], width: int, height: int, rank: int, world: int, device=None, process=None,
-                 filters: int = 0x94949494, p2p: bool = False):
+                 filters: int = 0x94949494, p2p: bool = False, p2p_dst=None):
         import torch
         self.torch = torch
         self.nodes, self.w, self.h, self.rank, self.world = nodes, width, height, rank, world
@@ -108,6 +108,7 @@ class BandedChain:
             self.pieces.append(p)
         self.tmp = [torch.empty((max(bh, 1), width, 4), dtype=torch.float32, device=self.device) for _ in range(2)]
         self.p2p = bool(p2p) and world > 1
+        self.p2p_dst = p2p_dst  # None: every rank ends with the frame (all-gather); int: only that rank does (gather)
         self._own_ptr, self._peer_ptr = None, {}
         if not self.p2p:
             self.frame = torch.empty((height, width, 4), dtype=torch.float32, device=self.device)
@@ -142,7 +143,10 @@ class BandedChain:
                                          devid=self.device.index)
         self._last_piece.buf_in_width, self._last_piece.buf_in_height = self.w, self.h
         row = b.out_y0 * self.w * 16
-        ptrs = [self._own_ptr + row] + [self._peer_ptr[r] + row for r in sorted(self._peer_ptr)]
+        if self.p2p_dst is None:
+            ptrs = [self._own_ptr + row] + [self._peer_ptr[r] + row for r in sorted(self._peer_ptr)]
+        else:  # gather to the exporting rank: one destination
+            ptrs = [(self._own_ptr if self.p2p_dst == self.rank else self._peer_ptr[self.p2p_dst]) + row]
         self._dsts = (C.c_void_p * len(ptrs))(*ptrs)
 
     def close(self):
@@ -174,7 +178,7 @@ class BandedChain:
                                                                self._dsts, C.c_void_p(stream)))
         # the stores of every rank must have landed before anyone reads its frame
         dist.barrier()
-        return self.frame
+        return self.frame if self.p2p_dst is None or self.p2p_dst == self.rank else None
 
     def band_rows(self, frame_in):
         """this rank's input rows of a full-frame host/device array"""

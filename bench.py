@@ -448,6 +448,26 @@ def run_b200(args):
             same2 = torch.tensor([int(torch.equal(out2.view(torch.int32), out_frame.view(torch.int32)))], dtype=torch.int32, device=dev)
             dist.all_reduce(same2, op=dist.ReduceOp.MIN)
             ch2.close()
+            # gather to the exporting rank only (what an export needs): every band has one destination
+            ch3 = bands.BandedChain(bnodes, w, h, rank, world, device=dev, p2p=True, p2p_dst=0)
+            for _ in range(3):
+                ch3(t_band, stream=stream)
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(args.steps):
+                out3 = ch3(t_band, stream=stream)
+            g1.record()
+            barrier()
+            t_g = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t_g, op=dist.ReduceOp.MAX)
+            same3 = torch.ones(1, dtype=torch.int32, device=dev)
+            if rank == 0:
+                same3[0] = int(torch.equal(out3.view(torch.int32), out_frame.view(torch.int32)))
+            dist.broadcast(same3, 0)
+            ch3.close()
+            banded["fused_p2p_gather_to_rank0"] = {"value": npx * args.steps / (float(t_g.item()) * 1e-3) / 1e6,
+                                                   "ms_per_frame": float(t_g.item()) / args.steps, "bit_identical_to_collective": bool(same3.item())}
             banded["fused_p2p"] = {"value": npx * args.steps / (float(t_c.item()) * 1e-3) / 1e6, "ms_per_frame": float(t_c.item()) / args.steps,
                                    "how": "colorout stores each pixel into every rank's frame (CUDA IPC peer mappings), then one barrier",
                                    "bit_identical_to_collective": bool(same2.item())}

@@ -103,7 +103,7 @@ def test_banded_nlm_chain_equals_per_band_oracle(built):
         assert (~taint[lo:hi]).mean() > 0.8
 
 
-def _nccl_worker(rank, world, port, w, h, q, p2p=False):
+def _nccl_worker(rank, world, port, w, h, q, p2p=False, p2p_dst=None):
     import torch
     import torch.distributed as dist
     import ansel_b200 as ab
@@ -115,7 +115,7 @@ def _nccl_worker(rank, world, port, w, h, q, p2p=False):
         mosaic = util.frame_natural(w, h, 11)
         nodes, _keep = _c2_nodes()
         dev = torch.device("cuda", rank)
-        ch = bands.BandedChain(nodes, w, h, rank, world, device=dev, p2p=p2p)
+        ch = bands.BandedChain(nodes, w, h, rank, world, device=dev, p2p=p2p, p2p_dst=p2p_dst)
         band = torch.from_numpy(np.ascontiguousarray(ch.band_rows(mosaic))).to(dev)
         one = bands.BandedChain(nodes, w, h, 0, 1, device=dev)
         want = one(torch.from_numpy(mosaic).to(dev), stream=torch.cuda.current_stream().cuda_stream)
@@ -124,7 +124,10 @@ def _nccl_worker(rank, world, port, w, h, q, p2p=False):
         for _ in range(2):                      # twice: the second pass overwrites frames the peers have already read
             frame = ch(band, stream=torch.cuda.current_stream().cuda_stream)
             torch.cuda.synchronize()
-            ok = ok and bool(torch.equal(frame.view(torch.int32), want.view(torch.int32)))
+            if frame is None:
+                ok = ok and p2p_dst is not None and rank != p2p_dst
+            else:
+                ok = ok and bool(torch.equal(frame.view(torch.int32), want.view(torch.int32)))
             dist.barrier()
         ch.close()
         q.put((rank, ok))
@@ -132,7 +135,7 @@ def _nccl_worker(rank, world, port, w, h, q, p2p=False):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("p2p", [False, True])
+@pytest.mark.parametrize("p2p", [False, True, "gather"])
 def test_banded_c2_all_gather_over_nccl(built, p2p):
     """needs >= 2 GPUs (gpurun --gpus 2): every rank ends with the untiled frame, bit for bit -- gathered by NCCL
     (p2p=False) or by colorout's own stores into the peers' frames over NVLink (p2p=True)."""
@@ -147,7 +150,7 @@ def test_banded_c2_all_gather_over_nccl(built, p2p):
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, 3000, 2000, q, p2p)) for r in range(world)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, 3000, 2000, q, bool(p2p), 0 if p2p == "gather" else None)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
