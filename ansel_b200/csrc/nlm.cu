@@ -17,6 +17,7 @@
 //   phase B1 threads = rows    : the running sum along each row                          -> D[row][col] (in place of S)
 //   phase B2 threads = pixels  : weights and accumulation; each thread owns a fixed set of chunk pixels and keeps
 //                                their RGBA sums in registers across all patches
+// and the phases of successive patches are software-pipelined (see nlm_chunks_kernel).
 // pixel_difference() is (d0*d0)*n0 + (d1*d1)*n1 + (d2*d2)*n2 and diff_of_pixels_diff() is
 // (a0*a0 - b0*b0)*n0 + ...: both are functions of the per-channel squares, so E holds exactly the reference's
 // intermediate values and the sums are formed in its order.
@@ -39,16 +40,7 @@ constexpr int SSTRIDE = SW + 1;                    // 83: odd, so lanes = rows h
 #ifndef NLM_MINB
 #define NLM_MINB 1
 #endif
-#ifndef NLM_UE
-#define NLM_UE 1
-#endif
 constexpr int NT = NLM_NT;
-constexpr int OWN = (MAX_CH * MAX_CW + NT - 1) / NT; // chunk pixels owned by one thread
-constexpr int UE = NLM_UE;
-#ifndef NLM_UB
-#define NLM_UB 1
-#endif
-constexpr int UB = NLM_UB;                            // owned pixels fetched together in phase B2                            // E entries fetched per thread before any is used
 
 struct patch_t
 {
@@ -89,239 +81,210 @@ __device__ __forceinline__ float diff_of_diffs(const float4 p1, const float4 p2,
   return (a0 * a0 - b0 * b0) * n[0] + (a1 * a1 - b1 * b1) * n[1] + (a2 * a2 - b2 * b2) * n[2];
 }
 
+// patch geometry of nlmeans_denoise() :345-372 for one chunk; uniform across the CTA
+struct patch_geo_t
+{
+  int srow, scol, row_min, row_max, row_top, row_bot, col_min, col_max, pcol_min, pcol_max;
+  long long poff;
+  bool valid;
+};
+__device__ __forceinline__ patch_geo_t patch_geo(const nlm_args_t &a, int p, int chunk_top, int chunk_bot, int chunk_left, int chunk_right)
+{
+  patch_geo_t g;
+  g.valid = p >= 0 && p < a.n_patches;
+  if(!g.valid) return g;
+  const int radius = a.radius, width = a.width, height = a.height;
+  g.srow = a.patches[p].rows;
+  g.scol = a.patches[p].cols;
+  g.row_min = max(chunk_top, max(0, -g.srow));
+  g.row_max = min(chunk_bot, height - max(0, g.srow));
+  g.valid = g.row_min < g.row_max;
+  g.row_top = max(g.row_min, max(radius, radius - g.srow));
+  g.row_bot = min(g.row_max, height - 1 - max(radius, radius + g.srow));
+  g.col_min = max(chunk_left, -g.scol);
+  g.col_max = min(chunk_right, width - g.scol);
+  g.pcol_min = chunk_left - min(radius, min(chunk_left, chunk_left + g.scol));
+  g.pcol_max = chunk_right + min(radius, min(width - chunk_right, width - (chunk_right + g.scol)));
+  g.poff = (long long)g.srow * width + g.scol;
+  return g;
+}
+
+// Software pipeline over the patches, two __syncthreads per patch.  Warps 0..2 ("serial") own the two recurrences,
+// the other warps ("parallel") own every global load and the accumulation:
+//     interval 1:  serial A(i)   -- column sums of patch i from E[i&1] into S[i&1]     | parallel B2(i-1) from S[(i-1)&1]
+//     interval 2:  serial B1(i)  -- distortions of patch i, in place in S[i&1]          | parallel E(i+1) into E[(i+1)&1]
+// so the recurrences (3 busy warps) run under the latency-bound parallel phases instead of between them.
+constexpr int SERIAL_T = 96;                       // >= SW columns and >= MAX_CH rows
+constexpr int PNT = NT - SERIAL_T;                 // parallel threads
+constexpr int OWNP = (MAX_CH * MAX_CW + PNT - 1) / PNT;
+static_assert(SERIAL_T >= SW && SERIAL_T >= MAX_CH, "serial warps must cover one row and one column of a chunk");
+
 __global__ void __launch_bounds__(NT, NLM_MINB) nlm_chunks_kernel(const __grid_constant__ nlm_args_t a)
 {
   extern __shared__ __align__(16) float smem[];
-  float *const E0 = smem;                      // [rows_e][SW] squared differences, channel 0
-  float *const E1 = E0 + a.plane_e;
-  float *const E2 = E1 + a.plane_e;
-  float *const S = E2 + a.plane_e;             // [chunk rows][SSTRIDE] column sums / distortions
+  float *const Ebuf = smem;                                    // 2 x 3 planes [rows_e][SW]
+  float *const Sbuf = smem + 6 * a.plane_e;                    // 2 x [chunk rows][SSTRIDE]
   const int tid = threadIdx.x;
+  const bool serial = tid < SERIAL_T;
+  const int ptid = tid - SERIAL_T;                             // index among the parallel threads
   const int it = blockIdx.x / a.n_cl, il = blockIdx.x - it * a.n_cl;
   const int chunk_top = it * a.chk_h, chunk_left = il * a.chk_w;
   const int chunk_bot = min(chunk_top + a.chk_h, a.height), chunk_right = min(chunk_left + a.chk_w, a.width);
   const int width = a.width, height = a.height, radius = a.radius;
   const int cbase = chunk_left - radius - 1;              // column of S[.][0] and E[.][0]
   const int ncols = (chunk_right + radius) - cbase;       // <= SW
+  const int s_plane = a.chk_h * SSTRIDE;
   const float4 *const in = a.in;
   const float n0 = a.norm[0], n1 = a.norm[1], n2 = a.norm[2];
 
-  // the pixels this thread owns: chunk-local (row, col) of pixel tid + k*NT, row-major over the chunk
+  // the pixels a parallel thread owns: pixel ptid + k*PNT of the chunk, row-major
   const int cw = chunk_right - chunk_left, ch = chunk_bot - chunk_top;
-  float4 acc[OWN];
-  int own[OWN]; // (image row << 16) | image column, or -1 when the slot lies beyond the chunk (frames < 32768 px a side)
+  float4 acc[OWNP];
+  int own[OWNP]; // (image row << 16) | image column, or -1 (frames < 32768 px a side)
 #pragma unroll
-  for(int k = 0; k < OWN; k++)
+  for(int k = 0; k < OWNP; k++)
   {
     acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int idx = tid + k * NT;
+    const int idx = ptid + k * PNT;
     const int rr = idx / cw;
-    own[k] = rr < ch ? (((chunk_top + rr) << 16) | (chunk_left + (idx - rr * cw))) : -1;
+    own[k] = (!serial && rr < ch) ? (((chunk_top + rr) << 16) | (chunk_left + (idx - rr * cw))) : -1;
   }
-  // phase E walks (row, col) entries tid, tid+NT, ... of a ncols-wide grid without dividing in the loop
-  const int e_r0 = tid / ncols, e_c0 = tid - e_r0 * ncols, e_dr = NT / ncols, e_dc = NT - e_dr * ncols;
+  // phase E walks (row, col) entries ptid, ptid+PNT, ... of an ncols-wide grid without dividing in the loop
+  const int e_r0 = ptid / ncols, e_c0 = ptid - e_r0 * ncols, e_dr = PNT / ncols, e_dc = PNT - e_dr * ncols;
 
-  for(int p = 0; p < a.n_patches; p++)
+  // ---- phase E: squared per-channel differences of every pixel pair the patch touches (parallel threads) --------
+  auto phase_e = [&](int p) {
+    const patch_geo_t g = patch_geo(a, p, chunk_top, chunk_bot, chunk_left, chunk_right);
+    if(!g.valid) return;
+    float *const E0 = Ebuf + (p & 1) * 3 * a.plane_e, *const E1 = E0 + a.plane_e, *const E2 = E1 + a.plane_e;
+    const int erow0 = g.row_min - radius;                         // image row of E[0][.]
+    const int n_erows = (g.row_max - g.row_min) + 2 * radius + 1; // rows row_min-radius .. row_max+radius
+    int rr = e_r0, cc = e_c0;
+    while(rr < n_erows)
+    {
+      const int r = erow0 + rr, col = cbase + cc;
+      if(col >= g.pcol_min && col < g.pcol_max && r >= 0 && r < height && r + g.srow >= 0 && r + g.srow < height)
+      {
+        const float4 *px = in + (size_t)r * width + col;
+        const float4 x = __ldg(px), y = __ldg(px + g.poff);
+        const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z;
+        const int e = rr * SW + cc;
+        E0[e] = d0 * d0;
+        E1[e] = d1 * d1;
+        E2[e] = d2 * d2;
+      }
+      rr += e_dr;
+      cc += e_dc;
+      if(cc >= ncols)
+      {
+        cc -= ncols;
+        rr++;
+      }
+    }
+  };
+  // ---- phase A: column sums down the rows, one serial thread per column ----------------------------------------
+  auto phase_a = [&](int p) {
+    const patch_geo_t g = patch_geo(a, p, chunk_top, chunk_bot, chunk_left, chunk_right);
+    if(!g.valid || tid >= ncols) return;
+    const float *const E0 = Ebuf + (p & 1) * 3 * a.plane_e, *const E1 = E0 + a.plane_e, *const E2 = E1 + a.plane_e;
+    float *const S = Sbuf + (p & 1) * s_plane;
+    const int erow0 = g.row_min - radius;
+    const int col = cbase + tid;
+    const bool live = col >= g.pcol_min && col < g.pcol_max;
+    float cs = 0.0f;
+    if(live)
+    { // init_column_sums(), :214-264, at row = row_min
+      const int row = g.row_min;
+      const int rmin = row - min(radius, min(row, row + g.srow));
+      const int rmax = row + min(radius, min(height - 1 - row, height - 1 - (row + g.srow)));
+      float sum = 0.0f;
+      for(int r = rmin; r <= rmax; r++)
+      {
+        const int e = (r - erow0) * SW + tid;
+        sum += E0[e] * n0 + E1[e] * n1 + E2[e] * n2; // pixel_difference(), :156-165
+      }
+      cs = sum;
+    }
+    // Rows [row_min, lim_a) add the entering row (:424-440), [lim_a, row_bot) add entering minus leaving (:441-466),
+    // rows >= max(row_top, row_bot) with a successor subtract the leaving row (:467-483).  All three are the middle
+    // formula with the absent row's squares replaced by +0 (x - 0 = x, and -(u+v+w) is formed by the same roundings
+    // as (-u)+(-v)+(-w)), so the loop is branch-free.
+    const int lim_a = min(g.row_top, g.row_bot);
+    int eb = (g.row_min + 1 + radius - erow0) * SW + tid, et = (g.row_min - radius - erow0) * SW + tid;
+    float *sp = S + tid;
+    for(int row = g.row_min; row < g.row_max; row++, eb += SW, et += SW, sp += SSTRIDE)
+    {
+      const bool use_b = live && row < g.row_bot;
+      const bool use_t = live && row >= lim_a && (row < g.row_bot || (row >= g.row_top && row + 1 < g.row_max));
+      const float b0 = use_b ? E0[eb] : 0.0f, b1 = use_b ? E1[eb] : 0.0f, b2 = use_b ? E2[eb] : 0.0f;
+      const float t0 = use_t ? E0[et] : 0.0f, t1 = use_t ? E1[et] : 0.0f, t2 = use_t ? E2[et] : 0.0f;
+      *sp = cs;
+      cs += (b0 - t0) * n0 + (b1 - t1) * n1 + (b2 - t2) * n2;
+    }
+  };
+  // ---- phase B1: running distortion along each row, one serial thread per row (:384-387,409) --------------------
+  auto phase_b1 = [&](int p) {
+    const patch_geo_t g = patch_geo(a, p, chunk_top, chunk_bot, chunk_left, chunk_right);
+    if(!g.valid || tid >= g.row_max - g.row_min || g.col_min >= g.col_max) return;
+    float *const Sr = Sbuf + (p & 1) * s_plane + tid * SSTRIDE - cbase; // Sr[col] = column sum of `col` for this row
+    float distortion = 0.0f;
+    for(int i = g.col_min - radius; i < min(g.col_min + radius, g.col_max); i++) distortion += Sr[i];
+    for(int col = g.col_min; col < g.col_max; col++)
+    {
+      distortion += (Sr[col + radius] - Sr[col - radius - 1]);
+      Sr[col - radius - 1] = distortion; // that slot is never read again: keep D[col] there
+    }
+  };
+  // ---- phase B2: weights and accumulation into the owned pixels' registers (parallel threads) -------------------
+  auto phase_b2 = [&](int p) {
+    const patch_geo_t g = patch_geo(a, p, chunk_top, chunk_bot, chunk_left, chunk_right);
+    if(!g.valid || g.col_min >= g.col_max) return;
+    const float *const S = Sbuf + (p & 1) * s_plane;
+#pragma unroll
+    for(int k = 0; k < OWNP; k++)
+    {
+      const int row = own[k] >> 16, col = own[k] & 0xffff;
+      if(own[k] < 0 || row < g.row_min || row >= g.row_max || col < g.col_min || col >= g.col_max) continue;
+      const float4 *px = in + (size_t)row * width + col;
+      const float4 q = __ldg(px + g.poff);
+      const float dist = S[(row - g.row_min) * SSTRIDE + (col - radius - 1 - cbase)];
+      float wt;
+      if(a.center_weight < 0)
+        wt = fast_mexp2(dist * a.sharpness); // :389-402
+      else
+      { // :404-420
+        const float4 c = __ldg(px);
+        const float d0 = c.x - q.x, d1 = c.y - q.y, d2 = c.z - q.z;
+        const float pd = d0 * d0 * a.cp_norm + d1 * d1 * a.cp_norm + d2 * d2 * a.cp_norm;
+        const float dissimilarity = (dist + pd) / (1.0f + a.center_weight);
+        wt = fast_mexp2(fmaxf(0.0f, dissimilarity * a.sharpness - 2.0f));
+      }
+      acc[k].x += q.x * wt;
+      acc[k].y += q.y * wt;
+      acc[k].z += q.z * wt;
+      acc[k].w += 1.0f * wt;
+    }
+  };
+
+  if(!serial) phase_e(0);
+  __syncthreads();
+  for(int i = 0; i <= a.n_patches; i++)
   {
-    const int srow = a.patches[p].rows, scol = a.patches[p].cols;
-    const int row_min = max(chunk_top, max(0, -srow)), row_max = min(chunk_bot, height - max(0, srow));
-    if(row_min >= row_max) continue; // uniform
-    const int row_top = max(row_min, max(radius, radius - srow));
-    const int row_bot = min(row_max, height - 1 - max(radius, radius + srow));
-    const int col_min = max(chunk_left, -scol), col_max = min(chunk_right, width - scol);
-    const int pcol_min = chunk_left - min(radius, min(chunk_left, chunk_left + scol));
-    const int pcol_max = chunk_right + min(radius, min(width - chunk_right, width - (chunk_right + scol)));
-    const long long poff = (long long)srow * width + scol; // patch offset in pixels
-    const int nrows = row_max - row_min;
-    const int erow0 = row_min - radius;                     // image row of E[0][.]
-    const int n_erows = nrows + 2 * radius + 1;             // rows row_min-radius .. row_max+radius
-
-    // ---- phase E: squared per-channel differences of every pixel pair the patch touches ---------------
-    {
-      int rr = e_r0, cc = e_c0;
-      while(rr < n_erows)
-      {
-        float4 x[UE], y[UE];
-        int slot[UE];
-#pragma unroll
-        for(int u = 0; u < UE; u++)
-        {
-          slot[u] = -1;
-          if(rr < n_erows)
-          {
-            const int r = erow0 + rr, col = cbase + cc;
-            if(col >= pcol_min && col < pcol_max && r >= 0 && r < height && r + srow >= 0 && r + srow < height)
-            {
-              const float4 *px = in + (size_t)r * width + col;
-              x[u] = __ldg(px);
-              y[u] = __ldg(px + poff);
-              slot[u] = rr * SW + cc;
-            }
-          }
-          rr += e_dr;
-          cc += e_dc;
-          if(cc >= ncols)
-          {
-            cc -= ncols;
-            rr++;
-          }
-        }
-#pragma unroll
-        for(int u = 0; u < UE; u++)
-          if(slot[u] >= 0)
-          {
-            const float d0 = x[u].x - y[u].x, d1 = x[u].y - y[u].y, d2 = x[u].z - y[u].z;
-            E0[slot[u]] = d0 * d0;
-            E1[slot[u]] = d1 * d1;
-            E2[slot[u]] = d2 * d2;
-          }
-      }
-    }
+    if(serial)
+      phase_a(i);
+    else
+      phase_b2(i - 1);
     __syncthreads();
-
-    // ---- phase A: column sums down the rows, one thread per column ---------------------------------
-    if(tid < ncols)
-    {
-      const int col = cbase + tid;
-      const bool live = col >= pcol_min && col < pcol_max;
-      float cs = 0.0f;
-      if(live)
-      { // init_column_sums(), :214-264, at row = row_min
-        const int row = row_min;
-        const int rmin = row - min(radius, min(row, row + srow));
-        const int rmax = row + min(radius, min(height - 1 - row, height - 1 - (row + srow)));
-        float sum = 0.0f;
-        for(int r = rmin; r <= rmax; r++)
-        {
-          const int e = (r - erow0) * SW + tid;
-          sum += E0[e] * n0 + E1[e] * n1 + E2[e] * n2; // pixel_difference(), :156-165
-        }
-        cs = sum;
-      }
-      // Rows [row_min, lim_a) add the entering row (:424-440), [lim_a, row_bot) add entering minus leaving
-      // (:441-466), rows >= max(row_top, row_bot) with a successor subtract the leaving row (:467-483).  All three
-      // are the middle formula with the absent row's squares replaced by +0 (x - 0 = x, and -(u+v+w) is formed by
-      // the same roundings as (-u)+(-v)+(-w)), so the loop is branch-free; operands of UA rows are fetched before
-      // any column sum is stored.
-      const int lim_a = min(row_top, row_bot);
-      #ifndef NLM_UA
-#define NLM_UA 1
-#endif
-      constexpr int UA = NLM_UA;
-      for(int row0 = row_min; row0 < row_max; row0 += UA)
-      {
-        float b0[UA], b1[UA], b2[UA], t0[UA], t1[UA], t2[UA];
-#pragma unroll
-        for(int u = 0; u < UA; u++)
-        {
-          const int row = row0 + u;
-          const bool use_b = live && row < row_bot && row < row_max;
-          const bool use_t = live && row >= lim_a && row < row_max && (row < row_bot || (row >= row_top && row + 1 < row_max));
-          const int eb = (row + 1 + radius - erow0) * SW + tid, et = (row - radius - erow0) * SW + tid;
-          b0[u] = use_b ? E0[eb] : 0.0f;
-          b1[u] = use_b ? E1[eb] : 0.0f;
-          b2[u] = use_b ? E2[eb] : 0.0f;
-          t0[u] = use_t ? E0[et] : 0.0f;
-          t1[u] = use_t ? E1[et] : 0.0f;
-          t2[u] = use_t ? E2[et] : 0.0f;
-        }
-#pragma unroll
-        for(int u = 0; u < UA; u++)
-        {
-          if(row0 + u >= row_max) break;
-          S[(row0 + u - row_min) * SSTRIDE + tid] = cs;
-          cs += (b0[u] - t0[u]) * n0 + (b1[u] - t1[u]) * n1 + (b2[u] - t2[u]) * n2;
-        }
-      }
-    }
+    if(serial)
+      phase_b1(i);
+    else
+      phase_e(i + 1);
     __syncthreads();
-
-    // ---- phase B1: running distortion along each row, one thread per row (:384-387,409) -----------
-    if(tid < nrows && col_min < col_max)
-    {
-      float *const Sr = S + tid * SSTRIDE - cbase; // Sr[col] = column sum of `col` for this row
-      float distortion = 0.0f;
-      for(int i = col_min - radius; i < min(col_min + radius, col_max); i++) distortion += Sr[i];
-      // D[col] is kept in the slot col-radius-1, which is behind every column sum still to be read; the operands of
-      // UC columns are fetched before the first of their results is stored
-      #ifndef NLM_UC
-#define NLM_UC 2
-#endif
-      constexpr int UC = NLM_UC;
-      for(int col0 = col_min; col0 < col_max; col0 += UC)
-      {
-        float hi[UC], lo[UC];
-#pragma unroll
-        for(int u = 0; u < UC; u++)
-          if(col0 + u < col_max)
-          {
-            hi[u] = Sr[col0 + u + radius];
-            lo[u] = Sr[col0 + u - radius - 1];
-          }
-#pragma unroll
-        for(int u = 0; u < UC; u++)
-          if(col0 + u < col_max)
-          {
-            distortion += (hi[u] - lo[u]);
-            Sr[col0 + u - radius - 1] = distortion;
-          }
-      }
-    }
-    __syncthreads();
-
-    // ---- phase B2: weights and accumulation into the owned pixels' registers ---------------------------
-    // (no barrier after it: the next patch's phase E touches neither S nor the accumulators)
-    if(col_min < col_max)
-    {
-#pragma unroll
-      for(int k0 = 0; k0 < OWN; k0 += UB)
-      { // operands of UB owned pixels first (independent loads in flight), then the arithmetic
-        float4 q[UB], c[UB];
-        float dist[UB];
-        bool on[UB];
-#pragma unroll
-        for(int u = 0; u < UB; u++)
-        {
-          on[u] = false;
-          if(k0 + u < OWN)
-          {
-            const int row = own[k0 + u] >> 16, col = own[k0 + u] & 0xffff;
-            on[u] = own[k0 + u] >= 0 && row >= row_min && row < row_max && col >= col_min && col < col_max;
-            if(on[u])
-            {
-              const float4 *px = in + (size_t)row * width + col;
-              q[u] = __ldg(px + poff);
-              if(a.center_weight >= 0) c[u] = __ldg(px);
-              dist[u] = S[(row - row_min) * SSTRIDE + (col - radius - 1 - cbase)];
-            }
-          }
-        }
-#pragma unroll
-        for(int u = 0; u < UB; u++)
-        {
-          if(!on[u]) continue;
-          float wt;
-          if(a.center_weight < 0)
-            wt = fast_mexp2(dist[u] * a.sharpness); // :389-402
-          else
-          { // :404-420
-            const float d0 = c[u].x - q[u].x, d1 = c[u].y - q[u].y, d2 = c[u].z - q[u].z;
-            const float pd = d0 * d0 * a.cp_norm + d1 * d1 * a.cp_norm + d2 * d2 * a.cp_norm;
-            const float dissimilarity = (dist[u] + pd) / (1.0f + a.center_weight);
-            wt = fast_mexp2(fmaxf(0.0f, dissimilarity * a.sharpness - 2.0f));
-          }
-          acc[k0 + u].x += q[u].x * wt;
-          acc[k0 + u].y += q[u].y * wt;
-          acc[k0 + u].z += q[u].z * wt;
-          acc[k0 + u].w += 1.0f * wt;
-        }
-      }
-    }
   }
 
   // ---- normalise (and blend) : :485-519 ---------------------------------------------------------------
 #pragma unroll
-  for(int k = 0; k < OWN; k++)
+  for(int k = 0; k < OWNP; k++)
   {
     if(own[k] < 0) continue;
     const float4 v = acc[k];
@@ -738,7 +701,7 @@ int nlmeans_denoise_dev(const float *d_in, float *d_out, int width, int height, 
   B200_CUDA_TRY(cudaGetDevice(&dev));
   if(!attr_set[dev & 15])
   {
-    const int smem_max = (3 * (MAX_CH + 2 * MAX_RADIUS + 1) * SW + MAX_CH * SSTRIDE) * (int)sizeof(float);
+    const int smem_max = 2 * (3 * (MAX_CH + 2 * MAX_RADIUS + 1) * SW + MAX_CH * SSTRIDE) * (int)sizeof(float);
     B200_CUDA_TRY(cudaFuncSetAttribute(nlm_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     B200_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin[dev & 15], cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     B200_CUDA_TRY(cudaFuncSetAttribute(nlm_chunks_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin[dev & 15]));
@@ -753,7 +716,7 @@ int nlmeans_denoise_dev(const float *d_in, float *d_out, int width, int height, 
     nlm_chunks_win_kernel<<<(unsigned)(n_ct * a.n_cl), WNT, (size_t)win_bytes, stream>>>(a);
   else
   {
-    const int smem_bytes = (3 * a.plane_e + a.chk_h * SSTRIDE) * (int)sizeof(float);
+    const int smem_bytes = 2 * (3 * a.plane_e + a.chk_h * SSTRIDE) * (int)sizeof(float); // E and S double-buffered
     nlm_chunks_kernel<<<(unsigned)(n_ct * a.n_cl), NT, smem_bytes, stream>>>(a);
   }
   B200_CUDA_TRY(cudaGetLastError());
