@@ -7,7 +7,12 @@ namespace b200
 {
 int rcd_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters,
                      const float processed_maximum[3], cudaStream_t stream);
+int demosaic_green_eq_dev(const float *d_in, float *d_tmp0, float *d_tmp1, double *d_partial, int width, int height, uint32_t dsc_filters, int x, int y,
+                          unsigned green_eq, float threshold, const float **d_result, cudaStream_t s);
+int demosaic_green_eq_partial_doubles();
+int demosaic_color_smoothing_dev(float *d_out, int width, int height, int passes, cudaStream_t s);
 }
+#define DT_IMAGE_4BAYER (1u << 14) /* common/image.h:139 */
 using namespace b200;
 
 #define DEMOSAIC_DUAL 2048 /* iop/demosaic.c:109 */
@@ -31,22 +36,33 @@ extern "C" int b200_demosaic_process_dev(const b200_piece_t *piece, const void *
   // demosaic.c:1071 -- fold the ROI origin into the CFA phase for the tile-local algorithms
   const uint32_t filters = b200_roi_filters(piece->filters, piece->roi_in.x, piece->roi_in.y);
   if(filters == 9u) return fail(B200_ERR_UNSUPPORTED, "demosaic: X-Trans sensors are not built (SURVEY.md 8f rank 4)");
-  if(d->green_eq != 0) return fail(B200_ERR_UNSUPPORTED, "demosaic: green equilibration is not built (8f rank 4)");
-  if(d->color_smoothing != 0) return fail(B200_ERR_UNSUPPORTED, "demosaic: colour smoothing is not built (8f rank 4)");
+  if(d->green_eq > 3) return fail(B200_ERR_ARG, "demosaic: green_eq %u", d->green_eq);
+  if(piece->image_flags & DT_IMAGE_4BAYER) return fail(B200_ERR_UNSUPPORTED, "demosaic: four-colour Bayer sensors are not built");
   if(d->demosaicing_method & DEMOSAIC_DUAL) return fail(B200_ERR_UNSUPPORTED, "demosaic: dual demosaic is not built (8f rank 4)");
   // roi_out has the size of roi_in with origin 0 for the full demosaicers (demosaic.c:1052-1054)
   if(piece->roi_out.width != piece->roi_in.width || piece->roi_out.height != piece->roi_in.height)
     return fail(B200_ERR_UNSUPPORTED, "demosaic: roi_out %dx%d != roi_in %dx%d (downsampling paths are not built)",
                 piece->roi_out.width, piece->roi_out.height, piece->roi_in.width, piece->roi_in.height);
 
-  switch(d->demosaicing_method)
-  {
-    case B200_DEMOSAIC_RCD:
-      return rcd_demosaic_dev((const float *)d_in, (float *)d_out, piece->roi_in.width, piece->roi_in.height, filters,
-                              piece->processed_maximum, (cudaStream_t)stream);
-    default:
-      return fail(B200_ERR_UNSUPPORTED, "demosaic: method %u is not built", d->demosaicing_method);
+  if(d->demosaicing_method != B200_DEMOSAIC_RCD) return fail(B200_ERR_UNSUPPORTED, "demosaic: method %u is not built", d->demosaicing_method);
+  const int width = piece->roi_in.width, height = piece->roi_in.height;
+  cudaStream_t s = (cudaStream_t)stream;
+  const float *mosaic = (const float *)d_in;
+  if(d->green_eq != 0)
+  { // demosaic.c:1137-1170: the equalised mosaic replaces the input of the demosaicer
+    const size_t n = (size_t)width * height;
+    void *t0 = nullptr, *t1 = nullptr, *pd = nullptr;
+    if((rc = scratch(SLOT_TMP0, n * sizeof(float), &t0))) return rc;
+    if((rc = scratch(SLOT_TMP1, n * sizeof(float), &t1))) return rc;
+    if((rc = scratch(SLOT_SMALL, (size_t)demosaic_green_eq_partial_doubles() * sizeof(double), &pd))) return rc;
+    const float threshold = 0.0001f * piece->exif_iso; // :1049
+    if((rc = demosaic_green_eq_dev(mosaic, (float *)t0, (float *)t1, (double *)pd, width, height, piece->filters, piece->roi_in.x, piece->roi_in.y,
+                                   d->green_eq, threshold, &mosaic, s)))
+      return rc;
   }
+  if((rc = rcd_demosaic_dev(mosaic, (float *)d_out, width, height, filters, piece->processed_maximum, s))) return rc;
+  if(d->color_smoothing) rc = demosaic_color_smoothing_dev((float *)d_out, piece->roi_out.width, piece->roi_out.height, (int)d->color_smoothing, s); // :1249-1250
+  return rc;
 }
 
 extern "C" int b200_demosaic_process_host(const b200_piece_t *piece, const void *in, void *out)

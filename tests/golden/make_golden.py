@@ -72,3 +72,7 @@ np.savez_compressed(os.path.join(OUT, "diffuse.npz"), img=img,
 wp = util.profile_pair(util.REC2020_TO_XYZ_D50)
 rgb, lab = util.hdr_rgba(120, 80, 51), util.lab_scene(120, 80, 52)
 np.savez_compressed(os.path.join(OUT, "labglue.npz"), rgb=rgb, lab=lab, lab_of_rgb=util.ref_rgb_to_lab(rgb, wp), rgb_of_lab=util.ref_lab_to_rgb(lab, wp))
+rgba = util.hdr_rgba(90, 70, 61)
+mos = util.frame_natural(128, 96, 62, iso=400.0)
+np.savez_compressed(os.path.join(OUT, "demosaic_extra.npz"), rgba=rgba, mosaic=mos, smoothed2=util.ref_color_smoothing(rgba, 2),
+                    geq_local=util.ref_green_eq(mos, util.BAYER["RGGB"], 1, iso=400.0), geq_both=util.ref_green_eq(mos, util.BAYER["RGGB"], 3, iso=400.0))

@@ -338,3 +338,35 @@ def test_nlmeans_iop_oracle_equals_reference(scale, pipe, prev):
             got = util.oracle_nlmeans_iop(img, d, scale, dec, mask)
             want = util.ref_nlmeans_iop(img, d, scale, pipe, prev, mask)
             assert same_bits(got, want).all()
+
+
+@need_ref
+@pytest.mark.parametrize("passes", [1, 3, 5])
+def test_color_smoothing_oracle_equals_reference(passes):
+    """iop/demosaic/basic.c color_smoothing cut verbatim (median network, alpha lane as scratch)."""
+    for (w, h) in ((200, 150), (33, 17), (3, 3), (2, 5)):
+        img = util.hdr_rgba(w, h, 4) if w > 8 else util.rgba_test_image(w, h, 4)
+        assert same_bits(util.oracle_color_smoothing(img, passes), util.ref_color_smoothing(img, passes)).all()
+
+
+@need_ref
+@pytest.mark.parametrize("name", list(util.BAYER))
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_green_eq_oracle_equals_reference(name, mode):
+    """green_equilibration_lavg / _favg cut verbatim; ROI phases; the reference called with one thread so that its
+    reduction order is the raster order the oracle uses."""
+    os.environ["OMP_NUM_THREADS"] = "1"
+    for (w, h), (x, y), iso in (((214, 135), (0, 0), 100.0), ((101, 77), (1, 0), 800.0), ((64, 48), (1, 1), 6400.0), ((5, 4), (0, 1), 100.0)):
+        m = util.frame_natural(w, h, 9, filters=util.BAYER[name], iso=iso)
+        got, want = util.oracle_green_eq(m, util.BAYER[name], mode, x, y, iso), util.ref_green_eq(m, util.BAYER[name], mode, x, y, iso)
+        if mode == 1:
+            assert same_bits(got, want).all()
+        else:  # the full average's sums are an OpenMP reduction: order-dependent in the last bits of a double
+            assert util.ulp_distance(got, want).max() <= 1 and (~same_bits(got, want)).mean() < 1e-3
+
+
+def test_demosaic_extras_oracle_equals_golden():
+    g = _golden("demosaic_extra.npz")
+    assert same_bits(util.oracle_color_smoothing(g["rgba"], 2), g["smoothed2"]).all()
+    assert same_bits(util.oracle_green_eq(g["mosaic"], util.BAYER["RGGB"], 1, iso=400.0), g["geq_local"]).all()
+    assert util.ulp_distance(util.oracle_green_eq(g["mosaic"], util.BAYER["RGGB"], 3, iso=400.0), g["geq_both"]).max() <= 1

@@ -1,0 +1,78 @@
+"""GPU parity of the demosaic module's optional passes (green equilibration before RCD, median colour smoothing after
+it) through b200_demosaic_process_*, against the oracle (pinned to iop/demosaic/basic.c cut verbatim)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def same_bits(a, b):
+    return (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+
+
+def cuda_demosaic(mosaic, filters, green_eq=0, smoothing=0, x=0, y=0, iso=100.0, host=False):
+    import torch
+    import ansel_b200 as ab
+    ab.init()
+    h, w = mosaic.shape
+    d = ab.demosaic_data(ab.DEMOSAIC_RCD)
+    d.green_eq, d.color_smoothing = green_eq, smoothing
+    piece = ab.make_piece(w, h, filters=filters, data=d, devid=0, roi_x=x, roi_y=y, exif_iso=iso)
+    if host:
+        out = np.zeros((h, w, 4), np.float32)
+        ab.check(ab.lib().b200_demosaic_process_host(C.byref(piece), mosaic.ctypes.data, out.ctypes.data))
+        return out
+    d_in = torch.from_numpy(np.ascontiguousarray(mosaic)).cuda()
+    d_out = torch.zeros((h, w, 4), device="cuda")
+    ab.check(ab.lib().b200_demosaic_process_dev(C.byref(piece), d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    return d_out.cpu().numpy()
+
+
+@pytest.mark.parametrize("passes", [1, 2, 5])
+def test_color_smoothing_bit_exact(built, passes):
+    """smoothing acts on the demosaicer's output: the oracle pass is run on the CUDA RCD result"""
+    f = util.BAYER["RGGB"]
+    m = util.frame_natural(801, 533, 3, filters=f)
+    plain = cuda_demosaic(m, f)
+    got = cuda_demosaic(m, f, smoothing=passes, host=(passes == 2))
+    assert same_bits(got, util.oracle_color_smoothing(plain, passes)).all()
+
+
+@pytest.mark.parametrize("name", list(util.BAYER))
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_green_equilibration_then_rcd(built, name, mode):
+    f = util.BAYER[name]
+    for (w, h), (x, y), iso in (((640, 427), (0, 0), 100.0), ((333, 222), (1, 0), 1600.0), ((128, 96), (1, 1), 6400.0)):
+        m = util.frame_natural(w, h, 9, filters=f, iso=iso)
+        got = cuda_demosaic(m, f, green_eq=mode, x=x, y=y, iso=iso)
+        eq = util.oracle_green_eq(m, f, mode, x, y, iso)
+        roi_f = np.uint32(util.roi_filters(f, x, y)) if hasattr(util, "roi_filters") else None
+        import ansel_b200 as ab
+        rf = ab.lib().b200_roi_filters(C.c_uint32(f), x, y)
+        want = util.oracle_rcd(eq, rf)
+        defined = (util.oracle_rcd_mask(eq, rf) & 1) == 0
+        if mode == 1:
+            assert (same_bits(got[..., :3], want[..., :3]).all(axis=2) | ~defined).all()
+        else:
+            # the full average's green ratio comes from a differently ordered double sum: the equalised mosaic may differ by
+            # one ULP on rare sites, which RCD then carries into their neighbourhood
+            bad = (~same_bits(got[..., :3], want[..., :3])).any(axis=2) & defined
+            assert bad.mean() < 1e-3 and np.abs(got[..., :3] - want[..., :3])[defined].max() < 1e-5
+
+
+def test_both_passes_full_frame(built):
+    """45 MP: equilibration + RCD + 2 smoothing passes run, are deterministic and finite; a flat mosaic is a fixed point."""
+    f = util.BAYER["RGGB"]
+    w, h = util.SIZE_45MP
+    m = util.frame_natural(w, h, util.SEEDS[1])
+    a = cuda_demosaic(m, f, green_eq=3, smoothing=2)
+    b = cuda_demosaic(m, f, green_eq=3, smoothing=2)
+    assert same_bits(a, b).all() and np.isfinite(a).all()
+    flat = np.full((512, 768), 0.25, np.float32)
+    out = cuda_demosaic(flat, f, green_eq=3, smoothing=1)
+    assert np.abs(out[8:-8, 8:-8, :3] - 0.25).max() < 1e-6

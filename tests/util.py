@@ -602,3 +602,61 @@ def ref_nlmeans_iop(img, data, roi_scale=1.0, pipe_type=1, has_preview=0, mask_d
     assert f(fptr(src), fptr(out), w, h, (C.c_float * 4)(data.radius, data.strength, data.luma, data.chroma), C.c_double(roi_scale),
              pipe_type, has_preview, mask_display) == 0
     return np.array(out)
+
+
+# ---- demosaic: green equilibration and colour smoothing ---------------------------------------------------
+def _geq(lib, fn, mosaic, filters, x, y, thr=None):
+    h, w = mosaic.shape
+    src = aligned_empty(mosaic.shape)
+    src[...] = mosaic
+    out = aligned_empty(mosaic.shape)
+    f = getattr(lib, fn)
+    f.restype = None
+    args = [fptr(out), fptr(src), w, h, C.c_uint32(filters), x, y]
+    if thr is not None:
+        args.append(C.c_float(thr))
+    f(*args)
+    return np.array(out)
+
+
+def oracle_green_eq(mosaic, filters, mode, x=0, y=0, iso=100.0):
+    """mode: dt_iop_demosaic_greeneq_t 1 local, 2 full, 3 both (iop/demosaic.c:1137-1170)"""
+    thr = np.float32(0.0001) * np.float32(iso)
+    m = mosaic
+    if mode in (2, 3):
+        m = _geq(oracle(), "orc_green_eq_favg", m, filters, x, y)
+    if mode in (1, 3):
+        m = _geq(oracle(), "orc_green_eq_lavg", m, filters, x, y, thr)
+    return m
+
+
+def ref_green_eq(mosaic, filters, mode, x=0, y=0, iso=100.0, kind="strict"):
+    lib = ref(kind)
+    if lib is None:
+        return None
+    thr = np.float32(0.0001) * np.float32(iso)
+    m = mosaic
+    if mode in (2, 3):
+        m = _geq(lib, "ref_green_eq_favg", m, filters, x, y)
+    if mode in (1, 3):
+        m = _geq(lib, "ref_green_eq_lavg", m, filters, x, y, thr)
+    return m
+
+
+def _smooth(lib, fn, rgba, passes):
+    h, w = rgba.shape[:2]
+    buf = aligned_empty(rgba.shape)
+    buf[...] = rgba
+    f = getattr(lib, fn)
+    f.restype = None
+    f(fptr(buf), w, h, passes)
+    return np.array(buf)
+
+
+def oracle_color_smoothing(rgba, passes):
+    return _smooth(oracle(), "orc_color_smoothing", rgba, passes)
+
+
+def ref_color_smoothing(rgba, passes, kind="strict"):
+    lib = ref(kind)
+    return None if lib is None else _smooth(lib, "ref_color_smoothing", rgba, passes)
