@@ -40,6 +40,10 @@ struct filmic_args_t
   float grey_source, black_source, dynamic_range, output_power, agx_beta_hue;
   float black, white;
   int copy_alpha;
+  // colour sciences before AgX
+  int version, preserve_color;
+  float saturation, sigma_toe, sigma_shoulder, norm_min, norm_max;
+  float work_lum[4]; // row 1 of the work profile's RGB -> XYZ matrix
 };
 
 // ---- host-side set-up: plain C float arithmetic + the host libm (cosf, sinf, powf) --------------
@@ -389,6 +393,40 @@ __device__ void gamut_check_rgb(const float (*m_out)[4], const float (*m_in)[4],
   for(int c = 0; c < 4; c++) out[c] = CLAMPG(out[c], 0.f, white);
 }
 
+// gamut_mapping_simd(), :1986-2030 (filmic_desaturate_v4 :1779-1816, gamut_check_Yrg_filmic_simd :1928-1946)
+__device__ void gamut_map(const filmic_args_t &a, float Yf[4], const float Yr[4], float saturation, float res[4])
+{
+  Yf[2] = Yr[2];
+  Yf[3] = Yr[3];
+  Yf[0] = CLAMPG(Yf[0], Y31_TO_Y06(a.black), Y31_TO_Y06(a.white));
+  {
+    const float c_o = Yr[1] * Yr[0];
+    float c_f = Yf[1] * Yf[0];
+    const float delta = saturation * (c_o - c_f);
+    const bool brightens = (Yf[0] > Yr[0]), resat = (c_o < c_f), desat = (c_o > c_f);
+    const bool u_resat = (saturation > 0.f), u_desat = (saturation < 0.f);
+    c_f = (brightens && resat) ? (c_o + c_f) / 2.f : (((u_resat && desat) || u_desat) ? c_f + delta : c_f);
+    Yf[1] = fmaxf(c_f / Yf[0], 0.f);
+  }
+  {
+    const float y1 = Yf[1] * Yf[2] + 0.21902143f, y2 = Yf[1] * Yf[3] + 0.54371398f;
+    float max_c = Yf[1];
+    if(y1 < 0.f) max_c = fminf(-0.21902143f / Yf[2], max_c);
+    if(y2 < 0.f) max_c = fminf(-0.54371398f / Yf[3], max_c);
+    if(y1 + y2 > 1.f) max_c = fminf((1.f - 0.21902143f - 0.54371398f) / (Yf[2] + Yf[3]), max_c);
+    Yf[1] = max_c;
+  }
+  if(!a.use_output_profile)
+    gamut_check_rgb(a.output, a.input, a.black, a.white, Yf, res);
+  else
+  {
+    float px[4], lms[4];
+    gamut_check_rgb(a.export_output, a.export_input, a.black, a.white, Yf, px);
+    mat4(a.export_input, px, lms);
+    mat4(a.output, lms, res);
+  }
+}
+
 __global__ void __launch_bounds__(128) filmic_agx_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, size_t npx,
                                                          const __grid_constant__ filmic_args_t a)
 {
@@ -456,39 +494,175 @@ __global__ void __launch_bounds__(128) filmic_agx_kernel(const float4 *__restric
   const float Yr[4] = { Yo[0], Yo[1], (norm_mix > 1e-9f) ? r_mix / norm_mix : Yo[2], (norm_mix > 1e-9f) ? g_mix / norm_mix : Yo[3] };
   Yf[1] = chroma_final;
 
-  // gamut_mapping_simd(), :1986-2030, saturation = 0
-  Yf[2] = Yr[2];
-  Yf[3] = Yr[3];
-  Yf[0] = CLAMPG(Yf[0], Y31_TO_Y06(a.black), Y31_TO_Y06(a.white));
-  { // filmic_desaturate_v4(), :1779-1816
-    const float saturation = 0.f;
-    const float c_o = Yr[1] * Yr[0];
-    float c_f = Yf[1] * Yf[0];
-    const float delta = saturation * (c_o - c_f);
-    const bool brightens = (Yf[0] > Yr[0]), resat = (c_o < c_f), desat = (c_o > c_f);
-    const bool u_resat = (saturation > 0.f), u_desat = (saturation < 0.f);
-    c_f = (brightens && resat) ? (c_o + c_f) / 2.f : (((u_resat && desat) || u_desat) ? c_f + delta : c_f);
-    Yf[1] = fmaxf(c_f / Yf[0], 0.f);
-  }
-  { // gamut_check_Yrg_filmic_simd(), :1928-1946
-    const float y1 = Yf[1] * Yf[2] + 0.21902143f, y2 = Yf[1] * Yf[3] + 0.54371398f;
-    float max_c = Yf[1];
-    if(y1 < 0.f) max_c = fminf(-0.21902143f / Yf[2], max_c);
-    if(y2 < 0.f) max_c = fminf(-0.54371398f / Yf[3], max_c);
-    if(y1 + y2 > 1.f) max_c = fminf((1.f - 0.21902143f - 0.54371398f) / (Yf[2] + Yf[3]), max_c);
-    Yf[1] = max_c;
-  }
   float res[4];
-  if(!a.use_output_profile)
-    gamut_check_rgb(a.output, a.input, a.black, a.white, Yf, res);
-  else
-  {
-    float px[4], lms[4];
-    gamut_check_rgb(a.export_output, a.export_input, a.black, a.white, Yf, px);
-    mat4(a.export_input, px, lms);
-    mat4(a.output, lms, res);
-  }
+  gamut_map(a, Yf, Yr, 0.f, res);
   if(a.copy_alpha) res[3] = p.w; // dt_iop_alpha_copy when the pipe displays a mask (:2893-2894)
+  __stcs(out + k, make_float4(res[0], res[1], res[2], res[3]));
+}
+
+// ---- the colour sciences before AgX (filmicrgb.c:2857-2887): "v3 (2019)" .. "v7 (2023)" ------------------------
+#define NORM_MIN 1.52587890625e-05f // math/math.h:37
+__device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); } // clamp_simd
+__device__ __forceinline__ float log_tm(const f32m::tables_t &tb, const filmic_args_t &a, float x)
+{ // log_tonemapping(), :1047-1051
+  return clamp01((f32m::log2f_(tb, x / a.grey_source) - a.black_source) / a.dynamic_range);
+}
+__device__ __forceinline__ float lum_work(const filmic_args_t &a, const float p[4]) { return a.work_lum[0] * p[0] + a.work_lum[1] * p[1] + a.work_lum[2] * p[2]; }
+__device__ float pixel_norm(const filmic_args_t &a, const float p[4], int variant)
+{ // get_pixel_norm_simd(), :976-1038
+  switch(variant)
+  {
+    case 1: return fmaxf(fmaxf(p[0], p[1]), p[2]);
+    case 3:
+    { // pixel_rgb_norm_power_simd(), :949-967
+      float num = 0.0f, den = 0.0f;
+#pragma unroll
+      for(int c = 0; c < 3; c++)
+      {
+        const float v = fabsf(p[c]);
+        const float sq = v * v;
+        const float cu = sq * v;
+        num += cu;
+        den += sq;
+      }
+      return num / fmaxf(den, 1e-12f);
+    }
+    case 4: return sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+    case 5: return sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]) * 0.5773502691896258f;
+    default: return lum_work(a, p);
+  }
+}
+__device__ float desat_v1(const f32m::tables_t &tb, const filmic_args_t &a, float x)
+{ // filmic_desaturate_v1(), :1164-1175
+  const float rt = x, rs = 1.0f - x;
+  const float kt = f32m::expf_(tb, -0.5f * rt * rt / a.sigma_toe), ks = f32m::expf_(tb, -0.5f * rs * rs / a.sigma_shoulder);
+  return 1.0f - clamp01((kt + ks) / a.saturation);
+}
+__device__ float desat_v2(const f32m::tables_t &tb, const filmic_args_t &a, float x)
+{ // filmic_desaturate_v2(), :1178-1189
+  const float rt = x, rs = 1.0f - x;
+  const float sat2 = 0.5f / sqrtf(a.saturation);
+  const float kt = f32m::expf_(tb, -rt * rt / a.sigma_toe * sat2), ks = f32m::expf_(tb, -rs * rs / a.sigma_shoulder * sat2);
+  return (a.saturation - (kt + ks) * (a.saturation));
+}
+__device__ float curve_out(const f32m::tables_t &tb, const filmic_args_t &a, float x, float lo)
+{
+  return f32m::powf_(tb, CLAMPF(spline_eval(tb, x, a.spline), lo, a.spline.y[4]), a.output_power);
+}
+__device__ void norm_tm_v4(const f32m::tables_t &tb, const filmic_args_t &a, const float in[4], int variant, float o[4])
+{ // norm_tone_mapping_v4_simd(), :2106-2131
+  float norm = CLAMPF(pixel_norm(a, in, variant), a.norm_min, a.norm_max);
+  float ratios[4];
+#pragma unroll
+  for(int c = 0; c < 4; c++) ratios[c] = in[c] / norm;
+  norm = log_tm(tb, a, norm);
+  norm = curve_out(tb, a, norm, a.spline.y[0]);
+#pragma unroll
+  for(int c = 0; c < 4; c++) o[c] = ratios[c] * norm;
+}
+__device__ void rgb_tm_v4(const f32m::tables_t &tb, const filmic_args_t &a, const float in[4], float o[4])
+{ // RGB_tone_mapping_v4_simd(), :2133-2149
+#pragma unroll
+  for(int c = 0; c < 3; c++) o[c] = curve_out(tb, a, log_tm(tb, a, in[c]), 0.f);
+  o[3] = in[3];
+}
+
+__global__ void __launch_bounds__(128) filmic_legacy_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, size_t npx, const filmic_args_t a)
+{
+  __shared__ double tabs[f32m::SMEM_DOUBLES];
+  const f32m::tables_t tb = f32m::stage_tables(tabs, threadIdx.x, 128);
+  __syncthreads();
+  const size_t k = (size_t)blockIdx.x * 128 + threadIdx.x;
+  if(k >= npx) return;
+  const float4 p = __ldcs(in + k);
+  const float pix[4] = { p.x, p.y, p.z, p.w };
+  float res[4] = { 0.f, 0.f, 0.f, p.w };
+  if(a.version >= 3)
+  { // filmic_chroma_v4 :2153-2198, filmic_split_v4 :2201-2243, filmic_v5 :2247-2299
+    float po[4], Yo[4], Yf[4];
+    float saturation = a.saturation;
+    bool clamp_chroma = false;
+    if(a.version == 4)
+    {
+      float naive[4], maxrgb[4];
+      rgb_tm_v4(tb, a, pix, naive);
+      norm_tm_v4(tb, a, pix, 1, maxrgb);
+#pragma unroll
+      for(int c = 0; c < 4; c++) po[c] = (0.5f + a.saturation) * maxrgb[c];
+#pragma unroll
+      for(int c = 0; c < 4; c++) po[c] = (0.5f - a.saturation) * naive[c] + po[c];
+      saturation = 0.f;
+      clamp_chroma = true;
+    }
+    else if(a.preserve_color == 0)
+    {
+      rgb_tm_v4(tb, a, pix, po);
+      clamp_chroma = true;
+    }
+    else
+      norm_tm_v4(tb, a, pix, a.preserve_color, po);
+    rgb_to_ych(pix, a.input, Yo);
+    rgb_to_ych(po, a.input, Yf);
+    if(clamp_chroma) Yf[1] = fminf(Yo[1], Yf[1]);
+    gamut_map(a, Yf, Yo, saturation, res);
+  }
+  else if(a.preserve_color == 0)
+  { // filmic_split_v1 :1534-1571, filmic_split_v2_v3 :1575-1612; lane 3 is not written by the reference: the input's is kept
+    float temp[4];
+#pragma unroll
+    for(int c = 0; c < 3; c++) temp[c] = log_tm(tb, a, fmaxf(pix[c], NORM_MIN));
+    const float lum = lum_work(a, temp);
+    const float desat = a.version == 0 ? desat_v1(tb, a, lum) : desat_v2(tb, a, lum);
+#pragma unroll
+    for(int c = 0; c < 3; c++) res[c] = curve_out(tb, a, lum + desat * (temp[c] - lum), a.spline.y[0]); // linear_saturation :1193-1196
+  }
+  else
+  { // filmic_chroma_v1 :1616-1666, filmic_chroma_v2_v3 :1670-1737
+    float norm = fmaxf(pixel_norm(a, pix, a.preserve_color), NORM_MIN);
+    float ratios[4];
+#pragma unroll
+    for(int c = 0; c < 4; c++) ratios[c] = pix[c] / norm;
+    const float min_ratios = fminf(fminf(ratios[0], ratios[1]), ratios[2]);
+    if(min_ratios < 0.0f)
+    {
+#pragma unroll
+      for(int c = 0; c < 4; c++) ratios[c] -= min_ratios;
+    }
+    norm = log_tm(tb, a, norm);
+    if(a.version == 0)
+    {
+      const float desat = desat_v1(tb, a, norm);
+#pragma unroll
+      for(int c = 0; c < 4; c++) ratios[c] *= norm;
+      const float lum = lum_work(a, ratios);
+#pragma unroll
+      for(int c = 0; c < 3; c++) ratios[c] = (lum + desat * (ratios[c] - lum)) / norm;
+      norm = curve_out(tb, a, norm, a.spline.y[0]);
+#pragma unroll
+      for(int c = 0; c < 4; c++) res[c] = ratios[c] * norm;
+    }
+    else
+    {
+      const float desat = desat_v2(tb, a, norm);
+      norm = curve_out(tb, a, norm, a.spline.y[0]);
+#pragma unroll
+      for(int c = 0; c < 3; c++) ratios[c] = fmaxf(ratios[c] + (1.0f - ratios[c]) * (1.0f - desat), 0.0f);
+      if(a.version == 2) norm /= fmaxf(pixel_norm(a, ratios, a.preserve_color), NORM_MIN);
+#pragma unroll
+      for(int c = 0; c < 4; c++) res[c] = ratios[c] * norm;
+      const float max_pix = fmaxf(fmaxf(res[0], res[1]), res[2]);
+      if(max_pix > 1.0f)
+      {
+#pragma unroll
+        for(int c = 0; c < 4; c++)
+        {
+          ratios[c] = fmaxf(ratios[c] + (1.0f - max_pix), 0.0f);
+          res[c] = ratios[c] * norm;
+        }
+      }
+    }
+  }
+  if(a.copy_alpha) res[3] = p.w;
   __stcs(out + k, make_float4(res[0], res[1], res[2], res[3]));
 }
 
@@ -508,8 +682,7 @@ static int check_fl(const b200_piece_t *piece, const void *in, void *out)
   if(!piece->data || piece->data_size < sizeof(b200_filmicrgb_piece_t))
     return fail(B200_ERR_ARG, "filmicrgb: piece->data is not a b200_filmicrgb_piece_t");
   const b200_filmicrgb_data_t *d = &((const b200_filmicrgb_piece_t *)piece->data)->data;
-  if(d->version < 5 || d->version > 9)
-    return fail(B200_ERR_UNSUPPORTED, "filmicrgb: colour science %d is not built (only the AgX family, 5..9; SURVEY.md 8a16)", d->version);
+  if(d->version < 0 || d->version > 9) return fail(B200_ERR_ARG, "filmicrgb: colour science %d", d->version);
   if(!d->hl_deprecated)
     return fail(B200_ERR_UNSUPPORTED, "filmicrgb: the deprecated highlight reconstruction is not built (SURVEY.md 8a16)");
   return B200_OK;
@@ -544,7 +717,18 @@ extern "C" int b200_filmicrgb_process_dev(const b200_piece_t *piece, const void 
   a.copy_alpha = (piece->mask_display & B200_DISPLAY_MASK) ? 1 : 0;
   const size_t npx = (size_t)piece->roi_out.width * piece->roi_out.height;
   if(!npx) return B200_OK;
-  filmic_agx_kernel<<<(unsigned)((npx + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const float4 *)d_in, (float4 *)d_out, npx, a);
+  a.version = d->version;
+  a.preserve_color = d->preserve_color;
+  a.saturation = d->saturation;
+  a.sigma_toe = d->sigma_toe;
+  a.sigma_shoulder = d->sigma_shoulder;
+  a.norm_min = d->grey_source * exp2f(d->dynamic_range * 0.f + d->black_source); // exp_tonemapping_v2(), :1054-1059, at 0 and 1
+  a.norm_max = d->grey_source * exp2f(d->dynamic_range * 1.f + d->black_source);
+  for(int c = 0; c < 3; c++) a.work_lum[c] = fp->work_profile.matrix_in[1][c];
+  if(d->version >= 5)
+    filmic_agx_kernel<<<(unsigned)((npx + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const float4 *)d_in, (float4 *)d_out, npx, a);
+  else
+    filmic_legacy_kernel<<<(unsigned)((npx + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const float4 *)d_in, (float4 *)d_out, npx, a);
   B200_CUDA_TRY(cudaGetLastError());
   return B200_OK;
 }

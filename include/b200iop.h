@@ -298,7 +298,7 @@ typedef struct b200_filmicrgb_data_t
       reconstruct_structure_vs_texture;
   float normalize, dynamic_range, saturation, output_power, contrast, sigma_toe, sigma_shoulder, noise_level;
   int preserve_color;
-  int version; /* dt_iop_filmicrgb_colorscience_type_t: 5..9 = the AgX (v8) family */
+  int version; /* dt_iop_filmicrgb_colorscience_type_t: 0..4 = "v3 (2019)".."v7 (2023)", 5..9 = the AgX (v8) family */
   int spline_version;
   int high_quality_reconstruction;
   int hl_deprecated;
@@ -328,9 +328,11 @@ typedef struct b200_filmicrgb_piece_t
   b200_profile_matrices_t export_profile;
 } b200_filmicrgb_piece_t;
 
-/* process(), filmicrgb.c:2707-2895.  Built: the AgX colour sciences (version 5..9) with the highlight
- * reconstruction at its deprecation sentinel (hl_deprecated, the default).  v1..v5 and the legacy
- * reconstruction return B200_ERR_UNSUPPORTED. */
+/* process(), filmicrgb.c:2707-2895.  Built: every colour science -- the AgX family (version 5..9, :2495-2587) and the
+ * earlier ones (0..4: filmic_split/chroma_v1, _v2_v3, _v4, filmic_v5, :1534-1737,2153-2299) with any chroma-preservation
+ * norm -- with the highlight reconstruction at its deprecation sentinel (hl_deprecated, the default).  The legacy
+ * wavelet highlight reconstruction returns B200_ERR_UNSUPPORTED; so does a work profile with tone curves
+ * (the luminance norm then needs its LUTs). */
 int b200_filmicrgb_process_host(const b200_piece_t *piece, const void *in, void *out);
 int b200_filmicrgb_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
 /* tiling_callback(), filmicrgb.c:2668-2704 */

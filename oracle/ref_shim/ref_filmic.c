@@ -164,3 +164,49 @@ void ref_filmic_prepare(int version, const float work_in[9], const float work_ou
     for(int i = 0; i < 3; i++)
       for(int j = 0; j < 4; j++) out[12 * k + 4 * i + j] = M[k][i][j];
 }
+
+/* the non-AgX branches of process(), filmicrgb.c:2857-2887: filmic_v5 and the v1..v4 colour sciences with and
+ * without chroma preservation.  Same profile conventions as ref_filmic_agx(). */
+int ref_filmic_legacy(const float *in, float *out, size_t width, size_t height, const void *data, const float work_in[9],
+                      const float work_out[9], const float *export_in, const float *export_out)
+{
+  dt_iop_filmicrgb_data_t *data_ = aligned_alloc(64, ((sizeof(dt_iop_filmicrgb_data_t) + 63) / 64) * 64);
+  memcpy(data_, data, sizeof(*data_));
+  const dt_iop_filmicrgb_data_t *const d = data_;
+  dt_iop_order_iccprofile_info_t work_, expo_;
+  fill_profile(&work_, work_in, work_out);
+  if(export_in) fill_profile(&expo_, export_in, export_out);
+  const dt_iop_order_iccprofile_info_t *const work_profile = &work_, *const export_profile = export_in ? &expo_ : NULL;
+  const size_t ch = 4;
+  const float white_display = powf(d->spline.y[4], d->output_power);
+  const float black_display = powf(d->spline.y[0], d->output_power);
+  int rc = 0;
+  if(d->version == DT_FILMIC_COLORSCIENCE_V5)
+    filmic_v5(in, out, work_profile, export_profile, d, d->spline, width, height, ch, black_display, white_display);
+  else if(d->preserve_color == DT_FILMIC_METHOD_NONE)
+  {
+    if(d->version == DT_FILMIC_COLORSCIENCE_V1)
+      filmic_split_v1(in, out, work_profile, d, d->spline, width, height);
+    else if(d->version == DT_FILMIC_COLORSCIENCE_V2 || d->version == DT_FILMIC_COLORSCIENCE_V3)
+      filmic_split_v2_v3(in, out, work_profile, d, d->spline, width, height);
+    else if(d->version == DT_FILMIC_COLORSCIENCE_V4)
+      filmic_split_v4(in, out, work_profile, export_profile, d, d->spline, d->preserve_color, width, height, ch, d->version, black_display,
+                      white_display);
+    else
+      rc = 1;
+  }
+  else
+  {
+    if(d->version == DT_FILMIC_COLORSCIENCE_V1)
+      filmic_chroma_v1(in, out, work_profile, d, d->spline, d->preserve_color, width, height);
+    else if(d->version == DT_FILMIC_COLORSCIENCE_V2 || d->version == DT_FILMIC_COLORSCIENCE_V3)
+      filmic_chroma_v2_v3(in, out, work_profile, d, d->spline, d->preserve_color, width, height, ch, d->version);
+    else if(d->version == DT_FILMIC_COLORSCIENCE_V4)
+      filmic_chroma_v4(in, out, work_profile, export_profile, d, d->spline, d->preserve_color, width, height, ch, d->version, black_display,
+                       white_display);
+    else
+      rc = 1;
+  }
+  free(data_);
+  return rc;
+}

@@ -386,6 +386,40 @@ static inline void gamut_check_rgb(const m34 m_out, const m34 m_in, float black,
   for(int c = 0; c < 4; c++) out[c] = CLAMP(out[c], 0.f, white);
 }
 
+/* gamut_mapping_simd(), :1986-2030 (filmic_desaturate_v4 :1779-1816, gamut_check_Yrg_filmic_simd :1928-1946) */
+static inline void gamut_map(float Yf[4], const float Yr[4], float saturation, const filmic_mats_t *m, float black, float white, float *out)
+{
+  Yf[2] = Yr[2];
+  Yf[3] = Yr[3];
+  Yf[0] = CLAMP(Yf[0], Y31_TO_Y06(black), Y31_TO_Y06(white));
+  {
+    const float c_o = Yr[1] * Yr[0];
+    float c_f = Yf[1] * Yf[0];
+    const float delta = saturation * (c_o - c_f);
+    const int brightens = (Yf[0] > Yr[0]), resat = (c_o < c_f), desat = (c_o > c_f);
+    const int u_resat = (saturation > 0.f), u_desat = (saturation < 0.f);
+    c_f = (brightens && resat) ? (c_o + c_f) / 2.f : (((u_resat && desat) || u_desat) ? c_f + delta : c_f);
+    Yf[1] = fmaxf(c_f / Yf[0], 0.f);
+  }
+  {
+    const float y1 = Yf[1] * Yf[2] + 0.21902143f, y2 = Yf[1] * Yf[3] + 0.54371398f;
+    float max_c = Yf[1];
+    if(y1 < 0.f) max_c = fminf(-0.21902143f / Yf[2], max_c);
+    if(y2 < 0.f) max_c = fminf(-0.54371398f / Yf[3], max_c);
+    if(y1 + y2 > 1.f) max_c = fminf((1.f - 0.21902143f - 0.54371398f) / (Yf[2] + Yf[3]), max_c);
+    Yf[1] = max_c;
+  }
+  if(!m->use_output_profile)
+  {
+    gamut_check_rgb(m->output, m->input, black, white, Yf, out);
+    return;
+  }
+  float px[4], lms[4];
+  gamut_check_rgb(m->export_output, m->export_input, black, white, Yf, px);
+  mat4(m->export_input, px, lms);
+  mat4(m->output, lms, out);
+}
+
 static inline void agx_pixel(const float *in, float *out, const b200_filmicrgb_data_t *d, const filmic_mats_t *m, float black, float white)
 {
   float pix[4] = { in[0], in[1], in[2], in[3] };
@@ -440,37 +474,7 @@ static inline void agx_pixel(const float *in, float *out, const b200_filmicrgb_d
   float Yr[4] = { Yo[0], Yo[1], (norm_mix > 1e-9f) ? r_mix / norm_mix : Yo[2], (norm_mix > 1e-9f) ? g_mix / norm_mix : Yo[3] };
   Yf[1] = chroma_final;
 
-  /* gamut_mapping_simd :1986-2030 with saturation 0 */
-  Yf[2] = Yr[2];
-  Yf[3] = Yr[3];
-  Yf[0] = CLAMP(Yf[0], Y31_TO_Y06(black), Y31_TO_Y06(white));
-  { /* filmic_desaturate_v4 :1779-1816, saturation = 0 */
-    const float saturation = 0.f;
-    const float c_o = Yr[1] * Yr[0];
-    float c_f = Yf[1] * Yf[0];
-    const float delta = saturation * (c_o - c_f);
-    const int brightens = (Yf[0] > Yr[0]), resat = (c_o < c_f), desat = (c_o > c_f);
-    const int u_resat = (saturation > 0.f), u_desat = (saturation < 0.f);
-    c_f = (brightens && resat) ? (c_o + c_f) / 2.f : (((u_resat && desat) || u_desat) ? c_f + delta : c_f);
-    Yf[1] = fmaxf(c_f / Yf[0], 0.f);
-  }
-  { /* gamut_check_Yrg_filmic_simd :1928-1946 */
-    const float y1 = Yf[1] * Yf[2] + 0.21902143f, y2 = Yf[1] * Yf[3] + 0.54371398f;
-    float max_c = Yf[1];
-    if(y1 < 0.f) max_c = fminf(-0.21902143f / Yf[2], max_c);
-    if(y2 < 0.f) max_c = fminf(-0.54371398f / Yf[3], max_c);
-    if(y1 + y2 > 1.f) max_c = fminf((1.f - 0.21902143f - 0.54371398f) / (Yf[2] + Yf[3]), max_c);
-    Yf[1] = max_c;
-  }
-  if(!m->use_output_profile)
-  {
-    gamut_check_rgb(m->output, m->input, black, white, Yf, out);
-    return;
-  }
-  float px[4], lms[4];
-  gamut_check_rgb(m->export_output, m->export_input, black, white, Yf, px);
-  mat4(m->export_input, px, lms);
-  mat4(m->output, lms, out);
+  gamut_map(Yf, Yr, 0.f, m, black, white, out);
 }
 
 static void to_m34(m34 dst, const float src9[9])
@@ -521,5 +525,187 @@ int orc_filmic_agx(const float *in, float *out, size_t width, size_t height, con
   const size_t n = width * height;
 #pragma omp parallel for schedule(static)
   for(size_t k = 0; k < n; k++) agx_pixel(in + 4 * k, out + 4 * k, d, &m, black, white);
+  return 0;
+}
+
+
+/* ---- the colour sciences before AgX (filmicrgb.c:2857-2887): v3 (2019) .. v7 (2023) -------------------------- */
+#define NORM_MIN 1.52587890625e-05f /* math/math.h:37 */
+static inline float clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); } /* clamp_simd, math/openmp_maths.h:128-131 */
+static inline float log_tm(float x, const b200_filmicrgb_data_t *d)
+{ /* log_tonemapping :1047-1051 */
+  return clamp01((f32m_log2f(x / d->grey_source) - d->black_source) / d->dynamic_range);
+}
+static inline float exp_tm_v2(float x, const b200_filmicrgb_data_t *d)
+{ /* :1054-1059 */
+  return d->grey_source * f32m_exp2f(d->dynamic_range * x + d->black_source);
+}
+static inline float lum_work(const float p[4], const m34 work_in)
+{ /* dt_ioppr_get_rgb_matrix_luminance, linear profile: iop_profile.h:640-655 */
+  return work_in[1][0] * p[0] + work_in[1][1] * p[1] + work_in[1][2] * p[2];
+}
+static inline float pixel_norm(const float p[4], int variant, const m34 work_in)
+{ /* get_pixel_norm_simd :976-1038 */
+  switch(variant)
+  {
+    case 1: return fmaxf(fmaxf(p[0], p[1]), p[2]);
+    case 3:
+    { /* pixel_rgb_norm_power_simd :949-967 */
+      float num = 0.0f, den = 0.0f;
+      for(int c = 0; c < 3; c++)
+      {
+        const float v = fabsf(p[c]);
+        const float sq = v * v;
+        const float cu = sq * v;
+        num += cu;
+        den += sq;
+      }
+      return num / fmaxf(den, 1e-12f);
+    }
+    case 4: return sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+    case 5: return sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]) * 0.5773502691896258f;
+    default: return lum_work(p, work_in);
+  }
+}
+static inline float desat_v1(float x, const b200_filmicrgb_data_t *d)
+{ /* filmic_desaturate_v1 :1164-1175 */
+  const float rt = x, rs = 1.0f - x;
+  const float kt = f32m_expf(-0.5f * rt * rt / d->sigma_toe), ks = f32m_expf(-0.5f * rs * rs / d->sigma_shoulder);
+  return 1.0f - clamp01((kt + ks) / d->saturation);
+}
+static inline float desat_v2(float x, const b200_filmicrgb_data_t *d)
+{ /* filmic_desaturate_v2 :1178-1189 */
+  const float rt = x, rs = 1.0f - x;
+  const float sat2 = 0.5f / sqrtf(d->saturation);
+  const float kt = f32m_expf(-rt * rt / d->sigma_toe * sat2), ks = f32m_expf(-rs * rs / d->sigma_shoulder * sat2);
+  return (d->saturation - (kt + ks) * (d->saturation));
+}
+static inline float curve_out(float x, float lo, const b200_filmicrgb_data_t *d)
+{ /* spline, clamp to [lo, y4], display transfer function */
+  return f32m_powf(CLAMPF(spline_eval(x, &d->spline), lo, d->spline.y[4]), d->output_power);
+}
+/* filmic_split_v1 :1534-1571 and filmic_split_v2_v3 :1575-1612 differ by the desaturation only; lane 3 is not written */
+static inline void split_v123(const float *in, float *out, const b200_filmicrgb_data_t *d, const m34 work_in, int v1)
+{
+  float temp[4];
+  for(int c = 0; c < 3; c++) temp[c] = log_tm(fmaxf(in[c], NORM_MIN), d);
+  const float lum = lum_work(temp, work_in);
+  const float desat = v1 ? desat_v1(lum, d) : desat_v2(lum, d);
+  for(int c = 0; c < 3; c++) out[c] = curve_out(lum + desat * (temp[c] - lum), d->spline.y[0], d); /* linear_saturation :1193-1196 */
+}
+static inline void chroma_v1(const float *in, float *out, const b200_filmicrgb_data_t *d, const m34 work_in)
+{ /* :1616-1666 */
+  float ratios[4];
+  float norm = fmaxf(pixel_norm(in, d->preserve_color, work_in), NORM_MIN);
+  for(int c = 0; c < 4; c++) ratios[c] = in[c] / norm;
+  const float min_ratios = fminf(fminf(ratios[0], ratios[1]), ratios[2]);
+  if(min_ratios < 0.0f)
+    for(int c = 0; c < 4; c++) ratios[c] -= min_ratios;
+  norm = log_tm(norm, d);
+  const float desat = desat_v1(norm, d);
+  for(int c = 0; c < 4; c++) ratios[c] *= norm;
+  const float lum = lum_work(ratios, work_in);
+  for(int c = 0; c < 3; c++) ratios[c] = (lum + desat * (ratios[c] - lum)) / norm;
+  norm = curve_out(norm, d->spline.y[0], d);
+  for(int c = 0; c < 4; c++) out[c] = ratios[c] * norm;
+}
+static inline void chroma_v2_v3(const float *in, float *out, const b200_filmicrgb_data_t *d, const m34 work_in)
+{ /* :1670-1737 */
+  float norm = fmaxf(pixel_norm(in, d->preserve_color, work_in), NORM_MIN);
+  float ratios[4];
+  for(int c = 0; c < 4; c++) ratios[c] = in[c] / norm;
+  const float min_ratios = fminf(fminf(ratios[0], ratios[1]), ratios[2]);
+  if(min_ratios < 0.0f)
+    for(int c = 0; c < 4; c++) ratios[c] -= min_ratios;
+  norm = log_tm(norm, d);
+  const float desat = desat_v2(norm, d);
+  norm = curve_out(norm, d->spline.y[0], d);
+  for(int c = 0; c < 3; c++) ratios[c] = fmaxf(ratios[c] + (1.0f - ratios[c]) * (1.0f - desat), 0.0f);
+  if(d->version == 2) norm /= fmaxf(pixel_norm(ratios, d->preserve_color, work_in), NORM_MIN);
+  for(int c = 0; c < 4; c++) out[c] = ratios[c] * norm;
+  const float max_pix = fmaxf(fmaxf(out[0], out[1]), out[2]);
+  if(max_pix > 1.0f)
+    for(int c = 0; c < 4; c++)
+    {
+      ratios[c] = fmaxf(ratios[c] + (1.0f - max_pix), 0.0f);
+      out[c] = ratios[c] * norm;
+    }
+}
+static inline void norm_tm_v4(const float *in, int variant, const b200_filmicrgb_data_t *d, const m34 work_in, float nmin, float nmax, float *o)
+{ /* norm_tone_mapping_v4_simd :2106-2131 */
+  float norm = CLAMPF(pixel_norm(in, variant, work_in), nmin, nmax);
+  float ratios[4];
+  for(int c = 0; c < 4; c++) ratios[c] = in[c] / norm;
+  norm = log_tm(norm, d);
+  norm = curve_out(norm, d->spline.y[0], d);
+  for(int c = 0; c < 4; c++) o[c] = ratios[c] * norm;
+}
+static inline void rgb_tm_v4(const float *in, const b200_filmicrgb_data_t *d, float *o)
+{ /* RGB_tone_mapping_v4_simd :2133-2149 */
+  for(int c = 0; c < 3; c++) o[c] = curve_out(log_tm(in[c], d), 0.f, d);
+  o[3] = in[3];
+}
+static inline void v4_v5_pixel(const float *in, float *out, const b200_filmicrgb_data_t *d, const filmic_mats_t *m, const m34 work_in, float nmin,
+                               float nmax, float black, float white)
+{ /* filmic_chroma_v4 :2153-2198, filmic_split_v4 :2201-2243, filmic_v5 :2247-2299 */
+  float po[4], Yo[4], Yf[4];
+  float saturation = d->saturation;
+  int clamp_chroma = 0;
+  if(d->version == 4)
+  {
+    float naive[4], maxrgb[4];
+    rgb_tm_v4(in, d, naive);
+    norm_tm_v4(in, 1, d, work_in, nmin, nmax, maxrgb);
+    for(int c = 0; c < 4; c++) po[c] = (0.5f + d->saturation) * maxrgb[c];
+    for(int c = 0; c < 4; c++) po[c] = (0.5f - d->saturation) * naive[c] + po[c];
+    saturation = 0.f;
+    clamp_chroma = 1;
+  }
+  else if(d->preserve_color == 0)
+  {
+    rgb_tm_v4(in, d, po);
+    clamp_chroma = 1;
+  }
+  else
+    norm_tm_v4(in, d->preserve_color, d, work_in, nmin, nmax, po);
+  rgb_to_ych(in, m->input, Yo);
+  rgb_to_ych(po, m->input, Yf);
+  if(clamp_chroma) Yf[1] = fminf(Yo[1], Yf[1]);
+  gamut_map(Yf, Yo, saturation, m, black, white, out);
+}
+
+/* process() for version < 5 (reconstruction at its deprecation sentinel).  Lane 3 of split v1..v3 is left as found.
+ * Returns 0, or 3 for what is not restated. */
+int orc_filmic_legacy(const float *in, float *out, size_t width, size_t height, const b200_filmicrgb_data_t *d, const float work_in[9],
+                      const float work_out[9], const float *export_in, const float *export_out)
+{
+  if(d->version < 0 || d->version > 4 || !d->hl_deprecated) return 3;
+  m34 wi, wo, ei, eo;
+  to_m34(wi, work_in);
+  to_m34(wo, work_out);
+  if(export_in)
+  {
+    to_m34(ei, export_in);
+    to_m34(eo, export_out);
+  }
+  filmic_mats_t m;
+  prepare(&m, d->version, wi, wo, export_in ? &ei : NULL, export_in ? &eo : NULL);
+  const float white = f32m_powf(d->spline.y[4], d->output_power), black = f32m_powf(d->spline.y[0], d->output_power);
+  const float nmin = exp_tm_v2(0.f, d), nmax = exp_tm_v2(1.f, d);
+  const size_t n = width * height;
+#pragma omp parallel for schedule(static)
+  for(size_t k = 0; k < n; k++)
+  {
+    const float *pi = in + 4 * k;
+    float *po = out + 4 * k;
+    if(d->version >= 3)
+      v4_v5_pixel(pi, po, d, &m, wi, nmin, nmax, black, white);
+    else if(d->preserve_color == 0)
+      split_v123(pi, po, d, wi, d->version == 0);
+    else if(d->version == 0)
+      chroma_v1(pi, po, d, wi);
+    else
+      chroma_v2_v3(pi, po, d, wi);
+  }
   return 0;
 }

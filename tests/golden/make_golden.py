@@ -76,3 +76,10 @@ rgba = util.hdr_rgba(90, 70, 61)
 mos = util.frame_natural(128, 96, 62, iso=400.0)
 np.savez_compressed(os.path.join(OUT, "demosaic_extra.npz"), rgba=rgba, mosaic=mos, smoothed2=util.ref_color_smoothing(rgba, 2),
                     geq_local=util.ref_green_eq(mos, util.BAYER["RGGB"], 1, iso=400.0), geq_both=util.ref_green_eq(mos, util.BAYER["RGGB"], 3, iso=400.0))
+img = util.hdr_rgba(96, 64, 71)
+save = dict(img=img)
+for version, pc in ((0, 0), (0, 3), (1, 0), (2, 5), (3, 0), (3, 2), (4, 1)):
+    blob = util.ref_filmic_commit(util.filmic_default_params(version=version, preserve_color=pc, saturation=10.0))
+    save[f"data_v{version}_n{pc}"] = blob
+    save[f"out_v{version}_n{pc}"] = util.ref_filmic_legacy(img, blob, work, export)
+np.savez_compressed(os.path.join(OUT, "filmic_legacy.npz"), **save)

@@ -370,3 +370,28 @@ def test_demosaic_extras_oracle_equals_golden():
     assert same_bits(util.oracle_color_smoothing(g["rgba"], 2), g["smoothed2"]).all()
     assert same_bits(util.oracle_green_eq(g["mosaic"], util.BAYER["RGGB"], 1, iso=400.0), g["geq_local"]).all()
     assert util.ulp_distance(util.oracle_green_eq(g["mosaic"], util.BAYER["RGGB"], 3, iso=400.0), g["geq_both"]).max() <= 1
+
+
+LEGACY_EXTRA = [{}, dict(saturation=20.0), dict(saturation=-15.0, shadows=0, highlights=2, contrast=1.4)]
+
+
+@need_ref
+@pytest.mark.parametrize("version", [0, 1, 2, 3, 4])
+def test_filmic_legacy_oracle_equals_reference(version):
+    """filmic_split/chroma_v1, _v2_v3, _v4 and filmic_v5 cut verbatim from filmicrgb.c, every norm, with/without an
+    export profile; piece->data from the reference's own commit_params()."""
+    work, export = util.profile_pair(util.REC2020_TO_XYZ_D50), util.profile_pair(util.SRGB_TO_XYZ_D50)
+    img = util.hdr_rgba(160, 100, 7)
+    for pc in range(6):
+        for extra in LEGACY_EXTRA:
+            blob = util.ref_filmic_commit(util.filmic_default_params(version=version, preserve_color=pc, **extra))
+            for ex in (export, None):
+                assert same_bits(util.oracle_filmic_legacy(img, blob, work, ex), util.ref_filmic_legacy(img, blob, work, ex)).all(), (pc, extra)
+
+
+def test_filmic_legacy_oracle_equals_golden():
+    g = _golden("filmic_legacy.npz")
+    work, export = util.profile_pair(util.REC2020_TO_XYZ_D50), util.profile_pair(util.SRGB_TO_XYZ_D50)
+    for key in [k for k in g.files if k.startswith("out_")]:
+        tag = key[4:]
+        assert same_bits(util.oracle_filmic_legacy(g["img"], g["data_" + tag], work, export), g[key]).all(), tag

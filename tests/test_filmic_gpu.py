@@ -90,3 +90,39 @@ def test_filmic_45mp_matches_oracle(built):
     got = cuda_filmic(img, blob)
     want = util.oracle_filmic_agx(img, blob, WORK, EXPORT)
     assert same_bits(got, want).all()
+
+
+# ---- the colour sciences before AgX ("v3 (2019)" .. "v7 (2023)") ---------------------------------------------------
+def legacy_cases():
+    g = np.load(os.path.join(util.GOLDEN_DIR, "filmic_legacy.npz"))
+    return g, sorted(k[5:] for k in g.files if k.startswith("data_"))
+
+
+@pytest.mark.parametrize("export", [True, False])
+def test_filmic_legacy_bit_exact(built, export):
+    """every committed data block (versions 0..4, several norms) on a fresh scene-referred frame, all four lanes"""
+    g, tags = legacy_cases()
+    img = util.hdr_rgba(700, 467, 12)
+    for tag in tags:
+        blob = g["data_" + tag]
+        got = cuda_filmic(img, blob, EXPORT if export else None)
+        want = util.oracle_filmic_legacy(img, blob, WORK, EXPORT if export else None)
+        assert same_bits(got, want).all(), tag
+
+
+def test_filmic_legacy_golden_and_host(built):
+    g, tags = legacy_cases()
+    for tag in tags:
+        got = cuda_filmic(g["img"], g["data_" + tag], EXPORT, host=True)
+        lanes = 3 if tag in ("v0_n0", "v1_n0") else 4          # split v1..v3 leave lane 3 as found; here: the input's alpha
+        assert same_bits(got[..., :lanes], g["out_" + tag][..., :lanes]).all(), tag
+
+
+@pytest.mark.skipif(util.ref("strict") is None, reason="needs the reference build (authoring container)")
+def test_filmic_legacy_all_norms_live(built):
+    """where the reference is present: every version x norm x parameter set from its own commit_params()"""
+    img = util.hdr_rgba(320, 200, 3)
+    for version in range(5):
+        for pc in range(6):
+            blob = util.ref_filmic_commit(util.filmic_default_params(version=version, preserve_color=pc, saturation=-15.0, shadows=0, highlights=2))
+            assert same_bits(cuda_filmic(img, blob, EXPORT), util.oracle_filmic_legacy(img, blob, WORK, EXPORT)).all(), (version, pc)

@@ -430,6 +430,33 @@ def oracle_filmic_agx(rgba, data_blob, work, export=None):
     return dst
 
 
+def ref_filmic_legacy(rgba, data_blob, work, export=None, kind="strict"):
+    """the v1..v5 colour sciences through the reference's own functions; lanes a branch does not write keep the input's"""
+    lib = ref(kind)
+    h, w = rgba.shape[:2]
+    src, dst = aligned_empty(rgba.shape), aligned_empty(rgba.shape)
+    src[...] = rgba
+    dst[...] = rgba
+    keep = [_f9(work[0]), _f9(work[1]), _f9(export[0]) if export else None, _f9(export[1]) if export else None]
+    lib.ref_filmic_legacy.restype = C.c_int
+    assert lib.ref_filmic_legacy(fptr(src), fptr(dst), C.c_size_t(w), C.c_size_t(h), data_blob.ctypes.data_as(C.c_void_p), *keep) == 0
+    return np.array(dst)
+
+
+def oracle_filmic_legacy(rgba, data_blob, work, export=None):
+    h, w = rgba.shape[:2]
+    src = np.ascontiguousarray(rgba)
+    dst = src.copy()
+    keep = [_f9(work[0]), _f9(work[1]), _f9(export[0]) if export else None, _f9(export[1]) if export else None]
+    data = aligned_empty((832,), np.uint8)
+    data[:] = data_blob
+    f = oracle().orc_filmic_legacy
+    f.restype = C.c_int
+    rc = f(fptr(src), fptr(dst), C.c_size_t(w), C.c_size_t(h), data.ctypes.data_as(C.c_void_p), *keep)
+    assert rc == 0, rc
+    return dst
+
+
 def filmic_prepare(lib, fn, version, work, export=None):
     out = np.zeros(72, np.float32)
     keep = [_f9(work[0]), _f9(work[1]), _f9(export[0]) if export else None, _f9(export[1]) if export else None]
