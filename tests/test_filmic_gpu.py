@@ -75,7 +75,7 @@ def test_filmic_host_entry_alpha_and_unsupported(built):
     c = cuda_filmic(img, blob, mask_display=1)
     assert (c[..., 3] == img[..., 3]).all() and same_bits(c[..., :3], a[..., :3]).all()
     old = blob.copy()
-    old[72:76].view(np.int32)[0] = 3   # version = v6 (2022): not an AgX science
+    old[84:88].view(np.int32)[0] = 0   # hl_deprecated = 0: the legacy wavelet highlight reconstruction is asked for
     fp = ab.filmic_piece(old, WORK, EXPORT)
     piece = ab.make_piece(320, 200, filters=0, channels=4, devid=0)
     piece.data, piece.data_size = C.addressof(fp), C.sizeof(fp)
