@@ -7,6 +7,7 @@ namespace b200
 {
 int rcd_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters,
                      const float processed_maximum[3], cudaStream_t stream);
+int amaze_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters, const float processed_maximum[3], cudaStream_t stream);
 int demosaic_green_eq_dev(const float *d_in, float *d_tmp0, float *d_tmp1, double *d_partial, int width, int height, uint32_t dsc_filters, int x, int y,
                           unsigned green_eq, float threshold, const float **d_result, cudaStream_t s);
 int demosaic_green_eq_partial_doubles();
@@ -44,7 +45,8 @@ extern "C" int b200_demosaic_process_dev(const b200_piece_t *piece, const void *
     return fail(B200_ERR_UNSUPPORTED, "demosaic: roi_out %dx%d != roi_in %dx%d (downsampling paths are not built)",
                 piece->roi_out.width, piece->roi_out.height, piece->roi_in.width, piece->roi_in.height);
 
-  if(d->demosaicing_method != B200_DEMOSAIC_RCD) return fail(B200_ERR_UNSUPPORTED, "demosaic: method %u is not built", d->demosaicing_method);
+  if(d->demosaicing_method != B200_DEMOSAIC_RCD && d->demosaicing_method != B200_DEMOSAIC_AMAZE)
+    return fail(B200_ERR_UNSUPPORTED, "demosaic: method %u is not built", d->demosaicing_method);
   const int width = piece->roi_in.width, height = piece->roi_in.height;
   cudaStream_t s = (cudaStream_t)stream;
   const float *mosaic = (const float *)d_in;
@@ -60,7 +62,11 @@ extern "C" int b200_demosaic_process_dev(const b200_piece_t *piece, const void *
                                    d->green_eq, threshold, &mosaic, s)))
       return rc;
   }
-  if((rc = rcd_demosaic_dev(mosaic, (float *)d_out, width, height, filters, piece->processed_maximum, s))) return rc;
+  if(d->demosaicing_method == B200_DEMOSAIC_AMAZE)
+    rc = amaze_demosaic_dev(mosaic, (float *)d_out, width, height, filters, piece->processed_maximum, s); // demosaic.c:1227
+  else
+    rc = rcd_demosaic_dev(mosaic, (float *)d_out, width, height, filters, piece->processed_maximum, s);
+  if(rc) return rc;
   if(d->color_smoothing) rc = demosaic_color_smoothing_dev((float *)d_out, piece->roi_out.width, piece->roi_out.height, (int)d->color_smoothing, s); // :1249-1250
   return rc;
 }

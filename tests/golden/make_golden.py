@@ -83,3 +83,5 @@ for version, pc in ((0, 0), (0, 3), (1, 0), (2, 5), (3, 0), (3, 2), (4, 1)):
     save[f"data_v{version}_n{pc}"] = blob
     save[f"out_v{version}_n{pc}"] = util.ref_filmic_legacy(img, blob, work, export)
 np.savez_compressed(os.path.join(OUT, "filmic_legacy.npz"), **save)
+mos = util.frame_natural(300, 200, 81)
+np.savez_compressed(os.path.join(OUT, "amaze.npz"), mosaic=mos, rgb_carried=util.ref_amaze(mos, util.BAYER["RGGB"]))

@@ -395,3 +395,34 @@ def test_filmic_legacy_oracle_equals_golden():
     for key in [k for k in g.files if k.startswith("out_")]:
         tag = key[4:]
         assert same_bits(util.oracle_filmic_legacy(g["img"], g["data_" + tag], work, export), g[key]).all(), tag
+
+
+@need_ref
+@pytest.mark.parametrize("name", list(util.BAYER))
+def test_amaze_oracle_equals_reference(name):
+    """iop/demosaic/amaze.cc compiled in place, one thread (its scratch is carried from tile to tile in raster order:
+    oracle scratch_mode 0); several tiles, ragged edges, clip points above and below the data."""
+    f = util.BAYER[name]
+    for (w, h), pm, gain in (((320, 240), (1.0, 1.0, 1.0), 1.0), ((501, 333), (0.8, 1.0, 0.9), 1.3), ((129, 161), (2.0, 2.0, 2.0), 1.0), ((33, 34), (1.0, 1.0, 1.0), 1.0)):
+        m = (util.frame_natural(w, h, 5, filters=f) * gain).astype(np.float32)
+        assert same_bits(util.oracle_amaze(m, f, pm, 0), util.ref_amaze(m, f, pm)).all()
+
+
+@need_ref
+def test_amaze_edge_inputs_and_scratch_modes():
+    f = util.BAYER["RGGB"]
+    for kind in ("zeros", "ones", "impulses", "negative", "tiny"):
+        m = util.frame_edge(300, 200, kind)
+        assert same_bits(util.oracle_amaze(m, f, scratch_mode=0), util.ref_amaze(m, f)).all(), kind
+    # the reference is thread-count dependent through its carried scratch; zeroing it per tile moves only a few pixels
+    m = util.frame_natural(1300, 900, 6)
+    a0, a1 = util.oracle_amaze(m, f, scratch_mode=0), util.oracle_amaze(m, f, scratch_mode=1)
+    moved = (~same_bits(a0, a1)).any(axis=2).mean()
+    assert 0 < moved < 1e-3
+    r8 = util.ref_amaze(m, f, threads=8)
+    assert (~same_bits(r8, a0)).any(axis=2).mean() < 1e-3      # ... as many as the reference moves by itself
+
+
+def test_amaze_oracle_equals_golden():
+    g = _golden("amaze.npz")
+    assert same_bits(util.oracle_amaze(g["mosaic"], util.BAYER["RGGB"], scratch_mode=0)[..., :3], g["rgb_carried"][..., :3]).all()

@@ -687,3 +687,32 @@ def oracle_color_smoothing(rgba, passes):
 def ref_color_smoothing(rgba, passes, kind="strict"):
     lib = ref(kind)
     return None if lib is None else _smooth(lib, "ref_color_smoothing", rgba, passes)
+
+
+# ---- AMaZE demosaic ---------------------------------------------------------------------------------------
+def oracle_amaze(mosaic, filters, pm=(1.0, 1.0, 1.0), scratch_mode=1):
+    """scratch_mode 0: one scratch carried from tile to tile (= the reference with one thread); 1: zeroed per tile (what
+    the CUDA kernel computes); 2: NaN-filled per tile.  Lane 3 is not written (comes back 0)."""
+    h, w = mosaic.shape
+    src = np.ascontiguousarray(mosaic)
+    out = np.zeros((h, w, 4), np.float32)
+    f = oracle().orc_amaze_demosaic
+    f.restype = C.c_int
+    assert f(fptr(out), fptr(src), w, h, C.c_uint32(filters), (C.c_float * 3)(*pm), scratch_mode) == 0
+    return out
+
+
+def ref_amaze(mosaic, filters, pm=(1.0, 1.0, 1.0), kind="strict", threads=1):
+    lib = ref(kind)
+    if lib is None:
+        return None
+    C.CDLL("libgomp.so.1").omp_set_num_threads(threads)
+    h, w = mosaic.shape
+    src = aligned_empty(mosaic.shape)
+    src[...] = mosaic
+    out = aligned_empty((h, w, 4))
+    out[...] = 0
+    lib.ref_amaze_demosaic.restype = C.c_int
+    lib.ref_amaze_demosaic(fptr(out), fptr(src), w, h, C.c_uint32(filters), (C.c_float * 3)(*pm))
+    C.CDLL("libgomp.so.1").omp_set_num_threads(os.cpu_count() or 1)
+    return np.array(out)
