@@ -19,7 +19,8 @@
  *        1  scratch zeroed before every tile                        == what a GPU kernel with fresh scratch computes
  *        2  scratch filled with NaN before every tile               -> marks every result that reads stale scratch
  * Mixed precision of the source is kept: `0.5 - varwt`, `cfa * 2.0 / ...`, `2.0 * (...)` are double expressions.
- * Pinned bit-for-bit against amaze.cc compiled in place (oracle/_ref, ref_amaze.cc).
+ * Evaluated with flush-to-zero / denormals-are-zero like the reference's pipe threads; pinned bit-for-bit against
+ * amaze.cc compiled in place and run in the same mode (oracle/_ref, ref_amaze.cc).
  */
 #include "oracle_common.h"
 #include <stdlib.h>
@@ -77,6 +78,7 @@ static void fill_scratch(char *buffer, size_t bytes, int mode)
 
 int orc_amaze_demosaic(float *out, const float *in, int width, int height, uint32_t filters, const float processed_maximum[3], int scratch_mode)
 {
+  orc_fp_fast_mode(); /* the pipe's threads run with FTZ|DAZ (darktable.c:877, common/dtpthread.c:54) */
   const int winx = 0, winy = 0;
   const float clip_pt = fminf(processed_maximum[0], fminf(processed_maximum[1], processed_maximum[2]));
   const float clip_pt8 = 0.8f * clip_pt;

@@ -707,6 +707,7 @@ def ref_amaze(mosaic, filters, pm=(1.0, 1.0, 1.0), kind="strict", threads=1):
     if lib is None:
         return None
     C.CDLL("libgomp.so.1").omp_set_num_threads(threads)
+    oracle().orc_fp_fast_mode()      # FTZ|DAZ on this thread, as the reference's pipe threads have it (darktable.c:877)
     h, w = mosaic.shape
     src = aligned_empty(mosaic.shape)
     src[...] = mosaic
