@@ -207,68 +207,63 @@ __global__ void __launch_bounds__(NT, 1) amaze_tiles_kernel(const amaze_args_t a
     __syncthreads();
 
     // ---- tile load with the mirrored 16-px border at the frame edges, :357-455 -----------------------------------
-    for(int rr = y4; rr < rr1; rr += RG4)
+    // The reference fills nine regions one after the other with the linear index rr*ts + cc and no bound on it: when the
+    // frame edge sits less than 16 px before the tile edge, the right border runs over into column 0.. of the next row
+    // (replacing what the left border put there) and the lower border runs past row 159 into the padding and the
+    // Nyquist flags.  Both reach kept pixels, so the regions are written with the same indices in the same order.
+#define PUT(idx_, src_)                         \
+  do                                            \
+  {                                             \
+    const float t_ = __ldg(a.in + (src_));      \
+    cfa[idx_] = t_;                             \
+    rgbgreen[idx_] = t_;                        \
+  } while(0)
     {
-      const int cc = x160;
-      if(cc < cc1)
+      const int ncc = ccmax - ccmin;
+      // upper border, inner part, lower border (:357-391): pairwise disjoint targets
+      if(rrmin > 0)
+        for(int k = tid; k < 16 * ncc; k += NT)
+        {
+          const int rr = k / ncc, cc = ccmin + (k - rr * ncc);
+          PUT(rr * TS + cc, (size_t)(32 - rr + top) * width + (cc + left));
+        }
+      for(int rr = rrmin + y4; rr < rrmax; rr += RG4)
       {
-        const bool in_r = rr >= rrmin && rr < rrmax, in_c = cc >= ccmin && cc < ccmax;
-        const bool top_b = rrmin > 0 && rr < 16, bot_b = rrmax < rr1 && rr >= rrmax && rr < rrmax + 16;
-        const bool left_b = ccmin > 0 && cc < 16, right_b = ccmax < cc1 && cc >= ccmax && cc < ccmax + 16;
-        int row = -1, col = -1;
-        if(in_r && in_c)
-        {
-          row = rr + top;
-          col = cc + left;
-        }
-        else if(in_c && top_b)
-        {
-          row = 32 - rr + top;
-          col = cc + left;
-        }
-        else if(in_c && bot_b)
-        {
-          row = height - (rr - rrmax) - 2;
-          col = left + cc;
-        }
-        else if(in_r && left_b)
-        {
-          row = rr + top;
-          col = 32 - cc + left;
-        }
-        else if(in_r && right_b)
-        {
-          row = top + rr;
-          col = width - (cc - ccmax) - 2;
-        }
-        else if(top_b && left_b)
-        { // the corners mirror about row/column 32, not 16 (:411-449)
-          row = 32 - rr;
-          col = 32 - cc;
-        }
-        else if(bot_b && right_b)
-        {
-          row = height - (rr - rrmax) - 2;
-          col = width - (cc - ccmax) - 2;
-        }
-        else if(top_b && right_b)
-        {
-          row = 32 - rr;
-          col = width - (cc - ccmax) - 2;
-        }
-        else if(bot_b && left_b)
-        {
-          row = height - (rr - rrmax) - 2;
-          col = 32 - cc;
-        }
-        if(row >= 0)
-        {
-          const float v = __ldg(a.in + (size_t)row * width + col);
-          cfa[rr * TS + cc] = v;
-          rgbgreen[rr * TS + cc] = v;
-        }
+        const int cc = x160;
+        if(cc >= ccmin && cc < ccmax) PUT(rr * TS + cc, (size_t)(rr + top) * width + (cc + left));
       }
+      if(rrmax < rr1)
+        for(int k = tid; k < 16 * ncc; k += NT)
+        {
+          const int rr = k / ncc, cc = ccmin + (k - rr * ncc);
+          PUT((rrmax + rr) * TS + cc, (size_t)(height - rr - 2) * width + (left + cc));
+        }
+      __syncthreads();
+      if(ccmin > 0) // left border, :395-403
+        for(int k = tid; k < 16 * (rrmax - rrmin); k += NT)
+        {
+          const int rr = rrmin + (k >> 4), cc = k & 15;
+          PUT(rr * TS + cc, (size_t)(rr + top) * width + (32 - cc + left));
+        }
+      __syncthreads();
+      if(ccmax < cc1) // right border, :406-414
+        for(int k = tid; k < 16 * (rrmax - rrmin); k += NT)
+        {
+          const int rr = rrmin + (k >> 4), cc = k & 15;
+          PUT(rr * TS + ccmax + cc, (size_t)(top + rr) * width + (width - cc - 2));
+        }
+      __syncthreads();
+      // the corners mirror about row/column 32, not 16 (:417-455); in the reference's order
+      if(rrmin > 0 && ccmin > 0 && tid < 256) PUT((tid >> 4) * TS + (tid & 15), (size_t)(32 - (tid >> 4)) * width + (32 - (tid & 15)));
+      __syncthreads();
+      if(rrmax < rr1 && ccmax < cc1 && tid < 256)
+        PUT((rrmax + (tid >> 4)) * TS + ccmax + (tid & 15), (size_t)(height - (tid >> 4) - 2) * width + (width - (tid & 15) - 2));
+      __syncthreads();
+      if(rrmin > 0 && ccmax < cc1 && tid < 256) PUT((tid >> 4) * TS + ccmax + (tid & 15), (size_t)(32 - (tid >> 4)) * width + (width - (tid & 15) - 2));
+      __syncthreads();
+      if(rrmax < rr1 && ccmin > 0 && tid < 256) PUT((rrmax + (tid >> 4)) * TS + (tid & 15), (size_t)(height - (tid >> 4) - 2) * width + (32 - (tid & 15)));
     }
+#undef PUT
     __syncthreads();
 
     // ---- gradients and direction weights, :460-470 ---------------------------------------------------------------

@@ -81,6 +81,9 @@ def test_amaze_45mp_properties(built):
     a = cuda_amaze(m, f)
     b = cuda_amaze(m, f)
     assert same_bits(a, b).all(), "not deterministic"
-    assert np.isfinite(a).all() and a[..., :3].min() >= 0.0 and a[..., :3].max() <= 1.0
+    # clampnan (amaze.cc:60-75) only touches non-finite values: finite overshoot outside [0,1] is reference behaviour
+    assert np.isfinite(a).all()
+    g = a[1::2, 0::2, 1]  # a green site of RGGB keeps its CFA sample
+    assert same_bits(g[16:-16, 16:-16], m[1::2, 0::2][16:-16, 16:-16]).all()
     flat = np.full((512, 768), 0.25, np.float32)
     assert np.abs(cuda_amaze(flat, f)[..., :3] - 0.25).max() < 1e-6
