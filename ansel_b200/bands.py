@@ -66,7 +66,8 @@ def chain_cuts(nodes: list[Node], width: int, height: int) -> tuple[int, int, in
         align = align * a // math.gcd(align, a)
     if nodes and nodes[0].op == "demosaic" and not any(overlaps[1:]):
         g, h_, a_ = C.c_int(), C.c_int(), C.c_int()
-        L.b200_demosaic_band_grid(None, C.byref(g), C.byref(h_), C.byref(a_))
+        piece = ab.make_piece(width, height, filters=0x94949494, channels=1, data=nodes[0].data)
+        L.b200_demosaic_band_grid(C.byref(piece), C.byref(g), C.byref(h_), C.byref(a_))
         return g.value, h_.value, a_.value
     return 1, sum(overlaps), align
 

@@ -65,7 +65,19 @@ extern "C" int b200_band_plan(int height, int n_bands, int grid, int halo, int a
 // the block grid and halo under which banded RCD equals the untiled frame bit for bit (rcd.c:71-75)
 extern "C" void b200_demosaic_band_grid(const b200_piece_t *piece, int *grid, int *halo, int *align)
 {
-  (void)piece;
+  if(piece && piece->data)
+  {
+    const b200_demosaic_data_t *d = (const b200_demosaic_data_t *)piece->data;
+    if((d->demosaicing_method & ~1024u) != B200_DEMOSAIC_RCD)
+    { // AMaZE mirrors at its own tile origin: no cut reproduces the untiled frame; bands are tiling.c tiles
+      b200_tiling_t t;
+      b200_demosaic_tiling(piece, &t);
+      if(grid) *grid = 1;
+      if(halo) *halo = (int)t.overlap;
+      if(align) *align = (int)t.yalign;
+      return;
+    }
+  }
   if(grid) *grid = 94;
   if(halo) *halo = 9;
   if(align) *align = 2;

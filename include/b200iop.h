@@ -439,6 +439,10 @@ int b200_colorout_process_scatter_dev(const b200_piece_t *piece, const void *d_i
 int b200_ipc_export(void *d_ptr, unsigned char handle[B200_IPC_HANDLE_BYTES]);
 int b200_ipc_import(const unsigned char handle[B200_IPC_HANDLE_BYTES], void **d_ptr);
 int b200_ipc_release(void *d_ptr);
+/* Row grid, halo and alignment for b200_band_plan() under which a banded demosaic equals the untiled frame bit
+ * for bit: RCD's 94-row blocks with a 9-row halo (rcd.c:71-75).  AMaZE mirrors the frame edge at its own tile
+ * origin (amaze.cc:357-455), so no cut reproduces the untiled frame: grid 1 and the tiling_callback() overlap
+ * (demosaic.c:1916-2013) come back, i.e. bands are tiles of develop/tiling.c.  piece == NULL means RCD. */
 void b200_demosaic_band_grid(const b200_piece_t *piece, int *grid, int *halo, int *align);
 
 /* ---- the libm the kernels use ------------------------------------------------------------------

@@ -161,3 +161,17 @@ def test_product_never_references_the_oracle():
     assert not bad, bad
     out = subprocess.run(["ldd", os.path.join(ROOT, "ansel_b200", "libb200iop.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_band_grid_follows_the_demosaic_method(built):
+    """RCD bands cut on its 94-row block grid (bit-identical to the untiled frame); AMaZE bands are tiling.c tiles"""
+    import ansel_b200 as ab
+    L = ab.lib()
+    g, h, a = C.c_int(), C.c_int(), C.c_int()
+    L.b200_demosaic_band_grid(None, C.byref(g), C.byref(h), C.byref(a))
+    assert (g.value, h.value, a.value) == (94, 9, 2)
+    for method, want in ((ab.DEMOSAIC_RCD, (94, 9, 2)), (ab.DEMOSAIC_AMAZE, (1, 5, 2))):
+        d = ab.demosaic_data(method=method)
+        piece = ab.make_piece(640, 480, filters=0x94949494, channels=1, data=d)
+        L.b200_demosaic_band_grid(C.byref(piece), C.byref(g), C.byref(h), C.byref(a))
+        assert (g.value, h.value, a.value) == want
