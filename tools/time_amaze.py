@@ -13,3 +13,9 @@ for _ in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); run(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
 print("AMaZE 45MP median ms", np.median(ts), "MP/s", w*h/np.median(ts)/1e3)
+import time
+mh = m.cpu().numpy()
+for thr in (os.cpu_count() or 1, max(1, (os.cpu_count() or 2) // 2)):
+    util.ref_amaze(mh[:1024], util.BAYER["RGGB"], kind="fast", threads=thr)
+    t0 = time.perf_counter(); util.ref_amaze(mh, util.BAYER["RGGB"], kind="fast", threads=thr); dt = time.perf_counter() - t0
+    print("reference amaze.cc (release flags) 45MP incl. buffer copies", thr, "threads:", round(dt * 1e3, 1), "ms")
