@@ -17,14 +17,22 @@
 //         row in parallel;
 //   * mixed precision of the source is kept (`0.5 - varwt`, `cfa * 2.0 / ...`, `2.0 * (...)` are double).
 // 14 float planes of 160x160 per tile (1.45 MB) do not fit in shared memory: each persistent CTA owns a scratch region
-// in global memory that stays L2-resident while it is being worked on.  First version: correctness first.
+// in global memory; the row-sequential refinements stage their half plane in shared memory, the chain sweeps fetch the
+// operands of four steps at a time.
 #include "runtime.h"
 #include <math.h>
 
 namespace
 {
 constexpr int TS = 160, TSH = TS / 2;
-constexpr int NT = 640;            // 160 columns x 4 row groups, or 80 site columns x 8 row groups
+#ifndef AMAZE_NT
+#define AMAZE_NT 640
+#endif
+#ifndef AMAZE_MINB
+#define AMAZE_MINB 1
+#endif
+constexpr int NT = AMAZE_NT;       // a multiple of 160: 160 columns x NT/160 row groups, or 80 site columns x NT/80 row groups
+static_assert(NT % TS == 0 && NT >= 640, "the chain sweeps need 2 x 304 threads");
 constexpr int RG4 = NT / TS, RG8 = NT / TSH;
 constexpr size_t FULL = sizeof(float) * TS * TS, HALF = sizeof(float) * TS * TSH, PAD = 2 * 64;
 constexpr size_t SCRATCH_BYTES = 14 * FULL + TS * TSH + 18 * PAD; // amaze.cc:283 without the alignment slack
@@ -116,6 +124,51 @@ __device__ float cd_update(float prev, float cur, float next, float ap, float ac
   return cd;
 }
 
+// One chain of that sweep: elements i0, i0 + S, ... (n of them), neighbours of a site at +-N (S = 2N).  Everything a
+// step reads except `prev` is original data (the chain only ever rewrites elements behind it), so the operands of four
+// steps are fetched together before the dependent arithmetic runs: one memory round trip per four steps.
+template <int S, int N> __device__ __forceinline__ void cd_chain(float *cd, const float *alt, const float *cfa, int i0, int n, bool green, float clip_pt)
+{
+  float prev = cd[i0 - S], cur = cd[i0], ap = alt[i0 - S], ac = alt[i0], lo = cfa[i0 - N];
+  for(int k = 0; k < n; k += 4)
+  {
+    const int i = i0 + k * S;
+    float nx[4], an[4], cf[4], hi[4];
+#pragma unroll
+    for(int u = 0; u < 4; u++)
+    { // reads past the end of a short chain stay inside the scratch region and are not used
+      nx[u] = cd[i + (u + 1) * S];
+      an[u] = alt[i + (u + 1) * S];
+      cf[u] = cfa[i + u * S];
+      hi[u] = cfa[i + u * S + N];
+    }
+#pragma unroll
+    for(int u = 0; u < 4; u++)
+      if(k + u < n)
+      {
+        const float nv = cd_update(prev, cur, nx[u], ap, ac, an[u], green, cf[u], lo, hi[u], clip_pt);
+        cd[i + u * S] = nv;
+        prev = nv;
+        cur = nx[u];
+        ap = ac;
+        ac = an[u];
+        lo = hi[u];
+      }
+  }
+}
+
+// a half plane (160 x 80 floats) to and from shared memory for the row-sequential refinements
+constexpr int ROW_T = 96; // the three warps that hold a row's 80 sites
+__device__ __forceinline__ void stage_in(float *sm, const float *g, int tid)
+{
+  for(int k = tid; k < TS * TSH / 4; k += NT) reinterpret_cast<float4 *>(sm)[k] = reinterpret_cast<const float4 *>(g)[k];
+}
+__device__ __forceinline__ void stage_out(float *g, const float *sm, int tid)
+{
+  for(int k = tid; k < TS * TSH / 4; k += NT) reinterpret_cast<float4 *>(g)[k] = reinterpret_cast<const float4 *>(sm)[k];
+}
+__device__ __forceinline__ void row_barrier() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
+
 #define FULL_LOOP(a)                                   \
   for(int rr = (a) + y4; rr < rr1 - (a); rr += RG4)    \
   {                                                    \
@@ -140,9 +193,31 @@ __device__ float cd_update(float prev, float cur, float next, float ap, float ac
   }              \
   }
 
-__global__ void __launch_bounds__(NT, 1) amaze_tiles_kernel(const amaze_args_t a)
+#ifdef B200_AMAZE_PROF
+// development aid (tools/prof_amaze.py): cycles of CTA 0 between the section marks, summed over its tiles
+__device__ unsigned long long g_amaze_prof[40];
+#define AMAZE_PROF_MARK()                                         \
+  do                                                              \
+  {                                                               \
+    if(blockIdx.x == 0 && tid == 0)                               \
+    {                                                             \
+      const long long now_ = clock64();                           \
+      g_amaze_prof[prof_k] += (unsigned long long)(now_ - prof_t); \
+      prof_t = now_;                                              \
+    }                                                             \
+    prof_k++;                                                     \
+  } while(0)
+#else
+#define AMAZE_PROF_MARK() \
+  do                      \
+  {                       \
+  } while(0)
+#endif
+
+__global__ void __launch_bounds__(NT, AMAZE_MINB) amaze_tiles_kernel(const amaze_args_t a)
 {
   __shared__ int s_ny[4];
+  extern __shared__ __align__(16) float s_half[]; // TS * TSH floats
   const int tid = threadIdx.x;
   const int x160 = tid % TS, y4 = tid / TS, x80 = tid % TSH, y8 = tid / TSH;
   const uint32_t f = a.filters;
@@ -189,6 +264,10 @@ __global__ void __launch_bounds__(NT, 1) amaze_tiles_kernel(const amaze_args_t a
 
   for(int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x)
   {
+#ifdef B200_AMAZE_PROF
+    int prof_k = 0;
+    long long prof_t = clock64();
+#endif
     const int ty = tile / a.ntx, tx = tile - ty * a.ntx;
     const int top = -16 + ty * (TS - 32), left = -16 + tx * (TS - 32);
     const int bottom = min(top + TS, height + 16), right = min(left + TS, width + 16);
@@ -206,6 +285,7 @@ __global__ void __launch_bounds__(NT, 1) amaze_tiles_kernel(const amaze_args_t a
     if(tid < 4) s_ny[tid] = (tid == 0) ? (1 << 30) : (tid == 2 ? (1 << 30) : -1); // start row (min), end row (max), start col (min), end col (max)
     __syncthreads();
 
+    AMAZE_PROF_MARK();
     // ---- tile load with the mirrored 16-px border at the frame edges, :357-455 -----------------------------------
     // The reference fills nine regions one after the other with the linear index rr*ts + cc and no bound on it: when the
     // frame edge sits less than 16 px before the tile edge, the right border runs over into column 0.. of the next row
@@ -266,6 +346,7 @@ __global__ void __launch_bounds__(NT, 1) amaze_tiles_kernel(const amaze_args_t a
 #undef PUT
     __syncthreads();
 
+    AMAZE_PROF_MARK();
     // ---- gradients and direction weights, :460-470 ---------------------------------------------------------------
     FULL_LOOP(2)
     const float delh = fabsf(cfa[i + 1] - cfa[i - 1]);
@@ -276,6 +357,7 @@ __global__ void __launch_bounds__(NT, 1) amaze_tiles_kernel(const amaze_args_t a
     END_LOOP
     __syncthreads();
 
+    AMAZE_PROF_MARK();
     // ---- vertical / horizontal colour differences, :474-577 ------------------------------------------------------
     FULL_LOOP(4)
     const bool fcswitch = ((fc(rr, 4, f) & 1) ^ ((cc - 4) & 1)) != 0;
@@ -329,38 +411,27 @@ __global__ void __launch_bounds__(NT, 1) amaze_tiles_kernel(const amaze_args_t a
     END_LOOP
     __syncthreads();
 
+    AMAZE_PROF_MARK();
     // ---- smaller-variance choice and saturation bounds, in place in raster order, :580-686 -----------------------
     // hcd: one thread per (row, column parity) walks its row; vcd: one thread per (column, row parity) walks its column
+    // The two sweeps touch different planes and run side by side on the two halves of the CTA.
     {
       const int nrows = rr1 - 8, ncols = cc1 - 8; // rows / columns 4 .. rr1-5 / cc1-5
-      for(int t = tid; t < 2 * nrows; t += NT)
+      if(tid < 2 * nrows)
       {
-        const int rr = 4 + (t >> 1), q = t & 1;
-        const bool g0 = (fc(rr, 4, f) & 1) != 0; // kind of the site at column 4
-        float prev = hcd[rr * TS + 4 + q - 2];
-        for(int cc = 4 + q; cc < cc1 - 4; cc += 2)
-        {
-          const int i = rr * TS + cc;
-          const bool green = g0 ^ (((cc - 4) & 1) != 0);
-          const float nv = cd_update(prev, hcd[i], hcd[i + 2], hcdalt[i - 2], hcdalt[i], hcdalt[i + 2], green, cfa[i], cfa[i - 1], cfa[i + 1], clip_pt);
-          hcd[i] = nv;
-          prev = nv;
-        }
+        const int rr = 4 + (tid >> 1), q = tid & 1;
+        const bool green = ((fc(rr, 4, f) & 1) != 0) ^ (q != 0);
+        cd_chain<2, 1>(hcd, hcdalt, cfa, rr * TS + 4 + q, (cc1 - 8 - q + 1) >> 1, green, clip_pt);
       }
-      for(int t = tid; t < 2 * ncols; t += NT)
+      else if(tid >= NT / 2 && tid - NT / 2 < 2 * ncols)
       {
+        const int t = tid - NT / 2;
         const int cc = 4 + (t >> 1), q = t & 1;
-        float prev = vcd[(4 + q - 2) * TS + cc];
-        for(int rr = 4 + q; rr < rr1 - 4; rr += 2)
-        {
-          const int i = rr * TS + cc;
-          const bool green = ((fc(rr, 4, f) & 1) != 0) ^ (((cc - 4) & 1) != 0);
-          const float nv = cd_update(prev, vcd[i], vcd[i + v2], vcdalt[i - v2], vcdalt[i], vcdalt[i + v2], green, cfa[i], cfa[i - v1], cfa[i + v1], clip_pt);
-          vcd[i] = nv;
-          prev = nv;
-        }
+        const bool green = ((fc(4 + q, 4, f) & 1) != 0) ^ (((cc - 4) & 1) != 0);
+        cd_chain<2 * TS, TS>(vcd, vcdalt, cfa, (4 + q) * TS + cc, (rr1 - 8 - q + 1) >> 1, green, clip_pt);
       }
     }
+    AMAZE_PROF_MARK(); // chains done (thread 0 walks an hcd row)
     __syncthreads();
     FULL_LOOP(4)
     const bool green = ((fc(rr, 4, f) & 1) ^ ((cc - 4) & 1)) != 0;
@@ -368,6 +439,7 @@ __global__ void __launch_bounds__(NT, 1) amaze_tiles_kernel(const amaze_args_t a
     END_LOOP
     __syncthreads();
 
+    AMAZE_PROF_MARK();
     // ---- adaptive H/V weight at R/B sites, :688-746 --------------------------------------------------------------
     SITE_LOOP(6)
     const float uave = vcd[i] + vcd[i - v1] + vcd[i - v2] + vcd[i - v3];
@@ -396,6 +468,7 @@ __global__ void __launch_bounds__(NT, 1) amaze_tiles_kernel(const amaze_args_t a
       hvwt[i >> 1] = diffwt;
     END_LOOP
 
+    AMAZE_PROF_MARK();
     // ---- Nyquist texture test, :748-815 (cddiffsq and delhvsqsum are complete: barrier above) --------------------
     SITE_LOOP(6)
     const float t
@@ -471,18 +544,27 @@ __global__ void __launch_bounds__(NT, 1) amaze_tiles_kernel(const amaze_args_t a
     }
     __syncthreads();
 
+    AMAZE_PROF_MARK();
     // ---- hvwt refined in place, row after row (:893-899); then green at R/B sites (:901-911) ---------------------
-    for(int rr = 8; rr < rr1 - 8; rr++)
-    {
-      const int i = rr * TS + 8 + (fc(rr, 2, f) & 1) + 2 * tid;
-      if(tid < TSH && i < rr * TS + cc1 - 8)
+    // (the half plane is staged in shared memory: 144 dependent rows at shared-memory latency, three warps and a named barrier)
+    stage_in(s_half, hvwt, tid);
+    __syncthreads();
+    if(tid < ROW_T)
+      for(int rr = 8; rr < rr1 - 8; rr++)
       {
-        const float hvwtalt = XDIV4(hvwt[(i - m1) >> 1] + hvwt[(i + p1) >> 1] + hvwt[(i - p1) >> 1] + hvwt[(i + m1) >> 1]);
-        const float cur = hvwt[i >> 1];
-        hvwt[i >> 1] = fabsf(0.5f - cur) < fabsf(0.5f - hvwtalt) ? hvwtalt : cur;
+        const int i = rr * TS + 8 + (fc(rr, 2, f) & 1) + 2 * tid;
+        if(tid < TSH && i < rr * TS + cc1 - 8)
+        {
+          const float hvwtalt = XDIV4(s_half[(i - m1) >> 1] + s_half[(i + p1) >> 1] + s_half[(i - p1) >> 1] + s_half[(i + m1) >> 1]);
+          const float cur = s_half[i >> 1];
+          s_half[i >> 1] = fabsf(0.5f - cur) < fabsf(0.5f - hvwtalt) ? hvwtalt : cur;
+        }
+        row_barrier();
       }
-      __syncthreads();
-    }
+    __syncthreads();
+    stage_out(hvwt, s_half, tid);
+    __syncthreads();
+    AMAZE_PROF_MARK(); // hvwt rows done
     SITE_LOOP(8)
     Dgrb0[i >> 1] = mixf(hvwt[i >> 1], vcd[i], hcd[i]);
     const float g = cfa[i] + Dgrb0[i >> 1];
@@ -493,6 +575,7 @@ __global__ void __launch_bounds__(NT, 1) amaze_tiles_kernel(const amaze_args_t a
     END_LOOP
     __syncthreads();
 
+    AMAZE_PROF_MARK();
     // ---- Nyquist refinement with green curvatures, :918-955 ------------------------------------------------------
     if(doNyquist)
     {
@@ -516,6 +599,7 @@ __global__ void __launch_bounds__(NT, 1) amaze_tiles_kernel(const amaze_args_t a
     }
     __syncthreads();
 
+    AMAZE_PROF_MARK();
     // ---- diagonal gradients, :957-981 (delp/delm/Dgrbsq1* take over cddiffsq / delm / their own planes) ------------
     for(int rr = 6 + y8; rr < rr1 - 6; rr += RG8)
     {
@@ -541,6 +625,7 @@ __global__ void __launch_bounds__(NT, 1) amaze_tiles_kernel(const amaze_args_t a
     }
     __syncthreads();
 
+    AMAZE_PROF_MARK();
     // ---- diagonal interpolation of the opposite colour, :986-1104 (rbm/rbp take over vcd, pmwt takes delhvsqsum) ----
     SITE_LOOP(8)
     const int j = i >> 1;
@@ -600,23 +685,32 @@ __global__ void __launch_bounds__(NT, 1) amaze_tiles_kernel(const amaze_args_t a
     END_LOOP
     __syncthreads();
 
+    AMAZE_PROF_MARK();
     // ---- pmwt refined in place, row after row (:1111-1118); then R+B (:1120-1121) ---------------------------------
-    for(int rr = 10; rr < rr1 - 10; rr++)
-    {
-      const int i = rr * TS + 10 + (fc(rr, 2, f) & 1) + 2 * tid;
-      if(tid < TSH && i < rr * TS + cc1 - 10)
+    stage_in(s_half, pmwt, tid);
+    __syncthreads();
+    if(tid < ROW_T)
+      for(int rr = 10; rr < rr1 - 10; rr++)
       {
-        const float pmwtalt = XDIV4(pmwt[(i - m1) >> 1] + pmwt[(i + p1) >> 1] + pmwt[(i - p1) >> 1] + pmwt[(i + m1) >> 1]);
-        if(fabsf(0.5f - pmwt[i >> 1]) < fabsf(0.5f - pmwtalt)) pmwt[i >> 1] = pmwtalt;
+        const int i = rr * TS + 10 + (fc(rr, 2, f) & 1) + 2 * tid;
+        if(tid < TSH && i < rr * TS + cc1 - 10)
+        {
+          const float pmwtalt = XDIV4(s_half[(i - m1) >> 1] + s_half[(i + p1) >> 1] + s_half[(i - p1) >> 1] + s_half[(i + m1) >> 1]);
+          if(fabsf(0.5f - s_half[i >> 1]) < fabsf(0.5f - pmwtalt)) s_half[i >> 1] = pmwtalt;
+        }
+        row_barrier();
       }
-      __syncthreads();
-    }
+    __syncthreads();
+    stage_out(pmwt, s_half, tid);
+    __syncthreads();
+    AMAZE_PROF_MARK(); // pmwt rows done
     SITE_LOOP(10)
     const int j = i >> 1;
     rbint[j] = XDIV2(cfa[i] + rbm[j] * (1.f - pmwt[j]) + rbp[j] * pmwt[j]);
     END_LOOP
     __syncthreads();
 
+    AMAZE_PROF_MARK();
     // ---- green re-interpolated where the diagonal direction discriminates better, :1127-1241 ----------------------
     SITE_LOOP(12)
     const int j = i >> 1;
@@ -661,6 +755,7 @@ __global__ void __launch_bounds__(NT, 1) amaze_tiles_kernel(const amaze_args_t a
     END_LOOP
     __syncthreads();
 
+    AMAZE_PROF_MARK();
     // ---- chroma: split G-B out of G-R (:1247-1253) ------------------------------------------------------------------
     for(int rr = 13 - a.ey + 2 * y8; rr < rr1 - 12; rr += 2 * RG8)
     {
@@ -672,6 +767,7 @@ __global__ void __launch_bounds__(NT, 1) amaze_tiles_kernel(const amaze_args_t a
       }
     }
     __syncthreads();
+    AMAZE_PROF_MARK();
     // ---- ... and interpolate each at the other colour's sites from its diagonal neighbours (:1255-1289) -------------
     SITE_LOOP(14)
     const int c = 1 - fc(rr, cc, f) / 2;
@@ -688,6 +784,7 @@ __global__ void __launch_bounds__(NT, 1) amaze_tiles_kernel(const amaze_args_t a
     END_LOOP
     __syncthreads();
 
+    AMAZE_PROF_MARK();
     // ---- output, :1291-1407: alpha is not written by the reference; 0 here ------------------------------------------
     FULL_LOOP(16)
     const int row = rr + top, col = cc + left;
@@ -717,6 +814,7 @@ __global__ void __launch_bounds__(NT, 1) amaze_tiles_kernel(const amaze_args_t a
       __stcs(reinterpret_cast<float4 *>(a.out + 4 * ((size_t)row * width + col)), make_float4(r, clampnan(rgbgreen[i], 0.0f, 1.0f), b, 0.0f));
     }
     END_LOOP
+    AMAZE_PROF_MARK();
   }
 }
 } // namespace
@@ -730,6 +828,11 @@ int amaze_demosaic_dev(const float *d_in, float *d_out, int width, int height, u
   if(width < 1 || height < 1) return B200_OK;
   // the mirrored border reads rows / columns up to 32 (:363,:414): smaller frames are out-of-bounds reads in the reference
   if(width < 33 || height < 33) return fail(B200_ERR_UNSUPPORTED, "AMaZE: frames under 33 px a side are undefined in the reference");
+  // the sweeps below take the colour of a site from its row and column parity
+  for(int r = 0; r < 8; r++)
+    for(int c = 0; c < 2; c++)
+      if(b200_fc(r, c, filters) != b200_fc(r & 1, c, filters))
+        return fail(B200_ERR_UNSUPPORTED, "AMaZE: filters 0x%08x is not a 2x2 Bayer pattern", filters);
   amaze_args_t a;
   a.in = d_in;
   a.out = d_out;
@@ -766,14 +869,35 @@ int amaze_demosaic_dev(const float *d_in, float *d_out, int width, int height, u
     a.ey = 1;
     a.ex = 1;
   }
-  int grid = 2 * sm_count();
+  // persistent CTAs: as many as are resident at once (register-limited), each with its own scratch region
+  static int per_sm[16] = { 0 };
+  int dev = 0;
+  B200_CUDA_TRY(cudaGetDevice(&dev));
+  if(!per_sm[dev & 15])
+  {
+    B200_CUDA_TRY(cudaFuncSetAttribute(amaze_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HALF));
+    int n = 0;
+    B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, amaze_tiles_kernel, NT, HALF));
+    per_sm[dev & 15] = n < 1 ? 1 : n;
+  }
+  int grid = per_sm[dev & 15] * sm_count();
   if(grid > a.ntiles) grid = a.ntiles;
   void *scr = nullptr;
   int rc = scratch(SLOT_TMP2, (size_t)grid * SCRATCH_STRIDE, &scr);
   if(rc) return rc;
   a.scratch = (char *)scr;
-  amaze_tiles_kernel<<<grid, NT, 0, stream>>>(a);
+  amaze_tiles_kernel<<<grid, NT, HALF, stream>>>(a);
   B200_CUDA_TRY(cudaGetLastError());
   return B200_OK;
 }
 } // namespace b200
+
+#ifdef B200_AMAZE_PROF
+extern "C" int b200_amaze_prof(unsigned long long *out, int n, int reset)
+{
+  unsigned long long z[40] = { 0 };
+  if(out && cudaMemcpyFromSymbol(out, g_amaze_prof, sizeof(unsigned long long) * (n < 40 ? n : 40)) != cudaSuccess) return 1;
+  if(reset && cudaMemcpyToSymbol(g_amaze_prof, z, sizeof(z)) != cudaSuccess) return 1;
+  return 0;
+}
+#endif

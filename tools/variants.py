@@ -8,6 +8,7 @@ from ansel_b200 import build as B
 SETS = {
     "rcd": ("rcd.cu", "quick_time.py", {"rg8_u1": ["-DRCD_RG=8", "-DRCD_UNROLL=1"], "rg8_u2": ["-DRCD_RG=8", "-DRCD_UNROLL=2"], "rg7_u1": ["-DRCD_RG=7"]}),
     "nlm": ("nlm.cu", "time_nlm.py", {'nt512_2224': ['-DNLM_NT=512', '-DNLM_UB=2', '-DNLM_UE=2', '-DNLM_UA=2', '-DNLM_UC=4'], 'nt384_3448': ['-DNLM_NT=384', '-DNLM_UB=3', '-DNLM_UE=4', '-DNLM_UA=4', '-DNLM_UC=8'], 'nt384_2224': ['-DNLM_NT=384', '-DNLM_UB=2', '-DNLM_UE=2', '-DNLM_UA=2', '-DNLM_UC=4'], 'nt256_4448': ['-DNLM_NT=256', '-DNLM_UB=4', '-DNLM_UE=4', '-DNLM_UA=4', '-DNLM_UC=8'], 'nt512_1112': ['-DNLM_NT=512', '-DNLM_UB=1', '-DNLM_UE=1', '-DNLM_UA=1', '-DNLM_UC=2']}),
+    "amaze": ("amaze.cu", "time_amaze_gpu.py", {"nt640_b1": [], "nt960_b1": ["-DAMAZE_NT=960"], "nt640_b2": ["-DAMAZE_MINB=2"], "nt800_b1": ["-DAMAZE_NT=800"]}),
 }
 OUT = os.path.join(ROOT, "tools", "variants")
 os.makedirs(OUT, exist_ok=True)
