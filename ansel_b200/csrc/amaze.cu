@@ -29,7 +29,7 @@ constexpr int TS = 160, TSH = TS / 2;
 #define AMAZE_NT 640
 #endif
 #ifndef AMAZE_MINB
-#define AMAZE_MINB 1
+#define AMAZE_MINB 2
 #endif
 constexpr int NT = AMAZE_NT;       // a multiple of 160: 160 columns x NT/160 row groups, or 80 site columns x NT/80 row groups
 static_assert(NT % TS == 0 && NT >= 640, "the chain sweeps need 2 x 304 threads");

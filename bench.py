@@ -398,6 +398,20 @@ def run_b200(args):
                 ts.append(a0.elapsed_time(a1))
             m = float(np.median(ts))
             other[label] = {"ms": m, "MP_per_s": npx / m / 1e3, "algorithmic_GBps": 32 * npx / (m * 1e-3) / 1e9}
+        # the second demosaicer of the north star on the bench frame (20 B/px at the module boundary)
+        d_amz = ab.demosaic_data(ab.DEMOSAIC_AMAZE)
+        p_amz = ab.make_piece(w, h, filters=filters, data=d_amz, devid=local)
+        ts = []
+        for k in range(4):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            ab.check(L.b200_demosaic_process_dev(p_amz, t_mosaic.data_ptr(), t_rgb[1].data_ptr(), stream))
+            a1.record()
+            torch.cuda.synchronize()
+            if k:
+                ts.append(a0.elapsed_time(a1))
+        m = float(np.median(ts))
+        other["demosaic_amaze"] = {"ms": m, "MP_per_s": npx / m / 1e3, "algorithmic_GBps": 20 * npx / (m * 1e-3) / 1e9}
 
     # ---- second mode at N>1: ONE frame cut into row bands + all-gather ---------
     banded = None
