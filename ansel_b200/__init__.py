@@ -329,6 +329,10 @@ DIFFUSE_PRESETS = {
                          anisotropy_third=4.0, anisotropy_fourth=4.0, first=1.0, second=1.0, third=1.0, fourth=1.0),
     # "bloom" :422-438
     "bloom": dict(iterations=1, radius=32, regularization=0.0, variance_threshold=0.0, first=0.5, second=0.5, third=0.5, fourth=0.5),
+    # "inpaint highlights" :518-538: the luminance mask (threshold > 0) with its noise-seeded start image
+    "inpaint_highlights": dict(iterations=32, radius=4, radius_center=0, sharpness=0.0, threshold=1.41, variance_threshold=0.0,
+                               regularization=0.0, anisotropy_first=0.0, anisotropy_second=0.0, anisotropy_third=0.0,
+                               anisotropy_fourth=2.0, first=0.0, second=0.0, third=0.0, fourth=0.5),
 }
 
 

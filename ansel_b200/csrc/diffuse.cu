@@ -17,6 +17,7 @@
 // Arithmetic contract: the reference source under C float semantics (no contraction, IEEE div/sqrt), as
 // restated in oracle/restate/diffuse_oracle.c, which is bit-identical to diffuse.c's own process().
 #include "runtime.h"
+#include "flt32_math.cuh"
 #include <math.h>
 
 namespace
@@ -125,18 +126,88 @@ __device__ __forceinline__ void make_kernel(float c2, float cs, float cos2, floa
   k[8] = b11;
 }
 
-// heat_PDE_diffusion(), :760-953, has_mask == 0
+// ---- luminance mask (threshold > 0): build_mask :1109-1119, inpaint_mask :1122-1152 -----------------------------
+// iop/noise_generator.h: splitmix32 :36-43, xoshiro128plus :54-70, gaussian_noise :82-96 (Box-Muller on glibc
+// logf / sinf / cosf -> flt32_math.cuh).
+__device__ __forceinline__ uint32_t splitmix32(uint64_t seed)
+{
+  uint64_t r = (seed ^ (seed >> 33)) * 0x62a9d9ed799705f5ull;
+  r = (r ^ (r >> 28)) * 0xcb24d0a5c88c35b3ull;
+  return (uint32_t)(r >> 32);
+}
+__device__ __forceinline__ float xoshiro128plus(uint32_t (&st)[4])
+{
+  const uint32_t result = st[0] + st[3];
+  const uint32_t t = st[1] << 9;
+  st[2] ^= st[0];
+  st[3] ^= st[1];
+  st[1] ^= st[2];
+  st[0] ^= st[3];
+  st[2] ^= t;
+  st[3] = (st[3] << 11) | (st[3] >> 21);
+  return (float)(result >> 8) * 0x1.0p-24f;
+}
+__device__ __forceinline__ float gaussian_noise(const f32m::tables_t &tb, float mu, float sigma, bool flip, uint32_t (&st)[4])
+{
+  const float u1 = fmaxf(xoshiro128plus(st), 1.17549435e-38f);
+  const float u2 = xoshiro128plus(st);
+  const float radius = sqrtf(-2.0f * f32m::logf_(tb, u1));
+  const float angle = (float)(6.283185307179586 * (double)u2); // 2.f * M_PI * u2 is a double product in the source
+  const float noise = flip ? radius * f32m::cosf_(angle) : radius * f32m::sinf_(angle);
+  return noise * sigma + mu;
+}
+// one thread per pixel: the mask byte, and the start image -- the input outside the mask, |noise around the input| inside
+__global__ void __launch_bounds__(NT) mask_inpaint_kernel(const float4 *__restrict__ in, float4 *__restrict__ inpainted, unsigned char *__restrict__ mask,
+                                                          size_t npx, unsigned width, float threshold)
+{
+  const size_t px = (size_t)blockIdx.x * NT + threadIdx.x;
+  if(px >= npx) return;
+  const float4 v = __ldg(in + px);
+  const bool m = v.x > threshold || v.y > threshold || v.z > threshold;
+  mask[px] = m ? 1 : 0;
+  if(!m)
+  {
+    inpainted[px] = v;
+    return;
+  }
+  const f32m::tables_t tb = f32m::global_tables();
+  // the reference seeds from the FLOAT index k = 4*px and k / width (:1132-1136)
+  const size_t k = 4 * px;
+  const uint32_t i = (uint32_t)(k / width);
+  const uint32_t j = (uint32_t)(k - i);
+  uint32_t st[4] = { splitmix32((uint64_t)(uint32_t)(j + 1u)), splitmix32((uint64_t)(uint32_t)(j + 1u) * (uint64_t)(uint32_t)(i + 3u)), splitmix32(1337), splitmix32(666) };
+  xoshiro128plus(st);
+  xoshiro128plus(st);
+  xoshiro128plus(st);
+  xoshiro128plus(st);
+  const bool flip = (i % 2u) || (j % 2u);
+  float4 o;
+  o.x = fabsf(gaussian_noise(tb, v.x, v.x, flip, st));
+  o.y = fabsf(gaussian_noise(tb, v.y, v.y, flip, st));
+  o.z = fabsf(gaussian_noise(tb, v.z, v.z, flip, st));
+  o.w = fabsf(gaussian_noise(tb, v.w, v.w, flip, st));
+  inpainted[px] = o;
+}
+
+// heat_PDE_diffusion(), :760-953; mask == nullptr is has_mask == 0
 // R holds (HF/safe(LF))^2 of this band per float -- every pixel's term is needed by its nine neighbours, so it is
 // computed once where LF is produced (the previous, coarser PDE step or the last B-spline pass) instead of nine
 // times here: one IEEE division per float instead of nine.  HFnext/Rnext: the next finer band, whose LF is `out`.
 __global__ void __launch_bounds__(NT) heat_pde_kernel(const float *__restrict__ HF, const float *__restrict__ LF, const float *__restrict__ R,
-                                                      float *__restrict__ out, const float *__restrict__ HFnext, float *__restrict__ Rnext, int w4,
-                                                      int width, int height, int mult, const pde_t p)
+                                                      float *__restrict__ out, const float *__restrict__ HFnext, float *__restrict__ Rnext,
+                                                      const unsigned char *__restrict__ mask, int w4, int width, int height, int mult, const pde_t p)
 {
   const int x = blockIdx.x * NT + threadIdx.x, i = blockIdx.y;
   if(x >= w4) return;
   const int j = x >> 2, c = x & 3;
   const size_t rn[3] = { (size_t)w4 * max(i - mult, 0), (size_t)w4 * i, (size_t)w4 * min(i + mult, height - 1) };
+  if(mask && !mask[(size_t)i * width + j])
+  { // :938-947: outside the mask the band is only added back
+    const float o = max_zero(__ldg(HF + rn[1] + x) + __ldg(LF + rn[1] + x));
+    out[rn[1] + x] = o;
+    if(Rnext) Rnext[rn[1] + x] = ratio_sq(__ldg(HFnext + rn[1] + x), o);
+    return;
+  }
   const int cn[3] = { 4 * max(j - mult, 0) + c, x, 4 * min(j + mult, width - 1) + c };
   float hf[9], lf[9];
 #pragma unroll
@@ -220,8 +291,6 @@ static int check_df(const b200_piece_t *piece, const void *in, void *out)
   if(!piece || !in || !out) return fail(B200_ERR_ARG, "diffuse: NULL argument");
   if(!piece->data || piece->data_size < sizeof(b200_diffuse_data_t)) return fail(B200_ERR_ARG, "diffuse: piece->data is not a b200_diffuse_data_t");
   const b200_diffuse_data_t *d = (const b200_diffuse_data_t *)piece->data;
-  if(d->threshold > 0.f)
-    return fail(B200_ERR_UNSUPPORTED, "diffuse: the luminance mask / noise inpainting (threshold > 0) is not built");
   if(in == out) return fail(B200_ERR_ARG, "diffuse: in-place processing is not supported");
   if(piece->roi_in.width != piece->roi_out.width || piece->roi_in.height != piece->roi_out.height)
     return fail(B200_ERR_ARG, "diffuse: roi_in and roi_out differ in size");
@@ -244,12 +313,13 @@ extern "C" int b200_diffuse_process_dev(const b200_piece_t *piece, const void *d
   const int scales = scale_count(d, zoom);
 
   void *base = nullptr;
-  if((rc = scratch(SLOT_TMP0, (size_t)(scales + 7) * n * sizeof(float), &base))) return rc;
+  if((rc = scratch(SLOT_TMP0, (size_t)(scales + 7) * n * sizeof(float) + n / 4, &base))) return rc;
   float *p = (float *)base;
   float *HF[MAX_SCALES];
   for(int s = 0; s < scales; s++, p += n) HF[s] = p;
   float *const LF_odd = p, *const LF_even = p + n, *const temp1 = p + 2 * n, *const temp2 = p + 3 * n, *const vtmp = p + 4 * n;
   float *Rbuf[2] = { p + 5 * n, p + 6 * n }; // energy terms of the band being solved / of the next one
+  unsigned char *mask = nullptr;            // one byte per pixel, behind the float planes
 
   // wavelets_process() :985-1000, :1057-1075: per-call constants
   pde_t pde;
@@ -265,6 +335,14 @@ extern "C" int b200_diffuse_process_dev(const b200_piece_t *piece, const void *d
   const int w4 = 4 * width;
   const dim3 grid((w4 + NT - 1) / NT, height);        // PDE: one thread per float
   const dim3 grid_px((width + NT - 1) / NT, height);  // B-spline passes: one thread per pixel
+  if(d->threshold > 0.f)
+  { // :1207-1218: mask of the pixels above the threshold, noise-seeded start image in temp1
+    mask = (unsigned char *)(p + 7 * n);
+    const size_t npx = n / 4;
+    mask_inpaint_kernel<<<(unsigned)((npx + NT - 1) / NT), NT, 0, st>>>((const float4 *)d_in, (float4 *)temp1, mask, npx, (unsigned)width, d->threshold);
+    B200_CUDA_TRY(cudaGetLastError());
+    d_in = temp1;
+  }
   for(int it = 0; it < iterations; it++)
   {
     const float *temp_in = it == 0 ? (const float *)d_in : (it % 2 == 0 ? temp1 : temp2);
@@ -298,7 +376,7 @@ extern "C" int b200_diffuse_process_dev(const b200_piece_t *piece, const void *d
       const float *bin = count == 0 ? residual : (count % 2 != 0 ? temp : residual);
       float *bout = count == 0 ? temp : (count % 2 != 0 ? residual : temp);
       if(s == 0) bout = temp_out;
-      heat_pde_kernel<<<grid, NT, 0, st>>>(HF[s], bin, Rbuf[count & 1], bout, s > 0 ? HF[s - 1] : nullptr, s > 0 ? Rbuf[(count + 1) & 1] : nullptr, w4,
+      heat_pde_kernel<<<grid, NT, 0, st>>>(HF[s], bin, Rbuf[count & 1], bout, s > 0 ? HF[s - 1] : nullptr, s > 0 ? Rbuf[(count + 1) & 1] : nullptr, mask, w4,
                                            width, height, 1 << s, pde);
       count++;
     }

@@ -313,4 +313,51 @@ __device__ __forceinline__ float powf_(const tables_t &tb, float x, float y)
   kd -= EXP2_SHIFT_SCALED;
   return (float)exp2_tail(tb, ki, ki + sign_bias, ylogx - kd, EXP2_C0, EXP2_C1, EXP2_C2);
 }
+// ---- s_sinf.c / s_cosf.c / sincosf.h (reached through iop/noise_generator.h:93-96 with arguments 2*pi*u) ------
+// |x| < 120: the pi/4 polynomial and the single multiply-subtract reduction.  Larger arguments need glibc's
+// table-driven reduction, which nothing on this path calls: NaN, so a misuse shows.
+constexpr double SC_HPI_INV = 0x1.45F306DC9C883p+23, SC_HPI = 0x1.921FB54442D18p0;
+constexpr double SC_C1 = -0x1.ffffffd0c621cp-2, SC_C2 = 0x1.55553e1068f19p-5, SC_C3 = -0x1.6c087e89a359dp-10, SC_C4 = 0x1.99343027bf8c3p-16;
+constexpr double SC_S1 = -0x1.555545995a603p-3, SC_S2 = 0x1.1107605230bc4p-7, SC_S3 = -0x1.994eb3774cf24p-13;
+
+__device__ __forceinline__ uint32_t abstop12(float x) { return (__float_as_uint(x) >> 20) & 0x7ffu; }
+// sinf_poly(): sine polynomial for even n, cosine for odd; neg selects __sincosf_table[1]
+__device__ __forceinline__ float sinf_poly(double x, double x2, bool neg, int n)
+{
+  if((n & 1) == 0)
+  {
+    const double x3 = x * x2;
+    const double s1 = fma(x2, SC_S3, SC_S2);
+    const double x7 = x3 * x2;
+    const double s = fma(x3, SC_S1, x);
+    return (float)fma(x7, s1, s);
+  }
+  const double sg = neg ? -1.0 : 1.0;
+  const double x4 = x2 * x2;
+  const double c2 = fma(x2, sg * SC_C4, sg * SC_C3);
+  const double c1 = fma(x2, sg * SC_C1, sg);
+  const double x6 = x4 * x2;
+  const double c = fma(x4, sg * SC_C2, c1);
+  return (float)fma(x6, c2, c);
+}
+template <bool COS> __device__ __forceinline__ float sincosf_(float y)
+{
+  double x = (double)y;
+  if(abstop12(y) < abstop12(0x1.921FB6p-1f))
+  {
+    if(abstop12(y) < abstop12(0x1p-12f)) return COS ? 1.0f : y;
+    return sinf_poly(x, x * x, false, COS ? 1 : 0);
+  }
+  if(abstop12(y) < abstop12(120.0f))
+  {
+    const double r = x * SC_HPI_INV;
+    const int n = (__double2int_rz(r) + 0x800000) >> 24;
+    x = fma(-(double)n, SC_HPI, x);
+    const double s = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+    return sinf_poly(x * s, x * x, (n & 2) != 0, COS ? (n ^ 1) : n);
+  }
+  return CUDART_NAN_F;
+}
+__device__ __forceinline__ float sinf_(float y) { return sincosf_<false>(y); }
+__device__ __forceinline__ float cosf_(float y) { return sincosf_<true>(y); }
 } // namespace f32m

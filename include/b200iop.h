@@ -370,7 +370,7 @@ typedef struct b200_diffuse_data_t
   float regularization;     /* 0 */
   float variance_threshold; /* 0 */
   float anisotropy_first, anisotropy_second, anisotropy_third, anisotropy_fourth;
-  float threshold;          /* luminance masking threshold; > 0 (inpainting mask) is not built */
+  float threshold;          /* luminance masking threshold; > 0: only pixels above it are solved, from a noise-seeded start */
   float first, second, third, fourth;
   int radius_center;
 } b200_diffuse_data_t;
@@ -455,7 +455,9 @@ enum
   B200_FLT32_EXP2F = 1,
   B200_FLT32_LOGF = 2,
   B200_FLT32_LOG2F = 3,
-  B200_FLT32_POWF = 4
+  B200_FLT32_POWF = 4,
+  B200_FLT32_SINF = 5, /* |x| < 120 */
+  B200_FLT32_COSF = 6
 };
 int b200_flt32_eval_dev(int fn, const float *d_x, const float *d_y, float *d_out, size_t n, void *stream);
 

@@ -9,8 +9,9 @@
  * dt_fast_expf :254-267; system/simd.h: dt_simd_max_zero :107-114; develop/imageop.c:134-137.
  *
  * Pinned bit-for-bit against the reference's own process() cut verbatim out of diffuse.c (oracle/_ref,
- * ref_diffuse.c).  The luminance mask (threshold > 0: build_mask/inpaint_mask, a noise-seeded inpainting)
- * is not restated; such parameter sets return 2.
+ * ref_diffuse.c), the luminance mask included (threshold > 0: build_mask :1109-1119, inpaint_mask :1122-1152 with
+ * iop/noise_generator.h splitmix32 :36-43, xoshiro128plus :54-70, gaussian_noise :82-96 -- glibc logf/sinf/cosf
+ * through flt32_math.h).
  */
 #include "oracle_common.h"
 #include "flt32_math.h"
@@ -131,8 +132,67 @@ static inline void make_kernel(float c2, float cs, float cos2, float sin2, int t
   k[8] = b11;
 }
 
-/* heat_PDE_diffusion(), :760-953, has_mask == 0 */
-static void heat_pde(const float *HF, const float *LF, float *out, int width, int height, int mult, const pde_t *p)
+/* iop/noise_generator.h */
+static inline uint32_t splitmix32(const uint64_t seed)
+{ /* :36-43 */
+  uint64_t result = (seed ^ (seed >> 33)) * 0x62a9d9ed799705f5ul;
+  result = (result ^ (result >> 28)) * 0xcb24d0a5c88c35b3ul;
+  return (uint32_t)(result >> 32);
+}
+static inline float xoshiro128plus(uint32_t state[4])
+{ /* :54-70 */
+  const uint32_t result = state[0] + state[3];
+  const uint32_t t = state[1] << 9;
+  state[2] ^= state[0];
+  state[3] ^= state[1];
+  state[1] ^= state[2];
+  state[0] ^= state[3];
+  state[2] ^= t;
+  state[3] = (state[3] << 11) | (state[3] >> 21);
+  return (float)(result >> 8) * 0x1.0p-24f;
+}
+static inline float gaussian_noise(float mu, float sigma, int flip, uint32_t state[4])
+{ /* :82-96: Box-Muller; `2.f * M_PI * u2` is a double product rounded to float at the call */
+  const float u1 = fmaxf(xoshiro128plus(state), 1.17549435e-38f);
+  const float u2 = xoshiro128plus(state);
+  const float radius = sqrtf(-2.0f * f32m_logf(u1));
+  const float angle = (float)(2.0 * 3.14159265358979323846 * (double)u2);
+  const float noise = flip ? radius * f32m_cosf(angle) : radius * f32m_sinf(angle);
+  return noise * sigma + mu;
+}
+/* build_mask(), :1109-1119 */
+static void build_mask(const float *in, uint8_t *mask, float threshold, size_t npx)
+{
+  for(size_t k = 0; k < npx; k++) mask[k] = (in[4 * k] > threshold || in[4 * k + 1] > threshold || in[4 * k + 2] > threshold);
+}
+/* inpaint_mask(), :1122-1152: the seed mixes the FLOAT index k with k / width, as the reference writes it */
+static void inpaint_mask(float *inpainted, const float *original, const uint8_t *mask, size_t width, size_t height)
+{
+#pragma omp parallel
+  {
+    orc_fp_fast_mode();
+#pragma omp for
+    for(size_t k = 0; k < height * width * 4; k += 4)
+    {
+      if(mask[k / 4])
+      {
+        const uint32_t i = (uint32_t)(k / width);
+        const uint32_t j = (uint32_t)(k - i);
+        uint32_t state[4] = { splitmix32(j + 1), splitmix32((uint64_t)(j + 1) * (i + 3)), splitmix32(1337), splitmix32(666) };
+        xoshiro128plus(state);
+        xoshiro128plus(state);
+        xoshiro128plus(state);
+        xoshiro128plus(state);
+        for(int c = 0; c < 4; c++) inpainted[k + c] = fabsf(gaussian_noise(original[k + c], original[k + c], i % 2 || j % 2, state));
+      }
+      else
+        for(int c = 0; c < 4; c++) inpainted[k + c] = original[k + c];
+    }
+  }
+}
+
+/* heat_PDE_diffusion(), :760-953; mask == NULL is has_mask == 0 */
+static void heat_pde(const float *HF, const float *LF, const uint8_t *mask, float *out, int width, int height, int mult, const pde_t *p)
 {
 #pragma omp parallel
   {
@@ -152,6 +212,11 @@ static void heat_pde(const float *HF, const float *LF, float *out, int width, in
             lf[3 * ii + jj] = LF + 4 * (in[ii] + jn[jj]);
           }
         float *o = out + 4 * ((size_t)i * width + j);
+        if(mask && !mask[(size_t)i * width + j])
+        { /* :938-947: outside the mask the scale is only recombined */
+          for(int c = 0; c < 4; c++) o[c] = max_zero(hf[4][c] + lf[4][c]);
+          continue;
+        }
         for(int c = 0; c < 4; c++)
         {
           float energy = 0.f;
@@ -231,7 +296,6 @@ void orc_diffuse_plan(const b200_diffuse_data_t *d, float zoom, int scales, floa
 /* process(), :1155-1259 */
 int orc_diffuse(const float *in, float *out, int width, int height, const b200_diffuse_data_t *d, float iscale, float roi_scale)
 {
-  if(d->threshold > 0.f) return 2;
   const size_t n = (size_t)width * height * 4;
   const float zoom = iscale / roi_scale;
   const int iterations = imax((int)ceilf((float)d->iterations), 1);
@@ -248,6 +312,14 @@ int orc_diffuse(const float *in, float *out, int width, int height, const b200_d
   {
     p.anisotropy[k] = sqf(an[k]);
     p.isotropy[k] = an[k] == 0.f ? 0 : (an[k] > 0.f ? 1 : 2);
+  }
+  uint8_t *mask = NULL;
+  if(d->threshold > 0.f)
+  { /* :1207-1218 */
+    mask = malloc((size_t)width * height);
+    build_mask(in, mask, d->threshold, (size_t)width * height);
+    inpaint_mask(temp1, in, mask, (size_t)width, (size_t)height);
+    in = temp1;
   }
   for(int it = 0; it < iterations; it++)
   {
@@ -275,11 +347,12 @@ int orc_diffuse(const float *in, float *out, int width, int height, const b200_d
       const float *bin = count == 0 ? residual : (count % 2 != 0 ? temp : residual);
       float *bout = count == 0 ? temp : (count % 2 != 0 ? residual : temp);
       if(s == 0) bout = temp_out;
-      heat_pde(HF[s], bin, bout, width, height, 1 << s, &p);
+      heat_pde(HF[s], bin, mask, bout, width, height, 1 << s, &p);
       count++;
     }
   }
   for(int s = 0; s < scales; s++) free(HF[s]);
+  free(mask);
   free(temp1);
   free(temp2);
   free(LF_odd);

@@ -313,4 +313,85 @@ static inline float f32m_powf(float x, float y)
   e = e * s;
   return (float)e;
 }
+
+/* ---- sinf / cosf: sysdeps/ieee754/flt-32/{s_sinf.c,s_cosf.c,sincosf.h,s_sincosf_data.c} ---------------------
+ * Reached by the reference through iop/noise_generator.h:93-96 (Box-Muller), with arguments 2*pi*u, u in [0,1).
+ * Restated for |x| < 120 (the pi/4 polynomial and the single multiply-subtract reduction); the table-driven
+ * reduction of larger arguments is not needed on this path and returns NaN here so a misuse cannot go unnoticed.
+ * __sincosf_table cross-checked against the .rodata of this image's libm.so.6 (x86-64: TOINT_INTRINSICS 0). */
+#define F32M_SC_HPI_INV 0x1.45F306DC9C883p+23
+#define F32M_SC_HPI 0x1.921FB54442D18p0
+#define F32M_SC_C1 -0x1.ffffffd0c621cp-2
+#define F32M_SC_C2 0x1.55553e1068f19p-5
+#define F32M_SC_C3 -0x1.6c087e89a359dp-10
+#define F32M_SC_C4 0x1.99343027bf8c3p-16
+#define F32M_SC_S1 -0x1.555545995a603p-3
+#define F32M_SC_S2 0x1.1107605230bc4p-7
+#define F32M_SC_S3 -0x1.994eb3774cf24p-13
+
+static inline uint32_t f32m_abstop12(float x) { return (f32m_asuint(x) >> 20) & 0x7ff; }
+
+/* sinf_poly(): sine polynomial for even n, cosine for odd; `neg` selects __sincosf_table[1] (cosine coefficients negated) */
+static inline float f32m_sinf_poly(double x, double x2, int neg, int n)
+{
+  if((n & 1) == 0)
+  {
+    const double x3 = x * x2;
+    const double s1 = F32M_FMA(x2, F32M_SC_S3, F32M_SC_S2);
+    const double x7 = x3 * x2;
+    const double s = F32M_FMA(x3, F32M_SC_S1, x);
+    return (float)F32M_FMA(x7, s1, s);
+  }
+  const double sg = neg ? -1.0 : 1.0;
+  const double x4 = x2 * x2;
+  const double c2 = F32M_FMA(x2, sg * F32M_SC_C4, sg * F32M_SC_C3);
+  const double c1 = F32M_FMA(x2, sg * F32M_SC_C1, sg * 1.0);
+  const double x6 = x4 * x2;
+  const double c = F32M_FMA(x4, sg * F32M_SC_C2, c1);
+  return (float)F32M_FMA(x6, c2, c);
+}
+/* reduce_fast(): x - n*pi/2 with n = round(x * 2/pi), the quadrant */
+static inline double f32m_reduce_fast(double x, int *np)
+{
+  const double r = x * F32M_SC_HPI_INV;
+  const int n = ((int32_t)r + 0x800000) >> 24;
+  *np = n;
+  return F32M_FMA(-(double)n, F32M_SC_HPI, x);
+}
+static const double f32m_sc_sign[4] = { 1.0, -1.0, -1.0, 1.0 };
+
+static inline float f32m_sinf(float y)
+{
+  double x = y;
+  if(f32m_abstop12(y) < f32m_abstop12(0x1.921FB6p-1f))
+  {
+    if(f32m_abstop12(y) < f32m_abstop12(0x1p-12f)) return y;
+    return f32m_sinf_poly(x, x * x, 0, 0);
+  }
+  if(f32m_abstop12(y) < f32m_abstop12(120.0f))
+  {
+    int n;
+    x = f32m_reduce_fast(x, &n);
+    const double s = f32m_sc_sign[n & 3];
+    return f32m_sinf_poly(x * s, x * x, (n & 2) != 0, n);
+  }
+  return NAN;
+}
+static inline float f32m_cosf(float y)
+{
+  double x = y;
+  if(f32m_abstop12(y) < f32m_abstop12(0x1.921FB6p-1f))
+  {
+    if(f32m_abstop12(y) < f32m_abstop12(0x1p-12f)) return 1.0f;
+    return f32m_sinf_poly(x, x * x, 0, 1);
+  }
+  if(f32m_abstop12(y) < f32m_abstop12(120.0f))
+  {
+    int n;
+    x = f32m_reduce_fast(x, &n);
+    const double s = f32m_sc_sign[n & 3];
+    return f32m_sinf_poly(x * s, x * x, (n & 2) != 0, n ^ 1);
+  }
+  return NAN;
+}
 #endif

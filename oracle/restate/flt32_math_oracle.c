@@ -19,6 +19,8 @@ ARRAY1(orc_exp2f_array, f32m_exp2f)
 ARRAY1(orc_logf_array, f32m_logf)
 ARRAY1(orc_log2f_array, f32m_log2f)
 ARRAY2(orc_powf_array, f32m_powf)
+ARRAY1(orc_sinf_array, f32m_sinf)
+ARRAY1(orc_cosf_array, f32m_cosf)
 
 /* the system libm, called through volatile function pointers so nothing is folded or vectorised */
 static float (*volatile sys_expf)(float) = expf;
@@ -26,8 +28,12 @@ static float (*volatile sys_exp2f)(float) = exp2f;
 static float (*volatile sys_logf)(float) = logf;
 static float (*volatile sys_log2f)(float) = log2f;
 static float (*volatile sys_powf)(float, float) = powf;
+static float (*volatile sys_sinf)(float) = sinf;
+static float (*volatile sys_cosf)(float) = cosf;
 ARRAY1(sys_expf_array, sys_expf)
 ARRAY1(sys_exp2f_array, sys_exp2f)
 ARRAY1(sys_logf_array, sys_logf)
 ARRAY1(sys_log2f_array, sys_log2f)
 ARRAY2(sys_powf_array, sys_powf)
+ARRAY1(sys_sinf_array, sys_sinf)
+ARRAY1(sys_cosf_array, sys_cosf)

@@ -68,7 +68,7 @@ import ansel_b200 as ab  # noqa: E402
 import test_cpu_oracle_pin as pin  # noqa: E402
 img = util.hdr_rgba(140, 101, 41)
 np.savez_compressed(os.path.join(OUT, "diffuse.npz"), img=img,
-                    **{k: util.ref_diffuse(img, ab.diffuse_data(**pin._diffuse_cases()[k])) for k in ("sharpen_demosaic_aa", "gradient_sharpen")})
+                    **{k: util.ref_diffuse(img, ab.diffuse_data(**pin._diffuse_cases()[k])) for k in ("sharpen_demosaic_aa", "gradient_sharpen", "inpaint_highlights")})
 wp = util.profile_pair(util.REC2020_TO_XYZ_D50)
 rgb, lab = util.hdr_rgba(120, 80, 51), util.lab_scene(120, 80, 52)
 np.savez_compressed(os.path.join(OUT, "labglue.npz"), rgb=rgb, lab=lab, lab_of_rgb=util.ref_rgb_to_lab(rgb, wp), rgb_of_lab=util.ref_lab_to_rgb(lab, wp))

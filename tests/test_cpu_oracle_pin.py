@@ -1,5 +1,6 @@
 """CPU tests: the oracle against (a) the reference's own sources compiled here (oracle/_ref, when
 present) and (b) the committed golden vectors those sources produced (tests/golden, always)."""
+import ctypes as C
 import os
 
 import numpy as np
@@ -284,6 +285,8 @@ def _diffuse_cases():
     out["gradient_sharpen"] = dict(iterations=2, radius=16, radius_center=4, sharpness=0.3, regularization=3.0, variance_threshold=-1.0,
                                    anisotropy_first=-3.0, anisotropy_second=2.0, anisotropy_third=-0.5, anisotropy_fourth=5.0,
                                    first=0.3, second=-0.6, third=0.8, fourth=-1.0)
+    out["masked_all_orders"] = dict(iterations=2, radius=8, threshold=0.5, regularization=1.5, anisotropy_first=1.0, anisotropy_second=-1.0,
+                                    anisotropy_third=-2.0, anisotropy_fourth=3.0, first=0.5, second=0.3, third=-0.2, fourth=0.1)
     return out
 
 
@@ -301,8 +304,25 @@ def test_diffuse_oracle_equals_reference(name):
 def test_diffuse_oracle_equals_golden():
     import ansel_b200 as ab
     g = _golden("diffuse.npz")
-    for name in ("sharpen_demosaic_aa", "gradient_sharpen"):
+    for name in ("sharpen_demosaic_aa", "gradient_sharpen", "inpaint_highlights"):
         assert same_bits(util.oracle_diffuse(g["img"], ab.diffuse_data(**_diffuse_cases()[name])), g[name]).all()
+
+
+def test_libm_sinf_cosf_restatement_equals_system_libm():
+    """glibc sinf/cosf as iop/noise_generator.h:93-96 reaches them: EVERY argument the Box-Muller call can produce,
+    (float)(2*pi*k/2^24), plus a stride through all floats below 120."""
+    L = util.oracle()
+    FP = C.POINTER(C.c_float)
+
+    def run(fn, x):
+        out = np.empty_like(x)
+        getattr(L, fn)(x.ctypes.data_as(FP), out.ctypes.data_as(FP), C.c_size_t(x.size))
+        return out
+    k = np.arange(1 << 24, dtype=np.float64)
+    u = np.arange(0, 0x42F00000, 211, dtype=np.uint32)
+    for x in (((2.0 * np.pi) * (k * 2.0 ** -24)).astype(np.float32), np.concatenate([u.view(np.float32), (u | 0x80000000).view(np.float32)])):
+        for f in ("sinf", "cosf"):
+            assert (run(f"orc_{f}_array", x).view(np.uint32) == run(f"sys_{f}_array", x).view(np.uint32)).all(), f
 
 
 WORK_PROFILE = util.profile_pair(util.REC2020_TO_XYZ_D50)

@@ -57,7 +57,7 @@ def test_diffuse_zoom_changes_scale_count(built, zoom):
 def test_diffuse_golden_and_host_entry(built):
     import ansel_b200 as ab
     g = np.load(os.path.join(util.GOLDEN_DIR, "diffuse.npz"))
-    for name in ("sharpen_demosaic_aa", "gradient_sharpen"):
+    for name in ("sharpen_demosaic_aa", "gradient_sharpen", "inpaint_highlights"):
         d = ab.diffuse_data(**_diffuse_cases()[name])
         assert same_bits(cuda_diffuse(g["img"], d, host=True), g[name]).all()
 
@@ -103,10 +103,17 @@ def test_diffuse_45mp_properties(built):
     torch.cuda.empty_cache()
 
 
-def test_luminance_mask_is_refused(built):
+def test_luminance_mask_inpainting(built):
+    """threshold > 0: mask, Box-Muller noise start image (device glibc logf/sinf/cosf), masked PDE; full preset count"""
     import ansel_b200 as ab
-    ab.init()
-    piece = ab.make_piece(16, 16, filters=0, channels=4, data=ab.diffuse_data(threshold=1.0))
-    buf = np.zeros((16, 16, 4), np.float32)
-    out = np.zeros_like(buf)
-    assert ab.lib().b200_diffuse_process_host(C.byref(piece), buf.ctypes.data, out.ctypes.data) == ab.B200_ERR_UNSUPPORTED
+    d = ab.diffuse_data(**ab.DIFFUSE_PRESETS["inpaint_highlights"])
+    assert d.iterations == 32 and d.threshold > 0
+    img = (util.rgba_scene(200, 150, 4) * 2.5).astype(np.float32)
+    assert (img[..., :3] > d.threshold).any(-1).mean() > 0.02
+    assert same_bits(cuda_diffuse(img, d), util.oracle_diffuse(img, d)).all()
+    # a frame wide enough that the seed's float index passes 2^24, and one with every pixel masked
+    img = (util.rgba_scene(3000, 1500, 6) * 2.5).astype(np.float32)
+    d = ab.diffuse_data(**_diffuse_cases()["masked_all_orders"])
+    assert same_bits(cuda_diffuse(img, d), util.oracle_diffuse(img, d)).all()
+    img = np.full((40, 50, 4), 3.0, np.float32)
+    assert same_bits(cuda_diffuse(img, d), util.oracle_diffuse(img, d)).all()

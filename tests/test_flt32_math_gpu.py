@@ -66,3 +66,13 @@ def test_device_powf(built):
         tiny = (np.abs(x) < 1.2e-38) | (np.abs(y) < 1.2e-38) | (np.abs(b) < 1.2e-38) | (np.abs(a) < 1.2e-38)
         bad = ~same & ~tiny
         assert not bad.any(), f"{int(bad.sum())} mismatches, e.g. {x[bad][:3]} ^ {y[bad][:3]}: dev {a[bad][:3]} host {b[bad][:3]}"
+
+
+@pytest.mark.parametrize("fn,name", [(5, "sinf"), (6, "cosf")])
+def test_device_sinf_cosf(built, fn, name):
+    """every argument the Box-Muller call of iop/noise_generator.h can produce, plus random |x| < 120"""
+    rng = np.random.default_rng(23)
+    k = np.arange(1 << 24, dtype=np.float64)
+    x = np.ascontiguousarray(np.concatenate([((2.0 * np.pi) * (k * 2.0 ** -24)).astype(np.float32), rng.uniform(-119.9, 119.9, N).astype(np.float32),
+                                             np.array([0.0, -0.0, 1e-5, -1e-5, 0.7853981, 0.7853982], np.float32)]))
+    _assert_same(_device(fn, x), _host(name, x), x)
