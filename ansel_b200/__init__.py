@@ -121,6 +121,12 @@ class ProfileMatrices(C.Structure):
     _fields_ = [("matrix_in", (C.c_float * 4) * 3), ("matrix_out", (C.c_float * 4) * 3)]
 
 
+class ProfileCurves(C.Structure):
+    """b200_profile_curves_t: tone curves of a matrix profile (lut_in / lut_out, 65536 floats each, host memory)."""
+    _fields_ = [("lut_in", C.POINTER(C.c_float) * 3), ("lut_out", C.POINTER(C.c_float) * 3),
+                ("unbounded_coeffs_in", (C.c_float * 3) * 3), ("unbounded_coeffs_out", (C.c_float * 3) * 3), ("identity", C.c_uint64)]
+
+
 class B200Error(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libb200iop error {code}: {msg}")
@@ -352,6 +358,21 @@ CS_LAB, CS_RGB = 1, 2
 
 def nlmeans_data(radius: float = 2.0, strength: float = 50.0, luma: float = 0.5, chroma: float = 1.0) -> NlmeansData:
     return NlmeansData(radius, strength, luma, chroma)
+
+
+def profile_curves(lut_in, co_in, lut_out, co_out, identity: int = 0) -> ProfileCurves:
+    """lut_*: float32 arrays (3, 65536), kept alive on the returned struct; co_*: (3, 3) unbounded coefficients."""
+    import numpy as np
+    pc = ProfileCurves()
+    pc._keep = [np.ascontiguousarray(lut_in, np.float32), np.ascontiguousarray(lut_out, np.float32)]
+    for k in range(3):
+        pc.lut_in[k] = pc._keep[0][k].ctypes.data_as(C.POINTER(C.c_float))
+        pc.lut_out[k] = pc._keep[1][k].ctypes.data_as(C.POINTER(C.c_float))
+        for j in range(3):
+            pc.unbounded_coeffs_in[k][j] = float(co_in[k][j])
+            pc.unbounded_coeffs_out[k][j] = float(co_out[k][j])
+    pc.identity = identity
+    return pc
 
 
 def profile_matrices(matrix_in, matrix_out) -> ProfileMatrices:

@@ -19,12 +19,11 @@
 // --fmad=false, so the only fused operations are the explicit ones below.
 #include "runtime.h"
 #include "flt32_math.cuh"
+#include "trc.cuh"
 #include <mutex>
 
 namespace
 {
-constexpr int LUTN = B200_LUT_SAMPLES;
-
 struct conv_args_t
 {
   const float4 *in;
@@ -62,26 +61,6 @@ template <bool CONTRACT> __device__ __forceinline__ float4 mat4(const float *m, 
     o[i] = acc;
   }
   return make_float4(o[0], o[1], o[2], o[3]);
-}
-
-// extrapolate_lut(), iop_profile.h:536-545
-template <bool CONTRACT, bool DECODE_LOOP> __device__ __forceinline__ float lut_lerp(const float *lut, float v)
-{
-  const float scaled = v * (float)(LUTN - 1);
-  const float ft = scaled > 0.0f ? (scaled < (float)(LUTN - 1) ? scaled : (float)(LUTN - 1)) : 0.0f; // CLAMPS: NaN -> 0
-  const int t = (ft < (float)(LUTN - 2)) ? (int)ft : LUTN - 2;
-  const float f = ft - (float)t;
-  const float l1 = __ldg(lut + t), l2 = __ldg(lut + t + 1);
-  if(!CONTRACT) return __fadd_rn(__fmul_rn(l1, 1.0f - f), __fmul_rn(l2, f));
-  return DECODE_LOOP ? __fmaf_rn(l2, f, __fmul_rn(l1, 1.0f - f)) : __fmaf_rn(l1, 1.0f - f, __fmul_rn(l2, f));
-}
-
-// dt_ioppr_eval_trc(), iop_profile.h:577-580
-template <bool CONTRACT, bool DECODE_LOOP>
-__device__ __forceinline__ float eval_trc(const f32m::tables_t &tb, float x, const float *lut, const float *co)
-{
-  if(x < 1.0f) return lut_lerp<CONTRACT, DECODE_LOOP>(lut, x);
-  return co[1] * f32m::powf_(tb, x * co[0], co[2]);
 }
 
 __device__ __forceinline__ float clamp01(float v) { return v > 1.0f ? 1.0f : (v < 0.0f ? 0.0f : v); }
@@ -142,8 +121,10 @@ lut_entry_t g_luts[LUT_CACHE];
 unsigned long long g_stamp = 0;
 std::mutex g_lut_mu;
 
+} // namespace
+
 // returns a device pointer holding the three curves of one side (3*LUTN floats)
-int device_curves(const float *const host[3], uint64_t identity, int side, cudaStream_t stream, const float **out)
+int b200::device_curves(const float *const host[3], uint64_t identity, int side, cudaStream_t stream, const float **out)
 {
   using namespace b200;
   int dev = 0;
@@ -198,7 +179,6 @@ int device_curves(const float *const host[3], uint64_t identity, int side, cudaS
   *out = g_luts[slot].d;
   return B200_OK;
 }
-} // namespace
 
 using namespace b200;
 

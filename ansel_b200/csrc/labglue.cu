@@ -5,6 +5,7 @@
 // iop/nlmeans.c process_cpu :416-456, tiling_callback :400-414.
 // Pointwise, 32 B/px at the boundary: HBM-bound streaming kernels (float4 in, float4 out).
 #include "runtime.h"
+#include "trc.cuh"
 #include <math.h>
 
 namespace b200
@@ -73,6 +74,43 @@ __global__ void __launch_bounds__(256) lab_to_rgb_kernel(const float4 *__restric
   const float X = 0.9642f * lab_f_inv(fx), Y = 1.0f * lab_f_inv(fy), Z = 0.8249f * lab_f_inv(fz);
   out[k] = make_float4(row(M.m + 0, X, Y, Z), row(M.m + 3, X, Y, Z), row(M.m + 6, X, Y, Z), p.w);
 }
+// the same two conversions for a profile with tone curves (_apply_tonecurves :332-373): lut_in before the matrix,
+// lut_out after it, each only on the channels that have a curve (nullptr = linear channel)
+struct curves_t
+{
+  const float *lut[3];
+  float co[9];
+};
+__global__ void __launch_bounds__(256) rgb_to_lab_trc_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, size_t n, const m3_t M, const curves_t cv)
+{
+  const size_t k = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if(k >= n) return;
+  const f32m::tables_t tb = f32m::global_tables();
+  float4 p = in[k];
+  if(cv.lut[0]) p.x = eval_trc<false, true>(tb, p.x, cv.lut[0], cv.co + 0);
+  if(cv.lut[1]) p.y = eval_trc<false, true>(tb, p.y, cv.lut[1], cv.co + 3);
+  if(cv.lut[2]) p.z = eval_trc<false, true>(tb, p.z, cv.lut[2], cv.co + 6);
+  const float fx = lab_f(divc(row(M.m + 0, p.x, p.y, p.z), 0.9642f));
+  const float fy = lab_f(row(M.m + 3, p.x, p.y, p.z));
+  const float fz = lab_f(divc(row(M.m + 6, p.x, p.y, p.z), 0.8249f));
+  out[k] = make_float4(116.0f * fy - 16.0f, 500.0f * (fx - fy), 200.0f * (fy - fz), p.w);
+}
+__global__ void __launch_bounds__(256) lab_to_rgb_trc_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, size_t n, const m3_t M, const curves_t cv)
+{
+  const size_t k = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if(k >= n) return;
+  const f32m::tables_t tb = f32m::global_tables();
+  const float4 p = in[k];
+  const float fy = divc(p.x + 16.0f, 116.0f);
+  const float fx = divc(p.y, 500.0f) + fy;
+  const float fz = fy - divc(p.z, 200.0f);
+  const float X = 0.9642f * lab_f_inv(fx), Y = 1.0f * lab_f_inv(fy), Z = 0.8249f * lab_f_inv(fz);
+  float4 o = make_float4(row(M.m + 0, X, Y, Z), row(M.m + 3, X, Y, Z), row(M.m + 6, X, Y, Z), p.w);
+  if(cv.lut[0]) o.x = eval_trc<false, false>(tb, o.x, cv.lut[0], cv.co + 0);
+  if(cv.lut[1]) o.y = eval_trc<false, false>(tb, o.y, cv.lut[1], cv.co + 3);
+  if(cv.lut[2]) o.z = eval_trc<false, false>(tb, o.z, cv.lut[2], cv.co + 6);
+  out[k] = o;
+}
 __global__ void copy_alpha_kernel2(const float4 *__restrict__ in, float4 *__restrict__ out, size_t n)
 {
   const size_t k = (size_t)blockIdx.x * 256 + threadIdx.x;
@@ -82,8 +120,26 @@ __global__ void copy_alpha_kernel2(const float4 *__restrict__ in, float4 *__rest
 
 using namespace b200;
 
+static int transform(const void *d_in, void *d_out, int width, int height, int cst_from, int cst_to, const b200_profile_matrices_t *wp,
+                     const b200_profile_curves_t *curves, int nonlinearlut, void *stream);
 extern "C" int b200_colorspace_transform_dev(const void *d_in, void *d_out, int width, int height, int cst_from, int cst_to,
                                              const b200_profile_matrices_t *wp, int nonlinearlut, void *stream)
+{
+  return transform(d_in, d_out, width, height, cst_from, cst_to, wp, nullptr, nonlinearlut, stream);
+}
+extern "C" int b200_colorspace_transform_trc_dev(const void *d_in, void *d_out, int width, int height, int cst_from, int cst_to,
+                                                 const b200_profile_matrices_t *wp, const b200_profile_curves_t *curves, void *stream)
+{
+  if(!curves) return fail(B200_ERR_ARG, "colorspace_transform_trc: NULL curves");
+  for(int k = 0; k < 3; k++)
+    if(!curves->lut_in[k] || !curves->lut_out[k]) return fail(B200_ERR_ARG, "colorspace_transform_trc: NULL curve");
+  // dt_ioppr_init_unbounded_coeffs, iop_profile.c:303-329: the flag counts the INPUT curves only and gates both directions
+  int nonlinearlut = 0;
+  for(int k = 0; k < 3; k++) nonlinearlut += curves->lut_in[k][0] >= 0.0f;
+  return transform(d_in, d_out, width, height, cst_from, cst_to, wp, nonlinearlut ? curves : nullptr, 0, stream);
+}
+static int transform(const void *d_in, void *d_out, int width, int height, int cst_from, int cst_to, const b200_profile_matrices_t *wp,
+                     const b200_profile_curves_t *curves, int nonlinearlut, void *stream)
 {
   if(!d_in || !d_out || !wp) return fail(B200_ERR_ARG, "colorspace_transform: NULL argument");
   if(width <= 0 || height <= 0) return B200_OK;
@@ -94,7 +150,7 @@ extern "C" int b200_colorspace_transform_dev(const void *d_in, void *d_out, int 
     if(d_in != d_out) B200_CUDA_TRY(cudaMemcpyAsync(d_out, d_in, n * 16, cudaMemcpyDeviceToDevice, s));
     return B200_OK;
   }
-  if(nonlinearlut) return fail(B200_ERR_UNSUPPORTED, "colorspace_transform: work profiles with tone curves are not built");
+  if(nonlinearlut) return fail(B200_ERR_UNSUPPORTED, "colorspace_transform: a work profile with tone curves goes through b200_colorspace_transform_trc_dev");
   if(isnan(wp->matrix_in[0][0]) || isnan(wp->matrix_out[0][0]))
     return fail(B200_ERR_UNSUPPORTED, "colorspace_transform: not a matrix profile (the reference falls back to lcms2)");
   m3_t M;
@@ -103,13 +159,41 @@ extern "C" int b200_colorspace_transform_dev(const void *d_in, void *d_out, int 
   {
     for(int i = 0; i < 3; i++)
       for(int j = 0; j < 3; j++) M.m[3 * i + j] = wp->matrix_in[i][j];
-    rgb_to_lab_kernel<<<grid, 256, 0, s>>>((const float4 *)d_in, (float4 *)d_out, n, M);
+    if(curves)
+    {
+      curves_t cv;
+      const float *d = nullptr;
+      int rc = device_curves(curves->lut_in, curves->identity, 2, s, &d);
+      if(rc) return rc;
+      for(int k = 0; k < 3; k++)
+      {
+        cv.lut[k] = curves->lut_in[k][0] >= 0.0f ? d + (size_t)k * B200_LUT_SAMPLES : nullptr;
+        for(int j = 0; j < 3; j++) cv.co[3 * k + j] = curves->unbounded_coeffs_in[k][j];
+      }
+      rgb_to_lab_trc_kernel<<<grid, 256, 0, s>>>((const float4 *)d_in, (float4 *)d_out, n, M, cv);
+    }
+    else
+      rgb_to_lab_kernel<<<grid, 256, 0, s>>>((const float4 *)d_in, (float4 *)d_out, n, M);
   }
   else if(cst_from == B200_CS_LAB && cst_to == B200_CS_RGB)
   {
     for(int i = 0; i < 3; i++)
       for(int j = 0; j < 3; j++) M.m[3 * i + j] = wp->matrix_out[i][j];
-    lab_to_rgb_kernel<<<grid, 256, 0, s>>>((const float4 *)d_in, (float4 *)d_out, n, M);
+    if(curves)
+    {
+      curves_t cv;
+      const float *d = nullptr;
+      int rc = device_curves(curves->lut_out, curves->identity, 3, s, &d);
+      if(rc) return rc;
+      for(int k = 0; k < 3; k++)
+      {
+        cv.lut[k] = curves->lut_out[k][0] >= 0.0f ? d + (size_t)k * B200_LUT_SAMPLES : nullptr;
+        for(int j = 0; j < 3; j++) cv.co[3 * k + j] = curves->unbounded_coeffs_out[k][j];
+      }
+      lab_to_rgb_trc_kernel<<<grid, 256, 0, s>>>((const float4 *)d_in, (float4 *)d_out, n, M, cv);
+    }
+    else
+      lab_to_rgb_kernel<<<grid, 256, 0, s>>>((const float4 *)d_in, (float4 *)d_out, n, M);
   }
   else
     return fail(B200_ERR_ARG, "colorspace_transform: invalid conversion from %d to %d", cst_from, cst_to); // :594

@@ -51,4 +51,8 @@ int copy_d2h(void *dst, const void *src, size_t bytes, cudaStream_t stream);
 
 // per-thread non-blocking stream used by the *_process_host entry points
 int host_stream(cudaStream_t *s);
+
+// Device copy of three tone curves (3 * B200_LUT_SAMPLES floats), cached per device by `identity` and `side`
+// (0 = decoding / source, 1 = encoding / target); identity 0 = upload every time.  color.cu.
+int device_curves(const float *const host[3], uint64_t identity, int side, cudaStream_t stream, const float **out);
 } // namespace b200

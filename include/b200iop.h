@@ -400,8 +400,9 @@ void b200_nlmeans_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
 /* ---- RGB <-> Lab between modules of different colour space ------------------------------------------
  * dt_colorspaces_apply_profile(), colorprofiles/iop_profile.c:1300-1359 -> dt_ioppr_transform_matrix :566-596
  * -> _transform_rgb_to_lab_matrix :376-420 / _transform_lab_to_rgb_matrix :422-464, for the pipe's work
- * profile.  Built for linear work profiles (nonlinearlut == 0: linear Rec2020, the default, and every other
- * "linear ..." built-in); a work profile with tone curves returns B200_ERR_UNSUPPORTED.
+ * profile.  b200_colorspace_transform_dev is the linear-profile call (nonlinearlut == 0: linear Rec2020, the default,
+ * and every other "linear ..." built-in; nonlinearlut != 0 is refused there); a work profile with tone curves goes
+ * through b200_colorspace_transform_trc_dev with its curves (_apply_tonecurves :332-373).
  * cst: dt_iop_colorspace_type_t (pixel/format.h): 1 = IOP_CS_LAB, 2 = IOP_CS_RGB.  d_in == d_out allowed.
  * RGB -> Lab leaves lane 3 as the reference does (not written: in place it keeps the pixel's alpha, which is
  * what this entry stores); Lab -> RGB copies the input alpha. */
@@ -409,6 +410,23 @@ void b200_nlmeans_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
 #define B200_CS_RGB 2
 int b200_colorspace_transform_dev(const void *d_in, void *d_out, int width, int height, int cst_from, int cst_to,
                                   const b200_profile_matrices_t *work_profile, int nonlinearlut, void *stream);
+/* Tone curves of a matrix profile, dt_iop_order_iccprofile_info_t (colorprofiles/iop_profile.h:137-156): lut_in /
+ * lut_out are host arrays of B200_LUT_SAMPLES floats (lutsize 65536, the only size the reference uses), lut[k][0] < 0
+ * marks channel k linear; unbounded_coeffs_* are the {a, b, c} of b * (a x)^c past 1.0.  As in the reference the
+ * profile counts as non-linear by its INPUT curves alone (dt_ioppr_init_unbounded_coeffs, iop_profile.c:303-329):
+ * with three linear lut_in the call equals the linear one whatever lut_out holds.  RGB -> Lab: a channel without a
+ * curve and lane 3 keep the pixel's values (the reference's in-place behaviour).  identity != 0 caches the device
+ * copy of the curves. */
+typedef struct b200_profile_curves_t
+{
+  const float *lut_in[3];
+  const float *lut_out[3];
+  float unbounded_coeffs_in[3][3];
+  float unbounded_coeffs_out[3][3];
+  uint64_t identity;
+} b200_profile_curves_t;
+int b200_colorspace_transform_trc_dev(const void *d_in, void *d_out, int width, int height, int cst_from, int cst_to,
+                                      const b200_profile_matrices_t *work_profile, const b200_profile_curves_t *curves, void *stream);
 
 /* ---- sharding one frame over several GPUs ---------------------------------------
  * Row bands = full-width tiles of the reference's tiling engine (src/develop/tiling.c:723-1075).

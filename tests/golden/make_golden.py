@@ -71,7 +71,10 @@ np.savez_compressed(os.path.join(OUT, "diffuse.npz"), img=img,
                     **{k: util.ref_diffuse(img, ab.diffuse_data(**pin._diffuse_cases()[k])) for k in ("sharpen_demosaic_aa", "gradient_sharpen", "inpaint_highlights")})
 wp = util.profile_pair(util.REC2020_TO_XYZ_D50)
 rgb, lab = util.hdr_rgba(120, 80, 51), util.lab_scene(120, 80, 52)
-np.savez_compressed(os.path.join(OUT, "labglue.npz"), rgb=rgb, lab=lab, lab_of_rgb=util.ref_rgb_to_lab(rgb, wp), rgb_of_lab=util.ref_lab_to_rgb(lab, wp))
+sp = util.profile_pair(util.SRGB_TO_XYZ_D50)
+dec, cdec, enc, cenc = pin._srgb_curves(False)
+np.savez_compressed(os.path.join(OUT, "labglue.npz"), rgb=rgb, lab=lab, lab_of_rgb=util.ref_rgb_to_lab(rgb, wp), rgb_of_lab=util.ref_lab_to_rgb(lab, wp),
+                    lab_of_rgb_trc=util.ref_rgb_to_lab_trc(rgb, sp, dec, cdec, enc, cenc), rgb_of_lab_trc=util.ref_lab_to_rgb_trc(lab, sp, dec, cdec, enc, cenc))
 rgba = util.hdr_rgba(90, 70, 61)
 mos = util.frame_natural(128, 96, 62, iso=400.0)
 np.savez_compressed(os.path.join(OUT, "demosaic_extra.npz"), rgba=rgba, mosaic=mos, smoothed2=util.ref_color_smoothing(rgba, 2),

@@ -344,6 +344,36 @@ def test_lab_glue_oracle_equals_golden():
     g = _golden("labglue.npz")
     assert same_bits(util.oracle_rgb_to_lab(g["rgb"], WORK_PROFILE), g["lab_of_rgb"]).all()
     assert same_bits(util.oracle_lab_to_rgb(g["lab"], WORK_PROFILE), g["rgb_of_lab"]).all()
+    d, cd, e, ce = _srgb_curves(False)
+    assert same_bits(util.oracle_rgb_to_lab_trc(g["rgb"], SRGB_PROFILE, d, cd), g["lab_of_rgb_trc"]).all()
+    assert same_bits(util.oracle_lab_to_rgb_trc(g["lab"], SRGB_PROFILE, e, ce), g["rgb_of_lab_trc"]).all()
+
+
+SRGB_PROFILE = util.profile_pair(util.SRGB_TO_XYZ_D50)
+
+
+def _srgb_curves(partial):
+    """the sRGB TRC as lut_in (decode) / lut_out (encode); partial: one channel of each marked linear"""
+    d, e = util.srgb_decode_lut(), util.srgb_encode_lut()
+    if partial:
+        d[1, 0] = -1.0
+        e[2, 0] = -1.0
+    return d, util.fit_unbounded_coeffs(d), e, util.fit_unbounded_coeffs(e)
+
+
+@need_ref
+@pytest.mark.parametrize("partial", [False, True])
+def test_lab_glue_with_tone_curves_oracle_equals_reference(partial):
+    """_apply_tonecurves + the two matrix loops cut verbatim, for a profile with tone curves (sRGB)"""
+    d, cd, e, ce = _srgb_curves(partial)
+    rgb, lab = util.hdr_rgba(333, 217, 6), util.lab_scene(333, 217, 6)
+    assert same_bits(util.oracle_rgb_to_lab_trc(rgb, SRGB_PROFILE, d, cd), util.ref_rgb_to_lab_trc(rgb, SRGB_PROFILE, d, cd, e, ce)).all()
+    assert same_bits(util.oracle_lab_to_rgb_trc(lab, SRGB_PROFILE, e, ce), util.ref_lab_to_rgb_trc(lab, SRGB_PROFILE, d, cd, e, ce)).all()
+    # the flag comes from the input curves alone: three linear lut_in switch the output curves off as well
+    d[:, 0] = -1.0
+    cd = util.fit_unbounded_coeffs(d)
+    assert same_bits(util.ref_lab_to_rgb_trc(lab, SRGB_PROFILE, d, cd, e, ce), util.ref_lab_to_rgb(lab, SRGB_PROFILE)).all()
+    assert same_bits(util.ref_rgb_to_lab_trc(rgb, SRGB_PROFILE, d, cd, e, ce), util.ref_rgb_to_lab(rgb, SRGB_PROFILE)).all()
 
 
 @need_ref

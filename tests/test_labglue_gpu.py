@@ -61,6 +61,51 @@ def test_golden_and_dispatch(built):
     assert cuda_transform(g["rgb"], 0, ab.CS_LAB)[0] == ab.B200_ERR_ARG              # "invalid conversion", :594
 
 
+def cuda_transform_trc(img, cst_from, cst_to, curves, inplace=False):
+    import torch
+    import ansel_b200 as ab
+    ab.init()
+    h, w = img.shape[:2]
+    pm = ab.profile_matrices(*util.profile_pair(util.SRGB_TO_XYZ_D50))
+    d_in = torch.from_numpy(np.ascontiguousarray(img)).cuda()
+    d_out = d_in if inplace else d_in.clone()        # a channel without a curve and lane 3 keep the pixel (in-place behaviour)
+    f = ab.lib().b200_colorspace_transform_trc_dev
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(ab.ProfileMatrices), C.POINTER(ab.ProfileCurves), C.c_void_p]
+    rc = f(d_in.data_ptr(), d_out.data_ptr(), w, h, cst_from, cst_to, C.byref(pm), C.byref(curves), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return rc, d_out.cpu().numpy()
+
+
+@pytest.mark.parametrize("partial", [False, True])
+@pytest.mark.parametrize("inplace", [False, True])
+def test_glue_with_tone_curves_bit_exact(built, partial, inplace):
+    """a work profile with tone curves (sRGB): lut_in before the matrix, lut_out after it, per channel"""
+    import ansel_b200 as ab
+    from test_cpu_oracle_pin import _srgb_curves, SRGB_PROFILE
+    d, cd, e, ce = _srgb_curves(partial)
+    cv = ab.profile_curves(d, cd, e, ce, identity=0x51 + partial)
+    rgb, lab = util.hdr_rgba(1000, 700, 6), util.lab_scene(1000, 700, 6)
+    rc, got = cuda_transform_trc(rgb, ab.CS_RGB, ab.CS_LAB, cv, inplace)
+    assert rc == 0 and same_bits(got, util.oracle_rgb_to_lab_trc(rgb, SRGB_PROFILE, d, cd)).all()
+    rc, got = cuda_transform_trc(lab, ab.CS_LAB, ab.CS_RGB, cv, inplace)
+    assert rc == 0 and same_bits(got, util.oracle_lab_to_rgb_trc(lab, SRGB_PROFILE, e, ce)).all()
+
+
+def test_glue_tone_curves_golden_and_flag(built):
+    import ansel_b200 as ab
+    from test_cpu_oracle_pin import _srgb_curves, SRGB_PROFILE
+    g = np.load(os.path.join(util.GOLDEN_DIR, "labglue.npz"))
+    d, cd, e, ce = _srgb_curves(False)
+    cv = ab.profile_curves(d, cd, e, ce)
+    assert same_bits(cuda_transform_trc(g["rgb"], ab.CS_RGB, ab.CS_LAB, cv)[1][..., :3], g["lab_of_rgb_trc"][..., :3]).all()
+    assert same_bits(cuda_transform_trc(g["lab"], ab.CS_LAB, ab.CS_RGB, cv)[1], g["rgb_of_lab_trc"]).all()
+    # three linear input curves: the profile counts as linear and lut_out is ignored (iop_profile.c:303-329)
+    d[:, 0] = -1.0
+    cv = ab.profile_curves(d, util.fit_unbounded_coeffs(d), e, ce)
+    rc, got = cuda_transform_trc(g["lab"], ab.CS_LAB, ab.CS_RGB, cv)
+    assert rc == 0 and same_bits(got, util.oracle_lab_to_rgb(g["lab"], SRGB_PROFILE)).all()
+
+
 def test_round_trip_45mp(built):
     """full size: RGB -> Lab -> RGB returns the in-gamut input to ~1e-5 (Halley cube root, one step)."""
     import ansel_b200 as ab

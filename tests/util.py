@@ -603,6 +603,40 @@ def ref_lab_to_rgb(img, work, kind="strict"):
     return None if lib is None else _glue(lib, "ref_lab_to_rgb", img, work, 2)
 
 
+def _glue_trc(lib, fn, img, mats, luts, coeffs):
+    """luts / coeffs: one (3 x 65536, 3 x 3) pair per argument the entry takes, in order"""
+    h, w = img.shape[:2]
+    src = aligned_empty(img.shape)
+    src[...] = img
+    out = aligned_empty(img.shape)
+    out[...] = img            # in place is how the pipe calls it: unwritten lanes keep the pixel
+    f = getattr(lib, fn)
+    f.restype = C.c_int
+    m = [(C.c_float * 9)(*np.asarray(x, np.float32).reshape(-1)) for x in mats]
+    keep = [np.ascontiguousarray(x, np.float32) for x in luts]
+    co = [(C.c_float * 9)(*np.asarray(x, np.float32).reshape(-1)) for x in coeffs]
+    assert f(fptr(src), fptr(out), w, h, *m, *[fptr(x) for x in keep], *co) == 0
+    return np.array(out)
+
+
+def oracle_rgb_to_lab_trc(img, work, lut_in, co_in):
+    return _glue_trc(oracle(), "orc_rgb_to_lab_trc", img, (work[0],), (lut_in,), (co_in,))
+
+
+def oracle_lab_to_rgb_trc(img, work, lut_out, co_out):
+    return _glue_trc(oracle(), "orc_lab_to_rgb_trc", img, (work[1],), (lut_out,), (co_out,))
+
+
+def ref_rgb_to_lab_trc(img, work, lut_in, co_in, lut_out, co_out, kind="strict"):
+    lib = ref(kind)
+    return None if lib is None else _glue_trc(lib, "ref_rgb_to_lab_trc", img, work, (lut_in, lut_out), (co_in, co_out))
+
+
+def ref_lab_to_rgb_trc(img, work, lut_in, co_in, lut_out, co_out, kind="strict"):
+    lib = ref(kind)
+    return None if lib is None else _glue_trc(lib, "ref_lab_to_rgb_trc", img, work, (lut_in, lut_out), (co_in, co_out))
+
+
 def oracle_nlmeans_iop(img, data, roi_scale=1.0, decimate=0, mask_display=0):
     h, w = img.shape[:2]
     src = aligned_empty(img.shape)
