@@ -307,7 +307,7 @@ extern "C" int b200_diffuse_process_dev(const b200_piece_t *piece, const void *d
   const int width = piece->roi_out.width, height = piece->roi_out.height;
   if(width <= 0 || height <= 0) return B200_OK;
   const size_t n = (size_t)width * height * 4;
-  const float zoom = piece->iscale / (float)piece->roi_in.scale; // dt_dev_get_module_scale, develop/imageop.c:134-137
+  const float zoom = (float)((double)piece->iscale / piece->roi_in.scale); // dt_dev_get_module_scale, develop/imageop.c:134-137 (double division)
   const int it_f = (int)ceilf((float)d->iterations);
   const int iterations = it_f > 1 ? it_f : 1;
   const int scales = scale_count(d, zoom);
@@ -408,7 +408,7 @@ extern "C" void b200_diffuse_tiling(const b200_piece_t *piece, b200_tiling_t *ti
 {
   if(!piece || !tiling || !piece->data) return;
   const b200_diffuse_data_t *d = (const b200_diffuse_data_t *)piece->data;
-  const float zoom = piece->iscale / (float)piece->roi_in.scale;
+  const float zoom = (float)((double)piece->iscale / piece->roi_in.scale);
   const int scales = scale_count(d, zoom);
   tiling->factor = 6.0625f + scales;
   tiling->factor_cl = 6.0625f + scales;

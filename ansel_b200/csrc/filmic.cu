@@ -683,9 +683,13 @@ static int check_fl(const b200_piece_t *piece, const void *in, void *out)
     return fail(B200_ERR_ARG, "filmicrgb: piece->data is not a b200_filmicrgb_piece_t");
   const b200_filmicrgb_data_t *d = &((const b200_filmicrgb_piece_t *)piece->data)->data;
   if(d->version < 0 || d->version > 9) return fail(B200_ERR_ARG, "filmicrgb: colour science %d", d->version);
-  if(!d->hl_deprecated)
-    return fail(B200_ERR_UNSUPPORTED, "filmicrgb: the deprecated highlight reconstruction is not built (SURVEY.md 8a16)");
   return B200_OK;
+}
+
+namespace b200
+{
+int filmic_reconstruct_dev(const b200_piece_t *piece, const b200_filmicrgb_data_t *d, const float *d_in, const float **d_use, cudaStream_t st);
+int filmic_reconstruct_scales(const b200_piece_t *piece);
 }
 
 extern "C" int b200_filmicrgb_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream)
@@ -717,6 +721,12 @@ extern "C" int b200_filmicrgb_process_dev(const b200_piece_t *piece, const void 
   a.copy_alpha = (piece->mask_display & B200_DISPLAY_MASK) ? 1 : 0;
   const size_t npx = (size_t)piece->roi_out.width * piece->roi_out.height;
   if(!npx) return B200_OK;
+  if(!d->hl_deprecated)
+  { // :2729-2838: edits that still carry a reconstruction threshold get their clipped highlights inpainted first
+    const float *use = (const float *)d_in;
+    if((rc = filmic_reconstruct_dev(piece, d, (const float *)d_in, &use, (cudaStream_t)stream))) return rc;
+    d_in = use;
+  }
   a.version = d->version;
   a.preserve_color = d->preserve_color;
   a.saturation = d->saturation;
@@ -751,11 +761,11 @@ extern "C" int b200_filmicrgb_process_host(const b200_piece_t *piece, const void
   return B200_OK;
 }
 
-// tiling_callback(), filmicrgb.c:2668-2704 with the reconstruction deprecated: in + out, no overlap
+// tiling_callback(), filmicrgb.c:2668-2704
 extern "C" void b200_filmicrgb_tiling(const b200_piece_t *piece, b200_tiling_t *tiling)
 {
   if(!piece || !tiling) return;
-  tiling->factor = 2.0f;
+  tiling->factor = 2.0f; // reconstruction deprecated (every new edit): in + out, pointwise
   tiling->factor_cl = 2.0f;
   tiling->maxbuf = 1.0f;
   tiling->maxbuf_cl = 1.0f;
@@ -763,4 +773,10 @@ extern "C" void b200_filmicrgb_tiling(const b200_piece_t *piece, b200_tiling_t *
   tiling->overlap = 0;
   tiling->xalign = 1;
   tiling->yalign = 1;
+  if(!piece->data || piece->data_size < sizeof(b200_filmicrgb_piece_t)) return;
+  const b200_filmicrgb_data_t *d = &((const b200_filmicrgb_piece_t *)piece->data)->data;
+  if(d->hl_deprecated) return;
+  tiling->factor = 9.0f; // in + out + 2 * tmp + 2 * LF + 2 * temp + ratios
+  tiling->factor_cl = 9.0f;
+  tiling->overlap = 1u << filmic_reconstruct_scales(piece);
 }

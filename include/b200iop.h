@@ -330,9 +330,11 @@ typedef struct b200_filmicrgb_piece_t
 
 /* process(), filmicrgb.c:2707-2895.  Built: every colour science -- the AgX family (version 5..9, :2495-2587) and the
  * earlier ones (0..4: filmic_split/chroma_v1, _v2_v3, _v4, filmic_v5, :1534-1737,2153-2299) with any chroma-preservation
- * norm -- with the highlight reconstruction at its deprecation sentinel (hl_deprecated, the default).  The legacy
- * wavelet highlight reconstruction returns B200_ERR_UNSUPPORTED; so does a work profile with tone curves
- * (the luminance norm then needs its LUTs). */
+ * norm -- and, for edits that still carry a reconstruction threshold (hl_deprecated == 0; off by default), the wavelet
+ * highlight reconstruction in front of them (:1201-1532, 2729-2838; reads piece->buf_in_*, iscale and roi_in.scale
+ * for its scale count, and synchronises the stream once to learn whether anything is clipped).  The display of the
+ * clipping mask is GUI state and stays in the reference.  A work profile with tone curves is not representable in
+ * b200_profile_matrices_t (the luminance norm then needs its LUTs). */
 int b200_filmicrgb_process_host(const b200_piece_t *piece, const void *in, void *out);
 int b200_filmicrgb_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
 /* tiling_callback(), filmicrgb.c:2668-2704 */

@@ -210,3 +210,60 @@ int ref_filmic_legacy(const float *in, float *out, size_t width, size_t height, 
   free(data_);
   return rc;
 }
+
+/* The highlight reconstruction in front of the tone mapping, process() filmicrgb.c:2729-2838, replayed on the cut
+ * functions (mask_clipped_pixels :1201, inpaint_noise :1230, reconstruct_highlights :1430, compute_ratios :2604,
+ * restore_ratios :2622).  Returns 1 with the reconstructed frame in `out`, 0 when fewer than 10 pixels are clipped
+ * (out = in: tone mapping reads the input), -1 on allocation failure.  mask_out (optional): the clipping mask. */
+int ref_filmic_reconstruct(const float *in, float *out, float *mask_out, size_t width, size_t height, const void *data, float iscale,
+                           double roi_scale, int buf_w, int buf_h)
+{
+  dt_iop_filmicrgb_data_t *data_ = aligned_alloc(64, ((sizeof(dt_iop_filmicrgb_data_t) + 63) / 64) * 64);
+  memcpy(data_, data, sizeof(*data_));
+  const dt_iop_filmicrgb_data_t *const d = data_;
+  dt_dev_pixelpipe_t pipe_ = { DT_DEV_PIXELPIPE_EXPORT, iscale };
+  const dt_dev_pixelpipe_t *const pipe = &pipe_;
+  dt_dev_pixelpipe_iop_t piece_;
+  memset(&piece_, 0, sizeof(piece_));
+  piece_.data = data_;
+  piece_.buf_in = (dt_iop_roi_t){ 0, 0, buf_w, buf_h, 1.0 };
+  piece_.buf_out = piece_.buf_in;
+  const dt_dev_pixelpipe_iop_t *const piece = &piece_;
+  dt_iop_roi_t roi = { 0, 0, (int)width, (int)height, roi_scale };
+  const dt_iop_roi_t *const roi_in = &roi, *const roi_out = &roi;
+  const size_t ch = 4, npx = width * height;
+  int rc = 0;
+  float *mask = aligned_alloc(64, ((npx * sizeof(float) + 63) / 64) * 64);
+  float *inpainted = aligned_alloc(64, npx * 4 * sizeof(float));
+  float *norms = aligned_alloc(64, ((npx * sizeof(float) + 63) / 64) * 64);
+  float *ratios = aligned_alloc(64, npx * 4 * sizeof(float));
+  float *reconstructed = out;
+  const float scale = fmaxf(dt_dev_get_module_scale(pipe, roi_in), 1.f);
+  const int recover_highlights = mask_clipped_pixels(in, mask, d->normalize, d->reconstruct_feather, roi_out->width, roi_out->height, 4);
+  if(mask_out) memcpy(mask_out, mask, npx * sizeof(float));
+  if(recover_highlights)
+  {
+    rc = 1;
+    inpaint_noise(in, mask, inpainted, d->noise_level / scale, d->reconstruct_threshold, d->noise_distribution, roi_out->width, roi_out->height);
+    if(reconstruct_highlights(pipe, inpainted, mask, reconstructed, DT_FILMIC_RECONSTRUCT_RGB, ch, d, piece, roi_in, roi_out)) rc = -1;
+    if(rc == 1 && d->high_quality_reconstruction > 0)
+      for(int i = 0; i < d->high_quality_reconstruction; i++)
+      {
+        compute_ratios(reconstructed, norms, ratios, NULL, DT_FILMIC_METHOD_EUCLIDEAN_NORM_V1, roi_out->width, roi_out->height);
+        if(reconstruct_highlights(pipe, ratios, mask, reconstructed, DT_FILMIC_RECONSTRUCT_RATIOS, ch, d, piece, roi_in, roi_out))
+        {
+          rc = -1;
+          break;
+        }
+        restore_ratios(reconstructed, norms, roi_out->width, roi_out->height);
+      }
+  }
+  else
+    memcpy(out, in, npx * 4 * sizeof(float));
+  free(mask);
+  free(inpainted);
+  free(norms);
+  free(ratios);
+  free(data_);
+  return rc;
+}

@@ -28,6 +28,7 @@ static inline int orc_fc(size_t row, size_t col, uint32_t filters)
 
 /* flush-to-zero / denormals-are-zero for the calling thread: system/fp_mode.h:45-62 */
 void orc_fp_fast_mode(void);
+void orc_fp_fast_mode_all(void);
 
 #ifdef __cplusplus
 }

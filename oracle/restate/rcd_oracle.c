@@ -38,6 +38,15 @@ void orc_fp_fast_mode(void)
 #endif
 }
 
+/* the same on every thread of the OpenMP pool (shared with the reference build loaded into this process): the
+ * reference's pipe threads all run with FTZ|DAZ (darktable.c:877, common/dtpthread.c:54) */
+void orc_fp_fast_mode_all(void)
+{
+  orc_fp_fast_mode();
+#pragma omp parallel
+  orc_fp_fast_mode();
+}
+
 static inline float pos(float v) { return fmaxf(0.0f, v); }
 /* fmaxf()/compare that let a NaN through: used when the never-written scratch is filled with NaN
  * so that every value the reference derives from uninitialised memory stays marked */

@@ -88,3 +88,12 @@ for version, pc in ((0, 0), (0, 3), (1, 0), (2, 5), (3, 0), (3, 2), (4, 1)):
 np.savez_compressed(os.path.join(OUT, "filmic_legacy.npz"), **save)
 mos = util.frame_natural(300, 200, 81)
 np.savez_compressed(os.path.join(OUT, "amaze.npz"), mosaic=mos, rgb_carried=util.ref_amaze(mos, util.BAYER["RGGB"]))
+
+img = (util.rgba_scene(150, 110, 71) * 2.0).astype(np.float32)
+rec = {"img": img}
+for name, over in pin.RECONSTRUCT_CASES.items():
+    blob = util.ref_filmic_commit(util.filmic_default_params(**over))
+    rc, frame, mask = util.ref_filmic_reconstruct(img, blob)
+    assert rc == 1
+    rec["data_" + name], rec["frame_" + name], rec["mask_" + name] = blob, frame, mask
+np.savez_compressed(os.path.join(OUT, "filmic_reconstruct.npz"), **rec)

@@ -476,3 +476,39 @@ def test_amaze_edge_inputs_and_scratch_modes():
 def test_amaze_oracle_equals_golden():
     g = _golden("amaze.npz")
     assert same_bits(util.oracle_amaze(g["mosaic"], util.BAYER["RGGB"], scratch_mode=0)[..., :3], g["rgb_carried"][..., :3]).all()
+
+
+# ---- filmic's highlight reconstruction (a16) ------------------------------------------------------------------------
+RECONSTRUCT_CASES = {
+    "rgb_only_gaussian": dict(reconstruct_threshold=0.0, reconstruct_feather=3.0, reconstruct_bloom_vs_details=40.0, reconstruct_grey_vs_color=-30.0,
+                              reconstruct_structure_vs_texture=20.0, noise_level=0.2, high_quality_reconstruction=0, noise_distribution=1),
+    "default_poisson": dict(reconstruct_threshold=-1.0, noise_level=0.1),                      # hq 1, poissonian, sliders at +100 %
+    "two_passes_uniform_v3": dict(reconstruct_threshold=-0.5, reconstruct_feather=1.5, reconstruct_bloom_vs_details=-50.0, reconstruct_grey_vs_color=10.0,
+                                  reconstruct_structure_vs_texture=-70.0, noise_level=0.5, high_quality_reconstruction=2, noise_distribution=0, version=2),
+}
+
+
+def _reconstruct_frames():
+    return {"scene": (util.rgba_scene(333, 217, 4) * 2.0).astype(np.float32), "hdr": util.hdr_rgba(200, 150, 3),
+            "dark": (util.rgba_scene(100, 80, 4) * 0.01).astype(np.float32), "tiny": (util.rgba_scene(7, 5, 4) * 3).astype(np.float32)}
+
+
+@need_ref
+@pytest.mark.parametrize("name", list(RECONSTRUCT_CASES))
+def test_filmic_reconstruct_oracle_equals_reference(name):
+    """process() :2729-2838 replayed on mask_clipped_pixels / inpaint_noise / reconstruct_highlights / compute_ratios /
+    restore_ratios cut verbatim; every noise distribution, 0-2 ratio passes, zoomed pipes, a frame with nothing to recover"""
+    d = util.ref_filmic_commit(util.filmic_default_params(**RECONSTRUCT_CASES[name]))
+    assert d[84:88].view(np.int32)[0] == 0                   # hl_deprecated off: the path is live
+    for fname, img in _reconstruct_frames().items():
+        for kw in ({}, dict(iscale=2.0, roi_scale=0.3, buf=(4000, 3000))):
+            r, o = util.ref_filmic_reconstruct(img, d, **kw), util.oracle_filmic_reconstruct(img, d, **kw)
+            assert r[0] == o[0] == (0 if fname == "dark" else 1), fname
+            assert same_bits(r[2], o[2]).all() and same_bits(r[1], o[1]).all(), (fname, kw)
+
+
+def test_filmic_reconstruct_oracle_equals_golden():
+    g = _golden("filmic_reconstruct.npz")
+    for name in RECONSTRUCT_CASES:
+        rc, frame, mask = util.oracle_filmic_reconstruct(g["img"], g["data_" + name])
+        assert rc == 1 and same_bits(frame, g["frame_" + name]).all() and same_bits(mask, g["mask_" + name]).all()

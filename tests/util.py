@@ -457,6 +457,30 @@ def oracle_filmic_legacy(rgba, data_blob, work, export=None):
     return dst
 
 
+def _filmic_reconstruct(lib, fn, rgba, data_blob, iscale, roi_scale, buf):
+    h, w = rgba.shape[:2]
+    src, dst, mask = aligned_empty(rgba.shape), aligned_empty(rgba.shape), aligned_empty((h, w))
+    src[...] = rgba
+    dst[...] = 0
+    f = getattr(lib, fn)
+    f.restype = C.c_int
+    oracle().orc_fp_fast_mode_all()   # values next to FLT_MIN occur here (lane 3): every thread flushes, like the pipe's
+    bw, bh = buf if buf else (w, h)
+    rc = f(fptr(src), fptr(dst), fptr(mask), C.c_size_t(w), C.c_size_t(h), data_blob.ctypes.data_as(C.c_void_p), C.c_float(iscale), C.c_double(roi_scale),
+           int(bw), int(bh))
+    return rc, np.array(dst), np.array(mask)
+
+
+def ref_filmic_reconstruct(rgba, data_blob, iscale=1.0, roi_scale=1.0, buf=None, kind="strict"):
+    """process() :2729-2838 on the cut functions: (recovered?, frame the tone mapping reads, clipping mask)"""
+    lib = ref(kind)
+    return None if lib is None else _filmic_reconstruct(lib, "ref_filmic_reconstruct", rgba, data_blob, iscale, roi_scale, buf)
+
+
+def oracle_filmic_reconstruct(rgba, data_blob, iscale=1.0, roi_scale=1.0, buf=None):
+    return _filmic_reconstruct(oracle(), "orc_filmic_reconstruct", rgba, data_blob, iscale, roi_scale, buf)
+
+
 def filmic_prepare(lib, fn, version, work, export=None):
     out = np.zeros(72, np.float32)
     keep = [_f9(work[0]), _f9(work[1]), _f9(export[0]) if export else None, _f9(export[1]) if export else None]
