@@ -10,7 +10,9 @@
 //
 // Everything is pointwise or a separable 5-tap stencil: HBM-bound streaming kernels, one thread per pixel (float4).
 // Per scale: 2 blurs (4 passes) + detail split + accumulation = ~15 RGBA plane passes; 1 + iterations reconstructions.
+#ifndef B200_KERNELS_ON_CPU // tests/emul compiles the kernels of this file with g++ to check them against the oracle without a GPU
 #include "runtime.h"
+#endif
 #include "flt32_math.cuh"
 #include <math.h>
 
@@ -22,9 +24,13 @@ constexpr int MAX_SCALES = 10;
 // IEEE division by a constant: nvcc turns `x / c` into `x * (1/c)` under -ftz=true (see labglue.cu)
 __device__ __forceinline__ float divc(float a, float b)
 {
+#ifdef __CUDA_ARCH__
   float q;
   asm("div.rn.ftz.f32 %0, %1, %2;" : "=f"(q) : "f"(a), "f"(b));
   return q;
+#else
+  return a / b; // host pass: never called by the product
+#endif
 }
 __device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
 __device__ __forceinline__ float fmaxabsf(float a, float b) { return (fabsf(a) > fabsf(b) && !isnan(a)) ? a : (isnan(b) ? 0.f : b); }
@@ -242,6 +248,7 @@ __global__ void __launch_bounds__(NT) restore_kernel(float4 *__restrict__ rec, c
 }
 } // namespace
 
+#ifndef B200_KERNELS_ON_CPU
 namespace b200
 {
 // get_scales(), filmicrgb.c:1414-1431
@@ -333,3 +340,4 @@ int filmic_reconstruct_dev(const b200_piece_t *piece, const b200_filmicrgb_data_
   return B200_OK;
 }
 } // namespace b200
+#endif // B200_KERNELS_ON_CPU

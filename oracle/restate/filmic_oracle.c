@@ -13,8 +13,8 @@
  *
  * Pinned bit-for-bit (tests/test_cpu_oracle_pin.py) against those very functions cut verbatim out of
  * filmicrgb.c and compiled with C-standard semantics (oracle/_ref/libref_strict.so, ref_filmic.c).
- * powf/log2f are glibc's (flt32_math.h).  Other colour sciences (v1..v5) and the deprecated
- * highlight reconstruction are not restated.
+ * powf/log2f are glibc's (flt32_math.h).  The colour sciences before AgX follow further down (orc_filmic_legacy);
+ * the highlight reconstruction in front of either is filmic_reconstruct_oracle.c.
  */
 #include "oracle_common.h"
 #include "flt32_math.h"
@@ -506,11 +506,12 @@ void orc_filmic_prepare(int version, const float work_in[9], const float work_ou
   memcpy(out + 60, m.outset, 48);
 }
 
-/* the AgX branch of process().  Returns 0, or 3 for what is not restated. */
+/* the AgX branch of process(): the tone mapping itself; with hl_deprecated == 0 the caller feeds it the frame
+ * orc_filmic_reconstruct() (filmic_reconstruct_oracle.c) returns.  Returns 0, or 3 for another colour science. */
 int orc_filmic_agx(const float *in, float *out, size_t width, size_t height, const b200_filmicrgb_data_t *d,
                    const float work_in[9], const float work_out[9], const float *export_in, const float *export_out)
 {
-  if(d->version < 5 || d->version > 9 || !d->hl_deprecated) return 3;
+  if(d->version < 5 || d->version > 9) return 3;
   m34 wi, wo, ei, eo;
   to_m34(wi, work_in);
   to_m34(wo, work_out);
@@ -679,7 +680,7 @@ static inline void v4_v5_pixel(const float *in, float *out, const b200_filmicrgb
 int orc_filmic_legacy(const float *in, float *out, size_t width, size_t height, const b200_filmicrgb_data_t *d, const float work_in[9],
                       const float work_out[9], const float *export_in, const float *export_out)
 {
-  if(d->version < 0 || d->version > 4 || !d->hl_deprecated) return 3;
+  if(d->version < 0 || d->version > 4) return 3;
   m34 wi, wo, ei, eo;
   to_m34(wi, work_in);
   to_m34(wo, work_out);
