@@ -39,7 +39,8 @@ class Piece(C.Structure):
                 ("channels", C.c_uint32), ("processed_maximum", C.c_float * 4), ("wb_coeffs", C.c_float * 4),
                 ("buf_in_width", C.c_int), ("buf_in_height", C.c_int), ("pipe_type", C.c_int),
                 ("mask_display", C.c_int), ("iscale", C.c_double), ("exif_iso", C.c_float),
-                ("image_flags", C.c_uint32), ("devid", C.c_int), ("data", C.c_void_p), ("data_size", C.c_size_t)]
+                ("image_flags", C.c_uint32), ("devid", C.c_int), ("datatype", C.c_int), ("data", C.c_void_p),
+                ("data_size", C.c_size_t)]
 
 
 class DemosaicData(C.Structure):
@@ -125,6 +126,45 @@ class ProfileCurves(C.Structure):
     """b200_profile_curves_t: tone curves of a matrix profile (lut_in / lut_out, 65536 floats each, host memory)."""
     _fields_ = [("lut_in", C.POINTER(C.c_float) * 3), ("lut_out", C.POINTER(C.c_float) * 3),
                 ("unbounded_coeffs_in", (C.c_float * 3) * 3), ("unbounded_coeffs_out", (C.c_float * 3) * 3), ("identity", C.c_uint64)]
+
+
+TYPE_UNKNOWN, TYPE_FLOAT, TYPE_UINT16, TYPE_UINT8 = range(4)
+HIGHLIGHTS_CLIP, HIGHLIGHTS_LCH, HIGHLIGHTS_INPAINT, HIGHLIGHTS_LAPLACIAN, HIGHLIGHTS_HARMONIC = range(5)
+EXPORT_UINT8, EXPORT_UINT8_SWAP, EXPORT_UINT16 = range(3)
+
+
+class DngGainMap(C.Structure):
+    """b200_dng_gain_map_t header == dt_dng_gain_map_t (src/common/dng_opcode.h:37-55); map_gain[] follows it."""
+    _fields_ = [("top", C.c_uint32), ("left", C.c_uint32), ("bottom", C.c_uint32), ("right", C.c_uint32), ("plane", C.c_uint32),
+                ("planes", C.c_uint32), ("row_pitch", C.c_uint32), ("col_pitch", C.c_uint32), ("map_points_v", C.c_uint32),
+                ("map_points_h", C.c_uint32), ("map_spacing_v", C.c_double), ("map_spacing_h", C.c_double),
+                ("map_origin_v", C.c_double), ("map_origin_h", C.c_double), ("map_planes", C.c_uint32)]
+
+
+class RawprepareData(C.Structure):
+    """b200_rawprepare_data_t == dt_iop_rawprepare_data_t (src/iop/rawprepare.c:94-111)."""
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("sub", C.c_float * 4),
+                ("div", C.c_float * 4), ("raw_black_level", C.c_uint16), ("raw_white_point", C.c_uint16),
+                ("apply_gainmaps", C.c_int), ("gainmaps", C.c_void_p * 4)]
+
+
+class TemperatureData(C.Structure):
+    """b200_temperature_data_t == dt_iop_temperature_data_t (src/iop/temperature.c:150-153)."""
+    _fields_ = [("coeffs", C.c_float * 4)]
+
+
+class HighlightsData(C.Structure):
+    """b200_highlights_data_t == dt_iop_highlights_params_t (src/iop/highlights/common.h:456-476)."""
+    _fields_ = [("mode", C.c_int), ("blendL", C.c_float), ("blendC", C.c_float), ("blendh", C.c_float), ("clip", C.c_float),
+                ("noise_level", C.c_float), ("iterations", C.c_int), ("scales", C.c_int), ("reconstructing", C.c_float),
+                ("combine", C.c_float), ("debugmode", C.c_int), ("solid_color", C.c_float)]
+
+
+class ExposureData(C.Structure):
+    """b200_exposure_data_t == dt_iop_exposure_data_t (src/iop/exposure.c:116-124,151-157)."""
+    _fields_ = [("mode", C.c_int), ("p_black", C.c_float), ("p_exposure", C.c_float), ("deflicker_percentile", C.c_float),
+                ("deflicker_target_level", C.c_float), ("compensate_exposure_bias", C.c_int), ("deflicker", C.c_int),
+                ("black", C.c_float), ("scale", C.c_float)]
 
 
 class B200Error(RuntimeError):
@@ -382,3 +422,54 @@ def profile_matrices(matrix_in, matrix_out) -> ProfileMatrices:
             for c in range(3):
                 getattr(pm, name)[r][c] = float(m[r][c])
     return pm
+
+
+def rawprepare_data(sub, div, x: int = 0, y: int = 0, gain=None, spacing=(0.0, 0.0), origin=(0.0, 0.0)) -> RawprepareData:
+    """sub/div: the four per-site black levels and ranges commit_params() leaves (rawprepare.c:722-750); gain: None or a
+    float32 array [4, map_h, map_w] (spacing/origin = (h, v), relative to the full image)."""
+    import numpy as np
+    d = RawprepareData()
+    d.x, d.y = x, y
+    for k in range(4):
+        d.sub[k], d.div[k] = sub[k], div[k]
+    if gain is not None:
+        gain = np.ascontiguousarray(gain, dtype=np.float32)
+        _, mh, mw = gain.shape
+        keep = []
+        for f in range(4):
+            buf = (C.c_uint8 * (C.sizeof(DngGainMap) + 4 + 4 * mw * mh))()  # map_gain[] starts at offsetof == sizeof - padding
+            hdr = DngGainMap.from_buffer(buf)
+            hdr.map_points_h, hdr.map_points_v = mw, mh
+            hdr.map_spacing_h, hdr.map_spacing_v = spacing
+            hdr.map_origin_h, hdr.map_origin_v = origin
+            C.memmove(C.addressof(buf) + DngGainMap.map_planes.offset + 4, gain[f].ctypes.data, 4 * mw * mh)
+            keep.append(buf)
+            d.gainmaps[f] = C.addressof(buf)
+        d.apply_gainmaps = 1
+        d._keepalive = keep
+    return d
+
+
+def temperature_data(coeffs) -> TemperatureData:
+    d = TemperatureData()
+    for k in range(4):
+        d.coeffs[k] = coeffs[k] if k < len(coeffs) else 0.0
+    return d
+
+
+def highlights_data(mode: int = HIGHLIGHTS_CLIP, clip: float = 1.0) -> HighlightsData:
+    d = HighlightsData()
+    d.mode, d.clip, d.blendL, d.iterations, d.scales, d.reconstructing, d.combine = mode, clip, 1.0, 30, 8, 0.4, 2.0
+    return d
+
+
+def exposure_data(black: float = 0.0, exposure_ev: float = 0.0) -> ExposureData:
+    """black/scale as _process_common_setup() derives them (exposure.c:433-470): white = exp2f(-exposure),
+    scale = 1.0 / (white - black) with a double division."""
+    import numpy as np
+    d = ExposureData()
+    d.p_black, d.p_exposure, d.deflicker_percentile, d.deflicker_target_level = black, exposure_ev, 50.0, -4.0
+    d.black = black
+    white = np.exp2(np.float32(-exposure_ev), dtype=np.float32)
+    d.scale = float(np.float32(1.0 / float(white - np.float32(black))))
+    return d

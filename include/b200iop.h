@@ -67,6 +67,15 @@ enum
   B200_PIPE_THUMBNAIL = 4
 };
 
+/* dt_iop_buffer_type_t, src/pixel/format.h:54-59 (same values) */
+enum
+{
+  B200_TYPE_UNKNOWN = 0,
+  B200_TYPE_FLOAT = 1,
+  B200_TYPE_UINT16 = 2,
+  B200_TYPE_UINT8 = 3
+};
+
 /* Exactly the fields the hot-path process() bodies read from `piece`, `pipe` and `self`
  * (SURVEY.md appendix D): dt_dev_pixelpipe_iop_t src/develop/pixelpipe_hb.h:101-166,
  * dt_iop_buffer_dsc_t src/pixel/format.h:80-119. */
@@ -86,6 +95,8 @@ typedef struct b200_piece_t
   float exif_iso;              /* self->dev->image_storage.exif_iso */
   uint32_t image_flags;        /* self->dev->image_storage.flags */
   int devid;                   /* pipe->devid: CUDA device ordinal, < 0 = current device */
+  int datatype;                /* piece->dsc_in.datatype (B200_TYPE_*); read by rawprepare only.  Occupies what was
+                                  padding: the struct's size and every other offset are unchanged */
   const void *data;            /* piece->data: the module's b200_<op>_data_t */
   size_t data_size;            /* piece->data_size */
 } b200_piece_t;
@@ -464,6 +475,129 @@ int b200_ipc_release(void *d_ptr);
  * origin (amaze.cc:357-455), so no cut reproduces the untiled frame: grid 1 and the tiling_callback() overlap
  * (demosaic.c:1916-2013) come back, i.e. bands are tiles of develop/tiling.c.  piece == NULL means RCD. */
 void b200_demosaic_band_grid(const b200_piece_t *piece, int *grid, int *halo, int *align);
+
+/* ==== the modules either side of the demosaic .. colorout path ============ */
+
+/* ---- rawprepare (src/iop/rawprepare.c): sensor data -> normalised float mosaic ------------------------------- */
+/* dt_dng_gain_map_t, src/common/dng_opcode.h:37-55 (identical layout; host memory) */
+typedef struct b200_dng_gain_map_t
+{
+  uint32_t top, left, bottom, right, plane, planes, row_pitch, col_pitch;
+  uint32_t map_points_v, map_points_h;
+  double map_spacing_v, map_spacing_h, map_origin_v, map_origin_h;
+  uint32_t map_planes;
+  float map_gain[];
+} b200_dng_gain_map_t;
+/* dt_iop_rawprepare_data_t, rawprepare.c:94-111 (identical layout) */
+typedef struct b200_rawprepare_data_t
+{
+  int32_t x, y, width, height; /* sensor border trim */
+  float sub[4];                /* black level per CFA site of the 2x2 block */
+  float div[4];                /* white - black */
+  struct
+  {
+    uint16_t raw_black_level, raw_white_point;
+  } rawprepare;
+  int apply_gainmaps;
+  b200_dng_gain_map_t *gainmaps[4]; /* one per site of the RGGB block when apply_gainmaps */
+} b200_rawprepare_data_t;
+/* process() :466-633.  Input: roi_in.width x roi_in.height samples of piece->datatype (uint16 or float mosaic when
+ * piece->filters != 0 and channels == 1, else `channels` floats per pixel); output roi_out floats.  Gain maps are
+ * bilinearly interpolated per site (:592-630).  process_cl() :636-760 is the same arithmetic. */
+int b200_rawprepare_process_host(const b200_piece_t *piece, const void *in, void *out);
+int b200_rawprepare_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
+void b200_rawprepare_tiling(const b200_piece_t *piece, b200_tiling_t *tiling); /* default_tiling_callback, imageop.c */
+
+/* ---- temperature (src/iop/temperature.c): white-balance multipliers ---------------------------------------------- */
+/* dt_iop_temperature_data_t, temperature.c:150-153 */
+typedef struct b200_temperature_data_t
+{
+  float coeffs[4];
+} b200_temperature_data_t;
+/* process() :486-608: Bayer mosaic (coefficient by FC at roi_out origin), X-Trans mosaic (FCxtrans), or `channels`
+ * floats per pixel (alpha carried; copied from the input when a mask is displayed) */
+int b200_temperature_process_host(const b200_piece_t *piece, const void *in, void *out);
+int b200_temperature_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
+void b200_temperature_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
+
+/* ---- highlights (src/iop/highlights.c): clip mode + the "nothing to reconstruct" bypass -------------------------- */
+enum
+{
+  B200_HIGHLIGHTS_CLIP = 0,
+  B200_HIGHLIGHTS_LCH = 1,
+  B200_HIGHLIGHTS_INPAINT = 2,
+  B200_HIGHLIGHTS_LAPLACIAN = 3,
+  B200_HIGHLIGHTS_HARMONIC = 4
+};
+/* dt_iop_highlights_data_t == dt_iop_highlights_params_t, iop/highlights/common.h:456-476 (identical layout) */
+typedef struct b200_highlights_data_t
+{
+  int mode;
+  float blendL, blendC, blendh;
+  float clip;
+  float noise_level;
+  int iterations;
+  int scales;
+  float reconstructing;
+  float combine;
+  int debugmode;
+  float solid_color;
+} b200_highlights_data_t;
+/* process() :679-789: counts the samples above the mode's threshold (_hl_count_clipped :266-292); fewer than 25 ->
+ * the input is copied through; else process_clip (iop/highlights/clip.c:60-85).  Built: mode CLIP, and the modes that
+ * fall back to it on non-mosaic input (LCh, colour inpainting).  The reconstruction modes on a mosaic (LCh's
+ * long-double arithmetic, inpainting, guided Laplacians, harmonic transposition) return B200_ERR_UNSUPPORTED.
+ * The count and the branch stay on the device: no host round trip. */
+int b200_highlights_process_host(const b200_piece_t *piece, const void *in, void *out);
+int b200_highlights_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
+void b200_highlights_tiling(const b200_piece_t *piece, b200_tiling_t *tiling); /* :575-644 */
+
+/* ---- the three of them in one pass over the sensor data (pipe-level fusion) ---------------------------------------
+ * What rawprepare -> temperature -> highlights(clip) compute on a Bayer mosaic, sample by sample in the same order
+ * and precision, without the two intermediate float planes: bit-identical to calling the three entry points one
+ * after the other (tests/test_zz_pipe_ends_gpu.py).  pieces: [0] rawprepare's, [1] temperature's, [2] highlights'
+ * (NULL = module disabled).  26 -> 8 bytes per sample of HBM traffic for uint16 input. */
+int b200_rawfront_process_dev(const b200_piece_t *rawprepare, const b200_piece_t *temperature, const b200_piece_t *highlights,
+                              const void *d_in, void *d_out, void *stream);
+
+/* ---- exposure (src/iop/exposure.c) ------------------------------------------------------------------------------- */
+/* dt_iop_exposure_data_t, exposure.c:151-157 with dt_iop_exposure_params_t :116-124 (identical layout) */
+typedef struct b200_exposure_data_t
+{
+  struct
+  {
+    int mode;
+    float black, exposure, deflicker_percentile, deflicker_target_level;
+    int compensate_exposure_bias;
+  } params;
+  int deflicker;
+  float black; /* as _process_common_setup() :433-470 left them */
+  float scale;
+} b200_exposure_data_t;
+/* process() :501-544: (in - black) * scale on every float of the pixel (alpha included when channels == 4) */
+int b200_exposure_process_host(const b200_piece_t *piece, const void *in, void *out);
+int b200_exposure_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
+void b200_exposure_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
+
+/* ---- gamma (src/iop/gamma.c): the pipe's last module, float RGBA -> uint8 BGRA for the display --------------------- */
+/* process() :367-377 with no mask or channel display: _copy_output :352-364 (the fourth byte of every output pixel is
+ * not written).  Mask and false-colour displays (GUI previews) return B200_ERR_UNSUPPORTED. */
+int b200_gamma_process_host(const b200_piece_t *piece, const void *in, void *out);
+int b200_gamma_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
+void b200_gamma_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
+
+/* ---- the export's down-conversion of the float backbuffer (src/imageio/imageio_core.c:706-738) ---------------------
+ * B200_EXPORT_UINT8 _clamp_float_to_uint8, B200_EXPORT_UINT8_SWAP _swap_byteorder_float_to_uint8 (BGRA),
+ * B200_EXPORT_UINT16 _export_final_buffer_to_uint16.  Done on the device, the read-back of a finished frame is 4 or
+ * 8 bytes per pixel instead of 16. */
+enum
+{
+  B200_EXPORT_UINT8 = 0,
+  B200_EXPORT_UINT8_SWAP = 1,
+  B200_EXPORT_UINT16 = 2
+};
+int b200_export_convert_dev(const void *d_in, void *d_out, size_t width, size_t height, int format, void *stream);
+int b200_export_convert_host(const void *in, void *out, size_t width, size_t height, int format);
 
 /* ---- the libm the kernels use ------------------------------------------------------------------
  * Device restatement of glibc 2.39's single-precision expf/exp2f/logf/log2f/powf (the functions the

@@ -1,0 +1,54 @@
+/* oracle/_ref wrapper: highlights (clip mode and the "nothing to reconstruct" bypass).  TEST INFRASTRUCTURE ONLY.
+ *
+ * oracle/Makefile cuts verbatim into oracle/_ref/gen_highlights.c:
+ *     iop/highlights/common.h :218 (DT_HL_MIN_CLIPPED_PIXELS), :431-476 (mode enum, params == data)
+ *     iop/highlights/clip.c   :60-85  process_clip
+ *     iop/highlights.c        :232-302 _hl_count_thresholds, _hl_count_clipped, _hl_copy_input;  :679-789 process()
+ * The reconstruction modes (LCh, colour inpainting, guided Laplacians, harmonic transposition) are separate translation
+ * units of 18 k lines that are not built here: their entry points abort (the tests reach them only through the bypass).
+ */
+#include "ref_piece.h"
+#include "gen_imageop_math.c"
+#include <stdio.h>
+static inline void dt_iop_image_copy_by_size(float *const out, const float *const in, const size_t width, const size_t height, const size_t ch)
+{ /* common/imagebuf.h:91-95 -> dt_iop_image_copy: a copy */
+  memcpy(out, in, sizeof(float) * width * height * ch);
+}
+typedef struct dt_iop_highlights_gui_data_t { int show_visualize; } dt_iop_highlights_gui_data_t;
+#define dt_iop_gui_data(self) NULL
+#define DT_DEV_PIXELPIPE_DISPLAY_PASSTHRU (1 << 12)
+static inline uint32_t dt_dev_get_roi_filters(const dt_dev_pixelpipe_iop_t *piece, const dt_iop_roi_t *roi)
+{ /* only the visualisation and colour-inpainting branches read the shifted word; neither is entered here */
+  return piece->dsc_in.filters;
+}
+#define NOT_BUILT(name) do { fprintf(stderr, "oracle/_ref: highlights %s is not built\n", name); abort(); } while(0)
+#define process_visualize(...) NOT_BUILT("process_visualize")
+#define process_inpaint_xtrans(...) NOT_BUILT("process_inpaint_xtrans")
+#define process_inpaint_bayer(...) NOT_BUILT("process_inpaint_bayer")
+#define process_lch_xtrans(...) NOT_BUILT("process_lch_xtrans")
+#define process_lch_bayer(...) NOT_BUILT("process_lch_bayer")
+static inline int process_laplacian_stub(void) { NOT_BUILT("process_laplacian"); return 1; }
+#define process_laplacian(...) process_laplacian_stub()
+#define process_harmonic(...) process_laplacian_stub()
+#define process highlights_process
+#include "gen_highlights.c"
+#undef process
+
+int ref_highlights(const float *in, float *out, int x, int y, int width, int height, uint32_t filters, int channels, int mode, float clip,
+                   const float processed_maximum[4], int mask_display)
+{
+  dt_iop_highlights_data_t d;
+  memset(&d, 0, sizeof(d));
+  d.mode = mode;
+  d.clip = clip;
+  dt_dev_pixelpipe_t pipe = { 1, mask_display, 1.0f, 0 };
+  dt_dev_pixelpipe_iop_t piece;
+  memset(&piece, 0, sizeof(piece));
+  piece.data = &d;
+  piece.roi_in = piece.roi_out = (dt_iop_roi_t){ x, y, width, height, 1.0 };
+  piece.dsc_in.filters = filters;
+  piece.dsc_in.channels = channels;
+  for(int k = 0; k < 4; k++) piece.dsc_in.processed_maximum[k] = processed_maximum[k];
+  return highlights_process(NULL, &pipe, &piece, in, out);
+}
+size_t ref_highlights_sizeof_data(void) { return sizeof(dt_iop_highlights_data_t); }

@@ -1,0 +1,226 @@
+/* CPU restatement of the pointwise modules either side of the demosaic .. colorout path: rawprepare, temperature,
+ * highlights (clip mode and the bypass) in front; exposure, gamma and the export's float -> integer conversions behind.
+ * TEST INFRASTRUCTURE ONLY.
+ *
+ * Follows /root/reference/src:
+ *   iop/rawprepare.c    compute_proper_crop :206-210, BL :413-418, process() :466-633
+ *   iop/temperature.c   process() :486-608  (FC / FCxtrans: develop/imageop_math.h:190-222)
+ *   iop/highlights.c    _hl_count_thresholds :232-253, _hl_count_clipped :266-292, _hl_copy_input :296-302,
+ *                       process() :679-789;  iop/highlights/clip.c process_clip :60-85
+ *   iop/exposure.c      process() :501-544
+ *   iop/gamma.c         _copy_output :352-364 (process() :367-377 without mask/channel display)
+ *   imageio/imageio_core.c  _clamp_float_to_uint8 :706-714, _swap_byteorder_float_to_uint8 :717-728,
+ *                           _export_final_buffer_to_uint16 :731-738
+ * Pinned bit-for-bit against those lines cut verbatim (oracle/_ref: ref_rawprepare.c, ref_temperature.c,
+ * ref_highlights.c, ref_exposure.c, ref_pipe_end.c) by tests/test_cpu_pipe_ends.py.
+ */
+#include "oracle_common.h"
+#include "b200iop.h"
+#include <string.h>
+
+/* ---- rawprepare ------------------------------------------------------------------------------------------------- */
+static int proper_crop(double roi_scale, int value) { return (int)roundf((double)value * roi_scale); } /* the double product is
+                                                                                    converted to float by roundf's prototype */
+
+/* in: roi_in samples; out: roi_out floats (x channels).  gain: NULL or the four maps (host pointers inside d). */
+int orc_rawprepare(const b200_piece_t *piece, const void *ivoid, void *ovoid)
+{
+  const b200_rawprepare_data_t *d = (const b200_rawprepare_data_t *)piece->data;
+  const int width = piece->roi_out.width, height = piece->roi_out.height, input_width = piece->roi_in.width;
+  const int roi_x = piece->roi_out.x, roi_y = piece->roi_out.y;
+  const int cfa_x = roi_x + d->x, cfa_y = roi_y + d->y;
+  const int csx = proper_crop(piece->roi_in.scale, d->x), csy = proper_crop(piece->roi_in.scale, d->y);
+  float *const out = (float *)ovoid;
+  const int mosaic = piece->filters && piece->channels == 1;
+
+  if(mosaic && (piece->datatype == B200_TYPE_UINT16 || piece->datatype == B200_TYPE_FLOAT))
+  {
+    float inv_div[4];
+    for(int k = 0; k < 4; k++) inv_div[k] = 1.0f / d->div[k];
+    for(int j = 0; j < height; j++)
+      for(int i = 0; i < width; i++)
+      {
+        const int id = (((j + cfa_y) & 1) << 1) + ((cfa_x + i) & 1);
+        const size_t pin = (size_t)input_width * (j + csy) + csx + i;
+        const float v = piece->datatype == B200_TYPE_UINT16 ? (float)((const uint16_t *)ivoid)[pin] : ((const float *)ivoid)[pin];
+        out[(size_t)j * width + i] = (v - d->sub[id]) * inv_div[id];
+      }
+  }
+  else
+  {
+    const float *const in = (const float *)ivoid;
+    const float sub = d->sub[0], div = d->div[0];
+    const int ch = (int)piece->channels;
+    for(int j = 0; j < height; j++)
+      for(int i = 0; i < width; i++)
+        for(int c = 0; c < ch; c++)
+        {
+          /* the reference's index is `(size_t)ch * (int product)`: the inner product is int arithmetic */
+          const size_t pin = (size_t)ch * (input_width * (j + csy) + csx + i) + c;
+          const size_t pout = (size_t)ch * (j * width + i) + c;
+          out[pout] = (in[pin] - sub) / div;
+        }
+  }
+
+  if(mosaic && d->apply_gainmaps)
+  {
+    const b200_dng_gain_map_t *const g0 = d->gainmaps[0];
+    const uint32_t map_w = g0->map_points_h, map_h = g0->map_points_v;
+    const float im_to_rel_x = 1.0f / piece->buf_in_width, im_to_rel_y = 1.0f / piece->buf_in_height;
+    const float rel_to_map_x = 1.0f / g0->map_spacing_h, rel_to_map_y = 1.0f / g0->map_spacing_v; /* double division, then float */
+    const float map_origin_h = g0->map_origin_h, map_origin_v = g0->map_origin_v;
+    for(int j = 0; j < height; j++)
+    {
+      /* CLAMP(float, int 0, uint32): the comparisons and the result are float */
+      float y_map = ((roi_y + csy + j) * im_to_rel_y - map_origin_v) * rel_to_map_y;
+      y_map = y_map < 0 ? (float)0 : (y_map > (float)map_h ? (float)map_h : y_map);
+      const uint32_t y_i0 = (uint32_t)(y_map < (float)(map_h - 1) ? y_map : (float)(map_h - 1));
+      const uint32_t y_i1 = (y_i0 + 1 < map_h - 1) ? y_i0 + 1 : map_h - 1;
+      const float y_frac = y_map - y_i0;
+      for(int i = 0; i < width; i++)
+      {
+        const int id = (((j + roi_y + d->y) & 1) << 1) + ((i + roi_x + d->x) & 1);
+        float x_map = ((roi_x + csx + i) * im_to_rel_x - map_origin_h) * rel_to_map_x;
+        x_map = x_map < 0 ? (float)0 : (x_map > (float)map_w ? (float)map_w : x_map);
+        const uint32_t x_i0 = (uint32_t)(x_map < (float)(map_w - 1) ? x_map : (float)(map_w - 1));
+        const uint32_t x_i1 = (x_i0 + 1 < map_w - 1) ? x_i0 + 1 : map_w - 1;
+        const float x_frac = x_map - x_i0;
+        const float *row0 = &d->gainmaps[id]->map_gain[y_i0 * map_w], *row1 = &d->gainmaps[id]->map_gain[y_i1 * map_w];
+        const float gain_top = (1.0f - x_frac) * row0[x_i0] + x_frac * row0[x_i1];
+        const float gain_bottom = (1.0f - x_frac) * row1[x_i0] + x_frac * row1[x_i1];
+        out[j * width + i] *= (1.0f - y_frac) * gain_top + y_frac * gain_bottom;
+      }
+    }
+  }
+  return 0;
+}
+
+/* ---- temperature ------------------------------------------------------------------------------------------------ */
+static int fc_xtrans(int row, int col, int roi_x, int roi_y, const uint8_t xtrans[6][6])
+{
+  return xtrans[(row + 600 + roi_y) % 6][(col + 600 + roi_x) % 6];
+}
+int orc_temperature(const b200_piece_t *piece, const float *in, float *out)
+{
+  const b200_temperature_data_t *d = (const b200_temperature_data_t *)piece->data;
+  const int width = piece->roi_out.width, height = piece->roi_out.height;
+  const uint32_t filters = piece->filters;
+  if(filters == 9u)
+  {
+    for(int j = 0; j < height; j++)
+      for(int i = 0; i < width; i++)
+        out[(size_t)j * width + i] = in[(size_t)j * width + i] * d->coeffs[fc_xtrans(j, i % 12, piece->roi_out.x, piece->roi_out.y, piece->xtrans)];
+  }
+  else if(filters)
+  {
+    for(int j = 0; j < height; j++)
+      for(int i = 0; i < width; i++)
+        out[(size_t)j * width + i] = in[(size_t)j * width + i] * d->coeffs[orc_fc(j + piece->roi_out.y, i + piece->roi_out.x, filters)];
+  }
+  else
+  {
+    const size_t ch = piece->channels, npixels = (size_t)width * height;
+    for(size_t k = 0; k < npixels; k++)
+    {
+      for(int c = 0; c < 3; c++) out[ch * k + c] = in[ch * k + c] * d->coeffs[c];
+      if(ch == 4) out[4 * k + 3] = in[4 * k + 3]; /* other channel counts leave the rest of the pixel unwritten */
+    }
+    if((piece->mask_display & 1) && ch == 4)
+      for(size_t k = 3; k < npixels * 4; k += 4) out[k] = in[k];
+  }
+  return 0;
+}
+
+/* ---- highlights --------------------------------------------------------------------------------------------------- */
+/* returns 0 and the number of samples counted as clipped in *n_clipped; -1 for a mode that is not restated */
+int orc_highlights(const b200_piece_t *piece, const float *in, float *out, size_t *n_clipped)
+{
+  const b200_highlights_data_t *data = (const b200_highlights_data_t *)piece->data;
+  const uint32_t filters = piece->filters;
+  const size_t n_pixels = (size_t)piece->roi_out.width * piece->roi_out.height;
+  float pmax[4];
+  for(int c = 0; c < 4; c++) pmax[c] = (piece->processed_maximum[c] > 0.f) ? piece->processed_maximum[c] : 1.0f;
+  const float clip = data->clip * fminf(pmax[0], fminf(pmax[1], pmax[2]));
+  float thresholds[4];
+  float factor = 0.f;
+  if(data->mode == B200_HIGHLIGHTS_INPAINT) factor = 0.987f;
+  if(data->mode == B200_HIGHLIGHTS_LAPLACIAN || data->mode == B200_HIGHLIGHTS_HARMONIC) factor = 0.995f;
+  for(int c = 0; c < 3; c++) thresholds[c] = (factor > 0.f) ? factor * data->clip * pmax[c] : clip;
+  thresholds[3] = clip;
+
+  size_t clipped = 0;
+  const size_t ch = filters ? 1 : piece->channels;
+  if(filters)
+  {
+    const float raw_threshold = fminf(fminf(thresholds[0], thresholds[1]), thresholds[2]);
+    for(size_t k = 0; k < n_pixels; k++) clipped += (in[k] > raw_threshold);
+  }
+  else
+  {
+    const size_t n_colours = ch < 3 ? ch : 3;
+    for(size_t k = 0; k < n_pixels; k++)
+    {
+      int over = 0;
+      for(size_t c = 0; c < n_colours; c++) over |= (in[k * ch + c] > thresholds[c]);
+      clipped += (over != 0);
+    }
+  }
+  if(n_clipped) *n_clipped = clipped;
+  if(clipped < 25)
+  {
+    memcpy(out, in, sizeof(float) * n_pixels * ch);
+    return 0;
+  }
+  /* past the bypass: the reconstruction modes are not restated (on non-mosaic input LCh and inpainting are process_clip) */
+  if(data->mode == B200_HIGHLIGHTS_LAPLACIAN || data->mode == B200_HIGHLIGHTS_HARMONIC) return -1;
+  if(filters && data->mode != B200_HIGHLIGHTS_CLIP) return -1;
+  for(size_t k = 0; k < ch * n_pixels; k++) out[k] = clip < in[k] ? clip : in[k];
+  /* dt_iop_alpha_copy assumes four floats per pixel whatever the buffer holds: on a mosaic it would run past both buffers */
+  if((piece->mask_display & 1) && !filters && ch == 4)
+    for(size_t k = 3; k < n_pixels * 4; k += 4) out[k] = in[k];
+  return 0;
+}
+
+/* ---- exposure ----------------------------------------------------------------------------------------------------- */
+int orc_exposure(const b200_piece_t *piece, const float *in, float *out)
+{
+  const b200_exposure_data_t *d = (const b200_exposure_data_t *)piece->data;
+  const size_t n = (size_t)piece->channels * piece->roi_out.width * piece->roi_out.height;
+  for(size_t k = 0; k < n; k++) out[k] = (in[k] - d->black) * d->scale;
+  if(piece->mask_display & 1)
+    for(size_t k = 3; k < (size_t)piece->roi_out.width * piece->roi_out.height * 4; k += 4) out[k] = in[k];
+  return 0;
+}
+
+/* ---- the float -> integer ends -------------------------------------------------------------------------------------- */
+/* C's (int)float on the reference's hardware: cvttss2si, INT_MIN for NaN and out-of-range */
+static int cvtt(float f) { return (f >= -2147483648.0f && f < 2147483648.0f) ? (int)f : (int)0x80000000u; }
+
+void orc_gamma_copy_output(const float *in, uint8_t *out, size_t npixels)
+{
+  for(size_t j = 0; j < 4 * npixels; j += 4)
+    for(size_t c = 0; c < 3; c++) out[j + 2 - c] = (uint8_t)cvtt(fminf(roundf(255.0f * fmaxf(in[j + c], 0.0f)), 255.0f));
+}
+static float clampf(float a, float mn, float mx) { return a >= mn ? (a <= mx ? a : mx) : mn; } /* CLAMPF, math/math.h:91 */
+void orc_export_convert(const float *in, void *out, size_t npixels, int format)
+{
+  if(format == B200_EXPORT_UINT8)
+    for(size_t k = 0; k < 4 * npixels; k++) ((uint8_t *)out)[k] = (uint8_t)cvtt(clampf(roundf(in[k] * 255.f), 0.f, 255.f));
+  else if(format == B200_EXPORT_UINT8_SWAP)
+    for(size_t k = 0; k < npixels; k++)
+    {
+      uint8_t *o = (uint8_t *)out + 4 * k;
+      o[0] = (uint8_t)cvtt(clampf(roundf(in[4 * k + 2] * 255.f), 0.f, 255.f));
+      o[1] = (uint8_t)cvtt(clampf(roundf(in[4 * k + 1] * 255.f), 0.f, 255.f));
+      o[2] = (uint8_t)cvtt(clampf(roundf(in[4 * k + 0] * 255.f), 0.f, 255.f));
+      o[3] = (uint8_t)cvtt(clampf(roundf(in[4 * k + 3] * 255.f), 0.f, 255.f));
+    }
+  else
+    for(size_t k = 0; k < 4 * npixels; k++)
+    {
+      /* glib's CLAMP: x > high ? high : (x < low ? low : x) -- NaN passes through to the conversion */
+      const float x = roundf(in[k] * 65535.f);
+      const float c = x > 65535.f ? 65535.f : (x < 0.f ? 0.f : x);
+      ((uint16_t *)out)[k] = (uint16_t)cvtt(c);
+    }
+}

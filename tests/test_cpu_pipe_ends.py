@@ -1,0 +1,218 @@
+"""CPU: the oracle of the modules either side of the demosaic .. colorout path (rawprepare, temperature, highlights' clip
+mode and bypass, exposure, gamma, the export's float -> integer conversions) pinned bit for bit against the reference's
+own lines compiled in place (oracle/_ref, strict build), and against the golden vectors those builds produced
+(tests/golden/pipe_ends.npz), which travel to the GPU box."""
+import os
+
+import numpy as np
+import pytest
+
+import ansel_b200 as ab
+import pipe_ends_util as pe
+import util
+
+
+def same_bits(a, b):
+    return (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build():
+    import subprocess
+    subprocess.run(["make", "-s", "-C", util.ORACLE_DIR, "oracle"], check=True)   # dependency-tracked; oracle/_ref comes from build()
+    if util.ref("strict") is None and os.path.isdir("/root/reference/src"):
+        util.build_oracle()
+
+
+need_ref = pytest.mark.skipif(util.ref("strict") is None and not os.path.isdir("/root/reference/src"),
+                              reason="oracle/_ref not built (no /root/reference)")
+
+SUB = (512.0, 520.0, 508.0, 515.0)
+DIV = (15871.0, 15863.0, 15875.0, 15868.0)
+
+
+def gain_maps(mw=9, mh=7, seed=3):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:mh, 0:mw]
+    r2 = ((xx / (mw - 1) - 0.5) ** 2 + (yy / (mh - 1) - 0.5) ** 2)
+    return np.stack([(1.0 + (0.6 + 0.1 * f) * r2 + rng.normal(0, 0.01, r2.shape)).astype(np.float32) for f in range(4)])
+
+
+RAWPREPARE_CASES = {
+    "uint16": dict(),
+    "uint16_crop": dict(x=3, y=5),
+    "uint16_odd_sizes": dict(size=(131, 77), x=1, y=0),
+    "uint16_roi": dict(x=2, y=2, out=(7, 4, 90, 50)),
+    "float_mosaic": dict(datatype=ab.TYPE_FLOAT, x=4, y=1),
+    "uint16_scaled": dict(x=8, y=6, scale=0.5),
+    "uint16_gainmaps": dict(x=2, y=4, gain=True),
+    "rgba_predownsampled": dict(datatype=ab.TYPE_FLOAT, filters=0, channels=4, x=2, y=3),
+    "mono_unknown_type": dict(datatype=ab.TYPE_UNKNOWN, filters=0, channels=1),
+}
+
+
+def rawprepare_case(name, size=(206, 120)):
+    kw = dict(RAWPREPARE_CASES[name])
+    w, h = kw.pop("size", size)
+    gain = gain_maps() if kw.pop("gain", False) else None
+    spacing, origin = (1.0 / 8, 1.0 / 6), (0.01, -0.02)
+    d = ab.rawprepare_data(SUB, DIV, kw.pop("x", 0), kw.pop("y", 0), gain=gain, spacing=spacing, origin=origin)
+    ch, datatype = kw.get("channels", 1), kw.get("datatype", ab.TYPE_UINT16)
+    raw = pe.sensor_frame(w * ch, h, 11)
+    src = raw if datatype == ab.TYPE_UINT16 else raw.astype(np.float32)
+    piece = pe.rawprepare_piece(w, h, d, **kw)
+    return piece, src, dict(gain=gain, spacing=spacing, origin=origin)
+
+
+@need_ref
+@pytest.mark.parametrize("name", list(RAWPREPARE_CASES))
+def test_rawprepare_oracle_equals_reference(name):
+    piece, src, g = rawprepare_case(name)
+    want = pe.ref_rawprepare(piece, src, **g)
+    assert same_bits(pe.oracle_rawprepare(piece, src), want).all()
+    assert np.isfinite(want).all() and want.std() > 0
+
+
+TEMPERATURE_CASES = {
+    "bayer": dict(),
+    "bayer_roi_odd": dict(x=3, y=1, size=(131, 77)),
+    "bayer_gbrg": dict(filters=util.BAYER["GBRG"], x=1, y=2),
+    "xtrans": dict(filters=9, xtrans=pe.XTRANS, x=4, y=5, size=(133, 70)),
+    "rgba": dict(filters=0, channels=4),
+    "rgba_mask": dict(filters=0, channels=4, mask_display=1),
+}
+COEFFS = (2.13, 1.0, 1.57, 1.02)
+
+
+def temperature_case(name):
+    kw = dict(TEMPERATURE_CASES[name])
+    w, h = kw.pop("size", (206, 120))
+    piece = pe.mosaic_piece(w, h, ab.temperature_data(COEFFS), **kw)
+    img = util.rgba_test_image(w, h, 5) if piece.channels == 4 else util.frame_natural(w, h, 5)
+    return piece, img
+
+
+@need_ref
+@pytest.mark.parametrize("name", list(TEMPERATURE_CASES))
+def test_temperature_oracle_equals_reference(name):
+    piece, img = temperature_case(name)
+    assert same_bits(pe.oracle_temperature(piece, img), pe.ref_temperature(piece, img)).all()
+
+
+HIGHLIGHTS_CASES = {
+    "clip_mosaic": dict(),
+    "clip_mosaic_wb_maximum": dict(pm=(2.13, 1.0, 1.57, 0.0), clip=0.9),
+    "clip_mosaic_24_clipped": dict(n_clipped=24),          # one short of DT_HL_MIN_CLIPPED_PIXELS: copied through
+    "clip_mosaic_25_clipped": dict(n_clipped=25),
+    "clip_rgba": dict(filters=0, channels=4),
+    "clip_rgba_mask_zero_maximum": dict(filters=0, channels=4, mask_display=1, pm=(0.0, 0.0, 0.0, 0.0)),
+    "lch_on_rgba_is_clip": dict(filters=0, channels=4, mode=ab.HIGHLIGHTS_LCH),
+    "harmonic_bypass": dict(mode=ab.HIGHLIGHTS_HARMONIC, n_clipped=3),   # the default mode on a frame with nothing to reconstruct
+    "inpaint_bypass_rgba": dict(filters=0, channels=4, mode=ab.HIGHLIGHTS_INPAINT, n_clipped=10),
+}
+
+
+def highlights_case(name, size=(206, 120)):
+    kw = dict(HIGHLIGHTS_CASES[name])
+    w, h = size
+    mode, clip, n = kw.pop("mode", ab.HIGHLIGHTS_CLIP), kw.pop("clip", 1.0), kw.pop("n_clipped", None)
+    piece = pe.mosaic_piece(w, h, ab.highlights_data(mode, clip), **kw)
+    rng = np.random.default_rng(8)
+    if piece.channels == 4:
+        img = util.rgba_test_image(w, h, 6, lo=0.0, hi=0.8 if n is not None else 1.3)
+        if n is not None:
+            ys, xs = rng.choice(h * w, n, replace=False) // w, rng.choice(h * w, n, replace=False) % w
+            img[ys[:n], xs[:n], rng.integers(0, 3, n)] = 1.5
+    else:
+        img = np.minimum(util.frame_natural(w, h, 6) * (0.7 if n is not None else 1.6), 3.0).astype(np.float32)
+        if n is not None:
+            img = np.minimum(img, 0.8)
+            k = rng.choice(h * w, n, replace=False)
+            img.reshape(-1)[k] = 1.25
+    img.reshape(-1)[7] = np.nan
+    return piece, img
+
+
+@need_ref
+@pytest.mark.parametrize("name", list(HIGHLIGHTS_CASES))
+def test_highlights_oracle_equals_reference(name):
+    piece, img = highlights_case(name)
+    rc, got, n = pe.oracle_highlights(piece, img)
+    assert rc == 0
+    want = pe.ref_highlights(piece, img)
+    assert same_bits(got, want).all()
+    if "bypass" in name or "24" in name:
+        assert n < 25 and same_bits(want, img).all()
+    else:
+        assert n >= 25 and not same_bits(want, img).all()
+
+
+def test_highlights_oracle_refuses_reconstruction_modes():
+    piece, img = highlights_case("clip_mosaic")
+    for mode in (ab.HIGHLIGHTS_LCH, ab.HIGHLIGHTS_INPAINT, ab.HIGHLIGHTS_LAPLACIAN, ab.HIGHLIGHTS_HARMONIC):
+        p = pe.mosaic_piece(206, 120, ab.highlights_data(mode, 1.0))
+        assert pe.oracle_highlights(p, img)[0] == -1
+
+
+EXPOSURE_CASES = {"rgba": dict(channels=4), "rgba_mask": dict(channels=4, mask_display=1), "mono": dict(channels=1)}
+
+
+def exposure_case(name):
+    kw = EXPOSURE_CASES[name]
+    w, h = 203, 117
+    piece = pe.mosaic_piece(w, h, ab.exposure_data(-0.00024, 0.7), filters=0, **kw)
+    img = util.rgba_test_image(w, h, 4) if kw["channels"] == 4 else util.frame_natural(w, h, 4)
+    return piece, img
+
+
+@need_ref
+@pytest.mark.parametrize("name", list(EXPOSURE_CASES))
+def test_exposure_oracle_equals_reference(name):
+    piece, img = exposure_case(name)
+    assert same_bits(pe.oracle_exposure(piece, img), pe.ref_exposure(piece, img)).all()
+
+
+@need_ref
+def test_exposure_data_layout_is_the_reference_struct():
+    lib = util.ref("strict")
+    for fn in ("ref_exposure_sizeof_data", "ref_exposure_offsetof_black", "ref_rawprepare_sizeof_data", "ref_highlights_sizeof_data"):
+        getattr(lib, fn).restype = C_size_t
+    import ctypes as C
+    assert lib.ref_exposure_sizeof_data() == C.sizeof(ab.ExposureData) and lib.ref_exposure_offsetof_black() == ab.ExposureData.black.offset
+    assert lib.ref_rawprepare_sizeof_data() == C.sizeof(ab.RawprepareData)
+    assert lib.ref_highlights_sizeof_data() == C.sizeof(ab.HighlightsData)
+
+
+import ctypes  # noqa: E402
+C_size_t = ctypes.c_size_t
+
+
+@need_ref
+def test_float_to_integer_ends_oracle_equals_reference():
+    img = pe.awkward_rgba(211, 97, 12)
+    got, want = pe.oracle_gamma(img), pe.ref_gamma(img)
+    assert (got == want).all() and (want[..., 3] == 0x5A).all()      # the fourth byte is never written
+    for fmt in (ab.EXPORT_UINT8, ab.EXPORT_UINT8_SWAP, ab.EXPORT_UINT16):
+        assert (pe.oracle_export(img, fmt) == pe.ref_export(img, fmt)).all()
+
+
+def _golden():
+    return np.load(os.path.join(util.GOLDEN_DIR, "pipe_ends.npz"))
+
+
+def test_pipe_ends_oracle_equals_golden():
+    """the same cases as above against the outputs the reference builds gave in the authoring container"""
+    g = _golden()
+    for name in RAWPREPARE_CASES:
+        piece, src, _ = rawprepare_case(name)
+        assert same_bits(pe.oracle_rawprepare(piece, src), g["rawprepare_" + name]).all()
+    for name in TEMPERATURE_CASES:
+        assert same_bits(pe.oracle_temperature(*temperature_case(name)), g["temperature_" + name]).all()
+    for name in HIGHLIGHTS_CASES:
+        assert same_bits(pe.oracle_highlights(*highlights_case(name))[1], g["highlights_" + name]).all()
+    for name in EXPOSURE_CASES:
+        assert same_bits(pe.oracle_exposure(*exposure_case(name)), g["exposure_" + name]).all()
+    img = pe.awkward_rgba(211, 97, 12)
+    assert (pe.oracle_gamma(img) == g["gamma"]).all()
+    for fmt in (ab.EXPORT_UINT8, ab.EXPORT_UINT8_SWAP, ab.EXPORT_UINT16):
+        assert (pe.oracle_export(img, fmt) == g[f"export_{fmt}"]).all()
