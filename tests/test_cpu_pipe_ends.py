@@ -51,7 +51,7 @@ RAWPREPARE_CASES = {
 }
 
 
-def rawprepare_case(name, size=(206, 120)):
+def rawprepare_case(name, size=(134, 78)):
     kw = dict(RAWPREPARE_CASES[name])
     w, h = kw.pop("size", size)
     gain = gain_maps() if kw.pop("gain", False) else None
@@ -86,7 +86,7 @@ COEFFS = (2.13, 1.0, 1.57, 1.02)
 
 def temperature_case(name):
     kw = dict(TEMPERATURE_CASES[name])
-    w, h = kw.pop("size", (206, 120))
+    w, h = kw.pop("size", (134, 78))
     piece = pe.mosaic_piece(w, h, ab.temperature_data(COEFFS), **kw)
     img = util.rgba_test_image(w, h, 5) if piece.channels == 4 else util.frame_natural(w, h, 5)
     return piece, img
@@ -112,7 +112,7 @@ HIGHLIGHTS_CASES = {
 }
 
 
-def highlights_case(name, size=(206, 120)):
+def highlights_case(name, size=(134, 78)):
     kw = dict(HIGHLIGHTS_CASES[name])
     w, h = size
     mode, clip, n = kw.pop("mode", ab.HIGHLIGHTS_CLIP), kw.pop("clip", 1.0), kw.pop("n_clipped", None)
@@ -150,7 +150,7 @@ def test_highlights_oracle_equals_reference(name):
 def test_highlights_oracle_refuses_reconstruction_modes():
     piece, img = highlights_case("clip_mosaic")
     for mode in (ab.HIGHLIGHTS_LCH, ab.HIGHLIGHTS_INPAINT, ab.HIGHLIGHTS_LAPLACIAN, ab.HIGHLIGHTS_HARMONIC):
-        p = pe.mosaic_piece(206, 120, ab.highlights_data(mode, 1.0))
+        p = pe.mosaic_piece(134, 78, ab.highlights_data(mode, 1.0))
         assert pe.oracle_highlights(p, img)[0] == -1
 
 
@@ -159,7 +159,7 @@ EXPOSURE_CASES = {"rgba": dict(channels=4), "rgba_mask": dict(channels=4, mask_d
 
 def exposure_case(name):
     kw = EXPOSURE_CASES[name]
-    w, h = 203, 117
+    w, h = 131, 75
     piece = pe.mosaic_piece(w, h, ab.exposure_data(-0.00024, 0.7), filters=0, **kw)
     img = util.rgba_test_image(w, h, 4) if kw["channels"] == 4 else util.frame_natural(w, h, 4)
     return piece, img
@@ -189,7 +189,7 @@ C_size_t = ctypes.c_size_t
 
 @need_ref
 def test_float_to_integer_ends_oracle_equals_reference():
-    img = pe.awkward_rgba(211, 97, 12)
+    img = pe.awkward_rgba(141, 67, 12)
     got, want = pe.oracle_gamma(img), pe.ref_gamma(img)
     assert (got == want).all() and (want[..., 3] == 0x5A).all()      # the fourth byte is never written
     for fmt in (ab.EXPORT_UINT8, ab.EXPORT_UINT8_SWAP, ab.EXPORT_UINT16):
@@ -212,7 +212,7 @@ def test_pipe_ends_oracle_equals_golden():
         assert same_bits(pe.oracle_highlights(*highlights_case(name))[1], g["highlights_" + name]).all()
     for name in EXPOSURE_CASES:
         assert same_bits(pe.oracle_exposure(*exposure_case(name)), g["exposure_" + name]).all()
-    img = pe.awkward_rgba(211, 97, 12)
+    img = pe.awkward_rgba(141, 67, 12)
     assert (pe.oracle_gamma(img) == g["gamma"]).all()
     for fmt in (ab.EXPORT_UINT8, ab.EXPORT_UINT8_SWAP, ab.EXPORT_UINT16):
         assert (pe.oracle_export(img, fmt) == g[f"export_{fmt}"]).all()
