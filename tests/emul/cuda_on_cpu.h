@@ -14,6 +14,11 @@ struct float4
   float x, y, z, w;
 };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{ x, y, z, w }; }
+struct uint2
+{
+  unsigned x, y;
+};
+static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{ x, y }; }
 struct dim3
 {
   unsigned x, y, z;
@@ -67,6 +72,12 @@ static inline int __syncthreads_count(int p) { return p; }
 static inline int atomicAdd(int *p, int v)
 {
   const int old = *p;
+  *p += v;
+  return old;
+}
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v)
+{
+  const unsigned long long old = *p;
   *p += v;
   return old;
 }

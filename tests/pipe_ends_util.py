@@ -18,11 +18,11 @@ def vp(a: np.ndarray):
     return a.ctypes.data_as(VP)
 
 
-def sensor_frame(w: int, h: int, seed: int, black: int = 512, white: int = 16383, clipped: int = 60) -> np.ndarray:
+def sensor_frame(w: int, h: int, seed: int, black: int = 512, white: int = 16383, clipped: int = 60, level: float = 0.9) -> np.ndarray:
     """uint16 RGGB sensor data: the natural test scene scaled into [black, white] with `clipped` blown samples"""
     m = util.frame_natural(w, h, seed)
     rng = np.random.default_rng(seed + 5)
-    raw = np.clip(np.rint(m * (white - black) * 0.9 + black + rng.normal(0, 3, m.shape)), 0, 65535)
+    raw = np.clip(np.rint(m * (white - black) * level + black + rng.normal(0, 3, m.shape)), 0, 65535)
     if clipped:
         ys, xs = rng.integers(0, h, clipped), rng.integers(0, w, clipped)
         raw[ys, xs] = white + rng.integers(0, 40, clipped)

@@ -1,0 +1,139 @@
+"""CPU: the kernels of ansel_b200/csrc/pipe_ends.cu compiled with g++ through tests/emul/cuda_on_cpu.h, run thread by
+thread in the order the entry points launch them, and compared with the oracle bit for bit on the cases of
+tests/test_cpu_pipe_ends.py.  This checks arithmetic, indexing and the host-side set-up those kernels share with the
+product (fill_prepare, make_thresholds); nvcc's code generation and the launch code are what the `-m gpu` tests see."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import ansel_b200 as ab
+import pipe_ends_util as pe
+import test_cpu_pipe_ends as cases
+import util
+
+EMUL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul")
+same_bits = cases.same_bits
+
+
+@pytest.fixture(scope="module")
+def emul():
+    so = os.path.join(EMUL, "libemul_pipe_ends.so")
+    srcs = [os.path.join(EMUL, "emul_pipe_ends.cpp"), os.path.join(EMUL, "cuda_on_cpu.h"), os.path.join(util.ROOT, "ansel_b200", "csrc", "pipe_ends.cu"),
+            os.path.join(util.ROOT, "include", "b200iop.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.run(["g++", "-O1", "-std=c++17", "-fno-fast-math", "-ffp-contract=off", "-I", EMUL, "-shared", "-fPIC", "-o", so, srcs[0]], check=True)
+    subprocess.run(["make", "-s", "-C", util.ORACLE_DIR, "oracle"], check=True)
+    return C.CDLL(so)
+
+
+@pytest.mark.parametrize("name", list(cases.RAWPREPARE_CASES))
+def test_rawprepare_kernels_equal_oracle(emul, name):
+    piece, src, _ = cases.rawprepare_case(name)
+    want = pe.oracle_rawprepare(piece, src)
+    got = np.full_like(want, -7.0)
+    assert emul.emul_rawprepare(C.byref(piece), pe.vp(src), pe.vp(got)) == 0
+    assert same_bits(got, want).all()
+
+
+@pytest.mark.parametrize("name", list(cases.TEMPERATURE_CASES))
+def test_temperature_kernels_equal_oracle(emul, name):
+    piece, img = cases.temperature_case(name)
+    want = pe.oracle_temperature(piece, img)
+    got = np.full_like(want, -7.0)
+    assert emul.emul_temperature(C.byref(piece), pe.vp(img), pe.vp(got)) == 0
+    assert same_bits(got, want).all()
+
+
+@pytest.mark.parametrize("name", list(cases.HIGHLIGHTS_CASES))
+def test_highlights_kernels_equal_oracle(emul, name):
+    piece, img = cases.highlights_case(name)
+    rc, want, n_want = pe.oracle_highlights(piece, img)
+    got, n = np.full_like(want, -7.0), C.c_ulonglong(0)
+    assert emul.emul_highlights(C.byref(piece), pe.vp(img), pe.vp(got), C.byref(n)) == 0 and rc == 0
+    assert n.value == n_want and same_bits(got, want).all()
+
+
+def test_highlights_kernels_refuse_reconstruction_past_the_bypass(emul):
+    _, img = cases.highlights_case("clip_mosaic")
+    piece = pe.mosaic_piece(img.shape[1], img.shape[0], ab.highlights_data(ab.HIGHLIGHTS_HARMONIC, 1.0))
+    got, n = np.zeros_like(img), C.c_ulonglong(0)
+    assert emul.emul_highlights(C.byref(piece), pe.vp(img), pe.vp(got), C.byref(n)) == 3 and n.value >= 25
+
+
+@pytest.mark.parametrize("name", list(cases.EXPOSURE_CASES))
+def test_exposure_kernel_equals_oracle(emul, name):
+    piece, img = cases.exposure_case(name)
+    want = pe.oracle_exposure(piece, img)
+    got = np.full_like(want, -7.0)
+    assert emul.emul_exposure(C.byref(piece), pe.vp(img), pe.vp(got)) == 0
+    assert same_bits(got, want).all()
+
+
+def test_float_to_integer_kernels_equal_oracle(emul):
+    img = pe.awkward_rgba(141, 67, 12)
+    npx = C.c_size_t(img.shape[0] * img.shape[1])
+    got = np.full(img.shape, 0x5A, np.uint8)
+    emul.emul_gamma(pe.vp(img), pe.vp(got), npx)
+    assert (got == pe.oracle_gamma(img)).all()
+    for fmt in (ab.EXPORT_UINT8, ab.EXPORT_UINT8_SWAP, ab.EXPORT_UINT16):
+        got = np.zeros(img.shape, pe.EXPORT_DTYPE[fmt])
+        emul.emul_export(pe.vp(img), pe.vp(got), npx, fmt)
+        assert (got == pe.oracle_export(img, fmt)).all()
+
+
+FRONT_CASES = {
+    "uint16_all_three": dict(),
+    "uint16_crop_gainmaps": dict(x=3, y=5, gain=True),
+    "float_all_three": dict(datatype=ab.TYPE_FLOAT, x=2, y=2),
+    "uint16_bypass": dict(clipped=7, level=0.3),                        # fewer than 25 blown samples: highlights copies through
+    "uint16_no_highlights": dict(highlights=False),
+    "uint16_rawprepare_only": dict(highlights=False, temperature=False, x=1, y=1),
+    "uint16_no_temperature": dict(temperature=False),
+    "uint16_odd_width_roi": dict(size=(131, 77), x=1, y=0, out=(3, 2, 101, 60)),
+}
+
+
+def front_case(name, size=(134, 78)):
+    """-> (pieces [rawprepare, temperature or None, highlights or None], sensor data)"""
+    kw = dict(FRONT_CASES[name])
+    w, h = kw.pop("size", size)
+    gain = cases.gain_maps() if kw.pop("gain", False) else None
+    d = ab.rawprepare_data(cases.SUB, cases.DIV, kw.pop("x", 0), kw.pop("y", 0), gain=gain, spacing=(1.0 / 8, 1.0 / 6), origin=(0.01, -0.02))
+    datatype = kw.pop("datatype", ab.TYPE_UINT16)
+    raw = pe.sensor_frame(w, h, 11, clipped=kw.pop("clipped", 60), level=kw.pop("level", 0.9))
+    src = raw if datatype == ab.TYPE_UINT16 else raw.astype(np.float32)
+    with_t, with_h = kw.pop("temperature", True), kw.pop("highlights", True)
+    rp = pe.rawprepare_piece(w, h, d, datatype=datatype, **kw)
+    ow, oh, ox, oy = rp.roi_out.width, rp.roi_out.height, rp.roi_out.x, rp.roi_out.y
+    tp = pe.mosaic_piece(ow, oh, ab.temperature_data(cases.COEFFS), x=ox, y=oy) if with_t else None
+    pm = (cases.COEFFS[0], cases.COEFFS[1], cases.COEFFS[2], 0.0) if with_t else (1.0, 1.0, 1.0, 0.0)   # temperature's commit scales the maximum
+    hp = pe.mosaic_piece(ow, oh, ab.highlights_data(ab.HIGHLIGHTS_CLIP, 0.98), x=ox, y=oy, pm=pm) if with_h else None
+    return [rp, tp, hp], src
+
+
+def oracle_front(pieces, src):
+    """the three modules one after the other through the oracle"""
+    rp, tp, hp = pieces
+    frame = pe.oracle_rawprepare(rp, src)
+    if tp is not None:
+        frame = pe.oracle_temperature(tp, frame)
+    n = None
+    if hp is not None:
+        rc, frame, n = pe.oracle_highlights(hp, frame)
+        assert rc == 0
+    return frame, n
+
+
+@pytest.mark.parametrize("name", list(FRONT_CASES))
+def test_fused_raw_front_kernels_equal_the_oracle_chain(emul, name):
+    pieces, src = front_case(name)
+    want, n = oracle_front(pieces, src)
+    if pieces[2] is not None:
+        assert (n < 25) == ("bypass" in name)
+    got = np.full_like(want, -7.0)
+    ptr = [C.byref(p) if p is not None else None for p in pieces]
+    assert emul.emul_rawfront(ptr[0], ptr[1], ptr[2], pe.vp(src), pe.vp(got)) == 0
+    assert same_bits(got, want).all()
