@@ -59,7 +59,8 @@ class PipeNode(C.Structure):
 
 
 _mod = None
-ADAPTED_OPS = ("demosaic", "colorin", "colorout", "denoiseprofile", "filmicrgb", "bilat", "diffuse", "nlmeans")
+ADAPTED_OPS = ("demosaic", "colorin", "colorout", "denoiseprofile", "filmicrgb", "bilat", "diffuse", "nlmeans",
+               "rawprepare", "temperature", "highlights", "exposure", "gamma")
 
 
 def modlib() -> C.CDLL:
@@ -135,23 +136,26 @@ def make_pipe(devid: int = 0, pipe_type: int = 1, stream: int | None = None, exi
 
 
 def make_piece_iop(op: str, width: int, height: int, data, *, channels_in: int, channels_out: int,
-                   filters: int = 0, processed_maximum=(1.0, 1.0, 1.0, 1.0), wb=(2.0, 1.0, 1.5, 0.0)) -> PipeIop:
+                   filters: int = 0, processed_maximum=(1.0, 1.0, 1.0, 1.0), wb=(2.0, 1.0, 1.5, 0.0),
+                   type_in: int = 1, type_out: int = 1) -> PipeIop:
+    """type_in / type_out: dt_iop_buffer_type_t of the two cachelines (1 float, 2 uint16, 3 uint8)"""
     m = Module()
     m.op = op.encode()
     piece = PipeIop()
     piece._keepalive = (m, data)  # noqa
     piece.module = C.pointer(m)
-    piece.data = C.cast(C.pointer(data), C.c_void_p)
-    piece.data_size = C.sizeof(data)
+    if data is not None:
+        piece.data = C.cast(C.pointer(data), C.c_void_p)
+        piece.data_size = C.sizeof(data)
     piece.enabled = 1
     roi = Roi(0, 0, width, height, 1.0)
     piece.buf_in = piece.buf_out = piece.roi_in = piece.roi_out = roi
     piece.process_cl_ready = 1
     piece.process_tiling_ready = 1
-    for dsc, ch in ((piece.dsc_in, channels_in), (piece.dsc_out, channels_out)):
+    for dsc, ch, ty in ((piece.dsc_in, channels_in, type_in), (piece.dsc_out, channels_out, type_out)):
         dsc.channels = ch
-        dsc.datatype = 1  # TYPE_FLOAT
-        dsc.bpp = 4 * ch
+        dsc.datatype = ty
+        dsc.bpp = {1: 4, 2: 2, 3: 1}[ty] * ch
         dsc.filters = filters if ch == 1 else 0
         for k in range(4):
             dsc.processed_maximum[k] = processed_maximum[k]

@@ -111,6 +111,7 @@ static inline void b200_piece_from_dt(b200_piece_t *p, const dt_iop_module_t *se
   for(int i = 0; i < 6; i++)
     for(int j = 0; j < 6; j++) p->xtrans[i][j] = piece->dsc_in.xtrans[i][j];
   p->channels = piece->dsc_in.channels;
+  p->datatype = piece->dsc_in.datatype;
   for(int k = 0; k < 4; k++)
   {
     p->processed_maximum[k] = piece->dsc_in.processed_maximum[k];

@@ -42,6 +42,13 @@ ADAPT(diffuse)        /* src/iop/diffuse.c:1155 (process), :1486 (process_cl), :
 ADAPT(nlmeans)        /* src/iop/nlmeans.c:458 (process), :150-398 (process_cl), :400 (tiling_callback) */
 ADAPT(bilat)          /* src/iop/bilat.c:336 (process), :313-334 (process_cl), :296 (commit: tiling off) */
 
+/* the modules either side of that path: sensor data in, display/export integers out */
+ADAPT(rawprepare)  /* src/iop/rawprepare.c:467 (process), :636 (process_cl); default_tiling_callback */
+ADAPT(temperature) /* src/iop/temperature.c:487 (process), :611 (process_cl) */
+ADAPT(highlights)  /* src/iop/highlights.c:680 (process), :464 (process_cl), :575 (tiling_callback) */
+ADAPT(exposure)    /* src/iop/exposure.c:503 (process), :473 (process_cl) */
+ADAPT(gamma)       /* src/iop/gamma.c:367 (process), :461 (process_cl) */
+
 /* filmic reads two pipe-level profiles next to piece->data (filmicrgb.c:2714-2715); the adapter flattens the
  * three into the b200_filmicrgb_piece_t the library takes.  A soft-proof profile (data->softproof_mode != 0,
  * _filmic_get_output_profile :2650-2666) is resolved by the reference's own dt_colorspaces_add_profile() in

@@ -66,6 +66,64 @@ def test_no_cuda_device_fails_loudly(built):
         assert (out == -3.0).all(), op
 
 
+def test_pipe_end_modules_fail_loudly_without_a_device(built):
+    """rawprepare, temperature, highlights, exposure, gamma, the export conversion: refusal, nothing computed on the CPU"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import ansel_b200 as ab
+    L = ab.lib()
+    raw = np.full((64, 64), 1000, np.uint16)
+    mosaic, rgba = np.zeros((64, 64), np.float32), np.zeros((64, 64, 4), np.float32)
+    cases = dict(rawprepare=(ab.rawprepare_data((512,) * 4, (15000,) * 4), raw, 1), temperature=(ab.temperature_data((2, 1, 1.5, 1)), mosaic, 1),
+                 highlights=(ab.highlights_data(), mosaic, 1), exposure=(ab.exposure_data(0.0, 0.5), rgba, 4), gamma=(None, rgba, 4))
+    for op, (data, src, ch) in cases.items():
+        pc = ab.make_piece(64, 64, filters=0x94949494 if ch == 1 else 0, channels=ch, data=data)
+        pc.datatype = ab.TYPE_UINT16 if op == "rawprepare" else ab.TYPE_FLOAT
+        out = np.full((64, 64, 4), -3.0, np.float32)
+        assert getattr(L, f"b200_{op}_process_host")(pc, src.ctypes.data, out.ctypes.data) != 0, op
+        assert b"CUDA" in L.b200_last_error() or b"device" in L.b200_last_error(), op
+        assert (out == -3.0).all(), op
+    out = np.full((64, 64, 4), 7, np.uint16)
+    assert L.b200_export_convert_host(rgba.ctypes.data, out.ctypes.data, 64, 64, ab.EXPORT_UINT16) != 0
+    assert (out == 7).all()
+
+
+def test_pipe_end_tiling_callbacks(built):
+    """default_tiling_callback (develop/tiling.c:1423-1463) for rawprepare (TILING_FULL_ROI), temperature, exposure, gamma;
+    highlights' own (iop/highlights.c:575-644)"""
+    import ansel_b200 as ab
+    L = ab.lib()
+    t = ab.Tiling()
+    piece = ab.make_piece(6000, 4000, data=ab.rawprepare_data((512,) * 4, (15000,) * 4), out_width=5990, out_height=3990)
+    L.b200_rawprepare_tiling(piece, t)
+    want = np.float32(1.0) + (np.float32(5990) * np.float32(3990)) / (np.float32(6000) * np.float32(4000))
+    assert (t.overlap, t.xalign, t.yalign) == (4, 2, 2) and np.float32(t.factor) == want
+    piece = ab.make_piece(6000, 4000, filters=9, data=ab.temperature_data((2, 1, 1.5, 1)))
+    L.b200_temperature_tiling(piece, t)
+    assert (t.overlap, t.xalign, t.yalign, t.factor) == (0, 3, 3, 2.0)
+    for op, data in (("exposure", ab.exposure_data()), ("gamma", None)):
+        piece = ab.make_piece(6000, 4000, filters=0, channels=4, data=data)
+        getattr(L, f"b200_{op}_tiling")(piece, t)
+        assert (t.overlap, t.xalign, t.yalign, t.factor) == (0, 1, 1, 2.0), op
+    piece = ab.make_piece(6000, 4000, data=ab.highlights_data(ab.HIGHLIGHTS_LCH))
+    L.b200_highlights_tiling(piece, t)
+    assert (t.overlap, t.xalign, t.yalign, t.factor) == (1, 2, 2, 2.0)
+    d = ab.highlights_data(ab.HIGHLIGHTS_HARMONIC)
+    piece = ab.make_piece(6000, 4000, data=d)
+    L.b200_highlights_tiling(piece, t)
+    # scales = 8: final_radius = 256 / 4 = 64 -> 6 scales -> radius 64 -> overlap 64 * 1.5 / 4
+    assert (t.overlap, t.xalign, t.yalign) == (24, 2, 2) and abs(t.factor - 16.0) < 1e-6 and abs(t.factor_cl - 20.0) < 1e-6
+
+
+def test_piece_datatype_fills_padding(built):
+    """b200_piece_t gained `datatype` where the compiler had padding: size and the offsets of its neighbours are unchanged"""
+    import ansel_b200 as ab
+    import ansel_b200.dtsurface as ds
+    assert C.sizeof(ab.Piece) == 184 and ab.Piece.devid.offset == 160 and ab.Piece.datatype.offset == 164 and ab.Piece.data.offset == 168
+    assert ds.modlib().b200_dt_surface_probe(10) == C.sizeof(ab.Piece)
+
+
 def _shift_dcraw(filters, x, y):
     """ColorFilterArray::shiftDcrawFilter (rawspeed ColorFilterArray.cpp:143-170) in Python ints."""
     if abs(x) & 1:
