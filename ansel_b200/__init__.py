@@ -131,6 +131,7 @@ class ProfileCurves(C.Structure):
 TYPE_UNKNOWN, TYPE_FLOAT, TYPE_UINT16, TYPE_UINT8 = range(4)
 HIGHLIGHTS_CLIP, HIGHLIGHTS_LCH, HIGHLIGHTS_INPAINT, HIGHLIGHTS_LAPLACIAN, HIGHLIGHTS_HARMONIC = range(5)
 EXPORT_UINT8, EXPORT_UINT8_SWAP, EXPORT_UINT16 = range(3)
+INTERPOLATION_BILINEAR, INTERPOLATION_BICUBIC, INTERPOLATION_MITCHELL = range(3)
 
 
 class DngGainMap(C.Structure):
@@ -165,6 +166,11 @@ class ExposureData(C.Structure):
     _fields_ = [("mode", C.c_int), ("p_black", C.c_float), ("p_exposure", C.c_float), ("deflicker_percentile", C.c_float),
                 ("deflicker_target_level", C.c_float), ("compensate_exposure_bias", C.c_int), ("deflicker", C.c_int),
                 ("black", C.c_float), ("scale", C.c_float)]
+
+
+class FinalscaleData(C.Structure):
+    """b200_finalscale_data_t: dt_iop_finalscale_data_t's dummy int + the user-preference interpolator the adapter resolves."""
+    _fields_ = [("dummy", C.c_int), ("interpolator", C.c_int)]
 
 
 class B200Error(RuntimeError):
@@ -476,4 +482,10 @@ def exposure_data(black: float = 0.0, exposure_ev: float = 0.0) -> ExposureData:
     d.black = black
     white = np.exp2(np.float32(-exposure_ev), dtype=np.float32)
     d.scale = float(np.float32(1.0 / float(white - np.float32(black))))
+    return d
+
+
+def finalscale_data(interpolator: int = INTERPOLATION_MITCHELL) -> FinalscaleData:
+    d = FinalscaleData()
+    d.interpolator = interpolator
     return d

@@ -579,6 +579,35 @@ int b200_exposure_process_host(const b200_piece_t *piece, const void *in, void *
 int b200_exposure_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
 void b200_exposure_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
 
+/* ---- finalscale (src/iop/finalscale.c): the export's final resampling ------------------------------------------- */
+/* enum dt_interpolation_type, src/pixel/interpolation.h:38-44 (same values) */
+enum
+{
+  B200_INTERPOLATION_BILINEAR = 0,
+  B200_INTERPOLATION_BICUBIC = 1,
+  B200_INTERPOLATION_MITCHELL = 2 /* DT_INTERPOLATION_DEFAULT */
+};
+/* dt_iop_finalscale_data_t (finalscale.c:46-51: one dummy int) + the interpolator process() resolves from the user
+ * preference (dt_interpolation_new(DT_INTERPOLATION_USERPREF), plugins/lighttable/export/pixel_interpolator): the
+ * adapter passes its id, the library reads no configuration */
+typedef struct b200_finalscale_data_t
+{
+  int dummy;
+  int interpolator; /* B200_INTERPOLATION_* */
+} b200_finalscale_data_t;
+/* process() :117-131 = dt_iop_clip_and_zoom_roi -> _interpolation_resample_plain (pixel/interpolation.c:897-1027) with
+ * both ROI origins zeroed: roi_in.width x height RGBA at roi_in.scale -> roi_out.width x height at roi_out.scale.  The
+ * two per-axis tap plans (_prepare_resampling_plan :710-893) are built on the host as in the reference; every output
+ * pixel accumulates its taps in the reference's order (rows, then columns within a row), negative and non-finite
+ * results become 0.  Equal scales (or roi_out.scale == 1) copy rows. */
+int b200_finalscale_process_host(const b200_piece_t *piece, const void *in, void *out);
+int b200_finalscale_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
+void b200_finalscale_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
+/* One axis of the plan, for inspection (lengths[out], kernel/index concatenated, at most max_taps): returns the number of
+ * taps, -1 for scale == 1 (no resampling), < -1 on error */
+int b200_resampling_plan(int interpolator, int in, int in_x0, int out, int out_x0, float scale, int *lengths, float *kernel, int *index,
+                         int max_taps);
+
 /* ---- gamma (src/iop/gamma.c): the pipe's last module, float RGBA -> uint8 BGRA for the display --------------------- */
 /* process() :367-377 with no mask or channel display: _copy_output :352-364 (the fourth byte of every output pixel is
  * not written).  Mask and false-colour displays (GUI previews) return B200_ERR_UNSUPPORTED. */

@@ -215,3 +215,44 @@ def awkward_rgba(w: int, h: int, seed: int) -> np.ndarray:
     flat[k[200:300]] = (rng.integers(0, 256, 100) + 0.5) / np.float32(255.0)
     flat[k[300:400]] = (rng.integers(0, 65536, 100) + 0.5) / np.float32(65535.0)
     return img
+
+
+# ---- finalscale ---------------------------------------------------------------------------------------------------------
+def _plan(lib, fn, interpolator, n_in, in_x0, n_out, out_x0, scale):
+    per = 160
+    lengths, kernel, index = np.zeros(n_out, np.int32), np.zeros(per * n_out, np.float32), np.zeros(per * n_out, np.int32)
+    f = getattr(lib, fn)
+    f.restype = C.c_int
+    f.argtypes = [C.c_int] * 5 + [C.c_float, VP, VP, VP, C.c_int]
+    n = f(interpolator, n_in, in_x0, n_out, out_x0, scale, vp(lengths), vp(kernel), vp(index), per * n_out)
+    return n, lengths, kernel[:max(n, 0)], index[:max(n, 0)]
+
+
+def oracle_plan(*a):
+    return _plan(util.oracle(), "orc_resampling_plan", *a)
+
+
+def ref_plan(*a, kind="strict"):
+    lib = util.ref(kind)
+    return None if lib is None else _plan(lib, "ref_resampling_plan", *a)
+
+
+def _finalscale(lib, fn, img, out_w, out_h, in_scale, out_scale, interpolator):
+    h, w = img.shape[:2]
+    src, out = util.aligned_empty(img.shape), util.aligned_empty((out_h, out_w, 4))
+    src[...] = img
+    out[...] = -7.0
+    f = getattr(lib, fn)
+    f.restype = C.c_int
+    f.argtypes = [VP, VP, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int]
+    assert f(vp(src), vp(out), w, h, in_scale, out_w, out_h, out_scale, interpolator) == 0
+    return np.array(out)
+
+
+def oracle_finalscale(img, out_w, out_h, in_scale, out_scale, interpolator):
+    return _finalscale(util.oracle(), "orc_finalscale", img, out_w, out_h, in_scale, out_scale, interpolator)
+
+
+def ref_finalscale(img, out_w, out_h, in_scale, out_scale, interpolator, kind="strict"):
+    lib = util.ref(kind)
+    return None if lib is None else _finalscale(lib, "ref_finalscale", img, out_w, out_h, in_scale, out_scale, interpolator)

@@ -196,6 +196,52 @@ def test_float_to_integer_ends_oracle_equals_reference():
         assert (pe.oracle_export(img, fmt) == pe.ref_export(img, fmt)).all()
 
 
+FINALSCALE_CASES = {
+    # name: (input w, h, input scale, output scale, interpolator); output size = round(input * out / in) as modify_roi_in implies
+    "export_half_mitchell": (161, 97, 1.0, 0.5, ab.INTERPOLATION_MITCHELL),
+    "export_third_bicubic": (173, 101, 1.0, 0.3333, ab.INTERPOLATION_BICUBIC),
+    "export_0p77_bilinear": (150, 90, 1.0, 0.77, ab.INTERPOLATION_BILINEAR),
+    "tiny_thumbnail_mitchell": (160, 120, 1.0, 0.06, ab.INTERPOLATION_MITCHELL),
+    "darkroom_upscale_mitchell": (90, 60, 1.0, 1.7, ab.INTERPOLATION_MITCHELL),
+    "darkroom_upscale_bicubic": (70, 50, 1.0, 2.0, ab.INTERPOLATION_BICUBIC),
+    "upscale_bilinear": (64, 48, 1.0, 1.25, ab.INTERPOLATION_BILINEAR),
+    "same_scale_is_a_copy": (80, 60, 0.5, 0.5, ab.INTERPOLATION_MITCHELL),
+}
+
+
+def finalscale_case(name):
+    w, h, si, so, itor = FINALSCALE_CASES[name]
+    img = util.rgba_test_image(w, h, 17, lo=-0.2, hi=1.5)
+    img[3, 3, 1] = np.nan
+    img[h // 2, w // 2, 0] = np.inf
+    ow, oh = (w - 10, h - 7) if si == so else (int(round(w * so / si)), int(round(h * so / si)))
+    return img, ow, oh, si, so, itor
+
+
+@need_ref
+@pytest.mark.parametrize("itor", [ab.INTERPOLATION_BILINEAR, ab.INTERPOLATION_BICUBIC, ab.INTERPOLATION_MITCHELL])
+@pytest.mark.parametrize("scale", [0.5, 0.3333, 0.77, 0.06, 0.999, 1.001, 1.7, 2.0, 3.3])
+def test_resampling_plan_oracle_equals_reference(itor, scale):
+    """_prepare_resampling_plan cut verbatim: lengths, normalised taps (bit for bit) and clipped indexes of one axis"""
+    n_in = 400
+    for x0_in, x0_out in ((0, 0), (13, 7)):
+        n_out = max(int(n_in * scale) - x0_out, 4)
+        n, l, k, i = pe.oracle_plan(itor, n_in, x0_in, n_out, x0_out, scale)
+        rn, rl, rk, ri = pe.ref_plan(itor, n_in, x0_in, n_out, x0_out, scale)
+        assert n == rn and n > 0 and (l == rl).all() and (i == ri).all() and same_bits(k, rk).all()
+    assert pe.oracle_plan(itor, n_in, 0, n_in, 0, 1.0)[0] == -1 == pe.ref_plan(itor, n_in, 0, n_in, 0, 1.0)[0]
+
+
+@need_ref
+@pytest.mark.parametrize("name", list(FINALSCALE_CASES))
+def test_finalscale_oracle_equals_reference(name):
+    args = finalscale_case(name)
+    want = pe.ref_finalscale(*args)
+    assert same_bits(pe.oracle_finalscale(*args), want).all()
+    if "copy" not in name:       # resampled pixels are clipped at 0 and never non-finite; copied rows are what they were
+        assert (want >= 0).all() and np.isfinite(want).all() and want.std() > 0
+
+
 def _golden():
     return np.load(os.path.join(util.GOLDEN_DIR, "pipe_ends.npz"))
 
@@ -212,6 +258,8 @@ def test_pipe_ends_oracle_equals_golden():
         assert same_bits(pe.oracle_highlights(*highlights_case(name))[1], g["highlights_" + name]).all()
     for name in EXPOSURE_CASES:
         assert same_bits(pe.oracle_exposure(*exposure_case(name)), g["exposure_" + name]).all()
+    for name in FINALSCALE_CASES:
+        assert same_bits(pe.oracle_finalscale(*finalscale_case(name)), g["finalscale_" + name]).all()
     img = pe.awkward_rgba(141, 67, 12)
     assert (pe.oracle_gamma(img) == g["gamma"]).all()
     for fmt in (ab.EXPORT_UINT8, ab.EXPORT_UINT8_SWAP, ab.EXPORT_UINT16):
