@@ -49,6 +49,43 @@ ADAPT(highlights)  /* src/iop/highlights.c:680 (process), :464 (process_cl), :57
 ADAPT(exposure)    /* src/iop/exposure.c:503 (process), :473 (process_cl) */
 ADAPT(gamma)       /* src/iop/gamma.c:367 (process), :461 (process_cl) */
 
+/* finalscale's data block is one dummy int (finalscale.c:46-51); its process() resolves the interpolator from the user
+ * preference: dt_interpolation_new(DT_INTERPOLATION_USERPREF) (develop/imageop_math.c:150).  In the reference tree the
+ * adapter passes that interpolator's id; standing alone, dt_surface.h keeps the preference in a variable. */
+int b200_userpref_interpolator = B200_INTERPOLATION_MITCHELL; /* plugins/lighttable/export/pixel_interpolator, default "mitchell" */
+static void finalscale_view(b200_finalscale_data_t *fd, b200_piece_t *p)
+{
+  fd->dummy = 0;
+  fd->interpolator = b200_userpref_interpolator; /* = dt_interpolation_new(DT_INTERPOLATION_USERPREF)->id */
+  p->data = fd;
+  p->data_size = sizeof(*fd);
+}
+int dt_iop_finalscale__process(struct dt_iop_module_t *self, const dt_dev_pixelpipe_t *pipe, const dt_dev_pixelpipe_iop_t *piece,
+                               const void *const i, void *const o)
+{
+  b200_piece_t p;
+  b200_finalscale_data_t fd;
+  b200_piece_from_dt(&p, self, pipe, piece);
+  finalscale_view(&fd, &p);
+  return b200_finalscale_process_host(&p, i, o);
+}
+int dt_iop_finalscale__process_cl(struct dt_iop_module_t *self, const dt_dev_pixelpipe_t *pipe, const dt_dev_pixelpipe_iop_t *piece,
+                                  cl_mem dev_in, cl_mem dev_out)
+{
+  b200_piece_t p;
+  b200_finalscale_data_t fd;
+  b200_piece_from_dt(&p, self, pipe, piece);
+  finalscale_view(&fd, &p);
+  return b200_finalscale_process_dev(&p, dev_in, dev_out, pipe->stream) == 0 ? TRUE : FALSE;
+}
+void dt_iop_finalscale__tiling_callback(struct dt_iop_module_t *self, const dt_dev_pixelpipe_t *pipe,
+                                        const dt_dev_pixelpipe_iop_t *piece, dt_develop_tiling_t *tiling)
+{
+  b200_piece_t p;
+  b200_piece_from_dt(&p, self, pipe, piece);
+  b200_finalscale_tiling(&p, tiling);
+}
+
 /* filmic reads two pipe-level profiles next to piece->data (filmicrgb.c:2714-2715); the adapter flattens the
  * three into the b200_filmicrgb_piece_t the library takes.  A soft-proof profile (data->softproof_mode != 0,
  * _filmic_get_output_profile :2650-2666) is resolved by the reference's own dt_colorspaces_add_profile() in

@@ -84,6 +84,10 @@ def test_pipe_end_modules_fail_loudly_without_a_device(built):
         assert getattr(L, f"b200_{op}_process_host")(pc, src.ctypes.data, out.ctypes.data) != 0, op
         assert b"CUDA" in L.b200_last_error() or b"device" in L.b200_last_error(), op
         assert (out == -3.0).all(), op
+    pc = ab.make_piece(64, 64, filters=0, channels=4, data=ab.finalscale_data(), out_width=32, out_height=32)
+    pc.roi_out.scale = 0.5
+    out = np.full((32, 32, 4), -3.0, np.float32)
+    assert L.b200_finalscale_process_host(pc, rgba.ctypes.data, out.ctypes.data) != 0 and (out == -3.0).all()
     out = np.full((64, 64, 4), 7, np.uint16)
     assert L.b200_export_convert_host(rgba.ctypes.data, out.ctypes.data, 64, 64, ab.EXPORT_UINT16) != 0
     assert (out == 7).all()
@@ -106,6 +110,9 @@ def test_pipe_end_tiling_callbacks(built):
         piece = ab.make_piece(6000, 4000, filters=0, channels=4, data=data)
         getattr(L, f"b200_{op}_tiling")(piece, t)
         assert (t.overlap, t.xalign, t.yalign, t.factor) == (0, 1, 1, 2.0), op
+    piece = ab.make_piece(6000, 4000, filters=0, channels=4, data=ab.finalscale_data(), out_width=3000, out_height=2000)
+    L.b200_finalscale_tiling(piece, t)
+    assert (t.overlap, t.xalign, t.yalign, t.factor) == (4, 1, 1, 1.25)      # IOP_FLAGS_TILING_FULL_ROI
     piece = ab.make_piece(6000, 4000, data=ab.highlights_data(ab.HIGHLIGHTS_LCH))
     L.b200_highlights_tiling(piece, t)
     assert (t.overlap, t.xalign, t.yalign, t.factor) == (1, 2, 2, 2.0)

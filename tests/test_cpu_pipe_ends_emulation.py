@@ -137,3 +137,34 @@ def test_fused_raw_front_kernels_equal_the_oracle_chain(emul, name):
     ptr = [C.byref(p) if p is not None else None for p in pieces]
     assert emul.emul_rawfront(ptr[0], ptr[1], ptr[2], pe.vp(src), pe.vp(got)) == 0
     assert same_bits(got, want).all()
+
+
+# ---- finalscale: ansel_b200/csrc/resample.cu -------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def emul_resample():
+    so = os.path.join(EMUL, "libemul_resample.so")
+    srcs = [os.path.join(EMUL, "emul_resample.cpp"), os.path.join(EMUL, "cuda_on_cpu.h"), os.path.join(util.ROOT, "ansel_b200", "csrc", "resample.cu"),
+            os.path.join(util.ROOT, "include", "b200iop.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.run(["g++", "-O1", "-std=c++17", "-fno-fast-math", "-ffp-contract=off", "-I", EMUL, "-shared", "-fPIC", "-o", so, srcs[0]], check=True)
+    subprocess.run(["make", "-s", "-C", util.ORACLE_DIR, "oracle"], check=True)
+    return C.CDLL(so)
+
+
+@pytest.mark.parametrize("itor", [ab.INTERPOLATION_BILINEAR, ab.INTERPOLATION_BICUBIC, ab.INTERPOLATION_MITCHELL])
+@pytest.mark.parametrize("scale", [0.5, 0.3333, 0.77, 0.06, 0.999, 1.001, 1.7, 2.0, 3.3])
+def test_product_plan_builder_equals_oracle(emul_resample, itor, scale):
+    """build_axis_plan (the host code the product runs) against the oracle's plan: lengths, taps bit for bit, indexes"""
+    n_in = 400
+    for x0_in, x0_out in ((0, 0), (13, 7)):
+        n_out = max(int(n_in * scale) - x0_out, 4)
+        n, l, k, i = pe._plan(emul_resample, "emul_resampling_plan", itor, n_in, x0_in, n_out, x0_out, scale)
+        on, ol, ok, oi = pe.oracle_plan(itor, n_in, x0_in, n_out, x0_out, scale)
+        assert n == on and n > 0 and (l == ol).all() and (i == oi).all() and same_bits(k, ok).all()
+    assert pe._plan(emul_resample, "emul_resampling_plan", itor, n_in, 0, n_in, 0, 1.0)[0] == -1
+
+
+@pytest.mark.parametrize("name", list(cases.FINALSCALE_CASES))
+def test_finalscale_kernels_equal_oracle(emul_resample, name):
+    args = cases.finalscale_case(name)
+    assert same_bits(pe._finalscale(emul_resample, "emul_finalscale", *args), pe.oracle_finalscale(*args)).all()

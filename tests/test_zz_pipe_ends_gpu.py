@@ -235,3 +235,56 @@ def test_adapters_and_device_resident_export_chain(built):
     ep = pe.mosaic_piece(w, h, datas["exposure"], filters=0, channels=4)
     want = pe.oracle_gamma(pe.oracle_exposure(ep, rgb), fill=0x5A)
     assert (got_rows := (out[..., :3] == want[..., :3]).all(axis=2))[defined].all(), int((~got_rows & defined).sum())
+
+
+# ---- finalscale ---------------------------------------------------------------------------------------------------------------
+def finalscale_piece(in_w, in_h, in_scale, out_w, out_h, out_scale, itor):
+    import ansel_b200 as ab
+    p = ab.make_piece(in_w, in_h, filters=0, channels=4, data=ab.finalscale_data(itor), out_width=out_w, out_height=out_h, devid=0)
+    p.roi_in.scale, p.roi_out.scale = in_scale, out_scale
+    p.roi_in.x, p.roi_in.y, p.roi_out.x, p.roi_out.y = 11, 5, 3, 2      # process() zeroes the origins: they must not matter
+    return p
+
+
+@pytest.mark.parametrize("name", list(cases.FINALSCALE_CASES))
+def test_finalscale_bit_exact(built, name):
+    img, ow, oh, si, so, itor = cases.finalscale_case(name)
+    want = pe.oracle_finalscale(img, ow, oh, si, so, itor)
+    piece = finalscale_piece(img.shape[1], img.shape[0], si, ow, oh, so, itor)
+    for run in (run_dev, run_host):
+        rc, got = run("finalscale", piece, img, want.shape)
+        assert rc == 0 and same_bits(got, want).all(), run.__name__
+    g = np.load(os.path.join(util.GOLDEN_DIR, "pipe_ends.npz"))
+    assert same_bits(got, g["finalscale_" + name]).all()
+
+
+def test_finalscale_plan_equals_oracle(built):
+    """the host code the product runs (b200_resampling_plan) against the oracle's plan"""
+    import ansel_b200 as ab
+    for itor in (ab.INTERPOLATION_BILINEAR, ab.INTERPOLATION_BICUBIC, ab.INTERPOLATION_MITCHELL):
+        for scale in (0.5, 0.3333, 0.06, 1.7, 3.3):
+            n_out = max(int(400 * scale) - 7, 4)
+            n, l, k, i = pe._plan(ab.lib(), "b200_resampling_plan", itor, 400, 13, n_out, 7, scale)
+            on, ol, ok, oi = pe.oracle_plan(itor, 400, 13, n_out, 7, scale)
+            assert n == on and (l == ol).all() and (i == oi).all() and same_bits(k, ok).all()
+
+
+def test_finalscale_export_sizes(built):
+    """a 12 MP frame down to 2048 px wide, and the 45 MP frame to half size through a size-independent property: a constant
+    image stays that constant wherever the taps are normalised (every output pixel, both axes)"""
+    import torch
+    import ansel_b200 as ab
+    ab.init()
+    img = util.rgba_test_image(4000, 3000, 23, lo=0.0, hi=1.2)
+    so = 2048 / 4000
+    ow, oh = 2048, int(round(3000 * so))
+    piece = finalscale_piece(4000, 3000, 1.0, ow, oh, so, ab.INTERPOLATION_MITCHELL)
+    rc, got = run_dev("finalscale", piece, img, (oh, ow, 4))
+    assert rc == 0 and same_bits(got, pe.oracle_finalscale(img, ow, oh, 1.0, so, ab.INTERPOLATION_MITCHELL)).all()
+    w, h = util.SIZE_45MP
+    d_in = torch.full((h, w, 4), 0.5, dtype=torch.float32, device="cuda")
+    d_out = torch.zeros((h // 2, w // 2, 4), dtype=torch.float32, device="cuda")
+    piece = finalscale_piece(w, h, 1.0, w // 2, h // 2, 0.5, ab.INTERPOLATION_BICUBIC)
+    assert ab.lib().b200_finalscale_process_dev(C.byref(piece), d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream) == 0
+    torch.cuda.synchronize()
+    assert float((d_out - 0.5).abs().max()) < 1e-6
