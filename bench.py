@@ -229,6 +229,110 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------
+def pipe_ends_extras(ab, ds, util, L, M, torch, w, h, local, dev, stream, conv_in, conv_out, d_cin, d_cout):
+    """Per-module device times of rawprepare / temperature / highlights(clip) / their fused pass / exposure / gamma /
+    finalscale at the bench frame size, and the sensor-to-display chain end to end: uint16 sensor data up (2 B/px), uint8
+    display pixels down (4 B/px), rawprepare -> temperature -> highlights -> demosaic(RCD) -> colorin -> colorout -> gamma
+    through the C module adapters with two frames in flight."""
+    npx = w * h
+    wb = (2.13, 1.0, 1.57, 1.02)
+    pm = (wb[0], wb[1], wb[2], 0.0)
+    filters = util.BAYER["RGGB"]
+    sub, div = (512.0, 520.0, 508.0, 515.0), (15871.0, 15863.0, 15875.0, 15868.0)
+    rng = np.random.default_rng(SEED)
+    raw = np.clip(util.frame_natural(w, h, SEED) * 15871.0 * 0.45 + 512.0 + rng.normal(0, 3, (h, w)), 0, 16383).astype(np.uint16)
+    raw[rng.integers(0, h, 4000), rng.integers(0, w, 4000)] = 16383           # blown samples: highlights takes the clip branch
+    d_rp, d_tp, d_hl = ab.rawprepare_data(sub, div), ab.temperature_data(wb), ab.highlights_data(ab.HIGHLIGHTS_CLIP, 1.0)
+    d_ex, d_fs, d_dem = ab.exposure_data(0.0, 0.5), ab.finalscale_data(ab.INTERPOLATION_MITCHELL), ab.demosaic_data(ab.DEMOSAIC_RCD)
+
+    def piece(data, ch, datatype=ab.TYPE_FLOAT, pmax=(1.0, 1.0, 1.0, 1.0), out=None):
+        p = ab.make_piece(w, h, filters=filters if ch == 1 else 0, channels=ch, data=data, processed_maximum=pmax, devid=local,
+                          out_width=out[0] if out else None, out_height=out[1] if out else None)
+        p.datatype = datatype
+        return p
+
+    p_rp, p_tp, p_hl = piece(d_rp, 1, ab.TYPE_UINT16), piece(d_tp, 1), piece(d_hl, 1, pmax=pm)
+    p_ex, p_gm = piece(d_ex, 4), piece(None, 4)
+    p_fs = piece(d_fs, 4, out=(w // 2, h // 2))
+    p_fs.roi_out.scale = 0.5
+    t_raw = torch.from_numpy(raw).to(dev)
+    t_m = [torch.empty((h, w), dtype=torch.float32, device=dev) for _ in range(2)]
+    t_rgba = torch.rand((h, w, 4), dtype=torch.float32, device=dev)
+    t_out = torch.empty((h, w, 4), dtype=torch.float32, device=dev)
+    t_u8 = torch.zeros((h, w, 4), dtype=torch.uint8, device=dev)
+
+    def timed(call, reps=5):
+        call()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            call()
+            a1.record()
+            torch.cuda.synchronize()
+            ts.append(a0.elapsed_time(a1))
+        return float(np.median(ts))
+
+    res = {}
+
+    def report(label, ms, bytes_per_px):
+        res[label] = {"ms": ms, "MP_per_s": npx / ms / 1e3, "algorithmic_GBps": bytes_per_px * npx / (ms * 1e-3) / 1e9,
+                      "algorithmic_bytes_per_px": bytes_per_px}
+
+    report("rawprepare_uint16", timed(lambda: ab.check(L.b200_rawprepare_process_dev(p_rp, t_raw.data_ptr(), t_m[0].data_ptr(), stream))), 6)
+    report("temperature", timed(lambda: ab.check(L.b200_temperature_process_dev(p_tp, t_m[0].data_ptr(), t_m[1].data_ptr(), stream))), 8)
+    report("highlights_clip", timed(lambda: ab.check(L.b200_highlights_process_dev(p_hl, t_m[1].data_ptr(), t_m[0].data_ptr(), stream))), 8)
+    report("rawfront_fused_uint16", timed(lambda: ab.check(L.b200_rawfront_process_dev(p_rp, p_tp, p_hl, t_raw.data_ptr(), t_m[0].data_ptr(), stream))), 6)
+    report("exposure", timed(lambda: ab.check(L.b200_exposure_process_dev(p_ex, t_rgba.data_ptr(), t_out.data_ptr(), stream))), 32)
+    report("gamma_uint8", timed(lambda: ab.check(L.b200_gamma_process_dev(p_gm, t_rgba.data_ptr(), t_u8.data_ptr(), stream))), 20)
+    report("export_uint16", timed(lambda: ab.check(L.b200_export_convert_dev(t_rgba.data_ptr(), t_out.data_ptr(), w, h, ab.EXPORT_UINT16, stream))), 24)
+    report("finalscale_half_mitchell", timed(lambda: ab.check(L.b200_finalscale_process_dev(p_fs, t_rgba.data_ptr(), t_out.data_ptr(), stream))), 20)
+
+    # sensor-to-display chain, end to end
+    order = [("rawprepare", d_rp, 1, 1, 2, 1, (1.0,) * 4), ("temperature", d_tp, 1, 1, 1, 1, (1.0,) * 4), ("highlights", d_hl, 1, 1, 1, 1, pm),
+             ("demosaic", d_dem, 1, 4, 1, 1, pm), ("colorin", d_cin, 4, 4, 1, 1, pm), ("colorout", d_cout, 4, 4, 1, 1, pm), ("gamma", None, 4, 4, 1, 3, pm)]
+    pieces = [ds.make_piece_iop(op, w, h, data, channels_in=ci, channels_out=co, filters=filters, processed_maximum=pmx, wb=wb, type_in=ti, type_out=to)
+              for op, data, ci, co, ti, to, pmx in order]
+    nodes = (ds.PipeNode * len(order))()
+    for k, (op, *_rest) in enumerate(order):
+        nodes[k].process_cl = C.cast(getattr(M, f"dt_iop_{op}__process_cl"), C.c_void_p)
+        nodes[k].module = pieces[k].module
+        nodes[k].piece = C.pointer(pieces[k])
+    pipe = ds.make_pipe(devid=local, stream=None)
+    DEPTH, steps = 2, 12
+    queue = M.b200_pipe_queue_new(DEPTH)
+    try:
+        h_in = torch.from_numpy(raw).pin_memory()
+        h_out = [torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory() for _ in range(DEPTH)]
+
+        def run(n):
+            tickets = []
+            for i in range(n):
+                t = M.b200_pixelpipe_submit(queue, C.byref(pipe), nodes, len(order), h_in.data_ptr(), h_out[i % DEPTH].data_ptr())
+                if t < 0:
+                    raise RuntimeError("chain failed: " + L.b200_last_error().decode())
+                tickets.append(t)
+                if i >= DEPTH - 1 and M.b200_pixelpipe_wait(queue, tickets[i - DEPTH + 1]) != 0:
+                    raise RuntimeError("wait failed: " + L.b200_last_error().decode())
+            if M.b200_pixelpipe_wait(queue, tickets[-1]) != 0:
+                raise RuntimeError("wait failed: " + L.b200_last_error().decode())
+
+        run(3)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run(steps)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    finally:
+        M.b200_pipe_queue_free(queue)
+    res["sensor_to_display_e2e"] = {"value": npx * steps / dt / 1e6, "unit": UNIT, "steps": steps, "h2d_bytes_per_step": 2 * npx, "d2h_bytes_per_step": 4 * npx,
+                                    "chain": "rawprepare(uint16) -> temperature -> highlights(clip) -> demosaic(RCD) -> colorin -> colorout -> gamma(uint8)",
+                                    "path": "dt_iop_<op>__process_cl adapters via b200_pixelpipe_submit/_wait, 2 frames in flight, pinned host buffers",
+                                    "mean_display_value": float(h_out[0][..., :3].float().mean())}
+    return res
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -412,6 +516,12 @@ def run_b200(args):
                 ts.append(a0.elapsed_time(a1))
         m = float(np.median(ts))
         other["demosaic_amaze"] = {"ms": m, "MP_per_s": npx / m / 1e3, "algorithmic_GBps": 20 * npx / (m * 1e-3) / 1e9}
+
+        # the modules either side of the path and the sensor-to-display chain; never part of the headline
+        try:
+            other["pipe_ends"] = pipe_ends_extras(ab, ds, util, L, M, torch, w, h, local, dev, stream, conv_in, conv_out, d_cin, d_cout)
+        except Exception as e:  # reported, not fatal: these figures sit beside the benchmark, not in it
+            other["pipe_ends"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
     # ---- second mode at N>1: ONE frame cut into row bands + all-gather ---------
     banded = None
