@@ -8,6 +8,7 @@ namespace b200
 int rcd_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters,
                      const float processed_maximum[3], cudaStream_t stream);
 int amaze_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters, const float processed_maximum[3], cudaStream_t stream);
+int ppg_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters, float median_thrs, cudaStream_t s);
 int demosaic_green_eq_dev(const float *d_in, float *d_tmp0, float *d_tmp1, double *d_partial, int width, int height, uint32_t dsc_filters, int x, int y,
                           unsigned green_eq, float threshold, const float **d_result, cudaStream_t s);
 int demosaic_green_eq_partial_doubles();
@@ -45,7 +46,7 @@ extern "C" int b200_demosaic_process_dev(const b200_piece_t *piece, const void *
     return fail(B200_ERR_UNSUPPORTED, "demosaic: roi_out %dx%d != roi_in %dx%d (downsampling paths are not built)",
                 piece->roi_out.width, piece->roi_out.height, piece->roi_in.width, piece->roi_in.height);
 
-  if(d->demosaicing_method != B200_DEMOSAIC_RCD && d->demosaicing_method != B200_DEMOSAIC_AMAZE)
+  if(d->demosaicing_method != B200_DEMOSAIC_RCD && d->demosaicing_method != B200_DEMOSAIC_AMAZE && d->demosaicing_method != B200_DEMOSAIC_PPG)
     return fail(B200_ERR_UNSUPPORTED, "demosaic: method %u is not built", d->demosaicing_method);
   const int width = piece->roi_in.width, height = piece->roi_in.height;
   cudaStream_t s = (cudaStream_t)stream;
@@ -62,7 +63,9 @@ extern "C" int b200_demosaic_process_dev(const b200_piece_t *piece, const void *
                                    d->green_eq, threshold, &mosaic, s)))
       return rc;
   }
-  if(d->demosaicing_method == B200_DEMOSAIC_AMAZE)
+  if(d->demosaicing_method == B200_DEMOSAIC_PPG)
+    rc = ppg_demosaic_dev(mosaic, (float *)d_out, width, height, filters, d->median_thrs, s); // demosaic.c:1218-1226
+  else if(d->demosaicing_method == B200_DEMOSAIC_AMAZE)
     rc = amaze_demosaic_dev(mosaic, (float *)d_out, width, height, filters, piece->processed_maximum, s); // demosaic.c:1227
   else
     rc = rcd_demosaic_dev(mosaic, (float *)d_out, width, height, filters, piece->processed_maximum, s);
@@ -87,8 +90,9 @@ extern "C" int b200_demosaic_process_host(const b200_piece_t *piece, const void 
   if((rc = copy_h2d(d_in, in, npx_in * sizeof(float), s))) return rc;
   // The caller's cacheline may hold anything; the reference leaves the alpha of the outer 3 px
   // and (for frames under 16 px) the whole buffer as found.  Start from the caller's bytes only
-  // in the too-small case; otherwise every pixel is overwritten.
-  if(piece->roi_in.width < 16 || piece->roi_in.height < 16)
+  // in the too-small case and for PPG (which, like the reference, keeps the alpha of the outer three pixels);
+  // otherwise every pixel is overwritten.
+  if(piece->roi_in.width < 16 || piece->roi_in.height < 16 || ((const b200_demosaic_data_t *)piece->data)->demosaicing_method == B200_DEMOSAIC_PPG)
     if((rc = copy_h2d(d_out, out, npx_out * 4 * sizeof(float), s))) return rc;
   if((rc = b200_demosaic_process_dev(piece, d_in, d_out, (void *)s))) return rc;
   if((rc = copy_d2h(out, d_out, npx_out * 4 * sizeof(float), s))) return rc;

@@ -1,0 +1,214 @@
+// PPG demosaic (the reference's fallback Bayer method) and its optional pre-median.
+//
+// Reference: iop/demosaic/ppg.c demosaic_ppg :21-211; iop/demosaic/basic.c pre_median_b :136-180; dispatch
+// iop/demosaic.c:1218-1226.
+//
+// The reference makes three passes over the frame: a border average into the outer three pixels, the green plane of the
+// interior, then red and blue in place from the greens around each pixel.  The in-place pass only ever reads values it
+// does not write (a site's own colour and the greens), so every output pixel is a pure function of the mosaic within
+// +-4 pixels.  The kernel computes it that way: one thread per pixel re-derives the (at most five) greens it needs from
+// the mosaic, which L1/L2 serve, and stores the pixel once -- 20 bytes per pixel of HBM traffic (4 in, 16 out) instead
+// of the 52 the three passes would move.  Arithmetic and its order are the reference's, so results are bit-identical.
+#ifndef B200_KERNELS_ON_CPU // tests/emul compiles the kernels of this file with g++ to check them against the oracle without a GPU
+#include "runtime.h"
+#endif
+#include <math.h>
+
+namespace
+{
+constexpr int PNT = 256;
+
+struct ppg_frame_t
+{
+  const float *in;    // the mosaic as the module received it (border averages read this)
+  const float *input; // the pre-median'ed mosaic when the threshold is > 0, else == in (interior reads this)
+  int width, height;
+  unsigned filters; // ROI-shifted
+};
+
+__device__ __forceinline__ int ppg_fc(int row, int col, unsigned filters) { return (filters >> ((((row << 1) & 14) + (col & 1)) << 1)) & 3; }
+__device__ __forceinline__ bool in_ring(const ppg_frame_t &F, int y, int x) { return y < 3 || y >= F.height - 3 || x < 3 || x >= F.width - 3; }
+
+// channel c of a pixel of the three-pixel border as ppg.c:31-56 leaves it: the average of the 3x3 neighbours of that
+// colour that lie inside the frame (raster order), or the site's own sample for its own colour / when there is none
+__device__ float border_value(const ppg_frame_t &F, int j, int i, int c)
+{
+  const float own = F.in[(size_t)j * F.width + i];
+  if(c == ppg_fc(j, i, F.filters)) return own;
+  float sum = 0.0f, count = 0.0f;
+  for(int y = j - 1; y != j + 2; y++)
+    for(int x = i - 1; x != i + 2; x++)
+      if(y >= 0 && x >= 0 && y < F.height && x < F.width && ppg_fc(y, x, F.filters) == c)
+      {
+        sum += F.in[(size_t)y * F.width + x];
+        count += 1.0f;
+      }
+  return count > 0.0f ? sum / count : own;
+}
+
+// the green of pixel (y, x) after the first two passes: :70-131 in the interior, the border average elsewhere
+__device__ float green_at(const ppg_frame_t &F, int y, int x)
+{
+  if(in_ring(F, y, x)) return border_value(F, y, x, 1);
+  const int w = F.width;
+  const float *b = F.input + (size_t)y * w + x;
+  const float pc = b[0];
+  const int c = ppg_fc(y, x, F.filters);
+  if(c != 0 && c != 2) return pc;
+  const float pym = b[-w], pym2 = b[-2 * w], pym3 = b[-3 * w], pyM = b[w], pyM2 = b[2 * w], pyM3 = b[3 * w];
+  const float pxm = b[-1], pxm2 = b[-2], pxm3 = b[-3], pxM = b[1], pxM2 = b[2], pxM3 = b[3];
+  const float guessx = (pxm + pc + pxM) * 2.0f - pxM2 - pxm2;
+  const float diffx = (fabsf(pxm2 - pc) + fabsf(pxM2 - pc) + fabsf(pxm - pxM)) * 3.0f + (fabsf(pxM3 - pxM) + fabsf(pxm3 - pxm)) * 2.0f;
+  const float guessy = (pym + pc + pyM) * 2.0f - pyM2 - pym2;
+  const float diffy = (fabsf(pym2 - pc) + fabsf(pyM2 - pc) + fabsf(pym - pyM)) * 3.0f + (fabsf(pyM3 - pyM) + fabsf(pym3 - pym)) * 2.0f;
+  if(diffx > diffy) return fmaxf(fminf(guessy * .25f, fmaxf(pym, pyM)), fminf(pym, pyM));
+  return fmaxf(fminf(guessx * .25f, fmaxf(pxm, pxM)), fminf(pxm, pxM));
+}
+// a site's own sample as the output buffer holds it after the first two passes
+__device__ __forceinline__ float own_at(const ppg_frame_t &F, int y, int x)
+{
+  return (in_ring(F, y, x) ? F.in : F.input)[(size_t)y * F.width + x];
+}
+
+__global__ void __launch_bounds__(PNT) ppg_kernel(ppg_frame_t F, float4 *__restrict__ out)
+{
+  const int i = blockIdx.x * PNT + threadIdx.x, j = blockIdx.y;
+  if(i >= F.width) return;
+  const size_t p = (size_t)j * F.width + i;
+  const int c = ppg_fc(j, i, F.filters);
+  const bool ring = in_ring(F, j, i);
+  float4 o;
+  o.w = ring ? out[p].w : 0.0f; // the border loop does not write alpha, the green pass writes 0
+  if(j == 0 || i == 0 || j == F.height - 1 || i == F.width - 1)
+  { // outermost pixels: not touched by the red/blue pass
+    o.x = border_value(F, j, i, 0);
+    o.y = border_value(F, j, i, 1);
+    o.z = border_value(F, j, i, 2);
+    out[p] = o;
+    return;
+  }
+  const float g = green_at(F, j, i);
+  float r, b;
+  if(c & 1)
+  { // green site :151-169: red and blue from the two pairs of direct neighbours
+    const float gt = green_at(F, j - 1, i), gb = green_at(F, j + 1, i), gl = green_at(F, j, i - 1), gr = green_at(F, j, i + 1);
+    const float vert = (own_at(F, j - 1, i) + own_at(F, j + 1, i) + 2.0f * g - gt - gb) * .5f;
+    const float horz = (own_at(F, j, i - 1) + own_at(F, j, i + 1) + 2.0f * g - gl - gr) * .5f;
+    if(ppg_fc(j, i + 1, F.filters) == 0)
+    { // red neighbours in the row, blue ones in the column
+      b = vert;
+      r = horz;
+    }
+    else
+    {
+      r = vert;
+      b = horz;
+    }
+  }
+  else
+  { // red or blue site :170-203: the other of the two from the diagonal neighbours, along the flatter diagonal
+    const float ntl = own_at(F, j - 1, i - 1), ntr = own_at(F, j - 1, i + 1), nbl = own_at(F, j + 1, i - 1), nbr = own_at(F, j + 1, i + 1);
+    const float gtl = green_at(F, j - 1, i - 1), gtr = green_at(F, j - 1, i + 1), gbl = green_at(F, j + 1, i - 1), gbr = green_at(F, j + 1, i + 1);
+    const float diff1 = fabsf(ntl - nbr) + fabsf(gtl - g) + fabsf(gbr - g);
+    const float guess1 = ntl + nbr + 2.0f * g - gtl - gbr;
+    const float diff2 = fabsf(ntr - nbl) + fabsf(gtr - g) + fabsf(gbl - g);
+    const float guess2 = ntr + nbl + 2.0f * g - gtr - gbl;
+    float other;
+    if(diff1 > diff2)
+      other = guess2 * .5f;
+    else if(diff1 < diff2)
+      other = guess1 * .5f;
+    else
+      other = (guess1 + guess2) * .25f;
+    const float own = own_at(F, j, i);
+    r = c == 0 ? own : other;
+    b = c == 0 ? other : own;
+  }
+  o.x = r;
+  o.y = g;
+  o.z = b;
+  out[p] = o;
+}
+
+// pre_median_b with one pass :136-180: green sites of the interior become a thresholded median of their nine green
+// neighbours (the reference's exchange sort, compare for compare, so that NaNs land where they land there)
+__global__ void __launch_bounds__(PNT) pre_median_kernel(const float *__restrict__ in, float *__restrict__ out, int width, int height, unsigned filters,
+                                                         float threshold)
+{
+  const int col = blockIdx.x * PNT + threadIdx.x, row = blockIdx.y;
+  if(col >= width) return;
+  const size_t p = (size_t)row * width + col;
+  const float centre = in[p];
+  const int c = ppg_fc(row, col, filters);
+  // the row loop starts at column 3 or 4, whichever is green, and steps by two: the green sites of that row
+  if(row < 3 || row >= height - 3 || col < 3 || col >= width - 3 || (c != 1 && c != 3))
+  {
+    out[p] = centre;
+    return;
+  }
+  float med[9];
+  int cnt = 0;
+  {
+    const int dy[9] = { -2, -1, -1, 0, 0, 0, 1, 1, 2 }, dx[9] = { 0, -1, 1, -2, 0, 2, -1, 1, 0 };
+#pragma unroll
+    for(int k = 0; k < 9; k++)
+    {
+      const float v = in[p + (ptrdiff_t)width * dy[k] + dx[k]];
+      if(fabsf(v - centre) < threshold)
+      {
+        med[k] = v;
+        cnt++;
+      }
+      else
+        med[k] = 64.0f + v;
+    }
+  }
+#pragma unroll
+  for(int a = 0; a < 8; a++)
+#pragma unroll
+    for(int b = a + 1; b < 9; b++)
+      if(med[a] > med[b])
+      {
+        const float t = med[b];
+        med[b] = med[a];
+        med[a] = t;
+      }
+  float result = med[4] - 64.0f;
+  if(cnt != 1)
+  { // med[(cnt - 1) / 2] without indexing the register array dynamically; cnt == 0 reads med[0] like (0 - 1) / 2 == 0 in C
+    const int k = (cnt - 1) / 2;
+    result = med[0];
+#pragma unroll
+    for(int q = 1; q < 5; q++)
+      if(k == q) result = med[q];
+  }
+  out[p] = result;
+}
+} // namespace
+
+#ifndef B200_KERNELS_ON_CPU
+namespace b200
+{
+// demosaic.c:1218-1226: d_in = the (green-equilibrated) mosaic, filters = ROI-shifted word, out keeps the alpha of its
+// outer three pixels
+int ppg_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters, float median_thrs, cudaStream_t s)
+{
+  if(width < 8 || height < 8) return fail(B200_ERR_UNSUPPORTED, "demosaic: PPG on a %dx%d frame (the reference's border loop does not terminate under 6 px)", width, height);
+  if(height > 65535) return fail(B200_ERR_ARG, "demosaic: PPG frame height %d", height);
+  ppg_frame_t F = { d_in, d_in, width, height, filters };
+  const dim3 grid((unsigned)((width + PNT - 1) / PNT), (unsigned)height);
+  if(median_thrs > 0.0f)
+  {
+    void *med = nullptr;
+    int rc = scratch(SLOT_TMP2, (size_t)width * height * sizeof(float), &med);
+    if(rc) return rc;
+    pre_median_kernel<<<grid, PNT, 0, s>>>(d_in, (float *)med, width, height, filters, median_thrs);
+    B200_CUDA_TRY(cudaGetLastError());
+    F.input = (const float *)med;
+  }
+  ppg_kernel<<<grid, PNT, 0, s>>>(F, (float4 *)d_out);
+  B200_CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+} // namespace b200
+#endif

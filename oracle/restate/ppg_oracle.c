@@ -1,0 +1,146 @@
+/* CPU restatement of the PPG demosaicer (the reference's fallback Bayer method).  TEST INFRASTRUCTURE ONLY.
+ *
+ * Follows /root/reference/src/iop/demosaic/ppg.c demosaic_ppg :21-211 (border average :28-56, optional pre-median :57-67,
+ * green interpolation :70-131, red/blue interpolation in place :136-203) and iop/demosaic/basic.c pre_median_b :136-180.
+ * Pinned bit-for-bit against those lines cut verbatim (oracle/_ref: ref_ppg.c).  The caller passes the ROI-shifted
+ * filters word and an output buffer whose outer three pixels keep their alpha, as in the reference.
+ */
+#include "oracle_common.h"
+#include <stdlib.h>
+#include <string.h>
+
+static void pre_median(float *out, const float *in, int width, int height, uint32_t filters, float threshold)
+{
+  memcpy(out, in, sizeof(float) * (size_t)width * height);
+  static const int lim[5] = { 0, 1, 2, 1, 0 };
+  for(int row = 3; row < height - 3; row++)
+  {
+    int col = 3;
+    if(orc_fc(row, col, filters) != 1 && orc_fc(row, col, filters) != 3) col++;
+    for(; col < width - 3; col += 2)
+    {
+      const float *pixi = in + (size_t)width * row + col;
+      float med[9];
+      int cnt = 0, k = 0;
+      for(int i = 0; i < 5; i++)
+        for(int j = -lim[i]; j <= lim[i]; j += 2)
+        {
+          const float v = pixi[width * (i - 2) + j];
+          if(fabsf(v - pixi[0]) < threshold)
+          {
+            med[k++] = v;
+            cnt++;
+          }
+          else
+            med[k++] = 64.0f + v;
+        }
+      for(int i = 0; i < 8; i++)
+        for(int ii = i + 1; ii < 9; ii++)
+          if(med[i] > med[ii])
+          {
+            const float t = med[ii];
+            med[ii] = med[i];
+            med[i] = t;
+          }
+      out[(size_t)width * row + col] = (cnt == 1 ? med[4] - 64.0f : med[(cnt - 1) / 2]);
+    }
+  }
+}
+
+int orc_demosaic_ppg(float *out, const float *in, int width, int height, uint32_t filters, float thrs)
+{
+  /* the three-pixel border: average of the neighbours of each colour inside the frame */
+  for(int j = 0; j < height; j++)
+    for(int i = 0; i < width; i++)
+    {
+      if(i == 3 && j >= 3 && j < height - 3) i = width - 3;
+      if(i == width) break;
+      float sum[8] = { 0 };
+      for(int y = j - 1; y != j + 2; y++)
+        for(int x = i - 1; x != i + 2; x++)
+          if(y >= 0 && x >= 0 && y < height && x < width)
+          {
+            const int f = orc_fc(y, x, filters);
+            sum[f] += in[(size_t)y * width + x];
+            sum[f + 4]++;
+          }
+      const int f = orc_fc(j, i, filters);
+      for(int c = 0; c < 3; c++)
+        out[4 * ((size_t)j * width + i) + c] = (c != f && sum[c + 4] > 0.0f) ? sum[c] / sum[c + 4] : in[(size_t)j * width + i];
+    }
+  const float *input = in;
+  float *med = NULL;
+  if(thrs > 0.0f)
+  {
+    med = malloc(sizeof(float) * (size_t)width * height);
+    pre_median(med, in, width, height, filters, thrs);
+    input = med;
+  }
+  /* green */
+  for(int j = 3; j < height - 3; j++)
+    for(int i = 3; i < width - 3; i++)
+    {
+      const float *b = input + (size_t)width * j + i;
+      float *o = out + 4 * ((size_t)width * j + i);
+      const int c = orc_fc(j, i, filters);
+      const float pc = b[0];
+      if(c == 0 || c == 2)
+      {
+        o[c] = pc;
+        const float pym = b[-width], pym2 = b[-2 * width], pym3 = b[-3 * width], pyM = b[width], pyM2 = b[2 * width], pyM3 = b[3 * width];
+        const float pxm = b[-1], pxm2 = b[-2], pxm3 = b[-3], pxM = b[1], pxM2 = b[2], pxM3 = b[3];
+        const float guessx = (pxm + pc + pxM) * 2.0f - pxM2 - pxm2;
+        const float diffx = (fabsf(pxm2 - pc) + fabsf(pxM2 - pc) + fabsf(pxm - pxM)) * 3.0f + (fabsf(pxM3 - pxM) + fabsf(pxm3 - pxm)) * 2.0f;
+        const float guessy = (pym + pc + pyM) * 2.0f - pyM2 - pym2;
+        const float diffy = (fabsf(pym2 - pc) + fabsf(pyM2 - pc) + fabsf(pym - pyM)) * 3.0f + (fabsf(pyM3 - pyM) + fabsf(pym3 - pym)) * 2.0f;
+        if(diffx > diffy)
+          o[1] = fmaxf(fminf(guessy * .25f, fmaxf(pym, pyM)), fminf(pym, pyM));
+        else
+          o[1] = fmaxf(fminf(guessx * .25f, fmaxf(pxm, pxM)), fminf(pxm, pxM));
+      }
+      else
+        o[1] = pc;
+      o[3] = 0.0f; /* the other colours of the pixel are written by the next pass */
+    }
+  /* red and blue, in place: every value read here is one this pass does not write */
+  for(int j = 1; j < height - 1; j++)
+    for(int i = 1; i < width - 1; i++)
+    {
+      float *buf = out + 4 * ((size_t)width * j + i);
+      const int c = orc_fc(j, i, filters);
+      const int w4 = 4 * width;
+      float color[4] = { buf[0], buf[1], buf[2], buf[3] };
+      if(c & 1)
+      {
+        const float *nt = buf - w4, *nb = buf + w4, *nl = buf - 4, *nr = buf + 4;
+        if(orc_fc(j, i + 1, filters) == 0)
+        {
+          color[2] = (nt[2] + nb[2] + 2.0f * color[1] - nt[1] - nb[1]) * .5f;
+          color[0] = (nl[0] + nr[0] + 2.0f * color[1] - nl[1] - nr[1]) * .5f;
+        }
+        else
+        {
+          color[0] = (nt[0] + nb[0] + 2.0f * color[1] - nt[1] - nb[1]) * .5f;
+          color[2] = (nl[2] + nr[2] + 2.0f * color[1] - nl[1] - nr[1]) * .5f;
+        }
+      }
+      else
+      {
+        const float *ntl = buf - 4 - w4, *ntr = buf + 4 - w4, *nbl = buf - 4 + w4, *nbr = buf + 4 + w4;
+        const int o = c == 0 ? 2 : 0; /* a red site gets blue, a blue site red */
+        const float diff1 = fabsf(ntl[o] - nbr[o]) + fabsf(ntl[1] - color[1]) + fabsf(nbr[1] - color[1]);
+        const float guess1 = ntl[o] + nbr[o] + 2.0f * color[1] - ntl[1] - nbr[1];
+        const float diff2 = fabsf(ntr[o] - nbl[o]) + fabsf(ntr[1] - color[1]) + fabsf(nbl[1] - color[1]);
+        const float guess2 = ntr[o] + nbl[o] + 2.0f * color[1] - ntr[1] - nbl[1];
+        if(diff1 > diff2)
+          color[o] = guess2 * .5f;
+        else if(diff1 < diff2)
+          color[o] = guess1 * .5f;
+        else
+          color[o] = (guess1 + guess2) * .25f;
+      }
+      memcpy(buf, color, sizeof(color));
+    }
+  free(med);
+  return 0;
+}

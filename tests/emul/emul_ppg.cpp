@@ -1,0 +1,22 @@
+/* Test infrastructure: the kernels of ansel_b200/csrc/ppg.cu compiled with g++ and run thread by thread on the CPU, in
+ * the order ppg_demosaic_dev() launches them.  Not part of the product. */
+#define B200_KERNELS_ON_CPU
+#include "cuda_on_cpu.h"
+#include "../../include/b200iop.h"
+#include "../../ansel_b200/csrc/ppg.cu"
+#include <vector>
+
+extern "C" int emul_demosaic_ppg(float *out, const float *in, int width, int height, unsigned filters, float median_thrs)
+{
+  ppg_frame_t F = { in, in, width, height, filters };
+  const dim3 grid((unsigned)((width + PNT - 1) / PNT), (unsigned)height);
+  std::vector<float> med;
+  if(median_thrs > 0.0f)
+  {
+    med.resize((size_t)width * height);
+    emulate(grid, PNT, pre_median_kernel, in, med.data(), width, height, filters, median_thrs);
+    F.input = med.data();
+  }
+  emulate(grid, PNT, ppg_kernel, F, (float4 *)out);
+  return 0;
+}

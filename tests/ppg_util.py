@@ -1,0 +1,63 @@
+"""Helpers for the PPG demosaicer's tests: the oracle (oracle/restate/ppg_oracle.c), the reference's own lines compiled
+in place (oracle/_ref: ref_ppg.c) and the product's kernels run on the CPU (tests/emul/emul_ppg.cpp).  Checkers only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import util
+
+EMUL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul")
+ALPHA_FILL = -7.0      # the reference leaves the alpha of the outer three pixels as it finds it
+
+CASES = {
+    # name: (width, height, Bayer pattern, median threshold, special samples)
+    "rggb": (206, 120, "RGGB", 0.0, True),
+    "bggr_median": (117, 131, "BGGR", 0.05, True),
+    "grbg_median_wide": (300, 40, "GRBG", 0.5, False),
+    "gbrg": (134, 78, "GBRG", 0.0, False),
+    "smallest": (8, 9, "RGGB", 0.05, False),
+    "sixteen": (16, 16, "GBRG", 0.0, False),
+}
+
+
+def case(name):
+    w, h, pat, thrs, special = CASES[name]
+    m = util.frame_natural(w, h, 3, filters=util.BAYER[pat])
+    if special:
+        m[5, 5], m[20, 8], m[7, 30], m[40, 41] = np.nan, np.inf, -1.0, 0.0
+    return m, util.BAYER[pat], thrs
+
+
+def _run(lib, fn, mosaic, filters, thrs):
+    h, w = mosaic.shape
+    out, src = util.aligned_empty((h, w, 4)), util.aligned_empty(mosaic.shape)
+    out[...] = ALPHA_FILL
+    src[...] = mosaic
+    f = getattr(lib, fn)
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_float]
+    assert f(out.ctypes.data, src.ctypes.data, w, h, filters, thrs) == 0
+    return np.array(out)
+
+
+def oracle_ppg(mosaic, filters, thrs=0.0):
+    return _run(util.oracle(), "orc_demosaic_ppg", mosaic, filters, thrs)
+
+
+def ref_ppg(mosaic, filters, thrs=0.0, kind="strict"):
+    lib = util.ref(kind)
+    return None if lib is None else _run(lib, "ref_demosaic_ppg", mosaic, filters, thrs)
+
+
+def emul_lib():
+    so = os.path.join(EMUL, "libemul_ppg.so")
+    srcs = [os.path.join(EMUL, "emul_ppg.cpp"), os.path.join(EMUL, "cuda_on_cpu.h"), os.path.join(util.ROOT, "ansel_b200", "csrc", "ppg.cu")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.run(["g++", "-O1", "-std=c++17", "-fno-fast-math", "-ffp-contract=off", "-I", EMUL, "-shared", "-fPIC", "-o", so, srcs[0]], check=True)
+    return C.CDLL(so)
+
+
+def emul_ppg(mosaic, filters, thrs=0.0):
+    return _run(emul_lib(), "emul_demosaic_ppg", mosaic, filters, thrs)

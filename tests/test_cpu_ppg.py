@@ -1,0 +1,62 @@
+"""CPU: the PPG demosaicer's oracle pinned bit for bit to iop/demosaic/ppg.c + basic.c pre_median compiled in place, to
+the golden vectors those builds produced, and the product's fused kernel (one pass instead of the reference's three)
+run on the CPU against the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import ppg_util as pu
+import util
+
+
+def same_bits(a, b):
+    return (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build():
+    subprocess.run(["make", "-s", "-C", util.ORACLE_DIR, "oracle"], check=True)
+    if util.ref("strict") is None and os.path.isdir("/root/reference/src"):
+        util.build_oracle()
+
+
+need_ref = pytest.mark.skipif(util.ref("strict") is None and not os.path.isdir("/root/reference/src"), reason="oracle/_ref not built (no /root/reference)")
+
+
+@need_ref
+@pytest.mark.parametrize("name", list(pu.CASES))
+def test_ppg_oracle_equals_reference(name):
+    m, filters, thrs = pu.case(name)
+    want = pu.ref_ppg(m, filters, thrs)
+    assert same_bits(pu.oracle_ppg(m, filters, thrs), want).all()
+    h, w = m.shape
+    assert (want[3:h - 3, 3:w - 3, 3] == 0.0).all() and (want[0, :, 3] == pu.ALPHA_FILL).all() and (want[:, 2, 3] == pu.ALPHA_FILL).all()
+
+
+@need_ref
+def test_pre_median_changes_the_result():
+    m, filters, _ = pu.case("rggb")
+    assert not same_bits(pu.ref_ppg(m, filters, 0.0), pu.ref_ppg(m, filters, 0.05)).all()
+
+
+def test_ppg_oracle_equals_golden():
+    g = np.load(os.path.join(util.GOLDEN_DIR, "ppg.npz"))
+    for name in pu.CASES:
+        assert same_bits(pu.oracle_ppg(*pu.case(name)), g[name]).all(), name
+
+
+@pytest.mark.parametrize("name", list(pu.CASES))
+def test_fused_ppg_kernel_equals_oracle(name):
+    """ansel_b200/csrc/ppg.cu: pre_median_kernel + ppg_kernel, thread by thread on the CPU"""
+    m, filters, thrs = pu.case(name)
+    assert same_bits(pu.emul_ppg(m, filters, thrs), pu.oracle_ppg(m, filters, thrs)).all()
+
+
+@pytest.mark.parametrize("pattern", list(util.BAYER))
+def test_fused_ppg_kernel_every_phase_and_ragged_size(pattern):
+    for w, h in ((33, 20), (64, 47), (9, 8)):
+        m = util.frame_natural(w, h, 9, filters=util.BAYER[pattern])
+        for thrs in (0.0, 0.1):
+            assert same_bits(pu.emul_ppg(m, util.BAYER[pattern], thrs), pu.oracle_ppg(m, util.BAYER[pattern], thrs)).all()

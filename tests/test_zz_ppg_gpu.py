@@ -1,0 +1,81 @@
+"""GPU parity: the PPG demosaicer through b200_demosaic_process_* against the oracle, bit for bit (alpha included: 0 in
+the interior, as found in the outer three pixels).  The oracle is pinned to iop/demosaic/ppg.c (tests/test_cpu_ppg.py)
+and the fused kernel already agrees with it on the CPU.  Sorted last: written after the round's GPU budget was spent, so
+these tests have not run on a B200 yet."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import ppg_util as pu
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def same_bits(a, b):
+    return (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+
+
+def cuda_ppg(mosaic, filters, thrs=0.0, x=0, y=0, host=False, green_eq=0, smoothing=0):
+    import torch
+    import ansel_b200 as ab
+    ab.init()
+    h, w = mosaic.shape
+    d = ab.demosaic_data(ab.DEMOSAIC_PPG)
+    d.median_thrs, d.green_eq, d.color_smoothing = thrs, green_eq, smoothing
+    piece = ab.make_piece(w, h, filters=filters, data=d, devid=0, roi_x=x, roi_y=y)
+    if host:
+        out = np.full((h, w, 4), pu.ALPHA_FILL, np.float32)
+        ab.check(ab.lib().b200_demosaic_process_host(C.byref(piece), mosaic.ctypes.data, out.ctypes.data))
+        return out
+    d_in = torch.from_numpy(np.ascontiguousarray(mosaic)).cuda()
+    d_out = torch.full((h, w, 4), pu.ALPHA_FILL, device="cuda")
+    ab.check(ab.lib().b200_demosaic_process_dev(C.byref(piece), d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    return d_out.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", list(pu.CASES))
+def test_ppg_bit_exact(built, name):
+    m, filters, thrs = pu.case(name)
+    want = pu.oracle_ppg(m, filters, thrs)
+    for host in (False, True):
+        assert same_bits(cuda_ppg(m, filters, thrs, host=host), want).all(), host
+    g = np.load(os.path.join(util.GOLDEN_DIR, "ppg.npz"))
+    assert same_bits(cuda_ppg(m, filters, thrs), g[name]).all()
+
+
+@pytest.mark.parametrize("pattern", list(util.BAYER))
+def test_ppg_sizes_and_roi_phase(built, pattern):
+    import ansel_b200 as ab
+    f = util.BAYER[pattern]
+    for w, h in ((1300, 900), (501, 333), (9, 8)):
+        m = util.frame_natural(w, h, 5, filters=f)
+        assert same_bits(cuda_ppg(m, f, 0.02), pu.oracle_ppg(m, f, 0.02)).all()
+    m = util.frame_natural(640, 427, 7, filters=f)
+    for (x, y) in ((1, 0), (0, 1), (1, 1)):      # the ROI origin shifts the CFA phase (dt_dev_get_roi_filters)
+        rf = ab.lib().b200_roi_filters(C.c_uint32(f), x, y)
+        assert same_bits(cuda_ppg(m, f, x=x, y=y), pu.oracle_ppg(m, rf)).all()
+
+
+def test_ppg_45mp_and_module_passes(built):
+    """BASELINE's frame size; green equilibration in front and colour smoothing behind, as demosaic.c:1137-1250 orders them"""
+    import ansel_b200 as ab
+    w, h = util.SIZE_45MP
+    m = util.frame_natural(w, h, 11)
+    assert same_bits(cuda_ppg(m, util.BAYER["RGGB"]), pu.oracle_ppg(m, util.BAYER["RGGB"])).all()
+    m = util.frame_natural(900, 600, 12)
+    f = util.BAYER["RGGB"]
+    eq = util.oracle_green_eq(m, f, 1)                       # local average
+    want = util.oracle_color_smoothing(pu.oracle_ppg(eq, f, 0.0), 2)
+    got = cuda_ppg(m, f, green_eq=1, smoothing=2)
+    assert same_bits(got[..., :3], want[..., :3]).all()
+
+
+def test_ppg_refuses_tiny_frames(built):
+    import ansel_b200 as ab
+    with pytest.raises(ab.B200Error) as e:
+        cuda_ppg(np.zeros((6, 6), np.float32), util.BAYER["RGGB"])
+    assert e.value.code == ab.B200_ERR_UNSUPPORTED
