@@ -173,6 +173,18 @@ class FinalscaleData(C.Structure):
     _fields_ = [("dummy", C.c_int), ("interpolator", C.c_int)]
 
 
+ADAPTATION_LINEAR_BRADFORD, ADAPTATION_CAT16, ADAPTATION_FULL_BRADFORD, ADAPTATION_XYZ, ADAPTATION_RGB = range(5)
+
+
+class ChannelmixerPiece(C.Structure):
+    """b200_channelmixerrgb_piece_t: dt_iop_channelmixer_rbg_data_t (src/iop/channelmixerrgb.c:259-272; 64-byte aligned, 192 bytes)
+    + the work profile's matrices process() fetches.  Must live at a 64-byte aligned address (channelmixer_piece())."""
+    _fields_ = [("MIX", (C.c_float * 4) * 4), ("saturation", C.c_float * 4), ("lightness", C.c_float * 4), ("grey", C.c_float * 4),
+                ("illuminant", C.c_float * 4), ("p", C.c_float), ("gamut", C.c_float), ("apply_grey", C.c_int), ("clip", C.c_int),
+                ("adaptation", C.c_int), ("illuminant_type", C.c_int), ("version", C.c_int), ("_pad0", C.c_uint8 * 36),
+                ("work_in", (C.c_float * 4) * 3), ("work_out", (C.c_float * 4) * 3), ("_pad1", C.c_uint8 * 32)]
+
+
 class B200Error(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libb200iop error {code}: {msg}")
@@ -180,7 +192,7 @@ class B200Error(RuntimeError):
 
 
 OPS = ("demosaic", "colorin", "colorout", "denoiseprofile", "filmicrgb", "bilat", "diffuse", "nlmeans",
-       "rawprepare", "temperature", "highlights", "exposure", "gamma", "finalscale")
+       "rawprepare", "temperature", "highlights", "exposure", "gamma", "finalscale", "channelmixerrgb")
 
 _lib = None
 
@@ -490,3 +502,25 @@ def finalscale_data(interpolator: int = INTERPOLATION_MITCHELL) -> FinalscaleDat
     d = FinalscaleData()
     d.interpolator = interpolator
     return d
+
+
+def channelmixer_piece(work, *, adaptation: int = ADAPTATION_CAT16, illuminant=(0.95, 1.0, 0.85), mix=None, saturation=(0.0, 0.0, 0.0),
+                       lightness=(0.0, 0.0, 0.0), grey=(0.0, 0.0, 0.0), p: float = 0.9, gamut: float = 1.0, clip: int = 1, apply_grey: int = 0,
+                       version: int = 2) -> ChannelmixerPiece:
+    """work: (matrix_in, matrix_out) 3x3 arrays of the pipe's work profile; the rest as commit_params() (channelmixerrgb.c:2290-2440)
+    leaves it: illuminant in the adaptation's LMS/XYZ space, mix = 3x3 rows (identity by default)."""
+    import numpy as np
+    assert C.sizeof(ChannelmixerPiece) == 320
+    raw = np.zeros(C.sizeof(ChannelmixerPiece) + 64, np.uint8)
+    off = (-raw.ctypes.data) % 64
+    cp = ChannelmixerPiece.from_buffer(raw, off)
+    cp._keepalive = raw  # noqa
+    mix = np.eye(3, dtype=np.float32) if mix is None else np.asarray(mix, np.float32)
+    for i in range(3):
+        for j in range(3):
+            cp.MIX[i][j] = float(mix[i][j])
+            cp.work_in[i][j] = float(work[0][i][j])
+            cp.work_out[i][j] = float(work[1][i][j])
+        cp.saturation[i], cp.lightness[i], cp.grey[i], cp.illuminant[i] = saturation[i], lightness[i], grey[i], illuminant[i]
+    cp.p, cp.gamut, cp.apply_grey, cp.clip, cp.adaptation, cp.version = p, gamut, apply_grey, clip, adaptation, version
+    return cp

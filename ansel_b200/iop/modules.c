@@ -9,6 +9,8 @@
  * Return conventions: process() 0 = success; process_cl() TRUE = success.
  */
 #include "dt_surface.h"
+#include <math.h>
+#include <string.h>
 
 #define ADAPT(op)                                                                                         \
   int dt_iop_##op##__process(struct dt_iop_module_t *self, const dt_dev_pixelpipe_t *pipe,                \
@@ -48,6 +50,48 @@ ADAPT(temperature) /* src/iop/temperature.c:487 (process), :611 (process_cl) */
 ADAPT(highlights)  /* src/iop/highlights.c:680 (process), :464 (process_cl), :575 (tiling_callback) */
 ADAPT(exposure)    /* src/iop/exposure.c:503 (process), :473 (process_cl) */
 ADAPT(gamma)       /* src/iop/gamma.c:367 (process), :461 (process_cl) */
+
+/* colour calibration reads the work profile next to piece->data (channelmixerrgb.c:1926, :1936-1942); everything of its
+ * process() that precedes the switch on data->adaptation -- the GUI's colour-checker fit and illuminant detection, the
+ * re-derivation of data->illuminant for DT_ILLUMINANT_CAMERA from the image metadata (:1986-2014) -- stays in the
+ * reference and runs before this call. */
+static int channelmixer_view(b200_channelmixerrgb_piece_t *cp, b200_piece_t *p, const dt_dev_pixelpipe_t *pipe, const dt_dev_pixelpipe_iop_t *piece)
+{
+  if(!piece->data || piece->data_size < sizeof(b200_channelmixerrgb_data_t)) return 1;
+  memcpy(&cp->data, piece->data, sizeof(b200_channelmixerrgb_data_t));
+  const dt_iop_order_iccprofile_info_t *const work = dt_ioppr_get_pipe_work_profile_info(pipe); /* = dt_ioppr_get_pipe_current_profile_info(self, pipe) */
+  if(!work) return 1; /* the reference would multiply by uninitialised matrices: refuse */
+  memcpy(cp->work_profile.matrix_in, work->matrix_in, sizeof(work->matrix_in));
+  memcpy(cp->work_profile.matrix_out, work->matrix_out, sizeof(work->matrix_out));
+  p->data = cp;
+  p->data_size = sizeof(*cp);
+  return 0;
+}
+int dt_iop_channelmixerrgb__process(struct dt_iop_module_t *self, const dt_dev_pixelpipe_t *pipe, const dt_dev_pixelpipe_iop_t *piece,
+                                    const void *const i, void *const o)
+{
+  b200_piece_t p;
+  b200_channelmixerrgb_piece_t cp;
+  b200_piece_from_dt(&p, self, pipe, piece);
+  if(channelmixer_view(&cp, &p, pipe, piece)) return 1;
+  return b200_channelmixerrgb_process_host(&p, i, o);
+}
+int dt_iop_channelmixerrgb__process_cl(struct dt_iop_module_t *self, const dt_dev_pixelpipe_t *pipe, const dt_dev_pixelpipe_iop_t *piece,
+                                       cl_mem dev_in, cl_mem dev_out)
+{
+  b200_piece_t p;
+  b200_channelmixerrgb_piece_t cp;
+  b200_piece_from_dt(&p, self, pipe, piece);
+  if(channelmixer_view(&cp, &p, pipe, piece)) return FALSE;
+  return b200_channelmixerrgb_process_dev(&p, dev_in, dev_out, pipe->stream) == 0 ? TRUE : FALSE;
+}
+void dt_iop_channelmixerrgb__tiling_callback(struct dt_iop_module_t *self, const dt_dev_pixelpipe_t *pipe,
+                                             const dt_dev_pixelpipe_iop_t *piece, dt_develop_tiling_t *tiling)
+{
+  b200_piece_t p;
+  b200_piece_from_dt(&p, self, pipe, piece);
+  b200_channelmixerrgb_tiling(&p, tiling);
+}
 
 /* finalscale's data block is one dummy int (finalscale.c:46-51); its process() resolves the interpolator from the user
  * preference: dt_interpolation_new(DT_INTERPOLATION_USERPREF) (develop/imageop_math.c:150).  In the reference tree the

@@ -579,6 +579,46 @@ int b200_exposure_process_host(const b200_piece_t *piece, const void *in, void *
 int b200_exposure_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
 void b200_exposure_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
 
+/* ---- colour calibration (src/iop/channelmixerrgb.c) ------------------------------------------------------------ */
+/* dt_adaptation_t, src/pixel/chromatic_adaptation.h:34-42 (same values) */
+enum
+{
+  B200_ADAPTATION_LINEAR_BRADFORD = 0,
+  B200_ADAPTATION_CAT16 = 1,
+  B200_ADAPTATION_FULL_BRADFORD = 2,
+  B200_ADAPTATION_XYZ = 3,
+  B200_ADAPTATION_RGB = 4
+};
+/* dt_iop_channelmixer_rbg_data_t, channelmixerrgb.c:259-272 (identical layout: 64-byte aligned, 192 bytes) */
+typedef struct b200_channelmixerrgb_data_t
+{
+  float MIX[4][4] __attribute__((aligned(64))); /* dt_colormatrix_t: the 3x3 channel mix, rows padded to 4 */
+  float saturation[4] __attribute__((aligned(16)));
+  float lightness[4] __attribute__((aligned(16)));
+  float grey[4] __attribute__((aligned(16)));
+  float illuminant[4] __attribute__((aligned(16))); /* in the adaptation's LMS (or XYZ) space */
+  float p, gamut;
+  int apply_grey;
+  int clip;
+  int adaptation;      /* B200_ADAPTATION_* */
+  int illuminant_type; /* dt_illuminant_t; read by the reference's process() before the pixel loop, not by the library */
+  int version;         /* dt_iop_channelmixer_rgb_version_t: 0 (2020), 1 (2021), 2 (Apr 2021) */
+} b200_channelmixerrgb_data_t;
+/* what the pixel loop reads: piece->data plus the work profile's matrices process() fetches (:1926, :1936-1942) */
+typedef struct b200_channelmixerrgb_piece_t
+{
+  b200_channelmixerrgb_data_t data;
+  b200_profile_matrices_t work_profile;
+} b200_channelmixerrgb_piece_t;
+/* process() :1920-2078 from the switch on data->adaptation on: loop_switch() :765-959 = chromatic adaptation (Bradford
+ * linear / full, CAT16, XYZ, none) + channel mix + gamut compression in xyY/uvY (gamut_mapping :641-706) + the
+ * colourfulness / brightness adjustment (luma_chroma :707-763) + optional grey output, with every clip of the reference.
+ * What precedes the switch stays the reference's C: the GUI's colour-checker fit and illuminant detection, and the
+ * re-derivation of data->illuminant for the "as shot in camera" illuminant from the image metadata (:1986-2014). */
+int b200_channelmixerrgb_process_host(const b200_piece_t *piece, const void *in, void *out);
+int b200_channelmixerrgb_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
+void b200_channelmixerrgb_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
+
 /* ---- finalscale (src/iop/finalscale.c): the export's final resampling ------------------------------------------- */
 /* enum dt_interpolation_type, src/pixel/interpolation.h:38-44 (same values) */
 enum

@@ -27,6 +27,8 @@ for name in t.HIGHLIGHTS_CASES:
     save["highlights_" + name] = pe.ref_highlights(*t.highlights_case(name))
 for name in t.EXPOSURE_CASES:
     save["exposure_" + name] = pe.ref_exposure(*t.exposure_case(name))
+for name in t.CHANNELMIXER_CASES:
+    save["channelmixerrgb_" + name] = pe.ref_channelmixerrgb(*t.channelmixer_case(name))
 for name in t.FINALSCALE_CASES:
     save["finalscale_" + name] = pe.ref_finalscale(*t.finalscale_case(name))
 img = pe.awkward_rgba(141, 67, 12)

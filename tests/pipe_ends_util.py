@@ -256,3 +256,27 @@ def oracle_finalscale(img, out_w, out_h, in_scale, out_scale, interpolator):
 def ref_finalscale(img, out_w, out_h, in_scale, out_scale, interpolator, kind="strict"):
     lib = util.ref(kind)
     return None if lib is None else _finalscale(lib, "ref_finalscale", img, out_w, out_h, in_scale, out_scale, interpolator)
+
+
+# ---- colour calibration (channelmixerrgb) -------------------------------------------------------------------------------
+def oracle_channelmixerrgb(img, cp):
+    h, w = img.shape[:2]
+    out = np.full_like(img, -7.0)
+    f = util.oracle().orc_channelmixerrgb
+    f.restype = C.c_int
+    assert f(vp(np.ascontiguousarray(img)), vp(out), w, h, C.byref(cp)) == 0
+    return out
+
+
+def ref_channelmixerrgb(img, cp, kind="strict"):
+    lib = util.ref(kind)
+    if lib is None:
+        return None
+    h, w = img.shape[:2]
+    src, out = util.aligned_empty(img.shape), util.aligned_empty(img.shape)
+    src[...] = img
+    out[...] = -7.0
+    f = lib.ref_channelmixerrgb
+    f.restype = C.c_int
+    assert f(vp(src), vp(out), w, h, C.byref(cp), C.byref(cp, ab.ChannelmixerPiece.work_in.offset), C.byref(cp, ab.ChannelmixerPiece.work_out.offset)) == 0
+    return np.array(out)

@@ -88,6 +88,11 @@ def test_pipe_end_modules_fail_loudly_without_a_device(built):
     pc.roi_out.scale = 0.5
     out = np.full((32, 32, 4), -3.0, np.float32)
     assert L.b200_finalscale_process_host(pc, rgba.ctypes.data, out.ctypes.data) != 0 and (out == -3.0).all()
+    cp = ab.channelmixer_piece(util.profile_pair(util.REC2020_TO_XYZ_D50))
+    pc = ab.make_piece(64, 64, filters=0, channels=4)
+    pc.data, pc.data_size = C.addressof(cp), C.sizeof(cp)
+    out = np.full((64, 64, 4), -3.0, np.float32)
+    assert L.b200_channelmixerrgb_process_host(pc, rgba.ctypes.data, out.ctypes.data) != 0 and (out == -3.0).all()
     out = np.full((64, 64, 4), 7, np.uint16)
     assert L.b200_export_convert_host(rgba.ctypes.data, out.ctypes.data, 64, 64, ab.EXPORT_UINT16) != 0
     assert (out == 7).all()
@@ -106,7 +111,7 @@ def test_pipe_end_tiling_callbacks(built):
     piece = ab.make_piece(6000, 4000, filters=9, data=ab.temperature_data((2, 1, 1.5, 1)))
     L.b200_temperature_tiling(piece, t)
     assert (t.overlap, t.xalign, t.yalign, t.factor) == (0, 3, 3, 2.0)
-    for op, data in (("exposure", ab.exposure_data()), ("gamma", None)):
+    for op, data in (("exposure", ab.exposure_data()), ("gamma", None), ("channelmixerrgb", None)):
         piece = ab.make_piece(6000, 4000, filters=0, channels=4, data=data)
         getattr(L, f"b200_{op}_tiling")(piece, t)
         assert (t.overlap, t.xalign, t.yalign, t.factor) == (0, 1, 1, 2.0), op

@@ -242,6 +242,61 @@ def test_finalscale_oracle_equals_reference(name):
         assert (want >= 0).all() and np.isfinite(want).all() and want.std() > 0
 
 
+WORK = util.profile_pair(util.REC2020_TO_XYZ_D50)
+MIX = [[1.1, -0.05, -0.05], [0.02, 0.95, 0.03], [-0.1, 0.0, 1.1]]
+CHANNELMIXER_CASES = {
+    # the module's default (CAT16, version 3, clip, gamut compression 1) and one case per branch of loop_switch
+    "cat16_v3_default": dict(adaptation=ab.ADAPTATION_CAT16, illuminant=(0.93, 1.02, 0.71)),
+    "cat16_v3_tuned": dict(adaptation=ab.ADAPTATION_CAT16, illuminant=(0.93, 1.02, 0.71), mix=MIX, saturation=(0.1, -0.2, 0.05), lightness=(0.05, 0.1, -0.1)),
+    "bradford_full_v2_noclip": dict(adaptation=ab.ADAPTATION_FULL_BRADFORD, version=1, clip=0, illuminant=(1.05, 1.0, 0.6), mix=MIX, p=0.8, gamut=2.5),
+    "bradford_linear_v1": dict(adaptation=ab.ADAPTATION_LINEAR_BRADFORD, version=0, illuminant=(1.05, 1.0, 0.6), saturation=(0.3, 0.1, -0.2)),
+    "xyz_no_gamut": dict(adaptation=ab.ADAPTATION_XYZ, illuminant=(0.9, 1.0, 0.7), gamut=0.0, mix=MIX),
+    "rgb_bypass_mix_only": dict(adaptation=ab.ADAPTATION_RGB, mix=MIX, clip=0, lightness=(0.2, 0.2, 0.2)),
+    "grey_output": dict(adaptation=ab.ADAPTATION_CAT16, illuminant=(0.93, 1.02, 0.71), apply_grey=1, grey=(0.3, 0.5, 0.2)),
+    "unhandled_adaptation_writes_nothing": dict(adaptation=5),
+}
+
+
+def channelmixer_case(name):
+    img = util.hdr_rgba(131, 75, 3)
+    img[3, 3, :3] = np.nan
+    img[4, 4, 0] = np.inf
+    img[5, 5, :3] = (-0.5, 0.2, 0.1)
+    img[6, 6, :3] = 0.0
+    img[7, 7, :3] = 1e-7
+    return img, ab.channelmixer_piece(WORK, **CHANNELMIXER_CASES[name])
+
+
+@need_ref
+@pytest.mark.parametrize("name", list(CHANNELMIXER_CASES))
+def test_channelmixerrgb_oracle_equals_reference(name):
+    img, cp = channelmixer_case(name)
+    want = pe.ref_channelmixerrgb(img, cp)
+    assert same_bits(pe.oracle_channelmixerrgb(img, cp), want).all()
+    assert same_bits(want[..., 3], img[..., 3]).all() != ("unhandled" in name)
+
+
+@need_ref
+def test_channelmixerrgb_oracle_every_branch_combination():
+    img = channelmixer_case("cat16_v3_default")[0]
+    for ad in range(5):
+        for ver in range(3):
+            for clip in (0, 1):
+                cp = ab.channelmixer_piece(WORK, adaptation=ad, version=ver, clip=clip, illuminant=(0.93, 1.02, 0.71), mix=MIX, saturation=(0.1, -0.2, 0.05),
+                                           lightness=(0.05, 0.1, -0.1), p=0.85, gamut=1.5)
+                assert same_bits(pe.oracle_channelmixerrgb(img, cp), pe.ref_channelmixerrgb(img, cp)).all(), (ad, ver, clip)
+
+
+@need_ref
+def test_channelmixerrgb_data_layout_is_the_reference_struct():
+    import ctypes as C
+    r = util.ref("strict")
+    r.ref_channelmixerrgb_sizeof_data.restype = r.ref_channelmixerrgb_offsetof.restype = C.c_size_t
+    P = ab.ChannelmixerPiece
+    assert r.ref_channelmixerrgb_sizeof_data() == P.work_in.offset == 192
+    assert [r.ref_channelmixerrgb_offsetof(i) for i in range(5)] == [P.saturation.offset, P.illuminant.offset, P.p.offset, P.adaptation.offset, P.version.offset]
+
+
 def _golden():
     return np.load(os.path.join(util.GOLDEN_DIR, "pipe_ends.npz"))
 
@@ -260,6 +315,8 @@ def test_pipe_ends_oracle_equals_golden():
         assert same_bits(pe.oracle_exposure(*exposure_case(name)), g["exposure_" + name]).all()
     for name in FINALSCALE_CASES:
         assert same_bits(pe.oracle_finalscale(*finalscale_case(name)), g["finalscale_" + name]).all()
+    for name in CHANNELMIXER_CASES:
+        assert same_bits(pe.oracle_channelmixerrgb(*channelmixer_case(name)), g["channelmixerrgb_" + name]).all()
     img = pe.awkward_rgba(141, 67, 12)
     assert (pe.oracle_gamma(img) == g["gamma"]).all()
     for fmt in (ab.EXPORT_UINT8, ab.EXPORT_UINT8_SWAP, ab.EXPORT_UINT16):

@@ -168,3 +168,39 @@ def test_product_plan_builder_equals_oracle(emul_resample, itor, scale):
 def test_finalscale_kernels_equal_oracle(emul_resample, name):
     args = cases.finalscale_case(name)
     assert same_bits(pe._finalscale(emul_resample, "emul_finalscale", *args), pe.oracle_finalscale(*args)).all()
+
+
+# ---- colour calibration: ansel_b200/csrc/channelmixer.cu -------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def emul_channelmixer():
+    so = os.path.join(EMUL, "libemul_channelmixer.so")
+    srcs = [os.path.join(EMUL, "emul_channelmixer.cpp"), os.path.join(EMUL, "cuda_on_cpu.h"), os.path.join(util.ROOT, "ansel_b200", "csrc", "channelmixer.cu"),
+            os.path.join(util.ROOT, "ansel_b200", "csrc", "flt32_math.cuh"), os.path.join(util.ROOT, "include", "b200iop.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.run(["g++", "-O1", "-std=c++17", "-fno-fast-math", "-ffp-contract=off", "-I", EMUL, "-shared", "-fPIC", "-o", so, srcs[0]], check=True)
+    subprocess.run(["make", "-s", "-C", util.ORACLE_DIR, "oracle"], check=True)
+    return C.CDLL(so)
+
+
+def _emul_channelmixer(lib, img, cp):
+    out = np.full_like(img, -7.0)
+    lib.emul_channelmixerrgb(pe.vp(np.ascontiguousarray(img)), pe.vp(out), img.shape[1], img.shape[0], C.byref(cp))
+    return out
+
+
+@pytest.mark.parametrize("name", list(cases.CHANNELMIXER_CASES))
+def test_channelmixer_kernel_equals_oracle(emul_channelmixer, name):
+    img, cp = cases.channelmixer_case(name)
+    assert same_bits(_emul_channelmixer(emul_channelmixer, img, cp), pe.oracle_channelmixerrgb(img, cp)).all()
+
+
+def test_channelmixer_kernel_every_branch_combination(emul_channelmixer):
+    img = cases.channelmixer_case("cat16_v3_default")[0]
+    for ad in range(5):
+        for ver in range(3):
+            for clip in (0, 1):
+                for grey in (0, 1):
+                    for gamut in (0.0, 1.5):
+                        cp = ab.channelmixer_piece(cases.WORK, adaptation=ad, version=ver, clip=clip, apply_grey=grey, illuminant=(0.93, 1.02, 0.71), mix=cases.MIX,
+                                                   saturation=(0.1, -0.2, 0.05), lightness=(0.05, 0.1, -0.1), grey=(0.3, 0.5, 0.2), p=0.85, gamut=gamut)
+                        assert same_bits(_emul_channelmixer(emul_channelmixer, img, cp), pe.oracle_channelmixerrgb(img, cp)).all(), (ad, ver, clip, grey, gamut)

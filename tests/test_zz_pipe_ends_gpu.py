@@ -288,3 +288,56 @@ def test_finalscale_export_sizes(built):
     assert ab.lib().b200_finalscale_process_dev(C.byref(piece), d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream) == 0
     torch.cuda.synchronize()
     assert float((d_out - 0.5).abs().max()) < 1e-6
+
+
+# ---- colour calibration (channelmixerrgb) ---------------------------------------------------------------------------------------
+def channelmixer_gpu(img, cp, host=False):
+    import ansel_b200 as ab
+    piece = ab.make_piece(img.shape[1], img.shape[0], filters=0, channels=4, devid=0)
+    piece.data, piece.data_size = C.addressof(cp), C.sizeof(cp)
+    return (run_host if host else run_dev)("channelmixerrgb", piece, img, img.shape)
+
+
+@pytest.mark.parametrize("name", list(cases.CHANNELMIXER_CASES))
+def test_channelmixerrgb_bit_exact(built, name):
+    img, cp = cases.channelmixer_case(name)
+    want = pe.oracle_channelmixerrgb(img, cp)
+    for host in (False, True):
+        rc, got = channelmixer_gpu(img, cp, host)
+        assert rc == 0 and same_bits(got, want).all(), host
+    g = np.load(os.path.join(util.GOLDEN_DIR, "pipe_ends.npz"))
+    assert same_bits(got, g["channelmixerrgb_" + name]).all()
+
+
+def test_channelmixerrgb_every_branch_combination_and_a_large_frame(built):
+    import ansel_b200 as ab
+    img = cases.channelmixer_case("cat16_v3_default")[0]
+    for ad in range(5):
+        for ver in range(3):
+            for clip in (0, 1):
+                for grey in (0, 1):
+                    cp = ab.channelmixer_piece(cases.WORK, adaptation=ad, version=ver, clip=clip, apply_grey=grey, illuminant=(0.93, 1.02, 0.71), mix=cases.MIX,
+                                               saturation=(0.1, -0.2, 0.05), lightness=(0.05, 0.1, -0.1), grey=(0.3, 0.5, 0.2), p=0.85, gamut=1.5)
+                    rc, got = channelmixer_gpu(img, cp)
+                    assert rc == 0 and same_bits(got, pe.oracle_channelmixerrgb(img, cp)).all(), (ad, ver, clip, grey)
+    big = util.hdr_rgba(4000, 3000, 9)
+    cp = ab.channelmixer_piece(cases.WORK, adaptation=ab.ADAPTATION_CAT16, illuminant=(0.93, 1.02, 0.71), mix=cases.MIX, saturation=(0.1, -0.2, 0.05))
+    rc, got = channelmixer_gpu(big, cp)
+    assert rc == 0 and same_bits(got, pe.oracle_channelmixerrgb(big, cp)).all()
+
+
+def test_channelmixerrgb_adapter(built):
+    """dt_iop_channelmixerrgb__process with the work profile on the pipe; without one the adapter refuses"""
+    import ansel_b200 as ab
+    import ansel_b200.dtsurface as ds
+    ab.init()
+    M = ds.modlib()
+    img, cp = cases.channelmixer_case("cat16_v3_tuned")
+    h, w = img.shape[:2]
+    piece = ds.make_piece_iop("channelmixerrgb", w, h, cp, channels_in=4, channels_out=4)
+    piece.data_size = 192                                   # the reference's own data block is what piece->data holds
+    out = np.zeros_like(img)
+    pipe = ds.make_pipe(devid=0, work_profile=ds.profile_info(*cases.WORK))
+    assert M.dt_iop_channelmixerrgb__process(piece.module, C.byref(pipe), C.byref(piece), img.ctypes.data, out.ctypes.data) == 0
+    assert same_bits(out, pe.oracle_channelmixerrgb(img, cp)).all()
+    assert M.dt_iop_channelmixerrgb__process(piece.module, C.byref(ds.make_pipe(devid=0)), C.byref(piece), img.ctypes.data, out.ctypes.data) != 0
