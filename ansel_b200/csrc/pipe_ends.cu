@@ -276,6 +276,92 @@ __global__ void __launch_bounds__(NT) count_pixels_kernel(const float *__restric
 #endif
 }
 
+// ---- highlights, colour inpainting on a Bayer mosaic (iop/highlights/inpaint.c:63-82, lch.c interpolate_color :206-303) ----
+// Along a line, a running ratio between neighbouring sites (decayed over unclipped pairs) restores a clipped sample from
+// its neighbour; the four directions are averaged.  Each line is a serial recurrence, the lines are independent: one
+// thread per row runs passes 0 and 1, then one thread per column runs passes 2 and 3.
+struct inpaint_t
+{
+  float clips[4]; // 0.987 * clip * processed_maximum per colour
+  unsigned filters; // ROI-shifted
+  int width, height;
+};
+__device__ void inpaint_line(const float *__restrict__ ivoid, float *__restrict__ ovoid, const inpaint_t &A, int dim, int dir, int other, int pass)
+{
+  float ratio = 1.0f;
+  int i = dim ? other : 0, j = dim ? 0 : other;
+  const ptrdiff_t offs = (ptrdiff_t)(dim ? A.width : 1) * dir;
+  const int n = dim ? A.height : A.width;
+  const int beg = dir == 1 ? 0 : n - 1, end = dir == 1 ? n : -1;
+  const size_t first = dim ? i + (size_t)beg * A.width : beg + (size_t)j * A.width;
+  const float *in = ivoid + first;
+  float *out = ovoid + first;
+  for(int k = beg; k != end; k += dir)
+  {
+    if(dim == 1)
+      j = k;
+    else
+      i = k;
+    if(i == 0 || i == A.width - 1 || j == 0 || j == A.height - 1)
+    {
+      if(pass == 3) out[0] = in[0];
+    }
+    else
+    {
+      const float clip0 = pick4(A.clips, fc(j, i, A.filters));
+      const float clip1 = pick4(A.clips, fc(dim ? (j + 1) : j, dim ? i : (i + 1), A.filters));
+      const float v0 = in[0], v1 = in[offs];
+      if(v0 < clip0 && v0 > 1e-5f && v1 < clip1 && v1 > 1e-5f)
+      { // both unclipped: ratio = in[odd] / in[even], exponential decay
+        if(k & 1)
+          ratio = (3.0f * ratio + v0 / v1) / 4.0f;
+        else
+          ratio = (3.0f * ratio + v1 / v0) / 4.0f;
+      }
+      if(v0 >= clip0 - 1e-5f)
+      {
+        float add;
+        if(v1 >= clip1 - 1e-5f)
+          add = fmaxf(clip0, clip1);
+        else if(k & 1)
+          add = v1 * ratio;
+        else
+          add = v1 / ratio;
+        if(pass == 0)
+          out[0] = add;
+        else if(pass == 3)
+          out[0] = (out[0] + add) / 4.0f;
+        else
+          out[0] += add;
+      }
+      else if(pass == 3)
+        out[0] = v0;
+    }
+    out += offs;
+    in += offs;
+  }
+}
+// `counter`: the clipped-sample count of the bypass test; under 25 the frame is copied through (by the column kernel)
+__global__ void __launch_bounds__(128) inpaint_rows_kernel(const float *__restrict__ in, float *__restrict__ out, inpaint_t A, const unsigned long long *counter)
+{
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  if(j >= A.height || *counter < 25ull) return;
+  inpaint_line(in, out, A, 0, 1, j, 0);
+  inpaint_line(in, out, A, 0, -1, j, 1);
+}
+__global__ void __launch_bounds__(128) inpaint_cols_kernel(const float *__restrict__ in, float *__restrict__ out, inpaint_t A, const unsigned long long *counter)
+{
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  if(i >= A.width) return;
+  if(*counter < 25ull)
+  {
+    for(int j = 0; j < A.height; j++) out[(size_t)j * A.width + i] = in[(size_t)j * A.width + i];
+    return;
+  }
+  inpaint_line(in, out, A, 1, 1, i, 2);
+  inpaint_line(in, out, A, 1, -1, i, 3);
+}
+
 // ---- the float -> integer ends ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned gamma_byte(float x)
 { // (uint8_t)(fminf(roundf(255.0f * fmaxf(in, 0.0f)), 255.0f)), gamma.c:361
@@ -615,7 +701,19 @@ extern "C" int b200_highlights_process_dev(const b200_piece_t *piece, const void
     B200_CUDA_TRY(cudaGetLastError());
     return B200_OK;
   }
-  // a reconstruction mode: only its bypass is built, so the host has to know which way the frame goes
+  if(mosaic && piece->filters != 9u && d->mode == B200_HIGHLIGHTS_INPAINT)
+  { // process() :735-746; the bypass stays on the device: the kernels read the counter
+    float pmax[4];
+    for(int c = 0; c < 4; c++) pmax[c] = (piece->processed_maximum[c] > 0.f) ? piece->processed_maximum[c] : 1.0f;
+    inpaint_t A = { { 0.987f * d->clip * pmax[0], 0.987f * d->clip * pmax[1], 0.987f * d->clip * pmax[2], clip },
+                    b200_roi_filters(piece->filters, piece->roi_in.x, piece->roi_in.y), width, height };
+    inpaint_rows_kernel<<<(unsigned)((height + 127) / 128), 128, 0, s>>>((const float *)d_in, (float *)d_out, A, counter);
+    B200_CUDA_TRY(cudaGetLastError());
+    inpaint_cols_kernel<<<(unsigned)((width + 127) / 128), 128, 0, s>>>((const float *)d_in, (float *)d_out, A, counter);
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+  }
+  // another reconstruction mode: only its bypass is built, so the host has to know which way the frame goes
   unsigned long long n_clipped = 0;
   B200_CUDA_TRY(cudaMemcpyAsync(&n_clipped, counter, sizeof(n_clipped), cudaMemcpyDeviceToHost, s));
   B200_CUDA_TRY(cudaStreamSynchronize(s));

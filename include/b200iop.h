@@ -544,10 +544,12 @@ typedef struct b200_highlights_data_t
   float solid_color;
 } b200_highlights_data_t;
 /* process() :679-789: counts the samples above the mode's threshold (_hl_count_clipped :266-292); fewer than 25 ->
- * the input is copied through; else process_clip (iop/highlights/clip.c:60-85).  Built: mode CLIP, and the modes that
- * fall back to it on non-mosaic input (LCh, colour inpainting).  The reconstruction modes on a mosaic (LCh's
- * long-double arithmetic, inpainting, guided Laplacians, harmonic transposition) return B200_ERR_UNSUPPORTED.
- * The count and the branch stay on the device: no host round trip. */
+ * the input is copied through.  Past the bypass, built: mode CLIP (process_clip, iop/highlights/clip.c:60-85; also
+ * what LCh and colour inpainting run on non-mosaic input) and colour inpainting on a Bayer mosaic
+ * (process_inpaint_bayer, iop/highlights/inpaint.c:63-82: four directional line recurrences, averaged).  For these the
+ * count and the branch stay on the device: no host round trip.  LCh on a mosaic (long-double arithmetic in the
+ * reference), X-Trans inpainting, guided Laplacians and harmonic transposition return B200_ERR_UNSUPPORTED when the
+ * frame does not take the bypass (the host reads the count once to know). */
 int b200_highlights_process_host(const b200_piece_t *piece, const void *in, void *out);
 int b200_highlights_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
 void b200_highlights_tiling(const b200_piece_t *piece, b200_tiling_t *tiling); /* :575-644 */

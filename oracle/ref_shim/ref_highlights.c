@@ -3,8 +3,9 @@
  * oracle/Makefile cuts verbatim into oracle/_ref/gen_highlights.c:
  *     iop/highlights/common.h :218 (DT_HL_MIN_CLIPPED_PIXELS), :431-476 (mode enum, params == data)
  *     iop/highlights/clip.c   :60-85  process_clip
+ *     iop/highlights/lch.c    :206-303 interpolate_color;  iop/highlights/inpaint.c :63-82 process_inpaint_bayer
  *     iop/highlights.c        :232-302 _hl_count_thresholds, _hl_count_clipped, _hl_copy_input;  :679-789 process()
- * The reconstruction modes (LCh, colour inpainting, guided Laplacians, harmonic transposition) are separate translation
+ * The other reconstruction modes (LCh, X-Trans inpainting, guided Laplacians, harmonic transposition) are separate translation
  * units of 18 k lines that are not built here: their entry points abort (the tests reach them only through the bypass).
  */
 #include "ref_piece.h"
@@ -17,14 +18,30 @@ static inline void dt_iop_image_copy_by_size(float *const out, const float *cons
 typedef struct dt_iop_highlights_gui_data_t { int show_visualize; } dt_iop_highlights_gui_data_t;
 #define dt_iop_gui_data(self) NULL
 #define DT_DEV_PIXELPIPE_DISPLAY_PASSTHRU (1 << 12)
+/* develop/imageop.c:139-142 -> imageio/imageio_rawspeed.cc:146-151 -> rawspeed's ColorFilterArray::shiftDcrawFilter
+ * (third party, not under /root/reference/src; ColorFilterArray.cpp:143-170 restated): an odd x swaps the two colours of
+ * every row pair of the 8x2 pattern word, y rotates it by four bits per row */
 static inline uint32_t dt_dev_get_roi_filters(const dt_dev_pixelpipe_iop_t *piece, const dt_iop_roi_t *roi)
-{ /* only the visualisation and colour-inpainting branches read the shifted word; neither is entered here */
-  return piece->dsc_in.filters;
+{
+  uint32_t filters = piece->dsc_in.filters;
+  if(!filters || filters == 9u) return filters;
+  int x = roi->x, y = roi->y;
+  if(abs(x) & 1)
+    for(int n = 0; n < 8; n++)
+    {
+      const int i = n * 4, j = i + 2;
+      const uint32_t t = ((filters >> i) ^ (filters >> j)) & 3u;
+      filters ^= (t << i) | (t << j);
+    }
+  if(y == 0) return filters;
+  y *= 4;
+  y = y >= 0 ? y % 32 : 32 - ((-y) % 32);
+  if(y != 0 && y != 32) filters = (filters >> y) | (filters << (32 - y));
+  return filters;
 }
 #define NOT_BUILT(name) do { fprintf(stderr, "oracle/_ref: highlights %s is not built\n", name); abort(); } while(0)
 #define process_visualize(...) NOT_BUILT("process_visualize")
 #define process_inpaint_xtrans(...) NOT_BUILT("process_inpaint_xtrans")
-#define process_inpaint_bayer(...) NOT_BUILT("process_inpaint_bayer")
 #define process_lch_xtrans(...) NOT_BUILT("process_lch_xtrans")
 #define process_lch_bayer(...) NOT_BUILT("process_lch_bayer")
 static inline int process_laplacian_stub(void) { NOT_BUILT("process_laplacian"); return 1; }

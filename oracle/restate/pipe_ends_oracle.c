@@ -6,7 +6,8 @@
  *   iop/rawprepare.c    compute_proper_crop :206-210, BL :413-418, process() :466-633
  *   iop/temperature.c   process() :486-608  (FC / FCxtrans: develop/imageop_math.h:190-222)
  *   iop/highlights.c    _hl_count_thresholds :232-253, _hl_count_clipped :266-292, _hl_copy_input :296-302,
- *                       process() :679-789;  iop/highlights/clip.c process_clip :60-85
+ *                       process() :679-789;  iop/highlights/clip.c process_clip :60-85;  iop/highlights/inpaint.c
+ *                       process_inpaint_bayer :63-82 with iop/highlights/lch.c interpolate_color :206-303
  *   iop/exposure.c      process() :501-544
  *   iop/gamma.c         _copy_output :352-364 (process() :367-377 without mask/channel display)
  *   imageio/imageio_core.c  _clamp_float_to_uint8 :706-714, _swap_byteorder_float_to_uint8 :717-728,
@@ -132,6 +133,83 @@ int orc_temperature(const b200_piece_t *piece, const float *in, float *out)
 }
 
 /* ---- highlights --------------------------------------------------------------------------------------------------- */
+/* dt_dev_get_roi_filters (develop/imageop.c:139-142): the CFA word seen from the ROI origin.  The shift itself is
+ * rawspeed's ColorFilterArray::shiftDcrawFilter (third party, pinned submodule external/rawspeed; ColorFilterArray.cpp:
+ * 143-170), restated: odd x swaps the colours of each horizontal pair, y rotates by one row (four bits) per step. */
+static uint32_t roi_filters(uint32_t filters, int x, int y)
+{
+  if(!filters || filters == 9u) return filters;
+  if((x < 0 ? -x : x) & 1)
+    for(int n = 0; n < 8; n++)
+    {
+      const int i = n * 4, j = i + 2;
+      const uint32_t t = ((filters >> i) ^ (filters >> j)) & 3u;
+      filters ^= (t << i) | (t << j);
+    }
+  y *= 4;
+  y = y >= 0 ? y % 32 : 32 - ((-y) % 32);
+  if(y != 0 && y != 32) filters = (filters >> y) | (filters << (32 - y));
+  return filters;
+}
+
+/* one line of the colour inpainting, lch.c:206-303: a running ratio between neighbouring sites of the line, decayed
+ * exponentially over unclipped pairs, restores a clipped sample from its neighbour; four passes (row left-to-right,
+ * right-to-left, column down, up) are averaged.  dim 0 = along a row (`other` = the row), 1 = along a column. */
+static void interpolate_color(const float *ivoid, float *ovoid, int width, int height, int dim, int dir, int other, const float *clip, uint32_t filters,
+                              int pass)
+{
+  float ratio = 1.0f;
+  int i = 0, j = 0;
+  if(dim == 0) j = other; else i = other;
+  ptrdiff_t offs = dim ? width : 1;
+  if(dir < 0) offs = -offs;
+  const int n = dim ? height : width;
+  const int beg = dir == 1 ? 0 : n - 1, end = dir == 1 ? n : -1;
+  const float *in = ivoid + (dim ? i + (size_t)beg * width : beg + (size_t)j * width);
+  float *out = ovoid + (in - ivoid);
+  for(int k = beg; k != end; k += dir)
+  {
+    if(dim == 1) j = k; else i = k;
+    const float clip0 = clip[orc_fc(j, i, filters)];
+    const float clip1 = clip[orc_fc(dim ? (j + 1) : j, dim ? i : (i + 1), filters)];
+    if(i == 0 || i == width - 1 || j == 0 || j == height - 1)
+    {
+      if(pass == 3) out[0] = in[0];
+    }
+    else
+    {
+      if(in[0] < clip0 && in[0] > 1e-5f)
+        if(in[offs] < clip1 && in[offs] > 1e-5f)
+        {
+          if(k & 1)
+            ratio = (3.0f * ratio + in[0] / in[offs]) / 4.0f;
+          else
+            ratio = (3.0f * ratio + in[offs] / in[0]) / 4.0f;
+        }
+      if(in[0] >= clip0 - 1e-5f)
+      {
+        float add = 0.0f;
+        if(in[offs] >= clip1 - 1e-5f)
+          add = fmaxf(clip0, clip1);
+        else if(k & 1)
+          add = in[offs] * ratio;
+        else
+          add = in[offs] / ratio;
+        if(pass == 0)
+          out[0] = add;
+        else if(pass == 3)
+          out[0] = (out[0] + add) / 4.0f;
+        else
+          out[0] += add;
+      }
+      else if(pass == 3)
+        out[0] = in[0];
+    }
+    out += offs;
+    in += offs;
+  }
+}
+
 /* returns 0 and the number of samples counted as clipped in *n_clipped; -1 for a mode that is not restated */
 int orc_highlights(const b200_piece_t *piece, const float *in, float *out, size_t *n_clipped)
 {
@@ -173,6 +251,23 @@ int orc_highlights(const b200_piece_t *piece, const float *in, float *out, size_
   }
   /* past the bypass: the reconstruction modes are not restated (on non-mosaic input LCh and inpainting are process_clip) */
   if(data->mode == B200_HIGHLIGHTS_LAPLACIAN || data->mode == B200_HIGHLIGHTS_HARMONIC) return -1;
+  if(filters && filters != 9u && data->mode == B200_HIGHLIGHTS_INPAINT)
+  { /* process() :735-746 */
+    const float clips[4] = { 0.987f * data->clip * pmax[0], 0.987f * data->clip * pmax[1], 0.987f * data->clip * pmax[2], clip };
+    const int w = piece->roi_out.width, h = piece->roi_out.height;
+    const uint32_t shifted = roi_filters(filters, piece->roi_in.x, piece->roi_in.y); /* :691 */
+    for(int j = 0; j < h; j++)
+    {
+      interpolate_color(in, out, w, h, 0, 1, j, clips, shifted, 0);
+      interpolate_color(in, out, w, h, 0, -1, j, clips, shifted, 1);
+    }
+    for(int i = 0; i < w; i++)
+    {
+      interpolate_color(in, out, w, h, 1, 1, i, clips, shifted, 2);
+      interpolate_color(in, out, w, h, 1, -1, i, clips, shifted, 3);
+    }
+    return 0;
+  }
   if(filters && data->mode != B200_HIGHLIGHTS_CLIP) return -1;
   for(size_t k = 0; k < ch * n_pixels; k++) out[k] = clip < in[k] ? clip : in[k];
   /* dt_iop_alpha_copy assumes four floats per pixel whatever the buffer holds: on a mosaic it would run past both buffers */

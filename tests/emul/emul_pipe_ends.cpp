@@ -78,7 +78,8 @@ extern "C" int emul_temperature(const b200_piece_t *piece, const float *in, floa
 }
 
 /* -> 0 ok, 3 = a reconstruction mode past its bypass (B200_ERR_UNSUPPORTED) */
-extern "C" int emul_highlights(const b200_piece_t *piece, const float *in, float *out, unsigned long long *n_clipped)
+/* shifted_filters: b200_roi_filters(piece->filters, roi_in.x, roi_in.y), a host function of the product the caller evaluates */
+extern "C" int emul_highlights(const b200_piece_t *piece, const float *in, float *out, unsigned long long *n_clipped, unsigned shifted_filters)
 {
   const b200_highlights_data_t *d = (const b200_highlights_data_t *)piece->data;
   const int w = piece->roi_out.width, h = piece->roi_out.height;
@@ -93,6 +94,15 @@ extern "C" int emul_highlights(const b200_piece_t *piece, const float *in, float
   else
     emulate(dim3((unsigned)((npx + NT - 1) / NT)), NT, count_pixels_kernel, in, npx, ch, thresholds[0], thresholds[1], thresholds[2], &counter);
   *n_clipped = counter;
+  if(mosaic && piece->filters != 9u && d->mode == B200_HIGHLIGHTS_INPAINT)
+  {
+    float pmax[4];
+    for(int c = 0; c < 4; c++) pmax[c] = (piece->processed_maximum[c] > 0.f) ? piece->processed_maximum[c] : 1.0f;
+    inpaint_t A = { { 0.987f * d->clip * pmax[0], 0.987f * d->clip * pmax[1], 0.987f * d->clip * pmax[2], clip }, shifted_filters, w, h };
+    emulate(dim3((unsigned)((h + 127) / 128)), 128, inpaint_rows_kernel, in, out, A, (const unsigned long long *)&counter);
+    emulate(dim3((unsigned)((w + 127) / 128)), 128, inpaint_cols_kernel, in, out, A, (const unsigned long long *)&counter);
+    return 0;
+  }
   const bool clip_mode = d->mode == B200_HIGHLIGHTS_CLIP || (!mosaic && (d->mode == B200_HIGHLIGHTS_LCH || d->mode == B200_HIGHLIGHTS_INPAINT));
   if(clip_mode)
     emulate(dim3(flat_grid(n)), NT, flat_kernel<OP_CLIP>, in, out, n, clip, 0.0f, (piece->mask_display & 1) ? 1 : 0, (const unsigned long long *)&counter);

@@ -52,7 +52,8 @@ def test_highlights_kernels_equal_oracle(emul, name):
     piece, img = cases.highlights_case(name)
     rc, want, n_want = pe.oracle_highlights(piece, img)
     got, n = np.full_like(want, -7.0), C.c_ulonglong(0)
-    assert emul.emul_highlights(C.byref(piece), pe.vp(img), pe.vp(got), C.byref(n)) == 0 and rc == 0
+    shifted = ab.lib().b200_roi_filters(C.c_uint32(piece.filters), piece.roi_in.x, piece.roi_in.y)
+    assert emul.emul_highlights(C.byref(piece), pe.vp(img), pe.vp(got), C.byref(n), C.c_uint32(shifted)) == 0 and rc == 0
     assert n.value == n_want and same_bits(got, want).all()
 
 
@@ -60,7 +61,7 @@ def test_highlights_kernels_refuse_reconstruction_past_the_bypass(emul):
     _, img = cases.highlights_case("clip_mosaic")
     piece = pe.mosaic_piece(img.shape[1], img.shape[0], ab.highlights_data(ab.HIGHLIGHTS_HARMONIC, 1.0))
     got, n = np.zeros_like(img), C.c_ulonglong(0)
-    assert emul.emul_highlights(C.byref(piece), pe.vp(img), pe.vp(got), C.byref(n)) == 3 and n.value >= 25
+    assert emul.emul_highlights(C.byref(piece), pe.vp(img), pe.vp(got), C.byref(n), C.c_uint32(piece.filters)) == 3 and n.value >= 25
 
 
 @pytest.mark.parametrize("name", list(cases.EXPOSURE_CASES))
