@@ -8,6 +8,9 @@ namespace b200
 int rcd_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters,
                      const float processed_maximum[3], cudaStream_t stream);
 int amaze_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters, const float processed_maximum[3], cudaStream_t stream);
+int vng_demosaic_dev(const float *d_in, float *d_out, int width, int height, int x0, int y0, uint32_t filters, int lin_slot, cudaStream_t s);
+int dual_demosaic_dev(float *d_rgb, const float *d_raw, int width, int height, int x0, int y0, uint32_t filters, const float wb[4], float dual_threshold,
+                      cudaStream_t s);
 int ppg_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters, float median_thrs, cudaStream_t s);
 int demosaic_green_eq_dev(const float *d_in, float *d_tmp0, float *d_tmp1, double *d_partial, int width, int height, uint32_t dsc_filters, int x, int y,
                           unsigned green_eq, float threshold, const float **d_result, cudaStream_t s);
@@ -40,14 +43,17 @@ extern "C" int b200_demosaic_process_dev(const b200_piece_t *piece, const void *
   if(filters == 9u) return fail(B200_ERR_UNSUPPORTED, "demosaic: X-Trans sensors are not built (SURVEY.md 8f rank 4)");
   if(d->green_eq > 3) return fail(B200_ERR_ARG, "demosaic: green_eq %u", d->green_eq);
   if(piece->image_flags & DT_IMAGE_4BAYER) return fail(B200_ERR_UNSUPPORTED, "demosaic: four-colour Bayer sensors are not built");
-  if(d->demosaicing_method & DEMOSAIC_DUAL) return fail(B200_ERR_UNSUPPORTED, "demosaic: dual demosaic is not built (8f rank 4)");
   // roi_out has the size of roi_in with origin 0 for the full demosaicers (demosaic.c:1052-1054)
   if(piece->roi_out.width != piece->roi_in.width || piece->roi_out.height != piece->roi_in.height)
     return fail(B200_ERR_UNSUPPORTED, "demosaic: roi_out %dx%d != roi_in %dx%d (downsampling paths are not built)",
                 piece->roi_out.width, piece->roi_out.height, piece->roi_in.width, piece->roi_in.height);
 
-  if(d->demosaicing_method != B200_DEMOSAIC_RCD && d->demosaicing_method != B200_DEMOSAIC_AMAZE && d->demosaicing_method != B200_DEMOSAIC_PPG)
+  const uint32_t method = d->demosaicing_method & ~(uint32_t)DEMOSAIC_DUAL;
+  const bool dual = (d->demosaicing_method & DEMOSAIC_DUAL) != 0;
+  if(method != B200_DEMOSAIC_RCD && method != B200_DEMOSAIC_AMAZE && method != B200_DEMOSAIC_PPG && method != B200_DEMOSAIC_VNG4)
     return fail(B200_ERR_UNSUPPORTED, "demosaic: method %u is not built", d->demosaicing_method);
+  if(dual && method != B200_DEMOSAIC_RCD && method != B200_DEMOSAIC_AMAZE)
+    return fail(B200_ERR_UNSUPPORTED, "demosaic: dual demosaic is RCD + VNG4 or AMaZE + VNG4 (method %u)", d->demosaicing_method);
   const int width = piece->roi_in.width, height = piece->roi_in.height;
   cudaStream_t s = (cudaStream_t)stream;
   const float *mosaic = (const float *)d_in;
@@ -63,13 +69,18 @@ extern "C" int b200_demosaic_process_dev(const b200_piece_t *piece, const void *
                                    d->green_eq, threshold, &mosaic, s)))
       return rc;
   }
-  if(d->demosaicing_method == B200_DEMOSAIC_PPG)
+  if(method == B200_DEMOSAIC_VNG4)
+    rc = vng_demosaic_dev(mosaic, (float *)d_out, width, height, piece->roi_in.x, piece->roi_in.y, piece->filters, SLOT_TMP3, s); // demosaic.c:1172-1175
+  else if(method == B200_DEMOSAIC_PPG)
     rc = ppg_demosaic_dev(mosaic, (float *)d_out, width, height, filters, d->median_thrs, s); // demosaic.c:1218-1226
-  else if(d->demosaicing_method == B200_DEMOSAIC_AMAZE)
+  else if(method == B200_DEMOSAIC_AMAZE)
     rc = amaze_demosaic_dev(mosaic, (float *)d_out, width, height, filters, piece->processed_maximum, s); // demosaic.c:1227
   else
     rc = rcd_demosaic_dev(mosaic, (float *)d_out, width, height, filters, piece->processed_maximum, s);
   if(rc) return rc;
+  // demosaic.c:1243-1247: the blend reads the module's own input (not the green-equilibrated copy) and the sensor's filters word
+  if(dual && (rc = dual_demosaic_dev((float *)d_out, (const float *)d_in, width, height, piece->roi_in.x, piece->roi_in.y, piece->filters, piece->wb_coeffs, d->dual_thrs, s)))
+    return rc;
   if(d->color_smoothing) rc = demosaic_color_smoothing_dev((float *)d_out, piece->roi_out.width, piece->roi_out.height, (int)d->color_smoothing, s); // :1249-1250
   return rc;
 }
