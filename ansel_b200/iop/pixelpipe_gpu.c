@@ -61,28 +61,85 @@ static int ensure(b200_pipe_buffers_t *b, int k, size_t bytes)
   return 0;
 }
 
+/* both buffers large enough for every cacheline of the chain (fusion changes which buffer a module lands in) */
+static int size_buffers(const b200_pipe_node_t *nodes, int n_nodes, b200_pipe_buffers_t *bufs)
+{
+  size_t need = 0;
+  for(int k = 0; k < n_nodes; k++)
+  {
+    const size_t bi = buffer_bytes(&nodes[k].piece->dsc_in, &nodes[k].piece->roi_in);
+    const size_t bo = buffer_bytes(&nodes[k].piece->dsc_out, &nodes[k].piece->roi_out);
+    if(bi > need) need = bi;
+    if(bo > need) need = bo;
+  }
+  return ensure(bufs, 0, need) || ensure(bufs, 1, need);
+}
+
+/* ---- pipe-level fusion of the raw front ------------------------------------------------------------------------
+ * rawprepare -> temperature -> highlights are three pointwise modules over the mosaic; one after the other they move
+ * 26 bytes per sample through HBM, as one pass over the sensor data 8 (b200_rawfront_process_dev, bit-identical).  The
+ * decision belongs to the pipe, where the reference's pixelpipe_process_on_GPU walks its nodes: when the chain starts
+ * with rawprepare and the following nodes are temperature and/or highlights in clip mode, they run as one launch and
+ * the intermediate cachelines are never produced.  Anything the fused entry point refuses (X-Trans, another highlights
+ * mode, mask display) runs module by module as before.  Returns the number of nodes consumed (0 = not fused), < 0 on error. */
+#include <string.h>
+int b200_rawfront_process_dev(const b200_piece_t *rawprepare, const b200_piece_t *temperature, const b200_piece_t *highlights, const void *d_in,
+                              void *d_out, void *stream);
+int b200_pipe_fusion_enabled = 1; /* set to 0 to run every module on its own (parity tests compare the two) */
+static int fuse_raw_front(const dt_dev_pixelpipe_t *pipe, const b200_pipe_node_t *nodes, int n_nodes, void *d_in, void *d_out)
+{
+  if(!b200_pipe_fusion_enabled || n_nodes < 2 || !nodes[0].module || strcmp(nodes[0].module->op, "rawprepare")) return 0;
+  b200_piece_t p[3];
+  const b200_piece_t *tp = NULL, *hp = NULL;
+  int used = 1;
+  b200_piece_from_dt(&p[0], nodes[0].module, pipe, nodes[0].piece);
+  if(nodes[used].module && !strcmp(nodes[used].module->op, "temperature"))
+  {
+    b200_piece_from_dt(&p[1], nodes[used].module, pipe, nodes[used].piece);
+    tp = &p[1];
+    used++;
+  }
+  if(used < n_nodes && nodes[used].module && !strcmp(nodes[used].module->op, "highlights"))
+  {
+    b200_piece_from_dt(&p[2], nodes[used].module, pipe, nodes[used].piece);
+    hp = &p[2];
+    used++;
+  }
+  if(used < 2) return 0;
+  const int rc = b200_rawfront_process_dev(&p[0], tp, hp, d_in, d_out, pipe->stream);
+  if(rc == B200_ERR_UNSUPPORTED) return 0;
+  return rc ? -1 : used;
+}
+/* run nodes [0, n_nodes) with ping-pong buffers; *last = index of the buffer holding the final output */
+static int run_chain(const dt_dev_pixelpipe_t *pipe, const b200_pipe_node_t *nodes, int n_nodes, b200_pipe_buffers_t *bufs, int *last)
+{
+  int k = 0, cur = 0;
+  const int fused = fuse_raw_front(pipe, nodes, n_nodes, bufs->buf[0], bufs->buf[1]);
+  if(fused < 0) return 1;
+  if(fused > 0)
+  {
+    k = fused;
+    cur = 1;
+  }
+  for(; k < n_nodes; k++, cur ^= 1)
+    if(!nodes[k].process_cl(nodes[k].module, pipe, nodes[k].piece, bufs->buf[cur], bufs->buf[cur ^ 1])) return 1;
+  *last = cur;
+  return 0;
+}
+
 /* Returns 0 on success (process() convention).  host_in is the first node's input cacheline,
  * host_out the last node's output cacheline. */
 int b200_pixelpipe_process_on_gpu(const dt_dev_pixelpipe_t *pipe, const b200_pipe_node_t *nodes, int n_nodes,
                                   b200_pipe_buffers_t *bufs, const void *host_in, void *host_out)
 {
   if(!pipe || !nodes || n_nodes < 1 || !bufs || !host_in || !host_out) return 1;
-  size_t need[2] = { 0, 0 };
-  for(int k = 0; k < n_nodes; k++)
-  {
-    const size_t bi = buffer_bytes(&nodes[k].piece->dsc_in, &nodes[k].piece->roi_in);
-    const size_t bo = buffer_bytes(&nodes[k].piece->dsc_out, &nodes[k].piece->roi_out);
-    if(bi > need[k & 1]) need[k & 1] = bi;
-    if(bo > need[(k + 1) & 1]) need[(k + 1) & 1] = bo;
-  }
-  if(ensure(bufs, 0, need[0]) || ensure(bufs, 1, need[1])) return 1;
-
+  if(size_buffers(nodes, n_nodes, bufs)) return 1;
   const size_t in_bytes = buffer_bytes(&nodes[0].piece->dsc_in, &nodes[0].piece->roi_in);
   if(b200_copy_host_to_device(bufs->buf[0], host_in, in_bytes, pipe->stream)) return 1;
-  for(int k = 0; k < n_nodes; k++)
-    if(!nodes[k].process_cl(nodes[k].module, pipe, nodes[k].piece, bufs->buf[k & 1], bufs->buf[(k + 1) & 1])) return 1;
+  int out_buf = 0;
+  if(run_chain(pipe, nodes, n_nodes, bufs, &out_buf)) return 1;
   const dt_dev_pixelpipe_iop_t *last = nodes[n_nodes - 1].piece;
-  if(b200_copy_device_to_host(host_out, bufs->buf[n_nodes & 1], buffer_bytes(&last->dsc_out, &last->roi_out), pipe->stream))
+  if(b200_copy_device_to_host(host_out, bufs->buf[out_buf], buffer_bytes(&last->dsc_out, &last->roi_out), pipe->stream))
     return 1;
   return b200_stream_synchronize(pipe->stream);
 }
@@ -141,15 +198,7 @@ long b200_pixelpipe_submit(b200_pipe_queue_t *q, const dt_dev_pixelpipe_t *pipe,
   void *const st = q->stream[slot];
   b200_pipe_buffers_t *const bufs = &q->bufs[slot];
   if(b200_stream_synchronize(st)) return -1;
-  size_t need[2] = { 0, 0 };
-  for(int k = 0; k < n_nodes; k++)
-  {
-    const size_t bi = buffer_bytes(&nodes[k].piece->dsc_in, &nodes[k].piece->roi_in);
-    const size_t bo = buffer_bytes(&nodes[k].piece->dsc_out, &nodes[k].piece->roi_out);
-    if(bi > need[k & 1]) need[k & 1] = bi;
-    if(bo > need[(k + 1) & 1]) need[(k + 1) & 1] = bo;
-  }
-  if(ensure(bufs, 0, need[0]) || ensure(bufs, 1, need[1])) return -1;
+  if(size_buffers(nodes, n_nodes, bufs)) return -1;
   if(b200_copy_host_to_device(bufs->buf[0], host_in, buffer_bytes(&nodes[0].piece->dsc_in, &nodes[0].piece->roi_in), st)) return -1;
   if(q->submitted > 0)
   { /* one module chain at a time on the device */
@@ -158,11 +207,11 @@ long b200_pixelpipe_submit(b200_pipe_queue_t *q, const dt_dev_pixelpipe_t *pipe,
   }
   dt_dev_pixelpipe_t p = *pipe;
   p.stream = st;
-  for(int k = 0; k < n_nodes; k++)
-    if(!nodes[k].process_cl(nodes[k].module, &p, nodes[k].piece, bufs->buf[k & 1], bufs->buf[(k + 1) & 1])) return -1;
+  int out_buf = 0;
+  if(run_chain(&p, nodes, n_nodes, bufs, &out_buf)) return -1;
   if(b200_event_record(q->compute_done[slot], st)) return -1;
   const dt_dev_pixelpipe_iop_t *last = nodes[n_nodes - 1].piece;
-  if(b200_copy_device_to_host(host_out, bufs->buf[n_nodes & 1], buffer_bytes(&last->dsc_out, &last->roi_out), st)) return -1;
+  if(b200_copy_device_to_host(host_out, bufs->buf[out_buf], buffer_bytes(&last->dsc_out, &last->roi_out), st)) return -1;
   return (long)(q->submitted++);
 }
 /* Block until the frame of `ticket` is in its host_out.  Returns 0 on success. */

@@ -328,7 +328,7 @@ def pipe_ends_extras(ab, ds, util, L, M, torch, w, h, local, dev, stream, conv_i
         M.b200_pipe_queue_free(queue)
     res["sensor_to_display_e2e"] = {"value": npx * steps / dt / 1e6, "unit": UNIT, "steps": steps, "h2d_bytes_per_step": 2 * npx, "d2h_bytes_per_step": 4 * npx,
                                     "chain": "rawprepare(uint16) -> temperature -> highlights(clip) -> demosaic(RCD) -> colorin -> colorout -> gamma(uint8)",
-                                    "path": "dt_iop_<op>__process_cl adapters via b200_pixelpipe_submit/_wait, 2 frames in flight, pinned host buffers",
+                                    "path": "dt_iop_<op>__process_cl adapters via b200_pixelpipe_submit/_wait (the raw front fused into one launch by the pipe glue), 2 frames in flight, pinned host buffers",
                                     "mean_display_value": float(h_out[0][..., :3].float().mean())}
     return res
 

@@ -220,11 +220,18 @@ def test_adapters_and_device_resident_export_chain(built):
         nodes[k].module = pieces[k].module
         nodes[k].piece = C.pointer(pieces[k])
     out = np.full((h, w, 4), 0x5A, np.uint8)
+    unfused = np.full((h, w, 4), 0x5A, np.uint8)
+    fusion = C.c_int.in_dll(M, "b200_pipe_fusion_enabled")       # the raw front runs as one launch by default
     bufs = M.b200_pipe_buffers_new()
     try:
+        assert fusion.value == 1
         assert M.b200_pixelpipe_process_on_gpu(C.byref(pipe), nodes, len(spec), bufs, raw.ctypes.data, out.ctypes.data) == 0
+        fusion.value = 0
+        assert M.b200_pixelpipe_process_on_gpu(C.byref(pipe), nodes, len(spec), bufs, raw.ctypes.data, unfused.ctypes.data) == 0
     finally:
+        fusion.value = 1
         M.b200_pipe_buffers_free(bufs)
+    assert (out[..., :3] == unfused[..., :3]).all()              # module by module: the same bytes
     # the oracle chain on the same data
     rp = pe.rawprepare_piece(w, h, datas["rawprepare"])
     tp = pe.mosaic_piece(w, h, datas["temperature"])
