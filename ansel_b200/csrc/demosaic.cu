@@ -11,6 +11,8 @@ int amaze_demosaic_dev(const float *d_in, float *d_out, int width, int height, u
 int vng_demosaic_dev(const float *d_in, float *d_out, int width, int height, int x0, int y0, uint32_t filters, int lin_slot, cudaStream_t s);
 int dual_demosaic_dev(float *d_rgb, const float *d_raw, int width, int height, int x0, int y0, uint32_t filters, const float wb[4], float dual_threshold,
                       cudaStream_t s);
+int passthrough_demosaic_dev(const float *d_in, float *d_out, int width, int height, int colour, uint32_t filters, int x0, int y0, const uint8_t xtrans[6][6],
+                             cudaStream_t s);
 int ppg_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters, float median_thrs, cudaStream_t s);
 int demosaic_green_eq_dev(const float *d_in, float *d_tmp0, float *d_tmp1, double *d_partial, int width, int height, uint32_t dsc_filters, int x, int y,
                           unsigned green_eq, float threshold, const float **d_result, cudaStream_t s);
@@ -21,6 +23,9 @@ int demosaic_color_smoothing_dev(float *d_out, int width, int height, int passes
 using namespace b200;
 
 #define DEMOSAIC_DUAL 2048 /* iop/demosaic.c:109 */
+
+// methods that, like the reference, leave (part of) the alpha lane as they find it
+static bool keeps_alpha(uint32_t m) { return m == B200_DEMOSAIC_PPG || m == 3u || m == 4u; }
 
 static int check_piece(const b200_piece_t *piece, const void *in, void *out)
 {
@@ -40,6 +45,23 @@ extern "C" int b200_demosaic_process_dev(const b200_piece_t *piece, const void *
   const b200_demosaic_data_t *d = (const b200_demosaic_data_t *)piece->data;
   // demosaic.c:1071 -- fold the ROI origin into the CFA phase for the tile-local algorithms
   const uint32_t filters = b200_roi_filters(piece->filters, piece->roi_in.x, piece->roi_in.y);
+  // the passthrough methods come first and take any sensor (demosaic.c:1111-1118); colour smoothing still follows (:1249),
+  // green equilibration does not apply
+  {
+    const uint32_t m = d->demosaicing_method;
+    const bool mono = m == 3u, colour = m == 4u; // commit_params() :2196-2199 folds the X-Trans ids (1027, 1029) onto these
+    if(mono || colour)
+    {
+      if(piece->roi_out.width != piece->roi_in.width || piece->roi_out.height != piece->roi_in.height)
+        return fail(B200_ERR_UNSUPPORTED, "demosaic: passthrough with roi_out != roi_in");
+      rc = passthrough_demosaic_dev((const float *)d_in, (float *)d_out, piece->roi_in.width, piece->roi_in.height, colour ? 1 : 0, piece->filters,
+                                    piece->roi_in.x, piece->roi_in.y, piece->xtrans, (cudaStream_t)stream);
+      if(rc) return rc;
+      if(d->color_smoothing)
+        rc = demosaic_color_smoothing_dev((float *)d_out, piece->roi_out.width, piece->roi_out.height, (int)d->color_smoothing, (cudaStream_t)stream);
+      return rc;
+    }
+  }
   if(filters == 9u) return fail(B200_ERR_UNSUPPORTED, "demosaic: X-Trans sensors are not built (SURVEY.md 8f rank 4)");
   if(d->green_eq > 3) return fail(B200_ERR_ARG, "demosaic: green_eq %u", d->green_eq);
   if(piece->image_flags & DT_IMAGE_4BAYER) return fail(B200_ERR_UNSUPPORTED, "demosaic: four-colour Bayer sensors are not built");
@@ -103,7 +125,7 @@ extern "C" int b200_demosaic_process_host(const b200_piece_t *piece, const void 
   // and (for frames under 16 px) the whole buffer as found.  Start from the caller's bytes only
   // in the too-small case and for PPG (which, like the reference, keeps the alpha of the outer three pixels);
   // otherwise every pixel is overwritten.
-  if(piece->roi_in.width < 16 || piece->roi_in.height < 16 || ((const b200_demosaic_data_t *)piece->data)->demosaicing_method == B200_DEMOSAIC_PPG)
+  if(piece->roi_in.width < 16 || piece->roi_in.height < 16 || keeps_alpha(((const b200_demosaic_data_t *)piece->data)->demosaicing_method))
     if((rc = copy_h2d(d_out, out, npx_out * 4 * sizeof(float), s))) return rc;
   if((rc = b200_demosaic_process_dev(piece, d_in, d_out, (void *)s))) return rc;
   if((rc = copy_d2h(out, d_out, npx_out * 4 * sizeof(float), s))) return rc;

@@ -184,11 +184,49 @@ __global__ void __launch_bounds__(PNT) pre_median_kernel(const float *__restrict
   }
   out[p] = result;
 }
+// the two passthrough methods, iop/demosaic/passthrough.c:22-88: every channel = the sample (monochrome sensors), or the
+// sample in its CFA colour and zeros elsewhere (debug view).  Lane 3 is not written by the reference: kept.  The Bayer
+// colour is taken from the sensor's filters word at the frame's own coordinates (demosaic.c:1117 passes roi_out with its
+// origin zeroed), the X-Trans colour through roi_in.
+__global__ void __launch_bounds__(PNT) passthrough_kernel(const float *__restrict__ in, float4 *__restrict__ out, int width, int height, int colour,
+                                                          unsigned filters, int x0, int y0, const unsigned char *__restrict__ xtrans36)
+{
+  const int col = blockIdx.x * PNT + threadIdx.x, row = blockIdx.y;
+  if(col >= width) return;
+  const size_t p = (size_t)row * width + col;
+  const float v = in[p];
+  float4 o = make_float4(v, v, v, out[p].w);
+  if(colour)
+  {
+    const int ch = filters == 9u ? xtrans36[((row + 600 + y0) % 6) * 6 + (col + 600 + x0) % 6] : ppg_fc(row, col, filters);
+    o.x = ch == 0 ? v : 0.0f;
+    o.y = ch == 1 ? v : 0.0f;
+    o.z = ch == 2 ? v : 0.0f;
+  }
+  out[p] = o;
+}
 } // namespace
 
 #ifndef B200_KERNELS_ON_CPU
 namespace b200
 {
+// demosaic.c:1111-1118.  filters: piece->dsc_in.filters (not ROI-shifted); xtrans: piece->dsc_in.xtrans (used when filters == 9)
+int passthrough_demosaic_dev(const float *d_in, float *d_out, int width, int height, int colour, uint32_t filters, int x0, int y0, const uint8_t xtrans[6][6],
+                             cudaStream_t s)
+{
+  if(height > 65535) return fail(B200_ERR_ARG, "demosaic: frame height %d", height);
+  void *dx = nullptr;
+  if(colour && filters == 9u)
+  {
+    int rc = scratch(SLOT_SMALL + 3, 64, &dx);
+    if(rc) return rc;
+    B200_CUDA_TRY(cudaMemcpyAsync(dx, xtrans, 36, cudaMemcpyHostToDevice, s)); // pageable source: staged before the call returns
+  }
+  passthrough_kernel<<<dim3((unsigned)((width + PNT - 1) / PNT), (unsigned)height), PNT, 0, s>>>(d_in, (float4 *)d_out, width, height, colour, filters, x0, y0,
+                                                                                                 (const unsigned char *)dx);
+  B200_CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
 // demosaic.c:1218-1226: d_in = the (green-equilibrated) mosaic, filters = ROI-shifted word, out keeps the alpha of its
 // outer three pixels
 int ppg_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters, float median_thrs, cudaStream_t s)

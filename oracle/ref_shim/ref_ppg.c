@@ -2,13 +2,11 @@
  *
  * iop/demosaic/ppg.c and basic.c are fragments that demosaic.c #includes; oracle/Makefile cuts verbatim into
  * oracle/_ref/gen_demosaic_ppg.c:  basic.c :129-186 (SWAP, pre_median_b, pre_median),  ppg.c :21-211 (demosaic_ppg).
+ * iop/demosaic/passthrough.c :21-87 (passthrough_monochrome, passthrough_color) rides along.
  * demosaic.c:1218-1226 calls it with roi_out's origin zeroed and the ROI-shifted filters word.
  */
 #include "ref_piece.h"
-static inline int FC(const size_t row, const size_t col, const uint32_t filters)
-{ /* develop/imageop_math.h:190-193 */
-  return filters >> (((row << 1 & 14) + (col & 1)) << 1) & 3;
-}
+#include "gen_imageop_math.c" /* develop/imageop_math.h:175-219: dt_iop_alpha_copy, FC, FCxtrans */
 static inline void dt_iop_image_copy_by_size(float *const out, const float *const in, const size_t width, const size_t height, const size_t ch)
 { /* common/imagebuf.h:91-95 */
   memcpy(out, in, sizeof(float) * width * height * ch);
@@ -22,4 +20,15 @@ int ref_demosaic_ppg(float *out, const float *in, int width, int height, uint32_
 {
   const dt_iop_roi_t roi = { 0, 0, width, height, 1.0 };
   return demosaic_ppg(out, in, &roi, &roi, filters, median_thrs);
+}
+
+/* demosaic.c:1111-1118: roi_out arrives with its origin zeroed, roi_in keeps the ROI origin; filters = the sensor's word */
+int ref_demosaic_passthrough(float *out, const float *in, int width, int height, int x, int y, uint32_t filters, const uint8_t xtrans[36], int colour)
+{
+  dt_iop_roi_t roi_in = { x, y, width, height, 1.0 }, roi_out = { 0, 0, width, height, 1.0 };
+  if(colour)
+    passthrough_color(out, in, &roi_out, &roi_in, filters, (const uint8_t(*)[6])xtrans);
+  else
+    passthrough_monochrome(out, in, &roi_out, &roi_in);
+  return 0;
 }

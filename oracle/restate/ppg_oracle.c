@@ -144,3 +144,25 @@ int orc_demosaic_ppg(float *out, const float *in, int width, int height, uint32_
   free(med);
   return 0;
 }
+
+/* the passthrough methods, iop/demosaic/passthrough.c:22-87 (dispatch demosaic.c:1111-1118): roi_out's origin is zeroed by
+ * process(), so the Bayer colour ignores the ROI origin while the X-Trans colour (FCxtrans with roi_in) follows it.
+ * Lane 3 of the output is not written. */
+int orc_demosaic_passthrough(float *out, const float *in, int width, int height, int x, int y, uint32_t filters, const uint8_t xtrans[36], int colour)
+{
+  for(int row = 0; row < height; row++)
+    for(int col = 0; col < width; col++)
+    {
+      const float val = in[(size_t)row * width + col];
+      float *o = out + 4 * ((size_t)row * width + col);
+      if(!colour)
+        o[0] = o[1] = o[2] = val;
+      else
+      {
+        const int ch = filters != 9u ? orc_fc(row, col, filters) : xtrans[((row + 600 + y) % 6) * 6 + (col + 600 + x) % 6];
+        o[0] = o[1] = o[2] = 0.0f;
+        o[ch] = val;
+      }
+    }
+  return 0;
+}

@@ -20,3 +20,9 @@ extern "C" int emul_demosaic_ppg(float *out, const float *in, int width, int hei
   emulate(grid, PNT, ppg_kernel, F, (float4 *)out);
   return 0;
 }
+
+extern "C" int emul_demosaic_passthrough(float *out, const float *in, int width, int height, int x, int y, unsigned filters, const unsigned char *xtrans36, int colour)
+{
+  emulate(dim3((unsigned)((width + PNT - 1) / PNT), (unsigned)height), PNT, passthrough_kernel, in, (float4 *)out, width, height, colour, filters, x, y, xtrans36);
+  return 0;
+}

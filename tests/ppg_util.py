@@ -61,3 +61,32 @@ def emul_lib():
 
 def emul_ppg(mosaic, filters, thrs=0.0):
     return _run(emul_lib(), "emul_demosaic_ppg", mosaic, filters, thrs)
+
+
+XTRANS = np.array([[1, 1, 0, 1, 1, 2], [1, 1, 2, 1, 1, 0], [2, 0, 1, 0, 2, 1], [1, 1, 2, 1, 1, 0], [1, 1, 0, 1, 1, 2], [0, 2, 1, 2, 0, 1]], np.uint8)
+
+
+def _passthrough(lib, fn, mosaic, filters, x, y, colour):
+    h, w = mosaic.shape
+    out, src = util.aligned_empty((h, w, 4)), util.aligned_empty(mosaic.shape)
+    out[...] = ALPHA_FILL
+    src[...] = mosaic
+    xt = np.ascontiguousarray(XTRANS)
+    f = getattr(lib, fn)
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_int]
+    assert f(out.ctypes.data, src.ctypes.data, w, h, x, y, filters, xt.ctypes.data, colour) == 0
+    return np.array(out)
+
+
+def oracle_passthrough(m, filters, x=0, y=0, colour=0):
+    return _passthrough(util.oracle(), "orc_demosaic_passthrough", m, filters, x, y, colour)
+
+
+def ref_passthrough(m, filters, x=0, y=0, colour=0, kind="strict"):
+    lib = util.ref(kind)
+    return None if lib is None else _passthrough(lib, "ref_demosaic_passthrough", m, filters, x, y, colour)
+
+
+def emul_passthrough(m, filters, x=0, y=0, colour=0):
+    return _passthrough(emul_lib(), "emul_demosaic_passthrough", m, filters, x, y, colour)

@@ -60,3 +60,23 @@ def test_fused_ppg_kernel_every_phase_and_ragged_size(pattern):
         m = util.frame_natural(w, h, 9, filters=util.BAYER[pattern])
         for thrs in (0.0, 0.1):
             assert same_bits(pu.emul_ppg(m, util.BAYER[pattern], thrs), pu.oracle_ppg(m, util.BAYER[pattern], thrs)).all()
+
+
+PASSTHROUGH = [(util.BAYER["RGGB"], 0, 0), (util.BAYER["GBRG"], 3, 1), (9, 0, 0), (9, 4, 5)]
+
+
+@need_ref
+@pytest.mark.parametrize("filters,x,y", PASSTHROUGH)
+def test_passthrough_oracle_equals_reference(filters, x, y):
+    m = util.frame_natural(77, 50, 2)
+    for colour in (0, 1):
+        want = pu.ref_passthrough(m, filters, x, y, colour)
+        assert same_bits(pu.oracle_passthrough(m, filters, x, y, colour), want).all()
+        assert (want[..., 3] == pu.ALPHA_FILL).all()
+
+
+@pytest.mark.parametrize("filters,x,y", PASSTHROUGH)
+def test_passthrough_kernel_equals_oracle(filters, x, y):
+    m = util.frame_natural(77, 50, 2)
+    for colour in (0, 1):
+        assert same_bits(pu.emul_passthrough(m, filters, x, y, colour), pu.oracle_passthrough(m, filters, x, y, colour)).all()

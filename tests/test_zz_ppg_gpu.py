@@ -79,3 +79,24 @@ def test_ppg_refuses_tiny_frames(built):
     with pytest.raises(ab.B200Error) as e:
         cuda_ppg(np.zeros((6, 6), np.float32), util.BAYER["RGGB"])
     assert e.value.code == ab.B200_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("filters,x,y", [(util.BAYER["RGGB"], 0, 0), (util.BAYER["GBRG"], 3, 1), (9, 0, 0), (9, 4, 5)])
+def test_passthrough_methods_bit_exact(built, filters, x, y):
+    """methods 3 (monochrome) and 4 (photosite colour), iop/demosaic/passthrough.c, on Bayer and X-Trans descriptors"""
+    import torch
+    import ansel_b200 as ab
+    ab.init()
+    m = util.frame_natural(777, 500, 2)
+    h, w = m.shape
+    for method, colour in ((3, 0), (4, 1)):
+        d = ab.demosaic_data(method)
+        piece = ab.make_piece(w, h, filters=filters, data=d, devid=0, roi_x=x, roi_y=y)
+        for i in range(6):
+            for j in range(6):
+                piece.xtrans[i][j] = int(pu.XTRANS[i][j])
+        d_in = torch.from_numpy(m).cuda()
+        d_out = torch.full((h, w, 4), pu.ALPHA_FILL, device="cuda")
+        ab.check(ab.lib().b200_demosaic_process_dev(C.byref(piece), d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert same_bits(d_out.cpu().numpy(), pu.oracle_passthrough(m, filters, x, y, colour)).all(), (method, filters)
