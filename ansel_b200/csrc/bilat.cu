@@ -168,6 +168,11 @@ __global__ void ll_writeback_kernel(const float4 *__restrict__ in, float4 *__res
 }
 } // namespace
 
+namespace b200
+{
+int bilateral_grid_dev(const float *d_in, float *d_out, int width, int height, float sigma_s, float sigma_r, float detail, cudaStream_t s);
+size_t bilateral_grid_bytes(int width, int height, float sigma_s, float sigma_r);
+}
 using namespace b200;
 
 // dt_iop_bilat_params_t == dt_iop_bilat_data_t, iop/bilat.c:78-110
@@ -176,8 +181,7 @@ static int check_bl(const b200_piece_t *piece, const void *in, void *out)
   if(!piece || !in || !out) return fail(B200_ERR_ARG, "bilat: NULL argument");
   if(!piece->data || piece->data_size < sizeof(b200_bilat_data_t)) return fail(B200_ERR_ARG, "bilat: piece->data is not a b200_bilat_data_t");
   const b200_bilat_data_t *d = (const b200_bilat_data_t *)piece->data;
-  if(d->mode != B200_BILAT_LOCAL_LAPLACIAN)
-    return fail(B200_ERR_UNSUPPORTED, "bilat: the bilateral-grid mode is not built (SURVEY.md 8a18 names the local Laplacian)");
+  if(d->mode != B200_BILAT_LOCAL_LAPLACIAN && d->mode != B200_BILAT_BILATERAL) return fail(B200_ERR_ARG, "bilat: mode %d", d->mode);
   if(in == out) return fail(B200_ERR_ARG, "bilat: in-place processing is not supported");
   return B200_OK;
 }
@@ -190,6 +194,11 @@ extern "C" int b200_bilat_process_dev(const b200_piece_t *piece, const void *d_i
   const b200_bilat_data_t *d = (const b200_bilat_data_t *)piece->data;
   cudaStream_t s = (cudaStream_t)stream;
   const int wd = piece->roi_in.width, ht = piece->roi_in.height;
+  if(d->mode == B200_BILAT_BILATERAL)
+  { // bilat.c:341-353; the alpha copy of :361 is what the slice already does
+    const float scale = (float)((double)(float)piece->iscale / piece->roi_in.scale); // dt_dev_get_module_scale: float / double
+    return bilateral_grid_dev((const float *)d_in, (float *)d_out, wd, ht, d->sigma_s / scale, d->sigma_r, d->detail, s);
+  }
   // local_laplacian(i, o, w, h, d->midtone, d->sigma_s, d->sigma_r, d->detail, 0), bilat.c:354
   const float sigma = d->midtone, shadows = d->sigma_s, highlights = d->sigma_r, clarity = d->detail;
   if(wd <= 1 || ht <= 1) return B200_OK; // :366: returns without touching the output
@@ -315,6 +324,23 @@ extern "C" int b200_bilat_process_host(const b200_piece_t *piece, const void *in
 extern "C" void b200_bilat_tiling(const b200_piece_t *piece, b200_tiling_t *tiling)
 {
   if(!piece || !tiling) return;
+  if(piece->data && ((const b200_bilat_data_t *)piece->data)->mode == B200_BILAT_BILATERAL)
+  { // bilat.c:259-280.  The reference's figures add three grid rows per OpenMP thread of scratch; the device needs the grid only
+    const b200_bilat_data_t *d = (const b200_bilat_data_t *)piece->data;
+    const float scale = (float)((double)(float)piece->iscale / piece->roi_in.scale);
+    const float sigma_s = d->sigma_s / scale;
+    const size_t basebuffer = sizeof(float) * piece->channels * (size_t)piece->roi_in.width * piece->roi_in.height;
+    const size_t grid = bilateral_grid_bytes(piece->roi_in.width, piece->roi_in.height, sigma_s, d->sigma_r);
+    tiling->factor = 2.0f + (float)grid / basebuffer;
+    tiling->factor_cl = 2.0f + (float)(2 * grid) / basebuffer; // dt_bilateral_memory_use with OpenCL: two grids
+    tiling->maxbuf = fmaxf(1.0f, (float)grid / basebuffer);
+    tiling->maxbuf_cl = tiling->maxbuf;
+    tiling->overhead = 0;
+    tiling->overlap = (unsigned)ceilf(4 * sigma_s);
+    tiling->xalign = 1;
+    tiling->yalign = 1;
+    return;
+  }
   tiling->factor = 2.0f;
   tiling->factor_cl = 2.0f;
   tiling->maxbuf = 1.0f;

@@ -358,7 +358,7 @@ int b200_filmicrgb_process_dev(const b200_piece_t *piece, const void *d_in, void
 /* tiling_callback(), filmicrgb.c:2668-2704 */
 void b200_filmicrgb_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
 
-/* ---- local contrast (src/iop/bilat.c), local-Laplacian mode ------------------------------------ */
+/* ---- local contrast (src/iop/bilat.c): local-Laplacian and bilateral-grid modes ------------------ */
 enum
 { /* dt_iop_bilat_mode_t, bilat.c:71-76 */
   B200_BILAT_BILATERAL = 0,
@@ -373,7 +373,10 @@ typedef struct b200_bilat_data_t
   float detail;  /* clarity, default 0.25 */
   float midtone; /* default 0.5 */
 } b200_bilat_data_t;
-/* process(), bilat.c:336-360 -> local_laplacian_internal(), pixel/locallaplacian.c:354-563.  Lab RGBA in/out;
+/* process(), bilat.c:336-360.  Mode 1 -> local_laplacian_internal(), pixel/locallaplacian.c:354-563.  Mode 0 -> the bilateral
+ * grid of pixel/bilateral.c (init, splat, blur, slice :157-393) with sigma_s divided by the module scale (piece->iscale /
+ * roi_in.scale); the reference's splat rounds differently for different OpenMP thread counts (one horizontal slice per
+ * thread, partial grids added afterwards): the result here is the one-slice, raster-order one.  Lab RGBA in/out;
  * channels 1,2 are copied, channel 3 carried through from the input. */
 int b200_bilat_process_host(const b200_piece_t *piece, const void *in, void *out);
 int b200_bilat_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);

@@ -79,16 +79,6 @@ def test_local_laplacian_full_frame_properties(built):
     torch.cuda.empty_cache()
 
 
-def test_bilateral_mode_is_refused(built):
-    import ansel_b200 as ab
-    ab.init()
-    data = ab.bilat_data(mode=0)
-    piece = ab.make_piece(16, 16, data=data)
-    buf = np.zeros((16, 16, 4), np.float32)
-    out = np.zeros_like(buf)
-    assert ab.lib().b200_bilat_process_host(C.byref(piece), buf.ctypes.data, out.ctypes.data) == ab.B200_ERR_UNSUPPORTED
-
-
 def test_tiny_frames_are_refused(built):
     """min(w,h) in {2,3}: the reference indexes padded[-1] (locallaplacian.c:417); refused, not guessed."""
     import ansel_b200 as ab
