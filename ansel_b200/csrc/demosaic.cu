@@ -8,7 +8,8 @@ namespace b200
 int rcd_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters,
                      const float processed_maximum[3], cudaStream_t stream);
 int amaze_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters, const float processed_maximum[3], cudaStream_t stream);
-int vng_demosaic_dev(const float *d_in, float *d_out, int width, int height, int x0, int y0, uint32_t filters, int lin_slot, cudaStream_t s);
+int vng_demosaic_dev(const float *d_in, float *d_out, int width, int height, int x0, int y0, uint32_t filters, const uint8_t *xtrans36, int lin_slot,
+                     cudaStream_t s);
 int dual_demosaic_dev(float *d_rgb, const float *d_raw, int width, int height, int x0, int y0, uint32_t filters, const float wb[4], float dual_threshold,
                       cudaStream_t s);
 int passthrough_demosaic_dev(const float *d_in, float *d_out, int width, int height, int colour, uint32_t filters, int x0, int y0, const uint8_t xtrans[6][6],
@@ -25,7 +26,7 @@ using namespace b200;
 #define DEMOSAIC_DUAL 2048 /* iop/demosaic.c:109 */
 
 // methods that, like the reference, leave (part of) the alpha lane as they find it
-static bool keeps_alpha(uint32_t m) { return m == B200_DEMOSAIC_PPG || m == 3u || m == 4u; }
+static bool keeps_alpha(uint32_t m) { return m == B200_DEMOSAIC_PPG || m == 3u || m == 4u || m == 1024u; }
 
 static int check_piece(const b200_piece_t *piece, const void *in, void *out)
 {
@@ -62,7 +63,19 @@ extern "C" int b200_demosaic_process_dev(const b200_piece_t *piece, const void *
       return rc;
     }
   }
-  if(filters == 9u) return fail(B200_ERR_UNSUPPORTED, "demosaic: X-Trans sensors are not built (SURVEY.md 8f rank 4)");
+  if(filters == 9u)
+  { // demosaic.c:1119-1131: VNG is what every X-Trans method below Markesteijn resolves to (DT_IOP_DEMOSAIC_VNG = 1024)
+    if(d->demosaicing_method != 1024u)
+      return fail(B200_ERR_UNSUPPORTED, "demosaic: X-Trans method %u is not built (VNG is; Markesteijn and FDC are not)", d->demosaicing_method);
+    if(piece->roi_out.width != piece->roi_in.width || piece->roi_out.height != piece->roi_in.height)
+      return fail(B200_ERR_UNSUPPORTED, "demosaic: roi_out != roi_in (downsampling paths are not built)");
+    rc = vng_demosaic_dev((const float *)d_in, (float *)d_out, piece->roi_in.width, piece->roi_in.height, piece->roi_in.x, piece->roi_in.y, 9u,
+                          &piece->xtrans[0][0], SLOT_TMP3, (cudaStream_t)stream);
+    if(rc) return rc;
+    if(d->color_smoothing)
+      rc = demosaic_color_smoothing_dev((float *)d_out, piece->roi_out.width, piece->roi_out.height, (int)d->color_smoothing, (cudaStream_t)stream);
+    return rc;
+  }
   if(d->green_eq > 3) return fail(B200_ERR_ARG, "demosaic: green_eq %u", d->green_eq);
   if(piece->image_flags & DT_IMAGE_4BAYER) return fail(B200_ERR_UNSUPPORTED, "demosaic: four-colour Bayer sensors are not built");
   // roi_out has the size of roi_in with origin 0 for the full demosaicers (demosaic.c:1052-1054)
@@ -92,7 +105,7 @@ extern "C" int b200_demosaic_process_dev(const b200_piece_t *piece, const void *
       return rc;
   }
   if(method == B200_DEMOSAIC_VNG4)
-    rc = vng_demosaic_dev(mosaic, (float *)d_out, width, height, piece->roi_in.x, piece->roi_in.y, piece->filters, SLOT_TMP3, s); // demosaic.c:1172-1175
+    rc = vng_demosaic_dev(mosaic, (float *)d_out, width, height, piece->roi_in.x, piece->roi_in.y, piece->filters, nullptr, SLOT_TMP3, s); // demosaic.c:1172-1175
   else if(method == B200_DEMOSAIC_PPG)
     rc = ppg_demosaic_dev(mosaic, (float *)d_out, width, height, filters, d->median_thrs, s); // demosaic.c:1218-1226
   else if(method == B200_DEMOSAIC_AMAZE)

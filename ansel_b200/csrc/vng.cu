@@ -21,7 +21,18 @@ namespace
 {
 constexpr int VNT = 128;
 
-__device__ __forceinline__ int vfc(int row, int col, unsigned filters) { return (filters >> ((((row << 1) & 14) + (col & 1)) << 1)) & 3; }
+// the CFA seen by fcol (develop/imageop_math.h:207-214): a Bayer word (the four-colour one, second green = 3), or 9 and the
+// sensor's 6x6 X-Trans table
+struct cfa_t
+{
+  unsigned filters;
+  unsigned char xtrans[36];
+};
+__device__ __forceinline__ int vfc(int row, int col, const cfa_t &F)
+{
+  if(F.filters == 9u) return F.xtrans[((row + 600) % 6) * 6 + (col + 600) % 6];
+  return (F.filters >> ((((row << 1) & 14) + (col & 1)) << 1)) & 3;
+}
 __device__ __forceinline__ float lane(const float4 &p, int c) { return c == 0 ? p.x : (c == 1 ? p.y : (c == 2 ? p.z : p.w)); }
 __device__ __forceinline__ void set_lane(float4 &p, int c, float v)
 {
@@ -33,10 +44,11 @@ __device__ __forceinline__ void set_lane(float4 &p, int c, float v)
 
 // bilinear interpolation with four colours (the second green is colour 3), basic.c:20-125
 __global__ void __launch_bounds__(VNT) lin_interpolate_kernel(const float *__restrict__ in, float4 *__restrict__ out, int width, int height, int x0, int y0,
-                                                              unsigned filters4)
+                                                              const cfa_t filters4)
 {
   const int col = blockIdx.x * VNT + threadIdx.x, row = blockIdx.y;
   if(col >= width) return;
+  const int colors = filters4.filters == 9u ? 3 : 4; // X-Trans: lane 3 is not a colour and is not written (kept by vng_kernel)
   const int f = vfc(row + y0, col + x0, filters4);
   const float own = in[(size_t)row * width + col];
   float4 o;
@@ -59,7 +71,7 @@ __global__ void __launch_bounds__(VNT) lin_interpolate_kernel(const float *__res
             }
         }
 #pragma unroll
-    for(int c = 0; c < 4; c++) set_lane(o, c, (c != f && count[c] != 0) ? sum[c] / (float)count[c] : own);
+    for(int c = 0; c < 4; c++) set_lane(o, c, c >= colors ? 0.0f : ((c != f && count[c] != 0) ? sum[c] / (float)count[c] : own));
   }
   else
   { // weights 1 (diagonal), 2 (edge), 4 (never: the centre is the pixel's own colour); :68-124
@@ -81,7 +93,7 @@ __global__ void __launch_bounds__(VNT) lin_interpolate_kernel(const float *__res
           }
       }
 #pragma unroll
-    for(int c = 0; c < 4; c++) set_lane(o, c, c == f ? own : sum[c] / (float)tot[c]);
+    for(int c = 0; c < 4; c++) set_lane(o, c, c >= colors ? 0.0f : (c == f ? own : sum[c] / (float)tot[c]));
   }
   out[(size_t)row * width + col] = o;
 }
@@ -105,15 +117,17 @@ __constant__ signed char c_chood[16] = { -1, -1, -1, 0, -1, +1, 0, +1, +1, +1, +
 // vng.c:77-186 as a function of the bilinear image; the two greens are averaged on the way out (:193-197), the fourth
 // lane keeps the second green like the reference's buffer does
 __global__ void __launch_bounds__(VNT) vng_kernel(const float4 *__restrict__ lin, float4 *__restrict__ out, int width, int height, int x0, int y0,
-                                                  unsigned filters4)
+                                                  const cfa_t filters4)
 {
   const int col = blockIdx.x * VNT + threadIdx.x, row = blockIdx.y;
   if(col >= width) return;
+  const bool xtrans = filters4.filters == 9u;
+  const int colors = xtrans ? 3 : 4, period_row = xtrans ? 6 : 8, period_col = xtrans ? 6 : 2;
   const float4 *pix = lin + (size_t)row * width + col;
   float4 o = pix[0];
   if(row >= 2 && col >= 2 && row < height - 2 && col < width - 2)
   {
-    const int prow = (row + y0) % 8, pcol = (col + x0) % 2;
+    const int prow = (row + y0) % period_row, pcol = (col + x0) % period_col;
     float gval[8] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
     for(int t = 0; t < 64; t++)
     {
@@ -152,7 +166,8 @@ __global__ void __launch_bounds__(VNT) vng_kernel(const float4 *__restrict__ lin
           const bool far = vfc(prow + y, pcol + x, filters4) != color && vfc(prow + y * 2, pcol + x * 2, filters4) == color;
           const float mid = far ? (own + lane(pix[(y * width + x) * 2], color)) * 0.5f : 0.f;
 #pragma unroll
-          for(int c = 0; c < 4; c++) sum[c] += (c == color && far) ? mid : lane(near, c);
+          for(int c = 0; c < 4; c++)
+            if(c < colors) sum[c] += (c == color && far) ? mid : lane(near, c);
           num++;
         }
       }
@@ -162,14 +177,18 @@ __global__ void __launch_bounds__(VNT) vng_kernel(const float4 *__restrict__ lin
         if(c == color) base = sum[c];
 #pragma unroll
       for(int c = 0; c < 4; c++)
-      {
-        float tot = own;
-        if(c != color) tot += (sum[c] - base) / (float)num;
-        set_lane(o, c, tot);
-      }
+        if(c < colors)
+        {
+          float tot = own;
+          if(c != color) tot += (sum[c] - base) / (float)num;
+          set_lane(o, c, tot);
+        }
     }
   }
-  o.y = (o.y + o.w) / 2.0f;
+  if(xtrans)
+    o.w = out[(size_t)row * width + col].w; // the reference leaves lane 3 to whatever its buffers held: kept as found
+  else
+    o.y = (o.y + o.w) / 2.0f;
   out[(size_t)row * width + col] = o;
 }
 
@@ -244,6 +263,14 @@ __global__ void __launch_bounds__(256) dual_blend_kernel(float4 *__restrict__ rg
 
 // ---- host-side set-up shared with tests/emul ----------------------------------------------------------------------------------
 inline unsigned four_colour_word(unsigned filters) { return (filters & 3) == 1 ? (filters | 0x03030303u) : (filters | 0x0c0c0c0cu); } // vng.c:68-73
+inline cfa_t make_cfa(unsigned filters, const unsigned char *xtrans36)
+{
+  cfa_t F;
+  memset(&F, 0, sizeof(F));
+  F.filters = filters == 9u ? 9u : four_colour_word(filters);
+  if(filters == 9u && xtrans36) memcpy(F.xtrans, xtrans36, 36);
+  return F;
+}
 // dt_masks_blur_9x9_coeff :159-192 (host libm expf, as in the reference)
 inline void blur9_coeff(blur9_t *B, float sigma)
 {
@@ -273,14 +300,15 @@ int demosaic_color_smoothing_dev(float *d_out, int width, int height, int passes
 
 // vng_interpolate(out, in, roo, roi, piece->dsc_in.filters, ..., FALSE), demosaic.c:1172-1175: filters is the sensor word,
 // the ROI origin enters through x0 / y0.  lin_slot: the scratch slot for the bilinear image.
-int vng_demosaic_dev(const float *d_in, float *d_out, int width, int height, int x0, int y0, uint32_t filters, int lin_slot, cudaStream_t s)
+int vng_demosaic_dev(const float *d_in, float *d_out, int width, int height, int x0, int y0, uint32_t filters, const uint8_t *xtrans36, int lin_slot,
+                     cudaStream_t s)
 {
   if(width < 5 || height < 5 || height > 65535) return fail(B200_ERR_UNSUPPORTED, "demosaic: VNG4 on a %dx%d frame", width, height);
   void *lin = nullptr;
   int rc = scratch(lin_slot, (size_t)width * height * 16, &lin);
   if(rc) return rc;
   const dim3 grid((unsigned)((width + VNT - 1) / VNT), (unsigned)height);
-  const unsigned f4 = four_colour_word(filters);
+  const cfa_t f4 = make_cfa(filters, xtrans36);
   lin_interpolate_kernel<<<grid, VNT, 0, s>>>(d_in, (float4 *)lin, width, height, x0, y0, f4);
   B200_CUDA_TRY(cudaGetLastError());
   vng_kernel<<<grid, VNT, 0, s>>>((const float4 *)lin, (float4 *)d_out, width, height, x0, y0, f4);
@@ -300,7 +328,7 @@ int dual_demosaic_dev(float *d_rgb, const float *d_raw, int width, int height, i
   if((rc = scratch(SLOT_TMP1, n * 16, &vng))) return rc;
   if((rc = scratch(SLOT_TMP2, n * 4, &tmp))) return rc;
   if((rc = scratch(SLOT_TMP3, n * 4, &blend))) return rc;
-  if((rc = vng_demosaic_dev(d_raw, (float *)vng, width, height, x0, y0, filters, SLOT_TMP0, s))) return rc;
+  if((rc = vng_demosaic_dev(d_raw, (float *)vng, width, height, x0, y0, filters, nullptr, SLOT_TMP0, s))) return rc;
   if((rc = demosaic_color_smoothing_dev((float *)vng, width, height, 2, s))) return rc;
   const dim3 grid((unsigned)((width + VNT - 1) / VNT), (unsigned)height);
   detail_luma_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const float4 *)d_rgb, (float *)tmp, n, wb[0], wb[1], wb[2]);

@@ -55,3 +55,8 @@ int ref_dual_demosaic(float *rgb, const float *raw, int width, int height, int x
   return dual_demosaic(&pipe, &piece, rgb, raw, &roi_out, &roi_in, filters, NULL, mask, dual_threshold);
 }
 void ref_blur_9x9_coeff(float *c, float sigma) { dt_masks_blur_9x9_coeff(c, sigma); }
+int ref_vng_interpolate_xtrans(float *out, const float *in, int width, int height, int x, int y, const uint8_t xtrans[36], int only_linear)
+{
+  const dt_iop_roi_t roi_in = { x, y, width, height, 1.0 }, roi_out = { 0, 0, width, height, 1.0 };
+  return vng_interpolate(out, in, &roi_out, &roi_in, 9u, (const uint8_t(*)[6])xtrans, only_linear);
+}

@@ -35,10 +35,15 @@ static const signed char vng_terms[] = {
 static const signed char vng_chood[] = { -1, -1, -1, 0, -1, +1, 0, +1, +1, +1, +1, 0, +1, -1, 0, -1 };
 
 static uint32_t four_colour_word(uint32_t filters) { return (filters & 3) == 1 ? (filters | 0x03030303u) : (filters | 0x0c0c0c0cu); }
+/* fcol, develop/imageop_math.h:207-214: Bayer word or the 6x6 X-Trans table (FCxtrans :197-204 without a roi) */
+static const uint8_t (*g_xtrans)[6]; /* set for the duration of a call when filters == 9; the oracle is single-threaded here */
+static int fcolour(int row, int col, uint32_t filters) { return filters == 9u ? g_xtrans[(row + 600) % 6][(col + 600) % 6] : orc_fc(row, col, filters); }
+#define orc_fc(r, c, f) fcolour((r), (c), (f))
 
 /* bilinear interpolation with four colours, basic.c:20-125; (x, y): roi_in origin */
 void orc_lin_interpolate(float *out, const float *in, int width, int height, int x0, int y0, uint32_t filters4)
 {
+  const int colors = filters4 == 9u ? 3 : 4, size = filters4 == 9u ? 6 : 16;
   for(int row = 0; row < height; row++)
     for(int col = 0; col < width; col++)
     {
@@ -54,7 +59,7 @@ void orc_lin_interpolate(float *out, const float *in, int width, int height, int
             count[f]++;
           }
       const int f = orc_fc(row + y0, col + x0, filters4);
-      for(int c = 0; c < 4; c++)
+      for(int c = 0; c < colors; c++)
         out[4 * (row * width + col) + c] = (c != f && count[c] != 0) ? sum[c] / count[c] : in[row * width + col];
     }
   for(int row = 1; row < height - 1; row++)
@@ -62,12 +67,12 @@ void orc_lin_interpolate(float *out, const float *in, int width, int height, int
     {
       float sum[4] = { 0.0f };
       int tot[4] = { 0 };
-      const int f = orc_fc(row % 16 + y0, col % 16 + x0, filters4);
+      const int f = orc_fc(row % size + y0, col % size + x0, filters4);
       for(int y = -1; y <= 1; y++)
         for(int x = -1; x <= 1; x++)
         {
           const int weight = 1 << ((y == 0) + (x == 0));
-          const int color = orc_fc(row % 16 + y + y0, col % 16 + x + x0, filters4);
+          const int color = orc_fc(row % size + y + y0, col % size + x + x0, filters4);
           if(color == f) continue;
           sum[color] += in[(row + y) * width + col + x] * weight;
           tot[color] += weight;
@@ -75,7 +80,7 @@ void orc_lin_interpolate(float *out, const float *in, int width, int height, int
       float *buf = out + 4 * (row * width + col);
       /* the table lists the colours other than f in ascending order and leaves out the last one the loop counter skips */
       int written = 0;
-      for(int c = 0; c < 4 && written < 3; c++)
+      for(int c = 0; c < colors && written < colors - 1; c++)
         if(c != f)
         {
           buf[c] = sum[c] / tot[c];
@@ -88,11 +93,12 @@ void orc_lin_interpolate(float *out, const float *in, int width, int height, int
 /* VNG proper, vng.c:77-186, as a function of the bilinear image `lin`: out = lin on the two-pixel border */
 static void vng_from_linear(float *out, const float *lin, int width, int height, int x0, int y0, uint32_t filters4)
 {
+  const int colors = filters4 == 9u ? 3 : 4, period_row = filters4 == 9u ? 6 : 8, period_col = filters4 == 9u ? 6 : 2;
   memcpy(out, lin, sizeof(float) * 4 * width * height);
   for(int row = 2; row < height - 2; row++)
     for(int col = 2; col < width - 2; col++)
     {
-      const int prow = (row + y0) % 8, pcol = (col + x0) % 2;
+      const int prow = (row + y0) % period_row, pcol = (col + x0) % period_col;
       const float *pix = lin + 4 * (row * width + col);
       float gval[8] = { 0.0f };
       const signed char *cp = vng_terms;
@@ -127,7 +133,7 @@ static void vng_from_linear(float *out, const float *lin, int width, int height,
                             ? (y * width + x) * 8 + color : 0;
         if(gval[g] <= thold)
         {
-          for(int c = 0; c < 4; c++)
+          for(int c = 0; c < colors; c++)
             if(c == color && far)
               sum[c] += (pix[c] + pix[far]) * 0.5f;
             else
@@ -136,7 +142,7 @@ static void vng_from_linear(float *out, const float *lin, int width, int height,
         }
       }
       float *o = out + 4 * (row * width + col);
-      for(int c = 0; c < 4; c++)
+      for(int c = 0; c < colors; c++)
       {
         float tot = pix[color];
         if(c != color) tot += (sum[c] - sum[color]) / num;
@@ -146,6 +152,7 @@ static void vng_from_linear(float *out, const float *lin, int width, int height,
 }
 
 /* filters: the sensor word (not ROI-shifted; the origin enters through x0, y0 as in the reference) */
+int orc_vng_interpolate_xtrans(float *out, const float *in, int width, int height, int x0, int y0, const uint8_t xtrans[36], int only_linear);
 int orc_vng_interpolate(float *out, const float *in, int width, int height, int x0, int y0, uint32_t filters, int only_linear)
 {
   const uint32_t filters4 = four_colour_word(filters);
@@ -284,5 +291,23 @@ int orc_dual_demosaic(float *rgb, const float *raw, int width, int height, int x
   for(size_t idx = 0; idx < n; idx++)
     for(int c = 0; c < 4; c++) rgb[4 * idx + c] = mask ? blend[idx] : blend[idx] * (rgb[4 * idx + c] - vng[4 * idx + c]) + vng[4 * idx + c];
   free(blend), free(vng);
+  return 0;
+}
+
+/* X-Trans (filters == 9): three colours, 6x6 periods, no green averaging; lane 3 of `out` is not written for the bilinear
+ * pixels and is uninitialised memory in the reference for the VNG pixels (its row buffer is malloc'ed): left as found here. */
+int orc_vng_interpolate_xtrans(float *out, const float *in, int width, int height, int x0, int y0, const uint8_t xtrans[36], int only_linear)
+{
+  g_xtrans = (const uint8_t(*)[6])xtrans;
+  if(only_linear)
+  {
+    orc_lin_interpolate(out, in, width, height, x0, y0, 9u);
+    return 0;
+  }
+  float *lin = malloc(sizeof(float) * 4 * width * height);
+  memcpy(lin, out, sizeof(float) * 4 * width * height); /* carries lane 3 */
+  orc_lin_interpolate(lin, in, width, height, x0, y0, 9u);
+  vng_from_linear(out, lin, width, height, x0, y0, 9u);
+  free(lin);
   return 0;
 }

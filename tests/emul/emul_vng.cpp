@@ -8,10 +8,15 @@
 #include "../../ansel_b200/csrc/vng.cu"
 #include <vector>
 
+extern "C" int emul_vng_cfa(float *out, const float *in, int width, int height, int x0, int y0, unsigned filters, const unsigned char *xtrans36, int only_linear);
 extern "C" int emul_vng(float *out, const float *in, int width, int height, int x0, int y0, unsigned filters, int only_linear)
 {
+  return emul_vng_cfa(out, in, width, height, x0, y0, filters, nullptr, only_linear);
+}
+extern "C" int emul_vng_cfa(float *out, const float *in, int width, int height, int x0, int y0, unsigned filters, const unsigned char *xtrans36, int only_linear)
+{
   const dim3 grid((unsigned)((width + VNT - 1) / VNT), (unsigned)height);
-  const unsigned f4 = four_colour_word(filters);
+  const cfa_t f4 = make_cfa(filters, xtrans36);
   std::vector<float4> lin((size_t)width * height);
   emulate(grid, VNT, lin_interpolate_kernel, in, only_linear ? (float4 *)out : lin.data(), width, height, x0, y0, f4);
   if(!only_linear) emulate(grid, VNT, vng_kernel, (const float4 *)lin.data(), (float4 *)out, width, height, x0, y0, f4);

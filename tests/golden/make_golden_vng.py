@@ -16,6 +16,10 @@ for name in vu.CASES:
     m, filters, x, y = vu.case(name)
     save["vng_" + name] = vu.ref_vng(m, filters, x, y)
     save["dual_" + name] = vu.ref_dual(vu.sharp_frame(m, filters, x, y), m, filters, x, y, 0.2)
+for name in vu.XTRANS_CASES:
+    m, x, y = vu.xtrans_case(name)
+    save["xtrans_" + name] = vu.ref_vng_xtrans(m, x, y)
+    save["xtrans_" + name][..., 3] = 0.0        # lane 3 is uninitialised memory in the reference: not a golden value
 out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "vng.npz")
 np.savez_compressed(out, **save)
 print("written", out, os.path.getsize(out) // 1024, "KiB")

@@ -69,3 +69,22 @@ def test_dual_kernels_equal_oracle(name):
     rgb = vu.sharp_frame(m, filters, x, y)
     for thr in THRESHOLDS:
         assert same_bits(vu.emul_dual(rgb, m, filters, x, y, thr), vu.oracle_dual(rgb, m, filters, x, y, thr)).all(), thr
+
+
+@need_ref
+@pytest.mark.parametrize("name", list(vu.XTRANS_CASES))
+def test_vng_xtrans_oracle_equals_reference(name):
+    """the X-Trans branch of vng_interpolate (three colours, 6x6 periods); lane 3 is uninitialised memory in the reference"""
+    m, x, y = vu.xtrans_case(name)
+    for lin in (1, 0):
+        assert same_bits(vu.oracle_vng_xtrans(m, x, y, lin)[..., :3], vu.ref_vng_xtrans(m, x, y, lin)[..., :3]).all(), lin
+
+
+@pytest.mark.parametrize("name", list(vu.XTRANS_CASES))
+def test_vng_xtrans_kernels_equal_oracle(name):
+    m, x, y = vu.xtrans_case(name)
+    g = np.load(os.path.join(util.GOLDEN_DIR, "vng.npz"))
+    for lin in (1, 0):
+        got = vu.emul_vng_xtrans(m, x, y, lin)
+        assert same_bits(got[..., :3], vu.oracle_vng_xtrans(m, x, y, lin)[..., :3]).all(), lin
+    assert same_bits(got[..., :3], g["xtrans_" + name][..., :3]).all() and (got[..., 3] == -7.0).all()

@@ -102,3 +102,30 @@ def test_dual_refuses_other_pairs(built):
     with pytest.raises(ab.B200Error) as e:
         cuda_demosaic(np.zeros((64, 64), np.float32), util.BAYER["RGGB"], ab.DEMOSAIC_PPG | DUAL)
     assert e.value.code == ab.B200_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("name", list(vu.XTRANS_CASES))
+def test_vng_xtrans_bit_exact(built, name):
+    """X-Trans sensors: method DT_IOP_DEMOSAIC_VNG (1024) through the module; lane 3 is not a result (kept as found)"""
+    import torch
+    import ansel_b200 as ab
+    ab.init()
+    m, x, y = vu.xtrans_case(name)
+    h, w = m.shape
+    d = ab.demosaic_data(1024)
+    piece = ab.make_piece(w, h, filters=9, data=d, devid=0, roi_x=x, roi_y=y)
+    for i in range(6):
+        for j in range(6):
+            piece.xtrans[i][j] = int(vu.XTRANS[i][j])
+    d_in = torch.from_numpy(np.ascontiguousarray(m)).cuda()
+    d_out = torch.full((h, w, 4), -7.0, device="cuda")
+    ab.check(ab.lib().b200_demosaic_process_dev(C.byref(piece), d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    assert same_bits(got[..., :3], vu.oracle_vng_xtrans(m, x, y)[..., :3]).all() and (got[..., 3] == -7.0).all()
+    host = np.full((h, w, 4), -7.0, np.float32)
+    ab.check(ab.lib().b200_demosaic_process_host(C.byref(piece), m.ctypes.data, host.ctypes.data))
+    assert same_bits(host, got).all()
+    d2 = ab.demosaic_data(1025)                                   # Markesteijn: not built
+    piece.data = C.cast(C.pointer(d2), C.c_void_p)
+    assert ab.lib().b200_demosaic_process_dev(C.byref(piece), d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream) == ab.B200_ERR_UNSUPPORTED

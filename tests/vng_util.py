@@ -107,3 +107,43 @@ def emul_dual(rgb, m, filters, x, y, thr):
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_float, _SMOOTH]
     assert f(out.ctypes.data, src.ctypes.data, w, h, x, y, filters, (C.c_float * 4)(*WB), thr, smooth) == 0
     return np.array(out)
+
+
+# ---- X-Trans (filters == 9): three colours, lane 3 is not a result ----------------------------------------------------------
+XTRANS = np.array([[1, 1, 0, 1, 1, 2], [1, 1, 2, 1, 1, 0], [2, 0, 1, 0, 2, 1], [1, 1, 2, 1, 1, 0], [1, 1, 0, 1, 1, 2], [0, 2, 1, 2, 0, 1]], np.uint8)
+XTRANS_CASES = {"origin": (134, 78, 0, 0), "roi": (131, 77, 1, 4), "roi2": (64, 48, 3, 2), "small": (30, 17, 5, 5)}
+
+
+def xtrans_case(name):
+    w, h, x, y = XTRANS_CASES[name]
+    m = util.frame_natural(w, h, 6)
+    if h > 40:
+        m[5, 5], m[20, 8] = np.nan, 0.0
+        m[30:36, 30:36] = 0.25
+    return m, x, y
+
+
+def _vng_xtrans(lib, fn, m, x, y, lin=0, extra=()):
+    h, w = m.shape
+    out, src = util.aligned_empty((h, w, 4)), util.aligned_empty(m.shape)
+    out[...] = -7.0
+    src[...] = m
+    xt = np.ascontiguousarray(XTRANS)
+    f = getattr(lib, fn)
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_uint32] * len(extra) + [C.c_void_p, C.c_int]
+    assert f(out.ctypes.data, src.ctypes.data, w, h, x, y, *extra, xt.ctypes.data, lin) == 0
+    return np.array(out)
+
+
+def oracle_vng_xtrans(m, x=0, y=0, lin=0):
+    return _vng_xtrans(util.oracle(), "orc_vng_interpolate_xtrans", m, x, y, lin)
+
+
+def ref_vng_xtrans(m, x=0, y=0, lin=0, kind="strict"):
+    lib = util.ref(kind)
+    return None if lib is None else _vng_xtrans(lib, "ref_vng_interpolate_xtrans", m, x, y, lin)
+
+
+def emul_vng_xtrans(m, x=0, y=0, lin=0):
+    return _vng_xtrans(emul_lib(), "emul_vng_cfa", m, x, y, lin, extra=(9,))
