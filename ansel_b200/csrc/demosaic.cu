@@ -14,6 +14,7 @@ int dual_demosaic_dev(float *d_rgb, const float *d_raw, int width, int height, i
                       cudaStream_t s);
 int passthrough_demosaic_dev(const float *d_in, float *d_out, int width, int height, int colour, uint32_t filters, int x0, int y0, const uint8_t xtrans[6][6],
                              cudaStream_t s);
+int downsample_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters, cudaStream_t s);
 int ppg_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters, float median_thrs, cudaStream_t s);
 int demosaic_green_eq_dev(const float *d_in, float *d_tmp0, float *d_tmp1, double *d_partial, int width, int height, uint32_t dsc_filters, int x, int y,
                           unsigned green_eq, float threshold, const float **d_result, cudaStream_t s);
@@ -62,6 +63,16 @@ extern "C" int b200_demosaic_process_dev(const b200_piece_t *piece, const void *
         rc = demosaic_color_smoothing_dev((float *)d_out, piece->roi_out.width, piece->roi_out.height, (int)d->color_smoothing, (cudaStream_t)stream);
       return rc;
     }
+  }
+  if(d->demosaicing_method == 7u)
+  { // DT_IOP_DEMOSAIC_DOWNSAMPLE, demosaic.c:1101-1108: half-size output (modify_roi_out :940-952), then the guided-Laplacian
+    // post-filter when data->color_smoothing asks for iterations of it
+    if(filters == 9u || (piece->image_flags & DT_IMAGE_4BAYER)) return fail(B200_ERR_UNSUPPORTED, "demosaic: downsample is built for three-colour Bayer sensors");
+    if(d->color_smoothing) return fail(B200_ERR_UNSUPPORTED, "demosaic: the guided-Laplacian post-filter of the downsample method is not built");
+    if(piece->roi_out.width != (piece->roi_in.width + 1) / 2 || piece->roi_out.height != (piece->roi_in.height + 1) / 2)
+      return fail(B200_ERR_ARG, "demosaic: downsample wants roi_out = (roi_in + 1) / 2, got %dx%d for %dx%d", piece->roi_out.width, piece->roi_out.height,
+                  piece->roi_in.width, piece->roi_in.height);
+    return downsample_demosaic_dev((const float *)d_in, (float *)d_out, piece->roi_in.width, piece->roi_in.height, filters, (cudaStream_t)stream);
   }
   if(filters == 9u)
   { // demosaic.c:1119-1131: VNG is what every X-Trans method below Markesteijn resolves to (DT_IOP_DEMOSAIC_VNG = 1024)
@@ -163,6 +174,15 @@ extern "C" void b200_demosaic_tiling(const b200_piece_t *piece, b200_tiling_t *t
   tiling->maxbuf = 1.0f;
   tiling->maxbuf_cl = 1.0f;
   tiling->overhead = 0;
+  if(method == 7u)
+  { // DT_IOP_DEMOSAIC_DOWNSAMPLE, :1928-1936
+    tiling->factor = 1.0f + ioratio + (d->color_smoothing ? 7.0f * ioratio : 0.0f);
+    tiling->factor_cl = tiling->factor;
+    tiling->xalign = 1;
+    tiling->yalign = 1;
+    tiling->overlap = (piece->filters == 9u) ? 18 : 16;
+    return;
+  }
   if(method == B200_DEMOSAIC_RCD)
   {
     // the CPU figure counts per-thread tile scratch; the device keeps its tiles in shared memory
@@ -171,8 +191,8 @@ extern "C" void b200_demosaic_tiling(const b200_piece_t *piece, b200_tiling_t *t
     tiling->overlap = 10;
     tiling->factor_cl = tiling->factor; // no full-frame temporaries on the device (reference: +3, rcd.c:671-686)
   }
-  else if(method == B200_DEMOSAIC_AMAZE || method == B200_DEMOSAIC_PPG)
-  {
+  else if(method == B200_DEMOSAIC_AMAZE || method == B200_DEMOSAIC_PPG || method == 3u || method == 4u)
+  { // PPG, the passthrough methods, AMaZE :1937-1950
     tiling->xalign = 2;
     tiling->yalign = 2;
     tiling->overlap = 5;

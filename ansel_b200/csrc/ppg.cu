@@ -205,11 +205,50 @@ __global__ void __launch_bounds__(PNT) passthrough_kernel(const float *__restric
   }
   out[p] = o;
 }
+// the half-size "downsample" method, demosaic.c:480-532 (Bayer, three colours): the mean of each colour's samples in the 2x2
+// block behind the output pixel, the block clamped into the frame at odd edges; alpha 0
+__global__ void __launch_bounds__(PNT) downsample_kernel(const float *__restrict__ in, float4 *__restrict__ out, int width, int height, int out_width, unsigned filters)
+{
+  const int x = blockIdx.x * PNT + threadIdx.x, y = blockIdx.y;
+  if(x >= out_width) return;
+  const int px = min(2 * x, width - 1), py = min(2 * y, height - 1);
+  float cam[3] = { 0.f, 0.f, 0.f };
+  int samples[3] = { 0, 0, 0 };
+#pragma unroll
+  for(int j = 0; j < 2; j++)
+#pragma unroll
+    for(int i = 0; i < 2; i++)
+    {
+      const int xx = min(px + i, width - 1), yy = min(py + j, height - 1);
+      const int c = ppg_fc(yy, xx, filters);
+      const float v = in[(size_t)yy * width + xx];
+#pragma unroll
+      for(int q = 0; q < 3; q++)
+        if(q == c)
+        {
+          cam[q] += v;
+          samples[q]++;
+        }
+    }
+#pragma unroll
+  for(int q = 0; q < 3; q++)
+    if(samples[q] > 0) cam[q] /= (float)samples[q];
+  out[(size_t)y * out_width + x] = make_float4(cam[0], cam[1], cam[2], 0.0f);
+}
 } // namespace
 
 #ifndef B200_KERNELS_ON_CPU
 namespace b200
 {
+// demosaic.c:1101-1108 for a three-colour Bayer sensor; out is (width + 1) / 2 x (height + 1) / 2
+int downsample_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters, cudaStream_t s)
+{
+  const int ow = (width + 1) / 2, oh = (height + 1) / 2;
+  if(oh > 65535) return fail(B200_ERR_ARG, "demosaic: frame height %d", height);
+  downsample_kernel<<<dim3((unsigned)((ow + PNT - 1) / PNT), (unsigned)oh), PNT, 0, s>>>(d_in, (float4 *)d_out, width, height, ow, filters);
+  B200_CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
 // demosaic.c:1111-1118.  filters: piece->dsc_in.filters (not ROI-shifted); xtrans: piece->dsc_in.xtrans (used when filters == 9)
 int passthrough_demosaic_dev(const float *d_in, float *d_out, int width, int height, int colour, uint32_t filters, int x0, int y0, const uint8_t xtrans[6][6],
                              cudaStream_t s)

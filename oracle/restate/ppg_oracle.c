@@ -166,3 +166,30 @@ int orc_demosaic_passthrough(float *out, const float *in, int width, int height,
     }
   return 0;
 }
+
+/* the half-size "downsample" method for a Bayer sensor, demosaic.c:480-532: every output pixel is the 2x2 block behind it, each
+ * colour the mean of its samples in the block (clamped to the frame at odd edges); alpha 0 */
+int orc_demosaic_downsample(float *out, const float *in, int width, int height, uint32_t filters)
+{
+  const int ow = (width + 1) / 2, oh = (height + 1) / 2;
+  for(int y = 0; y < oh; y++)
+    for(int x = 0; x < ow; x++)
+    {
+      float cam[4] = { 0.0f };
+      int samples[4] = { 0 };
+      const int px = 2 * x < width - 1 ? 2 * x : width - 1, py = 2 * y < height - 1 ? 2 * y : height - 1;
+      for(int j = 0; j < 2; j++)
+        for(int i = 0; i < 2; i++)
+        {
+          const int xx = px + i < width - 1 ? px + i : width - 1, yy = py + j < height - 1 ? py + j : height - 1;
+          const int c = orc_fc(yy, xx, filters);
+          cam[c] += in[(size_t)yy * width + xx];
+          samples[c]++;
+        }
+      for(int c = 0; c < 4; c++)
+        if(samples[c] > 0) cam[c] /= (float)samples[c];
+      float *o = out + 4 * ((size_t)y * ow + x);
+      o[0] = cam[0], o[1] = cam[1], o[2] = cam[2], o[3] = 0.0f;
+    }
+  return 0;
+}

@@ -26,3 +26,10 @@ extern "C" int emul_demosaic_passthrough(float *out, const float *in, int width,
   emulate(dim3((unsigned)((width + PNT - 1) / PNT), (unsigned)height), PNT, passthrough_kernel, in, (float4 *)out, width, height, colour, filters, x, y, xtrans36);
   return 0;
 }
+
+extern "C" int emul_demosaic_downsample(float *out, const float *in, int width, int height, unsigned filters)
+{
+  const int ow = (width + 1) / 2, oh = (height + 1) / 2;
+  emulate(dim3((unsigned)((ow + PNT - 1) / PNT), (unsigned)oh), PNT, downsample_kernel, in, (float4 *)out, width, height, ow, filters);
+  return 0;
+}

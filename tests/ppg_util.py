@@ -90,3 +90,28 @@ def ref_passthrough(m, filters, x=0, y=0, colour=0, kind="strict"):
 
 def emul_passthrough(m, filters, x=0, y=0, colour=0):
     return _passthrough(emul_lib(), "emul_demosaic_passthrough", m, filters, x, y, colour)
+
+
+def _downsample(lib, fn, mosaic, filters):
+    h, w = mosaic.shape
+    out, src = util.aligned_empty(((h + 1) // 2, (w + 1) // 2, 4)), util.aligned_empty(mosaic.shape)
+    out[...] = ALPHA_FILL
+    src[...] = mosaic
+    f = getattr(lib, fn)
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32]
+    assert f(out.ctypes.data, src.ctypes.data, w, h, filters) == 0
+    return np.array(out)
+
+
+def oracle_downsample(m, filters):
+    return _downsample(util.oracle(), "orc_demosaic_downsample", m, filters)
+
+
+def ref_downsample(m, filters, kind="strict"):
+    lib = util.ref(kind)
+    return None if lib is None else _downsample(lib, "ref_demosaic_downsample", m, filters)
+
+
+def emul_downsample(m, filters):
+    return _downsample(emul_lib(), "emul_demosaic_downsample", m, filters)

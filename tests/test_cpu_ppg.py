@@ -80,3 +80,15 @@ def test_passthrough_kernel_equals_oracle(filters, x, y):
     m = util.frame_natural(77, 50, 2)
     for colour in (0, 1):
         assert same_bits(pu.emul_passthrough(m, filters, x, y, colour), pu.oracle_passthrough(m, filters, x, y, colour)).all()
+
+
+@pytest.mark.parametrize("pattern", list(util.BAYER))
+def test_downsample_oracle_reference_and_kernel(pattern):
+    """the half-size method (demosaic.c:480-532) on even and odd frame sizes"""
+    f = util.BAYER[pattern]
+    for w, h in ((64, 48), (77, 51), (9, 8)):
+        m = util.frame_natural(w, h, 4, filters=f)
+        want = pu.oracle_downsample(m, f)
+        if util.ref("strict") is not None:
+            assert same_bits(want, pu.ref_downsample(m, f)).all()
+        assert same_bits(pu.emul_downsample(m, f), want).all()

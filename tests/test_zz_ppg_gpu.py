@@ -100,3 +100,22 @@ def test_passthrough_methods_bit_exact(built, filters, x, y):
         ab.check(ab.lib().b200_demosaic_process_dev(C.byref(piece), d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
         assert same_bits(d_out.cpu().numpy(), pu.oracle_passthrough(m, filters, x, y, colour)).all(), (method, filters)
+
+
+def test_downsample_method_bit_exact(built):
+    """method 7 (half-size), demosaic.c:480-532, even and odd frame sizes; its post-filter is refused"""
+    import torch
+    import ansel_b200 as ab
+    ab.init()
+    for pat, f in util.BAYER.items():
+        for w, h in ((1300, 900), (777, 501)):
+            m = util.frame_natural(w, h, 4, filters=f)
+            d = ab.demosaic_data(7)
+            piece = ab.make_piece(w, h, filters=f, data=d, devid=0, out_width=(w + 1) // 2, out_height=(h + 1) // 2)
+            d_in = torch.from_numpy(m).cuda()
+            d_out = torch.full(((h + 1) // 2, (w + 1) // 2, 4), -7.0, device="cuda")
+            ab.check(ab.lib().b200_demosaic_process_dev(C.byref(piece), d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            torch.cuda.synchronize()
+            assert same_bits(d_out.cpu().numpy(), pu.oracle_downsample(m, f)).all(), (pat, w, h)
+    d.color_smoothing = 1
+    assert ab.lib().b200_demosaic_process_dev(C.byref(piece), d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream) == ab.B200_ERR_UNSUPPORTED
