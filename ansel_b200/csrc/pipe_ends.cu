@@ -12,6 +12,8 @@
 #include "runtime.h"
 #include <initializer_list>
 #endif
+#include "x87.cuh"
+#include <float.h>
 #include <math.h>
 #include <string.h>
 
@@ -362,6 +364,76 @@ __global__ void __launch_bounds__(128) inpaint_cols_kernel(const float *__restri
   inpaint_line(in, out, A, 1, -1, i, 3);
 }
 
+// ---- highlights, LCh reconstruction on a Bayer mosaic (iop/highlights/lch.c:315-411) --------------------------------------------
+// Every 2x2 block with a clipped sample is rebuilt from the lightness / chroma / hue of its clipped and unclipped values.  The
+// reference multiplies and divides by long double constants (SQRT3, SQRT12): x87.cuh performs those three operations exactly.
+// filters: the sensor's word, the ROI origin enters through x0 / y0 (process_lch_bayer reads piece->dsc_in.filters).
+__global__ void __launch_bounds__(NT) lch_bayer_kernel(const float *__restrict__ ivoid, float *__restrict__ ovoid, int width, int height, int x0, int y0,
+                                                       unsigned filters, float clip, const unsigned long long *counter)
+{
+  const int i = blockIdx.x * NT + threadIdx.x, j = blockIdx.y;
+  if(i >= width) return;
+  const float *in = ivoid + (size_t)width * j + i;
+  float *out = ovoid + (size_t)width * j + i;
+  if(*counter < 25ull)
+  { // the bypass: fewer than DT_HL_MIN_CLIPPED_PIXELS samples over the threshold, the frame is copied through
+    out[0] = in[0];
+    return;
+  }
+  if(i == width - 1 || j == height - 1)
+  {
+    out[0] = clip < in[0] ? clip : in[0];
+    return;
+  }
+  bool clipped = false;
+  float R = 0.0f, Gmin = FLT_MAX, Gmax = -FLT_MAX, B = 0.0f;
+#pragma unroll
+  for(int jj = 0; jj <= 1; jj++)
+#pragma unroll
+    for(int ii = 0; ii <= 1; ii++)
+    {
+      const float val = in[(size_t)jj * width + ii];
+      clipped = clipped || (val > clip);
+      const int c = fc(j + jj + y0, i + ii + x0, filters);
+      if(c == 0)
+        R = val;
+      else if(c == 1)
+      {
+        Gmin = Gmin < val ? Gmin : val;
+        Gmax = Gmax > val ? Gmax : val;
+      }
+      else if(c == 2)
+        B = val;
+    }
+  if(!clipped)
+  {
+    out[0] = in[0];
+    return;
+  }
+  const float Ro = R < clip ? R : clip, Go = Gmin < clip ? Gmin : clip, Bo = B < clip ? B : clip;
+  const float L = divr(R + Gmax + B, 3.0f);
+  float C = x87::mul_sqrt3(R - Gmax);
+  float H = 2.0f * B - Gmax - R;
+  const float Co = x87::mul_sqrt3(Ro - Go);
+  const float Ho = 2.0f * Bo - Go - Ro;
+  if(R != Gmax && Gmax != B)
+  {
+    const float ratio = sqrtf((Co * Co + Ho * Ho) / (C * C + H * H));
+    C *= ratio;
+    H *= ratio;
+  }
+  const float t = L - divr(H, 6.0f);
+  const int c = fc(j + y0, i + x0, filters);
+  float v;
+  if(c == 0)
+    v = x87::add_div_sqrt12(t, C, +1);
+  else if(c == 1)
+    v = x87::add_div_sqrt12(t, C, -1);
+  else
+    v = L + divr(H, 3.0f);
+  out[0] = v;
+}
+
 // ---- the float -> integer ends ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned gamma_byte(float x)
 { // (uint8_t)(fminf(roundf(255.0f * fmaxf(in, 0.0f)), 255.0f)), gamma.c:361
@@ -698,6 +770,13 @@ extern "C" int b200_highlights_process_dev(const b200_piece_t *piece, const void
   if(clip_mode)
   { // count and branch stay on the device
     flat_kernel<OP_CLIP><<<flat_grid(n), NT, 0, s>>>((const float *)d_in, (float *)d_out, n, clip, 0.0f, (piece->mask_display & 1) ? 1 : 0, counter);
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+  }
+  if(mosaic && piece->filters != 9u && d->mode == B200_HIGHLIGHTS_LCH)
+  { // process() :748-757; the kernel reads the counter for the bypass
+    lch_bayer_kernel<<<dim3((unsigned)((width + NT - 1) / NT), (unsigned)height), NT, 0, s>>>((const float *)d_in, (float *)d_out, width, height, piece->roi_out.x,
+                                                                                             piece->roi_out.y, piece->filters, clip, counter);
     B200_CUDA_TRY(cudaGetLastError());
     return B200_OK;
   }

@@ -3,9 +3,10 @@
  * oracle/Makefile cuts verbatim into oracle/_ref/gen_highlights.c:
  *     iop/highlights/common.h :218 (DT_HL_MIN_CLIPPED_PIXELS), :431-476 (mode enum, params == data)
  *     iop/highlights/clip.c   :60-85  process_clip
+ *     iop/highlights/common.h :618-619 SQRT3, SQRT12 (long double);  iop/highlights/lch.c :315-411 process_lch_bayer
  *     iop/highlights/lch.c    :206-303 interpolate_color;  iop/highlights/inpaint.c :63-82 process_inpaint_bayer
  *     iop/highlights.c        :232-302 _hl_count_thresholds, _hl_count_clipped, _hl_copy_input;  :679-789 process()
- * The other reconstruction modes (LCh, X-Trans inpainting, guided Laplacians, harmonic transposition) are separate translation
+ * The other reconstruction modes (X-Trans LCh and inpainting, guided Laplacians, harmonic transposition) are separate translation
  * units of 18 k lines that are not built here: their entry points abort (the tests reach them only through the bypass).
  */
 #include "ref_piece.h"
@@ -43,7 +44,6 @@ static inline uint32_t dt_dev_get_roi_filters(const dt_dev_pixelpipe_iop_t *piec
 #define process_visualize(...) NOT_BUILT("process_visualize")
 #define process_inpaint_xtrans(...) NOT_BUILT("process_inpaint_xtrans")
 #define process_lch_xtrans(...) NOT_BUILT("process_lch_xtrans")
-#define process_lch_bayer(...) NOT_BUILT("process_lch_bayer")
 static inline int process_laplacian_stub(void) { NOT_BUILT("process_laplacian"); return 1; }
 #define process_laplacian(...) process_laplacian_stub()
 #define process_harmonic(...) process_laplacian_stub()

@@ -17,6 +17,7 @@
  */
 #include "oracle_common.h"
 #include "b200iop.h"
+#include <float.h>
 #include <string.h>
 
 /* ---- rawprepare ------------------------------------------------------------------------------------------------- */
@@ -210,6 +211,65 @@ static void interpolate_color(const float *ivoid, float *ovoid, int width, int h
   }
 }
 
+/* LCh reconstruction on a Bayer mosaic, lch.c:315-411: every 2x2 block with a clipped sample is rebuilt from its clipped and
+ * unclipped lightness / chroma / hue.  SQRT3 and SQRT12 are long double literals in the reference (common.h:618-619): the
+ * products, the quotients and the sums they enter are x87 operations, rounded to float on assignment -- restated with the
+ * same types.  filters: the sensor word; the ROI origin enters through x0, y0. */
+static void lch_bayer(const float *ivoid, float *ovoid, int width, int height, int x0, int y0, uint32_t filters, float clip)
+{
+  static const long double SQRT3 = 1.7320508075688772935274463415058723669L, SQRT12 = 3.4641016151377545870548926830117447339L;
+  for(int j = 0; j < height; j++)
+    for(int i = 0; i < width; i++)
+    {
+      float *const out = ovoid + (size_t)width * j + i;
+      const float *const in = ivoid + (size_t)width * j + i;
+      if(i == width - 1 || j == height - 1)
+      {
+        out[0] = clip < in[0] ? clip : in[0];
+        continue;
+      }
+      int clipped = 0;
+      float R = 0.0f, Gmin = FLT_MAX, Gmax = -FLT_MAX, B = 0.0f;
+      for(int jj = 0; jj <= 1; jj++)
+        for(int ii = 0; ii <= 1; ii++)
+        {
+          const float val = in[(size_t)jj * width + ii];
+          clipped = (clipped || (val > clip));
+          switch(orc_fc(j + jj + y0, i + ii + x0, filters))
+          {
+            case 0: R = val; break;
+            case 1:
+              Gmin = Gmin < val ? Gmin : val; /* MIN(Gmin, val) */
+              Gmax = Gmax > val ? Gmax : val; /* MAX(Gmax, val) */
+              break;
+            case 2: B = val; break;
+          }
+        }
+      if(!clipped)
+      {
+        out[0] = in[0];
+        continue;
+      }
+      const float Ro = R < clip ? R : clip, Go = Gmin < clip ? Gmin : clip, Bo = B < clip ? B : clip; /* MIN(x, clip) */
+      const float L = (R + Gmax + B) / 3.0f;
+      float C = SQRT3 * (R - Gmax);
+      float H = 2.0f * B - Gmax - R;
+      const float Co = SQRT3 * (Ro - Go);
+      const float Ho = 2.0f * Bo - Go - Ro;
+      if(R != Gmax && Gmax != B)
+      {
+        const float ratio = sqrtf((Co * Co + Ho * Ho) / (C * C + H * H));
+        C *= ratio;
+        H *= ratio;
+      }
+      float RGB[3];
+      RGB[0] = L - H / 6.0f + C / SQRT12;
+      RGB[1] = L - H / 6.0f - C / SQRT12;
+      RGB[2] = L + H / 3.0f;
+      out[0] = RGB[orc_fc(j + y0, i + x0, filters)];
+    }
+}
+
 /* returns 0 and the number of samples counted as clipped in *n_clipped; -1 for a mode that is not restated */
 int orc_highlights(const b200_piece_t *piece, const float *in, float *out, size_t *n_clipped)
 {
@@ -266,6 +326,11 @@ int orc_highlights(const b200_piece_t *piece, const float *in, float *out, size_
       interpolate_color(in, out, w, h, 1, 1, i, clips, shifted, 2);
       interpolate_color(in, out, w, h, 1, -1, i, clips, shifted, 3);
     }
+    return 0;
+  }
+  if(filters && filters != 9u && data->mode == B200_HIGHLIGHTS_LCH)
+  { /* process() :748-757: process_lch_bayer reads piece->dsc_in.filters with the ROI origin added to its coordinates */
+    lch_bayer(in, out, piece->roi_out.width, piece->roi_out.height, piece->roi_out.x, piece->roi_out.y, filters, clip);
     return 0;
   }
   if(filters && data->mode != B200_HIGHLIGHTS_CLIP) return -1;

@@ -94,6 +94,12 @@ extern "C" int emul_highlights(const b200_piece_t *piece, const float *in, float
   else
     emulate(dim3((unsigned)((npx + NT - 1) / NT)), NT, count_pixels_kernel, in, npx, ch, thresholds[0], thresholds[1], thresholds[2], &counter);
   *n_clipped = counter;
+  if(mosaic && piece->filters != 9u && d->mode == B200_HIGHLIGHTS_LCH)
+  {
+    emulate(dim3((unsigned)((w + NT - 1) / NT), (unsigned)h), NT, lch_bayer_kernel, in, out, w, h, piece->roi_out.x, piece->roi_out.y, (unsigned)piece->filters, clip,
+            (const unsigned long long *)&counter);
+    return 0;
+  }
   if(mosaic && piece->filters != 9u && d->mode == B200_HIGHLIGHTS_INPAINT)
   {
     float pmax[4];

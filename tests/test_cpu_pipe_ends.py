@@ -112,6 +112,9 @@ HIGHLIGHTS_CASES = {
     "inpaint_mosaic": dict(mode=ab.HIGHLIGHTS_INPAINT, clip=0.95),                    # colour inpainting along rows and columns
     "inpaint_mosaic_wb_roi": dict(mode=ab.HIGHLIGHTS_INPAINT, clip=0.9, pm=(2.13, 1.0, 1.57, 0.0), x=3, y=1, filters=util.BAYER["GBRG"]),
     "inpaint_mosaic_bypass": dict(mode=ab.HIGHLIGHTS_INPAINT, n_clipped=5),
+    "lch_mosaic": dict(mode=ab.HIGHLIGHTS_LCH, clip=0.95),                            # 2x2 blocks rebuilt in LCh, long double constants
+    "lch_mosaic_wb_roi": dict(mode=ab.HIGHLIGHTS_LCH, clip=0.9, pm=(2.13, 1.0, 1.57, 0.0), x=3, y=1, filters=util.BAYER["GRBG"]),
+    "lch_mosaic_bypass": dict(mode=ab.HIGHLIGHTS_LCH, n_clipped=12),
 }
 
 
@@ -152,7 +155,7 @@ def test_highlights_oracle_equals_reference(name):
 
 def test_highlights_oracle_refuses_reconstruction_modes():
     piece, img = highlights_case("clip_mosaic")
-    for mode in (ab.HIGHLIGHTS_LCH, ab.HIGHLIGHTS_LAPLACIAN, ab.HIGHLIGHTS_HARMONIC):
+    for mode in (ab.HIGHLIGHTS_LAPLACIAN, ab.HIGHLIGHTS_HARMONIC):
         p = pe.mosaic_piece(134, 78, ab.highlights_data(mode, 1.0))
         assert pe.oracle_highlights(p, img)[0] == -1
 

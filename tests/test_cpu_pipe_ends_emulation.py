@@ -205,3 +205,15 @@ def test_channelmixer_kernel_every_branch_combination(emul_channelmixer):
                         cp = ab.channelmixer_piece(cases.WORK, adaptation=ad, version=ver, clip=clip, apply_grey=grey, illuminant=(0.93, 1.02, 0.71), mix=cases.MIX,
                                                    saturation=(0.1, -0.2, 0.05), lightness=(0.05, 0.1, -0.1), grey=(0.3, 0.5, 0.2), p=0.85, gamut=gamut)
                         assert same_bits(_emul_channelmixer(emul_channelmixer, img, cp), pe.oracle_channelmixerrgb(img, cp)).all(), (ad, ver, clip, grey, gamut)
+
+
+def test_x87_operations_equal_the_host_long_double():
+    """ansel_b200/csrc/x87.cuh (the three 80-bit operations of the LCh highlight reconstruction in integer arithmetic) against the
+    host's own long double on 60 million operands: denormals, signed zeros, near-cancellations included"""
+    exe = os.path.join(EMUL, "x87_selftest")
+    src = os.path.join(EMUL, "x87_selftest.cpp")
+    dep = os.path.join(util.ROOT, "ansel_b200", "csrc", "x87.cuh")
+    if not os.path.exists(exe) or max(os.path.getmtime(src), os.path.getmtime(dep)) > os.path.getmtime(exe):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fno-fast-math", "-ffp-contract=off", "-I", EMUL, "-o", exe, src], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "0 mismatches" in r.stdout, r.stdout[-500:]

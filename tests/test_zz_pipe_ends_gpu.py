@@ -84,7 +84,7 @@ def test_highlights_bit_exact(built, name):
 def test_highlights_refuses_reconstruction_past_the_bypass(built):
     import ansel_b200 as ab
     _, img = cases.highlights_case("clip_mosaic")
-    for mode in (ab.HIGHLIGHTS_LCH, ab.HIGHLIGHTS_LAPLACIAN, ab.HIGHLIGHTS_HARMONIC):
+    for mode in (ab.HIGHLIGHTS_LAPLACIAN, ab.HIGHLIGHTS_HARMONIC):
         piece = pe.mosaic_piece(img.shape[1], img.shape[0], ab.highlights_data(mode, 1.0))
         rc, got = run_dev("highlights", piece, img, img.shape)
         assert rc == ab.B200_ERR_UNSUPPORTED and b"clipped" in ab.lib().b200_last_error()
