@@ -434,6 +434,188 @@ __global__ void __launch_bounds__(NT) lch_bayer_kernel(const float *__restrict__
   out[0] = v;
 }
 
+// ---- the X-Trans variants of the two reconstructions (lch.c:66-204, :412-537; inpaint.c:84-104) -------------------------------------
+struct xtable_t
+{
+  unsigned char v[36]; // piece->dsc_in.xtrans
+  int x0, y0;          // roi_in origin
+};
+__device__ __forceinline__ int fcx(const xtable_t &X, int row, int col) { return X.v[((row + 600 + X.y0) % 6) * 6 + (col + 600 + X.x0) % 6]; } // FCxtrans
+__device__ __forceinline__ float pick4r(const float *a, int k) { return (k & 2) ? ((k & 1) ? a[3] : a[2]) : ((k & 1) ? a[1] : a[0]); }
+__device__ __forceinline__ void set4r(float *a, int k, float v)
+{
+  if(k == 1) a[1] = v;
+  else if(k == 2) a[2] = v;
+  else if(k == 3) a[3] = v;
+}
+// interp_pix_xtrans :66-88
+__device__ __forceinline__ float interp_pix_xtrans(int ratio_next, float next, float clip0, float clip_next, const float *ratios)
+{
+  const float clip_val = fmaxf(clip0, clip_next);
+  if(next >= clip_next - 1e-5f) return clip_val;
+  if(ratio_next > 0) return fminf(next / pick4r(ratios, ratio_next), clip_val);
+  return fminf(next * pick4r(ratios, -ratio_next), clip_val);
+}
+// the colour-transition table roff[f0][f1] :104: RG 1, RB 2, GB 3, negative = inverted
+__device__ __forceinline__ int roff(int f0, int f1) { return f0 == f1 ? 0 : (f0 < f1 ? -(f0 + f1) : (f0 + f1)); }
+// interpolate_color_xtrans :90-204: three running ratios (one per colour pair) instead of Bayer's one
+__device__ void inpaint_line_xtrans(const float *__restrict__ ivoid, float *__restrict__ ovoid, const inpaint_t &A, const xtable_t &X, int dim, int dir, int other,
+                                    int pass)
+{
+  float ratios[4] = { 1.0f, 1.0f, 1.0f, 1.0f };
+  int i = dim ? other : 0, j = dim ? 0 : other;
+  const ptrdiff_t offs = (ptrdiff_t)(dim ? A.width : 1) * dir;
+  const ptrdiff_t offl = offs - (dim ? 1 : A.width), offr = offs + (dim ? 1 : A.width);
+  const int n = dim ? A.height : A.width;
+  const int beg = dir == 1 ? 0 : n - 1, end = dir == 1 ? n : -1;
+  const size_t first = dim ? i + (size_t)beg * A.width : beg + (size_t)j * A.width;
+  const float *in = ivoid + first;
+  float *out = ovoid + first;
+  const float clip_max = fmaxf(fmaxf(A.clips[0], A.clips[1]), A.clips[2]);
+  for(int k = beg; k != end; k += dir)
+  {
+    if(dim == 1)
+      j = k;
+    else
+      i = k;
+    if(i == 0 || i == A.width - 1 || j == 0 || j == A.height - 1)
+    {
+      if(pass == 3) out[0] = fminf(clip_max, in[0]);
+    }
+    else
+    {
+      const int f0 = fcx(X, j, i), f1 = fcx(X, dim ? (j + dir) : j, dim ? i : (i + dir));
+      const float clip0 = pick4(A.clips, f0), clip1 = pick4(A.clips, f1);
+      const float v0 = in[0], v1 = in[offs];
+      if((f0 != f1) && (v0 < clip0 && v0 > 1e-5f) && (v1 < clip1 && v1 > 1e-5f))
+      {
+        const int r = roff(f0, f1);
+        if(r > 0)
+          set4r(ratios, r, (3.f * pick4r(ratios, r) + (v1 / v0)) / 4.f);
+        else
+          set4r(ratios, -r, (3.f * pick4r(ratios, -r) + (v0 / v1)) / 4.f);
+      }
+      if(v0 >= clip0 - 1e-5f)
+      {
+        float add;
+        if(f0 != f1)
+          add = interp_pix_xtrans(roff(f0, f1), v1, clip0, clip1, ratios);
+        else
+        { // at the start of a 2x2 green block: look diagonally
+          const int fl = fcx(X, dim ? (j + dir) : (j - 1), dim ? (i - 1) : (i + dir)), fr = fcx(X, dim ? (j + dir) : (j + 1), dim ? (i + 1) : (i + dir));
+          add = (fl != f0) ? interp_pix_xtrans(roff(f0, fl), in[offl], clip0, pick4(A.clips, fl), ratios)
+                           : interp_pix_xtrans(roff(f0, fr), in[offr], clip0, pick4(A.clips, fr), ratios);
+        }
+        if(pass == 0)
+          out[0] = add;
+        else if(pass == 3)
+          out[0] = fminf(clip_max, (out[0] + add) / 4.0f);
+        else
+          out[0] += add;
+      }
+      else if(pass == 3)
+        out[0] = v0;
+    }
+    out += offs;
+    in += offs;
+  }
+}
+__global__ void __launch_bounds__(128) inpaint_rows_xtrans_kernel(const float *__restrict__ in, float *__restrict__ out, inpaint_t A, xtable_t X,
+                                                                  const unsigned long long *counter)
+{
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  if(j >= A.height || *counter < 25ull) return;
+  inpaint_line_xtrans(in, out, A, X, 0, 1, j, 0);
+  inpaint_line_xtrans(in, out, A, X, 0, -1, j, 1);
+}
+__global__ void __launch_bounds__(128) inpaint_cols_xtrans_kernel(const float *__restrict__ in, float *__restrict__ out, inpaint_t A, xtable_t X,
+                                                                  const unsigned long long *counter)
+{
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  if(i >= A.width) return;
+  if(*counter < 25ull)
+  {
+    for(int j = 0; j < A.height; j++) out[(size_t)j * A.width + i] = in[(size_t)j * A.width + i];
+    return;
+  }
+  inpaint_line_xtrans(in, out, A, X, 1, 1, i, 2);
+  inpaint_line_xtrans(in, out, A, X, 1, -1, i, 3);
+}
+// process_lch_xtrans :412-537.  The reference's ring buffer `cl` says whether any of this and the two previous columns has a
+// clipped sample in rows j-1..j+1: recomputed per pixel here.
+__global__ void __launch_bounds__(NT) lch_xtrans_kernel(const float *__restrict__ ivoid, float *__restrict__ ovoid, int width, int height, xtable_t X, float clip,
+                                                        const unsigned long long *counter)
+{
+  const int i = blockIdx.x * NT + threadIdx.x, j = blockIdx.y;
+  if(i >= width) return;
+  const float *in = ivoid + (size_t)width * j + i;
+  float *out = ovoid + (size_t)width * j + i;
+  if(*counter < 25ull)
+  {
+    out[0] = in[0];
+    return;
+  }
+  if(i < 2 || i > width - 3 || j < 2 || j > height - 3)
+  {
+    out[0] = clip < in[0] ? clip : in[0];
+    return;
+  }
+  bool clipped = in[0] > clip;
+  if(!clipped)
+  {
+    bool cl = false;
+    for(int ii = -2; ii <= 0; ii++) cl = cl || (in[-width + ii] > clip) || (in[ii] > clip) || (in[width + ii] > clip);
+    clipped = cl;
+    if(clipped)
+      for(int offset_j = -2; offset_j <= 0; offset_j++)
+        for(int offset_i = -2; offset_i <= 0; offset_i++)
+          if(clipped)
+          { // a 3x3 block touching the pixel without any clipping: no reconstruction
+            clipped = false;
+            for(int jj = offset_j; jj <= offset_j + 2; jj++)
+              for(int ii = offset_i; ii <= offset_i + 2; ii++) clipped = clipped || (in[(ptrdiff_t)jj * width + ii] > clip);
+          }
+  }
+  if(!clipped)
+  {
+    out[0] = in[0];
+    return;
+  }
+  float mean[3] = { 0.0f, 0.0f, 0.0f }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+  int cnt[3] = { 0, 0, 0 };
+  for(int jj = -1; jj <= 1; jj++)
+    for(int ii = -1; ii <= 1; ii++)
+    {
+      const float val = in[(ptrdiff_t)jj * width + ii];
+      const int c = fcx(X, j + jj, i + ii);
+#pragma unroll
+      for(int q = 0; q < 3; q++)
+        if(q == c)
+        {
+          mean[q] += val;
+          cnt[q]++;
+          mx[q] = mx[q] > val ? mx[q] : val;
+        }
+    }
+  const float m0 = mean[0] / (float)cnt[0], m1 = mean[1] / (float)cnt[1], m2 = mean[2] / (float)cnt[2];
+  const float Ro = m0 < clip ? m0 : clip, Go = m1 < clip ? m1 : clip, Bo = m2 < clip ? m2 : clip;
+  const float R = mx[0], G = mx[1], B = mx[2];
+  const float L = divr(R + G + B, 3.0f);
+  float C = x87::mul_sqrt3(R - G);
+  float H = 2.0f * B - G - R;
+  const float Co = x87::mul_sqrt3(Ro - Go);
+  const float Ho = 2.0f * Bo - Go - Ro;
+  if(R != G && G != B)
+  {
+    const float ratio = sqrtf((Co * Co + Ho * Ho) / (C * C + H * H));
+    C *= ratio;
+    H *= ratio;
+  }
+  const float t = L - divr(H, 6.0f);
+  const int c = fcx(X, j, i);
+  out[0] = c == 0 ? x87::add_div_sqrt12(t, C, +1) : (c == 1 ? x87::add_div_sqrt12(t, C, -1) : L + divr(H, 3.0f));
+}
+
 // ---- the float -> integer ends ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned gamma_byte(float x)
 { // (uint8_t)(fminf(roundf(255.0f * fmaxf(in, 0.0f)), 255.0f)), gamma.c:361
@@ -770,6 +952,30 @@ extern "C" int b200_highlights_process_dev(const b200_piece_t *piece, const void
   if(clip_mode)
   { // count and branch stay on the device
     flat_kernel<OP_CLIP><<<flat_grid(n), NT, 0, s>>>((const float *)d_in, (float *)d_out, n, clip, 0.0f, (piece->mask_display & 1) ? 1 : 0, counter);
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+  }
+  if(mosaic && piece->filters == 9u && (d->mode == B200_HIGHLIGHTS_LCH || d->mode == B200_HIGHLIGHTS_INPAINT))
+  { // the X-Trans variants :735-757; FCxtrans takes roi_in
+    xtable_t X;
+    for(int r = 0; r < 6; r++)
+      for(int c = 0; c < 6; c++)
+      {
+        if(piece->xtrans[r][c] > 2) return fail(B200_ERR_ARG, "highlights: xtrans[%d][%d] = %d", r, c, piece->xtrans[r][c]);
+        X.v[r * 6 + c] = piece->xtrans[r][c];
+      }
+    X.x0 = piece->roi_in.x;
+    X.y0 = piece->roi_in.y;
+    if(d->mode == B200_HIGHLIGHTS_LCH)
+      lch_xtrans_kernel<<<dim3((unsigned)((width + NT - 1) / NT), (unsigned)height), NT, 0, s>>>((const float *)d_in, (float *)d_out, width, height, X, clip, counter);
+    else
+    {
+      float pmax[4];
+      for(int c = 0; c < 4; c++) pmax[c] = (piece->processed_maximum[c] > 0.f) ? piece->processed_maximum[c] : 1.0f;
+      const inpaint_t A = { { 0.987f * d->clip * pmax[0], 0.987f * d->clip * pmax[1], 0.987f * d->clip * pmax[2], clip }, 9u, width, height };
+      inpaint_rows_xtrans_kernel<<<(unsigned)((height + 127) / 128), 128, 0, s>>>((const float *)d_in, (float *)d_out, A, X, counter);
+      inpaint_cols_xtrans_kernel<<<(unsigned)((width + 127) / 128), 128, 0, s>>>((const float *)d_in, (float *)d_out, A, X, counter);
+    }
     B200_CUDA_TRY(cudaGetLastError());
     return B200_OK;
   }

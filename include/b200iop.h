@@ -556,12 +556,12 @@ typedef struct b200_highlights_data_t
 } b200_highlights_data_t;
 /* process() :679-789: counts the samples above the mode's threshold (_hl_count_clipped :266-292); fewer than 25 ->
  * the input is copied through.  Past the bypass, built: mode CLIP (process_clip, iop/highlights/clip.c:60-85; also
- * what LCh and colour inpainting run on non-mosaic input) and, on a Bayer mosaic, LCh (process_lch_bayer,
- * iop/highlights/lch.c:315-411; its long-double products, quotients and sums in integer arithmetic, x87.cuh) and colour
- * inpainting (process_inpaint_bayer, iop/highlights/inpaint.c:63-82: four directional line recurrences, averaged).
- * For these the count and the branch stay on the device: no host round trip.  The X-Trans variants of LCh and inpainting,
- * guided Laplacians and harmonic transposition return B200_ERR_UNSUPPORTED when the frame does not take the bypass (the
- * host reads the count once to know). */
+ * what LCh and colour inpainting run on non-mosaic input) and, on Bayer and X-Trans mosaics alike, LCh (process_lch_bayer /
+ * process_lch_xtrans, iop/highlights/lch.c:315-537; their long-double products, quotients and sums in integer arithmetic,
+ * x87.cuh) and colour inpainting (process_inpaint_bayer / _xtrans, iop/highlights/inpaint.c:63-104: four directional line
+ * recurrences, averaged).  For these the count and the branch stay on the device: no host round trip.  Guided Laplacians
+ * and harmonic transposition return B200_ERR_UNSUPPORTED when the frame does not take the bypass (the host reads the
+ * count once to know). */
 int b200_highlights_process_host(const b200_piece_t *piece, const void *in, void *out);
 int b200_highlights_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
 void b200_highlights_tiling(const b200_piece_t *piece, b200_tiling_t *tiling); /* :575-644 */

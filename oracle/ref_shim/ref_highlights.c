@@ -4,9 +4,10 @@
  *     iop/highlights/common.h :218 (DT_HL_MIN_CLIPPED_PIXELS), :431-476 (mode enum, params == data)
  *     iop/highlights/clip.c   :60-85  process_clip
  *     iop/highlights/common.h :618-619 SQRT3, SQRT12 (long double);  iop/highlights/lch.c :315-411 process_lch_bayer
+ *     iop/highlights/lch.c    :65-204 interp_pix_xtrans, interpolate_color_xtrans;  :412-537 process_lch_xtrans
  *     iop/highlights/lch.c    :206-303 interpolate_color;  iop/highlights/inpaint.c :63-82 process_inpaint_bayer
  *     iop/highlights.c        :232-302 _hl_count_thresholds, _hl_count_clipped, _hl_copy_input;  :679-789 process()
- * The other reconstruction modes (X-Trans LCh and inpainting, guided Laplacians, harmonic transposition) are separate translation
+ * The other reconstruction modes ( guided Laplacians, harmonic transposition) are separate translation
  * units of 18 k lines that are not built here: their entry points abort (the tests reach them only through the bypass).
  */
 #include "ref_piece.h"
@@ -42,8 +43,6 @@ static inline uint32_t dt_dev_get_roi_filters(const dt_dev_pixelpipe_iop_t *piec
 }
 #define NOT_BUILT(name) do { fprintf(stderr, "oracle/_ref: highlights %s is not built\n", name); abort(); } while(0)
 #define process_visualize(...) NOT_BUILT("process_visualize")
-#define process_inpaint_xtrans(...) NOT_BUILT("process_inpaint_xtrans")
-#define process_lch_xtrans(...) NOT_BUILT("process_lch_xtrans")
 static inline int process_laplacian_stub(void) { NOT_BUILT("process_laplacian"); return 1; }
 #define process_laplacian(...) process_laplacian_stub()
 #define process_harmonic(...) process_laplacian_stub()
@@ -51,6 +50,9 @@ static inline int process_laplacian_stub(void) { NOT_BUILT("process_laplacian");
 #include "gen_highlights.c"
 #undef process
 
+static uint8_t ref_highlights_xtrans[6][6];
+/* the sensor's X-Trans table for the following ref_highlights() calls with filters == 9 */
+void ref_highlights_set_xtrans(const uint8_t xtrans[36]) { memcpy(ref_highlights_xtrans, xtrans, 36); }
 int ref_highlights(const float *in, float *out, int x, int y, int width, int height, uint32_t filters, int channels, int mode, float clip,
                    const float processed_maximum[4], int mask_display)
 {
@@ -66,6 +68,7 @@ int ref_highlights(const float *in, float *out, int x, int y, int width, int hei
   piece.dsc_in.filters = filters;
   piece.dsc_in.channels = channels;
   for(int k = 0; k < 4; k++) piece.dsc_in.processed_maximum[k] = processed_maximum[k];
+  memcpy(piece.dsc_in.xtrans, ref_highlights_xtrans, 36);
   return highlights_process(NULL, &pipe, &piece, in, out);
 }
 size_t ref_highlights_sizeof_data(void) { return sizeof(dt_iop_highlights_data_t); }

@@ -270,6 +270,140 @@ static void lch_bayer(const float *ivoid, float *ovoid, int width, int height, i
     }
 }
 
+/* ---- the X-Trans variants: lch.c interp_pix_xtrans :66-88, interpolate_color_xtrans :90-204, process_lch_xtrans :412-537,
+ * inpaint.c process_inpaint_xtrans :84-104.  FCxtrans(row, col, roi, xtrans) = xtrans[(row + 600 + roi.y) % 6][(col + 600 + roi.x) % 6] */
+typedef struct { const uint8_t (*xtrans)[6]; int x0, y0; } xt_t;
+static int fcx(const xt_t *X, int row, int col) { return X->xtrans[(row + 600 + X->y0) % 6][(col + 600 + X->x0) % 6]; }
+static float interp_pix_xtrans(int ratio_next, ptrdiff_t offset_next, float clip0, float clip_next, const float *in, const float *ratios)
+{
+  const float clip_val = fmaxf(clip0, clip_next);
+  if(in[offset_next] >= clip_next - 1e-5f) return clip_val;
+  if(ratio_next > 0) return fminf(in[offset_next] / ratios[ratio_next], clip_val);
+  return fminf(in[offset_next] * ratios[-ratio_next], clip_val);
+}
+static void interpolate_color_xtrans(const float *ivoid, float *ovoid, int width, int height, int dim, int dir, int other, const float *clip, const xt_t *X,
+                                     int pass)
+{
+  static const int roff[3][3] = { { 0, -1, -2 }, { 1, 0, -3 }, { 2, 3, 0 } };
+  float ratios[4] = { 1.0f, 1.0f, 1.0f, 1.0f };
+  int i = (dim == 0) ? 0 : other, j = (dim == 0) ? other : 0;
+  const ptrdiff_t offs = (ptrdiff_t)(dim ? width : 1) * ((dir < 0) ? -1 : 1);
+  const ptrdiff_t offl = offs - (dim ? 1 : width), offr = offs + (dim ? 1 : width);
+  const int n = dim ? height : width, beg = dir == 1 ? 0 : n - 1, end = dir == 1 ? n : -1;
+  const float *in = ivoid + (dim ? (size_t)i + (size_t)beg * width : (size_t)beg + (size_t)j * width);
+  float *out = ovoid + (in - ivoid);
+  for(int k = beg; k != end; k += dir)
+  {
+    if(dim == 1) j = k; else i = k;
+    const int f0 = fcx(X, j, i), f1 = fcx(X, dim ? (j + dir) : j, dim ? i : (i + dir));
+    const int fl = fcx(X, dim ? (j + dir) : (j - 1), dim ? (i - 1) : (i + dir)), fr = fcx(X, dim ? (j + dir) : (j + 1), dim ? (i + 1) : (i + dir));
+    const float clip0 = clip[f0], clip1 = clip[f1], clipl = clip[fl], clipr = clip[fr];
+    const float clip_max = fmaxf(fmaxf(clip[0], clip[1]), clip[2]);
+    if(i == 0 || i == width - 1 || j == 0 || j == height - 1)
+    {
+      if(pass == 3) out[0] = fminf(clip_max, in[0]);
+    }
+    else
+    {
+      if((f0 != f1) && (in[0] < clip0 && in[0] > 1e-5f) && (in[offs] < clip1 && in[offs] > 1e-5f))
+      {
+        const int r = roff[f0][f1];
+        if(r > 0)
+          ratios[r] = (3.f * ratios[r] + (in[offs] / in[0])) / 4.f;
+        else
+          ratios[-r] = (3.f * ratios[-r] + (in[0] / in[offs])) / 4.f;
+      }
+      if(in[0] >= clip0 - 1e-5f)
+      {
+        float add;
+        if(f0 != f1)
+          add = interp_pix_xtrans(roff[f0][f1], offs, clip0, clip1, in, ratios);
+        else
+          add = (fl != f0) ? interp_pix_xtrans(roff[f0][fl], offl, clip0, clipl, in, ratios) : interp_pix_xtrans(roff[f0][fr], offr, clip0, clipr, in, ratios);
+        if(pass == 0)
+          out[0] = add;
+        else if(pass == 3)
+          out[0] = fminf(clip_max, (out[0] + add) / 4.0f);
+        else
+          out[0] += add;
+      }
+      else if(pass == 3)
+        out[0] = in[0];
+    }
+    out += offs;
+    in += offs;
+  }
+}
+static void lch_xtrans(const float *ivoid, float *ovoid, int width, int height, const xt_t *X, float clip)
+{
+  static const long double SQRT3 = 1.7320508075688772935274463415058723669L, SQRT12 = 3.4641016151377545870548926830117447339L;
+  for(int j = 0; j < height; j++)
+  {
+    int cl = 0; /* clipping of the vertical triplets of this and the two previous columns */
+    for(int i = 0; i < width; i++)
+    {
+      const float *in = ivoid + (size_t)width * j + i;
+      float *out = ovoid + (size_t)width * j + i;
+      cl = (cl << 1) & 6;
+      if(j >= 2 && j <= height - 3) cl |= (in[-width] > clip) | (in[0] > clip) | (in[width] > clip);
+      if(i < 2 || i > width - 3 || j < 2 || j > height - 3)
+      {
+        out[0] = clip < in[0] ? clip : in[0];
+        continue;
+      }
+      int clipped = (in[0] > clip);
+      if(!clipped)
+      {
+        clipped = cl;
+        if(clipped)
+          for(int offset_j = -2; offset_j <= 0; offset_j++)
+            for(int offset_i = -2; offset_i <= 0; offset_i++)
+              if(clipped)
+              {
+                clipped = 0;
+                for(int jj = offset_j; jj <= offset_j + 2; jj++)
+                  for(int ii = offset_i; ii <= offset_i + 2; ii++) clipped = (clipped || (in[(ptrdiff_t)jj * width + ii] > clip));
+              }
+      }
+      if(!clipped)
+      {
+        out[0] = in[0];
+        continue;
+      }
+      float mean[3] = { 0.0f, 0.0f, 0.0f }, RGBmax[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+      int cnt[3] = { 0, 0, 0 };
+      for(int jj = -1; jj <= 1; jj++)
+        for(int ii = -1; ii <= 1; ii++)
+        {
+          const float val = in[(ptrdiff_t)jj * width + ii];
+          const int c = fcx(X, j + jj, i + ii);
+          mean[c] += val;
+          cnt[c]++;
+          RGBmax[c] = RGBmax[c] > val ? RGBmax[c] : val;
+        }
+      const float m0 = mean[0] / cnt[0], m1 = mean[1] / cnt[1], m2 = mean[2] / cnt[2];
+      const float Ro = m0 < clip ? m0 : clip, Go = m1 < clip ? m1 : clip, Bo = m2 < clip ? m2 : clip;
+      const float R = RGBmax[0], G = RGBmax[1], B = RGBmax[2];
+      const float L = (R + G + B) / 3.0f;
+      float C = SQRT3 * (R - G);
+      float H = 2.0f * B - G - R;
+      const float Co = SQRT3 * (Ro - Go);
+      const float Ho = 2.0f * Bo - Go - Ro;
+      if(R != G && G != B)
+      {
+        const float ratio = sqrtf((Co * Co + Ho * Ho) / (C * C + H * H));
+        C *= ratio;
+        H *= ratio;
+      }
+      float RGB[3];
+      RGB[0] = L - H / 6.0f + C / SQRT12;
+      RGB[1] = L - H / 6.0f - C / SQRT12;
+      RGB[2] = L + H / 3.0f;
+      out[0] = RGB[fcx(X, j, i)];
+    }
+  }
+}
+
 /* returns 0 and the number of samples counted as clipped in *n_clipped; -1 for a mode that is not restated */
 int orc_highlights(const b200_piece_t *piece, const float *in, float *out, size_t *n_clipped)
 {
@@ -325,6 +459,28 @@ int orc_highlights(const b200_piece_t *piece, const float *in, float *out, size_
     {
       interpolate_color(in, out, w, h, 1, 1, i, clips, shifted, 2);
       interpolate_color(in, out, w, h, 1, -1, i, clips, shifted, 3);
+    }
+    return 0;
+  }
+  if(filters == 9u && (data->mode == B200_HIGHLIGHTS_LCH || data->mode == B200_HIGHLIGHTS_INPAINT))
+  {
+    const xt_t X = { piece->xtrans, piece->roi_in.x, piece->roi_in.y };
+    const int w = piece->roi_out.width, h = piece->roi_out.height;
+    if(data->mode == B200_HIGHLIGHTS_LCH)
+      lch_xtrans(in, out, w, h, &X, clip);
+    else
+    {
+      const float clips[4] = { 0.987f * data->clip * pmax[0], 0.987f * data->clip * pmax[1], 0.987f * data->clip * pmax[2], clip };
+      for(int j = 0; j < h; j++)
+      {
+        interpolate_color_xtrans(in, out, w, h, 0, 1, j, clips, &X, 0);
+        interpolate_color_xtrans(in, out, w, h, 0, -1, j, clips, &X, 1);
+      }
+      for(int i = 0; i < w; i++)
+      {
+        interpolate_color_xtrans(in, out, w, h, 1, 1, i, clips, &X, 2);
+        interpolate_color_xtrans(in, out, w, h, 1, -1, i, clips, &X, 3);
+      }
     }
     return 0;
   }

@@ -94,6 +94,25 @@ extern "C" int emul_highlights(const b200_piece_t *piece, const float *in, float
   else
     emulate(dim3((unsigned)((npx + NT - 1) / NT)), NT, count_pixels_kernel, in, npx, ch, thresholds[0], thresholds[1], thresholds[2], &counter);
   *n_clipped = counter;
+  if(mosaic && piece->filters == 9u && (d->mode == B200_HIGHLIGHTS_LCH || d->mode == B200_HIGHLIGHTS_INPAINT))
+  {
+    xtable_t X;
+    for(int r = 0; r < 6; r++)
+      for(int c = 0; c < 6; c++) X.v[r * 6 + c] = piece->xtrans[r][c];
+    X.x0 = piece->roi_in.x;
+    X.y0 = piece->roi_in.y;
+    if(d->mode == B200_HIGHLIGHTS_LCH)
+      emulate(dim3((unsigned)((w + NT - 1) / NT), (unsigned)h), NT, lch_xtrans_kernel, in, out, w, h, X, clip, (const unsigned long long *)&counter);
+    else
+    {
+      float pmax[4];
+      for(int c = 0; c < 4; c++) pmax[c] = (piece->processed_maximum[c] > 0.f) ? piece->processed_maximum[c] : 1.0f;
+      const inpaint_t A = { { 0.987f * d->clip * pmax[0], 0.987f * d->clip * pmax[1], 0.987f * d->clip * pmax[2], clip }, 9u, w, h };
+      emulate(dim3((unsigned)((h + 127) / 128)), 128, inpaint_rows_xtrans_kernel, in, out, A, X, (const unsigned long long *)&counter);
+      emulate(dim3((unsigned)((w + 127) / 128)), 128, inpaint_cols_xtrans_kernel, in, out, A, X, (const unsigned long long *)&counter);
+    }
+    return 0;
+  }
   if(mosaic && piece->filters != 9u && d->mode == B200_HIGHLIGHTS_LCH)
   {
     emulate(dim3((unsigned)((w + NT - 1) / NT), (unsigned)h), NT, lch_bayer_kernel, in, out, w, h, piece->roi_out.x, piece->roi_out.y, (unsigned)piece->filters, clip,

@@ -131,6 +131,8 @@ def ref_highlights(piece, img: np.ndarray, kind="strict"):
     src, out = util.aligned_empty(img.shape), util.aligned_empty(img.shape)
     src[...] = img
     out[...] = -7.0
+    xt = np.ascontiguousarray(np.array([[piece.xtrans[i][j] for j in range(6)] for i in range(6)], np.uint8))
+    lib.ref_highlights_set_xtrans(vp(xt))
     f = lib.ref_highlights
     f.restype = C.c_int
     pm = (C.c_float * 4)(*piece.processed_maximum)

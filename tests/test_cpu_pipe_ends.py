@@ -115,6 +115,9 @@ HIGHLIGHTS_CASES = {
     "lch_mosaic": dict(mode=ab.HIGHLIGHTS_LCH, clip=0.95),                            # 2x2 blocks rebuilt in LCh, long double constants
     "lch_mosaic_wb_roi": dict(mode=ab.HIGHLIGHTS_LCH, clip=0.9, pm=(2.13, 1.0, 1.57, 0.0), x=3, y=1, filters=util.BAYER["GRBG"]),
     "lch_mosaic_bypass": dict(mode=ab.HIGHLIGHTS_LCH, n_clipped=12),
+    "lch_xtrans": dict(mode=ab.HIGHLIGHTS_LCH, clip=0.95, filters=9, xtrans=pe.XTRANS, x=1, y=4),
+    "inpaint_xtrans_wb": dict(mode=ab.HIGHLIGHTS_INPAINT, clip=0.9, filters=9, xtrans=pe.XTRANS, x=3, y=2, pm=(2.13, 1.0, 1.57, 0.0)),
+    "clip_xtrans": dict(filters=9, xtrans=pe.XTRANS),
 }
 
 
