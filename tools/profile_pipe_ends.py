@@ -51,6 +51,10 @@ for method in (ab.DEMOSAIC_PPG, ab.DEMOSAIC_VNG4, ab.DEMOSAIC_RCD | 2048):
     d = ab.demosaic_data(method)
     d.median_thrs, d.dual_thrs = 0.02, 0.2
     go(L.b200_demosaic_process_dev(piece(d, 1), m0.data_ptr(), b.data_ptr(), s))
+p_lc = piece(ab.highlights_data(ab.HIGHLIGHTS_LCH, 1.0), 1, pm=(wb[0], wb[1], wb[2], 0.0))
+go(L.b200_highlights_process_dev(p_lc, m1.data_ptr(), m0.data_ptr(), s))
+lab = a * torch.tensor([100.0, 60.0, 60.0, 1.0], device="cuda")
+go(L.b200_bilat_process_dev(piece(ab.bilat_data(sigma_r=5.0, sigma_s=50.0, detail=0.5, mode=0), 4), lab.data_ptr(), b.data_ptr(), s))
 go(L.b200_exposure_process_dev(piece(ab.exposure_data(0.0, 0.5), 4), a.data_ptr(), b.data_ptr(), s))
 cp = ab.channelmixer_piece(util.profile_pair(util.REC2020_TO_XYZ_D50), illuminant=(0.93, 1.02, 0.71))
 pc = piece(None, 4)
