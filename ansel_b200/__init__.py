@@ -185,6 +185,11 @@ class ChannelmixerPiece(C.Structure):
                 ("work_in", (C.c_float * 4) * 3), ("work_out", (C.c_float * 4) * 3), ("_pad1", C.c_uint8 * 32)]
 
 
+class FlipData(C.Structure):
+    """b200_flip_data_t == dt_iop_flip_params_t (src/iop/flip.c:74-79): dt_image_orientation_t."""
+    _fields_ = [("orientation", C.c_int)]
+
+
 class B200Error(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libb200iop error {code}: {msg}")
@@ -192,7 +197,7 @@ class B200Error(RuntimeError):
 
 
 OPS = ("demosaic", "colorin", "colorout", "denoiseprofile", "filmicrgb", "bilat", "diffuse", "nlmeans",
-       "rawprepare", "temperature", "highlights", "exposure", "gamma", "finalscale", "channelmixerrgb")
+       "rawprepare", "temperature", "highlights", "exposure", "gamma", "finalscale", "channelmixerrgb", "initialscale", "flip")
 
 _lib = None
 

@@ -154,6 +154,41 @@ __global__ void __launch_bounds__(RNT) copy_rows_kernel(const float4 *__restrict
   const int ox = blockIdx.x * RNT + threadIdx.x, oy = blockIdx.y;
   if(ox < out_w) out[(size_t)oy * out_w + ox] = in[(size_t)oy * in_w + ox];
 }
+// the 1:1 path with ROI origins :916-932: the output is a crop of the input at (dx, dy) = roi_out - roi_in
+__global__ void __launch_bounds__(RNT) crop_rows_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int in_w, int out_w, int dx, int dy)
+{
+  const int ox = blockIdx.x * RNT + threadIdx.x, oy = blockIdx.y;
+  if(ox < out_w) out[(size_t)oy * out_w + ox] = in[(size_t)(oy + dy) * in_w + ox + dx];
+}
+// dt_imageio_flip_buffers, imageio/imageio_core.c:258-297: pixel (i, j) of the input lands at |sj| jj + |si| ii + sj j + si i
+// (in pixels here; `ch` floats per pixel)
+__global__ void __launch_bounds__(RNT) flip_kernel(const float *__restrict__ in, float *__restrict__ out, int width, int height, int ch, int orientation)
+{
+  const int i = blockIdx.x * RNT + threadIdx.x, j = blockIdx.y;
+  if(i >= width) return;
+  long ii = 0, jj = 0, si = 1, sj = width;
+  if(orientation & 4)
+  {
+    sj = 1;
+    si = height;
+  }
+  if(orientation & 1)
+  {
+    jj = height - 1;
+    sj = -sj;
+  }
+  if(orientation & 2)
+  {
+    ii = width - 1;
+    si = -si;
+  }
+  const long o = (sj < 0 ? -sj : sj) * jj + (si < 0 ? -si : si) * ii + sj * j + si * i;
+  const size_t p = (size_t)j * width + i;
+  if(ch == 4)
+    ((float4 *)out)[o] = ((const float4 *)in)[p];
+  else
+    for(int c = 0; c < ch; c++) out[(size_t)o * ch + c] = in[p * ch + c];
+}
 } // namespace
 
 #ifndef B200_KERNELS_ON_CPU
@@ -174,7 +209,17 @@ extern "C" int b200_resampling_plan(int interpolator, int in, int in_x0, int out
   return (int)P.kernel.size();
 }
 
+static int clip_and_zoom_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream, bool keep_origins);
 extern "C" int b200_finalscale_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream)
+{
+  return clip_and_zoom_dev(piece, d_in, d_out, stream, false); // process() :117-131 zeroes the origins of both ROIs
+}
+extern "C" int b200_initialscale_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream)
+{
+  return clip_and_zoom_dev(piece, d_in, d_out, stream, true); // iop/initialscale.c:122-129: the ROIs as they are
+}
+// dt_iop_clip_and_zoom_roi (develop/imageop_math.c:146-152) -> _interpolation_resample_plain
+static int clip_and_zoom_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream, bool keep_origins)
 {
   if(!piece || !d_in || !d_out) return fail(B200_ERR_ARG, "finalscale: NULL argument");
   if(!piece->data || piece->data_size < sizeof(b200_finalscale_data_t)) return fail(B200_ERR_ARG, "finalscale: piece->data is not a b200_finalscale_data_t");
@@ -188,16 +233,23 @@ extern "C" int b200_finalscale_process_dev(const b200_piece_t *piece, const void
   if(rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   const dim3 grid((unsigned)((out_w + RNT - 1) / RNT), (unsigned)out_h);
+  const int in_x = keep_origins ? piece->roi_in.x : 0, in_y = keep_origins ? piece->roi_in.y : 0;
+  const int out_x = keep_origins ? piece->roi_out.x : 0, out_y = keep_origins ? piece->roi_out.y : 0;
   if(piece->roi_out.scale == 1.f || piece->roi_out.scale == piece->roi_in.scale)
   {
-    if(out_w > in_w || out_h > in_h) return fail(B200_ERR_ARG, "finalscale: 1:1 copy of %dx%d out of %dx%d", out_w, out_h, in_w, in_h);
-    copy_rows_kernel<<<grid, RNT, 0, s>>>((const float4 *)d_in, (float4 *)d_out, in_w, out_w);
+    const int dx = out_x - in_x, dy = out_y - in_y;
+    if(dx < 0 || dy < 0 || dx + out_w > in_w || dy + out_h > in_h)
+      return fail(B200_ERR_ARG, "finalscale: 1:1 copy of %dx%d at %d,%d out of %dx%d", out_w, out_h, dx, dy, in_w, in_h);
+    if(dx == 0 && dy == 0)
+      copy_rows_kernel<<<grid, RNT, 0, s>>>((const float4 *)d_in, (float4 *)d_out, in_w, out_w);
+    else
+      crop_rows_kernel<<<grid, RNT, 0, s>>>((const float4 *)d_in, (float4 *)d_out, in_w, out_w, dx, dy);
     B200_CUDA_TRY(cudaGetLastError());
     return B200_OK;
   }
   const float resample_scale = (float)(piece->roi_out.scale / piece->roi_in.scale); // :939, a double division stored in a float
   axis_plan_t H, V;
-  if(!build_axis_plan(itor, in_w, 0, out_w, 0, resample_scale, H) || !build_axis_plan(itor, in_h, 0, out_h, 0, resample_scale, V))
+  if(!build_axis_plan(itor, in_w, in_x, out_w, out_x, resample_scale, H) || !build_axis_plan(itor, in_h, in_y, out_h, out_y, resample_scale, V))
     return fail(B200_ERR_ARG, "finalscale: resampling scale rounds to 1 between different ROI scales");
   // one upload: [hlen | hoff | hidx | vlen | voff | vidx | hker | vker]
   const size_t nh = H.kernel.size(), nv = V.kernel.size();
@@ -225,7 +277,10 @@ extern "C" int b200_finalscale_process_dev(const b200_piece_t *piece, const void
   return B200_OK;
 }
 
-extern "C" int b200_finalscale_process_host(const b200_piece_t *piece, const void *in, void *out)
+static int clip_and_zoom_host(const b200_piece_t *piece, const void *in, void *out, bool keep_origins);
+extern "C" int b200_finalscale_process_host(const b200_piece_t *piece, const void *in, void *out) { return clip_and_zoom_host(piece, in, out, false); }
+extern "C" int b200_initialscale_process_host(const b200_piece_t *piece, const void *in, void *out) { return clip_and_zoom_host(piece, in, out, true); }
+static int clip_and_zoom_host(const b200_piece_t *piece, const void *in, void *out, bool keep_origins)
 {
   if(!piece || !in || !out) return fail(B200_ERR_ARG, "finalscale: NULL argument");
   if(piece->roi_in.width < 1 || piece->roi_in.height < 1 || piece->roi_out.width < 1 || piece->roi_out.height < 1)
@@ -239,7 +294,7 @@ extern "C" int b200_finalscale_process_host(const b200_piece_t *piece, const voi
   if((rc = scratch(SLOT_IN, in_bytes, &d_in))) return rc;
   if((rc = scratch(SLOT_OUT, out_bytes, &d_out))) return rc;
   if((rc = copy_h2d(d_in, in, in_bytes, s))) return rc;
-  if((rc = b200_finalscale_process_dev(piece, d_in, d_out, (void *)s))) return rc;
+  if((rc = clip_and_zoom_dev(piece, d_in, d_out, (void *)s, keep_origins))) return rc;
   if((rc = copy_d2h(out, d_out, out_bytes, s))) return rc;
   B200_CUDA_TRY(cudaStreamSynchronize(s));
   return B200_OK;
@@ -259,3 +314,54 @@ extern "C" void b200_finalscale_tiling(const b200_piece_t *piece, b200_tiling_t 
   t->yalign = 1;
 }
 #endif // B200_KERNELS_ON_CPU
+
+#ifndef B200_KERNELS_ON_CPU
+extern "C" void b200_initialscale_tiling(const b200_piece_t *piece, b200_tiling_t *t) { b200_finalscale_tiling(piece, t); } // same flags, no callback of its own
+
+// ---- flip -------------------------------------------------------------------------------------------------------------------------
+extern "C" int b200_flip_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream)
+{
+  if(!piece || !d_in || !d_out) return fail(B200_ERR_ARG, "flip: NULL argument");
+  if(!piece->data || piece->data_size < sizeof(b200_flip_data_t)) return fail(B200_ERR_ARG, "flip: piece->data is not a b200_flip_data_t");
+  if(d_in == d_out) return fail(B200_ERR_ARG, "flip: in-place processing is not supported");
+  const int w = piece->roi_in.width, h = piece->roi_in.height, ch = (int)piece->channels;
+  const int orientation = ((const b200_flip_data_t *)piece->data)->orientation;
+  if(w < 1 || h < 1 || h > 65535 || ch < 1) return fail(B200_ERR_ARG, "flip: %d x %d x %d", w, h, ch);
+  if(orientation < 0 || orientation > 7) return fail(B200_ERR_ARG, "flip: orientation %d", orientation);
+  int rc = bind_device(piece->devid);
+  if(rc) return rc;
+  flip_kernel<<<dim3((unsigned)((w + RNT - 1) / RNT), (unsigned)h), RNT, 0, (cudaStream_t)stream>>>((const float *)d_in, (float *)d_out, w, h, ch, orientation);
+  B200_CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+extern "C" int b200_flip_process_host(const b200_piece_t *piece, const void *in, void *out)
+{
+  if(!piece || !in || !out) return fail(B200_ERR_ARG, "flip: NULL argument");
+  if(piece->roi_in.width < 1 || piece->roi_in.height < 1 || piece->channels < 1) return fail(B200_ERR_ARG, "flip: empty ROI");
+  int rc = bind_device(piece->devid);
+  if(rc) return rc;
+  const size_t bytes = (size_t)piece->roi_in.width * piece->roi_in.height * piece->channels * sizeof(float);
+  void *d_in = nullptr, *d_out = nullptr;
+  cudaStream_t s;
+  if((rc = host_stream(&s))) return rc;
+  if((rc = scratch(SLOT_IN, bytes, &d_in))) return rc;
+  if((rc = scratch(SLOT_OUT, bytes, &d_out))) return rc;
+  if((rc = copy_h2d(d_in, in, bytes, s))) return rc;
+  if((rc = b200_flip_process_dev(piece, d_in, d_out, (void *)s))) return rc;
+  if((rc = copy_d2h(out, d_out, bytes, s))) return rc;
+  B200_CUDA_TRY(cudaStreamSynchronize(s));
+  return B200_OK;
+}
+extern "C" void b200_flip_tiling(const b200_piece_t *piece, b200_tiling_t *t)
+{ // flip.c tiling_callback: in + out, no overlap; the module does not define alignment
+  if(!piece || !t) return;
+  t->factor = 2.0f;
+  t->factor_cl = 2.0f;
+  t->maxbuf = 1.0f;
+  t->maxbuf_cl = 1.0f;
+  t->overhead = 0;
+  t->overlap = 0;
+  t->xalign = 1;
+  t->yalign = 1;
+}
+#endif

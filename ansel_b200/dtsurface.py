@@ -60,7 +60,7 @@ class PipeNode(C.Structure):
 
 _mod = None
 ADAPTED_OPS = ("demosaic", "colorin", "colorout", "denoiseprofile", "filmicrgb", "bilat", "diffuse", "nlmeans",
-               "rawprepare", "temperature", "highlights", "exposure", "gamma", "finalscale", "channelmixerrgb")
+               "rawprepare", "temperature", "highlights", "exposure", "gamma", "finalscale", "channelmixerrgb", "initialscale", "flip")
 
 
 def modlib() -> C.CDLL:

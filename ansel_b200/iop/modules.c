@@ -130,6 +130,34 @@ void dt_iop_finalscale__tiling_callback(struct dt_iop_module_t *self, const dt_d
   b200_finalscale_tiling(&p, tiling);
 }
 
+ADAPT(flip) /* src/iop/flip.c:388 (process), :403 (process_cl); default_tiling_callback */
+/* initialscale resamples like finalscale, with the user's interpolator and the ROIs as they are (iop/initialscale.c:122-129) */
+int dt_iop_initialscale__process(struct dt_iop_module_t *self, const dt_dev_pixelpipe_t *pipe, const dt_dev_pixelpipe_iop_t *piece,
+                                 const void *const i, void *const o)
+{
+  b200_piece_t p;
+  b200_finalscale_data_t fd;
+  b200_piece_from_dt(&p, self, pipe, piece);
+  finalscale_view(&fd, &p);
+  return b200_initialscale_process_host(&p, i, o);
+}
+int dt_iop_initialscale__process_cl(struct dt_iop_module_t *self, const dt_dev_pixelpipe_t *pipe, const dt_dev_pixelpipe_iop_t *piece,
+                                    cl_mem dev_in, cl_mem dev_out)
+{
+  b200_piece_t p;
+  b200_finalscale_data_t fd;
+  b200_piece_from_dt(&p, self, pipe, piece);
+  finalscale_view(&fd, &p);
+  return b200_initialscale_process_dev(&p, dev_in, dev_out, pipe->stream) == 0 ? TRUE : FALSE;
+}
+void dt_iop_initialscale__tiling_callback(struct dt_iop_module_t *self, const dt_dev_pixelpipe_t *pipe,
+                                          const dt_dev_pixelpipe_iop_t *piece, dt_develop_tiling_t *tiling)
+{
+  b200_piece_t p;
+  b200_piece_from_dt(&p, self, pipe, piece);
+  b200_initialscale_tiling(&p, tiling);
+}
+
 /* filmic reads two pipe-level profiles next to piece->data (filmicrgb.c:2714-2715); the adapter flattens the
  * three into the b200_filmicrgb_piece_t the library takes.  A soft-proof profile (data->softproof_mode != 0,
  * _filmic_get_output_profile :2650-2666) is resolved by the reference's own dt_colorspaces_add_profile() in

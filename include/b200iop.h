@@ -662,6 +662,27 @@ void b200_finalscale_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
 int b200_resampling_plan(int interpolator, int in, int in_x0, int out, int out_x0, float scale, int *lengths, float *kernel, int *index,
                          int max_taps);
 
+/* ---- initialscale (src/iop/initialscale.c): the darkroom's first resampling ---------------------------------------- */
+/* process() :122-129 = dt_iop_clip_and_zoom_roi with both ROIs as they are: the resampler of finalscale with the ROI origins in
+ * its tap plans (and, between equal scales, a crop at roi_out - roi_in).  piece->data: a b200_finalscale_data_t (the module's
+ * own data block is a dummy int; the interpolator is the user preference the adapter resolves). */
+int b200_initialscale_process_host(const b200_piece_t *piece, const void *in, void *out);
+int b200_initialscale_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
+void b200_initialscale_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
+
+/* ---- flip (src/iop/flip.c): orientation ---------------------------------------------------------------------------- */
+/* dt_iop_flip_data_t == dt_iop_flip_params_t, flip.c:74-79: dt_image_orientation_t (common/image.h:213-231): bit 0 flip y,
+ * bit 1 flip x, bit 2 swap x and y (the output then has roi_in.height columns) */
+typedef struct b200_flip_data_t
+{
+  int orientation;
+} b200_flip_data_t;
+/* process() :388-400 -> dt_imageio_flip_buffers (imageio/imageio_core.c:258-297) on roi_in.width x roi_in.height pixels of
+ * piece->channels floats */
+int b200_flip_process_host(const b200_piece_t *piece, const void *in, void *out);
+int b200_flip_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);
+void b200_flip_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
+
 /* ---- gamma (src/iop/gamma.c): the pipe's last module, float RGBA -> uint8 BGRA for the display --------------------- */
 /* process() :367-377 with no mask or channel display: _copy_output :352-364 (the fourth byte of every output pixel is
  * not written).  Mask and false-colour displays (GUI previews) return B200_ERR_UNSUPPORTED. */

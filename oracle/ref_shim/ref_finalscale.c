@@ -47,3 +47,12 @@ int ref_resampling_plan(int interpolator, int in, int in_x0, int out, int out_x0
   free(l);
   return n;
 }
+
+/* dt_iop_clip_and_zoom_roi with the ROIs as given (initialscale, iop/initialscale.c:122-129) */
+int ref_clip_and_zoom(const float *in, float *out, int in_x, int in_y, int in_w, int in_h, double in_scale, int out_x, int out_y, int out_w, int out_h,
+                      double out_scale, int interpolator)
+{
+  dt_iop_roi_t roi_in = { in_x, in_y, in_w, in_h, in_scale }, roi_out = { out_x, out_y, out_w, out_h, out_scale };
+  _interpolation_resample_plain(&dt_interpolator[interpolator], out, &roi_out, in, &roi_in);
+  return 0;
+}

@@ -99,12 +99,22 @@ int orc_resampling_plan(int interpolator, int in, int in_x0, int out, int out_x0
   return n;
 }
 
-/* process(): the origins of both ROIs are zeroed, sizes and scales kept */
+int orc_clip_and_zoom(const float *in, float *out, int in_x, int in_y, int in_w, int in_h, double in_scale, int out_x, int out_y, int out_w, int out_h,
+                      double out_scale, int interpolator);
+/* finalscale's process(): the origins of both ROIs are zeroed, sizes and scales kept */
 int orc_finalscale(const float *in, float *out, int in_w, int in_h, double in_scale, int out_w, int out_h, double out_scale, int interpolator)
+{
+  return orc_clip_and_zoom(in, out, 0, 0, in_w, in_h, in_scale, 0, 0, out_w, out_h, out_scale, interpolator);
+}
+/* dt_iop_clip_and_zoom_roi -> _interpolation_resample_plain :897-1027 with the ROIs as given (initialscale's process(),
+ * iop/initialscale.c:122-129): the ROI origins enter the tap plans, and the 1:1 path copies from (roi_out - roi_in) */
+int orc_clip_and_zoom(const float *in, float *out, int in_x, int in_y, int in_w, int in_h, double in_scale, int out_x, int out_y, int out_w, int out_h,
+                      double out_scale, int interpolator)
 {
   if(out_scale == 1.f || out_scale == in_scale)
   {
-    for(int y = 0; y < out_h; y++) memcpy(out + (size_t)4 * out_w * y, in + (size_t)4 * in_w * y, sizeof(float) * 4 * out_w);
+    for(int y = 0; y < out_h; y++)
+      memcpy(out + (size_t)4 * out_w * y, in + (size_t)4 * in_w * (y + (out_y - in_y)) + (size_t)4 * (out_x - in_x), sizeof(float) * 4 * out_w);
     return 0;
   }
   const float resample_scale = out_scale / in_scale; /* a double division, rounded to float */
@@ -113,8 +123,8 @@ int orc_finalscale(const float *in, float *out, int in_w, int in_h, double in_sc
   int *hl = malloc(sizeof(int) * out_w), *vl = malloc(sizeof(int) * out_h);
   int *hi = malloc(sizeof(int) * (size_t)per * out_w), *vi = malloc(sizeof(int) * (size_t)per * out_h);
   float *hk = malloc(sizeof(float) * (size_t)per * out_w), *vk = malloc(sizeof(float) * (size_t)per * out_h);
-  const int nh = orc_resampling_plan(interpolator, in_w, 0, out_w, 0, resample_scale, hl, hk, hi, per * out_w);
-  const int nv = orc_resampling_plan(interpolator, in_h, 0, out_h, 0, resample_scale, vl, vk, vi, per * out_h);
+  const int nh = orc_resampling_plan(interpolator, in_w, in_x, out_w, out_x, resample_scale, hl, hk, hi, per * out_w);
+  const int nv = orc_resampling_plan(interpolator, in_h, in_y, out_h, out_y, resample_scale, vl, vk, vi, per * out_h);
   int rc = (nh < 0 || nv < 0) ? 1 : 0;
   if(!rc)
   {
@@ -147,4 +157,32 @@ int orc_finalscale(const float *in, float *out, int in_w, int in_h, double in_sc
   }
   free(hl), free(vl), free(hi), free(vi), free(hk), free(vk);
   return rc;
+}
+
+/* flip: dt_imageio_flip_buffers, imageio/imageio_core.c:258-297 as iop/flip.c process() :388-400 calls it (bpp bytes per pixel,
+ * input rows of `width` pixels; orientation: 1 flip y, 2 flip x, 4 swap x and y -- the output then has rows of `height` pixels) */
+int orc_flip(const void *in, void *out, int bpp, int width, int height, int orientation)
+{
+  const char *src = in;
+  char *dst = out;
+  long ii = 0, jj = 0, si = bpp, sj = (long)width * bpp;
+  if(orientation & 4)
+  {
+    sj = bpp;
+    si = (long)height * bpp;
+  }
+  if(orientation & 1)
+  {
+    jj = height - 1;
+    sj = -sj;
+  }
+  if(orientation & 2)
+  {
+    ii = width - 1;
+    si = -si;
+  }
+  for(int j = 0; j < height; j++)
+    for(int i = 0; i < width; i++)
+      memcpy(dst + labs(sj) * jj + labs(si) * ii + sj * j + si * i, src + ((size_t)j * width + i) * bpp, bpp);
+  return 0;
 }

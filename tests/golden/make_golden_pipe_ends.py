@@ -29,6 +29,10 @@ for name in t.EXPOSURE_CASES:
     save["exposure_" + name] = pe.ref_exposure(*t.exposure_case(name))
 for name in t.CHANNELMIXER_CASES:
     save["channelmixerrgb_" + name] = pe.ref_channelmixerrgb(*t.channelmixer_case(name))
+for name in t.INITIALSCALE_CASES:
+    save["initialscale_" + name] = pe.ref_clip_and_zoom(*t.initialscale_case(name))
+for orientation in range(8):
+    save[f"flip_{orientation}"] = pe.ref_flip(util.rgba_test_image(37, 23, 3), orientation)
 for name in t.FINALSCALE_CASES:
     save["finalscale_" + name] = pe.ref_finalscale(*t.finalscale_case(name))
 img = pe.awkward_rgba(141, 67, 12)

@@ -282,3 +282,47 @@ def ref_channelmixerrgb(img, cp, kind="strict"):
     f.restype = C.c_int
     assert f(vp(src), vp(out), w, h, C.byref(cp), C.byref(cp, ab.ChannelmixerPiece.work_in.offset), C.byref(cp, ab.ChannelmixerPiece.work_out.offset)) == 0
     return np.array(out)
+
+
+# ---- initialscale (clip and zoom with ROI origins) and flip -----------------------------------------------------------------
+def _clip_and_zoom(lib, fn, img, roi_in, roi_out, interpolator):
+    """roi = (x, y, width, height, scale); img holds roi_in"""
+    src, out = util.aligned_empty(img.shape), util.aligned_empty((roi_out[3], roi_out[2], 4))
+    src[...] = img
+    out[...] = -7.0
+    f = getattr(lib, fn)
+    f.restype = C.c_int
+    f.argtypes = [VP, VP] + [C.c_int] * 4 + [C.c_double] + [C.c_int] * 4 + [C.c_double, C.c_int]
+    assert f(vp(src), vp(out), *roi_in, *roi_out, interpolator) == 0
+    return np.array(out)
+
+
+def oracle_clip_and_zoom(img, roi_in, roi_out, interpolator):
+    return _clip_and_zoom(util.oracle(), "orc_clip_and_zoom", img, roi_in, roi_out, interpolator)
+
+
+def ref_clip_and_zoom(img, roi_in, roi_out, interpolator, kind="strict"):
+    lib = util.ref(kind)
+    return None if lib is None else _clip_and_zoom(lib, "ref_clip_and_zoom", img, roi_in, roi_out, interpolator)
+
+
+def _flip(lib, fn, img, orientation, ch_arg):
+    h, w = img.shape[:2]
+    ch = img.shape[2] if img.ndim == 3 else 1
+    src = util.aligned_empty(img.shape)
+    src[...] = img
+    out = util.aligned_empty((w, h) + img.shape[2:]) if orientation & 4 else util.aligned_empty(img.shape)
+    out[...] = -7.0
+    f = getattr(lib, fn)
+    f.restype = C.c_int
+    assert f(vp(src), vp(out), ch * 4 if ch_arg == "bpp" else ch, w, h, orientation) == 0
+    return np.array(out)
+
+
+def oracle_flip(img, orientation):
+    return _flip(util.oracle(), "orc_flip", img, orientation, "bpp")
+
+
+def ref_flip(img, orientation, kind="strict"):
+    lib = util.ref(kind)
+    return None if lib is None else _flip(lib, "ref_flip", img, orientation, "bpp")

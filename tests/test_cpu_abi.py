@@ -88,6 +88,10 @@ def test_pipe_end_modules_fail_loudly_without_a_device(built):
     pc.roi_out.scale = 0.5
     out = np.full((32, 32, 4), -3.0, np.float32)
     assert L.b200_finalscale_process_host(pc, rgba.ctypes.data, out.ctypes.data) != 0 and (out == -3.0).all()
+    for op, data in (("flip", ab.FlipData(5)), ("initialscale", ab.finalscale_data())):
+        pc = ab.make_piece(64, 64, filters=0, channels=4, data=data)
+        out = np.full((64, 64, 4), -3.0, np.float32)
+        assert getattr(L, f"b200_{op}_process_host")(pc, rgba.ctypes.data, out.ctypes.data) != 0 and (out == -3.0).all(), op
     cp = ab.channelmixer_piece(util.profile_pair(util.REC2020_TO_XYZ_D50))
     pc = ab.make_piece(64, 64, filters=0, channels=4)
     pc.data, pc.data_size = C.addressof(cp), C.sizeof(cp)

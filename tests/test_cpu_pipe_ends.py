@@ -306,6 +306,36 @@ def test_channelmixerrgb_data_layout_is_the_reference_struct():
     assert [r.ref_channelmixerrgb_offsetof(i) for i in range(5)] == [P.saturation.offset, P.illuminant.offset, P.p.offset, P.adaptation.offset, P.version.offset]
 
 
+INITIALSCALE_CASES = {
+    # name: (full image w, h; roi_in (x, y, w, h, scale); roi_out (x, y, w, h, scale); interpolator): what the darkroom asks of the module
+    "zoomed_out_region": ((40, 30, 160, 110, 1.0), (12, 9, 48, 33, 0.3), ab.INTERPOLATION_MITCHELL),
+    "half_size_bicubic": ((0, 0, 151, 97, 1.0), (0, 0, 75, 48, 0.5), ab.INTERPOLATION_BICUBIC),
+    "crop_at_equal_scale": ((10, 20, 120, 90, 1.0), (25, 31, 60, 40, 1.0), ab.INTERPOLATION_MITCHELL),
+    "upscaled_region_bilinear": ((30, 20, 60, 50, 1.0), (45, 30, 80, 60, 1.5), ab.INTERPOLATION_BILINEAR),
+}
+
+
+def initialscale_case(name):
+    roi_in, roi_out, itor = INITIALSCALE_CASES[name]
+    img = util.rgba_test_image(roi_in[2], roi_in[3], 19, lo=-0.2, hi=1.5)
+    return img, roi_in, roi_out, itor
+
+
+@need_ref
+@pytest.mark.parametrize("name", list(INITIALSCALE_CASES))
+def test_initialscale_oracle_equals_reference(name):
+    args = initialscale_case(name)
+    assert same_bits(pe.oracle_clip_and_zoom(*args), pe.ref_clip_and_zoom(*args)).all()
+
+
+@need_ref
+@pytest.mark.parametrize("orientation", range(8))
+def test_flip_oracle_equals_reference(orientation):
+    for img in (util.rgba_test_image(37, 23, 3), util.frame_natural(41, 19, 3)):
+        want = pe.ref_flip(img, orientation)
+        assert same_bits(pe.oracle_flip(img, orientation), want).all() and (want != -7.0).all()
+
+
 def _golden():
     return np.load(os.path.join(util.GOLDEN_DIR, "pipe_ends.npz"))
 
@@ -326,6 +356,10 @@ def test_pipe_ends_oracle_equals_golden():
         assert same_bits(pe.oracle_finalscale(*finalscale_case(name)), g["finalscale_" + name]).all()
     for name in CHANNELMIXER_CASES:
         assert same_bits(pe.oracle_channelmixerrgb(*channelmixer_case(name)), g["channelmixerrgb_" + name]).all()
+    for name in INITIALSCALE_CASES:
+        assert same_bits(pe.oracle_clip_and_zoom(*initialscale_case(name)), g["initialscale_" + name]).all()
+    for orientation in range(8):
+        assert same_bits(pe.oracle_flip(util.rgba_test_image(37, 23, 3), orientation), g[f"flip_{orientation}"]).all()
     img = pe.awkward_rgba(141, 67, 12)
     assert (pe.oracle_gamma(img) == g["gamma"]).all()
     for fmt in (ab.EXPORT_UINT8, ab.EXPORT_UINT8_SWAP, ab.EXPORT_UINT16):

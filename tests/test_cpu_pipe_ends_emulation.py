@@ -217,3 +217,15 @@ def test_x87_operations_equal_the_host_long_double():
         subprocess.run(["g++", "-O2", "-std=c++17", "-fno-fast-math", "-ffp-contract=off", "-I", EMUL, "-o", exe, src], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "0 mismatches" in r.stdout, r.stdout[-500:]
+
+
+@pytest.mark.parametrize("name", list(cases.INITIALSCALE_CASES))
+def test_initialscale_kernels_equal_oracle(emul_resample, name):
+    args = cases.initialscale_case(name)
+    assert same_bits(pe._clip_and_zoom(emul_resample, "emul_clip_and_zoom", *args), pe.oracle_clip_and_zoom(*args)).all()
+
+
+@pytest.mark.parametrize("orientation", range(8))
+def test_flip_kernel_equals_oracle(emul_resample, orientation):
+    for img in (util.rgba_test_image(37, 23, 3), util.frame_natural(41, 19, 3), util.rgba_test_image(300, 5, 4)):
+        assert same_bits(pe._flip(emul_resample, "emul_flip", img, orientation, "ch"), pe.oracle_flip(img, orientation)).all()

@@ -348,3 +348,29 @@ def test_channelmixerrgb_adapter(built):
     assert M.dt_iop_channelmixerrgb__process(piece.module, C.byref(pipe), C.byref(piece), img.ctypes.data, out.ctypes.data) == 0
     assert same_bits(out, pe.oracle_channelmixerrgb(img, cp)).all()
     assert M.dt_iop_channelmixerrgb__process(piece.module, C.byref(ds.make_pipe(devid=0)), C.byref(piece), img.ctypes.data, out.ctypes.data) != 0
+
+
+# ---- initialscale and flip ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(cases.INITIALSCALE_CASES))
+def test_initialscale_bit_exact(built, name):
+    import ansel_b200 as ab
+    img, roi_in, roi_out, itor = cases.initialscale_case(name)
+    want = pe.oracle_clip_and_zoom(img, roi_in, roi_out, itor)
+    p = ab.make_piece(roi_in[2], roi_in[3], filters=0, channels=4, data=ab.finalscale_data(itor), out_width=roi_out[2], out_height=roi_out[3], devid=0)
+    p.roi_in.x, p.roi_in.y, p.roi_in.scale = roi_in[0], roi_in[1], roi_in[4]
+    p.roi_out.x, p.roi_out.y, p.roi_out.scale = roi_out[0], roi_out[1], roi_out[4]
+    for run in (run_dev, run_host):
+        rc, got = run("initialscale", p, img, want.shape)
+        assert rc == 0 and same_bits(got, want).all(), run.__name__
+
+
+@pytest.mark.parametrize("orientation", range(8))
+def test_flip_bit_exact(built, orientation):
+    import ansel_b200 as ab
+    for img, ch in ((util.rgba_test_image(1237, 823, 3), 4), (util.frame_natural(641, 419, 3), 1)):
+        want = pe.oracle_flip(img, orientation)
+        d = ab.FlipData(orientation)
+        p = ab.make_piece(img.shape[1], img.shape[0], filters=0, channels=ch, data=d, devid=0)
+        for run in (run_dev, run_host):
+            rc, got = run("flip", p, img, want.shape)
+            assert rc == 0 and same_bits(got, want).all(), (run.__name__, ch)
