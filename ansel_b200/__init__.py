@@ -220,6 +220,7 @@ def lib() -> C.CDLL:
             getattr(L, f"b200_{op}_tiling").restype = None
         L.b200_rawfront_process_dev.argtypes = [C.POINTER(Piece), C.POINTER(Piece), C.POINTER(Piece), C.c_void_p, C.c_void_p, C.c_void_p]
         L.b200_resampling_plan.argtypes = [C.c_int] * 5 + [C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.b200_basebuffer_upload_dev.argtypes = [C.POINTER(Piece), C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]
         L.b200_export_convert_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]
         L.b200_export_convert_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]
         L.b200_apply_conversion_dev.argtypes = [C.POINTER(Conversion), C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,

@@ -365,3 +365,23 @@ extern "C" void b200_flip_tiling(const b200_piece_t *piece, b200_tiling_t *t)
   t->yalign = 1;
 }
 #endif
+
+#ifndef B200_KERNELS_ON_CPU
+// ---- basebuffer: the crop of the sensor buffer is the upload -------------------------------------------------------------------------
+extern "C" int b200_basebuffer_upload_dev(const b200_piece_t *piece, const void *host_full, int iwidth, int iheight, size_t bpp, void *d_out, void *stream)
+{
+  if(!piece || !host_full || !d_out) return fail(B200_ERR_ARG, "basebuffer: NULL argument");
+  if(iwidth < 1 || iheight < 1 || bpp < 1 || piece->roi_out.width < 1 || piece->roi_out.height < 1) return fail(B200_ERR_ARG, "basebuffer: empty buffer or ROI");
+  int rc = bind_device(piece->devid);
+  if(rc) return rc;
+  // basebuffer.c:127-139: the crop origin clamped at 0, its size clamped to what the buffer holds from there
+  const size_t x = piece->roi_out.x > 0 ? (size_t)piece->roi_out.x : 0, y = piece->roi_out.y > 0 ? (size_t)piece->roi_out.y : 0;
+  if(x >= (size_t)iwidth || y >= (size_t)iheight) return fail(B200_ERR_ARG, "basebuffer: roi_out origin %zu,%zu outside the %dx%d buffer", x, y, iwidth, iheight);
+  const size_t in_width = (size_t)piece->roi_out.width < (size_t)iwidth - x ? (size_t)piece->roi_out.width : (size_t)iwidth - x;
+  const size_t in_height = (size_t)piece->roi_out.height < (size_t)iheight - y ? (size_t)piece->roi_out.height : (size_t)iheight - y;
+  const size_t in_stride = (size_t)iwidth * bpp, out_stride = (size_t)piece->roi_out.width * bpp;
+  B200_CUDA_TRY(cudaMemcpy2DAsync(d_out, out_stride, (const char *)host_full + y * in_stride + x * bpp, in_stride, in_width * bpp, in_height, cudaMemcpyHostToDevice,
+                                  (cudaStream_t)stream));
+  return B200_OK;
+}
+#endif

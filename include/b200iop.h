@@ -662,6 +662,14 @@ void b200_finalscale_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
 int b200_resampling_plan(int interpolator, int in, int in_x0, int out, int out_x0, float scale, int *lengths, float *kernel, int *index,
                          int max_taps);
 
+/* ---- basebuffer (src/iop/basebuffer.c): the pipe's first node, sensor buffer -> first cacheline ------------------------- */
+/* process() :119-160 copies the crop roi_out out of the full-size buffer the mipmap cache holds (host memory, pipe->iwidth x
+ * pipe->iheight samples of dsc_in.bpp bytes) into the module's output.  On the device that copy IS the upload: one strided
+ * host-to-device transfer into the device cacheline, nothing else touches the bytes.  bpp: piece->dsc_in.bpp (2 for uint16
+ * sensor data, 4 for float mosaics, 16 for float RGBA).  Rows or columns of roi_out beyond the buffer are left as found, as
+ * in the reference (:133-134). */
+int b200_basebuffer_upload_dev(const b200_piece_t *piece, const void *host_full, int iwidth, int iheight, size_t bpp, void *d_out, void *stream);
+
 /* ---- initialscale (src/iop/initialscale.c): the darkroom's first resampling ---------------------------------------- */
 /* process() :122-129 = dt_iop_clip_and_zoom_roi with both ROIs as they are: the resampler of finalscale with the ROI origins in
  * its tap plans (and, between equal scales, a crop at roi_out - roi_in).  piece->data: a b200_finalscale_data_t (the module's

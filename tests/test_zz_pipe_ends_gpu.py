@@ -374,3 +374,23 @@ def test_flip_bit_exact(built, orientation):
         for run in (run_dev, run_host):
             rc, got = run("flip", p, img, want.shape)
             assert rc == 0 and same_bits(got, want).all(), (run.__name__, ch)
+
+
+def test_basebuffer_upload_is_the_crop(built):
+    """basebuffer.c:119-160: the crop of the full sensor buffer, as one strided upload (uint16 and float RGBA)"""
+    import torch
+    import ansel_b200 as ab
+    ab.init()
+    for full, bpp in ((pe.sensor_frame(301, 200, 3), 2), (util.rgba_test_image(301, 200, 3), 16)):
+        ih, iw = full.shape[:2]
+        for (x, y, w, h) in ((0, 0, iw, ih), (17, 9, 120, 80), (250, 150, 100, 90)):      # the last one runs past the buffer
+            piece = ab.make_piece(w, h, filters=0, channels=1, devid=0)
+            piece.roi_out.x, piece.roi_out.y = x, y
+            d_out = torch.full((h, w * bpp), 0x5A, dtype=torch.uint8, device="cuda")
+            ab.check(ab.lib().b200_basebuffer_upload_dev(C.byref(piece), full.ctypes.data, iw, ih, bpp, d_out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            torch.cuda.synchronize()
+            want = np.full((h, w * bpp), 0x5A, np.uint8)
+            src = np.ascontiguousarray(full).view(np.uint8).reshape(ih, iw * bpp)
+            cw, chh = min(w, iw - x), min(h, ih - y)
+            want[:chh, :cw * bpp] = src[y:y + chh, x * bpp:(x + cw) * bpp]
+            assert (d_out.cpu().numpy() == want).all(), (bpp, x, y, w, h)
