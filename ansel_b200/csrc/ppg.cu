@@ -235,6 +235,126 @@ __global__ void __launch_bounds__(PNT) downsample_kernel(const float *__restrict
     if(samples[q] > 0) cam[q] /= (float)samples[q];
   out[(size_t)y * out_width + x] = make_float4(cam[0], cam[1], cam[2], 0.0f);
 }
+// The same method on an X-Trans sensor, demosaic.c:543-666.  A 2x2 block of the 6x6 pattern misses one or two colours; a missing
+// colour is rebuilt from the nearest same-colour photosite of each quadrant around the block centre (8x8 window, first in raster
+// order wins a tie), bilinear inside the rectangle those four span, their plain mean when the frame edge hides a quadrant.
+// The reference walks the window once and sorts sites into quadrants; a site's quadrant is a function of its position alone, so
+// four 4x4 walks in the same order find the same sites with nothing indexed at run time.  ("nearest overall", the reference's last
+// fallback, is only reached when no quadrant found anything, i.e. when it is still 0.)
+//
+// The sensor's table arrives as two 36-bit words (rows 0-2, rows 3-5, two bits a site) already rotated by roi_in's origin.
+struct xtrans_words_t
+{
+  unsigned long long lo, hi;
+};
+__device__ __forceinline__ int xw_colour(const xtrans_words_t &T, int r6, int c6)
+{
+  const unsigned long long w = r6 < 3 ? T.lo : T.hi;
+  return (int)(w >> (((r6 < 3 ? r6 : r6 - 3) * 6 + c6) * 2)) & 3;
+}
+struct quadrant_t
+{
+  float value, dist;
+  int x, y;
+  bool found;
+};
+template <int Q>
+__device__ __forceinline__ quadrant_t nearest_in_quadrant(const float *__restrict__ in, int width, int height, int px, int py, const xtrans_words_t &T, int colour)
+{
+  quadrant_t q = { 0.0f, INFINITY, 0, 0, false };
+  const float cx = px + 0.5f, cy = py + 0.5f;
+  const int xs = (Q & 1) ? px + 1 : px - 3, ys = (Q & 2) ? py + 1 : py - 3;
+  int r6 = (ys + 6) % 6;
+#pragma unroll
+  for(int j = 0; j < 4; j++)
+  {
+    const int yy = ys + j;
+    int c6 = (xs + 6) % 6;
+#pragma unroll
+    for(int i = 0; i < 4; i++)
+    {
+      const int xx = xs + i;
+      if(yy >= 0 && yy < height && xx >= 0 && xx < width && xw_colour(T, r6, c6) == colour)
+      {
+        const float dx = xx - cx, dy = yy - cy;
+        const float d2 = dx * dx + dy * dy;
+        if(d2 < q.dist)
+        {
+          q.dist = d2;
+          q.value = in[(size_t)yy * width + xx];
+          q.x = xx;
+          q.y = yy;
+          q.found = true;
+        }
+      }
+      c6 = c6 == 5 ? 0 : c6 + 1;
+    }
+    r6 = r6 == 5 ? 0 : r6 + 1;
+  }
+  return q;
+}
+__device__ float xtrans_missing_colour(const float *__restrict__ in, int width, int height, int px, int py, const xtrans_words_t &T, int colour)
+{
+  const quadrant_t q0 = nearest_in_quadrant<0>(in, width, height, px, py, T, colour), q1 = nearest_in_quadrant<1>(in, width, height, px, py, T, colour),
+                   q2 = nearest_in_quadrant<2>(in, width, height, px, py, T, colour), q3 = nearest_in_quadrant<3>(in, width, height, px, py, T, colour);
+  if(q0.found && q1.found && q2.found && q3.found)
+  {
+    const float cx = px + 0.5f, cy = py + 0.5f;
+    const float x_left = 0.5f * (q0.x + q2.x), x_right = 0.5f * (q1.x + q3.x), y_top = 0.5f * (q0.y + q1.y), y_bottom = 0.5f * (q2.y + q3.y);
+    const float tx = fminf(fmaxf((cx - x_left) / fmaxf(x_right - x_left, 1e-6f), 0.0f), 1.0f);
+    const float ty = fminf(fmaxf((cy - y_top) / fmaxf(y_bottom - y_top, 1e-6f), 0.0f), 1.0f);
+    const float top = q0.value + tx * (q1.value - q0.value);
+    const float bottom = q2.value + tx * (q3.value - q2.value);
+    return top + ty * (bottom - top);
+  }
+  float sum = 0.0f;
+  int count = 0;
+  if(q0.found) sum += q0.value, count++;
+  if(q1.found) sum += q1.value, count++;
+  if(q2.found) sum += q2.value, count++;
+  if(q3.found) sum += q3.value, count++;
+  return count > 0 ? sum / (float)count : 0.0f;
+}
+__global__ void __launch_bounds__(PNT) downsample_xtrans_kernel(const float *__restrict__ in, float4 *__restrict__ out, int width, int height, int out_width,
+                                                                xtrans_words_t T)
+{
+  const int x = blockIdx.x * PNT + threadIdx.x, y = blockIdx.y;
+  if(x >= out_width) return;
+  const int px = min(2 * x, width - 1), py = min(2 * y, height - 1);
+  float rgb[3] = { 0.f, 0.f, 0.f };
+  int samples[3] = { 0, 0, 0 };
+#pragma unroll
+  for(int j = 0; j < 2; j++)
+#pragma unroll
+    for(int i = 0; i < 2; i++)
+    {
+      const int xx = min(px + i, width - 1), yy = min(py + j, height - 1);
+      const int c = xw_colour(T, yy % 6, xx % 6);
+      const float v = in[(size_t)yy * width + xx];
+#pragma unroll
+      for(int q = 0; q < 3; q++)
+        if(q == c)
+        {
+          rgb[q] += v;
+          samples[q]++;
+        }
+    }
+#pragma unroll
+  for(int q = 0; q < 3; q++) rgb[q] = samples[q] > 0 ? rgb[q] / (float)samples[q] : xtrans_missing_colour(in, width, height, px, py, T, q);
+  out[(size_t)y * out_width + x] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
+}
+// the table FCxtrans() sees through roi_in (develop/imageop_math.h:216-219), packed for xw_colour()
+inline xtrans_words_t pack_xtrans(const unsigned char *xtrans36, int x0, int y0)
+{
+  xtrans_words_t T = { 0ull, 0ull };
+  for(int r = 0; r < 6; r++)
+    for(int c = 0; c < 6; c++)
+    {
+      const unsigned long long v = xtrans36[((r + y0 + 600) % 6) * 6 + (c + x0 + 600) % 6] & 3u;
+      (r < 3 ? T.lo : T.hi) |= v << (((r % 3) * 6 + c) * 2);
+    }
+  return T;
+}
 } // namespace
 
 #ifndef B200_KERNELS_ON_CPU
@@ -246,6 +366,16 @@ int downsample_demosaic_dev(const float *d_in, float *d_out, int width, int heig
   const int ow = (width + 1) / 2, oh = (height + 1) / 2;
   if(oh > 65535) return fail(B200_ERR_ARG, "demosaic: frame height %d", height);
   downsample_kernel<<<dim3((unsigned)((ow + PNT - 1) / PNT), (unsigned)oh), PNT, 0, s>>>(d_in, (float4 *)d_out, width, height, ow, filters);
+  B200_CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+// demosaic.c:1103-1104 for an X-Trans sensor: (x0, y0) = roi_in's origin, xtrans = piece->dsc_in.xtrans
+int downsample_xtrans_demosaic_dev(const float *d_in, float *d_out, int width, int height, int x0, int y0, const uint8_t xtrans[6][6], cudaStream_t s)
+{
+  const int ow = (width + 1) / 2, oh = (height + 1) / 2;
+  if(oh > 65535) return fail(B200_ERR_ARG, "demosaic: frame height %d", height);
+  downsample_xtrans_kernel<<<dim3((unsigned)((ow + PNT - 1) / PNT), (unsigned)oh), PNT, 0, s>>>(d_in, (float4 *)d_out, width, height, ow,
+                                                                                              pack_xtrans(&xtrans[0][0], x0, y0));
   B200_CUDA_TRY(cudaGetLastError());
   return B200_OK;
 }

@@ -3,7 +3,7 @@
  * iop/demosaic/ppg.c and basic.c are fragments that demosaic.c #includes; oracle/Makefile cuts verbatim into
  * oracle/_ref/gen_demosaic_ppg.c:  basic.c :129-186 (SWAP, pre_median_b, pre_median),  ppg.c :21-211 (demosaic_ppg).
  * iop/demosaic/passthrough.c :21-87 (passthrough_monochrome, passthrough_color) and iop/demosaic.c :480-532
- * (_downsample_bayer_half_size) ride along.
+ * (_downsample_bayer_half_size) and :543-666 (_downsample_xtrans_missing_colour, _downsample_xtrans_half_size) ride along.
  * demosaic.c:1218-1226 calls it with roi_out's origin zeroed and the ROI-shifted filters word.
  */
 #include "ref_piece.h"
@@ -43,5 +43,13 @@ int ref_demosaic_downsample(float *out, const float *in, int width, int height, 
   const dt_iop_roi_t roi_in = { 0, 0, width, height, 1.0 }, roi_out = { 0, 0, (width + 1) / 2, (height + 1) / 2, 1.0 };
   const double cam_to_rgb[3][4] = { { 0 } };
   _downsample_bayer_half_size(out, in, &roi_out, &roi_in, filters, 0, cam_to_rgb);
+  return 0;
+}
+
+/* demosaic.c:1103-1104 for an X-Trans sensor, post-filter off: roi_in keeps the ROI origin (FCxtrans adds it), xtrans = dsc_in.xtrans */
+int ref_demosaic_downsample_xtrans(float *out, const float *in, int width, int height, int x, int y, const uint8_t xtrans[36])
+{
+  const dt_iop_roi_t roi_in = { x, y, width, height, 1.0 }, roi_out = { 0, 0, (width + 1) / 2, (height + 1) / 2, 1.0 };
+  _downsample_xtrans_half_size(out, in, &roi_out, &roi_in, (const uint8_t(*)[6])xtrans);
   return 0;
 }

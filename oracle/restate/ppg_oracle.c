@@ -193,3 +193,70 @@ int orc_demosaic_downsample(float *out, const float *in, int width, int height, 
     }
   return 0;
 }
+
+/* demosaic.c:543-615: a colour the 2x2 block does not sample.  The nearest same-colour photosite of each quadrant around the
+ * block centre, searched over x in [px-3, px+4], y in [py-3, py+4] clamped into the frame (first found wins ties, raster order);
+ * four quadrants -> bilinear inside the rectangle of their mean coordinates; fewer -> the mean of those found; none -> the
+ * nearest sample overall (0 when there is none) */
+static inline int xt_colour(int row, int col, int x0, int y0, const uint8_t *xtrans) { return xtrans[((row + y0 + 600) % 6) * 6 + (col + x0 + 600) % 6]; }
+static float xt_missing(const float *in, int width, int height, int x0, int y0, int px, int py, const uint8_t *xtrans, int colour)
+{
+  const float cx = px + 0.5f, cy = py + 0.5f;
+  const int xmin = px - 3 > 0 ? px - 3 : 0, xmax = px + 4 < width - 1 ? px + 4 : width - 1;
+  const int ymin = py - 3 > 0 ? py - 3 : 0, ymax = py + 4 < height - 1 ? py + 4 : height - 1;
+  float qv[4] = { 0.0f }, qd[4] = { INFINITY, INFINITY, INFINITY, INFINITY }, nearest = 0.0f, nearest_d = INFINITY;
+  int qx[4] = { 0 }, qy[4] = { 0 }, found[4] = { 0 };
+  for(int yy = ymin; yy <= ymax; yy++)
+    for(int xx = xmin; xx <= xmax; xx++)
+    {
+      if(xt_colour(yy, xx, x0, y0, xtrans) != colour) continue;
+      const float dx = xx - cx, dy = yy - cy;
+      const float d2 = dx * dx + dy * dy;
+      const float v = in[(size_t)yy * width + xx];
+      if(d2 < nearest_d) nearest_d = d2, nearest = v;
+      const int q = (yy > cy ? 2 : 0) + (xx > cx ? 1 : 0);
+      if(d2 < qd[q]) qd[q] = d2, qv[q] = v, qx[q] = xx, qy[q] = yy, found[q] = 1;
+    }
+  if(found[0] && found[1] && found[2] && found[3])
+  {
+    const float xl = 0.5f * (qx[0] + qx[2]), xr = 0.5f * (qx[1] + qx[3]), yt = 0.5f * (qy[0] + qy[1]), yb = 0.5f * (qy[2] + qy[3]);
+    const float wx = xr - xl > 1e-6f ? xr - xl : 1e-6f, wy = yb - yt > 1e-6f ? yb - yt : 1e-6f;
+    float tx = (cx - xl) / wx, ty = (cy - yt) / wy;
+    tx = tx < 0.0f ? 0.0f : (tx > 1.0f ? 1.0f : tx); /* CLAMP = MIN(MAX(x, lo), hi) on finite values */
+    ty = ty < 0.0f ? 0.0f : (ty > 1.0f ? 1.0f : ty);
+    const float top = qv[0] + tx * (qv[1] - qv[0]);
+    const float bottom = qv[2] + tx * (qv[3] - qv[2]);
+    return top + ty * (bottom - top);
+  }
+  float sum = 0.0f;
+  int count = 0;
+  for(int q = 0; q < 4; q++)
+    if(found[q]) sum += qv[q], count++;
+  return count > 0 ? sum / (float)count : nearest;
+}
+
+/* the half-size method on an X-Trans sensor, demosaic.c:624-666: the colours sampled in the 2x2 block are their means, the others
+ * come from xt_missing(); alpha 0.  (x0, y0) = roi_in's origin on the sensor. */
+int orc_demosaic_downsample_xtrans(float *out, const float *in, int width, int height, int x0, int y0, const uint8_t xtrans[36])
+{
+  const int ow = (width + 1) / 2, oh = (height + 1) / 2;
+  for(int y = 0; y < oh; y++)
+    for(int x = 0; x < ow; x++)
+    {
+      float rgb[3] = { 0.0f };
+      int samples[3] = { 0 };
+      const int px = 2 * x < width - 1 ? 2 * x : width - 1, py = 2 * y < height - 1 ? 2 * y : height - 1;
+      for(int j = 0; j < 2; j++)
+        for(int i = 0; i < 2; i++)
+        {
+          const int xx = px + i < width - 1 ? px + i : width - 1, yy = py + j < height - 1 ? py + j : height - 1;
+          const int c = xt_colour(yy, xx, x0, y0, xtrans);
+          rgb[c] += in[(size_t)yy * width + xx];
+          samples[c]++;
+        }
+      float *o = out + 4 * ((size_t)y * ow + x);
+      for(int c = 0; c < 3; c++) o[c] = samples[c] > 0 ? rgb[c] / (float)samples[c] : xt_missing(in, width, height, x0, y0, px, py, xtrans, c);
+      o[3] = 0.0f;
+    }
+  return 0;
+}

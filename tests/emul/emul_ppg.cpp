@@ -33,3 +33,10 @@ extern "C" int emul_demosaic_downsample(float *out, const float *in, int width, 
   emulate(dim3((unsigned)((ow + PNT - 1) / PNT), (unsigned)oh), PNT, downsample_kernel, in, (float4 *)out, width, height, ow, filters);
   return 0;
 }
+
+extern "C" int emul_demosaic_downsample_xtrans(float *out, const float *in, int width, int height, int x, int y, const unsigned char *xtrans36)
+{
+  const int ow = (width + 1) / 2, oh = (height + 1) / 2;
+  emulate(dim3((unsigned)((ow + PNT - 1) / PNT), (unsigned)oh), PNT, downsample_xtrans_kernel, in, (float4 *)out, width, height, ow, pack_xtrans(xtrans36, x, y));
+  return 0;
+}

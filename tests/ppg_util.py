@@ -115,3 +115,29 @@ def ref_downsample(m, filters, kind="strict"):
 
 def emul_downsample(m, filters):
     return _downsample(emul_lib(), "emul_demosaic_downsample", m, filters)
+
+
+def _downsample_xtrans(lib, fn, mosaic, x, y, xtrans):
+    h, w = mosaic.shape
+    out, src = util.aligned_empty(((h + 1) // 2, (w + 1) // 2, 4)), util.aligned_empty(mosaic.shape)
+    out[...] = ALPHA_FILL
+    src[...] = mosaic
+    xt = np.ascontiguousarray(xtrans, np.uint8)
+    f = getattr(lib, fn)
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    assert f(out.ctypes.data, src.ctypes.data, w, h, x, y, xt.ctypes.data) == 0
+    return np.array(out)
+
+
+def oracle_downsample_xtrans(m, x, y, xtrans):
+    return _downsample_xtrans(util.oracle(), "orc_demosaic_downsample_xtrans", m, x, y, xtrans)
+
+
+def ref_downsample_xtrans(m, x, y, xtrans, kind="strict"):
+    lib = util.ref(kind)
+    return None if lib is None else _downsample_xtrans(lib, "ref_demosaic_downsample_xtrans", m, x, y, xtrans)
+
+
+def emul_downsample_xtrans(m, x, y, xtrans):
+    return _downsample_xtrans(emul_lib(), "emul_demosaic_downsample_xtrans", m, x, y, xtrans)

@@ -92,3 +92,36 @@ def test_downsample_oracle_reference_and_kernel(pattern):
         if util.ref("strict") is not None:
             assert same_bits(want, pu.ref_downsample(m, f)).all()
         assert same_bits(pu.emul_downsample(m, f), want).all()
+
+
+@pytest.mark.parametrize("case", ["origin", "roi", "roi2", "small", "sliver", "column"])
+def test_downsample_xtrans_oracle_reference_and_kernel(case):
+    """the half-size method on an X-Trans sensor (demosaic.c:543-666): missing colours from the quadrant search, ROI origins that
+    rotate the pattern, odd sizes, NaN and flat patches, and frames so thin that quadrants are hidden by the edge"""
+    import vng_util as vu
+    if case in vu.XTRANS_CASES:
+        m, x, y = vu.xtrans_case(case)
+    else:
+        w, h, x, y = {"sliver": (41, 2, 2, 3), "column": (1, 9, 4, 1)}[case]
+        m = util.frame_natural(w, h, 8)
+    want = pu.oracle_downsample_xtrans(m, x, y, vu.XTRANS)
+    assert want.shape == ((m.shape[0] + 1) // 2, (m.shape[1] + 1) // 2, 4) and (want[..., 3] == 0).all()
+    if util.ref("strict") is not None:
+        assert same_bits(want, pu.ref_downsample_xtrans(m, x, y, vu.XTRANS)).all()
+    assert same_bits(pu.emul_downsample_xtrans(m, x, y, vu.XTRANS), want).all()
+
+
+def test_downsample_xtrans_random_tables():
+    """any 6x6 table with values 0..2 (not only Fuji's): a colour absent from the whole window resolves to 0"""
+    import vng_util as vu
+    rng = np.random.default_rng(77)
+    for k in range(12):
+        xt = rng.integers(0, 3, (6, 6)).astype(np.uint8)
+        if k == 0:
+            xt[...] = 1
+        w, h, x, y = int(rng.integers(1, 40)), int(rng.integers(1, 40)), int(rng.integers(0, 12)), int(rng.integers(0, 12))
+        m = util.frame_natural(w, h, 20 + k)
+        want = pu.oracle_downsample_xtrans(m, x, y, xt)
+        if util.ref("strict") is not None:
+            assert same_bits(want, pu.ref_downsample_xtrans(m, x, y, xt)).all(), k
+        assert same_bits(pu.emul_downsample_xtrans(m, x, y, xt), want).all(), k

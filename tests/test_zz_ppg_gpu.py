@@ -119,3 +119,24 @@ def test_downsample_method_bit_exact(built):
             assert same_bits(d_out.cpu().numpy(), pu.oracle_downsample(m, f)).all(), (pat, w, h)
     d.color_smoothing = 1
     assert ab.lib().b200_demosaic_process_dev(C.byref(piece), d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream) == ab.B200_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("name", ["origin", "roi", "small"])
+def test_downsample_xtrans_bit_exact(built, name):
+    """method 7 on an X-Trans sensor, demosaic.c:543-666, through the module (roi_in's origin rotates the pattern)"""
+    import torch
+    import ansel_b200 as ab
+    import vng_util as vu
+    ab.init()
+    m, x, y = vu.xtrans_case(name)
+    h, w = m.shape
+    d = ab.demosaic_data(7)
+    piece = ab.make_piece(w, h, filters=9, data=d, devid=0, roi_x=x, roi_y=y, out_width=(w + 1) // 2, out_height=(h + 1) // 2)
+    for i in range(6):
+        for j in range(6):
+            piece.xtrans[i][j] = int(vu.XTRANS[i][j])
+    d_in = torch.from_numpy(np.ascontiguousarray(m)).cuda()
+    d_out = torch.full(((h + 1) // 2, (w + 1) // 2, 4), -7.0, device="cuda")
+    ab.check(ab.lib().b200_demosaic_process_dev(C.byref(piece), d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert same_bits(d_out.cpu().numpy(), pu.oracle_downsample_xtrans(m, x, y, vu.XTRANS)).all()
