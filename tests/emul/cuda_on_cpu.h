@@ -89,12 +89,13 @@ template <typename K, typename... A> static void emulate(dim3 grid, unsigned thr
   _mm_setcsr(_mm_getcsr() | 0x8040u);
   blockDim = dim3(threads);
   gridDim = grid;
-  for(unsigned by = 0; by < grid.y; by++)
-    for(unsigned bx = 0; bx < grid.x; bx++)
-      for(unsigned t = 0; t < threads; t++)
-      {
-        blockIdx = dim3(bx, by);
-        threadIdx = dim3(t);
-        kernel(args...);
-      }
+  for(unsigned bz = 0; bz < grid.z; bz++)
+    for(unsigned by = 0; by < grid.y; by++)
+      for(unsigned bx = 0; bx < grid.x; bx++)
+        for(unsigned t = 0; t < threads; t++)
+        {
+          blockIdx = dim3(bx, by, bz);
+          threadIdx = dim3(t);
+          kernel(args...);
+        }
 }

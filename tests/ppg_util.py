@@ -51,9 +51,9 @@ def ref_ppg(mosaic, filters, thrs=0.0, kind="strict"):
     return None if lib is None else _run(lib, "ref_demosaic_ppg", mosaic, filters, thrs)
 
 
-def emul_lib():
-    so = os.path.join(EMUL, "libemul_ppg.so")
-    srcs = [os.path.join(EMUL, "emul_ppg.cpp"), os.path.join(EMUL, "cuda_on_cpu.h"), os.path.join(util.ROOT, "ansel_b200", "csrc", "ppg.cu")]
+def emul_lib(name="ppg"):
+    so = os.path.join(EMUL, "libemul_%s.so" % name)
+    srcs = [os.path.join(EMUL, "emul_%s.cpp" % name), os.path.join(EMUL, "cuda_on_cpu.h"), os.path.join(util.ROOT, "ansel_b200", "csrc", "%s.cu" % name)]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.run(["g++", "-O1", "-std=c++17", "-fno-fast-math", "-ffp-contract=off", "-I", EMUL, "-shared", "-fPIC", "-o", so, srcs[0]], check=True)
     return C.CDLL(so)
@@ -141,3 +141,28 @@ def ref_downsample_xtrans(m, x, y, xtrans, kind="strict"):
 
 def emul_downsample_xtrans(m, x, y, xtrans):
     return _downsample_xtrans(emul_lib(), "emul_demosaic_downsample_xtrans", m, x, y, xtrans)
+
+
+def _postfilter(lib, fn, rgba, iterations):
+    h, w = rgba.shape[:2]
+    buf = util.aligned_empty((h, w, 4))
+    buf[...] = rgba
+    f = getattr(lib, fn)
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    util.oracle().orc_fp_fast_mode_all()  # FTZ|DAZ on every worker thread, as the pipe's have it
+    assert f(buf.ctypes.data, w, h, iterations) == 0
+    return np.array(buf)
+
+
+def oracle_postfilter(rgba, iterations):
+    return _postfilter(util.oracle(), "orc_demosaic_downsample_postfilter", rgba, iterations)
+
+
+def ref_postfilter(rgba, iterations, kind="strict"):
+    lib = util.ref(kind)
+    return None if lib is None else _postfilter(lib, "ref_demosaic_downsample_postfilter", rgba, iterations)
+
+
+def emul_postfilter(rgba, iterations):
+    return _postfilter(emul_lib("demosaic_postfilter"), "emul_demosaic_downsample_postfilter", rgba, iterations)

@@ -125,3 +125,22 @@ def test_downsample_xtrans_random_tables():
         if util.ref("strict") is not None:
             assert same_bits(want, pu.ref_downsample_xtrans(m, x, y, xt)).all(), k
         assert same_bits(pu.emul_downsample_xtrans(m, x, y, xt), want).all(), k
+
+
+@pytest.mark.parametrize("size,iterations", [((64, 48), 1), ((33, 21), 3), ((5, 4), 2), ((1, 1), 1), ((2, 7), 1), ((300, 3), 2)])
+def test_downsample_postfilter_oracle_reference_and_kernels(size, iterations):
+    """the guided-Laplacian post-filter of the half-size method (demosaic.c:681-926) on half-size frames with NaN, inf, zero
+    and flat patches; one to three iterations; frames thinner than the 5x5 patch"""
+    w, h = size
+    f = util.BAYER["RGGB"]
+    half = pu.oracle_downsample(util.frame_natural(2 * w, 2 * h, 11 + w, filters=f), f)
+    if w >= 40 and h >= 40:
+        half[5, 5, 0] = np.nan
+        half[10:14, 10:14, :3] = 0.25
+        half[20, 20, :3] = 0
+        half[30, 30, 1] = np.inf
+    want = pu.oracle_postfilter(half, iterations)
+    assert (want[..., 3] == 0).all() and not same_bits(want, half).all() or w == 1
+    if util.ref("strict") is not None:
+        assert same_bits(want, pu.ref_postfilter(half, iterations)).all()
+    assert same_bits(pu.emul_postfilter(half, iterations), want).all()

@@ -103,7 +103,7 @@ def test_passthrough_methods_bit_exact(built, filters, x, y):
 
 
 def test_downsample_method_bit_exact(built):
-    """method 7 (half-size), demosaic.c:480-532, even and odd frame sizes; its post-filter is refused"""
+    """method 7 (half-size), demosaic.c:480-532, even and odd frame sizes"""
     import torch
     import ansel_b200 as ab
     ab.init()
@@ -117,8 +117,28 @@ def test_downsample_method_bit_exact(built):
             ab.check(ab.lib().b200_demosaic_process_dev(C.byref(piece), d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream))
             torch.cuda.synchronize()
             assert same_bits(d_out.cpu().numpy(), pu.oracle_downsample(m, f)).all(), (pat, w, h)
-    d.color_smoothing = 1
-    assert ab.lib().b200_demosaic_process_dev(C.byref(piece), d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream) == ab.B200_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("iterations", [1, 3])
+def test_downsample_postfilter_bit_exact(built, iterations):
+    """method 7 with data->color_smoothing iterations of the guided-Laplacian post-filter (demosaic.c:681-926, :1108)"""
+    import torch
+    import ansel_b200 as ab
+    ab.init()
+    f = util.BAYER["GRBG"]
+    w, h = 1301, 902
+    m = util.frame_natural(w, h, 9, filters=f)
+    m[100:140, 100:140] = 0.25
+    m[300, 300] = np.nan
+    d = ab.demosaic_data(7)
+    d.color_smoothing = iterations
+    piece = ab.make_piece(w, h, filters=f, data=d, devid=0, out_width=(w + 1) // 2, out_height=(h + 1) // 2)
+    d_in = torch.from_numpy(m).cuda()
+    d_out = torch.full(((h + 1) // 2, (w + 1) // 2, 4), -7.0, device="cuda")
+    ab.check(ab.lib().b200_demosaic_process_dev(C.byref(piece), d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    want = pu.oracle_postfilter(pu.oracle_downsample(m, f), iterations)
+    assert same_bits(d_out.cpu().numpy(), want).all()
 
 
 @pytest.mark.parametrize("name", ["origin", "roi", "small"])
