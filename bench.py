@@ -304,6 +304,18 @@ def pipe_ends_extras(ab, ds, util, L, M, torch, w, h, local, dev, stream, conv_i
         dd.median_thrs, dd.dual_thrs = 0.02, 0.2
         p_d = piece(dd, 1)
         report(label, lambda: ab.check(L.b200_demosaic_process_dev(p_d, t_m[0].data_ptr(), t_dem.data_ptr(), stream)), 20, reps=3)
+    # the half-size method (algorithmic bytes per INPUT pixel: 4 in + 16 / 4 out), its post-filter, and the X-Trans variant
+    hw, hh = (w + 1) // 2, (h + 1) // 2
+    for label, smoothing, xtrans in (("demosaic_downsample", 0, False), ("demosaic_downsample_postfilter1", 1, False), ("demosaic_downsample_xtrans", 0, True)):
+        dd = ab.demosaic_data(7)
+        dd.color_smoothing = smoothing
+        p_d = piece(dd, 1, out=(hw, hh))
+        if xtrans:
+            p_d.filters = 9
+            for i, rowv in enumerate(((1, 1, 0, 1, 1, 2), (1, 1, 2, 1, 1, 0), (2, 0, 1, 0, 2, 1), (1, 1, 2, 1, 1, 0), (1, 1, 0, 1, 1, 2), (0, 2, 1, 2, 0, 1))):
+                for j, v in enumerate(rowv):
+                    p_d.xtrans[i][j] = v
+        report(label, lambda: ab.check(L.b200_demosaic_process_dev(p_d, t_m[0].data_ptr(), t_dem.data_ptr(), stream)), 8, reps=3)
     cp = ab.channelmixer_piece(util.profile_pair(util.REC2020_TO_XYZ_D50), illuminant=(0.93, 1.02, 0.71))
     p_cm = piece(None, 4)
     p_cm.data, p_cm.data_size = C.addressof(cp), C.sizeof(cp)
