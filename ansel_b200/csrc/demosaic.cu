@@ -16,6 +16,7 @@ int passthrough_demosaic_dev(const float *d_in, float *d_out, int width, int hei
                              cudaStream_t s);
 int downsample_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters, cudaStream_t s);
 int demosaic_postfilter_dev(float *d_rgba, int width, int height, int iterations, cudaStream_t s);
+int downsample4_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters, const double cam_to_rgb[3][4], cudaStream_t s);
 int downsample_xtrans_demosaic_dev(const float *d_in, float *d_out, int width, int height, int x0, int y0, const uint8_t xtrans[6][6], cudaStream_t s);
 int ppg_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters, float median_thrs, cudaStream_t s);
 int demosaic_green_eq_dev(const float *d_in, float *d_tmp0, float *d_tmp1, double *d_partial, int width, int height, uint32_t dsc_filters, int x, int y,
@@ -69,13 +70,14 @@ extern "C" int b200_demosaic_process_dev(const b200_piece_t *piece, const void *
   if(d->demosaicing_method == 7u)
   { // DT_IOP_DEMOSAIC_DOWNSAMPLE, demosaic.c:1101-1108: half-size output (modify_roi_out :940-952), then the guided-Laplacian
     // post-filter when data->color_smoothing asks for iterations of it
-    if(filters != 9u && (piece->image_flags & DT_IMAGE_4BAYER)) return fail(B200_ERR_UNSUPPORTED, "demosaic: downsample is not built for four-colour Bayer sensors");
     if(piece->roi_out.width != (piece->roi_in.width + 1) / 2 || piece->roi_out.height != (piece->roi_in.height + 1) / 2)
       return fail(B200_ERR_ARG, "demosaic: downsample wants roi_out = (roi_in + 1) / 2, got %dx%d for %dx%d", piece->roi_out.width, piece->roi_out.height,
                   piece->roi_in.width, piece->roi_in.height);
     if(filters == 9u)
       rc = downsample_xtrans_demosaic_dev((const float *)d_in, (float *)d_out, piece->roi_in.width, piece->roi_in.height, piece->roi_in.x, piece->roi_in.y,
                                           piece->xtrans, (cudaStream_t)stream);
+    else if(piece->image_flags & DT_IMAGE_4BAYER)
+      rc = downsample4_demosaic_dev((const float *)d_in, (float *)d_out, piece->roi_in.width, piece->roi_in.height, filters, d->CAM_to_RGB, (cudaStream_t)stream);
     else
       rc = downsample_demosaic_dev((const float *)d_in, (float *)d_out, piece->roi_in.width, piece->roi_in.height, filters, (cudaStream_t)stream);
     if(rc) return rc;

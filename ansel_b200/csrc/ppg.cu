@@ -235,6 +235,50 @@ __global__ void __launch_bounds__(PNT) downsample_kernel(const float *__restrict
     if(samples[q] > 0) cam[q] /= (float)samples[q];
   out[(size_t)y * out_width + x] = make_float4(cam[0], cam[1], cam[2], 0.0f);
 }
+// the same for a four-colour Bayer sensor (demosaic.c:514-521): four camera primaries, then R, G, B = CAM_to_RGB rows times them,
+// products and sums in double, the running value rounded to float after every term as the reference's float accumulator is
+struct cam_to_rgb_t
+{
+  double m[12];
+};
+__global__ void __launch_bounds__(PNT) downsample4_kernel(const float *__restrict__ in, float4 *__restrict__ out, int width, int height, int out_width, unsigned filters,
+                                                          cam_to_rgb_t M)
+{
+  const int x = blockIdx.x * PNT + threadIdx.x, y = blockIdx.y;
+  if(x >= out_width) return;
+  const int px = min(2 * x, width - 1), py = min(2 * y, height - 1);
+  float cam[4] = { 0.f, 0.f, 0.f, 0.f };
+  int samples[4] = { 0, 0, 0, 0 };
+#pragma unroll
+  for(int j = 0; j < 2; j++)
+#pragma unroll
+    for(int i = 0; i < 2; i++)
+    {
+      const int xx = min(px + i, width - 1), yy = min(py + j, height - 1);
+      const int c = ppg_fc(yy, xx, filters);
+      const float v = in[(size_t)yy * width + xx];
+#pragma unroll
+      for(int q = 0; q < 4; q++)
+        if(q == c)
+        {
+          cam[q] += v;
+          samples[q]++;
+        }
+    }
+#pragma unroll
+  for(int q = 0; q < 4; q++)
+    if(samples[q] > 0) cam[q] /= (float)samples[q];
+  float rgb[3];
+#pragma unroll
+  for(int c = 0; c < 3; c++)
+  {
+    float acc = 0.0f;
+#pragma unroll
+    for(int k = 0; k < 4; k++) acc = (float)((double)acc + M.m[4 * c + k] * (double)cam[k]);
+    rgb[c] = acc;
+  }
+  out[(size_t)y * out_width + x] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
+}
 // The same method on an X-Trans sensor, demosaic.c:543-666.  A 2x2 block of the 6x6 pattern misses one or two colours; a missing
 // colour is rebuilt from the nearest same-colour photosite of each quadrant around the block centre (8x8 window, first in raster
 // order wins a tie), bilinear inside the rectangle those four span, their plain mean when the frame edge hides a quadrant.
@@ -366,6 +410,17 @@ int downsample_demosaic_dev(const float *d_in, float *d_out, int width, int heig
   const int ow = (width + 1) / 2, oh = (height + 1) / 2;
   if(oh > 65535) return fail(B200_ERR_ARG, "demosaic: frame height %d", height);
   downsample_kernel<<<dim3((unsigned)((ow + PNT - 1) / PNT), (unsigned)oh), PNT, 0, s>>>(d_in, (float4 *)d_out, width, height, ow, filters);
+  B200_CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+// demosaic.c:1106-1107 for a four-colour Bayer sensor; cam_to_rgb = data->CAM_to_RGB
+int downsample4_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters, const double cam_to_rgb[3][4], cudaStream_t s)
+{
+  const int ow = (width + 1) / 2, oh = (height + 1) / 2;
+  if(oh > 65535) return fail(B200_ERR_ARG, "demosaic: frame height %d", height);
+  cam_to_rgb_t M;
+  for(int k = 0; k < 12; k++) M.m[k] = cam_to_rgb[k / 4][k % 4];
+  downsample4_kernel<<<dim3((unsigned)((ow + PNT - 1) / PNT), (unsigned)oh), PNT, 0, s>>>(d_in, (float4 *)d_out, width, height, ow, filters, M);
   B200_CUDA_TRY(cudaGetLastError());
   return B200_OK;
 }

@@ -53,3 +53,11 @@ int ref_demosaic_downsample_xtrans(float *out, const float *in, int width, int h
   _downsample_xtrans_half_size(out, in, &roi_out, &roi_in, (const uint8_t(*)[6])xtrans);
   return 0;
 }
+
+/* the same for a four-colour Bayer sensor (img->flags & DT_IMAGE_4BAYER): the camera primaries go through data->CAM_to_RGB */
+int ref_demosaic_downsample4(float *out, const float *in, int width, int height, uint32_t filters, const double cam_to_rgb[12])
+{
+  const dt_iop_roi_t roi_in = { 0, 0, width, height, 1.0 }, roi_out = { 0, 0, (width + 1) / 2, (height + 1) / 2, 1.0 };
+  _downsample_bayer_half_size(out, in, &roi_out, &roi_in, filters, 1, (const double(*)[4])cam_to_rgb);
+  return 0;
+}

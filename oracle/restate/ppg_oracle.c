@@ -260,3 +260,36 @@ int orc_demosaic_downsample_xtrans(float *out, const float *in, int width, int h
     }
   return 0;
 }
+
+/* demosaic.c:514-521, four-colour Bayer sensors: each of R, G, B starts at 0.0f and takes CAM_to_RGB[c][k] * cam[k] for k = 0..3,
+ * every product and sum in double, the running value rounded to float after each term */
+int orc_demosaic_downsample4(float *out, const float *in, int width, int height, uint32_t filters, const double cam_to_rgb[12])
+{
+  const int ow = (width + 1) / 2, oh = (height + 1) / 2;
+  for(int y = 0; y < oh; y++)
+    for(int x = 0; x < ow; x++)
+    {
+      float cam[4] = { 0.0f };
+      int samples[4] = { 0 };
+      const int px = 2 * x < width - 1 ? 2 * x : width - 1, py = 2 * y < height - 1 ? 2 * y : height - 1;
+      for(int j = 0; j < 2; j++)
+        for(int i = 0; i < 2; i++)
+        {
+          const int xx = px + i < width - 1 ? px + i : width - 1, yy = py + j < height - 1 ? py + j : height - 1;
+          const int c = orc_fc(yy, xx, filters);
+          cam[c] += in[(size_t)yy * width + xx];
+          samples[c]++;
+        }
+      for(int c = 0; c < 4; c++)
+        if(samples[c] > 0) cam[c] /= (float)samples[c];
+      float *o = out + 4 * ((size_t)y * ow + x);
+      for(int c = 0; c < 3; c++)
+      {
+        float acc = 0.0f;
+        for(int k = 0; k < 4; k++) acc = (float)((double)acc + cam_to_rgb[4 * c + k] * (double)cam[k]);
+        o[c] = acc;
+      }
+      o[3] = 0.0f;
+    }
+  return 0;
+}

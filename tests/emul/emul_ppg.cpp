@@ -40,3 +40,12 @@ extern "C" int emul_demosaic_downsample_xtrans(float *out, const float *in, int 
   emulate(dim3((unsigned)((ow + PNT - 1) / PNT), (unsigned)oh), PNT, downsample_xtrans_kernel, in, (float4 *)out, width, height, ow, pack_xtrans(xtrans36, x, y));
   return 0;
 }
+
+extern "C" int emul_demosaic_downsample4(float *out, const float *in, int width, int height, unsigned filters, const double *cam_to_rgb)
+{
+  const int ow = (width + 1) / 2, oh = (height + 1) / 2;
+  cam_to_rgb_t M;
+  for(int k = 0; k < 12; k++) M.m[k] = cam_to_rgb[k];
+  emulate(dim3((unsigned)((ow + PNT - 1) / PNT), (unsigned)oh), PNT, downsample4_kernel, in, (float4 *)out, width, height, ow, filters, M);
+  return 0;
+}

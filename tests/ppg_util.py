@@ -166,3 +166,32 @@ def ref_postfilter(rgba, iterations, kind="strict"):
 
 def emul_postfilter(rgba, iterations):
     return _postfilter(emul_lib("demosaic_postfilter"), "emul_demosaic_downsample_postfilter", rgba, iterations)
+
+
+CYGM_TO_RGB = np.array([[0.82, -1.27, 0.31, 1.14], [-0.35, 1.61, 0.48, -0.74], [1.03, -0.22, -0.67, 0.86]], np.float64) / 3.0
+
+
+def _downsample4(lib, fn, mosaic, filters, cam_to_rgb):
+    h, w = mosaic.shape
+    out, src = util.aligned_empty(((h + 1) // 2, (w + 1) // 2, 4)), util.aligned_empty(mosaic.shape)
+    out[...] = ALPHA_FILL
+    src[...] = mosaic
+    mat = np.ascontiguousarray(cam_to_rgb, np.float64)
+    f = getattr(lib, fn)
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_void_p]
+    assert f(out.ctypes.data, src.ctypes.data, w, h, filters, mat.ctypes.data) == 0
+    return np.array(out)
+
+
+def oracle_downsample4(m, filters, cam_to_rgb=CYGM_TO_RGB):
+    return _downsample4(util.oracle(), "orc_demosaic_downsample4", m, filters, cam_to_rgb)
+
+
+def ref_downsample4(m, filters, cam_to_rgb=CYGM_TO_RGB, kind="strict"):
+    lib = util.ref(kind)
+    return None if lib is None else _downsample4(lib, "ref_demosaic_downsample4", m, filters, cam_to_rgb)
+
+
+def emul_downsample4(m, filters, cam_to_rgb=CYGM_TO_RGB):
+    return _downsample4(emul_lib(), "emul_demosaic_downsample4", m, filters, cam_to_rgb)

@@ -144,3 +144,16 @@ def test_downsample_postfilter_oracle_reference_and_kernels(size, iterations):
     if util.ref("strict") is not None:
         assert same_bits(want, pu.ref_postfilter(half, iterations)).all()
     assert same_bits(pu.emul_postfilter(half, iterations), want).all()
+
+
+@pytest.mark.parametrize("filters", [0xb4b4b4b4, 0x1e4e1e4e, 0xe1e4e1e4])
+def test_downsample_four_colour_oracle_reference_and_kernel(filters):
+    """four-colour Bayer sensors (CYGM / RGBE words) through CAM_to_RGB, demosaic.c:514-521: double products, float accumulator"""
+    for w, h in ((64, 48), (77, 51), (3, 1)):
+        m = util.frame_natural(w, h, 31)
+        if w > 10:
+            m[7, 9], m[20, 21] = np.nan, 1e30
+        want = pu.oracle_downsample4(m, filters)
+        if util.ref("strict") is not None:
+            assert same_bits(want, pu.ref_downsample4(m, filters)).all()
+        assert same_bits(pu.emul_downsample4(m, filters), want).all()

@@ -160,3 +160,23 @@ def test_downsample_xtrans_bit_exact(built, name):
     ab.check(ab.lib().b200_demosaic_process_dev(C.byref(piece), d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     assert same_bits(d_out.cpu().numpy(), pu.oracle_downsample_xtrans(m, x, y, vu.XTRANS)).all()
+
+
+def test_downsample_four_colour_bit_exact(built):
+    """method 7 on a four-colour Bayer sensor (image_flags & DT_IMAGE_4BAYER): data->CAM_to_RGB, demosaic.c:514-521"""
+    import torch
+    import ansel_b200 as ab
+    ab.init()
+    f, (w, h) = 0xb4b4b4b4, (1203, 801)
+    m = util.frame_natural(w, h, 31)
+    d = ab.demosaic_data(7)
+    for r in range(3):
+        for k in range(4):
+            d.CAM_to_RGB[r][k] = float(pu.CYGM_TO_RGB[r, k])
+    piece = ab.make_piece(w, h, filters=f, data=d, devid=0, out_width=(w + 1) // 2, out_height=(h + 1) // 2)
+    piece.image_flags = 16384  # DT_IMAGE_4BAYER, common/image.h
+    d_in = torch.from_numpy(m).cuda()
+    d_out = torch.full(((h + 1) // 2, (w + 1) // 2, 4), -7.0, device="cuda")
+    ab.check(ab.lib().b200_demosaic_process_dev(C.byref(piece), d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert same_bits(d_out.cpu().numpy(), pu.oracle_downsample4(m, f)).all()
