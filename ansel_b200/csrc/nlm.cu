@@ -22,7 +22,10 @@
 // (a0*a0 - b0*b0)*n0 + ...: both are functions of the per-channel squares, so E holds exactly the reference's
 // intermediate values and the sums are formed in its order.
 // Not HBM bound by construction (~9 kflop/px at K=7); reported against FP32 issue.
+#ifndef B200_KERNELS_ON_CPU // tests/emul compiles the group kernel's phases with g++ to check them against the oracle without a GPU
 #include "runtime.h"
+#include <math_constants.h>
+#endif
 #include <math.h>
 #include <stdlib.h>
 
@@ -47,6 +50,13 @@ struct patch_t
   short rows, cols;
 };
 
+__device__ __forceinline__ float fast_mexp2(float x) // math/math.h:290-301
+{
+  const int i1 = 0x3f800000, i2 = 0x3f000000;
+  const int k0 = i1 + (int)(x * (float)(i2 - i1));
+  return __int_as_float(k0 >= 0x800000 ? k0 : 0);
+}
+#ifndef B200_KERNELS_ON_CPU
 struct nlm_args_t
 {
   const float4 *in;
@@ -63,12 +73,6 @@ struct nlm_args_t
   int cols_w, sstride_w; // window variant: columns of a window row, odd pitch of its sum planes
 };
 
-__device__ __forceinline__ float fast_mexp2(float x) // math/math.h:290-301
-{
-  const int i1 = 0x3f800000, i2 = 0x3f000000;
-  const int k0 = i1 + (int)(x * (float)(i2 - i1));
-  return __int_as_float(k0 >= 0x800000 ? k0 : 0);
-}
 __device__ __forceinline__ float pixdiff(const float4 a, const float4 b, const float *n) // :156-165
 {
   const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z;
@@ -584,6 +588,10 @@ __global__ void __launch_bounds__(WNT, 1) nlm_chunks_win_kernel(const __grid_con
   }
 }
 
+#endif // B200_KERNELS_ON_CPU
+
+#include "nlm_group.cuh"
+
 // scatter(), :95-104: evaluated in double, truncated to int
 int scatter(float scale, float scattering, int i1, int i2)
 {
@@ -626,8 +634,144 @@ int slice_width(int width) // :299-312
   }
   return sl;
 }
+
+// ---- host side of the group kernel: geometry of the window and of the column-sum planes, patches in flight ---------
+// false: the chunk window plus two planes do not fit `smem_optin` bytes (or the radius is beyond the kernel's rings)
+bool grp_plan(grp_args_t &g, int n_patches, int width, int height, int radius, float center_weight, float sharpness, const float norm[4],
+              const float weight[4], const float invert[4], int skip_blend, int shift_max, int smem_optin, int g_cap)
+{
+  if(radius > 2) return false; // the rings of 7 and 9 rows do not fit the register file next to the pixel sums
+  g.n_patches = n_patches;
+  g.width = width;
+  g.height = height;
+  g.chk_h = slice_height(height);
+  g.chk_w = slice_width(width);
+  g.n_cl = (width + g.chk_w - 1) / g.chk_w;
+  g.radius = radius;
+  g.center_weight = center_weight;
+  g.sharpness = sharpness;
+  const int pw = 2 * radius + 1;
+  g.cp_norm = center_weight * pw * pw; // compute_center_pixel_norm(), :147-153
+  g.div_d = 1.0f + center_weight;      // :416
+  g.div_rcp = 1.0f / g.div_d;
+  for(int c = 0; c < 4; c++)
+  {
+    g.norm[c] = norm[c];
+    g.weight[c] = weight[c];
+    g.invert[c] = invert[c];
+  }
+  g.skip_blend = skip_blend;
+  g.hs = shift_max;
+  g.wrows = g.chk_h + 2 * radius + 1 + 2 * shift_max;
+  g.wcols = g.chk_w + 2 * radius + 2 * shift_max;
+  g.wpitch = g.wcols;
+  g.wplane = g.wrows * g.wpitch;
+  g.spitch = (g.chk_w + 2 * radius + 1) | 1;
+  g.splane = (g.chk_h + 1) * g.spitch;
+  if(g.chk_h > MAX_CH || g.chk_w > MAX_CW) return false;
+  const long long wbytes = 3LL * g.wplane * 4, sbytes = (long long)g.splane * 4;
+  if(wbytes + 2 * sbytes > smem_optin) return false;
+  int G = (int)((smem_optin - wbytes) / sbytes);
+  G = (G < g_cap ? G : g_cap);
+  G = (G < GRP_MAXG ? G : GRP_MAXG) & ~1;
+  if(G < 2) return false;
+  g.G = G;
+  return true;
+}
+int grp_pairs_per_thread(const grp_args_t &g) { return (((g.chk_h + 1) / 2) * g.chk_w + GRP_NT - 1) / GRP_NT; }
+size_t grp_smem_bytes(const grp_args_t &g) { return ((size_t)3 * g.wplane + (size_t)g.G * g.splane) * sizeof(float); }
+// Markstein's division is the reference's division as long as nothing underflows on the way; where it could (x below
+// 2^-44 with these bounds) the weight is 1 whatever the last bit of the quotient, because x / d * sharpness < 2^-24
+// vanishes against the 2 it is subtracted from.
+bool grp_division_by_constant(const grp_args_t &g)
+{
+  return !(g.center_weight < 0) && g.div_d >= 1.0f && g.div_d <= 1048576.0f && g.sharpness > 0.0f && g.sharpness <= 1048576.0f;
+}
+// define_patches(), :107-145; returns the largest |shift|
+int grp_define_patches(patch_t *patches, int search_radius, float scale, float scattering, int decimate)
+{
+  int k = 0, dec = decimate, shift_max = 0;
+  for(int ri = -search_radius; ri <= search_radius; ri++)
+    for(int ci = -search_radius; ci <= search_radius; ci++)
+    {
+      if(dec && (++dec & 1)) continue;
+      patches[k].rows = (short)scatter(scale, scattering, ri, ci);
+      patches[k].cols = (short)scatter(scale, scattering, ci, ri);
+      const int ar = abs((int)patches[k].rows), ac = abs((int)patches[k].cols);
+      if(ar > shift_max) shift_max = ar;
+      if(ac > shift_max) shift_max = ac;
+      k++;
+    }
+  return shift_max;
+}
+
+#ifndef B200_KERNELS_ON_CPU
+template <int R, int KP> cudaError_t launch_group_r(const grp_args_t &g, bool norm1, bool profiled, bool divc, unsigned grid, size_t smem, cudaStream_t stream)
+{
+#define GRP_LAUNCH(N1, PR, DC)                                                                                         \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    cudaError_t e = cudaFuncSetAttribute(nlm_group_kernel<R, N1, PR, DC, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if(e != cudaSuccess) return e;                                                                                     \
+    nlm_group_kernel<R, N1, PR, DC, KP><<<grid, GRP_NT, smem, stream>>>(g);                                                \
+    return cudaGetLastError();                                                                                         \
+  } while(0)
+  if(!profiled)
+  {
+    if(norm1) GRP_LAUNCH(true, false, false);
+    GRP_LAUNCH(false, false, false);
+  }
+  if(divc)
+  {
+    if(norm1) GRP_LAUNCH(true, true, true);
+    GRP_LAUNCH(false, true, true);
+  }
+  if(norm1) GRP_LAUNCH(true, true, false);
+  GRP_LAUNCH(false, true, false);
+#undef GRP_LAUNCH
+}
+
+// the group kernel, if the chunk window and two or more planes of column sums fit; *launched tells
+int launch_group(const nlm_args_t &a, int shift_max, int smem_optin, int n_chunks, cudaStream_t stream, int *launched)
+{
+  *launched = 0;
+  grp_args_t g;
+  g.in = a.in;
+  g.out = a.out;
+  g.patches = a.patches;
+  int g_cap = GRP_MAXG;
+  if(const char *e = getenv("B200_NLM_G")) g_cap = atoi(e);
+  if(!grp_plan(g, a.n_patches, a.width, a.height, a.radius, a.center_weight, a.sharpness, a.norm, a.weight, a.invert, a.skip_blend,
+               shift_max, smem_optin, g_cap))
+    return B200_OK;
+  const bool profiled = !(a.center_weight < 0);
+  const bool norm1 = a.norm[0] == 1.0f && a.norm[1] == 1.0f && a.norm[2] == 1.0f;
+  const bool divc = grp_division_by_constant(g) && !getenv("B200_NLM_IEEE_DIV");
+  cudaError_t e;
+  const size_t smem = grp_smem_bytes(g);
+  const unsigned grid = (unsigned)n_chunks;
+  if(grp_pairs_per_thread(g) <= GRP_KP_MIN)
+    switch(a.radius)
+    {
+      case 0: e = launch_group_r<0, GRP_KP_MIN>(g, norm1, profiled, divc, grid, smem, stream); break;
+      case 1: e = launch_group_r<1, GRP_KP_MIN>(g, norm1, profiled, divc, grid, smem, stream); break;
+      default: e = launch_group_r<2, GRP_KP_MIN>(g, norm1, profiled, divc, grid, smem, stream); break;
+    }
+  else
+    switch(a.radius)
+    {
+      case 0: e = launch_group_r<0, GRP_KP_MAX>(g, norm1, profiled, divc, grid, smem, stream); break;
+      case 1: e = launch_group_r<1, GRP_KP_MAX>(g, norm1, profiled, divc, grid, smem, stream); break;
+      default: e = launch_group_r<2, GRP_KP_MAX>(g, norm1, profiled, divc, grid, smem, stream); break;
+    }
+  if(e != cudaSuccess) return ::b200::fail(B200_ERR_CUDA, "nlmeans: group kernel launch: %s", cudaGetErrorString(e));
+  *launched = 1;
+  return B200_OK;
+}
+#endif // B200_KERNELS_ON_CPU
 } // namespace
 
+#ifndef B200_KERNELS_ON_CPU
 namespace b200
 {
 // nlmeans_denoise(), :315-532, on device RGBA buffers.  in != out.
@@ -641,17 +785,7 @@ int nlmeans_denoise_dev(const float *d_in, float *d_out, int width, int height, 
   if(decimate) n_patches = (n_patches + 1) / 2;
   patch_t *h_patches = (patch_t *)malloc(sizeof(patch_t) * (size_t)n_patches);
   if(!h_patches) return fail(B200_ERR_NOMEM, "nlmeans: host allocation");
-  { // define_patches(), :107-145
-    int k = 0, dec = decimate;
-    for(int ri = -search_radius; ri <= search_radius; ri++)
-      for(int ci = -search_radius; ci <= search_radius; ci++)
-      {
-        if(dec && (++dec & 1)) continue;
-        h_patches[k].rows = (short)scatter(scale, scattering, ri, ci);
-        h_patches[k].cols = (short)scatter(scale, scattering, ci, ri);
-        k++;
-      }
-  }
+  const int h_shift_max = grp_define_patches(h_patches, search_radius, scale, scattering, decimate);
   void *d_patches = nullptr;
   int rc = scratch(SLOT_SMALL + 1, sizeof(patch_t) * (size_t)n_patches, &d_patches);
   if(rc)
@@ -706,6 +840,14 @@ int nlmeans_denoise_dev(const float *d_in, float *d_out, int width, int height, 
     B200_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin[dev & 15], cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     B200_CUDA_TRY(cudaFuncSetAttribute(nlm_chunks_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin[dev & 15]));
     attr_set[dev & 15] = true;
+  }
+  // The group kernel (nlm_group.cuh) wherever the pixels a chunk reads for every patch, plus at least two planes of
+  // column sums, fit the shared memory of an SM: every module default does (K = 7 with P <= 4 and no scattering).
+  if(!getenv("B200_NLM_CHUNKS") && !getenv("B200_NLM_WINDOW"))
+  {
+    int launched = 0;
+    if((rc = launch_group(a, h_shift_max, smem_optin[dev & 15], n_ct * a.n_cl, stream, &launched))) return rc;
+    if(launched) return B200_OK;
   }
   const long long win_bytes = 2LL * a.rows_e * a.cols_w * 16 + 2LL * a.chk_h * a.sstride_w * 4;
   // Measured at 45 MP, K=7, P=1: E-plane kernel 126 ms, window kernel 137 ms (both bit-exact; the window kernel
@@ -770,3 +912,4 @@ int denoiseprofile_nlmeans_dev(const b200_piece_t *piece, const b200_denoiseprof
   return denoise_vst_backward(piece, d, d_out, npx, true, s);
 }
 } // namespace b200
+#endif // B200_KERNELS_ON_CPU

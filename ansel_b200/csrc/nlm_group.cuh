@@ -1,0 +1,554 @@
+// Non-local means, the group kernel: the pixels a chunk can touch live in shared memory once, G patch offsets are in
+// flight at a time, and every thread works in every phase.  Included by nlm.cu inside its anonymous namespace.
+//
+// Reference: src/pixel/nlmeans_core.c nlmeans_denoise :315-532 (what fixes the float rounding order: the column sums
+// run down the rows of a chunk :424-483 from init_column_sums :214-264, the distortion runs along each row :384-409,
+// the output accumulates patch after patch :396-420).  Those three orders are sequential per (patch, column),
+// per (patch, row) and per pixel -- and nothing else is: different patches have independent column sums and
+// distortions.  So per group of G patches
+//   phase A   thread = (two patches, column)  column sums down the rows, squared differences formed on the fly from the
+//                                             window, the 2*radius+1 rows of a patch kept in registers -> S[g][row][col]
+//   phase B1  thread = (patch, row)           running distortion along the row, in place in S
+//   phase B2  thread = its pixels (in pairs)  weights and accumulation in patch order, sums in registers for all patches
+// with one __syncthreads between phases.  The inner arithmetic works on pairs of floats (FADD2 / FMUL2 / FFMA2, the
+// packed FP32 instructions of sm_100): two patches of one column in phase A, two vertically adjacent pixels in phase B2.
+// ptxas contracts a packed multiply feeding a packed add into FFMA2 even under --fmad=false, so such pairs of
+// operations are never both packed here (the product or the sum is formed per lane); tests/test_cpu_abi.py counts the
+// FFMA2 in the SASS.  The division by the constant 1 + center_weight is Markstein's sequence (q0 = x*rcp, r = fma(-q0,
+// d, x), q = fma(r, rcp, q0)): correctly rounded for every x when rcp = RN(1/d) and nothing underflows (Markstein
+// 1990; Brisebarre, Muller, Raina 2004, section 1), i.e. identical to the reference's divss; the host restricts it
+// to parameter ranges where an underflowing x cannot change the weight (see nlmeans_denoise_dev).
+//
+// Chunks whose rows or columns leave the frame for some patch take the scalar paths below (validity tests per row,
+// per pixel); they restate the same formulas and are what the packed paths are checked against.
+
+constexpr int GRP_NT = 384;   // 64x72 chunk = 2304 pixel pairs = 6 per thread
+constexpr int GRP_MAXG = 8;
+constexpr int GRP_KP_MAX = (((MAX_CH + 1) / 2) * MAX_CW + GRP_NT - 1) / GRP_NT; // pixel pairs a thread owns: 7 at most,
+constexpr int GRP_KP_MIN = 6;                                                   // 6 for chunks of up to 64 rows (a template parameter: registers)
+
+// ---- pairs of floats ------------------------------------------------------------------------------------------
+#ifdef B200_KERNELS_ON_CPU
+struct f2
+{
+  float x, y;
+};
+static inline f2 mk2(float x, float y) { return f2{ x, y }; }
+static inline f2 add2(f2 a, f2 b) { return f2{ a.x + b.x, a.y + b.y }; }
+static inline f2 sub2(f2 a, f2 b) { return f2{ a.x - b.x, a.y - b.y }; }
+static inline f2 mul2(f2 a, f2 b) { return f2{ a.x * b.x, a.y * b.y }; }
+static inline f2 fma2(f2 a, f2 b, f2 c) { return f2{ fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y) }; }
+static inline f2 neg2(f2 a) { return f2{ -a.x, -a.y }; }
+#else
+typedef float2 f2;
+__device__ __forceinline__ f2 mk2(float x, float y) { return make_float2(x, y); }
+__device__ __forceinline__ unsigned long long f2_bits(f2 a)
+{
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ f2 bits_f2(unsigned long long r)
+{
+  f2 a;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
+  return a;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b)
+{
+  unsigned long long c;
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(c) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return bits_f2(c);
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b)
+{
+  unsigned long long c;
+  asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(c) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return bits_f2(c);
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b)
+{
+  unsigned long long c;
+  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(c) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return bits_f2(c);
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c)
+{
+  unsigned long long d;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+  return bits_f2(d);
+}
+__device__ __forceinline__ f2 neg2(f2 a) { return make_float2(-a.x, -a.y); }
+#endif
+
+struct grp_args_t
+{
+  const float4 *in;
+  float4 *out;
+  const patch_t *patches;
+  int n_patches, width, height, chk_h, chk_w, n_cl, radius;
+  float center_weight, sharpness, cp_norm, div_d, div_rcp;
+  float norm[4], weight[4], invert[4];
+  int skip_blend;
+  int hs;             // largest |row shift| or |column shift| of the patch list
+  int wcols, wrows;   // window: chunk + radius + hs on every side (+1 row)
+  int wpitch, wplane; // floats per window row, per window plane (three planes: the channels)
+  int spitch, splane; // column sums / distortions of one patch: floats per row (odd), floats per plane
+  int G;              // patches in flight, even
+};
+
+struct chunk_t
+{
+  int top, bot, left, right, ch, cw;
+  int cbase, ncols; // image column of S[.][0] (a column of zeros), columns of S
+  int wr0, wc0;     // image row / column of window entry (0, 0)
+};
+
+__device__ __forceinline__ chunk_t chunk_of(const grp_args_t &a, int block)
+{
+  chunk_t c;
+  const int it = block / a.n_cl, il = block - it * a.n_cl;
+  c.top = it * a.chk_h;
+  c.left = il * a.chk_w;
+  c.bot = min(c.top + a.chk_h, a.height);
+  c.right = min(c.left + a.chk_w, a.width);
+  c.ch = c.bot - c.top;
+  c.cw = c.right - c.left;
+  c.cbase = c.left - a.radius - 1;
+  c.ncols = c.cw + 2 * a.radius + 1;
+  c.wr0 = c.top - a.radius - a.hs;
+  c.wc0 = c.left - a.radius - a.hs;
+  return c;
+}
+
+// patch geometry of nlmeans_denoise() :345-372 for one chunk, plus the rows on which both pixels of a pair exist
+struct pgeo_t
+{
+  int srow, scol, row_min, row_max, col_min, col_max, pcol_min, pcol_max, lo, hi;
+  bool valid;
+};
+__device__ __forceinline__ pgeo_t patch_geo_grp(const grp_args_t &a, const chunk_t &c, int p)
+{
+  pgeo_t g;
+  g.valid = p < a.n_patches;
+  if(!g.valid) return g;
+  const int radius = a.radius, width = a.width, height = a.height;
+  g.srow = a.patches[p].rows;
+  g.scol = a.patches[p].cols;
+  g.row_min = max(c.top, max(0, -g.srow));
+  g.row_max = min(c.bot, height - max(0, g.srow));
+  g.valid = g.row_min < g.row_max;
+  g.col_min = max(c.left, -g.scol);
+  g.col_max = min(c.right, width - g.scol);
+  g.pcol_min = c.left - min(radius, min(c.left, c.left + g.scol));
+  g.pcol_max = c.right + min(radius, min(width - c.right, width - (c.right + g.scol)));
+  g.lo = max(0, -g.srow);                // rows rho with rho and rho + srow inside the frame: lo <= rho < hi
+  g.hi = height - max(0, g.srow);
+  return g;
+}
+// every row the column sums of this chunk read exists for this patch (no top / bottom edge of the frame in reach)
+__device__ __forceinline__ bool rows_regular(const grp_args_t &a, const chunk_t &c, const pgeo_t &g)
+{
+  return c.top - a.radius >= g.lo && c.bot - 1 + a.radius < g.hi;
+}
+
+template <bool NORM1> __device__ __forceinline__ float pd3(float e0, float e1, float e2, float n0, float n1, float n2)
+{ // pixel_difference(), :156-165, from the squares
+  return NORM1 ? (e0 + e1) + e2 : (e0 * n0 + e1 * n1) + e2 * n2;
+}
+
+// ---- the window: every pixel this chunk reads, for every patch, once ---------------------------------------------
+__device__ __forceinline__ void grp_fill(const grp_args_t &a, const chunk_t &c, float *W, int tid)
+{
+  const int n = a.wrows * a.wcols;
+  for(int idx = tid; idx < n; idx += GRP_NT)
+  {
+    const int wi = idx / a.wcols, wj = idx - wi * a.wcols;
+    const int r = c.wr0 + wi, col = c.wc0 + wj;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if(r >= 0 && r < a.height && col >= 0 && col < a.width) v = __ldg(a.in + (size_t)r * a.width + col);
+    const int o = wi * a.wpitch + wj;
+    W[o] = v.x;
+    W[o + a.wplane] = v.y;
+    W[o + 2 * a.wplane] = v.z;
+  }
+}
+
+// ---- phase A -----------------------------------------------------------------------------------------------------
+// one patch, one column, every edge case: rows that do not exist for the patch count as zero squares, which is what
+// the three branches of :424-483 and the row range of init_column_sums() :232-233 amount to (nlm.cu phase_a).
+template <int R, bool NORM1>
+__device__ void grp_colsum_one(const grp_args_t &a, const chunk_t &c, const float *W, float *Sg, const pgeo_t &g, int k)
+{
+  const int col = c.cbase + k, spitch = a.spitch, wpitch = a.wpitch;
+  float *sp = Sg + (g.row_min - c.top) * spitch + k;
+  if(!(col >= g.pcol_min && col < g.pcol_max))
+  {
+    for(int row = g.row_min; row < g.row_max; row++, sp += spitch) *sp = 0.0f;
+    return;
+  }
+  const float *const W0 = W, *const W1 = W + a.wplane, *const W2 = W1 + a.wplane;
+  const float n0 = a.norm[0], n1 = a.norm[1], n2 = a.norm[2];
+  const int sh = g.srow * wpitch + g.scol;
+  int o = (g.row_min - R - c.wr0) * wpitch + (col - c.wc0);
+  int rho = g.row_min - R;
+  float ring[2 * R + 1][3];
+  float cs = 0.0f;
+#pragma unroll
+  for(int i = 0; i < 2 * R + 1; i++, o += wpitch, rho++)
+  {
+    float e0 = 0.0f, e1 = 0.0f, e2 = 0.0f;
+    if(rho >= g.lo && rho < g.hi)
+    {
+      const float d0 = W0[o] - W0[o + sh], d1 = W1[o] - W1[o + sh], d2 = W2[o] - W2[o + sh];
+      e0 = d0 * d0;
+      e1 = d1 * d1;
+      e2 = d2 * d2;
+      cs += pd3<NORM1>(e0, e1, e2, n0, n1, n2);
+    }
+    ring[i][0] = e0;
+    ring[i][1] = e1;
+    ring[i][2] = e2;
+  }
+  for(int row = g.row_min; row < g.row_max;)
+  {
+#pragma unroll
+    for(int s = 0; s < 2 * R + 1; s++)
+    {
+      if(row < g.row_max)
+      {
+        *sp = cs;
+        sp += spitch;
+        if(row + 1 < g.row_max)
+        {
+          float e0 = 0.0f, e1 = 0.0f, e2 = 0.0f;
+          if(rho >= g.lo && rho < g.hi)
+          {
+            const float d0 = W0[o] - W0[o + sh], d1 = W1[o] - W1[o + sh], d2 = W2[o] - W2[o + sh];
+            e0 = d0 * d0;
+            e1 = d1 * d1;
+            e2 = d2 * d2;
+          }
+          cs += pd3<NORM1>(e0 - ring[s][0], e1 - ring[s][1], e2 - ring[s][2], n0, n1, n2); // diff_of_pixels_diff(), :168-180
+          ring[s][0] = e0;
+          ring[s][1] = e1;
+          ring[s][2] = e2;
+        }
+        o += wpitch;
+        rho++;
+        row++;
+      }
+    }
+  }
+}
+
+// two patches of one column whose rows are all regular and whose column is live for both: lane x = patch ga, lane y = gb
+template <int R, bool NORM1>
+__device__ void grp_colsum_pair(const grp_args_t &a, const chunk_t &c, const float *W, float *Sa, float *Sb, const pgeo_t &ga,
+                                const pgeo_t &gb, int k)
+{
+  const int col = c.cbase + k, spitch = a.spitch, wpitch = a.wpitch;
+  const float *const W0 = W, *const W1 = W + a.wplane, *const W2 = W1 + a.wplane;
+  const f2 n0 = mk2(a.norm[0], a.norm[0]), n1 = mk2(a.norm[1], a.norm[1]), n2 = mk2(a.norm[2], a.norm[2]);
+  const int sha = ga.srow * wpitch + ga.scol, shb = gb.srow * wpitch + gb.scol;
+  int o = (c.top - R - c.wr0) * wpitch + (col - c.wc0);
+  float *spa = Sa + k, *spb = Sb + k;
+  f2 ring[2 * R + 1][3];
+  f2 cs = mk2(0.0f, 0.0f);
+#pragma unroll
+  for(int i = 0; i < 2 * R + 1; i++, o += wpitch)
+  {
+    const float x0 = W0[o], x1 = W1[o], x2 = W2[o];
+    const f2 d0 = sub2(mk2(x0, x0), mk2(W0[o + sha], W0[o + shb]));
+    const f2 d1 = sub2(mk2(x1, x1), mk2(W1[o + sha], W1[o + shb]));
+    const f2 d2 = sub2(mk2(x2, x2), mk2(W2[o + sha], W2[o + shb]));
+    const f2 e0 = mul2(d0, d0), e1 = mul2(d1, d1), e2 = mul2(d2, d2);
+    ring[i][0] = e0;
+    ring[i][1] = e1;
+    ring[i][2] = e2;
+    if(NORM1)
+      cs = add2(cs, add2(add2(e0, e1), e2));
+    else
+    { // products packed, sums per lane (a packed product feeding a packed sum would be contracted)
+      const f2 s0 = mul2(e0, n0), s1 = mul2(e1, n1), s2 = mul2(e2, n2);
+      cs = add2(cs, mk2((s0.x + s1.x) + s2.x, (s0.y + s1.y) + s2.y));
+    }
+  }
+  for(int row = c.top; row < c.bot;)
+  {
+#pragma unroll
+    for(int s = 0; s < 2 * R + 1; s++)
+    {
+      if(row < c.bot)
+      {
+        *spa = cs.x;
+        *spb = cs.y;
+        spa += spitch;
+        spb += spitch;
+        if(row + 1 < c.bot)
+        {
+          const float x0 = W0[o], x1 = W1[o], x2 = W2[o];
+          const f2 d0 = sub2(mk2(x0, x0), mk2(W0[o + sha], W0[o + shb]));
+          const f2 d1 = sub2(mk2(x1, x1), mk2(W1[o + sha], W1[o + shb]));
+          const f2 d2 = sub2(mk2(x2, x2), mk2(W2[o + sha], W2[o + shb]));
+          const f2 e0 = mul2(d0, d0), e1 = mul2(d1, d1), e2 = mul2(d2, d2);
+          const f2 u0 = sub2(e0, ring[s][0]), u1 = sub2(e1, ring[s][1]), u2 = sub2(e2, ring[s][2]);
+          if(NORM1)
+            cs = add2(cs, add2(add2(u0, u1), u2));
+          else
+          {
+            const f2 s0 = mul2(u0, n0), s1 = mul2(u1, n1), s2 = mul2(u2, n2);
+            cs = add2(cs, mk2((s0.x + s1.x) + s2.x, (s0.y + s1.y) + s2.y));
+          }
+          ring[s][0] = e0;
+          ring[s][1] = e1;
+          ring[s][2] = e2;
+        }
+        o += wpitch;
+        row++;
+      }
+    }
+  }
+}
+
+template <int R, bool NORM1>
+__device__ __forceinline__ void grp_phase_a(const grp_args_t &a, const chunk_t &c, const float *W, float *S, int p0, int tid)
+{
+  const int npairs = a.G / 2;
+  for(int t = tid; t < npairs * c.ncols; t += GRP_NT)
+  {
+    const int pi = t / c.ncols, k = t - pi * c.ncols;
+    const int pa = p0 + 2 * pi;
+    const pgeo_t ga = patch_geo_grp(a, c, pa), gb = patch_geo_grp(a, c, pa + 1);
+    float *const Sa = S + (2 * pi) * a.splane, *const Sb = Sa + a.splane;
+    const int col = c.cbase + k;
+    const bool la = ga.valid && col >= ga.pcol_min && col < ga.pcol_max, lb = gb.valid && col >= gb.pcol_min && col < gb.pcol_max;
+    if(ga.valid && gb.valid && la && lb && rows_regular(a, c, ga) && rows_regular(a, c, gb))
+      grp_colsum_pair<R, NORM1>(a, c, W, Sa, Sb, ga, gb, k);
+    else
+    {
+      if(ga.valid) grp_colsum_one<R, NORM1>(a, c, W, Sa, ga, k);
+      if(gb.valid) grp_colsum_one<R, NORM1>(a, c, W, Sb, gb, k);
+    }
+  }
+}
+
+// ---- phase B1: running distortion along each row (:384-387, 409), in place: D[col] lands in slot col - left ----------
+__device__ __forceinline__ void grp_phase_b1(const grp_args_t &a, const chunk_t &c, float *S, int p0, int tid)
+{
+  const int radius = a.radius;
+  for(int t = tid; t < a.G * c.ch; t += GRP_NT)
+  {
+    const int gi = t / c.ch, rr = t - gi * c.ch;
+    const pgeo_t g = patch_geo_grp(a, c, p0 + gi);
+    const int row = c.top + rr;
+    if(!g.valid || row < g.row_min || row >= g.row_max || g.col_min >= g.col_max) continue;
+    float *const Sr = S + gi * a.splane + rr * a.spitch - c.cbase; // Sr[col] = column sum of `col` for this row
+    float distortion = 0.0f;
+    for(int i = g.col_min - radius; i < min(g.col_min + radius, g.col_max); i++) distortion += Sr[i];
+    for(int col = g.col_min; col < g.col_max; col++)
+    {
+      distortion += (Sr[col + radius] - Sr[col - radius - 1]);
+      Sr[col - radius - 1] = distortion; // that slot is never read again
+    }
+  }
+}
+
+// ---- phase B2 --------------------------------------------------------------------------------------------------
+template <int KP> struct grp_thread_t
+{
+  float acc[KP][8]; // x y z w of the upper pixel (lane x of the pairs), then of the lower one -- stored as x x y y z z w w
+  float ctr[KP][6]; // the pixels themselves: c0 c0' c1 c1' c2 c2'
+  int wofs[KP];     // window offset of the upper pixel, -1: no such pair
+  int sofs[KP];     // offset of its distortion in a plane of S
+  unsigned lower;       // bit k: the lower pixel of pair k belongs to the chunk
+};
+
+template <int KP>
+__device__ __forceinline__ void grp_own_init(const grp_args_t &a, const chunk_t &c, const float *W, grp_thread_t<KP> &st, int tid)
+{
+  st.lower = 0u;
+#pragma unroll
+  for(int k = 0; k < KP; k++)
+  {
+    const int j = tid + k * GRP_NT;
+    const int pr = j / c.cw, pc = j - pr * c.cw;
+#pragma unroll
+    for(int i = 0; i < 8; i++) st.acc[k][i] = 0.0f;
+    st.wofs[k] = -1;
+    st.sofs[k] = 0;
+#pragma unroll
+    for(int i = 0; i < 6; i++) st.ctr[k][i] = 0.0f;
+    if(2 * pr < c.ch)
+    {
+      const int wo = (c.top + 2 * pr - c.wr0) * a.wpitch + (c.left + pc - c.wc0);
+      st.wofs[k] = wo;
+      st.sofs[k] = 2 * pr * a.spitch + pc;
+      if(2 * pr + 1 < c.ch) st.lower |= 1u << k;
+      st.ctr[k][0] = W[wo];
+      st.ctr[k][1] = W[wo + a.wpitch];
+      st.ctr[k][2] = W[wo + a.wplane];
+      st.ctr[k][3] = W[wo + a.wplane + a.wpitch];
+      st.ctr[k][4] = W[wo + 2 * a.wplane];
+      st.ctr[k][5] = W[wo + 2 * a.wplane + a.wpitch];
+    }
+  }
+}
+
+// :389-420 for one pixel
+template <bool PROFILED>
+__device__ __forceinline__ float grp_weight(const grp_args_t &a, float dist, float c0, float c1, float c2, float q0, float q1, float q2)
+{
+  if(!PROFILED) return fast_mexp2(dist * a.sharpness);
+  const float d0 = c0 - q0, d1 = c1 - q1, d2 = c2 - q2;
+  const float pd = d0 * d0 * a.cp_norm + d1 * d1 * a.cp_norm + d2 * d2 * a.cp_norm;
+  const float dissimilarity = (dist + pd) / a.div_d;
+  return fast_mexp2(fmaxf(0.0f, dissimilarity * a.sharpness - 2.0f));
+}
+
+template <bool PROFILED, bool DIVC, int KP>
+__device__ __forceinline__ void grp_phase_b2(const grp_args_t &a, const chunk_t &c, const float *W, const float *S, grp_thread_t<KP> &st,
+                                             int p0, int tid)
+{
+  const float *const W0 = W, *const W1 = W + a.wplane, *const W2 = W1 + a.wplane;
+  const int wpitch = a.wpitch, spitch = a.spitch;
+  for(int gi = 0; gi < a.G; gi++)
+  {
+    const pgeo_t g = patch_geo_grp(a, c, p0 + gi);
+    if(!g.valid || g.col_min >= g.col_max) continue; // uniform
+    const float *const Sg = S + gi * a.splane;
+    const int sh = g.srow * wpitch + g.scol;
+    const bool inside = g.row_min == c.top && g.row_max == c.bot && g.col_min == c.left && g.col_max == c.right;
+    if(inside)
+    {
+      const f2 cp = mk2(a.cp_norm, a.cp_norm), sharp = mk2(a.sharpness, a.sharpness);
+      const f2 dd = mk2(a.div_d, a.div_d), rcp = mk2(a.div_rcp, a.div_rcp);
+#pragma unroll
+      for(int k = 0; k < KP; k++)
+      {
+        if(st.wofs[k] < 0) continue;
+        const int wo = st.wofs[k] + sh;
+        const f2 q0 = mk2(W0[wo], W0[wo + wpitch]), q1 = mk2(W1[wo], W1[wo + wpitch]), q2 = mk2(W2[wo], W2[wo + wpitch]);
+        const float *const sp = Sg + st.sofs[k];
+        const f2 dist = mk2(sp[0], sp[spitch]);
+        f2 t;
+        if(PROFILED)
+        { // :404-420
+          const f2 d0 = sub2(mk2(st.ctr[k][0], st.ctr[k][1]), q0), d1 = sub2(mk2(st.ctr[k][2], st.ctr[k][3]), q1),
+                   d2 = sub2(mk2(st.ctr[k][4], st.ctr[k][5]), q2);
+          const f2 e0 = mul2(mul2(d0, d0), cp), e1 = mul2(mul2(d1, d1), cp), e2 = mul2(mul2(d2, d2), cp);
+          const f2 x = add2(dist, mk2((e0.x + e1.x) + e2.x, (e0.y + e1.y) + e2.y));
+          f2 q;
+          if(DIVC)
+          { // x / d, correctly rounded (see the head of this file); +inf would come out as NaN
+            const f2 qa = mul2(x, rcp);
+            const f2 r = fma2(neg2(qa), dd, x);
+            q = fma2(r, rcp, qa);
+            q.x = (x.x == CUDART_INF_F) ? x.x : q.x;
+            q.y = (x.y == CUDART_INF_F) ? x.y : q.y;
+          }
+          else
+            q = mk2(x.x / a.div_d, x.y / a.div_d);
+          const f2 u = mul2(q, sharp);
+          t = mk2(fmaxf(0.0f, u.x - 2.0f), fmaxf(0.0f, u.y - 2.0f));
+        }
+        else
+          t = mul2(dist, sharp); // :389-402
+        const float wx = fast_mexp2(t.x), wy = fast_mexp2(t.y);
+        // out += pixel * wt: products per lane, sums packed
+        const f2 a0 = add2(mk2(st.acc[k][0], st.acc[k][1]), mk2(q0.x * wx, q0.y * wy));
+        const f2 a1 = add2(mk2(st.acc[k][2], st.acc[k][3]), mk2(q1.x * wx, q1.y * wy));
+        const f2 a2 = add2(mk2(st.acc[k][4], st.acc[k][5]), mk2(q2.x * wx, q2.y * wy));
+        const f2 a3 = add2(mk2(st.acc[k][6], st.acc[k][7]), mk2(wx, wy));
+        st.acc[k][0] = a0.x;
+        st.acc[k][1] = a0.y;
+        st.acc[k][2] = a1.x;
+        st.acc[k][3] = a1.y;
+        st.acc[k][4] = a2.x;
+        st.acc[k][5] = a2.y;
+        st.acc[k][6] = a3.x;
+        st.acc[k][7] = a3.y;
+      }
+    }
+    else
+    { // a patch that leaves the frame somewhere in this chunk: pixel by pixel
+#pragma unroll
+      for(int k = 0; k < KP; k++)
+      {
+        if(st.wofs[k] < 0) continue;
+        const int rr = st.sofs[k] / spitch, pc = st.sofs[k] - rr * spitch;
+        const int col = c.left + pc;
+        if(col < g.col_min || col >= g.col_max) continue;
+#pragma unroll
+        for(int l = 0; l < 2; l++)
+        {
+          const int row = c.top + rr + l;
+          if(row < g.row_min || row >= g.row_max) continue;
+          const int wo = st.wofs[k] + l * wpitch + sh;
+          const float q0 = W0[wo], q1 = W1[wo], q2 = W2[wo];
+          const float wt = grp_weight<PROFILED>(a, Sg[st.sofs[k] + l * spitch], st.ctr[k][0 + l], st.ctr[k][2 + l], st.ctr[k][4 + l], q0, q1, q2);
+          st.acc[k][0 + l] += q0 * wt;
+          st.acc[k][2 + l] += q1 * wt;
+          st.acc[k][4 + l] += q2 * wt;
+          st.acc[k][6 + l] += 1.0f * wt;
+        }
+      }
+    }
+  }
+}
+
+// ---- normalise (and blend), :485-519 -----------------------------------------------------------------------------
+template <int KP>
+__device__ __forceinline__ void grp_finish(const grp_args_t &a, const chunk_t &c, const grp_thread_t<KP> &st, int tid)
+{
+#pragma unroll
+  for(int k = 0; k < KP; k++)
+  {
+    if(st.wofs[k] < 0) continue;
+    const int rr = st.sofs[k] / a.spitch, pc = st.sofs[k] - rr * a.spitch;
+#pragma unroll
+    for(int l = 0; l < 2; l++)
+    {
+      if(l == 1 && !((st.lower >> k) & 1u)) continue;
+      const size_t gidx = (size_t)(c.top + rr + l) * a.width + (c.left + pc);
+      const float vx = st.acc[k][0 + l], vy = st.acc[k][2 + l], vz = st.acc[k][4 + l], vw = st.acc[k][6 + l];
+      float4 o;
+      if(a.skip_blend)
+        o = make_float4(vx / vw, vy / vw, vz / vw, vw / vw);
+      else
+      {
+        const float4 i4 = __ldg(a.in + gidx);
+        o.x = (i4.x * a.invert[0]) + (vx / vw * a.weight[0]);
+        o.y = (i4.y * a.invert[1]) + (vy / vw * a.weight[1]);
+        o.z = (i4.z * a.invert[2]) + (vz / vw * a.weight[2]);
+        o.w = (i4.w * a.invert[3]) + (vw / vw * a.weight[3]);
+      }
+      a.out[gidx] = o;
+    }
+  }
+}
+
+#ifndef B200_KERNELS_ON_CPU
+template <int R, bool NORM1, bool PROFILED, bool DIVC, int KP>
+__global__ void __launch_bounds__(GRP_NT, 1) nlm_group_kernel(const __grid_constant__ grp_args_t a)
+{
+  extern __shared__ __align__(16) float smem[];
+  float *const W = smem, *const S = smem + 3 * a.wplane;
+  const int tid = threadIdx.x;
+  const chunk_t c = chunk_of(a, blockIdx.x);
+  grp_fill(a, c, W, tid);
+  __syncthreads();
+  grp_thread_t<KP> st;
+  grp_own_init(a, c, W, st, tid);
+  for(int p0 = 0; p0 < a.n_patches; p0 += a.G)
+  {
+    grp_phase_a<R, NORM1>(a, c, W, S, p0, tid);
+    __syncthreads();
+    grp_phase_b1(a, c, S, p0, tid);
+    __syncthreads();
+    grp_phase_b2<PROFILED, DIVC, KP>(a, c, W, S, st, p0, tid);
+    __syncthreads();
+  }
+  grp_finish(a, c, st, tid);
+}
+#endif

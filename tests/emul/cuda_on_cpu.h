@@ -51,6 +51,12 @@ static inline float __uint_as_float(uint32_t u)
   memcpy(&f, &u, 4);
   return f;
 }
+static inline float __int_as_float(int i)
+{
+  float f;
+  memcpy(&f, &i, 4);
+  return f;
+}
 static inline long long __double_as_longlong(double d)
 {
   long long u;
