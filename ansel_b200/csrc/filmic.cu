@@ -17,6 +17,7 @@
 // polynomial) + 5 sqrtf + ~30 IEEE divisions per pixel: FP64/XU-issue bound by an order of magnitude,
 // not HBM bound; reported as such.
 #include "runtime.h"
+#include <stddef.h>
 #include "flt32_math.cuh"
 #include <float.h>
 #include <math.h>
@@ -773,8 +774,11 @@ extern "C" void b200_filmicrgb_tiling(const b200_piece_t *piece, b200_tiling_t *
   tiling->overlap = 0;
   tiling->xalign = 1;
   tiling->yalign = 1;
-  if(!piece->data || piece->data_size < sizeof(b200_filmicrgb_piece_t)) return;
-  const b200_filmicrgb_data_t *d = &((const b200_filmicrgb_piece_t *)piece->data)->data;
+  // the data block is the first member of b200_filmicrgb_piece_t and the only one read here: the module adapter passes
+  // the reference's own piece->data (sizeof(dt_iop_filmicrgb_data_t)), library callers the flattened piece
+  static_assert(offsetof(b200_filmicrgb_piece_t, data) == 0, "data must lead b200_filmicrgb_piece_t");
+  if(!piece->data || piece->data_size < sizeof(b200_filmicrgb_data_t)) return;
+  const b200_filmicrgb_data_t *d = (const b200_filmicrgb_data_t *)piece->data;
   if(d->hl_deprecated) return;
   tiling->factor = 9.0f; // in + out + 2 * tmp + 2 * LF + 2 * temp + ratios
   tiling->factor_cl = 9.0f;

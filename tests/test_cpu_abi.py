@@ -249,3 +249,49 @@ def test_band_grid_follows_the_demosaic_method(built):
         piece = ab.make_piece(640, 480, filters=0x94949494, channels=1, data=d)
         L.b200_demosaic_band_grid(C.byref(piece), C.byref(g), C.byref(h), C.byref(a))
         assert (g.value, h.value, a.value) == want
+
+
+def test_filmic_tiling_through_the_adapter_with_reconstruction_live(built):
+    """tiling_callback(), filmicrgb.c:2668-2704: the reference's own piece->data (sizeof(dt_iop_filmicrgb_data_t), not the
+    flattened piece the library entry points take) must report 9 buffers and 2^scales overlap while hl_deprecated == 0"""
+    import ansel_b200 as ab
+    import ansel_b200.dtsurface as ds
+    g = np.load(os.path.join(util.GOLDEN_DIR, "filmic_reconstruct.npz"))
+    blob = np.ascontiguousarray(g["data_default_poisson"], np.uint8)
+    fdata = (C.c_uint8 * blob.size).from_buffer_copy(blob.tobytes())
+    assert blob.size == 832
+    piece = ds.make_piece_iop("filmicrgb", 6000, 4000, fdata, channels_in=4, channels_out=4)
+    work, export = util.profile_pair(util.REC2020_TO_XYZ_D50), util.profile_pair(util.SRGB_TO_XYZ_D50)
+    pipe = ds.make_pipe(devid=-1, work_profile=ds.profile_info(*work), output_profile=ds.profile_info(*export))
+    t = ab.Tiling()
+    ds.modlib().dt_iop_filmicrgb__tiling_callback(piece.module, C.byref(pipe), C.byref(piece), C.byref(t))
+    f = util.oracle().orc_filmic_reconstruct_scales
+    f.restype = C.c_int
+    assert t.factor == 9.0 and t.overlap == 1 << f(C.c_float(1.0), C.c_double(1.0), 6000, 4000)
+    # ... and a pointwise module again once the reconstruction is deprecated (every new edit)
+    blob2 = np.ascontiguousarray(np.load(os.path.join(util.GOLDEN_DIR, "filmic_data.npz"))["default_v8"], np.uint8)
+    fdata2 = (C.c_uint8 * blob2.size).from_buffer_copy(blob2.tobytes())
+    piece2 = ds.make_piece_iop("filmicrgb", 6000, 4000, fdata2, channels_in=4, channels_out=4)
+    ds.modlib().dt_iop_filmicrgb__tiling_callback(piece2.module, C.byref(pipe), C.byref(piece2), C.byref(t))
+    assert (t.factor, t.overlap) == (2.0, 0)
+
+
+def test_packed_fp32_is_never_contracted_in_the_nlm_group_kernel(built):
+    """ptxas turns a packed multiply feeding a packed add into FFMA2 even under --fmad=false (nlm_group.cuh): the only FFMA2
+    allowed in the group kernels are the two of Markstein's division per owned pixel pair, and only in the variants using it"""
+    so = os.path.join(ROOT, "ansel_b200", "libb200iop.so")
+    r = subprocess.run(["cuobjdump", "-sass", "-fun", "nlm_group_kernel", so], capture_output=True, text=True)
+    if r.returncode != 0 or "Function" not in r.stdout:
+        r = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-300:]
+    seen = 0
+    for body in re.split(r"\n\s*Function : ", r.stdout)[1:]:
+        name = body.split("\n", 1)[0]
+        m = re.search(r"nlm_group_kernelILi(\d)ELb([01])ELb([01])ELb([01])ELi(\d)E", name)
+        if not m:
+            continue
+        seen += 1
+        divc, kp = m.group(4) == "1", int(m.group(5))
+        assert len(re.findall(r"\bFFMA2\b", body)) == (2 * kp if divc else 0), name
+        assert len(re.findall(r"\bFMUL2\b", body)) > 0 and len(re.findall(r"\bFADD2\b", body)) > 0, name
+    assert seen >= 12
