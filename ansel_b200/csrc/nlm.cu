@@ -640,7 +640,7 @@ int slice_width(int width) // :299-312
 bool grp_plan(grp_args_t &g, int n_patches, int width, int height, int radius, float center_weight, float sharpness, const float norm[4],
               const float weight[4], const float invert[4], int skip_blend, int shift_max, int smem_optin, int g_cap)
 {
-  if(radius > 2) return false; // the rings of 7 and 9 rows do not fit the register file next to the pixel sums
+  if(radius < 1 || radius > 2) return false; // the rings of 7 and 9 rows do not fit the register file next to the pixel sums
   g.n_patches = n_patches;
   g.width = width;
   g.height = height;
@@ -664,14 +664,12 @@ bool grp_plan(grp_args_t &g, int n_patches, int width, int height, int radius, f
   g.hs = shift_max;
   g.wrows = g.chk_h + 2 * radius + 1 + 2 * shift_max;
   g.wcols = g.chk_w + 2 * radius + 2 * shift_max;
-  g.wpitch = g.wcols;
-  g.wplane = g.wrows * g.wpitch;
-  g.spitch = (g.chk_w + 2 * radius + 1) | 1;
-  g.splane = (g.chk_h + 1) * g.spitch;
-  if(g.chk_h > MAX_CH || g.chk_w > MAX_CW) return false;
-  const long long wbytes = 3LL * g.wplane * 4, sbytes = (long long)g.splane * 4;
-  if(wbytes + 2 * sbytes > smem_optin) return false;
-  int G = (int)((smem_optin - wbytes) / sbytes);
+  g.splane = (g.chk_h + 1) * GRP_SP;
+  if(g.chk_h > MAX_CH || g.chk_w > MAX_CW || g.wcols > GRP_WP_WIDE || g.chk_w + 2 * radius + 1 > GRP_SP) return false;
+  g.wp = g.wcols <= GRP_WP_NARROW ? GRP_WP_NARROW : GRP_WP_WIDE;
+  const long long wbytes = (long long)g.wrows * 3 * g.wp * 4, sbytes = (long long)g.splane * 4;
+  if(wbytes + 2 * sbytes + GRP_MAXG * 4 > smem_optin) return false;
+  int G = (int)((smem_optin - wbytes - GRP_MAXG * 4) / sbytes);
   G = (G < g_cap ? G : g_cap);
   G = (G < GRP_MAXG ? G : GRP_MAXG) & ~1;
   if(G < 2) return false;
@@ -679,13 +677,14 @@ bool grp_plan(grp_args_t &g, int n_patches, int width, int height, int radius, f
   return true;
 }
 int grp_pairs_per_thread(const grp_args_t &g) { return (((g.chk_h + 1) / 2) * g.chk_w + GRP_NT - 1) / GRP_NT; }
-size_t grp_smem_bytes(const grp_args_t &g) { return ((size_t)3 * g.wplane + (size_t)g.G * g.splane) * sizeof(float); }
+size_t grp_smem_bytes(const grp_args_t &g) { return ((size_t)g.wrows * 3 * g.wp + (size_t)g.G * g.splane + GRP_MAXG) * sizeof(float); }
 // Markstein's division is the reference's division as long as nothing underflows on the way; where it could (x below
 // 2^-44 with these bounds) the weight is 1 whatever the last bit of the quotient, because x / d * sharpness < 2^-24
-// vanishes against the 2 it is subtracted from.
+// vanishes against the 2 it is subtracted from.  An infinite x enters the sequence as FLT_MAX: FLT_MAX / d * sharpness
+// is beyond 128 with these bounds, so its weight is the 0 the reference gets from the infinity.
 bool grp_division_by_constant(const grp_args_t &g)
 {
-  return !(g.center_weight < 0) && g.div_d >= 1.0f && g.div_d <= 1048576.0f && g.sharpness > 0.0f && g.sharpness <= 1048576.0f;
+  return !(g.center_weight < 0) && g.div_d >= 1.0f && g.div_d <= 1048576.0f && g.sharpness >= 1e-30f && g.sharpness <= 1048576.0f;
 }
 // define_patches(), :107-145; returns the largest |shift|
 int grp_define_patches(patch_t *patches, int search_radius, float scale, float scattering, int decimate)
@@ -706,14 +705,14 @@ int grp_define_patches(patch_t *patches, int search_radius, float scale, float s
 }
 
 #ifndef B200_KERNELS_ON_CPU
-template <int R, int KP> cudaError_t launch_group_r(const grp_args_t &g, bool norm1, bool profiled, bool divc, unsigned grid, size_t smem, cudaStream_t stream)
+template <int R, int WP, int KP> cudaError_t launch_group_r(const grp_args_t &g, bool norm1, bool profiled, bool divc, unsigned grid, size_t smem, cudaStream_t stream)
 {
 #define GRP_LAUNCH(N1, PR, DC)                                                                                         \
   do                                                                                                                   \
   {                                                                                                                    \
-    cudaError_t e = cudaFuncSetAttribute(nlm_group_kernel<R, N1, PR, DC, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    cudaError_t e = cudaFuncSetAttribute(nlm_group_kernel<R, WP, N1, PR, DC, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if(e != cudaSuccess) return e;                                                                                     \
-    nlm_group_kernel<R, N1, PR, DC, KP><<<grid, GRP_NT, smem, stream>>>(g);                                                \
+    nlm_group_kernel<R, WP, N1, PR, DC, KP><<<grid, GRP_NT, smem, stream>>>(g);                                                \
     return cudaGetLastError();                                                                                         \
   } while(0)
   if(!profiled)
@@ -750,20 +749,18 @@ int launch_group(const nlm_args_t &a, int shift_max, int smem_optin, int n_chunk
   cudaError_t e;
   const size_t smem = grp_smem_bytes(g);
   const unsigned grid = (unsigned)n_chunks;
-  if(grp_pairs_per_thread(g) <= GRP_KP_MIN)
-    switch(a.radius)
-    {
-      case 0: e = launch_group_r<0, GRP_KP_MIN>(g, norm1, profiled, divc, grid, smem, stream); break;
-      case 1: e = launch_group_r<1, GRP_KP_MIN>(g, norm1, profiled, divc, grid, smem, stream); break;
-      default: e = launch_group_r<2, GRP_KP_MIN>(g, norm1, profiled, divc, grid, smem, stream); break;
-    }
-  else
-    switch(a.radius)
-    {
-      case 0: e = launch_group_r<0, GRP_KP_MAX>(g, norm1, profiled, divc, grid, smem, stream); break;
-      case 1: e = launch_group_r<1, GRP_KP_MAX>(g, norm1, profiled, divc, grid, smem, stream); break;
-      default: e = launch_group_r<2, GRP_KP_MAX>(g, norm1, profiled, divc, grid, smem, stream); break;
-    }
+  const int variant = (a.radius == 2 ? 4 : 0) + (g.wp == GRP_WP_WIDE ? 2 : 0) + (grp_pairs_per_thread(g) > GRP_KP_MIN ? 1 : 0);
+  switch(variant)
+  {
+    case 0: e = launch_group_r<1, GRP_WP_NARROW, GRP_KP_MIN>(g, norm1, profiled, divc, grid, smem, stream); break;
+    case 1: e = launch_group_r<1, GRP_WP_NARROW, GRP_KP_MAX>(g, norm1, profiled, divc, grid, smem, stream); break;
+    case 2: e = launch_group_r<1, GRP_WP_WIDE, GRP_KP_MIN>(g, norm1, profiled, divc, grid, smem, stream); break;
+    case 3: e = launch_group_r<1, GRP_WP_WIDE, GRP_KP_MAX>(g, norm1, profiled, divc, grid, smem, stream); break;
+    case 4: e = launch_group_r<2, GRP_WP_NARROW, GRP_KP_MIN>(g, norm1, profiled, divc, grid, smem, stream); break;
+    case 5: e = launch_group_r<2, GRP_WP_NARROW, GRP_KP_MAX>(g, norm1, profiled, divc, grid, smem, stream); break;
+    case 6: e = launch_group_r<2, GRP_WP_WIDE, GRP_KP_MIN>(g, norm1, profiled, divc, grid, smem, stream); break;
+    default: e = launch_group_r<2, GRP_WP_WIDE, GRP_KP_MAX>(g, norm1, profiled, divc, grid, smem, stream); break;
+  }
   if(e != cudaSuccess) return ::b200::fail(B200_ERR_CUDA, "nlmeans: group kernel launch: %s", cudaGetErrorString(e));
   *launched = 1;
   return B200_OK;

@@ -8,16 +8,22 @@
 // distortions.  So per group of G patches
 //   phase A   thread = (two patches, column)  column sums down the rows, squared differences formed on the fly from the
 //                                             window, the 2*radius+1 rows of a patch kept in registers -> S[g][row][col]
-//   phase B1  thread = (patch, row)           running distortion along the row, in place in S
+//   phase B1  thread = (patch, two rows)      running distortion along the rows, in place in S, the last 2*radius+1
+//                                             column sums of a row kept in registers
 //   phase B2  thread = its pixels (in pairs)  weights and accumulation in patch order, sums in registers for all patches
 // with one __syncthreads between phases.  The inner arithmetic works on pairs of floats (FADD2 / FMUL2 / FFMA2, the
-// packed FP32 instructions of sm_100): two patches of one column in phase A, two vertically adjacent pixels in phase B2.
-// ptxas contracts a packed multiply feeding a packed add into FFMA2 even under --fmad=false, so such pairs of
-// operations are never both packed here (the product or the sum is formed per lane); tests/test_cpu_abi.py counts the
-// FFMA2 in the SASS.  The division by the constant 1 + center_weight is Markstein's sequence (q0 = x*rcp, r = fma(-q0,
-// d, x), q = fma(r, rcp, q0)): correctly rounded for every x when rcp = RN(1/d) and nothing underflows (Markstein
-// 1990; Brisebarre, Muller, Raina 2004, section 1), i.e. identical to the reference's divss; the host restricts it
-// to parameter ranges where an underflowing x cannot change the weight (see nlmeans_denoise_dev).
+// packed FP32 instructions of sm_100): two patches of one column in phase A, two rows in phase B1, two vertically
+// adjacent pixels in phase B2.  ptxas contracts a packed multiply feeding a packed add into FFMA2 even under
+// --fmad=false, so such pairs of operations are never both packed here (the product or the sum is formed per lane);
+// tests/test_cpu_abi.py counts the FFMA2 in the SASS.  The division by the constant 1 + center_weight is Markstein's
+// sequence (q0 = x*rcp, r = fma(-q0, d, x), q = fma(r, rcp, q0)): correctly rounded for every x when rcp = RN(1/d) and
+// nothing underflows (Markstein 1990; Brisebarre, Muller, Raina 2004, section 1), i.e. identical to the reference's
+// divss; the host restricts it to parameter ranges where an underflowing x cannot change the weight
+// (grp_division_by_constant in nlm.cu).
+//
+// Shared memory: the window as rows of three channel lines of WP floats (every offset between a pixel, its
+// channels and the row below is a compile-time constant), then G planes of column sums with rows of GRP_SP floats
+// (odd: a warp whose lanes are rows hits 32 banks).
 //
 // Chunks whose rows or columns leave the frame for some patch take the scalar paths below (validity tests per row,
 // per pixel); they restate the same formulas and are what the packed paths are checked against.
@@ -26,6 +32,10 @@ constexpr int GRP_NT = 384;   // 64x72 chunk = 2304 pixel pairs = 6 per thread
 constexpr int GRP_MAXG = 8;
 constexpr int GRP_KP_MAX = (((MAX_CH + 1) / 2) * MAX_CW + GRP_NT - 1) / GRP_NT; // pixel pairs a thread owns: 7 at most,
 constexpr int GRP_KP_MIN = 6;                                                   // 6 for chunks of up to 64 rows (a template parameter: registers)
+// WP (template parameter): floats of one channel line of the window, >= chunk + 2 * (radius + largest shift) columns; 96 holds every
+// unscattered search radius up to 10, 128 shifts up to 26.  One window row is 3 * WP floats.
+constexpr int GRP_WP_NARROW = 96, GRP_WP_WIDE = 128;
+constexpr int GRP_SP = MAX_CW + 2 * 2 + 1;     // 77: columns of column sums at radius <= 2, odd
 
 // ---- pairs of floats ------------------------------------------------------------------------------------------
 #ifdef B200_KERNELS_ON_CPU
@@ -39,6 +49,8 @@ static inline f2 sub2(f2 a, f2 b) { return f2{ a.x - b.x, a.y - b.y }; }
 static inline f2 mul2(f2 a, f2 b) { return f2{ a.x * b.x, a.y * b.y }; }
 static inline f2 fma2(f2 a, f2 b, f2 c) { return f2{ fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y) }; }
 static inline f2 neg2(f2 a) { return f2{ -a.x, -a.y }; }
+static inline float min_nan(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
+static inline int __float2int_rz(float x) { return (int)x; } // cvttss2si: INT_MIN beyond the range, where the device saturates (same below -2^31)
 #else
 typedef float2 f2;
 __device__ __forceinline__ f2 mk2(float x, float y) { return make_float2(x, y); }
@@ -79,6 +91,12 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c)
   return bits_f2(d);
 }
 __device__ __forceinline__ f2 neg2(f2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float min_nan(float a, float b) // a NaN stays a NaN (fminf drops it)
+{
+  float r;
+  asm("min.NaN.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
 #endif
 
 struct grp_args_t
@@ -90,11 +108,11 @@ struct grp_args_t
   float center_weight, sharpness, cp_norm, div_d, div_rcp;
   float norm[4], weight[4], invert[4];
   int skip_blend;
-  int hs;             // largest |row shift| or |column shift| of the patch list
-  int wcols, wrows;   // window: chunk + radius + hs on every side (+1 row)
-  int wpitch, wplane; // floats per window row, per window plane (three planes: the channels)
-  int spitch, splane; // column sums / distortions of one patch: floats per row (odd), floats per plane
-  int G;              // patches in flight, even
+  int hs;           // largest |row shift| or |column shift| of the patch list
+  int wcols, wrows; // window: chunk + radius + hs on every side (+1 row)
+  int wp;           // floats of one channel line of the window (the kernel's WP): GRP_WP_NARROW or GRP_WP_WIDE, >= wcols
+  int splane;       // floats of one plane of column sums / distortions: (chk_h + 1) * GRP_SP
+  int G;            // patches in flight, even
 };
 
 struct chunk_t
@@ -102,6 +120,8 @@ struct chunk_t
   int top, bot, left, right, ch, cw;
   int cbase, ncols; // image column of S[.][0] (a column of zeros), columns of S
   int wr0, wc0;     // image row / column of window entry (0, 0)
+  bool interior;    // no patch leaves the frame anywhere in this chunk's reach: every patch is valid, its rows regular, it covers
+                    // the chunk, and every column but S[.][0] is live -- the packed paths without a geometry test
 };
 
 __device__ __forceinline__ chunk_t chunk_of(const grp_args_t &a, int block)
@@ -118,6 +138,9 @@ __device__ __forceinline__ chunk_t chunk_of(const grp_args_t &a, int block)
   c.ncols = c.cw + 2 * a.radius + 1;
   c.wr0 = c.top - a.radius - a.hs;
   c.wc0 = c.left - a.radius - a.hs;
+  const int reach = a.radius + a.hs;
+  c.interior = c.top - reach >= 0 && c.bot + reach <= a.height && c.left - reach >= 0 && c.right + reach <= a.width
+               && c.cw >= 2 * a.radius + 1;
   return c;
 }
 
@@ -151,6 +174,11 @@ __device__ __forceinline__ bool rows_regular(const grp_args_t &a, const chunk_t 
 {
   return c.top - a.radius >= g.lo && c.bot - 1 + a.radius < g.hi;
 }
+// the patch covers the whole chunk: no pixel of it is skipped (:351-366)
+__device__ __forceinline__ bool covers_chunk(const chunk_t &c, const pgeo_t &g)
+{
+  return g.row_min == c.top && g.row_max == c.bot && g.col_min == c.left && g.col_max == c.right;
+}
 
 template <bool NORM1> __device__ __forceinline__ float pd3(float e0, float e1, float e2, float n0, float n1, float n2)
 { // pixel_difference(), :156-165, from the squares
@@ -158,7 +186,7 @@ template <bool NORM1> __device__ __forceinline__ float pd3(float e0, float e1, f
 }
 
 // ---- the window: every pixel this chunk reads, for every patch, once ---------------------------------------------
-__device__ __forceinline__ void grp_fill(const grp_args_t &a, const chunk_t &c, float *W, int tid)
+template <int WP> __device__ __forceinline__ void grp_fill(const grp_args_t &a, const chunk_t &c, float *W, int tid)
 {
   const int n = a.wrows * a.wcols;
   for(int idx = tid; idx < n; idx += GRP_NT)
@@ -167,40 +195,39 @@ __device__ __forceinline__ void grp_fill(const grp_args_t &a, const chunk_t &c, 
     const int r = c.wr0 + wi, col = c.wc0 + wj;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if(r >= 0 && r < a.height && col >= 0 && col < a.width) v = __ldg(a.in + (size_t)r * a.width + col);
-    const int o = wi * a.wpitch + wj;
-    W[o] = v.x;
-    W[o + a.wplane] = v.y;
-    W[o + 2 * a.wplane] = v.z;
+    float *const w = W + wi * (3 * WP) + wj;
+    w[0] = v.x;
+    w[WP] = v.y;
+    w[2 * WP] = v.z;
   }
 }
 
 // ---- phase A -----------------------------------------------------------------------------------------------------
 // one patch, one column, every edge case: rows that do not exist for the patch count as zero squares, which is what
 // the three branches of :424-483 and the row range of init_column_sums() :232-233 amount to (nlm.cu phase_a).
-template <int R, bool NORM1>
+template <int WP, int R, bool NORM1>
 __device__ void grp_colsum_one(const grp_args_t &a, const chunk_t &c, const float *W, float *Sg, const pgeo_t &g, int k)
 {
-  const int col = c.cbase + k, spitch = a.spitch, wpitch = a.wpitch;
-  float *sp = Sg + (g.row_min - c.top) * spitch + k;
+  const int col = c.cbase + k;
+  float *sp = Sg + (g.row_min - c.top) * GRP_SP + k;
   if(!(col >= g.pcol_min && col < g.pcol_max))
   {
-    for(int row = g.row_min; row < g.row_max; row++, sp += spitch) *sp = 0.0f;
+    for(int row = g.row_min; row < g.row_max; row++, sp += GRP_SP) *sp = 0.0f;
     return;
   }
-  const float *const W0 = W, *const W1 = W + a.wplane, *const W2 = W1 + a.wplane;
   const float n0 = a.norm[0], n1 = a.norm[1], n2 = a.norm[2];
-  const int sh = g.srow * wpitch + g.scol;
-  int o = (g.row_min - R - c.wr0) * wpitch + (col - c.wc0);
+  const float *x = W + (g.row_min - R - c.wr0) * (3 * WP) + (col - c.wc0);
+  const float *y = x + g.srow * (3 * WP) + g.scol;
   int rho = g.row_min - R;
   float ring[2 * R + 1][3];
   float cs = 0.0f;
 #pragma unroll
-  for(int i = 0; i < 2 * R + 1; i++, o += wpitch, rho++)
+  for(int i = 0; i < 2 * R + 1; i++, x += (3 * WP), y += (3 * WP), rho++)
   {
     float e0 = 0.0f, e1 = 0.0f, e2 = 0.0f;
     if(rho >= g.lo && rho < g.hi)
     {
-      const float d0 = W0[o] - W0[o + sh], d1 = W1[o] - W1[o + sh], d2 = W2[o] - W2[o + sh];
+      const float d0 = x[0] - y[0], d1 = x[WP] - y[WP], d2 = x[2 * WP] - y[2 * WP];
       e0 = d0 * d0;
       e1 = d1 * d1;
       e2 = d2 * d2;
@@ -218,13 +245,13 @@ __device__ void grp_colsum_one(const grp_args_t &a, const chunk_t &c, const floa
       if(row < g.row_max)
       {
         *sp = cs;
-        sp += spitch;
+        sp += GRP_SP;
         if(row + 1 < g.row_max)
         {
           float e0 = 0.0f, e1 = 0.0f, e2 = 0.0f;
           if(rho >= g.lo && rho < g.hi)
           {
-            const float d0 = W0[o] - W0[o + sh], d1 = W1[o] - W1[o + sh], d2 = W2[o] - W2[o + sh];
+            const float d0 = x[0] - y[0], d1 = x[WP] - y[WP], d2 = x[2 * WP] - y[2 * WP];
             e0 = d0 * d0;
             e1 = d1 * d1;
             e2 = d2 * d2;
@@ -234,7 +261,8 @@ __device__ void grp_colsum_one(const grp_args_t &a, const chunk_t &c, const floa
           ring[s][1] = e1;
           ring[s][2] = e2;
         }
-        o += wpitch;
+        x += (3 * WP);
+        y += (3 * WP);
         rho++;
         row++;
       }
@@ -242,114 +270,212 @@ __device__ void grp_colsum_one(const grp_args_t &a, const chunk_t &c, const floa
   }
 }
 
-// two patches of one column whose rows are all regular and whose column is live for both: lane x = patch ga, lane y = gb
-template <int R, bool NORM1>
+// the squares of one window row for two patches: lane x = patch a, lane y = patch b
+template <int WP> __device__ __forceinline__ void grp_squares2(const float *x, const float *ya, const float *yb, f2 &e0, f2 &e1, f2 &e2)
+{
+  const float x0 = x[0], x1 = x[WP], x2 = x[2 * WP];
+  const f2 d0 = sub2(mk2(x0, x0), mk2(ya[0], yb[0]));
+  const f2 d1 = sub2(mk2(x1, x1), mk2(ya[WP], yb[WP]));
+  const f2 d2 = sub2(mk2(x2, x2), mk2(ya[2 * WP], yb[2 * WP]));
+  // squares per lane: they feed packed differences and sums, and ptxas would contract a packed square into those (FFMA2)
+  e0 = mk2(d0.x * d0.x, d0.y * d0.y);
+  e1 = mk2(d1.x * d1.x, d1.y * d1.y);
+  e2 = mk2(d2.x * d2.x, d2.y * d2.y);
+}
+template <bool NORM1> __device__ __forceinline__ f2 grp_pd2(f2 u0, f2 u1, f2 u2, f2 n0, f2 n1, f2 n2)
+{
+  if(NORM1) return add2(add2(u0, u1), u2);
+  // products packed, sums per lane (a packed product feeding a packed sum would be contracted)
+  const f2 s0 = mul2(u0, n0), s1 = mul2(u1, n1), s2 = mul2(u2, n2);
+  return mk2((s0.x + s1.x) + s2.x, (s0.y + s1.y) + s2.y);
+}
+
+// two patches of one column whose rows are all regular and whose column is live for both
+template <int WP, int R, bool NORM1>
 __device__ void grp_colsum_pair(const grp_args_t &a, const chunk_t &c, const float *W, float *Sa, float *Sb, const pgeo_t &ga,
                                 const pgeo_t &gb, int k)
 {
-  const int col = c.cbase + k, spitch = a.spitch, wpitch = a.wpitch;
-  const float *const W0 = W, *const W1 = W + a.wplane, *const W2 = W1 + a.wplane;
+  const int col = c.cbase + k;
   const f2 n0 = mk2(a.norm[0], a.norm[0]), n1 = mk2(a.norm[1], a.norm[1]), n2 = mk2(a.norm[2], a.norm[2]);
-  const int sha = ga.srow * wpitch + ga.scol, shb = gb.srow * wpitch + gb.scol;
-  int o = (c.top - R - c.wr0) * wpitch + (col - c.wc0);
+  const float *x = W + (c.top - R - c.wr0) * (3 * WP) + (col - c.wc0);
+  const float *ya = x + ga.srow * (3 * WP) + ga.scol, *yb = x + gb.srow * (3 * WP) + gb.scol;
   float *spa = Sa + k, *spb = Sb + k;
   f2 ring[2 * R + 1][3];
   f2 cs = mk2(0.0f, 0.0f);
 #pragma unroll
-  for(int i = 0; i < 2 * R + 1; i++, o += wpitch)
+  for(int i = 0; i < 2 * R + 1; i++)
   {
-    const float x0 = W0[o], x1 = W1[o], x2 = W2[o];
-    const f2 d0 = sub2(mk2(x0, x0), mk2(W0[o + sha], W0[o + shb]));
-    const f2 d1 = sub2(mk2(x1, x1), mk2(W1[o + sha], W1[o + shb]));
-    const f2 d2 = sub2(mk2(x2, x2), mk2(W2[o + sha], W2[o + shb]));
-    const f2 e0 = mul2(d0, d0), e1 = mul2(d1, d1), e2 = mul2(d2, d2);
-    ring[i][0] = e0;
-    ring[i][1] = e1;
-    ring[i][2] = e2;
-    if(NORM1)
-      cs = add2(cs, add2(add2(e0, e1), e2));
-    else
-    { // products packed, sums per lane (a packed product feeding a packed sum would be contracted)
-      const f2 s0 = mul2(e0, n0), s1 = mul2(e1, n1), s2 = mul2(e2, n2);
-      cs = add2(cs, mk2((s0.x + s1.x) + s2.x, (s0.y + s1.y) + s2.y));
-    }
+    grp_squares2<WP>(x + i * (3 * WP), ya + i * (3 * WP), yb + i * (3 * WP), ring[i][0], ring[i][1], ring[i][2]);
+    cs = add2(cs, grp_pd2<NORM1>(ring[i][0], ring[i][1], ring[i][2], n0, n1, n2));
   }
-  for(int row = c.top; row < c.bot;)
+  x += (2 * R + 1) * (3 * WP);
+  ya += (2 * R + 1) * (3 * WP);
+  yb += (2 * R + 1) * (3 * WP);
+  // rows top .. bot-1: store the sum, then slide it down by one row (the last row has no successor to slide to)
+  int left = c.ch;
+  for(; left > 2 * R + 1; left -= 2 * R + 1)
   {
 #pragma unroll
     for(int s = 0; s < 2 * R + 1; s++)
     {
-      if(row < c.bot)
+      spa[s * GRP_SP] = cs.x;
+      spb[s * GRP_SP] = cs.y;
+      f2 e0, e1, e2;
+      grp_squares2<WP>(x + s * (3 * WP), ya + s * (3 * WP), yb + s * (3 * WP), e0, e1, e2);
+      cs = add2(cs, grp_pd2<NORM1>(sub2(e0, ring[s][0]), sub2(e1, ring[s][1]), sub2(e2, ring[s][2]), n0, n1, n2));
+      ring[s][0] = e0;
+      ring[s][1] = e1;
+      ring[s][2] = e2;
+    }
+    x += (2 * R + 1) * (3 * WP);
+    ya += (2 * R + 1) * (3 * WP);
+    yb += (2 * R + 1) * (3 * WP);
+    spa += (2 * R + 1) * GRP_SP;
+    spb += (2 * R + 1) * GRP_SP;
+  }
+#pragma unroll
+  for(int s = 0; s < 2 * R + 1; s++)
+  {
+    if(s < left)
+    {
+      spa[s * GRP_SP] = cs.x;
+      spb[s * GRP_SP] = cs.y;
+      if(s + 1 < left)
       {
-        *spa = cs.x;
-        *spb = cs.y;
-        spa += spitch;
-        spb += spitch;
-        if(row + 1 < c.bot)
-        {
-          const float x0 = W0[o], x1 = W1[o], x2 = W2[o];
-          const f2 d0 = sub2(mk2(x0, x0), mk2(W0[o + sha], W0[o + shb]));
-          const f2 d1 = sub2(mk2(x1, x1), mk2(W1[o + sha], W1[o + shb]));
-          const f2 d2 = sub2(mk2(x2, x2), mk2(W2[o + sha], W2[o + shb]));
-          const f2 e0 = mul2(d0, d0), e1 = mul2(d1, d1), e2 = mul2(d2, d2);
-          const f2 u0 = sub2(e0, ring[s][0]), u1 = sub2(e1, ring[s][1]), u2 = sub2(e2, ring[s][2]);
-          if(NORM1)
-            cs = add2(cs, add2(add2(u0, u1), u2));
-          else
-          {
-            const f2 s0 = mul2(u0, n0), s1 = mul2(u1, n1), s2 = mul2(u2, n2);
-            cs = add2(cs, mk2((s0.x + s1.x) + s2.x, (s0.y + s1.y) + s2.y));
-          }
-          ring[s][0] = e0;
-          ring[s][1] = e1;
-          ring[s][2] = e2;
-        }
-        o += wpitch;
-        row++;
+        f2 e0, e1, e2;
+        grp_squares2<WP>(x + s * (3 * WP), ya + s * (3 * WP), yb + s * (3 * WP), e0, e1, e2);
+        cs = add2(cs, grp_pd2<NORM1>(sub2(e0, ring[s][0]), sub2(e1, ring[s][1]), sub2(e2, ring[s][2]), n0, n1, n2));
       }
     }
   }
 }
 
-template <int R, bool NORM1>
-__device__ __forceinline__ void grp_phase_a(const grp_args_t &a, const chunk_t &c, const float *W, float *S, int p0, int tid)
+// the patches of a group as phase B2 wants them: their window shifts, in shared memory
+template <int WP> __device__ __forceinline__ int grp_shift(const grp_args_t &a, int p) { return a.patches[p].rows * (3 * WP) + a.patches[p].cols; }
+
+template <int WP, int R, bool NORM1>
+__device__ __forceinline__ void grp_phase_a(const grp_args_t &a, const chunk_t &c, const float *W, float *S, int *shifts, int p0, int tid)
 {
   const int npairs = a.G / 2;
+  if(tid < a.G) shifts[tid] = p0 + tid < a.n_patches ? grp_shift<WP>(a, p0 + tid) : 0;
   for(int t = tid; t < npairs * c.ncols; t += GRP_NT)
   {
     const int pi = t / c.ncols, k = t - pi * c.ncols;
     const int pa = p0 + 2 * pi;
-    const pgeo_t ga = patch_geo_grp(a, c, pa), gb = patch_geo_grp(a, c, pa + 1);
     float *const Sa = S + (2 * pi) * a.splane, *const Sb = Sa + a.splane;
+    if(c.interior && pa + 1 < a.n_patches)
+    {
+      if(k == 0)
+      { // the column of zeros left of the first live one (:228-231)
+        for(int rr = 0; rr < c.ch; rr++) Sa[rr * GRP_SP] = Sb[rr * GRP_SP] = 0.0f;
+      }
+      else
+      {
+        pgeo_t ga, gb;
+        ga.srow = a.patches[pa].rows;
+        ga.scol = a.patches[pa].cols;
+        gb.srow = a.patches[pa + 1].rows;
+        gb.scol = a.patches[pa + 1].cols;
+        grp_colsum_pair<WP, R, NORM1>(a, c, W, Sa, Sb, ga, gb, k);
+      }
+      continue;
+    }
+    const pgeo_t ga = patch_geo_grp(a, c, pa), gb = patch_geo_grp(a, c, pa + 1);
     const int col = c.cbase + k;
     const bool la = ga.valid && col >= ga.pcol_min && col < ga.pcol_max, lb = gb.valid && col >= gb.pcol_min && col < gb.pcol_max;
     if(ga.valid && gb.valid && la && lb && rows_regular(a, c, ga) && rows_regular(a, c, gb))
-      grp_colsum_pair<R, NORM1>(a, c, W, Sa, Sb, ga, gb, k);
+      grp_colsum_pair<WP, R, NORM1>(a, c, W, Sa, Sb, ga, gb, k);
     else
     {
-      if(ga.valid) grp_colsum_one<R, NORM1>(a, c, W, Sa, ga, k);
-      if(gb.valid) grp_colsum_one<R, NORM1>(a, c, W, Sb, gb, k);
+      if(ga.valid) grp_colsum_one<WP, R, NORM1>(a, c, W, Sa, ga, k);
+      if(gb.valid) grp_colsum_one<WP, R, NORM1>(a, c, W, Sb, gb, k);
     }
   }
 }
 
 // ---- phase B1: running distortion along each row (:384-387, 409), in place: D[col] lands in slot col - left ----------
-__device__ __forceinline__ void grp_phase_b1(const grp_args_t &a, const chunk_t &c, float *S, int p0, int tid)
+// one row, every case
+__device__ __forceinline__ void grp_row_one(float *Sr /* Sr[col] = column sum of `col` */, const pgeo_t &g, int radius)
 {
-  const int radius = a.radius;
-  for(int t = tid; t < a.G * c.ch; t += GRP_NT)
+  float distortion = 0.0f;
+  for(int i = g.col_min - radius; i < min(g.col_min + radius, g.col_max); i++) distortion += Sr[i];
+  for(int col = g.col_min; col < g.col_max; col++)
   {
-    const int gi = t / c.ch, rr = t - gi * c.ch;
-    const pgeo_t g = patch_geo_grp(a, c, p0 + gi);
-    const int row = c.top + rr;
-    if(!g.valid || row < g.row_min || row >= g.row_max || g.col_min >= g.col_max) continue;
-    float *const Sr = S + gi * a.splane + rr * a.spitch - c.cbase; // Sr[col] = column sum of `col` for this row
-    float distortion = 0.0f;
-    for(int i = g.col_min - radius; i < min(g.col_min + radius, g.col_max); i++) distortion += Sr[i];
-    for(int col = g.col_min; col < g.col_max; col++)
+    distortion += (Sr[col + radius] - Sr[col - radius - 1]);
+    Sr[col - radius - 1] = distortion; // that slot is never read again
+  }
+}
+// two rows (lane x: row, lane y: row + half) of a patch with at least 2*R+1 columns; the column sum leaving the window
+// is the one read 2*R+1 steps earlier
+template <int R> __device__ __forceinline__ void grp_row_pair(float *Sx, float *Sy, const pgeo_t &g)
+{
+  float *px = Sx + g.col_min - R - 1, *py = Sy + g.col_min - R - 1; // slot of D[col_min], column sum leaving at col_min
+  f2 ring[2 * R + 1];
+  f2 distortion = mk2(0.0f, 0.0f);
+  ring[0] = mk2(px[0], py[0]);
+#pragma unroll
+  for(int i = 1; i < 2 * R + 1; i++)
+  {
+    ring[i] = mk2(px[i], py[i]);
+    distortion = add2(distortion, ring[i]);
+  }
+  int left = g.col_max - g.col_min;
+  for(; left >= 2 * R + 1; left -= 2 * R + 1)
+  {
+#pragma unroll
+    for(int s = 0; s < 2 * R + 1; s++)
     {
-      distortion += (Sr[col + radius] - Sr[col - radius - 1]);
-      Sr[col - radius - 1] = distortion; // that slot is never read again
+      const f2 in = mk2(px[s + 2 * R + 1], py[s + 2 * R + 1]);
+      distortion = add2(distortion, sub2(in, ring[s]));
+      ring[s] = in;
+      px[s] = distortion.x;
+      py[s] = distortion.y;
+    }
+    px += 2 * R + 1;
+    py += 2 * R + 1;
+  }
+#pragma unroll
+  for(int s = 0; s < 2 * R + 1; s++)
+  {
+    if(s < left)
+    {
+      const f2 in = mk2(px[s + 2 * R + 1], py[s + 2 * R + 1]);
+      distortion = add2(distortion, sub2(in, ring[s]));
+      px[s] = distortion.x;
+      py[s] = distortion.y;
+    }
+  }
+}
+
+template <int R> __device__ __forceinline__ void grp_phase_b1(const grp_args_t &a, const chunk_t &c, float *S, int p0, int tid)
+{
+  const int half = (c.ch + 1) / 2;
+  for(int t = tid; t < a.G * half; t += GRP_NT)
+  {
+    const int gi = t / half, rr = t - gi * half;
+    float *const Sx = S + gi * a.splane + rr * GRP_SP - c.cbase, *const Sy = Sx + half * GRP_SP;
+    if(c.interior)
+    {
+      if(p0 + gi >= a.n_patches) continue;
+      pgeo_t g;
+      g.col_min = c.left;
+      g.col_max = c.right;
+      if(rr + half < c.ch)
+        grp_row_pair<R>(Sx, Sy, g);
+      else
+        grp_row_one(Sx, g, R);
+      continue;
+    }
+    const pgeo_t g = patch_geo_grp(a, c, p0 + gi);
+    if(!g.valid || g.col_min >= g.col_max) continue;
+    const int rx = c.top + rr, ry = rx + half;
+    const bool vx = rx >= g.row_min && rx < g.row_max, vy = ry >= g.row_min && ry < g.row_max;
+    if(vx && vy && g.col_max - g.col_min >= 2 * R + 1)
+      grp_row_pair<R>(Sx, Sy, g);
+    else
+    {
+      if(vx) grp_row_one(Sx, g, R);
+      if(vy) grp_row_one(Sy, g, R);
     }
   }
 }
@@ -357,17 +483,18 @@ __device__ __forceinline__ void grp_phase_b1(const grp_args_t &a, const chunk_t 
 // ---- phase B2 --------------------------------------------------------------------------------------------------
 template <int KP> struct grp_thread_t
 {
-  float acc[KP][8]; // x y z w of the upper pixel (lane x of the pairs), then of the lower one -- stored as x x y y z z w w
+  float acc[KP][8]; // sums of the upper pixel (even slots) and of the lower pixel (odd slots): x x' y y' z z' w w'
   float ctr[KP][6]; // the pixels themselves: c0 c0' c1 c1' c2 c2'
-  int wofs[KP];     // window offset of the upper pixel, -1: no such pair
+  int wofs[KP];     // window offset of the upper pixel (the chunk's first pixel for a pair that does not exist: harmless reads, never stored)
   int sofs[KP];     // offset of its distortion in a plane of S
-  unsigned lower;       // bit k: the lower pixel of pair k belongs to the chunk
+  unsigned upper;   // bit k: pair k exists
+  unsigned lower;   // bit k: its lower pixel belongs to the chunk
 };
 
-template <int KP>
+template <int WP, int KP>
 __device__ __forceinline__ void grp_own_init(const grp_args_t &a, const chunk_t &c, const float *W, grp_thread_t<KP> &st, int tid)
 {
-  st.lower = 0u;
+  st.lower = st.upper = 0u;
 #pragma unroll
   for(int k = 0; k < KP; k++)
   {
@@ -375,23 +502,22 @@ __device__ __forceinline__ void grp_own_init(const grp_args_t &a, const chunk_t 
     const int pr = j / c.cw, pc = j - pr * c.cw;
 #pragma unroll
     for(int i = 0; i < 8; i++) st.acc[k][i] = 0.0f;
-    st.wofs[k] = -1;
+    st.wofs[k] = (c.top - c.wr0) * (3 * WP) + (c.left - c.wc0); // the chunk's first pixel: any patch shift stays inside the window
     st.sofs[k] = 0;
-#pragma unroll
-    for(int i = 0; i < 6; i++) st.ctr[k][i] = 0.0f;
     if(2 * pr < c.ch)
     {
-      const int wo = (c.top + 2 * pr - c.wr0) * a.wpitch + (c.left + pc - c.wc0);
-      st.wofs[k] = wo;
-      st.sofs[k] = 2 * pr * a.spitch + pc;
+      st.wofs[k] = (c.top + 2 * pr - c.wr0) * (3 * WP) + (c.left + pc - c.wc0);
+      st.sofs[k] = 2 * pr * GRP_SP + pc;
+      st.upper |= 1u << k;
       if(2 * pr + 1 < c.ch) st.lower |= 1u << k;
-      st.ctr[k][0] = W[wo];
-      st.ctr[k][1] = W[wo + a.wpitch];
-      st.ctr[k][2] = W[wo + a.wplane];
-      st.ctr[k][3] = W[wo + a.wplane + a.wpitch];
-      st.ctr[k][4] = W[wo + 2 * a.wplane];
-      st.ctr[k][5] = W[wo + 2 * a.wplane + a.wpitch];
     }
+    const float *const w = W + st.wofs[k];
+    st.ctr[k][0] = w[0];
+    st.ctr[k][1] = w[(3 * WP)];
+    st.ctr[k][2] = w[WP];
+    st.ctr[k][3] = w[(3 * WP) + WP];
+    st.ctr[k][4] = w[2 * WP];
+    st.ctr[k][5] = w[(3 * WP) + 2 * WP];
   }
 }
 
@@ -405,78 +531,92 @@ __device__ __forceinline__ float grp_weight(const grp_args_t &a, float dist, flo
   const float dissimilarity = (dist + pd) / a.div_d;
   return fast_mexp2(fmaxf(0.0f, dissimilarity * a.sharpness - 2.0f));
 }
-
-template <bool PROFILED, bool DIVC, int KP>
-__device__ __forceinline__ void grp_phase_b2(const grp_args_t &a, const chunk_t &c, const float *W, const float *S, grp_thread_t<KP> &st,
-                                             int p0, int tid)
+// dt_fast_mexp2f(), math/math.h:290-301, as the accumulation sees it: where the reference returns 0 this returns a
+// subnormal, which every consumer (flush-to-zero multiplies and adds, like the reference's DAZ) reads as +0
+__device__ __forceinline__ float grp_mexp2_daz(float x)
 {
-  const float *const W0 = W, *const W1 = W + a.wplane, *const W2 = W1 + a.wplane;
-  const int wpitch = a.wpitch, spitch = a.spitch;
+  return __int_as_float(max(0x3f800000 + __float2int_rz(x * -8388608.0f), 0x007fffff));
+}
+
+// every pixel pair of the thread for one patch that covers the chunk: Wq = window + the patch's shift, Sg = its distortions
+template <int WP, bool PROFILED, bool DIVC, int KP>
+__device__ __forceinline__ void grp_accumulate_pairs(const grp_args_t &a, const float *Wq, const float *Sg, grp_thread_t<KP> &st)
+{
+  const f2 cp = mk2(a.cp_norm, a.cp_norm), sharp = mk2(a.sharpness, a.sharpness);
+  const f2 ndd = mk2(-a.div_d, -a.div_d), rcp = mk2(a.div_rcp, a.div_rcp);
+#pragma unroll
+  for(int k = 0; k < KP; k++)
+  {
+    const float *const w = Wq + st.wofs[k];
+    const f2 q0 = mk2(w[0], w[(3 * WP)]), q1 = mk2(w[WP], w[(3 * WP) + WP]), q2 = mk2(w[2 * WP], w[(3 * WP) + 2 * WP]);
+    const float *const sp = Sg + st.sofs[k];
+    const f2 dist = mk2(sp[0], sp[GRP_SP]);
+    f2 t;
+    if(PROFILED)
+    { // :404-420
+      const f2 d0 = sub2(mk2(st.ctr[k][0], st.ctr[k][1]), q0), d1 = sub2(mk2(st.ctr[k][2], st.ctr[k][3]), q1),
+               d2 = sub2(mk2(st.ctr[k][4], st.ctr[k][5]), q2);
+      const f2 e0 = mul2(mul2(d0, d0), cp), e1 = mul2(mul2(d1, d1), cp), e2 = mul2(mul2(d2, d2), cp);
+      f2 x = add2(dist, mk2((e0.x + e1.x) + e2.x, (e0.y + e1.y) + e2.y));
+      f2 q;
+      if(DIVC)
+      { // x / d, correctly rounded (see the head of this file).  +inf would come out of the sequence as NaN: FLT_MAX in
+        // its place gives the same weight, 0 (the host checked FLT_MAX / d * sharpness > 128); a NaN stays one
+        x = mk2(min_nan(x.x, 3.402823466e38f), min_nan(x.y, 3.402823466e38f));
+        const f2 qa = mul2(x, rcp);
+        const f2 r = fma2(qa, ndd, x);
+        q = fma2(r, rcp, qa);
+      }
+      else
+        q = mk2(x.x / a.div_d, x.y / a.div_d);
+      const f2 u = mul2(q, sharp);
+      t = mk2(fmaxf(0.0f, u.x - 2.0f), fmaxf(0.0f, u.y - 2.0f));
+    }
+    else
+      t = mul2(dist, sharp); // :389-402
+    const float wx = grp_mexp2_daz(t.x), wy = grp_mexp2_daz(t.y);
+    // out += pixel * wt: products per lane, sums packed
+    const f2 a0 = add2(mk2(st.acc[k][0], st.acc[k][1]), mk2(q0.x * wx, q0.y * wy));
+    const f2 a1 = add2(mk2(st.acc[k][2], st.acc[k][3]), mk2(q1.x * wx, q1.y * wy));
+    const f2 a2 = add2(mk2(st.acc[k][4], st.acc[k][5]), mk2(q2.x * wx, q2.y * wy));
+    const f2 a3 = add2(mk2(st.acc[k][6], st.acc[k][7]), mk2(wx, wy));
+    st.acc[k][0] = a0.x;
+    st.acc[k][1] = a0.y;
+    st.acc[k][2] = a1.x;
+    st.acc[k][3] = a1.y;
+    st.acc[k][4] = a2.x;
+    st.acc[k][5] = a2.y;
+    st.acc[k][6] = a3.x;
+    st.acc[k][7] = a3.y;
+  }
+}
+
+template <int WP, bool PROFILED, bool DIVC, int KP>
+__device__ __forceinline__ void grp_phase_b2(const grp_args_t &a, const chunk_t &c, const float *W, const float *S, const int *shifts,
+                                             grp_thread_t<KP> &st, int p0, int tid)
+{
+  if(c.interior)
+  {
+    const int n = min(a.G, a.n_patches - p0);
+    const float *Sg = S;
+    for(int gi = 0; gi < n; gi++, Sg += a.splane) grp_accumulate_pairs<WP, PROFILED, DIVC, KP>(a, W + shifts[gi], Sg, st);
+    return;
+  }
   for(int gi = 0; gi < a.G; gi++)
   {
     const pgeo_t g = patch_geo_grp(a, c, p0 + gi);
     if(!g.valid || g.col_min >= g.col_max) continue; // uniform
     const float *const Sg = S + gi * a.splane;
-    const int sh = g.srow * wpitch + g.scol;
-    const bool inside = g.row_min == c.top && g.row_max == c.bot && g.col_min == c.left && g.col_max == c.right;
-    if(inside)
-    {
-      const f2 cp = mk2(a.cp_norm, a.cp_norm), sharp = mk2(a.sharpness, a.sharpness);
-      const f2 dd = mk2(a.div_d, a.div_d), rcp = mk2(a.div_rcp, a.div_rcp);
-#pragma unroll
-      for(int k = 0; k < KP; k++)
-      {
-        if(st.wofs[k] < 0) continue;
-        const int wo = st.wofs[k] + sh;
-        const f2 q0 = mk2(W0[wo], W0[wo + wpitch]), q1 = mk2(W1[wo], W1[wo + wpitch]), q2 = mk2(W2[wo], W2[wo + wpitch]);
-        const float *const sp = Sg + st.sofs[k];
-        const f2 dist = mk2(sp[0], sp[spitch]);
-        f2 t;
-        if(PROFILED)
-        { // :404-420
-          const f2 d0 = sub2(mk2(st.ctr[k][0], st.ctr[k][1]), q0), d1 = sub2(mk2(st.ctr[k][2], st.ctr[k][3]), q1),
-                   d2 = sub2(mk2(st.ctr[k][4], st.ctr[k][5]), q2);
-          const f2 e0 = mul2(mul2(d0, d0), cp), e1 = mul2(mul2(d1, d1), cp), e2 = mul2(mul2(d2, d2), cp);
-          const f2 x = add2(dist, mk2((e0.x + e1.x) + e2.x, (e0.y + e1.y) + e2.y));
-          f2 q;
-          if(DIVC)
-          { // x / d, correctly rounded (see the head of this file); +inf would come out as NaN
-            const f2 qa = mul2(x, rcp);
-            const f2 r = fma2(neg2(qa), dd, x);
-            q = fma2(r, rcp, qa);
-            q.x = (x.x == CUDART_INF_F) ? x.x : q.x;
-            q.y = (x.y == CUDART_INF_F) ? x.y : q.y;
-          }
-          else
-            q = mk2(x.x / a.div_d, x.y / a.div_d);
-          const f2 u = mul2(q, sharp);
-          t = mk2(fmaxf(0.0f, u.x - 2.0f), fmaxf(0.0f, u.y - 2.0f));
-        }
-        else
-          t = mul2(dist, sharp); // :389-402
-        const float wx = fast_mexp2(t.x), wy = fast_mexp2(t.y);
-        // out += pixel * wt: products per lane, sums packed
-        const f2 a0 = add2(mk2(st.acc[k][0], st.acc[k][1]), mk2(q0.x * wx, q0.y * wy));
-        const f2 a1 = add2(mk2(st.acc[k][2], st.acc[k][3]), mk2(q1.x * wx, q1.y * wy));
-        const f2 a2 = add2(mk2(st.acc[k][4], st.acc[k][5]), mk2(q2.x * wx, q2.y * wy));
-        const f2 a3 = add2(mk2(st.acc[k][6], st.acc[k][7]), mk2(wx, wy));
-        st.acc[k][0] = a0.x;
-        st.acc[k][1] = a0.y;
-        st.acc[k][2] = a1.x;
-        st.acc[k][3] = a1.y;
-        st.acc[k][4] = a2.x;
-        st.acc[k][5] = a2.y;
-        st.acc[k][6] = a3.x;
-        st.acc[k][7] = a3.y;
-      }
-    }
+    const float *const Wq = W + g.srow * (3 * WP) + g.scol;
+    if(covers_chunk(c, g))
+      grp_accumulate_pairs<WP, PROFILED, DIVC, KP>(a, Wq, Sg, st);
     else
     { // a patch that leaves the frame somewhere in this chunk: pixel by pixel
 #pragma unroll
       for(int k = 0; k < KP; k++)
       {
-        if(st.wofs[k] < 0) continue;
-        const int rr = st.sofs[k] / spitch, pc = st.sofs[k] - rr * spitch;
+        if(!((st.upper >> k) & 1u)) continue;
+        const int rr = st.sofs[k] / GRP_SP, pc = st.sofs[k] - rr * GRP_SP;
         const int col = c.left + pc;
         if(col < g.col_min || col >= g.col_max) continue;
 #pragma unroll
@@ -484,9 +624,9 @@ __device__ __forceinline__ void grp_phase_b2(const grp_args_t &a, const chunk_t 
         {
           const int row = c.top + rr + l;
           if(row < g.row_min || row >= g.row_max) continue;
-          const int wo = st.wofs[k] + l * wpitch + sh;
-          const float q0 = W0[wo], q1 = W1[wo], q2 = W2[wo];
-          const float wt = grp_weight<PROFILED>(a, Sg[st.sofs[k] + l * spitch], st.ctr[k][0 + l], st.ctr[k][2 + l], st.ctr[k][4 + l], q0, q1, q2);
+          const float *const w = Wq + st.wofs[k] + l * (3 * WP);
+          const float q0 = w[0], q1 = w[WP], q2 = w[2 * WP];
+          const float wt = grp_weight<PROFILED>(a, Sg[st.sofs[k] + l * GRP_SP], st.ctr[k][0 + l], st.ctr[k][2 + l], st.ctr[k][4 + l], q0, q1, q2);
           st.acc[k][0 + l] += q0 * wt;
           st.acc[k][2 + l] += q1 * wt;
           st.acc[k][4 + l] += q2 * wt;
@@ -504,8 +644,8 @@ __device__ __forceinline__ void grp_finish(const grp_args_t &a, const chunk_t &c
 #pragma unroll
   for(int k = 0; k < KP; k++)
   {
-    if(st.wofs[k] < 0) continue;
-    const int rr = st.sofs[k] / a.spitch, pc = st.sofs[k] - rr * a.spitch;
+    if(!((st.upper >> k) & 1u)) continue;
+    const int rr = st.sofs[k] / GRP_SP, pc = st.sofs[k] - rr * GRP_SP;
 #pragma unroll
     for(int l = 0; l < 2; l++)
     {
@@ -529,24 +669,25 @@ __device__ __forceinline__ void grp_finish(const grp_args_t &a, const chunk_t &c
 }
 
 #ifndef B200_KERNELS_ON_CPU
-template <int R, bool NORM1, bool PROFILED, bool DIVC, int KP>
+template <int R, int WP, bool NORM1, bool PROFILED, bool DIVC, int KP>
 __global__ void __launch_bounds__(GRP_NT, 1) nlm_group_kernel(const __grid_constant__ grp_args_t a)
 {
   extern __shared__ __align__(16) float smem[];
-  float *const W = smem, *const S = smem + 3 * a.wplane;
+  float *const W = smem, *const S = smem + a.wrows * (3 * WP);
+  int *const shifts = reinterpret_cast<int *>(S + a.G * a.splane); // GRP_MAXG ints behind the planes
   const int tid = threadIdx.x;
   const chunk_t c = chunk_of(a, blockIdx.x);
-  grp_fill(a, c, W, tid);
+  grp_fill<WP>(a, c, W, tid);
   __syncthreads();
   grp_thread_t<KP> st;
-  grp_own_init(a, c, W, st, tid);
+  grp_own_init<WP>(a, c, W, st, tid);
   for(int p0 = 0; p0 < a.n_patches; p0 += a.G)
   {
-    grp_phase_a<R, NORM1>(a, c, W, S, p0, tid);
+    grp_phase_a<WP, R, NORM1>(a, c, W, S, shifts, p0, tid);
     __syncthreads();
-    grp_phase_b1(a, c, S, p0, tid);
+    grp_phase_b1<R>(a, c, S, p0, tid);
     __syncthreads();
-    grp_phase_b2<PROFILED, DIVC, KP>(a, c, W, S, st, p0, tid);
+    grp_phase_b2<WP, PROFILED, DIVC, KP>(a, c, W, S, shifts, st, p0, tid);
     __syncthreads();
   }
   grp_finish(a, c, st, tid);

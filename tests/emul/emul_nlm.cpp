@@ -7,38 +7,41 @@
 #include "../../ansel_b200/csrc/nlm.cu"
 #include <vector>
 
-template <int R, bool NORM1, bool PROFILED, bool DIVC, int KP> static void run_chunks(const grp_args_t &a, int n_chunks)
+template <int R, int WP, bool NORM1, bool PROFILED, bool DIVC, int KP> static void run_chunks(const grp_args_t &a, int n_chunks)
 {
-  std::vector<float> smem((size_t)3 * a.wplane + (size_t)a.G * a.splane);
+  std::vector<float> smem((size_t)a.wrows * 3 * WP + (size_t)a.G * a.splane + GRP_MAXG);
   std::vector<grp_thread_t<KP>> st(GRP_NT);
-  float *const W = smem.data(), *const S = W + 3 * a.wplane;
+  float *const W = smem.data(), *const S = W + a.wrows * 3 * WP;
+  int *const shifts = reinterpret_cast<int *>(S + a.G * a.splane);
   for(int b = 0; b < n_chunks; b++)
   {
     for(auto &v : smem) v = __builtin_nanf(""); // whatever a phase reads must have been written by an earlier one
     const chunk_t c = chunk_of(a, b);
-    for(int t = 0; t < GRP_NT; t++) grp_fill(a, c, W, t);
-    for(int t = 0; t < GRP_NT; t++) grp_own_init(a, c, W, st[t], t);
+    for(int t = 0; t < GRP_NT; t++) grp_fill<WP>(a, c, W, t);
+    for(int t = 0; t < GRP_NT; t++) grp_own_init<WP>(a, c, W, st[t], t);
     for(int p0 = 0; p0 < a.n_patches; p0 += a.G)
     {
-      for(int t = 0; t < GRP_NT; t++) grp_phase_a<R, NORM1>(a, c, W, S, p0, t);
-      for(int t = 0; t < GRP_NT; t++) grp_phase_b1(a, c, S, p0, t);
-      for(int t = 0; t < GRP_NT; t++) grp_phase_b2<PROFILED, DIVC, KP>(a, c, W, S, st[t], p0, t);
+      for(int t = 0; t < GRP_NT; t++) grp_phase_a<WP, R, NORM1>(a, c, W, S, shifts, p0, t);
+      for(int t = 0; t < GRP_NT; t++) grp_phase_b1<R>(a, c, S, p0, t);
+      for(int t = 0; t < GRP_NT; t++) grp_phase_b2<WP, PROFILED, DIVC, KP>(a, c, W, S, shifts, st[t], p0, t);
     }
     for(int t = 0; t < GRP_NT; t++) grp_finish(a, c, st[t], t);
   }
 }
 
-template <int R, int KP> static void run_rk(const grp_args_t &a, int n, bool norm1, bool profiled, bool divc)
+template <int R, int WP, int KP> static void run_rk(const grp_args_t &a, int n, bool norm1, bool profiled, bool divc)
 {
   if(!profiled)
-    return norm1 ? run_chunks<R, true, false, false, KP>(a, n) : run_chunks<R, false, false, false, KP>(a, n);
-  if(divc) return norm1 ? run_chunks<R, true, true, true, KP>(a, n) : run_chunks<R, false, true, true, KP>(a, n);
-  return norm1 ? run_chunks<R, true, true, false, KP>(a, n) : run_chunks<R, false, true, false, KP>(a, n);
+    return norm1 ? run_chunks<R, WP, true, false, false, KP>(a, n) : run_chunks<R, WP, false, false, false, KP>(a, n);
+  if(divc) return norm1 ? run_chunks<R, WP, true, true, true, KP>(a, n) : run_chunks<R, WP, false, true, true, KP>(a, n);
+  return norm1 ? run_chunks<R, WP, true, true, false, KP>(a, n) : run_chunks<R, WP, false, true, false, KP>(a, n);
 }
 template <int R> static void run_r(const grp_args_t &a, int n, bool norm1, bool profiled, bool divc)
 {
-  if(grp_pairs_per_thread(a) <= GRP_KP_MIN) return run_rk<R, GRP_KP_MIN>(a, n, norm1, profiled, divc);
-  return run_rk<R, GRP_KP_MAX>(a, n, norm1, profiled, divc);
+  const bool tall = grp_pairs_per_thread(a) > GRP_KP_MIN;
+  if(a.wp == GRP_WP_NARROW)
+    return tall ? run_rk<R, GRP_WP_NARROW, GRP_KP_MAX>(a, n, norm1, profiled, divc) : run_rk<R, GRP_WP_NARROW, GRP_KP_MIN>(a, n, norm1, profiled, divc);
+  return tall ? run_rk<R, GRP_WP_WIDE, GRP_KP_MAX>(a, n, norm1, profiled, divc) : run_rk<R, GRP_WP_WIDE, GRP_KP_MIN>(a, n, norm1, profiled, divc);
 }
 
 /* same arguments as b200_nlmeans_denoise_dev on host buffers; smem_bytes = what an SM offers, g_cap = patches in flight at most,
@@ -65,11 +68,9 @@ extern "C" int emul_nlmeans_group(const float *in, float *out, int width, int he
   const int n_ct = (height + g.chk_h - 1) / g.chk_h;
   const bool profiled = !(center_weight < 0), norm1 = norm[0] == 1.0f && norm[1] == 1.0f && norm[2] == 1.0f;
   const bool divc = grp_division_by_constant(g) && !ieee_div;
-  switch(radius)
-  {
-    case 0: run_r<0>(g, n_ct * g.n_cl, norm1, profiled, divc); break;
-    case 1: run_r<1>(g, n_ct * g.n_cl, norm1, profiled, divc); break;
-    default: run_r<2>(g, n_ct * g.n_cl, norm1, profiled, divc); break;
-  }
+  if(radius == 1)
+    run_r<1>(g, n_ct * g.n_cl, norm1, profiled, divc);
+  else
+    run_r<2>(g, n_ct * g.n_cl, norm1, profiled, divc);
   return g.G;
 }

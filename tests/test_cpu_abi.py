@@ -278,20 +278,19 @@ def test_filmic_tiling_through_the_adapter_with_reconstruction_live(built):
 
 def test_packed_fp32_is_never_contracted_in_the_nlm_group_kernel(built):
     """ptxas turns a packed multiply feeding a packed add into FFMA2 even under --fmad=false (nlm_group.cuh): the only FFMA2
-    allowed in the group kernels are the two of Markstein's division per owned pixel pair, and only in the variants using it"""
+    allowed in the group kernels are the two of Markstein's division per owned pixel pair (the accumulation loop exists twice:
+    chunks in the interior of the frame, and patches that cover a chunk at its edge), and only in the variants using it"""
     so = os.path.join(ROOT, "ansel_b200", "libb200iop.so")
-    r = subprocess.run(["cuobjdump", "-sass", "-fun", "nlm_group_kernel", so], capture_output=True, text=True)
-    if r.returncode != 0 or "Function" not in r.stdout:
-        r = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True)
+    r = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-300:]
     seen = 0
     for body in re.split(r"\n\s*Function : ", r.stdout)[1:]:
         name = body.split("\n", 1)[0]
-        m = re.search(r"nlm_group_kernelILi(\d)ELb([01])ELb([01])ELb([01])ELi(\d)E", name)
+        m = re.search(r"nlm_group_kernelILi(\d)ELi(\d+)ELb([01])ELb([01])ELb([01])ELi(\d)E", name)
         if not m:
             continue
         seen += 1
-        divc, kp = m.group(4) == "1", int(m.group(5))
-        assert len(re.findall(r"\bFFMA2\b", body)) == (2 * kp if divc else 0), name
+        divc, kp = m.group(5) == "1", int(m.group(6))
+        assert len(re.findall(r"\bFFMA2\b", body)) == (4 * kp if divc else 0), name
         assert len(re.findall(r"\bFMUL2\b", body)) > 0 and len(re.findall(r"\bFADD2\b", body)) > 0, name
     assert seen >= 12

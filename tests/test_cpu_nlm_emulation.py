@@ -40,7 +40,7 @@ def emul_nlm(lib, img, *, scattering=0.0, scale=1.0, luma=1.0, chroma=1.0, cente
 
 
 # the parameter sets of tests/test_nlm_gpu.py that the group kernel takes (patch radius <= 2, window in shared memory), and more
-CONFIGS = [dict(), dict(P=2, K=4, scattering=0.5), dict(K=2, P=1, scattering=1.0, scale=0.7), dict(P=0, K=3), dict(K=5, decimate=1),
+CONFIGS = [dict(), dict(P=2, K=4, scattering=0.5), dict(K=2, P=1, scattering=1.0, scale=0.7), dict(P=2, K=3), dict(K=5, decimate=1),
            dict(center_weight=-1.0, sharpness=0.01, luma=0.8, chroma=0.6, K=3, P=2), dict(norm=(0.7, 1.3, 0.9, 1.0), K=3),
            dict(norm=(0.7, 1.3, 0.9, 1.0), K=2, P=2, center_weight=-1.0, sharpness=0.02), dict(center_weight=0.37, sharpness=0.02, K=3),
            dict(center_weight=0.0, K=2), dict(center_weight=3.0, sharpness=0.001, K=2, luma=0.5)]
@@ -87,5 +87,6 @@ def test_flat_dark_and_extreme_pixels(emul):
 def test_plan_refuses_what_does_not_fit(emul):
     img = (util.rgba_scene(100, 80, 2) * 60).astype(np.float32)
     assert emul_nlm(emul, img, P=3, K=2)[0] == 0          # rings of 7 rows: the chunk kernel keeps them
+    assert emul_nlm(emul, img, P=0, K=3)[0] == 0          # single-pixel patches: the chunk kernel keeps them
     assert emul_nlm(emul, img, K=7, scattering=1.0)[0] == 0  # shifts of 85 px: no window
     assert emul_nlm(emul, img, smem=48 * 1024)[0] == 0
