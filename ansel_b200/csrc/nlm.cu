@@ -712,7 +712,10 @@ template <int R, int WP, int KP> cudaError_t launch_group_r(const grp_args_t &g,
   {                                                                                                                    \
     cudaError_t e = cudaFuncSetAttribute(nlm_group_kernel<R, WP, N1, PR, DC, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if(e != cudaSuccess) return e;                                                                                     \
-    nlm_group_kernel<R, WP, N1, PR, DC, KP><<<grid, GRP_NT, smem, stream>>>(g);                                                \
+    {                                                                                                                  \
+      ::b200::timed_launch timed(::b200::TIMED_NLM, stream);                                                           \
+      nlm_group_kernel<R, WP, N1, PR, DC, KP><<<grid, GRP_NT, smem, stream>>>(g);                                      \
+    }                                                                                                                  \
     return cudaGetLastError();                                                                                         \
   } while(0)
   if(!profiled)

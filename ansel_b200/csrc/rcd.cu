@@ -539,7 +539,10 @@ int rcd_demosaic_dev(const float *d_in, float *d_out, int width, int height, uin
   a.revscaler = 1.0f / a.scaler;
   a.nv = 1 + (height - 2 * RING - 1) / KEEP;
   a.nh = 1 + (width - 2 * RING - 1) / KEEP;
-  rcd_tiles_kernel<<<(unsigned)(a.nv * a.nh), NT, smem_bytes, stream>>>(a);
+  {
+    timed_launch timed(TIMED_RCD, stream);
+    rcd_tiles_kernel<<<(unsigned)(a.nv * a.nh), NT, smem_bytes, stream>>>(a);
+  }
   B200_CUDA_TRY(cudaGetLastError());
   return B200_OK;
 }

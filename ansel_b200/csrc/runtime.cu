@@ -1,6 +1,7 @@
 // libb200iop.so runtime: errors, device binding, per-thread scratch, host<->device staging.
 // Counterpart of the reference's OpenCL runtime (src/common/opencl.c) for CUDA on B200.
 #include "runtime.h"
+#include <vector>
 #include <string.h>
 #include <atomic>
 #include <cstdarg>
@@ -241,10 +242,80 @@ int copy_d2h(void *dst, const void *src, size_t bytes, cudaStream_t stream)
   (void)done;
   return B200_OK;
 }
+// ---- launch timing of the headline kernels ----------------------------------------------------------------
+namespace
+{
+std::atomic<bool> g_timing(false);
+std::mutex g_timing_mu;
+struct timed_pair
+{
+  cudaEvent_t e0, e1;
+};
+std::vector<timed_pair> g_timed[TIMED_COUNT];
+const char *const g_timed_names[TIMED_COUNT] = { "nlm_group_kernel", "rcd_tiles_kernel" };
+} // namespace
+bool timing_enabled() { return g_timing.load(std::memory_order_relaxed); }
+void timing_mark(int which, bool end, cudaStream_t stream)
+{
+  std::lock_guard<std::mutex> lock(g_timing_mu);
+  if(which < 0 || which >= TIMED_COUNT) return;
+  if(!end)
+  {
+    timed_pair p = { nullptr, nullptr };
+    if(cudaEventCreate(&p.e0) != cudaSuccess || cudaEventCreate(&p.e1) != cudaSuccess) return;
+    cudaEventRecord(p.e0, stream);
+    g_timed[which].push_back(p);
+  }
+  else if(!g_timed[which].empty())
+    cudaEventRecord(g_timed[which].back().e1, stream);
+}
 } // namespace b200
 
 // ---- exported C ABI ---------------------------------------------------------------------
 using namespace b200;
+
+extern "C" int b200_kernel_timing(int enable)
+{
+  std::lock_guard<std::mutex> lock(g_timing_mu);
+  for(auto &v : g_timed)
+  {
+    for(auto &p : v)
+    {
+      cudaEventDestroy(p.e0);
+      cudaEventDestroy(p.e1);
+    }
+    v.clear();
+  }
+  g_timing.store(enable != 0);
+  return B200_OK;
+}
+
+extern "C" int b200_kernel_timing_read(const char *kernel, double *sum_ms, int *count)
+{
+  if(!kernel || !sum_ms || !count) return fail(B200_ERR_ARG, "kernel_timing_read: null argument");
+  std::lock_guard<std::mutex> lock(g_timing_mu);
+  for(int k = 0; k < TIMED_COUNT; k++)
+    if(!strcmp(kernel, g_timed_names[k]))
+    {
+      double sum = 0.0;
+      int n = 0;
+      for(auto &p : g_timed[k])
+      {
+        float ms = 0.0f;
+        if(cudaEventSynchronize(p.e1) != cudaSuccess || cudaEventElapsedTime(&ms, p.e0, p.e1) != cudaSuccess)
+        {
+          cudaGetLastError();
+          continue;
+        }
+        sum += ms;
+        n++;
+      }
+      *sum_ms = sum;
+      *count = n;
+      return B200_OK;
+    }
+  return fail(B200_ERR_ARG, "kernel_timing_read: no timed kernel named %s", kernel);
+}
 
 extern "C" int b200_abi_version(void) { return B200_ABI_VERSION; }
 

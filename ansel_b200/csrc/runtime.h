@@ -52,6 +52,31 @@ int copy_d2h(void *dst, const void *src, size_t bytes, cudaStream_t stream);
 // per-thread non-blocking stream used by the *_process_host entry points
 int host_stream(cudaStream_t *s);
 
+// Launch timing of the headline kernels (b200_kernel_timing, b200_kernel_timing_read): when enabled, a pair of CUDA
+// events brackets the launch on the stream it goes to.  One `if` per launch when disabled.
+enum
+{
+  TIMED_NLM = 0,
+  TIMED_RCD = 1,
+  TIMED_COUNT = 2
+};
+bool timing_enabled();
+void timing_mark(int which, bool end, cudaStream_t stream);
+struct timed_launch
+{ // brackets the statement(s) between construction and destruction
+  int which;
+  cudaStream_t stream;
+  bool on;
+  timed_launch(int w, cudaStream_t s) : which(w), stream(s), on(timing_enabled())
+  {
+    if(on) timing_mark(which, false, stream);
+  }
+  ~timed_launch()
+  {
+    if(on) timing_mark(which, true, stream);
+  }
+};
+
 // Device copy of three tone curves (3 * B200_LUT_SAMPLES floats), cached per device by `identity` and `side`
 // (0 = decoding / source, 1 = encoding / target); identity 0 = upload every time.  color.cu.
 int device_curves(const float *const host[3], uint64_t identity, int side, cudaStream_t stream, const float **out);

@@ -111,6 +111,13 @@ void b200_shutdown(void);
 int b200_device_count(void);
 /* thread-local, never NULL */
 const char *b200_last_error(void);
+/* Launch timing of the two headline kernels, for benchmarks: while enabled, every launch of `nlm_group_kernel` (non-local
+ * means, nlm_group.cuh) and `rcd_tiles_kernel` (RCD demosaic, rcd.cu) is bracketed by a pair of CUDA events on the stream it
+ * is launched on.  b200_kernel_timing(1) clears what was recorded and starts, (0) clears and stops;
+ * b200_kernel_timing_read() waits for the recorded launches of one kernel and returns their summed duration and count.
+ * No counterpart in the reference (its OpenCL path profiles through dt_opencl_events_*, src/common/opencl.c). */
+int b200_kernel_timing(int enable);
+int b200_kernel_timing_read(const char *kernel, double *sum_ms, int *count);
 
 /* ---- device memory for callers that keep buffers resident between modules --------------------
  * The counterparts of dt_opencl_alloc_device_buffer / dt_opencl_copy_host_to_device /

@@ -510,6 +510,23 @@ void orc_dn_plan_export(const b200_denoiseprofile_data_t *d, float roi_scale, in
   memcpy(out + 40, pl.bb, 16);
   memcpy(out + 44, pl.sigma_band, 28);
 }
+/* the same for the non-local-means mode (nlmeans_precondition(), denoiseprofile.c:1500-1533): what bench.py's CPU arm hands to the
+ * reference's own precondition_v2 / backtransform_v2 around nlmeans_denoise() */
+void orc_dn_plan_export_nlm(const b200_denoiseprofile_data_t *d, float roi_scale, int buf_w, int buf_h, const float wb_coeffs[4],
+                            const float pm[4], float out[51])
+{
+  wavelet_plan_t pl;
+  make_plan_ex(&pl, d, roi_scale, buf_w, buf_h, wb_coeffs, pm, 1);
+  memset(out, 0, 51 * sizeof(float));
+  out[0] = (float)pl.max_scale;
+  memcpy(out + 1, pl.wb, 16);
+  memcpy(out + 5, pl.p, 16);
+  out[9] = pl.a_eff;
+  out[10] = pl.b;
+  out[11] = pl.bias_eff;
+  memcpy(out + 36, pl.aa, 16);
+  memcpy(out + 40, pl.bb, 16);
+}
 void orc_dn_vst(int forward, const b200_denoiseprofile_data_t *d, float roi_scale, int buf_w, int buf_h,
                 const float wb_coeffs[4], const float pm[4], const float *in, float *out, size_t npx)
 {
