@@ -20,6 +20,7 @@ B200_OK, B200_ERR_CUDA, B200_ERR_ARG, B200_ERR_UNSUPPORTED, B200_ERR_NODEVICE, B
 PIPE_NONE, PIPE_EXPORT, PIPE_FULL, PIPE_PREVIEW, PIPE_THUMBNAIL = range(5)
 
 DEMOSAIC_PPG, DEMOSAIC_AMAZE, DEMOSAIC_VNG4, DEMOSAIC_RCD, DEMOSAIC_LMMSE = 0, 1, 2, 5, 6
+GREEN_EQ_NO, GREEN_EQ_LOCAL, GREEN_EQ_FULL, GREEN_EQ_BOTH = 0, 1, 2, 3  # dt_iop_demosaic_greeneq_t, iop/demosaic.c:146-149
 
 
 class Roi(C.Structure):

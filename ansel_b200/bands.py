@@ -64,12 +64,21 @@ def chain_cuts(nodes: list[Node], width: int, height: int) -> tuple[int, int, in
     align = 1
     for a in aligns:
         align = align * a // math.gcd(align, a)
-    if nodes and nodes[0].op == "demosaic" and not any(overlaps[1:]):
+    extra = 0
+    if nodes and nodes[0].op == "demosaic":
+        dd = nodes[0].data
+        # green equilibration FULL / BOTH averages the two greens over the buffer it is given (basic.c:296-329): every band
+        # would get its own scale -- the reference's tiling has the same flaw and the module asks for no tiling then
+        if int(getattr(dd, "green_eq", 0)) in (ab.GREEN_EQ_FULL, ab.GREEN_EQ_BOTH):
+            raise NotImplementedError("demosaic: full-frame green equilibration needs whole-frame sums -- run it as replicas")
+        # every colour-smoothing pass reads one more ring of border-treated pixels next to a cut (basic.c:192-246)
+        extra = int(getattr(dd, "color_smoothing", 0))
+    if nodes and nodes[0].op == "demosaic" and not any(overlaps[1:]) and not extra:
         g, h_, a_ = C.c_int(), C.c_int(), C.c_int()
         piece = ab.make_piece(width, height, filters=0x94949494, channels=1, data=nodes[0].data)
         L.b200_demosaic_band_grid(C.byref(piece), C.byref(g), C.byref(h_), C.byref(a_))
         return g.value, h_.value, a_.value
-    return 1, sum(overlaps), align
+    return 1, sum(overlaps) + extra, align
 
 
 class _DeviceArray:
@@ -111,9 +120,17 @@ class BandedChain:
         self.p2p = bool(p2p) and world > 1
         self.p2p_dst = p2p_dst  # None: every rank ends with the frame (all-gather); int: only that rank does (gather)
         self._own_ptr, self._peer_ptr = None, {}
+        heights = [q.out_y1 - q.out_y0 for q in self.bands]
+        self.equal_bands = len(set(heights)) == 1 and all(q.out_y0 == r * heights[0] for r, q in enumerate(self.bands))
+        self.collective = ("one ncclAllGather of the finished RGBA bands straight into the frame (equal bands, no copy)" if self.equal_bands else
+                           "one ncclAllGather of the finished RGBA bands through slots of the tallest band, then device copies into the frame")
+        self.slots = None
         if not self.p2p:
             self.frame = torch.empty((height, width, 4), dtype=torch.float32, device=self.device)
+            if world > 1 and not self.equal_bands:
+                self.slots = torch.empty((world, max(heights), width, 4), dtype=torch.float32, device=self.device)
         else:
+            self.collective = "none: the last kernel stores into the peers' frames (CUDA IPC), then one barrier"
             self._map_peer_frames()
 
     # ---- the gather fused into the last kernel (b200_colorout_process_scatter_dev) -----------------------------
@@ -199,22 +216,33 @@ class BandedChain:
 
     def assemble(self, mine, mode: str = "allgather", dst_rank: int = 0):
         """mode 'allgather': every rank returns the finished frame; 'gather': only dst_rank does (others None).
-        Bands differ in height (cuts sit on the block grid), so the exchange is one broadcast per band --
-        NCCL runs them back to back on its own stream; the bytes moved equal an all-gather's."""
+        ONE collective moves the pixels: ncclAllGather (dist.all_gather_into_tensor).  Bands of equal height are gathered
+        straight into the frame (each rank's chain writes its band where the collective expects it: no copy at all); bands of
+        unequal height (cuts on a block grid) go through slots of the tallest band's size and are copied out on the device."""
         torch = self.torch
         b = self.band
-        if b.out_y1 > b.out_y0:
-            self.frame[b.out_y0:b.out_y1].copy_(mine)
+        own = self.frame[b.out_y0:b.out_y1]
         if self.world == 1:
+            if b.out_y1 > b.out_y0:
+                own.copy_(mine)
             return self.frame
         import torch.distributed as dist
         if mode == "allgather":
-            works = [dist.broadcast(self.frame[q.out_y0:q.out_y1], src=r, async_op=True)
-                     for r, q in enumerate(self.bands) if q.out_y1 > q.out_y0]
-            for wk in works:
-                wk.wait()
+            if self.equal_bands:
+                own.copy_(mine)
+                dist.all_gather_into_tensor(self.frame, own)
+            else:
+                slot = self.slots[self.rank]
+                if b.out_y1 > b.out_y0:
+                    slot[:b.out_y1 - b.out_y0].copy_(mine)
+                dist.all_gather_into_tensor(self.slots.view(-1, self.w, 4), slot)  # the concatenated form: rank r's slot is rows r*maxh..
+                for r, q in enumerate(self.bands):
+                    if q.out_y1 > q.out_y0:
+                        self.frame[q.out_y0:q.out_y1].copy_(self.slots[r, :q.out_y1 - q.out_y0])
             return self.frame
         if mode == "gather":
+            if b.out_y1 > b.out_y0:
+                own.copy_(mine)
             ops = []
             if self.rank == dst_rank:
                 ops = [dist.P2POp(dist.irecv, self.frame[q.out_y0:q.out_y1], r) for r, q in enumerate(self.bands)

@@ -68,7 +68,7 @@ extern "C" void b200_demosaic_band_grid(const b200_piece_t *piece, int *grid, in
   if(piece && piece->data)
   {
     const b200_demosaic_data_t *d = (const b200_demosaic_data_t *)piece->data;
-    if((d->demosaicing_method & ~1024u) != B200_DEMOSAIC_RCD)
+    if((d->demosaicing_method & ~2048u) != B200_DEMOSAIC_RCD) /* 2048 = DEMOSAIC_DUAL: the VNG4 half blends in pointwise */
     { // AMaZE mirrors at its own tile origin: no cut reproduces the untiled frame; bands are tiling.c tiles
       b200_tiling_t t;
       b200_demosaic_tiling(piece, &t);

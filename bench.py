@@ -4,28 +4,58 @@
   python bench.py --gpus N --steps K --warmup W              # this repo's B200 path
   python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path (oracle/_ref)
 
-Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): one synthetic 45.44 MP RGGB Bayer frame
-(8256x5504, D-natural, seed 20260922) per step through  demosaic(RCD) -> colorin(matrix) ->
-colorout(matrix + sRGB tone curve).  A "step" is one frame through that chain.
+Workload (BASELINE.json configs[2], SURVEY.md 8d "C3", the pipe north_star sets its target on): one synthetic 45.44 MP RGGB
+Bayer frame (8256x5504, D-natural, seed 20260922) per step through
+    demosaic(RCD) -> denoiseprofile(non-local means, P = 1, K = 7) -> colorin(matrix) -> filmicrgb(v8 defaults).
+A "step" is one frame through that chain.
   value : device-resident chain throughput, MP/s, frames already in HBM, CUDA-event timed.
   e2e   : the same chain through the C module adapters and the device-resident pixelpipe glue
           (ansel_b200/iop/), host (pinned) buffers in and out, H2D + D2H inside the timed region.
-Multi-GPU (torchrun): frames are independent, each rank develops its own frame per step, no
-data-path collective (weak scaling, SURVEY.md 8e "batch (C5) replicas").
+  config.c2 : the lighter chain of configs[1] (RCD -> colorin -> colorout), same frame, device-resident.
+Multi-GPU (torchrun): frames are independent, each rank develops its own frame per step, no data-path collective (weak
+scaling, SURVEY.md 8e "batch (C5) replicas"); `banded_one_frame` reports the second mode, ONE frame in row bands.
 """
 from __future__ import annotations
 
-import argparse
-import ctypes as C
-import json
 import os
 import sys
-import threading
-import time
+
+
+def _physical_cores() -> int:
+    """cores this process may run on, one per (package, core) pair"""
+    try:
+        allowed = os.sched_getaffinity(0)
+    except AttributeError:
+        allowed = set(range(os.cpu_count() or 1))
+    seen, cpu, phys = set(), None, None
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("processor"):
+                cpu = int(line.split(":")[1])
+            elif line.startswith("physical id"):
+                phys = int(line.split(":")[1])
+            elif line.startswith("core id") and cpu in allowed:
+                seen.add((phys, int(line.split(":")[1])))
+    except OSError:
+        pass
+    return len(seen) or max(1, len(allowed) // 2)
+
+
+# The CPU arm is OpenMP: BASELINE.md section 3 asks for one thread per physical core, bound (OMP_PROC_BIND=close).  libgomp reads
+# these when it is loaded, so they are set before anything imports it -- and a launcher's OMP_NUM_THREADS=1 (torchrun exports it to
+# every rank) is not the machine's answer: it is overridden, a user's explicit B200_BENCH_OMP_THREADS is kept.
+_CPU_THREADS = int(os.environ.get("B200_BENCH_OMP_THREADS", "0")) or _physical_cores()
+os.environ["OMP_NUM_THREADS"] = str(_CPU_THREADS)
+os.environ.setdefault("OMP_PROC_BIND", "close")
+os.environ.setdefault("OMP_PLACES", "cores")
+
+import argparse  # noqa: E402
+import ctypes as C  # noqa: E402
+import json  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-# The CPU arm uses whatever OpenMP placement the environment asks for (OMP_PROC_BIND / OMP_PLACES /
-# OMP_NUM_THREADS); by default libgomp's own default: all host threads, unbound.
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
@@ -37,10 +67,17 @@ import numpy as np  # noqa: E402
 
 METRIC = "megapixels/sec full develop pipe @45MP"
 UNIT = "MP/s"
-WORKLOAD = "C2: 45MP RGGB Bayer (8256x5504) -> demosaic(RCD) -> colorin(matrix) -> colorout(matrix+sRGB TRC)"
+WORKLOAD = ("C3: 45MP RGGB Bayer (8256x5504) -> demosaic(RCD) -> denoiseprofile(non-local means P=1 K=7) -> colorin(matrix) "
+            "-> filmicrgb(v8 defaults)")
+WORKLOAD_C2 = "C2: 45MP RGGB Bayer (8256x5504) -> demosaic(RCD) -> colorin(matrix) -> colorout(matrix+sRGB TRC)"
 W45, H45 = 8256, 5504
 SEED = 20260922
-ALGO_BYTES_PER_PX = {"demosaic": 20, "colorin": 32, "colorout": 32}
+WB = (2.0, 1.0, 1.5, 0.0)           # white-balance coefficients the denoise profile sees (the tests' values)
+ALGO_BYTES_PER_PX = {"demosaic": 20, "denoiseprofile": 32, "colorin": 32, "filmicrgb": 32, "colorout": 32}
+# non-local means, arithmetic per pixel and patch as the reference's loops write it (nlmeans_core.c:384-483): column sums 12 (x 1.07
+# for the halo columns and rows), running distortion 2, weight and accumulation 24 -> 38.8 flop; 225 patches at K = 7
+NLM_FLOP_PER_PX_PATCH = 12 * 1.07 + 2 + 24
+FP32_PEAK_TFLOPS = 148 * 4 * 32 * 2 * 1.965e9 / 1e12   # 148 SMs x 4 schedulers x one packed (2-wide) 32-lane FP32 instruction per clock
 
 
 def parse():
@@ -74,15 +111,29 @@ def peaks():
 # CPU arm: the reference's own sources compiled by oracle/Makefile (oracle/_ref), else the port
 # ------------------------------------------------------------------------------------------
 class CpuChain:
-    def __init__(self, w, h):
+    """The C3 chain (or C2) on the host cores, module by module as pixelpipe_process_on_CPU calls them: rcd_demosaic ->
+    [precondition_v2 -> nlmeans_denoise -> backtransform_v2] (process_nlmeans_cpu, denoiseprofile.c:1599-1648) ->
+    dt_colorspaces_apply_matrix_conversion (colorin) -> filmic's AgX loop.  Runs on any frame height (bounded samples)."""
+
+    def __init__(self, w, h, chain="c3"):
         import util
-        self.util = util
-        self.w, self.h = w, h
+        import ansel_b200 as ab
+        self.util, self.ab = util, ab
+        self.w, self.h, self.chain = w, h, chain
         self.kind = "reference" if util.ref("fast") is not None else "port"
+        self.lib = util.ref("fast") if self.kind == "reference" else util.oracle()
         self.enc = util.srgb_encode_lut()
         self.co_t = util.fit_unbounded_coeffs(self.enc)
         self.rgb = [util.aligned_empty((h, w, 4)) for _ in range(3)]
-        self.fp = C.POINTER(C.c_float)
+        self.work = util.profile_pair(util.REC2020_TO_XYZ_D50)
+        self.export = util.profile_pair(util.SRGB_TO_XYZ_D50)
+        self.fblob = np.ascontiguousarray(np.load(os.path.join(util.GOLDEN_DIR, "filmic_data.npz"))["default_v8"])
+        self.dn = ab.denoiseprofile_data(ab.DENOISE_NLMEANS, radius=1, nbhood=7)
+        plan = np.zeros(51, np.float32)
+        f4 = lambda v: (C.c_float * 4)(*v)  # noqa: E731
+        util.oracle().orc_dn_plan_export_nlm(C.byref(self.dn), C.c_float(1.0), w, h, f4(WB), f4((1.0, 1.0, 1.0, 1.0)), util.fptr(plan))
+        self.vst = dict(wb=f4(plan[1:5]), p=f4(plan[5:9]), a=C.c_float(plan[9]), b=C.c_float(plan[10]), bias=C.c_float(plan[11]))
+        self.f9 = [np.ascontiguousarray(m, np.float32).reshape(-1).copy() for m in (*self.work, *self.export)]
 
     def _conv(self, src, dst, matrix, lut_t=None, co_t=None):
         u = self.util
@@ -90,49 +141,66 @@ class CpuChain:
         lt = u.fptr(lut_t) if lut_t is not None else None
         ct = u.fptr(np.ascontiguousarray(co_t, np.float32).reshape(-1)) if co_t is not None else None
         if self.kind == "reference":
-            f = u.ref("fast").ref_apply_matrix_conversion
+            f = self.lib.ref_apply_matrix_conversion
             f.restype = C.c_int
             f(u.fptr(src), u.fptr(dst), C.c_size_t(self.w), C.c_size_t(self.h), u.fptr(m), None, C.c_int(0), None, None, lt, ct)
         else:
-            f = u.oracle().orc_apply_matrix_conversion
+            f = self.lib.orc_apply_matrix_conversion
             f.restype = C.c_int
             f(u.fptr(src), u.fptr(dst), C.c_size_t(self.w), C.c_size_t(self.h), u.fptr(m), None, C.c_int(0), None, None, lt, ct,
               C.c_int(u.FP_CONTRACT))
 
+    def _denoise(self, src, tmp, dst):
+        u, v, w, h = self.util, self.vst, self.w, self.h
+        if self.kind != "reference":
+            f = self.lib.orc_denoiseprofile_nlmeans
+            f.restype = C.c_int
+            f(u.fptr(src), u.fptr(dst), w, h, C.byref(self.dn), C.c_float(1.0), 1, (C.c_float * 4)(*WB), (C.c_float * 4)(1.0, 1.0, 1.0, 1.0))
+            return
+        L = self.lib
+        L.ref_dn_precondition_v2(u.fptr(src), u.fptr(tmp), w, h, v["a"], v["p"], v["b"], v["wb"])
+        norm = np.float32(0.045) / np.float32(9.0)           # nlmeans_norm(), denoiseprofile.c:1456-1470, P = 1
+        L.ref_nlmeans_denoise(u.fptr(tmp), u.fptr(dst), w, h, C.c_float(0.0), C.c_float(1.0), C.c_float(1.0), C.c_float(1.0),
+                              C.c_float(self.dn.central_pixel_weight), C.c_float(norm), 1, 7, 0, (C.c_float * 4)(1.0, 1.0, 1.0, 1.0))
+        L.ref_dn_backtransform_v2(u.fptr(dst), w, h, v["a"], v["p"], v["b"], v["bias"], v["wb"])
+
+    def _filmic(self, src, dst):
+        u = self.util
+        f = self.lib.ref_filmic_agx if self.kind == "reference" else self.lib.orc_filmic_agx
+        f(u.fptr(src), u.fptr(dst), C.c_size_t(self.w), C.c_size_t(self.h), self.fblob.ctypes.data_as(C.c_void_p), *[u.fptr(m) for m in self.f9])
+
     def step(self, mosaic):
         u = self.util
         pm = (C.c_float * 3)(1.0, 1.0, 1.0)
-        lib = u.ref("fast") if self.kind == "reference" else u.oracle()
-        name = "ref_rcd_demosaic" if self.kind == "reference" else "orc_rcd_demosaic"
-        f = getattr(lib, name)
+        f = getattr(self.lib, "ref_rcd_demosaic" if self.kind == "reference" else "orc_rcd_demosaic")
         f.restype = C.c_int
-        f(u.fptr(self.rgb[0]), u.fptr(mosaic), self.w, self.h, C.c_uint32(u.BAYER["RGGB"]), pm, C.c_float(0.0))
-        self._conv(self.rgb[0], self.rgb[1], u.MATRIX_CAM_TO_REC2020)
-        self._conv(self.rgb[1], self.rgb[2], u.MATRIX_REC2020_TO_SRGB, self.enc, self.co_t)
-        return self.rgb[2]
+        a, b, c = self.rgb
+        f(u.fptr(a), u.fptr(mosaic), self.w, self.h, C.c_uint32(u.BAYER["RGGB"]), pm, C.c_float(0.0))
+        if self.chain == "c2":
+            self._conv(a, b, u.MATRIX_CAM_TO_REC2020)
+            self._conv(b, c, u.MATRIX_REC2020_TO_SRGB, self.enc, self.co_t)
+            return c
+        self._denoise(a, b, c)
+        self._conv(c, a, u.MATRIX_CAM_TO_REC2020)
+        self._filmic(a, b)
+        return b
 
 
-def tune_cpu_threads(chain, mosaic):
-    """The reference's CPU path is OpenMP; give it the thread count it runs fastest with on this host (all logical
-    CPUs, or one per physical core when SMT hurts this bandwidth-bound chain).  Returns the count chosen."""
-    n_all = os.cpu_count() or 1
-    if "OMP_NUM_THREADS" in os.environ:
-        return int(os.environ["OMP_NUM_THREADS"])
-    try:
-        omp = C.CDLL("libgomp.so.1")
-    except OSError:
-        return n_all
-    best_n, best_t = n_all, None
-    for n in sorted({n_all, max(1, n_all // 2)}, reverse=True):
-        omp.omp_set_num_threads(n)
-        chain.step(mosaic)                       # first touch / thread start-up
-        t0 = time.perf_counter()
-        chain.step(mosaic)
-        t = time.perf_counter() - t0
-        if best_t is None or t < best_t:
-            best_n, best_t = n, t
-    omp.omp_set_num_threads(best_n)
-    return best_n
+def cpu_sample_rows(w, h, budget_s, steps):
+    """rows of the frame one CPU step develops so that `steps` steps fit `budget_s` seconds: a full-width strip (the chunk
+    grids of the tiled modules keep their widths; the strip height keeps a multiple of 64 rows = the NLM chunk rows of this frame)"""
+    probe_h = 256
+    chain = CpuChain(w, probe_h)
+    import util
+    mosaic = util.frame_natural(w, probe_h, SEED)
+    chain.step(mosaic)
+    t0 = time.perf_counter()
+    chain.step(mosaic)
+    per_row = (time.perf_counter() - t0) / probe_h
+    rows = int(budget_s / max(steps, 1) / per_row)
+    if rows >= h:
+        return h, per_row
+    return max(256, rows // 64 * 64), per_row
 
 
 def time_cpu(chain, mosaic, warm, steps):
@@ -152,22 +220,25 @@ def run_reference(args):
         return
     import util
     w, h = args.width, args.height
-    mosaic = util.frame_natural(w, h, SEED)
-    chain = CpuChain(w, h)
-    cores = tune_cpu_threads(chain, mosaic)
-    ts = time_cpu(chain, mosaic, max(args.warmup, 2), args.steps)
-    total = float(np.sum(ts))
-    mps = w * h * len(ts) / total / 1e6
+    warm, steps = max(args.warmup, 3), max(args.steps, 1)
+    rows, per_row = cpu_sample_rows(w, h, 150.0, warm + steps)
+    mosaic = util.frame_natural(w, h, SEED)[:rows].copy()
+    chain = CpuChain(w, rows)
+    ts = time_cpu(chain, mosaic, warm, steps)
+    med = float(np.median(ts))
+    mps = w * rows / med / 1e6
+    sample = (f"{len(ts)} steps after {warm} warm-ups, each the top {rows} rows of the {w}x{h} frame through the chain "
+              f"({'the whole frame' if rows == h else 'a bounded sample: the full frame would take %.1f s per step' % (per_row * h)}); median step")
     line = {
         "impl": "reference", "metric": METRIC, "value": mps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * med, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frame": f"{w}x{h}", "cpu_threads": cores, "host_logical_cpus": os.cpu_count(),
+        "config": {"workload": WORKLOAD, "frame": f"{w}x{h}", "cpu_threads": _CPU_THREADS, "host_logical_cpus": os.cpu_count(),
+                   "omp": {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OMP_PROC_BIND", "OMP_PLACES")},
                    "what": "reference sources compiled in place (oracle/_ref, release flags)" if chain.kind == "reference"
                    else "oracle port (oracle/_ref not built)",
-                   "step_ms": [round(1e3 * t, 1) for t in ts]},
-        "cpu_baseline": {"value": mps, "unit": UNIT, "cores": cores, "kind": chain.kind,
-                         "sample": f"{len(ts)} full {w}x{h} frames through the chain, one per step"},
+                   "sample_rows": rows, "step_ms": [round(1e3 * t, 1) for t in ts]},
+        "cpu_baseline": {"value": mps, "unit": UNIT, "cores": _CPU_THREADS, "kind": chain.kind, "sample": sample},
         "e2e": {"value": mps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -416,6 +487,56 @@ def run_pipe_ends_only(args):
     print(json.dumps(res))
 
 
+def bind_near_gpu(local):
+    """N > 1: run this rank (and allocate its pinned host buffers: first touch) on the CPUs of the GPU's NUMA node.  Returns a note."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return "no NUMA node reported for the GPU"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"NUMA node {node}: no allowed CPU"
+        os.sched_setaffinity(0, cpus)
+        return f"NUMA node {node}, {len(cpus)} CPUs"
+    except Exception as e:  # affinity is an optimisation, never a requirement
+        return f"unbound ({type(e).__name__})"
+
+
+class DeviceChain:
+    """a chain of modules on device-resident buffers through the C ABI (b200_<op>_process_dev), per-module CUDA events on request"""
+
+    def __init__(self, ab, torch, ops, w, h, dev, stream):
+        self.ab, self.torch, self.ops, self.stream = ab, torch, ops, stream
+        self.L = ab.lib()
+        self.bufs = [torch.empty((h, w, 4), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.fns = [getattr(self.L, f"b200_{op}_process_dev") for op, _ in ops]
+
+    def step(self, src, record=False):
+        torch, ab = self.torch, self.ab
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.ops) + 1)] if record else None
+        cur = src
+        for k, ((op, piece), fn) in enumerate(zip(self.ops, self.fns)):
+            if record:
+                evs[k].record()
+            dst = self.bufs[k & 1]
+            ab.check(fn(piece, cur.data_ptr(), dst.data_ptr(), self.stream))
+            cur = dst
+        if record:
+            evs[-1].record()
+        self.out = cur
+        return evs
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -429,10 +550,12 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = bind_near_gpu(local) if world > 1 else "single rank: all host CPUs (the CPU baseline runs on them)"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ab.init()
     L = ab.lib()
+    L.b200_kernel_timing_read.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     w, h = args.width, args.height
     npx = w * h
 
@@ -444,72 +567,77 @@ def run_b200(args):
     L.b200_fit_unbounded_coeffs(lut_ptrs, co_t.ctypes.data)
     conv_in = ab.make_conversion(util.MATRIX_CAM_TO_REC2020, identity=0x1001)
     conv_out = ab.make_conversion(util.MATRIX_REC2020_TO_SRGB, lut_target=enc, coeffs_target=co_t, identity=0x1002)
+    work, export = util.profile_pair(util.REC2020_TO_XYZ_D50), util.profile_pair(util.SRGB_TO_XYZ_D50)
+    fblob = np.ascontiguousarray(np.load(os.path.join(util.GOLDEN_DIR, "filmic_data.npz"))["default_v8"], np.uint8)
     d_dem, d_cin, d_cout = ab.demosaic_data(ab.DEMOSAIC_RCD), ab.colorin_data(conv_in), ab.colorout_data(conv_out)
-    p_dem = ab.make_piece(w, h, filters=filters, data=d_dem, devid=local)
-    p_cin = ab.make_piece(w, h, filters=0, channels=4, data=d_cin, devid=local)
-    p_cout = ab.make_piece(w, h, filters=0, channels=4, data=d_cout, devid=local)
+    d_dn = ab.denoiseprofile_data(ab.DENOISE_NLMEANS, radius=1, nbhood=7)
+    d_fp = ab.filmic_piece(fblob, work, export)
+
+    def piece_of(data, ch):
+        p = ab.make_piece(w, h, filters=filters if ch == 1 else 0, channels=ch, devid=local)
+        p.data, p.data_size = C.addressof(data), C.sizeof(data)
+        return p
 
     dev = torch.device("cuda", local)
-    t_mosaic = torch.from_numpy(mosaic).to(dev)
-    t_rgb = [torch.empty((h, w, 4), dtype=torch.float32, device=dev) for _ in range(3)]
     stream = torch.cuda.current_stream().cuda_stream
-    mod_ms = {"demosaic": [], "colorin": [], "colorout": []}
-    launches = [0]
-
-    def step(record=False):
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
-        if record:
-            evs[0].record()
-        ab.check(L.b200_demosaic_process_dev(p_dem, t_mosaic.data_ptr(), t_rgb[0].data_ptr(), stream))
-        if record:
-            evs[1].record()
-        ab.check(L.b200_colorin_process_dev(p_cin, t_rgb[0].data_ptr(), t_rgb[1].data_ptr(), stream))
-        if record:
-            evs[2].record()
-        ab.check(L.b200_colorout_process_dev(p_cout, t_rgb[1].data_ptr(), t_rgb[2].data_ptr(), stream))
-        if record:
-            evs[3].record()
-        launches[0] += 4  # rcd_ring_kernel, rcd_tiles_kernel, convert_kernel x2
-        return evs
+    t_mosaic = torch.from_numpy(mosaic).to(dev)
+    c3 = DeviceChain(ab, torch, [("demosaic", piece_of(d_dem, 1)), ("denoiseprofile", piece_of(d_dn, 4)), ("colorin", piece_of(d_cin, 4)),
+                                 ("filmicrgb", piece_of(d_fp, 4))], w, h, dev, stream)
+    c2 = DeviceChain(ab, torch, [("demosaic", piece_of(d_dem, 1)), ("colorin", piece_of(d_cin, 4)), ("colorout", piece_of(d_cout, 4))], w, h, dev, stream)
+    c2.bufs = c3.bufs                       # the two chains never run at the same time
+    # kernels per step: rcd_ring + rcd_tiles | vst_forward + nlm_group + vst_backward | convert | filmic_agx
+    LAUNCHES_C3 = 2 + 3 + 1 + 1
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-
-    # ---- timed region: exactly K steps, device-resident ----------------------------------------
-    launches[0] = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+    def timed_steps(chain, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        all_evs = [step(record=True) for _ in range(args.steps)]
+        all_evs = [chain.step(t_mosaic, record=True) for _ in range(steps)]
         e1.record()
         barrier()
-    ms = e0.elapsed_time(e1)
-    for evs in all_evs:
-        mod_ms["demosaic"].append(evs[0].elapsed_time(evs[1]))
-        mod_ms["colorin"].append(evs[1].elapsed_time(evs[2]))
-        mod_ms["colorout"].append(evs[2].elapsed_time(evs[3]))
-    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_max = float(t_ms.item())
+        t_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        mod = {op: float(np.mean([evs[k].elapsed_time(evs[k + 1]) for evs in all_evs])) for k, (op, _) in enumerate(chain.ops)}
+        return float(t_ms.item()), mod
+
+    for _ in range(max(args.warmup, 3)):
+        c3.step(t_mosaic)
+    barrier()
+
+    # ---- timed region: exactly K steps, device-resident, the two headline kernels bracketed by events on their stream ----
+    L.b200_kernel_timing(1)
+    with ClockSampler(local) as clk:
+        ms_max, mod_ms = timed_steps(c3, args.steps)
+    ksum, kcnt = C.c_double(), C.c_int()
+    kernel_ms = {}
+    for name in ("nlm_group_kernel", "rcd_tiles_kernel"):
+        ab.check(L.b200_kernel_timing_read(name.encode(), C.byref(ksum), C.byref(kcnt)))
+        kernel_ms[name] = (ksum.value / kcnt.value) if kcnt.value else None
+    L.b200_kernel_timing(0)
     value = world * npx * args.steps / (ms_max * 1e-3) / 1e6
-    gpu_launches = launches[0]
+    gpu_launches = LAUNCHES_C3 * args.steps
+
+    # ---- the lighter chain of configs[1], same frame, for continuity with round 1 --------------------------
+    for _ in range(3):
+        c2.step(t_mosaic)
+    c2_ms, c2_mod = timed_steps(c2, args.steps)
+    c2_line = {"workload": WORKLOAD_C2, "value": world * npx * args.steps / (c2_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": c2_ms / args.steps,
+               "per_module_ms": c2_mod}
 
     # ---- e2e: host buffers through the C module adapters + device-resident pipe glue -----------
     M = ds.modlib()
-    pipe = ds.make_pipe(devid=local, stream=None)
-    nodes = (ds.PipeNode * 3)()
-    pieces = [ds.make_piece_iop("demosaic", w, h, d_dem, channels_in=1, channels_out=4, filters=filters),
-              ds.make_piece_iop("colorin", w, h, d_cin, channels_in=4, channels_out=4),
-              ds.make_piece_iop("colorout", w, h, d_cout, channels_in=4, channels_out=4)]
-    for k, op in enumerate(("demosaic", "colorin", "colorout")):
+    pipe = ds.make_pipe(devid=local, stream=None, work_profile=ds.profile_info(*work), output_profile=ds.profile_info(*export))
+    fdata = (C.c_uint8 * fblob.size).from_buffer_copy(fblob.tobytes())
+    chain_ops = [("demosaic", d_dem, 1), ("denoiseprofile", d_dn, 4), ("colorin", d_cin, 4), ("filmicrgb", fdata, 4)]
+    pieces = [ds.make_piece_iop(op, w, h, data, channels_in=ch, channels_out=4, filters=filters if ch == 1 else 0, wb=WB) for op, data, ch in chain_ops]
+    nodes = (ds.PipeNode * len(chain_ops))()
+    for k, (op, _d, _c) in enumerate(chain_ops):
         nodes[k].process_cl = C.cast(getattr(M, f"dt_iop_{op}__process_cl"), C.c_void_p)
         nodes[k].module = pieces[k].module
         nodes[k].piece = C.pointer(pieces[k])
@@ -523,7 +651,7 @@ def run_b200(args):
     def e2e_run(n):
         tickets = []
         for i in range(n):
-            t = M.b200_pixelpipe_submit(queue, C.byref(pipe), nodes, 3, h_in.data_ptr(), h_out[i % DEPTH].data_ptr())
+            t = M.b200_pixelpipe_submit(queue, C.byref(pipe), nodes, len(chain_ops), h_in.data_ptr(), h_out[i % DEPTH].data_ptr())
             if t < 0:
                 raise RuntimeError("e2e chain failed: " + L.b200_last_error().decode())
             tickets.append(t)
@@ -540,13 +668,15 @@ def run_b200(args):
     e2e_run(args.e2e_steps)
     barrier()
     e2e_s = time.perf_counter() - t0
+    # the adapters must give what the ABI chain gives
+    e2e_same = bool(torch.equal(h_out[(args.e2e_steps - 1) % DEPTH].to(dev).view(torch.int32), c3_out_bits(c3, t_mosaic, torch)))
     # the synchronous single-frame call, for reference (one frame at a time: upload, chain, read back)
     bufs = M.b200_pipe_buffers_new()
     for _ in range(2):
-        M.b200_pixelpipe_process_on_gpu(C.byref(pipe), nodes, 3, bufs, h_in.data_ptr(), h_out[0].data_ptr())
+        M.b200_pixelpipe_process_on_gpu(C.byref(pipe), nodes, len(chain_ops), bufs, h_in.data_ptr(), h_out[0].data_ptr())
     t1 = time.perf_counter()
     for _ in range(4):
-        if M.b200_pixelpipe_process_on_gpu(C.byref(pipe), nodes, 3, bufs, h_in.data_ptr(), h_out[0].data_ptr()) != 0:
+        if M.b200_pixelpipe_process_on_gpu(C.byref(pipe), nodes, len(chain_ops), bufs, h_in.data_ptr(), h_out[0].data_ptr()) != 0:
             raise RuntimeError("e2e chain failed: " + L.b200_last_error().decode())
     e2e_sync_ms = (time.perf_counter() - t1) / 4 * 1e3
     M.b200_pipe_buffers_free(bufs)
@@ -555,23 +685,19 @@ def run_b200(args):
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = world * npx * args.e2e_steps / float(t_e.item()) / 1e6
     M.b200_pipe_queue_free(queue)
+    del h_out
 
     # ---- the other modules of SURVEY.md 8a at the same frame size (outside the timed region; N=1 only) ----
     other = None
+    t_rgb = c3.bufs
     if world == 1 and not args.no_other_modules:
         other = {}
-        work, export = util.profile_pair(util.REC2020_TO_XYZ_D50), util.profile_pair(util.SRGB_TO_XYZ_D50)
-        fblob = np.load(os.path.join(util.GOLDEN_DIR, "filmic_data.npz"))["default_v8"]
-        fp = ab.filmic_piece(fblob, work, export)
         cases = [("denoiseprofile_wavelets", "denoiseprofile", ab.denoiseprofile_data(ab.DENOISE_WAVELETS), 2),
-                 ("denoiseprofile_nlmeans_K7_P1", "denoiseprofile", ab.denoiseprofile_data(ab.DENOISE_NLMEANS, radius=1, nbhood=7), 1),
-                 ("filmicrgb_v8_agx", "filmicrgb", fp, 3),
                  ("diffuse_sharpen_demosaic_1it_5scales", "diffuse", ab.diffuse_data(**ab.DIFFUSE_PRESETS["sharpen_demosaic_aa"]), 2),
                  ("bilat_local_laplacian", "bilat", ab.bilat_data(), 2)]
         t_rgb[0].copy_(torch.rand((h, w, 4), device=dev))
         for label, op, data, reps in cases:
-            pc = ab.make_piece(w, h, filters=0, channels=4, devid=local)
-            pc.data, pc.data_size = C.addressof(data), C.sizeof(data)
+            pc = piece_of(data, 4)
             fn = getattr(L, f"b200_{op}_process_dev")
             ab.check(fn(pc, t_rgb[0].data_ptr(), t_rgb[1].data_ptr(), stream))
             torch.cuda.synchronize()
@@ -586,8 +712,7 @@ def run_b200(args):
             m = float(np.median(ts))
             other[label] = {"ms": m, "MP_per_s": npx / m / 1e3, "algorithmic_GBps": 32 * npx / (m * 1e-3) / 1e9}
         # the second demosaicer of the north star on the bench frame (20 B/px at the module boundary)
-        d_amz = ab.demosaic_data(ab.DEMOSAIC_AMAZE)
-        p_amz = ab.make_piece(w, h, filters=filters, data=d_amz, devid=local)
+        p_amz = piece_of(ab.demosaic_data(ab.DEMOSAIC_AMAZE), 1)
         ts = []
         for k in range(4):
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -603,105 +728,54 @@ def run_b200(args):
         # the modules either side of the path and the sensor-to-display chain; never part of the headline
         other["pipe_ends"] = pipe_ends_in_child(w, h, local)
 
-    # ---- second mode at N>1: ONE frame cut into row bands + all-gather ---------
+    # ---- second mode at N>1: ONE frame cut into row bands + one all-gather ---------
     banded = None
     if world > 1:
-        from ansel_b200 import bands
-        bnodes = [bands.Node("demosaic", d_dem, channels_in=1), bands.Node("colorin", d_cin), bands.Node("colorout", d_cout)]
-        frame0 = util.frame_natural(w, h, SEED)          # the same frame on every rank
-        ch = bands.BandedChain(bnodes, w, h, rank, world, device=dev)
-        t_band = torch.from_numpy(np.ascontiguousarray(ch.band_rows(frame0))).to(dev)
-        for _ in range(3):
-            ch(t_band, stream=stream)
-        barrier()
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b0.record()
-        for _ in range(args.steps):
-            out_frame = ch(t_band, stream=stream)
-        b1.record()
-        barrier()
-        t_b = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t_b, op=dist.ReduceOp.MAX)
-        # every rank must now hold the frame rank 0 computes untiled
-        same = torch.ones(1, dtype=torch.int32, device=dev)
-        if rank == 0:
-            t_full = torch.from_numpy(frame0).to(dev)
-            ab.check(L.b200_demosaic_process_dev(p_dem, t_full.data_ptr(), t_rgb[0].data_ptr(), stream))
-            ab.check(L.b200_colorin_process_dev(p_cin, t_rgb[0].data_ptr(), t_rgb[1].data_ptr(), stream))
-            ab.check(L.b200_colorout_process_dev(p_cout, t_rgb[1].data_ptr(), t_rgb[2].data_ptr(), stream))
-            same[0] = int(torch.equal(out_frame.view(torch.int32), t_rgb[2].view(torch.int32)))
-        dist.broadcast(same, 0)
-        banded = {"value": npx * args.steps / (float(t_b.item()) * 1e-3) / 1e6, "unit": UNIT, "ms_per_frame": float(t_b.item()) / args.steps,
-                  "collective": "all-gather of finished RGBA bands (one ncclBroadcast per band, NVLink)",
-                  "cuts": "RCD 94-row block grid, 9-row halo", "bit_identical_to_untiled": bool(same.item()),
-                  "gathered_bytes_per_frame": 16 * npx}
-        # the same, with the gather fused into colorout's stores (peer frames mapped over CUDA IPC)
-        try:
-            ch2 = bands.BandedChain(bnodes, w, h, rank, world, device=dev, p2p=True)
-            for _ in range(3):
-                ch2(t_band, stream=stream)
-            barrier()
-            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            c0.record()
-            for _ in range(args.steps):
-                out2 = ch2(t_band, stream=stream)
-            c1.record()
-            barrier()
-            t_c = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
-            dist.all_reduce(t_c, op=dist.ReduceOp.MAX)
-            same2 = torch.tensor([int(torch.equal(out2.view(torch.int32), out_frame.view(torch.int32)))], dtype=torch.int32, device=dev)
-            dist.all_reduce(same2, op=dist.ReduceOp.MIN)
-            ch2.close()
-            # gather to the exporting rank only (what an export needs): every band has one destination
-            ch3 = bands.BandedChain(bnodes, w, h, rank, world, device=dev, p2p=True, p2p_dst=0)
-            for _ in range(3):
-                ch3(t_band, stream=stream)
-            barrier()
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record()
-            for _ in range(args.steps):
-                out3 = ch3(t_band, stream=stream)
-            g1.record()
-            barrier()
-            t_g = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
-            dist.all_reduce(t_g, op=dist.ReduceOp.MAX)
-            same3 = torch.ones(1, dtype=torch.int32, device=dev)
-            if rank == 0:
-                same3[0] = int(torch.equal(out3.view(torch.int32), out_frame.view(torch.int32)))
-            dist.broadcast(same3, 0)
-            ch3.close()
-            banded["fused_p2p_gather_to_rank0"] = {"value": npx * args.steps / (float(t_g.item()) * 1e-3) / 1e6,
-                                                   "ms_per_frame": float(t_g.item()) / args.steps, "bit_identical_to_collective": bool(same3.item())}
-            banded["fused_p2p"] = {"value": npx * args.steps / (float(t_c.item()) * 1e-3) / 1e6, "ms_per_frame": float(t_c.item()) / args.steps,
-                                   "how": "colorout stores each pixel into every rank's frame (CUDA IPC peer mappings), then one barrier",
-                                   "bit_identical_to_collective": bool(same2.item())}
-        except Exception as e:  # no peer access on this box: keep the NCCL number
-            banded["fused_p2p"] = {"unavailable": str(e)[:200]}
+        banded = banded_modes(args, ab, util, torch, dist, world, rank, dev, stream, w, h, npx, barrier,
+                              dict(dem=d_dem, dn=d_dn, cin=d_cin, cout=d_cout, fp=d_fp), c3, c2)
 
-    # ---- roofline of the dominant kernel (RCD tiles) --------------------------------------------
+    # ---- roofline of the dominant kernel (non-local means) and of RCD ------------------------------------
     peak, peak_src = peaks()
-    dem_ms = float(np.mean(mod_ms["demosaic"]))
-    achieved = ALGO_BYTES_PER_PX["demosaic"] * npx / (dem_ms * 1e-3) / 1e9
-    traffic = None
+    nlm_ms = kernel_ms["nlm_group_kernel"]
+    traffic = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("rcd_tiles_kernel_dram_bytes_per_launch")
+            traffic = json.load(open(tpath))
         except Exception:
-            traffic = None
-    per_module = {k: {"ms": float(np.mean(v)), "algorithmic_GBps": ALGO_BYTES_PER_PX[k] * npx / (float(np.mean(v)) * 1e-3) / 1e9,
-                      "frac_of_hbm_peak": ALGO_BYTES_PER_PX[k] * npx / (float(np.mean(v)) * 1e-3) / 1e9 / peak}
-                  for k, v in mod_ms.items()}
+            traffic = {}
+    per_module = {k: {"ms": v, "algorithmic_GBps": ALGO_BYTES_PER_PX[k] * npx / (v * 1e-3) / 1e9,
+                      "frac_of_hbm_peak": ALGO_BYTES_PER_PX[k] * npx / (v * 1e-3) / 1e9 / peak} for k, v in mod_ms.items()}
+    chain_bytes = sum(ALGO_BYTES_PER_PX[k] for k in mod_ms)
+    roof = None
+    if nlm_ms:
+        achieved = ALGO_BYTES_PER_PX["denoiseprofile"] * npx / (nlm_ms * 1e-3) / 1e9
+        flops = NLM_FLOP_PER_PX_PATCH * 225 * npx / (nlm_ms * 1e-3) / 1e12
+        roof = {"bound": "hbm", "kernel": "nlm_group_kernel (non-local means, 225 patches; the vst kernels either side are < 2% of the module)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get("nlm_group_kernel_dram_bytes_per_launch"),
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX["denoiseprofile"] * npx, "avg_launch_ms": nlm_ms,
+                "launches_timed": args.steps, "share_of_step": nlm_ms / (ms_max / args.steps),
+                "fp32": {"achieved_tflops": flops, "peak_tflops": FP32_PEAK_TFLOPS, "frac": flops / FP32_PEAK_TFLOPS,
+                         "flop_per_pixel": NLM_FLOP_PER_PX_PATCH * 225,
+                         "note": "the kernel is arithmetic-bound by construction (8.7 kflop per pixel against 32 B): the FP32 fraction is the meaningful one; "
+                                 "peak = one packed FP32 instruction per scheduler and clock at 1965 MHz, unfused (bit parity forbids FMA contraction)"},
+                "chain": {"algorithmic_bytes_per_px": chain_bytes, "achieved_GBps": chain_bytes * npx / (ms_max / args.steps * 1e-3) / 1e9,
+                          "frac": chain_bytes * npx / (ms_max / args.steps * 1e-3) / 1e9 / peak},
+                "rcd_tiles_kernel": None if not kernel_ms["rcd_tiles_kernel"] else {
+                    "avg_launch_ms": kernel_ms["rcd_tiles_kernel"], "achieved": ALGO_BYTES_PER_PX["demosaic"] * npx / (kernel_ms["rcd_tiles_kernel"] * 1e-3) / 1e9,
+                    "frac": ALGO_BYTES_PER_PX["demosaic"] * npx / (kernel_ms["rcd_tiles_kernel"] * 1e-3) / 1e9 / peak,
+                    "traffic": traffic.get("rcd_tiles_kernel_dram_bytes_per_launch")}}
 
     # ---- CPU baseline, rank 0 at N=1 only, bounded sample ---------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        chain = CpuChain(w, h)
-        cores = tune_cpu_threads(chain, mosaic)
-        ts = time_cpu(chain, mosaic, 1, 4)
-        cpu = {"value": w * h / float(np.median(ts)) / 1e6, "unit": UNIT, "cores": cores, "kind": chain.kind,
-               "sample": f"4 full {w}x{h} frames through the same chain after 1 warm-up (median), "
-                         f"{'reference sources, release flags, ' if chain.kind == 'reference' else 'oracle port, '}OpenMP, thread count tuned (all logical CPUs or one per core, whichever is faster)"}
+        rows, per_row = cpu_sample_rows(w, h, 20.0, 4)
+        chain = CpuChain(w, rows)
+        ts = time_cpu(chain, mosaic[:rows].copy(), 1, 3)
+        cpu = {"value": w * rows / float(np.median(ts)) / 1e6, "unit": UNIT, "cores": _CPU_THREADS, "kind": chain.kind,
+               "sample": f"3 steps after 1 warm-up (median), each the top {rows} rows of the {w}x{h} frame through the same chain, "
+                         f"{'reference sources, release flags, ' if chain.kind == 'reference' else 'oracle port, '}OpenMP, {_CPU_THREADS} threads "
+                         f"(one per physical core), OMP_PROC_BIND={os.environ.get('OMP_PROC_BIND')}"}
 
     if rank == 0:
         line = {
@@ -710,19 +784,16 @@ def run_b200(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frame": f"{w}x{h}", "frames_per_step": world,
                        "parallelism": f"{world} independent frame replicas, no data-path collective",
-                       "l2": "inputs larger than L2: 182 MB mosaic + 3 x 727 MB RGBA per step vs 126 MB L2",
-                       "fp": "RCD: C-standard float semantics (no contraction); colour: reference release-build contraction",
-                       "per_module": per_module},
+                       "l2": "inputs larger than L2: 182 MB mosaic + 2 x 727 MB RGBA ping-pong per step vs 126 MB L2",
+                       "fp": "C-standard float semantics (no contraction) = the strict build of the reference's sources; colorin: the release build's contraction",
+                       "per_module": per_module, "host_binding": numa, "c2": c2_line},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * npx, "d2h_bytes_per_step": 16 * npx,
                     "steps": args.e2e_steps,
                     "path": "dt_iop_<op>__process_cl adapters via b200_pixelpipe_submit/_wait, 2 frames in flight, pinned host buffers",
-                    "single_frame_sync_ms": e2e_sync_ms},
+                    "single_frame_sync_ms": e2e_sync_ms, "bit_identical_to_the_abi_chain": e2e_same},
             "gpu_launches": gpu_launches,
             "clocks": clk.summary(),
-            "roofline": {"bound": "hbm", "kernel": "rcd_tiles_kernel (+rcd_ring_kernel, <1% of the pair)", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX["demosaic"] * npx,
-                         "avg_launch_ms": dem_ms},
+            "roofline": roof,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
@@ -733,6 +804,96 @@ def run_b200(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def c3_out_bits(chain, t_mosaic, torch):
+    chain.step(t_mosaic)
+    torch.cuda.synchronize()
+    return chain.out.view(torch.int32)
+
+
+def banded_modes(args, ab, util, torch, dist, world, rank, dev, stream, w, h, npx, barrier, d, c3, c2):
+    """ONE frame over the ranks in row bands (ansel_b200/bands.py): the C3 chain (tiling.c-style cuts: halo = the modules' overlaps,
+    one all-gather of the finished bands) and the C2 chain (RCD block-grid cuts, bit-identical to the untiled frame; NCCL and the
+    gather fused into colorout's stores)."""
+    from ansel_b200 import bands
+    out = {}
+    frame0 = util.frame_natural(w, h, SEED)          # the same frame on every rank
+    t_full = torch.from_numpy(frame0).to(dev)
+
+    def timed(chain, t_band, steps):
+        for _ in range(3):
+            chain(t_band, stream=stream)
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(steps):
+            res = chain(t_band, stream=stream)
+        b1.record()
+        barrier()
+        t_b = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_b, op=dist.ReduceOp.MAX)
+        return float(t_b.item()) / steps, res
+
+    # C3 in bands
+    try:
+        nodes3 = [bands.Node("demosaic", d["dem"], channels_in=1), bands.Node("denoiseprofile", d["dn"]), bands.Node("colorin", d["cin"]),
+                  bands.Node("filmicrgb", d["fp"])]
+        ch = bands.BandedChain(nodes3, w, h, rank, world, device=dev)
+        t_band = torch.from_numpy(np.ascontiguousarray(ch.band_rows(frame0))).to(dev)
+        ms, frame = timed(ch, t_band, args.steps)
+        c3.step(t_full)
+        torch.cuda.synchronize()
+        diff = (frame - c3.out).abs()
+        ndiff = torch.tensor([float((frame.view(torch.int32) != c3.out.view(torch.int32)).sum().item()), float(diff.max().item())], dtype=torch.float64, device=dev)
+        dist.all_reduce(ndiff, op=dist.ReduceOp.MAX)
+        one_ms = torch.tensor([0.0], dtype=torch.float64, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        c3.step(t_full)
+        e1.record()
+        torch.cuda.synchronize()
+        one_ms[0] = e0.elapsed_time(e1)
+        dist.all_reduce(one_ms, op=dist.ReduceOp.MAX)
+        out["c3"] = {"workload": WORKLOAD, "value": npx / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_frame": ms, "one_gpu_ms_per_frame": float(one_ms.item()),
+                     "speedup_over_one_gpu": float(one_ms.item()) / ms, "scaling": "strong",
+                     "cuts": f"tiling.c-style full-width tiles, halo {ch.halo} rows = the sum of the modules' tiling_callback overlaps",
+                     "collective": ch.collective, "gathered_bytes_per_frame": 16 * npx,
+                     "vs_untiled": {"floats_differing": int(ndiff[0].item()), "max_abs": float(ndiff[1].item()),
+                                    "why": "the reference's own tiles differ from its untiled frame the same way: RCD's tile grid and the non-local-means "
+                                           "chunk grid start at the tile origin (tests/test_bands_gpu.py checks each band against the oracle on the same cuts)"}}
+    except Exception as e:
+        out["c3"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
+    # C2 in bands: NCCL exchange, then the gather fused into colorout
+    try:
+        nodes2 = [bands.Node("demosaic", d["dem"], channels_in=1), bands.Node("colorin", d["cin"]), bands.Node("colorout", d["cout"])]
+        ch = bands.BandedChain(nodes2, w, h, rank, world, device=dev)
+        t_band = torch.from_numpy(np.ascontiguousarray(ch.band_rows(frame0))).to(dev)
+        ms, frame = timed(ch, t_band, args.steps)
+        c2.step(t_full)
+        torch.cuda.synchronize()
+        same = torch.tensor([int(torch.equal(frame.view(torch.int32), c2.out.view(torch.int32)))], dtype=torch.int32, device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        out["c2"] = {"workload": WORKLOAD_C2, "value": npx / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_frame": ms, "collective": ch.collective,
+                     "cuts": "RCD 94-row block grid, 9-row halo", "bit_identical_to_untiled": bool(same.item()), "gathered_bytes_per_frame": 16 * npx}
+        ref_frame = frame.clone()
+        for key, dst in (("fused_p2p", None), ("fused_p2p_gather_to_rank0", 0)):
+            try:
+                chp = bands.BandedChain(nodes2, w, h, rank, world, device=dev, p2p=True, p2p_dst=dst)
+                msp, fr = timed(chp, t_band, args.steps)
+                ok = torch.ones(1, dtype=torch.int32, device=dev)
+                if fr is not None:
+                    ok[0] = int(torch.equal(fr.view(torch.int32), ref_frame.view(torch.int32)))
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                chp.close()
+                out["c2"][key] = {"value": npx / (msp * 1e-3) / 1e6, "ms_per_frame": msp, "bit_identical_to_collective": bool(ok.item()),
+                                  "how": "colorout stores each pixel into the destination frames itself (CUDA IPC peer mappings), then one barrier"}
+            except Exception as e:  # no peer access on this box: keep the NCCL number
+                out["c2"][key] = {"unavailable": str(e)[:200]}
+    except Exception as e:
+        out["c2"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+    return out
 
 
 if __name__ == "__main__":

@@ -64,6 +64,22 @@ def test_chain_cuts_follow_the_modules(built):
     assert g == 1 and halo == 10 + 1 + 7 and align == 2          # demosaic.c:1972-1982 + denoiseprofile.c:803-811
     with pytest.raises(NotImplementedError):
         bands.chain_cuts([bands.Node("bilat", ab.bilat_data())], 800, 600)
+    # whole-frame green sums: refused; colour smoothing: one more halo row per pass, tiling.c-style cuts (no block grid)
+    for mode in (ab.GREEN_EQ_FULL, ab.GREEN_EQ_BOTH):
+        dd = ab.demosaic_data(ab.DEMOSAIC_RCD)
+        dd.green_eq = mode
+        with pytest.raises(NotImplementedError):
+            bands.chain_cuts([bands.Node("demosaic", dd, channels_in=1), cin], 8256, 5504)
+    dd = ab.demosaic_data(ab.DEMOSAIC_RCD)
+    dd.green_eq, dd.color_smoothing = ab.GREEN_EQ_LOCAL, 3
+    g, halo, align = bands.chain_cuts([bands.Node("demosaic", dd, channels_in=1), cin], 8256, 5504)
+    assert g == 1 and halo == 10 + 3
+    # the dual demosaic (RCD | 2048) blends pointwise: still on RCD's block grid; AMaZE is not
+    g2, h2, a2 = C.c_int(), C.c_int(), C.c_int()
+    for method, want in ((ab.DEMOSAIC_RCD | 2048, 94), (ab.DEMOSAIC_AMAZE, 1)):
+        piece = ab.make_piece(800, 600, filters=0x94949494, channels=1, data=ab.demosaic_data(method))
+        ab.lib().b200_demosaic_band_grid(C.byref(piece), C.byref(g2), C.byref(h2), C.byref(a2))
+        assert g2.value == want
     with pytest.raises(NotImplementedError):
         bands.chain_cuts([bands.Node("denoiseprofile", ab.denoiseprofile_data(ab.DENOISE_WAVELETS))], 800, 600)
 
@@ -107,16 +123,24 @@ def _worker(rank, world, port, mode, w, h, q):
         mosaic = np.random.default_rng(7).random((h, w), dtype=np.float32)
         nodes = [bands.Node("demosaic", ab.demosaic_data(ab.DEMOSAIC_RCD), channels_in=1),
                  bands.Node("colorin", ab.colorin_data(ab.make_conversion(util.MATRIX_CAM_TO_REC2020)))]
+        tiles = mode.endswith("-tiles")   # a module with an overlap in the chain: tiling.c-style cuts, equal bands, gathered in place
+        if tiles:
+            nodes.insert(1, bands.Node("denoiseprofile", ab.denoiseprofile_data(ab.DENOISE_NLMEANS, radius=1, nbhood=7)))
+            mode = mode[:-6]
         ch = bands.BandedChain(nodes, w, h, rank, world, process=_process)
         band_in = torch.from_numpy(np.ascontiguousarray(ch.band_rows(mosaic)))
         frame = ch(band_in, mode=mode)
         want = standin_pointwise(standin_demosaic(mosaic, 0))
+        if tiles:
+            want = standin_pointwise(want)
         if frame is None:
             ok = mode == "gather" and rank != 0
         else:
             got = frame.numpy()
             # ch0 of the untiled stand-in clips its window at the FRAME edge only; ch1, ch2 are global row / block ids
-            ok = bool((got == want).all())
+            # (ch2 follows the band-local block grid, which tiling.c-style cuts do not align with the frame's)
+            ok = bool((got[..., :2] == want[..., :2]).all()) if tiles else bool((got == want).all())
+            ok = ok and ch.equal_bands == tiles and "one ncclAllGather" in ch.collective
         q.put((rank, ok, [(b.out_y0, b.out_y1) for b in ch.bands]))
     finally:
         dist.destroy_process_group()
@@ -130,13 +154,13 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,mode", [(2, "allgather"), (3, "allgather"), (2, "gather")])
+@pytest.mark.parametrize("world,mode", [(2, "allgather"), (3, "allgather"), (2, "gather"), (2, "allgather-tiles"), (4, "allgather-tiles")])
 def test_banded_chain_over_gloo(built, world, mode):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, mode, 96, 700, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, mode, 96, 704 if mode.endswith("-tiles") else 700, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]

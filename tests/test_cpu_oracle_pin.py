@@ -512,3 +512,31 @@ def test_filmic_reconstruct_oracle_equals_golden():
     for name in RECONSTRUCT_CASES:
         rc, frame, mask = util.oracle_filmic_reconstruct(g["img"], g["data_" + name])
         assert rc == 1 and same_bits(frame, g["frame_" + name]).all() and same_bits(mask, g["mask_" + name]).all()
+
+
+@need_ref
+def test_denoiseprofile_nlmeans_module_is_the_reference_pieces_in_order():
+    """process_nlmeans_cpu(), denoiseprofile.c:1599-1648, composed from the reference's own precondition_v2, nlmeans_denoise and
+    backtransform_v2 with the parameters nlmeans_precondition() :1500-1533 derives (exported by the oracle's NLM plan): what
+    bench.py's CPU arm runs for the denoise node of the C3 chain, and what the oracle's module-level entry point restates"""
+    import ctypes as C
+    import ansel_b200 as ab
+    O, R = util.oracle(), util.ref("strict")
+    f4 = lambda v: (C.c_float * 4)(*v)  # noqa: E731
+    w, h = 300, 200
+    img = util.rgba_scene(w, h, 5)
+    d = ab.denoiseprofile_data(ab.DENOISE_NLMEANS, radius=1, nbhood=7)
+    wbc, pm = (2.0, 1.0, 1.5, 0.0), (1.0, 1.0, 1.0, 1.0)
+    plan = np.zeros(51, np.float32)
+    O.orc_dn_plan_export_nlm(C.byref(d), C.c_float(1.0), w, h, f4(wbc), f4(pm), util.fptr(plan))
+    wb, p, a_eff, b, bias = plan[1:5], plan[5:9], plan[9], plan[10], plan[11]
+    pre = np.zeros_like(img)
+    R.ref_dn_precondition_v2(util.fptr(img), util.fptr(pre), w, h, C.c_float(a_eff), f4(p), C.c_float(b), f4(wb))
+    nlm = util.ref_nlmeans(pre, kind="strict", sharpness=float(np.float32(0.045) / np.float32(9)), center_weight=float(np.float32(d.central_pixel_weight)), P=1, K=7)
+    buf = np.ascontiguousarray(nlm)
+    R.ref_dn_backtransform_v2(util.fptr(buf), w, h, C.c_float(a_eff), f4(p), C.c_float(b), C.c_float(bias), f4(wb))
+    f = O.orc_denoiseprofile_nlmeans
+    f.restype = C.c_int
+    want = np.zeros_like(img)
+    assert f(util.fptr(img), util.fptr(want), w, h, C.byref(d), C.c_float(1.0), 1, f4(wbc), f4(pm)) == 0
+    assert same_bits(buf, want).all()
