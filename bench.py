@@ -712,7 +712,8 @@ def run_b200(args):
             m = float(np.median(ts))
             other[label] = {"ms": m, "MP_per_s": npx / m / 1e3, "algorithmic_GBps": 32 * npx / (m * 1e-3) / 1e9}
         # the second demosaicer of the north star on the bench frame (20 B/px at the module boundary)
-        p_amz = piece_of(ab.demosaic_data(ab.DEMOSAIC_AMAZE), 1)
+        d_amz = ab.demosaic_data(ab.DEMOSAIC_AMAZE)   # the piece points at it: keep it alive
+        p_amz = piece_of(d_amz, 1)
         ts = []
         for k in range(4):
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

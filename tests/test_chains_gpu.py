@@ -92,6 +92,14 @@ def test_c3_chain_bit_exact(built):
     assert same_bits(g.cpu().numpy(), o).all()
 
 
+def test_c3_chain_full_width_strip_bit_exact(built):
+    """C3 on a strip as wide as the 45 MP bench frame (8256 x 600): RCD's 88 tile columns, the 115 chunk columns of the
+    non-local means and the pointwise kernels' row geometry are the frame's own"""
+    dev, g, o, _k = _front(util.SIZE_45MP[0], 600, util.SEEDS[2], K=7)
+    g, o = _filmic(dev, g, o)
+    assert same_bits(g.cpu().numpy(), o).all()
+
+
 def test_c4_chain_bit_exact(built):
     """C4: RCD -> denoiseprofile -> colorin -> diffuse (stock sharpen preset) -> filmic -> [RGB->Lab] local
     contrast [Lab->RGB] -> colorout (matrix + sRGB curve)."""

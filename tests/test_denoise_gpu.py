@@ -114,6 +114,14 @@ def test_wavelet_denoise_tiny_image_is_a_copy(built):
     assert same_bits(got, img).all()
 
 
+def test_wavelet_denoise_full_width_strip_matches_oracle(built):
+    """a strip as wide as the 45 MP bench frame (8256 px): the row geometry of the decompose tiles is the frame's own"""
+    import ansel_b200 as ab
+    img = util.rgba_scene(util.SIZE_45MP[0], 600, 11)
+    data = ab.denoiseprofile_data(ab.DENOISE_WAVELETS)
+    assert_close_ulp(run_denoise(img, data), util.oracle_denoise_wavelets(img, data))
+
+
 def test_wavelet_denoise_12mp_matches_oracle(built):
     import ansel_b200 as ab
     img = util.rgba_scene(4000, 3000, util.SEEDS[0])

@@ -80,6 +80,14 @@ def test_diffuse_large_radius_many_scales(built):
     assert same_bits(cuda_diffuse(img, d), util.oracle_diffuse(img, d)).all()
 
 
+def test_diffuse_full_width_strip_bit_exact(built):
+    """a strip as wide as the 45 MP bench frame (8256 px)"""
+    import ansel_b200 as ab
+    img = util.rgba_scene(util.SIZE_45MP[0], 600, 12)
+    d = ab.diffuse_data(**_diffuse_cases()["sharpen_demosaic_aa"])
+    assert same_bits(cuda_diffuse(img, d), util.oracle_diffuse(img, d)).all()
+
+
 def test_diffuse_12mp_matches_oracle(built):
     import ansel_b200 as ab
     img = util.rgba_scene(4000, 3000, util.SEEDS[0])

@@ -86,12 +86,48 @@ def test_nlmeans_24mp_bit_exact(built):
     assert same_bits(got, want).all()
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(P=2, K=5), dict(center_weight=-1.0, sharpness=0.01, luma=0.8, chroma=0.6, K=4, P=2, norm=(0.7, 1.3, 0.9, 1.0))])
+def test_nlmeans_full_width_strip_bit_exact(built, kw):
+    """a strip as wide as the 45 MP bench frame: the chunk grid across the row (114 full columns + the 48-px remainder) and the
+    group kernel's window at the right edge are the frame's own"""
+    w, h = util.SIZE_45MP[0], 600
+    img = (util.rgba_scene(w, h, 7, noise=0.02) * 60).astype(np.float32)
+    got = cuda_nlm(img, **kw)
+    want = util.oracle_nlmeans(img, **kw)
+    bad = ~same_bits(got, want)
+    assert not bad.any(), f"{int(bad.sum())} floats differ, first {np.argwhere(bad)[:4].tolist()}"
+
+
 def test_nlmeans_45mp_deterministic(built):
     w, h = util.SIZE_45MP
     img = (util.rgba_scene(w, h, util.SEEDS[2], noise=0.02) * 60).astype(np.float32)
     a = cuda_nlm(img)
     assert np.isfinite(a).all()
     assert same_bits(a, cuda_nlm(img)).all()
+
+
+def test_chunk_kernel_is_bit_exact_too(built, monkeypatch):
+    """the round-1 kernel (one chunk per CTA, patches one after the other): what runs where the group kernel's window does not fit"""
+    monkeypatch.setenv("B200_NLM_CHUNKS", "1")
+    for cfg in (0, 1, 4, 6):
+        img = (util.rgba_scene(301, 203, 2, noise=0.02) * 60).astype(np.float32)
+        kw = CONFIGS[cfg]
+        assert same_bits(cuda_nlm(img, **kw), util.oracle_nlmeans(img, **kw)).all(), cfg
+
+
+def test_extreme_pixels_through_the_group_kernel(built):
+    """zeros (weights of exactly 1), infinities, NaN, values next to FLT_MAX and subnormals: Markstein's division, the clamp in
+    front of it and the packed lanes must leave what the reference leaves (tests/test_cpu_nlm_emulation.py has the same frame)"""
+    img = (util.rgba_scene(160, 130, 4, noise=0.02) * 60).astype(np.float32)
+    img[20:60, 30:90, :3] = 0.0
+    img[70:90, 10:50, :3] = 1e-30
+    img[100, 100, :3] = (np.inf, 1.0, 2.0)
+    img[101, 120, :3] = (np.nan, 1.0, 2.0)
+    img[110, 20, :3] = (3e38, -3e38, 1e19)
+    img[5, 5, :3] = (1e-40, 1e-44, 0.0)
+    for kw in (dict(K=3), dict(K=3, center_weight=-1.0, sharpness=0.01), dict(K=2, P=2, norm=(0.5, 2.0, 1.5, 1.0))):
+        bad = ~same_bits(cuda_nlm(img, **kw), util.oracle_nlmeans(img, **kw))
+        assert not bad.any(), f"{kw}: {int(bad.sum())} floats differ, first {np.argwhere(bad)[:4].tolist()}"
 
 
 def test_window_kernel_is_bit_exact_too(built, monkeypatch):

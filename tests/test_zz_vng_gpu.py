@@ -68,14 +68,20 @@ def test_dual_rcd_vng4_bit_exact(built, name):
     m, filters, x, y = vu.case(name)
     m = np.nan_to_num(m)
     rf = ab.lib().b200_roi_filters(C.c_uint32(filters), x, y)
-    sharp = util.oracle_rcd(m, rf)
+    sharp = np.ascontiguousarray(util.oracle_rcd(m, rf), np.float32)
     undefined = (util.oracle_rcd_mask(m, rf) & 1) != 0
+    far = np.ones(m.shape, bool)
     if undefined.any():
-        pytest.skip("this geometry has undefined RCD sites feeding the 9x9 mask blur")
+        # rcd.c leaves those sites to uninitialised scratch: the oracle blend is fed what the device left there, and pixels within
+        # reach of one (3x3 Scharr, then the 9x9 blur of the mask) are not compared
+        import scipy.ndimage as ndi
+        sharp = np.where(undefined[..., None], cuda_demosaic(m, filters, ab.DEMOSAIC_RCD, x, y), sharp)
+        far = ~ndi.binary_dilation(undefined, iterations=6)
+        assert far.mean() > 0.5
     for thr in (0.2, 1.0):
         want = vu.oracle_dual(sharp, m, filters, x, y, thr)
         got = cuda_demosaic(m, filters, ab.DEMOSAIC_RCD | DUAL, x, y, dual_thrs=thr)
-        assert same_bits(got[..., :3], want[..., :3]).all(), thr     # lane 3 of the sharp frame is the demosaicer's business (alpha)
+        assert same_bits(got[..., :3], want[..., :3])[far].all(), thr     # lane 3 of the sharp frame is the demosaicer's business (alpha)
 
 
 def test_dual_on_a_frame_without_undefined_rcd_sites_and_with_amaze(built):
