@@ -49,13 +49,23 @@ class Node:
     channels_in: int = 4
 
 
+def needs_whole_frame(n: Node) -> bool:
+    """modules whose result depends on statistics or structures of the whole frame: the local Laplacian pyramid (bilat) and the
+    wavelet thresholds of the profiled denoise (both refuse tiling in the reference too)"""
+    return n.op in WHOLE_FRAME_OPS or (n.op == "denoiseprofile" and n.data.mode not in (ab.DENOISE_NLMEANS, ab.DENOISE_NLMEANS_AUTO))
+
+
 def chain_cuts(nodes: list[Node], width: int, height: int) -> tuple[int, int, int]:
     """(grid, halo, align) for a chain, from each module's own tiling numbers."""
     L = ab.lib()
     overlaps, aligns = [], []
     for n in nodes:
-        if n.op in WHOLE_FRAME_OPS or (n.op == "denoiseprofile" and n.data.mode not in (ab.DENOISE_NLMEANS, ab.DENOISE_NLMEANS_AUTO)):
-            raise NotImplementedError(f"{n.op}: needs whole-frame statistics -- run it as replicas (SURVEY.md 8e)")
+        if needs_whole_frame(n):
+            raise NotImplementedError(f"{n.op}: needs whole-frame statistics -- run it as replicas or in a SegmentedChain (SURVEY.md 8e)")
+        if n.op == "colorspace":
+            overlaps.append(0)
+            aligns.append(1)
+            continue
         piece = ab.make_piece(width, height, filters=0x94949494 if n.channels_in == 1 else 0, channels=n.channels_in, data=n.data)
         t = ab.Tiling()
         getattr(L, f"b200_{n.op}_tiling")(C.byref(piece), C.byref(t))
@@ -88,7 +98,13 @@ class _DeviceArray:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
 
 
-def _cuda_process(op, piece, src, dst, stream):
+def _cuda_process(op, piece, src, dst, stream, node=None):
+    if op == "colorspace":   # the pipe's RGB <-> Lab glue between modules (pixelpipe_hb.c dt_ioppr_transform_image_colorspace): pointwise
+        cst_from, cst_to, pm = node.data
+        f = ab.lib().b200_colorspace_transform_dev
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(ab.ProfileMatrices), C.c_int, C.c_void_p]
+        ab.check(f(src.data_ptr(), dst.data_ptr(), piece.roi_in.width, piece.roi_in.height, cst_from, cst_to, C.byref(pm), 0, stream))
+        return
     ab.check(getattr(ab.lib(), f"b200_{op}_process_dev")(C.byref(piece), src.data_ptr(), dst.data_ptr(), stream))
 
 
@@ -112,7 +128,8 @@ class BandedChain:
         bh = self.band.in_y1 - self.band.in_y0
         self.pieces = []
         for n in nodes:
-            p = ab.make_piece(width, max(bh, 1), filters=filters if n.channels_in == 1 else 0, channels=n.channels_in, data=n.data,
+            p = ab.make_piece(width, max(bh, 1), filters=filters if n.channels_in == 1 else 0, channels=n.channels_in,
+                              data=None if n.op == "colorspace" else n.data,
                               roi_y=self.band.in_y0, devid=self.device.index if self.device.type == "cuda" else -1)
             p.buf_in_width, p.buf_in_height = width, height  # the full frame, as tiling.c leaves piece->buf_in
             self.pieces.append(p)
@@ -189,7 +206,7 @@ class BandedChain:
             src = band_in
             for k, (n, p) in enumerate(zip(self.nodes[:-1], self.pieces[:-1])):
                 dst = self.tmp[k & 1]
-                self.process(n.op, p, src, dst, stream)
+                self._run(n, p, src, dst, stream)
                 src = dst
             kept = src[b.out_y0 - b.in_y0:b.out_y1 - b.in_y0]      # pointwise last module: only the owned rows
             ab.check(ab.lib().b200_colorout_process_scatter_dev(C.byref(self._last_piece), C.c_void_p(kept.data_ptr()), len(self._dsts),
@@ -210,9 +227,15 @@ class BandedChain:
         src = band_in
         for k, (n, p) in enumerate(zip(self.nodes, self.pieces)):
             dst = self.tmp[k & 1]
-            self.process(n.op, p, src, dst, stream)
+            self._run(n, p, src, dst, stream)
             src = dst
         return src[b.out_y0 - b.in_y0:b.out_y1 - b.in_y0]
+
+    def _run(self, n, p, src, dst, stream):
+        if self.process is _cuda_process:
+            _cuda_process(n.op, p, src, dst, stream, node=n)
+        else:
+            self.process(n.op, p, src, dst, stream)
 
     def assemble(self, mine, mode: str = "allgather", dst_rank: int = 0):
         """mode 'allgather': every rank returns the finished frame; 'gather': only dst_rank does (others None).
@@ -259,3 +282,59 @@ class BandedChain:
         if self.p2p:
             return self.run_scatter(band_in, stream)
         return self.assemble(self.run_band(band_in, stream), mode)
+
+
+class SegmentedChain:
+    """A chain with whole-frame modules in it, over several GPUs (BASELINE.json configs[3], "C4"): the nodes are cut into
+    banded segments at every module that needs the whole frame (needs_whole_frame).  A banded segment runs as a BandedChain on
+    this rank's rows (its own cuts: halo = its modules' overlaps); in front of a whole-frame module ONE all-gather assembles
+    the frame on every rank, the module runs on the full frame on every rank (replicated: its result is the untiled one, bit for
+    bit), and the next banded segment cuts its input rows out of that frame locally.  One more all-gather ends the chain.
+    Collectives per frame: 1 + the number of whole-frame modules."""
+
+    def __init__(self, nodes: list[Node], width: int, height: int, rank: int, world: int, device=None, process=None, filters: int = 0x94949494):
+        import torch
+        self.torch = torch
+        self.w, self.h, self.rank, self.world = width, height, rank, world
+        self.device = device if device is not None else torch.device("cpu")
+        self.process = process or _cuda_process
+        self.segments = []   # ("bands", BandedChain) | ("whole", node, piece)
+        run = []
+        for n in nodes:
+            if needs_whole_frame(n):
+                if run:
+                    self.segments.append(("bands", BandedChain(run, width, height, rank, world, device=self.device, process=process, filters=filters)))
+                    run = []
+                p = ab.make_piece(width, height, filters=0, channels=n.channels_in, data=n.data, devid=self.device.index if self.device.type == "cuda" else -1)
+                self.segments.append(("whole", n, p))
+            else:
+                run.append(n)
+        if run:
+            self.segments.append(("bands", BandedChain(run, width, height, rank, world, device=self.device, process=process, filters=filters)))
+        self.full = [torch.empty((height, width, 4), dtype=torch.float32, device=self.device) for _ in range(2)] if any(s[0] == "whole" for s in self.segments) else None
+        self.collectives = sum(1 for s in self.segments if s[0] == "bands")
+        self.plan = [(s[0], [n.op for n in s[1].nodes], s[1].halo) if s[0] == "bands" else ("whole", [s[1].op], None) for s in self.segments]
+
+    def band_rows(self, frame_in):
+        seg = self.segments[0]
+        return seg[1].band_rows(frame_in) if seg[0] == "bands" else frame_in
+
+    def __call__(self, first_in, stream=0):
+        """first_in: this rank's input rows of the first banded segment (band_rows of the frame input).  Returns the frame."""
+        cur_full, cur = None, first_in
+        for k, seg in enumerate(self.segments):
+            if seg[0] == "bands":
+                ch = seg[1]
+                band_in = cur if cur_full is None else ch.band_rows(cur_full)
+                cur_full = ch.assemble(ch.run_band(band_in, stream), "allgather")
+                cur = None
+            else:
+                _kind, n, p = seg
+                src = cur_full if cur_full is not None else cur
+                dst = self.full[0] if src.data_ptr() != self.full[0].data_ptr() else self.full[1]
+                if self.process is _cuda_process:
+                    _cuda_process(n.op, p, src, dst, stream, node=n)
+                else:
+                    self.process(n.op, p, src, dst, stream)
+                cur_full = dst
+        return cur_full

@@ -14,6 +14,7 @@
 // Cost model per scale (45 MP): decompose reads the input through L1/L2 (25 taps), writes coarse +
 // detail (32 B/px), ~1 k instructions/px -> instruction bound; synthesize streams 48 B/px.
 #include "runtime.h"
+#include "packed_f32.cuh"
 #include "flt32_math.cuh"
 #include <math.h>
 #include <string.h>
@@ -33,7 +34,16 @@ __device__ __forceinline__ float mexp2_float(float x)
 
 constexpr int DEC_BX = 32, DEC_BY = 8;
 
-// eaw.c:242-326: one thread per pixel, taps rows-outer / columns-inner, clamp-to-edge
+// max(0, t) the way `(0 > t) ? 0 : t` reads for a NaN (it stays one; fmaxf would drop it)
+__device__ __forceinline__ float max0_keep_nan(float t)
+{
+  float r;
+  asm("max.NaN.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(t), "f"(0.0f));
+  return r;
+}
+
+// eaw.c:242-326: one thread per pixel, taps rows-outer / columns-inner, clamp-to-edge.  The two channel pairs of a pixel
+// (x y | z w) are the lanes of the packed FP32 instructions: they sit in adjacent registers as the 16-byte load delivers them.
 __global__ void __launch_bounds__(DEC_BX *DEC_BY)
     eaw_decompose_kernel(float4 *__restrict__ coarse, const float4 *__restrict__ in, float4 *__restrict__ detail,
                          double *__restrict__ partial, int mult, float inv_sigma2, int width, int height)
@@ -43,33 +53,43 @@ __global__ void __launch_bounds__(DEC_BX *DEC_BY)
   if(i < width && j < height)
   {
     const float4 px = __ldg(in + (size_t)j * width + i);
-    float sum[4] = { 0.f, 0.f, 0.f, 0.f }, wgt = 0.f; // the four wgt lanes of the reference hold the same number
-    const float filter[5] = { 1.0f / 16.0f, 4.0f / 16.0f, 6.0f / 16.0f, 4.0f / 16.0f, 1.0f / 16.0f };
+    // the 25 taps, clamped to the frame: five row pointers, five column offsets
+    const float4 *row[5];
+    int xs[5];
+#pragma unroll
+    for(int k = 0; k < 5; k++)
+    {
+      row[k] = in + (size_t)min(max(j + mult * (k - 2), 0), height - 1) * width;
+      xs[k] = min(max(i + mult * (k - 2), 0), width - 1);
+    }
+    constexpr float filter[5] = { 1.0f / 16.0f, 4.0f / 16.0f, 6.0f / 16.0f, 4.0f / 16.0f, 1.0f / 16.0f };
+    f2 sxy = mk2(0.f, 0.f), szw = mk2(0.f, 0.f); // sum[0..1], sum[2..3]
+    float wgt = 0.f;                              // the four wgt lanes of the reference hold the same number
+    const f2 pxy = mk2(px.x, px.y);
 #pragma unroll
     for(int jj = 0; jj < 5; jj++)
     {
-      const int y = min(max(j + mult * (jj - 2), 0), height - 1);
 #pragma unroll
       for(int ii = 0; ii < 5; ii++)
       {
-        const int x = min(max(i + mult * (ii - 2), 0), width - 1);
-        const float4 q = __ldg(in + (size_t)y * width + x);
-        const float d0 = px.x - q.x, d1 = px.y - q.y, d2 = px.z - q.z;
-        const float dot = (d0 * d0 + d1 * d1 + d2 * d2) * inv_sigma2;
-        const float t = dot * 0.02f - 9.0f;
-        const float w = (filter[ii] * filter[jj]) * mexp2_float((0 > t) ? 0.0f : t);
+        const float4 q = __ldg(row[jj] + xs[ii]);
+        const f2 dxy = sub2(pxy, mk2(q.x, q.y));
+        const float d2 = px.z - q.z;
+        const float dot = (dxy.x * dxy.x + dxy.y * dxy.y + d2 * d2) * inv_sigma2;
+        const float t = max0_keep_nan(dot * 0.02f - 9.0f);
+        // mexp2_float(), math/math.h:303-317
+        const float k0 = (float)0x3f800000u + t * ((float)0x3f000000u - (float)0x3f800000u);
+        const float w = (filter[ii] * filter[jj]) * __int_as_float(k0 >= (float)0x800000u ? (int)k0 : 0);
         wgt += w;
-        sum[0] += w * q.x;
-        sum[1] += w * q.y;
-        sum[2] += w * q.z;
-        sum[3] += w * q.w;
+        sxy = add2(sxy, mk2(w * q.x, w * q.y)); // products per lane, sums packed
+        szw = add2(szw, mk2(w * q.z, w * q.w));
       }
     }
     float4 c, d;
-    c.x = sum[0] / wgt;
-    c.y = sum[1] / wgt;
-    c.z = sum[2] / wgt;
-    c.w = sum[3] / wgt;
+    c.x = sxy.x / wgt;
+    c.y = sxy.y / wgt;
+    c.z = szw.x / wgt;
+    c.w = szw.y / wgt;
     d.x = px.x - c.x;
     d.y = px.y - c.y;
     d.z = px.z - c.z;

@@ -28,6 +28,7 @@
 #endif
 #include <math.h>
 #include <stdlib.h>
+#include "packed_f32.cuh"
 
 namespace
 {
@@ -677,6 +678,7 @@ bool grp_plan(grp_args_t &g, int n_patches, int width, int height, int radius, f
   return true;
 }
 int grp_pairs_per_thread(const grp_args_t &g) { return (((g.chk_h + 1) / 2) * g.chk_w + GRP_NT - 1) / GRP_NT; }
+size_t grp_pipe_smem_bytes(const grp_args_t &g) { return ((size_t)g.wrows * 3 * g.wp + (size_t)2 * PIPE_SLOTS * g.splane) * sizeof(float); }
 size_t grp_smem_bytes(const grp_args_t &g) { return ((size_t)g.wrows * 3 * g.wp + (size_t)g.G * g.splane + GRP_MAXG) * sizeof(float); }
 // Markstein's division is the reference's division as long as nothing underflows on the way; where it could (x below
 // 2^-44 with these bounds) the weight is 1 whatever the last bit of the quotient, because x / d * sharpness < 2^-24
@@ -704,7 +706,42 @@ int grp_define_patches(patch_t *patches, int search_radius, float scale, float s
   return shift_max;
 }
 
+// the pipelined kernel (nlm_pipe_kernel): chunks of up to 64 rows, the narrow window, a ring of PIPE_SLOTS pair slots
+bool grp_pipe_fits(const grp_args_t &g, int smem_optin)
+{
+  return g.wp == GRP_WP_NARROW && ((g.chk_h + 1) / 2) * g.chk_w <= PIPE_KP * PIPE_ACC_T
+         && (long long)grp_pipe_smem_bytes(g) <= smem_optin;
+}
+
 #ifndef B200_KERNELS_ON_CPU
+template <int R> cudaError_t launch_pipe_r(const grp_args_t &g, bool norm1, bool profiled, bool divc, unsigned grid, size_t smem, cudaStream_t stream)
+{
+#define PIPE_LAUNCH(N1, PR, DC)                                                                                        \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    cudaError_t e = cudaFuncSetAttribute(nlm_pipe_kernel<R, GRP_WP_NARROW, N1, PR, DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if(e != cudaSuccess) return e;                                                                                     \
+    {                                                                                                                  \
+      ::b200::timed_launch timed(::b200::TIMED_NLM, stream);                                                           \
+      nlm_pipe_kernel<R, GRP_WP_NARROW, N1, PR, DC><<<grid, PIPE_NT, smem, stream>>>(g);                               \
+    }                                                                                                                  \
+    return cudaGetLastError();                                                                                         \
+  } while(0)
+  if(!profiled)
+  {
+    if(norm1) PIPE_LAUNCH(true, false, false);
+    PIPE_LAUNCH(false, false, false);
+  }
+  if(divc)
+  {
+    if(norm1) PIPE_LAUNCH(true, true, true);
+    PIPE_LAUNCH(false, true, true);
+  }
+  if(norm1) PIPE_LAUNCH(true, true, false);
+  PIPE_LAUNCH(false, true, false);
+#undef PIPE_LAUNCH
+}
+
 template <int R, int WP, int KP> cudaError_t launch_group_r(const grp_args_t &g, bool norm1, bool profiled, bool divc, unsigned grid, size_t smem, cudaStream_t stream)
 {
 #define GRP_LAUNCH(N1, PR, DC)                                                                                         \
@@ -750,8 +787,16 @@ int launch_group(const nlm_args_t &a, int shift_max, int smem_optin, int n_chunk
   const bool norm1 = a.norm[0] == 1.0f && a.norm[1] == 1.0f && a.norm[2] == 1.0f;
   const bool divc = grp_division_by_constant(g) && !getenv("B200_NLM_IEEE_DIV");
   cudaError_t e;
-  const size_t smem = grp_smem_bytes(g);
   const unsigned grid = (unsigned)n_chunks;
+  if(grp_pipe_fits(g, smem_optin) && !getenv("B200_NLM_NO_PIPE"))
+  {
+    const size_t psmem = grp_pipe_smem_bytes(g);
+    e = a.radius == 1 ? launch_pipe_r<1>(g, norm1, profiled, divc, grid, psmem, stream) : launch_pipe_r<2>(g, norm1, profiled, divc, grid, psmem, stream);
+    if(e != cudaSuccess) return ::b200::fail(B200_ERR_CUDA, "nlmeans: pipelined kernel launch: %s", cudaGetErrorString(e));
+    *launched = 1;
+    return B200_OK;
+  }
+  const size_t smem = grp_smem_bytes(g);
   const int variant = (a.radius == 2 ? 4 : 0) + (g.wp == GRP_WP_WIDE ? 2 : 0) + (grp_pairs_per_thread(g) > GRP_KP_MIN ? 1 : 0);
   switch(variant)
   {

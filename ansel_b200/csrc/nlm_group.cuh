@@ -37,68 +37,6 @@ constexpr int GRP_KP_MIN = 6;                                                   
 constexpr int GRP_WP_NARROW = 96, GRP_WP_WIDE = 128;
 constexpr int GRP_SP = MAX_CW + 2 * 2 + 1;     // 77: columns of column sums at radius <= 2, odd
 
-// ---- pairs of floats ------------------------------------------------------------------------------------------
-#ifdef B200_KERNELS_ON_CPU
-struct f2
-{
-  float x, y;
-};
-static inline f2 mk2(float x, float y) { return f2{ x, y }; }
-static inline f2 add2(f2 a, f2 b) { return f2{ a.x + b.x, a.y + b.y }; }
-static inline f2 sub2(f2 a, f2 b) { return f2{ a.x - b.x, a.y - b.y }; }
-static inline f2 mul2(f2 a, f2 b) { return f2{ a.x * b.x, a.y * b.y }; }
-static inline f2 fma2(f2 a, f2 b, f2 c) { return f2{ fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y) }; }
-static inline f2 neg2(f2 a) { return f2{ -a.x, -a.y }; }
-static inline float min_nan(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
-static inline int __float2int_rz(float x) { return (int)x; } // cvttss2si: INT_MIN beyond the range, where the device saturates (same below -2^31)
-#else
-typedef float2 f2;
-__device__ __forceinline__ f2 mk2(float x, float y) { return make_float2(x, y); }
-__device__ __forceinline__ unsigned long long f2_bits(f2 a)
-{
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
-  return r;
-}
-__device__ __forceinline__ f2 bits_f2(unsigned long long r)
-{
-  f2 a;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
-  return a;
-}
-__device__ __forceinline__ f2 add2(f2 a, f2 b)
-{
-  unsigned long long c;
-  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(c) : "l"(f2_bits(a)), "l"(f2_bits(b)));
-  return bits_f2(c);
-}
-__device__ __forceinline__ f2 sub2(f2 a, f2 b)
-{
-  unsigned long long c;
-  asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(c) : "l"(f2_bits(a)), "l"(f2_bits(b)));
-  return bits_f2(c);
-}
-__device__ __forceinline__ f2 mul2(f2 a, f2 b)
-{
-  unsigned long long c;
-  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(c) : "l"(f2_bits(a)), "l"(f2_bits(b)));
-  return bits_f2(c);
-}
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c)
-{
-  unsigned long long d;
-  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
-  return bits_f2(d);
-}
-__device__ __forceinline__ f2 neg2(f2 a) { return make_float2(-a.x, -a.y); }
-__device__ __forceinline__ float min_nan(float a, float b) // a NaN stays a NaN (fminf drops it)
-{
-  float r;
-  asm("min.NaN.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
-  return r;
-}
-#endif
-
 struct grp_args_t
 {
   const float4 *in;
@@ -186,10 +124,10 @@ template <bool NORM1> __device__ __forceinline__ float pd3(float e0, float e1, f
 }
 
 // ---- the window: every pixel this chunk reads, for every patch, once ---------------------------------------------
-template <int WP> __device__ __forceinline__ void grp_fill(const grp_args_t &a, const chunk_t &c, float *W, int tid)
+template <int WP, int NTHREADS = GRP_NT> __device__ __forceinline__ void grp_fill(const grp_args_t &a, const chunk_t &c, float *W, int tid)
 {
   const int n = a.wrows * a.wcols;
-  for(int idx = tid; idx < n; idx += GRP_NT)
+  for(int idx = tid; idx < n; idx += NTHREADS)
   {
     const int wi = idx / a.wcols, wj = idx - wi * a.wcols;
     const int r = c.wr0 + wi, col = c.wc0 + wj;
@@ -353,6 +291,39 @@ __device__ void grp_colsum_pair(const grp_args_t &a, const chunk_t &c, const flo
 // the patches of a group as phase B2 wants them: their window shifts, in shared memory
 template <int WP> __device__ __forceinline__ int grp_shift(const grp_args_t &a, int p) { return a.patches[p].rows * (3 * WP) + a.patches[p].cols; }
 
+// phase A for one thread: column k (0 = the column of zeros) of patches pa and pa + 1 into the planes Sa, Sb
+template <int WP, int R, bool NORM1>
+__device__ __forceinline__ void grp_scan_column(const grp_args_t &a, const chunk_t &c, const float *W, float *Sa, float *Sb, int pa, int k)
+{
+  if(c.interior && pa + 1 < a.n_patches)
+  {
+    if(k == 0)
+    { // the column of zeros left of the first live one (:228-231)
+      for(int rr = 0; rr < c.ch; rr++) Sa[rr * GRP_SP] = Sb[rr * GRP_SP] = 0.0f;
+    }
+    else
+    {
+      pgeo_t ga, gb;
+      ga.srow = a.patches[pa].rows;
+      ga.scol = a.patches[pa].cols;
+      gb.srow = a.patches[pa + 1].rows;
+      gb.scol = a.patches[pa + 1].cols;
+      grp_colsum_pair<WP, R, NORM1>(a, c, W, Sa, Sb, ga, gb, k);
+    }
+    return;
+  }
+  const pgeo_t ga = patch_geo_grp(a, c, pa), gb = patch_geo_grp(a, c, pa + 1);
+  const int col = c.cbase + k;
+  const bool la = ga.valid && col >= ga.pcol_min && col < ga.pcol_max, lb = gb.valid && col >= gb.pcol_min && col < gb.pcol_max;
+  if(ga.valid && gb.valid && la && lb && rows_regular(a, c, ga) && rows_regular(a, c, gb))
+    grp_colsum_pair<WP, R, NORM1>(a, c, W, Sa, Sb, ga, gb, k);
+  else
+  {
+    if(ga.valid) grp_colsum_one<WP, R, NORM1>(a, c, W, Sa, ga, k);
+    if(gb.valid) grp_colsum_one<WP, R, NORM1>(a, c, W, Sb, gb, k);
+  }
+}
+
 template <int WP, int R, bool NORM1>
 __device__ __forceinline__ void grp_phase_a(const grp_args_t &a, const chunk_t &c, const float *W, float *S, int *shifts, int p0, int tid)
 {
@@ -361,35 +332,8 @@ __device__ __forceinline__ void grp_phase_a(const grp_args_t &a, const chunk_t &
   for(int t = tid; t < npairs * c.ncols; t += GRP_NT)
   {
     const int pi = t / c.ncols, k = t - pi * c.ncols;
-    const int pa = p0 + 2 * pi;
-    float *const Sa = S + (2 * pi) * a.splane, *const Sb = Sa + a.splane;
-    if(c.interior && pa + 1 < a.n_patches)
-    {
-      if(k == 0)
-      { // the column of zeros left of the first live one (:228-231)
-        for(int rr = 0; rr < c.ch; rr++) Sa[rr * GRP_SP] = Sb[rr * GRP_SP] = 0.0f;
-      }
-      else
-      {
-        pgeo_t ga, gb;
-        ga.srow = a.patches[pa].rows;
-        ga.scol = a.patches[pa].cols;
-        gb.srow = a.patches[pa + 1].rows;
-        gb.scol = a.patches[pa + 1].cols;
-        grp_colsum_pair<WP, R, NORM1>(a, c, W, Sa, Sb, ga, gb, k);
-      }
-      continue;
-    }
-    const pgeo_t ga = patch_geo_grp(a, c, pa), gb = patch_geo_grp(a, c, pa + 1);
-    const int col = c.cbase + k;
-    const bool la = ga.valid && col >= ga.pcol_min && col < ga.pcol_max, lb = gb.valid && col >= gb.pcol_min && col < gb.pcol_max;
-    if(ga.valid && gb.valid && la && lb && rows_regular(a, c, ga) && rows_regular(a, c, gb))
-      grp_colsum_pair<WP, R, NORM1>(a, c, W, Sa, Sb, ga, gb, k);
-    else
-    {
-      if(ga.valid) grp_colsum_one<WP, R, NORM1>(a, c, W, Sa, ga, k);
-      if(gb.valid) grp_colsum_one<WP, R, NORM1>(a, c, W, Sb, gb, k);
-    }
+    float *const Sa = S + (2 * pi) * a.splane;
+    grp_scan_column<WP, R, NORM1>(a, c, W, Sa, Sa + a.splane, p0 + 2 * pi, k);
   }
 }
 
@@ -447,36 +391,42 @@ template <int R> __device__ __forceinline__ void grp_row_pair(float *Sx, float *
   }
 }
 
+// phase B1 for one thread: rows rr and rr + half of patch p, whose plane is Sp
+template <int R> __device__ __forceinline__ void grp_scan_rows(const grp_args_t &a, const chunk_t &c, float *Sp, int p, int rr, int half)
+{
+  float *const Sx = Sp + rr * GRP_SP - c.cbase, *const Sy = Sx + half * GRP_SP;
+  if(c.interior)
+  {
+    if(p >= a.n_patches) return;
+    pgeo_t g;
+    g.col_min = c.left;
+    g.col_max = c.right;
+    if(rr + half < c.ch)
+      grp_row_pair<R>(Sx, Sy, g);
+    else
+      grp_row_one(Sx, g, R);
+    return;
+  }
+  const pgeo_t g = patch_geo_grp(a, c, p);
+  if(!g.valid || g.col_min >= g.col_max) return;
+  const int rx = c.top + rr, ry = rx + half;
+  const bool vx = rx >= g.row_min && rx < g.row_max, vy = ry >= g.row_min && ry < g.row_max;
+  if(vx && vy && g.col_max - g.col_min >= 2 * R + 1)
+    grp_row_pair<R>(Sx, Sy, g);
+  else
+  {
+    if(vx) grp_row_one(Sx, g, R);
+    if(vy) grp_row_one(Sy, g, R);
+  }
+}
+
 template <int R> __device__ __forceinline__ void grp_phase_b1(const grp_args_t &a, const chunk_t &c, float *S, int p0, int tid)
 {
   const int half = (c.ch + 1) / 2;
   for(int t = tid; t < a.G * half; t += GRP_NT)
   {
     const int gi = t / half, rr = t - gi * half;
-    float *const Sx = S + gi * a.splane + rr * GRP_SP - c.cbase, *const Sy = Sx + half * GRP_SP;
-    if(c.interior)
-    {
-      if(p0 + gi >= a.n_patches) continue;
-      pgeo_t g;
-      g.col_min = c.left;
-      g.col_max = c.right;
-      if(rr + half < c.ch)
-        grp_row_pair<R>(Sx, Sy, g);
-      else
-        grp_row_one(Sx, g, R);
-      continue;
-    }
-    const pgeo_t g = patch_geo_grp(a, c, p0 + gi);
-    if(!g.valid || g.col_min >= g.col_max) continue;
-    const int rx = c.top + rr, ry = rx + half;
-    const bool vx = rx >= g.row_min && rx < g.row_max, vy = ry >= g.row_min && ry < g.row_max;
-    if(vx && vy && g.col_max - g.col_min >= 2 * R + 1)
-      grp_row_pair<R>(Sx, Sy, g);
-    else
-    {
-      if(vx) grp_row_one(Sx, g, R);
-      if(vy) grp_row_one(Sy, g, R);
-    }
+    grp_scan_rows<R>(a, c, S + gi * a.splane, p0 + gi, rr, half);
   }
 }
 
@@ -491,14 +441,14 @@ template <int KP> struct grp_thread_t
   unsigned lower;   // bit k: its lower pixel belongs to the chunk
 };
 
-template <int WP, int KP>
+template <int WP, int KP, int NTHREADS = GRP_NT>
 __device__ __forceinline__ void grp_own_init(const grp_args_t &a, const chunk_t &c, const float *W, grp_thread_t<KP> &st, int tid)
 {
   st.lower = st.upper = 0u;
 #pragma unroll
   for(int k = 0; k < KP; k++)
   {
-    const int j = tid + k * GRP_NT;
+    const int j = tid + k * NTHREADS;
     const int pr = j / c.cw, pc = j - pr * c.cw;
 #pragma unroll
     for(int i = 0; i < 8; i++) st.acc[k][i] = 0.0f;
@@ -591,6 +541,42 @@ __device__ __forceinline__ void grp_accumulate_pairs(const grp_args_t &a, const 
   }
 }
 
+// phase B2 for one thread and one patch of a chunk that is not in the interior of the frame
+template <int WP, bool PROFILED, bool DIVC, int KP>
+__device__ __forceinline__ void grp_accumulate_edge(const grp_args_t &a, const chunk_t &c, const float *W, const float *Sg, grp_thread_t<KP> &st, int p)
+{
+  const pgeo_t g = patch_geo_grp(a, c, p);
+  if(!g.valid || g.col_min >= g.col_max) return; // uniform
+  const float *const Wq = W + g.srow * (3 * WP) + g.scol;
+  if(covers_chunk(c, g))
+  {
+    grp_accumulate_pairs<WP, PROFILED, DIVC, KP>(a, Wq, Sg, st);
+    return;
+  }
+  // a patch that leaves the frame somewhere in this chunk: pixel by pixel
+#pragma unroll
+  for(int k = 0; k < KP; k++)
+  {
+    if(!((st.upper >> k) & 1u)) continue;
+    const int rr = st.sofs[k] / GRP_SP, pc = st.sofs[k] - rr * GRP_SP;
+    const int col = c.left + pc;
+    if(col < g.col_min || col >= g.col_max) continue;
+#pragma unroll
+    for(int l = 0; l < 2; l++)
+    {
+      const int row = c.top + rr + l;
+      if(row < g.row_min || row >= g.row_max) continue;
+      const float *const w = Wq + st.wofs[k] + l * (3 * WP);
+      const float q0 = w[0], q1 = w[WP], q2 = w[2 * WP];
+      const float wt = grp_weight<PROFILED>(a, Sg[st.sofs[k] + l * GRP_SP], st.ctr[k][0 + l], st.ctr[k][2 + l], st.ctr[k][4 + l], q0, q1, q2);
+      st.acc[k][0 + l] += q0 * wt;
+      st.acc[k][2 + l] += q1 * wt;
+      st.acc[k][4 + l] += q2 * wt;
+      st.acc[k][6 + l] += 1.0f * wt;
+    }
+  }
+}
+
 template <int WP, bool PROFILED, bool DIVC, int KP>
 __device__ __forceinline__ void grp_phase_b2(const grp_args_t &a, const chunk_t &c, const float *W, const float *S, const int *shifts,
                                              grp_thread_t<KP> &st, int p0, int tid)
@@ -602,39 +588,7 @@ __device__ __forceinline__ void grp_phase_b2(const grp_args_t &a, const chunk_t 
     for(int gi = 0; gi < n; gi++, Sg += a.splane) grp_accumulate_pairs<WP, PROFILED, DIVC, KP>(a, W + shifts[gi], Sg, st);
     return;
   }
-  for(int gi = 0; gi < a.G; gi++)
-  {
-    const pgeo_t g = patch_geo_grp(a, c, p0 + gi);
-    if(!g.valid || g.col_min >= g.col_max) continue; // uniform
-    const float *const Sg = S + gi * a.splane;
-    const float *const Wq = W + g.srow * (3 * WP) + g.scol;
-    if(covers_chunk(c, g))
-      grp_accumulate_pairs<WP, PROFILED, DIVC, KP>(a, Wq, Sg, st);
-    else
-    { // a patch that leaves the frame somewhere in this chunk: pixel by pixel
-#pragma unroll
-      for(int k = 0; k < KP; k++)
-      {
-        if(!((st.upper >> k) & 1u)) continue;
-        const int rr = st.sofs[k] / GRP_SP, pc = st.sofs[k] - rr * GRP_SP;
-        const int col = c.left + pc;
-        if(col < g.col_min || col >= g.col_max) continue;
-#pragma unroll
-        for(int l = 0; l < 2; l++)
-        {
-          const int row = c.top + rr + l;
-          if(row < g.row_min || row >= g.row_max) continue;
-          const float *const w = Wq + st.wofs[k] + l * (3 * WP);
-          const float q0 = w[0], q1 = w[WP], q2 = w[2 * WP];
-          const float wt = grp_weight<PROFILED>(a, Sg[st.sofs[k] + l * GRP_SP], st.ctr[k][0 + l], st.ctr[k][2 + l], st.ctr[k][4 + l], q0, q1, q2);
-          st.acc[k][0 + l] += q0 * wt;
-          st.acc[k][2 + l] += q1 * wt;
-          st.acc[k][4 + l] += q2 * wt;
-          st.acc[k][6 + l] += 1.0f * wt;
-        }
-      }
-    }
-  }
+  for(int gi = 0; gi < a.G; gi++) grp_accumulate_edge<WP, PROFILED, DIVC, KP>(a, c, W, S + gi * a.splane, st, p0 + gi);
 }
 
 // ---- normalise (and blend), :485-519 -----------------------------------------------------------------------------
@@ -691,5 +645,78 @@ __global__ void __launch_bounds__(GRP_NT, 1) nlm_group_kernel(const __grid_const
     __syncthreads();
   }
   grp_finish(a, c, st, tid);
+}
+#endif
+
+// ---- the same phases as a pipeline: scan warps run ahead of the accumulating warps --------------------------------------------
+// 512 threads: two scan groups of 128 (phases A and B1 of a patch pair each, pairs dealt alternately) fill a ring of PIPE_SLOTS
+// pair slots (2 planes each) in shared memory; 256 accumulating threads (9 pixel pairs each) drain it in patch order (phase B2).
+// Named barriers: FULL[slot] (scan group arrives, accumulators wait), EMPTY[slot] (accumulators arrive, the scan group that
+// wants the slot waits), one barrier per scan group between its phases A and B1.  The accumulators need 3.5 times the
+// registers of the scan threads: setmaxnreg moves them (the block is launched with 128 per thread).
+constexpr int PIPE_NT = 512, PIPE_SCAN_GROUP = 128, PIPE_ACC_T = 256, PIPE_KP = 9, PIPE_SLOTS = 3;
+constexpr int PIPE_SCAN_REGS = 80, PIPE_ACC_REGS = 176; // 256 x 80 + 256 x 176 = the register file
+constexpr int PIPE_BAR_FULL = 1, PIPE_BAR_EMPTY = PIPE_BAR_FULL + PIPE_SLOTS, PIPE_BAR_GROUP = PIPE_BAR_EMPTY + PIPE_SLOTS;
+static_assert(((MAX_CH - 5 + 1) / 2) * MAX_CW <= PIPE_KP * PIPE_ACC_T, "chunks of up to 64 rows: 9 pixel pairs per accumulating thread");
+
+#ifndef B200_KERNELS_ON_CPU
+__device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <int R, int WP, bool NORM1, bool PROFILED, bool DIVC>
+__global__ void __launch_bounds__(PIPE_NT, 1) nlm_pipe_kernel(const __grid_constant__ grp_args_t a)
+{
+  extern __shared__ __align__(16) float smem[];
+  float *const W = smem, *const S = smem + a.wrows * (3 * WP);
+  const int tid = threadIdx.x;
+  const chunk_t c = chunk_of(a, blockIdx.x);
+  grp_fill<WP, PIPE_NT>(a, c, W, tid);
+  __syncthreads();
+  const int npairs = (a.n_patches + 1) / 2;
+  if(tid < 2 * PIPE_SCAN_GROUP)
+  {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PIPE_SCAN_REGS));
+    const int group = tid / PIPE_SCAN_GROUP, t = tid - group * PIPE_SCAN_GROUP;
+    const int half = (c.ch + 1) / 2;
+    for(int q = group; q < npairs; q += 2)
+    {
+      const int slot = q % PIPE_SLOTS;
+      float *const Sa = S + (2 * slot) * a.splane, *const Sb = Sa + a.splane;
+      if(q >= PIPE_SLOTS) named_sync(PIPE_BAR_EMPTY + slot, PIPE_SCAN_GROUP + PIPE_ACC_T);
+      if(t < c.ncols) grp_scan_column<WP, R, NORM1>(a, c, W, Sa, Sb, 2 * q, t);
+      named_sync(PIPE_BAR_GROUP + group, PIPE_SCAN_GROUP);
+      if(t < 2 * half)
+      {
+        const int gi = t / half;
+        grp_scan_rows<R>(a, c, gi ? Sb : Sa, 2 * q + gi, t - gi * half, half);
+      }
+      named_arrive(PIPE_BAR_FULL + slot, PIPE_SCAN_GROUP + PIPE_ACC_T);
+    }
+  }
+  else
+  {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PIPE_ACC_REGS));
+    const int ta = tid - 2 * PIPE_SCAN_GROUP;
+    grp_thread_t<PIPE_KP> st;
+    grp_own_init<WP, PIPE_KP, PIPE_ACC_T>(a, c, W, st, ta);
+    for(int q = 0; q < npairs; q++)
+    {
+      const int slot = q % PIPE_SLOTS;
+      const float *const Sa = S + (2 * slot) * a.splane;
+      named_sync(PIPE_BAR_FULL + slot, PIPE_SCAN_GROUP + PIPE_ACC_T);
+      if(c.interior)
+      {
+        grp_accumulate_pairs<WP, PROFILED, DIVC, PIPE_KP>(a, W + grp_shift<WP>(a, 2 * q), Sa, st);
+        if(2 * q + 1 < a.n_patches) grp_accumulate_pairs<WP, PROFILED, DIVC, PIPE_KP>(a, W + grp_shift<WP>(a, 2 * q + 1), Sa + a.splane, st);
+      }
+      else
+      {
+        grp_accumulate_edge<WP, PROFILED, DIVC, PIPE_KP>(a, c, W, Sa, st, 2 * q);
+        grp_accumulate_edge<WP, PROFILED, DIVC, PIPE_KP>(a, c, W, Sa + a.splane, st, 2 * q + 1);
+      }
+      if(q + PIPE_SLOTS < npairs) named_arrive(PIPE_BAR_EMPTY + slot, PIPE_SCAN_GROUP + PIPE_ACC_T);
+    }
+    grp_finish(a, c, st, ta);
+  }
 }
 #endif

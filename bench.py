@@ -90,6 +90,8 @@ def parse():
     ap.add_argument("--height", type=int, default=H45)
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batch", action="store_true", help="skip the 64-frame batch export (BASELINE.json configs[4])")
+    ap.add_argument("--c4", action="store_true", help="at N > 1: also the 100 MP C4 chain over the ranks (always run at N = 4, the configuration BASELINE.json names)")
     ap.add_argument("--no-other-modules", action="store_true", help="skip the untimed per-module table of the non-C2 modules")
     ap.add_argument("--pipe-ends-only", action="store_true",
                     help="internal: run the pipe-end module table in this process and print it as one JSON object (the main run calls this in a "
@@ -687,6 +689,15 @@ def run_b200(args):
     M.b200_pipe_queue_free(queue)
     del h_out
 
+    # ---- C5: the batch export, frames dealt to the ranks ---------------------------------------------------
+    batch = None
+    if not args.no_batch:
+        try:
+            batch = batch_export(ab, ds, util, L, M, torch, dist, world, rank, local, w, h, barrier,
+                                 dict(dem=d_dem, dn=d_dn, cin=d_cin, cout=d_cout, fdata=fdata, work_info=ds.profile_info(*work), export_info=ds.profile_info(*export)))
+        except Exception as e:
+            batch = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
     # ---- the other modules of SURVEY.md 8a at the same frame size (outside the timed region; N=1 only) ----
     other = None
     t_rgb = c3.bufs
@@ -732,6 +743,8 @@ def run_b200(args):
     # ---- second mode at N>1: ONE frame cut into row bands + one all-gather ---------
     banded = None
     if world > 1:
+        del c2_mod
+        torch.cuda.empty_cache()
         banded = banded_modes(args, ab, util, torch, dist, world, rank, dev, stream, w, h, npx, barrier,
                               dict(dem=d_dem, dn=d_dn, cin=d_cin, cout=d_cout, fp=d_fp), c3, c2)
 
@@ -802,9 +815,134 @@ def run_b200(args):
             line["config"]["other_modules_45mp"] = other
         if banded is not None:
             line["banded_one_frame"] = banded
+        if batch is not None:
+            line["batch_export_c5"] = batch
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def batch_export(ab, ds, util, L, M, torch, dist, world, rank, local, w, h, barrier, datas, n_frames=64):
+    """BASELINE.json configs[4] ("C5"): a batch of 64 x 45 MP frames through the full export pipe -- uint16 sensor data up, uint8 display
+    pixels down: rawprepare -> temperature -> highlights(clip) -> demosaic(RCD) -> denoiseprofile(NLM) -> colorin -> filmicrgb ->
+    colorout -> gamma -- the frames dealt to the ranks (64 / N each), every frame through the C module adapters and the device-resident
+    pipe glue with two frames in flight.  Frames are independent: no collective moves pixels."""
+    npx = w * h
+    wb = (2.13, 1.0, 1.57, 1.02)
+    pm = (wb[0], wb[1], wb[2], 0.0)
+    filters = util.BAYER["RGGB"]
+    sub, div = (512.0, 520.0, 508.0, 515.0), (15871.0, 15863.0, 15875.0, 15868.0)
+    rng = np.random.default_rng(SEED + rank)
+    raw = np.clip(util.frame_natural(w, h, SEED + rank) * 15871.0 * 0.45 + 512.0 + rng.normal(0, 3, (h, w)), 0, 16383).astype(np.uint16)
+    raw[rng.integers(0, h, 4000), rng.integers(0, w, 4000)] = 16383
+    d_rp, d_tp, d_hl = ab.rawprepare_data(sub, div), ab.temperature_data(wb), ab.highlights_data(ab.HIGHLIGHTS_CLIP, 1.0)
+    order = [("rawprepare", d_rp, 1, 1, 2, 1, (1.0,) * 4), ("temperature", d_tp, 1, 1, 1, 1, (1.0,) * 4), ("highlights", d_hl, 1, 1, 1, 1, pm),
+             ("demosaic", datas["dem"], 1, 4, 1, 1, pm), ("denoiseprofile", datas["dn"], 4, 4, 1, 1, pm), ("colorin", datas["cin"], 4, 4, 1, 1, pm),
+             ("filmicrgb", datas["fdata"], 4, 4, 1, 1, pm), ("colorout", datas["cout"], 4, 4, 1, 1, pm), ("gamma", None, 4, 4, 1, 3, pm)]
+    pieces = [ds.make_piece_iop(op, w, h, data, channels_in=ci, channels_out=co, filters=filters, processed_maximum=pmx, wb=wb, type_in=ti, type_out=to)
+              for op, data, ci, co, ti, to, pmx in order]
+    nodes = (ds.PipeNode * len(order))()
+    for k, (op, *_rest) in enumerate(order):
+        nodes[k].process_cl = C.cast(getattr(M, f"dt_iop_{op}__process_cl"), C.c_void_p)
+        nodes[k].module = pieces[k].module
+        nodes[k].piece = C.pointer(pieces[k])
+    pipe = ds.make_pipe(devid=local, stream=None, work_profile=datas["work_info"], output_profile=datas["export_info"])
+    DEPTH = 2
+    mine = n_frames // world + (1 if rank < n_frames % world else 0)
+    queue = M.b200_pipe_queue_new(DEPTH)
+    try:
+        h_in = torch.from_numpy(raw).pin_memory()
+        h_out = [torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory() for _ in range(DEPTH)]
+
+        def run(n):
+            tickets = []
+            for i in range(n):
+                t = M.b200_pixelpipe_submit(queue, C.byref(pipe), nodes, len(order), h_in.data_ptr(), h_out[i % DEPTH].data_ptr())
+                if t < 0:
+                    raise RuntimeError("chain failed: " + L.b200_last_error().decode())
+                tickets.append(t)
+                if i >= DEPTH - 1 and M.b200_pixelpipe_wait(queue, tickets[i - DEPTH + 1]) != 0:
+                    raise RuntimeError("wait failed: " + L.b200_last_error().decode())
+            if tickets and M.b200_pixelpipe_wait(queue, tickets[-1]) != 0:
+                raise RuntimeError("wait failed: " + L.b200_last_error().decode())
+
+        run(2)
+        barrier()
+        t0 = time.perf_counter()
+        run(mine)
+        barrier()
+        dt = time.perf_counter() - t0
+        mean = float(h_out[0][..., :3].float().mean())
+    finally:
+        M.b200_pipe_queue_free(queue)
+    t_e = torch.tensor([dt], dtype=torch.float64, device=torch.device("cuda", local))
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    dt = float(t_e.item())
+    return {"workload": "C5: 64 x 45MP frames, full export pipe: rawprepare(uint16) -> temperature -> highlights(clip) -> demosaic(RCD) -> "
+                        "denoiseprofile(NLM P=1 K=7) -> colorin -> filmicrgb -> colorout -> gamma(uint8)",
+            "value": npx * n_frames / dt / 1e6, "unit": UNIT, "frames": n_frames, "frames_per_rank": mine, "seconds": dt,
+            "h2d_bytes_per_frame": 2 * npx, "d2h_bytes_per_frame": 4 * npx,
+            "path": "dt_iop_<op>__process_cl adapters via b200_pixelpipe_submit/_wait (raw front fused by the pipe glue), 2 frames in flight per rank, pinned host buffers",
+            "collective": "none: frames are independent (SURVEY.md 8e); one frame over several GPUs is `banded_one_frame`",
+            "mean_display_value": mean}
+
+
+def c4_mode(args, ab, util, torch, dist, world, rank, dev, stream, barrier, d):
+    """C4: 100 MP Bayer (11648x8736) -> demosaic(RCD) -> denoiseprofile(NLM) -> colorin -> diffuse(sharpen) -> filmicrgb -> [RGB->Lab]
+    bilat(local Laplacian) [Lab->RGB] -> colorout, ONE frame over the ranks (ansel_b200/bands.py SegmentedChain): two banded segments
+    around the local Laplacian, which runs on the whole frame on every rank after an all-gather (its pyramid reaches across the
+    frame; the reference refuses to tile it: bilat.c:310-311)."""
+    from ansel_b200 import bands
+    w, h = 11648, 8736
+    npx = w * h
+    frame0 = util.frame_natural(w, h, SEED)
+    work = util.profile_pair(util.REC2020_TO_XYZ_D50)
+    pm = ab.profile_matrices(*work)
+    dd = ab.diffuse_data(**ab.DIFFUSE_PRESETS["sharpen_demosaic_aa"])
+    nodes = [bands.Node("demosaic", d["dem"], channels_in=1), bands.Node("denoiseprofile", d["dn"]), bands.Node("colorin", d["cin"]),
+             bands.Node("diffuse", dd), bands.Node("filmicrgb", d["fp"]), bands.Node("colorspace", (ab.CS_RGB, ab.CS_LAB, pm)),
+             bands.Node("bilat", ab.bilat_data()), bands.Node("colorspace", (ab.CS_LAB, ab.CS_RGB, pm)), bands.Node("colorout", d["cout"])]
+    ch = bands.SegmentedChain(nodes, w, h, rank, world, device=dev)
+    t_band = torch.from_numpy(np.ascontiguousarray(ch.band_rows(frame0))).to(dev)
+    steps = 3
+    ch(t_band, stream=stream)
+    barrier()
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record()
+    for _ in range(steps):
+        frame = ch(t_band, stream=stream)
+    b1.record()
+    barrier()
+    t_b = torch.tensor([b0.elapsed_time(b1) / steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(t_b, op=dist.ReduceOp.MAX)
+    res = {"workload": "C4: 100MP RGGB Bayer (11648x8736) -> demosaic(RCD) -> denoiseprofile(NLM P=1 K=7) -> colorin -> diffuse(sharpen demosaicing) -> "
+                       "filmicrgb -> [RGB->Lab] bilat(local Laplacian) [Lab->RGB] -> colorout",
+           "value": npx / (float(t_b.item()) * 1e-3) / 1e6, "unit": UNIT, "ms_per_frame": float(t_b.item()), "n_gpus": world, "scaling": "strong",
+           "plan": [list(p) for p in ch.plan], "collectives_per_frame": ch.collectives,
+           "collective": "ncclAllGather of the finished RGBA bands, once in front of the whole-frame local Laplacian and once at the end"}
+    # rank 0: the same chain untiled on one GPU, for the speed-up and the distance
+    stat = torch.zeros(3, dtype=torch.float64, device=dev)
+    if rank == 0:
+        one = bands.SegmentedChain(nodes, w, h, 0, 1, device=dev)
+        t_full = torch.from_numpy(frame0).to(dev)
+        one(t_full, stream=stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ref = one(t_full, stream=stream)
+        e1.record()
+        torch.cuda.synchronize()
+        stat[0] = e0.elapsed_time(e1)
+        stat[1] = float((frame.view(torch.int32) != ref.view(torch.int32)).sum().item())
+        stat[2] = float((frame - ref).abs().nan_to_num(0.0).max().item())
+        del one, ref, t_full
+    dist.broadcast(stat, 0)
+    res.update({"one_gpu_ms_per_frame": float(stat[0].item()), "speedup_over_one_gpu": float(stat[0].item()) / float(t_b.item()),
+                "vs_untiled": {"floats_differing": int(stat[1].item()), "max_abs": float(stat[2].item()),
+                               "why": "the banded segments are the reference's own tiles (RCD tile grid, NLM chunk grid and the diffuse wavelet borders follow the tile "
+                                      "origin); the local Laplacian itself is computed on the whole frame"}})
+    return res
 
 
 def c3_out_bits(chain, t_mosaic, torch):
@@ -865,6 +1003,14 @@ def banded_modes(args, ab, util, torch, dist, world, rank, dev, stream, w, h, np
                                            "chunk grid start at the tile origin (tests/test_bands_gpu.py checks each band against the oracle on the same cuts)"}}
     except Exception as e:
         out["c3"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
+    # C4: the 100 MP full pipe over the ranks, whole-frame local Laplacian inside (BASELINE.json configs[3] names 4 GPUs)
+    if world == 4 or args.c4:
+        try:
+            out["c4"] = c4_mode(args, ab, util, torch, dist, world, rank, dev, stream, barrier, d)
+        except Exception as e:
+            out["c4"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
 
     # C2 in bands: NCCL exchange, then the gather fused into colorout
     try:

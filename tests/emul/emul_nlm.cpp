@@ -29,6 +29,58 @@ template <int R, int WP, bool NORM1, bool PROFILED, bool DIVC, int KP> static vo
   }
 }
 
+/* the pipelined kernel's order of work: per patch pair, scan group (phase A, then phase B1) into its slot of the ring, then the 256
+ * accumulating threads; what the emulation cannot see is the barrier protocol between them */
+template <int R, int WP, bool NORM1, bool PROFILED, bool DIVC> static void run_pipe_chunks(const grp_args_t &a, int n_chunks)
+{
+  std::vector<float> smem((size_t)a.wrows * 3 * WP + (size_t)2 * PIPE_SLOTS * a.splane);
+  std::vector<grp_thread_t<PIPE_KP>> st(PIPE_ACC_T);
+  float *const W = smem.data(), *const S = W + a.wrows * 3 * WP;
+  const int npairs = (a.n_patches + 1) / 2;
+  for(int b = 0; b < n_chunks; b++)
+  {
+    for(auto &v : smem) v = __builtin_nanf("");
+    const chunk_t c = chunk_of(a, b);
+    const int half = (c.ch + 1) / 2;
+    for(int t = 0; t < PIPE_NT; t++) grp_fill<WP, PIPE_NT>(a, c, W, t);
+    for(int t = 0; t < PIPE_ACC_T; t++) grp_own_init<WP, PIPE_KP, PIPE_ACC_T>(a, c, W, st[t], t);
+    for(int q = 0; q < npairs; q++)
+    {
+      const int slot = q % PIPE_SLOTS;
+      float *const Sa = S + (2 * slot) * a.splane, *const Sb = Sa + a.splane;
+      for(int t = 0; t < PIPE_SCAN_GROUP; t++)
+        if(t < c.ncols) grp_scan_column<WP, R, NORM1>(a, c, W, Sa, Sb, 2 * q, t);
+      for(int t = 0; t < PIPE_SCAN_GROUP; t++)
+        if(t < 2 * half)
+        {
+          const int gi = t / half;
+          grp_scan_rows<R>(a, c, gi ? Sb : Sa, 2 * q + gi, t - gi * half, half);
+        }
+      for(int t = 0; t < PIPE_ACC_T; t++)
+      {
+        if(c.interior)
+        {
+          grp_accumulate_pairs<WP, PROFILED, DIVC, PIPE_KP>(a, W + grp_shift<WP>(a, 2 * q), Sa, st[t]);
+          if(2 * q + 1 < a.n_patches) grp_accumulate_pairs<WP, PROFILED, DIVC, PIPE_KP>(a, W + grp_shift<WP>(a, 2 * q + 1), Sb, st[t]);
+        }
+        else
+        {
+          grp_accumulate_edge<WP, PROFILED, DIVC, PIPE_KP>(a, c, W, Sa, st[t], 2 * q);
+          grp_accumulate_edge<WP, PROFILED, DIVC, PIPE_KP>(a, c, W, Sb, st[t], 2 * q + 1);
+        }
+      }
+    }
+    for(int t = 0; t < PIPE_ACC_T; t++) grp_finish(a, c, st[t], t);
+  }
+}
+template <int R> static void run_pipe(const grp_args_t &a, int n, bool norm1, bool profiled, bool divc)
+{
+  if(!profiled)
+    return norm1 ? run_pipe_chunks<R, GRP_WP_NARROW, true, false, false>(a, n) : run_pipe_chunks<R, GRP_WP_NARROW, false, false, false>(a, n);
+  if(divc) return norm1 ? run_pipe_chunks<R, GRP_WP_NARROW, true, true, true>(a, n) : run_pipe_chunks<R, GRP_WP_NARROW, false, true, true>(a, n);
+  return norm1 ? run_pipe_chunks<R, GRP_WP_NARROW, true, true, false>(a, n) : run_pipe_chunks<R, GRP_WP_NARROW, false, true, false>(a, n);
+}
+
 template <int R, int WP, int KP> static void run_rk(const grp_args_t &a, int n, bool norm1, bool profiled, bool divc)
 {
   if(!profiled)
@@ -45,10 +97,11 @@ template <int R> static void run_r(const grp_args_t &a, int n, bool norm1, bool 
 }
 
 /* same arguments as b200_nlmeans_denoise_dev on host buffers; smem_bytes = what an SM offers, g_cap = patches in flight at most,
- * ieee_div: the plain division instead of Markstein's sequence.  Returns the patches in flight, 0 = the plan does not fit. */
+ * ieee_div: the plain division instead of Markstein's sequence; pipe: the pipelined kernel's order of work.  Returns the patches in
+ * flight, 0 = the plan does not fit. */
 extern "C" int emul_nlmeans_group(const float *in, float *out, int width, int height, float scattering, float scale, float luma, float chroma,
                                   float center_weight, float sharpness, int radius, int search_radius, int decimate, const float *norm,
-                                  int smem_bytes, int g_cap, int ieee_div)
+                                  int smem_bytes, int g_cap, int ieee_div, int pipe)
 {
   _mm_setcsr(_mm_getcsr() | 0x8040u);
   int n_patches = (2 * search_radius + 1) * (2 * search_radius + 1);
@@ -68,6 +121,15 @@ extern "C" int emul_nlmeans_group(const float *in, float *out, int width, int he
   const int n_ct = (height + g.chk_h - 1) / g.chk_h;
   const bool profiled = !(center_weight < 0), norm1 = norm[0] == 1.0f && norm[1] == 1.0f && norm[2] == 1.0f;
   const bool divc = grp_division_by_constant(g) && !ieee_div;
+  if(pipe)
+  { /* returns -1 where the pipelined kernel does not take the frame (the launcher then uses the group kernel) */
+    if(!grp_pipe_fits(g, smem_bytes)) return -1;
+    if(radius == 1)
+      run_pipe<1>(g, n_ct * g.n_cl, norm1, profiled, divc);
+    else
+      run_pipe<2>(g, n_ct * g.n_cl, norm1, profiled, divc);
+    return g.G;
+  }
   if(radius == 1)
     run_r<1>(g, n_ct * g.n_cl, norm1, profiled, divc);
   else

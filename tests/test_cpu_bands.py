@@ -168,3 +168,61 @@ def test_banded_chain_over_gloo(built, world, mode):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res), res
+
+
+# ---- whole-frame modules inside a banded chain (C4): SegmentedChain over gloo ----------------------------------
+def standin_whole(rgba):
+    """needs the whole frame: every pixel minus the frame mean of its lane (like a pyramid's coarsest level reaching everywhere)"""
+    return (rgba - rgba.reshape(-1, 4).mean(axis=0, dtype=np.float64).astype(np.float32)).astype(np.float32)
+
+
+def _process_seg(op, piece, src, dst, stream):
+    a = src.numpy()
+    if op == "demosaic":
+        r = standin_demosaic(a, piece.roi_in.y)[..., :4]
+        r[..., 2] = 0.0                                   # the band-local block index is not a frame property
+    elif op == "bilat":
+        r = standin_whole(a[: piece.roi_in.height])
+    else:
+        r = standin_pointwise(a[: piece.roi_in.height])
+    dst.numpy()[: r.shape[0]] = r
+
+
+def _seg_worker(rank, world, port, w, h, q):
+    import torch
+    import torch.distributed as dist
+    import ansel_b200 as ab
+    from ansel_b200 import bands
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        mosaic = np.random.default_rng(9).random((h, w), dtype=np.float32)
+        cin = bands.Node("colorin", ab.colorin_data(ab.make_conversion(util.MATRIX_CAM_TO_REC2020)))
+        nodes = [bands.Node("demosaic", ab.demosaic_data(ab.DEMOSAIC_RCD), channels_in=1),
+                 bands.Node("denoiseprofile", ab.denoiseprofile_data(ab.DENOISE_NLMEANS, radius=1, nbhood=7)), cin,
+                 bands.Node("bilat", ab.bilat_data()), cin, cin]
+        ch = bands.SegmentedChain(nodes, w, h, rank, world, process=_process_seg)
+        frame = ch(torch.from_numpy(np.ascontiguousarray(ch.band_rows(mosaic)))).numpy()
+        d = standin_demosaic(mosaic, 0)
+        d[..., 2] = 0.0
+        want = standin_pointwise(standin_pointwise(standin_whole(standin_pointwise(standin_pointwise(d)))))
+        ok = bool((frame == want).all()) and ch.collectives == 2 and [p[0] for p in ch.plan] == ["bands", "whole", "bands"]
+        q.put((rank, ok, ch.plan))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_segmented_chain_with_a_whole_frame_module_over_gloo(built, world):
+    """banded segment -> all-gather -> whole-frame module on every rank -> banded segment -> all-gather == the untiled chain"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_seg_worker, args=(r, world, port, 96, 704, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res), res

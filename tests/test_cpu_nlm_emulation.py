@@ -30,12 +30,12 @@ def emul():
 
 
 def emul_nlm(lib, img, *, scattering=0.0, scale=1.0, luma=1.0, chroma=1.0, center_weight=0.1, sharpness=0.005, P=1, K=7, decimate=0,
-             norm=(1.0, 1.0, 1.0, 1.0), smem=SMEM, g_cap=8, ieee_div=0):
+             norm=(1.0, 1.0, 1.0, 1.0), smem=SMEM, g_cap=8, ieee_div=0, pipe=0):
     h, w = img.shape[:2]
     src = np.ascontiguousarray(img)
     out = np.full_like(src, np.nan)
     G = lib.emul_nlmeans_group(util.fptr(src), util.fptr(out), w, h, C.c_float(scattering), C.c_float(scale), C.c_float(luma), C.c_float(chroma),
-                               C.c_float(center_weight), C.c_float(sharpness), P, K, decimate, (C.c_float * 4)(*norm), smem, g_cap, ieee_div)
+                               C.c_float(center_weight), C.c_float(sharpness), P, K, decimate, (C.c_float * 4)(*norm), smem, g_cap, ieee_div, pipe)
     return G, out
 
 
@@ -57,6 +57,20 @@ def test_group_kernel_phases_equal_oracle(emul, size, cfg):
     want = util.oracle_nlmeans(img, **kw)
     bad = ~same_bits(got, want)
     assert not bad.any(), f"G={G}: {int(bad.sum())} floats differ, first {np.argwhere(bad)[:4].tolist()}"
+
+
+@pytest.mark.parametrize("cfg", range(len(CONFIGS)))
+@pytest.mark.parametrize("size", [(200, 150), (73, 61), (145, 121), (301, 128)])
+def test_pipelined_kernel_phases_equal_oracle(emul, size, cfg):
+    """the same phases in the pipelined kernel's order: a patch pair per slot of the ring, 256 accumulating threads with 9 pixel pairs each"""
+    w, h = size
+    img = (util.rgba_scene(w, h, 5, noise=0.02) * 60).astype(np.float32)
+    kw = CONFIGS[cfg]
+    G, got = emul_nlm(emul, img, pipe=1, **kw)
+    if G == -1:
+        pytest.skip("the pipelined kernel does not take this configuration (wide window or tall chunks)")
+    bad = ~same_bits(got, util.oracle_nlmeans(img, **kw))
+    assert not bad.any(), f"{int(bad.sum())} floats differ, first {np.argwhere(bad)[:4].tolist()}"
 
 
 @pytest.mark.parametrize("g_cap,ieee", [(2, 0), (4, 1), (6, 0)])
