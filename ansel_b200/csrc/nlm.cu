@@ -51,10 +51,20 @@ struct patch_t
   short rows, cols;
 };
 
+// C's (int)float on the reference's hardware is cvttss2si: the "integer indefinite" 0x80000000 for a NaN and for anything
+// beyond the int range, where the device's conversion saturates (and turns a NaN into 0)
+__device__ __forceinline__ int cvtt_x86(float v)
+{
+#ifdef B200_KERNELS_ON_CPU
+  return (int)v;
+#else
+  return (fabsf(v) < 2147483648.0f) ? __float2int_rz(v) : (int)0x80000000;
+#endif
+}
 __device__ __forceinline__ float fast_mexp2(float x) // math/math.h:290-301
 {
   const int i1 = 0x3f800000, i2 = 0x3f000000;
-  const int k0 = i1 + (int)(x * (float)(i2 - i1));
+  const int k0 = (int)((unsigned)i1 + (unsigned)cvtt_x86(x * (float)(i2 - i1))); // the sum wraps like the reference's two's-complement add
   return __int_as_float(k0 >= 0x800000 ? k0 : 0);
 }
 #ifndef B200_KERNELS_ON_CPU

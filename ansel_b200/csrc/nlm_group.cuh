@@ -208,13 +208,31 @@ __device__ void grp_colsum_one(const grp_args_t &a, const chunk_t &c, const floa
   }
 }
 
-// the squares of one window row for two patches: lane x = patch a, lane y = patch b
-template <int WP> __device__ __forceinline__ void grp_squares2(const float *x, const float *ya, const float *yb, f2 &e0, f2 &e1, f2 &e2)
+// one window row as phase A reads it for two patches: the pixel, and the pixels at the two patch offsets
+struct grp_row9_t
 {
-  const float x0 = x[0], x1 = x[WP], x2 = x[2 * WP];
-  const f2 d0 = sub2(mk2(x0, x0), mk2(ya[0], yb[0]));
-  const f2 d1 = sub2(mk2(x1, x1), mk2(ya[WP], yb[WP]));
-  const f2 d2 = sub2(mk2(x2, x2), mk2(ya[2 * WP], yb[2 * WP]));
+  float x0, x1, x2, a0, a1, a2, b0, b1, b2;
+};
+template <int WP> __device__ __forceinline__ grp_row9_t grp_load_row(const float *x, const float *ya, const float *yb)
+{
+  grp_row9_t r;
+  r.x0 = x[0];
+  r.x1 = x[WP];
+  r.x2 = x[2 * WP];
+  r.a0 = ya[0];
+  r.a1 = ya[WP];
+  r.a2 = ya[2 * WP];
+  r.b0 = yb[0];
+  r.b1 = yb[WP];
+  r.b2 = yb[2 * WP];
+  return r;
+}
+// its squared differences: lane x = patch a, lane y = patch b
+__device__ __forceinline__ void grp_squares2(const grp_row9_t &r, f2 &e0, f2 &e1, f2 &e2)
+{
+  const f2 d0 = sub2(mk2(r.x0, r.x0), mk2(r.a0, r.b0));
+  const f2 d1 = sub2(mk2(r.x1, r.x1), mk2(r.a1, r.b1));
+  const f2 d2 = sub2(mk2(r.x2, r.x2), mk2(r.a2, r.b2));
   // squares per lane: they feed packed differences and sums, and ptxas would contract a packed square into those (FFMA2)
   e0 = mk2(d0.x * d0.x, d0.y * d0.y);
   e1 = mk2(d1.x * d1.x, d1.y * d1.y);
@@ -228,51 +246,59 @@ template <bool NORM1> __device__ __forceinline__ f2 grp_pd2(f2 u0, f2 u1, f2 u2,
   return mk2((s0.x + s1.x) + s2.x, (s0.y + s1.y) + s2.y);
 }
 
-// two patches of one column whose rows are all regular and whose column is live for both
+// two patches of one column whose rows are all regular and whose column is live for both.  The running sum is the only thing a
+// row hands to the next one: the nine window values of row r + 1 are fetched before row r is worked on, so their
+// shared-memory latency runs under its arithmetic (the window has a spare row behind the last one read).
 template <int WP, int R, bool NORM1>
 __device__ void grp_colsum_pair(const grp_args_t &a, const chunk_t &c, const float *W, float *Sa, float *Sb, const pgeo_t &ga,
                                 const pgeo_t &gb, int k)
 {
+  constexpr int RP = 3 * WP, N = 2 * R + 1;
   const int col = c.cbase + k;
   const f2 n0 = mk2(a.norm[0], a.norm[0]), n1 = mk2(a.norm[1], a.norm[1]), n2 = mk2(a.norm[2], a.norm[2]);
-  const float *x = W + (c.top - R - c.wr0) * (3 * WP) + (col - c.wc0);
-  const float *ya = x + ga.srow * (3 * WP) + ga.scol, *yb = x + gb.srow * (3 * WP) + gb.scol;
+  const float *x = W + (c.top - R - c.wr0) * RP + (col - c.wc0);
+  const float *ya = x + ga.srow * RP + ga.scol, *yb = x + gb.srow * RP + gb.scol;
   float *spa = Sa + k, *spb = Sb + k;
-  f2 ring[2 * R + 1][3];
+  f2 ring[N][3];
   f2 cs = mk2(0.0f, 0.0f);
+  grp_row9_t nxt = grp_load_row<WP>(x, ya, yb);
 #pragma unroll
-  for(int i = 0; i < 2 * R + 1; i++)
+  for(int i = 0; i < N; i++)
   {
-    grp_squares2<WP>(x + i * (3 * WP), ya + i * (3 * WP), yb + i * (3 * WP), ring[i][0], ring[i][1], ring[i][2]);
+    const grp_row9_t cur = nxt;
+    nxt = grp_load_row<WP>(x + (i + 1) * RP, ya + (i + 1) * RP, yb + (i + 1) * RP);
+    grp_squares2(cur, ring[i][0], ring[i][1], ring[i][2]);
     cs = add2(cs, grp_pd2<NORM1>(ring[i][0], ring[i][1], ring[i][2], n0, n1, n2));
   }
-  x += (2 * R + 1) * (3 * WP);
-  ya += (2 * R + 1) * (3 * WP);
-  yb += (2 * R + 1) * (3 * WP);
+  x += N * RP;
+  ya += N * RP;
+  yb += N * RP;
   // rows top .. bot-1: store the sum, then slide it down by one row (the last row has no successor to slide to)
   int left = c.ch;
-  for(; left > 2 * R + 1; left -= 2 * R + 1)
+  for(; left > N; left -= N)
   {
 #pragma unroll
-    for(int s = 0; s < 2 * R + 1; s++)
+    for(int s = 0; s < N; s++)
     {
+      const grp_row9_t cur = nxt;
+      nxt = grp_load_row<WP>(x + (s + 1) * RP, ya + (s + 1) * RP, yb + (s + 1) * RP);
       spa[s * GRP_SP] = cs.x;
       spb[s * GRP_SP] = cs.y;
       f2 e0, e1, e2;
-      grp_squares2<WP>(x + s * (3 * WP), ya + s * (3 * WP), yb + s * (3 * WP), e0, e1, e2);
+      grp_squares2(cur, e0, e1, e2);
       cs = add2(cs, grp_pd2<NORM1>(sub2(e0, ring[s][0]), sub2(e1, ring[s][1]), sub2(e2, ring[s][2]), n0, n1, n2));
       ring[s][0] = e0;
       ring[s][1] = e1;
       ring[s][2] = e2;
     }
-    x += (2 * R + 1) * (3 * WP);
-    ya += (2 * R + 1) * (3 * WP);
-    yb += (2 * R + 1) * (3 * WP);
-    spa += (2 * R + 1) * GRP_SP;
-    spb += (2 * R + 1) * GRP_SP;
+    x += N * RP;
+    ya += N * RP;
+    yb += N * RP;
+    spa += N * GRP_SP;
+    spb += N * GRP_SP;
   }
 #pragma unroll
-  for(int s = 0; s < 2 * R + 1; s++)
+  for(int s = 0; s < N; s++)
   {
     if(s < left)
     {
@@ -280,8 +306,10 @@ __device__ void grp_colsum_pair(const grp_args_t &a, const chunk_t &c, const flo
       spb[s * GRP_SP] = cs.y;
       if(s + 1 < left)
       {
+        const grp_row9_t cur = nxt;
+        if(s + 2 < left) nxt = grp_load_row<WP>(x + (s + 1) * RP, ya + (s + 1) * RP, yb + (s + 1) * RP);
         f2 e0, e1, e2;
-        grp_squares2<WP>(x + s * (3 * WP), ya + s * (3 * WP), yb + s * (3 * WP), e0, e1, e2);
+        grp_squares2(cur, e0, e1, e2);
         cs = add2(cs, grp_pd2<NORM1>(sub2(e0, ring[s][0]), sub2(e1, ring[s][1]), sub2(e2, ring[s][2]), n0, n1, n2));
       }
     }
@@ -483,9 +511,14 @@ __device__ __forceinline__ float grp_weight(const grp_args_t &a, float dist, flo
 }
 // dt_fast_mexp2f(), math/math.h:290-301, as the accumulation sees it: where the reference returns 0 this returns a
 // subnormal, which every consumer (flush-to-zero multiplies and adds, like the reference's DAZ) reads as +0
-__device__ __forceinline__ float grp_mexp2_daz(float x)
+// ANY: x may be negative or a NaN (the weights of the plain non-local means, :389-402): the conversion then has to be the
+// reference's cvttss2si.  Otherwise x is max(0, .) of something (:404-420): never a NaN, and x * -2^23 saturates at the same
+// INT_MIN on both machines.
+template <bool ANY> __device__ __forceinline__ float grp_mexp2_daz(float x)
 {
-  return __int_as_float(max(0x3f800000 + __float2int_rz(x * -8388608.0f), 0x007fffff));
+  const float v = x * -8388608.0f;
+  const int k = ANY ? cvtt_x86(v) : __float2int_rz(v);
+  return __int_as_float(max((int)(0x3f800000u + (unsigned)k), 0x007fffff));
 }
 
 // every pixel pair of the thread for one patch that covers the chunk: Wq = window + the patch's shift, Sg = its distortions
@@ -524,7 +557,7 @@ __device__ __forceinline__ void grp_accumulate_pairs(const grp_args_t &a, const 
     }
     else
       t = mul2(dist, sharp); // :389-402
-    const float wx = grp_mexp2_daz(t.x), wy = grp_mexp2_daz(t.y);
+    const float wx = grp_mexp2_daz<!PROFILED>(t.x), wy = grp_mexp2_daz<!PROFILED>(t.y);
     // out += pixel * wt: products per lane, sums packed
     const f2 a0 = add2(mk2(st.acc[k][0], st.acc[k][1]), mk2(q0.x * wx, q0.y * wy));
     const f2 a1 = add2(mk2(st.acc[k][2], st.acc[k][3]), mk2(q1.x * wx, q1.y * wy));

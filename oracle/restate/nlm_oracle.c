@@ -138,6 +138,7 @@ int orc_nlmeans_denoise(const float *inbuf, float *outbuf, int width, int height
   for(int it = 0; it < n_ct; it++)
     for(int il = 0; il < n_cl; il++)
     {
+      orc_fp_fast_mode(); /* the pipe's threads run with FTZ|DAZ (darktable.c:877, common/dtpthread.c:54): a weighted sum next to FLT_MIN flushes */
       const int chunk_top = it * chk_h, chunk_left = il * chk_w;
       float scratch[SLICE_WIDTH + 2 * 8 + 1 + 48];
       float *const col_sums = scratch + (radius + 1) - chunk_left;

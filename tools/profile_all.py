@@ -16,6 +16,7 @@ def run(op, data, src, dst, ww=w, hh=h, ch=4, filters=0):
 enc = util.srgb_encode_lut()
 conv_in = ab.make_conversion(util.MATRIX_CAM_TO_REC2020)
 conv_out = ab.make_conversion(util.MATRIX_REC2020_TO_SRGB, lut_target=enc, coeffs_target=util.fit_unbounded_coeffs(enc))
+run("demosaic", ab.demosaic_data(ab.DEMOSAIC_AMAZE), mosaic, a, ch=1, filters=util.BAYER["RGGB"])
 run("demosaic", ab.demosaic_data(ab.DEMOSAIC_RCD), mosaic, a, ch=1, filters=util.BAYER["RGGB"])
 run("colorin", ab.colorin_data(conv_in), a, b)
 run("denoiseprofile", ab.denoiseprofile_data(ab.DENOISE_WAVELETS), b, a)
