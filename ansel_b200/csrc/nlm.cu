@@ -688,7 +688,7 @@ bool grp_plan(grp_args_t &g, int n_patches, int width, int height, int radius, f
   return true;
 }
 int grp_pairs_per_thread(const grp_args_t &g) { return (((g.chk_h + 1) / 2) * g.chk_w + GRP_NT - 1) / GRP_NT; }
-size_t grp_pipe_smem_bytes(const grp_args_t &g) { return ((size_t)g.wrows * 3 * g.wp + (size_t)2 * PIPE_SLOTS * g.splane) * sizeof(float); }
+size_t grp_pipe_smem_bytes(const grp_args_t &g, int wp) { return ((size_t)g.wrows * 3 * wp + (size_t)2 * PIPE_SLOTS * g.splane + (size_t)g.n_patches) * sizeof(float); }
 size_t grp_smem_bytes(const grp_args_t &g) { return ((size_t)g.wrows * 3 * g.wp + (size_t)g.G * g.splane + GRP_MAXG) * sizeof(float); }
 // Markstein's division is the reference's division as long as nothing underflows on the way; where it could (x below
 // 2^-44 with these bounds) the weight is 1 whatever the last bit of the quotient, because x / d * sharpness < 2^-24
@@ -716,24 +716,24 @@ int grp_define_patches(patch_t *patches, int search_radius, float scale, float s
   return shift_max;
 }
 
+constexpr int PIPE_DEFAULT_CFG = 0;
 // the pipelined kernel (nlm_pipe_kernel): chunks of up to 64 rows, the narrow window, a ring of PIPE_SLOTS pair slots
-bool grp_pipe_fits(const grp_args_t &g, int smem_optin)
+bool grp_pipe_fits(const grp_args_t &g, int smem_optin, int wp)
 {
-  return g.wp == GRP_WP_NARROW && ((g.chk_h + 1) / 2) * g.chk_w <= PIPE_KP * PIPE_ACC_T
-         && (long long)grp_pipe_smem_bytes(g) <= smem_optin;
+  return g.wcols <= PIPE_WCOLS_MAX && g.chk_h <= PIPE_MAX_ROWS && (long long)grp_pipe_smem_bytes(g, wp) <= smem_optin;
 }
 
 #ifndef B200_KERNELS_ON_CPU
-template <int R> cudaError_t launch_pipe_r(const grp_args_t &g, bool norm1, bool profiled, bool divc, unsigned grid, size_t smem, cudaStream_t stream)
+template <int R, int CFG> cudaError_t launch_pipe_r(const grp_args_t &g, bool norm1, bool profiled, bool divc, unsigned grid, size_t smem, cudaStream_t stream)
 {
 #define PIPE_LAUNCH(N1, PR, DC)                                                                                        \
   do                                                                                                                   \
   {                                                                                                                    \
-    cudaError_t e = cudaFuncSetAttribute(nlm_pipe_kernel<R, GRP_WP_NARROW, N1, PR, DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    cudaError_t e = cudaFuncSetAttribute(nlm_pipe_kernel<R, N1, PR, DC, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if(e != cudaSuccess) return e;                                                                                     \
     {                                                                                                                  \
       ::b200::timed_launch timed(::b200::TIMED_NLM, stream);                                                           \
-      nlm_pipe_kernel<R, GRP_WP_NARROW, N1, PR, DC><<<grid, PIPE_NT, smem, stream>>>(g);                               \
+      nlm_pipe_kernel<R, N1, PR, DC, CFG><<<grid, pipe_cfg<CFG>::NT, smem, stream>>>(g);                              \
     }                                                                                                                  \
     return cudaGetLastError();                                                                                         \
   } while(0)
@@ -798,10 +798,16 @@ int launch_group(const nlm_args_t &a, int shift_max, int smem_optin, int n_chunk
   const bool divc = grp_division_by_constant(g) && !getenv("B200_NLM_IEEE_DIV");
   cudaError_t e;
   const unsigned grid = (unsigned)n_chunks;
-  if(grp_pipe_fits(g, smem_optin) && !getenv("B200_NLM_NO_PIPE"))
+  int shape = PIPE_DEFAULT_CFG;
+  if(const char *v = getenv("B200_NLM_PIPE_CFG")) shape = atoi(v) ? 1 : 0;
+  const int pipe_wp = shape == 1 ? pipe_cfg<1>::WP : pipe_cfg<0>::WP;
+  if(grp_pipe_fits(g, smem_optin, pipe_wp) && !getenv("B200_NLM_NO_PIPE"))
   {
-    const size_t psmem = grp_pipe_smem_bytes(g);
-    e = a.radius == 1 ? launch_pipe_r<1>(g, norm1, profiled, divc, grid, psmem, stream) : launch_pipe_r<2>(g, norm1, profiled, divc, grid, psmem, stream);
+    const size_t psmem = grp_pipe_smem_bytes(g, pipe_wp);
+    if(shape == 1)
+      e = a.radius == 1 ? launch_pipe_r<1, 1>(g, norm1, profiled, divc, grid, psmem, stream) : launch_pipe_r<2, 1>(g, norm1, profiled, divc, grid, psmem, stream);
+    else
+      e = a.radius == 1 ? launch_pipe_r<1, 0>(g, norm1, profiled, divc, grid, psmem, stream) : launch_pipe_r<2, 0>(g, norm1, profiled, divc, grid, psmem, stream);
     if(e != cudaSuccess) return ::b200::fail(B200_ERR_CUDA, "nlmeans: pipelined kernel launch: %s", cudaGetErrorString(e));
     *launched = 1;
     return B200_OK;

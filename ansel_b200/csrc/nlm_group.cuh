@@ -459,14 +459,33 @@ template <int R> __device__ __forceinline__ void grp_phase_b1(const grp_args_t &
 }
 
 // ---- phase B2 --------------------------------------------------------------------------------------------------
-template <int KP> struct grp_thread_t
+// Two ways of dealing the pixel pairs of a chunk to the accumulating threads.  grp_thread_t: pair j = tid + k * NTHREADS in raster
+// order (any chunk height, any thread count; the offsets of every pair live in registers).  grp_strip_t: a thread owns the pairs
+// of ONE pair of rows at columns i, i + L, i + 2L, ...: the offsets of pair k are those of pair 0 plus k * L, immediates of the
+// load instructions.  L = 8: a warp holds 8 lanes on each of 4 row pairs that lie 4 row pairs apart, 72 columns = 9 pairs per
+// thread; with an odd window pitch (3 * WP) and the odd pitch of the planes the four row pairs of a warp start 8 banks apart:
+// no bank conflicts in phase B2, whatever the patch shift.  L = 12: thread ta owns row pair ta / 12, 6 pairs per thread.
+template <int KP_> struct grp_thread_t
 {
+  static constexpr int KP = KP_;
   float acc[KP][8]; // sums of the upper pixel (even slots) and of the lower pixel (odd slots): x x' y y' z z' w w'
   float ctr[KP][6]; // the pixels themselves: c0 c0' c1 c1' c2 c2'
-  int wofs[KP];     // window offset of the upper pixel (the chunk's first pixel for a pair that does not exist: harmless reads, never stored)
-  int sofs[KP];     // offset of its distortion in a plane of S
+  int wofs_[KP];    // window offset of the upper pixel (the chunk's first pixel for a pair that does not exist: harmless reads, never stored)
+  int sofs_[KP];    // offset of its distortion in a plane of S
   unsigned upper;   // bit k: pair k exists
   unsigned lower;   // bit k: its lower pixel belongs to the chunk
+  __device__ __forceinline__ int wofs(int k) const { return wofs_[k]; }
+  __device__ __forceinline__ int sofs(int k) const { return sofs_[k]; }
+};
+template <int KP_, int L_> struct grp_strip_t
+{
+  static constexpr int KP = KP_, L = L_;
+  float acc[KP][8];
+  float ctr[KP][6];
+  int wofs0, sofs0; // of pair 0 (row pair 0 for a thread whose row pair is below the chunk: harmless reads, never stored)
+  unsigned upper, lower;
+  __device__ __forceinline__ int wofs(int k) const { return wofs0 + k * L; }
+  __device__ __forceinline__ int sofs(int k) const { return sofs0 + k * L; }
 };
 
 template <int WP, int KP, int NTHREADS = GRP_NT>
@@ -480,16 +499,60 @@ __device__ __forceinline__ void grp_own_init(const grp_args_t &a, const chunk_t 
     const int pr = j / c.cw, pc = j - pr * c.cw;
 #pragma unroll
     for(int i = 0; i < 8; i++) st.acc[k][i] = 0.0f;
-    st.wofs[k] = (c.top - c.wr0) * (3 * WP) + (c.left - c.wc0); // the chunk's first pixel: any patch shift stays inside the window
-    st.sofs[k] = 0;
+    st.wofs_[k] = (c.top - c.wr0) * (3 * WP) + (c.left - c.wc0); // the chunk's first pixel: any patch shift stays inside the window
+    st.sofs_[k] = 0;
     if(2 * pr < c.ch)
     {
-      st.wofs[k] = (c.top + 2 * pr - c.wr0) * (3 * WP) + (c.left + pc - c.wc0);
-      st.sofs[k] = 2 * pr * GRP_SP + pc;
+      st.wofs_[k] = (c.top + 2 * pr - c.wr0) * (3 * WP) + (c.left + pc - c.wc0);
+      st.sofs_[k] = 2 * pr * GRP_SP + pc;
       st.upper |= 1u << k;
       if(2 * pr + 1 < c.ch) st.lower |= 1u << k;
     }
-    const float *const w = W + st.wofs[k];
+    const float *const w = W + st.wofs_[k];
+    st.ctr[k][0] = w[0];
+    st.ctr[k][1] = w[(3 * WP)];
+    st.ctr[k][2] = w[WP];
+    st.ctr[k][3] = w[(3 * WP) + WP];
+    st.ctr[k][4] = w[2 * WP];
+    st.ctr[k][5] = w[(3 * WP) + 2 * WP];
+  }
+}
+// row pair and first column of accumulating thread ta of a strip ownership
+template <int L> __device__ __forceinline__ void grp_strip_of(int ta, int &pr, int &i)
+{
+  if(L == 8)
+  {
+    const int wa = ta >> 5, l = ta & 31;
+    i = l & 7;
+    pr = (wa & 3) + 4 * (l >> 3) + 16 * (wa >> 2);
+  }
+  else
+  {
+    pr = ta / L;
+    i = ta - pr * L;
+  }
+}
+template <int WP, int KP, int L>
+__device__ __forceinline__ void grp_own_init(const grp_args_t &a, const chunk_t &c, const float *W, grp_strip_t<KP, L> &st, int ta)
+{
+  int pr, i;
+  grp_strip_of<L>(ta, pr, i);
+  const bool rows = 2 * pr < c.ch;
+  const int r0 = rows ? 2 * pr : 0;
+  st.wofs0 = (c.top + r0 - c.wr0) * (3 * WP) + (c.left + i - c.wc0);
+  st.sofs0 = r0 * GRP_SP + i;
+  st.lower = st.upper = 0u;
+#pragma unroll
+  for(int k = 0; k < KP; k++)
+  {
+#pragma unroll
+    for(int j = 0; j < 8; j++) st.acc[k][j] = 0.0f;
+    if(rows && i + k * L < c.cw)
+    {
+      st.upper |= 1u << k;
+      if(2 * pr + 1 < c.ch) st.lower |= 1u << k;
+    }
+    const float *const w = W + st.wofs(k);
     st.ctr[k][0] = w[0];
     st.ctr[k][1] = w[(3 * WP)];
     st.ctr[k][2] = w[WP];
@@ -522,17 +585,18 @@ template <bool ANY> __device__ __forceinline__ float grp_mexp2_daz(float x)
 }
 
 // every pixel pair of the thread for one patch that covers the chunk: Wq = window + the patch's shift, Sg = its distortions
-template <int WP, bool PROFILED, bool DIVC, int KP>
-__device__ __forceinline__ void grp_accumulate_pairs(const grp_args_t &a, const float *Wq, const float *Sg, grp_thread_t<KP> &st)
+template <int WP, bool PROFILED, bool DIVC, class ST>
+__device__ __forceinline__ void grp_accumulate_pairs(const grp_args_t &a, const float *Wq, const float *Sg, ST &st)
 {
+  constexpr int KP = ST::KP;
   const f2 cp = mk2(a.cp_norm, a.cp_norm), sharp = mk2(a.sharpness, a.sharpness);
   const f2 ndd = mk2(-a.div_d, -a.div_d), rcp = mk2(a.div_rcp, a.div_rcp);
 #pragma unroll
   for(int k = 0; k < KP; k++)
   {
-    const float *const w = Wq + st.wofs[k];
+    const float *const w = Wq + st.wofs(k);
     const f2 q0 = mk2(w[0], w[(3 * WP)]), q1 = mk2(w[WP], w[(3 * WP) + WP]), q2 = mk2(w[2 * WP], w[(3 * WP) + 2 * WP]);
-    const float *const sp = Sg + st.sofs[k];
+    const float *const sp = Sg + st.sofs(k);
     const f2 dist = mk2(sp[0], sp[GRP_SP]);
     f2 t;
     if(PROFILED)
@@ -575,15 +639,16 @@ __device__ __forceinline__ void grp_accumulate_pairs(const grp_args_t &a, const 
 }
 
 // phase B2 for one thread and one patch of a chunk that is not in the interior of the frame
-template <int WP, bool PROFILED, bool DIVC, int KP>
-__device__ __forceinline__ void grp_accumulate_edge(const grp_args_t &a, const chunk_t &c, const float *W, const float *Sg, grp_thread_t<KP> &st, int p)
+template <int WP, bool PROFILED, bool DIVC, class ST>
+__device__ __forceinline__ void grp_accumulate_edge(const grp_args_t &a, const chunk_t &c, const float *W, const float *Sg, ST &st, int p)
 {
+  constexpr int KP = ST::KP;
   const pgeo_t g = patch_geo_grp(a, c, p);
   if(!g.valid || g.col_min >= g.col_max) return; // uniform
   const float *const Wq = W + g.srow * (3 * WP) + g.scol;
   if(covers_chunk(c, g))
   {
-    grp_accumulate_pairs<WP, PROFILED, DIVC, KP>(a, Wq, Sg, st);
+    grp_accumulate_pairs<WP, PROFILED, DIVC>(a, Wq, Sg, st);
     return;
   }
   // a patch that leaves the frame somewhere in this chunk: pixel by pixel
@@ -591,7 +656,7 @@ __device__ __forceinline__ void grp_accumulate_edge(const grp_args_t &a, const c
   for(int k = 0; k < KP; k++)
   {
     if(!((st.upper >> k) & 1u)) continue;
-    const int rr = st.sofs[k] / GRP_SP, pc = st.sofs[k] - rr * GRP_SP;
+    const int rr = st.sofs(k) / GRP_SP, pc = st.sofs(k) - rr * GRP_SP;
     const int col = c.left + pc;
     if(col < g.col_min || col >= g.col_max) continue;
 #pragma unroll
@@ -599,9 +664,9 @@ __device__ __forceinline__ void grp_accumulate_edge(const grp_args_t &a, const c
     {
       const int row = c.top + rr + l;
       if(row < g.row_min || row >= g.row_max) continue;
-      const float *const w = Wq + st.wofs[k] + l * (3 * WP);
+      const float *const w = Wq + st.wofs(k) + l * (3 * WP);
       const float q0 = w[0], q1 = w[WP], q2 = w[2 * WP];
-      const float wt = grp_weight<PROFILED>(a, Sg[st.sofs[k] + l * GRP_SP], st.ctr[k][0 + l], st.ctr[k][2 + l], st.ctr[k][4 + l], q0, q1, q2);
+      const float wt = grp_weight<PROFILED>(a, Sg[st.sofs(k) + l * GRP_SP], st.ctr[k][0 + l], st.ctr[k][2 + l], st.ctr[k][4 + l], q0, q1, q2);
       st.acc[k][0 + l] += q0 * wt;
       st.acc[k][2 + l] += q1 * wt;
       st.acc[k][4 + l] += q2 * wt;
@@ -618,21 +683,22 @@ __device__ __forceinline__ void grp_phase_b2(const grp_args_t &a, const chunk_t 
   {
     const int n = min(a.G, a.n_patches - p0);
     const float *Sg = S;
-    for(int gi = 0; gi < n; gi++, Sg += a.splane) grp_accumulate_pairs<WP, PROFILED, DIVC, KP>(a, W + shifts[gi], Sg, st);
+    for(int gi = 0; gi < n; gi++, Sg += a.splane) grp_accumulate_pairs<WP, PROFILED, DIVC>(a, W + shifts[gi], Sg, st);
     return;
   }
-  for(int gi = 0; gi < a.G; gi++) grp_accumulate_edge<WP, PROFILED, DIVC, KP>(a, c, W, S + gi * a.splane, st, p0 + gi);
+  for(int gi = 0; gi < a.G; gi++) grp_accumulate_edge<WP, PROFILED, DIVC>(a, c, W, S + gi * a.splane, st, p0 + gi);
 }
 
 // ---- normalise (and blend), :485-519 -----------------------------------------------------------------------------
-template <int KP>
-__device__ __forceinline__ void grp_finish(const grp_args_t &a, const chunk_t &c, const grp_thread_t<KP> &st, int tid)
+template <class ST>
+__device__ __forceinline__ void grp_finish(const grp_args_t &a, const chunk_t &c, const ST &st, int tid)
 {
+  constexpr int KP = ST::KP;
 #pragma unroll
   for(int k = 0; k < KP; k++)
   {
     if(!((st.upper >> k) & 1u)) continue;
-    const int rr = st.sofs[k] / GRP_SP, pc = st.sofs[k] - rr * GRP_SP;
+    const int rr = st.sofs(k) / GRP_SP, pc = st.sofs(k) - rr * GRP_SP;
 #pragma unroll
     for(int l = 0; l < 2; l++)
     {
@@ -682,72 +748,99 @@ __global__ void __launch_bounds__(GRP_NT, 1) nlm_group_kernel(const __grid_const
 #endif
 
 // ---- the same phases as a pipeline: scan warps run ahead of the accumulating warps --------------------------------------------
-// 512 threads: two scan groups of 128 (phases A and B1 of a patch pair each, pairs dealt alternately) fill a ring of PIPE_SLOTS
-// pair slots (2 planes each) in shared memory; 256 accumulating threads (9 pixel pairs each) drain it in patch order (phase B2).
+// Two scan groups of 128 threads (phases A and B1 of a patch pair each, pairs dealt alternately) fill a ring of PIPE_SLOTS pair
+// slots (2 planes each) in shared memory; ACC_T accumulating threads (KP pixel pairs each) drain it in patch order (phase B2).
 // Named barriers: FULL[slot] (scan group arrives, accumulators wait), EMPTY[slot] (accumulators arrive, the scan group that
-// wants the slot waits), one barrier per scan group between its phases A and B1.  The accumulators need 3.5 times the
-// registers of the scan threads: setmaxnreg moves them (the block is launched with 128 per thread).
-constexpr int PIPE_NT = 512, PIPE_SCAN_GROUP = 128, PIPE_ACC_T = 256, PIPE_KP = 9, PIPE_SLOTS = 3;
-constexpr int PIPE_SCAN_REGS = 80, PIPE_ACC_REGS = 176; // 256 x 80 + 256 x 176 = the register file
+// wants the slot waits), one barrier per scan group between its phases A and B1.  The accumulators need two to three times the
+// registers of the scan threads: setmaxnreg moves them.  Two shapes (pipe_cfg): 256 accumulating threads with 9 pixel pairs each
+// (512 threads, launched with 128 registers) or 384 with 6 (640 threads, launched with 96): the second trades instruction-level
+// for thread-level parallelism -- three accumulating warps per scheduler instead of two.
+// Phase B1 runs on the upper half of a scan group (warps 2 and 3: warp 3 has no column in phase A, warp 2 eleven), so that the
+// four schedulers of the SM see the same number of busy scan warps.
+constexpr int PIPE_SCAN_GROUP = 128, PIPE_SLOTS = 3;
+template <int CFG> struct pipe_cfg;
+template <> struct pipe_cfg<0>
+{
+  static constexpr int ACC_T = 256, KP = 9, L = 8, WP = 97, SCAN_REGS = 80, ACC_REGS = 176, NT = 2 * PIPE_SCAN_GROUP + ACC_T; // 256 x 80 + 256 x 176 = the register file
+};
+template <> struct pipe_cfg<1>
+{
+  static constexpr int ACC_T = 384, KP = 6, L = 12, WP = 98, SCAN_REGS = 64, ACC_REGS = 128, NT = 2 * PIPE_SCAN_GROUP + ACC_T; // 256 x 64 + 384 x 128 = the register file
+};
+constexpr int PIPE_MAX_ROWS = 64; // chunks of up to 64 rows: 2 * 32 row pairs = the 64 threads of phase B1, 2304 pixel pairs at most
 constexpr int PIPE_BAR_FULL = 1, PIPE_BAR_EMPTY = PIPE_BAR_FULL + PIPE_SLOTS, PIPE_BAR_GROUP = PIPE_BAR_EMPTY + PIPE_SLOTS;
-static_assert(((MAX_CH - 5 + 1) / 2) * MAX_CW <= PIPE_KP * PIPE_ACC_T, "chunks of up to 64 rows: 9 pixel pairs per accumulating thread");
+static_assert(pipe_cfg<0>::KP * pipe_cfg<0>::L >= MAX_CW && pipe_cfg<0>::ACC_T / pipe_cfg<0>::L * 2 >= PIPE_MAX_ROWS
+              && pipe_cfg<1>::KP * pipe_cfg<1>::L >= MAX_CW && pipe_cfg<1>::ACC_T / pipe_cfg<1>::L * 2 >= PIPE_MAX_ROWS,
+              "every pixel pair of a 64-row chunk has an accumulating thread");
+constexpr int PIPE_WCOLS_MAX = 96; // window columns the pipelined kernel takes: both pitches (pipe_cfg::WP) hold them
+// thread t of a scan group in phase B1: its index among the 2 * half row tasks, or -1
+__device__ __forceinline__ int pipe_b1_task(int t, int half)
+{
+  const int tb = t - (PIPE_SCAN_GROUP - PIPE_MAX_ROWS);
+  return tb >= 0 && tb < 2 * half ? tb : -1;
+}
 
 #ifndef B200_KERNELS_ON_CPU
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-template <int R, int WP, bool NORM1, bool PROFILED, bool DIVC>
-__global__ void __launch_bounds__(PIPE_NT, 1) nlm_pipe_kernel(const __grid_constant__ grp_args_t a)
+template <int R, bool NORM1, bool PROFILED, bool DIVC, int CFG>
+__global__ void __launch_bounds__(pipe_cfg<CFG>::NT, 1) nlm_pipe_kernel(const __grid_constant__ grp_args_t a)
 {
+  using cfg = pipe_cfg<CFG>;
+  constexpr int NT = cfg::NT, ACC_T = cfg::ACC_T, WP = cfg::WP;
   extern __shared__ __align__(16) float smem[];
   float *const W = smem, *const S = smem + a.wrows * (3 * WP);
+  int *const shifts = reinterpret_cast<int *>(S + 2 * PIPE_SLOTS * a.splane); // window shift of every patch
   const int tid = threadIdx.x;
   const chunk_t c = chunk_of(a, blockIdx.x);
-  grp_fill<WP, PIPE_NT>(a, c, W, tid);
+  grp_fill<WP, NT>(a, c, W, tid);
+  for(int p = tid; p < a.n_patches; p += NT) shifts[p] = grp_shift<WP>(a, p);
   __syncthreads();
   const int npairs = (a.n_patches + 1) / 2;
   if(tid < 2 * PIPE_SCAN_GROUP)
   {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PIPE_SCAN_REGS));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(cfg::SCAN_REGS));
     const int group = tid / PIPE_SCAN_GROUP, t = tid - group * PIPE_SCAN_GROUP;
     const int half = (c.ch + 1) / 2;
+    const int tb = pipe_b1_task(t, half);
     for(int q = group; q < npairs; q += 2)
     {
       const int slot = q % PIPE_SLOTS;
       float *const Sa = S + (2 * slot) * a.splane, *const Sb = Sa + a.splane;
-      if(q >= PIPE_SLOTS) named_sync(PIPE_BAR_EMPTY + slot, PIPE_SCAN_GROUP + PIPE_ACC_T);
+      if(q >= PIPE_SLOTS) named_sync(PIPE_BAR_EMPTY + slot, PIPE_SCAN_GROUP + ACC_T);
       if(t < c.ncols) grp_scan_column<WP, R, NORM1>(a, c, W, Sa, Sb, 2 * q, t);
       named_sync(PIPE_BAR_GROUP + group, PIPE_SCAN_GROUP);
-      if(t < 2 * half)
+      if(tb >= 0)
       {
-        const int gi = t / half;
-        grp_scan_rows<R>(a, c, gi ? Sb : Sa, 2 * q + gi, t - gi * half, half);
+        const int gi = tb / half;
+        grp_scan_rows<R>(a, c, gi ? Sb : Sa, 2 * q + gi, tb - gi * half, half);
       }
-      named_arrive(PIPE_BAR_FULL + slot, PIPE_SCAN_GROUP + PIPE_ACC_T);
+      named_arrive(PIPE_BAR_FULL + slot, PIPE_SCAN_GROUP + ACC_T);
     }
   }
   else
   {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PIPE_ACC_REGS));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(cfg::ACC_REGS));
     const int ta = tid - 2 * PIPE_SCAN_GROUP;
-    grp_thread_t<PIPE_KP> st;
-    grp_own_init<WP, PIPE_KP, PIPE_ACC_T>(a, c, W, st, ta);
+    grp_strip_t<cfg::KP, cfg::L> st;
+    grp_own_init<WP>(a, c, W, st, ta);
     for(int q = 0; q < npairs; q++)
     {
       const int slot = q % PIPE_SLOTS;
       const float *const Sa = S + (2 * slot) * a.splane;
-      named_sync(PIPE_BAR_FULL + slot, PIPE_SCAN_GROUP + PIPE_ACC_T);
+      named_sync(PIPE_BAR_FULL + slot, PIPE_SCAN_GROUP + ACC_T);
       if(c.interior)
       {
-        grp_accumulate_pairs<WP, PROFILED, DIVC, PIPE_KP>(a, W + grp_shift<WP>(a, 2 * q), Sa, st);
-        if(2 * q + 1 < a.n_patches) grp_accumulate_pairs<WP, PROFILED, DIVC, PIPE_KP>(a, W + grp_shift<WP>(a, 2 * q + 1), Sa + a.splane, st);
+        grp_accumulate_pairs<WP, PROFILED, DIVC>(a, W + shifts[2 * q], Sa, st);
+        if(2 * q + 1 < a.n_patches) grp_accumulate_pairs<WP, PROFILED, DIVC>(a, W + shifts[2 * q + 1], Sa + a.splane, st);
       }
       else
       {
-        grp_accumulate_edge<WP, PROFILED, DIVC, PIPE_KP>(a, c, W, Sa, st, 2 * q);
-        grp_accumulate_edge<WP, PROFILED, DIVC, PIPE_KP>(a, c, W, Sa + a.splane, st, 2 * q + 1);
+        grp_accumulate_edge<WP, PROFILED, DIVC>(a, c, W, Sa, st, 2 * q);
+        grp_accumulate_edge<WP, PROFILED, DIVC>(a, c, W, Sa + a.splane, st, 2 * q + 1);
       }
-      if(q + PIPE_SLOTS < npairs) named_arrive(PIPE_BAR_EMPTY + slot, PIPE_SCAN_GROUP + PIPE_ACC_T);
+      if(q + PIPE_SLOTS < npairs) named_arrive(PIPE_BAR_EMPTY + slot, PIPE_SCAN_GROUP + ACC_T);
     }
     grp_finish(a, c, st, ta);
   }

@@ -31,11 +31,13 @@ template <int R, int WP, bool NORM1, bool PROFILED, bool DIVC, int KP> static vo
 
 /* the pipelined kernel's order of work: per patch pair, scan group (phase A, then phase B1) into its slot of the ring, then the 256
  * accumulating threads; what the emulation cannot see is the barrier protocol between them */
-template <int R, int WP, bool NORM1, bool PROFILED, bool DIVC> static void run_pipe_chunks(const grp_args_t &a, int n_chunks)
+template <int R, bool NORM1, bool PROFILED, bool DIVC, int CFG> static void run_pipe_chunks(const grp_args_t &a, int n_chunks)
 {
-  std::vector<float> smem((size_t)a.wrows * 3 * WP + (size_t)2 * PIPE_SLOTS * a.splane);
-  std::vector<grp_thread_t<PIPE_KP>> st(PIPE_ACC_T);
+  constexpr int PIPE_NT = pipe_cfg<CFG>::NT, PIPE_ACC_T = pipe_cfg<CFG>::ACC_T, WP = pipe_cfg<CFG>::WP;
+  std::vector<float> smem((size_t)a.wrows * 3 * WP + (size_t)2 * PIPE_SLOTS * a.splane + a.n_patches);
+  std::vector<grp_strip_t<pipe_cfg<CFG>::KP, pipe_cfg<CFG>::L>> st(PIPE_ACC_T);
   float *const W = smem.data(), *const S = W + a.wrows * 3 * WP;
+  int *const shifts = reinterpret_cast<int *>(S + 2 * PIPE_SLOTS * a.splane);
   const int npairs = (a.n_patches + 1) / 2;
   for(int b = 0; b < n_chunks; b++)
   {
@@ -43,7 +45,9 @@ template <int R, int WP, bool NORM1, bool PROFILED, bool DIVC> static void run_p
     const chunk_t c = chunk_of(a, b);
     const int half = (c.ch + 1) / 2;
     for(int t = 0; t < PIPE_NT; t++) grp_fill<WP, PIPE_NT>(a, c, W, t);
-    for(int t = 0; t < PIPE_ACC_T; t++) grp_own_init<WP, PIPE_KP, PIPE_ACC_T>(a, c, W, st[t], t);
+    for(int t = 0; t < PIPE_NT; t++)
+      for(int p = t; p < a.n_patches; p += PIPE_NT) shifts[p] = grp_shift<WP>(a, p);
+    for(int t = 0; t < PIPE_ACC_T; t++) grp_own_init<WP>(a, c, W, st[t], t);
     for(int q = 0; q < npairs; q++)
     {
       const int slot = q % PIPE_SLOTS;
@@ -51,34 +55,37 @@ template <int R, int WP, bool NORM1, bool PROFILED, bool DIVC> static void run_p
       for(int t = 0; t < PIPE_SCAN_GROUP; t++)
         if(t < c.ncols) grp_scan_column<WP, R, NORM1>(a, c, W, Sa, Sb, 2 * q, t);
       for(int t = 0; t < PIPE_SCAN_GROUP; t++)
-        if(t < 2 * half)
+      {
+        const int tb = pipe_b1_task(t, half);
+        if(tb >= 0)
         {
-          const int gi = t / half;
-          grp_scan_rows<R>(a, c, gi ? Sb : Sa, 2 * q + gi, t - gi * half, half);
+          const int gi = tb / half;
+          grp_scan_rows<R>(a, c, gi ? Sb : Sa, 2 * q + gi, tb - gi * half, half);
         }
+      }
       for(int t = 0; t < PIPE_ACC_T; t++)
       {
         if(c.interior)
         {
-          grp_accumulate_pairs<WP, PROFILED, DIVC, PIPE_KP>(a, W + grp_shift<WP>(a, 2 * q), Sa, st[t]);
-          if(2 * q + 1 < a.n_patches) grp_accumulate_pairs<WP, PROFILED, DIVC, PIPE_KP>(a, W + grp_shift<WP>(a, 2 * q + 1), Sb, st[t]);
+          grp_accumulate_pairs<WP, PROFILED, DIVC>(a, W + shifts[2 * q], Sa, st[t]);
+          if(2 * q + 1 < a.n_patches) grp_accumulate_pairs<WP, PROFILED, DIVC>(a, W + shifts[2 * q + 1], Sb, st[t]);
         }
         else
         {
-          grp_accumulate_edge<WP, PROFILED, DIVC, PIPE_KP>(a, c, W, Sa, st[t], 2 * q);
-          grp_accumulate_edge<WP, PROFILED, DIVC, PIPE_KP>(a, c, W, Sb, st[t], 2 * q + 1);
+          grp_accumulate_edge<WP, PROFILED, DIVC>(a, c, W, Sa, st[t], 2 * q);
+          grp_accumulate_edge<WP, PROFILED, DIVC>(a, c, W, Sb, st[t], 2 * q + 1);
         }
       }
     }
     for(int t = 0; t < PIPE_ACC_T; t++) grp_finish(a, c, st[t], t);
   }
 }
-template <int R> static void run_pipe(const grp_args_t &a, int n, bool norm1, bool profiled, bool divc)
+template <int R, int CFG> static void run_pipe(const grp_args_t &a, int n, bool norm1, bool profiled, bool divc)
 {
   if(!profiled)
-    return norm1 ? run_pipe_chunks<R, GRP_WP_NARROW, true, false, false>(a, n) : run_pipe_chunks<R, GRP_WP_NARROW, false, false, false>(a, n);
-  if(divc) return norm1 ? run_pipe_chunks<R, GRP_WP_NARROW, true, true, true>(a, n) : run_pipe_chunks<R, GRP_WP_NARROW, false, true, true>(a, n);
-  return norm1 ? run_pipe_chunks<R, GRP_WP_NARROW, true, true, false>(a, n) : run_pipe_chunks<R, GRP_WP_NARROW, false, true, false>(a, n);
+    return norm1 ? run_pipe_chunks<R, true, false, false, CFG>(a, n) : run_pipe_chunks<R, false, false, false, CFG>(a, n);
+  if(divc) return norm1 ? run_pipe_chunks<R, true, true, true, CFG>(a, n) : run_pipe_chunks<R, false, true, true, CFG>(a, n);
+  return norm1 ? run_pipe_chunks<R, true, true, false, CFG>(a, n) : run_pipe_chunks<R, false, true, false, CFG>(a, n);
 }
 
 template <int R, int WP, int KP> static void run_rk(const grp_args_t &a, int n, bool norm1, bool profiled, bool divc)
@@ -123,11 +130,12 @@ extern "C" int emul_nlmeans_group(const float *in, float *out, int width, int he
   const bool divc = grp_division_by_constant(g) && !ieee_div;
   if(pipe)
   { /* returns -1 where the pipelined kernel does not take the frame (the launcher then uses the group kernel) */
-    if(!grp_pipe_fits(g, smem_bytes)) return -1;
-    if(radius == 1)
-      run_pipe<1>(g, n_ct * g.n_cl, norm1, profiled, divc);
+    if(!grp_pipe_fits(g, smem_bytes, pipe == 2 ? pipe_cfg<1>::WP : pipe_cfg<0>::WP)) return -1;
+    const int n = n_ct * g.n_cl; /* pipe: 1 = 256 accumulating threads x 9 pixel pairs, 2 = 384 x 6 */
+    if(pipe == 2)
+      radius == 1 ? run_pipe<1, 1>(g, n, norm1, profiled, divc) : run_pipe<2, 1>(g, n, norm1, profiled, divc);
     else
-      run_pipe<2>(g, n_ct * g.n_cl, norm1, profiled, divc);
+      radius == 1 ? run_pipe<1, 0>(g, n, norm1, profiled, divc) : run_pipe<2, 0>(g, n, norm1, profiled, divc);
     return g.G;
   }
   if(radius == 1)
