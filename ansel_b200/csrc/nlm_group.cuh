@@ -381,38 +381,47 @@ __device__ __forceinline__ void grp_row_one(float *Sr /* Sr[col] = column sum of
 // is the one read 2*R+1 steps earlier
 template <int R> __device__ __forceinline__ void grp_row_pair(float *Sx, float *Sy, const pgeo_t &g)
 {
+  constexpr int N = 2 * R + 1;
   float *px = Sx + g.col_min - R - 1, *py = Sy + g.col_min - R - 1; // slot of D[col_min], column sum leaving at col_min
-  f2 ring[2 * R + 1];
+  f2 ring[N];
   f2 distortion = mk2(0.0f, 0.0f);
   ring[0] = mk2(px[0], py[0]);
 #pragma unroll
-  for(int i = 1; i < 2 * R + 1; i++)
+  for(int i = 1; i < N; i++)
   {
     ring[i] = mk2(px[i], py[i]);
     distortion = add2(distortion, ring[i]);
   }
-  int left = g.col_max - g.col_min;
-  for(; left >= 2 * R + 1; left -= 2 * R + 1)
-  {
+  // the column sums entering the window are fetched a block of N ahead of their use: only the running sum itself is a chain.
+  // (The last fetch reads up to N floats behind the row's last column sum: the next row of the plane, or what follows the planes.)
+  f2 nxt[N];
 #pragma unroll
-    for(int s = 0; s < 2 * R + 1; s++)
+  for(int s = 0; s < N; s++) nxt[s] = mk2(px[s + N], py[s + N]);
+  int left = g.col_max - g.col_min;
+  for(; left >= N; left -= N)
+  {
+    f2 cur[N];
+#pragma unroll
+    for(int s = 0; s < N; s++) cur[s] = nxt[s];
+#pragma unroll
+    for(int s = 0; s < N; s++) nxt[s] = mk2(px[s + 2 * N], py[s + 2 * N]);
+#pragma unroll
+    for(int s = 0; s < N; s++)
     {
-      const f2 in = mk2(px[s + 2 * R + 1], py[s + 2 * R + 1]);
-      distortion = add2(distortion, sub2(in, ring[s]));
-      ring[s] = in;
+      distortion = add2(distortion, sub2(cur[s], ring[s]));
+      ring[s] = cur[s];
       px[s] = distortion.x;
       py[s] = distortion.y;
     }
-    px += 2 * R + 1;
-    py += 2 * R + 1;
+    px += N;
+    py += N;
   }
 #pragma unroll
-  for(int s = 0; s < 2 * R + 1; s++)
+  for(int s = 0; s < N; s++)
   {
     if(s < left)
     {
-      const f2 in = mk2(px[s + 2 * R + 1], py[s + 2 * R + 1]);
-      distortion = add2(distortion, sub2(in, ring[s]));
+      distortion = add2(distortion, sub2(nxt[s], ring[s]));
       px[s] = distortion.x;
       py[s] = distortion.y;
     }
@@ -467,7 +476,7 @@ template <int R> __device__ __forceinline__ void grp_phase_b1(const grp_args_t &
 // no bank conflicts in phase B2, whatever the patch shift.  L = 12: thread ta owns row pair ta / 12, 6 pairs per thread.
 template <int KP_> struct grp_thread_t
 {
-  static constexpr int KP = KP_;
+  static constexpr int KP = KP_, IL = 1;
   float acc[KP][8]; // sums of the upper pixel (even slots) and of the lower pixel (odd slots): x x' y y' z z' w w'
   float ctr[KP][6]; // the pixels themselves: c0 c0' c1 c1' c2 c2'
   int wofs_[KP];    // window offset of the upper pixel (the chunk's first pixel for a pair that does not exist: harmless reads, never stored)
@@ -479,7 +488,7 @@ template <int KP_> struct grp_thread_t
 };
 template <int KP_, int L_> struct grp_strip_t
 {
-  static constexpr int KP = KP_, L = L_;
+  static constexpr int KP = KP_, L = L_, IL = KP_ % 3 == 0 && KP_ > 6 ? 3 : 2; // pairs in flight in phase B2
   float acc[KP][8];
   float ctr[KP][6];
   int wofs0, sofs0; // of pair 0 (row pair 0 for a thread whose row pair is below the chunk: harmless reads, never stored)
@@ -585,56 +594,116 @@ template <bool ANY> __device__ __forceinline__ float grp_mexp2_daz(float x)
 }
 
 // every pixel pair of the thread for one patch that covers the chunk: Wq = window + the patch's shift, Sg = its distortions
-template <int WP, bool PROFILED, bool DIVC, class ST>
+// The chain of one pixel pair is some twenty dependent operations long; left alone, ptxas walks the pairs one after the other
+// through ten scratch registers.  The pairs are therefore taken IL at a time, stage by stage: IL independent chains in flight.
+template <int WP, bool PROFILED, bool DIVC, class ST, int IL = ST::IL>
 __device__ __forceinline__ void grp_accumulate_pairs(const grp_args_t &a, const float *Wq, const float *Sg, ST &st)
 {
   constexpr int KP = ST::KP;
+  static_assert(KP % IL == 0, "pairs per thread come in whole batches");
   const f2 cp = mk2(a.cp_norm, a.cp_norm), sharp = mk2(a.sharpness, a.sharpness);
   const f2 ndd = mk2(-a.div_d, -a.div_d), rcp = mk2(a.div_rcp, a.div_rcp);
 #pragma unroll
-  for(int k = 0; k < KP; k++)
+  for(int k0 = 0; k0 < KP; k0 += IL)
   {
-    const float *const w = Wq + st.wofs(k);
-    const f2 q0 = mk2(w[0], w[(3 * WP)]), q1 = mk2(w[WP], w[(3 * WP) + WP]), q2 = mk2(w[2 * WP], w[(3 * WP) + 2 * WP]);
-    const float *const sp = Sg + st.sofs(k);
-    const f2 dist = mk2(sp[0], sp[GRP_SP]);
-    f2 t;
+    f2 q0[IL], q1[IL], q2[IL], t[IL];
+#pragma unroll
+    for(int j = 0; j < IL; j++)
+    {
+      const float *const w = Wq + st.wofs(k0 + j);
+      q0[j] = mk2(w[0], w[(3 * WP)]);
+      q1[j] = mk2(w[WP], w[(3 * WP) + WP]);
+      q2[j] = mk2(w[2 * WP], w[(3 * WP) + 2 * WP]);
+      const float *const sp = Sg + st.sofs(k0 + j);
+      t[j] = mk2(sp[0], sp[GRP_SP]); // the distortion
+    }
     if(PROFILED)
     { // :404-420
-      const f2 d0 = sub2(mk2(st.ctr[k][0], st.ctr[k][1]), q0), d1 = sub2(mk2(st.ctr[k][2], st.ctr[k][3]), q1),
-               d2 = sub2(mk2(st.ctr[k][4], st.ctr[k][5]), q2);
-      const f2 e0 = mul2(mul2(d0, d0), cp), e1 = mul2(mul2(d1, d1), cp), e2 = mul2(mul2(d2, d2), cp);
-      f2 x = add2(dist, mk2((e0.x + e1.x) + e2.x, (e0.y + e1.y) + e2.y));
-      f2 q;
+      f2 e0[IL], e1[IL], e2[IL];
+#pragma unroll
+      for(int j = 0; j < IL; j++)
+      {
+        const int k = k0 + j;
+        e0[j] = sub2(mk2(st.ctr[k][0], st.ctr[k][1]), q0[j]);
+        e1[j] = sub2(mk2(st.ctr[k][2], st.ctr[k][3]), q1[j]);
+        e2[j] = sub2(mk2(st.ctr[k][4], st.ctr[k][5]), q2[j]);
+      }
+#pragma unroll
+      for(int j = 0; j < IL; j++)
+      {
+        e0[j] = mul2(e0[j], e0[j]);
+        e1[j] = mul2(e1[j], e1[j]);
+        e2[j] = mul2(e2[j], e2[j]);
+      }
+#pragma unroll
+      for(int j = 0; j < IL; j++)
+      {
+        e0[j] = mul2(e0[j], cp);
+        e1[j] = mul2(e1[j], cp);
+        e2[j] = mul2(e2[j], cp);
+      }
+#pragma unroll
+      for(int j = 0; j < IL; j++) e0[j] = mk2(e0[j].x + e1[j].x, e0[j].y + e1[j].y);
+#pragma unroll
+      for(int j = 0; j < IL; j++) e0[j] = mk2(e0[j].x + e2[j].x, e0[j].y + e2[j].y);
+#pragma unroll
+      for(int j = 0; j < IL; j++) t[j] = add2(t[j], e0[j]);
       if(DIVC)
       { // x / d, correctly rounded (see the head of this file).  +inf would come out of the sequence as NaN: FLT_MAX in
         // its place gives the same weight, 0 (the host checked FLT_MAX / d * sharpness > 128); a NaN stays one
-        x = mk2(min_nan(x.x, 3.402823466e38f), min_nan(x.y, 3.402823466e38f));
-        const f2 qa = mul2(x, rcp);
-        const f2 r = fma2(qa, ndd, x);
-        q = fma2(r, rcp, qa);
+#pragma unroll
+        for(int j = 0; j < IL; j++) t[j] = mk2(min_nan(t[j].x, 3.402823466e38f), min_nan(t[j].y, 3.402823466e38f));
+#pragma unroll
+        for(int j = 0; j < IL; j++) e1[j] = mul2(t[j], rcp);
+#pragma unroll
+        for(int j = 0; j < IL; j++) e2[j] = fma2(e1[j], ndd, t[j]);
+#pragma unroll
+        for(int j = 0; j < IL; j++) t[j] = fma2(e2[j], rcp, e1[j]);
       }
       else
-        q = mk2(x.x / a.div_d, x.y / a.div_d);
-      const f2 u = mul2(q, sharp);
-      t = mk2(fmaxf(0.0f, u.x - 2.0f), fmaxf(0.0f, u.y - 2.0f));
+      {
+#pragma unroll
+        for(int j = 0; j < IL; j++) t[j] = mk2(t[j].x / a.div_d, t[j].y / a.div_d);
+      }
+#pragma unroll
+      for(int j = 0; j < IL; j++) t[j] = mul2(t[j], sharp);
+#pragma unroll
+      for(int j = 0; j < IL; j++) t[j] = mk2(t[j].x - 2.0f, t[j].y - 2.0f);
+#pragma unroll
+      for(int j = 0; j < IL; j++) t[j] = mk2(fmaxf(0.0f, t[j].x), fmaxf(0.0f, t[j].y));
     }
     else
-      t = mul2(dist, sharp); // :389-402
-    const float wx = grp_mexp2_daz<!PROFILED>(t.x), wy = grp_mexp2_daz<!PROFILED>(t.y);
+    {
+#pragma unroll
+      for(int j = 0; j < IL; j++) t[j] = mul2(t[j], sharp); // :389-402
+    }
+#pragma unroll
+    for(int j = 0; j < IL; j++) t[j] = mk2(grp_mexp2_daz<!PROFILED>(t[j].x), grp_mexp2_daz<!PROFILED>(t[j].y)); // the weights
     // out += pixel * wt: products per lane, sums packed
-    const f2 a0 = add2(mk2(st.acc[k][0], st.acc[k][1]), mk2(q0.x * wx, q0.y * wy));
-    const f2 a1 = add2(mk2(st.acc[k][2], st.acc[k][3]), mk2(q1.x * wx, q1.y * wy));
-    const f2 a2 = add2(mk2(st.acc[k][4], st.acc[k][5]), mk2(q2.x * wx, q2.y * wy));
-    const f2 a3 = add2(mk2(st.acc[k][6], st.acc[k][7]), mk2(wx, wy));
-    st.acc[k][0] = a0.x;
-    st.acc[k][1] = a0.y;
-    st.acc[k][2] = a1.x;
-    st.acc[k][3] = a1.y;
-    st.acc[k][4] = a2.x;
-    st.acc[k][5] = a2.y;
-    st.acc[k][6] = a3.x;
-    st.acc[k][7] = a3.y;
+#pragma unroll
+    for(int j = 0; j < IL; j++)
+    {
+      q0[j] = mk2(q0[j].x * t[j].x, q0[j].y * t[j].y);
+      q1[j] = mk2(q1[j].x * t[j].x, q1[j].y * t[j].y);
+      q2[j] = mk2(q2[j].x * t[j].x, q2[j].y * t[j].y);
+    }
+#pragma unroll
+    for(int j = 0; j < IL; j++)
+    {
+      const int k = k0 + j;
+      const f2 a0 = add2(mk2(st.acc[k][0], st.acc[k][1]), q0[j]);
+      const f2 a1 = add2(mk2(st.acc[k][2], st.acc[k][3]), q1[j]);
+      const f2 a2 = add2(mk2(st.acc[k][4], st.acc[k][5]), q2[j]);
+      const f2 a3 = add2(mk2(st.acc[k][6], st.acc[k][7]), t[j]);
+      st.acc[k][0] = a0.x;
+      st.acc[k][1] = a0.y;
+      st.acc[k][2] = a1.x;
+      st.acc[k][3] = a1.y;
+      st.acc[k][4] = a2.x;
+      st.acc[k][5] = a2.y;
+      st.acc[k][6] = a3.x;
+      st.acc[k][7] = a3.y;
+    }
   }
 }
 
@@ -750,13 +819,13 @@ __global__ void __launch_bounds__(GRP_NT, 1) nlm_group_kernel(const __grid_const
 // ---- the same phases as a pipeline: scan warps run ahead of the accumulating warps --------------------------------------------
 // Two scan groups of 128 threads (phases A and B1 of a patch pair each, pairs dealt alternately) fill a ring of PIPE_SLOTS pair
 // slots (2 planes each) in shared memory; ACC_T accumulating threads (KP pixel pairs each) drain it in patch order (phase B2).
+// The scan groups run phase A only; phase B1 (6 % of the work, but a chain of 72 dependent steps) is done by two of the accumulating
+// warps in front of phase B2: the accumulators have the slack, the scan groups are the critical path.
 // Named barriers: FULL[slot] (scan group arrives, accumulators wait), EMPTY[slot] (accumulators arrive, the scan group that
-// wants the slot waits), one barrier per scan group between its phases A and B1.  The accumulators need two to three times the
+// wants the slot waits), one barrier among the accumulators between phases B1 and B2.  The accumulators need two to three times the
 // registers of the scan threads: setmaxnreg moves them.  Two shapes (pipe_cfg): 256 accumulating threads with 9 pixel pairs each
 // (512 threads, launched with 128 registers) or 384 with 6 (640 threads, launched with 96): the second trades instruction-level
 // for thread-level parallelism -- three accumulating warps per scheduler instead of two.
-// Phase B1 runs on the upper half of a scan group (warps 2 and 3: warp 3 has no column in phase A, warp 2 eleven), so that the
-// four schedulers of the SM see the same number of busy scan warps.
 constexpr int PIPE_SCAN_GROUP = 128, PIPE_SLOTS = 3;
 template <int CFG> struct pipe_cfg;
 template <> struct pipe_cfg<0>
@@ -765,19 +834,34 @@ template <> struct pipe_cfg<0>
 };
 template <> struct pipe_cfg<1>
 {
-  static constexpr int ACC_T = 384, KP = 6, L = 12, WP = 98, SCAN_REGS = 64, ACC_REGS = 128, NT = 2 * PIPE_SCAN_GROUP + ACC_T; // 256 x 64 + 384 x 128 = the register file
+  static constexpr int ACC_T = 384, KP = 6, L = 12, WP = 98, SCAN_REGS = 64, ACC_REGS = 112, NT = 2 * PIPE_SCAN_GROUP + ACC_T; // launched with 96: the scan warps give 8 x 32, the accumulating warps take 12 x 16
 };
+// setmaxnreg.inc only ever gets what setmaxnreg.dec of the same block released: a shape that asks for more waits forever
+template <int CFG> constexpr bool pipe_regs_balance()
+{
+  using c = pipe_cfg<CFG>;
+  constexpr int launch = 65536 / c::NT / 8 * 8;
+  return 2 * PIPE_SCAN_GROUP * (launch - c::SCAN_REGS) >= c::ACC_T * (c::ACC_REGS - launch) && c::ACC_REGS % 8 == 0 && c::SCAN_REGS % 8 == 0;
+}
+static_assert(pipe_regs_balance<0>() && pipe_regs_balance<1>(), "the accumulating warps take no more registers than the scan warps release");
 constexpr int PIPE_MAX_ROWS = 64; // chunks of up to 64 rows: 2 * 32 row pairs = the 64 threads of phase B1, 2304 pixel pairs at most
-constexpr int PIPE_BAR_FULL = 1, PIPE_BAR_EMPTY = PIPE_BAR_FULL + PIPE_SLOTS, PIPE_BAR_GROUP = PIPE_BAR_EMPTY + PIPE_SLOTS;
+constexpr int PIPE_BAR_FULL = 1, PIPE_BAR_EMPTY = PIPE_BAR_FULL + PIPE_SLOTS, PIPE_BAR_ACC = PIPE_BAR_EMPTY + PIPE_SLOTS;
 static_assert(pipe_cfg<0>::KP * pipe_cfg<0>::L >= MAX_CW && pipe_cfg<0>::ACC_T / pipe_cfg<0>::L * 2 >= PIPE_MAX_ROWS
               && pipe_cfg<1>::KP * pipe_cfg<1>::L >= MAX_CW && pipe_cfg<1>::ACC_T / pipe_cfg<1>::L * 2 >= PIPE_MAX_ROWS,
               "every pixel pair of a 64-row chunk has an accumulating thread");
 constexpr int PIPE_WCOLS_MAX = 96; // window columns the pipelined kernel takes: both pitches (pipe_cfg::WP) hold them
-// thread t of a scan group in phase B1: its index among the 2 * half row tasks, or -1
-__device__ __forceinline__ int pipe_b1_task(int t, int half)
+// accumulating thread ta in phase B1: its index among the 2 * half row tasks of a patch pair (two rows of one patch each), or -1.
+// The tasks go to the accumulating warps 2 and 3: schedulers 2 and 3 of the SM, which carry the lighter scan warps.
+__device__ __forceinline__ int pipe_b1_task(int ta, int half)
 {
-  const int tb = t - (PIPE_SCAN_GROUP - PIPE_MAX_ROWS);
+  const int tb = ta - PIPE_MAX_ROWS;
   return tb >= 0 && tb < 2 * half ? tb : -1;
+}
+template <int R> __device__ __forceinline__ void pipe_b1(const grp_args_t &a, const chunk_t &c, float *Sa, int p0, int tb, int half)
+{
+  if(tb < 0) return;
+  const int gi = tb / half;
+  grp_scan_rows<R>(a, c, Sa + gi * a.splane, p0 + gi, tb - gi * half, half);
 }
 
 #ifndef B200_KERNELS_ON_CPU
@@ -802,20 +886,12 @@ __global__ void __launch_bounds__(pipe_cfg<CFG>::NT, 1) nlm_pipe_kernel(const __
   {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(cfg::SCAN_REGS));
     const int group = tid / PIPE_SCAN_GROUP, t = tid - group * PIPE_SCAN_GROUP;
-    const int half = (c.ch + 1) / 2;
-    const int tb = pipe_b1_task(t, half);
     for(int q = group; q < npairs; q += 2)
     {
       const int slot = q % PIPE_SLOTS;
       float *const Sa = S + (2 * slot) * a.splane, *const Sb = Sa + a.splane;
       if(q >= PIPE_SLOTS) named_sync(PIPE_BAR_EMPTY + slot, PIPE_SCAN_GROUP + ACC_T);
       if(t < c.ncols) grp_scan_column<WP, R, NORM1>(a, c, W, Sa, Sb, 2 * q, t);
-      named_sync(PIPE_BAR_GROUP + group, PIPE_SCAN_GROUP);
-      if(tb >= 0)
-      {
-        const int gi = tb / half;
-        grp_scan_rows<R>(a, c, gi ? Sb : Sa, 2 * q + gi, tb - gi * half, half);
-      }
       named_arrive(PIPE_BAR_FULL + slot, PIPE_SCAN_GROUP + ACC_T);
     }
   }
@@ -825,22 +901,37 @@ __global__ void __launch_bounds__(pipe_cfg<CFG>::NT, 1) nlm_pipe_kernel(const __
     const int ta = tid - 2 * PIPE_SCAN_GROUP;
     grp_strip_t<cfg::KP, cfg::L> st;
     grp_own_init<WP>(a, c, W, st, ta);
-    for(int q = 0; q < npairs; q++)
+    const int half = (c.ch + 1) / 2;
+    const int tb = pipe_b1_task(ta, half);
+    // two loops, not one with the test inside: what the edge path keeps alive (the chunk's geometry) would otherwise take its
+    // registers from the interior loop, where every register is a pixel pair more in flight
+    if(c.interior)
     {
-      const int slot = q % PIPE_SLOTS;
-      const float *const Sa = S + (2 * slot) * a.splane;
-      named_sync(PIPE_BAR_FULL + slot, PIPE_SCAN_GROUP + ACC_T);
-      if(c.interior)
+      for(int q = 0; q < npairs; q++)
       {
+        const int slot = q % PIPE_SLOTS;
+        const float *const Sa = S + (2 * slot) * a.splane;
+        named_sync(PIPE_BAR_FULL + slot, PIPE_SCAN_GROUP + ACC_T);
+        pipe_b1<R>(a, c, S + (2 * slot) * a.splane, 2 * q, tb, half);
+        named_sync(PIPE_BAR_ACC, ACC_T);
         grp_accumulate_pairs<WP, PROFILED, DIVC>(a, W + shifts[2 * q], Sa, st);
         if(2 * q + 1 < a.n_patches) grp_accumulate_pairs<WP, PROFILED, DIVC>(a, W + shifts[2 * q + 1], Sa + a.splane, st);
+        if(q + PIPE_SLOTS < npairs) named_arrive(PIPE_BAR_EMPTY + slot, PIPE_SCAN_GROUP + ACC_T);
       }
-      else
+    }
+    else
+    {
+      for(int q = 0; q < npairs; q++)
       {
+        const int slot = q % PIPE_SLOTS;
+        const float *const Sa = S + (2 * slot) * a.splane;
+        named_sync(PIPE_BAR_FULL + slot, PIPE_SCAN_GROUP + ACC_T);
+        pipe_b1<R>(a, c, S + (2 * slot) * a.splane, 2 * q, tb, half);
+        named_sync(PIPE_BAR_ACC, ACC_T);
         grp_accumulate_edge<WP, PROFILED, DIVC>(a, c, W, Sa, st, 2 * q);
         grp_accumulate_edge<WP, PROFILED, DIVC>(a, c, W, Sa + a.splane, st, 2 * q + 1);
+        if(q + PIPE_SLOTS < npairs) named_arrive(PIPE_BAR_EMPTY + slot, PIPE_SCAN_GROUP + ACC_T);
       }
-      if(q + PIPE_SLOTS < npairs) named_arrive(PIPE_BAR_EMPTY + slot, PIPE_SCAN_GROUP + ACC_T);
     }
     grp_finish(a, c, st, ta);
   }

@@ -54,15 +54,7 @@ template <int R, bool NORM1, bool PROFILED, bool DIVC, int CFG> static void run_
       float *const Sa = S + (2 * slot) * a.splane, *const Sb = Sa + a.splane;
       for(int t = 0; t < PIPE_SCAN_GROUP; t++)
         if(t < c.ncols) grp_scan_column<WP, R, NORM1>(a, c, W, Sa, Sb, 2 * q, t);
-      for(int t = 0; t < PIPE_SCAN_GROUP; t++)
-      {
-        const int tb = pipe_b1_task(t, half);
-        if(tb >= 0)
-        {
-          const int gi = tb / half;
-          grp_scan_rows<R>(a, c, gi ? Sb : Sa, 2 * q + gi, tb - gi * half, half);
-        }
-      }
+      for(int t = 0; t < PIPE_ACC_T; t++) pipe_b1<R>(a, c, Sa, 2 * q, pipe_b1_task(t, half), half);
       for(int t = 0; t < PIPE_ACC_T; t++)
       {
         if(c.interior)
