@@ -56,6 +56,16 @@ __host__ __device__ inline int mk_fc(const uint8_t *xt, int row, int col) { retu
 __device__ __forceinline__ const short *mk_hex(const mk_args_t &a, int row, int col) { return a.hex[(row + 600) % 3][(col + 600) % 3]; }
 __device__ __forceinline__ int mk_mirror(int n, int size) { return n >= size ? 2 * size - n - 2 : (n < 0 ? -n : n); } // TRANSLATE, :158
 __device__ __forceinline__ float mk_sqr(float x) { return x * x; }
+__device__ __forceinline__ float mk_div(float a, float b)
+{ // IEEE division, opaque to nvcc's x / c -> x * (1 / c) rewrite under -ftz=true (labglue.cu: divc); halving is exact either way
+#ifdef B200_KERNELS_ON_CPU
+  return a / b;
+#else
+  float q;
+  asm("div.rn.ftz.f32 %0, %1, %2;" : "=f"(q) : "f"(a), "f"(b));
+  return q;
+#endif
+}
 __device__ __forceinline__ float mk_clamps(float v, float l, float h) { return v > l ? (v < h ? v : h) : l; } // CLAMPS, math/math.h:78
 
 __device__ __forceinline__ mk_tile_t mk_tile_of(const mk_args_t &a, int t)
@@ -248,7 +258,7 @@ __device__ void mk_green_blocks(const mk_args_t &a, const mk_tile_t &T, float *P
         for(int ch = 0; ch < 4; ch += 2)
         {
           float *const Cp = P + (k * 3 + ch) * NPX + p;
-          Cp[0] = (g + 2.f * Cp[ha] + Cp[hb]) / 3.f;
+          Cp[0] = mk_div(g + 2.f * Cp[ha] + Cp[hb], 3.f);
         }
       }
       else

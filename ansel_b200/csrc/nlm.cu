@@ -716,7 +716,6 @@ int grp_define_patches(patch_t *patches, int search_radius, float scale, float s
   return shift_max;
 }
 
-constexpr int PIPE_DEFAULT_CFG = 0;
 // the pipelined kernel (nlm_pipe_kernel): chunks of up to 64 rows, the narrow window, a ring of PIPE_SLOTS pair slots
 bool grp_pipe_fits(const grp_args_t &g, int smem_optin, int wp)
 {
@@ -798,16 +797,11 @@ int launch_group(const nlm_args_t &a, int shift_max, int smem_optin, int n_chunk
   const bool divc = grp_division_by_constant(g) && !getenv("B200_NLM_IEEE_DIV");
   cudaError_t e;
   const unsigned grid = (unsigned)n_chunks;
-  int shape = PIPE_DEFAULT_CFG;
-  if(const char *v = getenv("B200_NLM_PIPE_CFG")) shape = atoi(v) ? 1 : 0;
-  const int pipe_wp = shape == 1 ? pipe_cfg<1>::WP : pipe_cfg<0>::WP;
+  const int pipe_wp = pipe_cfg<0>::WP;
   if(grp_pipe_fits(g, smem_optin, pipe_wp) && !getenv("B200_NLM_NO_PIPE"))
   {
     const size_t psmem = grp_pipe_smem_bytes(g, pipe_wp);
-    if(shape == 1)
-      e = a.radius == 1 ? launch_pipe_r<1, 1>(g, norm1, profiled, divc, grid, psmem, stream) : launch_pipe_r<2, 1>(g, norm1, profiled, divc, grid, psmem, stream);
-    else
-      e = a.radius == 1 ? launch_pipe_r<1, 0>(g, norm1, profiled, divc, grid, psmem, stream) : launch_pipe_r<2, 0>(g, norm1, profiled, divc, grid, psmem, stream);
+    e = a.radius == 1 ? launch_pipe_r<1, 0>(g, norm1, profiled, divc, grid, psmem, stream) : launch_pipe_r<2, 0>(g, norm1, profiled, divc, grid, psmem, stream);
     if(e != cudaSuccess) return ::b200::fail(B200_ERR_CUDA, "nlmeans: pipelined kernel launch: %s", cudaGetErrorString(e));
     *launched = 1;
     return B200_OK;

@@ -486,9 +486,9 @@ template <int KP_> struct grp_thread_t
   __device__ __forceinline__ int wofs(int k) const { return wofs_[k]; }
   __device__ __forceinline__ int sofs(int k) const { return sofs_[k]; }
 };
-template <int KP_, int L_> struct grp_strip_t
+template <int KP_, int L_, int IL_> struct grp_strip_t
 {
-  static constexpr int KP = KP_, L = L_, IL = KP_ % 3 == 0 && KP_ > 6 ? 3 : 2; // pairs in flight in phase B2
+  static constexpr int KP = KP_, L = L_, IL = IL_; // IL: pairs in flight in phase B2
   float acc[KP][8];
   float ctr[KP][6];
   int wofs0, sofs0; // of pair 0 (row pair 0 for a thread whose row pair is below the chunk: harmless reads, never stored)
@@ -541,8 +541,8 @@ template <int L> __device__ __forceinline__ void grp_strip_of(int ta, int &pr, i
     i = ta - pr * L;
   }
 }
-template <int WP, int KP, int L>
-__device__ __forceinline__ void grp_own_init(const grp_args_t &a, const chunk_t &c, const float *W, grp_strip_t<KP, L> &st, int ta)
+template <int WP, int KP, int L, int IL>
+__device__ __forceinline__ void grp_own_init(const grp_args_t &a, const chunk_t &c, const float *W, grp_strip_t<KP, L, IL> &st, int ta)
 {
   int pr, i;
   grp_strip_of<L>(ta, pr, i);
@@ -819,23 +819,24 @@ __global__ void __launch_bounds__(GRP_NT, 1) nlm_group_kernel(const __grid_const
 // ---- the same phases as a pipeline: scan warps run ahead of the accumulating warps --------------------------------------------
 // Two scan groups of 128 threads (phases A and B1 of a patch pair each, pairs dealt alternately) fill a ring of PIPE_SLOTS pair
 // slots (2 planes each) in shared memory; ACC_T accumulating threads (KP pixel pairs each) drain it in patch order (phase B2).
-// The scan groups run phase A only; phase B1 (6 % of the work, but a chain of 72 dependent steps) is done by two of the accumulating
-// warps in front of phase B2: the accumulators have the slack, the scan groups are the critical path.
 // Named barriers: FULL[slot] (scan group arrives, accumulators wait), EMPTY[slot] (accumulators arrive, the scan group that
-// wants the slot waits), one barrier among the accumulators between phases B1 and B2.  The accumulators need two to three times the
+// wants the slot waits), one barrier per scan group between its phases A and B1.  The accumulators need two to three times the
 // registers of the scan threads: setmaxnreg moves them.  Two shapes (pipe_cfg): 256 accumulating threads with 9 pixel pairs each
 // (512 threads, launched with 128 registers) or 384 with 6 (640 threads, launched with 96): the second trades instruction-level
 // for thread-level parallelism -- three accumulating warps per scheduler instead of two.
 constexpr int PIPE_SCAN_GROUP = 128, PIPE_SLOTS = 3;
-template <int CFG> struct pipe_cfg;
-template <> struct pipe_cfg<0>
+// Measured on a B200 at 45 MP (K = 7, P = 1; profiles/r02_nlm_pipe_ncu.md): 25.7 ms.  What was tried around this shape and lost:
+// three pixel pairs in flight in phase B2 (grp_accumulate_pairs<.., IL = 3>: the accumulators get faster, the frame does not -- their
+// loads arrive in bursts in front of the scan warps' loads, and the scan warps are the critical path: 25.7 ms with phase B1 where it
+// is, 28.9 ms before phase B1's loads ran a block ahead); phase B1 on two accumulating warps (the scan groups then run phase A only,
+// but the accumulators wait for a chain of 72 dependent steps every pair: 27.7 ms); 384 accumulating threads with 6 pairs each
+// (64 registers for the scan threads spill their rings: 30.3 ms).
+template <int CFG> struct pipe_cfg
 {
   static constexpr int ACC_T = 256, KP = 9, L = 8, WP = 97, SCAN_REGS = 80, ACC_REGS = 176, NT = 2 * PIPE_SCAN_GROUP + ACC_T; // 256 x 80 + 256 x 176 = the register file
+  static constexpr int IL = 1; // pixel pairs an accumulating thread keeps in flight in phase B2
 };
-template <> struct pipe_cfg<1>
-{
-  static constexpr int ACC_T = 384, KP = 6, L = 12, WP = 98, SCAN_REGS = 64, ACC_REGS = 112, NT = 2 * PIPE_SCAN_GROUP + ACC_T; // launched with 96: the scan warps give 8 x 32, the accumulating warps take 12 x 16
-};
+constexpr int PIPE_N_CFG = 1;
 // setmaxnreg.inc only ever gets what setmaxnreg.dec of the same block released: a shape that asks for more waits forever
 template <int CFG> constexpr bool pipe_regs_balance()
 {
@@ -843,18 +844,17 @@ template <int CFG> constexpr bool pipe_regs_balance()
   constexpr int launch = 65536 / c::NT / 8 * 8;
   return 2 * PIPE_SCAN_GROUP * (launch - c::SCAN_REGS) >= c::ACC_T * (c::ACC_REGS - launch) && c::ACC_REGS % 8 == 0 && c::SCAN_REGS % 8 == 0;
 }
-static_assert(pipe_regs_balance<0>() && pipe_regs_balance<1>(), "the accumulating warps take no more registers than the scan warps release");
+static_assert(pipe_regs_balance<0>(), "the accumulating warps take no more registers than the scan warps release");
 constexpr int PIPE_MAX_ROWS = 64; // chunks of up to 64 rows: 2 * 32 row pairs = the 64 threads of phase B1, 2304 pixel pairs at most
-constexpr int PIPE_BAR_FULL = 1, PIPE_BAR_EMPTY = PIPE_BAR_FULL + PIPE_SLOTS, PIPE_BAR_ACC = PIPE_BAR_EMPTY + PIPE_SLOTS;
-static_assert(pipe_cfg<0>::KP * pipe_cfg<0>::L >= MAX_CW && pipe_cfg<0>::ACC_T / pipe_cfg<0>::L * 2 >= PIPE_MAX_ROWS
-              && pipe_cfg<1>::KP * pipe_cfg<1>::L >= MAX_CW && pipe_cfg<1>::ACC_T / pipe_cfg<1>::L * 2 >= PIPE_MAX_ROWS,
+constexpr int PIPE_BAR_FULL = 1, PIPE_BAR_EMPTY = PIPE_BAR_FULL + PIPE_SLOTS, PIPE_BAR_GROUP = PIPE_BAR_EMPTY + PIPE_SLOTS;
+static_assert(pipe_cfg<0>::KP * pipe_cfg<0>::L >= MAX_CW && pipe_cfg<0>::ACC_T / pipe_cfg<0>::L * 2 >= PIPE_MAX_ROWS,
               "every pixel pair of a 64-row chunk has an accumulating thread");
-constexpr int PIPE_WCOLS_MAX = 96; // window columns the pipelined kernel takes: both pitches (pipe_cfg::WP) hold them
-// accumulating thread ta in phase B1: its index among the 2 * half row tasks of a patch pair (two rows of one patch each), or -1.
-// The tasks go to the accumulating warps 2 and 3: schedulers 2 and 3 of the SM, which carry the lighter scan warps.
-__device__ __forceinline__ int pipe_b1_task(int ta, int half)
+constexpr int PIPE_WCOLS_MAX = 96; // window columns the pipelined kernel takes (pipe_cfg::WP holds them)
+// phase B1 of a patch pair is 2 * half row tasks (two rows of one patch each).  They go to the upper half of the scan group (warp 3 has
+// no column in phase A, warp 2 eleven): the schedulers 2 and 3 of the SM, which carry the lighter scan warps.  -1: no task.
+__device__ __forceinline__ int pipe_b1_task(int t, int half)
 {
-  const int tb = ta - PIPE_MAX_ROWS;
+  const int tb = t - PIPE_MAX_ROWS;
   return tb >= 0 && tb < 2 * half ? tb : -1;
 }
 template <int R> __device__ __forceinline__ void pipe_b1(const grp_args_t &a, const chunk_t &c, float *Sa, int p0, int tb, int half)
@@ -886,12 +886,16 @@ __global__ void __launch_bounds__(pipe_cfg<CFG>::NT, 1) nlm_pipe_kernel(const __
   {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(cfg::SCAN_REGS));
     const int group = tid / PIPE_SCAN_GROUP, t = tid - group * PIPE_SCAN_GROUP;
+    const int half = (c.ch + 1) / 2;
+    const int tb = pipe_b1_task(t, half);
     for(int q = group; q < npairs; q += 2)
     {
       const int slot = q % PIPE_SLOTS;
       float *const Sa = S + (2 * slot) * a.splane, *const Sb = Sa + a.splane;
       if(q >= PIPE_SLOTS) named_sync(PIPE_BAR_EMPTY + slot, PIPE_SCAN_GROUP + ACC_T);
       if(t < c.ncols) grp_scan_column<WP, R, NORM1>(a, c, W, Sa, Sb, 2 * q, t);
+      named_sync(PIPE_BAR_GROUP + group, PIPE_SCAN_GROUP);
+      pipe_b1<R>(a, c, Sa, 2 * q, tb, half);
       named_arrive(PIPE_BAR_FULL + slot, PIPE_SCAN_GROUP + ACC_T);
     }
   }
@@ -899,10 +903,8 @@ __global__ void __launch_bounds__(pipe_cfg<CFG>::NT, 1) nlm_pipe_kernel(const __
   {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(cfg::ACC_REGS));
     const int ta = tid - 2 * PIPE_SCAN_GROUP;
-    grp_strip_t<cfg::KP, cfg::L> st;
+    grp_strip_t<cfg::KP, cfg::L, cfg::IL> st;
     grp_own_init<WP>(a, c, W, st, ta);
-    const int half = (c.ch + 1) / 2;
-    const int tb = pipe_b1_task(ta, half);
     // two loops, not one with the test inside: what the edge path keeps alive (the chunk's geometry) would otherwise take its
     // registers from the interior loop, where every register is a pixel pair more in flight
     if(c.interior)
@@ -912,8 +914,6 @@ __global__ void __launch_bounds__(pipe_cfg<CFG>::NT, 1) nlm_pipe_kernel(const __
         const int slot = q % PIPE_SLOTS;
         const float *const Sa = S + (2 * slot) * a.splane;
         named_sync(PIPE_BAR_FULL + slot, PIPE_SCAN_GROUP + ACC_T);
-        pipe_b1<R>(a, c, S + (2 * slot) * a.splane, 2 * q, tb, half);
-        named_sync(PIPE_BAR_ACC, ACC_T);
         grp_accumulate_pairs<WP, PROFILED, DIVC>(a, W + shifts[2 * q], Sa, st);
         if(2 * q + 1 < a.n_patches) grp_accumulate_pairs<WP, PROFILED, DIVC>(a, W + shifts[2 * q + 1], Sa + a.splane, st);
         if(q + PIPE_SLOTS < npairs) named_arrive(PIPE_BAR_EMPTY + slot, PIPE_SCAN_GROUP + ACC_T);
@@ -926,8 +926,6 @@ __global__ void __launch_bounds__(pipe_cfg<CFG>::NT, 1) nlm_pipe_kernel(const __
         const int slot = q % PIPE_SLOTS;
         const float *const Sa = S + (2 * slot) * a.splane;
         named_sync(PIPE_BAR_FULL + slot, PIPE_SCAN_GROUP + ACC_T);
-        pipe_b1<R>(a, c, S + (2 * slot) * a.splane, 2 * q, tb, half);
-        named_sync(PIPE_BAR_ACC, ACC_T);
         grp_accumulate_edge<WP, PROFILED, DIVC>(a, c, W, Sa, st, 2 * q);
         grp_accumulate_edge<WP, PROFILED, DIVC>(a, c, W, Sa + a.splane, st, 2 * q + 1);
         if(q + PIPE_SLOTS < npairs) named_arrive(PIPE_BAR_EMPTY + slot, PIPE_SCAN_GROUP + ACC_T);

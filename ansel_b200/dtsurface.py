@@ -55,7 +55,8 @@ PROCESS_CL = C.CFUNCTYPE(C.c_int, C.POINTER(Module), C.POINTER(Pipe), C.POINTER(
 
 
 class PipeNode(C.Structure):
-    _fields_ = [("process_cl", C.c_void_p), ("module", C.POINTER(Module)), ("piece", C.POINTER(PipeIop))]
+    _fields_ = [("process_cl", C.c_void_p), ("module", C.POINTER(Module)), ("piece", C.POINTER(PipeIop)),
+                ("blend", C.c_void_p), ("d_form_mask", C.c_void_p), ("d_mask", C.c_void_p)]   # blending: b200_blend_params_t * or NULL
 
 
 _mod = None

@@ -2,8 +2,9 @@
  * that matters for throughput -- upload the first module's input once, hand each module's output to
  * the next as a device buffer (the "borrow the cached vRAM payload" protocol, :219-224,317-328), and
  * read back only the last output (:456-463).  Host pointers in, host pointers out; the modules run
- * through their process_cl() adapters.  Cache keys, blending and the CPU fallback ladder stay in the
- * reference's own pixelpipe code and are not reproduced here.
+ * through their process_cl() adapters, each followed -- where the node carries blend parameters -- by the blend of the module's
+ * output over its input on the device (develop/pixelpipe_gpu.c:364-454 calls dt_develop_blend_process_cl there).  Cache keys and
+ * the CPU fallback ladder stay in the reference's own pixelpipe code and are not reproduced here.
  */
 #include "dt_surface.h"
 #include <stdlib.h>
@@ -16,6 +17,11 @@ typedef struct b200_pipe_node_t
   b200_process_cl_fn process_cl;   /* the module's process_cl() */
   struct dt_iop_module_t *module;
   const dt_dev_pixelpipe_iop_t *piece;
+  /* blending, develop/blend.c:657-860: NULL = the module has none.  d_form_mask: the raster / drawn mask of roi_out in device memory
+   * (the host rasterises forms; NULL without one); d_mask: receives the final mask when the module publishes it as a raster mask */
+  const b200_blend_params_t *blend;
+  const float *d_form_mask;
+  float *d_mask;
 } b200_pipe_node_t;
 
 /* provided by libb200iop.so (device memory for the chain; dt_opencl_alloc_device / copy analogues) */
@@ -89,6 +95,8 @@ int b200_pipe_fusion_enabled = 1; /* set to 0 to run every module on its own (pa
 static int fuse_raw_front(const dt_dev_pixelpipe_t *pipe, const b200_pipe_node_t *nodes, int n_nodes, void *d_in, void *d_out)
 {
   if(!b200_pipe_fusion_enabled || n_nodes < 2 || !nodes[0].module || strcmp(nodes[0].module->op, "rawprepare")) return 0;
+  for(int k = 0; k < n_nodes && k < 3; k++)
+    if(nodes[k].blend) return 0; /* a blended module keeps its own launch: the blend reads its input and its output */
   b200_piece_t p[3];
   const b200_piece_t *tp = NULL, *hp = NULL;
   int used = 1;
@@ -122,7 +130,15 @@ static int run_chain(const dt_dev_pixelpipe_t *pipe, const b200_pipe_node_t *nod
     cur = 1;
   }
   for(; k < n_nodes; k++, cur ^= 1)
+  {
     if(!nodes[k].process_cl(nodes[k].module, pipe, nodes[k].piece, bufs->buf[cur], bufs->buf[cur ^ 1])) return 1;
+    if(nodes[k].blend)
+    { /* anything the device blend does not take (feathering, ...) fails the chain: the caller runs this pipe the reference's way */
+      b200_piece_t p;
+      b200_piece_from_dt(&p, nodes[k].module, pipe, nodes[k].piece);
+      if(b200_blend_process_dev(&p, nodes[k].blend, bufs->buf[cur], bufs->buf[cur ^ 1], nodes[k].d_form_mask, nodes[k].d_mask, pipe->stream)) return 1;
+    }
+  }
   *last = cur;
   return 0;
 }

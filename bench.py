@@ -398,6 +398,26 @@ def pipe_ends_extras(ab, ds, util, L, M, torch, w, h, local, dev, stream, conv_i
     report("bilat_bilateral_grid_sigma50", lambda: ab.check(L.b200_bilat_process_dev(p_bl, t_lab.data_ptr(), t_out.data_ptr(), stream)), 32, reps=3)
     p_hi = piece(ab.highlights_data(ab.HIGHLIGHTS_INPAINT, 1.0), 1, pmax=pm)
     report("highlights_inpaint", lambda: ab.check(L.b200_highlights_process_dev(p_hi, t_m[1].data_ptr(), t_m[0].data_ptr(), stream)), 8, reps=3)
+    # X-Trans: Markesteijn with one pass (the default demosaicer of X-Trans frames)
+    p_mk = piece(ab.demosaic_data(1025), 1)
+    p_mk.filters = 9
+    for i, rowv in enumerate(((1, 1, 0, 1, 1, 2), (1, 1, 2, 1, 1, 0), (2, 0, 1, 0, 2, 1), (1, 1, 2, 1, 1, 0), (1, 1, 0, 1, 1, 2), (0, 2, 1, 2, 0, 1))):
+        for j, v in enumerate(rowv):
+            p_mk.xtrans[i][j] = v
+    report("demosaic_markesteijn_1pass_xtrans", lambda: ab.check(L.b200_demosaic_process_dev(p_mk, t_m[0].data_ptr(), t_dem.data_ptr(), stream)), 20, reps=3)
+    # blending of a module's output over its input: parametric mask on two channels + a drawn mask, one fused pass (52 B/px: in, out, form mask in; out)
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import blend_util as bu
+        bp = bu.params(mode="normal", opacity=70.0, mask_mode=bu.MASK_ENABLED | bu.MASK_SHAPE | bu.MASK_PARAMETRIC, drawn=1,
+                       channels={0: (0.05, 0.2, 0.8, 1.0), 5: (0.0, 0.0, 0.7, 0.9)})
+        t_form = torch.rand((h, w), dtype=torch.float32, device=dev)
+        p_b = piece(None, 4)
+        L.b200_blend_process_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        report("blend_rgb_scene_drawn_and_parametric",
+               lambda: ab.check(L.b200_blend_process_dev(C.byref(p_b), C.byref(bp), t_rgba.data_ptr(), t_out.data_ptr(), t_form.data_ptr(), None, stream)), 52)
+    except Exception as e:
+        res["blend_rgb_scene_drawn_and_parametric"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
     # sensor-to-display chain, end to end
     try:
@@ -618,7 +638,7 @@ def run_b200(args):
         ms_max, mod_ms = timed_steps(c3, args.steps)
     ksum, kcnt = C.c_double(), C.c_int()
     kernel_ms = {}
-    for name in ("nlm_group_kernel", "rcd_tiles_kernel"):
+    for name in ("nlm_kernel", "rcd_tiles_kernel"):
         ab.check(L.b200_kernel_timing_read(name.encode(), C.byref(ksum), C.byref(kcnt)))
         kernel_ms[name] = (ksum.value / kcnt.value) if kcnt.value else None
     L.b200_kernel_timing(0)
@@ -750,7 +770,7 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (non-local means) and of RCD ------------------------------------
     peak, peak_src = peaks()
-    nlm_ms = kernel_ms["nlm_group_kernel"]
+    nlm_ms = kernel_ms["nlm_kernel"]
     traffic = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -765,8 +785,8 @@ def run_b200(args):
     if nlm_ms:
         achieved = ALGO_BYTES_PER_PX["denoiseprofile"] * npx / (nlm_ms * 1e-3) / 1e9
         flops = NLM_FLOP_PER_PX_PATCH * 225 * npx / (nlm_ms * 1e-3) / 1e12
-        roof = {"bound": "hbm", "kernel": "nlm_group_kernel (non-local means, 225 patches; the vst kernels either side are < 2% of the module)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get("nlm_group_kernel_dram_bytes_per_launch"),
+        roof = {"bound": "hbm", "kernel": "nlm_pipe_kernel (non-local means, 225 patches; the vst kernels either side are < 2% of the module)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get("nlm_pipe_kernel_dram_bytes_per_launch"),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX["denoiseprofile"] * npx, "avg_launch_ms": nlm_ms,
                 "launches_timed": args.steps, "share_of_step": nlm_ms / (ms_max / args.steps),
                 "fp32": {"achieved_tflops": flops, "peak_tflops": FP32_PEAK_TFLOPS, "frac": flops / FP32_PEAK_TFLOPS,

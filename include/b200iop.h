@@ -737,6 +737,43 @@ enum
 };
 int b200_flt32_eval_dev(int fn, const float *d_x, const float *d_y, float *d_out, size_t n, void *stream);
 
+/* ---- blending of a module's output over its input: develop/blend.c dt_develop_blend_process :657-860 --------------------------------
+ * The members of dt_develop_blend_params_t (develop/blend.h:197-237, piece->blendop_data) the path reads, under their own names, then
+ * what the reference looks up on the host for the same call. */
+typedef struct b200_blend_params_t
+{
+  uint32_t mask_mode;        /* dt_develop_mask_mode_t: 1 enabled, 2 drawn mask, 4 parametric mask, 8 raster mask */
+  int32_t blend_cst;         /* dt_develop_blend_colorspace_t: 4 = DEVELOP_BLEND_CS_RGB_SCENE is built */
+  uint32_t blend_mode;       /* dt_develop_blend_mode_t, | 0x80000000 = DEVELOP_BLEND_REVERSE */
+  float blend_parameter;     /* exposure-like parameter of the operator, in EV */
+  float opacity;             /* 0 .. 100 */
+  uint32_t mask_combine;     /* dt_develop_mask_combine_mode_t: 1 inverted, 2 inclusive */
+  uint32_t blendif;          /* bits 0..3 / 4..7: gray, red, green, blue of the input / output take part; bit + 16: that channel inverted */
+  float feathering_radius;
+  uint32_t feathering_guide;
+  float blur_radius, contrast, brightness, details;
+  float blendif_parameters[64];    /* four limits per channel */
+  float blendif_boost_factors[16];
+  int32_t raster_used, drawn_used; /* dt_develop_blend_get_mask_usage() :262-320: the form mask passed is a raster mask / a drawn mask (or their
+                                      combination, _develop_blend_combine_masks :593-601) */
+  float luminance[3];              /* row Y of matrix_in of the pipe's current profile (dt_ioppr_get_rgb_matrix_luminance, iop_profile.h:637-654) */
+  int32_t profile_nonlinear;       /* that profile's nonlinearlut: must be 0 */
+  uint32_t mask_display;           /* pipe->mask_display: with B200_DISPLAY_MASK the alpha lane of the input is kept (:952-961) */
+} b200_blend_params_t;
+/* in: the module's input (roi_in, RGBA float), out: the module's output (roi_out, inside roi_in), blended in place with the mask in its
+ * alpha lane; form_mask: the raster / drawn mask of roi_out the host rasterised, or NULL; mask: receives the final mask (what the reference
+ * publishes as the module's raster mask, :892-950), or NULL.  Built: the scene-referred RGB space (develop/blends/blendif_rgb_jzczhz.c) with
+ * uniform, raster, drawn and parametric (gray, red, green, blue of input and output) masks, their exclusive / inclusive / inverted
+ * combinations, the mask tone curve and the sixteen blend operators.  B200_ERR_UNSUPPORTED (fall back to dt_develop_blend_process): feathering,
+ * blur and detail refinement of the mask, the JzCzhz channels, the other colour spaces.  mask_mode without the enabled bit: B200_OK, nothing
+ * touched. */
+int b200_blend_process_host(const b200_piece_t *piece, const b200_blend_params_t *bp, const void *in, void *out, const float *form_mask, float *mask);
+/* dt_develop_blend_process_cl() slot, develop/blend.c:1113-1604: device pointers */
+int b200_blend_process_dev(const b200_piece_t *piece, const b200_blend_params_t *bp, const void *d_in, void *d_out, const float *d_form_mask,
+                           float *d_mask, void *stream);
+/* tiling_callback_blendop(), develop/blend.c:1672-1691 */
+void b200_blend_tiling(const b200_piece_t *piece, b200_tiling_t *tiling);
+
 #ifdef __cplusplus
 }
 #endif

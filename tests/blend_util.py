@@ -1,0 +1,140 @@
+"""Helpers of the blending tests: the parameter block (same layout for the reference wrapper, the oracle and the product), cases."""
+import ctypes as C
+
+import numpy as np
+
+import util
+
+MASK_ENABLED, MASK_SHAPE, MASK_PARAMETRIC, MASK_RASTER = 1, 2, 4, 8
+COMBINE_INV, COMBINE_INCL = 1, 2
+CS_RGB_SCENE = 4
+REVERSE = 0x80000000
+MODES = {"normal": 0x18, "multiply": 0x04, "average": 0x05, "add": 0x06, "subtract": 0x07, "subtract_inverse": 0x25, "difference": 0x17,
+         "divide": 0x26, "divide_inverse": 0x27, "geometric_mean": 0x28, "harmonic_mean": 0x29, "luminance": 0x10, "chromaticity": 0x11,
+         "rgb_r": 0x21, "rgb_g": 0x22, "rgb_b": 0x23}
+LUMINANCE = (0.2627002120112671, 0.6779980715188708, 0.05930171646986196)   # row Y of linear Rec2020 -> XYZ
+
+
+class BlendParams(C.Structure):
+    _fields_ = [("mask_mode", C.c_uint32), ("blend_cst", C.c_int32), ("blend_mode", C.c_uint32), ("blend_parameter", C.c_float), ("opacity", C.c_float),
+                ("mask_combine", C.c_uint32), ("blendif", C.c_uint32), ("feathering_radius", C.c_float), ("feathering_guide", C.c_uint32),
+                ("blur_radius", C.c_float), ("contrast", C.c_float), ("brightness", C.c_float), ("details", C.c_float),
+                ("blendif_parameters", C.c_float * 64), ("blendif_boost_factors", C.c_float * 16), ("raster_used", C.c_int32), ("drawn_used", C.c_int32),
+                ("luminance", C.c_float * 3), ("profile_nonlinear", C.c_int32), ("mask_display", C.c_uint32)]
+
+
+def params(mode="normal", opacity=65.0, mask_mode=MASK_ENABLED, reverse=False, blend_parameter=0.0, combine=0, blendif=0, channels=None, boosts=None,
+           contrast=0.0, brightness=0.0, raster=0, drawn=0, mask_display=0, **extra):
+    """channels: {bit: (p0, p1, p2, p3)} of the parametric mask (bits 0..3 gray/R/G/B of the input, 4..7 of the output; bit + 16 in `blendif`
+    inverts a channel)"""
+    p = BlendParams()
+    p.mask_mode, p.blend_cst = mask_mode, CS_RGB_SCENE
+    p.blend_mode = MODES[mode] | (REVERSE if reverse else 0)
+    p.blend_parameter, p.opacity, p.mask_combine, p.blendif = blend_parameter, opacity, combine, blendif
+    p.contrast, p.brightness = contrast, brightness
+    for i in range(16):
+        p.blendif_parameters[4 * i:4 * i + 4] = (0.0, 0.0, 1.0, 1.0)
+    for bit, v in (channels or {}).items():
+        p.blendif_parameters[4 * bit:4 * bit + 4] = v
+        p.blendif |= 1 << bit
+    for bit, v in (boosts or {}).items():
+        p.blendif_boost_factors[bit] = v
+    p.raster_used, p.drawn_used, p.mask_display = raster, drawn, mask_display
+    p.luminance[:] = LUMINANCE
+    for k, v in extra.items():
+        setattr(p, k, v)
+    return p
+
+
+def frames(w=160, h=120, seed=1, xoffs=0, yoffs=0, iw=None, ih=None):
+    """a module's input (scene-referred, some values beyond 1, a few non-positive) and output, and a smooth form mask"""
+    rng = np.random.default_rng(seed)
+    iw, ih = iw or w + xoffs, ih or h + yoffs
+    a = (util.rgba_scene(iw, ih, seed, noise=0.02) * 1.8).astype(np.float32)
+    a[..., 3] = rng.random((ih, iw), dtype=np.float32)
+    a[3, 5, :3] = 0.0
+    a[7, 2, 1] = -0.01
+    b = (a[yoffs:yoffs + h, xoffs:xoffs + w] * rng.uniform(0.6, 1.5, (h, w, 1)) + rng.normal(0, 0.03, (h, w, 4))).astype(np.float32)
+    b[11, 4, :3] = 0.0
+    yy, xx = np.mgrid[0:h, 0:w]
+    form = np.clip(1.2 - np.hypot(yy - h * 0.4, xx - w * 0.55) / (0.5 * w), 0.0, 1.0).astype(np.float32)
+    return np.ascontiguousarray(a), np.ascontiguousarray(b), np.ascontiguousarray(form)
+
+
+def _run(lib, fn, a, b, p, form=None, xoffs=0, yoffs=0, want_mask=True):
+    ih, iw = a.shape[:2]
+    oh, ow = b.shape[:2]
+    out = util.aligned_empty(b.shape)
+    out[...] = b
+    src = util.aligned_empty(a.shape)
+    src[...] = a
+    mask = util.aligned_empty((oh, ow)) if want_mask else None
+    if mask is not None:
+        mask[...] = -3.0
+    f = getattr(lib, fn)
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.POINTER(BlendParams), C.c_void_p, C.c_void_p]
+    fm = None
+    if form is not None:
+        fm = util.aligned_empty(form.shape)
+        fm[...] = form
+    rc = f(src.ctypes.data, out.ctypes.data, iw, ih, ow, oh, xoffs, yoffs, C.byref(p), None if fm is None else fm.ctypes.data,
+           None if mask is None else mask.ctypes.data)
+    return rc, np.array(out), (None if mask is None else np.array(mask))
+
+
+def oracle(a, b, p, form=None, xoffs=0, yoffs=0):
+    return _run(util.oracle(), "orc_blend_process", a, b, p, form, xoffs, yoffs)
+
+
+def ref(a, b, p, form=None, xoffs=0, yoffs=0, kind="strict"):
+    lib = util.ref(kind)
+    return None if lib is None else _run(lib, "ref_blend_process", a, b, p, form, xoffs, yoffs)
+
+
+# the configurations every layer is checked on: (name, params kwargs, uses the form mask)
+CONFIGS = [(m, dict(mode=m), False) for m in MODES] + [
+    ("normal_reverse", dict(mode="normal", reverse=True, opacity=40.0), False),
+    ("multiply_param", dict(mode="multiply", blend_parameter=1.5), False),
+    ("divide_reverse", dict(mode="divide", reverse=True, blend_parameter=-0.5), False),
+    ("opacity_0", dict(opacity=0.0), False),
+    ("opacity_over", dict(opacity=130.0), False),
+    ("raster_only", dict(mask_mode=MASK_ENABLED | MASK_RASTER, raster=1), True),
+    ("drawn_only", dict(mask_mode=MASK_ENABLED | MASK_SHAPE, drawn=1), True),
+    ("drawn_inverted", dict(mask_mode=MASK_ENABLED | MASK_SHAPE, drawn=1, combine=COMBINE_INV), True),
+    ("parametric_gray_in", dict(mask_mode=MASK_ENABLED | MASK_PARAMETRIC, channels={0: (0.1, 0.3, 0.7, 0.9)}), False),
+    ("parametric_rgb_out", dict(mask_mode=MASK_ENABLED | MASK_PARAMETRIC, channels={5: (0.0, 0.0, 0.5, 0.8), 6: (0.2, 0.4, 1.0, 1.0), 3: (0.05, 0.2, 0.6, 0.7)}), False),
+    ("parametric_inverted_channel", dict(mask_mode=MASK_ENABLED | MASK_PARAMETRIC, channels={1: (0.2, 0.5, 0.8, 0.95)}, blendif=1 << 17), False),
+    ("parametric_inclusive", dict(mask_mode=MASK_ENABLED | MASK_PARAMETRIC, combine=COMBINE_INCL, channels={0: (0.1, 0.3, 0.7, 0.9), 7: (0.0, 0.1, 0.4, 0.6)}), False),
+    ("parametric_inclusive_inverted", dict(mask_mode=MASK_ENABLED | MASK_PARAMETRIC, combine=COMBINE_INCL | COMBINE_INV, channels={2: (0.1, 0.3, 0.7, 0.9)}), False),
+    ("parametric_boost", dict(mask_mode=MASK_ENABLED | MASK_PARAMETRIC, channels={0: (0.1, 0.3, 0.7, 0.9)}, boosts={0: 1.5}), False),
+    ("parametric_canceling", dict(mask_mode=MASK_ENABLED | MASK_PARAMETRIC, channels={1: (0.2, 0.5, 0.8, 0.95)}, blendif=(1 << 18)), False),
+    ("drawn_and_parametric", dict(mask_mode=MASK_ENABLED | MASK_SHAPE | MASK_PARAMETRIC, drawn=1, channels={0: (0.1, 0.3, 0.7, 0.9)}), True),
+    ("drawn_and_parametric_inv", dict(mask_mode=MASK_ENABLED | MASK_SHAPE | MASK_PARAMETRIC, drawn=1, combine=COMBINE_INV, channels={4: (0.1, 0.3, 0.7, 0.9)}), True),
+    ("raster_and_parametric_incl", dict(mask_mode=MASK_ENABLED | MASK_RASTER | MASK_PARAMETRIC, raster=1, combine=COMBINE_INCL, channels={0: (0.1, 0.3, 0.7, 0.9)}), True),
+    ("tone_curve", dict(mask_mode=MASK_ENABLED | MASK_SHAPE, drawn=1, contrast=0.4, brightness=0.2), True),
+    ("tone_curve_dark", dict(mask_mode=MASK_ENABLED | MASK_SHAPE, drawn=1, contrast=-0.3, brightness=-0.35), True),
+    ("tone_curve_extremes", dict(mask_mode=MASK_ENABLED | MASK_SHAPE, drawn=1, contrast=0.1, brightness=1.0), True),
+    ("tone_curve_extremes2", dict(mask_mode=MASK_ENABLED | MASK_SHAPE, drawn=1, contrast=0.1, brightness=-1.0), True),
+    ("mask_display", dict(mode="add", mask_display=1), False),
+    ("disabled", dict(mask_mode=0), False),
+]
+
+
+_EMUL = None
+
+
+def emul(a, b, p, form=None, xoffs=0, yoffs=0):
+    """ansel_b200/csrc/blend.cu compiled with g++ (tests/emul/emul_blend.cpp): the host-side plan and the kernel, thread by thread"""
+    global _EMUL
+    if _EMUL is None:
+        import os
+        import subprocess
+        here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul")
+        so = os.path.join(here, "libemul_blend.so")
+        srcs = [os.path.join(here, "emul_blend.cpp"), os.path.join(here, "cuda_on_cpu.h"), os.path.join(here, "..", "..", "ansel_b200", "csrc", "blend.cu"),
+                os.path.join(here, "..", "..", "include", "b200iop.h")]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.run(["g++", "-O1", "-std=c++17", "-fno-fast-math", "-ffp-contract=off", "-I", here, "-shared", "-fPIC", "-o", so, srcs[0]], check=True)
+        _EMUL = C.CDLL(so)
+    return _run(_EMUL, "emul_blend_process", a, b, p, form, xoffs, yoffs)

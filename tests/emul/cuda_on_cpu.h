@@ -33,6 +33,7 @@ static thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 #define __noinline__
 #define __restrict__
 #define __launch_bounds__(...)
+#define __grid_constant__
 #define __ldg(p) (*(p))
 #define __stcs(p, v) (*(p) = (v))
 #define __ldcs(p) (*(p))

@@ -35,7 +35,7 @@ template <int R, bool NORM1, bool PROFILED, bool DIVC, int CFG> static void run_
 {
   constexpr int PIPE_NT = pipe_cfg<CFG>::NT, PIPE_ACC_T = pipe_cfg<CFG>::ACC_T, WP = pipe_cfg<CFG>::WP;
   std::vector<float> smem((size_t)a.wrows * 3 * WP + (size_t)2 * PIPE_SLOTS * a.splane + a.n_patches);
-  std::vector<grp_strip_t<pipe_cfg<CFG>::KP, pipe_cfg<CFG>::L>> st(PIPE_ACC_T);
+  std::vector<grp_strip_t<pipe_cfg<CFG>::KP, pipe_cfg<CFG>::L, pipe_cfg<CFG>::IL>> st(PIPE_ACC_T);
   float *const W = smem.data(), *const S = W + a.wrows * 3 * WP;
   int *const shifts = reinterpret_cast<int *>(S + 2 * PIPE_SLOTS * a.splane);
   const int npairs = (a.n_patches + 1) / 2;
@@ -122,12 +122,9 @@ extern "C" int emul_nlmeans_group(const float *in, float *out, int width, int he
   const bool divc = grp_division_by_constant(g) && !ieee_div;
   if(pipe)
   { /* returns -1 where the pipelined kernel does not take the frame (the launcher then uses the group kernel) */
-    if(!grp_pipe_fits(g, smem_bytes, pipe == 2 ? pipe_cfg<1>::WP : pipe_cfg<0>::WP)) return -1;
-    const int n = n_ct * g.n_cl; /* pipe: 1 = 256 accumulating threads x 9 pixel pairs, 2 = 384 x 6 */
-    if(pipe == 2)
-      radius == 1 ? run_pipe<1, 1>(g, n, norm1, profiled, divc) : run_pipe<2, 1>(g, n, norm1, profiled, divc);
-    else
-      radius == 1 ? run_pipe<1, 0>(g, n, norm1, profiled, divc) : run_pipe<2, 0>(g, n, norm1, profiled, divc);
+    if(!grp_pipe_fits(g, smem_bytes, pipe_cfg<0>::WP)) return -1;
+    const int n = n_ct * g.n_cl;
+    radius == 1 ? run_pipe<1, 0>(g, n, norm1, profiled, divc) : run_pipe<2, 0>(g, n, norm1, profiled, divc);
     return g.G;
   }
   if(radius == 1)

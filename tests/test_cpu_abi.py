@@ -294,3 +294,35 @@ def test_packed_fp32_is_never_contracted_in_the_nlm_group_kernel(built):
         assert len(re.findall(r"\bFFMA2\b", body)) == (4 * kp if divc else 0), name
         assert len(re.findall(r"\bFMUL2\b", body)) > 0 and len(re.findall(r"\bFADD2\b", body)) > 0, name
     assert seen >= 12
+
+
+def test_packed_fp32_is_never_contracted_in_the_nlm_pipe_kernel(built):
+    """the same for the pipelined kernel: the accumulation of a patch is inlined four times (two patches of a pair, in the loop of interior
+    chunks and in the loop of edge chunks), Markstein's two FFMA2 per owned pixel pair each, 9 pairs per thread"""
+    so = os.path.join(ROOT, "ansel_b200", "libb200iop.so")
+    r = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-300:]
+    seen = 0
+    for body in re.split(r"\n\s*Function : ", r.stdout)[1:]:
+        name = body.split("\n", 1)[0]
+        m = re.search(r"nlm_pipe_kernelILi(\d)ELb([01])ELb([01])ELb([01])ELi(\d)E", name)
+        if not m:
+            continue
+        seen += 1
+        divc, kp = m.group(4) == "1", 9
+        assert len(re.findall(r"\bFFMA2\b", body)) == (8 * kp if divc else 0), name
+        assert len(re.findall(r"\bFMUL2\b", body)) > 0 and len(re.findall(r"\bFADD2\b", body)) > 0, name
+    assert seen >= 12
+
+
+def test_markesteijn_divides_by_three(built):
+    """nvcc rewrites `x / 3.f` into `x * 0.33333334f` under -ftz=true even with -prec-div=true (1-ulp differences in a tenth of the pixels on
+    the device, none in the CPU emulation): the kernel's division by 3 goes through div.rn.ftz.f32, which the rewrite does not see"""
+    so = os.path.join(ROOT, "ansel_b200", "libb200iop.so")
+    r = subprocess.run(["cuobjdump", "-sass", "-fun", "markesteijn_tiles_kernel", so], capture_output=True, text=True)
+    body = r.stdout
+    if "markesteijn_tiles_kernel" not in body:      # cuobjdump wants the mangled name on some versions: take the whole listing
+        r = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True)
+        body = [b for b in re.split(r"\n\s*Function : ", r.stdout) if b.startswith("_Z") and "markesteijn_tiles_kernel" in b.split("\n", 1)[0]][0]
+    assert not re.search(r"FMUL(\.FTZ)? R\d+, R\d+, 0\.33333", body)
+    assert len(re.findall(r"MUFU\.RCP", body)) >= 4

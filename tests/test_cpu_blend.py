@@ -1,0 +1,71 @@
+"""CPU: blending in the scene-referred RGB space.  The oracle is pinned bit for bit to develop/blend.c and develop/blends/blendif_rgb_jzczhz.c
+compiled in place (oracle/_ref: ref_blend.c) on every blend operator, mask source, combination and the mask tone curve; the product's
+plan and kernel, compiled with g++ and run thread by thread, equal the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+import blend_util as bu
+
+
+def same_bits(a, b):
+    return (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build():
+    subprocess.run(["make", "-s", "-C", util.ORACLE_DIR, "oracle"], check=True)
+    if util.ref("strict") is None and os.path.isdir("/root/reference/src"):
+        util.build_oracle()
+
+
+need_ref = pytest.mark.skipif(util.ref("strict") is None and not os.path.isdir("/root/reference/src"), reason="oracle/_ref not built (no /root/reference)")
+IDS = [c[0] for c in bu.CONFIGS]
+
+
+@need_ref
+@pytest.mark.parametrize("cfg", bu.CONFIGS, ids=IDS)
+def test_oracle_equals_reference(cfg):
+    name, kw, uses_form = cfg
+    a, b, form = bu.frames()
+    p = bu.params(**kw)
+    rc_r, out_r, mask_r = bu.ref(a, b, p, form if uses_form else None)
+    rc_o, out_o, mask_o = bu.oracle(a, b, p, form if uses_form else None)
+    assert rc_r == rc_o == 0
+    assert same_bits(out_o, out_r).all() and same_bits(mask_o, mask_r).all()
+    assert (name == "disabled") == np.array_equal(out_r, b)      # every other configuration changes the output
+
+
+@need_ref
+def test_oracle_equals_reference_with_roi_out_inside_roi_in():
+    a, b, form = bu.frames(100, 80, 2, xoffs=7, yoffs=5)
+    for name, kw, uses_form in bu.CONFIGS[::3]:
+        p = bu.params(**kw)
+        r, o = bu.ref(a, b, p, form if uses_form else None, 7, 5), bu.oracle(a, b, p, form if uses_form else None, 7, 5)
+        assert same_bits(o[1], r[1]).all() and same_bits(o[2], r[2]).all(), name
+
+
+@pytest.mark.parametrize("cfg", bu.CONFIGS, ids=IDS)
+def test_kernel_equals_oracle(cfg):
+    name, kw, uses_form = cfg
+    a, b, form = bu.frames(301, 77, 3)
+    p = bu.params(**kw)
+    rc_e, out_e, mask_e = bu.emul(a, b, p, form if uses_form else None)
+    rc_o, out_o, mask_o = bu.oracle(a, b, p, form if uses_form else None)
+    assert rc_e == rc_o == 0
+    assert same_bits(out_e, out_o).all() and same_bits(mask_e, mask_o).all()
+
+
+def test_kernel_with_offsets_and_what_is_refused():
+    a, b, form = bu.frames(100, 80, 2, xoffs=7, yoffs=5)
+    p = bu.params(mask_mode=bu.MASK_ENABLED | bu.MASK_SHAPE | bu.MASK_PARAMETRIC, drawn=1, channels={0: (0.1, 0.3, 0.7, 0.9), 6: (0.0, 0.0, 0.6, 0.9)})
+    e, o = bu.emul(a, b, p, form, 7, 5), bu.oracle(a, b, p, form, 7, 5)
+    assert same_bits(e[1], o[1]).all() and same_bits(e[2], o[2]).all()
+    a, b, form = bu.frames(64, 48, 4)
+    for kw in (dict(feathering_radius=5.0), dict(blur_radius=2.0), dict(details=0.5), dict(blend_cst=2), dict(profile_nonlinear=1),
+               dict(mask_mode=bu.MASK_ENABLED | bu.MASK_PARAMETRIC, channels={8: (0.1, 0.3, 0.7, 0.9)})):
+        p = bu.params(**kw)
+        assert bu.emul(a, b, p)[0] == -1 and bu.oracle(a, b, p)[0] == -1, kw
