@@ -91,6 +91,56 @@ def chain_cuts(nodes: list[Node], width: int, height: int) -> tuple[int, int, in
     return 1, sum(overlaps) + extra, align
 
 
+def nlm_slice_height(height: int) -> int:
+    """compute_slice_height(), pixel/nlmeans_core.c:267-295: the height of the chunks non-local means cuts a region of `height` rows into"""
+    SLICE = 60
+    if height % SLICE == 0:
+        return SLICE
+    best, best_incr = height % SLICE, 0
+    for incr in range(1, 10):
+        plus_rem = height % (SLICE + incr)
+        if plus_rem == 0:
+            return SLICE + incr
+        if plus_rem > best:
+            best_incr, best = incr, plus_rem
+        minus_rem = height % (SLICE - incr)
+        if minus_rem == 0:
+            return SLICE - incr
+        if minus_rem > best:
+            best_incr, best = -incr, minus_rem
+    return SLICE + best_incr
+
+
+def _uses_nlm(n: Node) -> bool:
+    return n.op == "nlmeans" or (n.op == "denoiseprofile" and n.data.mode in (ab.DENOISE_NLMEANS, ab.DENOISE_NLMEANS_AUTO))
+
+
+def widen_for_nlm(bands: list[Band], height: int, align: int, max_chunk: int = 64) -> list[Band]:
+    """Non-local means chunks the rows it is given by compute_slice_height(); chunks of up to 64 rows take the pipelined kernel
+    (nlm_group.cuh), taller ones the slower group kernel.  A band's input rows may always grow into the frame (more halo than the modules
+    ask for changes nothing in the rows kept), so each band takes the fewest extra rows -- in steps of the row alignment, below or above,
+    wherever the frame has them -- that bring its chunk height down to 64 or less."""
+    out = []
+    for b in bands:
+        y0, y1 = b.in_y0, b.in_y1
+        if y1 > y0 and nlm_slice_height(y1 - y0) > max_chunk:
+            found = None
+            for extra in range(align, 4 * max_chunk + 1, align):
+                for up in range(0, extra + 1, align):             # rows added on top; the rest below
+                    ny0, ny1 = y0 - up, y1 + (extra - up)
+                    if ny0 >= 0 and ny1 <= height and nlm_slice_height(ny1 - ny0) <= max_chunk:
+                        found = (ny0, ny1)
+                        break
+                if found:
+                    break
+            if found:
+                y0, y1 = found
+        nb = Band()
+        nb.out_y0, nb.out_y1, nb.in_y0, nb.in_y1 = b.out_y0, b.out_y1, y0, y1
+        out.append(nb)
+    return out
+
+
 class _DeviceArray:
     """a raw device allocation seen through __cuda_array_interface__ (zero-copy torch.as_tensor)"""
 
@@ -124,6 +174,8 @@ class BandedChain:
         self.process = process or _cuda_process
         self.grid, self.halo, self.align = chain_cuts(nodes, width, height)
         self.bands = plan(height, world, self.grid, self.halo, self.align)
+        if self.grid == 1 and any(_uses_nlm(n) for n in nodes):
+            self.bands = widen_for_nlm(self.bands, height, self.align)
         self.band = self.bands[rank]
         bh = self.band.in_y1 - self.band.in_y0
         self.pieces = []

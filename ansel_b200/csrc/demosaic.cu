@@ -19,7 +19,7 @@ int demosaic_postfilter_dev(float *d_rgba, int width, int height, int iterations
 int downsample4_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters, const double cam_to_rgb[3][4], cudaStream_t s);
 int downsample_xtrans_demosaic_dev(const float *d_in, float *d_out, int width, int height, int x0, int y0, const uint8_t xtrans[6][6], cudaStream_t s);
 int ppg_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters, float median_thrs, cudaStream_t s);
-int markesteijn_demosaic_dev(const float *d_in, float *d_out, int width, int height, int x0, int y0, const uint8_t xtrans[6][6], cudaStream_t stream);
+int markesteijn_demosaic_dev(const float *d_in, float *d_out, int width, int height, int x0, int y0, const uint8_t xtrans[6][6], int passes, cudaStream_t stream);
 int demosaic_green_eq_dev(const float *d_in, float *d_tmp0, float *d_tmp1, double *d_partial, int width, int height, uint32_t dsc_filters, int x, int y,
                           unsigned green_eq, float threshold, const float **d_result, cudaStream_t s);
 int demosaic_green_eq_partial_doubles();
@@ -31,7 +31,7 @@ using namespace b200;
 #define DEMOSAIC_DUAL 2048 /* iop/demosaic.c:109 */
 
 // methods that, like the reference, leave (part of) the alpha lane as they find it
-static bool keeps_alpha(uint32_t m) { return m == B200_DEMOSAIC_PPG || m == 3u || m == 4u || m == 1024u || m == 1025u; }
+static bool keeps_alpha(uint32_t m) { return m == B200_DEMOSAIC_PPG || m == 3u || m == 4u || m == 1024u || m == 1025u || m == 1026u; }
 
 static int check_piece(const b200_piece_t *piece, const void *in, void *out)
 {
@@ -85,17 +85,17 @@ extern "C" int b200_demosaic_process_dev(const b200_piece_t *piece, const void *
     return demosaic_postfilter_dev((float *)d_out, piece->roi_out.width, piece->roi_out.height, (int)d->color_smoothing, (cudaStream_t)stream);
   }
   if(filters == 9u)
-  { // demosaic.c:1119-1131: Markesteijn with one pass (DT_IOP_DEMOSAIC_MARKESTEIJN = 1025, the default of X-Trans frames, :1085);
-    // VNG is what every X-Trans method below it resolves to (DT_IOP_DEMOSAIC_VNG = 1024)
-    if(d->demosaicing_method != 1024u && d->demosaicing_method != 1025u)
-      return fail(B200_ERR_UNSUPPORTED, "demosaic: X-Trans method %u is not built (VNG and Markesteijn 1-pass are; the 3-pass variant and FDC are not)",
+  { // demosaic.c:1119-1131: Markesteijn with one pass (DT_IOP_DEMOSAIC_MARKESTEIJN = 1025, the default of X-Trans frames, :1085) or three
+    // (DT_IOP_DEMOSAIC_MARKESTEIJN_3 = 1026); VNG is what every X-Trans method below them resolves to (DT_IOP_DEMOSAIC_VNG = 1024)
+    if(d->demosaicing_method != 1024u && d->demosaicing_method != 1025u && d->demosaicing_method != 1026u)
+      return fail(B200_ERR_UNSUPPORTED, "demosaic: X-Trans method %u is not built (VNG and Markesteijn are; FDC and Markesteijn 3-pass + VNG are not)",
                   d->demosaicing_method);
     if(piece->roi_out.width != piece->roi_in.width || piece->roi_out.height != piece->roi_in.height)
       return fail(B200_ERR_UNSUPPORTED, "demosaic: roi_out != roi_in (downsampling paths are not built)");
-    if(d->demosaicing_method == 1025u)
+    if(d->demosaicing_method == 1025u || d->demosaicing_method == 1026u)
     {
       rc = markesteijn_demosaic_dev((const float *)d_in, (float *)d_out, piece->roi_in.width, piece->roi_in.height, piece->roi_in.x, piece->roi_in.y,
-                                    piece->xtrans, (cudaStream_t)stream);
+                                    piece->xtrans, d->demosaicing_method == 1025u ? 1 : 3, (cudaStream_t)stream);
       if(rc) return rc;
       if(d->color_smoothing)
         rc = demosaic_color_smoothing_dev((float *)d_out, piece->roi_out.width, piece->roi_out.height, (int)d->color_smoothing, (cudaStream_t)stream);

@@ -1,7 +1,8 @@
-// Frank Markesteijn's demosaicer for X-Trans sensors, one pass, for B200 / sm_100a.
+// Frank Markesteijn's demosaicer for X-Trans sensors, one and three passes, for B200 / sm_100a.
 //
 // What the reference computes: src/iop/demosaic/markesteijn.c xtrans_markesteijn_interpolate :47-521 with passes == 1 (the default
-// demosaicer of every X-Trans frame, iop/demosaic.c:1085).  Parity contract: bit-identical to that source under C float semantics
+// demosaicer of every X-Trans frame, iop/demosaic.c:1085) and passes == 3 (eight directions, a border of 17, two more rounds that
+// recompute green from the closer interpolated values).  Parity contract: bit-identical to that source under C float semantics
 // (oracle/restate/markesteijn_oracle.c, pinned against the lines compiled in place).
 // What shapes the kernel:
 //   * the reference works in tiles of 122x122 with a border of 12, mirrored beyond the frame; every stage is local, but the first
@@ -16,8 +17,8 @@
 //     per pixel, in registers), red at blue and blue at red, the 2x2 green blocks (planes 0 and 1 only: the reference's loop
 //     stops there with four directions), squared YPbPr differences, 3x3 homogeneity counts, 5x5 sums of those (the reference
 //     rolls them in uint8 arithmetic: same sums), the average of the most homogeneous directions.
-// Scratch per resident CTA, in global memory (L2): 4 directions x 3 channels + 4 derivative planes of 122x122 floats
-// (952 KB; the homogeneity counts, 4 x 14.9 KB, live in shared memory).  Planes are split by direction and channel so that a
+// Scratch per resident CTA, in global memory (L2): directions x 3 channels + one derivative plane per direction of 122x122 floats
+// (952 KB with four directions, 1.9 MB with eight; the homogeneity counts, 14.9 KB per direction, live in shared memory).  Planes are split by direction and channel so that a
 // warp reads consecutive floats.  Algorithmic bytes: 20 B/px.
 #ifndef B200_KERNELS_ON_CPU // tests/emul compiles the stages of this file with g++ to check them against the oracle without a GPU
 #include "runtime.h"
@@ -28,18 +29,24 @@
 
 namespace
 {
-constexpr int TS = 122, NPX = TS * TS, PAD = 12, STEP = TS - 2 * PAD;
+constexpr int TS = 122, NPX = TS * TS;
 constexpr int MK_NT = 1024;
-constexpr int MK_PLANES = 16; // 12 colour planes (direction * 3 + channel), 4 derivative planes
 constexpr int MK_MAX_CLASSES = 20; // (first row, three phases, last row) x (three phases, last column)
+// what the number of passes decides, :64, :106, :305, :357, :376, :419-452
+template <int PASSES> struct mk_geo
+{
+  static constexpr int NDIR = PASSES > 1 ? 8 : 4, PAD = PASSES > 1 ? 17 : 12, STEP = TS - 2 * PAD;
+  static constexpr int PLANES = 4 * NDIR; // colour planes (direction * 3 + channel), then one derivative plane per direction
+  static constexpr int PAD_SG = PASSES > 1 ? 5 : 6, PAD_RB = PASSES > 1 ? 5 : 6, PAD_G22 = PASSES > 1 ? 4 : 8, PAD_YUV = PASSES > 1 ? 13 : 8;
+};
 
 struct mk_args_t
 {
   const float *in;
   float4 *out;
-  float *scratch;     // MK_PLANES * NPX floats per CTA
+  float *scratch;     // mk_geo::PLANES * NPX floats per CTA
   const short *start; // [class][NPX]: the record of the walk
-  int width, height, ntx, ntiles;
+  int width, height, ntx, ntiles, pad, step;
   int sgrow, sgcol;
   short hex[3][3][8];
   uint8_t xt[36];     // the sensor's pattern seen from the region's origin: xt[r][c] = xtrans[(r + roi.y) % 6][(c + roi.x) % 6]
@@ -72,10 +79,10 @@ __device__ __forceinline__ mk_tile_t mk_tile_of(const mk_args_t &a, int t)
 {
   mk_tile_t T;
   const int ty = t / a.ntx, tx = t - ty * a.ntx;
-  T.top = -PAD + ty * STEP;
-  T.left = -PAD + tx * STEP;
-  T.nrow = min(TS, a.height + PAD - T.top);
-  T.ncol = min(TS, a.width + PAD - T.left);
+  T.top = -a.pad + ty * a.step;
+  T.left = -a.pad + tx * a.step;
+  T.nrow = min(TS, a.height + a.pad - T.top);
+  T.ncol = min(TS, a.width + a.pad - T.left);
   const int rc = ty == 0 ? a.cls_first_row : (T.nrow == TS ? a.cls_row[(T.top + 600) % 6] : a.cls_last_row), cc = T.ncol == TS ? a.cls_col[(T.left + 600) % 6] : a.cls_last_col;
   T.cls = rc * a.n_col_classes + cc;
   return T;
@@ -135,6 +142,19 @@ __device__ __forceinline__ void mk_minmax6(const float *G, const short *hex, flo
     if(mx < v) mx = v;
   }
 }
+// the bounds of green of a red/blue pixel p (row, col), :203-231, from the record of the walk; G: plane 0, green
+__device__ __forceinline__ void mk_bounds(const mk_args_t &a, const mk_tile_t &T, const float *G, const short *start, int p, const short *hex, float &mn, float &mx)
+{
+  mn = FLT_MAX;
+  mx = 0.0f;
+  const int s = start[p];
+  if(s >= 0)
+  {
+    const int sr = s / TS, sc = s - sr * TS;
+    mk_minmax6(G + s, mk_hex(a, T.top + sr, T.left + sc), mn, mx);
+    if(s != p && mx == 0.0f) mk_minmax6(G + p, hex, mn, mx); // the loop's marker of a new pair: the second pixel goes on by itself
+  }
+}
 __device__ void mk_green(const mk_args_t &a, const mk_tile_t &T, float *P, int tid, int nt)
 {
   const int nr = T.nrow - 6, nc = T.ncol - 6;
@@ -148,15 +168,8 @@ __device__ void mk_green(const mk_args_t &a, const mk_tile_t &T, float *P, int t
     if(f == 1) continue;
     const int p = r * TS + c;
     const short *const hex = mk_hex(a, row, col);
-    // the bounds, :203-231
-    float mn = FLT_MAX, mx = 0.0f;
-    const int s = start[p];
-    if(s >= 0)
-    {
-      const int sr = s / TS, sc = s - sr * TS;
-      mk_minmax6(G + s, mk_hex(a, T.top + sr, T.left + sc), mn, mx);
-      if(s != p && mx == 0.0f) mk_minmax6(G + p, hex, mn, mx); // the loop's marker of a new pair: the second pixel goes on by itself
-    }
+    float mn, mx;
+    mk_bounds(a, T, G, start, p, hex, mn, mx);
     const float *const N = P + f * NPX + p; // plane 0, the pixel's own colour: natives
     const float *const g = G + p;
     float color[4];
@@ -172,11 +185,12 @@ __device__ void mk_green(const mk_args_t &a, const mk_tile_t &T, float *P, int t
 }
 
 // ---- stage 2, :304-354: red and blue at the solitary greens ---------------------------------------------------------------
-__device__ void mk_solitary(const mk_args_t &a, const mk_tile_t &T, float *P, int tid, int nt)
+// P: the first of the four direction planes the pass works on (planes 0-3 in the first pass, 4-7 afterwards); G0: plane 0's green
+__device__ void mk_solitary(const mk_args_t &a, const mk_tile_t &T, float *P, int pad, int tid, int nt)
 {
   const int mrow = T.top + T.nrow, mcol = T.left + T.ncol;
-  const int row0 = (T.top - a.sgrow + 6 + 2) / 3 * 3 + a.sgrow, col0 = (T.left - a.sgcol + 6 + 2) / 3 * 3 + a.sgcol;
-  const int nr = row0 < mrow - 6 ? (mrow - 6 - row0 + 2) / 3 : 0, nc = col0 < mcol - 6 ? (mcol - 6 - col0 + 2) / 3 : 0;
+  const int row0 = (T.top - a.sgrow + pad + 2) / 3 * 3 + a.sgrow, col0 = (T.left - a.sgcol + pad + 2) / 3 * 3 + a.sgcol;
+  const int nr = row0 < mrow - pad ? (mrow - pad - row0 + 2) / 3 : 0, nc = col0 < mcol - pad ? (mcol - pad - col0 + 2) / 3 : 0;
   for(int idx = tid; idx < nr * nc; idx += nt)
   {
     const int row = row0 + 3 * (idx / nc), col = col0 + 3 * (idx % nc);
@@ -212,13 +226,13 @@ __device__ void mk_solitary(const mk_args_t &a, const mk_tile_t &T, float *P, in
 }
 
 // ---- stage 3, :356-373: red at the blue pixels, blue at the red ones ----------------------------------------------------------
-__device__ void mk_red_blue(const mk_args_t &a, const mk_tile_t &T, float *P, int tid, int nt)
+__device__ void mk_red_blue(const mk_args_t &a, const mk_tile_t &T, float *P, int pad, int tid, int nt)
 {
-  const int nr = T.nrow - 12, nc = T.ncol - 12;
+  const int nr = T.nrow - 2 * pad, nc = T.ncol - 2 * pad;
   if(nr <= 0 || nc <= 0) return;
   for(int idx = tid; idx < nr * nc; idx += nt)
   {
-    const int r = 6 + idx / nc, c0 = 6 + idx % nc, row = T.top + r, col = T.left + c0;
+    const int r = pad + idx / nc, c0 = pad + idx % nc, row = T.top + r, col = T.left + c0;
     const int f = 2 - mk_fc(a.xt, row, col);
     if(f == 1) continue;
     const int p = r * TS + c0;
@@ -235,19 +249,19 @@ __device__ void mk_red_blue(const mk_args_t &a, const mk_tile_t &T, float *P, in
   }
 }
 
-// ---- stage 4, :375-399: red and blue in the 2x2 blocks of green (planes 0 and 1) ------------------------------------------------
-__device__ void mk_green_blocks(const mk_args_t &a, const mk_tile_t &T, float *P, int tid, int nt)
+// ---- stage 4, :375-399: red and blue in the 2x2 blocks of green: NK = directions / 2 planes (the loop `d += 2` over the directions) ----
+template <int NK> __device__ void mk_green_blocks(const mk_args_t &a, const mk_tile_t &T, float *P, int pad, int tid, int nt)
 {
-  const int nr = T.nrow - 16, nc = T.ncol - 16;
+  const int nr = T.nrow - 2 * pad, nc = T.ncol - 2 * pad;
   if(nr <= 0 || nc <= 0) return;
   for(int idx = tid; idx < nr * nc; idx += nt)
   {
-    const int r = 8 + idx / nc, c0 = 8 + idx % nc, row = T.top + r, col = T.left + c0;
+    const int r = pad + idx / nc, c0 = pad + idx % nc, row = T.top + r, col = T.left + c0;
     if(!((row - a.sgrow) % 3) || !((col - a.sgcol) % 3)) continue;
     const int p = r * TS + c0;
     const short *const hex = mk_hex(a, row, col);
 #pragma unroll
-    for(int k = 0; k < 2; k++)
+    for(int k = 0; k < NK; k++)
     {
       const int ha = hex[2 * k], hb = hex[2 * k + 1];
       const float *const Gp = P + (k * 3 + 1) * NPX + p;
@@ -289,37 +303,41 @@ __device__ __forceinline__ mk_yuv_t mk_yuv(const float *R, const float *G, const
   t.v = (r - t.y) * 0.67815f;
   return t;
 }
-__device__ void mk_derivatives(const mk_args_t &a, const mk_tile_t &T, float *P, int tid, int nt)
+template <int PASSES> __device__ void mk_derivatives(const mk_args_t &a, const mk_tile_t &T, float *P, int tid, int nt)
 {
-  const int nr = T.nrow - 18, nc = T.ncol - 18;
+  using geo = mk_geo<PASSES>;
+  constexpr int pad = geo::PAD_YUV + 1;
+  const int nr = T.nrow - 2 * pad, nc = T.ncol - 2 * pad;
   if(nr <= 0 || nc <= 0) return;
-  for(int idx = tid; idx < 4 * nr * nc; idx += nt)
+  for(int idx = tid; idx < geo::NDIR * nr * nc; idx += nt)
   {
     const int d = idx / (nr * nc), k = idx - d * (nr * nc);
-    const int p = (9 + k / nc) * TS + 9 + k % nc;
-    const int f = d == 0 ? 1 : (d == 1 ? TS : (d == 2 ? TS + 1 : TS - 1));
+    const int p = (pad + k / nc) * TS + pad + k % nc;
+    const int dd = d & 3, f = dd == 0 ? 1 : (dd == 1 ? TS : (dd == 2 ? TS + 1 : TS - 1));
     const float *const R = P + (d * 3 + 0) * NPX, *const G = R + NPX, *const B = G + NPX;
     const mk_yuv_t c = mk_yuv(R, G, B, p), hi = mk_yuv(R, G, B, p + f), lo = mk_yuv(R, G, B, p - f);
-    P[(12 + d) * NPX + p] = mk_sqr(2 * c.y - hi.y - lo.y) + mk_sqr(2 * c.u - hi.u - lo.u) + mk_sqr(2 * c.v - hi.v - lo.v);
+    P[(3 * geo::NDIR + d) * NPX + p] = mk_sqr(2 * c.y - hi.y - lo.y) + mk_sqr(2 * c.u - hi.u - lo.u) + mk_sqr(2 * c.v - hi.v - lo.v);
   }
 }
 
 // ---- stage 6, :450-464: homogeneity counts ----------------------------------------------------------------------------------
-__device__ void mk_homogeneity(const mk_args_t &a, const mk_tile_t &T, const float *P, uint8_t *homo, int tid, int nt)
+template <int PASSES> __device__ void mk_homogeneity(const mk_args_t &a, const mk_tile_t &T, const float *P, uint8_t *homo, int tid, int nt)
 {
-  const int nr = T.nrow - 20, nc = T.ncol - 20;
+  using geo = mk_geo<PASSES>;
+  constexpr int pad = geo::PAD_YUV + 2, NDIR = geo::NDIR;
+  const int nr = T.nrow - 2 * pad, nc = T.ncol - 2 * pad;
   if(nr <= 0 || nc <= 0) return;
-  const float *const D = P + 12 * NPX;
+  const float *const D = P + 3 * NDIR * NPX;
   for(int idx = tid; idx < nr * nc; idx += nt)
   {
-    const int p = (10 + idx / nc) * TS + 10 + idx % nc;
+    const int p = (pad + idx / nc) * TS + pad + idx % nc;
     float tr = FLT_MAX;
 #pragma unroll
-    for(int d = 0; d < 4; d++)
+    for(int d = 0; d < NDIR; d++)
       if(tr > D[d * NPX + p]) tr = D[d * NPX + p];
     tr *= 8;
 #pragma unroll
-    for(int d = 0; d < 4; d++)
+    for(int d = 0; d < NDIR; d++)
     {
       int n = 0;
 #pragma unroll
@@ -332,16 +350,18 @@ __device__ void mk_homogeneity(const mk_args_t &a, const mk_tile_t &T, const flo
 }
 
 // ---- stage 7, :466-515: 5x5 sums of the counts, the average of the most homogeneous directions --------------------------------
-__device__ void mk_average(const mk_args_t &a, const mk_tile_t &T, const float *P, const uint8_t *homo, int tid, int nt)
+template <int PASSES> __device__ void mk_average(const mk_args_t &a, const mk_tile_t &T, const float *P, const uint8_t *homo, int tid, int nt)
 {
+  using geo = mk_geo<PASSES>;
+  constexpr int PAD = geo::PAD, NDIR = geo::NDIR;
   const int nr = T.nrow - 2 * PAD, nc = T.ncol - 2 * PAD;
   if(nr <= 0 || nc <= 0) return;
   for(int idx = tid; idx < nr * nc; idx += nt)
   {
     const int r = PAD + idx / nc, c = PAD + idx % nc, p = r * TS + c;
-    int hm[4], maxval = 0;
+    int hm[NDIR], maxval = 0;
 #pragma unroll
-    for(int d = 0; d < 4; d++)
+    for(int d = 0; d < NDIR; d++)
     {
       int s = 0;
 #pragma unroll
@@ -352,9 +372,17 @@ __device__ void mk_average(const mk_args_t &a, const mk_tile_t &T, const float *
       maxval = max(maxval, s);
     }
     maxval -= maxval >> 3;
+#pragma unroll
+    for(int d = 0; d < NDIR - 4; d++)
+    { // :497-503: of a direction and its second-round twin the less homogeneous one drops out
+      if(hm[d] < hm[d + 4])
+        hm[d] = 0;
+      else if(hm[d] > hm[d + 4])
+        hm[d + 4] = 0;
+    }
     float avg[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
 #pragma unroll
-    for(int d = 0; d < 4; d++)
+    for(int d = 0; d < NDIR; d++)
       if(hm[d] >= maxval)
       {
         avg[0] += P[(d * 3 + 0) * NPX + p];
@@ -369,11 +397,46 @@ __device__ void mk_average(const mk_args_t &a, const mk_tile_t &T, const float *
   }
 }
 
-#ifndef B200_KERNELS_ON_CPU
-__global__ void __launch_bounds__(MK_NT, 1) markesteijn_tiles_kernel(const __grid_constant__ mk_args_t a)
+// ---- the rounds after the first (three passes): planes 0-3 copied to 4-7 (:275-281), then green again from the closer interpolated values,
+// :284-302 (P: planes 4-7; G0: plane 0's green for the bounds).  The pixels it reads are green ones, the pixels it writes are not.
+__device__ void mk_copy_planes(float *P, int tid, int nt)
 {
+  for(int idx = tid; idx < 12 * NPX; idx += nt) P[12 * NPX + idx] = P[idx];
+}
+__device__ void mk_recalc_green(const mk_args_t &a, const mk_tile_t &T, float *P, const float *G0, int tid, int nt)
+{
+  const int nr = T.nrow - 12, nc = T.ncol - 12;
+  if(nr <= 0 || nc <= 0) return;
+  const short *const start = a.start + (size_t)T.cls * NPX;
+  for(int idx = tid; idx < nr * nc; idx += nt)
+  {
+    const int r = 6 + idx / nc, c = 6 + idx % nc, row = T.top + r, col = T.left + c;
+    const int f = mk_fc(a.xt, row, col);
+    if(f == 1) continue;
+    const int p = r * TS + c;
+    const short *const hex = mk_hex(a, row, col);
+    float mn, mx;
+    mk_bounds(a, T, G0, start, p, hex, mn, mx);
+    const int flip = !((row - a.sgrow) % 3);
+#pragma unroll
+    for(int d = 3; d < 6; d++)
+    {
+      const int pl = (d - 2) ^ flip;
+      float *const Gp = P + (pl * 3 + 1) * NPX + p;
+      const float *const Fp = P + (pl * 3 + f) * NPX + p;
+      const int h = hex[d];
+      const float val = Gp[-2 * h] + 2 * Gp[h] - Fp[-2 * h] - 2 * Fp[h] + 3 * Fp[0];
+      Gp[0] = mk_clamps(mk_div(val, 3.0f), mn, mx);
+    }
+  }
+}
+
+#ifndef B200_KERNELS_ON_CPU
+template <int PASSES> __global__ void __launch_bounds__(MK_NT, 1) markesteijn_tiles_kernel(const __grid_constant__ mk_args_t a)
+{
+  using geo = mk_geo<PASSES>;
   extern __shared__ uint8_t mk_homo[];
-  float *const P = a.scratch + (size_t)blockIdx.x * MK_PLANES * NPX;
+  float *const P = a.scratch + (size_t)blockIdx.x * geo::PLANES * NPX;
   const int tid = threadIdx.x;
   for(int t = blockIdx.x; t < a.ntiles; t += gridDim.x)
   {
@@ -382,17 +445,31 @@ __global__ void __launch_bounds__(MK_NT, 1) markesteijn_tiles_kernel(const __gri
     __syncthreads();
     mk_green(a, T, P, tid, MK_NT);
     __syncthreads();
-    mk_solitary(a, T, P, tid, MK_NT);
+    for(int pass = 0; pass < PASSES; pass++)
+    {
+      float *const Pp = pass ? P + 12 * NPX : P;
+      if(pass == 1)
+      {
+        mk_copy_planes(P, tid, MK_NT);
+        __syncthreads();
+      }
+      if(pass)
+      {
+        mk_recalc_green(a, T, Pp, P + NPX, tid, MK_NT);
+        __syncthreads();
+      }
+      mk_solitary(a, T, Pp, geo::PAD_SG, tid, MK_NT);
+      __syncthreads();
+      mk_red_blue(a, T, Pp, geo::PAD_RB, tid, MK_NT);
+      __syncthreads();
+      mk_green_blocks<geo::NDIR / 2>(a, T, Pp, geo::PAD_G22, tid, MK_NT);
+      __syncthreads();
+    }
+    mk_derivatives<PASSES>(a, T, P, tid, MK_NT);
     __syncthreads();
-    mk_red_blue(a, T, P, tid, MK_NT);
+    mk_homogeneity<PASSES>(a, T, P, mk_homo, tid, MK_NT);
     __syncthreads();
-    mk_green_blocks(a, T, P, tid, MK_NT);
-    __syncthreads();
-    mk_derivatives(a, T, P, tid, MK_NT);
-    __syncthreads();
-    mk_homogeneity(a, T, P, mk_homo, tid, MK_NT);
-    __syncthreads();
-    mk_average(a, T, P, mk_homo, tid, MK_NT);
+    mk_average<PASSES>(a, T, P, mk_homo, tid, MK_NT);
     __syncthreads();
   }
 }
@@ -461,10 +538,11 @@ void mk_walk(short *start, const uint8_t *xt, int sgrow, int top, int left, int 
   }
 }
 
-// tiles (top = -12 + k * 98 < height - 12, left likewise) and their classes: full tiles by the phase of their origin (three of them:
-// 98 = 2 mod 6), the last row / column by its size; one record of the walk per class.  Nonzero: too many classes.
+// tiles (top = -pad + k * step < height - pad, left likewise: pad 12, step 98 with one pass, 17 and 88 with three) and their classes: full
+// tiles by the phase of their origin (three of them: 98 = 2 and 88 = 4 mod 6), the last row / column by its size; one record of the walk per class.  Nonzero: too many classes.
 int mk_build_classes(mk_args_t &a, std::vector<short> &maps)
 {
+  const int PAD = a.pad, STEP = a.step;
   a.ntx = (a.width + STEP - 1) / STEP;
   const int nty = (a.height + STEP - 1) / STEP;
   a.ntiles = a.ntx * nty;
@@ -509,12 +587,33 @@ int mk_build_classes(mk_args_t &a, std::vector<short> &maps)
 #ifndef B200_KERNELS_ON_CPU
 struct mk_plan_t
 { // what depends on the geometry only: built once per (frame size, origin, pattern), kept on the device
-  int width = 0, height = 0, rx = 0, ry = 0, dev = -1;
+  int width = 0, height = 0, rx = 0, ry = 0, dev = -1, passes = 0;
   uint8_t xtrans[36] = { 0 };
   mk_args_t a;
   short *d_start = nullptr;
 };
 mk_plan_t g_plan[2];
+
+template <int PASSES> int mk_launch(mk_args_t &a, int dev, cudaStream_t stream)
+{
+  using geo = mk_geo<PASSES>;
+  static bool attr_set[16] = { false };
+  const int smem = geo::NDIR * NPX;
+  if(!attr_set[dev & 15])
+  {
+    B200_CUDA_TRY(cudaFuncSetAttribute(markesteijn_tiles_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set[dev & 15] = true;
+  }
+  int grid = b200::sm_count();
+  if(grid > a.ntiles) grid = a.ntiles;
+  void *scr = nullptr;
+  int rc = b200::scratch(b200::SLOT_TMP2, (size_t)grid * geo::PLANES * NPX * sizeof(float), &scr);
+  if(rc) return rc;
+  a.scratch = (float *)scr;
+  markesteijn_tiles_kernel<PASSES><<<grid, MK_NT, smem, stream>>>(a);
+  B200_CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
 int g_plan_next = 0;
 #endif
 } // namespace
@@ -522,15 +621,16 @@ int g_plan_next = 0;
 #ifndef B200_KERNELS_ON_CPU
 namespace b200
 {
-// xtrans_markesteijn_interpolate(), markesteijn.c:47-521, passes == 1.  (x0, y0): origin of the region on the sensor.
-int markesteijn_demosaic_dev(const float *d_in, float *d_out, int width, int height, int x0, int y0, const uint8_t xtrans[6][6], cudaStream_t stream)
+// xtrans_markesteijn_interpolate(), markesteijn.c:47-521, passes == 1 or 3.  (x0, y0): origin of the region on the sensor.
+int markesteijn_demosaic_dev(const float *d_in, float *d_out, int width, int height, int x0, int y0, const uint8_t xtrans[6][6], int passes, cudaStream_t stream)
 {
+  if(passes != 1 && passes != 3) return fail(B200_ERR_ARG, "Markesteijn: %d passes", passes);
   if(width < 1 || height < 1) return B200_OK;
   int dev = 0;
   B200_CUDA_TRY(cudaGetDevice(&dev));
   mk_plan_t *plan = nullptr;
   for(auto &q : g_plan)
-    if(q.d_start && q.dev == dev && q.width == width && q.height == height && q.rx == x0 && q.ry == y0 && !memcmp(q.xtrans, xtrans, 36)) plan = &q;
+    if(q.d_start && q.dev == dev && q.passes == passes && q.width == width && q.height == height && q.rx == x0 && q.ry == y0 && !memcmp(q.xtrans, xtrans, 36)) plan = &q;
   if(!plan)
   {
     plan = &g_plan[g_plan_next];
@@ -545,6 +645,8 @@ int markesteijn_demosaic_dev(const float *d_in, float *d_out, int width, int hei
     memset(&a, 0, sizeof(a));
     a.width = width;
     a.height = height;
+    a.pad = passes == 1 ? mk_geo<1>::PAD : mk_geo<3>::PAD;
+    a.step = passes == 1 ? mk_geo<1>::STEP : mk_geo<3>::STEP;
     for(int r = 0; r < 6; r++)
       for(int c = 0; c < 6; c++) a.xt[r * 6 + c] = xtrans[(r + y0 + 600) % 6][(c + x0 + 600) % 6];
     mk_hexagons(a);
@@ -559,26 +661,14 @@ int markesteijn_demosaic_dev(const float *d_in, float *d_out, int width, int hei
     plan->rx = x0;
     plan->ry = y0;
     plan->dev = dev;
+    plan->passes = passes;
     memcpy(plan->xtrans, xtrans, 36);
   }
   mk_args_t a = plan->a;
   a.in = d_in;
   a.out = (float4 *)d_out;
-  static bool attr_set[16] = { false };
-  const int smem = 4 * NPX;
-  if(!attr_set[dev & 15])
-  {
-    B200_CUDA_TRY(cudaFuncSetAttribute(markesteijn_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set[dev & 15] = true;
-  }
-  int grid = sm_count();
-  if(grid > a.ntiles) grid = a.ntiles;
-  void *scr = nullptr;
-  int rc = scratch(SLOT_TMP2, (size_t)grid * MK_PLANES * NPX * sizeof(float), &scr);
+  const int rc = passes == 1 ? mk_launch<1>(a, dev, stream) : mk_launch<3>(a, dev, stream);
   if(rc) return rc;
-  a.scratch = (float *)scr;
-  markesteijn_tiles_kernel<<<grid, MK_NT, smem, stream>>>(a);
-  B200_CUDA_TRY(cudaGetLastError());
   return B200_OK;
 }
 } // namespace b200

@@ -174,10 +174,10 @@ typedef struct b200_demosaic_data_t
  * VNG4 under the detail mask of develop/masks/detail.c; data->dual_thrs, piece->wb_coeffs), green equilibration in front
  * (data->green_eq) and median colour smoothing behind (data->color_smoothing); the two passthrough methods (3 monochrome,
  * 4 photosite colour; passthrough.c) for any sensor; for X-Trans sensors (filters == 9, piece->xtrans) Markesteijn with one pass
- * (method 1025, the default of X-Trans frames; markesteijn.c:47-521) and VNG (method 1024, the X-Trans branch of vng.c); the
+ * (method 1025, the default of X-Trans frames; markesteijn.c:47-521) or three (method 1026) and VNG (method 1024, the X-Trans branch of vng.c); the
  * half-size downsample (method 7, iop/demosaic.c:480-532 Bayer, :543-666 X-Trans; roi_out =
  * (roi_in + 1) / 2; four-colour Bayer sensors through data->CAM_to_RGB) and its guided-Laplacian post-filter (:681-926;
- * data->color_smoothing iterations).  LMMSE, Markesteijn with three passes and FDC, the full-size demosaicers on four-colour Bayer sensors and
+ * data->color_smoothing iterations).  LMMSE, FDC, Markesteijn 3-pass + VNG, the full-size demosaicers on four-colour Bayer sensors and
  * the GUI's mask display return B200_ERR_UNSUPPORTED. */
 int b200_demosaic_process_host(const b200_piece_t *piece, const void *in, void *out);
 /* process_cl() slot, iop/demosaic/rcd.c:568-850: device pointers, `stream` is a cudaStream_t (NULL = default) */

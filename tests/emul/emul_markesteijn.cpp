@@ -7,23 +7,26 @@
 #include "../../ansel_b200/csrc/markesteijn.cu"
 #include <vector>
 
-extern "C" int emul_markesteijn(float *out, const float *in, int width, int height, int x0, int y0, const unsigned char *xtrans36, int nthreads, int ascending)
+template <int PASSES> static int emul_run(float *out, const float *in, int width, int height, int x0, int y0, const unsigned char *xtrans36, int nthreads, int ascending)
 {
+  using geo = mk_geo<PASSES>;
   _mm_setcsr(_mm_getcsr() | 0x8040u);
   mk_args_t a;
   memset(&a, 0, sizeof(a));
   a.width = width;
   a.height = height;
+  a.pad = geo::PAD;
+  a.step = geo::STEP;
   for(int r = 0; r < 6; r++)
     for(int c = 0; c < 6; c++) a.xt[r * 6 + c] = xtrans36[((r + y0 + 600) % 6) * 6 + (c + x0 + 600) % 6];
   mk_hexagons(a);
-  a.ntx = (width + STEP - 1) / STEP;
-  const int nty = (height + STEP - 1) / STEP;
+  a.ntx = (width + geo::STEP - 1) / geo::STEP;
+  const int nty = (height + geo::STEP - 1) / geo::STEP;
   a.ntiles = a.ntx * nty;
   a.in = in;
   a.out = (float4 *)out;
-  std::vector<float> P((size_t)MK_PLANES * NPX, __builtin_nanf(""));
-  std::vector<uint8_t> homo(4 * NPX, 0xff);
+  std::vector<float> P((size_t)geo::PLANES * NPX, __builtin_nanf(""));
+  std::vector<uint8_t> homo(geo::NDIR * NPX, 0xff);
   std::vector<short> start(NPX);
   a.start = start.data();
   for(int t = 0; t < a.ntiles; t++)
@@ -39,25 +42,38 @@ extern "C" int emul_markesteijn(float *out, const float *in, int width, int heig
   }
     STAGE(mk_load(a, T, P.data(), tid, nthreads))
     STAGE(mk_green(a, T, P.data(), tid, nthreads))
-    STAGE(mk_solitary(a, T, P.data(), tid, nthreads))
-    STAGE(mk_red_blue(a, T, P.data(), tid, nthreads))
-    STAGE(mk_green_blocks(a, T, P.data(), tid, nthreads))
-    STAGE(mk_derivatives(a, T, P.data(), tid, nthreads))
-    STAGE(mk_homogeneity(a, T, P.data(), homo.data(), tid, nthreads))
-    STAGE(mk_average(a, T, P.data(), homo.data(), tid, nthreads))
+    for(int pass = 0; pass < PASSES; pass++)
+    {
+      float *const Pp = pass ? P.data() + 12 * NPX : P.data();
+      if(pass == 1) STAGE(mk_copy_planes(P.data(), tid, nthreads))
+      if(pass) STAGE(mk_recalc_green(a, T, Pp, P.data() + NPX, tid, nthreads))
+      STAGE(mk_solitary(a, T, Pp, geo::PAD_SG, tid, nthreads))
+      STAGE(mk_red_blue(a, T, Pp, geo::PAD_RB, tid, nthreads))
+      STAGE(mk_green_blocks<geo::NDIR / 2>(a, T, Pp, geo::PAD_G22, tid, nthreads))
+    }
+    STAGE(mk_derivatives<PASSES>(a, T, P.data(), tid, nthreads))
+    STAGE(mk_homogeneity<PASSES>(a, T, P.data(), homo.data(), tid, nthreads))
+    STAGE(mk_average<PASSES>(a, T, P.data(), homo.data(), tid, nthreads))
 #undef STAGE
   }
   return 0;
 }
 
+extern "C" int emul_markesteijn(float *out, const float *in, int width, int height, int x0, int y0, const unsigned char *xtrans36, int nthreads, int ascending, int passes)
+{
+  return passes == 3 ? emul_run<3>(out, in, width, height, x0, y0, xtrans36, nthreads, ascending) : emul_run<1>(out, in, width, height, x0, y0, xtrans36, nthreads, ascending);
+}
+
 /* the classes of tiles the product builds for a frame: the class of every tile and, per class, the record of the walk -- compared by the
  * test with a walk of each tile on its own.  Returns the number of classes, -1 if two tiles of one class walk differently. */
-extern "C" int emul_markesteijn_classes(int width, int height, int x0, int y0, const unsigned char *xtrans36)
+extern "C" int emul_markesteijn_classes(int width, int height, int x0, int y0, const unsigned char *xtrans36, int passes)
 {
   mk_args_t a;
   memset(&a, 0, sizeof(a));
   a.width = width;
   a.height = height;
+  a.pad = passes == 3 ? mk_geo<3>::PAD : mk_geo<1>::PAD;
+  a.step = passes == 3 ? mk_geo<3>::STEP : mk_geo<1>::STEP;
   for(int r = 0; r < 6; r++)
     for(int c = 0; c < 6; c++) a.xt[r * 6 + c] = xtrans36[((r + y0 + 600) % 6) * 6 + (c + x0 + 600) % 6];
   mk_hexagons(a);

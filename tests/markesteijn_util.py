@@ -61,7 +61,7 @@ def emul_lib():
     return _EMUL
 
 
-def emul(m, x=0, y=0, nthreads=96, ascending=0):
+def emul(m, x=0, y=0, nthreads=96, ascending=0, passes=1):
     """the kernel's stages run thread by thread on the CPU, the threads of a stage in descending (or ascending) order"""
     h, w = m.shape
     out, src = util.aligned_empty((h, w, 4)), util.aligned_empty(m.shape)
@@ -69,13 +69,13 @@ def emul(m, x=0, y=0, nthreads=96, ascending=0):
     src[...] = m
     xt = np.ascontiguousarray(XTRANS)
     f = emul_lib().emul_markesteijn
-    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
-    assert f(out.ctypes.data, src.ctypes.data, w, h, x, y, xt.ctypes.data, nthreads, ascending) == 0
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    assert f(out.ctypes.data, src.ctypes.data, w, h, x, y, xt.ctypes.data, nthreads, ascending, passes) == 0
     return np.array(out)
 
 
-def emul_classes(w, h, x, y, xtrans=None):
+def emul_classes(w, h, x, y, xtrans=None, passes=1):
     xt = np.ascontiguousarray(XTRANS if xtrans is None else xtrans)
     f = emul_lib().emul_markesteijn_classes
-    f.argtypes = [C.c_int] * 4 + [C.c_void_p]
-    return f(w, h, x, y, xt.ctypes.data)
+    f.argtypes = [C.c_int] * 4 + [C.c_void_p, C.c_int]
+    return f(w, h, x, y, xt.ctypes.data, passes)

@@ -226,3 +226,21 @@ def test_segmented_chain_with_a_whole_frame_module_over_gloo(built, world):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res), res
+
+
+def test_band_rows_widened_until_non_local_means_chunks_fit_the_pipelined_kernel():
+    """bands.nlm_slice_height restates compute_slice_height() (the oracle's copy is pinned to the reference's); widen_for_nlm only ever adds
+    input rows inside the frame, keeps the kept rows and the row alignment, and ends with chunks of 64 rows or less"""
+    import ctypes as C
+    import util
+    from ansel_b200 import bands
+    o = util.oracle()
+    for hgt in list(range(16, 400)) + [2752, 2770, 2788, 4418, 5504, 8736]:
+        assert bands.nlm_slice_height(hgt) == o.orc_nlm_slice_height(hgt), hgt
+    for height, n, halo in ((5504, 2, 18), (5504, 4, 18), (5504, 8, 18), (8736, 2, 50), (8736, 4, 50), (3000, 3, 18), (999 * 2, 5, 20)):
+        before = bands.plan(height, n, 1, halo, 2)
+        after = bands.widen_for_nlm(before, height, 2)
+        for b, a in zip(before, after):
+            assert (a.out_y0, a.out_y1) == (b.out_y0, b.out_y1)
+            assert 0 <= a.in_y0 <= b.in_y0 and b.in_y1 <= a.in_y1 <= height and a.in_y0 % 2 == 0
+            assert bands.nlm_slice_height(a.in_y1 - a.in_y0) <= 64

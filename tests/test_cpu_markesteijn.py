@@ -1,5 +1,5 @@
 """CPU: Markesteijn's X-Trans demosaicer.  The oracle is pinned bit for bit to iop/demosaic/markesteijn.c :25-523 compiled in place
-(one and three passes) and to the golden vectors that build produced; the stages of the product's kernel (one pass), compiled with g++
+(one and three passes) and to the golden vectors that build produced; the stages of the product's kernel (one and three passes), compiled with g++
 and run thread by thread in either order, equal the oracle; the classes of tiles the product ships one record of the loop
 :199-246 for are checked against a walk of every tile on its own."""
 import os
@@ -55,28 +55,31 @@ def test_oracle_equals_reference_on_other_seeds_and_a_dark_frame():
     assert same_bits(mu.oracle(m, 2, 1, 1), mu.ref(m, 2, 1, 1)).all()
 
 
+@pytest.mark.parametrize("passes", [1, 3])
 @pytest.mark.parametrize("ascending", [0, 1])
 @pytest.mark.parametrize("name", list(mu.CASES))
-def test_kernel_stages_equal_oracle(name, ascending):
+def test_kernel_stages_equal_oracle(name, ascending, passes):
     """no stage reads what another thread of the same stage writes: both thread orders give the oracle's bits"""
     m, x, y = mu.case(name)
-    assert same_bits(mu.emul(m, x, y, 96, ascending), mu.oracle(m, x, y, 1)).all()
+    assert same_bits(mu.emul(m, x, y, 96, ascending, passes), mu.oracle(m, x, y, passes)).all()
 
 
 def test_kernel_stages_on_a_dark_frame_and_other_thread_counts():
     m = np.zeros((150, 140), np.float32)
     m[70:80, 60:90] = 0.5
-    want = mu.oracle(m, 2, 1, 1)
-    for nt in (1, 37, 1024):
-        assert same_bits(mu.emul(m, 2, 1, nt), want).all(), nt
+    for passes in (1, 3):
+        want = mu.oracle(m, 2, 1, passes)
+        for nt in (1, 37, 1024):
+            assert same_bits(mu.emul(m, 2, 1, nt, 0, passes), want).all(), (passes, nt)
 
 
 @pytest.mark.parametrize("geom", [(8256, 5504, 0, 0), (6000, 4000, 3, 5), (4896, 3264, 1, 2), (98, 98, 0, 0), (99, 197, 4, 1), (300, 210, 0, 0), (30, 17, 2, 3)])
 def test_tile_classes_walk_like_every_tile_on_its_own(geom):
     """-1: two tiles of a class walk differently; -2: too many classes; -3: a red/blue pixel the walk never writes (the reference would read
     what the previous tile left there)"""
-    n = mu.emul_classes(*geom)
-    assert 1 <= n <= 20, n
+    for passes in (1, 3):
+        n = mu.emul_classes(*geom, passes=passes)
+        assert 1 <= n <= 20, (passes, n)
 
 
 def test_tile_classes_with_a_permuted_pattern():

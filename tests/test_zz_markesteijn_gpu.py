@@ -1,4 +1,4 @@
-"""B200: Markesteijn's X-Trans demosaicer (one pass, method 1025) through the C ABI and the module adapter, bit for bit against the oracle
+"""B200: Markesteijn's X-Trans demosaicer (one pass, method 1025; three passes, method 1026) through the C ABI and the module adapter, bit for bit against the oracle
 (itself pinned to iop/demosaic/markesteijn.c compiled in place) and the golden vectors of the reference's build."""
 import ctypes as C
 import os
@@ -46,15 +46,17 @@ def cuda(ab, m, x, y, method=1025, host=False, smoothing=0):
     return d_out.cpu().numpy()
 
 
+@pytest.mark.parametrize("passes", [1, 3])
 @pytest.mark.parametrize("name", list(mu.CASES))
-def test_markesteijn_bit_exact(built, name):
+def test_markesteijn_bit_exact(built, name, passes):
     m, x, y = mu.case(name)
-    want = mu.oracle(m, x, y, 1)
-    got = cuda(built, m, x, y)
+    method = 1025 if passes == 1 else 1026
+    want = mu.oracle(m, x, y, passes)
+    got = cuda(built, m, x, y, method=method)
     assert same_bits(got[..., :3], want[..., :3]).all() and (got[..., 3] == -7.0).all()   # lane 3 is not a result: kept as found
-    assert same_bits(cuda(built, m, x, y, host=True), got).all()
+    assert same_bits(cuda(built, m, x, y, method=method, host=True), got).all()
     g = np.load(os.path.join(util.GOLDEN_DIR, "markesteijn.npz"))
-    assert same_bits(got[..., :3], g["p1_" + name][..., :3]).all()
+    assert same_bits(got[..., :3], g[f"p{passes}_{name}"][..., :3]).all()
 
 
 def test_markesteijn_larger_frames_second_call_and_a_dark_frame(built):
@@ -63,19 +65,20 @@ def test_markesteijn_larger_frames_second_call_and_a_dark_frame(built):
         want = mu.oracle(m, x, y, 1)
         for _ in range(2):                       # the second call runs on the cached plan of the frame's geometry
             assert same_bits(cuda(built, m, x, y)[..., :3], want[..., :3]).all(), (w, h)
+        assert same_bits(cuda(built, m, x, y, method=1026)[..., :3], mu.oracle(m, x, y, 3)[..., :3]).all(), (w, h)
     m = np.zeros((300, 260), np.float32)         # every maximum of green is 0.0f, the loop's marker of a new pair
     m[70:180, 60:190] = 0.5
     assert same_bits(cuda(built, m, 2, 1)[..., :3], mu.oracle(m, 2, 1, 1)[..., :3]).all()
 
 
-def test_markesteijn_with_colour_smoothing_and_the_three_pass_variant_refused(built):
+def test_markesteijn_with_colour_smoothing_and_fdc_refused(built):
     ab = built
     m, x, y = mu.case("roi2")
     want = util.oracle_color_smoothing(mu.oracle(m, x, y, 1), 2)
     got = cuda(ab, m, x, y, smoothing=2)
     assert same_bits(got[..., :3], want[..., :3]).all()
     with pytest.raises(ab.B200Error) as e:
-        cuda(ab, m, x, y, method=1026)
+        cuda(ab, m, x, y, method=1028)           # DT_IOP_DEMOSAIC_FDC
     assert e.value.code == ab.B200_ERR_UNSUPPORTED
 
 

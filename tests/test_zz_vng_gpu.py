@@ -132,6 +132,6 @@ def test_vng_xtrans_bit_exact(built, name):
     host = np.full((h, w, 4), -7.0, np.float32)
     ab.check(ab.lib().b200_demosaic_process_host(C.byref(piece), m.ctypes.data, host.ctypes.data))
     assert same_bits(host, got).all()
-    d2 = ab.demosaic_data(1026)                                   # Markesteijn with three passes: not built
+    d2 = ab.demosaic_data(1028)                                   # frequency-domain chroma: not built
     piece.data = C.cast(C.pointer(d2), C.c_void_p)
     assert ab.lib().b200_demosaic_process_dev(C.byref(piece), d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream) == ab.B200_ERR_UNSUPPORTED

@@ -7,7 +7,8 @@ ab.init()
 w, h = util.SIZE_45MP
 m = torch.from_numpy(util.frame_natural(w, h, 3)).cuda()
 out = torch.empty((h, w, 4), device="cuda")
-d = ab.demosaic_data(1025)
+passes = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+d = ab.demosaic_data(1025 if passes == 1 else 1026)
 piece = ab.make_piece(w, h, filters=9, data=d, devid=0)
 for i in range(6):
     for j in range(6):
@@ -18,4 +19,4 @@ run(); torch.cuda.synchronize(); ts = []
 for _ in range(5):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); run(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
-print(f"Markesteijn 1-pass 45MP median ms {np.median(ts):.2f}  MP/s {w*h/np.median(ts)/1e3:.0f}  ({20*w*h/np.median(ts)/1e6:.0f} GB/s algorithmic)")
+print(f"Markesteijn {passes}-pass 45MP median ms {np.median(ts):.2f}  MP/s {w*h/np.median(ts)/1e3:.0f}  ({20*w*h/np.median(ts)/1e6:.0f} GB/s algorithmic)")
