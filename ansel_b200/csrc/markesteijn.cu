@@ -625,6 +625,12 @@ namespace b200
 int markesteijn_demosaic_dev(const float *d_in, float *d_out, int width, int height, int x0, int y0, const uint8_t xtrans[6][6], int passes, cudaStream_t stream)
 {
   if(passes != 1 && passes != 3) return fail(B200_ERR_ARG, "Markesteijn: %d passes", passes);
+  { // the mirrored border (:158, TRANSLATE) reads row / column `pad` and 2 * size - (size + pad - 1) - 2: smaller frames are out-of-bounds reads
+    // in the reference
+    const int pad = passes == 1 ? mk_geo<1>::PAD : mk_geo<3>::PAD;
+    if(width > 0 && height > 0 && (width <= pad || height <= pad))
+      return fail(B200_ERR_UNSUPPORTED, "Markesteijn: frames of %d px or less a side are undefined in the reference with %d pass(es)", pad, passes);
+  }
   if(width < 1 || height < 1) return B200_OK;
   int dev = 0;
   B200_CUDA_TRY(cudaGetDevice(&dev));

@@ -801,7 +801,11 @@ int launch_group(const nlm_args_t &a, int shift_max, int smem_optin, int n_chunk
   if(grp_pipe_fits(g, smem_optin, pipe_wp) && !getenv("B200_NLM_NO_PIPE"))
   {
     const size_t psmem = grp_pipe_smem_bytes(g, pipe_wp);
-    e = a.radius == 1 ? launch_pipe_r<1, 0>(g, norm1, profiled, divc, grid, psmem, stream) : launch_pipe_r<2, 0>(g, norm1, profiled, divc, grid, psmem, stream);
+    const bool halves = !getenv("B200_NLM_WHOLE_SLOTS"); // development switch: the whole-pair slots everywhere
+    if(halves)
+      e = a.radius == 1 ? launch_pipe_r<1, 0>(g, norm1, profiled, divc, grid, psmem, stream) : launch_pipe_r<2, 0>(g, norm1, profiled, divc, grid, psmem, stream);
+    else
+      e = a.radius == 1 ? launch_pipe_r<1, 1>(g, norm1, profiled, divc, grid, psmem, stream) : launch_pipe_r<2, 1>(g, norm1, profiled, divc, grid, psmem, stream);
     if(e != cudaSuccess) return ::b200::fail(B200_ERR_CUDA, "nlmeans: pipelined kernel launch: %s", cudaGetErrorString(e));
     *launched = 1;
     return B200_OK;

@@ -760,14 +760,14 @@ __device__ __forceinline__ void grp_phase_b2(const grp_args_t &a, const chunk_t 
 
 // ---- normalise (and blend), :485-519 -----------------------------------------------------------------------------
 template <class ST>
-__device__ __forceinline__ void grp_finish(const grp_args_t &a, const chunk_t &c, const ST &st, int tid)
-{
+__device__ __forceinline__ void grp_finish(const grp_args_t &a, const chunk_t &c, const ST &st, int tid, int row_off = 0)
+{ // row_off: chunk row of the plane row 0 the thread's offsets count from (the half-height slots: 32 for the lower half)
   constexpr int KP = ST::KP;
 #pragma unroll
   for(int k = 0; k < KP; k++)
   {
     if(!((st.upper >> k) & 1u)) continue;
-    const int rr = st.sofs(k) / GRP_SP, pc = st.sofs(k) - rr * GRP_SP;
+    const int rl = st.sofs(k) / GRP_SP, pc = st.sofs(k) - rl * GRP_SP, rr = rl + row_off;
 #pragma unroll
     for(int l = 0; l < 2; l++)
     {
@@ -835,8 +835,9 @@ template <int CFG> struct pipe_cfg
 {
   static constexpr int ACC_T = 256, KP = 9, L = 8, WP = 97, SCAN_REGS = 80, ACC_REGS = 176, NT = 2 * PIPE_SCAN_GROUP + ACC_T; // 256 x 80 + 256 x 176 = the register file
   static constexpr int IL = 1; // pixel pairs an accumulating thread keeps in flight in phase B2
+  static constexpr bool HALVES = CFG == 0; // half-height slots (PIPE2_SLOTS) in the chunks that take them; CFG 1: whole-pair slots everywhere
 };
-constexpr int PIPE_N_CFG = 1;
+constexpr int PIPE_N_CFG = 2;
 // setmaxnreg.inc only ever gets what setmaxnreg.dec of the same block released: a shape that asks for more waits forever
 template <int CFG> constexpr bool pipe_regs_balance()
 {
@@ -864,6 +865,110 @@ template <int R> __device__ __forceinline__ void pipe_b1(const grp_args_t &a, co
   grp_scan_rows<R>(a, c, Sa + gi * a.splane, p0 + gi, tb - gi * half, half);
 }
 
+// ---- half-height slots: phase B1 of one half under phase A of the next ------------------------------------------------------------
+// In chunks of exactly 64 rows in the interior of the frame (all but the frame's rim) a slot holds HALF a patch pair: the column sums of
+// rows 0..31 or 32..63 (two planes of 32 x GRP_SP floats), six slots in the room of the three whole-pair ones.  A scan group's warps
+// 0..2 run phase A down a column as before -- the running sum and the ring of squares simply carry over from row 31 to row 32 -- and hand
+// each finished half to the group's warp 3, which runs phase B1 on it (2 patches x 16 row pairs = its 32 lanes) while they are already in
+// the next half.  The accumulating warps 0..3 own the row pairs of the upper halves, 4..7 those of the lower ones (grp_strip_of), and
+// drain their own sequence of slots.  Barriers: FULL[slot] (warp 3 arrives, one accumulating half waits), EMPTY[slot] (that half arrives,
+// the scan warps that want the slot wait), HANDOVER[group] (scan warps and warp 3 meet: the half is written, and warp 3 is done with the
+// one before).
+constexpr int PIPE2_SLOTS = 6, PIPE2_HROWS = 32, PIPE2_HSP = PIPE2_HROWS * GRP_SP; // floats of a half plane
+constexpr int PIPE2_A_T = 96, PIPE2_ACC_HALF = 128;
+constexpr int PIPE2_BAR_FULL = 1, PIPE2_BAR_EMPTY = PIPE2_BAR_FULL + PIPE2_SLOTS, PIPE2_BAR_HANDOVER = PIPE2_BAR_EMPTY + PIPE2_SLOTS; // 1..6, 7..12, 13..14
+static_assert(PIPE2_BAR_HANDOVER + 2 <= 16, "sixteen named barriers per block");
+static_assert(2 * PIPE2_SLOTS * PIPE2_HSP <= 2 * PIPE_SLOTS * (MAX_CH + 1) * GRP_SP, "the half slots fit the room of the whole-pair slots");
+
+// phase A of two patches down one column, as a resumable walk: init() takes in the 2 * R + 1 rows above the chunk's first one, step<S>()
+// stores the sums of a row and slides to the next (S = that row's place in the ring, row mod (2 * R + 1))
+template <int WP, int R, bool NORM1> struct grp_colwalk_t
+{
+  static constexpr int RP = 3 * WP, N = 2 * R + 1;
+  f2 ring[N][3];
+  f2 cs;
+  grp_row9_t nxt;
+  const float *x, *ya, *yb;
+  __device__ __forceinline__ void init(const grp_args_t &a, const chunk_t &c, const float *W, int pa, int k)
+  {
+    const int col = c.cbase + k;
+    x = W + (c.top - R - c.wr0) * RP + (col - c.wc0);
+    ya = x + a.patches[pa].rows * RP + a.patches[pa].cols;
+    const int pb = pa + 1 < a.n_patches ? pa + 1 : pa; // the last patch of an odd list walks alone: its twin is itself, its plane unread
+    yb = x + a.patches[pb].rows * RP + a.patches[pb].cols;
+    cs = mk2(0.0f, 0.0f);
+    nxt = grp_load_row<WP>(x, ya, yb);
+#pragma unroll
+    for(int i = 0; i < N; i++)
+    {
+      const grp_row9_t cur = nxt;
+      nxt = grp_load_row<WP>(x + (i + 1) * RP, ya + (i + 1) * RP, yb + (i + 1) * RP);
+      grp_squares2(cur, ring[i][0], ring[i][1], ring[i][2]);
+      cs = add2(cs, grp_pd2<NORM1>(ring[i][0], ring[i][1], ring[i][2], mk2(a.norm[0], a.norm[0]), mk2(a.norm[1], a.norm[1]), mk2(a.norm[2], a.norm[2])));
+    }
+    x += N * RP;
+    ya += N * RP;
+    yb += N * RP;
+  }
+  // one row: its sums go to spa[0] / spb[0]; the window row that enters is the one fetched a step ago (the window has a spare row behind
+  // the last one a chunk reads)
+  template <int S> __device__ __forceinline__ void step(const grp_args_t &a, float *spa, float *spb)
+  {
+    const grp_row9_t cur = nxt;
+    x += RP;
+    ya += RP;
+    yb += RP;
+    nxt = grp_load_row<WP>(x, ya, yb);
+    *spa = cs.x;
+    *spb = cs.y;
+    f2 e0, e1, e2;
+    grp_squares2(cur, e0, e1, e2);
+    cs = add2(cs, grp_pd2<NORM1>(sub2(e0, ring[S][0]), sub2(e1, ring[S][1]), sub2(e2, ring[S][2]), mk2(a.norm[0], a.norm[0]), mk2(a.norm[1], a.norm[1]),
+                                 mk2(a.norm[2], a.norm[2])));
+    ring[S][0] = e0;
+    ring[S][1] = e1;
+    ring[S][2] = e2;
+  }
+  // 32 rows of a half plane starting at ring place S0 (R == 1: three places)
+  template <int S0> __device__ __forceinline__ void half(const grp_args_t &a, float *spa, float *spb)
+  {
+    static_assert(R == 1, "the half walk is written for rings of three rows");
+    int r = 0;
+    if(S0 == 2)
+    {
+      step<2>(a, spa, spb);
+      r = 1;
+    }
+    else if(S0 == 1)
+    {
+      step<1>(a, spa, spb);
+      step<2>(a, spa + GRP_SP, spb + GRP_SP);
+      r = 2;
+    }
+    for(; r + 3 <= PIPE2_HROWS; r += 3)
+    {
+      step<0>(a, spa + r * GRP_SP, spb + r * GRP_SP);
+      step<1>(a, spa + (r + 1) * GRP_SP, spb + (r + 1) * GRP_SP);
+      step<2>(a, spa + (r + 2) * GRP_SP, spb + (r + 2) * GRP_SP);
+    }
+    if(r < PIPE2_HROWS) step<0>(a, spa + r * GRP_SP, spb + r * GRP_SP), r++;
+    if(r < PIPE2_HROWS) step<1>(a, spa + r * GRP_SP, spb + r * GRP_SP);
+  }
+};
+// where a chunk takes the half-height pipeline
+__device__ __forceinline__ bool pipe2_takes(const grp_args_t &a, const chunk_t &c, int radius) { return radius == 1 && c.interior && c.ch == 2 * PIPE2_HROWS && a.n_patches >= 2; }
+// phase B1 of one half for lane l of the group's warp 3: rows rr and rr + 16 of patch gi (planes Sa, Sa + PIPE2_HSP hold rows h0 .. h0 + 31)
+template <int R> __device__ __forceinline__ void pipe2_b1(const grp_args_t &a, const chunk_t &c, float *Sa, int p0, int l)
+{
+  const int gi = l >> 4, rr = l & 15;
+  if(p0 + gi >= a.n_patches) return;
+  float *const Sx = Sa + gi * PIPE2_HSP + rr * GRP_SP - c.cbase, *const Sy = Sx + (PIPE2_HROWS / 2) * GRP_SP;
+  pgeo_t g;
+  g.col_min = c.left;
+  g.col_max = c.right;
+  grp_row_pair<R>(Sx, Sy, g);
+}
+
 #ifndef B200_KERNELS_ON_CPU
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -882,6 +987,72 @@ __global__ void __launch_bounds__(pipe_cfg<CFG>::NT, 1) nlm_pipe_kernel(const __
   for(int p = tid; p < a.n_patches; p += NT) shifts[p] = grp_shift<WP>(a, p);
   __syncthreads();
   const int npairs = (a.n_patches + 1) / 2;
+  if constexpr(cfg::HALVES && R == 1)
+  if(pipe2_takes(a, c, R))
+  { // ---- half-height slots (see PIPE2_SLOTS) ----
+    if(tid < 2 * PIPE_SCAN_GROUP)
+    {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(cfg::SCAN_REGS));
+      const int group = tid / PIPE_SCAN_GROUP, t = tid - group * PIPE_SCAN_GROUP;
+      if(t < PIPE2_A_T)
+      {
+        const bool live = t >= 1 && t < c.ncols;
+        for(int q = group; q < npairs; q += 2)
+        {
+          grp_colwalk_t<WP, R, NORM1> walk;
+          if(live) walk.init(a, c, W, 2 * q, t);
+#pragma unroll
+          for(int hh = 0; hh < 2; hh++)
+          {
+            const int w = 2 * q + hh, slot = w % PIPE2_SLOTS;
+            float *const Sa = S + slot * (2 * PIPE2_HSP) + t, *const Sb = Sa + PIPE2_HSP;
+            if(w >= PIPE2_SLOTS) named_sync(PIPE2_BAR_EMPTY + slot, PIPE2_A_T + PIPE2_ACC_HALF);
+            if(live)
+            {
+              if(hh == 0)
+                walk.template half<0>(a, Sa, Sb);
+              else
+                walk.template half<(PIPE2_HROWS % 3)>(a, Sa, Sb);
+            }
+            else if(t == 0)
+              for(int rr = 0; rr < PIPE2_HROWS; rr++) Sa[rr * GRP_SP] = Sb[rr * GRP_SP] = 0.0f; // the column of zeros left of the first live one (:228-231)
+            named_sync(PIPE2_BAR_HANDOVER + group, PIPE_SCAN_GROUP);
+          }
+        }
+      }
+      else
+      {
+        const int l = t - PIPE2_A_T;
+        for(int q = group; q < npairs; q += 2)
+          for(int hh = 0; hh < 2; hh++)
+          {
+            const int slot = (2 * q + hh) % PIPE2_SLOTS;
+            named_sync(PIPE2_BAR_HANDOVER + group, PIPE_SCAN_GROUP);
+            pipe2_b1<R>(a, c, S + slot * (2 * PIPE2_HSP), 2 * q, l);
+            named_arrive(PIPE2_BAR_FULL + slot, 32 + PIPE2_ACC_HALF);
+          }
+      }
+    }
+    else
+    {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(cfg::ACC_REGS));
+      const int ta = tid - 2 * PIPE_SCAN_GROUP, hh = ta / PIPE2_ACC_HALF;
+      grp_strip_t<cfg::KP, cfg::L, cfg::IL> st;
+      grp_own_init<WP>(a, c, W, st, ta);
+      st.sofs0 -= hh * PIPE2_HROWS * GRP_SP; // the planes of a slot start at the half's first row
+      for(int q = 0; q < npairs; q++)
+      {
+        const int w = 2 * q + hh, slot = w % PIPE2_SLOTS;
+        const float *const Sa = S + slot * (2 * PIPE2_HSP);
+        named_sync(PIPE2_BAR_FULL + slot, 32 + PIPE2_ACC_HALF);
+        grp_accumulate_pairs<WP, PROFILED, DIVC>(a, W + shifts[2 * q], Sa, st);
+        if(2 * q + 1 < a.n_patches) grp_accumulate_pairs<WP, PROFILED, DIVC>(a, W + shifts[2 * q + 1], Sa + PIPE2_HSP, st);
+        if(w + PIPE2_SLOTS < 2 * npairs) named_arrive(PIPE2_BAR_EMPTY + slot, PIPE2_A_T + PIPE2_ACC_HALF);
+      }
+      grp_finish(a, c, st, ta, hh * PIPE2_HROWS);
+    }
+    return;
+  }
   if(tid < 2 * PIPE_SCAN_GROUP)
   {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(cfg::SCAN_REGS));

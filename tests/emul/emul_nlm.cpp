@@ -31,6 +31,7 @@ template <int R, int WP, bool NORM1, bool PROFILED, bool DIVC, int KP> static vo
 
 /* the pipelined kernel's order of work: per patch pair, scan group (phase A, then phase B1) into its slot of the ring, then the 256
  * accumulating threads; what the emulation cannot see is the barrier protocol between them */
+extern "C" int emul_nlm_halves_chunks = 0; /* chunks the last calls ran through the half-height slots (the tests check that some did) */
 template <int R, bool NORM1, bool PROFILED, bool DIVC, int CFG> static void run_pipe_chunks(const grp_args_t &a, int n_chunks)
 {
   constexpr int PIPE_NT = pipe_cfg<CFG>::NT, PIPE_ACC_T = pipe_cfg<CFG>::ACC_T, WP = pipe_cfg<CFG>::WP;
@@ -48,6 +49,46 @@ template <int R, bool NORM1, bool PROFILED, bool DIVC, int CFG> static void run_
     for(int t = 0; t < PIPE_NT; t++)
       for(int p = t; p < a.n_patches; p += PIPE_NT) shifts[p] = grp_shift<WP>(a, p);
     for(int t = 0; t < PIPE_ACC_T; t++) grp_own_init<WP>(a, c, W, st[t], t);
+    if(pipe_cfg<CFG>::HALVES && pipe2_takes(a, c, R))
+    { /* the half-height slots: per patch pair, upper then lower half: phase A of the 96 scan threads (their walks carry over), phase B1 of the
+         32 lanes of warp 3, phase B2 of the accumulating half that owns those rows */
+      if constexpr(R == 1)
+      {
+        emul_nlm_halves_chunks++;
+        for(int t = 0; t < PIPE_ACC_T; t++) st[t].sofs0 -= (t / PIPE2_ACC_HALF) * PIPE2_HROWS * GRP_SP;
+        std::vector<grp_colwalk_t<WP, R, NORM1>> walk(PIPE2_A_T);
+        for(int q = 0; q < npairs; q++)
+        {
+          for(int t = 1; t < PIPE2_A_T && t < c.ncols; t++) walk[t].init(a, c, W, 2 * q, t);
+          for(int hh = 0; hh < 2; hh++)
+          {
+            const int slot = (2 * q + hh) % PIPE2_SLOTS;
+            float *const Sh = S + slot * (2 * PIPE2_HSP);
+            for(int t = 0; t < PIPE2_A_T; t++)
+            {
+              float *const Sa = Sh + t, *const Sb = Sa + PIPE2_HSP;
+              if(t >= 1 && t < c.ncols)
+              {
+                if(hh == 0)
+                  walk[t].template half<0>(a, Sa, Sb);
+                else
+                  walk[t].template half<(PIPE2_HROWS % 3)>(a, Sa, Sb);
+              }
+              else if(t == 0)
+                for(int rr = 0; rr < PIPE2_HROWS; rr++) Sa[rr * GRP_SP] = Sb[rr * GRP_SP] = 0.0f;
+            }
+            for(int l = 0; l < 32; l++) pipe2_b1<R>(a, c, Sh, 2 * q, l);
+            for(int t = hh * PIPE2_ACC_HALF; t < (hh + 1) * PIPE2_ACC_HALF; t++)
+            {
+              grp_accumulate_pairs<WP, PROFILED, DIVC>(a, W + shifts[2 * q], Sh, st[t]);
+              if(2 * q + 1 < a.n_patches) grp_accumulate_pairs<WP, PROFILED, DIVC>(a, W + shifts[2 * q + 1], Sh + PIPE2_HSP, st[t]);
+            }
+          }
+        }
+        for(int t = 0; t < PIPE_ACC_T; t++) grp_finish(a, c, st[t], t, (t / PIPE2_ACC_HALF) * PIPE2_HROWS);
+      }
+      continue;
+    }
     for(int q = 0; q < npairs; q++)
     {
       const int slot = q % PIPE_SLOTS;
@@ -123,8 +164,11 @@ extern "C" int emul_nlmeans_group(const float *in, float *out, int width, int he
   if(pipe)
   { /* returns -1 where the pipelined kernel does not take the frame (the launcher then uses the group kernel) */
     if(!grp_pipe_fits(g, smem_bytes, pipe_cfg<0>::WP)) return -1;
-    const int n = n_ct * g.n_cl;
-    radius == 1 ? run_pipe<1, 0>(g, n, norm1, profiled, divc) : run_pipe<2, 0>(g, n, norm1, profiled, divc);
+    const int n = n_ct * g.n_cl; /* pipe: 1 = half-height slots where a chunk takes them, 2 = whole-pair slots everywhere */
+    if(pipe == 2)
+      radius == 1 ? run_pipe<1, 1>(g, n, norm1, profiled, divc) : run_pipe<2, 1>(g, n, norm1, profiled, divc);
+    else
+      radius == 1 ? run_pipe<1, 0>(g, n, norm1, profiled, divc) : run_pipe<2, 0>(g, n, norm1, profiled, divc);
     return g.G;
   }
   if(radius == 1)

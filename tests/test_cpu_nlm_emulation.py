@@ -59,19 +59,27 @@ def test_group_kernel_phases_equal_oracle(emul, size, cfg):
     assert not bad.any(), f"G={G}: {int(bad.sum())} floats differ, first {np.argwhere(bad)[:4].tolist()}"
 
 
+@pytest.mark.parametrize("slots", [1, 2])
 @pytest.mark.parametrize("cfg", range(len(CONFIGS)))
-@pytest.mark.parametrize("size", [(200, 150), (73, 61), (145, 121), (301, 128)])
-def test_pipelined_kernel_phases_equal_oracle(emul, size, cfg):
+@pytest.mark.parametrize("size", [(200, 150), (73, 61), (145, 121), (301, 128), (360, 256), (220, 192)])
+def test_pipelined_kernel_phases_equal_oracle(emul, size, cfg, slots):
     """the same phases in the pipelined kernel's order: a patch pair per slot of the ring, 256 accumulating threads with 9 pixel pairs each
-    (strip ownership)"""
+    (strip ownership).  slots 1: half-height slots in the 64-row chunks of the frame's interior (heights 256 and 192 cut into such chunks; the
+    other sizes, and every chunk on the rim, take the whole-pair slots); slots 2: whole-pair slots everywhere"""
     w, h = size
     img = (util.rgba_scene(w, h, 5, noise=0.02) * 60).astype(np.float32)
     kw = CONFIGS[cfg]
-    G, got = emul_nlm(emul, img, pipe=1, **kw)
+    before = C.c_int.in_dll(emul, "emul_nlm_halves_chunks").value
+    G, got = emul_nlm(emul, img, pipe=slots, **kw)
+    took_halves = C.c_int.in_dll(emul, "emul_nlm_halves_chunks").value - before
     if G == -1:
         pytest.skip("the pipelined kernel does not take this configuration (wide window or tall chunks)")
     bad = ~same_bits(got, util.oracle_nlmeans(img, **kw))
     assert not bad.any(), f"{int(bad.sum())} floats differ, first {np.argwhere(bad)[:4].tolist()}"
+    if slots == 2 or kw.get("P", 1) != 1:
+        assert took_halves == 0
+    elif size in ((360, 256), (220, 192)) and kw.get("K", 7) <= 7 and not kw.get("scattering"):
+        assert took_halves > 0, "no chunk took the half-height slots"
 
 
 @pytest.mark.parametrize("g_cap,ieee", [(2, 0), (4, 1), (6, 0)])

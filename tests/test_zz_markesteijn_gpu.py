@@ -51,6 +51,11 @@ def cuda(ab, m, x, y, method=1025, host=False, smoothing=0):
 def test_markesteijn_bit_exact(built, name, passes):
     m, x, y = mu.case(name)
     method = 1025 if passes == 1 else 1026
+    if min(m.shape) <= (12 if passes == 1 else 17):     # the reference mirrors out of its input there: refused
+        with pytest.raises(built.B200Error) as e:
+            cuda(built, m, x, y, method=method)
+        assert e.value.code == built.B200_ERR_UNSUPPORTED
+        return
     want = mu.oracle(m, x, y, passes)
     got = cuda(built, m, x, y, method=method)
     assert same_bits(got[..., :3], want[..., :3]).all() and (got[..., 3] == -7.0).all()   # lane 3 is not a result: kept as found
