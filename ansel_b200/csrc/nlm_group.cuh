@@ -825,7 +825,8 @@ __global__ void __launch_bounds__(GRP_NT, 1) nlm_group_kernel(const __grid_const
 // (512 threads, launched with 128 registers) or 384 with 6 (640 threads, launched with 96): the second trades instruction-level
 // for thread-level parallelism -- three accumulating warps per scheduler instead of two.
 constexpr int PIPE_SCAN_GROUP = 128, PIPE_SLOTS = 3;
-// Measured on a B200 at 45 MP (K = 7, P = 1; profiles/r02_nlm_pipe_ncu.md): 25.7 ms.  What was tried around this shape and lost:
+// Measured on a B200 at 45 MP (K = 7, P = 1; profiles/r02_nlm_pipe_ncu.md): 25.7 ms with whole-pair slots, 22.7 ms with the half-height
+// slots below.  What was tried around this shape and lost:
 // three pixel pairs in flight in phase B2 (grp_accumulate_pairs<.., IL = 3>: the accumulators get faster, the frame does not -- their
 // loads arrive in bursts in front of the scan warps' loads, and the scan warps are the critical path: 25.7 ms with phase B1 where it
 // is, 28.9 ms before phase B1's loads ran a block ahead); phase B1 on two accumulating warps (the scan groups then run phase A only,
@@ -873,7 +874,8 @@ template <int R> __device__ __forceinline__ void pipe_b1(const grp_args_t &a, co
 // the next half.  The accumulating warps 0..3 own the row pairs of the upper halves, 4..7 those of the lower ones (grp_strip_of), and
 // drain their own sequence of slots.  Barriers: FULL[slot] (warp 3 arrives, one accumulating half waits), EMPTY[slot] (that half arrives,
 // the scan warps that want the slot wait), HANDOVER[group] (scan warps and warp 3 meet: the half is written, and warp 3 is done with the
-// one before).
+// one before).  A slot is filled by the two groups in turn, three pairs apart; the group that fills it next reaches EMPTY[slot] only after it
+// has written a half that needed the other group's previous half consumed, i.e. long after the other group passed the same barrier.
 constexpr int PIPE2_SLOTS = 6, PIPE2_HROWS = 32, PIPE2_HSP = PIPE2_HROWS * GRP_SP; // floats of a half plane
 constexpr int PIPE2_A_T = 96, PIPE2_ACC_HALF = 128;
 constexpr int PIPE2_BAR_FULL = 1, PIPE2_BAR_EMPTY = PIPE2_BAR_FULL + PIPE2_SLOTS, PIPE2_BAR_HANDOVER = PIPE2_BAR_EMPTY + PIPE2_SLOTS; // 1..6, 7..12, 13..14
