@@ -19,6 +19,7 @@ int demosaic_postfilter_dev(float *d_rgba, int width, int height, int iterations
 int downsample4_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters, const double cam_to_rgb[3][4], cudaStream_t s);
 int downsample_xtrans_demosaic_dev(const float *d_in, float *d_out, int width, int height, int x0, int y0, const uint8_t xtrans[6][6], cudaStream_t s);
 int ppg_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters, float median_thrs, cudaStream_t s);
+int lmmse_demosaic_dev(const float *d_in, float *d_out, int width, int height, uint32_t filters, int mode, const float processed_maximum[3], cudaStream_t stream);
 int markesteijn_demosaic_dev(const float *d_in, float *d_out, int width, int height, int x0, int y0, const uint8_t xtrans[6][6], int passes, cudaStream_t stream);
 int demosaic_green_eq_dev(const float *d_in, float *d_tmp0, float *d_tmp1, double *d_partial, int width, int height, uint32_t dsc_filters, int x, int y,
                           unsigned green_eq, float threshold, const float **d_result, cudaStream_t s);
@@ -117,7 +118,7 @@ extern "C" int b200_demosaic_process_dev(const b200_piece_t *piece, const void *
 
   const uint32_t method = d->demosaicing_method & ~(uint32_t)DEMOSAIC_DUAL;
   const bool dual = (d->demosaicing_method & DEMOSAIC_DUAL) != 0;
-  if(method != B200_DEMOSAIC_RCD && method != B200_DEMOSAIC_AMAZE && method != B200_DEMOSAIC_PPG && method != B200_DEMOSAIC_VNG4)
+  if(method != B200_DEMOSAIC_RCD && method != B200_DEMOSAIC_AMAZE && method != B200_DEMOSAIC_PPG && method != B200_DEMOSAIC_VNG4 && method != B200_DEMOSAIC_LMMSE)
     return fail(B200_ERR_UNSUPPORTED, "demosaic: method %u is not built", d->demosaicing_method);
   if(dual && method != B200_DEMOSAIC_RCD && method != B200_DEMOSAIC_AMAZE)
     return fail(B200_ERR_UNSUPPORTED, "demosaic: dual demosaic is RCD + VNG4 or AMaZE + VNG4 (method %u)", d->demosaicing_method);
@@ -140,6 +141,8 @@ extern "C" int b200_demosaic_process_dev(const b200_piece_t *piece, const void *
     rc = vng_demosaic_dev(mosaic, (float *)d_out, width, height, piece->roi_in.x, piece->roi_in.y, piece->filters, nullptr, SLOT_TMP3, s); // demosaic.c:1172-1175
   else if(method == B200_DEMOSAIC_PPG)
     rc = ppg_demosaic_dev(mosaic, (float *)d_out, width, height, filters, d->median_thrs, s); // demosaic.c:1218-1226
+  else if(method == B200_DEMOSAIC_LMMSE)
+    rc = lmmse_demosaic_dev(mosaic, (float *)d_out, width, height, filters, (int)d->lmmse_refine, piece->processed_maximum, s); // demosaic.c:1189-1216
   else if(method == B200_DEMOSAIC_AMAZE)
     rc = amaze_demosaic_dev(mosaic, (float *)d_out, width, height, filters, piece->processed_maximum, s); // demosaic.c:1227
   else
@@ -211,6 +214,12 @@ extern "C" void b200_demosaic_tiling(const b200_piece_t *piece, b200_tiling_t *t
     tiling->yalign = 2;
     tiling->overlap = 10;
     tiling->factor_cl = tiling->factor; // no full-frame temporaries on the device (reference: +3, rcd.c:671-686)
+  }
+  else if(method == B200_DEMOSAIC_LMMSE)
+  { // :1983-1993
+    tiling->xalign = 2;
+    tiling->yalign = 2;
+    tiling->overlap = 10;
   }
   else if(method == B200_DEMOSAIC_AMAZE || method == B200_DEMOSAIC_PPG || method == 3u || method == 4u)
   { // PPG, the passthrough methods, AMaZE :1937-1950

@@ -169,7 +169,8 @@ typedef struct b200_demosaic_data_t
 
 #define B200_DEMOSAIC_DUAL 2048 /* DEMOSAIC_DUAL, iop/demosaic.c:109: or-ed into the method */
 /* process(), iop/demosaic.c:1043-1253: in = 1-channel float mosaic roi_in, out = RGBA float roi_out.  Built for Bayer
- * sensors: RCD (iop/demosaic/rcd.c), AMaZE (amaze.cc), PPG with its optional pre-median (ppg.c, basic.c:136-186;
+ * sensors: RCD (iop/demosaic/rcd.c), AMaZE (amaze.cc), LMMSE (lmmse.c; data->lmmse_refine; every tile from zeroed planes, where the
+ * reference carries them from tile to tile: DESIGN.md row f12), PPG with its optional pre-median (ppg.c, basic.c:136-186;
  * data->median_thrs), VNG4 (vng.c, basic.c lin_interpolate), the dual demosaic RCD|DUAL and AMaZE|DUAL (dual.c: blend with
  * VNG4 under the detail mask of develop/masks/detail.c; data->dual_thrs, piece->wb_coeffs), green equilibration in front
  * (data->green_eq) and median colour smoothing behind (data->color_smoothing); the two passthrough methods (3 monochrome,
@@ -177,7 +178,7 @@ typedef struct b200_demosaic_data_t
  * (method 1025, the default of X-Trans frames; markesteijn.c:47-521) or three (method 1026) and VNG (method 1024, the X-Trans branch of vng.c); the
  * half-size downsample (method 7, iop/demosaic.c:480-532 Bayer, :543-666 X-Trans; roi_out =
  * (roi_in + 1) / 2; four-colour Bayer sensors through data->CAM_to_RGB) and its guided-Laplacian post-filter (:681-926;
- * data->color_smoothing iterations).  LMMSE, FDC, Markesteijn 3-pass + VNG, the full-size demosaicers on four-colour Bayer sensors and
+ * data->color_smoothing iterations).  FDC, Markesteijn 3-pass + VNG, the full-size demosaicers on four-colour Bayer sensors and
  * the GUI's mask display return B200_ERR_UNSUPPORTED. */
 int b200_demosaic_process_host(const b200_piece_t *piece, const void *in, void *out);
 /* process_cl() slot, iop/demosaic/rcd.c:568-850: device pointers, `stream` is a cudaStream_t (NULL = default) */

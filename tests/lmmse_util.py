@@ -39,3 +39,28 @@ def oracle(m, filters, mode, carry=0):
 def ref(m, filters, mode, kind="strict"):
     lib = util.ref(kind)
     return None if lib is None else _run(lib, "ref_lmmse", m, filters, mode)
+
+
+_EMUL = None
+
+
+def emul(m, filters, mode, nthreads=96, ascending=0):
+    """ansel_b200/csrc/lmmse.cu compiled with g++ (tests/emul/emul_lmmse.cpp): the stages thread by thread, tile after tile"""
+    global _EMUL
+    if _EMUL is None:
+        import os
+        import subprocess
+        here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul")
+        so = os.path.join(here, "libemul_lmmse.so")
+        srcs = [os.path.join(here, "emul_lmmse.cpp"), os.path.join(here, "cuda_on_cpu.h"), os.path.join(here, "..", "..", "ansel_b200", "csrc", "lmmse.cu")]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.run(["g++", "-O1", "-std=c++17", "-fno-fast-math", "-ffp-contract=off", "-I", here, "-shared", "-fPIC", "-o", so, srcs[0]], check=True)
+        _EMUL = C.CDLL(so)
+    h, w = m.shape
+    out, src = util.aligned_empty((h, w, 4)), util.aligned_empty(m.shape)
+    out[...] = -7.0
+    src[...] = m
+    f = _EMUL.emul_lmmse
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int]
+    assert f(out.ctypes.data, src.ctypes.data, w, h, filters, mode, (C.c_float * 3)(*PMAX), nthreads, ascending) == 0
+    return np.array(out)
