@@ -298,7 +298,8 @@ def test_packed_fp32_is_never_contracted_in_the_nlm_group_kernel(built):
 
 def test_packed_fp32_is_never_contracted_in_the_nlm_pipe_kernel(built):
     """the same for the pipelined kernel: the accumulation of a patch is inlined four times (two patches of a pair, in the loop of interior
-    chunks and in the loop of edge chunks), Markstein's two FFMA2 per owned pixel pair each, 9 pairs per thread"""
+    chunks and in the loop of edge chunks) -- six times where the half-height slots are compiled in (radius 1, shape 0) -- with Markstein's two
+    FFMA2 per owned pixel pair each, 9 pairs per thread"""
     so = os.path.join(ROOT, "ansel_b200", "libb200iop.so")
     r = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-300:]
@@ -310,7 +311,8 @@ def test_packed_fp32_is_never_contracted_in_the_nlm_pipe_kernel(built):
             continue
         seen += 1
         divc, kp = m.group(4) == "1", 9
-        assert len(re.findall(r"\bFFMA2\b", body)) == (8 * kp if divc else 0), name
+        inlined = 6 if (m.group(1) == "1" and m.group(5) == "0") else 4
+        assert len(re.findall(r"\bFFMA2\b", body)) == (2 * inlined * kp if divc else 0), name
         assert len(re.findall(r"\bFMUL2\b", body)) > 0 and len(re.findall(r"\bFADD2\b", body)) > 0, name
     assert seen >= 12
 
