@@ -171,7 +171,10 @@ int b200::device_curves(const float *const host[3], uint64_t identity, int side,
   }
   for(int c = 0; c < 3; c++)
     B200_CUDA_TRY(cudaMemcpyAsync(g_luts[slot].d + (size_t)c * LUTN, host[c], sizeof(float) * LUTN, cudaMemcpyHostToDevice, stream));
-  // pageable sources are staged synchronously by the runtime, so the host arrays may change after return
+  // The entry is published to every stream of this device, so the upload has to have landed first: another pipe (preview and
+  // full start together, each on its own non-blocking stream) may hit the cache and launch before this stream got to the copy.
+  // Once per profile; it also makes pinned host arrays safe to change after return.
+  B200_CUDA_TRY(cudaStreamSynchronize(stream));
   g_luts[slot].identity = identity;
   g_luts[slot].dev = dev;
   g_luts[slot].side = side;

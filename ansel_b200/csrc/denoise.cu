@@ -568,6 +568,13 @@ int denoise_vst_backward(const b200_piece_t *piece, const b200_denoiseprofile_da
   B200_CUDA_TRY(cudaGetLastError());
   return B200_OK;
 }
+// dt_iop_alpha_copy() as both modes of denoiseprofile end with it when a mask is displayed (denoiseprofile.c:1645-1646)
+int denoise_alpha_copy(const float *d_in, float *d_out, size_t npx, cudaStream_t s)
+{
+  copy_alpha_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, s>>>((const float4 *)d_in, (float4 *)d_out, npx);
+  B200_CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
 } // namespace b200
 
 using namespace b200;

@@ -928,6 +928,7 @@ int denoise_vst_forward(const b200_piece_t *piece, const b200_denoiseprofile_dat
                         size_t npx, bool nlm, cudaStream_t s);
 int denoise_vst_backward(const b200_piece_t *piece, const b200_denoiseprofile_data_t *d, float *d_buf, size_t npx, bool nlm,
                          cudaStream_t s);
+int denoise_alpha_copy(const float *d_in, float *d_out, size_t npx, cudaStream_t s);
 
 // process_nlmeans_cpu(), denoiseprofile.c:1599-1648
 int denoiseprofile_nlmeans_dev(const b200_piece_t *piece, const b200_denoiseprofile_data_t *d, const float *d_in, float *d_out,
@@ -968,7 +969,9 @@ int denoiseprofile_nlmeans_dev(const b200_piece_t *piece, const b200_denoiseprof
   if((rc = nlmeans_denoise_dev((const float *)pre, d_out, width, height, scattering, scale, 1.0f, 1.0f, central_pixel_weight, norm, P,
                                K, 0, norm2, s)))
     return rc;
-  return denoise_vst_backward(piece, d, d_out, npx, true, s);
+  if((rc = denoise_vst_backward(piece, d, d_out, npx, true, s))) return rc;
+  if(piece->mask_display & B200_DISPLAY_MASK) return denoise_alpha_copy(d_in, d_out, npx, s); // :1645-1646
+  return B200_OK;
 }
 } // namespace b200
 #endif // B200_KERNELS_ON_CPU

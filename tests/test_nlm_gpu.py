@@ -44,12 +44,13 @@ def test_nlmeans_core_bit_exact(built, size, cfg):
     assert not bad.any(), f"{int(bad.sum())} floats differ, first {np.argwhere(bad)[:4].tolist()}"
 
 
-def run_module(img, data, pipe_type=1):
+def run_module(img, data, pipe_type=1, mask_display=0):
     import torch
     import ansel_b200 as ab
     ab.init()
     h, w = img.shape[:2]
     piece = ab.make_piece(w, h, filters=0, channels=4, data=data, devid=0, pipe_type=pipe_type)
+    piece.mask_display = mask_display
     d_in = torch.from_numpy(img).cuda()
     d_out = torch.zeros_like(d_in)
     ab.check(ab.lib().b200_denoiseprofile_process_dev(piece, d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream))
@@ -76,6 +77,19 @@ def test_denoiseprofile_nlmeans_module_bit_exact(built, new_vst, pipe):
     want = oracle_module(img, data, pipe)
     assert same_bits(got, want).all()
     assert np.abs(np.diff(got[..., 1], axis=1)).mean() < 0.9 * np.abs(np.diff(img[..., 1], axis=1)).mean()
+
+
+def test_denoiseprofile_nlmeans_keeps_the_alpha_of_a_displayed_mask(built):
+    """process_nlmeans_cpu() ends with dt_iop_alpha_copy() when the pipe displays a mask (denoiseprofile.c:1645-1646)."""
+    import ansel_b200 as ab
+    img = util.rgba_scene(300, 200, 6)
+    img[..., 3] = np.random.default_rng(6).random((200, 300), dtype=np.float32)
+    data = ab.denoiseprofile_data(ab.DENOISE_NLMEANS)
+    shown = run_module(img, data, mask_display=1)
+    plain = run_module(img, data)
+    assert same_bits(shown[..., 3], img[..., 3]).all()
+    assert same_bits(shown[..., :3], plain[..., :3]).all()
+    assert same_bits(plain, oracle_module(img, data)).all()
 
 
 def test_nlmeans_24mp_bit_exact(built):

@@ -111,11 +111,12 @@ def test_rcd_unsupported_is_loud(built):
     import ansel_b200 as ab
     ab.init()
     m = util.frame_uniform(64, 64, 1)
-    data = ab.demosaic_data(ab.DEMOSAIC_LMMSE)          # PPG, VNG4 and the dual blends are built; LMMSE and X-Trans are not
+    data = ab.demosaic_data(1028)                       # an X-Trans method (frequency-domain chroma) on a Bayer frame
     piece = ab.make_piece(64, 64, data=data, devid=0)
     out = np.zeros((64, 64, 4), np.float32)
     rc = ab.lib().b200_demosaic_process_host(piece, m.ctypes.data, out.ctypes.data)
     assert rc == ab.B200_ERR_UNSUPPORTED
+    assert (out == 0).all() and b"not built" in ab.lib().b200_last_error()
 
 
 @pytest.mark.parametrize("size", [util.SIZE_24MP, util.SIZE_45MP])
