@@ -219,6 +219,7 @@ def lib() -> C.CDLL:
             getattr(L, f"b200_{op}_process_dev").argtypes = [C.POINTER(Piece), C.c_void_p, C.c_void_p, C.c_void_p]
             getattr(L, f"b200_{op}_tiling").argtypes = [C.POINTER(Piece), C.POINTER(Tiling)]
             getattr(L, f"b200_{op}_tiling").restype = None
+        L.b200_highlights_laplacian_dev.argtypes = [C.POINTER(Piece), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.b200_rawfront_process_dev.argtypes = [C.POINTER(Piece), C.POINTER(Piece), C.POINTER(Piece), C.c_void_p, C.c_void_p, C.c_void_p]
         L.b200_resampling_plan.argtypes = [C.c_int] * 5 + [C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.b200_basebuffer_upload_dev.argtypes = [C.POINTER(Piece), C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]

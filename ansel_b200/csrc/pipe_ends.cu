@@ -916,6 +916,11 @@ extern "C" int b200_temperature_process_host(const b200_piece_t *piece, const vo
 extern "C" void b200_temperature_tiling(const b200_piece_t *piece, b200_tiling_t *t) { default_tiling(piece, t, false, true); }
 
 // ---- highlights --------------------------------------------------------------------------------------------------------------
+namespace b200
+{ // highlights_laplacian.cu
+int highlights_laplacian_dev(const b200_piece_t *piece, const b200_highlights_data_t *d, const void *d_in, void *d_out, const float clips[4],
+                             const float *normalization, cudaStream_t s);
+}
 extern "C" int b200_highlights_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream)
 {
   int rc = check_piece("highlights", piece, d_in, d_out, sizeof(b200_highlights_data_t));
@@ -1002,12 +1007,25 @@ extern "C" int b200_highlights_process_dev(const b200_piece_t *piece, const void
   unsigned long long n_clipped = 0;
   B200_CUDA_TRY(cudaMemcpyAsync(&n_clipped, counter, sizeof(n_clipped), cudaMemcpyDeviceToHost, s));
   B200_CUDA_TRY(cudaStreamSynchronize(s));
+  if(n_clipped >= 25ull && d->mode == B200_HIGHLIGHTS_LAPLACIAN) // process() :759-769: the thresholds of the count are the clips it hands over
+    return highlights_laplacian_dev(piece, d, d_in, d_out, thresholds, nullptr, s);
   if(n_clipped >= 25ull)
-    return fail(B200_ERR_UNSUPPORTED, "highlights: mode %d with %llu clipped samples (only clip mode and the bypass of the reconstruction modes are built)",
-                d->mode, n_clipped);
+    return fail(B200_ERR_UNSUPPORTED, "highlights: mode %d with %llu clipped samples (harmonic transposition is not built, only its bypass)", d->mode,
+                n_clipped);
   flat_kernel<OP_COPY><<<flat_grid(n), NT, 0, s>>>((const float *)d_in, (float *)d_out, n, 0.0f, 0.0f, 0, counter);
   B200_CUDA_TRY(cudaGetLastError());
   return B200_OK;
+}
+extern "C" int b200_highlights_laplacian_dev(const b200_piece_t *piece, const void *d_in, void *d_out, const float *normalization, void *stream)
+{
+  int rc = check_piece("highlights", piece, d_in, d_out, sizeof(b200_highlights_data_t));
+  if(rc) return rc;
+  if((rc = bind_device(piece->devid))) return rc;
+  const b200_highlights_data_t *d = (const b200_highlights_data_t *)piece->data;
+  if(d->mode != B200_HIGHLIGHTS_LAPLACIAN) return fail(B200_ERR_ARG, "highlights: mode %d is not the guided laplacians", d->mode);
+  float thresholds[4], clip;
+  make_thresholds(piece, thresholds, &clip);
+  return highlights_laplacian_dev(piece, d, d_in, d_out, thresholds, normalization, (cudaStream_t)stream);
 }
 extern "C" int b200_highlights_process_host(const b200_piece_t *piece, const void *in, void *out)
 {

@@ -398,6 +398,10 @@ def pipe_ends_extras(ab, ds, util, L, M, torch, w, h, local, dev, stream, conv_i
     report("bilat_bilateral_grid_sigma50", lambda: ab.check(L.b200_bilat_process_dev(p_bl, t_lab.data_ptr(), t_out.data_ptr(), stream)), 32, reps=3)
     p_hi = piece(ab.highlights_data(ab.HIGHLIGHTS_INPAINT, 1.0), 1, pmax=pm)
     report("highlights_inpaint", lambda: ab.check(L.b200_highlights_process_dev(p_hi, t_m[1].data_ptr(), t_m[0].data_ptr(), stream)), 8, reps=3)
+    hd = ab.highlights_data(ab.HIGHLIGHTS_LAPLACIAN, 1.0)     # iop/highlights/common.h:466-468: 30 iterations, diameter parameter 8
+    hd.iterations, hd.scales = 30, 8
+    p_hg = piece(hd, 1, pmax=pm)
+    report("highlights_guided_laplacians_30it", lambda: ab.check(L.b200_highlights_process_dev(p_hg, t_m[1].data_ptr(), t_m[0].data_ptr(), stream)), 8, reps=3)
     p_lm = piece(ab.demosaic_data(6), 1, pmax=pm)
     C.cast(p_lm.data, C.POINTER(ab.DemosaicData)).contents.lmmse_refine = 1
     report("demosaic_lmmse_median", lambda: ab.check(L.b200_demosaic_process_dev(p_lm, t_m[0].data_ptr(), t_dem.data_ptr(), stream)), 20, reps=3)

@@ -23,11 +23,9 @@ typedef struct dt_iop_highlights_gui_data_t { int show_visualize; } dt_iop_highl
 /* develop/imageop.c:139-142 -> imageio/imageio_rawspeed.cc:146-151 -> rawspeed's ColorFilterArray::shiftDcrawFilter
  * (third party, not under /root/reference/src; ColorFilterArray.cpp:143-170 restated): an odd x swaps the two colours of
  * every row pair of the 8x2 pattern word, y rotates it by four bits per row */
-static inline uint32_t dt_dev_get_roi_filters(const dt_dev_pixelpipe_iop_t *piece, const dt_iop_roi_t *roi)
+uint32_t ref_roi_filters(uint32_t filters, int x, int y)
 {
-  uint32_t filters = piece->dsc_in.filters;
   if(!filters || filters == 9u) return filters;
-  int x = roi->x, y = roi->y;
   if(abs(x) & 1)
     for(int n = 0; n < 8; n++)
     {
@@ -40,6 +38,10 @@ static inline uint32_t dt_dev_get_roi_filters(const dt_dev_pixelpipe_iop_t *piec
   y = y >= 0 ? y % 32 : 32 - ((-y) % 32);
   if(y != 0 && y != 32) filters = (filters >> y) | (filters << (32 - y));
   return filters;
+}
+static inline uint32_t dt_dev_get_roi_filters(const dt_dev_pixelpipe_iop_t *piece, const dt_iop_roi_t *roi)
+{
+  return ref_roi_filters(piece->dsc_in.filters, roi->x, roi->y);
 }
 #define NOT_BUILT(name) do { fprintf(stderr, "oracle/_ref: highlights %s is not built\n", name); abort(); } while(0)
 #define process_visualize(...) NOT_BUILT("process_visualize")

@@ -30,6 +30,9 @@ static inline int orc_fc(size_t row, size_t col, uint32_t filters)
 void orc_fp_fast_mode(void);
 void orc_fp_fast_mode_all(void);
 
+/* dt_dev_get_roi_filters (develop/imageop.c:139-142): the CFA word seen from a ROI origin (pipe_ends_oracle.c) */
+uint32_t orc_roi_filters(uint32_t filters, int x, int y);
+
 #ifdef __cplusplus
 }
 #endif

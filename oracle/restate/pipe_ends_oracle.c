@@ -137,7 +137,7 @@ int orc_temperature(const b200_piece_t *piece, const float *in, float *out)
 /* dt_dev_get_roi_filters (develop/imageop.c:139-142): the CFA word seen from the ROI origin.  The shift itself is
  * rawspeed's ColorFilterArray::shiftDcrawFilter (third party, pinned submodule external/rawspeed; ColorFilterArray.cpp:
  * 143-170), restated: odd x swaps the colours of each horizontal pair, y rotates by one row (four bits) per step. */
-static uint32_t roi_filters(uint32_t filters, int x, int y)
+uint32_t orc_roi_filters(uint32_t filters, int x, int y)
 {
   if(!filters || filters == 9u) return filters;
   if((x < 0 ? -x : x) & 1)
@@ -449,7 +449,7 @@ int orc_highlights(const b200_piece_t *piece, const float *in, float *out, size_
   { /* process() :735-746 */
     const float clips[4] = { 0.987f * data->clip * pmax[0], 0.987f * data->clip * pmax[1], 0.987f * data->clip * pmax[2], clip };
     const int w = piece->roi_out.width, h = piece->roi_out.height;
-    const uint32_t shifted = roi_filters(filters, piece->roi_in.x, piece->roi_in.y); /* :691 */
+    const uint32_t shifted = orc_roi_filters(filters, piece->roi_in.x, piece->roi_in.y); /* :691 */
     for(int j = 0; j < h; j++)
     {
       interpolate_color(in, out, w, h, 0, 1, j, clips, shifted, 0);

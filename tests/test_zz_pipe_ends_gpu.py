@@ -81,14 +81,16 @@ def test_highlights_bit_exact(built, name):
         assert rc == 0 and same_bits(got, want).all(), run.__name__
 
 
-def test_highlights_refuses_reconstruction_past_the_bypass(built):
+def test_highlights_refuses_harmonic_transposition_past_the_bypass(built):
     import ansel_b200 as ab
     _, img = cases.highlights_case("clip_mosaic")
-    for mode in (ab.HIGHLIGHTS_LAPLACIAN, ab.HIGHLIGHTS_HARMONIC):
-        piece = pe.mosaic_piece(img.shape[1], img.shape[0], ab.highlights_data(mode, 1.0))
-        rc, got = run_dev("highlights", piece, img, img.shape)
-        assert rc == ab.B200_ERR_UNSUPPORTED and b"clipped" in ab.lib().b200_last_error()
-        assert (got == -7.0).all()       # nothing written
+    piece = pe.mosaic_piece(img.shape[1], img.shape[0], ab.highlights_data(ab.HIGHLIGHTS_HARMONIC, 1.0))
+    rc, got = run_dev("highlights", piece, img, img.shape)
+    assert rc == ab.B200_ERR_UNSUPPORTED and b"clipped" in ab.lib().b200_last_error()
+    assert (got == -7.0).all()       # nothing written
+    piece = pe.mosaic_piece(img.shape[1], img.shape[0], ab.highlights_data(ab.HIGHLIGHTS_LAPLACIAN, 1.0))     # built: tests/test_zz_hl_laplacian_gpu.py
+    rc, got = run_dev("highlights", piece, img, img.shape)
+    assert rc == 0 and np.isfinite(got).all() and (got != img).any()
 
 
 def test_highlights_count_is_fresh_on_every_call(built):

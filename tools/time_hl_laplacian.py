@@ -1,0 +1,20 @@
+"""Development timing of highlights' guided laplacians at 45 MP (not the bench contract): usage  time_hl_laplacian.py [iterations [scales]]"""
+import sys, ctypes as C, os
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests")); sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np, torch, util, ansel_b200 as ab
+import hl_laplacian_util as hu
+ab.init()
+w, h = util.SIZE_45MP
+iterations = int(sys.argv[1]) if len(sys.argv) > 1 else 30      # iop/highlights/common.h:467-468: 30 iterations, scales parameter 8
+scales = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+img = hu.clipped_mosaic(w, h, 45, blobs=9)
+piece, d = hu.piece_of(ab, img, util.BAYER["RGGB"], iterations=iterations, scales=scales)
+m = torch.from_numpy(img).cuda()
+out = torch.empty_like(m)
+s = torch.cuda.current_stream().cuda_stream
+def run(): ab.check(ab.lib().b200_highlights_process_dev(piece, m.data_ptr(), out.data_ptr(), s))
+run(); torch.cuda.synchronize(); ts = []
+for _ in range(5):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); run(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+print(f"highlights guided laplacians 45MP, {iterations} iterations, scales {scales}: median ms {np.median(ts):.2f}  MP/s {w*h/np.median(ts)/1e3:.0f}")
