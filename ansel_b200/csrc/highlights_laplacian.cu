@@ -688,7 +688,7 @@ int highlights_laplacian_dev(const b200_piece_t *piece, const b200_highlights_da
         J.xt.v[r][c] = v;
       }
   for(int c = 0; c < 4; c++) J.clips.v[c] = clips[c];
-  const float module_scale = piece->iscale / (float)piece->roi_in.scale; // dt_dev_get_module_scale, develop/imageop.c:134-137
+  const float module_scale = (float)((double)piece->iscale / piece->roi_in.scale); // dt_dev_get_module_scale, develop/imageop.c:134-137: a double quotient
   J.iterations = d->iterations;
   J.scales = hl_scales(d->scales, module_scale);
   J.noise_level = d->noise_level / (DS_FACTOR * module_scale);
