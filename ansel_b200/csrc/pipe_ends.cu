@@ -279,40 +279,46 @@ __global__ void __launch_bounds__(NT) count_pixels_kernel(const float *__restric
 }
 
 // ---- highlights, colour inpainting on a Bayer mosaic (iop/highlights/inpaint.c:63-82, lch.c interpolate_color :206-303) ----
-// Along a line, a running ratio between neighbouring sites (decayed over unclipped pairs) restores a clipped sample from
-// its neighbour; the four directions are averaged.  Each line is a serial recurrence, the lines are independent: one
-// thread per row runs passes 0 and 1, then one thread per column runs passes 2 and 3.
+// Along a line, a running ratio between neighbouring sites (decayed over unclipped pairs) restores a clipped sample from its
+// neighbour; the four directions (along the row both ways, along the column both ways) are summed in that order and divided by four.
+// Each line of each direction is a serial recurrence, and nothing else is: the four directions run at once, one thread per line
+// (2 x height + 2 x width threads), each into a plane of its own, and a pointwise pass sums the planes in the reference's order.
+// A thread per ROW would make a warp touch 32 rows at once, so the row directions run on a transposed copy of the mosaic where
+// neighbouring rows are neighbouring addresses, like the columns of the frame itself; their two planes come back through a second
+// transposition that already adds them.  The operands of eight steps are fetched ahead of the recurrence.
 struct inpaint_t
 {
   float clips[4]; // 0.987 * clip * processed_maximum per colour
   unsigned filters; // ROI-shifted
   int width, height;
 };
-__device__ void inpaint_line(const float *__restrict__ ivoid, float *__restrict__ ovoid, const inpaint_t &A, int dim, int dir, int other, int pass)
+// one direction of one line.  dim 0: along row `other`, dim 1: down column `other`; (si, sj) = the strides of a column step and of a
+// row step in `in` and `plane`.  Only clipped sites are written (what the reference adds to its output there).
+__device__ void inpaint_chain(const float *__restrict__ in, float *__restrict__ plane, const inpaint_t &A, ptrdiff_t si, ptrdiff_t sj, int dim, int dir, int other)
 {
+  const int n = dim ? A.height : A.width, n_other = dim ? A.width : A.height;
+  if(other == 0 || other == n_other - 1) return; // a border line :232-235
+  const ptrdiff_t step = dim ? sj : si, line = (ptrdiff_t)other * (dim ? si : sj);
+  const int beg = dir == 1 ? 0 : n - 1;
   float ratio = 1.0f;
-  int i = dim ? other : 0, j = dim ? 0 : other;
-  const ptrdiff_t offs = (ptrdiff_t)(dim ? A.width : 1) * dir;
-  const int n = dim ? A.height : A.width;
-  const int beg = dir == 1 ? 0 : n - 1, end = dir == 1 ? n : -1;
-  const size_t first = dim ? i + (size_t)beg * A.width : beg + (size_t)j * A.width;
-  const float *in = ivoid + first;
-  float *out = ovoid + first;
-  for(int k = beg; k != end; k += dir)
+  for(int base = 0; base < n; base += 8)
   {
-    if(dim == 1)
-      j = k;
-    else
-      i = k;
-    if(i == 0 || i == A.width - 1 || j == 0 || j == A.height - 1)
+    float v[9];
+#pragma unroll
+    for(int m = 0; m < 9; m++)
     {
-      if(pass == 3) out[0] = in[0];
+      const int k = beg + min(base + m, n - 1) * dir;
+      v[m] = __ldg(in + line + (ptrdiff_t)k * step);
     }
-    else
+#pragma unroll
+    for(int m = 0; m < 8; m++)
     {
+      const int k = beg + (base + m) * dir;
+      if(base + m >= n || k == 0 || k == n - 1) continue; // the ends of the line are border sites
+      const int i = dim ? other : k, j = dim ? k : other;
       const float clip0 = pick4(A.clips, fc(j, i, A.filters));
       const float clip1 = pick4(A.clips, fc(dim ? (j + 1) : j, dim ? i : (i + 1), A.filters));
-      const float v0 = in[0], v1 = in[offs];
+      const float v0 = v[m], v1 = v[m + 1];
       if(v0 < clip0 && v0 > 1e-5f && v1 < clip1 && v1 > 1e-5f)
       { // both unclipped: ratio = in[odd] / in[even], exponential decay
         if(k & 1)
@@ -329,39 +335,68 @@ __device__ void inpaint_line(const float *__restrict__ ivoid, float *__restrict_
           add = v1 * ratio;
         else
           add = v1 / ratio;
-        if(pass == 0)
-          out[0] = add;
-        else if(pass == 3)
-          out[0] = (out[0] + add) / 4.0f;
-        else
-          out[0] += add;
+        plane[line + (ptrdiff_t)k * step] = add;
       }
-      else if(pass == 3)
-        out[0] = v0;
     }
-    out += offs;
-    in += offs;
   }
 }
-// `counter`: the clipped-sample count of the bypass test; under 25 the frame is copied through (by the column kernel)
-__global__ void __launch_bounds__(128) inpaint_rows_kernel(const float *__restrict__ in, float *__restrict__ out, inpaint_t A, const unsigned long long *counter)
+// `counter`: the clipped-sample count of the bypass test; under 25 the frame is copied through (by the last kernel) and nothing else runs
+// grid.y = the direction.  Rows: on the transposed mosaic (site (i, j) at i * height + j)
+__global__ void __launch_bounds__(128) inpaint_rows_kernel(const float *__restrict__ t_in, float *__restrict__ t_fwd, float *__restrict__ t_bwd, inpaint_t A,
+                                                           const unsigned long long *counter)
 {
   const int j = blockIdx.x * 128 + threadIdx.x;
   if(j >= A.height || *counter < 25ull) return;
-  inpaint_line(in, out, A, 0, 1, j, 0);
-  inpaint_line(in, out, A, 0, -1, j, 1);
+  inpaint_chain(t_in, blockIdx.y ? t_bwd : t_fwd, A, A.height, 1, 0, blockIdx.y ? -1 : 1, j);
 }
-__global__ void __launch_bounds__(128) inpaint_cols_kernel(const float *__restrict__ in, float *__restrict__ out, inpaint_t A, const unsigned long long *counter)
+__global__ void __launch_bounds__(128) inpaint_cols_kernel(const float *__restrict__ in, float *__restrict__ down, float *__restrict__ up, inpaint_t A,
+                                                           const unsigned long long *counter)
 {
   const int i = blockIdx.x * 128 + threadIdx.x;
-  if(i >= A.width) return;
-  if(*counter < 25ull)
+  if(i >= A.width || *counter < 25ull) return;
+  inpaint_chain(in, blockIdx.y ? up : down, A, 1, A.width, 1, blockIdx.y ? -1 : 1, i);
+}
+// out[x][y] = a[y][x] (+ b[y][x]): `a` has `cols` floats per row and `rows` rows.  32x32 tiles, block (32, 8).
+template <bool ADD>
+__global__ void __launch_bounds__(256) transpose_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out, int cols, int rows,
+                                                        const unsigned long long *counter)
+{
+  if(*counter < 25ull) return;
+#ifdef B200_KERNELS_ON_CPU // the harness runs threads one after the other: no staging through shared memory there
+  const int x = (int)blockIdx.x * 32 + (int)threadIdx.x % 32, y0 = (int)blockIdx.y * 32;
+  for(int y = y0 + (int)threadIdx.x / 32; y < min(y0 + 32, rows); y += 8)
+    if(x < cols) out[(size_t)x * rows + y] = ADD ? a[(size_t)y * cols + x] + b[(size_t)y * cols + x] : a[(size_t)y * cols + x];
+#else
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const int x = blockIdx.x * 32 + tx;
+  for(int r = ty; r < 32; r += 8)
   {
-    for(int j = 0; j < A.height; j++) out[(size_t)j * A.width + i] = in[(size_t)j * A.width + i];
-    return;
+    const int y = blockIdx.y * 32 + r;
+    if(x < cols && y < rows) tile[r][tx] = ADD ? __ldg(a + (size_t)y * cols + x) + __ldg(b + (size_t)y * cols + x) : __ldg(a + (size_t)y * cols + x);
   }
-  inpaint_line(in, out, A, 1, 1, i, 2);
-  inpaint_line(in, out, A, 1, -1, i, 3);
+  __syncthreads();
+  const int oy = blockIdx.y * 32 + tx; // the source row this lane writes
+  for(int r = ty; r < 32; r += 8)
+  {
+    const int ox = blockIdx.x * 32 + r;
+    if(ox < cols && oy < rows) out[(size_t)ox * rows + oy] = tile[tx][r];
+  }
+#endif
+}
+// the sum of the four directions in the reference's order, ((rows forward + rows backward) + down) + up, a quarter of it at the clipped
+// sites, the input elsewhere (:232-235, :290-299).  `down` may be `out`.
+__global__ void __launch_bounds__(NT) inpaint_sum_kernel(const float *__restrict__ in, const float *__restrict__ rows, const float *down, const float *__restrict__ up,
+                                                         float *out, inpaint_t A, const unsigned long long *counter)
+{
+  const int i = blockIdx.x * NT + threadIdx.x, j = blockIdx.y;
+  if(i >= A.width) return;
+  const size_t p = (size_t)j * A.width + i;
+  const float v0 = __ldg(in + p);
+  float o = v0;
+  if(*counter >= 25ull && i > 0 && i < A.width - 1 && j > 0 && j < A.height - 1 && v0 >= pick4(A.clips, fc(j, i, A.filters)) - 1e-5f)
+    o = (((__ldg(rows + p)) + down[p]) + __ldg(up + p)) / 4.0f;
+  out[p] = o;
 }
 
 // ---- highlights, LCh reconstruction on a Bayer mosaic (iop/highlights/lch.c:315-411) --------------------------------------------
@@ -997,9 +1032,20 @@ extern "C" int b200_highlights_process_dev(const b200_piece_t *piece, const void
     for(int c = 0; c < 4; c++) pmax[c] = (piece->processed_maximum[c] > 0.f) ? piece->processed_maximum[c] : 1.0f;
     inpaint_t A = { { 0.987f * d->clip * pmax[0], 0.987f * d->clip * pmax[1], 0.987f * d->clip * pmax[2], clip },
                     b200_roi_filters(piece->filters, piece->roi_in.x, piece->roi_in.y), width, height };
-    inpaint_rows_kernel<<<(unsigned)((height + 127) / 128), 128, 0, s>>>((const float *)d_in, (float *)d_out, A, counter);
+    void *t[4];
+    for(int k = 0; k < 4; k++)
+      if((rc = scratch(SLOT_TMP0 + k, npx * sizeof(float), &t[k]))) return rc;
+    float *t_in = (float *)t[0], *t_fwd = (float *)t[1], *t_bwd = (float *)t[2], *up = (float *)t[3], *rows = t_in, *down = (float *)d_out;
+    const dim3 tiles((unsigned)((width + 31) / 32), (unsigned)((height + 31) / 32)), tiles_t((unsigned)((height + 31) / 32), (unsigned)((width + 31) / 32));
+    transpose_kernel<false><<<tiles, 256, 0, s>>>((const float *)d_in, nullptr, t_in, width, height, counter);
     B200_CUDA_TRY(cudaGetLastError());
-    inpaint_cols_kernel<<<(unsigned)((width + 127) / 128), 128, 0, s>>>((const float *)d_in, (float *)d_out, A, counter);
+    inpaint_rows_kernel<<<dim3((unsigned)((height + 127) / 128), 2), 128, 0, s>>>(t_in, t_fwd, t_bwd, A, counter);
+    B200_CUDA_TRY(cudaGetLastError());
+    inpaint_cols_kernel<<<dim3((unsigned)((width + 127) / 128), 2), 128, 0, s>>>((const float *)d_in, down, up, A, counter);
+    B200_CUDA_TRY(cudaGetLastError());
+    transpose_kernel<true><<<tiles_t, 256, 0, s>>>(t_fwd, t_bwd, rows, height, width, counter); // back to the frame's layout, the two row directions added
+    B200_CUDA_TRY(cudaGetLastError());
+    inpaint_sum_kernel<<<dim3((unsigned)((width + NT - 1) / NT), (unsigned)height), NT, 0, s>>>((const float *)d_in, rows, down, up, (float *)d_out, A, counter);
     B200_CUDA_TRY(cudaGetLastError());
     return B200_OK;
   }

@@ -571,15 +571,15 @@ typedef struct b200_highlights_data_t
  * process_lch_xtrans, iop/highlights/lch.c:315-537; their long-double products, quotients and sums in integer arithmetic,
  * x87.cuh) and colour inpainting (process_inpaint_bayer / _xtrans, iop/highlights/inpaint.c:63-104: four directional line
  * recurrences, averaged).  For these the count and the branch stay on the device: no host round trip.  Guided Laplacians
- * (below) run on Bayer and RGBA input once the host has read the count; harmonic transposition returns B200_ERR_UNSUPPORTED
+ * (below) run once the host has read the count; harmonic transposition returns B200_ERR_UNSUPPORTED
  * when the frame does not take the bypass. */
-/* Mode LAPLACIAN past the bypass (process_laplacian, iop/highlights/laplacian.c:433-575) on a Bayer mosaic or on RGBA input: the
+/* Mode LAPLACIAN past the bypass (process_laplacian, iop/highlights/laplacian.c:433-575) on a Bayer or X-Trans mosaic or on RGBA input: the
  * frame gathered into [R, G, B, norm] and a clipping mask (iop/highlights/gather.c), the mask feathered by a box mean, both reduced
  * to a quarter, `iterations` rounds of guide_laplacians and heat_PDE_diffusion over the wavelet scales, enlarged and composited.
  * `normalization`: NULL in production.  The reference's vector (_compute_laplacian_normalization, gather.c:223-275) is an OpenMP
  * float reduction whose value depends on the thread count; the library sums in double in a fixed order.  A caller that has the
  * vector of one reference run (4 floats, host memory) passes it and gets that run's bits.  No bypass test here: the frame is
- * reconstructed whatever its count.  X-Trans: B200_ERR_UNSUPPORTED. */
+ * reconstructed whatever its count.  Frames under 8 px either way: B200_ERR_UNSUPPORTED (the reference's quarter-size planes vanish). */
 int b200_highlights_laplacian_dev(const b200_piece_t *piece, const void *d_in, void *d_out, const float *normalization, void *stream);
 int b200_highlights_process_host(const b200_piece_t *piece, const void *in, void *out);
 int b200_highlights_process_dev(const b200_piece_t *piece, const void *d_in, void *d_out, void *stream);

@@ -124,8 +124,16 @@ extern "C" int emul_highlights(const b200_piece_t *piece, const float *in, float
     float pmax[4];
     for(int c = 0; c < 4; c++) pmax[c] = (piece->processed_maximum[c] > 0.f) ? piece->processed_maximum[c] : 1.0f;
     inpaint_t A = { { 0.987f * d->clip * pmax[0], 0.987f * d->clip * pmax[1], 0.987f * d->clip * pmax[2], clip }, shifted_filters, w, h };
-    emulate(dim3((unsigned)((h + 127) / 128)), 128, inpaint_rows_kernel, in, out, A, (const unsigned long long *)&counter);
-    emulate(dim3((unsigned)((w + 127) / 128)), 128, inpaint_cols_kernel, in, out, A, (const unsigned long long *)&counter);
+    // the launch sequence of b200_highlights_process_dev; the planes start as NaN: only what a direction wrote may reach the output
+    const size_t npx = (size_t)w * h;
+    const unsigned long long *cnt = (const unsigned long long *)&counter;
+    std::vector<float> t_in(npx, NAN), t_fwd(npx, NAN), t_bwd(npx, NAN), up(npx, NAN);
+    float *rows = t_in.data(), *down = out;
+    emulate(dim3((unsigned)((w + 31) / 32), (unsigned)((h + 31) / 32)), 256, transpose_kernel<false>, in, (const float *)nullptr, t_in.data(), w, h, cnt);
+    emulate(dim3((unsigned)((h + 127) / 128), 2), 128, inpaint_rows_kernel, (const float *)t_in.data(), t_fwd.data(), t_bwd.data(), A, cnt);
+    emulate(dim3((unsigned)((w + 127) / 128), 2), 128, inpaint_cols_kernel, in, down, up.data(), A, cnt);
+    emulate(dim3((unsigned)((h + 31) / 32), (unsigned)((w + 31) / 32)), 256, transpose_kernel<true>, (const float *)t_fwd.data(), (const float *)t_bwd.data(), rows, h, w, cnt);
+    emulate(dim3((unsigned)((w + NT - 1) / NT), (unsigned)h), NT, inpaint_sum_kernel, in, (const float *)rows, (const float *)down, (const float *)up.data(), out, A, cnt);
     return 0;
   }
   const bool clip_mode = d->mode == B200_HIGHLIGHTS_CLIP || (!mosaic && (d->mode == B200_HIGHLIGHTS_LCH || d->mode == B200_HIGHLIGHTS_INPAINT));
