@@ -286,26 +286,55 @@ __global__ void __launch_bounds__(NT) hl_box_rows_kernel(const float4 *__restric
   out[row + j] = make_float4(L.x / hits, L.y / hits, L.z / hits, L.w / hits);
 }
 // Column pass (blur_vertical_1ch :891-913 and its 16-, 4- and 1-wide bodies): fractions enter and leave a float running sum, so
-// the order is the reference's: down the column, the leaving sample before the entering one.  One thread per float column.
-__global__ void __launch_bounds__(NT) hl_box_columns_kernel(const float *__restrict__ in, float *__restrict__ out, int height, size_t stride, int radius)
+// the order is the reference's: down the column, the leaving sample before the entering one.  One thread per float column; the
+// entering samples of eight rows are fetched ahead of the recurrence, the leaving ones are the entering ones of 2 * RADIUS + 1 rows
+// earlier and wait in registers.  Frames are at least 8 rows high (the caller refuses smaller ones).
+template <int RADIUS>
+__global__ void __launch_bounds__(NT) hl_box_columns_kernel(const float *__restrict__ in, float *__restrict__ out, int height, size_t stride)
 {
   const size_t x = (size_t)blockIdx.x * NT + threadIdx.x;
   if(x >= stride) return;
+  constexpr int W = 2 * RADIUS + 1;
   const float *col = in + x;
   float *dst = out + x;
+  float ring[W]; // before the step of row y: the samples of rows y - RADIUS - 1 .. y + RADIUS - 1, zeros outside the frame
+#pragma unroll
+  for(int q = 0; q < W; q++) ring[q] = 0.f;
   float L = 0.0f;
   int hits = 0;
-  for(int y = 0; y < min(radius, height); y++, hits++) L += __ldg(col + (size_t)y * stride);
-  for(int y = 0; y < height; y++)
+#pragma unroll
+  for(int y = 0; y < RADIUS; y++, hits++)
   {
-    if(y > radius) L -= __ldg(col + (size_t)(y - radius - 1) * stride);
-    if(y > radius && y + radius >= height) hits--;
-    if(y + radius < height)
+    const float v = __ldg(col + (size_t)y * stride);
+    L += v;
+#pragma unroll
+    for(int q = 0; q < W - 1; q++) ring[q] = ring[q + 1];
+    ring[W - 1] = v;
+  }
+  for(int base = 0; base < height; base += 8)
+  {
+    float enter[8];
+#pragma unroll
+    for(int m = 0; m < 8; m++) enter[m] = base + m + RADIUS < height ? __ldg(col + (size_t)(base + m + RADIUS) * stride) : 0.f;
+#pragma unroll
+    for(int m = 0; m < 8; m++)
     {
-      L += __ldg(col + (size_t)(y + radius) * stride);
-      if(y <= radius) hits++;
+      const int y = base + m;
+      if(y < height)
+      {
+        if(y > RADIUS) L -= ring[0];
+        if(y > RADIUS && y + RADIUS >= height) hits--;
+        if(y + RADIUS < height)
+        {
+          L += enter[m];
+          if(y <= RADIUS) hits++;
+        }
+        dst[(size_t)y * stride] = L / (float)hits;
+      }
+#pragma unroll
+      for(int q = 0; q < W - 1; q++) ring[q] = ring[q + 1];
+      ring[W - 1] = enter[m];
     }
-    dst[(size_t)y * stride] = L / (float)hits;
   }
 }
 
@@ -639,7 +668,7 @@ int hl_sequence(const hl_job_t &J, const hl_buffers_t &B, const void *d_in, void
     HL_LAUNCH(hl_gather_rgba_kernel, full, (const float4 *)d_in, B.interpolated, B.mask_a, J.width, J.clips, (const float *)B.norm);
   HL_LAUNCH(hl_box_rows_kernel, full, (const float4 *)B.mask_a, B.mask_b, J.width, 2);
   const size_t stride = (size_t)4 * J.width;
-  HL_LAUNCH(hl_box_columns_kernel, dim3((unsigned)((stride + NT - 1) / NT)), (const float *)B.mask_b, (float *)B.mask_a, J.height, stride, 2);
+  HL_LAUNCH(hl_box_columns_kernel<2>, dim3((unsigned)((stride + NT - 1) / NT)), (const float *)B.mask_b, (float *)B.mask_a, J.height, stride);
   HL_LAUNCH(hl_bilinear_kernel, ds, (const float4 *)B.mask_a, J.width, J.height, B.ds_mask, J.ds_width, J.ds_height);
   HL_LAUNCH(hl_bilinear_kernel, ds, (const float4 *)B.interpolated, J.width, J.height, B.ds_interpolated, J.ds_width, J.ds_height);
   for(int i = 0; i < J.iterations; i++)

@@ -57,6 +57,16 @@ def test_highlights_kernels_equal_oracle(emul, name):
     assert n.value == n_want and same_bits(got, want).all()
 
 
+def test_inpaint_kernels_on_a_frame_of_several_blocks(emul):
+    """more lines than one block of threads holds, ragged 32x32 tiles of the transposition, lines that end inside a group of eight steps"""
+    piece, img = cases.highlights_case("inpaint_mosaic_wb_roi", (301, 267))
+    rc, want, n_want = pe.oracle_highlights(piece, img)
+    got, n = np.full_like(want, -7.0), C.c_ulonglong(0)
+    shifted = ab.lib().b200_roi_filters(C.c_uint32(piece.filters), piece.roi_in.x, piece.roi_in.y)
+    assert emul.emul_highlights(C.byref(piece), pe.vp(img), pe.vp(got), C.byref(n), C.c_uint32(shifted)) == 0 and rc == 0
+    assert n.value == n_want and same_bits(got, want).all() and (got != img).mean() > 0.01
+
+
 def test_highlights_kernels_refuse_reconstruction_past_the_bypass(emul):
     _, img = cases.highlights_case("clip_mosaic")
     piece = pe.mosaic_piece(img.shape[1], img.shape[0], ab.highlights_data(ab.HIGHLIGHTS_HARMONIC, 1.0))
