@@ -493,35 +493,34 @@ __device__ __forceinline__ float interp_pix_xtrans(int ratio_next, float next, f
 }
 // the colour-transition table roff[f0][f1] :104: RG 1, RB 2, GB 3, negative = inverted
 __device__ __forceinline__ int roff(int f0, int f1) { return f0 == f1 ? 0 : (f0 < f1 ? -(f0 + f1) : (f0 + f1)); }
-// interpolate_color_xtrans :90-204: three running ratios (one per colour pair) instead of Bayer's one
-__device__ void inpaint_line_xtrans(const float *__restrict__ ivoid, float *__restrict__ ovoid, const inpaint_t &A, const xtable_t &X, int dim, int dir, int other,
-                                    int pass)
+// interpolate_color_xtrans :90-204: three running ratios (one per colour pair) instead of Bayer's one; one direction of one line, laid out and
+// fetched like inpaint_chain (the Bayer one): only clipped sites are written
+__device__ void inpaint_chain_xtrans(const float *__restrict__ in, float *__restrict__ plane, const inpaint_t &A, const xtable_t &X, ptrdiff_t si, ptrdiff_t sj,
+                                     int dim, int dir, int other)
 {
+  const int n = dim ? A.height : A.width, n_other = dim ? A.width : A.height;
+  if(other == 0 || other == n_other - 1) return; // a border line :118-121
+  const ptrdiff_t step = dim ? sj : si, across = dim ? si : sj, line = (ptrdiff_t)other * across;
+  const int beg = dir == 1 ? 0 : n - 1;
   float ratios[4] = { 1.0f, 1.0f, 1.0f, 1.0f };
-  int i = dim ? other : 0, j = dim ? 0 : other;
-  const ptrdiff_t offs = (ptrdiff_t)(dim ? A.width : 1) * dir;
-  const ptrdiff_t offl = offs - (dim ? 1 : A.width), offr = offs + (dim ? 1 : A.width);
-  const int n = dim ? A.height : A.width;
-  const int beg = dir == 1 ? 0 : n - 1, end = dir == 1 ? n : -1;
-  const size_t first = dim ? i + (size_t)beg * A.width : beg + (size_t)j * A.width;
-  const float *in = ivoid + first;
-  float *out = ovoid + first;
-  const float clip_max = fmaxf(fmaxf(A.clips[0], A.clips[1]), A.clips[2]);
-  for(int k = beg; k != end; k += dir)
+  for(int base = 0; base < n; base += 8)
   {
-    if(dim == 1)
-      j = k;
-    else
-      i = k;
-    if(i == 0 || i == A.width - 1 || j == 0 || j == A.height - 1)
+    float v[9];
+#pragma unroll
+    for(int m = 0; m < 9; m++)
     {
-      if(pass == 3) out[0] = fminf(clip_max, in[0]);
+      const int k = beg + min(base + m, n - 1) * dir;
+      v[m] = __ldg(in + line + (ptrdiff_t)k * step);
     }
-    else
+#pragma unroll
+    for(int m = 0; m < 8; m++)
     {
+      const int k = beg + (base + m) * dir;
+      if(base + m >= n || k == 0 || k == n - 1) continue;
+      const int i = dim ? other : k, j = dim ? k : other;
       const int f0 = fcx(X, j, i), f1 = fcx(X, dim ? (j + dir) : j, dim ? i : (i + dir));
       const float clip0 = pick4(A.clips, f0), clip1 = pick4(A.clips, f1);
-      const float v0 = in[0], v1 = in[offs];
+      const float v0 = v[m], v1 = v[m + 1];
       if((f0 != f1) && (v0 < clip0 && v0 > 1e-5f) && (v1 < clip1 && v1 > 1e-5f))
       {
         const int r = roff(f0, f1);
@@ -536,45 +535,49 @@ __device__ void inpaint_line_xtrans(const float *__restrict__ ivoid, float *__re
         if(f0 != f1)
           add = interp_pix_xtrans(roff(f0, f1), v1, clip0, clip1, ratios);
         else
-        { // at the start of a 2x2 green block: look diagonally
+        { // at the start of a 2x2 green block: look diagonally (one step on, one line to either side)
           const int fl = fcx(X, dim ? (j + dir) : (j - 1), dim ? (i - 1) : (i + dir)), fr = fcx(X, dim ? (j + dir) : (j + 1), dim ? (i + 1) : (i + dir));
-          add = (fl != f0) ? interp_pix_xtrans(roff(f0, fl), in[offl], clip0, pick4(A.clips, fl), ratios)
-                           : interp_pix_xtrans(roff(f0, fr), in[offr], clip0, pick4(A.clips, fr), ratios);
+          const float *next = in + line + (ptrdiff_t)(k + dir) * step;
+          add = (fl != f0) ? interp_pix_xtrans(roff(f0, fl), __ldg(next - across), clip0, pick4(A.clips, fl), ratios)
+                           : interp_pix_xtrans(roff(f0, fr), __ldg(next + across), clip0, pick4(A.clips, fr), ratios);
         }
-        if(pass == 0)
-          out[0] = add;
-        else if(pass == 3)
-          out[0] = fminf(clip_max, (out[0] + add) / 4.0f);
-        else
-          out[0] += add;
+        plane[line + (ptrdiff_t)k * step] = add;
       }
-      else if(pass == 3)
-        out[0] = v0;
     }
-    out += offs;
-    in += offs;
   }
 }
-__global__ void __launch_bounds__(128) inpaint_rows_xtrans_kernel(const float *__restrict__ in, float *__restrict__ out, inpaint_t A, xtable_t X,
-                                                                  const unsigned long long *counter)
-{
+__global__ void __launch_bounds__(128) inpaint_rows_xtrans_kernel(const float *__restrict__ t_in, float *__restrict__ t_fwd, float *__restrict__ t_bwd, inpaint_t A,
+                                                                  xtable_t X, const unsigned long long *counter)
+{ // on the transposed mosaic, like inpaint_rows_kernel
   const int j = blockIdx.x * 128 + threadIdx.x;
   if(j >= A.height || *counter < 25ull) return;
-  inpaint_line_xtrans(in, out, A, X, 0, 1, j, 0);
-  inpaint_line_xtrans(in, out, A, X, 0, -1, j, 1);
+  inpaint_chain_xtrans(t_in, blockIdx.y ? t_bwd : t_fwd, A, X, A.height, 1, 0, blockIdx.y ? -1 : 1, j);
 }
-__global__ void __launch_bounds__(128) inpaint_cols_xtrans_kernel(const float *__restrict__ in, float *__restrict__ out, inpaint_t A, xtable_t X,
-                                                                  const unsigned long long *counter)
+__global__ void __launch_bounds__(128) inpaint_cols_xtrans_kernel(const float *__restrict__ in, float *__restrict__ down, float *__restrict__ up, inpaint_t A,
+                                                                  xtable_t X, const unsigned long long *counter)
 {
   const int i = blockIdx.x * 128 + threadIdx.x;
+  if(i >= A.width || *counter < 25ull) return;
+  inpaint_chain_xtrans(in, blockIdx.y ? up : down, A, X, 1, A.width, 1, blockIdx.y ? -1 : 1, i);
+}
+// the four directions summed in the reference's order, capped at the largest clip value :114, :196-199
+__global__ void __launch_bounds__(NT) inpaint_sum_xtrans_kernel(const float *__restrict__ in, const float *__restrict__ rows, const float *down,
+                                                                const float *__restrict__ up, float *out, inpaint_t A, xtable_t X, const unsigned long long *counter)
+{
+  const int i = blockIdx.x * NT + threadIdx.x, j = blockIdx.y;
   if(i >= A.width) return;
-  if(*counter < 25ull)
+  const size_t p = (size_t)j * A.width + i;
+  const float v0 = __ldg(in + p);
+  float o = v0;
+  if(*counter >= 25ull)
   {
-    for(int j = 0; j < A.height; j++) out[(size_t)j * A.width + i] = in[(size_t)j * A.width + i];
-    return;
+    const float clip_max = fmaxf(fmaxf(A.clips[0], A.clips[1]), A.clips[2]);
+    if(i == 0 || i == A.width - 1 || j == 0 || j == A.height - 1)
+      o = fminf(clip_max, v0);
+    else if(v0 >= pick4(A.clips, fcx(X, j, i)) - 1e-5f)
+      o = fminf(clip_max, (((__ldg(rows + p)) + down[p]) + __ldg(up + p)) / 4.0f);
   }
-  inpaint_line_xtrans(in, out, A, X, 1, 1, i, 2);
-  inpaint_line_xtrans(in, out, A, X, 1, -1, i, 3);
+  out[p] = o;
 }
 // process_lch_xtrans :412-537.  The reference's ring buffer `cl` says whether any of this and the two previous columns has a
 // clipped sample in rows j-1..j+1: recomputed per pixel here.
@@ -951,6 +954,41 @@ extern "C" int b200_temperature_process_host(const b200_piece_t *piece, const vo
 extern "C" void b200_temperature_tiling(const b200_piece_t *piece, b200_tiling_t *t) { default_tiling(piece, t, false, true); }
 
 // ---- highlights --------------------------------------------------------------------------------------------------------------
+// colour inpainting, both mosaics: the mosaic transposed, the two row directions on the copy and the two column directions on the frame, the row
+// planes transposed back (and added on the way), the sum.  X = NULL: Bayer
+static int inpaint_sequence(const void *d_in, void *d_out, const inpaint_t &A, const xtable_t *X, const unsigned long long *counter, cudaStream_t s)
+{
+  const int width = A.width, height = A.height;
+  const size_t npx = (size_t)width * height;
+  void *t[4];
+  int rc;
+  for(int k = 0; k < 4; k++)
+    if((rc = scratch(SLOT_TMP0 + k, npx * sizeof(float), &t[k]))) return rc;
+  float *t_in = (float *)t[0], *t_fwd = (float *)t[1], *t_bwd = (float *)t[2], *up = (float *)t[3], *rows = t_in, *down = (float *)d_out;
+  const dim3 tiles((unsigned)((width + 31) / 32), (unsigned)((height + 31) / 32)), tiles_t((unsigned)((height + 31) / 32), (unsigned)((width + 31) / 32));
+  const dim3 by_row((unsigned)((height + 127) / 128), 2), by_col((unsigned)((width + 127) / 128), 2), px((unsigned)((width + NT - 1) / NT), (unsigned)height);
+  transpose_kernel<false><<<tiles, 256, 0, s>>>((const float *)d_in, nullptr, t_in, width, height, counter);
+  B200_CUDA_TRY(cudaGetLastError());
+  if(X)
+  {
+    inpaint_rows_xtrans_kernel<<<by_row, 128, 0, s>>>(t_in, t_fwd, t_bwd, A, *X, counter);
+    inpaint_cols_xtrans_kernel<<<by_col, 128, 0, s>>>((const float *)d_in, down, up, A, *X, counter);
+  }
+  else
+  {
+    inpaint_rows_kernel<<<by_row, 128, 0, s>>>(t_in, t_fwd, t_bwd, A, counter);
+    inpaint_cols_kernel<<<by_col, 128, 0, s>>>((const float *)d_in, down, up, A, counter);
+  }
+  B200_CUDA_TRY(cudaGetLastError());
+  transpose_kernel<true><<<tiles_t, 256, 0, s>>>(t_fwd, t_bwd, rows, height, width, counter); // back to the frame's layout, the two row directions added
+  B200_CUDA_TRY(cudaGetLastError());
+  if(X)
+    inpaint_sum_xtrans_kernel<<<px, NT, 0, s>>>((const float *)d_in, rows, down, up, (float *)d_out, A, *X, counter);
+  else
+    inpaint_sum_kernel<<<px, NT, 0, s>>>((const float *)d_in, rows, down, up, (float *)d_out, A, counter);
+  B200_CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
 namespace b200
 { // highlights_laplacian.cu
 int highlights_laplacian_dev(const b200_piece_t *piece, const b200_highlights_data_t *d, const void *d_in, void *d_out, const float clips[4],
@@ -1013,8 +1051,7 @@ extern "C" int b200_highlights_process_dev(const b200_piece_t *piece, const void
       float pmax[4];
       for(int c = 0; c < 4; c++) pmax[c] = (piece->processed_maximum[c] > 0.f) ? piece->processed_maximum[c] : 1.0f;
       const inpaint_t A = { { 0.987f * d->clip * pmax[0], 0.987f * d->clip * pmax[1], 0.987f * d->clip * pmax[2], clip }, 9u, width, height };
-      inpaint_rows_xtrans_kernel<<<(unsigned)((height + 127) / 128), 128, 0, s>>>((const float *)d_in, (float *)d_out, A, X, counter);
-      inpaint_cols_xtrans_kernel<<<(unsigned)((width + 127) / 128), 128, 0, s>>>((const float *)d_in, (float *)d_out, A, X, counter);
+      if((rc = inpaint_sequence(d_in, d_out, A, &X, counter, s))) return rc;
     }
     B200_CUDA_TRY(cudaGetLastError());
     return B200_OK;
@@ -1032,22 +1069,7 @@ extern "C" int b200_highlights_process_dev(const b200_piece_t *piece, const void
     for(int c = 0; c < 4; c++) pmax[c] = (piece->processed_maximum[c] > 0.f) ? piece->processed_maximum[c] : 1.0f;
     inpaint_t A = { { 0.987f * d->clip * pmax[0], 0.987f * d->clip * pmax[1], 0.987f * d->clip * pmax[2], clip },
                     b200_roi_filters(piece->filters, piece->roi_in.x, piece->roi_in.y), width, height };
-    void *t[4];
-    for(int k = 0; k < 4; k++)
-      if((rc = scratch(SLOT_TMP0 + k, npx * sizeof(float), &t[k]))) return rc;
-    float *t_in = (float *)t[0], *t_fwd = (float *)t[1], *t_bwd = (float *)t[2], *up = (float *)t[3], *rows = t_in, *down = (float *)d_out;
-    const dim3 tiles((unsigned)((width + 31) / 32), (unsigned)((height + 31) / 32)), tiles_t((unsigned)((height + 31) / 32), (unsigned)((width + 31) / 32));
-    transpose_kernel<false><<<tiles, 256, 0, s>>>((const float *)d_in, nullptr, t_in, width, height, counter);
-    B200_CUDA_TRY(cudaGetLastError());
-    inpaint_rows_kernel<<<dim3((unsigned)((height + 127) / 128), 2), 128, 0, s>>>(t_in, t_fwd, t_bwd, A, counter);
-    B200_CUDA_TRY(cudaGetLastError());
-    inpaint_cols_kernel<<<dim3((unsigned)((width + 127) / 128), 2), 128, 0, s>>>((const float *)d_in, down, up, A, counter);
-    B200_CUDA_TRY(cudaGetLastError());
-    transpose_kernel<true><<<tiles_t, 256, 0, s>>>(t_fwd, t_bwd, rows, height, width, counter); // back to the frame's layout, the two row directions added
-    B200_CUDA_TRY(cudaGetLastError());
-    inpaint_sum_kernel<<<dim3((unsigned)((width + NT - 1) / NT), (unsigned)height), NT, 0, s>>>((const float *)d_in, rows, down, up, (float *)d_out, A, counter);
-    B200_CUDA_TRY(cudaGetLastError());
-    return B200_OK;
+    return inpaint_sequence(d_in, d_out, A, nullptr, counter, s);
   }
   // another reconstruction mode: only its bypass is built, so the host has to know which way the frame goes
   unsigned long long n_clipped = 0;

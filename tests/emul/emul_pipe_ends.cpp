@@ -79,6 +79,32 @@ extern "C" int emul_temperature(const b200_piece_t *piece, const float *in, floa
 
 /* -> 0 ok, 3 = a reconstruction mode past its bypass (B200_ERR_UNSUPPORTED) */
 /* shifted_filters: b200_roi_filters(piece->filters, roi_in.x, roi_in.y), a host function of the product the caller evaluates */
+// the launch sequence of inpaint_sequence() (pipe_ends.cu); the planes start as NaN: only what a direction wrote may reach the output
+static void emul_inpaint(const float *in, float *out, const inpaint_t &A, const xtable_t *X, const unsigned long long *cnt)
+{
+  const int w = A.width, h = A.height;
+  const size_t npx = (size_t)w * h;
+  std::vector<float> t_in(npx, NAN), t_fwd(npx, NAN), t_bwd(npx, NAN), up(npx, NAN);
+  float *rows = t_in.data(), *down = out;
+  const dim3 by_row((unsigned)((h + 127) / 128), 2), by_col((unsigned)((w + 127) / 128), 2), px((unsigned)((w + NT - 1) / NT), (unsigned)h);
+  emulate(dim3((unsigned)((w + 31) / 32), (unsigned)((h + 31) / 32)), 256, transpose_kernel<false>, in, (const float *)nullptr, t_in.data(), w, h, cnt);
+  if(X)
+  {
+    emulate(by_row, 128, inpaint_rows_xtrans_kernel, (const float *)t_in.data(), t_fwd.data(), t_bwd.data(), A, *X, cnt);
+    emulate(by_col, 128, inpaint_cols_xtrans_kernel, in, down, up.data(), A, *X, cnt);
+  }
+  else
+  {
+    emulate(by_row, 128, inpaint_rows_kernel, (const float *)t_in.data(), t_fwd.data(), t_bwd.data(), A, cnt);
+    emulate(by_col, 128, inpaint_cols_kernel, in, down, up.data(), A, cnt);
+  }
+  emulate(dim3((unsigned)((h + 31) / 32), (unsigned)((w + 31) / 32)), 256, transpose_kernel<true>, (const float *)t_fwd.data(), (const float *)t_bwd.data(), rows, h, w, cnt);
+  if(X)
+    emulate(px, NT, inpaint_sum_xtrans_kernel, in, (const float *)rows, (const float *)down, (const float *)up.data(), out, A, *X, cnt);
+  else
+    emulate(px, NT, inpaint_sum_kernel, in, (const float *)rows, (const float *)down, (const float *)up.data(), out, A, cnt);
+}
+
 extern "C" int emul_highlights(const b200_piece_t *piece, const float *in, float *out, unsigned long long *n_clipped, unsigned shifted_filters)
 {
   const b200_highlights_data_t *d = (const b200_highlights_data_t *)piece->data;
@@ -108,8 +134,7 @@ extern "C" int emul_highlights(const b200_piece_t *piece, const float *in, float
       float pmax[4];
       for(int c = 0; c < 4; c++) pmax[c] = (piece->processed_maximum[c] > 0.f) ? piece->processed_maximum[c] : 1.0f;
       const inpaint_t A = { { 0.987f * d->clip * pmax[0], 0.987f * d->clip * pmax[1], 0.987f * d->clip * pmax[2], clip }, 9u, w, h };
-      emulate(dim3((unsigned)((h + 127) / 128)), 128, inpaint_rows_xtrans_kernel, in, out, A, X, (const unsigned long long *)&counter);
-      emulate(dim3((unsigned)((w + 127) / 128)), 128, inpaint_cols_xtrans_kernel, in, out, A, X, (const unsigned long long *)&counter);
+      emul_inpaint(in, out, A, &X, (const unsigned long long *)&counter);
     }
     return 0;
   }
@@ -124,16 +149,7 @@ extern "C" int emul_highlights(const b200_piece_t *piece, const float *in, float
     float pmax[4];
     for(int c = 0; c < 4; c++) pmax[c] = (piece->processed_maximum[c] > 0.f) ? piece->processed_maximum[c] : 1.0f;
     inpaint_t A = { { 0.987f * d->clip * pmax[0], 0.987f * d->clip * pmax[1], 0.987f * d->clip * pmax[2], clip }, shifted_filters, w, h };
-    // the launch sequence of b200_highlights_process_dev; the planes start as NaN: only what a direction wrote may reach the output
-    const size_t npx = (size_t)w * h;
-    const unsigned long long *cnt = (const unsigned long long *)&counter;
-    std::vector<float> t_in(npx, NAN), t_fwd(npx, NAN), t_bwd(npx, NAN), up(npx, NAN);
-    float *rows = t_in.data(), *down = out;
-    emulate(dim3((unsigned)((w + 31) / 32), (unsigned)((h + 31) / 32)), 256, transpose_kernel<false>, in, (const float *)nullptr, t_in.data(), w, h, cnt);
-    emulate(dim3((unsigned)((h + 127) / 128), 2), 128, inpaint_rows_kernel, (const float *)t_in.data(), t_fwd.data(), t_bwd.data(), A, cnt);
-    emulate(dim3((unsigned)((w + 127) / 128), 2), 128, inpaint_cols_kernel, in, down, up.data(), A, cnt);
-    emulate(dim3((unsigned)((h + 31) / 32), (unsigned)((w + 31) / 32)), 256, transpose_kernel<true>, (const float *)t_fwd.data(), (const float *)t_bwd.data(), rows, h, w, cnt);
-    emulate(dim3((unsigned)((w + NT - 1) / NT), (unsigned)h), NT, inpaint_sum_kernel, in, (const float *)rows, (const float *)down, (const float *)up.data(), out, A, cnt);
+    emul_inpaint(in, out, A, nullptr, (const unsigned long long *)&counter);
     return 0;
   }
   const bool clip_mode = d->mode == B200_HIGHLIGHTS_CLIP || (!mosaic && (d->mode == B200_HIGHLIGHTS_LCH || d->mode == B200_HIGHLIGHTS_INPAINT));

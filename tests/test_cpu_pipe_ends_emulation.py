@@ -57,9 +57,10 @@ def test_highlights_kernels_equal_oracle(emul, name):
     assert n.value == n_want and same_bits(got, want).all()
 
 
-def test_inpaint_kernels_on_a_frame_of_several_blocks(emul):
+@pytest.mark.parametrize("name", ["inpaint_mosaic_wb_roi", "inpaint_xtrans_wb"])
+def test_inpaint_kernels_on_a_frame_of_several_blocks(emul, name):
     """more lines than one block of threads holds, ragged 32x32 tiles of the transposition, lines that end inside a group of eight steps"""
-    piece, img = cases.highlights_case("inpaint_mosaic_wb_roi", (301, 267))
+    piece, img = cases.highlights_case(name, (301, 267))
     rc, want, n_want = pe.oracle_highlights(piece, img)
     got, n = np.full_like(want, -7.0), C.c_ulonglong(0)
     shifted = ab.lib().b200_roi_filters(C.c_uint32(piece.filters), piece.roi_in.x, piece.roi_in.y)

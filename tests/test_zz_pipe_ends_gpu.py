@@ -82,7 +82,7 @@ def test_highlights_bit_exact(built, name):
 
 
 @pytest.mark.parametrize("size", [(1037, 613), (2600, 1702)])
-@pytest.mark.parametrize("name", ["inpaint_mosaic", "inpaint_mosaic_wb_roi"])
+@pytest.mark.parametrize("name", ["inpaint_mosaic", "inpaint_mosaic_wb_roi", "inpaint_xtrans_wb"])
 def test_highlights_inpaint_larger_frames(built, name, size):
     """frames of several blocks of lines and of ragged 32x32 tiles: the four directions run at once, the row ones on a transposed copy"""
     piece, img = cases.highlights_case(name, size)
