@@ -1,11 +1,13 @@
-// Blending of a module's output over its input (mask + blend operator), scene-referred RGB space, for B200 / sm_100a.
+// Blending of a module's output over its input (mask + blend operator), scene-referred RGB space and Lab, for B200 / sm_100a.
 //
-// What the reference computes: develop/blend.c dt_develop_blend_process :657-860 with blend_cst == DEVELOP_BLEND_CS_RGB_SCENE:
-// the mask (uniform opacity | the raster / drawn mask the host rasterised | the parametric mask of
-// develop/blends/blendif_rgb_jzczhz.c :42-325 on the gray, red, green and blue channels of the module's input and output, combined
-// exclusively or inclusively, inverted or not | the mask tone curve :626-655), then one of the sixteen blend operators :328-649,
-// the result in place of the module's output with the mask in its alpha lane (:878-961).  Parity contract: bit-identical to those
-// lines under C float semantics (oracle/restate/blend_oracle.c, pinned against them compiled in place).
+// What the reference computes: develop/blend.c dt_develop_blend_process :657-860 with blend_cst == DEVELOP_BLEND_CS_RGB_SCENE or
+// DEVELOP_BLEND_CS_LAB: the mask (uniform opacity | the raster / drawn mask the host rasterised | the parametric mask of
+// develop/blends/blendif_rgb_jzczhz.c :42-325 on the gray, red, green and blue channels -- of develop/blends/blendif_lab.c :56-298 on
+// the L, a and b channels -- of the module's input and output, combined exclusively or inclusively, inverted or not | the mask tone
+// curve :626-655), then one of the sixteen blend operators of the RGB space (blendif_rgb_jzczhz.c :328-649) or one of the twenty-two
+// of the Lab space that stay in Lab (blendif_lab.c :302-1068), the result in place of the module's output with the mask in its alpha
+// lane.  Parity contract: bit-identical to those lines under C float semantics (oracle/restate/blend_oracle.c, pinned against them
+// compiled in place).
 //
 // The reference makes up to seven passes over full buffers (seed, one per parametric channel set, opacity, tone curve, a copy of
 // the output, the operator, the alpha copy).  Every one of them is pointwise, so the kernel is ONE pass: 16 B of input, 16 B of
@@ -13,8 +15,9 @@
 // 52 B/px algorithmic.  What the host decides once per call (which of the reference's branches a parameter block takes, the
 // slopes of the parametric channels, exp2f / expf of the parameters) arrives in the plan; what depends on the pixel is evaluated
 // here.  Not built (B200_ERR_UNSUPPORTED, the caller falls back to the reference's own path): feathering (guided filter), Gaussian
-// blur and detail refinement of the mask, the JzCzhz channels of the parametric mask, the GUI's channel display, the Lab, display
-// RGB and raw colour spaces.
+// blur and detail refinement of the mask; the channels and operators that need another colour space per pixel (Jz, Cz, hz of the RGB
+// space; chroma and hue, and the chromaticity / hue / colour / colour-adjustment operators, of the Lab space: atan2f, hypotf, the PQ
+// curve); the GUI's channel display; the display-RGB and raw colour spaces.
 #ifndef B200_KERNELS_ON_CPU // tests/emul compiles the kernel of this file with g++ to check it against the oracle without a GPU
 #include "runtime.h"
 #endif
@@ -28,8 +31,8 @@ enum
 {
   MASK_ENABLED = 1, MASK_SHAPE = 2, MASK_PARAMETRIC = 4, MASK_RASTER = 8, // dt_develop_mask_mode_t, blend.h:110-118
   COMBINE_INV = 1, COMBINE_INCL = 2,                                      // dt_develop_mask_combine_mode_t :120-131
-  BLENDIF_SIZE = 16, BLENDIF_ITEMS = 6, BLENDIF_RGB_MASK = 0x77FF,        // :188-191, :329
-  CS_RGB_SCENE = 4                                                         // :52-59
+  BLENDIF_SIZE = 16, BLENDIF_ITEMS = 6, BLENDIF_RGB_MASK = 0x77FF, BLENDIF_LAB_MASK = 0x3377, // :188-191, :329
+  CS_LAB = 2, CS_RGB_SCENE = 4                                             // :52-59
 };
 constexpr unsigned BLEND_REVERSE = 0x80000000u; // blend.h:106
 
@@ -40,6 +43,7 @@ struct blend_plan_t
   const float *form;
   float *mask_out;
   int iw, ow, oh, xoffs, yoffs;
+  int lab;       // the Lab space (develop/blends/blendif_lab.c) instead of scene-referred RGB
   int kind;      // 0: mask = opacity; 1: mask = form * opacity (a raster mask alone); 2: seed, then the parametric stage
   int seed_form; // kind 2: the seed is the form mask, else `fill`
   float fill, opacity;
@@ -47,7 +51,7 @@ struct blend_plan_t
   int inversed, inclusive;
   float pm_const;
   unsigned blendif;
-  float par[BLENDIF_ITEMS * 8]; // gray, red, green, blue of the input, then of the output: four limits and two slopes each
+  float par[BLENDIF_ITEMS * 8]; // gray, red, green, blue (Lab: L, a, b, unused) of the input, then of the output: four limits and two slopes each
   float lum[3];
   int tone;
   float contrast_e, brightness;
@@ -79,6 +83,23 @@ __device__ __forceinline__ float bl_channels(const float px[4], float t, unsigne
     if(blendif & (2u << c)) t *= bl_factor(px[c], (blendif >> 16) & (2u << c), par + BLENDIF_ITEMS * (1 + c));
   return t;
 }
+__device__ __forceinline__ float bl_divc(float a, float b)
+{ // IEEE division by a constant that is not a power of two: opaque to nvcc's x / c -> x * (1 / c) rewrite under -ftz=true
+#ifdef B200_KERNELS_ON_CPU
+  return a / b;
+#else
+  float q;
+  asm("div.rn.ftz.f32 %0, %1, %2;" : "=f"(q) : "f"(a), "f"(b));
+  return q;
+#endif
+}
+__device__ __forceinline__ float bl_channels_lab(const float px[4], float t, unsigned blendif, const float *par)
+{ // blendif_lab.c _blendif_combine_channels :139-173 without the chroma / hue pair (the plan refuses it): L / 100, a / 256, b / 256
+  if(blendif & 1u) t *= bl_factor(bl_divc(px[0], 100.0f), (blendif >> 16) & 1u, par);
+  if(blendif & 2u) t *= bl_factor(px[1] / 256.0f, (blendif >> 16) & 2u, par + BLENDIF_ITEMS);
+  if(blendif & 4u) t *= bl_factor(px[2] / 256.0f, (blendif >> 16) & 4u, par + BLENDIF_ITEMS * 2);
+  return t;
+}
 __device__ __forceinline__ float bl_mask(const blend_plan_t &pl, const float a[4], const float b[4], float form)
 {
   if(pl.kind == 0) return pl.opacity;
@@ -91,8 +112,17 @@ __device__ __forceinline__ float bl_mask(const blend_plan_t &pl, const float a[4
     m = pl.pm_const; // :233-240
   else
   { // :241-320
-    float t = bl_channels(a, 1.0f, pl.blendif, pl.par, pl.lum);
-    t = bl_channels(b, t, pl.blendif >> 4, pl.par + BLENDIF_ITEMS * 4, pl.lum);
+    float t;
+    if(pl.lab)
+    {
+      t = bl_channels_lab(a, 1.0f, pl.blendif, pl.par);
+      t = bl_channels_lab(b, t, pl.blendif >> 4, pl.par + BLENDIF_ITEMS * 4);
+    }
+    else
+    {
+      t = bl_channels(a, 1.0f, pl.blendif, pl.par, pl.lum);
+      t = bl_channels(b, t, pl.blendif >> 4, pl.par + BLENDIF_ITEMS * 4, pl.lum);
+    }
     if(pl.inclusive)
       m = pl.inversed ? g * (1.0f - m) * t : g * (1.0f - (1.0f - m) * t);
     else
@@ -203,6 +233,147 @@ __device__ __forceinline__ void bl_operator(unsigned mode, const float a[4], con
   out[3] = lo;
 }
 
+// ---- Lab, blendif_lab.c:302-1068: the pixels scaled to L / 100, a / 128, b / 128, blended between min = { 0, -1, -1 } and max = { 1, 1, 1 },
+// scaled back.  The four operators that go through LCh (chromaticity, hue, colour, colour adjustment) are refused by the plan.
+__device__ __forceinline__ float bl_clamp(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); } // _CLAMP :45-48
+// a and b follow the lightness: what multiply, overlay, softlight, hardlight, vividlight and linearlight do to them
+__device__ __forceinline__ void bl_lab_follow(const float ta[3], float tb[3], float o)
+{
+  const float f = fmaxf(ta[0], 0.01f);
+  tb[1] = bl_clamp(ta[1] * (1.0f - o) + (ta[1] + tb[1]) * tb[0] / f * o, -1.0f, 1.0f);
+  tb[2] = bl_clamp(ta[2] * (1.0f - o) + (ta[2] + tb[2]) * tb[0] / f * o, -1.0f, 1.0f);
+}
+__device__ __forceinline__ void bl_operator_lab(unsigned mode, const float a[4], const float b[4], float lo, float out[4])
+{
+  const float mn[3] = { 0.0f, -1.0f, -1.0f }, mx[3] = { 1.0f, 1.0f, 1.0f };
+  float ta[3] = { a[0] * (1 / 100.0f), a[1] * (1 / 128.0f), a[2] * (1 / 128.0f) }, tb[3] = { b[0] * (1 / 100.0f), b[1] * (1 / 128.0f), b[2] * (1 / 128.0f) };
+  const float lo2 = lo * lo;
+  // the shifted lightness of the "light" family: lmax = max[0] + |min[0]| = 1, la and lb in [0, lmax]
+  const float lmax = mx[0] + fabsf(mn[0]), halfmax = lmax / 2.0f, doublemax = lmax * 2.0f;
+  const float la = bl_clamp(ta[0] + fabsf(mn[0]), 0.0f, lmax), lb = bl_clamp(tb[0] + fabsf(mn[0]), 0.0f, lmax);
+  switch(mode & 0xFFu)
+  {
+    case 0x02: // lighten
+    case 0x03: // darken
+    {
+      const float pick = (mode & 0xFFu) == 0x02 ? (ta[0] > tb[0] ? ta[0] : tb[0]) : (ta[0] < tb[0] ? ta[0] : tb[0]);
+      tb[0] = bl_clamp(ta[0] * (1.0f - lo) + pick * lo, mn[0], mx[0]);
+      tb[1] = bl_clamp(ta[1] * (1.0f - fabsf(tb[0] - ta[0])) + 0.5f * (ta[1] + tb[1]) * fabsf(tb[0] - ta[0]), mn[1], mx[1]);
+      tb[2] = bl_clamp(ta[2] * (1.0f - fabsf(tb[0] - ta[0])) + 0.5f * (ta[2] + tb[2]) * fabsf(tb[0] - ta[0]), mn[2], mx[2]);
+      break;
+    }
+    case 0x04: // multiply
+      tb[0] = bl_clamp(ta[0] * (1.0f - lo) + (ta[0] * tb[0]) * lo, mn[0], mx[0]);
+      bl_lab_follow(ta, tb, lo);
+      break;
+    case 0x05: // average
+#pragma unroll
+      for(int c = 0; c < 3; c++) tb[c] = bl_clamp(ta[c] * (1.0f - lo) + (ta[c] + tb[c]) / 2.0f * lo, mn[c], mx[c]);
+      break;
+    case 0x06: // add
+#pragma unroll
+      for(int c = 0; c < 3; c++) tb[c] = bl_clamp(ta[c] * (1.0f - lo) + (ta[c] + tb[c]) * lo, mn[c], mx[c]);
+      break;
+    case 0x07: // subtract
+#pragma unroll
+      for(int c = 0; c < 3; c++) tb[c] = bl_clamp(ta[c] * (1.0f - lo) + ((tb[c] + ta[c]) - (fabsf(mn[c] + mx[c]))) * lo, mn[c], mx[c]);
+      break;
+    case 0x08: // difference (deprecated)
+#pragma unroll
+      for(int c = 0; c < 3; c++)
+      {
+        const float cmax = mx[c] + fabsf(mn[c]);
+        const float ca = bl_clamp(ta[c] + fabsf(mn[c]), 0.0f, cmax), cb = bl_clamp(tb[c] + fabsf(mn[c]), 0.0f, cmax);
+        tb[c] = bl_clamp(ca * (1.0f - lo) + fabsf(ca - cb) * lo, 0.0f, cmax) - fabsf(mn[c]);
+      }
+      break;
+    case 0x17: // difference
+#pragma unroll
+      for(int c = 0; c < 3; c++) tb[c] = fabsf(ta[c] - tb[c]) / fabsf(mx[c] - mn[c]);
+      tb[0] = fmaxf(tb[0], fmaxf(tb[1], tb[2]));
+      tb[0] = bl_clamp(ta[0] * (1.0f - lo) + tb[0] * lo, mn[0], mx[0]);
+      tb[1] = 0.0f;
+      tb[2] = 0.0f;
+      break;
+    case 0x09: // screen
+    {
+      tb[0] = bl_clamp(la * (1.0f - lo) + ((lmax - (lmax - la) * (lmax - lb))) * lo, 0.0f, lmax) - fabsf(mn[0]);
+      const float f = fmaxf(ta[0], 0.01f);
+      tb[1] = bl_clamp(ta[1] * (1.0f - lo) + 0.5f * (ta[1] + tb[1]) * tb[0] / f * lo, mn[1], mx[1]);
+      tb[2] = bl_clamp(ta[2] * (1.0f - lo) + 0.5f * (ta[2] + tb[2]) * tb[0] / f * lo, mn[2], mx[2]);
+      break;
+    }
+    case 0x0A: // overlay
+      tb[0] = bl_clamp(la * (1.0f - lo2) + (la > halfmax ? lmax - (lmax - doublemax * (la - halfmax)) * (lmax - lb) : (doublemax * la) * lb) * lo2, 0.0f, lmax)
+              - fabsf(mn[0]);
+      bl_lab_follow(ta, tb, lo2);
+      break;
+    case 0x0B: // softlight
+      tb[0] = bl_clamp(la * (1.0f - lo2) + (lb > halfmax ? lmax - (lmax - la) * (lmax - (lb - halfmax)) : la * (lb + halfmax)) * lo2, 0.0f, lmax) - fabsf(mn[0]);
+      bl_lab_follow(ta, tb, lo2);
+      break;
+    case 0x0C: // hardlight
+      tb[0] = bl_clamp(la * (1.0f - lo2) + (lb > halfmax ? lmax - (lmax - doublemax * (la - halfmax)) * (lmax - lb) : doublemax * la * lb) * lo2, 0.0f, lmax)
+              - fabsf(mn[0]);
+      bl_lab_follow(ta, tb, lo2);
+      break;
+    case 0x0D: // vividlight
+      tb[0] = bl_clamp(la * (1.0f - lo2)
+                           + (lb > halfmax ? (lb >= lmax ? lmax : la / (doublemax * (lmax - lb))) : (lb <= 0.0f ? 0.0f : lmax - (lmax - la) / (doublemax * lb))) * lo2,
+                       0.0f, lmax)
+              - fabsf(mn[0]);
+      bl_lab_follow(ta, tb, lo2);
+      break;
+    case 0x0E: // linearlight
+      tb[0] = bl_clamp(la * (1.0f - lo2) + (la + doublemax * lb - lmax) * lo2, 0.0f, lmax) - fabsf(mn[0]);
+      bl_lab_follow(ta, tb, lo2);
+      break;
+    case 0x0F: // pinlight
+      tb[0] = bl_clamp(la * (1.0f - lo2) + (lb > halfmax ? fmaxf(la, doublemax * (lb - halfmax)) : fminf(la, doublemax * lb)) * lo2, 0.0f, lmax) - fabsf(mn[0]);
+      tb[1] = bl_clamp(ta[1], mn[1], mx[1]);
+      tb[2] = bl_clamp(ta[2], mn[2], mx[2]);
+      break;
+    case 0x10: // lightness
+      tb[0] = bl_clamp(ta[0] * (1.0f - lo) + tb[0] * lo, mn[0], mx[0]);
+      tb[1] = bl_clamp(ta[1], mn[1], mx[1]);
+      tb[2] = bl_clamp(ta[2], mn[2], mx[2]);
+      break;
+    case 0x19: // normal, bounded
+#pragma unroll
+      for(int c = 0; c < 3; c++) tb[c] = bl_clamp(ta[c] * (1.0f - lo) + tb[c] * lo, mn[c], mx[c]);
+      break;
+    case 0x1A:
+    case 0x1E: // Lab lightness
+      tb[0] = ta[0] * (1.0f - lo) + tb[0] * lo;
+      tb[1] = ta[1];
+      tb[2] = ta[2];
+      break;
+    case 0x1F: // Lab a
+      tb[0] = ta[0];
+      tb[1] = ta[1] * (1.0f - lo) + tb[1] * lo;
+      tb[2] = ta[2];
+      break;
+    case 0x20: // Lab b
+      tb[0] = ta[0];
+      tb[1] = ta[1];
+      tb[2] = ta[2] * (1.0f - lo) + tb[2] * lo;
+      break;
+    case 0x1B: // Lab colour
+      tb[0] = ta[0];
+      tb[1] = ta[1] * (1.0f - lo) + tb[1] * lo;
+      tb[2] = ta[2] * (1.0f - lo) + tb[2] * lo;
+      break;
+    default: // normal
+#pragma unroll
+      for(int c = 0; c < 3; c++) tb[c] = ta[c] * (1.0f - lo) + tb[c] * lo;
+      break;
+  }
+  out[0] = tb[0] * 100.0f;
+  out[1] = tb[1] * 128.0f;
+  out[2] = tb[2] * 128.0f;
+  out[3] = lo;
+}
+
 __global__ void __launch_bounds__(256) blend_kernel(const __grid_constant__ blend_plan_t pl)
 {
   const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
@@ -212,7 +383,9 @@ __global__ void __launch_bounds__(256) blend_kernel(const __grid_constant__ blen
   const float a[4] = { av.x, av.y, av.z, av.w }, b[4] = { bv.x, bv.y, bv.z, bv.w };
   const float m = bl_mask(pl, a, b, pl.form ? __ldg(pl.form + o) : 0.0f);
   float res[4];
-  if(pl.reverse)
+  if(pl.lab)
+    bl_operator_lab(pl.mode, pl.reverse ? b : a, pl.reverse ? a : b, m, res);
+  else if(pl.reverse)
     bl_operator(pl.mode, b, a, pl.p, m, res);
   else
     bl_operator(pl.mode, a, b, pl.p, m, res);
@@ -221,7 +394,8 @@ __global__ void __launch_bounds__(256) blend_kernel(const __grid_constant__ blen
   if(pl.mask_out) pl.mask_out[o] = m;
 }
 
-// dt_develop_blendif_process_parameters(), blend.c:214-260, for the eight RGB channels (no Lab offset)
+// dt_develop_blendif_process_parameters(), blend.c:214-260, for the first eight channels (gray / R / G / B or L / a / b of input and output);
+// in Lab the limits of the a and b channels are offset by a half
 void bl_parameters(float *par, const b200_blend_params_t *d)
 {
   for(int i = 0; i < 8; i++)
@@ -231,7 +405,8 @@ void bl_parameters(float *par, const b200_blend_params_t *d)
     if(d->blendif & (1u << i))
     {
       const float boost = exp2f(d->blendif_boost_factors[i]);
-      for(int k = 0; k < 4; k++) p[k] = (b[k] - 0.0f) * boost;
+      const float offset = (d->blend_cst == CS_LAB && (i == 1 || i == 2 || i == 5 || i == 6)) ? 0.5f : 0.0f;
+      for(int k = 0; k < 4; k++) p[k] = (b[k] - offset) * boost;
       p[4] = 1.0f / fmaxf(0.001f, p[1] - p[0]);
       p[5] = 1.0f / fmaxf(0.001f, p[3] - p[2]);
       if(b[0] <= 0.0f && b[1] <= 0.0f) p[0] = p[1] = -INFINITY;
@@ -252,15 +427,24 @@ int bl_plan(blend_plan_t &pl, const b200_blend_params_t *d, bool have_form)
 {
   memset(&pl, 0, sizeof(pl));
   if(!(d->mask_mode & MASK_ENABLED)) return 1; // :673
-  if(d->blend_cst != CS_RGB_SCENE) return B200_ERR_UNSUPPORTED;
-  if(d->profile_nonlinear) return B200_ERR_UNSUPPORTED;
+  const bool lab = d->blend_cst == CS_LAB;
+  if(!lab && d->blend_cst != CS_RGB_SCENE) return B200_ERR_UNSUPPORTED;
+  if(!lab && d->profile_nonlinear) return B200_ERR_UNSUPPORTED;
   if(d->feathering_radius > 0.1f || d->blur_radius > 0.1f || d->details != 0.0f) return B200_ERR_UNSUPPORTED;
-  if((d->mask_mode & MASK_PARAMETRIC) && (d->blendif & 0x7700u)) return B200_ERR_UNSUPPORTED;
+  // channels of the parametric mask that need a colour-space conversion: Jz, Cz, hz of scene-referred RGB; chroma and hue of Lab
+  if((d->mask_mode & MASK_PARAMETRIC) && (d->blendif & (lab ? 0x3300u : 0x7700u))) return B200_ERR_UNSUPPORTED;
+  if(lab)
+  { // the operators through LCh (atan2f, hypotf, cosf, sinf): chromaticity, hue, colour, colour adjustment
+    const unsigned m = d->blend_mode & 0xFFu;
+    if(m == 0x11 || m == 0x12 || m == 0x13 || m == 0x16) return B200_ERR_UNSUPPORTED;
+  }
+  const unsigned channel_mask = lab ? (unsigned)BLENDIF_LAB_MASK : (unsigned)BLENDIF_RGB_MASK;
+  pl.lab = lab;
   bool parametric = false; // dt_develop_blend_get_mask_usage(), :290-312
   if(d->mask_mode & MASK_PARAMETRIC)
     for(unsigned ch = 0; ch < BLENDIF_SIZE; ch++)
     {
-      if(!(BLENDIF_RGB_MASK & (1u << ch)) || !(d->blendif & (1u << ch))) continue;
+      if(!(channel_mask & (1u << ch)) || !(d->blendif & (1u << ch))) continue;
       const float *c = d->blendif_parameters + 4 * ch;
       if(fabsf(c[0]) > 1e-6f || fabsf(c[1]) > 1e-6f || fabsf(c[2] - 1.0f) > 1e-6f || fabsf(c[3] - 1.0f) > 1e-6f) parametric = true;
     }
@@ -275,11 +459,11 @@ int bl_plan(blend_plan_t &pl, const b200_blend_params_t *d, bool have_form)
     pl.kind = 2;
     pl.seed_form = raster || drawn;
     pl.fill = (d->mask_combine & COMBINE_INCL) ? 0.0f : 1.0f;
-    const unsigned any_active = d->blendif & BLENDIF_RGB_MASK;
+    const unsigned any_active = d->blendif & channel_mask;
     pl.inclusive = (d->mask_combine & COMBINE_INCL) != 0;
     pl.inversed = (d->mask_combine & COMBINE_INV) != 0;
-    pl.blendif = d->blendif ^ (pl.inclusive ? (unsigned)BLENDIF_RGB_MASK << 16 : 0u);
-    const unsigned canceling = (pl.blendif >> 16) & ~pl.blendif & BLENDIF_RGB_MASK;
+    pl.blendif = d->blendif ^ (pl.inclusive ? channel_mask << 16 : 0u);
+    const unsigned canceling = (pl.blendif >> 16) & ~pl.blendif & channel_mask;
     if(!(d->mask_mode & MASK_PARAMETRIC) || (!canceling && !any_active))
       pl.pm = 0;
     else if(canceling || !any_active)

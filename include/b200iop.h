@@ -752,12 +752,12 @@ int b200_flt32_eval_dev(int fn, const float *d_x, const float *d_y, float *d_out
 typedef struct b200_blend_params_t
 {
   uint32_t mask_mode;        /* dt_develop_mask_mode_t: 1 enabled, 2 drawn mask, 4 parametric mask, 8 raster mask */
-  int32_t blend_cst;         /* dt_develop_blend_colorspace_t: 4 = DEVELOP_BLEND_CS_RGB_SCENE is built */
+  int32_t blend_cst;         /* dt_develop_blend_colorspace_t: 2 = DEVELOP_BLEND_CS_LAB and 4 = DEVELOP_BLEND_CS_RGB_SCENE are built */
   uint32_t blend_mode;       /* dt_develop_blend_mode_t, | 0x80000000 = DEVELOP_BLEND_REVERSE */
   float blend_parameter;     /* exposure-like parameter of the operator, in EV */
   float opacity;             /* 0 .. 100 */
   uint32_t mask_combine;     /* dt_develop_mask_combine_mode_t: 1 inverted, 2 inclusive */
-  uint32_t blendif;          /* bits 0..3 / 4..7: gray, red, green, blue of the input / output take part; bit + 16: that channel inverted */
+  uint32_t blendif;          /* bits 0..3 / 4..7: gray, red, green, blue (Lab: L, a, b) of the input / output take part; bit + 16: that channel inverted */
   float feathering_radius;
   uint32_t feathering_guide;
   float blur_radius, contrast, brightness, details;
@@ -773,9 +773,11 @@ typedef struct b200_blend_params_t
  * alpha lane; form_mask: the raster / drawn mask of roi_out the host rasterised, or NULL; mask: receives the final mask (what the reference
  * publishes as the module's raster mask, :892-950), or NULL.  Built: the scene-referred RGB space (develop/blends/blendif_rgb_jzczhz.c) with
  * uniform, raster, drawn and parametric (gray, red, green, blue of input and output) masks, their exclusive / inclusive / inverted
- * combinations, the mask tone curve and the sixteen blend operators.  B200_ERR_UNSUPPORTED (fall back to dt_develop_blend_process): feathering,
- * blur and detail refinement of the mask, the JzCzhz channels, the other colour spaces.  mask_mode without the enabled bit: B200_OK, nothing
- * touched. */
+ * combinations, the mask tone curve and the sixteen blend operators; the Lab space (develop/blends/blendif_lab.c, what local contrast and the
+ * other Lab modules blend in) with the same masks on the L, a and b channels and the twenty-two operators that stay in Lab.
+ * B200_ERR_UNSUPPORTED (fall back to dt_develop_blend_process): feathering, blur and detail refinement of the mask; the JzCzhz channels of the
+ * RGB space; chroma and hue channels and the chromaticity / hue / colour / colour-adjustment operators of the Lab space; the display-RGB and raw
+ * spaces.  mask_mode without the enabled bit: B200_OK, nothing touched. */
 int b200_blend_process_host(const b200_piece_t *piece, const b200_blend_params_t *bp, const void *in, void *out, const float *form_mask, float *mask);
 /* dt_develop_blend_process_cl() slot, develop/blend.c:1113-1604: device pointers */
 int b200_blend_process_dev(const b200_piece_t *piece, const b200_blend_params_t *bp, const void *d_in, void *d_out, const float *d_form_mask,

@@ -1,11 +1,14 @@
-/* CPU restatement of a module's blending (mask + blend operator) in the scene-referred RGB space.  TEST INFRASTRUCTURE ONLY.
+/* CPU restatement of a module's blending (mask + blend operator) in the scene-referred RGB space and in Lab.  TEST INFRASTRUCTURE ONLY.
  *
  * Follows /root/reference/src: develop/blend.c dt_develop_blend_process :657-860 (mask usage :262-320, post operations :427-469,
  * dt_develop_blendif_process_parameters :214-260, _develop_blend_process_mask_tone_curve :626-655) and
  * develop/blends/blendif_rgb_jzczhz.c (_blendif_compute_factor :42-73, the gray / red / green / blue channels :75-121,
  * _blendif_combine_channels :151-194, dt_develop_blendif_rgb_jzczhz_make_mask :196-325, the sixteen operators :328-585,
  * _choose_blend_func :587-649, dt_develop_blendif_rgb_jzczhz_blend :878-961).  Pinned bit-for-bit against those lines cut verbatim
- * (oracle/_ref: ref_blend.c).
+ * (oracle/_ref: ref_blend.c).  For blend_cst == DEVELOP_BLEND_CS_LAB: develop/blends/blendif_lab.c (the L / a / b / C / h channels :90-137,
+ * _blendif_combine_channels :139-173, dt_develop_blendif_lab_make_mask :175-298, the 26 operators :302-1068, _choose_blend_func
+ * :1070-1162, dt_develop_blendif_lab_blend :1302-1418), pinned against oracle/_ref: ref_blend_lab.c.  The C / h channels and the four
+ * LCh operators go through the host's atan2f / hypotf / cosf / sinf / fmodf, like the reference.
  *
  * Everything here is a function of one pixel of the module's input, the same pixel of its output and the same pixel of the form
  * mask (the raster / drawn mask the host rasterised): the reference's passes over whole buffers are folded into one evaluation per
@@ -23,7 +26,7 @@ enum
   MASK_ENABLED = 1, MASK_SHAPE = 2, MASK_PARAMETRIC = 4, MASK_RASTER = 8, /* dt_develop_mask_mode_t, blend.h:110-118 */
   COMBINE_INV = 1, COMBINE_INCL = 2,                                      /* dt_develop_mask_combine_mode_t :120-131 */
   BLENDIF_SIZE = 16, BLENDIF_ITEMS = 6, BLENDIF_RGB_MASK = 0x77FF,        /* :188-191, :329 */
-  CS_RGB_SCENE = 4,                                                        /* :52-59 */
+  BLENDIF_LAB_MASK = 0x3377, CS_LAB = 2, CS_RGB_SCENE = 4,                 /* :52-59 */
   DISPLAY_MASK = 1                                                         /* develop.h:123 */
 };
 #define BLEND_REVERSE 0x80000000u /* blend.h:106 */
@@ -45,7 +48,7 @@ typedef struct orc_blend_params_t
   uint32_t mask_display;           /* pipe->mask_display */
 } orc_blend_params_t;
 
-/* :214-260 for the RGB spaces (no Lab offset) */
+/* :214-260: in Lab the limits of the a and b channels are offset by a half */
 static void blendif_parameters(float *par, const orc_blend_params_t *d)
 {
   for(int i = 0; i < BLENDIF_SIZE; i++)
@@ -55,7 +58,8 @@ static void blendif_parameters(float *par, const orc_blend_params_t *d)
     if(d->blendif & (1u << i))
     {
       const float boost = exp2f(d->blendif_boost_factors[i]);
-      for(int k = 0; k < 4; k++) p[k] = (b[k] - 0.0f) * boost;
+      const float offset = (d->blend_cst == CS_LAB && (i == 1 || i == 2 || i == 5 || i == 6)) ? 0.5f : 0.0f;
+      for(int k = 0; k < 4; k++) p[k] = (b[k] - offset) * boost;
       p[4] = 1.0f / fmaxf(0.001f, p[1] - p[0]);
       p[5] = 1.0f / fmaxf(0.001f, p[3] - p[2]);
       if(b[0] <= 0.0f && b[1] <= 0.0f) p[0] = p[1] = -INFINITY;
@@ -94,6 +98,43 @@ static float blendif_channels(const float *px, float t, unsigned blendif, const 
   return t;
 }
 
+#define PI_F 3.14159265358979324f /* DT_M_PI_F, math/math.h */
+/* dt_Lab_2_LCH / dt_LCH_2_Lab, common/colorspaces_inline_conversions.h:594-615 */
+static void lab_to_lch(const float *lab, float *lch)
+{
+  float h = atan2f(lab[2], lab[1]);
+  if(h > 0.0f)
+    h = h / (2.0f * PI_F);
+  else
+    h = 1.0f - fabsf(h) / (2.0f * PI_F);
+  lch[0] = lab[0];
+  lch[1] = hypotf(lab[1], lab[2]);
+  lch[2] = h;
+}
+static void lch_to_lab(const float *lch, float *lab)
+{
+  lab[0] = lch[0];
+  lab[1] = cosf(2.0f * PI_F * lch[2]) * lch[1];
+  lab[2] = sinf(2.0f * PI_F * lch[2]) * lch[1];
+}
+/* blendif_lab.c:139-173 for one pixel: L, a, b, then chroma and hue together, of the channel set starting at bit 0 of `blendif` / at `par` */
+static float blendif_channels_lab(const float *px, float t, unsigned blendif, const float *par)
+{
+  if(blendif & 1u) t *= blendif_factor(px[0] / 100.0f, (blendif >> 16) & 1u, par);
+  if(blendif & 2u) t *= blendif_factor(px[1] / 256.0f, (blendif >> 16) & 2u, par + BLENDIF_ITEMS);
+  if(blendif & 4u) t *= blendif_factor(px[2] / 256.0f, (blendif >> 16) & 4u, par + BLENDIF_ITEMS * 2);
+  if(blendif & 0x300u)
+  {
+    const float c_scale = 1.0f / (128.0f * sqrtf(2.0f));
+    float lch[3], factor = 1.0f;
+    lab_to_lch(px, lch);
+    factor *= blendif_factor(lch[1] * c_scale, (blendif >> 16) & 0x100u, par + BLENDIF_ITEMS * 8);
+    factor *= blendif_factor(lch[2], (blendif >> 16) & 0x200u, par + BLENDIF_ITEMS * 9);
+    t *= factor;
+  }
+  return t;
+}
+
 typedef struct
 {
   int kind;        /* 0: mask = opacity; 1: mask = form * opacity (raster only); 2: seed, then the parametric stage */
@@ -120,8 +161,17 @@ static float plan_mask(const blend_plan_t *pl, const orc_blend_params_t *d, cons
     m = pl->pm_const; /* :233-240 */
   else
   { /* :241-320 */
-    float t = blendif_channels(a, 1.0f, pl->blendif, pl->par, d->luminance);
-    t = blendif_channels(b, t, pl->blendif >> 4, pl->par + BLENDIF_ITEMS * 4, d->luminance);
+    float t;
+    if(d->blend_cst == CS_LAB)
+    {
+      t = blendif_channels_lab(a, 1.0f, pl->blendif, pl->par);
+      t = blendif_channels_lab(b, t, pl->blendif >> 4, pl->par + BLENDIF_ITEMS * 4);
+    }
+    else
+    {
+      t = blendif_channels(a, 1.0f, pl->blendif, pl->par, d->luminance);
+      t = blendif_channels(b, t, pl->blendif >> 4, pl->par + BLENDIF_ITEMS * 4, d->luminance);
+    }
     if(pl->inclusive)
       m = pl->inversed ? g * (1.0f - m) * t : g * (1.0f - (1.0f - m) * t);
     else
@@ -194,7 +244,209 @@ static void blend_pixel(unsigned mode, const float *a, const float *b, float p, 
   out[3] = lo;
 }
 
-/* dt_develop_blend_process() for blend_cst == DEVELOP_BLEND_CS_RGB_SCENE.  in: the module's input (iw x ih RGBA), out: its output
+/* ---- Lab, blendif_lab.c:302-1068: a = the lower layer, b = the upper one, lo = the mask; the pixels are scaled to L / 100, a / 128, b / 128,
+ * blended between min = { 0, -1, -1 } and max = { 1, 1, 1 } and scaled back ---- */
+static float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); } /* _CLAMP :45-48 */
+static const float LAB_MIN[3] = { 0.0f, -1.0f, -1.0f }, LAB_MAX[3] = { 1.0f, 1.0f, 1.0f };
+/* the shifted lightness of the operators of the "light" family: la, lb in [0, lmax] */
+static void light_pair(const float *ta, const float *tb, float *la, float *lb, float *lmax)
+{
+  *lmax = LAB_MAX[0] + fabsf(LAB_MIN[0]);
+  *la = clampf(ta[0] + fabsf(LAB_MIN[0]), 0.0f, *lmax);
+  *lb = clampf(tb[0] + fabsf(LAB_MIN[0]), 0.0f, *lmax);
+}
+/* a and b follow the lightness: what multiply, overlay, softlight, hardlight, vividlight and linearlight do to them */
+static void follow(const float *ta, float *tb, float o)
+{
+  const float f = fmaxf(ta[0], 0.01f);
+  tb[1] = clampf(ta[1] * (1.0f - o) + (ta[1] + tb[1]) * tb[0] / f * o, LAB_MIN[1], LAB_MAX[1]);
+  tb[2] = clampf(ta[2] * (1.0f - o) + (ta[2] + tb[2]) * tb[0] / f * o, LAB_MIN[2], LAB_MAX[2]);
+}
+static void hue_towards(const float *tta, float *ttb, float lo)
+{ /* blend hue along the shortest distance on the colour circle :888-891 */
+  const float d = fabsf(tta[2] - ttb[2]);
+  const float s = d > 0.5f ? -lo * (1.0f - d) / d : lo;
+  ttb[2] = fmodf((tta[2] * (1.0f - s)) + ttb[2] * s + 1.0f, 1.0f);
+}
+static void lab_blend_pixel(unsigned mode, const float *a, const float *b, float lo, float *out)
+{
+  static const float scale[3] = { 1 / 100.0f, 1 / 128.0f, 1 / 128.0f }, rescale[3] = { 100.0f, 128.0f, 128.0f };
+  const float *mn = LAB_MIN, *mx = LAB_MAX;
+  float ta[3], tb[3];
+  for(int c = 0; c < 3; c++)
+  {
+    ta[c] = a[c] * scale[c];
+    tb[c] = b[c] * scale[c];
+  }
+  const float lo2 = lo * lo;
+  float la, lb, lmax;
+  switch(mode & 0xFFu)
+  {
+    case 0x02: /* lighten */
+    case 0x03: /* darken */
+    {
+      const float pick = (mode & 0xFFu) == 0x02 ? (ta[0] > tb[0] ? ta[0] : tb[0]) : (ta[0] < tb[0] ? ta[0] : tb[0]);
+      tb[0] = clampf(ta[0] * (1.0f - lo) + pick * lo, mn[0], mx[0]);
+      tb[1] = clampf(ta[1] * (1.0f - fabsf(tb[0] - ta[0])) + 0.5f * (ta[1] + tb[1]) * fabsf(tb[0] - ta[0]), mn[1], mx[1]);
+      tb[2] = clampf(ta[2] * (1.0f - fabsf(tb[0] - ta[0])) + 0.5f * (ta[2] + tb[2]) * fabsf(tb[0] - ta[0]), mn[2], mx[2]);
+      break;
+    }
+    case 0x04: /* multiply */
+      tb[0] = clampf(ta[0] * (1.0f - lo) + (ta[0] * tb[0]) * lo, mn[0], mx[0]);
+      follow(ta, tb, lo);
+      break;
+    case 0x05: /* average */
+      for(int c = 0; c < 3; c++) tb[c] = clampf(ta[c] * (1.0f - lo) + (ta[c] + tb[c]) / 2.0f * lo, mn[c], mx[c]);
+      break;
+    case 0x06: /* add */
+      for(int c = 0; c < 3; c++) tb[c] = clampf(ta[c] * (1.0f - lo) + (ta[c] + tb[c]) * lo, mn[c], mx[c]);
+      break;
+    case 0x07: /* subtract */
+      for(int c = 0; c < 3; c++) tb[c] = clampf(ta[c] * (1.0f - lo) + ((tb[c] + ta[c]) - (fabsf(mn[c] + mx[c]))) * lo, mn[c], mx[c]);
+      break;
+    case 0x08: /* difference (deprecated) */
+      for(int c = 0; c < 3; c++)
+      {
+        const float cmax = mx[c] + fabsf(mn[c]);
+        const float ca = clampf(ta[c] + fabsf(mn[c]), 0.0f, cmax), cb = clampf(tb[c] + fabsf(mn[c]), 0.0f, cmax);
+        tb[c] = clampf(ca * (1.0f - lo) + fabsf(ca - cb) * lo, 0.0f, cmax) - fabsf(mn[c]);
+      }
+      break;
+    case 0x17: /* difference */
+      for(int c = 0; c < 3; c++) tb[c] = fabsf(ta[c] - tb[c]) / fabsf(mx[c] - mn[c]);
+      tb[0] = fmaxf(tb[0], fmaxf(tb[1], tb[2]));
+      tb[0] = clampf(ta[0] * (1.0f - lo) + tb[0] * lo, mn[0], mx[0]);
+      tb[1] = 0.0f;
+      tb[2] = 0.0f;
+      break;
+    case 0x09: /* screen */
+    {
+      light_pair(ta, tb, &la, &lb, &lmax);
+      tb[0] = clampf(la * (1.0f - lo) + ((lmax - (lmax - la) * (lmax - lb))) * lo, 0.0f, lmax) - fabsf(mn[0]);
+      const float f = fmaxf(ta[0], 0.01f);
+      tb[1] = clampf(ta[1] * (1.0f - lo) + 0.5f * (ta[1] + tb[1]) * tb[0] / f * lo, mn[1], mx[1]);
+      tb[2] = clampf(ta[2] * (1.0f - lo) + 0.5f * (ta[2] + tb[2]) * tb[0] / f * lo, mn[2], mx[2]);
+      break;
+    }
+    case 0x0A: /* overlay */
+    {
+      light_pair(ta, tb, &la, &lb, &lmax);
+      const float halfmax = lmax / 2.0f, doublemax = lmax * 2.0f;
+      tb[0] = clampf(la * (1.0f - lo2) + (la > halfmax ? lmax - (lmax - doublemax * (la - halfmax)) * (lmax - lb) : (doublemax * la) * lb) * lo2, 0.0f, lmax)
+              - fabsf(mn[0]);
+      follow(ta, tb, lo2);
+      break;
+    }
+    case 0x0B: /* softlight */
+    {
+      light_pair(ta, tb, &la, &lb, &lmax);
+      const float halfmax = lmax / 2.0f;
+      tb[0] = clampf(la * (1.0f - lo2) + (lb > halfmax ? lmax - (lmax - la) * (lmax - (lb - halfmax)) : la * (lb + halfmax)) * lo2, 0.0f, lmax) - fabsf(mn[0]);
+      follow(ta, tb, lo2);
+      break;
+    }
+    case 0x0C: /* hardlight */
+    {
+      light_pair(ta, tb, &la, &lb, &lmax);
+      const float halfmax = lmax / 2.0f, doublemax = lmax * 2.0f;
+      tb[0] = clampf(la * (1.0f - lo2) + (lb > halfmax ? lmax - (lmax - doublemax * (la - halfmax)) * (lmax - lb) : doublemax * la * lb) * lo2, 0.0f, lmax)
+              - fabsf(mn[0]);
+      follow(ta, tb, lo2);
+      break;
+    }
+    case 0x0D: /* vividlight */
+    {
+      light_pair(ta, tb, &la, &lb, &lmax);
+      const float halfmax = lmax / 2.0f, doublemax = lmax * 2.0f;
+      tb[0] = clampf(la * (1.0f - lo2)
+                         + (lb > halfmax ? (lb >= lmax ? lmax : la / (doublemax * (lmax - lb))) : (lb <= 0.0f ? 0.0f : lmax - (lmax - la) / (doublemax * lb))) * lo2,
+                     0.0f, lmax)
+              - fabsf(mn[0]);
+      follow(ta, tb, lo2);
+      break;
+    }
+    case 0x0E: /* linearlight */
+    {
+      light_pair(ta, tb, &la, &lb, &lmax);
+      const float doublemax = lmax * 2.0f;
+      tb[0] = clampf(la * (1.0f - lo2) + (la + doublemax * lb - lmax) * lo2, 0.0f, lmax) - fabsf(mn[0]);
+      follow(ta, tb, lo2);
+      break;
+    }
+    case 0x0F: /* pinlight */
+    {
+      light_pair(ta, tb, &la, &lb, &lmax);
+      const float halfmax = lmax / 2.0f, doublemax = lmax * 2.0f;
+      tb[0] = clampf(la * (1.0f - lo2) + (lb > halfmax ? fmaxf(la, doublemax * (lb - halfmax)) : fminf(la, doublemax * lb)) * lo2, 0.0f, lmax) - fabsf(mn[0]);
+      tb[1] = clampf(ta[1], mn[1], mx[1]);
+      tb[2] = clampf(ta[2], mn[2], mx[2]);
+      break;
+    }
+    case 0x10: /* lightness */
+      tb[0] = clampf(ta[0] * (1.0f - lo) + tb[0] * lo, mn[0], mx[0]);
+      tb[1] = clampf(ta[1], mn[1], mx[1]);
+      tb[2] = clampf(ta[2], mn[2], mx[2]);
+      break;
+    case 0x11: /* chromaticity */
+    case 0x12: /* hue */
+    case 0x13: /* colour */
+    case 0x16: /* colour adjustment */
+    {
+      const unsigned m = mode & 0xFFu;
+      float tta[3], ttb[3];
+      for(int c = 0; c < 3; c++)
+      {
+        ta[c] = clampf(ta[c], mn[c], mx[c]);
+        tb[c] = clampf(tb[c], mn[c], mx[c]);
+      }
+      lab_to_lch(ta, tta);
+      lab_to_lch(tb, ttb);
+      if(m != 0x16) ttb[0] = tta[0];
+      if(m == 0x12)
+        ttb[1] = tta[1];
+      else
+        ttb[1] = (tta[1] * (1.0f - lo)) + ttb[1] * lo;
+      if(m == 0x11)
+        ttb[2] = tta[2];
+      else
+        hue_towards(tta, ttb, lo);
+      lch_to_lab(ttb, tb);
+      for(int c = 0; c < 3; c++) tb[c] = clampf(tb[c], mn[c], mx[c]);
+      break;
+    }
+    case 0x19: /* normal, bounded */
+      for(int c = 0; c < 3; c++) tb[c] = clampf(ta[c] * (1.0f - lo) + tb[c] * lo, mn[c], mx[c]);
+      break;
+    case 0x1A:
+    case 0x1E: /* Lab lightness */
+      tb[0] = ta[0] * (1.0f - lo) + tb[0] * lo;
+      tb[1] = ta[1];
+      tb[2] = ta[2];
+      break;
+    case 0x1F: /* Lab a */
+      tb[0] = ta[0];
+      tb[1] = ta[1] * (1.0f - lo) + tb[1] * lo;
+      tb[2] = ta[2];
+      break;
+    case 0x20: /* Lab b */
+      tb[0] = ta[0];
+      tb[1] = ta[1];
+      tb[2] = ta[2] * (1.0f - lo) + tb[2] * lo;
+      break;
+    case 0x1B: /* Lab colour */
+      tb[0] = ta[0];
+      tb[1] = ta[1] * (1.0f - lo) + tb[1] * lo;
+      tb[2] = ta[2] * (1.0f - lo) + tb[2] * lo;
+      break;
+    default: /* normal */
+      for(int c = 0; c < 3; c++) tb[c] = ta[c] * (1.0f - lo) + tb[c] * lo;
+      break;
+  }
+  for(int c = 0; c < 3; c++) out[c] = tb[c] * rescale[c];
+  out[3] = lo;
+}
+
+/* dt_develop_blend_process() for blend_cst == DEVELOP_BLEND_CS_RGB_SCENE and DEVELOP_BLEND_CS_LAB.  in: the module's input (iw x ih RGBA), out: its output
  * (ow x oh RGBA, roi_out at (xoffs, yoffs) inside roi_in), blended in place; form: the form mask of roi_out or NULL; mask_out: the final
  * mask or NULL.  0 = done (also when blending is off), -1 = not restated. */
 int orc_blend_process(const float *in, float *out, int iw, int ih, int ow, int oh, int xoffs, int yoffs, const orc_blend_params_t *d,
@@ -202,9 +454,11 @@ int orc_blend_process(const float *in, float *out, int iw, int ih, int ow, int o
 {
   (void)ih;
   if(!(d->mask_mode & MASK_ENABLED)) return 0; /* :673 */
-  if(d->blend_cst != CS_RGB_SCENE || d->profile_nonlinear) return -1;
+  const int lab = d->blend_cst == CS_LAB;
+  if(!lab && (d->blend_cst != CS_RGB_SCENE || d->profile_nonlinear)) return -1;
   if(d->feathering_radius > 0.1f || d->blur_radius > 0.1f || d->details != 0.0f) return -1;
-  if((d->mask_mode & MASK_PARAMETRIC) && (d->blendif & 0x7700u)) return -1;
+  if(!lab && (d->mask_mode & MASK_PARAMETRIC) && (d->blendif & 0x7700u)) return -1;
+  const unsigned channel_mask = lab ? (unsigned)BLENDIF_LAB_MASK : (unsigned)BLENDIF_RGB_MASK;
   orc_fp_fast_mode(); /* the pipe's threads run with FTZ|DAZ (darktable.c:877, common/dtpthread.c:54) */
   blend_plan_t pl;
   memset(&pl, 0, sizeof(pl));
@@ -212,7 +466,7 @@ int orc_blend_process(const float *in, float *out, int iw, int ih, int ow, int o
   if(d->mask_mode & MASK_PARAMETRIC)
     for(unsigned ch = 0; ch < BLENDIF_SIZE; ch++)
     {
-      if(!(BLENDIF_RGB_MASK & (1u << ch)) || !(d->blendif & (1u << ch))) continue;
+      if(!(channel_mask & (1u << ch)) || !(d->blendif & (1u << ch))) continue;
       const float *c = d->blendif_parameters + 4 * ch;
       if(fabsf(c[0]) > 1e-6f || fabsf(c[1]) > 1e-6f || fabsf(c[2] - 1.0f) > 1e-6f || fabsf(c[3] - 1.0f) > 1e-6f) parametric = 1;
     }
@@ -228,11 +482,11 @@ int orc_blend_process(const float *in, float *out, int iw, int ih, int ow, int o
     pl.seed_form = raster || drawn;
     pl.fill = (d->mask_combine & COMBINE_INCL) ? 0.0f : 1.0f;
     /* make_mask, :196-325 */
-    const unsigned any_active = d->blendif & BLENDIF_RGB_MASK;
+    const unsigned any_active = d->blendif & channel_mask;
     pl.inclusive = (d->mask_combine & COMBINE_INCL) != 0;
     pl.inversed = (d->mask_combine & COMBINE_INV) != 0;
-    pl.blendif = d->blendif ^ (pl.inclusive ? (unsigned)BLENDIF_RGB_MASK << 16 : 0u);
-    const unsigned canceling = (pl.blendif >> 16) & ~pl.blendif & BLENDIF_RGB_MASK;
+    pl.blendif = d->blendif ^ (pl.inclusive ? channel_mask << 16 : 0u);
+    const unsigned canceling = (pl.blendif >> 16) & ~pl.blendif & channel_mask;
     if(!(d->mask_mode & MASK_PARAMETRIC) || (!canceling && !any_active))
       pl.pm = 0;
     else if(canceling || !any_active)
@@ -258,7 +512,9 @@ int orc_blend_process(const float *in, float *out, int iw, int ih, int ow, int o
       float *b = out + 4 * ((size_t)y * ow + x);
       const float m = plan_mask(&pl, d, a, b, form ? form[(size_t)y * ow + x] : 0.0f);
       float res[4];
-      if(reverse)
+      if(lab)
+        lab_blend_pixel(d->blend_mode, reverse ? b : a, reverse ? a : b, m, res);
+      else if(reverse)
         blend_pixel(d->blend_mode, b, a, p, m, res);
       else
         blend_pixel(d->blend_mode, a, b, p, m, res);

@@ -7,11 +7,17 @@ import util
 
 MASK_ENABLED, MASK_SHAPE, MASK_PARAMETRIC, MASK_RASTER = 1, 2, 4, 8
 COMBINE_INV, COMBINE_INCL = 1, 2
-CS_RGB_SCENE = 4
+CS_LAB, CS_RGB_SCENE = 2, 4
 REVERSE = 0x80000000
 MODES = {"normal": 0x18, "multiply": 0x04, "average": 0x05, "add": 0x06, "subtract": 0x07, "subtract_inverse": 0x25, "difference": 0x17,
          "divide": 0x26, "divide_inverse": 0x27, "geometric_mean": 0x28, "harmonic_mean": 0x29, "luminance": 0x10, "chromaticity": 0x11,
          "rgb_r": 0x21, "rgb_g": 0x22, "rgb_b": 0x23}
+# the operators of the Lab space (develop/blends/blendif_lab.c _choose_blend_func :1070-1162)
+LAB_MODES = {"normal": 0x18, "bounded": 0x19, "lighten": 0x02, "darken": 0x03, "multiply": 0x04, "average": 0x05, "add": 0x06, "subtract": 0x07,
+             "difference_old": 0x08, "difference": 0x17, "screen": 0x09, "overlay": 0x0A, "softlight": 0x0B, "hardlight": 0x0C, "vividlight": 0x0D,
+             "linearlight": 0x0E, "pinlight": 0x0F, "lightness": 0x10, "chromaticity": 0x11, "hue": 0x12, "color": 0x13, "coloradjust": 0x16,
+             "lab_lightness": 0x1A, "lab_l": 0x1E, "lab_a": 0x1F, "lab_b": 0x20, "lab_color": 0x1B}
+LAB_LCH_MODES = ("chromaticity", "hue", "color", "coloradjust")      # through atan2f / hypotf / cosf / sinf: not built on the device
 LUMINANCE = (0.2627002120112671, 0.6779980715188708, 0.05930171646986196)   # row Y of linear Rec2020 -> XYZ
 
 
@@ -28,8 +34,9 @@ def params(mode="normal", opacity=65.0, mask_mode=MASK_ENABLED, reverse=False, b
     """channels: {bit: (p0, p1, p2, p3)} of the parametric mask (bits 0..3 gray/R/G/B of the input, 4..7 of the output; bit + 16 in `blendif`
     inverts a channel)"""
     p = BlendParams()
-    p.mask_mode, p.blend_cst = mask_mode, CS_RGB_SCENE
-    p.blend_mode = MODES[mode] | (REVERSE if reverse else 0)
+    cst = extra.pop("cst", CS_RGB_SCENE)
+    p.mask_mode, p.blend_cst = mask_mode, cst
+    p.blend_mode = (LAB_MODES if cst == CS_LAB else MODES)[mode] | (REVERSE if reverse else 0)
     p.blend_parameter, p.opacity, p.mask_combine, p.blendif = blend_parameter, opacity, combine, blendif
     p.contrast, p.brightness = contrast, brightness
     for i in range(16):
@@ -61,6 +68,25 @@ def frames(w=160, h=120, seed=1, xoffs=0, yoffs=0, iw=None, ih=None):
     return np.ascontiguousarray(a), np.ascontiguousarray(b), np.ascontiguousarray(form)
 
 
+def frames_lab(w=160, h=120, seed=1, xoffs=0, yoffs=0):
+    """the same for a Lab module: L in 0 .. 100 and a little beyond, a and b within +-90"""
+    a, b, form = frames(w, h, seed, xoffs, yoffs)
+    rng = np.random.default_rng(seed + 100)
+
+    def to_lab(x, shape):
+        lab = np.empty_like(x)
+        lab[..., 0] = x[..., 1] * np.float32(62.0) - np.float32(3.0)
+        lab[..., 1] = (x[..., 0] - x[..., 1]) * np.float32(140.0) + rng.normal(0, 6, shape).astype(np.float32)
+        lab[..., 2] = (x[..., 1] - x[..., 2]) * np.float32(140.0) + rng.normal(0, 6, shape).astype(np.float32)
+        lab[..., 3] = x[..., 3]
+        return np.ascontiguousarray(lab)
+
+    a, b = to_lab(a, a.shape[:2]), to_lab(b, b.shape[:2])
+    a[3, 5, 1:3] = 0.0                  # a grey pixel: atan2f(0, 0)
+    b[11, 4, 1:3] = (0.0, -4.0)
+    return a, b, form
+
+
 def _run(lib, fn, a, b, p, form=None, xoffs=0, yoffs=0, want_mask=True):
     ih, iw = a.shape[:2]
     oh, ow = b.shape[:2]
@@ -89,7 +115,7 @@ def oracle(a, b, p, form=None, xoffs=0, yoffs=0):
 
 def ref(a, b, p, form=None, xoffs=0, yoffs=0, kind="strict"):
     lib = util.ref(kind)
-    return None if lib is None else _run(lib, "ref_blend_process", a, b, p, form, xoffs, yoffs)
+    return None if lib is None else _run(lib, "ref_blend_lab_process" if p.blend_cst == CS_LAB else "ref_blend_process", a, b, p, form, xoffs, yoffs)
 
 
 # the configurations every layer is checked on: (name, params kwargs, uses the form mask)
@@ -119,6 +145,31 @@ CONFIGS = [(m, dict(mode=m), False) for m in MODES] + [
     ("mask_display", dict(mode="add", mask_display=1), False),
     ("disabled", dict(mask_mode=0), False),
 ]
+
+# Lab: every operator, then the mask sources and combinations on the Lab channels (bits 0..2 L/a/b and 8..9 C/h of the input, 4..6 and 12..13 of the output)
+_PAR = MASK_ENABLED | MASK_PARAMETRIC
+LAB_CONFIGS = [("lab_" + m, dict(cst=CS_LAB, mode=m), False) for m in LAB_MODES] + [
+    ("lab_overlay_reverse", dict(cst=CS_LAB, mode="overlay", reverse=True, opacity=40.0), False),
+    ("lab_multiply_drawn", dict(cst=CS_LAB, mode="multiply", mask_mode=MASK_ENABLED | MASK_SHAPE, drawn=1), True),
+    ("lab_vividlight_raster", dict(cst=CS_LAB, mode="vividlight", mask_mode=MASK_ENABLED | MASK_RASTER, raster=1, opacity=90.0), True),
+    ("lab_parametric_L_in", dict(cst=CS_LAB, mask_mode=_PAR, channels={0: (0.1, 0.3, 0.6, 0.8)}), False),
+    ("lab_parametric_ab_out", dict(cst=CS_LAB, mask_mode=_PAR, channels={5: (0.3, 0.45, 0.6, 0.7), 6: (0.2, 0.4, 1.0, 1.0), 2: (0.0, 0.0, 0.55, 0.65)}), False),
+    ("lab_parametric_inverted_a", dict(cst=CS_LAB, mask_mode=_PAR, channels={1: (0.35, 0.45, 0.55, 0.7)}, blendif=1 << 17), False),
+    ("lab_parametric_inclusive", dict(cst=CS_LAB, mask_mode=_PAR, combine=COMBINE_INCL, channels={0: (0.1, 0.3, 0.7, 0.9), 6: (0.4, 0.5, 0.6, 0.8)}), False),
+    ("lab_parametric_boost_L", dict(cst=CS_LAB, mask_mode=_PAR, channels={4: (0.1, 0.3, 0.7, 0.9)}, boosts={4: -0.5}), False),
+    ("lab_parametric_canceling", dict(cst=CS_LAB, mask_mode=_PAR, channels={2: (0.4, 0.5, 0.8, 0.95)}, blendif=(1 << 16)), False),
+    ("lab_parametric_chroma_hue_in", dict(cst=CS_LAB, mask_mode=_PAR, channels={8: (0.05, 0.15, 0.5, 0.7), 9: (0.1, 0.2, 0.6, 0.75)}), False),
+    ("lab_parametric_hue_out_inverted", dict(cst=CS_LAB, mask_mode=_PAR, channels={13: (0.3, 0.4, 0.7, 0.8), 0: (0.0, 0.0, 0.7, 0.9)}, blendif=1 << 29), False),
+    ("lab_drawn_and_parametric", dict(cst=CS_LAB, mode="softlight", mask_mode=MASK_ENABLED | MASK_SHAPE | MASK_PARAMETRIC, drawn=1, channels={0: (0.1, 0.3, 0.7, 0.9)}), True),
+    ("lab_tone_curve", dict(cst=CS_LAB, mask_mode=MASK_ENABLED | MASK_SHAPE, drawn=1, contrast=0.4, brightness=0.2), True),
+    ("lab_mask_display", dict(cst=CS_LAB, mode="add", mask_display=1), False),
+]
+
+
+def lab_on_device(cfg):
+    """what the library builds of a Lab configuration: everything but the LCh operators and the C / h channels of the parametric mask"""
+    name, kw, _ = cfg
+    return kw.get("mode", "normal") not in LAB_LCH_MODES and not any(ch in (8, 9, 12, 13) for ch in kw.get("channels", {}))
 
 
 _EMUL = None

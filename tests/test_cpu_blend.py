@@ -65,7 +65,49 @@ def test_kernel_with_offsets_and_what_is_refused():
     e, o = bu.emul(a, b, p, form, 7, 5), bu.oracle(a, b, p, form, 7, 5)
     assert same_bits(e[1], o[1]).all() and same_bits(e[2], o[2]).all()
     a, b, form = bu.frames(64, 48, 4)
-    for kw in (dict(feathering_radius=5.0), dict(blur_radius=2.0), dict(details=0.5), dict(blend_cst=2), dict(profile_nonlinear=1),
+    for kw in (dict(feathering_radius=5.0), dict(blur_radius=2.0), dict(details=0.5), dict(blend_cst=3), dict(profile_nonlinear=1),
                dict(mask_mode=bu.MASK_ENABLED | bu.MASK_PARAMETRIC, channels={8: (0.1, 0.3, 0.7, 0.9)})):
         p = bu.params(**kw)
         assert bu.emul(a, b, p)[0] == -1 and bu.oracle(a, b, p)[0] == -1, kw
+
+
+# ---- the Lab space (develop/blends/blendif_lab.c) ----------------------------------------------------------------------------------------
+LAB_IDS = [c[0] for c in bu.LAB_CONFIGS]
+
+
+@need_ref
+@pytest.mark.parametrize("cfg", bu.LAB_CONFIGS, ids=LAB_IDS)
+def test_lab_oracle_equals_reference(cfg):
+    """every operator of the Lab space, the L / a / b / C / h channels of the parametric mask, the other mask sources"""
+    name, kw, uses_form = cfg
+    a, b, form = bu.frames_lab()
+    p = bu.params(**kw)
+    rc_r, out_r, mask_r = bu.ref(a, b, p, form if uses_form else None)
+    rc_o, out_o, mask_o = bu.oracle(a, b, p, form if uses_form else None)
+    assert rc_r == rc_o == 0
+    assert same_bits(out_o, out_r).all() and same_bits(mask_o, mask_r).all()
+    assert not np.array_equal(out_r[..., :3], b[..., :3])
+
+
+@need_ref
+def test_lab_oracle_equals_reference_with_roi_out_inside_roi_in():
+    a, b, form = bu.frames_lab(100, 80, 2, xoffs=7, yoffs=5)
+    for name, kw, uses_form in bu.LAB_CONFIGS[::4]:
+        p = bu.params(**kw)
+        r, o = bu.ref(a, b, p, form if uses_form else None, 7, 5), bu.oracle(a, b, p, form if uses_form else None, 7, 5)
+        assert same_bits(o[1], r[1]).all() and same_bits(o[2], r[2]).all(), name
+
+
+@pytest.mark.parametrize("cfg", bu.LAB_CONFIGS, ids=LAB_IDS)
+def test_lab_kernel_equals_oracle(cfg):
+    """the kernel thread by thread; what goes through LCh is refused by the plan (the oracle follows the reference there too)"""
+    name, kw, uses_form = cfg
+    a, b, form = bu.frames_lab(301, 77, 3)
+    p = bu.params(**kw)
+    rc_e, out_e, mask_e = bu.emul(a, b, p, form if uses_form else None)
+    rc_o, out_o, mask_o = bu.oracle(a, b, p, form if uses_form else None)
+    assert rc_o == 0
+    if not bu.lab_on_device(cfg):
+        assert rc_e == -1 and np.array_equal(out_e, b)
+        return
+    assert rc_e == 0 and same_bits(out_e, out_o).all() and same_bits(mask_e, mask_o).all()

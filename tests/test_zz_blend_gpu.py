@@ -69,10 +69,41 @@ def test_blend_inside_roi_in_and_what_is_refused(built):
     got = cuda(ab, a, b, p, form, 7, 5)
     assert got[0] == 0 and same_bits(got[1], want[1]).all() and same_bits(got[2], want[2]).all()
     a, b, form = bu.frames(64, 48, 4)
-    for kw in (dict(feathering_radius=5.0), dict(blur_radius=2.0), dict(details=0.5), dict(blend_cst=2), dict(profile_nonlinear=1),
+    for kw in (dict(feathering_radius=5.0), dict(blur_radius=2.0), dict(details=0.5), dict(blend_cst=3), dict(profile_nonlinear=1),
                dict(mask_mode=bu.MASK_ENABLED | bu.MASK_PARAMETRIC, channels={8: (0.1, 0.3, 0.7, 0.9)})):
         rc, out, _ = cuda(ab, a, b, bu.params(**kw))
         assert rc == ab.B200_ERR_UNSUPPORTED and np.array_equal(out, b), kw
+
+
+@pytest.mark.parametrize("cfg", bu.LAB_CONFIGS, ids=[c[0] for c in bu.LAB_CONFIGS])
+def test_lab_blend_bit_exact(built, cfg):
+    """the Lab space (develop/blends/blendif_lab.c): the operators that stay in Lab and the L / a / b channels of the parametric mask are built,
+    what goes through LCh is refused with the output untouched"""
+    name, kw, uses_form = cfg
+    a, b, form = bu.frames_lab(301, 177, 3)
+    p = bu.params(**kw)
+    rc, out, mask = cuda(built, a, b, p, form if uses_form else None)
+    if not bu.lab_on_device(cfg):
+        assert rc == built.B200_ERR_UNSUPPORTED and np.array_equal(out, b)
+        return
+    rc_o, out_o, mask_o = bu.oracle(a, b, p, form if uses_form else None)
+    assert rc == 0 and rc_o == 0
+    assert same_bits(out, out_o).all() and same_bits(mask, mask_o).all()
+
+
+def test_lab_blend_on_a_large_frame(built):
+    """45 MP in Lab, the overlay operator under a parametric mask on L and b: a strip against the oracle, the rest deterministic"""
+    w, h = util.SIZE_45MP
+    rng = np.random.default_rng(9)
+    a = rng.random((h, w, 4), dtype=np.float32) * np.array([100.0, 160.0, 160.0, 1.0], np.float32) - np.array([0.0, 80.0, 80.0, 0.0], np.float32)
+    b = rng.random((h, w, 4), dtype=np.float32) * np.array([100.0, 160.0, 160.0, 1.0], np.float32) - np.array([0.0, 80.0, 80.0, 0.0], np.float32)
+    p = bu.params(cst=bu.CS_LAB, mode="overlay", opacity=80.0, mask_mode=bu.MASK_ENABLED | bu.MASK_PARAMETRIC,
+                  channels={0: (0.1, 0.3, 0.7, 0.9), 6: (0.3, 0.4, 0.6, 0.8)})
+    rc, out, _ = cuda(built, a, b, p)
+    rows = slice(3000, 3048)
+    want = bu.oracle(np.ascontiguousarray(a[rows]), np.ascontiguousarray(b[rows]), p)
+    assert rc == 0 and same_bits(out[rows], want[1]).all() and not np.array_equal(out[rows, :, :3], b[rows, :, :3])
+    assert same_bits(out, cuda(built, a, b, p)[1]).all()
 
 
 def test_blend_45mp_and_linearity_of_the_normal_operator(built):
