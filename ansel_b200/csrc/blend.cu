@@ -2,10 +2,10 @@
 //
 // What the reference computes: develop/blend.c dt_develop_blend_process :657-860 with blend_cst == DEVELOP_BLEND_CS_RGB_SCENE or
 // DEVELOP_BLEND_CS_LAB: the mask (uniform opacity | the raster / drawn mask the host rasterised | the parametric mask of
-// develop/blends/blendif_rgb_jzczhz.c :42-325 on the gray, red, green and blue channels -- of develop/blends/blendif_lab.c :56-298 on
-// the L, a and b channels -- of the module's input and output, combined exclusively or inclusively, inverted or not | the mask tone
-// curve :626-655), then one of the sixteen blend operators of the RGB space (blendif_rgb_jzczhz.c :328-649) or one of the twenty-two
-// of the Lab space that stay in Lab (blendif_lab.c :302-1068), the result in place of the module's output with the mask in its alpha
+// develop/blends/blendif_rgb_jzczhz.c :42-325 on the gray, red, green, blue, Jz, Cz and hz channels -- of develop/blends/blendif_lab.c :56-298 on
+// the L, a, b, chroma and hue channels -- of the module's input and output, combined exclusively or inclusively, inverted or not | the mask tone
+// curve :626-655), then one of the sixteen blend operators of the RGB space (blendif_rgb_jzczhz.c :328-649) or one of the twenty-six
+// of the Lab space (blendif_lab.c :302-1068), the result in place of the module's output with the mask in its alpha
 // lane.  Parity contract: bit-identical to those lines under C float semantics (oracle/restate/blend_oracle.c, pinned against them
 // compiled in place).
 //
@@ -15,12 +15,13 @@
 // 52 B/px algorithmic.  What the host decides once per call (which of the reference's branches a parameter block takes, the
 // slopes of the parametric channels, exp2f / expf of the parameters) arrives in the plan; what depends on the pixel is evaluated
 // here.  Not built (B200_ERR_UNSUPPORTED, the caller falls back to the reference's own path): feathering (guided filter), Gaussian
-// blur and detail refinement of the mask; the channels and operators that need another colour space per pixel (Jz, Cz, hz of the RGB
-// space; chroma and hue, and the chromaticity / hue / colour / colour-adjustment operators, of the Lab space: atan2f, hypotf, the PQ
-// curve); the GUI's channel display; the display-RGB and raw colour spaces.
+// blur and detail refinement of the mask; the GUI's channel display; the display-RGB and raw colour spaces.  The Jz, Cz, hz channels of
+// the RGB space, the chroma and hue channels and the four LCh operators of the Lab space go through glibc's powf / atan2f / hypotf / cosf /
+// sinf as restated in flt32_math.cuh.
 #ifndef B200_KERNELS_ON_CPU // tests/emul compiles the kernel of this file with g++ to check it against the oracle without a GPU
 #include "runtime.h"
 #endif
+#include "flt32_math.cuh"
 #include <float.h>
 #include <math.h>
 #include <string.h>
@@ -51,7 +52,9 @@ struct blend_plan_t
   int inversed, inclusive;
   float pm_const;
   unsigned blendif;
-  float par[BLENDIF_ITEMS * 8]; // gray, red, green, blue (Lab: L, a, b, unused) of the input, then of the output: four limits and two slopes each
+  float par[BLENDIF_ITEMS * BLENDIF_SIZE]; // per channel (blend.h:132-187): four limits and two slopes
+  float c_scale;                           // Lab: 1 / (128 * sqrt(2)), the scale of the chroma channel
+  float masking[9];                        // RGB: matrix_out of the masking profile (RGB -> XYZ D65), row by row
   float lum[3];
   int tone;
   float contrast_e, brightness;
@@ -76,7 +79,7 @@ __device__ __forceinline__ float bl_factor(float value, unsigned invert, const f
   return invert ? 1.0f - f : f;
 }
 __device__ __forceinline__ float bl_channels(const float px[4], float t, unsigned blendif, const float *par, const float *lum)
-{ // _blendif_combine_channels(), :151-194, without the JzCzhz set
+{ // _blendif_combine_channels(), :151-185: gray, red, green, blue; bl_jzczhz() is the rest of it
   if(blendif & 1u) t *= bl_factor(lum[0] * px[0] + lum[1] * px[1] + lum[2] * px[2], (blendif >> 16) & 1u, par);
 #pragma unroll
   for(int c = 0; c < 3; c++)
@@ -93,12 +96,72 @@ __device__ __forceinline__ float bl_divc(float a, float b)
   return q;
 #endif
 }
-__device__ __forceinline__ float bl_channels_lab(const float px[4], float t, unsigned blendif, const float *par)
-{ // blendif_lab.c _blendif_combine_channels :139-173 without the chroma / hue pair (the plan refuses it): L / 100, a / 256, b / 256
+// dt_Lab_2_LCH / dt_LCH_2_Lab, common/colorspaces_inline_conversions.h:594-615, on glibc's atan2f / hypotf / cosf / sinf (flt32_math.cuh)
+__device__ __forceinline__ void bl_lab_to_lch(const float lab[3], float lch[3])
+{
+  const float two_pi = 2.0f * 3.14159265358979324f;
+  float h = f32m::atan2f_(lab[2], lab[1]);
+  if(h > 0.0f)
+    h = bl_divc(h, two_pi);
+  else
+    h = 1.0f - bl_divc(fabsf(h), two_pi);
+  lch[0] = lab[0];
+  lch[1] = f32m::hypotf_(lab[1], lab[2]);
+  lch[2] = h;
+}
+__device__ __forceinline__ void bl_lch_to_lab(const float lch[3], float lab[3])
+{
+  const float two_pi = 2.0f * 3.14159265358979324f;
+  lab[0] = lch[0];
+  lab[1] = f32m::cosf_(two_pi * lch[2]) * lch[1];
+  lab[2] = f32m::sinf_(two_pi * lch[2]) * lch[1];
+}
+__device__ __forceinline__ float bl_channels_lab(const float px[4], float t, unsigned blendif, const float *par, float c_scale)
+{ // blendif_lab.c _blendif_combine_channels :139-173: L / 100, a / 256, b / 256, then chroma and hue together
   if(blendif & 1u) t *= bl_factor(bl_divc(px[0], 100.0f), (blendif >> 16) & 1u, par);
   if(blendif & 2u) t *= bl_factor(px[1] / 256.0f, (blendif >> 16) & 2u, par + BLENDIF_ITEMS);
   if(blendif & 4u) t *= bl_factor(px[2] / 256.0f, (blendif >> 16) & 4u, par + BLENDIF_ITEMS * 2);
+  if(blendif & 0x300u)
+  {
+    float lch[3], factor = 1.0f;
+    bl_lab_to_lch(px, lch);
+    factor *= bl_factor(lch[1] * c_scale, (blendif >> 16) & 0x100u, par + BLENDIF_ITEMS * 8);
+    factor *= bl_factor(lch[2], (blendif >> 16) & 0x200u, par + BLENDIF_ITEMS * 9);
+    t *= factor;
+  }
   return t;
+}
+// the Jz, Cz, hz channels of the RGB space, blendif_rgb_jzczhz.c:122-149: XYZ D65 through the masking profile's matrix (dt_mat3x4_mul_vec4,
+// system/simd.h:189-197), dt_XYZ_2_JzAzBz and dt_JzAzBz_2_JzCzhz (common/colorspaces_inline_conversions.h:672-722, :775-781) on glibc's powf,
+// atan2f and hypotf (flt32_math.cuh); the three factors multiplied together, then into the mask
+__device__ __forceinline__ float bl_jzczhz(const float px[4], float t, unsigned blendif, const float *par, const float *mo)
+{
+  if(!(blendif & 0x700u)) return t;
+  const f32m::tables_t tb = f32m::global_tables();
+  const float b = 1.15f, g = 0.66f, c1 = 0.8359375f, c2 = 18.8515625f, c3 = 18.6875f, n = 0.159301758f, p = 134.034375f, d = -0.56f, d0 = 1.6295499532821566e-11f;
+  float d65[3];
+#pragma unroll
+  for(int c = 0; c < 3; c++) d65[c] = mo[3 * c + 2] * px[2] + (mo[3 * c + 1] * px[1] + mo[3 * c] * px[0]);
+  const float xyz[3] = { b * d65[0] - (b - 1.0f) * d65[2], g * d65[1] - (g - 1.0f) * d65[0], d65[2] };
+  const float M[3][3] = { { 0.41478972f, 0.579999f, 0.0146480f }, { -0.2015100f, 1.120649f, 0.0531008f }, { -0.0166008f, 0.264800f, 0.6684799f } };
+  const float At[3][3] = { { 0.5f, 3.524000f, 0.199076f }, { 0.5f, -4.066708f, 1.096799f }, { 0.0f, 0.542708f, -1.295875f } };
+  float lms[3], jab[3];
+#pragma unroll
+  for(int i = 0; i < 3; i++)
+  {
+    float v = M[i][0] * xyz[0] + M[i][1] * xyz[1] + M[i][2] * xyz[2];
+    v = f32m::powf_(tb, fmaxf(bl_divc(v, 10000.f), 0.0f), n);
+    lms[i] = f32m::powf_(tb, (c1 + c2 * v) / (1.0f + c3 * v), p);
+  }
+#pragma unroll
+  for(int c = 0; c < 3; c++) jab[c] = At[0][c] * lms[0] + At[1][c] * lms[1] + At[2][c] * lms[2];
+  jab[0] = fmaxf(((1.0f + d) * jab[0]) / (1.0f + d * jab[0]) - d0, 0.f);
+  const float h = bl_divc(f32m::atan2f_(jab[2], jab[1]), 2.0f * 3.14159265358979324f);
+  const float jch[3] = { jab[0], f32m::hypotf_(jab[1], jab[2]), h >= 0.0f ? h : 1.0f + h };
+  float factor = 1.0f;
+#pragma unroll
+  for(int i = 0; i < 3; i++) factor *= bl_factor(jch[i], (blendif >> 16) & (0x100u << i), par + BLENDIF_ITEMS * (8 + i));
+  return t * factor;
 }
 __device__ __forceinline__ float bl_mask(const blend_plan_t &pl, const float a[4], const float b[4], float form)
 {
@@ -115,13 +178,15 @@ __device__ __forceinline__ float bl_mask(const blend_plan_t &pl, const float a[4
     float t;
     if(pl.lab)
     {
-      t = bl_channels_lab(a, 1.0f, pl.blendif, pl.par);
-      t = bl_channels_lab(b, t, pl.blendif >> 4, pl.par + BLENDIF_ITEMS * 4);
+      t = bl_channels_lab(a, 1.0f, pl.blendif, pl.par, pl.c_scale);
+      t = bl_channels_lab(b, t, pl.blendif >> 4, pl.par + BLENDIF_ITEMS * 4, pl.c_scale);
     }
     else
     {
       t = bl_channels(a, 1.0f, pl.blendif, pl.par, pl.lum);
+      t = bl_jzczhz(a, t, pl.blendif, pl.par, pl.masking);
       t = bl_channels(b, t, pl.blendif >> 4, pl.par + BLENDIF_ITEMS * 4, pl.lum);
+      t = bl_jzczhz(b, t, pl.blendif >> 4, pl.par + BLENDIF_ITEMS * 4, pl.masking);
     }
     if(pl.inclusive)
       m = pl.inversed ? g * (1.0f - m) * t : g * (1.0f - (1.0f - m) * t);
@@ -234,7 +299,7 @@ __device__ __forceinline__ void bl_operator(unsigned mode, const float a[4], con
 }
 
 // ---- Lab, blendif_lab.c:302-1068: the pixels scaled to L / 100, a / 128, b / 128, blended between min = { 0, -1, -1 } and max = { 1, 1, 1 },
-// scaled back.  The four operators that go through LCh (chromaticity, hue, colour, colour adjustment) are refused by the plan.
+// scaled back.
 __device__ __forceinline__ float bl_clamp(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); } // _CLAMP :45-48
 // a and b follow the lightness: what multiply, overlay, softlight, hardlight, vividlight and linearlight do to them
 __device__ __forceinline__ void bl_lab_follow(const float ta[3], float tb[3], float o)
@@ -338,6 +403,36 @@ __device__ __forceinline__ void bl_operator_lab(unsigned mode, const float a[4],
       tb[1] = bl_clamp(ta[1], mn[1], mx[1]);
       tb[2] = bl_clamp(ta[2], mn[2], mx[2]);
       break;
+    case 0x11: // chromaticity
+    case 0x12: // hue
+    case 0x13: // colour
+    case 0x16: // colour adjustment: the four operators through LCh :843-976
+    {
+      const unsigned m = mode & 0xFFu;
+      float tta[3], ttb[3];
+#pragma unroll
+      for(int c = 0; c < 3; c++)
+      {
+        ta[c] = bl_clamp(ta[c], mn[c], mx[c]);
+        tb[c] = bl_clamp(tb[c], mn[c], mx[c]);
+      }
+      bl_lab_to_lch(ta, tta);
+      bl_lab_to_lch(tb, ttb);
+      if(m != 0x16) ttb[0] = tta[0];
+      ttb[1] = m == 0x12 ? tta[1] : (tta[1] * (1.0f - lo)) + ttb[1] * lo;
+      if(m == 0x11)
+        ttb[2] = tta[2];
+      else
+      { // the hue along the shortest way round the circle :888-891
+        const float d = fabsf(tta[2] - ttb[2]);
+        const float sh = d > 0.5f ? -lo * (1.0f - d) / d : lo;
+        ttb[2] = fmodf((tta[2] * (1.0f - sh)) + ttb[2] * sh + 1.0f, 1.0f);
+      }
+      bl_lch_to_lab(ttb, tb);
+#pragma unroll
+      for(int c = 0; c < 3; c++) tb[c] = bl_clamp(tb[c], mn[c], mx[c]);
+      break;
+    }
     case 0x19: // normal, bounded
 #pragma unroll
       for(int c = 0; c < 3; c++) tb[c] = bl_clamp(ta[c] * (1.0f - lo) + tb[c] * lo, mn[c], mx[c]);
@@ -394,11 +489,10 @@ __global__ void __launch_bounds__(256) blend_kernel(const __grid_constant__ blen
   if(pl.mask_out) pl.mask_out[o] = m;
 }
 
-// dt_develop_blendif_process_parameters(), blend.c:214-260, for the first eight channels (gray / R / G / B or L / a / b of input and output);
-// in Lab the limits of the a and b channels are offset by a half
+// dt_develop_blendif_process_parameters(), blend.c:214-260; in Lab the limits of the a and b channels are offset by a half
 void bl_parameters(float *par, const b200_blend_params_t *d)
 {
-  for(int i = 0; i < 8; i++)
+  for(int i = 0; i < BLENDIF_SIZE; i++)
   {
     float *p = par + BLENDIF_ITEMS * i;
     const float *b = d->blendif_parameters + 4 * i;
@@ -431,13 +525,17 @@ int bl_plan(blend_plan_t &pl, const b200_blend_params_t *d, bool have_form)
   if(!lab && d->blend_cst != CS_RGB_SCENE) return B200_ERR_UNSUPPORTED;
   if(!lab && d->profile_nonlinear) return B200_ERR_UNSUPPORTED;
   if(d->feathering_radius > 0.1f || d->blur_radius > 0.1f || d->details != 0.0f) return B200_ERR_UNSUPPORTED;
-  // channels of the parametric mask that need a colour-space conversion: Jz, Cz, hz of scene-referred RGB; chroma and hue of Lab
-  if((d->mask_mode & MASK_PARAMETRIC) && (d->blendif & (lab ? 0x3300u : 0x7700u))) return B200_ERR_UNSUPPORTED;
-  if(lab)
-  { // the operators through LCh (atan2f, hypotf, cosf, sinf): chromaticity, hue, colour, colour adjustment
-    const unsigned m = d->blend_mode & 0xFFu;
-    if(m == 0x11 || m == 0x12 || m == 0x13 || m == 0x16) return B200_ERR_UNSUPPORTED;
+  { // dt_develop_blendif_init_masking_profile(), develop/blend.c:322-353: the profile's matrix_in taken to D65 by Bradford's matrix
+    const float M[3][3] = { { 0.9555766f, -0.0230393f, 0.0631636f }, { -0.0282895f, 1.0099416f, 0.0210077f }, { 0.0122982f, -0.0204830f, 1.3299098f } };
+    for(int y = 0; y < 3; y++)
+      for(int x = 0; x < 3; x++)
+      {
+        float sum = 0.0f;
+        for(int i = 0; i < 3; i++) sum += M[y][i] * d->matrix_in[3 * i + x];
+        pl.masking[3 * y + x] = sum;
+      }
   }
+  pl.c_scale = 1.0f / (128.0f * sqrtf(2.0f)); // blendif_lab.c:125
   const unsigned channel_mask = lab ? (unsigned)BLENDIF_LAB_MASK : (unsigned)BLENDIF_RGB_MASK;
   pl.lab = lab;
   bool parametric = false; // dt_develop_blend_get_mask_usage(), :290-312

@@ -23,6 +23,9 @@ __global__ void eval_kernel(int fn, const float *x, const float *y, float *out, 
     case B200_FLT32_LOG2F: r = f32m::log2f_(tb, x[k]); break;
     case B200_FLT32_SINF: r = f32m::sinf_(x[k]); break;
     case B200_FLT32_COSF: r = f32m::cosf_(x[k]); break;
+    case B200_FLT32_ATANF: r = f32m::atanf_(x[k]); break;
+    case B200_FLT32_ATAN2F: r = f32m::atan2f_(x[k], y[k]); break;
+    case B200_FLT32_HYPOTF: r = f32m::hypotf_(x[k], y[k]); break;
     default: r = f32m::powf_(tb, x[k], y[k]); break;
   }
   out[k] = r;
@@ -32,7 +35,8 @@ __global__ void eval_kernel(int fn, const float *x, const float *y, float *out, 
 using namespace b200;
 extern "C" int b200_flt32_eval_dev(int fn, const float *d_x, const float *d_y, float *d_out, size_t n, void *stream)
 {
-  if(fn < B200_FLT32_EXPF || fn > B200_FLT32_COSF || !d_x || !d_out || (fn == B200_FLT32_POWF && !d_y))
+  const bool two = fn == B200_FLT32_POWF || fn == B200_FLT32_ATAN2F || fn == B200_FLT32_HYPOTF;
+  if(fn < B200_FLT32_EXPF || fn > B200_FLT32_HYPOTF || !d_x || !d_out || (two && !d_y))
     return fail(B200_ERR_ARG, "flt32_eval: bad arguments");
   int rc = bind_device(-1);
   if(rc) return rc;

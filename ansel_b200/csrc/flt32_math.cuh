@@ -360,4 +360,94 @@ template <bool COS> __device__ __forceinline__ float sincosf_(float y)
 }
 __device__ __forceinline__ float sinf_(float y) { return sincosf_<false>(y); }
 __device__ __forceinline__ float cosf_(float y) { return sincosf_<true>(y); }
+
+// ---- atanf, atan2f, hypotf: glibc 2.39 sysdeps/ieee754/flt-32/{s_atanf,e_atan2f,e_hypotf}.c ----------------------------------------
+// The first two are the fdlibm float routines: reduction to four breakpoints, an 11-term odd polynomial split in two, head / tail
+// constants of the breakpoints; no FMA build exists, every operation is a float operation in source order (the library is compiled
+// with --fmad=false).  hypotf is one square root of the exact double sum of the squares.  What the reference calls them for:
+// dt_Lab_2_LCH and dt_JzAzBz_2_JzCzhz (common/colorspaces_inline_conversions.h:594-606, :775-781).
+__device__ __forceinline__ float atan_hi(int id) { return id == 0 ? 4.6364760399e-01f : (id == 1 ? 7.8539812565e-01f : (id == 2 ? 9.8279368877e-01f : 1.5707962513e+00f)); }
+__device__ __forceinline__ float atan_lo(int id) { return id == 0 ? 5.0121582440e-09f : (id == 1 ? 3.7748947079e-08f : (id == 2 ? 3.4473217170e-08f : 7.5497894159e-08f)); }
+__device__ __forceinline__ float atanf_(float x)
+{
+  const int hx = (int)__float_as_uint(x), ix = hx & 0x7fffffff;
+  int id;
+  if(ix >= 0x4c000000)
+  { // |x| >= 2^25
+    if(ix > 0x7f800000) return x + x;
+    return hx > 0 ? atan_hi(3) + atan_lo(3) : -atan_hi(3) - atan_lo(3);
+  }
+  if(ix < 0x3ee00000)
+  { // |x| < 0.4375
+    if(ix < 0x31000000) return x; // |x| < 2^-29
+    id = -1;
+  }
+  else
+  {
+    x = fabsf(x);
+    if(ix < 0x3f980000)
+    {
+      if(ix < 0x3f300000)
+      {
+        id = 0;
+        x = (2.0f * x - 1.0f) / (2.0f + x);
+      }
+      else
+      {
+        id = 1;
+        x = (x - 1.0f) / (x + 1.0f);
+      }
+    }
+    else if(ix < 0x401c0000)
+    {
+      id = 2;
+      x = (x - 1.5f) / (1.0f + 1.5f * x);
+    }
+    else
+    {
+      id = 3;
+      x = -1.0f / x;
+    }
+  }
+  const float z = x * x, w = z * z;
+  const float s1 = z * (3.3333334327e-01f + w * (1.4285714924e-01f + w * (9.0908870101e-02f + w * (6.6610731184e-02f + w * (4.9768779427e-02f + w * 1.6285819933e-02f)))));
+  const float s2 = w * (-2.0000000298e-01f + w * (-1.1111110449e-01f + w * (-7.6918758452e-02f + w * (-5.8335702866e-02f + w * -3.6531571299e-02f))));
+  if(id < 0) return x - x * (s1 + s2);
+  const float r = atan_hi(id) - ((x * (s1 + s2) - atan_lo(id)) - x);
+  return hx < 0 ? -r : r;
+}
+__device__ __forceinline__ float atan2f_(float y, float x)
+{
+  const float tiny = 1.0e-30f, pi_o_4 = 7.8539818525e-01f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f, pi_lo = -8.7422776573e-08f;
+  const int hx = (int)__float_as_uint(x), ix = hx & 0x7fffffff, hy = (int)__float_as_uint(y), iy = hy & 0x7fffffff;
+  if(ix > 0x7f800000 || iy > 0x7f800000) return x + y;
+  if(hx == 0x3f800000) return atanf_(y);
+  const int m = ((hy >> 31) & 1) | ((hx >> 30) & 2); // 2 * sign(x) + sign(y)
+  if(iy == 0) return m < 2 ? y : (m == 2 ? pi + tiny : -pi - tiny);
+  if(ix == 0) return hy < 0 ? -pi_o_2 - tiny : pi_o_2 + tiny;
+  if(ix == 0x7f800000)
+  {
+    if(iy == 0x7f800000) return m == 0 ? pi_o_4 + tiny : (m == 1 ? -pi_o_4 - tiny : (m == 2 ? 3.0f * pi_o_4 + tiny : -3.0f * pi_o_4 - tiny));
+    return m == 0 ? 0.0f : (m == 1 ? -0.0f : (m == 2 ? pi + tiny : -pi - tiny));
+  }
+  if(iy == 0x7f800000) return hy < 0 ? -pi_o_2 - tiny : pi_o_2 + tiny;
+  const int k = (iy - ix) >> 23;
+  float z;
+  if(k > 60)
+    z = pi_o_2 + 0.5f * pi_lo;
+  else if(hx < 0 && k < -60)
+    z = 0.0f;
+  else
+    z = atanf_(fabsf(y / x));
+  if(m == 0) return z;
+  if(m == 1) return __uint_as_float(__float_as_uint(z) ^ 0x80000000u);
+  if(m == 2) return pi - (z - pi_lo);
+  return (z - pi_lo) - pi;
+}
+__device__ __forceinline__ float hypotf_(float x, float y)
+{
+  const uint32_t ax = __float_as_uint(x) & 0x7fffffffu, ay = __float_as_uint(y) & 0x7fffffffu;
+  if(ax >= 0x7f800000u || ay >= 0x7f800000u) return (ax == 0x7f800000u || ay == 0x7f800000u) ? __int_as_float(0x7f800000) : x + y;
+  return (float)sqrt((double)x * (double)x + (double)y * (double)y);
+}
 } // namespace f32m

@@ -731,7 +731,7 @@ int b200_export_convert_dev(const void *d_in, void *d_out, size_t width, size_t 
 int b200_export_convert_host(const void *in, void *out, size_t width, size_t height, int format);
 
 /* ---- the libm the kernels use ------------------------------------------------------------------
- * Device restatement of glibc 2.39's single-precision expf/exp2f/logf/log2f/powf (the functions the
+ * Device restatement of glibc 2.39's single-precision expf/exp2f/logf/log2f/powf/sinf/cosf/atanf/atan2f/hypotf (the functions the
  * reference's CPU path calls; see ansel_b200/csrc/flt32_math.cuh).  Exposed so its bit-compatibility
  * with the host libm can be verified on the machine the pipe runs on. */
 enum
@@ -742,7 +742,10 @@ enum
   B200_FLT32_LOG2F = 3,
   B200_FLT32_POWF = 4,
   B200_FLT32_SINF = 5, /* |x| < 120 */
-  B200_FLT32_COSF = 6
+  B200_FLT32_COSF = 6,
+  B200_FLT32_ATANF = 7,
+  B200_FLT32_ATAN2F = 8, /* atan2f(x[k], y[k]): x is the ordinate */
+  B200_FLT32_HYPOTF = 9
 };
 int b200_flt32_eval_dev(int fn, const float *d_x, const float *d_y, float *d_out, size_t n, void *stream);
 
@@ -757,7 +760,8 @@ typedef struct b200_blend_params_t
   float blend_parameter;     /* exposure-like parameter of the operator, in EV */
   float opacity;             /* 0 .. 100 */
   uint32_t mask_combine;     /* dt_develop_mask_combine_mode_t: 1 inverted, 2 inclusive */
-  uint32_t blendif;          /* bits 0..3 / 4..7: gray, red, green, blue (Lab: L, a, b) of the input / output take part; bit + 16: that channel inverted */
+  uint32_t blendif;          /* dt_develop_blendif_channels_t: bits 0..3 / 4..7 gray, red, green, blue (Lab: L, a, b), bits 8..10 / 12..14 Jz, Cz, hz (Lab:
+                                chroma, hue) of the input / output take part; bit + 16: that channel inverted */
   float feathering_radius;
   uint32_t feathering_guide;
   float blur_radius, contrast, brightness, details;
@@ -768,15 +772,17 @@ typedef struct b200_blend_params_t
   float luminance[3];              /* row Y of matrix_in of the pipe's current profile (dt_ioppr_get_rgb_matrix_luminance, iop_profile.h:637-654) */
   int32_t profile_nonlinear;       /* that profile's nonlinearlut: must be 0 */
   uint32_t mask_display;           /* pipe->mask_display: with B200_DISPLAY_MASK the alpha lane of the input is kept (:952-961) */
+  float matrix_in[9];              /* that profile's matrix_in (RGB -> XYZ D50), row by row: what the Jz / Cz / hz channels of the parametric mask start
+                                      from (dt_develop_blendif_init_masking_profile, develop/blend.c:322-353); read only when bits 8..10 / 12..14 of
+                                      `blendif` are set in the RGB space */
 } b200_blend_params_t;
 /* in: the module's input (roi_in, RGBA float), out: the module's output (roi_out, inside roi_in), blended in place with the mask in its
  * alpha lane; form_mask: the raster / drawn mask of roi_out the host rasterised, or NULL; mask: receives the final mask (what the reference
  * publishes as the module's raster mask, :892-950), or NULL.  Built: the scene-referred RGB space (develop/blends/blendif_rgb_jzczhz.c) with
- * uniform, raster, drawn and parametric (gray, red, green, blue of input and output) masks, their exclusive / inclusive / inverted
+ * uniform, raster, drawn and parametric (gray, red, green, blue, Jz, Cz, hz of input and output) masks, their exclusive / inclusive / inverted
  * combinations, the mask tone curve and the sixteen blend operators; the Lab space (develop/blends/blendif_lab.c, what local contrast and the
- * other Lab modules blend in) with the same masks on the L, a and b channels and the twenty-two operators that stay in Lab.
- * B200_ERR_UNSUPPORTED (fall back to dt_develop_blend_process): feathering, blur and detail refinement of the mask; the JzCzhz channels of the
- * RGB space; chroma and hue channels and the chromaticity / hue / colour / colour-adjustment operators of the Lab space; the display-RGB and raw
+ * other Lab modules blend in) with the same masks on the L, a, b, chroma and hue channels and its twenty-six operators.
+ * B200_ERR_UNSUPPORTED (fall back to dt_develop_blend_process): feathering, blur and detail refinement of the mask; the display-RGB and raw
  * spaces.  mask_mode without the enabled bit: B200_OK, nothing touched. */
 int b200_blend_process_host(const b200_piece_t *piece, const b200_blend_params_t *bp, const void *in, void *out, const float *form_mask, float *mask);
 /* dt_develop_blend_process_cl() slot, develop/blend.c:1113-1604: device pointers */

@@ -7,12 +7,13 @@
  *     colorprofiles/iop_profile.h :637-654  dt_ioppr_get_rgb_matrix_luminance
  *     develop/blend.c   :214-260    dt_develop_blendif_process_parameters
  *                       :626-655    _develop_blend_process_mask_tone_curve
- *     develop/blends/blendif_rgb_jzczhz.c :33-121  _blendif_compute_factor, _blendif_gray, _blendif_rgb_red/green/blue
+ *     colorprofiles/iop_profile.h :680-693  dt_ioppr_rgb_matrix_to_xyz;  develop/blend.c :321-353  dt_develop_blendif_init_masking_profile
+ *     develop/blends/blendif_rgb_jzczhz.c :33-149  _blendif_compute_factor, _blendif_gray, _blendif_rgb_red/green/blue, _blendif_jzczhz
  *                       :150-326    _blendif_combine_channels, dt_develop_blendif_rgb_jzczhz_make_mask
  *                       :327-650    the sixteen blend operators, _choose_blend_func
  *                       :870-960    _copy_mask, dt_develop_blendif_rgb_jzczhz_blend
- * Not cut: the JzCzhz channels of the parametric mask (:122-149, the colour-science headers behind them) and the GUI's channel
- * display (:652-868); both are aborting stubs here and the wrapper refuses parameters that would reach them.
+ * common/colorspaces_inline_conversions.h (dt_XYZ_2_JzAzBz, dt_JzAzBz_2_JzCzhz behind the Jz / Cz / hz channels) is included unmodified.
+ * Not cut: the GUI's channel display (:652-868), an aborting stub.
  * ref_blend_process() below is dt_develop_blend_process (develop/blend.c:657-860) for blend_cst == DEVELOP_BLEND_CS_RGB_SCENE
  * without feathering, blur and detail refinement, with the form mask (raster / drawn, already combined) handed in by the caller.
  */
@@ -23,9 +24,10 @@
 typedef char dt_dev_operation_t[20]; /* history/history.h */
 struct dt_dev_pixelpipe_t;
 struct dt_dev_pixelpipe_iop_t;
+#include "common/colorspaces_inline_conversions.h"
 typedef struct dt_iop_order_iccprofile_info_t
 { /* the members the cut lines read (colorprofiles/iop_profile.h) */
-  dt_colormatrix_t matrix_in;
+  dt_colormatrix_t matrix_in, matrix_out, matrix_out_transposed;
   float *lut_in[3];
   float unbounded_coeffs_in[3][3];
   int lutsize, nonlinearlut;
@@ -60,21 +62,12 @@ static void dt_iop_image_mul_const(float *const buf, const float v, const size_t
 static void dt_iop_image_copy(float *const out, const float *const in, const size_t n) { memcpy(out, in, n * sizeof(float)); }
 static float *dt_pixelpipe_cache_alloc_align_float_cache(size_t n, int id) { (void)id; return aligned_alloc(64, ((n * sizeof(float) + 63) / 64) * 64); }
 #define dt_pixelpipe_cache_free_align(p) free((void *)(p))
-#include "gen_blend_a.c" /* enums, parameters, luminance, dt_develop_blendif_process_parameters, the RGB channels of the parametric mask */
-static inline void _blendif_jzczhz(const float *const restrict pixels, float *const restrict mask, const size_t stride,
-                                   const float *const restrict parameters, const unsigned int *const restrict invert_mask,
-                                   const dt_iop_order_iccprofile_info_t *const restrict profile)
-{
-  (void)pixels; (void)mask; (void)stride; (void)parameters; (void)invert_mask; (void)profile;
-  abort(); /* :122-149 not cut: ref_blend_process refuses parameters with a JzCzhz channel */
-}
-static int dt_develop_blendif_init_masking_profile(const struct dt_dev_pixelpipe_t *pipe, const struct dt_dev_pixelpipe_iop_t *piece,
-                                                   dt_iop_order_iccprofile_info_t *blending_profile, dt_develop_blend_colorspace_t cst)
-{ /* develop/blend.c:322-353 copies the pipe's current profile (and derives a D65 matrix_out only the JzCzhz channels read) */
-  (void)pipe; (void)piece; (void)cst;
-  *blending_profile = g_blend_profile;
-  return 1;
-}
+/* what dt_develop_blendif_init_masking_profile (cut below, :321-353) asks the pipe for: the wrapper's profile */
+#define dt_ioppr_get_pipe_current_profile_info(module, pipe) (&g_blend_profile)
+#define dt_ioppr_get_iop_work_profile_info(module, iop) (&g_blend_profile)
+#define dt_develop_blendif_init_masking_profile ref_blend_init_masking_profile
+#include "gen_blend_a.c" /* enums, parameters, luminance, dt_develop_blendif_process_parameters, dt_ioppr_rgb_matrix_to_xyz, the channels of the
+                            parametric mask, dt_develop_blendif_init_masking_profile */
 #include "gen_blend_b.c" /* _blendif_combine_channels, make_mask, the blend operators */
 static void _display_channel(const float *const restrict a, float *const restrict b, const float *const restrict mask, const size_t stride,
                              const dt_dev_pixelpipe_display_mask_t channel, const float *const restrict boost_factors,
@@ -102,11 +95,12 @@ typedef struct ref_blend_params_t
   float luminance[3];
   int32_t profile_nonlinear;
   uint32_t mask_display;
+  float matrix_in[9];
 } ref_blend_params_t;
 
 /* dt_develop_blend_process(), develop/blend.c:657-860, for the scene-referred RGB space.  in: roi_in (iw x ih), out: roi_out (ow x oh) at
  * offset (xoffs, yoffs) inside roi_in, blended in place; form: the raster / drawn mask of roi_out or NULL; mask_out: the final mask or NULL.
- * Returns 0, or -1 for what the wrapper does not reach (feathering, blur, detail refinement, JzCzhz channels, other colour spaces). */
+ * Returns 0, or -1 for what the wrapper does not reach (feathering, blur, detail refinement, other colour spaces). */
 int ref_blend_process(const float *in, float *out, int iw, int ih, int ow, int oh, int xoffs, int yoffs, const ref_blend_params_t *bp,
                       const float *form, float *mask_out)
 {
@@ -130,9 +124,10 @@ int ref_blend_process(const float *in, float *out, int iw, int ih, int ow, int o
   if(!(d.mask_mode & DEVELOP_MASK_ENABLED)) return 0; /* :673 */
   if(d.blend_cst != DEVELOP_BLEND_CS_RGB_SCENE || bp->profile_nonlinear) return -1;
   if(d.feathering_radius > 0.1f || d.blur_radius > 0.1f || d.details != 0.0f) return -1;
-  if((d.mask_mode & DEVELOP_MASK_PARAMETRIC) && (d.blendif & 0x7700)) return -1; /* Jz, Cz, hz in and out */
   memset(&g_blend_profile, 0, sizeof(g_blend_profile));
-  for(int k = 0; k < 3; k++) g_blend_profile.matrix_in[1][k] = bp->luminance[k];
+  for(int r = 0; r < 3; r++)
+    for(int k = 0; k < 3; k++) g_blend_profile.matrix_in[r][k] = bp->matrix_in[3 * r + k];
+  for(int k = 0; k < 3; k++) g_blend_profile.matrix_in[1][k] = bp->luminance[k]; /* what the gray channel reads */
   ref_blend_piece_t piece;
   memset(&piece, 0, sizeof(piece));
   piece.roi_in = (dt_iop_roi_t){ 0, 0, iw, ih, 1.0 };

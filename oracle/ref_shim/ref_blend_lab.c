@@ -81,6 +81,7 @@ typedef struct ref_blend_lab_params_t
   float luminance[3];
   int32_t profile_nonlinear;
   uint32_t mask_display;
+  float matrix_in[9];
 } ref_blend_lab_params_t;
 
 /* dt_develop_blend_process(), develop/blend.c:657-860, for the Lab space; arguments as ref_blend_process().  Returns 0, or -1 for what the

@@ -13,10 +13,11 @@
  * Everything here is a function of one pixel of the module's input, the same pixel of its output and the same pixel of the form
  * mask (the raster / drawn mask the host rasterised): the reference's passes over whole buffers are folded into one evaluation per
  * pixel, which is also how the CUDA kernel does it.  Not restated (the entry point returns -1, the product B200_ERR_UNSUPPORTED):
- * feathering (guided filter), Gaussian blur and detail refinement of the mask, the JzCzhz channels of the parametric mask, the GUI's
- * channel display, the other blend colour spaces.
+ * feathering (guided filter), Gaussian blur and detail refinement of the mask, the GUI's channel display, the display-RGB and raw blend
+ * colour spaces.
  */
 #include "oracle_common.h"
+#include "flt32_math.h"
 #include <float.h>
 #include <stdlib.h>
 #include <string.h>
@@ -46,6 +47,7 @@ typedef struct orc_blend_params_t
   float luminance[3];              /* row Y of the work profile's matrix_in */
   int32_t profile_nonlinear;
   uint32_t mask_display;           /* pipe->mask_display */
+  float matrix_in[9];              /* the work profile's matrix_in (RGB -> XYZ D50), row by row: what the Jz / Cz / hz channels start from */
 } orc_blend_params_t;
 
 /* :214-260: in Lab the limits of the a and b channels are offset by a half */
@@ -135,6 +137,54 @@ static float blendif_channels_lab(const float *px, float t, unsigned blendif, co
   return t;
 }
 
+/* ---- the Jz, Cz, hz channels of the RGB space, blendif_rgb_jzczhz.c:122-149 ---- */
+/* dt_develop_blendif_init_masking_profile(), develop/blend.c:322-353: the profile's matrix_in taken to D65 by Bradford's matrix */
+static void masking_matrix(const float *matrix_in, float out[3][3])
+{
+  static const float M[3][3] = { { 0.9555766f, -0.0230393f, 0.0631636f }, { -0.0282895f, 1.0099416f, 0.0210077f }, { 0.0122982f, -0.0204830f, 1.3299098f } };
+  for(int y = 0; y < 3; y++)
+    for(int x = 0; x < 3; x++)
+    {
+      float sum = 0.0f;
+      for(int i = 0; i < 3; i++) sum += M[y][i] * matrix_in[3 * i + x];
+      out[y][x] = sum;
+    }
+}
+/* dt_XYZ_2_JzAzBz + dt_JzAzBz_2_JzCzhz, common/colorspaces_inline_conversions.h:672-722, :775-781 */
+static void xyz_to_jzczhz(const float *xyz_d65, float *jch)
+{
+  const float b = 1.15f, g = 0.66f, c1 = 0.8359375f, c2 = 18.8515625f, c3 = 18.6875f, n = 0.159301758f, p = 134.034375f, d = -0.56f, d0 = 1.6295499532821566e-11f;
+  static const float M[3][3] = { { 0.41478972f, 0.579999f, 0.0146480f }, { -0.2015100f, 1.120649f, 0.0531008f }, { -0.0166008f, 0.264800f, 0.6684799f } };
+  static const float At[3][3] = { { 0.5f, 3.524000f, 0.199076f }, { 0.5f, -4.066708f, 1.096799f }, { 0.0f, 0.542708f, -1.295875f } };
+  float xyz[3], lms[3], jab[3];
+  xyz[0] = b * xyz_d65[0] - (b - 1.0f) * xyz_d65[2];
+  xyz[1] = g * xyz_d65[1] - (g - 1.0f) * xyz_d65[0];
+  xyz[2] = xyz_d65[2];
+  for(int i = 0; i < 3; i++)
+  {
+    lms[i] = M[i][0] * xyz[0] + M[i][1] * xyz[1] + M[i][2] * xyz[2];
+    lms[i] = f32m_powf(fmaxf(lms[i] / 10000.f, 0.0f), n);
+    lms[i] = f32m_powf((c1 + c2 * lms[i]) / (1.0f + c3 * lms[i]), p);
+  }
+  for(int c = 0; c < 3; c++) jab[c] = At[0][c] * lms[0] + At[1][c] * lms[1] + At[2][c] * lms[2];
+  jab[0] = fmaxf(((1.0f + d) * jab[0]) / (1.0f + d * jab[0]) - d0, 0.f);
+  const float h = f32m_atan2f(jab[2], jab[1]) / (2.0f * PI_F);
+  jch[0] = jab[0];
+  jch[1] = f32m_hypotf(jab[1], jab[2]);
+  jch[2] = h >= 0.0f ? h : 1.0f + h;
+}
+static float blendif_jzczhz(const float *px, float t, unsigned blendif, const float *par, const float (*mo)[3])
+{ /* :122-149 and its call :186-193: the three factors multiplied together, then into the mask */
+  if(!(blendif & 0x700u)) return t;
+  float xyz[3], jch[3];
+  /* dt_mat3x4_mul_vec4, system/simd.h:189-197: row0 * in[0], then row1 * in[1] + that, then row2 * in[2] + that */
+  for(int c = 0; c < 3; c++) xyz[c] = mo[c][2] * px[2] + (mo[c][1] * px[1] + mo[c][0] * px[0]);
+  xyz_to_jzczhz(xyz, jch);
+  float factor = 1.0f;
+  for(int i = 0; i < 3; i++) factor *= blendif_factor(jch[i], (blendif >> 16) & (0x100u << i), par + BLENDIF_ITEMS * (8 + i));
+  return t * factor;
+}
+
 typedef struct
 {
   int kind;        /* 0: mask = opacity; 1: mask = form * opacity (raster only); 2: seed, then the parametric stage */
@@ -145,6 +195,7 @@ typedef struct
   float pm_const;
   unsigned blendif;
   float par[BLENDIF_ITEMS * BLENDIF_SIZE];
+  float masking[3][3]; /* RGB space: matrix_out of the masking profile */
   int tone;        /* mask tone curve :626-655 */
   float contrast_e, brightness;
 } blend_plan_t;
@@ -170,7 +221,9 @@ static float plan_mask(const blend_plan_t *pl, const orc_blend_params_t *d, cons
     else
     {
       t = blendif_channels(a, 1.0f, pl->blendif, pl->par, d->luminance);
+      t = blendif_jzczhz(a, t, pl->blendif, pl->par, pl->masking);
       t = blendif_channels(b, t, pl->blendif >> 4, pl->par + BLENDIF_ITEMS * 4, d->luminance);
+      t = blendif_jzczhz(b, t, pl->blendif >> 4, pl->par + BLENDIF_ITEMS * 4, pl->masking);
     }
     if(pl->inclusive)
       m = pl->inversed ? g * (1.0f - m) * t : g * (1.0f - (1.0f - m) * t);
@@ -457,7 +510,6 @@ int orc_blend_process(const float *in, float *out, int iw, int ih, int ow, int o
   const int lab = d->blend_cst == CS_LAB;
   if(!lab && (d->blend_cst != CS_RGB_SCENE || d->profile_nonlinear)) return -1;
   if(d->feathering_radius > 0.1f || d->blur_radius > 0.1f || d->details != 0.0f) return -1;
-  if(!lab && (d->mask_mode & MASK_PARAMETRIC) && (d->blendif & 0x7700u)) return -1;
   const unsigned channel_mask = lab ? (unsigned)BLENDIF_LAB_MASK : (unsigned)BLENDIF_RGB_MASK;
   orc_fp_fast_mode(); /* the pipe's threads run with FTZ|DAZ (darktable.c:877, common/dtpthread.c:54) */
   blend_plan_t pl;
@@ -499,6 +551,7 @@ int orc_blend_process(const float *in, float *out, int iw, int ih, int ow, int o
       pl.pm = 2;
       blendif_parameters(pl.par, d);
     }
+    masking_matrix(d->matrix_in, pl.masking);
     pl.tone = (fabsf(d->contrast) >= 0.01f || fabsf(d->brightness) >= 0.01f) && pl.opacity > 1e-4f; /* :432, :463 */
     pl.contrast_e = expf(3.f * d->contrast);
     pl.brightness = d->brightness;

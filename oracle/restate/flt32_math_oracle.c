@@ -21,6 +21,9 @@ ARRAY1(orc_log2f_array, f32m_log2f)
 ARRAY2(orc_powf_array, f32m_powf)
 ARRAY1(orc_sinf_array, f32m_sinf)
 ARRAY1(orc_cosf_array, f32m_cosf)
+ARRAY1(orc_atanf_array, f32m_atanf)
+ARRAY2(orc_atan2f_array, f32m_atan2f)
+ARRAY2(orc_hypotf_array, f32m_hypotf)
 
 /* the system libm, called through volatile function pointers so nothing is folded or vectorised */
 static float (*volatile sys_expf)(float) = expf;
@@ -30,6 +33,9 @@ static float (*volatile sys_log2f)(float) = log2f;
 static float (*volatile sys_powf)(float, float) = powf;
 static float (*volatile sys_sinf)(float) = sinf;
 static float (*volatile sys_cosf)(float) = cosf;
+static float (*volatile sys_atanf)(float) = atanf;
+static float (*volatile sys_atan2f)(float, float) = atan2f;
+static float (*volatile sys_hypotf)(float, float) = hypotf;
 ARRAY1(sys_expf_array, sys_expf)
 ARRAY1(sys_exp2f_array, sys_exp2f)
 ARRAY1(sys_logf_array, sys_logf)
@@ -37,3 +43,6 @@ ARRAY1(sys_log2f_array, sys_log2f)
 ARRAY2(sys_powf_array, sys_powf)
 ARRAY1(sys_sinf_array, sys_sinf)
 ARRAY1(sys_cosf_array, sys_cosf)
+ARRAY1(sys_atanf_array, sys_atanf)
+ARRAY2(sys_atan2f_array, sys_atan2f)
+ARRAY2(sys_hypotf_array, sys_hypotf)

@@ -17,8 +17,10 @@ LAB_MODES = {"normal": 0x18, "bounded": 0x19, "lighten": 0x02, "darken": 0x03, "
              "difference_old": 0x08, "difference": 0x17, "screen": 0x09, "overlay": 0x0A, "softlight": 0x0B, "hardlight": 0x0C, "vividlight": 0x0D,
              "linearlight": 0x0E, "pinlight": 0x0F, "lightness": 0x10, "chromaticity": 0x11, "hue": 0x12, "color": 0x13, "coloradjust": 0x16,
              "lab_lightness": 0x1A, "lab_l": 0x1E, "lab_a": 0x1F, "lab_b": 0x20, "lab_color": 0x1B}
-LAB_LCH_MODES = ("chromaticity", "hue", "color", "coloradjust")      # through atan2f / hypotf / cosf / sinf: not built on the device
-LUMINANCE = (0.2627002120112671, 0.6779980715188708, 0.05930171646986196)   # row Y of linear Rec2020 -> XYZ
+LAB_LCH_MODES = ("chromaticity", "hue", "color", "coloradjust")      # through atan2f / hypotf / cosf / sinf (ansel_b200/csrc/flt32_math.cuh)
+# linear Rec2020 -> XYZ (D50), the work profile's matrix_in, row by row; its middle row is what the gray channel of the parametric mask weighs with
+MATRIX_IN = (0.6734241, 0.1656411, 0.1251286, 0.2790177, 0.6753402, 0.0456377, -0.0019300, 0.0299784, 0.7973330)
+LUMINANCE = MATRIX_IN[3:6]
 
 
 class BlendParams(C.Structure):
@@ -26,7 +28,7 @@ class BlendParams(C.Structure):
                 ("mask_combine", C.c_uint32), ("blendif", C.c_uint32), ("feathering_radius", C.c_float), ("feathering_guide", C.c_uint32),
                 ("blur_radius", C.c_float), ("contrast", C.c_float), ("brightness", C.c_float), ("details", C.c_float),
                 ("blendif_parameters", C.c_float * 64), ("blendif_boost_factors", C.c_float * 16), ("raster_used", C.c_int32), ("drawn_used", C.c_int32),
-                ("luminance", C.c_float * 3), ("profile_nonlinear", C.c_int32), ("mask_display", C.c_uint32)]
+                ("luminance", C.c_float * 3), ("profile_nonlinear", C.c_int32), ("mask_display", C.c_uint32), ("matrix_in", C.c_float * 9)]
 
 
 def params(mode="normal", opacity=65.0, mask_mode=MASK_ENABLED, reverse=False, blend_parameter=0.0, combine=0, blendif=0, channels=None, boosts=None,
@@ -48,6 +50,7 @@ def params(mode="normal", opacity=65.0, mask_mode=MASK_ENABLED, reverse=False, b
         p.blendif_boost_factors[bit] = v
     p.raster_used, p.drawn_used, p.mask_display = raster, drawn, mask_display
     p.luminance[:] = LUMINANCE
+    p.matrix_in[:] = MATRIX_IN
     for k, v in extra.items():
         setattr(p, k, v)
     return p
@@ -144,6 +147,12 @@ CONFIGS = [(m, dict(mode=m), False) for m in MODES] + [
     ("tone_curve_extremes2", dict(mask_mode=MASK_ENABLED | MASK_SHAPE, drawn=1, contrast=0.1, brightness=-1.0), True),
     ("mask_display", dict(mode="add", mask_display=1), False),
     ("disabled", dict(mask_mode=0), False),
+    # the Jz / Cz / hz channels (bits 8..10 of the input, 12..14 of the output): XYZ D65 through the masking profile, the PQ curve, atan2f / hypotf
+    ("parametric_jz_in", dict(mask_mode=MASK_ENABLED | MASK_PARAMETRIC, channels={8: (0.002, 0.006, 0.015, 0.02)}), False),
+    ("parametric_cz_hz_out", dict(mask_mode=MASK_ENABLED | MASK_PARAMETRIC, channels={13: (0.0, 0.0, 0.004, 0.008), 14: (0.1, 0.2, 0.7, 0.85)}), False),
+    ("parametric_jz_inverted_and_gray", dict(mask_mode=MASK_ENABLED | MASK_PARAMETRIC, channels={8: (0.001, 0.004, 0.012, 0.018), 0: (0.05, 0.2, 0.8, 1.0)}, blendif=1 << 24), False),
+    ("drawn_and_parametric_hz_boost", dict(mask_mode=MASK_ENABLED | MASK_SHAPE | MASK_PARAMETRIC, drawn=1, channels={10: (0.2, 0.3, 0.6, 0.7), 12: (0.002, 0.006, 1.0, 1.0)},
+                                           boosts={12: 1.0}), True),
 ]
 
 # Lab: every operator, then the mask sources and combinations on the Lab channels (bits 0..2 L/a/b and 8..9 C/h of the input, 4..6 and 12..13 of the output)
@@ -167,9 +176,8 @@ LAB_CONFIGS = [("lab_" + m, dict(cst=CS_LAB, mode=m), False) for m in LAB_MODES]
 
 
 def lab_on_device(cfg):
-    """what the library builds of a Lab configuration: everything but the LCh operators and the C / h channels of the parametric mask"""
-    name, kw, _ = cfg
-    return kw.get("mode", "normal") not in LAB_LCH_MODES and not any(ch in (8, 9, 12, 13) for ch in kw.get("channels", {}))
+    """what the library builds of a Lab configuration: all of it since the LCh operators and the C / h channels went in"""
+    return True
 
 
 _EMUL = None

@@ -65,8 +65,7 @@ def test_kernel_with_offsets_and_what_is_refused():
     e, o = bu.emul(a, b, p, form, 7, 5), bu.oracle(a, b, p, form, 7, 5)
     assert same_bits(e[1], o[1]).all() and same_bits(e[2], o[2]).all()
     a, b, form = bu.frames(64, 48, 4)
-    for kw in (dict(feathering_radius=5.0), dict(blur_radius=2.0), dict(details=0.5), dict(blend_cst=3), dict(profile_nonlinear=1),
-               dict(mask_mode=bu.MASK_ENABLED | bu.MASK_PARAMETRIC, channels={8: (0.1, 0.3, 0.7, 0.9)})):
+    for kw in (dict(feathering_radius=5.0), dict(blur_radius=2.0), dict(details=0.5), dict(blend_cst=3), dict(profile_nonlinear=1)):
         p = bu.params(**kw)
         assert bu.emul(a, b, p)[0] == -1 and bu.oracle(a, b, p)[0] == -1, kw
 

@@ -76,3 +76,22 @@ def test_device_sinf_cosf(built, fn, name):
     x = np.ascontiguousarray(np.concatenate([((2.0 * np.pi) * (k * 2.0 ** -24)).astype(np.float32), rng.uniform(-119.9, 119.9, N).astype(np.float32),
                                              np.array([0.0, -0.0, 1e-5, -1e-5, 0.7853981, 0.7853982], np.float32)]))
     _assert_same(_device(fn, x), _host(name, x), x)
+
+
+def test_device_atanf_atan2f_hypotf(built):
+    """what dt_Lab_2_LCH and dt_JzAzBz_2_JzCzhz call: the fdlibm float routines and the one-square-root hypotf of glibc 2.39"""
+    from test_cpu_flt32_math import _pairs
+    rng = np.random.default_rng(24)
+    x = np.ascontiguousarray(np.concatenate([_bits(rng, 2 * N), rng.uniform(-3, 3, N).astype(np.float32),
+                                             np.array([0.0, -0.0, 0.4375, 0.6875, 1.1875, 2.4375, np.inf, -np.inf, np.nan], np.float32)]))
+    _assert_same(_device(7, x), _host("atanf", x), x)
+    for y, x in _pairs(rng):
+        y, x = np.ascontiguousarray(y), np.ascontiguousarray(x)
+        for fn, name in ((8, "atan2f"), (9, "hypotf")):
+            a, b = _device(fn, y, x), _host(name, y, x)
+            same = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+            # subnormal arguments, quotients and results: the device flushes like the reference's pipe threads, this test's host thread does not
+            q = np.abs(y.astype(np.float64)) / np.maximum(np.abs(x.astype(np.float64)), 1e-300)
+            tiny = (np.abs(x) < 1.2e-38) | (np.abs(y) < 1.2e-38) | (np.abs(b) < 1.2e-38) | (np.abs(a) < 1.2e-38) | ((q < 1.2e-38) & (q > 0))
+            bad = ~same & ~tiny
+            assert not bad.any(), f"{name}: {int(bad.sum())} mismatches, e.g. {y[bad][:3]}, {x[bad][:3]}: dev {a[bad][:3]} host {b[bad][:3]}"

@@ -69,8 +69,7 @@ def test_blend_inside_roi_in_and_what_is_refused(built):
     got = cuda(ab, a, b, p, form, 7, 5)
     assert got[0] == 0 and same_bits(got[1], want[1]).all() and same_bits(got[2], want[2]).all()
     a, b, form = bu.frames(64, 48, 4)
-    for kw in (dict(feathering_radius=5.0), dict(blur_radius=2.0), dict(details=0.5), dict(blend_cst=3), dict(profile_nonlinear=1),
-               dict(mask_mode=bu.MASK_ENABLED | bu.MASK_PARAMETRIC, channels={8: (0.1, 0.3, 0.7, 0.9)})):
+    for kw in (dict(feathering_radius=5.0), dict(blur_radius=2.0), dict(details=0.5), dict(blend_cst=3), dict(profile_nonlinear=1)):
         rc, out, _ = cuda(ab, a, b, bu.params(**kw))
         assert rc == ab.B200_ERR_UNSUPPORTED and np.array_equal(out, b), kw
 
