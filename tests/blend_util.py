@@ -175,6 +175,17 @@ LAB_CONFIGS = [("lab_" + m, dict(cst=CS_LAB, mode=m), False) for m in LAB_MODES]
 ]
 
 
+def golden_configs():
+    """the configurations of tests/golden/blend.npz: every third one of each space, and everything that goes through powf / atan2f / hypotf"""
+    rgb = [c for k, c in enumerate(CONFIGS) if c[0] != "disabled" and (k % 3 == 0 or any(ch >= 8 for ch in c[1].get("channels", {})))]
+    lab = [c for k, c in enumerate(LAB_CONFIGS) if k % 3 == 0 or c[1].get("mode") in LAB_LCH_MODES or any(ch >= 8 for ch in c[1].get("channels", {}))]
+    return rgb + lab
+
+
+def golden_frames(kw):
+    return (frames_lab if kw.get("cst") == CS_LAB else frames)(96, 64, 7)
+
+
 def lab_on_device(cfg):
     """what the library builds of a Lab configuration: all of it since the LCh operators and the C / h channels went in"""
     return True

@@ -110,3 +110,15 @@ def test_lab_kernel_equals_oracle(cfg):
         assert rc_e == -1 and np.array_equal(out_e, b)
         return
     assert rc_e == 0 and same_bits(out_e, out_o).all() and same_bits(mask_e, mask_o).all()
+
+
+@pytest.mark.parametrize("cfg", bu.golden_configs(), ids=[c[0] for c in bu.golden_configs()])
+def test_oracle_and_kernel_against_the_committed_reference_output(cfg):
+    """tests/golden/blend.npz: what the reference's lines produced in the authoring container (tests/golden/make_golden_blend.py)"""
+    name, kw, uses_form = cfg
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "blend.npz"))
+    a, b, form = bu.golden_frames(kw)
+    p = bu.params(**kw)
+    for run in (bu.oracle, bu.emul):
+        rc, out, mask = run(a, b, p, form if uses_form else None)
+        assert rc == 0 and same_bits(out, g[name]).all() and same_bits(mask, g[name + "_mask"]).all(), run.__name__

@@ -61,6 +61,17 @@ def test_blend_bit_exact(built, cfg):
     assert rc == 0 and same_bits(out_h, out_o).all() and same_bits(mask_h, mask_o).all()
 
 
+@pytest.mark.parametrize("cfg", bu.golden_configs(), ids=[c[0] for c in bu.golden_configs()])
+def test_committed_reference_output(built, cfg):
+    """tests/golden/blend.npz: what the reference's own lines produced (tests/golden/make_golden_blend.py), both colour spaces"""
+    import os
+    name, kw, uses_form = cfg
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "blend.npz"))
+    a, b, form = bu.golden_frames(kw)
+    rc, out, mask = cuda(built, a, b, bu.params(**kw), form if uses_form else None)
+    assert rc == 0 and same_bits(out, g[name]).all() and same_bits(mask, g[name + "_mask"]).all()
+
+
 def test_blend_inside_roi_in_and_what_is_refused(built):
     ab = built
     a, b, form = bu.frames(100, 80, 2, xoffs=7, yoffs=5)
