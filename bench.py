@@ -423,8 +423,27 @@ def pipe_ends_extras(ab, ds, util, L, M, torch, w, h, local, dev, stream, conv_i
         L.b200_blend_process_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         report("blend_rgb_scene_drawn_and_parametric",
                lambda: ab.check(L.b200_blend_process_dev(C.byref(p_b), C.byref(bp), t_rgba.data_ptr(), t_out.data_ptr(), t_form.data_ptr(), None, stream)), 52)
+        # the same in Lab (what local contrast blends in): the overlay operator under a mask on lightness, chroma and hue of the input
+        bl = bu.params(cst=bu.CS_LAB, mode="overlay", opacity=70.0, mask_mode=bu.MASK_ENABLED | bu.MASK_SHAPE | bu.MASK_PARAMETRIC, drawn=1,
+                       channels={0: (0.05, 0.2, 0.8, 1.0), 8: (0.02, 0.1, 0.6, 0.8), 9: (0.1, 0.2, 0.7, 0.8)})
+        report("blend_lab_overlay_drawn_and_parametric_lch",
+               lambda: ab.check(L.b200_blend_process_dev(C.byref(p_b), C.byref(bl), t_lab.data_ptr(), t_out.data_ptr(), t_form.data_ptr(), None, stream)), 52)
+        # and with the Jz / Cz / hz channels of the RGB space (the PQ curve twice per channel, atan2f, hypotf per pixel of input and output)
+        bj = bu.params(mode="normal", opacity=70.0, mask_mode=bu.MASK_ENABLED | bu.MASK_PARAMETRIC,
+                       channels={8: (0.002, 0.006, 0.015, 0.02), 14: (0.1, 0.2, 0.7, 0.85)})
+        report("blend_rgb_scene_parametric_jzczhz",
+               lambda: ab.check(L.b200_blend_process_dev(C.byref(p_b), C.byref(bj), t_rgba.data_ptr(), t_out.data_ptr(), None, None, stream)), 48)
     except Exception as e:
-        res["blend_rgb_scene_drawn_and_parametric"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+        res.setdefault("blend_rgb_scene_drawn_and_parametric", {"unavailable": f"{type(e).__name__}: {e}"[:200]})
+    try:   # colour inpainting on an X-Trans mosaic (the Bayer one is `highlights_inpaint` above)
+        p_hx = piece(ab.highlights_data(ab.HIGHLIGHTS_INPAINT, 1.0), 1, pmax=pm)
+        p_hx.filters = 9
+        for i, rowv in enumerate(((1, 1, 0, 1, 1, 2), (1, 1, 2, 1, 1, 0), (2, 0, 1, 0, 2, 1), (1, 1, 2, 1, 1, 0), (1, 1, 0, 1, 1, 2), (0, 2, 1, 2, 0, 1))):
+            for j, v in enumerate(rowv):
+                p_hx.xtrans[i][j] = v
+        report("highlights_inpaint_xtrans", lambda: ab.check(L.b200_highlights_process_dev(p_hx, t_m[1].data_ptr(), t_m[0].data_ptr(), stream)), 8, reps=3)
+    except Exception as e:
+        res["highlights_inpaint_xtrans"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
     # sensor-to-display chain, end to end
     try:
