@@ -122,3 +122,59 @@ def test_oracle_and_kernel_against_the_committed_reference_output(cfg):
     for run in (bu.oracle, bu.emul):
         rc, out, mask = run(a, b, p, form if uses_form else None)
         assert rc == 0 and same_bits(out, g[name]).all() and same_bits(mask, g[name + "_mask"]).all(), run.__name__
+
+
+def random_parameter_block(rng):
+    """a parameter block drawn at random in either colour space: operator, opacity, reverse, mask sources, up to three parametric channels with
+    random limits, inversions and boosts, the combination mode, the mask tone curve, an earlier module's mask"""
+    lab = rng.random() < 0.5
+    modes = list((bu.LAB_MODES if lab else bu.MODES).keys())
+    kw = dict(mode=modes[rng.integers(len(modes))], opacity=float(rng.choice([0, 35, 70, 100, 140])), reverse=bool(rng.random() < 0.3),
+              blend_parameter=float(rng.choice([0, -1.5, 2.0])), combine=int(rng.integers(0, 4)))
+    if lab:
+        kw["cst"] = bu.CS_LAB
+    mask_mode, uses_form, r = bu.MASK_ENABLED, False, rng.random()
+    if r < 0.3:
+        mask_mode, kw["drawn"], uses_form = mask_mode | bu.MASK_SHAPE, 1, True
+    elif r < 0.45:
+        mask_mode, kw["raster"], uses_form = mask_mode | bu.MASK_RASTER, 1, True
+    if rng.random() < 0.6:
+        mask_mode |= bu.MASK_PARAMETRIC
+        allowed = [0, 1, 2, 4, 5, 6, 8, 9, 12, 13] if lab else [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 13, 14]
+        channels, blendif = {}, 0
+        for c in rng.choice(allowed, size=rng.integers(1, 4), replace=False):
+            v = np.sort(rng.random(4)).astype(float)
+            if not lab and c in (8, 12):
+                v = v * 0.02          # Jz of scene-referred pixels around 1 is about 0.01
+            if not lab and c in (9, 13):
+                v = v * 0.01
+            if rng.random() < 0.2:
+                v[0] = v[1] = 0.0     # open at the bottom
+            if rng.random() < 0.2:
+                v[2] = v[3] = 1.0     # open at the top
+            channels[int(c)] = tuple(v)
+            if rng.random() < 0.3:
+                blendif |= 1 << (16 + int(c))
+        kw["channels"], kw["blendif"] = channels, blendif
+        if rng.random() < 0.3:
+            kw["boosts"] = {list(channels)[0]: float(rng.choice([-1.0, 0.5, 2.0]))}
+    if rng.random() < 0.3:
+        kw["contrast"], kw["brightness"] = float(rng.uniform(-0.8, 0.8)), float(rng.uniform(-1.0, 1.0))
+    if rng.random() < 0.15:
+        kw["mask_display"] = 1
+    kw["mask_mode"] = mask_mode
+    return lab, kw, uses_form
+
+
+@need_ref
+def test_random_parameter_blocks_reference_oracle_and_kernel_agree():
+    rng = np.random.default_rng(123)
+    for trial in range(120):
+        lab, kw, uses_form = random_parameter_block(rng)
+        a, b, form = (bu.frames_lab if lab else bu.frames)(64, 40, int(rng.integers(1000)))
+        if rng.random() < 0.2:
+            a[5, 5, :3], b[6, 6, 1] = np.nan, np.inf
+        p, f = bu.params(**kw), (form if uses_form else None)
+        r, o, e = bu.ref(a, b, p, f), bu.oracle(a, b, p, f), bu.emul(a, b, p, f)
+        assert r[0] == o[0] == e[0] == 0, (trial, kw)
+        assert same_bits(o[1], r[1]).all() and same_bits(o[2], r[2]).all() and same_bits(e[1], o[1]).all() and same_bits(e[2], o[2]).all(), (trial, kw)
