@@ -121,3 +121,25 @@ def test_oracle_against_the_committed_reference_output(name):
     got, _ = hu.oracle(img, f, hu.clips_of(), norm=g[name + "_norm"], **kw)
     assert same_bits(got, g[name]).all()
     assert same_bits(hu.emul(img, f, hu.clips_of(), g[name + "_norm"], **kw), g[name]).all()
+
+
+def test_random_frames_and_parameters_reference_oracle_and_kernels_agree():
+    """frames from 8 px a side, the three layouts, ROI origins, zoom, the scale parameter from 0, noise and solid colour, clip levels"""
+    if util.ref("strict") is None:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(7)
+    for trial in range(40):
+        w, h, kind = int(rng.integers(8, 180)), int(rng.integers(8, 140)), int(rng.integers(3))
+        f = [RGGB, GBRG, util.BAYER["BGGR"]][rng.integers(3)] if kind == 0 else (9 if kind == 1 else 0)
+        kw = dict(iterations=int(rng.integers(1, 4)), scales=int(rng.integers(0, 10)), noise_level=float(rng.choice([0, 0.1, 0.5])),
+                  solid_color=float(rng.choice([0, 0.3, 1.0])), roi_scale=float(rng.choice([1.0, 0.5, 0.33])), iscale=float(rng.choice([1.0, 2.0])))
+        if f:
+            kw.update(x=int(rng.integers(0, 7)), y=int(rng.integers(0, 7)))
+        if f == 9:
+            kw["xtrans"] = hu.XTRANS
+        img = hu.clipped_mosaic(w, h, int(rng.integers(100)), blobs=3) if f else hu.clipped_rgba(w, h, int(rng.integers(100)))
+        clips = hu.clips_of(float(rng.choice([1.0, 0.8])), (float(rng.choice([1.0, 2.0])), 1.0, float(rng.choice([1.0, 1.5]))))
+        want, norm = hu.ref(img, f, clips, **kw)
+        got, _ = hu.oracle(img, f, clips, norm=norm, **kw)
+        assert same_bits(got, want).all(), (trial, w, h, f, kw)
+        assert same_bits(hu.emul(img, f, clips, norm, **kw), got).all(), (trial, w, h, f, kw)
