@@ -240,3 +240,18 @@ def test_initialscale_kernels_equal_oracle(emul_resample, name):
 def test_flip_kernel_equals_oracle(emul_resample, orientation):
     for img in (util.rgba_test_image(37, 23, 3), util.frame_natural(41, 19, 3), util.rgba_test_image(300, 5, 4)):
         assert same_bits(pe._flip(emul_resample, "emul_flip", img, orientation, "ch"), pe.oracle_flip(img, orientation)).all()
+
+
+def test_inpaint_kernels_on_random_frame_sizes(emul):
+    """colour inpainting, Bayer and X-Trans: frame sizes around the groups of eight steps, the 32x32 tiles of the transposition and the 128 lines of
+    a block, against the oracle (pinned on the reference's lines by tests/test_cpu_pipe_ends.py)"""
+    rng = np.random.default_rng(31)
+    sizes = [(9, 9), (16, 8), (33, 31), (64, 64), (65, 129), (130, 47)] + [(int(rng.integers(8, 200)), int(rng.integers(8, 160))) for _ in range(10)]
+    for k, size in enumerate(sizes):
+        name = ("inpaint_mosaic_wb_roi", "inpaint_xtrans_wb", "inpaint_mosaic")[k % 3]
+        piece, img = cases.highlights_case(name, size)
+        rc, want, n_want = pe.oracle_highlights(piece, img)
+        got, n = np.full_like(want, -7.0), C.c_ulonglong(0)
+        shifted = ab.lib().b200_roi_filters(C.c_uint32(piece.filters), piece.roi_in.x, piece.roi_in.y)
+        assert emul.emul_highlights(C.byref(piece), pe.vp(img), pe.vp(got), C.byref(n), C.c_uint32(shifted)) == 0 and rc == 0, (name, size)
+        assert n.value == n_want and same_bits(got, want).all(), (name, size)
