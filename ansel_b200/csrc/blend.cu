@@ -1,6 +1,7 @@
-// Blending of a module's output over its input (mask + blend operator), scene-referred RGB space and Lab, for B200 / sm_100a.
+// Blending of a module's output over its input (mask + blend operator): scene-referred RGB, display-referred RGB and Lab, for B200 / sm_100a.
 //
-// What the reference computes: develop/blend.c dt_develop_blend_process :657-860 with blend_cst == DEVELOP_BLEND_CS_RGB_SCENE or
+// What the reference computes: develop/blend.c dt_develop_blend_process :657-860 with blend_cst == DEVELOP_BLEND_CS_RGB_SCENE,
+// DEVELOP_BLEND_CS_RGB_DISPLAY (develop/blends/blendif_rgb_hsl.c: the same masks with H, S, L for Jz, Cz, hz, its 27 operators) or
 // DEVELOP_BLEND_CS_LAB: the mask (uniform opacity | the raster / drawn mask the host rasterised | the parametric mask of
 // develop/blends/blendif_rgb_jzczhz.c :42-325 on the gray, red, green, blue, Jz, Cz and hz channels -- of develop/blends/blendif_lab.c :56-298 on
 // the L, a, b, chroma and hue channels -- of the module's input and output, combined exclusively or inclusively, inverted or not | the mask tone
@@ -15,7 +16,7 @@
 // 52 B/px algorithmic.  What the host decides once per call (which of the reference's branches a parameter block takes, the
 // slopes of the parametric channels, exp2f / expf of the parameters) arrives in the plan; what depends on the pixel is evaluated
 // here.  Not built (B200_ERR_UNSUPPORTED, the caller falls back to the reference's own path): feathering (guided filter), Gaussian
-// blur and detail refinement of the mask; the GUI's channel display; the display-RGB and raw colour spaces.  The Jz, Cz, hz channels of
+// blur and detail refinement of the mask; the GUI's channel display; the raw colour space.  The Jz, Cz, hz channels of
 // the RGB space, the chroma and hue channels and the four LCh operators of the Lab space go through glibc's powf / atan2f / hypotf / cosf /
 // sinf as restated in flt32_math.cuh.
 #ifndef B200_KERNELS_ON_CPU // tests/emul compiles the kernel of this file with g++ to check it against the oracle without a GPU
@@ -33,7 +34,7 @@ enum
   MASK_ENABLED = 1, MASK_SHAPE = 2, MASK_PARAMETRIC = 4, MASK_RASTER = 8, // dt_develop_mask_mode_t, blend.h:110-118
   COMBINE_INV = 1, COMBINE_INCL = 2,                                      // dt_develop_mask_combine_mode_t :120-131
   BLENDIF_SIZE = 16, BLENDIF_ITEMS = 6, BLENDIF_RGB_MASK = 0x77FF, BLENDIF_LAB_MASK = 0x3377, // :188-191, :329
-  CS_LAB = 2, CS_RGB_SCENE = 4                                             // :52-59
+  CS_LAB = 2, CS_RGB_DISPLAY = 3, CS_RGB_SCENE = 4                         // :52-59
 };
 constexpr unsigned BLEND_REVERSE = 0x80000000u; // blend.h:106
 
@@ -45,6 +46,7 @@ struct blend_plan_t
   float *mask_out;
   int iw, ow, oh, xoffs, yoffs;
   int lab;       // the Lab space (develop/blends/blendif_lab.c) instead of scene-referred RGB
+  int display;   // the display-referred RGB space (develop/blends/blendif_rgb_hsl.c)
   int kind;      // 0: mask = opacity; 1: mask = form * opacity (a raster mask alone); 2: seed, then the parametric stage
   int seed_form; // kind 2: the seed is the form mask, else `fill`
   float fill, opacity;
@@ -163,6 +165,279 @@ __device__ __forceinline__ float bl_jzczhz(const float px[4], float t, unsigned 
   for(int i = 0; i < 3; i++) factor *= bl_factor(jch[i], (blendif >> 16) & (0x100u << i), par + BLENDIF_ITEMS * (8 + i));
   return t * factor;
 }
+// ---- display-referred RGB, blendif_rgb_hsl.c.  HSL / HSV: common/colorspaces_inline_conversions.h _dt_RGB_2_Hue :420-435, _dt_Hue_2_RGB
+// :438-484, dt_RGB_2_HSL :488-514, dt_HSL_2_RGB :517-528, dt_RGB_2_HSV :532-555, dt_HSV_2_RGB :558-564 ----
+__device__ __forceinline__ float bl_clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); } // clamp_simd, math/openmp_maths.h:128-131
+__device__ __forceinline__ float bl_rgb_to_hue(const float rgb[3], float max, float delta)
+{
+  float hue;
+  if(rgb[0] == max)
+    hue = (rgb[1] - rgb[2]) / delta;
+  else if(rgb[1] == max)
+    hue = 2.0f + (rgb[2] - rgb[0]) / delta;
+  else
+    hue = 4.0f + (rgb[0] - rgb[1]) / delta;
+  hue = bl_divc(hue, 6.0f);
+  if(hue < 0.0f) hue += 1.0f;
+  if(hue > 1.0f) hue -= 1.0f;
+  return hue;
+}
+__device__ __forceinline__ void bl_hue_to_rgb(float rgb[3], float H, float C, float min)
+{
+  const float h = H * 6.0f, i = floorf(h), f = h - i, fc = f * C, top = C + min, inc = fc + min, dec = top - fc;
+  // the source switches on (size_t)i: sextants 0..4 by value, anything else (5, negative, huge, NaN) takes the last branch; compared as floats
+  // here, because a conversion of a negative or NaN float to an unsigned integer saturates on the device and wraps on x86
+  if(i == 0.0f)
+  {
+    rgb[0] = top;
+    rgb[1] = inc;
+    rgb[2] = min;
+  }
+  else if(i == 1.0f)
+  {
+    rgb[0] = dec;
+    rgb[1] = top;
+    rgb[2] = min;
+  }
+  else if(i == 2.0f)
+  {
+    rgb[0] = min;
+    rgb[1] = top;
+    rgb[2] = inc;
+  }
+  else if(i == 3.0f)
+  {
+    rgb[0] = min;
+    rgb[1] = dec;
+    rgb[2] = top;
+  }
+  else if(i == 4.0f)
+  {
+    rgb[0] = inc;
+    rgb[1] = min;
+    rgb[2] = top;
+  }
+  else
+  {
+    rgb[0] = top;
+    rgb[1] = min;
+    rgb[2] = dec;
+  }
+}
+__device__ __forceinline__ void bl_rgb_to_hsl(const float rgb[3], float hsl[3])
+{
+  const float min = fminf(rgb[0], fminf(rgb[1], rgb[2])), max = fmaxf(rgb[0], fmaxf(rgb[1], rgb[2])), delta = max - min;
+  const float L = (max + min) / 2.0f;
+  float H = 0.0f, S = 0.0f;
+  if(fabsf(max) > 1e-6f && fabsf(delta) > 1e-6f)
+  {
+    S = L < 0.5f ? delta / (max + min) : delta / (2.0f - max - min);
+    H = bl_rgb_to_hue(rgb, max, delta);
+  }
+  hsl[0] = H;
+  hsl[1] = S;
+  hsl[2] = L;
+}
+__device__ __forceinline__ void bl_hsl_to_rgb(const float hsl[3], float rgb[3])
+{
+  const float L = hsl[2];
+  const float C = L < 0.5f ? L * hsl[1] : (1.0f - L) * hsl[1];
+  bl_hue_to_rgb(rgb, hsl[0], 2.0f * C, L - C);
+}
+__device__ __forceinline__ void bl_rgb_to_hsv(const float rgb[3], float hsv[3])
+{
+  const float min = fminf(rgb[0], fminf(rgb[1], rgb[2])), max = fmaxf(rgb[0], fmaxf(rgb[1], rgb[2])), delta = max - min;
+  float H = 0.0f, S = 0.0f;
+  if(fabsf(max) > 1e-6f && fabsf(delta) > 1e-6f)
+  {
+    S = delta / max;
+    H = bl_rgb_to_hue(rgb, max, delta);
+  }
+  hsv[0] = H;
+  hsv[1] = S;
+  hsv[2] = max;
+}
+__device__ __forceinline__ void bl_hsv_to_rgb(const float hsv[3], float rgb[3])
+{
+  const float C = hsv[1] * hsv[2];
+  bl_hue_to_rgb(rgb, hsv[0], C, hsv[2] - C);
+}
+// the H, S, L channels :149-163 and their call :206-215
+__device__ __forceinline__ float bl_hsl(const float px[4], float t, unsigned blendif, const float *par)
+{
+  if(!(blendif & 0x700u)) return t;
+  float hsl[3], factor = 1.0f;
+  bl_rgb_to_hsl(px, hsl);
+#pragma unroll
+  for(int i = 0; i < 3; i++) factor *= bl_factor(hsl[i], (blendif >> 16) & (0x100u << i), par + BLENDIF_ITEMS * (8 + i));
+  return t * factor;
+}
+// the operators :347-913
+__device__ __forceinline__ void bl_operator_display(unsigned mode, const float a[4], const float b[4], float lo, float out[4])
+{
+  const float lo2 = lo * lo, na = 1.0f - lo, na2 = 1.0f - lo2;
+  const unsigned m = mode & 0xFFu;
+  switch(m)
+  {
+    case 0x02:
+#pragma unroll
+      for(int k = 0; k < 3; k++) out[k] = bl_clamp01(a[k] * na + fmaxf(a[k], b[k]) * lo);
+      break;
+    case 0x03:
+#pragma unroll
+      for(int k = 0; k < 3; k++) out[k] = bl_clamp01(a[k] * na + fminf(a[k], b[k]) * lo);
+      break;
+    case 0x04:
+#pragma unroll
+      for(int k = 0; k < 3; k++) out[k] = bl_clamp01(a[k] * na + (a[k] * b[k]) * lo);
+      break;
+    case 0x05:
+#pragma unroll
+      for(int k = 0; k < 3; k++) out[k] = bl_clamp01(a[k] * na + (a[k] + b[k]) / 2.0f * lo);
+      break;
+    case 0x06:
+#pragma unroll
+      for(int k = 0; k < 3; k++) out[k] = bl_clamp01(a[k] * na + (a[k] + b[k]) * lo);
+      break;
+    case 0x07:
+#pragma unroll
+      for(int k = 0; k < 3; k++) out[k] = bl_clamp01(a[k] * na + ((b[k] + a[k]) - 1.0f) * lo);
+      break;
+    case 0x08:
+    case 0x17:
+#pragma unroll
+      for(int k = 0; k < 3; k++) out[k] = bl_clamp01(a[k] * na + fabsf(a[k] - b[k]) * lo);
+      break;
+    case 0x09: // screen
+#pragma unroll
+      for(int k = 0; k < 3; k++)
+      {
+        const float la = bl_clamp01(a[k]), lb = bl_clamp01(b[k]);
+        out[k] = bl_clamp01(la * na + (1.0f - (1.0f - la) * (1.0f - lb)) * lo);
+      }
+      break;
+    case 0x0A: // overlay
+    case 0x0C: // hardlight: the same with the test on the upper layer
+#pragma unroll
+      for(int k = 0; k < 3; k++)
+      {
+        const float la = bl_clamp01(a[k]), lb = bl_clamp01(b[k]);
+        out[k] = bl_clamp01(la * na2 + ((m == 0x0A ? la : lb) > 0.5f ? 1.0f - (1.0f - 2.0f * (la - 0.5f)) * (1.0f - lb) : 2.0f * la * lb) * lo2);
+      }
+      break;
+    case 0x0B: // softlight
+#pragma unroll
+      for(int k = 0; k < 3; k++)
+      {
+        const float la = bl_clamp01(a[k]), lb = bl_clamp01(b[k]);
+        out[k] = bl_clamp01(la * na2 + (lb > 0.5f ? 1.0f - (1.0f - la) * (1.0f - (lb - 0.5f)) : la * (lb + 0.5f)) * lo2);
+      }
+      break;
+    case 0x0D: // vividlight
+#pragma unroll
+      for(int k = 0; k < 3; k++)
+      {
+        const float la = bl_clamp01(a[k]), lb = bl_clamp01(b[k]);
+        out[k] = bl_clamp01(la * na2 + (lb > 0.5f ? (lb >= 1.0f ? 1.0f : la / (2.0f * (1.0f - lb))) : (lb <= 0.0f ? 0.0f : 1.0f - (1.0f - la) / (2.0f * lb))) * lo2);
+      }
+      break;
+    case 0x0E: // linearlight
+#pragma unroll
+      for(int k = 0; k < 3; k++)
+      {
+        const float la = bl_clamp01(a[k]), lb = bl_clamp01(b[k]);
+        out[k] = bl_clamp01(la * na2 + (la + 2.0f * lb - 1.0f) * lo2);
+      }
+      break;
+    case 0x0F: // pinlight
+#pragma unroll
+      for(int k = 0; k < 3; k++)
+      {
+        const float la = bl_clamp01(a[k]), lb = bl_clamp01(b[k]);
+        out[k] = bl_clamp01(la * na2 + (lb > 0.5f ? fmaxf(la, 2.0f * (lb - 0.5f)) : fminf(la, 2.0f * lb)) * lo2);
+      }
+      break;
+    case 0x10: // lightness
+    case 0x11: // chromaticity
+    case 0x12: // hue
+    case 0x13: // colour
+    case 0x16: // colour adjustment: through HSL :645-808
+    {
+      float ta[3], tb[3], tta[3], ttb[3];
+#pragma unroll
+      for(int k = 0; k < 3; k++)
+      {
+        ta[k] = bl_clamp01(a[k]);
+        tb[k] = bl_clamp01(b[k]);
+      }
+      bl_rgb_to_hsl(ta, tta);
+      bl_rgb_to_hsl(tb, ttb);
+      if(m == 0x10 || m == 0x11)
+        ttb[0] = tta[0];
+      else
+      { // the hue along the shortest way round the circle
+        const float d = fabsf(tta[0] - ttb[0]);
+        const float sh = d > 0.5f ? -lo * (1.0f - d) / d : lo;
+        ttb[0] = fmodf((tta[0] * (1.0f - sh)) + ttb[0] * sh + 1.0f, 1.0f);
+      }
+      ttb[1] = (m == 0x10 || m == 0x12) ? tta[1] : (tta[1] * (1.0f - lo)) + ttb[1] * lo;
+      if(m == 0x10)
+        ttb[2] = (tta[2] * (1.0f - lo)) + ttb[2] * lo;
+      else if(m != 0x16)
+        ttb[2] = tta[2];
+      bl_hsl_to_rgb(ttb, out);
+#pragma unroll
+      for(int k = 0; k < 3; k++) out[k] = bl_clamp01(out[k]);
+      break;
+    }
+    case 0x19: // normal, bounded
+#pragma unroll
+      for(int k = 0; k < 3; k++) out[k] = bl_clamp01(a[k] * na + b[k] * lo);
+      break;
+    case 0x1C: // HSV value
+    {
+      float ta[3], tb[3];
+      bl_rgb_to_hsv(a, ta);
+      bl_rgb_to_hsv(b, tb);
+      tb[0] = ta[0];
+      tb[1] = ta[1];
+      tb[2] = ta[2] * (1.0f - lo) + tb[2] * lo;
+      bl_hsv_to_rgb(tb, out);
+      break;
+    }
+    case 0x1D: // HSV colour: hue and saturation blended as a vector
+    {
+      const float two_pi = 2.0f * 3.14159265358979324f;
+      float ta[3], tb[3];
+      bl_rgb_to_hsv(a, ta);
+      bl_rgb_to_hsv(b, tb);
+      const float xa = ta[1] * f32m::cosf_(two_pi * ta[0]), ya = ta[1] * f32m::sinf_(two_pi * ta[0]);
+      const float xb = tb[1] * f32m::cosf_(two_pi * tb[0]), yb = tb[1] * f32m::sinf_(two_pi * tb[0]);
+      const float xc = xa * (1.0f - lo) + xb * lo, yc = ya * (1.0f - lo) + yb * lo;
+      tb[0] = bl_divc(f32m::atan2f_(yc, xc), two_pi);
+      if(tb[0] < 0.0f) tb[0] += 1.0f;
+      tb[1] = sqrtf(xc * xc + yc * yc);
+      tb[2] = ta[2];
+      bl_hsv_to_rgb(tb, out);
+      break;
+    }
+    case 0x21:
+    case 0x22:
+    case 0x23:
+    {
+      const int c = (int)m - 0x21;
+#pragma unroll
+      for(int k = 0; k < 3; k++) out[k] = (k == c) ? a[k] * (1.0f - lo) + b[k] * lo : a[k];
+      break;
+    }
+    default: // normal
+#pragma unroll
+      for(int k = 0; k < 3; k++) out[k] = a[k] * na + b[k] * lo;
+      break;
+  }
+  out[3] = lo;
+}
+
 __device__ __forceinline__ float bl_mask(const blend_plan_t &pl, const float a[4], const float b[4], float form)
 {
   if(pl.kind == 0) return pl.opacity;
@@ -184,9 +459,9 @@ __device__ __forceinline__ float bl_mask(const blend_plan_t &pl, const float a[4
     else
     {
       t = bl_channels(a, 1.0f, pl.blendif, pl.par, pl.lum);
-      t = bl_jzczhz(a, t, pl.blendif, pl.par, pl.masking);
+      t = pl.display ? bl_hsl(a, t, pl.blendif, pl.par) : bl_jzczhz(a, t, pl.blendif, pl.par, pl.masking);
       t = bl_channels(b, t, pl.blendif >> 4, pl.par + BLENDIF_ITEMS * 4, pl.lum);
-      t = bl_jzczhz(b, t, pl.blendif >> 4, pl.par + BLENDIF_ITEMS * 4, pl.masking);
+      t = pl.display ? bl_hsl(b, t, pl.blendif >> 4, pl.par + BLENDIF_ITEMS * 4) : bl_jzczhz(b, t, pl.blendif >> 4, pl.par + BLENDIF_ITEMS * 4, pl.masking);
     }
     if(pl.inclusive)
       m = pl.inversed ? g * (1.0f - m) * t : g * (1.0f - (1.0f - m) * t);
@@ -480,6 +755,8 @@ __global__ void __launch_bounds__(256) blend_kernel(const __grid_constant__ blen
   float res[4];
   if(pl.lab)
     bl_operator_lab(pl.mode, pl.reverse ? b : a, pl.reverse ? a : b, m, res);
+  else if(pl.display)
+    bl_operator_display(pl.mode, pl.reverse ? b : a, pl.reverse ? a : b, m, res);
   else if(pl.reverse)
     bl_operator(pl.mode, b, a, pl.p, m, res);
   else
@@ -521,8 +798,8 @@ int bl_plan(blend_plan_t &pl, const b200_blend_params_t *d, bool have_form)
 {
   memset(&pl, 0, sizeof(pl));
   if(!(d->mask_mode & MASK_ENABLED)) return 1; // :673
-  const bool lab = d->blend_cst == CS_LAB;
-  if(!lab && d->blend_cst != CS_RGB_SCENE) return B200_ERR_UNSUPPORTED;
+  const bool lab = d->blend_cst == CS_LAB, display = d->blend_cst == CS_RGB_DISPLAY;
+  if(!lab && !display && d->blend_cst != CS_RGB_SCENE) return B200_ERR_UNSUPPORTED;
   if(!lab && d->profile_nonlinear) return B200_ERR_UNSUPPORTED;
   if(d->feathering_radius > 0.1f || d->blur_radius > 0.1f || d->details != 0.0f) return B200_ERR_UNSUPPORTED;
   { // dt_develop_blendif_init_masking_profile(), develop/blend.c:322-353: the profile's matrix_in taken to D65 by Bradford's matrix
@@ -538,6 +815,7 @@ int bl_plan(blend_plan_t &pl, const b200_blend_params_t *d, bool have_form)
   pl.c_scale = 1.0f / (128.0f * sqrtf(2.0f)); // blendif_lab.c:125
   const unsigned channel_mask = lab ? (unsigned)BLENDIF_LAB_MASK : (unsigned)BLENDIF_RGB_MASK;
   pl.lab = lab;
+  pl.display = display;
   bool parametric = false; // dt_develop_blend_get_mask_usage(), :290-312
   if(d->mask_mode & MASK_PARAMETRIC)
     for(unsigned ch = 0; ch < BLENDIF_SIZE; ch++)

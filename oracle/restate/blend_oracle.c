@@ -7,8 +7,10 @@
  * _choose_blend_func :587-649, dt_develop_blendif_rgb_jzczhz_blend :878-961).  Pinned bit-for-bit against those lines cut verbatim
  * (oracle/_ref: ref_blend.c).  For blend_cst == DEVELOP_BLEND_CS_LAB: develop/blends/blendif_lab.c (the L / a / b / C / h channels :90-137,
  * _blendif_combine_channels :139-173, dt_develop_blendif_lab_make_mask :175-298, the 26 operators :302-1068, _choose_blend_func
- * :1070-1162, dt_develop_blendif_lab_blend :1302-1418), pinned against oracle/_ref: ref_blend_lab.c.  The C / h channels and the four
- * LCh operators go through the host's atan2f / hypotf / cosf / sinf / fmodf, like the reference.
+ * :1070-1162, dt_develop_blendif_lab_blend :1302-1418), pinned against oracle/_ref: ref_blend_lab.c.  For
+ * DEVELOP_BLEND_CS_RGB_DISPLAY: develop/blends/blendif_rgb_hsl.c (the gray / R / G / B / H / S / L channels :89-216, make_mask :218-345, the 27
+ * operators :347-913, _choose_blend_func :915-1007, dt_develop_blendif_rgb_hsl_blend :1204-1288) with dt_RGB_2_HSL, dt_RGB_2_HSV and back
+ * (common/colorspaces_inline_conversions.h:420-565), pinned against oracle/_ref: ref_blend_rgb_hsl.c.
  *
  * Everything here is a function of one pixel of the module's input, the same pixel of its output and the same pixel of the form
  * mask (the raster / drawn mask the host rasterised): the reference's passes over whole buffers are folded into one evaluation per
@@ -27,7 +29,7 @@ enum
   MASK_ENABLED = 1, MASK_SHAPE = 2, MASK_PARAMETRIC = 4, MASK_RASTER = 8, /* dt_develop_mask_mode_t, blend.h:110-118 */
   COMBINE_INV = 1, COMBINE_INCL = 2,                                      /* dt_develop_mask_combine_mode_t :120-131 */
   BLENDIF_SIZE = 16, BLENDIF_ITEMS = 6, BLENDIF_RGB_MASK = 0x77FF,        /* :188-191, :329 */
-  BLENDIF_LAB_MASK = 0x3377, CS_LAB = 2, CS_RGB_SCENE = 4,                 /* :52-59 */
+  BLENDIF_LAB_MASK = 0x3377, CS_LAB = 2, CS_RGB_DISPLAY = 3, CS_RGB_SCENE = 4, /* :52-59 */
   DISPLAY_MASK = 1                                                         /* develop.h:123 */
 };
 #define BLEND_REVERSE 0x80000000u /* blend.h:106 */
@@ -200,6 +202,7 @@ typedef struct
   float contrast_e, brightness;
 } blend_plan_t;
 
+static float blendif_hsl(const float *px, float t, unsigned blendif, const float *par); /* the display-referred space, below */
 static float plan_mask(const blend_plan_t *pl, const orc_blend_params_t *d, const float *a, const float *b, float form)
 {
   if(pl->kind == 0) return pl->opacity;
@@ -220,10 +223,12 @@ static float plan_mask(const blend_plan_t *pl, const orc_blend_params_t *d, cons
     }
     else
     {
+      const int display = d->blend_cst == CS_RGB_DISPLAY;
       t = blendif_channels(a, 1.0f, pl->blendif, pl->par, d->luminance);
-      t = blendif_jzczhz(a, t, pl->blendif, pl->par, pl->masking);
+      t = display ? blendif_hsl(a, t, pl->blendif, pl->par) : blendif_jzczhz(a, t, pl->blendif, pl->par, pl->masking);
       t = blendif_channels(b, t, pl->blendif >> 4, pl->par + BLENDIF_ITEMS * 4, d->luminance);
-      t = blendif_jzczhz(b, t, pl->blendif >> 4, pl->par + BLENDIF_ITEMS * 4, pl->masking);
+      t = display ? blendif_hsl(b, t, pl->blendif >> 4, pl->par + BLENDIF_ITEMS * 4)
+                  : blendif_jzczhz(b, t, pl->blendif >> 4, pl->par + BLENDIF_ITEMS * 4, pl->masking);
     }
     if(pl->inclusive)
       m = pl->inversed ? g * (1.0f - m) * t : g * (1.0f - (1.0f - m) * t);
@@ -499,7 +504,210 @@ static void lab_blend_pixel(unsigned mode, const float *a, const float *b, float
   out[3] = lo;
 }
 
-/* dt_develop_blend_process() for blend_cst == DEVELOP_BLEND_CS_RGB_SCENE and DEVELOP_BLEND_CS_LAB.  in: the module's input (iw x ih RGBA), out: its output
+/* ---- display-referred RGB, blendif_rgb_hsl.c ---- */
+static float clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); } /* clamp_simd, math/openmp_maths.h:128-131 */
+/* common/colorspaces_inline_conversions.h: _dt_RGB_2_Hue :420-435, _dt_Hue_2_RGB :438-484, dt_RGB_2_HSL :488-514, dt_HSL_2_RGB :517-528,
+ * dt_RGB_2_HSV :532-555, dt_HSV_2_RGB :558-564 */
+static float rgb_to_hue(const float *rgb, float max, float delta)
+{
+  float hue;
+  if(rgb[0] == max)
+    hue = (rgb[1] - rgb[2]) / delta;
+  else if(rgb[1] == max)
+    hue = 2.0f + (rgb[2] - rgb[0]) / delta;
+  else
+    hue = 4.0f + (rgb[0] - rgb[1]) / delta;
+  hue /= 6.0f;
+  if(hue < 0.0f) hue += 1.0f;
+  if(hue > 1.0f) hue -= 1.0f;
+  return hue;
+}
+static void hue_to_rgb(float *rgb, float H, float C, float min)
+{
+  const float h = H * 6.0f, i = floorf(h), f = h - i, fc = f * C, top = C + min, inc = fc + min, dec = top - fc;
+  const size_t i_idx = (size_t)i;
+  const float r[6][3] = { { top, inc, min }, { dec, top, min }, { min, top, inc }, { min, dec, top }, { inc, min, top }, { top, min, dec } };
+  const int k = i_idx < 5 ? (int)i_idx : 5;
+  for(int c = 0; c < 3; c++) rgb[c] = r[k][c];
+}
+static void rgb_to_hsl(const float *rgb, float *hsl)
+{
+  const float min = fminf(rgb[0], fminf(rgb[1], rgb[2])), max = fmaxf(rgb[0], fmaxf(rgb[1], rgb[2])), delta = max - min;
+  const float L = (max + min) / 2.0f;
+  float H = 0.0f, S = 0.0f;
+  if(fabsf(max) > 1e-6f && fabsf(delta) > 1e-6f)
+  {
+    S = L < 0.5f ? delta / (max + min) : delta / (2.0f - max - min);
+    H = rgb_to_hue(rgb, max, delta);
+  }
+  hsl[0] = H;
+  hsl[1] = S;
+  hsl[2] = L;
+}
+static void hsl_to_rgb(const float *hsl, float *rgb)
+{
+  const float L = hsl[2];
+  const float C = L < 0.5f ? L * hsl[1] : (1.0f - L) * hsl[1];
+  hue_to_rgb(rgb, hsl[0], 2.0f * C, L - C);
+}
+static void rgb_to_hsv(const float *rgb, float *hsv)
+{
+  const float min = fminf(rgb[0], fminf(rgb[1], rgb[2])), max = fmaxf(rgb[0], fmaxf(rgb[1], rgb[2])), delta = max - min;
+  float H = 0.0f, S = 0.0f;
+  if(fabsf(max) > 1e-6f && fabsf(delta) > 1e-6f)
+  {
+    S = delta / max;
+    H = rgb_to_hue(rgb, max, delta);
+  }
+  hsv[0] = H;
+  hsv[1] = S;
+  hsv[2] = max;
+}
+static void hsv_to_rgb(const float *hsv, float *rgb)
+{
+  const float C = hsv[1] * hsv[2];
+  hue_to_rgb(rgb, hsv[0], C, hsv[2] - C);
+}
+/* the H, S, L channels :149-163 and their call :206-215 */
+static float blendif_hsl(const float *px, float t, unsigned blendif, const float *par)
+{
+  if(!(blendif & 0x700u)) return t;
+  float hsl[3], factor = 1.0f;
+  rgb_to_hsl(px, hsl);
+  for(int i = 0; i < 3; i++) factor *= blendif_factor(hsl[i], (blendif >> 16) & (0x100u << i), par + BLENDIF_ITEMS * (8 + i));
+  return t * factor;
+}
+/* the operators :347-913: a = the lower layer, b = the upper one, lo = the mask */
+static void hsl_blend_pixel(unsigned mode, const float *a, const float *b, float lo, float *out)
+{
+  const float lo2 = lo * lo, na = 1.0f - lo, na2 = 1.0f - lo2;
+  const unsigned m = mode & 0xFFu;
+  switch(m)
+  {
+    case 0x02: for(int k = 0; k < 3; k++) out[k] = clamp01(a[k] * na + fmaxf(a[k], b[k]) * lo); break;        /* lighten */
+    case 0x03: for(int k = 0; k < 3; k++) out[k] = clamp01(a[k] * na + fminf(a[k], b[k]) * lo); break;        /* darken */
+    case 0x04: for(int k = 0; k < 3; k++) out[k] = clamp01(a[k] * na + (a[k] * b[k]) * lo); break;            /* multiply */
+    case 0x05: for(int k = 0; k < 3; k++) out[k] = clamp01(a[k] * na + (a[k] + b[k]) / 2.0f * lo); break;     /* average */
+    case 0x06: for(int k = 0; k < 3; k++) out[k] = clamp01(a[k] * na + (a[k] + b[k]) * lo); break;            /* add */
+    case 0x07: for(int k = 0; k < 3; k++) out[k] = clamp01(a[k] * na + ((b[k] + a[k]) - 1.0f) * lo); break;   /* subtract */
+    case 0x08:
+    case 0x17: for(int k = 0; k < 3; k++) out[k] = clamp01(a[k] * na + fabsf(a[k] - b[k]) * lo); break;       /* difference */
+    case 0x09: /* screen */
+      for(int k = 0; k < 3; k++)
+      {
+        const float la = clamp01(a[k]), lb = clamp01(b[k]);
+        out[k] = clamp01(la * na + (1.0f - (1.0f - la) * (1.0f - lb)) * lo);
+      }
+      break;
+    case 0x0A: /* overlay */
+    case 0x0C: /* hardlight: the same with the test on the upper layer */
+      for(int k = 0; k < 3; k++)
+      {
+        const float la = clamp01(a[k]), lb = clamp01(b[k]);
+        out[k] = clamp01(la * na2 + ((m == 0x0A ? la : lb) > 0.5f ? 1.0f - (1.0f - 2.0f * (la - 0.5f)) * (1.0f - lb) : 2.0f * la * lb) * lo2);
+      }
+      break;
+    case 0x0B: /* softlight */
+      for(int k = 0; k < 3; k++)
+      {
+        const float la = clamp01(a[k]), lb = clamp01(b[k]);
+        out[k] = clamp01(la * na2 + (lb > 0.5f ? 1.0f - (1.0f - la) * (1.0f - (lb - 0.5f)) : la * (lb + 0.5f)) * lo2);
+      }
+      break;
+    case 0x0D: /* vividlight */
+      for(int k = 0; k < 3; k++)
+      {
+        const float la = clamp01(a[k]), lb = clamp01(b[k]);
+        out[k] = clamp01(la * na2 + (lb > 0.5f ? (lb >= 1.0f ? 1.0f : la / (2.0f * (1.0f - lb))) : (lb <= 0.0f ? 0.0f : 1.0f - (1.0f - la) / (2.0f * lb))) * lo2);
+      }
+      break;
+    case 0x0E: /* linearlight */
+      for(int k = 0; k < 3; k++)
+      {
+        const float la = clamp01(a[k]), lb = clamp01(b[k]);
+        out[k] = clamp01(la * na2 + (la + 2.0f * lb - 1.0f) * lo2);
+      }
+      break;
+    case 0x0F: /* pinlight */
+      for(int k = 0; k < 3; k++)
+      {
+        const float la = clamp01(a[k]), lb = clamp01(b[k]);
+        out[k] = clamp01(la * na2 + (lb > 0.5f ? fmaxf(la, 2.0f * (lb - 0.5f)) : fminf(la, 2.0f * lb)) * lo2);
+      }
+      break;
+    case 0x10: /* lightness */
+    case 0x11: /* chromaticity */
+    case 0x12: /* hue */
+    case 0x13: /* colour */
+    case 0x16: /* colour adjustment: through HSL :645-808 */
+    {
+      float ta[3], tb[3], tta[3], ttb[3];
+      for(int k = 0; k < 3; k++)
+      {
+        ta[k] = clamp01(a[k]);
+        tb[k] = clamp01(b[k]);
+      }
+      rgb_to_hsl(ta, tta);
+      rgb_to_hsl(tb, ttb);
+      if(m == 0x10 || m == 0x11)
+        ttb[0] = tta[0];
+      else
+      { /* the hue along the shortest way round the circle */
+        const float d = fabsf(tta[0] - ttb[0]);
+        const float s = d > 0.5f ? -lo * (1.0f - d) / d : lo;
+        ttb[0] = fmodf((tta[0] * (1.0f - s)) + ttb[0] * s + 1.0f, 1.0f);
+      }
+      if(m == 0x10 || m == 0x12)
+        ttb[1] = tta[1];
+      else
+        ttb[1] = (tta[1] * (1.0f - lo)) + ttb[1] * lo;
+      if(m == 0x10)
+        ttb[2] = (tta[2] * (1.0f - lo)) + ttb[2] * lo;
+      else if(m != 0x16)
+        ttb[2] = tta[2];
+      hsl_to_rgb(ttb, out);
+      for(int k = 0; k < 3; k++) out[k] = clamp01(out[k]);
+      break;
+    }
+    case 0x19: for(int k = 0; k < 3; k++) out[k] = clamp01(a[k] * na + b[k] * lo); break; /* normal, bounded */
+    case 0x1C: /* HSV value */
+    {
+      float ta[3], tb[3];
+      rgb_to_hsv(a, ta);
+      rgb_to_hsv(b, tb);
+      tb[0] = ta[0];
+      tb[1] = ta[1];
+      tb[2] = ta[2] * (1.0f - lo) + tb[2] * lo;
+      hsv_to_rgb(tb, out);
+      break;
+    }
+    case 0x1D: /* HSV colour */
+    {
+      float ta[3], tb[3];
+      rgb_to_hsv(a, ta);
+      rgb_to_hsv(b, tb);
+      const float xa = ta[1] * f32m_cosf(2.0f * PI_F * ta[0]), ya = ta[1] * f32m_sinf(2.0f * PI_F * ta[0]);
+      const float xb = tb[1] * f32m_cosf(2.0f * PI_F * tb[0]), yb = tb[1] * f32m_sinf(2.0f * PI_F * tb[0]);
+      const float xc = xa * (1.0f - lo) + xb * lo, yc = ya * (1.0f - lo) + yb * lo;
+      tb[0] = f32m_atan2f(yc, xc) / (2.0f * PI_F);
+      if(tb[0] < 0.0f) tb[0] += 1.0f;
+      tb[1] = sqrtf(xc * xc + yc * yc);
+      tb[2] = ta[2];
+      hsv_to_rgb(tb, out);
+      break;
+    }
+    case 0x21:
+    case 0x22:
+    case 0x23:
+      for(int k = 0; k < 3; k++) out[k] = a[k];
+      out[m - 0x21] = a[m - 0x21] * (1.0f - lo) + b[m - 0x21] * lo;
+      break;
+    default: for(int k = 0; k < 3; k++) out[k] = a[k] * na + b[k] * lo; break; /* normal */
+  }
+  out[3] = lo;
+}
+
+/* dt_develop_blend_process() for blend_cst == DEVELOP_BLEND_CS_RGB_SCENE, DEVELOP_BLEND_CS_RGB_DISPLAY and DEVELOP_BLEND_CS_LAB.  in: the module's input (iw x ih RGBA), out: its output
  * (ow x oh RGBA, roi_out at (xoffs, yoffs) inside roi_in), blended in place; form: the form mask of roi_out or NULL; mask_out: the final
  * mask or NULL.  0 = done (also when blending is off), -1 = not restated. */
 int orc_blend_process(const float *in, float *out, int iw, int ih, int ow, int oh, int xoffs, int yoffs, const orc_blend_params_t *d,
@@ -507,8 +715,8 @@ int orc_blend_process(const float *in, float *out, int iw, int ih, int ow, int o
 {
   (void)ih;
   if(!(d->mask_mode & MASK_ENABLED)) return 0; /* :673 */
-  const int lab = d->blend_cst == CS_LAB;
-  if(!lab && (d->blend_cst != CS_RGB_SCENE || d->profile_nonlinear)) return -1;
+  const int lab = d->blend_cst == CS_LAB, display = d->blend_cst == CS_RGB_DISPLAY;
+  if(!lab && ((d->blend_cst != CS_RGB_SCENE && !display) || d->profile_nonlinear)) return -1;
   if(d->feathering_radius > 0.1f || d->blur_radius > 0.1f || d->details != 0.0f) return -1;
   const unsigned channel_mask = lab ? (unsigned)BLENDIF_LAB_MASK : (unsigned)BLENDIF_RGB_MASK;
   orc_fp_fast_mode(); /* the pipe's threads run with FTZ|DAZ (darktable.c:877, common/dtpthread.c:54) */
@@ -567,6 +775,8 @@ int orc_blend_process(const float *in, float *out, int iw, int ih, int ow, int o
       float res[4];
       if(lab)
         lab_blend_pixel(d->blend_mode, reverse ? b : a, reverse ? a : b, m, res);
+      else if(display)
+        hsl_blend_pixel(d->blend_mode, reverse ? b : a, reverse ? a : b, m, res);
       else if(reverse)
         blend_pixel(d->blend_mode, b, a, p, m, res);
       else

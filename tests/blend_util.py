@@ -7,7 +7,7 @@ import util
 
 MASK_ENABLED, MASK_SHAPE, MASK_PARAMETRIC, MASK_RASTER = 1, 2, 4, 8
 COMBINE_INV, COMBINE_INCL = 1, 2
-CS_LAB, CS_RGB_SCENE = 2, 4
+CS_LAB, CS_RGB_DISPLAY, CS_RGB_SCENE = 2, 3, 4
 REVERSE = 0x80000000
 MODES = {"normal": 0x18, "multiply": 0x04, "average": 0x05, "add": 0x06, "subtract": 0x07, "subtract_inverse": 0x25, "difference": 0x17,
          "divide": 0x26, "divide_inverse": 0x27, "geometric_mean": 0x28, "harmonic_mean": 0x29, "luminance": 0x10, "chromaticity": 0x11,
@@ -17,6 +17,11 @@ LAB_MODES = {"normal": 0x18, "bounded": 0x19, "lighten": 0x02, "darken": 0x03, "
              "difference_old": 0x08, "difference": 0x17, "screen": 0x09, "overlay": 0x0A, "softlight": 0x0B, "hardlight": 0x0C, "vividlight": 0x0D,
              "linearlight": 0x0E, "pinlight": 0x0F, "lightness": 0x10, "chromaticity": 0x11, "hue": 0x12, "color": 0x13, "coloradjust": 0x16,
              "lab_lightness": 0x1A, "lab_l": 0x1E, "lab_a": 0x1F, "lab_b": 0x20, "lab_color": 0x1B}
+# the operators of the display-referred RGB space (develop/blends/blendif_rgb_hsl.c _choose_blend_func :915-1007)
+DISPLAY_MODES = {"normal": 0x18, "bounded": 0x19, "lighten": 0x02, "darken": 0x03, "multiply": 0x04, "average": 0x05, "add": 0x06, "subtract": 0x07,
+                 "difference": 0x17, "screen": 0x09, "overlay": 0x0A, "softlight": 0x0B, "hardlight": 0x0C, "vividlight": 0x0D, "linearlight": 0x0E,
+                 "pinlight": 0x0F, "lightness": 0x10, "chromaticity": 0x11, "hue": 0x12, "color": 0x13, "coloradjust": 0x16, "hsv_value": 0x1C,
+                 "hsv_color": 0x1D, "rgb_r": 0x21, "rgb_g": 0x22, "rgb_b": 0x23}
 LAB_LCH_MODES = ("chromaticity", "hue", "color", "coloradjust")      # through atan2f / hypotf / cosf / sinf (ansel_b200/csrc/flt32_math.cuh)
 # linear Rec2020 -> XYZ (D50), the work profile's matrix_in, row by row; its middle row is what the gray channel of the parametric mask weighs with
 MATRIX_IN = (0.6734241, 0.1656411, 0.1251286, 0.2790177, 0.6753402, 0.0456377, -0.0019300, 0.0299784, 0.7973330)
@@ -38,7 +43,7 @@ def params(mode="normal", opacity=65.0, mask_mode=MASK_ENABLED, reverse=False, b
     p = BlendParams()
     cst = extra.pop("cst", CS_RGB_SCENE)
     p.mask_mode, p.blend_cst = mask_mode, cst
-    p.blend_mode = (LAB_MODES if cst == CS_LAB else MODES)[mode] | (REVERSE if reverse else 0)
+    p.blend_mode = {CS_LAB: LAB_MODES, CS_RGB_DISPLAY: DISPLAY_MODES}.get(cst, MODES)[mode] | (REVERSE if reverse else 0)
     p.blend_parameter, p.opacity, p.mask_combine, p.blendif = blend_parameter, opacity, combine, blendif
     p.contrast, p.brightness = contrast, brightness
     for i in range(16):
@@ -118,7 +123,8 @@ def oracle(a, b, p, form=None, xoffs=0, yoffs=0):
 
 def ref(a, b, p, form=None, xoffs=0, yoffs=0, kind="strict"):
     lib = util.ref(kind)
-    return None if lib is None else _run(lib, "ref_blend_lab_process" if p.blend_cst == CS_LAB else "ref_blend_process", a, b, p, form, xoffs, yoffs)
+    fn = {CS_LAB: "ref_blend_lab_process", CS_RGB_DISPLAY: "ref_blend_rgb_hsl_process"}.get(p.blend_cst, "ref_blend_process")
+    return None if lib is None else _run(lib, fn, a, b, p, form, xoffs, yoffs)
 
 
 # the configurations every layer is checked on: (name, params kwargs, uses the form mask)
@@ -175,15 +181,49 @@ LAB_CONFIGS = [("lab_" + m, dict(cst=CS_LAB, mode=m), False) for m in LAB_MODES]
 ]
 
 
+# display-referred RGB: every operator, then the mask sources and combinations on its channels (bits 0..3 gray/R/G/B and 8..10 H/S/L of the input,
+# 4..7 and 12..14 of the output)
+_D = dict(cst=CS_RGB_DISPLAY)
+DISPLAY_CONFIGS = [("display_" + m, dict(_D, mode=m), False) for m in DISPLAY_MODES] + [
+    ("display_overlay_reverse", dict(_D, mode="overlay", reverse=True, opacity=40.0), False),
+    ("display_hsv_color_drawn", dict(_D, mode="hsv_color", mask_mode=MASK_ENABLED | MASK_SHAPE, drawn=1), True),
+    ("display_vividlight_raster", dict(_D, mode="vividlight", mask_mode=MASK_ENABLED | MASK_RASTER, raster=1, opacity=90.0), True),
+    ("display_parametric_gray_in", dict(_D, mask_mode=_PAR, channels={0: (0.1, 0.3, 0.6, 0.8)}), False),
+    ("display_parametric_rgb_out", dict(_D, mask_mode=_PAR, channels={5: (0.0, 0.0, 0.5, 0.8), 6: (0.2, 0.4, 1.0, 1.0), 3: (0.05, 0.2, 0.6, 0.7)}), False),
+    ("display_parametric_hsl_in", dict(_D, mask_mode=_PAR, channels={8: (0.05, 0.15, 0.5, 0.7), 9: (0.1, 0.2, 0.8, 0.95), 10: (0.1, 0.3, 0.7, 0.9)}), False),
+    ("display_parametric_hue_out_inverted", dict(_D, mask_mode=_PAR, channels={12: (0.3, 0.4, 0.7, 0.8), 0: (0.0, 0.0, 0.7, 0.9)}, blendif=1 << 28), False),
+    ("display_parametric_inclusive", dict(_D, mask_mode=_PAR, combine=COMBINE_INCL, channels={0: (0.1, 0.3, 0.7, 0.9), 13: (0.1, 0.2, 0.6, 0.8)}), False),
+    ("display_drawn_and_parametric", dict(_D, mode="softlight", mask_mode=MASK_ENABLED | MASK_SHAPE | MASK_PARAMETRIC, drawn=1, channels={10: (0.1, 0.3, 0.7, 0.9)}), True),
+    ("display_tone_curve", dict(_D, mask_mode=MASK_ENABLED | MASK_SHAPE, drawn=1, contrast=0.4, brightness=0.2), True),
+    ("display_mask_display", dict(_D, mode="add", mask_display=1), False),
+]
+
+
+def frames_display(w=160, h=120, seed=1, xoffs=0, yoffs=0):
+    """the same for a display-referred module: most values in 0 .. 1, some beyond on either side, a grey and a black pixel"""
+    a, b, form = frames(w, h, seed, xoffs, yoffs)
+    a[..., :3] = a[..., :3] * np.float32(0.62) - np.float32(0.03)
+    b[..., :3] = b[..., :3] * np.float32(0.62) - np.float32(0.03)
+    a[4, 6, :3] = 0.4
+    b[4, 6, :3] = (0.2, 0.2, 0.7)
+    a[9, 9, :3] = 0.0
+    return a, b, form
+
+
 def golden_configs():
     """the configurations of tests/golden/blend.npz: every third one of each space, and everything that goes through powf / atan2f / hypotf"""
     rgb = [c for k, c in enumerate(CONFIGS) if c[0] != "disabled" and (k % 3 == 0 or any(ch >= 8 for ch in c[1].get("channels", {})))]
     lab = [c for k, c in enumerate(LAB_CONFIGS) if k % 3 == 0 or c[1].get("mode") in LAB_LCH_MODES or any(ch >= 8 for ch in c[1].get("channels", {}))]
-    return rgb + lab
+    display = [c for k, c in enumerate(DISPLAY_CONFIGS) if k % 3 == 0 or c[1].get("mode") in ("hsv_color", "hue", "color") or any(ch >= 8 for ch in c[1].get("channels", {}))]
+    return rgb + lab + display
+
+
+def frames_of(cst):
+    return {CS_LAB: frames_lab, CS_RGB_DISPLAY: frames_display}.get(cst, frames)
 
 
 def golden_frames(kw):
-    return (frames_lab if kw.get("cst") == CS_LAB else frames)(96, 64, 7)
+    return frames_of(kw.get("cst"))(96, 64, 7)
 
 
 def lab_on_device(cfg):

@@ -65,7 +65,7 @@ def test_kernel_with_offsets_and_what_is_refused():
     e, o = bu.emul(a, b, p, form, 7, 5), bu.oracle(a, b, p, form, 7, 5)
     assert same_bits(e[1], o[1]).all() and same_bits(e[2], o[2]).all()
     a, b, form = bu.frames(64, 48, 4)
-    for kw in (dict(feathering_radius=5.0), dict(blur_radius=2.0), dict(details=0.5), dict(blend_cst=3), dict(profile_nonlinear=1)):
+    for kw in (dict(feathering_radius=5.0), dict(blur_radius=2.0), dict(details=0.5), dict(blend_cst=1), dict(profile_nonlinear=1)):
         p = bu.params(**kw)
         assert bu.emul(a, b, p)[0] == -1 and bu.oracle(a, b, p)[0] == -1, kw
 
@@ -124,15 +124,44 @@ def test_oracle_and_kernel_against_the_committed_reference_output(cfg):
         assert rc == 0 and same_bits(out, g[name]).all() and same_bits(mask, g[name + "_mask"]).all(), run.__name__
 
 
+# ---- the display-referred RGB space (develop/blends/blendif_rgb_hsl.c) ----------------------------------------------------------------------
+DISPLAY_IDS = [c[0] for c in bu.DISPLAY_CONFIGS]
+
+
+@need_ref
+@pytest.mark.parametrize("cfg", bu.DISPLAY_CONFIGS, ids=DISPLAY_IDS)
+def test_display_oracle_equals_reference(cfg):
+    """every operator of the display-referred space, the gray / R / G / B / H / S / L channels of the parametric mask, the other mask sources"""
+    name, kw, uses_form = cfg
+    a, b, form = bu.frames_display()
+    p = bu.params(**kw)
+    rc_r, out_r, mask_r = bu.ref(a, b, p, form if uses_form else None)
+    rc_o, out_o, mask_o = bu.oracle(a, b, p, form if uses_form else None)
+    assert rc_r == rc_o == 0
+    assert same_bits(out_o, out_r).all() and same_bits(mask_o, mask_r).all()
+    assert not np.array_equal(out_r[..., :3], b[..., :3])
+
+
+@pytest.mark.parametrize("cfg", bu.DISPLAY_CONFIGS, ids=DISPLAY_IDS)
+def test_display_kernel_equals_oracle(cfg):
+    name, kw, uses_form = cfg
+    a, b, form = bu.frames_display(301, 77, 3)
+    p = bu.params(**kw)
+    rc_e, out_e, mask_e = bu.emul(a, b, p, form if uses_form else None)
+    rc_o, out_o, mask_o = bu.oracle(a, b, p, form if uses_form else None)
+    assert rc_e == rc_o == 0 and same_bits(out_e, out_o).all() and same_bits(mask_e, mask_o).all()
+
+
 def random_parameter_block(rng):
     """a parameter block drawn at random in either colour space: operator, opacity, reverse, mask sources, up to three parametric channels with
     random limits, inversions and boosts, the combination mode, the mask tone curve, an earlier module's mask"""
-    lab = rng.random() < 0.5
-    modes = list((bu.LAB_MODES if lab else bu.MODES).keys())
+    cst = (bu.CS_RGB_SCENE, bu.CS_LAB, bu.CS_RGB_DISPLAY)[rng.integers(3)]
+    lab = cst == bu.CS_LAB
+    modes = list({bu.CS_LAB: bu.LAB_MODES, bu.CS_RGB_DISPLAY: bu.DISPLAY_MODES}.get(cst, bu.MODES).keys())
     kw = dict(mode=modes[rng.integers(len(modes))], opacity=float(rng.choice([0, 35, 70, 100, 140])), reverse=bool(rng.random() < 0.3),
               blend_parameter=float(rng.choice([0, -1.5, 2.0])), combine=int(rng.integers(0, 4)))
-    if lab:
-        kw["cst"] = bu.CS_LAB
+    kw["cst"] = cst
+    scene = cst == bu.CS_RGB_SCENE
     mask_mode, uses_form, r = bu.MASK_ENABLED, False, rng.random()
     if r < 0.3:
         mask_mode, kw["drawn"], uses_form = mask_mode | bu.MASK_SHAPE, 1, True
@@ -144,9 +173,9 @@ def random_parameter_block(rng):
         channels, blendif = {}, 0
         for c in rng.choice(allowed, size=rng.integers(1, 4), replace=False):
             v = np.sort(rng.random(4)).astype(float)
-            if not lab and c in (8, 12):
+            if scene and c in (8, 12):
                 v = v * 0.02          # Jz of scene-referred pixels around 1 is about 0.01
-            if not lab and c in (9, 13):
+            if scene and c in (9, 13):
                 v = v * 0.01
             if rng.random() < 0.2:
                 v[0] = v[1] = 0.0     # open at the bottom
@@ -163,15 +192,16 @@ def random_parameter_block(rng):
     if rng.random() < 0.15:
         kw["mask_display"] = 1
     kw["mask_mode"] = mask_mode
-    return lab, kw, uses_form
+    return cst, kw, uses_form
 
 
 @need_ref
 def test_random_parameter_blocks_reference_oracle_and_kernel_agree():
+    """the three colour spaces"""
     rng = np.random.default_rng(123)
-    for trial in range(120):
-        lab, kw, uses_form = random_parameter_block(rng)
-        a, b, form = (bu.frames_lab if lab else bu.frames)(64, 40, int(rng.integers(1000)))
+    for trial in range(180):
+        cst, kw, uses_form = random_parameter_block(rng)
+        a, b, form = bu.frames_of(cst)(64, 40, int(rng.integers(1000)))
         if rng.random() < 0.2:
             a[5, 5, :3], b[6, 6, 1] = np.nan, np.inf
         p, f = bu.params(**kw), (form if uses_form else None)

@@ -80,7 +80,7 @@ def test_blend_inside_roi_in_and_what_is_refused(built):
     got = cuda(ab, a, b, p, form, 7, 5)
     assert got[0] == 0 and same_bits(got[1], want[1]).all() and same_bits(got[2], want[2]).all()
     a, b, form = bu.frames(64, 48, 4)
-    for kw in (dict(feathering_radius=5.0), dict(blur_radius=2.0), dict(details=0.5), dict(blend_cst=3), dict(profile_nonlinear=1)):
+    for kw in (dict(feathering_radius=5.0), dict(blur_radius=2.0), dict(details=0.5), dict(blend_cst=1), dict(profile_nonlinear=1)):
         rc, out, _ = cuda(ab, a, b, bu.params(**kw))
         assert rc == ab.B200_ERR_UNSUPPORTED and np.array_equal(out, b), kw
 
@@ -96,6 +96,18 @@ def test_lab_blend_bit_exact(built, cfg):
     if not bu.lab_on_device(cfg):
         assert rc == built.B200_ERR_UNSUPPORTED and np.array_equal(out, b)
         return
+    rc_o, out_o, mask_o = bu.oracle(a, b, p, form if uses_form else None)
+    assert rc == 0 and rc_o == 0
+    assert same_bits(out, out_o).all() and same_bits(mask, mask_o).all()
+
+
+@pytest.mark.parametrize("cfg", bu.DISPLAY_CONFIGS, ids=[c[0] for c in bu.DISPLAY_CONFIGS])
+def test_display_blend_bit_exact(built, cfg):
+    """the display-referred RGB space (develop/blends/blendif_rgb_hsl.c): its 27 operators, the H / S / L channels of the parametric mask"""
+    name, kw, uses_form = cfg
+    a, b, form = bu.frames_display(301, 177, 3)
+    p = bu.params(**kw)
+    rc, out, mask = cuda(built, a, b, p, form if uses_form else None)
     rc_o, out_o, mask_o = bu.oracle(a, b, p, form if uses_form else None)
     assert rc == 0 and rc_o == 0
     assert same_bits(out, out_o).all() and same_bits(mask, mask_o).all()
