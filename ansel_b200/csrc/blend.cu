@@ -1,4 +1,4 @@
-// Blending of a module's output over its input (mask + blend operator): scene-referred RGB, display-referred RGB and Lab, for B200 / sm_100a.
+// Blending of a module's output over its input (mask + blend operator): scene-referred RGB, display-referred RGB, Lab and raw, for B200 / sm_100a.
 //
 // What the reference computes: develop/blend.c dt_develop_blend_process :657-860 with blend_cst == DEVELOP_BLEND_CS_RGB_SCENE,
 // DEVELOP_BLEND_CS_RGB_DISPLAY (develop/blends/blendif_rgb_hsl.c: the same masks with H, S, L for Jz, Cz, hz, its 27 operators) or
@@ -16,7 +16,8 @@
 // 52 B/px algorithmic.  What the host decides once per call (which of the reference's branches a parameter block takes, the
 // slopes of the parametric channels, exp2f / expf of the parameters) arrives in the plan; what depends on the pixel is evaluated
 // here.  Not built (B200_ERR_UNSUPPORTED, the caller falls back to the reference's own path): feathering (guided filter), Gaussian
-// blur and detail refinement of the mask; the GUI's channel display; the raw colour space.  The Jz, Cz, hz channels of
+// blur and detail refinement of the mask; the GUI's channel display.  The raw space (develop/blends/blendif_raw.c, one float per site, no
+// parametric channels, 16 operators) has a kernel of its own, blend_raw_kernel.  The Jz, Cz, hz channels of
 // the RGB space, the chroma and hue channels and the four LCh operators of the Lab space go through glibc's powf / atan2f / hypotf / cosf /
 // sinf as restated in flt32_math.cuh.
 #ifndef B200_KERNELS_ON_CPU // tests/emul compiles the kernel of this file with g++ to check it against the oracle without a GPU
@@ -34,7 +35,7 @@ enum
   MASK_ENABLED = 1, MASK_SHAPE = 2, MASK_PARAMETRIC = 4, MASK_RASTER = 8, // dt_develop_mask_mode_t, blend.h:110-118
   COMBINE_INV = 1, COMBINE_INCL = 2,                                      // dt_develop_mask_combine_mode_t :120-131
   BLENDIF_SIZE = 16, BLENDIF_ITEMS = 6, BLENDIF_RGB_MASK = 0x77FF, BLENDIF_LAB_MASK = 0x3377, // :188-191, :329
-  CS_LAB = 2, CS_RGB_DISPLAY = 3, CS_RGB_SCENE = 4                         // :52-59
+  CS_RAW = 1, CS_LAB = 2, CS_RGB_DISPLAY = 3, CS_RGB_SCENE = 4             // :52-59
 };
 constexpr unsigned BLEND_REVERSE = 0x80000000u; // blend.h:106
 
@@ -47,6 +48,7 @@ struct blend_plan_t
   int iw, ow, oh, xoffs, yoffs;
   int lab;       // the Lab space (develop/blends/blendif_lab.c) instead of scene-referred RGB
   int display;   // the display-referred RGB space (develop/blends/blendif_rgb_hsl.c)
+  int raw;       // the raw space (develop/blends/blendif_raw.c): `in` and `out` hold one float per site
   int kind;      // 0: mask = opacity; 1: mask = form * opacity (a raster mask alone); 2: seed, then the parametric stage
   int seed_form; // kind 2: the seed is the form mask, else `fill`
   float fill, opacity;
@@ -744,6 +746,49 @@ __device__ __forceinline__ void bl_operator_lab(unsigned mode, const float a[4],
   out[3] = lo;
 }
 
+// ---- raw, blendif_raw.c:64-352: one sample per site; the operators of the display-referred space that work channel by channel, anything else
+// is the unbounded normal blend ----
+__device__ __forceinline__ float bl_operator_raw(unsigned mode, float a, float b, float lo)
+{
+  const float lo2 = lo * lo, na = 1.0f - lo, na2 = 1.0f - lo2;
+  const float la = bl_clamp01(a), lb = bl_clamp01(b);
+  switch(mode & 0xFFu)
+  {
+    case 0x02: return bl_clamp01(a * na + fmaxf(a, b) * lo);
+    case 0x03: return bl_clamp01(a * na + fminf(a, b) * lo);
+    case 0x04: return bl_clamp01(a * na + (a * b) * lo);
+    case 0x05: return bl_clamp01(a * na + (a + b) / 2.0f * lo);
+    case 0x06: return bl_clamp01(a * na + (a + b) * lo);
+    case 0x07: return bl_clamp01(a * na + ((b + a) - 1.0f) * lo);
+    case 0x08:
+    case 0x17: return bl_clamp01(a * na + fabsf(a - b) * lo);
+    case 0x09: return bl_clamp01(la * na + (1.0f - (1.0f - la) * (1.0f - lb)) * lo);
+    case 0x0A: return bl_clamp01(la * na2 + (la > 0.5f ? 1.0f - (1.0f - 2.0f * (la - 0.5f)) * (1.0f - lb) : 2.0f * la * lb) * lo2);
+    case 0x0B: return bl_clamp01(la * na2 + (lb > 0.5f ? 1.0f - (1.0f - la) * (1.0f - (lb - 0.5f)) : la * (lb + 0.5f)) * lo2);
+    case 0x0C: return bl_clamp01(la * na2 + (lb > 0.5f ? 1.0f - (1.0f - 2.0f * (la - 0.5f)) * (1.0f - lb) : 2.0f * la * lb) * lo2);
+    case 0x0D:
+      return bl_clamp01(la * na2 + (lb > 0.5f ? (lb >= 1.0f ? 1.0f : la / (2.0f * (1.0f - lb))) : (lb <= 0.0f ? 0.0f : 1.0f - (1.0f - la) / (2.0f * lb))) * lo2);
+    case 0x0E: return bl_clamp01(la * na2 + (la + 2.0f * lb - 1.0f) * lo2);
+    case 0x0F: return bl_clamp01(la * na2 + (lb > 0.5f ? fmaxf(la, 2.0f * (lb - 0.5f)) : fminf(la, 2.0f * lb)) * lo2);
+    case 0x19: return bl_clamp01(a * na + b * lo);
+    default: return a * na + b * lo;
+  }
+}
+// the raw space: 4 B of input, 4 B of output and 4 B of form mask in, 4 B out (+ 4 B of mask) per site
+__global__ void __launch_bounds__(256) blend_raw_kernel(const __grid_constant__ blend_plan_t pl)
+{
+  const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+  if(x >= pl.ow) return;
+  const size_t o = (size_t)y * pl.ow + x;
+  const float *in = (const float *)pl.in;
+  float *out = (float *)pl.out;
+  const float a = __ldg(in + (size_t)(y + pl.yoffs) * pl.iw + pl.xoffs + x), b = out[o];
+  const float none[4] = { 0.f, 0.f, 0.f, 0.f };
+  const float m = bl_mask(pl, none, none, pl.form ? __ldg(pl.form + o) : 0.0f);
+  out[o] = pl.reverse ? bl_operator_raw(pl.mode, b, a, m) : bl_operator_raw(pl.mode, a, b, m);
+  if(pl.mask_out) pl.mask_out[o] = m;
+}
+
 __global__ void __launch_bounds__(256) blend_kernel(const __grid_constant__ blend_plan_t pl)
 {
   const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
@@ -798,9 +843,9 @@ int bl_plan(blend_plan_t &pl, const b200_blend_params_t *d, bool have_form)
 {
   memset(&pl, 0, sizeof(pl));
   if(!(d->mask_mode & MASK_ENABLED)) return 1; // :673
-  const bool lab = d->blend_cst == CS_LAB, display = d->blend_cst == CS_RGB_DISPLAY;
-  if(!lab && !display && d->blend_cst != CS_RGB_SCENE) return B200_ERR_UNSUPPORTED;
-  if(!lab && d->profile_nonlinear) return B200_ERR_UNSUPPORTED;
+  const bool lab = d->blend_cst == CS_LAB, display = d->blend_cst == CS_RGB_DISPLAY, raw = d->blend_cst == CS_RAW;
+  if(!lab && !display && !raw && d->blend_cst != CS_RGB_SCENE) return B200_ERR_UNSUPPORTED;
+  if(!lab && !raw && d->profile_nonlinear) return B200_ERR_UNSUPPORTED;
   if(d->feathering_radius > 0.1f || d->blur_radius > 0.1f || d->details != 0.0f) return B200_ERR_UNSUPPORTED;
   { // dt_develop_blendif_init_masking_profile(), develop/blend.c:322-353: the profile's matrix_in taken to D65 by Bradford's matrix
     const float M[3][3] = { { 0.9555766f, -0.0230393f, 0.0631636f }, { -0.0282895f, 1.0099416f, 0.0210077f }, { 0.0122982f, -0.0204830f, 1.3299098f } };
@@ -816,6 +861,7 @@ int bl_plan(blend_plan_t &pl, const b200_blend_params_t *d, bool have_form)
   const unsigned channel_mask = lab ? (unsigned)BLENDIF_LAB_MASK : (unsigned)BLENDIF_RGB_MASK;
   pl.lab = lab;
   pl.display = display;
+  pl.raw = raw;
   bool parametric = false; // dt_develop_blend_get_mask_usage(), :290-312
   if(d->mask_mode & MASK_PARAMETRIC)
     for(unsigned ch = 0; ch < BLENDIF_SIZE; ch++)
@@ -840,8 +886,8 @@ int bl_plan(blend_plan_t &pl, const b200_blend_params_t *d, bool have_form)
     pl.inversed = (d->mask_combine & COMBINE_INV) != 0;
     pl.blendif = d->blendif ^ (pl.inclusive ? channel_mask << 16 : 0u);
     const unsigned canceling = (pl.blendif >> 16) & ~pl.blendif & channel_mask;
-    if(!(d->mask_mode & MASK_PARAMETRIC) || (!canceling && !any_active))
-      pl.pm = 0;
+    if(raw || !(d->mask_mode & MASK_PARAMETRIC) || (!canceling && !any_active))
+      pl.pm = 0; // the raw space has no channels: opacity and inversion only, blendif_raw.c:36-61
     else if(canceling || !any_active)
     {
       pl.pm = 1;
@@ -901,7 +947,10 @@ extern "C" int b200_blend_process_dev(const b200_piece_t *piece, const b200_blen
   pl.xoffs = piece->roi_out.x - piece->roi_in.x;
   pl.yoffs = piece->roi_out.y - piece->roi_in.y;
   const dim3 grid((unsigned)((pl.ow + 255) / 256), (unsigned)pl.oh);
-  blend_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pl);
+  if(pl.raw)
+    blend_raw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pl);
+  else
+    blend_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pl);
   B200_CUDA_TRY(cudaGetLastError());
   return B200_OK;
 }
@@ -911,14 +960,15 @@ extern "C" int b200_blend_process_host(const b200_piece_t *piece, const b200_ble
   int rc = blend_check(piece, bp, in, out);
   if(rc) return rc;
   if((rc = bind_device(piece->devid))) return rc;
-  const size_t ibytes = (size_t)piece->roi_in.width * piece->roi_in.height * 16, opx = (size_t)piece->roi_out.width * piece->roi_out.height;
+  const size_t bpp = bp->blend_cst == CS_RAW ? 4 : 16; // one float per site in the raw space
+  const size_t ibytes = (size_t)piece->roi_in.width * piece->roi_in.height * bpp, opx = (size_t)piece->roi_out.width * piece->roi_out.height;
   void *d_in = nullptr, *d_out = nullptr, *d_form = nullptr, *d_mask = nullptr;
   cudaStream_t s;
   if((rc = host_stream(&s))) return rc;
   if((rc = scratch(SLOT_IN, ibytes, &d_in))) return rc;
-  if((rc = scratch(SLOT_OUT, opx * 16, &d_out))) return rc;
+  if((rc = scratch(SLOT_OUT, opx * bpp, &d_out))) return rc;
   if((rc = copy_h2d(d_in, in, ibytes, s))) return rc;
-  if((rc = copy_h2d(d_out, out, opx * 16, s))) return rc;
+  if((rc = copy_h2d(d_out, out, opx * bpp, s))) return rc;
   if(form_mask)
   {
     if((rc = scratch(SLOT_TMP0, opx * 4, &d_form))) return rc;
@@ -926,7 +976,7 @@ extern "C" int b200_blend_process_host(const b200_piece_t *piece, const b200_ble
   }
   if(mask && (rc = scratch(SLOT_TMP1, opx * 4, &d_mask))) return rc;
   if((rc = b200_blend_process_dev(piece, bp, d_in, d_out, (const float *)d_form, (float *)d_mask, (void *)s))) return rc;
-  if((rc = copy_d2h(out, d_out, opx * 16, s))) return rc;
+  if((rc = copy_d2h(out, d_out, opx * bpp, s))) return rc;
   if(mask && (bp->mask_mode & MASK_ENABLED) && (rc = copy_d2h(mask, d_mask, opx * 4, s))) return rc;
   B200_CUDA_TRY(cudaStreamSynchronize(s));
   return B200_OK;

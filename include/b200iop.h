@@ -755,7 +755,8 @@ int b200_flt32_eval_dev(int fn, const float *d_x, const float *d_y, float *d_out
 typedef struct b200_blend_params_t
 {
   uint32_t mask_mode;        /* dt_develop_mask_mode_t: 1 enabled, 2 drawn mask, 4 parametric mask, 8 raster mask */
-  int32_t blend_cst;         /* dt_develop_blend_colorspace_t: 2 = DEVELOP_BLEND_CS_LAB, 3 = DEVELOP_BLEND_CS_RGB_DISPLAY and 4 = DEVELOP_BLEND_CS_RGB_SCENE are built */
+  int32_t blend_cst;         /* dt_develop_blend_colorspace_t: 1 = DEVELOP_BLEND_CS_RAW (buffers of one float per site), 2 = DEVELOP_BLEND_CS_LAB,
+                                3 = DEVELOP_BLEND_CS_RGB_DISPLAY, 4 = DEVELOP_BLEND_CS_RGB_SCENE */
   uint32_t blend_mode;       /* dt_develop_blend_mode_t, | 0x80000000 = DEVELOP_BLEND_REVERSE */
   float blend_parameter;     /* exposure-like parameter of the operator, in EV */
   float opacity;             /* 0 .. 100 */
@@ -777,13 +778,14 @@ typedef struct b200_blend_params_t
                                       `blendif` are set in the RGB space */
 } b200_blend_params_t;
 /* in: the module's input (roi_in, RGBA float), out: the module's output (roi_out, inside roi_in), blended in place with the mask in its
- * alpha lane; form_mask: the raster / drawn mask of roi_out the host rasterised, or NULL; mask: receives the final mask (what the reference
+ * alpha lane (no alpha lane in the raw space); form_mask: the raster / drawn mask of roi_out the host rasterised, or NULL; mask: receives the final mask (what the reference
  * publishes as the module's raster mask, :892-950), or NULL.  Built: the scene-referred RGB space (develop/blends/blendif_rgb_jzczhz.c) with
  * uniform, raster, drawn and parametric (gray, red, green, blue, Jz, Cz, hz of input and output) masks, their exclusive / inclusive / inverted
  * combinations, the mask tone curve and the sixteen blend operators; the Lab space (develop/blends/blendif_lab.c, what local contrast and the
  * other Lab modules blend in) with the same masks on the L, a, b, chroma and hue channels and its twenty-six operators; the display-referred
  * RGB space (develop/blends/blendif_rgb_hsl.c) with the gray, red, green, blue, H, S, L channels and its twenty-seven operators.
- * B200_ERR_UNSUPPORTED (fall back to dt_develop_blend_process): feathering, blur and detail refinement of the mask; the raw space.  mask_mode without the enabled bit: B200_OK, nothing touched. */
+ * The raw space (develop/blends/blendif_raw.c): `in` and `out` hold one float per site, uniform / raster / drawn masks, sixteen operators.
+ * B200_ERR_UNSUPPORTED (fall back to dt_develop_blend_process): feathering, blur and detail refinement of the mask.  mask_mode without the enabled bit: B200_OK, nothing touched. */
 int b200_blend_process_host(const b200_piece_t *piece, const b200_blend_params_t *bp, const void *in, void *out, const float *form_mask, float *mask);
 /* dt_develop_blend_process_cl() slot, develop/blend.c:1113-1604: device pointers */
 int b200_blend_process_dev(const b200_piece_t *piece, const b200_blend_params_t *bp, const void *d_in, void *d_out, const float *d_form_mask,

@@ -10,7 +10,9 @@
  * :1070-1162, dt_develop_blendif_lab_blend :1302-1418), pinned against oracle/_ref: ref_blend_lab.c.  For
  * DEVELOP_BLEND_CS_RGB_DISPLAY: develop/blends/blendif_rgb_hsl.c (the gray / R / G / B / H / S / L channels :89-216, make_mask :218-345, the 27
  * operators :347-913, _choose_blend_func :915-1007, dt_develop_blendif_rgb_hsl_blend :1204-1288) with dt_RGB_2_HSL, dt_RGB_2_HSV and back
- * (common/colorspaces_inline_conversions.h:420-565), pinned against oracle/_ref: ref_blend_rgb_hsl.c.
+ * (common/colorspaces_inline_conversions.h:420-565), pinned against oracle/_ref: ref_blend_rgb_hsl.c.  For DEVELOP_BLEND_CS_RAW (buffers of
+ * one float per site): develop/blends/blendif_raw.c (make_mask :36-61, the 16 operators :64-287, _choose_blend_func :290-352, the blend
+ * :355-409), pinned against oracle/_ref: ref_blend_raw.c.
  *
  * Everything here is a function of one pixel of the module's input, the same pixel of its output and the same pixel of the form
  * mask (the raster / drawn mask the host rasterised): the reference's passes over whole buffers are folded into one evaluation per
@@ -29,7 +31,7 @@ enum
   MASK_ENABLED = 1, MASK_SHAPE = 2, MASK_PARAMETRIC = 4, MASK_RASTER = 8, /* dt_develop_mask_mode_t, blend.h:110-118 */
   COMBINE_INV = 1, COMBINE_INCL = 2,                                      /* dt_develop_mask_combine_mode_t :120-131 */
   BLENDIF_SIZE = 16, BLENDIF_ITEMS = 6, BLENDIF_RGB_MASK = 0x77FF,        /* :188-191, :329 */
-  BLENDIF_LAB_MASK = 0x3377, CS_LAB = 2, CS_RGB_DISPLAY = 3, CS_RGB_SCENE = 4, /* :52-59 */
+  BLENDIF_LAB_MASK = 0x3377, CS_RAW = 1, CS_LAB = 2, CS_RGB_DISPLAY = 3, CS_RGB_SCENE = 4, /* :52-59 */
   DISPLAY_MASK = 1                                                         /* develop.h:123 */
 };
 #define BLEND_REVERSE 0x80000000u /* blend.h:106 */
@@ -707,7 +709,35 @@ static void hsl_blend_pixel(unsigned mode, const float *a, const float *b, float
   out[3] = lo;
 }
 
-/* dt_develop_blend_process() for blend_cst == DEVELOP_BLEND_CS_RGB_SCENE, DEVELOP_BLEND_CS_RGB_DISPLAY and DEVELOP_BLEND_CS_LAB.  in: the module's input (iw x ih RGBA), out: its output
+/* ---- raw, blendif_raw.c:64-352: one sample per site; the operators of the display-referred space that work channel by channel, anything
+ * else is the unbounded normal blend ---- */
+static float raw_blend_value(unsigned mode, float a, float b, float lo)
+{
+  const float lo2 = lo * lo, na = 1.0f - lo, na2 = 1.0f - lo2;
+  const float la = clamp01(a), lb = clamp01(b);
+  switch(mode & 0xFFu)
+  {
+    case 0x02: return clamp01(a * na + fmaxf(a, b) * lo);
+    case 0x03: return clamp01(a * na + fminf(a, b) * lo);
+    case 0x04: return clamp01(a * na + (a * b) * lo);
+    case 0x05: return clamp01(a * na + (a + b) / 2.0f * lo);
+    case 0x06: return clamp01(a * na + (a + b) * lo);
+    case 0x07: return clamp01(a * na + ((b + a) - 1.0f) * lo);
+    case 0x08:
+    case 0x17: return clamp01(a * na + fabsf(a - b) * lo);
+    case 0x09: return clamp01(la * na + (1.0f - (1.0f - la) * (1.0f - lb)) * lo);
+    case 0x0A: return clamp01(la * na2 + (la > 0.5f ? 1.0f - (1.0f - 2.0f * (la - 0.5f)) * (1.0f - lb) : 2.0f * la * lb) * lo2);
+    case 0x0B: return clamp01(la * na2 + (lb > 0.5f ? 1.0f - (1.0f - la) * (1.0f - (lb - 0.5f)) : la * (lb + 0.5f)) * lo2);
+    case 0x0C: return clamp01(la * na2 + (lb > 0.5f ? 1.0f - (1.0f - 2.0f * (la - 0.5f)) * (1.0f - lb) : 2.0f * la * lb) * lo2);
+    case 0x0D: return clamp01(la * na2 + (lb > 0.5f ? (lb >= 1.0f ? 1.0f : la / (2.0f * (1.0f - lb))) : (lb <= 0.0f ? 0.0f : 1.0f - (1.0f - la) / (2.0f * lb))) * lo2);
+    case 0x0E: return clamp01(la * na2 + (la + 2.0f * lb - 1.0f) * lo2);
+    case 0x0F: return clamp01(la * na2 + (lb > 0.5f ? fmaxf(la, 2.0f * (lb - 0.5f)) : fminf(la, 2.0f * lb)) * lo2);
+    case 0x19: return clamp01(a * na + b * lo);
+    default: return a * na + b * lo;
+  }
+}
+
+/* dt_develop_blend_process() for the four colour spaces (in the raw one the buffers hold one float per site instead of four).  in: the module's input (iw x ih RGBA), out: its output
  * (ow x oh RGBA, roi_out at (xoffs, yoffs) inside roi_in), blended in place; form: the form mask of roi_out or NULL; mask_out: the final
  * mask or NULL.  0 = done (also when blending is off), -1 = not restated. */
 int orc_blend_process(const float *in, float *out, int iw, int ih, int ow, int oh, int xoffs, int yoffs, const orc_blend_params_t *d,
@@ -715,8 +745,8 @@ int orc_blend_process(const float *in, float *out, int iw, int ih, int ow, int o
 {
   (void)ih;
   if(!(d->mask_mode & MASK_ENABLED)) return 0; /* :673 */
-  const int lab = d->blend_cst == CS_LAB, display = d->blend_cst == CS_RGB_DISPLAY;
-  if(!lab && ((d->blend_cst != CS_RGB_SCENE && !display) || d->profile_nonlinear)) return -1;
+  const int lab = d->blend_cst == CS_LAB, display = d->blend_cst == CS_RGB_DISPLAY, raw = d->blend_cst == CS_RAW;
+  if(!lab && !raw && ((d->blend_cst != CS_RGB_SCENE && !display) || d->profile_nonlinear)) return -1;
   if(d->feathering_radius > 0.1f || d->blur_radius > 0.1f || d->details != 0.0f) return -1;
   const unsigned channel_mask = lab ? (unsigned)BLENDIF_LAB_MASK : (unsigned)BLENDIF_RGB_MASK;
   orc_fp_fast_mode(); /* the pipe's threads run with FTZ|DAZ (darktable.c:877, common/dtpthread.c:54) */
@@ -747,8 +777,8 @@ int orc_blend_process(const float *in, float *out, int iw, int ih, int ow, int o
     pl.inversed = (d->mask_combine & COMBINE_INV) != 0;
     pl.blendif = d->blendif ^ (pl.inclusive ? channel_mask << 16 : 0u);
     const unsigned canceling = (pl.blendif >> 16) & ~pl.blendif & channel_mask;
-    if(!(d->mask_mode & MASK_PARAMETRIC) || (!canceling && !any_active))
-      pl.pm = 0;
+    if(raw || !(d->mask_mode & MASK_PARAMETRIC) || (!canceling && !any_active))
+      pl.pm = 0; /* the raw space has no channels: opacity and inversion only, blendif_raw.c:36-61 */
     else if(canceling || !any_active)
     {
       pl.pm = 1;
@@ -766,6 +796,20 @@ int orc_blend_process(const float *in, float *out, int iw, int ih, int ow, int o
   }
   const float p = exp2f(d->blend_parameter);
   const int reverse = (d->blend_mode & BLEND_REVERSE) == BLEND_REVERSE;
+  if(raw)
+  {
+    for(int y = 0; y < oh; y++)
+      for(int x = 0; x < ow; x++)
+      {
+        const float av = in[(size_t)(y + yoffs) * iw + xoffs + x];
+        float *bv = out + (size_t)y * ow + x;
+        const float none[4] = { 0.f, 0.f, 0.f, 0.f };
+        const float m = plan_mask(&pl, d, none, none, form ? form[(size_t)y * ow + x] : 0.0f);
+        *bv = reverse ? raw_blend_value(d->blend_mode, *bv, av, m) : raw_blend_value(d->blend_mode, av, *bv, m);
+        if(mask_out) mask_out[(size_t)y * ow + x] = m;
+      }
+    return 0;
+  }
   for(int y = 0; y < oh; y++)
     for(int x = 0; x < ow; x++)
     {

@@ -7,7 +7,7 @@ import util
 
 MASK_ENABLED, MASK_SHAPE, MASK_PARAMETRIC, MASK_RASTER = 1, 2, 4, 8
 COMBINE_INV, COMBINE_INCL = 1, 2
-CS_LAB, CS_RGB_DISPLAY, CS_RGB_SCENE = 2, 3, 4
+CS_RAW, CS_LAB, CS_RGB_DISPLAY, CS_RGB_SCENE = 1, 2, 3, 4
 REVERSE = 0x80000000
 MODES = {"normal": 0x18, "multiply": 0x04, "average": 0x05, "add": 0x06, "subtract": 0x07, "subtract_inverse": 0x25, "difference": 0x17,
          "divide": 0x26, "divide_inverse": 0x27, "geometric_mean": 0x28, "harmonic_mean": 0x29, "luminance": 0x10, "chromaticity": 0x11,
@@ -22,6 +22,9 @@ DISPLAY_MODES = {"normal": 0x18, "bounded": 0x19, "lighten": 0x02, "darken": 0x0
                  "difference": 0x17, "screen": 0x09, "overlay": 0x0A, "softlight": 0x0B, "hardlight": 0x0C, "vividlight": 0x0D, "linearlight": 0x0E,
                  "pinlight": 0x0F, "lightness": 0x10, "chromaticity": 0x11, "hue": 0x12, "color": 0x13, "coloradjust": 0x16, "hsv_value": 0x1C,
                  "hsv_color": 0x1D, "rgb_r": 0x21, "rgb_g": 0x22, "rgb_b": 0x23}
+# the operators of the raw space (develop/blends/blendif_raw.c _choose_blend_func :290-352); any other mode is the unbounded normal blend there
+RAW_MODES = {k: v for k, v in DISPLAY_MODES.items() if v <= 0x0F or v in (0x17, 0x18, 0x19)}
+RAW_MODES["lightness_is_normal_here"] = 0x10
 LAB_LCH_MODES = ("chromaticity", "hue", "color", "coloradjust")      # through atan2f / hypotf / cosf / sinf (ansel_b200/csrc/flt32_math.cuh)
 # linear Rec2020 -> XYZ (D50), the work profile's matrix_in, row by row; its middle row is what the gray channel of the parametric mask weighs with
 MATRIX_IN = (0.6734241, 0.1656411, 0.1251286, 0.2790177, 0.6753402, 0.0456377, -0.0019300, 0.0299784, 0.7973330)
@@ -43,7 +46,7 @@ def params(mode="normal", opacity=65.0, mask_mode=MASK_ENABLED, reverse=False, b
     p = BlendParams()
     cst = extra.pop("cst", CS_RGB_SCENE)
     p.mask_mode, p.blend_cst = mask_mode, cst
-    p.blend_mode = {CS_LAB: LAB_MODES, CS_RGB_DISPLAY: DISPLAY_MODES}.get(cst, MODES)[mode] | (REVERSE if reverse else 0)
+    p.blend_mode = {CS_LAB: LAB_MODES, CS_RGB_DISPLAY: DISPLAY_MODES, CS_RAW: RAW_MODES}.get(cst, MODES)[mode] | (REVERSE if reverse else 0)
     p.blend_parameter, p.opacity, p.mask_combine, p.blendif = blend_parameter, opacity, combine, blendif
     p.contrast, p.brightness = contrast, brightness
     for i in range(16):
@@ -123,7 +126,7 @@ def oracle(a, b, p, form=None, xoffs=0, yoffs=0):
 
 def ref(a, b, p, form=None, xoffs=0, yoffs=0, kind="strict"):
     lib = util.ref(kind)
-    fn = {CS_LAB: "ref_blend_lab_process", CS_RGB_DISPLAY: "ref_blend_rgb_hsl_process"}.get(p.blend_cst, "ref_blend_process")
+    fn = {CS_LAB: "ref_blend_lab_process", CS_RGB_DISPLAY: "ref_blend_rgb_hsl_process", CS_RAW: "ref_blend_raw_process"}.get(p.blend_cst, "ref_blend_process")
     return None if lib is None else _run(lib, fn, a, b, p, form, xoffs, yoffs)
 
 
@@ -210,16 +213,33 @@ def frames_display(w=160, h=120, seed=1, xoffs=0, yoffs=0):
     return a, b, form
 
 
+# raw: every operator, then the mask sources; the parametric mask has no channels here, a block that asks for one only takes the seeded path
+_R = dict(cst=CS_RAW)
+RAW_CONFIGS = [("raw_" + m, dict(_R, mode=m), False) for m in RAW_MODES] + [
+    ("raw_overlay_reverse", dict(_R, mode="overlay", reverse=True, opacity=40.0), False),
+    ("raw_multiply_drawn_inverted", dict(_R, mode="multiply", mask_mode=MASK_ENABLED | MASK_SHAPE, drawn=1, combine=COMBINE_INV), True),
+    ("raw_vividlight_raster", dict(_R, mode="vividlight", mask_mode=MASK_ENABLED | MASK_RASTER, raster=1, opacity=90.0), True),
+    ("raw_parametric_asked_for", dict(_R, mask_mode=_PAR, channels={0: (0.1, 0.3, 0.6, 0.8)}, combine=COMBINE_INCL), False),
+    ("raw_drawn_tone_curve", dict(_R, mode="softlight", mask_mode=MASK_ENABLED | MASK_SHAPE, drawn=1, contrast=0.4, brightness=0.2), True),
+]
+
+
+def frames_raw(w=160, h=120, seed=1, xoffs=0, yoffs=0):
+    """a mosaic-like pair: one float per site, most values in 0 .. 1, some beyond on either side"""
+    a, b, form = frames_display(w, h, seed, xoffs, yoffs)
+    return np.ascontiguousarray(a[..., 1]), np.ascontiguousarray(b[..., 1]), form
+
+
 def golden_configs():
     """the configurations of tests/golden/blend.npz: every third one of each space, and everything that goes through powf / atan2f / hypotf"""
     rgb = [c for k, c in enumerate(CONFIGS) if c[0] != "disabled" and (k % 3 == 0 or any(ch >= 8 for ch in c[1].get("channels", {})))]
     lab = [c for k, c in enumerate(LAB_CONFIGS) if k % 3 == 0 or c[1].get("mode") in LAB_LCH_MODES or any(ch >= 8 for ch in c[1].get("channels", {}))]
     display = [c for k, c in enumerate(DISPLAY_CONFIGS) if k % 3 == 0 or c[1].get("mode") in ("hsv_color", "hue", "color") or any(ch >= 8 for ch in c[1].get("channels", {}))]
-    return rgb + lab + display
+    return rgb + lab + display + RAW_CONFIGS[::3]
 
 
 def frames_of(cst):
-    return {CS_LAB: frames_lab, CS_RGB_DISPLAY: frames_display}.get(cst, frames)
+    return {CS_LAB: frames_lab, CS_RGB_DISPLAY: frames_display, CS_RAW: frames_raw}.get(cst, frames)
 
 
 def golden_frames(kw):

@@ -22,6 +22,9 @@ extern "C" int emul_blend_process(const float *in, float *out, int iw, int ih, i
   pl.oh = oh;
   pl.xoffs = xoffs;
   pl.yoffs = yoffs;
-  emulate(dim3((unsigned)((ow + 255) / 256), (unsigned)oh), 256, blend_kernel, pl);
+  if(pl.raw)
+    emulate(dim3((unsigned)((ow + 255) / 256), (unsigned)oh), 256, blend_raw_kernel, pl);
+  else
+    emulate(dim3((unsigned)((ow + 255) / 256), (unsigned)oh), 256, blend_kernel, pl);
   return 0;
 }

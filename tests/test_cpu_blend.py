@@ -65,7 +65,7 @@ def test_kernel_with_offsets_and_what_is_refused():
     e, o = bu.emul(a, b, p, form, 7, 5), bu.oracle(a, b, p, form, 7, 5)
     assert same_bits(e[1], o[1]).all() and same_bits(e[2], o[2]).all()
     a, b, form = bu.frames(64, 48, 4)
-    for kw in (dict(feathering_radius=5.0), dict(blur_radius=2.0), dict(details=0.5), dict(blend_cst=1), dict(profile_nonlinear=1)):
+    for kw in (dict(feathering_radius=5.0), dict(blur_radius=2.0), dict(details=0.5), dict(blend_cst=0), dict(profile_nonlinear=1)):
         p = bu.params(**kw)
         assert bu.emul(a, b, p)[0] == -1 and bu.oracle(a, b, p)[0] == -1, kw
 
@@ -152,12 +152,34 @@ def test_display_kernel_equals_oracle(cfg):
     assert rc_e == rc_o == 0 and same_bits(out_e, out_o).all() and same_bits(mask_e, mask_o).all()
 
 
+# ---- the raw space (develop/blends/blendif_raw.c): one float per site ------------------------------------------------------------------------
+@need_ref
+@pytest.mark.parametrize("cfg", bu.RAW_CONFIGS, ids=[c[0] for c in bu.RAW_CONFIGS])
+def test_raw_reference_oracle_and_kernel(cfg):
+    name, kw, uses_form = cfg
+    a, b, form = bu.frames_raw(203, 77, 3)
+    p, f = bu.params(**kw), None
+    if uses_form:
+        f = form
+    r, o, e = bu.ref(a, b, p, f), bu.oracle(a, b, p, f), bu.emul(a, b, p, f)
+    assert r[0] == o[0] == e[0] == 0
+    assert same_bits(o[1], r[1]).all() and same_bits(o[2], r[2]).all() and same_bits(e[1], o[1]).all() and same_bits(e[2], o[2]).all()
+    assert not np.array_equal(r[1], b)
+
+
+def test_raw_kernel_with_roi_out_inside_roi_in():
+    a, b, form = bu.frames_raw(100, 80, 2, xoffs=7, yoffs=5)
+    p = bu.params(cst=bu.CS_RAW, mode="screen", mask_mode=bu.MASK_ENABLED | bu.MASK_SHAPE, drawn=1, opacity=80.0)
+    e, o = bu.emul(a, b, p, form, 7, 5), bu.oracle(a, b, p, form, 7, 5)
+    assert e[0] == o[0] == 0 and same_bits(e[1], o[1]).all() and same_bits(e[2], o[2]).all()
+
+
 def random_parameter_block(rng):
     """a parameter block drawn at random in either colour space: operator, opacity, reverse, mask sources, up to three parametric channels with
     random limits, inversions and boosts, the combination mode, the mask tone curve, an earlier module's mask"""
-    cst = (bu.CS_RGB_SCENE, bu.CS_LAB, bu.CS_RGB_DISPLAY)[rng.integers(3)]
+    cst = (bu.CS_RGB_SCENE, bu.CS_LAB, bu.CS_RGB_DISPLAY, bu.CS_RAW)[rng.integers(4)]
     lab = cst == bu.CS_LAB
-    modes = list({bu.CS_LAB: bu.LAB_MODES, bu.CS_RGB_DISPLAY: bu.DISPLAY_MODES}.get(cst, bu.MODES).keys())
+    modes = list({bu.CS_LAB: bu.LAB_MODES, bu.CS_RGB_DISPLAY: bu.DISPLAY_MODES, bu.CS_RAW: bu.RAW_MODES}.get(cst, bu.MODES).keys())
     kw = dict(mode=modes[rng.integers(len(modes))], opacity=float(rng.choice([0, 35, 70, 100, 140])), reverse=bool(rng.random() < 0.3),
               blend_parameter=float(rng.choice([0, -1.5, 2.0])), combine=int(rng.integers(0, 4)))
     kw["cst"] = cst
@@ -197,13 +219,13 @@ def random_parameter_block(rng):
 
 @need_ref
 def test_random_parameter_blocks_reference_oracle_and_kernel_agree():
-    """the three colour spaces"""
+    """the four colour spaces"""
     rng = np.random.default_rng(123)
-    for trial in range(180):
+    for trial in range(240):
         cst, kw, uses_form = random_parameter_block(rng)
         a, b, form = bu.frames_of(cst)(64, 40, int(rng.integers(1000)))
         if rng.random() < 0.2:
-            a[5, 5, :3], b[6, 6, 1] = np.nan, np.inf
+            a[5, 5, ...], b[6, 6, ...] = np.nan, np.inf
         p, f = bu.params(**kw), (form if uses_form else None)
         r, o, e = bu.ref(a, b, p, f), bu.oracle(a, b, p, f), bu.emul(a, b, p, f)
         assert r[0] == o[0] == e[0] == 0, (trial, kw)

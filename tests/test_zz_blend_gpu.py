@@ -80,7 +80,7 @@ def test_blend_inside_roi_in_and_what_is_refused(built):
     got = cuda(ab, a, b, p, form, 7, 5)
     assert got[0] == 0 and same_bits(got[1], want[1]).all() and same_bits(got[2], want[2]).all()
     a, b, form = bu.frames(64, 48, 4)
-    for kw in (dict(feathering_radius=5.0), dict(blur_radius=2.0), dict(details=0.5), dict(blend_cst=1), dict(profile_nonlinear=1)):
+    for kw in (dict(feathering_radius=5.0), dict(blur_radius=2.0), dict(details=0.5), dict(blend_cst=0), dict(profile_nonlinear=1)):
         rc, out, _ = cuda(ab, a, b, bu.params(**kw))
         assert rc == ab.B200_ERR_UNSUPPORTED and np.array_equal(out, b), kw
 
@@ -111,6 +111,18 @@ def test_display_blend_bit_exact(built, cfg):
     rc_o, out_o, mask_o = bu.oracle(a, b, p, form if uses_form else None)
     assert rc == 0 and rc_o == 0
     assert same_bits(out, out_o).all() and same_bits(mask, mask_o).all()
+
+
+@pytest.mark.parametrize("cfg", bu.RAW_CONFIGS, ids=[c[0] for c in bu.RAW_CONFIGS])
+def test_raw_blend_bit_exact(built, cfg):
+    """the raw space (develop/blends/blendif_raw.c): buffers of one float per site, device and host entry points"""
+    name, kw, uses_form = cfg
+    a, b, form = bu.frames_raw(301, 177, 3)
+    p = bu.params(**kw)
+    rc_o, out_o, mask_o = bu.oracle(a, b, p, form if uses_form else None)
+    for host in (False, True):
+        rc, out, mask = cuda(built, a, b, p, form if uses_form else None, host=host)
+        assert rc == 0 and rc_o == 0 and same_bits(out, out_o).all() and same_bits(mask, mask_o).all(), host
 
 
 def test_lab_blend_on_a_large_frame(built):
