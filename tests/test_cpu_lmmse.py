@@ -67,3 +67,15 @@ def test_what_the_carried_planes_change():
         near_rim = (ys < 20) | (xs < 20) | (ys >= h - 20) | (xs >= w - 20)
         seam = lambda v: np.minimum(np.abs((v - 8) % 112), 112 - np.abs((v - 8) % 112)) <= 20   # noqa: E731
         assert (near_rim | seam(ys) | seam(xs)).all()
+
+
+def test_kernel_stages_on_random_frame_sizes_and_modes():
+    """sizes from 12 px, the four Bayer phases, the five refinement modes, three thread counts and both thread orders"""
+    rng = np.random.default_rng(5)
+    pats = ["RGGB", "BGGR", "GRBG", "GBRG"]
+    for trial in range(8):
+        w, h, mode, pat = int(rng.integers(12, 420)), int(rng.integers(12, 330)), int(rng.integers(0, 5)), pats[rng.integers(4)]
+        m = np.ascontiguousarray(util.frame_natural(w, h, int(rng.integers(50)), filters=util.BAYER[pat]), np.float32)
+        want = lu.oracle(m, util.BAYER[pat], mode, carry=0)
+        got = lu.emul(m, util.BAYER[pat], mode, nthreads=int(rng.choice([32, 96, 128])), ascending=int(rng.integers(2)))
+        assert same_bits(got, want).all(), (trial, w, h, mode, pat)

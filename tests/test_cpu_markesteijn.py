@@ -90,3 +90,15 @@ def test_tile_classes_walk_like_every_tile_on_its_own(geom):
 def test_tile_classes_with_a_permuted_pattern():
     xt = np.roll(np.roll(XTRANS, 2, axis=0), 1, axis=1)
     assert 1 <= mu.emul_classes(1000, 700, 0, 0, xt) <= 20
+
+
+def test_kernel_stages_on_random_frame_sizes_and_origins():
+    """frame sizes, ROI origins (the phase of the 6x6 pattern and of the hexagon walk), one and three passes, both thread orders"""
+    rng = np.random.default_rng(6)
+    for trial in range(5):
+        w, h, x, y = int(rng.integers(40, 400)), int(rng.integers(40, 300)), int(rng.integers(0, 12)), int(rng.integers(0, 12))
+        passes = int(rng.choice([1, 3]))
+        m = np.ascontiguousarray(util.frame_natural(w, h, int(rng.integers(50))), np.float32)
+        want = mu.oracle(m, x, y, passes)
+        got = mu.emul(m, x, y, nthreads=int(rng.choice([64, 96])), ascending=int(rng.integers(2)), passes=passes)
+        assert same_bits(got, want).all(), (trial, w, h, x, y, passes)
